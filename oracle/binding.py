@@ -1,0 +1,153 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for the two CPU checkers.
+
+* ``RefLib``    -> oracle/_ref/libcrfref.so : the unmodified ASR-CRaFT hot path (see oracle/ref_driver.cpp)
+* ``OracleLib`` -> oracle/libcrforacle.so   : our C restatement (oracle/crf_oracle.c)
+
+Both expose the same call shapes so tests can swap one for the other.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+MODEL_TYPES = {"stdframe": 0, "stdseg": 1, "stdseg_no_dur": 2,
+               "stdseg_no_dur_no_transftr": 3, "stdseg_no_dur_no_segtransftr": 4}
+
+
+class Config(C.Structure):
+    """Field order shared by crfref_config (ref_driver.cpp) and crforacle_config (crf_oracle.h)."""
+    _fields_ = [("model_type", C.c_uint32), ("n_labs", C.c_uint32), ("n_base_ftrs", C.c_uint32),
+                ("n_states", C.c_uint32), ("max_dur", C.c_uint32), ("n_actual_labs", C.c_uint32),
+                ("extract_seg_ftrs", C.c_uint32),
+                ("use_state_ftrs", C.c_uint32), ("state_fidx_start", C.c_uint32), ("state_fidx_end", C.c_uint32),
+                ("use_trans_ftrs", C.c_uint32), ("trans_fidx_start", C.c_uint32), ("trans_fidx_end", C.c_uint32),
+                ("use_state_bias", C.c_uint32), ("use_trans_bias", C.c_uint32),
+                ("state_bias_val", C.c_double), ("trans_bias_val", C.c_double)]
+
+
+def window_width(n_base_ftrs, max_dur, extract_seg_ftrs):
+    if max_dur == 1 or not extract_seg_ftrs:
+        return n_base_ftrs
+    return 8 * n_base_ftrs + max_dur
+
+
+def make_config(model_type="stdframe", n_labs=0, n_base_ftrs=0, n_states=1, max_dur=1, n_actual_labs=None,
+                extract_seg_ftrs=0, use_trans_ftrs=0, state_fidx=None, trans_fidx=None,
+                use_state_bias=1, use_trans_bias=1, state_bias_val=1.0, trans_bias_val=1.0):
+    w = window_width(n_base_ftrs, max_dur, extract_seg_ftrs)
+    if n_actual_labs is None:
+        n_actual_labs = n_labs // max_dur if model_type == "stdseg" else n_labs
+    s0, s1 = state_fidx if state_fidx is not None else (0, w - 1)
+    t0, t1 = trans_fidx if trans_fidx is not None else (0, w - 1)
+    return Config(MODEL_TYPES[model_type], n_labs, n_base_ftrs, n_states, max_dur, n_actual_labs,
+                  int(extract_seg_ftrs), 1, s0, s1, int(use_trans_ftrs), t0, t1,
+                  int(use_state_bias), int(use_trans_bias), state_bias_val, trans_bias_val)
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+class _Lib:
+    prefix = ""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self._fn("last_error").restype = C.c_char_p
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self._fn("last_error")().decode())
+
+    def lambda_len(self, cfg):
+        out = C.c_uint32(0)
+        self._check(self._fn("lambda_len")(C.byref(cfg), C.byref(out)))
+        return out.value
+
+    def fwdbwd(self, cfg, lam, off, ftrs, labs, n_threads=1):
+        lam = np.ascontiguousarray(lam, np.float64)
+        off = np.ascontiguousarray(off, np.uint32)
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        labs = np.ascontiguousarray(labs, np.uint32)
+        n = len(off) - 1
+        grad = np.zeros(len(lam), np.float64)
+        numer = np.zeros(n, np.float64)
+        logz = np.zeros(n, np.float64)
+        self._check(self._fn("fwdbwd_mt")(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(n),
+                                          _p(off, C.c_uint32), _p(ftrs, C.c_float), _p(labs, C.c_uint32),
+                                          _p(grad, C.c_double), _p(numer, C.c_double), _p(logz, C.c_double),
+                                          C.c_uint32(n_threads)))
+        return grad, numer, logz
+
+    def viterbi(self, cfg, lam, off, ftrs):
+        """Returns list of (labels, durs, phones) per utterance, path costs, logZ."""
+        lam = np.ascontiguousarray(lam, np.float64)
+        off = np.ascontiguousarray(off, np.uint32)
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        n = len(off) - 1
+        tot = int(off[-1])
+        lab = np.zeros(tot, np.uint32)
+        dur = np.zeros(tot, np.uint32)
+        phn = np.zeros(tot, np.uint32)
+        nseg = np.zeros(n, np.uint32)
+        cost = np.zeros(n, np.float32)
+        logz = np.zeros(n, np.float64)
+        self._check(self._fn("viterbi")(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(n),
+                                        _p(off, C.c_uint32), _p(ftrs, C.c_float), _p(lab, C.c_uint32),
+                                        _p(dur, C.c_uint32), _p(phn, C.c_uint32), _p(nseg, C.c_uint32),
+                                        _p(cost, C.c_float), _p(logz, C.c_double)))
+        segs = []
+        for u in range(n):
+            b, k = int(off[u]), int(nseg[u])
+            segs.append((lab[b:b + k].copy(), dur[b:b + k].copy(), phn[b:b + k].copy()))
+        return segs, cost, logz
+
+    def window_ftrs(self, cfg, ftrs):
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        T = ftrs.shape[0]
+        w = window_width(cfg.n_base_ftrs, cfg.max_dur, cfg.extract_seg_ftrs)
+        out = np.full((T, cfg.max_dur, w), np.nan, np.float32)
+        self._check(self._fn("window_ftrs")(C.byref(cfg), C.c_uint32(T), _p(ftrs, C.c_float), _p(out, C.c_float)))
+        return out
+
+    def window_labs(self, cfg, labs):
+        labs = np.ascontiguousarray(labs, np.uint32)
+        out = np.zeros((len(labs), 4), np.uint32)
+        self._check(self._fn("window_labs")(C.byref(cfg), C.c_uint32(len(labs)), _p(labs, C.c_uint32),
+                                            _p(out, C.c_uint32)))
+        return out
+
+
+class RefLib(_Lib):
+    prefix = "crfref_"
+
+    def __init__(self, path=None):
+        super().__init__(path or os.path.join(HERE, "_ref", "libcrfref.so"))
+
+    def viterbi_old(self, cfg, lam, off, ftrs):
+        lam = np.ascontiguousarray(lam, np.float64)
+        off = np.ascontiguousarray(off, np.uint32)
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        lab = np.zeros(int(off[-1]), np.uint32)
+        self._check(self.lib.crfref_viterbi_old(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)),
+                                                C.c_uint32(len(off) - 1), _p(off, C.c_uint32),
+                                                _p(ftrs, C.c_float), _p(lab, C.c_uint32)))
+        return lab
+
+
+class OracleLib(_Lib):
+    prefix = "crforacle_"
+
+    def __init__(self, path=None):
+        super().__init__(path or os.path.join(HERE, "libcrforacle.so"))
+
+
+def have_ref():
+    return os.path.exists(os.path.join(HERE, "_ref", "libcrfref.so"))
