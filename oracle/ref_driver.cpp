@@ -356,6 +356,11 @@ int crfref_viterbi(const crfref_config* c, const double* lambda, uint32_t lambda
 				if (startf > 0) min_idx = vd.ptrs[end][min_idx];
 				end = startf - 1;
 			}
+			if (min_idx < 0 && tl.empty()) {
+				/* "Could not reach end of utterance" (.cpp:2188-2195): the reference emits one dummy arc */
+				n_seg[u] = 0; path_cost[u] = minw; logZ[u] = zx;
+				continue;
+			}
 			if (tl.size() != labs.size()) throw std::runtime_error("traceback/FST segment count mismatch");
 			uint32_t base = frame_off[u];
 			n_seg[u] = (uint32_t)labs.size();
