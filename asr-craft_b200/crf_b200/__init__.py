@@ -1,0 +1,270 @@
+"""crf_b200 -- thin Python host layer over libcrfgpu.so (the C ABI declared in include/crfgpu.h).
+
+The product path is the CUDA library; this module only marshals numpy / pinned buffers through ctypes.
+Importing it never touches oracle/ and there is no CPU fallback: if libcrfgpu.so is missing, or no CUDA
+device is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libcrfgpu.so")
+
+MODEL_TYPES = {"stdframe": 0, "stdseg": 1, "stdseg_no_dur": 2,
+               "stdseg_no_dur_no_transftr": 3, "stdseg_no_dur_no_segtransftr": 4}
+LAB_BAD = 0xFFFFFFFF
+ERR_NAMES = {1: "ARG", 2: "UNSUPPORTED", 3: "CUDA", 4: "NUMERIC"}
+
+
+class CrfGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"crfgpu error {ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    """crfgpu_config (include/crfgpu.h), mirrors CRF_FeatureMap_config + CRF_Model geometry."""
+    _fields_ = [("model_type", C.c_uint32), ("n_labs", C.c_uint32), ("n_base_ftrs", C.c_uint32),
+                ("n_states", C.c_uint32), ("max_dur", C.c_uint32), ("n_actual_labs", C.c_uint32),
+                ("extract_seg_ftrs", C.c_uint32),
+                ("use_state_ftrs", C.c_uint32), ("state_fidx_start", C.c_uint32), ("state_fidx_end", C.c_uint32),
+                ("use_trans_ftrs", C.c_uint32), ("trans_fidx_start", C.c_uint32), ("trans_fidx_end", C.c_uint32),
+                ("use_state_bias", C.c_uint32), ("use_trans_bias", C.c_uint32),
+                ("state_bias_val", C.c_double), ("trans_bias_val", C.c_double)]
+
+
+def window_width(n_base_ftrs, max_dur, extract_seg_ftrs):
+    if max_dur == 1 or not extract_seg_ftrs:
+        return n_base_ftrs
+    return 8 * n_base_ftrs + max_dur
+
+
+def make_config(model_type="stdframe", n_labs=0, n_base_ftrs=0, n_states=1, max_dur=1, n_actual_labs=None,
+                extract_seg_ftrs=0, use_trans_ftrs=0, state_fidx=None, trans_fidx=None,
+                use_state_bias=1, use_trans_bias=1, state_bias_val=1.0, trans_bias_val=1.0):
+    """Same defaults as CRFTrain's set_fmap_config (CRFTrain/src/Main.cpp:372-430)."""
+    w = window_width(n_base_ftrs, max_dur, extract_seg_ftrs)
+    if n_actual_labs is None:
+        n_actual_labs = n_labs // max_dur if model_type == "stdseg" else n_labs
+    s0, s1 = state_fidx if state_fidx is not None else (0, w - 1)
+    t0, t1 = trans_fidx if trans_fidx is not None else (0, w - 1)
+    return Config(MODEL_TYPES[model_type], n_labs, n_base_ftrs, n_states, max_dur, n_actual_labs,
+                  int(extract_seg_ftrs), 1, s0, s1, int(use_trans_ftrs), t0, t1,
+                  int(use_state_bias), int(use_trans_bias), state_bias_val, trans_bias_val)
+
+
+def copy_config(cfg):
+    """Field-wise copy from any ctypes struct with the same field names (e.g. the oracle's Config)."""
+    return Config(*[getattr(cfg, f[0]) for f in Config._fields_])
+
+
+_lib = None
+
+SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_window_width", "crfgpu_lambda_len",
+           "crfgpu_index_maps", "crfgpu_set_lambda", "crfgpu_fwdbwd_batch", "crfgpu_viterbi_batch",
+           "crfgpu_expand_windows", "crfgpu_group_labels", "crfgpu_stage_batch", "crfgpu_fwdbwd_staged",
+           "crfgpu_viterbi_staged", "crfgpu_device_results", "crfgpu_fetch_fwdbwd", "crfgpu_fetch_viterbi",
+           "crfgpu_synchronize", "crfgpu_stream", "crfgpu_launch_count", "crfgpu_phase_ms",
+           "crfgpu_fetch_alpha_beta", "crfgpu_set_option", "crfgpu_host_alloc", "crfgpu_host_free"]
+
+
+def load_library(path=None):
+    """Loads libcrfgpu.so (raises if absent -- there is no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found: build it with `make -C asr-craft_b200` (or __graft_entry__.build())")
+    lib = C.CDLL(path)
+    lib.crfgpu_last_error.restype = C.c_char_p
+    lib.crfgpu_lambda_len.restype = C.c_uint32
+    lib.crfgpu_window_width.restype = C.c_uint32
+    lib.crfgpu_stream.restype = C.c_void_p
+    lib.crfgpu_launch_count.restype = C.c_uint64
+    lib.crfgpu_phase_ms.restype = C.c_double
+    for name in ("crfgpu_destroy", "crfgpu_lambda_len", "crfgpu_fwdbwd_staged", "crfgpu_viterbi_staged",
+                 "crfgpu_synchronize", "crfgpu_stream", "crfgpu_launch_count"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.crfgpu_phase_ms.argtypes = [C.c_void_p, C.c_char_p]
+    lib.crfgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.crfgpu_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    lib.crfgpu_host_free.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+class PinnedBuffer:
+    """Page-locked host array (cudaMallocHost) exposed as numpy."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = self.lib.crfgpu_host_alloc(C.byref(p), C.c_uint64(max(n, 1)))
+        if rc:
+            raise CrfGpuError(rc, self.lib.crfgpu_last_error().decode())
+        self.ptr = p
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr is not None:
+            self.array = None
+            self.lib.crfgpu_host_free(self.ptr)
+            self.ptr = None
+
+
+class CrfGpu:
+    """One device handle: CRF_Model + CRF_FeatureMap + grad builder + decoder for one geometry."""
+
+    def __init__(self, cfg, device=0):
+        self.lib = load_library()
+        self.cfg = copy_config(cfg)
+        h = C.c_void_p()
+        rc = self.lib.crfgpu_create(C.byref(self.cfg), C.c_int(device), C.byref(h))
+        if rc:
+            raise CrfGpuError(rc, self.lib.crfgpu_last_error().decode())
+        self.h = h
+        self.lambda_len = self.lib.crfgpu_lambda_len(self.h)
+        self._n_utt = 0
+        self._n_frames = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.crfgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise CrfGpuError(rc, self.lib.crfgpu_last_error().decode())
+
+    def set_option(self, name, value):
+        self._check(self.lib.crfgpu_set_option(self.h, name.encode(), int(value)))
+
+    def index_maps(self):
+        L = self.cfg.n_labs
+        s = np.zeros(L, np.uint32)
+        t = np.zeros((L, L), np.uint32)
+        self._check(self.lib.crfgpu_index_maps(self.h, _ptr(s, C.c_uint32), _ptr(t, C.c_uint32)))
+        return s, t
+
+    def set_lambda(self, lam):
+        lam = np.ascontiguousarray(lam, np.float64)
+        self._check(self.lib.crfgpu_set_lambda(self.h, _ptr(lam, C.c_double), C.c_uint32(len(lam))))
+
+    # ---- host-buffer calls --------------------------------------------------------------------
+    def fwdbwd(self, off, ftrs, labs, out=None):
+        off = np.ascontiguousarray(off, np.uint32)
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        labs = np.ascontiguousarray(labs, np.uint32)
+        n = len(off) - 1
+        if out is None:
+            out = (np.zeros(self.lambda_len, np.float64), np.zeros(n, np.float64), np.zeros(n, np.float64))
+        grad, numer, logz = out
+        self._check(self.lib.crfgpu_fwdbwd_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
+                                                 _ptr(labs, C.c_uint32), _ptr(grad, C.c_double),
+                                                 _ptr(numer, C.c_double), _ptr(logz, C.c_double)))
+        self._n_utt, self._n_frames = n, int(off[-1])
+        return grad, numer, logz
+
+    def viterbi(self, off, ftrs, raw=False):
+        off = np.ascontiguousarray(off, np.uint32)
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        n, tot = len(off) - 1, int(off[-1])
+        lab = np.zeros(tot, np.uint32)
+        dur = np.zeros(tot, np.uint32)
+        phn = np.zeros(tot, np.uint32)
+        nseg = np.zeros(n, np.uint32)
+        cost = np.zeros(n, np.float32)
+        self._check(self.lib.crfgpu_viterbi_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
+                                                  _ptr(lab, C.c_uint32), _ptr(dur, C.c_uint32), _ptr(phn, C.c_uint32),
+                                                  _ptr(nseg, C.c_uint32), _ptr(cost, C.c_float)))
+        self._n_utt, self._n_frames = n, tot
+        if raw:
+            return lab, dur, phn, nseg, cost
+        segs = []
+        for u in range(n):
+            b, k = int(off[u]), int(nseg[u])
+            segs.append((lab[b:b + k].copy(), dur[b:b + k].copy(), phn[b:b + k].copy()))
+        return segs, cost
+
+    def expand_windows(self, ftrs):
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        T = ftrs.shape[0]
+        w = window_width(self.cfg.n_base_ftrs, self.cfg.max_dur, self.cfg.extract_seg_ftrs)
+        out = np.zeros((T, self.cfg.max_dur, w), np.float32)
+        self._check(self.lib.crfgpu_expand_windows(self.h, C.c_uint32(T), _ptr(ftrs, C.c_float), _ptr(out, C.c_float)))
+        return out
+
+    def group_labels(self, labs):
+        labs = np.ascontiguousarray(labs, np.uint32)
+        out = np.zeros((len(labs), 4), np.uint32)
+        self._check(self.lib.crfgpu_group_labels(C.byref(self.cfg), C.c_uint32(len(labs)), _ptr(labs, C.c_uint32),
+                                                 _ptr(out, C.c_uint32)))
+        return out
+
+    # ---- device-resident calls ----------------------------------------------------------------
+    def stage(self, off, ftrs, labs=None):
+        off = np.ascontiguousarray(off, np.uint32)
+        ftrs = np.ascontiguousarray(ftrs, np.float32)
+        lp = None
+        if labs is not None:
+            labs = np.ascontiguousarray(labs, np.uint32)
+            lp = _ptr(labs, C.c_uint32)
+        n = len(off) - 1
+        self._check(self.lib.crfgpu_stage_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float), lp))
+        self._n_utt, self._n_frames = n, int(off[-1])
+
+    def fwdbwd_staged(self):
+        self._check(self.lib.crfgpu_fwdbwd_staged(self.h))
+
+    def viterbi_staged(self):
+        self._check(self.lib.crfgpu_viterbi_staged(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.crfgpu_synchronize(self.h))
+
+    def fetch_fwdbwd(self, out=None):
+        if out is None:
+            out = (np.zeros(self.lambda_len, np.float64), np.zeros(self._n_utt, np.float64),
+                   np.zeros(self._n_utt, np.float64))
+        grad, numer, logz = out
+        self._check(self.lib.crfgpu_fetch_fwdbwd(self.h, _ptr(grad, C.c_double), _ptr(numer, C.c_double),
+                                                 _ptr(logz, C.c_double)))
+        return grad, numer, logz
+
+    def device_results(self):
+        g, n, z = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.crfgpu_device_results(self.h, C.byref(g), C.byref(n), C.byref(z)))
+        return g.value, n.value, z.value
+
+    def fetch_alpha_beta(self):
+        L = self.cfg.n_labs
+        a = np.zeros((self._n_frames, L), np.float64)
+        b = np.zeros((self._n_frames, L), np.float64)
+        self._check(self.lib.crfgpu_fetch_alpha_beta(self.h, _ptr(a, C.c_double), _ptr(b, C.c_double)))
+        return a, b
+
+    def phase_ms(self, name):
+        return float(self.lib.crfgpu_phase_ms(self.h, name.encode()))
+
+    @property
+    def stream(self):
+        return self.lib.crfgpu_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.crfgpu_launch_count(self.h))

@@ -1,0 +1,834 @@
+// Device kernels of libcrfgpu (sm_100a).  See crf_kernels.cuh for the parameter blocks and DESIGN.md
+// for the data layout and the roofline that bounds each kernel.  Citations: ASR-CRaFT tree.
+#include "crf_kernels.cuh"
+
+#include <cfloat>
+
+namespace crfgpu {
+
+// =================================================================================================
+// helpers
+// =================================================================================================
+__device__ __forceinline__ int float_key(float f) {
+	// order-preserving map float -> int so that atomicMax(int) implements a float max
+	int i = __float_as_int(f);
+	return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) {
+	return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+constexpr int KEY_NEG_INF = (int)0x807fffff;  // float_key(-inf)
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void fill_f64_kernel(double* p, uint64_t n, double v) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_f32(float* p, uint64_t n, float v, cudaStream_t s) {
+	if (!n) return;
+	uint64_t b = (n + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+	fill_f32_kernel<<<(unsigned)b, 256, 0, s>>>(p, n, v);
+}
+void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t s) {
+	if (!n) return;
+	uint64_t b = (n + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+	fill_f64_kernel<<<(unsigned)b, 256, 0, s>>>(p, n, v);
+}
+
+// =================================================================================================
+// K7: segment windows.  One CTA per frame; thread f walks the window back from the last frame so the
+// running sum / max / min are accumulated in the reference's order
+// (CRF_InFtrStream_SeqMultiWindow.cpp: sample_ftrs :556-590, avg_ftrs :601-626, max_ftrs :637-666,
+//  min_ftrs :677-706, dur_ftrs :790-812; first_frame_ftrs for the non-segment mode).
+// =================================================================================================
+__global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
+	const uint32_t n = blockIdx.x;
+	if (n >= p.N) return;
+	const uint32_t t = p.frame_t[n];
+	const uint32_t dmax = min(t + 1, p.D);
+	float* out = p.X + (uint64_t)n * p.D * p.W;
+	const float* cur = p.base + (uint64_t)n * p.F;
+	if (p.seg_ftrs) {
+		for (uint32_t f = threadIdx.x; f < p.F; f += blockDim.x) {
+			float acc = 0.0f, amax = cur[f], amin = cur[f];
+			for (uint32_t d = 1; d <= dmax; d++) {
+				const float* wstart = cur - (uint64_t)(d - 1) * p.F;   // first frame of the window
+				const float v = wstart[f];
+				acc += v;
+				amax = v > amax ? v : amax;
+				amin = v < amin ? v : amin;
+				float* o = out + (uint64_t)(d - 1) * p.W;
+#pragma unroll
+				for (int k = 0; k < 5; k++) o[k * p.F + f] = wstart[(uint64_t)p.steps[(d - 1) * 5 + k] * p.F + f];
+				o[5 * p.F + f] = acc / (float)d;
+				o[6 * p.F + f] = amax;
+				o[7 * p.F + f] = amin;
+			}
+		}
+		for (uint32_t i = threadIdx.x; i < dmax * p.D; i += blockDim.x) {
+			const uint32_t d = i / p.D + 1, k = i % p.D;
+			out[(uint64_t)(d - 1) * p.W + 8 * p.F + k] = (k == d - 1) ? 1.0f : 0.0f;
+		}
+	} else {
+		for (uint32_t i = threadIdx.x; i < dmax * p.F; i += blockDim.x) {
+			const uint32_t d = i / p.F + 1, f = i % p.F;
+			out[(uint64_t)(d - 1) * p.W + f] = (cur - (uint64_t)(d - 1) * p.F)[f];
+		}
+	}
+	// windows that would start before the utterance are never read by the lattice; keep them zero
+	for (uint32_t i = dmax * p.W + threadIdx.x; i < p.D * p.W; i += blockDim.x) out[i] = 0.0f;
+}
+void launch_expand_windows(const ExpandParams& p, cudaStream_t s) {
+	if (p.N) expand_windows_kernel<<<p.N, 128, 0, s>>>(p);
+}
+
+// =================================================================================================
+// GEMM-1 (state scores): C[n][j] = sum_k A[n][k]*B[j][k] + bias[j]   (fp32 FFMA, 64x64x16 tiles)
+// replaces L virtual calls of CRF_StdFeatureMap::computeStateArrayValue per frame
+// (CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:65-81)
+// =================================================================================================
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+__global__ void __launch_bounds__(256) score_gemm_kernel(ScoreGemmParams p) {
+	__shared__ __align__(16) float As[SG_BK][SG_BM + 4];
+	__shared__ __align__(16) float Bs[SG_BK][SG_BN + 4];
+	const uint32_t m0 = blockIdx.x * SG_BM, n0 = blockIdx.y * SG_BN;
+	const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+	float acc[4][4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+	for (uint32_t k0 = 0; k0 < p.K; k0 += SG_BK) {
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const int idx = threadIdx.x + i * 256;
+			const int r = idx / SG_BK, kk = idx % SG_BK;
+			const uint32_t gm = m0 + r, gn = n0 + r, gk = k0 + kk;
+			As[kk][r] = (gm < p.M && gk < p.K) ? p.A[(uint64_t)gm * p.lda + gk] : 0.0f;
+			Bs[kk][r] = (gn < p.Ncols && gk < p.K) ? p.B[(uint64_t)gn * p.ldb + gk] : 0.0f;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int kk = 0; kk < SG_BK; kk++) {
+			const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+			const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+			const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const uint32_t gm = m0 + ty * 4 + i;
+		if (gm >= p.M) continue;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t gn = n0 + tx * 4 + j;
+			if (gn < p.Ncols) p.C[(uint64_t)gm * p.ldc + gn] = acc[i][j] + (p.bias ? p.bias[gn] : 0.0f);
+		}
+	}
+}
+void launch_score_gemm(const ScoreGemmParams& p, cudaStream_t s) {
+	if (!p.M || !p.Ncols) return;
+	dim3 grid((p.M + SG_BM - 1) / SG_BM, (p.Ncols + SG_BN - 1) / SG_BN);
+	score_gemm_kernel<<<grid, 256, 0, s>>>(p);
+}
+
+// =================================================================================================
+// Lattice recursions (K2/K3/K4), probability domain with per-frame log scales.
+//
+// Reference semantics (log domain, fp64): CRF_StdSegStateNode::computeAlpha / computeBeta / computeExpF /
+// computeAlphaSum (CRF/src/nodes/CRF_StdSegStateNode.cpp:135-186, 219-308, 343-438, 447-462); with
+// max_dur == 1 these are exactly CRF_StdStateNode's (CRF/src/nodes/CRF_StdStateNode.cpp:81-299), and the
+// N-state topology (CRF_StdNStateNode.cpp:110-365) is the same recursion with E == 0 on illegal pairs.
+//
+//   alpha_t[(d,y)] = S_t[(d,y)] + log sum_{q<avail(t-d)} exp(alpha_{t-d}[q] + M[q,(d,y)])     d <= t
+//                  = S_t[(d,y)]                                                               d == t+1
+// Here alpha_t[c] = m_t + log A_t[c] with max_c A_t[c] == 1, and G_t[c] = sum_q A_t[q]*E[q][c] is pushed
+// once per frame and consumed at t+d by block d, so each frame costs one [avail x L] mat-vec.
+// =================================================================================================
+__host__ __device__ __forceinline__ size_t dp_vec_bytes(uint32_t L, int U) {
+	return ((size_t)L * U * sizeof(float) + 15) / 16 * 16;
+}
+// the U per-slot values of row q of a [rows][U] shared-memory vector, as one vector load
+template <int U> __device__ __forceinline__ void load_slots(const float* base, uint32_t q, float (&out)[U]);
+template <> __device__ __forceinline__ void load_slots<1>(const float* base, uint32_t q, float (&out)[1]) { out[0] = base[q]; }
+template <> __device__ __forceinline__ void load_slots<2>(const float* base, uint32_t q, float (&out)[2]) {
+	const float2 v = reinterpret_cast<const float2*>(base)[q]; out[0] = v.x; out[1] = v.y;
+}
+template <> __device__ __forceinline__ void load_slots<4>(const float* base, uint32_t q, float (&out)[4]) {
+	const float4 v = reinterpret_cast<const float4*>(base)[q]; out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <> __device__ __forceinline__ void load_slots<8>(const float* base, uint32_t q, float (&out)[8]) {
+	const float4 v = reinterpret_cast<const float4*>(base)[2 * q], w = reinterpret_cast<const float4*>(base)[2 * q + 1];
+	out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; out[4] = w.x; out[5] = w.y; out[6] = w.z; out[7] = w.w;
+}
+
+template <int U>
+__global__ void __launch_bounds__(1024) forward_kernel(DpParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* a_s = reinterpret_cast<float*>(smem_raw);                              // [L][U], 16B aligned
+	double* m_ring = reinterpret_cast<double*>(smem_raw + dp_vec_bytes(p.L, U));  // [U][D]
+	double* mu_s = m_ring + (size_t)U * p.D;                                      // [U]
+	double* zsum_s = mu_s + U;                                                    // [U]
+	int* key_s = reinterpret_cast<int*>(zsum_s + U);                              // [2][U]
+	float* delta_s = reinterpret_cast<float*>(key_s + 2 * U);                     // [U][D+1] (index d, d==0 unused)
+	__shared__ uint32_t s_off[U], s_len[U];
+
+	const uint32_t c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const uint32_t L = p.L, Lp = p.Lp, P = p.P, D = p.D;
+	if (threadIdx.x < U) {
+		const uint32_t utt = p.grp_utt[blockIdx.x * U + threadIdx.x];
+		s_off[threadIdx.x] = utt == LAB_BAD ? 0 : p.off[utt];
+		s_len[threadIdx.x] = utt == LAB_BAD ? 0 : p.off[utt + 1] - p.off[utt];
+		key_s[threadIdx.x] = KEY_NEG_INF; key_s[U + threadIdx.x] = KEY_NEG_INF;
+		zsum_s[threadIdx.x] = 0.0;
+	}
+	__syncthreads();
+	uint32_t Tmax = 0;
+#pragma unroll
+	for (int u = 0; u < U; u++) Tmax = max(Tmax, s_len[u]);
+	const uint32_t my_d = (c < L) ? c / P + 1 : 0xffffu;  // duration block of my column
+
+	for (uint32_t t = 0; t < Tmax; t++) {
+		const uint32_t avail = P * min(t + 1, D);
+		// [A] per-slot scale bookkeeping: warp u serves slot u, lane d-1 serves duration d
+		for (uint32_t u = warp; u < U; u += n_warps) {
+			if (t < s_len[u]) {
+				double val = -DBL_MAX;
+				const uint32_t d = lane + 1;
+				if (d <= D) {
+					if (d <= t) val = m_ring[u * D + (t - d) % D] + p.Mmax;
+					else if (d == t + 1) val = 0.0;   // segment starts the utterance: alpha = S
+				}
+				const double mu = warp_max_d(val);
+				if (d <= D) delta_s[u * (D + 1) + d] = (val == -DBL_MAX) ? -INFINITY : (float)(val - mu);
+				if (lane == 0) mu_s[u] = mu;
+			}
+		}
+		__syncthreads();
+		// [B] log-domain candidate, block max per slot
+		float lr[U];
+		if (threadIdx.x < U) key_s[((t + 1) & 1) * U + threadIdx.x] = KEY_NEG_INF;   // reset next step's key
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			lr[u] = -INFINITY;
+			if (t < s_len[u] && c < avail) {
+				const uint64_t n = (uint64_t)s_off[u] + t;
+				float lg = 0.0f;
+				if (my_d <= t) lg = logf(p.G[(n - my_d) * Lp + c]);
+				lr[u] = p.S[n * Lp + c] + lg + delta_s[u * (D + 1) + my_d];
+			}
+			const float wm = warp_max(lr[u]);
+			if (lane == 0 && wm > -INFINITY) atomicMax(&key_s[(t & 1) * U + u], float_key(wm));
+		}
+		__syncthreads();
+		// [C] normalise, publish A_t
+		float part[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			part[u] = 0.0f;
+			if (t < s_len[u]) {
+				const float mx = key_float(key_s[(t & 1) * U + u]);
+				const float a = (c < avail) ? expf(lr[u] - mx) : 0.0f;
+				if (c < L) {
+					a_s[c * U + u] = a;
+					p.A[((uint64_t)s_off[u] + t) * Lp + c] = a;
+				}
+				part[u] = a;
+				if (c == 0) {
+					const double mt = mu_s[u] + (double)mx;
+					m_ring[u * D + t % D] = mt;
+					p.m[(uint64_t)s_off[u] + t] = mt;
+				}
+			} else if (c < L) a_s[c * U + u] = 0.0f;
+		}
+		// logZ = m_{T-1} + log sum_{q<avail(T-1)} A_{T-1}[q]   (computeAlphaSum, :447-462)
+		bool any_last = false;
+#pragma unroll
+		for (int u = 0; u < U; u++) any_last |= (t + 1 == s_len[u]);
+		if (any_last) {
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				if (t + 1 == s_len[u]) {
+					const double ws = warp_sum_d((double)part[u]);
+					if (lane == 0) atomicAdd(&zsum_s[u], ws);
+				}
+			}
+		}
+		__syncthreads();
+		if (any_last && threadIdx.x < U && t + 1 == s_len[threadIdx.x]) {
+			const uint32_t utt = p.grp_utt[blockIdx.x * U + threadIdx.x];
+			p.logZ[utt] = m_ring[threadIdx.x * D + t % D] + log(zsum_s[threadIdx.x]);
+		}
+		// [D] push: G_t[c] = sum_{q<avail} A_t[q] * E[q][c]
+		bool any_next = false;
+#pragma unroll
+		for (int u = 0; u < U; u++) any_next |= (t + 1 < s_len[u]);
+		if (any_next && c < L) {
+			float acc[U];
+#pragma unroll
+			for (int u = 0; u < U; u++) acc[u] = 0.0f;
+			const float* Ec = p.E + c;
+			uint32_t q = 0;
+			for (; q + 4 <= avail; q += 4) {
+				const float e0 = __ldg(Ec + (uint64_t)(q + 0) * Lp), e1 = __ldg(Ec + (uint64_t)(q + 1) * Lp);
+				const float e2 = __ldg(Ec + (uint64_t)(q + 2) * Lp), e3 = __ldg(Ec + (uint64_t)(q + 3) * Lp);
+				float a0[U], a1[U], a2[U], a3[U];
+				load_slots<U>(a_s, q + 0, a0); load_slots<U>(a_s, q + 1, a1);
+				load_slots<U>(a_s, q + 2, a2); load_slots<U>(a_s, q + 3, a3);
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					acc[u] = fmaf(a0[u], e0, acc[u]);
+					acc[u] = fmaf(a1[u], e1, acc[u]);
+					acc[u] = fmaf(a2[u], e2, acc[u]);
+					acc[u] = fmaf(a3[u], e3, acc[u]);
+				}
+			}
+			for (; q < avail; q++) {
+				const float e0 = __ldg(Ec + (uint64_t)q * Lp);
+				float a0[U];
+				load_slots<U>(a_s, q, a0);
+#pragma unroll
+				for (int u = 0; u < U; u++) acc[u] = fmaf(a0[u], e0, acc[u]);
+			}
+#pragma unroll
+			for (int u = 0; u < U; u++)
+				if (t + 1 < s_len[u]) p.G[((uint64_t)s_off[u] + t) * Lp + c] = acc[u];
+		}
+		// G_t[c] is read back only by this same thread (column c), A/a_s hazards are covered by the
+		// barriers of the next step before a_s is rewritten in [C].
+	}
+}
+
+static size_t dp_smem_bytes(const DpParams& p, int U) {
+	size_t b = dp_vec_bytes(p.L, U);                                  // a_s / v_s
+	b += sizeof(double) * ((size_t)U * p.D + 2 * U);                  // ring + two per-slot doubles
+	b += sizeof(int) * 2 * U;                                         // keys
+	b += sizeof(float) * 2 * (size_t)U * (p.D + 1);                   // delta, rsc
+	return b;
+}
+
+template <int U>
+static void launch_forward_u(const DpParams& p, cudaStream_t s) {
+	const unsigned threads = (p.L + 31) / 32 * 32;
+	const size_t smem = dp_smem_bytes(p, U);
+	cudaFuncSetAttribute(forward_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	forward_kernel<U><<<p.n_groups, threads, smem, s>>>(p);
+}
+void launch_forward(const DpParams& p, int U, cudaStream_t s) {
+	if (!p.n_groups) return;
+	switch (U) {
+		case 1: launch_forward_u<1>(p, s); break;
+		case 2: launch_forward_u<2>(p, s); break;
+		case 4: launch_forward_u<4>(p, s); break;
+		default: launch_forward_u<8>(p, s); break;
+	}
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward + posteriors.
+//   beta_t[q] = log sum_{d<=numNext} sum_y exp(M[q,(d,y)] + S_{t+d}[(d,y)] + beta_{t+d}[(d,y)])   (:219-308)
+// With w~_{t'}[c] = exp(S_{t'}[c] + beta_{t'}[c] - kappa_{t'}) (max 1) kept in G, frame t gathers
+// v[(d,y)] = w~_{t+d}[(d,y)] * exp(kappa_{t+d} - kappa*) and does one [L x numNext*P] mat-vec with E^T:
+// u[q] = sum_c E[q][c] v[c], beta_t[q] = kappa* + Mmax + log u[q] =: bbase_t + log u[q].
+//   gamma_t[c] = exp(alpha+beta-logZ) = A_t[c]*u[c]*exp(m_t + bbase_t - logZ)                       (:369-372)
+//   xi_t(q,c)  = A_{t-d}[q] * E[q][c] * R_t[c],  R_t[c] = exp(S_t[c]+beta_t[c]+m_{t-d}+Mmax-logZ)  (:389-397)
+// The kernel emits Dm = onehot(reference label) - gamma and R; the sums over frames are the two
+// reduce-GEMMs (state weights: Dm^T X, transition bias: A^T R).
+// -------------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(1024) backward_kernel(DpParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* v_s = reinterpret_cast<float*>(smem_raw);                              // [L][U], 16B aligned
+	double* k_ring = reinterpret_cast<double*>(smem_raw + dp_vec_bytes(p.L, U));  // [U][D]
+	double* base_s = k_ring + (size_t)U * p.D;                                    // [U]
+	double* sg_s = base_s + U;                                                    // [U] log gamma scale
+	int* key_s = reinterpret_cast<int*>(sg_s + U);                                // [2][U]
+	float* delta_s = reinterpret_cast<float*>(key_s + 2 * U);                     // [U][D+1]
+	float* rsc_s = delta_s + (size_t)U * (p.D + 1);                               // [U][D+1]
+	__shared__ uint32_t s_off[U], s_len[U];
+	__shared__ double s_logZ[U];
+
+	const uint32_t c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const uint32_t L = p.L, Lp = p.Lp, P = p.P, D = p.D;
+	if (threadIdx.x < U) {
+		const uint32_t utt = p.grp_utt[blockIdx.x * U + threadIdx.x];
+		s_off[threadIdx.x] = utt == LAB_BAD ? 0 : p.off[utt];
+		s_len[threadIdx.x] = utt == LAB_BAD ? 0 : p.off[utt + 1] - p.off[utt];
+		s_logZ[threadIdx.x] = utt == LAB_BAD ? 0.0 : p.logZ[utt];
+		key_s[threadIdx.x] = KEY_NEG_INF; key_s[U + threadIdx.x] = KEY_NEG_INF;
+	}
+	__syncthreads();
+	uint32_t Tmax = 0;
+#pragma unroll
+	for (int u = 0; u < U; u++) Tmax = max(Tmax, s_len[u]);
+	const uint32_t my_d = (c < L) ? c / P + 1 : 0xffffu;
+
+	for (uint32_t t = Tmax; t-- > 0;) {
+		const uint32_t avail = P * min(t + 1, D);
+		uint32_t nn_max = 0;   // largest numNext among the slots active at this step
+		// [A] scales: warp u serves slot u, lane d-1 serves duration d
+		for (uint32_t u = warp; u < U; u += n_warps) {
+			if (t < s_len[u]) {
+				const uint32_t numNext = min(s_len[u] - 1 - t, D);
+				const uint64_t n = (uint64_t)s_off[u] + t;
+				const uint32_t d = lane + 1;
+				double kv = -DBL_MAX;
+				if (d <= numNext) kv = k_ring[u * D + (t + d) % D];
+				const double kstar = warp_max_d(kv);
+				const double base = numNext ? kstar + p.Mmax : 0.0;   // tail: beta = 0 (setTailBeta)
+				if (d <= D) {
+					delta_s[u * (D + 1) + d] = (d <= numNext) ? (float)(kv - kstar) : -INFINITY;
+					// xi needs alpha of frame t-d: scale m_{t-d}
+					rsc_s[u * (D + 1) + d] = (d <= t) ? (float)(base + p.m[n - d] + p.Mmax - s_logZ[u]) : -INFINITY;
+				}
+				if (lane == 0) {
+					base_s[u] = base;
+					sg_s[u] = p.m[n] + base - s_logZ[u];
+					p.bbase[n] = base;
+				}
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++)
+			if (t < s_len[u]) nn_max = max(nn_max, min(s_len[u] - 1 - t, D));
+		__syncthreads();
+		// [B] gather v from the next numNext frames
+		if (threadIdx.x < U) key_s[((t + 1) & 1) * U + threadIdx.x] = KEY_NEG_INF;
+		if (c < L) {
+#pragma unroll
+			for (int u = 0; u < U; u++) {
+				float v = 0.0f;
+				if (t < s_len[u]) {
+					const uint32_t numNext = min(s_len[u] - 1 - t, D);
+					if (my_d <= numNext)
+						v = p.G[((uint64_t)s_off[u] + t + my_d) * Lp + c] * expf(delta_s[u * (D + 1) + my_d]);
+				}
+				v_s[c * U + u] = v;
+			}
+		}
+		__syncthreads();
+		// [C] u[q] = sum_c E[q][c] v[c]; posteriors
+		float uq[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) uq[u] = 0.0f;
+		if (c < avail && nn_max) {
+			const float* Eq = p.ET + c;
+			const uint32_t ncol = nn_max * P;
+			uint32_t k = 0;
+			for (; k + 4 <= ncol; k += 4) {
+				const float e0 = __ldg(Eq + (uint64_t)(k + 0) * Lp), e1 = __ldg(Eq + (uint64_t)(k + 1) * Lp);
+				const float e2 = __ldg(Eq + (uint64_t)(k + 2) * Lp), e3 = __ldg(Eq + (uint64_t)(k + 3) * Lp);
+				float v0[U], v1[U], v2[U], v3[U];
+				load_slots<U>(v_s, k + 0, v0); load_slots<U>(v_s, k + 1, v1);
+				load_slots<U>(v_s, k + 2, v2); load_slots<U>(v_s, k + 3, v3);
+#pragma unroll
+				for (int u = 0; u < U; u++) {
+					uq[u] = fmaf(v0[u], e0, uq[u]);
+					uq[u] = fmaf(v1[u], e1, uq[u]);
+					uq[u] = fmaf(v2[u], e2, uq[u]);
+					uq[u] = fmaf(v3[u], e3, uq[u]);
+				}
+			}
+			for (; k < ncol; k++) {
+				const float e0 = __ldg(Eq + (uint64_t)k * Lp);
+				float v0[U];
+				load_slots<U>(v_s, k, v0);
+#pragma unroll
+				for (int u = 0; u < U; u++) uq[u] = fmaf(v0[u], e0, uq[u]);
+			}
+		}
+		float lw[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			lw[u] = -INFINITY;
+			float gamma = 0.0f;
+			if (t < s_len[u] && c < L) {
+				const uint64_t n = (uint64_t)s_off[u] + t;
+				const bool tail = (t + 1 == s_len[u]);
+				if (c < avail) {
+					const float uu = tail ? 1.0f : uq[u];
+					const float lu = logf(uu);
+					lw[u] = p.S[n * Lp + c] + lu;
+					gamma = p.A[n * Lp + c] * expf(lu + (float)sg_s[u]);
+					p.Dm[n * Lp + c] = ((p.node_lab[n] == c) ? 1.0f : 0.0f) - gamma;
+					p.R[n * Lp + c] = (my_d <= t) ? expf(lw[u] + rsc_s[u * (D + 1) + my_d]) : 0.0f;
+					if (p.Uvec) p.Uvec[n * Lp + c] = uu;
+				} else {
+					p.Dm[n * Lp + c] = 0.0f;
+					p.R[n * Lp + c] = 0.0f;
+					if (p.Uvec) p.Uvec[n * Lp + c] = 0.0f;
+				}
+			}
+			const float wm = warp_max(lw[u]);
+			if (lane == 0 && wm > -INFINITY) atomicMax(&key_s[(t & 1) * U + u], float_key(wm));
+			if (p.mass) {
+				const float gs = warp_sum(gamma);
+				if (lane == 0 && t < s_len[u] && gs != 0.0f) atomicAdd(&p.mass[(uint64_t)s_off[u] + t], (double)gs);
+			}
+		}
+		__syncthreads();
+		// [D] publish w~_t and its scale
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			if (t < s_len[u]) {
+				const float mx = key_float(key_s[(t & 1) * U + u]);
+				const uint64_t n = (uint64_t)s_off[u] + t;
+				if (c < L) p.G[n * Lp + c] = (c < avail) ? expf(lw[u] - mx) : 0.0f;
+				if (c == 0) {
+					const double kap = base_s[u] + (double)mx;
+					k_ring[u * D + t % D] = kap;
+					p.kappa[n] = kap;
+				}
+			}
+		}
+		__syncthreads();   // k_ring / G of this frame are read by other threads in the next step
+	}
+}
+
+template <int U>
+static void launch_backward_u(const DpParams& p, cudaStream_t s) {
+	const unsigned threads = (p.L + 31) / 32 * 32;
+	const size_t smem = dp_smem_bytes(p, U);
+	cudaFuncSetAttribute(backward_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	backward_kernel<U><<<p.n_groups, threads, smem, s>>>(p);
+}
+void launch_backward(const DpParams& p, int U, cudaStream_t s) {
+	if (!p.n_groups) return;
+	switch (U) {
+		case 1: launch_backward_u<1>(p, s); break;
+		case 2: launch_backward_u<2>(p, s); break;
+		case 4: launch_backward_u<4>(p, s); break;
+		default: launch_backward_u<8>(p, s); break;
+	}
+}
+
+__global__ void dump_alpha_beta_kernel(DpParams p, uint32_t N, const uint32_t* frame_t, const uint32_t* frame_len,
+                                       double* alpha, double* beta) {
+	const uint64_t total = (uint64_t)N * p.L;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t n = i / p.L; const uint32_t c = (uint32_t)(i % p.L);
+		const uint32_t t = frame_t[n];
+		const uint32_t avail = p.P * min(t + 1, p.D);
+		double a = -DBL_MAX, b = -DBL_MAX;
+		if (c < avail) {
+			const float av = p.A[n * p.Lp + c];
+			a = av > 0.0f ? p.m[n] + log((double)av) : -INFINITY;
+			const float uv = p.Uvec[n * p.Lp + c];
+			b = uv > 0.0f ? p.bbase[n] + log((double)uv) : -INFINITY;
+		} else if (t + 1 == frame_len[n]) b = 0.0;   // setTailBeta writes all labels
+		alpha[i] = a; beta[i] = b;
+	}
+}
+void launch_dump_alpha_beta(const DpParams& p, uint32_t N, const uint32_t* frame_t, const uint32_t* frame_len,
+                            double* alpha, double* beta, cudaStream_t s) {
+	if (N) dump_alpha_beta_kernel<<<148 * 4, 256, 0, s>>>(p, N, frame_t, frame_len, alpha, beta);
+}
+
+// =================================================================================================
+// Reduce-GEMM: out[map(i,j)] += scale * sum_n A[n-shift][i] * B[n][j]   (fp32 tiles, fp64 atomics)
+// replaces the per-frame scatter of CRF_StdFeatureMap::computeStateExpF / computeTransExpF
+// (CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:130-223) and `grad -= ExpF` (CRF_NewGradBuilder.cpp:374-376).
+// =================================================================================================
+constexpr int RG_BI = 64, RG_BJ = 64, RG_BK = 16;
+__global__ void __launch_bounds__(256) reduce_gemm_kernel(ReduceGemmParams p) {
+	__shared__ __align__(16) float As[RG_BK][RG_BI];
+	__shared__ __align__(16) float Bs[RG_BK][RG_BJ];
+	const uint32_t i0 = blockIdx.x * RG_BI, j0 = blockIdx.y * RG_BJ;
+	const uint32_t ns = p.n0 + blockIdx.z * p.k_slab;
+	const uint32_t ne = min(ns + p.k_slab, p.n1);
+	const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+	float acc[4][4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+	for (uint32_t nb = ns; nb < ne; nb += RG_BK) {
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			const int idx = threadIdx.x + r * 256;
+			const int kk = idx / 64, col = idx % 64;
+			const uint32_t n = nb + kk;
+			float a = 0.0f, b = 0.0f;
+			if (n < ne) {
+				if (i0 + col < p.I) a = p.A[(uint64_t)(n - p.a_row_shift) * p.lda + i0 + col];
+				if (j0 + col < p.J) b = (j0 + col == p.ones_col) ? 1.0f : p.B[(uint64_t)n * p.ldb + j0 + col];
+			}
+			As[kk][col] = a; Bs[kk][col] = b;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int kk = 0; kk < RG_BK; kk++) {
+			const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+			const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+			const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+#pragma unroll
+				for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const uint32_t gi = i0 + ty * 4 + i;
+		if (gi >= p.I) continue;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t gj = j0 + tx * 4 + j;
+			if (gj >= p.J) continue;
+			const float v = acc[i][j];
+			if (v == 0.0f) continue;
+			if (p.mode == 0) {
+				const double sc = (gj == p.ones_col) ? p.ones_scale : p.scale;
+				atomicAdd(&p.out[(uint64_t)p.row_idx[gi] + gj], sc * (double)v);
+			} else {
+				const uint32_t idx = p.pair_idx[(uint64_t)gi * p.pair_ld + gj];
+				if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)p.Ew[(uint64_t)gi * p.e_ld + gj] * (double)v);
+			}
+		}
+	}
+}
+void launch_reduce_gemm(const ReduceGemmParams& p, cudaStream_t s) {
+	if (p.n1 <= p.n0 || !p.I || !p.J) return;
+	dim3 grid((p.I + RG_BI - 1) / RG_BI, (p.J + RG_BJ - 1) / RG_BJ, (p.n1 - p.n0 + p.k_slab - 1) / p.k_slab);
+	reduce_gemm_kernel<<<grid, 256, 0, s>>>(p);
+}
+
+// =================================================================================================
+// Empirical counts on the reference path and the numerator sum lambda.f (fp64, one warp per labelled node)
+// (CRF_StdFeatureMap::computeStateExpF/computeTransExpF `t_clab==clab` branches, :150-171, :205-220)
+// The state-feature empirical counts themselves ride in Dm (the onehot term); here only the
+// transition-bias counts and the numerator are produced.
+// =================================================================================================
+__global__ void __launch_bounds__(256) empirical_kernel(EmpiricalParams p) {
+	const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t n = warp_global; n < p.N; n += n_warps) {
+		const uint32_t lab = p.node_lab[n];
+		if (lab == LAB_BAD || lab >= p.L) continue;
+		const uint32_t d = lab / p.P;   // duration block (0-based); 0 for frame-level models
+		const float* x = p.X + (uint64_t)n * p.ldx + (uint64_t)d * p.W + p.sf0;
+		const double* lam = p.lambda + p.sidx[lab];
+		double acc = 0.0;
+		for (uint32_t f = lane; f < p.nSf; f += 32) acc += lam[f] * (double)x[f];
+		acc = warp_sum_d(acc);
+		if (lane == 0) {
+			if (p.use_state_bias) acc += lam[p.nSf] * p.state_bias_val;
+			const uint32_t pl = p.prev_lab[n];
+			if (pl != LAB_BAD && pl < p.L && p.use_trans_bias) {
+				const uint32_t ti = p.tidx[(uint64_t)pl * p.L + lab];
+				if (ti != 0xffffffffu) {
+					acc += p.lambda[ti] * p.trans_bias_val;
+					atomicAdd(&p.grad[ti], p.trans_bias_val);
+				}
+			}
+			atomicAdd(&p.numer[p.frame_utt[n]], acc);
+		}
+	}
+}
+void launch_empirical(const EmpiricalParams& p, cudaStream_t s) {
+	if (!p.N) return;
+	unsigned blocks = (p.N + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
+	empirical_kernel<<<blocks, 256, 0, s>>>(p);
+}
+
+// =================================================================================================
+// Viterbi scores in the reference's arithmetic: fp64, features in index order, separate multiply and
+// add (no FMA), bias last, then negate and narrow to float
+// (CRF_StdFeatureMap.cpp:65-81; CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:143)
+// =================================================================================================
+__global__ void __launch_bounds__(256) vit_scores_kernel(VitScoreParams p) {
+	const uint64_t total = (uint64_t)p.N * p.D * p.L;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t lab = (uint32_t)(i % p.L);
+		const uint64_t nd = i / p.L;
+		const uint32_t d = (uint32_t)(nd % p.D); const uint64_t n = nd / p.D;
+		if (d > p.frame_t[n]) { p.negS[i] = 0.0f; continue; }
+		const float* x = p.X + n * p.ldx + (uint64_t)d * p.W + p.sf0;
+		double acc = 0.0;
+		for (uint32_t f = 0; f < p.nSf; f++) acc = __dadd_rn(acc, __dmul_rn((double)x[f], p.Wd[(uint64_t)f * p.L + lab]));
+		if (p.use_bias) acc = __dadd_rn(acc, __dmul_rn(p.Wd[(uint64_t)p.nSf * p.L + lab], p.bias_val));
+		p.negS[i] = (float)(-acc);
+	}
+}
+void launch_vit_scores(const VitScoreParams& p, cudaStream_t s) {
+	const uint64_t total = (uint64_t)p.N * p.D * p.L;
+	if (!total) return;
+	uint64_t b = (total + 255) / 256; if (b > 148ull * 32) b = 148ull * 32;
+	vit_scores_kernel<<<(unsigned)b, 256, 0, s>>>(p);
+}
+
+// =================================================================================================
+// Viterbi recursion + traceback, one CTA per utterance, thread = (phone, sub-state) label.
+// Array restatement of the token-passing decoder with the free-phone LM and no beam
+// (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:116-166 state update, :246-415 within-phone,
+//  :435-543 cross-phone, :545-733 expansion order, :976-1106 pruning/kept list, :2156-2171 final
+//  argmin, :2204-2349 traceback; CRF_ViterbiNode::addNonEpsVtbState / choose_nState_Best_Seg .h:193-465).
+// All costs are float with the finite sentinel 99999.0; candidate order reproduces the reference's
+// first-arrival-wins tie-breaks (see DESIGN.md "Viterbi exactness").
+// =================================================================================================
+__device__ __forceinline__ uint32_t kept_phone(uint32_t i, uint32_t P, uint32_t g) {
+	// i-th phone of the kept list described by g: identity if g==0xff, else increasing order with g moved last
+	if (g == 0xffu) return i;
+	if (i + 1 == P) return g;
+	return i < g ? i : i + 1;
+}
+
+__global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	float* Wprev = reinterpret_cast<float*>(smem_raw);   // [L] kept weights of the previous frame
+	float* crossS = Wprev + p.L;                          // [P*P] when it fits, else unused
+	__shared__ uint32_t s_g;        // descriptor of the kept-list order of the previous frame
+	__shared__ int s_best;
+	const uint32_t u = blockIdx.x;
+	const uint32_t L = p.L, P = p.P, NS = p.NS, D = p.D;
+	const uint32_t off = p.off[u], T = p.off[u + 1] - p.off[u];
+	const uint32_t lab = threadIdx.x;
+	const bool cross_in_smem = ((size_t)P * P * sizeof(float) <= 96 * 1024);
+	if (cross_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) crossS[i] = p.crossT[i];
+	const float* crossT = cross_in_smem ? crossS : p.crossT;
+	float* candW = p.candW + (uint64_t)u * D * L;
+	int32_t* candP = p.candP + (uint64_t)u * D * L;
+	const uint32_t q = lab / NS, k = lab % NS;
+	const float my_diag = lab < L ? p.negDiag[lab] : 0.0f;
+	const float my_off = (lab < L && k > 0) ? p.negOff[lab] : 0.0f;
+	__syncthreads();
+
+	for (uint32_t s = 0; s < T; s++) {
+		// ---- candidates for segments starting at frame s ----
+		float cw = VIT_INF; int32_t cp = -1;
+		if (lab < L) {
+			if (s == 0) {
+				if (k == 0) cw = 0.0f + 0.0f;   // lm_start weight 0 + arc weight 0, trans_wt = 0.0 at node 0 (:444-447)
+			} else {
+				const uint32_t g = s_g;
+				bool seen = false;
+				if (k == 0) {
+					// cross-phone: scan the kept list of frame s-1 in list order; strict '<' keeps the first arrival
+					for (uint32_t i = 0; i < P; i++) {
+						const uint32_t pp = kept_phone(i, P, g);
+						if (NS == 1 && pp == q) continue;   // free-phone LM, 1 state: no arc to the same phone (:1332-1346)
+						const float base = Wprev[pp * NS + NS - 1] + 0.0f;
+						const float cost = base + crossT[(uint64_t)pp * P + q];
+						if (!seen || cost < cw) { cw = cost; cp = (int32_t)(pp * NS + NS - 1); seen = true; }
+					}
+				} else seen = true;   // the cross update created the slot with 99999.0 / -1 for inner sub-states
+				// within-phone: self vs advance from the previous sub-state, self only if strictly smaller (:338)
+				float w; int32_t ptr;
+				const float n1 = Wprev[lab] + my_diag;
+				if (k == 0) { w = n1; ptr = (int32_t)lab; }
+				else {
+					const float n2 = Wprev[lab - 1] + my_off;
+					if (n1 < n2) { w = n1; ptr = (int32_t)lab; } else { w = n2; ptr = (int32_t)lab - 1; }
+				}
+				if (k == 0 && !seen) { cw = w; cp = ptr; }         // no cross arc reached this phone (P == 1)
+				else if (w < cw) { cw = w; cp = ptr; }
+			}
+			candW[(uint64_t)(s % D) * L + lab] = cw;
+			candP[(uint64_t)(s % D) * L + lab] = cp;
+		}
+		__syncthreads();   // Wprev fully consumed
+		// ---- node s: add state values, best duration per (phone, sub-state); longest duration first ----
+		if (lab < L) {
+			const uint32_t dmax = min(s + 1, D);
+			float best = 0.0f; int32_t bptr = -1; uint32_t bdur = 0;
+			for (uint32_t d = dmax; d >= 1; d--) {
+				const uint32_t s0 = s - d + 1;
+				float w = (d == 1) ? cw : candW[(uint64_t)(s0 % D) * L + lab];
+				const int32_t ptr = (d == 1) ? cp : candP[(uint64_t)(s0 % D) * L + lab];
+				if (w < VIT_INF) w = w + p.negS[((uint64_t)(off + s) * D + (d - 1)) * L + lab];
+				if (d == dmax || w < best) { best = w; bptr = ptr; bdur = d; }
+			}
+			Wprev[lab] = best;
+			p.bp[(uint64_t)(off + s) * L + lab] = bptr < 0 ? (uint16_t)0xffff : (uint16_t)bptr;
+			p.bd[(uint64_t)(off + s) * L + lab] = (uint8_t)bdur;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			// a[s] := descriptor of the ARRIVAL order at start frame s; a[0] = identity.
+			// a[s>=1] (NS==1): head of kept(s-1) moved to the back; kept(s-1) = a[max(0, s-1-D+1)] = a[max(0, s-D)].
+			uint32_t a_s = 0xffu;
+			if (NS == 1 && P > 1 && s >= 1) {
+				const uint32_t j = s >= D ? s - D : 0;
+				const uint32_t aj = j == 0 ? 0xffu : p.gmove[off + j];
+				a_s = (aj == 0xffu) ? 0u : (aj == 0u ? 1u : 0u);     // head of the list described by aj
+			}
+			p.gmove[off + s] = (uint8_t)a_s;
+			// order of kept(s) feeds the cross scan of frame s+1: kept(s) = a[max(0, s-D+1)]
+			const uint32_t j2 = s + 1 >= D ? s + 1 - D : 0;
+			s_g = (j2 == 0) ? 0xffu : (j2 == s ? a_s : p.gmove[off + j2]);
+		}
+		__syncthreads();
+	}
+	// ---- final argmin over the kept list (first wins) and traceback ----
+	if (threadIdx.x == 0) {
+		uint32_t nseg = 0; float minw = VIT_INF; int best = -1;
+		if (T > 0) {
+			const uint32_t g = s_g;
+			for (uint32_t i = 0; i < P; i++) {
+				const uint32_t e = kept_phone(i, P, g) * NS + NS - 1;
+				const float w = Wprev[e];
+				if (w < minw) { minw = w; best = (int)e; }
+			}
+			if (best >= 0) {
+				int end = (int)T - 1; int cur = best;
+				uint32_t* ol = p.out_lab + off; uint32_t* od = p.out_dur + off; uint32_t* op = p.out_phn + off;
+				while (end >= 0) {
+					const uint32_t d = p.bd[(uint64_t)(off + end) * L + cur];
+					const uint16_t prev = p.bp[(uint64_t)(off + end) * L + cur];
+					const int start = end + 1 - (int)d;
+					ol[nseg] = (uint32_t)cur; od[nseg] = d;
+					if (start == 0) op[nseg] = (uint32_t)cur / NS;
+					else op[nseg] = ((uint32_t)cur % NS == 0 && (int)prev != cur) ? (uint32_t)cur / NS : LAB_BAD;
+					nseg++;
+					if (start == 0) break;
+					cur = (int)prev; end = start - 1;
+				}
+				for (uint32_t i = 0; i < nseg / 2; i++) {
+					uint32_t a;
+					a = ol[i]; ol[i] = ol[nseg - 1 - i]; ol[nseg - 1 - i] = a;
+					a = od[i]; od[i] = od[nseg - 1 - i]; od[nseg - 1 - i] = a;
+					a = op[i]; op[i] = op[nseg - 1 - i]; op[nseg - 1 - i] = a;
+				}
+			}
+		}
+		p.n_seg[u] = nseg; p.cost[u] = minw;
+	}
+}
+void launch_viterbi(const VitParams& p, cudaStream_t s) {
+	if (!p.n_utt) return;
+	const unsigned threads = (p.L + 31) / 32 * 32;
+	size_t smem = sizeof(float) * p.L;
+	if ((size_t)p.P * p.P * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * p.P;
+	cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(p);
+}
+
+}  // namespace crfgpu

@@ -1,0 +1,129 @@
+// Device kernels of libcrfgpu (sm_100a).  Declarations + parameter blocks; definitions in crf_kernels.cu.
+// Citations are relative to the ASR-CRaFT tree.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace crfgpu {
+
+constexpr uint32_t LAB_BAD = 0xffffffffu;
+constexpr float VIT_INF = 99999.0f;  // the decoder's finite "infinity" (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:124-128)
+
+// ---- window expansion (K7) ---------------------------------------------------------------------
+struct ExpandParams {
+	const float* base;        // [N][F]
+	const uint32_t* frame_t;  // [N] frame index inside its utterance
+	const uint32_t* steps;    // [D*5] sample offsets (host-computed, see sample_steps())
+	float* X;                 // [N][D][W]
+	uint32_t N, F, D, W;
+	uint32_t seg_ftrs;        // 1: [5 samples|avg|max|min|one-hot dur], 0: first frame of the window
+};
+void launch_expand_windows(const ExpandParams& p, cudaStream_t s);
+
+// ---- GEMM-1: state scores  S[n][col0+j] = sum_k A[n][k]*B[j][k] + bias[j] ----------------------
+struct ScoreGemmParams {
+	const float* A; uint64_t lda;     // [M][K] row stride lda (window features of one duration)
+	const float* B; uint32_t ldb;     // [Ncols][K] state weights
+	const float* bias;                // [Ncols] (already multiplied by stateBiasVal) or nullptr
+	float* C; uint32_t ldc;           // [M][ldc], written at column offset applied by the caller
+	uint32_t M, Ncols, K;
+	const uint32_t* frame_t; uint32_t min_t;  // rows with frame_t[n] < min_t are skipped (window d needs t >= d-1)
+};
+void launch_score_gemm(const ScoreGemmParams& p, cudaStream_t s);
+
+// ---- dense lattice recursions in the probability domain ----------------------------------------
+// One CTA owns U utterances ("slots"); thread c owns label column c.  L <= 1024.
+struct DpParams {
+	uint32_t L, Lp, P, D;       // labels, padded row stride, phones (= L / D), max duration
+	uint32_t n_groups;
+	const uint32_t* grp_utt;    // [n_groups*U] utterance id per slot, LAB_BAD = empty slot
+	const uint32_t* off;        // [n_utt+1]
+	const float* S;             // [N][Lp] state scores
+	const float* E;             // [L][Lp]  E[q*Lp+c]  = exp(M[q][c]-Mmax), 0 for illegal pairs
+	const float* ET;            // [L][Lp]  ET[c*Lp+q] = E[q][c]
+	float* A;                   // [N][Lp] alpha, max-normalised per frame (probability domain)
+	float* G;                   // [N][Lp] forward: pushed sums a_t*E ; backward: w~_t = exp(S+beta-kappa)
+	double* m;                  // [N] log scale of A
+	double* kappa;              // [N] log scale of w~
+	double* bbase;              // [N] beta_t[c] = bbase[n] + log(u[c]); u stored in U_out when requested
+	float* Uvec;                // [N][Lp] (optional, for alpha/beta dumps) unnormalised backward sums
+	double* logZ;               // [n_utt]
+	float* Dm;                  // [N][Lp] onehot(reference label) - gamma
+	float* R;                   // [N][Lp] exp(S+beta+m_{t-d}+Mmax-logZ), the right factor of xi
+	const uint32_t* node_lab;   // [N] label (incl. duration) of the reference segment ending here, or LAB_BAD
+	double Mmax;
+	double* mass;               // [N] sum_c gamma (posterior-mass check), optional
+};
+void launch_forward(const DpParams& p, int U, cudaStream_t s);
+void launch_backward(const DpParams& p, int U, cudaStream_t s);
+
+// ---- TN GEMM with fp64 scatter epilogue:  out[map(i,j)] += scale * sum_n A[n][i]*B[n][j] --------
+struct ReduceGemmParams {
+	const float* A; uint64_t lda;   // rows n in [n0,n1), A row used = n - a_row_shift
+	const float* B; uint64_t ldb;
+	uint32_t n0, n1, a_row_shift;
+	uint32_t I, J;                  // output tile extents
+	uint32_t ones_col;              // if < J: column j==ones_col of B is the constant 1 (bias feature)
+	double scale, ones_scale;       // ones_scale applies to the ones column instead of scale
+	// epilogue mode 0: out[row_idx[i] + j]           (state weights; row_idx = sidx of the label)
+	// epilogue mode 1: out[pair_idx[i*pair_ld + j]] += scale*Ew[i*e_ld+j]*sum  (transition bias; skip NO_IDX)
+	int mode;
+	const uint32_t* row_idx;
+	const uint32_t* pair_idx; uint32_t pair_ld;
+	const float* Ew; uint32_t e_ld;
+	double* out;
+	uint32_t k_slab;                // rows of n per CTA (split-K)
+};
+void launch_reduce_gemm(const ReduceGemmParams& p, cudaStream_t s);
+
+// ---- empirical counts and numerators on the reference path -------------------------------------
+struct EmpiricalParams {
+	const float* X; uint64_t ldx;     // window features [N][D][W] (ldx = D*W)
+	uint32_t W, sf0, nSf;
+	const uint32_t* node_lab;         // [N]
+	const uint32_t* prev_lab;         // [N] label of the previous reference segment or LAB_BAD
+	const uint32_t* frame_utt;        // [N] utterance of the frame
+	uint32_t N, L, P;
+	const double* lambda;
+	const uint32_t* sidx; const uint32_t* tidx;
+	int use_state_bias, use_trans_bias;
+	double state_bias_val, trans_bias_val;
+	double* grad;                     // transition-bias empirical counts are added here
+	double* numer;                    // [n_utt]
+};
+void launch_empirical(const EmpiricalParams& p, cudaStream_t s);
+
+// ---- Viterbi (token-passing decoder restated as arrays; free-phone LM, beam 0) ------------------
+struct VitScoreParams {
+	const float* X; uint64_t ldx;     // [N][D][W]
+	uint32_t W, sf0, nSf, N, D, L;
+	const uint32_t* frame_t;
+	const double* Wd;                 // [nSf+1][L] state weights transposed, last row = bias weight
+	int use_bias; double bias_val;
+	float* negS;                      // [N][D][L]  (float)(-S) computed in fp64 in the reference's order
+};
+void launch_vit_scores(const VitScoreParams& p, cudaStream_t s);
+
+struct VitParams {
+	uint32_t n_utt, L, P, NS, D;
+	const uint32_t* off;
+	const float* negS;                // [N][D][L]
+	const float* crossT;              // [P][P]  crossT[pp*P+q] = (float)(-M[end(pp)][start(q)])
+	const float* negDiag;             // [L]     (float)(-M[l][l])
+	const float* negOff;              // [L]     (float)(-M[l-1][l]) for sub-state > 0
+	float* candW; int32_t* candP;     // [n_utt][D][L] rings of candidates per start frame
+	float* keptW;                     // [n_utt][2][L]
+	uint16_t* bp; uint8_t* bd;        // [N][L] back pointer (label or 0xffff) and duration
+	uint8_t* gmove;                   // [N] which phone was moved to the back of the kept list (0xff none)
+	uint32_t* out_lab; uint32_t* out_dur; uint32_t* out_phn; uint32_t* n_seg; float* cost;
+};
+void launch_viterbi(const VitParams& p, cudaStream_t s);
+
+// ---- small helpers ------------------------------------------------------------------------------
+void launch_fill_f32(float* p, uint64_t n, float v, cudaStream_t s);
+void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t s);
+// alpha/beta in the log domain for tests: alpha = m + log A, beta = bbase + log U (LOG0 where undefined)
+void launch_dump_alpha_beta(const DpParams& p, uint32_t N, const uint32_t* frame_t, const uint32_t* frame_len,
+                            double* alpha, double* beta, cudaStream_t s);
+
+}  // namespace crfgpu

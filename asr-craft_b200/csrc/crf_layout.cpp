@@ -1,0 +1,110 @@
+#include "crf_layout.h"
+
+#include <cmath>
+#include <stdexcept>
+
+namespace crfgpu {
+
+uint32_t window_width(const crfgpu_config& c) {
+	// CRF_InFtrStream_SeqMultiWindow ctor (CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:50-125), no context frames
+	if (c.max_dur == 1 || !c.extract_seg_ftrs) return c.n_base_ftrs;
+	return 8 * c.n_base_ftrs + c.max_dur;
+}
+
+Layout build_layout(const crfgpu_config& c) {
+	Layout m;
+	if (c.n_states == 0 || c.n_labs == 0 || c.n_labs % c.n_states != 0)
+		throw std::runtime_error("CRF_StdFeatureMap: invalid state/label combination while computing transitions");
+	const uint32_t W = window_width(c);
+	if (c.use_state_ftrs && (c.state_fidx_end < c.state_fidx_start || c.state_fidx_end >= W))
+		throw std::runtime_error("state feature index range outside the window feature vector");
+	if (c.use_trans_ftrs && (c.trans_fidx_end < c.trans_fidx_start || c.trans_fidx_end >= W))
+		throw std::runtime_error("transition feature index range outside the window feature vector");
+	m.L = c.n_labs;
+	m.n_states = c.n_states;
+	m.n_act = c.n_labs / c.n_states;
+	m.nSf = c.use_state_ftrs ? c.state_fidx_end - c.state_fidx_start + 1 : 0;
+	m.nTf = c.use_trans_ftrs ? c.trans_fidx_end - c.trans_fidx_start + 1 : 0;
+	m.nS = m.nSf + (c.use_state_bias ? 1u : 0u);
+	m.nT = m.nTf + (c.use_trans_bias ? 1u : 0u);
+	// end->start block + self transitions + previous-sub-state transitions (:478-485)
+	const uint64_t n_pairs = (m.n_states == 1) ? uint64_t(m.n_act) * m.n_act
+	                                           : uint64_t(m.n_act) * m.n_act + m.L + (m.L - m.n_act);
+	const uint64_t len = uint64_t(m.nS) * m.L + uint64_t(m.nT) * n_pairs;
+	if (len >= 0xffffffffull) throw std::runtime_error("lambda vector does not fit 32-bit indexing");
+	m.len = uint32_t(len);
+	m.sidx.resize(m.L);
+	m.tidx.assign(size_t(m.L) * m.L, CRFGPU_NO_IDX);
+	const uint32_t L = m.L, N = m.n_states;
+	if (N == 1) {
+		// each label owns one contiguous block: [state funcs | for every previous label: trans funcs] (:295,365)
+		const uint32_t block = m.nS + L * m.nT;
+		for (uint32_t cl = 0; cl < L; cl++) {
+			m.sidx[cl] = cl * block;
+			for (uint32_t pl = 0; pl < L; pl++) m.tidx[size_t(pl) * L + cl] = cl * block + m.nS + pl * m.nT;
+		}
+	} else {
+		// per label: state funcs, self transition, then (start sub-state) one block per phone for the
+		// end->start arcs, or (inner sub-state) the single arc from the previous sub-state (:298-315, 369-405)
+		uint32_t pos = 0;
+		for (uint32_t cl = 0; cl < L; cl++) {
+			m.sidx[cl] = pos;
+			const uint32_t self = pos + m.nS;
+			m.tidx[size_t(cl) * L + cl] = self;
+			if (cl % N == 0) {
+				for (uint32_t ph = 0; ph < m.n_act; ph++) {
+					const uint32_t pl = ph * N + N - 1;
+					if (pl != cl) m.tidx[size_t(pl) * L + cl] = self + m.nT + ph * m.nT;
+				}
+				pos = self + (m.n_act + 1) * m.nT;
+			} else {
+				m.tidx[size_t(cl - 1) * L + cl] = self + m.nT;
+				pos = self + 2 * m.nT;
+			}
+		}
+	}
+	return m;
+}
+
+void group_labels(uint32_t D, uint32_t T, const uint32_t* labs, uint32_t* out4) {
+	for (size_t i = 0; i < size_t(T) * 4; i++) out4[i] = CRFGPU_LAB_BAD;
+	uint32_t run_start = 0;
+	while (run_start < T) {
+		uint32_t run_end = run_start;  // inclusive
+		while (run_end + 1 < T && labs[run_end + 1] == labs[run_start]) run_end++;
+		const uint32_t lab = labs[run_start], dur = run_end - run_start + 1;
+		if (lab != CRFGPU_LAB_BAD) {
+			if (dur <= D) {
+				uint32_t* o = out4 + 4 * size_t(run_end);
+				o[0] = lab; o[1] = run_start; o[2] = run_end; o[3] = 0;
+			} else {
+				// long runs are cut into ceil(dur/D) near-equal pieces, the longer ones first (:75-106)
+				const uint32_t pieces = (dur + D - 1) / D, base = dur / pieces, extra = dur % pieces;
+				uint32_t ps = run_start;
+				for (uint32_t r = 0; r < pieces; r++) {
+					const uint32_t pe = ps + base + (r < extra ? 1u : 0u) - 1;
+					uint32_t* o = out4 + 4 * size_t(pe);
+					o[0] = lab; o[1] = ps; o[2] = pe; o[3] = 1;
+					ps = pe + 1;
+				}
+			}
+		}
+		run_start = run_end + 1;
+	}
+}
+
+std::vector<uint32_t> sample_steps(uint32_t D) {
+	std::vector<uint32_t> steps(size_t(D) * 5);
+	for (uint32_t d = 1; d <= D; d++) {
+		// float one_tenth_win_len = cur_win_len * 0.1;  frameStep = (QNUInt32)ceil(one_tenth_win_len * i) - 1  (:569-573)
+		volatile float one_tenth = float(d * 0.1);
+		int k = 0;
+		for (int i = 1; i < 10; i += 2, k++) {
+			volatile float prod = one_tenth * float(i);
+			steps[size_t(d - 1) * 5 + k] = uint32_t(std::ceil(prod)) - 1;
+		}
+	}
+	return steps;
+}
+
+}  // namespace crfgpu

@@ -1,0 +1,39 @@
+// Host-side geometry of the CRF: lambda-vector layout, window widths, label grouping.
+// Product code (part of libcrfgpu.so).  Citations are relative to the ASR-CRaFT tree.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/crfgpu.h"
+
+namespace crfgpu {
+
+// Layout of the lambda vector as defined by CRF_StdFeatureMap::recalc and its index functions
+// (CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:280-320, 355-410, 472-517).
+struct Layout {
+	uint32_t L = 0;        // labels (stdseg: phones * max_dur)
+	uint32_t n_states = 1; // sub-states per phone
+	uint32_t n_act = 0;    // L / n_states ("numActualLabels" of the map)
+	uint32_t nSf = 0, nTf = 0;  // state / transition FEATURES per label (pair)
+	uint32_t nS = 0, nT = 0;    // state / transition FUNCTIONS (features + bias)
+	uint32_t len = 0;      // lambda length
+	std::vector<uint32_t> sidx;  // [L]
+	std::vector<uint32_t> tidx;  // [L*L] at [plab*L+clab]; CRFGPU_NO_IDX when the topology forbids the pair
+};
+
+// Throws std::runtime_error on the geometry errors the reference throws for.
+Layout build_layout(const crfgpu_config& c);
+
+uint32_t window_width(const crfgpu_config& c);
+
+// CRF_InLabStream_SeqMultiWindow (CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-306): per frame
+// (label,start,end,broken) on the frame where a (possibly split) reference segment ends, else LAB_BAD x4.
+void group_labels(uint32_t max_dur, uint32_t n_frames, const uint32_t* frame_labs, uint32_t* out4);
+
+// Sample offsets of CRF_InFtrStream_SeqMultiWindow::sample_ftrs (CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:556-590):
+// steps[(d-1)*5+k] = frame offset from the window start of the k-th sampled frame for duration d.
+// Computed on the host with the reference's own float arithmetic so the device never re-derives it.
+std::vector<uint32_t> sample_steps(uint32_t max_dur);
+
+}  // namespace crfgpu

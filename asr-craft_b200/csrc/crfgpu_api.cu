@@ -1,0 +1,649 @@
+// libcrfgpu.so -- C ABI (include/crfgpu.h) over the sm_100a kernels.  Host code here only stages
+// buffers, derives the device-side tables from lambda and sequences kernel launches on one stream.
+// There is no CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/crfgpu.h"
+#include "crf_kernels.cuh"
+#include "crf_layout.h"
+
+using namespace crfgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct ApiError : std::runtime_error {
+	int code;
+	ApiError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_OK(expr)                                                                                   \
+	do {                                                                                                \
+		cudaError_t e_ = (expr);                                                                        \
+		if (e_ != cudaSuccess)                                                                          \
+			throw ApiError(CRFGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+	} while (0)
+
+// growable device buffer
+struct DevBuf {
+	void* p = nullptr; size_t cap = 0;
+	void ensure(size_t bytes) {
+		if (bytes <= cap) return;
+		if (p) CUDA_OK(cudaFree(p));
+		p = nullptr; cap = 0;
+		size_t want = bytes + bytes / 8 + 256;
+		CUDA_OK(cudaMalloc(&p, want));
+		cap = want;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct crfgpu_ctx {
+	crfgpu_config cfg{};
+	Layout lay;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	uint32_t W = 0;          // window feature width
+	uint32_t Lp = 0;         // padded label stride
+	bool train_ok = false, decode_ok = false;
+	std::string train_why, decode_why;
+	uint64_t launches = 0;
+	int opt_slots = 0, opt_keep_lattice = 0; uint32_t opt_k_slab = 1024;
+
+	// model tables
+	bool have_lambda = false;
+	DevBuf d_lambda, d_sidx, d_tidx, d_Ws, d_bias, d_E, d_ET, d_steps;
+	DevBuf d_Wd, d_crossT, d_negDiag, d_negOff;
+	double Mmax = 0.0;
+
+	// staged batch
+	uint32_t n_utt = 0, N = 0; bool have_labels = false;
+	std::vector<uint32_t> h_off;
+	DevBuf d_off, d_base, d_frame_t, d_frame_utt, d_frame_len, d_node_lab, d_prev_lab, d_grp;
+	uint32_t n_groups = 0; int U = 1;
+	DevBuf d_X, d_S, d_A, d_G, d_m, d_kappa, d_bbase, d_Uvec, d_Dm, d_R, d_logZ, d_numer, d_grad;
+	bool fwdbwd_done = false;
+	// viterbi
+	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
+	bool viterbi_done = false;
+
+	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
+
+	const float* X() const { return (cfg.max_dur == 1) ? d_base.as<float>() : d_X.as<float>(); }
+	uint64_t ldx() const { return (uint64_t)cfg.max_dur * W; }
+};
+
+namespace {
+
+void phase_begin(crfgpu_ctx* h, const char* name) {
+	auto& ev = h->phases[name];
+	if (!ev.first) { CUDA_OK(cudaEventCreate(&ev.first)); CUDA_OK(cudaEventCreate(&ev.second)); }
+	CUDA_OK(cudaEventRecord(ev.first, h->stream));
+}
+void phase_end(crfgpu_ctx* h, const char* name) { CUDA_OK(cudaEventRecord(h->phases[name].second, h->stream)); }
+
+template <class T>
+void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+	b.ensure(v.size() * sizeof(T) + 16);
+	if (!v.empty()) CUDA_OK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+void check_kernel(crfgpu_ctx* h, int n_launches) {
+	h->launches += n_launches;
+	CUDA_OK(cudaGetLastError());
+}
+
+// Which paths the device implements for this geometry (anything else fails loudly, never emulated).
+void classify(crfgpu_ctx* h) {
+	const crfgpu_config& c = h->cfg;
+	h->train_ok = h->decode_ok = true;
+	if (c.use_trans_ftrs) {
+		h->train_ok = h->decode_ok = false;
+		h->train_why = h->decode_why = "transition FEATURES (crf_featuremap=stdtrans) are not implemented on the device yet; "
+		                               "transition bias only";
+		return;
+	}
+	if (c.model_type == CRFGPU_STDFRAME) {
+		if (c.max_dur != 1) { h->train_ok = h->decode_ok = false; h->train_why = h->decode_why = "stdframe requires label_maximum_duration == 1"; }
+	} else if (c.model_type == CRFGPU_STDSEG) {
+		h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
+		if (c.n_states != 1) { h->train_ok = false; h->train_why = "stdseg with crf_states > 1 throws in the reference (CRF_StateNode.cpp:497-502)"; }
+		if (c.n_labs % c.max_dur != 0) { h->train_ok = false; h->train_why = "stdseg: crf_label_size must be phones * label_maximum_duration"; }
+	} else if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
+		h->train_ok = false; h->train_why = "forward-backward for stdseg_no_dur_no_segtransftr is not implemented on the device yet";
+	} else {
+		h->train_ok = h->decode_ok = false;
+		h->train_why = h->decode_why = "model type not implemented on the device yet (stdseg_no_dur / stdseg_no_dur_no_transftr)";
+	}
+	if (h->train_ok && c.n_labs > 1024) { h->train_ok = false; h->train_why = "dense lattice kernels support crf_label_size <= 1024"; }
+	if (h->decode_ok && (c.n_labs > 1024 || c.max_dur > 255)) { h->decode_ok = false; h->decode_why = "Viterbi kernel supports crf_label_size <= 1024 and max duration <= 255"; }
+	if (h->train_ok && c.max_dur > 32) { h->train_ok = false; h->train_why = "lattice kernels support label_maximum_duration <= 32"; }
+}
+
+void require_train(crfgpu_ctx* h) {
+	if (!h->train_ok) throw ApiError(CRFGPU_ERR_UNSUPPORTED, h->train_why);
+	if (!h->have_lambda) throw ApiError(CRFGPU_ERR_ARG, "crfgpu_set_lambda has not been called");
+}
+void require_decode(crfgpu_ctx* h) {
+	if (!h->decode_ok) throw ApiError(CRFGPU_ERR_UNSUPPORTED, h->decode_why);
+	if (!h->have_lambda) throw ApiError(CRFGPU_ERR_ARG, "crfgpu_set_lambda has not been called");
+}
+
+// ---------------------------------------------------------------------------------------------
+void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	if (len != m.len) throw ApiError(CRFGPU_ERR_ARG, "lambda length " + std::to_string(len) + " != feature map length " + std::to_string(m.len));
+	const uint32_t L = m.L, Lp = h->Lp, nSf = m.nSf;
+	cudaStream_t s = h->stream;
+	h->d_lambda.ensure(sizeof(double) * (size_t)len + 16);
+	CUDA_OK(cudaMemcpyAsync(h->d_lambda.p, lam, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, s));
+
+	// transition scores: M[p][c] = lambda[tidx]*transBiasVal (CRF_StdFeatureMap.cpp:94-110 with no transition features)
+	std::vector<double> M((size_t)L * L, 0.0);
+	double Mmax = -DBL_MAX;
+	for (uint32_t p = 0; p < L; p++)
+		for (uint32_t cl = 0; cl < L; cl++) {
+			const uint32_t ti = m.tidx[(size_t)p * L + cl];
+			if (ti == CRFGPU_NO_IDX) continue;
+			double v = 0.0;
+			if (c.use_trans_bias) v += lam[ti] * c.trans_bias_val;
+			M[(size_t)p * L + cl] = v;
+			Mmax = std::max(Mmax, v);
+		}
+	if (Mmax == -DBL_MAX) Mmax = 0.0;
+	h->Mmax = Mmax;
+
+	if (h->train_ok) {
+		std::vector<float> Ws((size_t)L * std::max(nSf, 1u)), bias(L, 0.0f), E((size_t)L * Lp, 0.0f), ET((size_t)L * Lp, 0.0f);
+		for (uint32_t cl = 0; cl < L; cl++) {
+			const double* w = lam + m.sidx[cl];
+			for (uint32_t f = 0; f < nSf; f++) Ws[(size_t)cl * nSf + f] = (float)w[f];
+			if (c.use_state_bias) bias[cl] = (float)(w[nSf] * c.state_bias_val);
+		}
+		for (uint32_t p = 0; p < L; p++)
+			for (uint32_t cl = 0; cl < L; cl++)
+				if (m.tidx[(size_t)p * L + cl] != CRFGPU_NO_IDX) {
+					const float e = (float)std::exp(M[(size_t)p * L + cl] - Mmax);
+					E[(size_t)p * Lp + cl] = e; ET[(size_t)cl * Lp + p] = e;
+				}
+		upload(h->d_Ws, Ws, s); upload(h->d_bias, bias, s); upload(h->d_E, E, s); upload(h->d_ET, ET, s);
+		CUDA_OK(cudaStreamSynchronize(s));   // host vectors die at scope exit
+	}
+	if (h->decode_ok) {
+		// decoder tables in the reference's arithmetic: double score, negate, narrow to float
+		// (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:286,315,331,458)
+		const uint32_t NS = m.n_states, P = m.n_act;
+		std::vector<double> Wd((size_t)(nSf + 1) * L, 0.0);
+		for (uint32_t cl = 0; cl < L; cl++) {
+			const double* w = lam + m.sidx[cl];
+			for (uint32_t f = 0; f < nSf; f++) Wd[(size_t)f * L + cl] = w[f];
+			if (c.use_state_bias) Wd[(size_t)nSf * L + cl] = w[nSf];
+		}
+		std::vector<float> crossT((size_t)P * P), negDiag(L), negOff(L, 0.0f);
+		for (uint32_t pp = 0; pp < P; pp++)
+			for (uint32_t q = 0; q < P; q++) {
+				const uint32_t pe = pp * NS + NS - 1, cs = q * NS;
+				crossT[(size_t)pp * P + q] = (float)(-1 * M[(size_t)pe * L + cs]);
+			}
+		for (uint32_t l = 0; l < L; l++) {
+			negDiag[l] = (float)(-1 * M[(size_t)l * L + l]);
+			if (l % NS != 0) negOff[l] = (float)(-1 * M[(size_t)(l - 1) * L + l]);
+		}
+		upload(h->d_Wd, Wd, s); upload(h->d_crossT, crossT, s); upload(h->d_negDiag, negDiag, s); upload(h->d_negOff, negOff, s);
+		CUDA_OK(cudaStreamSynchronize(s));
+	}
+	h->have_lambda = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs) {
+	const crfgpu_config& c = h->cfg;
+	if (!off || !ftrs) throw ApiError(CRFGPU_ERR_ARG, "null input pointer");
+	if (off[0] != 0) throw ApiError(CRFGPU_ERR_ARG, "frame_off[0] must be 0");
+	for (uint32_t u = 0; u < n_utt; u++)
+		if (off[u + 1] <= off[u])
+			throw ApiError(CRFGPU_ERR_ARG, "utterance " + std::to_string(u) + " has no frames (reference: \"No features read from this sentence\")");
+	const uint32_t N = n_utt ? off[n_utt] : 0;
+	cudaStream_t s = h->stream;
+	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
+	h->fwdbwd_done = h->viterbi_done = false;
+	h->h_off.assign(off, off + n_utt + 1);
+
+	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
+	for (uint32_t u = 0; u < n_utt; u++)
+		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
+	upload(h->d_off, h->h_off, s); upload(h->d_frame_t, frame_t, s); upload(h->d_frame_utt, frame_utt, s); upload(h->d_frame_len, frame_len, s);
+	h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
+	if (N) CUDA_OK(cudaMemcpyAsync(h->d_base.p, ftrs, sizeof(float) * (size_t)N * c.n_base_ftrs, cudaMemcpyHostToDevice, s));
+
+	std::vector<uint32_t> node_lab, prev_lab;
+	if (labs) {
+		// node label = (dur-1)*nActualLabs + phone on the frame where a reference segment ends
+		// (CRF_NewGradBuilder_StdSeg.cpp:172-187); prev_lab = label of the preceding reference segment (:343-351).
+		// Frame-level models label every frame (window length 1 cuts every run into 1-frame pieces).
+		node_lab.assign(N, CRFGPU_LAB_BAD); prev_lab.assign(N, CRFGPU_LAB_BAD);
+		std::vector<uint32_t> rec;
+		for (uint32_t u = 0; u < n_utt; u++) {
+			const uint32_t T = off[u + 1] - off[u];
+			rec.resize((size_t)T * 4);
+			group_labels(c.max_dur, T, labs + off[u], rec.data());
+			uint32_t last = CRFGPU_LAB_BAD;
+			for (uint32_t t = 0; t < T; t++) {
+				prev_lab[off[u] + t] = last;
+				if (rec[4 * (size_t)t] != CRFGPU_LAB_BAD) {
+					const uint32_t dur = rec[4 * (size_t)t + 2] - rec[4 * (size_t)t + 1] + 1;
+					const uint32_t lab = (c.model_type == CRFGPU_STDSEG) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
+					node_lab[off[u] + t] = lab; last = lab;
+				}
+			}
+		}
+		upload(h->d_node_lab, node_lab, s); upload(h->d_prev_lab, prev_lab, s);
+	}
+	// utterances sorted by length (longest first) so the slots of one CTA finish together; reordering inside a
+	// minibatch does not change the gradient sum
+	std::vector<uint32_t> order(n_utt);
+	std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+	int U = h->opt_slots;
+	if (U != 1 && U != 2 && U != 4 && U != 8) {
+		U = 1;
+		while (U < 8 && n_utt / (U * 2) >= 148) U *= 2;
+	}
+	h->U = U;
+	h->n_groups = (n_utt + U - 1) / U;
+	std::vector<uint32_t> grp((size_t)h->n_groups * U, CRFGPU_LAB_BAD);
+	// deal utterances round-robin over the groups so every group gets a similar mix of lengths?  No:
+	// consecutive (similar-length) utterances share a CTA, which minimises idle slots.
+	for (uint32_t i = 0; i < n_utt; i++) grp[i] = order[i];
+	upload(h->d_grp, grp, s);
+	CUDA_OK(cudaStreamSynchronize(s));   // host staging vectors die here
+
+	if (c.max_dur > 1 && N) {
+		h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->W + 16);
+		phase_begin(h, "expand");
+		ExpandParams ep{h->d_base.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_steps.as<uint32_t>(), h->d_X.as<float>(),
+		                N, c.n_base_ftrs, c.max_dur, h->W, c.extract_seg_ftrs};
+		launch_expand_windows(ep, s);
+		check_kernel(h, 1);
+		phase_end(h, "expand");
+	}
+}
+
+DpParams dp_params(crfgpu_ctx* h) {
+	const crfgpu_config& c = h->cfg;
+	DpParams p{};
+	p.L = h->lay.L; p.Lp = h->Lp; p.D = c.max_dur; p.P = h->lay.L / c.max_dur;
+	p.n_groups = h->n_groups; p.grp_utt = h->d_grp.as<uint32_t>(); p.off = h->d_off.as<uint32_t>();
+	p.S = h->d_S.as<float>(); p.E = h->d_E.as<float>(); p.ET = h->d_ET.as<float>();
+	p.A = h->d_A.as<float>(); p.G = h->d_G.as<float>(); p.m = h->d_m.as<double>(); p.kappa = h->d_kappa.as<double>();
+	p.bbase = h->d_bbase.as<double>(); p.Uvec = h->opt_keep_lattice ? h->d_Uvec.as<float>() : nullptr;
+	p.logZ = h->d_logZ.as<double>(); p.Dm = h->d_Dm.as<float>(); p.R = h->d_R.as<float>();
+	p.node_lab = h->d_node_lab.as<uint32_t>(); p.Mmax = h->Mmax; p.mass = nullptr;
+	return p;
+}
+
+void fwdbwd_staged(crfgpu_ctx* h) {
+	require_train(h);
+	if (!h->have_labels) throw ApiError(CRFGPU_ERR_ARG, "training needs frame labels");
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	const uint32_t N = h->N, L = m.L, Lp = h->Lp, D = c.max_dur, P = L / D, nSf = m.nSf;
+	cudaStream_t s = h->stream;
+	const size_t NL = (size_t)N * Lp;
+	h->d_S.ensure(sizeof(float) * NL + 16); h->d_A.ensure(sizeof(float) * NL + 16); h->d_G.ensure(sizeof(float) * NL + 16);
+	h->d_Dm.ensure(sizeof(float) * NL + 16); h->d_R.ensure(sizeof(float) * NL + 16);
+	if (h->opt_keep_lattice) h->d_Uvec.ensure(sizeof(float) * NL + 16);
+	h->d_m.ensure(sizeof(double) * (size_t)N + 16); h->d_kappa.ensure(sizeof(double) * (size_t)N + 16); h->d_bbase.ensure(sizeof(double) * (size_t)N + 16);
+	h->d_logZ.ensure(sizeof(double) * (size_t)h->n_utt + 16); h->d_numer.ensure(sizeof(double) * (size_t)h->n_utt + 16);
+	h->d_grad.ensure(sizeof(double) * (size_t)m.len + 16);
+	CUDA_OK(cudaMemsetAsync(h->d_grad.p, 0, sizeof(double) * (size_t)m.len, s));
+	CUDA_OK(cudaMemsetAsync(h->d_numer.p, 0, sizeof(double) * (size_t)h->n_utt, s));
+	if (!N) { h->fwdbwd_done = true; return; }
+
+	// K1: state scores, one GEMM per duration block
+	phase_begin(h, "score");
+	for (uint32_t d = 0; d < D; d++) {
+		ScoreGemmParams g{};
+		g.A = h->X() + (size_t)d * h->W + c.state_fidx_start; g.lda = h->ldx();
+		const bool per_dur = (c.model_type == CRFGPU_STDSEG);
+		g.B = h->d_Ws.as<float>() + (per_dur ? (size_t)d * P * nSf : 0); g.ldb = nSf;
+		g.bias = h->d_bias.as<float>() + (per_dur ? (size_t)d * P : 0);
+		g.C = h->d_S.as<float>() + (size_t)d * P; g.ldc = Lp;
+		g.M = N; g.Ncols = P; g.K = nSf;
+		if (nSf == 0) {   // bias-only state functions: S = bias
+			throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
+		}
+		launch_score_gemm(g, s);
+		check_kernel(h, 1);
+	}
+	phase_end(h, "score");
+
+	DpParams p = dp_params(h);
+	phase_begin(h, "forward");
+	launch_forward(p, h->U, s); check_kernel(h, 1);
+	phase_end(h, "forward");
+	phase_begin(h, "backward");
+	launch_backward(p, h->U, s); check_kernel(h, 1);
+	phase_end(h, "backward");
+
+	// K4: expected-minus-empirical counts as two families of reduce-GEMMs
+	phase_begin(h, "xi");
+	if (c.use_trans_bias) {
+		for (uint32_t d = 1; d <= D; d++) {
+			if (d >= N) break;
+			ReduceGemmParams r{};
+			r.A = h->d_A.as<float>(); r.lda = Lp; r.a_row_shift = d;
+			r.B = h->d_R.as<float>() + (size_t)(d - 1) * P; r.ldb = Lp;
+			r.n0 = d; r.n1 = N; r.I = L; r.J = P; r.ones_col = 0xffffffffu;
+			r.scale = -c.trans_bias_val; r.ones_scale = 0.0; r.mode = 1;
+			r.pair_idx = h->d_tidx.as<uint32_t>() + (size_t)(d - 1) * P; r.pair_ld = L;
+			r.Ew = h->d_E.as<float>() + (size_t)(d - 1) * P; r.e_ld = Lp;
+			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab;
+			launch_reduce_gemm(r, s); check_kernel(h, 1);
+		}
+	}
+	phase_end(h, "xi");
+	phase_begin(h, "grad");
+	for (uint32_t d = 0; d < D; d++) {
+		ReduceGemmParams r{};
+		r.A = h->d_Dm.as<float>() + (size_t)d * P; r.lda = Lp; r.a_row_shift = 0;
+		r.B = h->X() + (size_t)d * h->W + c.state_fidx_start; r.ldb = h->ldx();
+		r.n0 = 0; r.n1 = N; r.I = P; r.J = nSf + (c.use_state_bias ? 1 : 0);
+		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu;
+		r.scale = 1.0; r.ones_scale = c.state_bias_val; r.mode = 0;
+		r.row_idx = h->d_sidx.as<uint32_t>() + (size_t)d * P;
+		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab;
+		launch_reduce_gemm(r, s); check_kernel(h, 1);
+	}
+	EmpiricalParams e{};
+	e.X = h->X(); e.ldx = h->ldx(); e.W = h->W; e.sf0 = c.state_fidx_start; e.nSf = nSf;
+	e.node_lab = h->d_node_lab.as<uint32_t>(); e.prev_lab = h->d_prev_lab.as<uint32_t>(); e.frame_utt = h->d_frame_utt.as<uint32_t>();
+	e.N = N; e.L = L; e.P = P; e.lambda = h->d_lambda.as<double>(); e.sidx = h->d_sidx.as<uint32_t>(); e.tidx = h->d_tidx.as<uint32_t>();
+	e.use_state_bias = c.use_state_bias; e.use_trans_bias = c.use_trans_bias;
+	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
+	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
+	launch_empirical(e, s); check_kernel(h, 1);
+	phase_end(h, "grad");
+	h->fwdbwd_done = true;
+}
+
+void viterbi_staged(crfgpu_ctx* h) {
+	require_decode(h);
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	const uint32_t N = h->N, L = m.L, D = c.max_dur, NS = m.n_states, P = m.n_act;
+	cudaStream_t s = h->stream;
+	h->d_negS.ensure(sizeof(float) * (size_t)N * D * L + 16);
+	h->d_candW.ensure(sizeof(float) * (size_t)h->n_utt * D * L + 16); h->d_candP.ensure(sizeof(int32_t) * (size_t)h->n_utt * D * L + 16);
+	h->d_bp.ensure(sizeof(uint16_t) * (size_t)N * L + 16); h->d_bd.ensure((size_t)N * L + 16); h->d_gmove.ensure((size_t)N + 16);
+	h->d_olab.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_odur.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_ophn.ensure(sizeof(uint32_t) * (size_t)N + 16);
+	h->d_nseg.ensure(sizeof(uint32_t) * (size_t)h->n_utt + 16); h->d_cost.ensure(sizeof(float) * (size_t)h->n_utt + 16);
+	if (!N) { h->viterbi_done = true; return; }
+	phase_begin(h, "viterbi_score");
+	VitScoreParams vs{};
+	vs.X = h->X(); vs.ldx = h->ldx(); vs.W = h->W; vs.sf0 = c.state_fidx_start; vs.nSf = m.nSf; vs.N = N; vs.D = D; vs.L = L;
+	vs.frame_t = h->d_frame_t.as<uint32_t>(); vs.Wd = h->d_Wd.as<double>(); vs.use_bias = c.use_state_bias; vs.bias_val = c.state_bias_val;
+	vs.negS = h->d_negS.as<float>();
+	launch_vit_scores(vs, s); check_kernel(h, 1);
+	phase_end(h, "viterbi_score");
+	phase_begin(h, "viterbi");
+	VitParams v{};
+	v.n_utt = h->n_utt; v.L = L; v.P = P; v.NS = NS; v.D = D; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
+	v.crossT = h->d_crossT.as<float>(); v.negDiag = h->d_negDiag.as<float>(); v.negOff = h->d_negOff.as<float>();
+	v.candW = h->d_candW.as<float>(); v.candP = h->d_candP.as<int32_t>(); v.keptW = nullptr;
+	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
+	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
+	v.n_seg = h->d_nseg.as<uint32_t>(); v.cost = h->d_cost.as<float>();
+	launch_viterbi(v, s); check_kernel(h, 1);
+	phase_end(h, "viterbi");
+	h->viterbi_done = true;
+}
+
+template <class F>
+int guarded(F&& f) {
+	try { f(); return CRFGPU_OK; }
+	catch (const ApiError& e) { g_err = e.what(); return e.code; }
+	catch (const std::exception& e) { g_err = e.what(); return CRFGPU_ERR_ARG; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* crfgpu_last_error(void) { return g_err.c_str(); }
+
+uint32_t crfgpu_window_width(const crfgpu_config* cfg) { return cfg ? window_width(*cfg) : 0; }
+
+int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
+	if (out) *out = nullptr;
+	crfgpu_ctx* h = nullptr;
+	int rc = guarded([&] {
+		if (!cfg || !out) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		int n_dev = 0;
+		cudaError_t e = cudaGetDeviceCount(&n_dev);
+		if (e != cudaSuccess || n_dev == 0)
+			throw ApiError(CRFGPU_ERR_CUDA, std::string("no usable CUDA device (libcrfgpu has no CPU fallback): ") +
+			                                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+		if (device < 0 || device >= n_dev) throw ApiError(CRFGPU_ERR_ARG, "device index out of range");
+		CUDA_OK(cudaSetDevice(device));
+		h = new crfgpu_ctx();
+		h->cfg = *cfg; h->device = device;
+		h->lay = build_layout(*cfg);
+		h->W = window_width(*cfg);
+		h->Lp = (h->lay.L + 31) / 32 * 32;
+		if (cfg->max_dur == 0) throw ApiError(CRFGPU_ERR_ARG, "the maximum duration of labels must be larger than 0");
+		classify(h);
+		CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+		upload(h->d_sidx, h->lay.sidx, h->stream); upload(h->d_tidx, h->lay.tidx, h->stream);
+		std::vector<uint32_t> steps = sample_steps(cfg->max_dur);
+		upload(h->d_steps, steps, h->stream);
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+		const char* env = getenv("CRFGPU_SLOTS");
+		if (env) h->opt_slots = atoi(env);
+		*out = h;
+	});
+	if (rc != CRFGPU_OK && h) { delete h; }
+	return rc;
+}
+
+int crfgpu_destroy(crfgpu_handle h) {
+	if (!h) return CRFGPU_OK;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	DevBuf* bufs[] = {&h->d_lambda, &h->d_sidx, &h->d_tidx, &h->d_Ws, &h->d_bias, &h->d_E, &h->d_ET, &h->d_steps, &h->d_Wd, &h->d_crossT,
+	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
+	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
+	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
+	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost};
+	for (DevBuf* b : bufs) b->release();
+	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
+	cudaStreamDestroy(h->stream);
+	delete h;
+	return CRFGPU_OK;
+}
+
+uint32_t crfgpu_lambda_len(crfgpu_handle h) { return h ? h->lay.len : 0; }
+
+int crfgpu_index_maps(crfgpu_handle h, uint32_t* state_idx, uint32_t* trans_idx) {
+	return guarded([&] {
+		if (!h || !state_idx || !trans_idx) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		std::memcpy(state_idx, h->lay.sidx.data(), sizeof(uint32_t) * h->lay.sidx.size());
+		std::memcpy(trans_idx, h->lay.tidx.data(), sizeof(uint32_t) * h->lay.tidx.size());
+	});
+}
+
+int crfgpu_set_lambda(crfgpu_handle h, const double* lambda, uint32_t len) {
+	return guarded([&] {
+		if (!h || !lambda) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		CUDA_OK(cudaSetDevice(h->device));
+		set_lambda(h, lambda, len);
+	});
+}
+
+int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		stage_batch(h, n_utt, frame_off, base_ftrs, frame_labs);
+	});
+}
+
+int crfgpu_fwdbwd_staged(crfgpu_handle h) {
+	return guarded([&] { if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle"); CUDA_OK(cudaSetDevice(h->device)); fwdbwd_staged(h); });
+}
+int crfgpu_viterbi_staged(crfgpu_handle h) {
+	return guarded([&] { if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle"); CUDA_OK(cudaSetDevice(h->device)); viterbi_staged(h); });
+}
+
+int crfgpu_device_results(crfgpu_handle h, double** d_grad, double** d_numer, double** d_logZ) {
+	return guarded([&] {
+		if (!h || !h->fwdbwd_done) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
+		if (d_grad) *d_grad = h->d_grad.as<double>();
+		if (d_numer) *d_numer = h->d_numer.as<double>();
+		if (d_logZ) *d_logZ = h->d_logZ.as<double>();
+	});
+}
+
+int crfgpu_fetch_fwdbwd(crfgpu_handle h, double* grad, double* numer, double* logZ) {
+	return guarded([&] {
+		if (!h || !h->fwdbwd_done) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
+		CUDA_OK(cudaSetDevice(h->device));
+		if (grad) CUDA_OK(cudaMemcpyAsync(grad, h->d_grad.p, sizeof(double) * (size_t)h->lay.len, cudaMemcpyDeviceToHost, h->stream));
+		if (numer && h->n_utt) CUDA_OK(cudaMemcpyAsync(numer, h->d_numer.p, sizeof(double) * (size_t)h->n_utt, cudaMemcpyDeviceToHost, h->stream));
+		if (logZ && h->n_utt) CUDA_OK(cudaMemcpyAsync(logZ, h->d_logZ.p, sizeof(double) * (size_t)h->n_utt, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+		// the lattice kernels write NaN/Inf only when a log-sum was empty or overflowed -- the cases in which the
+		// reference throws from logE/expE (CRF_LogMath.cpp:192-224)
+		if (logZ) for (uint32_t u = 0; u < h->n_utt; u++)
+			if (!std::isfinite(logZ[u])) throw ApiError(CRFGPU_ERR_NUMERIC, "non-finite log partition function for utterance " + std::to_string(u));
+	});
+}
+
+int crfgpu_fetch_viterbi(crfgpu_handle h, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg, float* path_cost) {
+	return guarded([&] {
+		if (!h || !h->viterbi_done) throw ApiError(CRFGPU_ERR_ARG, "no Viterbi results staged");
+		CUDA_OK(cudaSetDevice(h->device));
+		const size_t nb = sizeof(uint32_t) * (size_t)h->N;
+		if (out_lab && h->N) CUDA_OK(cudaMemcpyAsync(out_lab, h->d_olab.p, nb, cudaMemcpyDeviceToHost, h->stream));
+		if (out_dur && h->N) CUDA_OK(cudaMemcpyAsync(out_dur, h->d_odur.p, nb, cudaMemcpyDeviceToHost, h->stream));
+		if (out_phn && h->N) CUDA_OK(cudaMemcpyAsync(out_phn, h->d_ophn.p, nb, cudaMemcpyDeviceToHost, h->stream));
+		if (n_seg && h->n_utt) CUDA_OK(cudaMemcpyAsync(n_seg, h->d_nseg.p, sizeof(uint32_t) * (size_t)h->n_utt, cudaMemcpyDeviceToHost, h->stream));
+		if (path_cost && h->n_utt) CUDA_OK(cudaMemcpyAsync(path_cost, h->d_cost.p, sizeof(float) * (size_t)h->n_utt, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+	});
+}
+
+int crfgpu_fwdbwd_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
+                        double* grad, double* numer, double* logZ) {
+	int rc = guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		require_train(h);
+		if (!frame_labs) throw ApiError(CRFGPU_ERR_ARG, "training needs frame labels");
+		stage_batch(h, n_utt, frame_off, base_ftrs, frame_labs);
+		fwdbwd_staged(h);
+	});
+	if (rc != CRFGPU_OK) return rc;
+	return crfgpu_fetch_fwdbwd(h, grad, numer, logZ);
+}
+
+int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
+                         uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg, float* path_cost) {
+	int rc = guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		require_decode(h);
+		stage_batch(h, n_utt, frame_off, base_ftrs, nullptr);
+		viterbi_staged(h);
+	});
+	if (rc != CRFGPU_OK) return rc;
+	return crfgpu_fetch_viterbi(h, out_lab, out_dur, out_phn, n_seg, path_cost);
+}
+
+int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out) {
+	return guarded([&] {
+		if (!h || !base_ftrs || !out) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		CUDA_OK(cudaSetDevice(h->device));
+		const uint32_t off[2] = {0, n_frames};
+		if (!n_frames) return;
+		stage_batch(h, 1, off, base_ftrs, nullptr);
+		const size_t bytes = sizeof(float) * (size_t)n_frames * h->cfg.max_dur * h->W;
+		CUDA_OK(cudaMemcpyAsync(out, h->X(), bytes, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+	});
+}
+
+int crfgpu_group_labels(const crfgpu_config* cfg, uint32_t n_frames, const uint32_t* frame_labs, uint32_t* out4) {
+	return guarded([&] {
+		if (!cfg || !frame_labs || !out4) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		if (cfg->max_dur == 0) throw ApiError(CRFGPU_ERR_ARG, "the maximum duration of labels must be larger than 0");
+		group_labels(cfg->max_dur, n_frames, frame_labs, out4);
+	});
+}
+
+int crfgpu_synchronize(crfgpu_handle h) {
+	return guarded([&] { if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle"); CUDA_OK(cudaSetDevice(h->device)); CUDA_OK(cudaStreamSynchronize(h->stream)); });
+}
+void* crfgpu_stream(crfgpu_handle h) { return h ? (void*)h->stream : nullptr; }
+uint64_t crfgpu_launch_count(crfgpu_handle h) { return h ? h->launches : 0; }
+
+double crfgpu_phase_ms(crfgpu_handle h, const char* phase) {
+	if (!h || !phase) return -1.0;
+	auto it = h->phases.find(phase);
+	if (it == h->phases.end()) return -1.0;
+	float ms = -1.0f;
+	if (cudaEventSynchronize(it->second.second) != cudaSuccess) return -1.0;
+	if (cudaEventElapsedTime(&ms, it->second.first, it->second.second) != cudaSuccess) return -1.0;
+	return ms;
+}
+
+int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta) {
+	return guarded([&] {
+		if (!h || !h->fwdbwd_done || !alpha || !beta) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
+		if (!h->opt_keep_lattice) throw ApiError(CRFGPU_ERR_ARG, "set option keep_lattice=1 before running forward-backward");
+		CUDA_OK(cudaSetDevice(h->device));
+		const size_t n = (size_t)h->N * h->lay.L;
+		DevBuf da, db; da.ensure(sizeof(double) * n + 16); db.ensure(sizeof(double) * n + 16);
+		DpParams p = dp_params(h);
+		launch_dump_alpha_beta(p, h->N, h->d_frame_t.as<uint32_t>(), h->d_frame_len.as<uint32_t>(), da.as<double>(), db.as<double>(), h->stream);
+		check_kernel(h, 1);
+		CUDA_OK(cudaMemcpyAsync(alpha, da.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaMemcpyAsync(beta, db.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+		da.release(); db.release();
+	});
+}
+
+int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
+	return guarded([&] {
+		if (!h || !name) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		const std::string n(name);
+		if (n == "slots") h->opt_slots = (int)value;
+		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
+		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
+		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);
+	});
+}
+
+int crfgpu_host_alloc(void** p, uint64_t bytes) {
+	return guarded([&] { if (!p) throw ApiError(CRFGPU_ERR_ARG, "null argument"); CUDA_OK(cudaMallocHost(p, bytes ? bytes : 1)); });
+}
+int crfgpu_host_free(void* p) {
+	return guarded([&] { if (p) CUDA_OK(cudaFreeHost(p)); });
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+/*
+ * crfgpu.h -- C ABI of libcrfgpu.so, the B200 (sm_100a) implementation of ASR-CRaFT's CRF lattice
+ * hot path.  Plain pointers and sizes only; every entry point returns 0 on success or a CRFGPU_ERR_*
+ * code, never throws across the boundary, and fails loudly (no CPU fallback) when no CUDA device
+ * is usable.  One handle is thread-compatible (use one handle per host thread / per GPU).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the ASR-CRaFT tree):
+ *
+ *   crfgpu_create / crfgpu_lambda_len / crfgpu_index_maps
+ *       CRF_FeatureMap::createFeatureMap(cfg) + CRF_StdFeatureMap::recalc()       CRF/src/ftrmaps/CRF_FeatureMap.cpp:55-74,
+ *       and CRF_Model::setFeatureMap / setLabMaxDur / setNActualLabs / setModelType  CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:472-517,
+ *                                                                                   CRF/src/CRF_Model.cpp:75-87
+ *   crfgpu_set_lambda            CRF_Model::getLambda() being read by the nodes     CRF/src/CRF_Model.cpp:105-131
+ *   crfgpu_fwdbwd_batch          CRF_Minibatch_GradAccumulator::accumulateGradient  CRF/src/trainers/accumulators/CRF_Minibatch_GradAccumulator.cpp:201-322
+ *                                = a loop of CRF_GradBuilder::buildGradient         CRF/src/trainers/gradbuilders/CRF_GradBuilder.h:40
+ *                                (CRF_NewGradBuilder.cpp:48-382, CRF_NewGradBuilder_StdSeg.cpp:31-377)
+ *   crfgpu_viterbi_batch         CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode>::nStateDecode
+ *                                with lm_fst==NULL, beam 0                           CRF/src/decoders/CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398
+ *   crfgpu_expand_windows        CRF_InFtrStream_SeqMultiWindow::read_ftrs           CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:209-328
+ *   crfgpu_group_labels          CRF_InLabStream_SeqMultiWindow::nextseg/read_labs   CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-306
+ *
+ * Inputs are the UN-windowed streams (what the pfile / ilab hold): a ragged batch of utterances,
+ * `frame_off[n_utt+1]` frame offsets, `base_ftrs[sum T][n_base_ftrs]` floats and one phone label per
+ * frame.  The segment windows (CRF_InFtrStream_SeqMultiWindow) and the (label,start,end) grouping
+ * (CRF_InLabStream_SeqMultiWindow) are applied on the device / inside the call, so the D-fold inflated
+ * window stream never crosses PCIe.
+ */
+#ifndef CRFGPU_H
+#define CRFGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* modeltype, CRF/src/CRF.h:50 */
+enum {
+	CRFGPU_STDFRAME = 0,
+	CRFGPU_STDSEG = 1,
+	CRFGPU_STDSEG_NO_DUR = 2,
+	CRFGPU_STDSEG_NO_DUR_NO_TRANSFTR = 3,
+	CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR = 4
+};
+
+enum {
+	CRFGPU_OK = 0,
+	CRFGPU_ERR_ARG = 1,          /* bad argument / geometry (what the reference would throw runtime_error for) */
+	CRFGPU_ERR_UNSUPPORTED = 2,  /* valid in the reference, not implemented on the device yet (never silently emulated) */
+	CRFGPU_ERR_CUDA = 3,         /* CUDA runtime failure, including "no device" */
+	CRFGPU_ERR_NUMERIC = 4       /* posterior-mass check failed / empty log-sum (reference: overflow_error / runtime_error) */
+};
+
+#define CRFGPU_LAB_BAD 0xffffffffu  /* CRF_LAB_BAD, CRF/src/io/CRF_FeatureStream.h:15 */
+#define CRFGPU_NO_IDX 0xffffffffu   /* illegal N-state transition, CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:389,401 */
+
+/* Mirrors CRF_FeatureMap_config (CRF/src/ftrmaps/CRF_FeatureMap.h:24-47) + the CRF_Model geometry set by
+ * CRFTrain (CRFTrain/src/Main.cpp:539-575) + the window-stream options (CRFTrain/src/Main.cpp:508-515). */
+typedef struct crfgpu_config {
+	uint32_t model_type;        /* CRFGPU_STD* */
+	uint32_t n_labs;            /* crf_label_size (stdseg: phones * max_dur) */
+	uint32_t n_base_ftrs;       /* width of the un-windowed feature stream */
+	uint32_t n_states;          /* crf_states */
+	uint32_t max_dur;           /* label_maximum_duration == ftr1_window_len */
+	uint32_t n_actual_labs;     /* num_actual_labs */
+	uint32_t extract_seg_ftrs;  /* ftr1_extract_seg_ftr: windows carry [5 samples|avg|max|min|one-hot dur] */
+	uint32_t use_state_ftrs, state_fidx_start, state_fidx_end;   /* indices into the WINDOW feature vector, inclusive */
+	uint32_t use_trans_ftrs, trans_fidx_start, trans_fidx_end;
+	uint32_t use_state_bias, use_trans_bias;
+	double state_bias_val, trans_bias_val;
+} crfgpu_config;
+
+typedef struct crfgpu_ctx* crfgpu_handle;
+
+/* Error text of the last failing call on this thread (valid also when crfgpu_create failed). */
+const char* crfgpu_last_error(void);
+
+int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out);
+int crfgpu_destroy(crfgpu_handle h);
+
+uint32_t crfgpu_window_width(const crfgpu_config* cfg);
+uint32_t crfgpu_lambda_len(crfgpu_handle h);
+/* state_idx[n_labs], trans_idx[n_labs*n_labs] indexed [plab*n_labs+clab]; CRFGPU_NO_IDX for illegal pairs */
+int crfgpu_index_maps(crfgpu_handle h, uint32_t* state_idx, uint32_t* trans_idx);
+
+/* Copies lambda (host, double) to the device and derives the device-side tables. */
+int crfgpu_set_lambda(crfgpu_handle h, const double* lambda, uint32_t len);
+
+/* ---- host-buffer entry points (the drop-in calls; H2D + kernels + D2H inside) --------------------
+ * grad[lambda_len] is OVERWRITTEN with sum over the batch of (empirical - expected) feature counts,
+ * numer[n_utt] = sum lambda.f on the reference path, logZ[n_utt] = log partition function. */
+int crfgpu_fwdbwd_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off,
+                        const float* base_ftrs, const uint32_t* frame_labs,
+                        double* grad, double* numer, double* logZ);
+
+/* Best path per utterance as segments, written at out_*[frame_off[u] .. frame_off[u]+n_seg[u]):
+ * out_lab = sub-state label of the segment, out_dur = its duration in frames, out_phn = phone id
+ * emitted when the segment starts a phone (else CRFGPU_LAB_BAD), path_cost = float cost of the path
+ * (99999.0 and n_seg 0 when the end state cannot be reached, as the reference reports). */
+int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
+                         uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                         float* path_cost);
+
+/* Window features for one utterance, out[(t*max_dur + d-1)*window_width ...]; slots with d > t+1 are zero. */
+int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out);
+/* (label,start,end,broken) records per frame or CRFGPU_LAB_BAD x4 (host-side, no device work). */
+int crfgpu_group_labels(const crfgpu_config* cfg, uint32_t n_frames, const uint32_t* frame_labs, uint32_t* out4);
+
+/* ---- device-resident entry points (inputs already in HBM; used for kernel-only timing and by
+ * multi-GPU drivers that all-reduce the gradient in place before reading it back) ----------------- */
+/* Stage a batch: copies offsets/features/labels to the device (async on the handle's stream). */
+int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off,
+                       const float* base_ftrs, const uint32_t* frame_labs /* may be NULL for decode */);
+/* Run forward-backward+gradient on the staged batch; results stay on the device. */
+int crfgpu_fwdbwd_staged(crfgpu_handle h);
+/* Run Viterbi + traceback on the staged batch; results stay on the device. */
+int crfgpu_viterbi_staged(crfgpu_handle h);
+/* Device pointers of the staged results (valid until the next stage/destroy). */
+int crfgpu_device_results(crfgpu_handle h, double** d_grad, double** d_numer, double** d_logZ);
+int crfgpu_fetch_fwdbwd(crfgpu_handle h, double* grad, double* numer, double* logZ);
+int crfgpu_fetch_viterbi(crfgpu_handle h, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,
+                         uint32_t* n_seg, float* path_cost);
+int crfgpu_synchronize(crfgpu_handle h);
+/* The CUDA stream (cudaStream_t) all work of this handle is issued on. */
+void* crfgpu_stream(crfgpu_handle h);
+/* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+uint64_t crfgpu_launch_count(crfgpu_handle h);
+/* Elapsed device milliseconds of the named phase in the last staged run (CUDA events on the stream):
+ * "expand","score","forward","backward","xi","grad","viterbi_score","viterbi". <0 if unknown. */
+double crfgpu_phase_ms(crfgpu_handle h, const char* phase);
+
+/* Debug/test access to the lattice of the staged batch after crfgpu_fwdbwd_staged: log-domain
+ * alpha/beta [sum T][n_labs] as doubles (entries the reference never computes are -DBL_MAX). */
+int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta);
+
+/* Tuning / debug switches: "slots" (utterances per CTA in the lattice kernels: 0 auto,1,2,4,8),
+ * "k_slab" (frames per CTA in the reduce-GEMMs), "keep_lattice" (1: keep what crfgpu_fetch_alpha_beta needs). */
+int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value);
+
+/* Pinned host memory helpers for callers that want asynchronous copies. */
+int crfgpu_host_alloc(void** p, uint64_t bytes);
+int crfgpu_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,79 @@
+"""CPU tests of the drop-in boundary: libcrfgpu.so loads, exports every symbol include/crfgpu.h
+declares, its host-only entry points (window width, label grouping) agree with the oracle, and the
+compute entry points fail loudly -- never fall back -- when no CUDA device is usable."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import crf_b200
+from helpers import load_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "crfgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(crfgpu_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = crf_b200.load_library()
+    names = declared_symbols()
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(crf_b200.SYMBOLS) == names
+
+
+def test_config_struct_matches_oracle_layout():
+    from oracle.binding import Config as OConfig
+    assert [f[0] for f in OConfig._fields_] == [f[0] for f in crf_b200.Config._fields_]
+    assert C.sizeof(OConfig) == C.sizeof(crf_b200.Config) == 15 * 4 + 4 + 16
+
+
+def test_window_width():
+    lib = crf_b200.load_library()
+    for (F, D, seg, want) in [(105, 1, 0, 105), (105, 10, 1, 850), (64, 30, 1, 542), (9, 3, 0, 9)]:
+        cfg = crf_b200.make_config("stdseg", n_labs=D * 2, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=seg)
+        assert lib.crfgpu_window_width(C.byref(cfg)) == want
+
+
+@pytest.mark.parametrize("name", sorted(k for k in load_cases("window_golden.npz") if k.startswith("lab_")))
+def test_group_labels_matches_reference_golden(name):
+    c = load_cases("window_golden.npz")[name]
+    lib = crf_b200.load_library()
+    cfg = crf_b200.copy_config(c["cfg"])
+    labs = np.ascontiguousarray(c["labs"], np.uint32)
+    out = np.zeros((len(labs), 4), np.uint32)
+    rc = lib.crfgpu_group_labels(C.byref(cfg), C.c_uint32(len(labs)), labs.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                 out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert rc == 0
+    assert np.array_equal(out, c["out"])
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(crf_b200.CrfGpuError) as ei:
+        crf_b200.CrfGpu(crf_b200.make_config("stdframe", n_labs=4, n_base_ftrs=3))
+    assert ei.value.code == 3 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    """The package under asr-craft_b200/ must not reference oracle/ (checker only)."""
+    pkg = os.path.join(ROOT, "asr-craft_b200")
+    for dp, _, files in os.walk(pkg):
+        if "build" in dp:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                text = open(os.path.join(dp, f), errors="ignore").read()
+                assert "crf_oracle" not in text and "libcrforacle" not in text and "libcrfref" not in text, os.path.join(dp, f)

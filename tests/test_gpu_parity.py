@@ -1,0 +1,203 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI
+(libcrfgpu.so via crf_b200), against (a) golden vectors produced by the unmodified reference and
+(b) the C oracle on fresh seeded inputs.
+
+Tolerances (north_star: "fp32 relative tolerance, e.g. 1e-4"):
+  logZ, numerator : |gpu - ref| <= 1e-5 * max(1, |ref|)
+  gradient        : |gpu - ref| <= 1e-4 * max(|ref|) + 1e-4 * |ref|  (element-wise; the device computes
+                    scores and posteriors in fp32, the reference in fp64)
+  alpha / beta    : |gpu - ref| <= 1e-4 * max(1, |ref|) on every lattice entry whose posterior is
+                    above 1e-30 (entries below the fp32 range flush to -inf on the device)
+  Viterbi         : labels, durations, emitted phones and the float path cost are bit-exact.
+"""
+import numpy as np
+import pytest
+
+import crf_b200
+from oracle.binding import make_config
+from helpers import load_cases, split_segs, synth_batch
+
+pytestmark = pytest.mark.gpu
+
+TRAIN = load_cases("train_golden.npz")
+VIT = load_cases("viterbi_golden.npz")
+WIN = load_cases("window_golden.npz")
+
+
+def gpu(cfg):
+    return crf_b200.CrfGpu(crf_b200.copy_config(cfg))
+
+
+def assert_train_close(got, want, what=""):
+    g, n, z = got
+    gw, nw, zw = want
+    np.testing.assert_allclose(z, zw, rtol=1e-5, atol=1e-5, err_msg=f"logZ {what}")
+    np.testing.assert_allclose(n, nw, rtol=1e-5, atol=1e-5, err_msg=f"numerator {what}")
+    tol = 1e-4 * np.abs(gw).max() + 1e-4 * np.abs(gw)
+    bad = np.abs(g - gw) > tol
+    assert not bad.any(), f"gradient {what}: {bad.sum()} of {bad.size} entries off, worst {np.abs(g - gw).max():.3e} (|g|max {np.abs(gw).max():.3e})"
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN))
+@pytest.mark.parametrize("slots", [1, 4])
+def test_fwdbwd_matches_reference_golden(name, slots):
+    c = TRAIN[name]
+    m = gpu(c["cfg"])
+    assert m.lambda_len == len(c["lam"])
+    m.set_option("slots", slots)
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    m.close()
+
+
+def test_toy_known_answers_on_gpu():
+    c = TRAIN["toy_stdframe"]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    g, n, z = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    np.testing.assert_allclose(z, [5.488352272567, 4.152084629056, 5.488352272567], rtol=1e-6)
+    np.testing.assert_allclose(n, [-0.09, -0.01, -0.09], atol=1e-7)
+    assert abs(np.sum(g ** 2) - 41.991090456415) < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["frame61", "frame3state", "stdseg_small", "stdseg_cfg4_shape"])
+def test_fwdbwd_matches_oracle_fresh(oracle, kind):
+    rng = np.random.default_rng({"frame61": 1, "frame3state": 2, "stdseg_small": 3, "stdseg_cfg4_shape": 4}[kind])
+    if kind == "frame61":      # cfg2 geometry, short utterances
+        off, ftrs, labs = synth_batch(rng, 9, 20, 120, 105, 61, 2, 15)
+        cfg = make_config("stdframe", n_labs=61, n_base_ftrs=105)
+        scale = 0.25
+    elif kind == "frame3state":
+        off, ftrs, labs = synth_batch(rng, 5, 10, 60, 20, 12, 3, 9, states=3)
+        cfg = make_config("stdframe", n_labs=36, n_base_ftrs=20, n_states=3)
+        scale = 0.25
+    elif kind == "stdseg_small":
+        off, ftrs, labs = synth_batch(rng, 7, 1, 50, 8, 6, 1, 9)
+        cfg = make_config("stdseg", n_labs=6 * 5, n_base_ftrs=8, max_dur=5, n_actual_labs=6, extract_seg_ftrs=1)
+        scale = 0.05
+    else:                       # cfg4 geometry (61 phones x maxDur 10, 105 base features), tiny batch
+        off, ftrs, labs = synth_batch(rng, 3, 12, 40, 105, 61, 2, 14)
+        cfg = make_config("stdseg", n_labs=610, n_base_ftrs=105, max_dur=10, n_actual_labs=61, extract_seg_ftrs=1)
+        scale = 0.01
+    lam = rng.uniform(-scale, scale, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=4)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, kind)
+
+
+def test_alpha_beta_match_oracle(oracle):
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    off, ftrs, labs = synth_batch(rng, 1, 37, 37, 8, 6, 1, 9)
+    cfg = make_config("stdseg", n_labs=6 * 4, n_base_ftrs=8, max_dur=4, n_actual_labs=6, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.05, 0.05, oracle.lambda_len(cfg))
+    T, L = int(off[-1]), 24
+    a = np.zeros((T, L)); b = np.zeros((T, L)); g = np.zeros(len(lam)); nu = np.zeros(1); z = np.zeros(1)
+    P = lambda x, t: x.ctypes.data_as(C.POINTER(t))
+    rc = oracle.lib.crforacle_fwdbwd_dump(C.byref(cfg), P(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(T),
+                                          P(ftrs, C.c_float), P(labs, C.c_uint32), P(g, C.c_double), P(nu, C.c_double),
+                                          P(z, C.c_double), P(a, C.c_double), P(b, C.c_double))
+    assert rc == 0
+    m = gpu(cfg)
+    m.set_option("keep_lattice", 1)
+    m.set_lambda(lam)
+    m.stage(off, ftrs, labs)
+    m.fwdbwd_staged()
+    ga, gb = m.fetch_alpha_beta()
+    defined = a > -1e300
+    assert np.array_equal(defined, ga > -1e300)
+    post = np.where(defined & (b > -1e300), a + b - z[0], -np.inf)
+    live = post > np.log(1e-30)
+    np.testing.assert_allclose(ga[live], a[live], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(gb[live], b[live], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", sorted(VIT))
+def test_viterbi_bit_exact_vs_reference_golden(name):
+    c = VIT[name]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    segs, cost = m.viterbi(c["off"], c["ftrs"])
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s[0]) for s in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert np.array_equal(got[0], exp[0]), name
+        assert np.array_equal(got[1], exp[1]), name
+        assert np.array_equal(got[2], exp[2]), name
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
+    m.close()
+
+
+@pytest.mark.parametrize("P,N,D,segf,F", [(61, 3, 1, 0, 105), (61, 1, 1, 0, 105), (48, 1, 10, 1, 12), (20, 3, 4, 1, 9)])
+def test_viterbi_bit_exact_vs_oracle_fresh(oracle, P, N, D, segf, F):
+    rng = np.random.default_rng(P * 100 + N * 10 + D)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P * N, n_base_ftrs=F, n_states=N, max_dur=D,
+                      extract_seg_ftrs=segf)
+    lens = rng.integers(1, 120, 12)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    m = gpu(cfg)
+    for lam_kind in ("random", "ties", "quantised"):
+        n = oracle.lambda_len(cfg)
+        ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+        if lam_kind == "random":
+            lam = rng.uniform(-0.25, 0.25, n)
+        elif lam_kind == "ties":
+            lam = np.zeros(n)
+        else:
+            lam = np.round(rng.uniform(-1, 1, n) * 2) / 2
+            ftrs = (np.round(ftrs * 2) / 2).astype(np.float32)
+        want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs)
+        m.set_lambda(lam)
+        segs, cost = m.viterbi(off, ftrs)
+        for got, exp in zip(segs, want):
+            assert all(np.array_equal(x, y) for x, y in zip(got, exp)), lam_kind
+        assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32)), lam_kind
+
+
+@pytest.mark.parametrize("name", sorted(k for k in WIN if k.startswith("win_")))
+def test_window_expansion_bit_exact(name):
+    c = WIN[name]
+    m = gpu(c["cfg"])
+    got = m.expand_windows(c["x"])
+    exp = c["out"]
+    valid = ~np.isnan(exp)
+    assert np.array_equal(got[valid].view(np.uint32), exp[valid].view(np.uint32))
+    assert np.all(got[~valid] == 0)
+
+
+def test_unsupported_geometries_fail_loudly():
+    with pytest.raises(crf_b200.CrfGpuError) as ei:
+        m = gpu(make_config("stdframe", n_labs=5, n_base_ftrs=4, use_trans_ftrs=1))
+        m.set_lambda(np.zeros(m.lambda_len))
+        m.fwdbwd([0, 3], np.zeros((3, 4), np.float32), np.zeros(3, np.uint32))
+    assert ei.value.code == 2
+    m = gpu(make_config("stdframe", n_labs=5, n_base_ftrs=4))
+    m.set_lambda(np.zeros(m.lambda_len))
+    with pytest.raises(crf_b200.CrfGpuError):   # empty utterance: reference throws "No features read from this sentence"
+        m.fwdbwd([0, 0, 3], np.zeros((3, 4), np.float32), np.zeros(3, np.uint32))
+
+
+def test_size_independent_properties_full_cfg2_shape():
+    """At BASELINE cfg2 size (61 labels, 105 features, ~300-frame utterances): with lambda = 0 every path is
+    equally likely, so logZ = T*log(61) - and the gradient's state-bias block sums to zero per frame
+    (sum_c (onehot - gamma) = 0), a checksum that does not need the oracle."""
+    rng = np.random.default_rng(5)
+    off, ftrs, labs = synth_batch(rng, 64, 200, 400, 105, 61, 3, 20)
+    cfg = make_config("stdframe", n_labs=61, n_base_ftrs=105)
+    m = gpu(cfg)
+    m.set_lambda(np.zeros(m.lambda_len))
+    g, n, z = m.fwdbwd(off, ftrs, labs)
+    T = np.diff(off.astype(np.int64))
+    np.testing.assert_allclose(z, T * np.log(61.0), rtol=1e-6)
+    assert np.all(n == 0)
+    sidx, _ = m.index_maps()
+    bias = g[sidx + 105]
+    assert abs(bias.sum()) < 1e-3 * T.sum() * 1e-3 + 1e-2
+    lam = rng.uniform(-0.25, 0.25, m.lambda_len)
+    m.set_lambda(lam)
+    g, n, z = m.fwdbwd(off, ftrs, labs)
+    assert abs(g[sidx + 105].sum()) < 2e-2
+    assert np.all(n - z < 0)    # log-likelihood of the reference path is negative
