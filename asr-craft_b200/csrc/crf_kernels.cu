@@ -564,11 +564,14 @@ __global__ void __launch_bounds__(256) reduce_gemm_kernel(ReduceGemmParams p) {
 	const uint32_t ns = p.n0 + blockIdx.z * p.k_slab;
 	const uint32_t ne = min(ns + p.k_slab, p.n1);
 	const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-	float acc[4][4];
+	// fp32 products are chained over one 16-row tile only, then folded into fp64 accumulators: with
+	// ~10^5 frames per launch a pure fp32 chain drifts by ~1e-7 per add (systematically when many frames
+	// carry the same posterior), which would eat the 1e-4 gradient tolerance.
+	double acc[4][4];
 #pragma unroll
 	for (int i = 0; i < 4; i++)
 #pragma unroll
-		for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+		for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
 	for (uint32_t nb = ns; nb < ne; nb += RG_BK) {
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
@@ -583,6 +586,11 @@ __global__ void __launch_bounds__(256) reduce_gemm_kernel(ReduceGemmParams p) {
 			As[kk][col] = a; Bs[kk][col] = b;
 		}
 		__syncthreads();
+		float part[4][4];
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) part[i][j] = 0.0f;
 #pragma unroll
 		for (int kk = 0; kk < RG_BK; kk++) {
 			const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -591,8 +599,12 @@ __global__ void __launch_bounds__(256) reduce_gemm_kernel(ReduceGemmParams p) {
 #pragma unroll
 			for (int i = 0; i < 4; i++)
 #pragma unroll
-				for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+				for (int j = 0; j < 4; j++) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
 		}
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) acc[i][j] += (double)part[i][j];
 		__syncthreads();
 	}
 #pragma unroll
@@ -603,14 +615,14 @@ __global__ void __launch_bounds__(256) reduce_gemm_kernel(ReduceGemmParams p) {
 		for (int j = 0; j < 4; j++) {
 			const uint32_t gj = j0 + tx * 4 + j;
 			if (gj >= p.J) continue;
-			const float v = acc[i][j];
-			if (v == 0.0f) continue;
+			const double v = acc[i][j];
+			if (v == 0.0) continue;
 			if (p.mode == 0) {
 				const double sc = (gj == p.ones_col) ? p.ones_scale : p.scale;
-				atomicAdd(&p.out[(uint64_t)p.row_idx[gi] + gj], sc * (double)v);
+				atomicAdd(&p.out[(uint64_t)p.row_idx[gi] + gj], sc * v);
 			} else {
 				const uint32_t idx = p.pair_idx[(uint64_t)gi * p.pair_ld + gj];
-				if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)p.Ew[(uint64_t)gi * p.e_ld + gj] * (double)v);
+				if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)p.Ew[(uint64_t)gi * p.e_ld + gj] * v);
 			}
 		}
 	}

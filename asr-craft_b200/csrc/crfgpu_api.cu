@@ -285,6 +285,22 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	}
 }
 
+// [sum numer, sum logZ, n_utt, 0] behind the gradient so that a multi-GPU driver moves gradient and scalars
+// with ONE all-reduce (CRF_Minibatch_GradAccumulator.cpp:277-298 sums them next to the gradient)
+__global__ void tail_sums_kernel(const double* numer, const double* logZ, uint32_t n_utt, double* tail) {
+	__shared__ double sn[32], sz[32];
+	double a = 0.0, b = 0.0;
+	for (uint32_t i = threadIdx.x; i < n_utt; i += blockDim.x) { a += numer[i]; b += logZ[i]; }
+	for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+	if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = a; sz[threadIdx.x >> 5] = b; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double ta = 0.0, tb = 0.0;
+		for (uint32_t w = 0; w < blockDim.x / 32; w++) { ta += sn[w]; tb += sz[w]; }
+		tail[0] = ta; tail[1] = tb; tail[2] = (double)n_utt; tail[3] = 0.0;
+	}
+}
+
 DpParams dp_params(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	DpParams p{};
@@ -310,8 +326,8 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	if (h->opt_keep_lattice) h->d_Uvec.ensure(sizeof(float) * NL + 16);
 	h->d_m.ensure(sizeof(double) * (size_t)N + 16); h->d_kappa.ensure(sizeof(double) * (size_t)N + 16); h->d_bbase.ensure(sizeof(double) * (size_t)N + 16);
 	h->d_logZ.ensure(sizeof(double) * (size_t)h->n_utt + 16); h->d_numer.ensure(sizeof(double) * (size_t)h->n_utt + 16);
-	h->d_grad.ensure(sizeof(double) * (size_t)m.len + 16);
-	CUDA_OK(cudaMemsetAsync(h->d_grad.p, 0, sizeof(double) * (size_t)m.len, s));
+	h->d_grad.ensure(sizeof(double) * ((size_t)m.len + 4) + 16);
+	CUDA_OK(cudaMemsetAsync(h->d_grad.p, 0, sizeof(double) * ((size_t)m.len + 4), s));
 	CUDA_OK(cudaMemsetAsync(h->d_numer.p, 0, sizeof(double) * (size_t)h->n_utt, s));
 	if (!N) { h->fwdbwd_done = true; return; }
 
@@ -378,6 +394,8 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
 	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
 	launch_empirical(e, s); check_kernel(h, 1);
+	tail_sums_kernel<<<1, 256, 0, s>>>(h->d_numer.as<double>(), h->d_logZ.as<double>(), h->n_utt, h->d_grad.as<double>() + m.len);
+	check_kernel(h, 1);
 	phase_end(h, "grad");
 	h->fwdbwd_done = true;
 }

@@ -115,7 +115,8 @@ int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_of
 int crfgpu_fwdbwd_staged(crfgpu_handle h);
 /* Run Viterbi + traceback on the staged batch; results stay on the device. */
 int crfgpu_viterbi_staged(crfgpu_handle h);
-/* Device pointers of the staged results (valid until the next stage/destroy). */
+/* Device pointers of the staged results (valid until the next stage/destroy).  d_grad has lambda_len+4
+ * doubles: the gradient followed by [sum numer, sum logZ, n_utt, 0], so one all-reduce moves everything. */
 int crfgpu_device_results(crfgpu_handle h, double** d_grad, double** d_numer, double** d_logZ);
 int crfgpu_fetch_fwdbwd(crfgpu_handle h, double* grad, double* numer, double* logZ);
 int crfgpu_fetch_viterbi(crfgpu_handle h, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,

@@ -195,7 +195,7 @@ def test_size_independent_properties_full_cfg2_shape():
     assert np.all(n == 0)
     sidx, _ = m.index_maps()
     bias = g[sidx + 105]
-    assert abs(bias.sum()) < 1e-3 * T.sum() * 1e-3 + 1e-2
+    assert abs(bias.sum()) < 2e-2
     lam = rng.uniform(-0.25, 0.25, m.lambda_len)
     m.set_lambda(lam)
     g, n, z = m.fwdbwd(off, ftrs, labs)

@@ -1,0 +1,92 @@
+"""Seeded synthetic workloads of BASELINE.json's configs, shared by bench.py, the tests and
+__graft_entry__.smoke().  Pure numpy; reads only the committed shape fixture tests/golden/timit_shape.npz
+(utterance lengths and segment durations of the TIMIT train set), never /root/reference.
+
+Every function returns (cfg_kwargs, lam_seed_info, off, ftrs, labs) pieces as a dict so that both the
+oracle binding and crf_b200 can build their own Config from the same kwargs.
+"""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+N_PHONES = 61
+N_BASE_FTRS = 105
+
+
+def timit_shape():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "timit_shape.npz"))
+    return z["utt_len"].astype(np.int64), z["seg_cnt"].astype(np.int64), z["seg_dur"].astype(np.int64)
+
+
+def _features(rng, frame_phone, n_ftrs=N_BASE_FTRS, n_post=N_PHONES):
+    """First n_post dims: softmax(N(0,1) + 4*onehot(true phone)) (posterior-like); rest U[0,1) (attribute-like)."""
+    n = len(frame_phone)
+    logits = rng.standard_normal((n, n_post), dtype=np.float32)
+    logits[np.arange(n), frame_phone % n_post] += 4.0
+    logits -= logits.max(axis=1, keepdims=True)
+    np.exp(logits, out=logits)
+    logits /= logits.sum(axis=1, keepdims=True)
+    out = np.empty((n, n_ftrs), np.float32)
+    out[:, :n_post] = logits
+    if n_ftrs > n_post:
+        out[:, n_post:] = rng.random((n, n_ftrs - n_post), dtype=np.float32)
+    return out
+
+
+def timit_train_batch(first_utt=0, n_utt=3696, n_phones=N_PHONES):
+    """Utterances [first_utt, first_utt+n_utt) of the TIMIT-shaped train set: real lengths and segment
+    boundaries, phone ids U{0..n_phones-1} with no two adjacent segments equal (seed 9), features seed 2.
+    Labels and features of an utterance do not depend on which slice is requested."""
+    utt_len, seg_cnt, seg_dur = timit_shape()
+    seg_start = np.concatenate([[0], np.cumsum(seg_cnt)])
+    sel = range(first_utt, first_utt + n_utt)
+    lens = utt_len[first_utt:first_utt + n_utt]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    labs = np.empty(int(off[-1]), np.uint32)
+    ftrs = np.empty((int(off[-1]), N_BASE_FTRS), np.float32)
+    for k, u in enumerate(sel):
+        rl = np.random.default_rng([9, u])
+        durs = seg_dur[seg_start[u]:seg_start[u + 1]]
+        phones = np.empty(len(durs), np.int64)
+        prev = -1
+        for i in range(len(durs)):
+            p = int(rl.integers(0, n_phones))
+            while p == prev:
+                p = int(rl.integers(0, n_phones))
+            phones[i] = prev = p
+        fl = np.repeat(phones, durs)
+        labs[off[k]:off[k + 1]] = fl
+        ftrs[off[k]:off[k + 1]] = _features(np.random.default_rng([2, u]), fl)
+    return off, ftrs, labs
+
+
+def cfg2_kwargs():
+    """frame-level CRF, 61 labels, 1 state/phone, 105 features, state+transition bias (dim(lambda)=10 187)."""
+    return dict(model_type="stdframe", n_labs=N_PHONES, n_base_ftrs=N_BASE_FTRS)
+
+
+def cfg3_kwargs():
+    """3-state/phone frame CRF decoded through stdseg_no_dur_no_segtransftr with maxDur 1 (dim(lambda)=23 424)."""
+    return dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=3 * N_PHONES, n_base_ftrs=N_BASE_FTRS, n_states=3)
+
+
+def cfg4_kwargs():
+    """segmental stdseg, 61 phones x maxDur 10 = 610 labels, 850 segment features (dim(lambda)=891 210)."""
+    return dict(model_type="stdseg", n_labs=10 * N_PHONES, n_base_ftrs=N_BASE_FTRS, max_dur=10,
+                n_actual_labs=N_PHONES, extract_seg_ftrs=1)
+
+
+def cfg3_batch(n_utt=1680):
+    """1680 utterances, lengths round(N(304,80^2)) clipped to [92,778] (seed 4), features seed 5."""
+    rng = np.random.default_rng(4)
+    lens = np.clip(np.rint(rng.normal(304, 80, n_utt)), 92, 778).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    r5 = np.random.default_rng(5)
+    phone = r5.integers(0, N_PHONES, int(off[-1]))
+    return off, _features(r5, phone)
+
+
+def lam_for(name, n):
+    seed, scale = {"cfg2": (3, 0.25), "cfg3": (6, 0.25), "cfg4": (7, 0.01)}[name]
+    return np.random.default_rng(seed).uniform(-scale, scale, n)
