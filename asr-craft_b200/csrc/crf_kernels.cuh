@@ -57,6 +57,24 @@ struct DpParams {
 void launch_forward(const DpParams& p, int U, cudaStream_t s);
 void launch_backward(const DpParams& p, int U, cudaStream_t s);
 
+// ---- cluster-resident variant (crf_dp_cluster.cu): E sliced over the CTAs of a thread-block cluster ----
+struct ClusterDpParams : DpParams {
+	uint32_t CS, CW, CWp, CWt;    // cluster size, label columns per CTA, smem row stride, column-threads per slot quad
+	uint32_t n_clusters;
+	const uint32_t* cl_off;       // [n_clusters+1] offsets into cl_list
+	const uint32_t* cl_list;      // utterance ids in the order each cluster processes them
+	float* xch;                   // [n_clusters][2][UB][Lp] log-domain frame vectors exchanged through L2
+	float* xmax;                  // [n_clusters][2][CS][UB] per-CTA maxima of those vectors
+};
+struct ClusterPlan {
+	uint32_t CS, CW, CWp, CWt, threads;
+	int UB;                       // utterance slots advanced in lock-step by one cluster (multiple of 4)
+	size_t smem;
+};
+bool plan_cluster_dp(uint32_t L, uint32_t D, int max_smem_optin, ClusterPlan* plan, int ub_cap = 32);
+int max_active_clusters(const ClusterPlan& plan);
+cudaError_t launch_cluster_dp(bool backward, const ClusterDpParams& p, const ClusterPlan& plan, cudaStream_t s);
+
 // ---- TN GEMM with fp64 scatter epilogue:  out[map(i,j)] += scale * sum_n A[n][i]*B[n][j] --------
 struct ReduceGemmParams {
 	const float* A; uint64_t lda;   // rows n in [n0,n1), A row used = n - a_row_shift

@@ -64,7 +64,10 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0; uint32_t opt_k_slab = 1024;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 1, opt_cluster_slots = 0; uint32_t opt_k_slab = 1024;
+	int max_smem_optin = 0;
+	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
+	DevBuf d_cl_off, d_cl_list, d_xch, d_xmax;
 
 	// model tables
 	bool have_lambda = false;
@@ -272,6 +275,43 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// consecutive (similar-length) utterances share a CTA, which minimises idle slots.
 	for (uint32_t i = 0; i < n_utt; i++) grp[i] = order[i];
 	upload(h->d_grp, grp, s);
+	// cluster-resident lattice kernels: persistent clusters, utterances dealt longest-first to the least loaded
+	// cluster; inside a cluster the list order is the order slots are (re)filled
+	std::vector<uint32_t> cl_off, cl_list;
+	h->cluster_ok = false;
+	if (h->train_ok && h->opt_dp_impl == 1 && labs && n_utt) {
+		ClusterPlan plan{};
+		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
+		if (plan_cluster_dp(h->lay.L, c.max_dur, h->max_smem_optin, &plan, cap)) {
+			int avail_cl = max_active_clusters(plan);
+			// keep every cluster busy: shrink the slot count while there are fewer slot-loads than clusters
+			while (h->opt_cluster_slots <= 0 && plan.UB > 4 && avail_cl > 0 && (n_utt + plan.UB - 1) / plan.UB < (uint32_t)avail_cl) {
+				ClusterPlan smaller{};
+				if (!plan_cluster_dp(h->lay.L, c.max_dur, h->max_smem_optin, &smaller, plan.UB == 32 ? 16 : plan.UB == 16 ? 12 : plan.UB == 12 ? 8 : 4)) break;
+				if (smaller.CS != plan.CS) break;
+				plan = smaller; avail_cl = max_active_clusters(plan);
+			}
+			if (avail_cl > 0) {
+				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + plan.UB - 1) / plan.UB);
+				std::vector<std::vector<uint32_t>> lists(ncl);
+				std::vector<uint64_t> load(ncl, 0);
+				for (uint32_t i = 0; i < n_utt; i++) {
+					const uint32_t u = order[i];
+					const uint32_t k = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+					lists[k].push_back(u); load[k] += off[u + 1] - off[u];
+				}
+				cl_off.push_back(0);
+				for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
+				h->plan = plan; h->n_clusters = ncl; h->cluster_ok = true;
+				if (getenv("CRFGPU_VERBOSE"))
+					fprintf(stderr, "[crfgpu] cluster plan: CS=%u CW=%u UB=%d threads=%u smem=%zu, %u of %d resident clusters, %u utterances\n",
+					        plan.CS, plan.CW, plan.UB, plan.threads, plan.smem, ncl, avail_cl, n_utt);
+				upload(h->d_cl_off, cl_off, s); upload(h->d_cl_list, cl_list, s);
+				h->d_xch.ensure(sizeof(float) * (size_t)ncl * 2 * plan.UB * h->Lp + 16);
+				h->d_xmax.ensure(sizeof(float) * (size_t)ncl * 2 * plan.CS * plan.UB + 16);
+			}
+		}
+	}
 	CUDA_OK(cudaStreamSynchronize(s));   // host staging vectors die here
 
 	if (c.max_dur > 1 && N) {
@@ -350,12 +390,26 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	phase_end(h, "score");
 
 	DpParams p = dp_params(h);
-	phase_begin(h, "forward");
-	launch_forward(p, h->U, s); check_kernel(h, 1);
-	phase_end(h, "forward");
-	phase_begin(h, "backward");
-	launch_backward(p, h->U, s); check_kernel(h, 1);
-	phase_end(h, "backward");
+	if (h->cluster_ok) {
+		ClusterDpParams cp{};
+		static_cast<DpParams&>(cp) = p;
+		cp.CS = h->plan.CS; cp.CW = h->plan.CW; cp.CWp = h->plan.CWp; cp.CWt = h->plan.CWt; cp.n_clusters = h->n_clusters;
+		cp.cl_off = h->d_cl_off.as<uint32_t>(); cp.cl_list = h->d_cl_list.as<uint32_t>();
+		cp.xch = h->d_xch.as<float>(); cp.xmax = h->d_xmax.as<float>();
+		phase_begin(h, "forward");
+		CUDA_OK(launch_cluster_dp(false, cp, h->plan, s)); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		CUDA_OK(launch_cluster_dp(true, cp, h->plan, s)); check_kernel(h, 1);
+		phase_end(h, "backward");
+	} else {
+		phase_begin(h, "forward");
+		launch_forward(p, h->U, s); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		launch_backward(p, h->U, s); check_kernel(h, 1);
+		phase_end(h, "backward");
+	}
 
 	// K4: expected-minus-empirical counts as two families of reduce-GEMMs
 	phase_begin(h, "xi");
@@ -465,6 +519,7 @@ int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
 		h->Lp = (h->lay.L + 31) / 32 * 32;
 		if (cfg->max_dur == 0) throw ApiError(CRFGPU_ERR_ARG, "the maximum duration of labels must be larger than 0");
 		classify(h);
+		CUDA_OK(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 		CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 		upload(h->d_sidx, h->lay.sidx, h->stream); upload(h->d_tidx, h->lay.tidx, h->stream);
 		std::vector<uint32_t> steps = sample_steps(cfg->max_dur);
@@ -486,7 +541,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
-	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost};
+	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(h->stream);
@@ -653,6 +708,8 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		if (n == "slots") h->opt_slots = (int)value;
 		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
+		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E
+		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
 		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);
 	});
 }

@@ -39,12 +39,16 @@ def assert_train_close(got, want, what=""):
 
 
 @pytest.mark.parametrize("name", sorted(TRAIN))
-@pytest.mark.parametrize("slots", [1, 4])
-def test_fwdbwd_matches_reference_golden(name, slots):
+@pytest.mark.parametrize("impl", ["legacy_u1", "legacy_u4", "cluster", "cluster_u4"])
+def test_fwdbwd_matches_reference_golden(name, impl):
     c = TRAIN[name]
     m = gpu(c["cfg"])
     assert m.lambda_len == len(c["lam"])
-    m.set_option("slots", slots)
+    if impl.startswith("legacy"):
+        m.set_option("dp_impl", 0)
+        m.set_option("slots", int(impl[-1]))
+    elif impl == "cluster_u4":
+        m.set_option("cluster_slots", 4)
     m.set_lambda(c["lam"])
     got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
     assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
