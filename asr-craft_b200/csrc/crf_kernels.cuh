@@ -29,7 +29,8 @@ struct ScoreGemmParams {
 	uint32_t M, Ncols, K;
 	const uint32_t* frame_t; uint32_t min_t;  // rows with frame_t[n] < min_t are skipped (window d needs t >= d-1)
 };
-void launch_score_gemm(const ScoreGemmParams& p, cudaStream_t s);
+void launch_score_gemm(const ScoreGemmParams& p, cudaStream_t s);          // fp32 FFMA tiles (round-1 baseline)
+cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s); // tcgen05, split-bf16 operands (crf_tc_gemm.cu)
 
 // ---- dense lattice recursions in the probability domain ----------------------------------------
 // One CTA owns U utterances ("slots"); thread c owns label column c.  L <= 1024.
@@ -93,6 +94,8 @@ struct ReduceGemmParams {
 	uint32_t k_slab;                // rows of n per CTA (split-K)
 };
 void launch_reduce_gemm(const ReduceGemmParams& p, cudaStream_t s);
+// tcgen05 version; m_side_is_b picks which operand's columns ride on the 128-row MMA M side (the wider one should)
+cudaError_t launch_reduce_gemm_tc(const ReduceGemmParams& p, bool m_side_is_b, cudaStream_t s);
 
 // ---- empirical counts and numerators on the reference path -------------------------------------
 struct EmpiricalParams {

@@ -1,0 +1,322 @@
+// Tensor-core GEMMs of libcrfgpu (sm_100a): tcgen05.mma with fp32 accumulators in TMEM, operands carried as
+// bf16 hi/lo pairs (three MMAs per k-step: hi*hi + lo*hi + hi*lo, ~16 mantissa bits, measured worst relative
+// error 3e-6 on the probe in tools/tc_probe.cu).
+//
+//   score_gemm_tc   S[n][j]      = sum_k X[n][k] * W[j][k] + bias[j]                (GEMM-1, both operands K-major)
+//                   replaces L calls per frame of CRF_StdFeatureMap::computeStateArrayValue
+//                   (CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:65-81)
+//   reduce_gemm_tc  out[map(i,j)] += scale * sum_n A[n-shift][i] * B[n][j]          (GEMM-3 / Xi, both operands MN-major)
+//                   replaces the per-frame scatter of computeStateExpF / computeTransExpF (:130-223) and
+//                   `grad -= ExpF` (CRF/src/trainers/gradbuilders/CRF_NewGradBuilder.cpp:374-376)
+//
+// Structure of both kernels (one CTA = one 128 x 64 output tile, 160 threads):
+//   warps 0-3  producers: coalesced fp32 loads from HBM/L2 -> split into bf16 hi/lo in registers -> 16-byte stores into
+//              the no-swizzle canonical UMMA layout of a 4-stage ring; later the epilogue (warp w owns TMEM lanes 32w..32w+31)
+//   warp  4    one elected lane issues tcgen05.mma, releases ring stages with tcgen05.commit
+// (a tile that holds, or lies beyond, the constant-1 column takes the per-element path)
+// Register staging (instead of TMA) lets the loaders apply what these operands need on the way: the row shift of the
+// Xi product, the constant-1 bias feature, ragged bounds and 8-byte-aligned window rows.
+#include "crf_kernels.cuh"
+#include "tc05.cuh"
+
+namespace crfgpu {
+
+using namespace tc05;
+
+namespace {
+
+constexpr int BM = 128, BN = 64, KC = 32, STAGES = 4;
+constexpr uint32_t A_TILE = BM * KC * 2, B_TILE = BN * KC * 2;        // bytes of one bf16 tile
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;             // hi + lo of both operands = 24576
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;          // + barriers / alignment slack
+constexpr int N_PRODUCERS = 128;
+
+struct Ring {
+	uint64_t full[STAGES], empty[STAGES], done;
+	uint32_t tmem;
+};
+
+__device__ __forceinline__ void load8(const float* p, bool ok, bool vec2, float (&x)[8]) {
+	if (!ok) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) x[j] = 0.0f;
+	} else if (vec2) {
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const float2 v = __ldg(reinterpret_cast<const float2*>(p) + j); x[2 * j] = v.x; x[2 * j + 1] = v.y; }
+	} else {
+#pragma unroll
+		for (int j = 0; j < 8; j++) x[j] = __ldg(p + j);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM-1.  A = X rows (frames) x K features, B = W rows (labels) x K; both K-major.
+// smem vector (row r, k-group g) at (r/8)*512 + g*128 + (r%8)*16   (LBO 128, SBO 512)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(160, 2) score_gemm_tc_kernel(ScoreGemmParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+	const uint32_t n_chunks = (p.K + KC - 1) / KC;
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], N_PRODUCERS); mbar_init(&ring->empty[s], 1); }
+		mbar_init(&ring->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ring->tmem;
+
+	if (warp < 4) {
+		const bool a_vec2 = ((reinterpret_cast<uintptr_t>(p.A) & 7) == 0) && (p.lda % 2 == 0);
+		const bool b_vec2 = ((reinterpret_cast<uintptr_t>(p.B) & 7) == 0) && (p.ldb % 2 == 0);
+		const uint32_t r8 = lane & 7, g = lane >> 3;
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % STAGES, k0 = c * KC + g * 8;
+			float xa[4][8], xb[2][8];
+			// issue every load of the stage before waiting for the ring slot: the registers are the in-flight buffer
+#pragma unroll
+			for (int it = 0; it < 4; it++) {
+				const uint32_t r = (it * 4 + warp) * 8 + r8, gm = m0 + r;
+				const float* src = p.A + (uint64_t)gm * p.lda + k0;
+				if (gm < p.M && k0 + 8 <= p.K) load8(src, true, a_vec2, xa[it]);
+				else {
+#pragma unroll
+					for (int j = 0; j < 8; j++) xa[it][j] = (gm < p.M && k0 + j < p.K) ? __ldg(src + j) : 0.0f;
+				}
+			}
+#pragma unroll
+			for (int it = 0; it < 2; it++) {
+				const uint32_t r = (it * 4 + warp) * 8 + r8, gn = n0 + r;
+				const float* src = p.B + (uint64_t)gn * p.ldb + k0;
+				if (gn < p.Ncols && k0 + 8 <= p.K) load8(src, true, b_vec2, xb[it]);
+				else {
+#pragma unroll
+					for (int j = 0; j < 8; j++) xb[it][j] = (gn < p.Ncols && k0 + j < p.K) ? __ldg(src + j) : 0.0f;
+				}
+			}
+			if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
+			unsigned char* st = smem + s * STAGE_BYTES;
+#pragma unroll
+			for (int it = 0; it < 4; it++) {
+				uint4 h, l; split8(xa[it], h, l);
+				const uint32_t o = (it * 4 + warp) * 512 + g * 128 + r8 * 16;
+				*reinterpret_cast<uint4*>(st + o) = h; *reinterpret_cast<uint4*>(st + A_TILE + o) = l;
+			}
+#pragma unroll
+			for (int it = 0; it < 2; it++) {
+				uint4 h, l; split8(xb[it], h, l);
+				const uint32_t o = (it * 4 + warp) * 512 + g * 128 + r8 * 16;
+				*reinterpret_cast<uint4*>(st + 2 * A_TILE + o) = h; *reinterpret_cast<uint4*>(st + 2 * A_TILE + B_TILE + o) = l;
+			}
+			fence_proxy_async_smem();
+			mbar_arrive(&ring->full[s]);
+		}
+	} else if (lane == 0) {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, false, false);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % STAGES;
+			mbar_wait(&ring->full[s], (c / STAGES) & 1);
+			tc_fence_after();
+			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+			for (int ks = 0; ks < KC / 16; ks++) {
+				const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+				const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+				mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+				mma_ss(tmem, al, bh, idesc, true);
+				mma_ss(tmem, ah, bl, idesc, true);
+			}
+			mma_commit(&ring->empty[s]);
+		}
+		mma_commit(&ring->done);
+	}
+	// ---- epilogue: TMEM -> registers -> (+bias) -> shared transpose -> coalesced rows of S ----
+	if (warp < 4) {
+		mbar_wait(&ring->done, 0);
+		tc_fence_after();
+		float* Cs = reinterpret_cast<float*>(smem);       // [128][65], the ring is idle now
+		const uint32_t row = warp * 32 + lane;
+#pragma unroll
+		for (int c0 = 0; c0 < BN; c0 += 16) {
+			float v[16];
+			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+			tmem_ld_wait();
+#pragma unroll
+			for (int j = 0; j < 16; j++) Cs[row * 65 + c0 + j] = v[j];
+		}
+		tc_fence_before();
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		const uint32_t ncol = min((uint32_t)BN, p.Ncols - n0);
+		for (uint32_t i = tid; i < BM * BN; i += N_PRODUCERS) {
+			const uint32_t r = i / BN, j = i % BN, gm = m0 + r;
+			if (gm < p.M && j < ncol) p.C[(uint64_t)gm * p.ldc + n0 + j] = Cs[r * 65 + j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 4) tmem_dealloc(tmem, BN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM-3 / Xi.  Both operands are [frames][columns] row-major, i.e. MN-major with the reduction index slow.
+// SWAP = false: MMA M side = p.A columns (I), N side = p.B columns (J)     (Xi: I = L source labels, J = P)
+// SWAP = true : MMA M side = p.B columns (J), N side = p.A columns (I)     (state weights: J = features, I = P)
+// smem vector (frame k, column group rg) at rg*512 + k*16   (LBO 128 = 8 frames, SBO 512)
+// ------------------------------------------------------------------------------------------------
+template <bool SWAP>
+__global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	// M-side / N-side views of the two operands
+	const float* Mp = SWAP ? p.B : p.A; const uint64_t ldm = SWAP ? p.ldb : p.lda; const uint32_t Mext = SWAP ? p.J : p.I;
+	const float* Np = SWAP ? p.A : p.B; const uint64_t ldn = SWAP ? p.lda : p.ldb; const uint32_t Next = SWAP ? p.I : p.J;
+	const uint32_t m_shift = SWAP ? 0 : p.a_row_shift, n_shift = SWAP ? p.a_row_shift : 0;
+	const uint32_t m_ones = SWAP ? p.ones_col : 0xffffffffu, n_ones = SWAP ? 0xffffffffu : p.ones_col;
+	const uint32_t m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+	const uint32_t ns = p.n0 + blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.n1);
+	const uint32_t n_chunks = (ne - ns + KC - 1) / KC;
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], N_PRODUCERS); mbar_init(&ring->empty[s], 1); }
+		mbar_init(&ring->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ring->tmem;
+
+	if (warp < 4) {
+		const bool m_vec2 = ((reinterpret_cast<uintptr_t>(Mp) & 7) == 0) && (ldm % 2 == 0);
+		const bool n_vec2 = ((reinterpret_cast<uintptr_t>(Np) & 7) == 0) && (ldn % 2 == 0);
+		const uint32_t k8 = lane & 7, rgq = lane >> 3;
+		const uint32_t kk = warp * 8 + k8;                 // frame of this thread inside the chunk
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % STAGES, n = ns + c * KC + kk;
+			const bool n_ok = n < ne;
+			float xm[4][8], xn[2][8];
+#pragma unroll
+			for (int it = 0; it < 4; it++) {
+				const uint32_t col = m0 + (it * 4 + rgq) * 8;
+				const float* src = Mp + (uint64_t)(n - m_shift) * ldm + col;
+				if (n_ok && col + 8 <= Mext && m_ones >= col + 8) load8(src, true, m_vec2, xm[it]);
+				else {
+#pragma unroll
+					for (int j = 0; j < 8; j++) xm[it][j] = (!n_ok || col + j >= Mext) ? 0.0f : (col + j == m_ones ? 1.0f : __ldg(src + j));
+				}
+			}
+#pragma unroll
+			for (int it = 0; it < 2; it++) {
+				const uint32_t col = n0 + (it * 4 + rgq) * 8;
+				const float* src = Np + (uint64_t)(n - n_shift) * ldn + col;
+				if (n_ok && col + 8 <= Next && n_ones >= col + 8) load8(src, true, n_vec2, xn[it]);
+				else {
+#pragma unroll
+					for (int j = 0; j < 8; j++) xn[it][j] = (!n_ok || col + j >= Next) ? 0.0f : (col + j == n_ones ? 1.0f : __ldg(src + j));
+				}
+			}
+			if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
+			unsigned char* st = smem + s * STAGE_BYTES;
+#pragma unroll
+			for (int it = 0; it < 4; it++) {
+				uint4 h, l; split8(xm[it], h, l);
+				const uint32_t o = (it * 4 + rgq) * 512 + kk * 16;
+				*reinterpret_cast<uint4*>(st + o) = h; *reinterpret_cast<uint4*>(st + A_TILE + o) = l;
+			}
+#pragma unroll
+			for (int it = 0; it < 2; it++) {
+				uint4 h, l; split8(xn[it], h, l);
+				const uint32_t o = (it * 4 + rgq) * 512 + kk * 16;
+				*reinterpret_cast<uint4*>(st + 2 * A_TILE + o) = h; *reinterpret_cast<uint4*>(st + 2 * A_TILE + B_TILE + o) = l;
+			}
+			fence_proxy_async_smem();
+			mbar_arrive(&ring->full[s]);
+		}
+	} else if (lane == 0) {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, true, true);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % STAGES;
+			mbar_wait(&ring->full[s], (c / STAGES) & 1);
+			tc_fence_after();
+			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+			for (int ks = 0; ks < KC / 16; ks++) {
+				const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+				const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+				mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+				mma_ss(tmem, al, bh, idesc, true);
+				mma_ss(tmem, ah, bl, idesc, true);
+			}
+			mma_commit(&ring->empty[s]);
+		}
+		mma_commit(&ring->done);
+	}
+	// ---- epilogue: lane = M-side column, 64 N-side columns; fp64 atomics into the gradient ----
+	if (warp < 4 && n_chunks) {
+		mbar_wait(&ring->done, 0);
+		tc_fence_after();
+		const uint32_t gm = m0 + warp * 32 + lane;
+#pragma unroll
+		for (int c0 = 0; c0 < BN; c0 += 16) {
+			float v[16];
+			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+			tmem_ld_wait();
+			if (gm < Mext) {
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t gn = n0 + c0 + j;
+					if (gn >= Next || v[j] == 0.0f) continue;
+					const uint32_t gi = SWAP ? gn : gm, gj = SWAP ? gm : gn;
+					if (p.mode == 0) {
+						const double sc = (gj == p.ones_col) ? p.ones_scale : p.scale;
+						atomicAdd(&p.out[(uint64_t)__ldg(p.row_idx + gi) + gj], sc * (double)v[j]);
+					} else {
+						const uint32_t idx = __ldg(p.pair_idx + (uint64_t)gi * p.pair_ld + gj);
+						if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)__ldg(p.Ew + (uint64_t)gi * p.e_ld + gj) * (double)v[j]);
+					}
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 4) tmem_dealloc(tmem, BN);
+}
+
+}  // namespace
+
+cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
+	if (!p.M || !p.Ncols) return cudaSuccess;
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaError_t e = cudaFuncSetAttribute(score_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+		if (e != cudaSuccess) return e;
+		attr_done = true;
+	}
+	dim3 grid((p.M + BM - 1) / BM, (p.Ncols + BN - 1) / BN);
+	score_gemm_tc_kernel<<<grid, 160, SMEM_BYTES, s>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_gemm_tc(const ReduceGemmParams& p, bool m_side_is_b, cudaStream_t s) {
+	if (p.n1 <= p.n0 || !p.I || !p.J) return cudaSuccess;
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaError_t e = cudaFuncSetAttribute(reduce_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+		if (e != cudaSuccess) return e;
+		attr_done = true;
+	}
+	const uint32_t Mext = m_side_is_b ? p.J : p.I, Next = m_side_is_b ? p.I : p.J;
+	dim3 grid((Mext + BM - 1) / BM, (Next + BN - 1) / BN, (p.n1 - p.n0 + p.k_slab - 1) / p.k_slab);
+	if (m_side_is_b) reduce_gemm_tc_kernel<true><<<grid, 160, SMEM_BYTES, s>>>(p);
+	else reduce_gemm_tc_kernel<false><<<grid, 160, SMEM_BYTES, s>>>(p);
+	return cudaGetLastError();
+}
+
+}  // namespace crfgpu

@@ -64,7 +64,7 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 1, opt_cluster_slots = 0; uint32_t opt_k_slab = 1024;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 1, opt_cluster_slots = 0, opt_gemm_impl = 1; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	DevBuf d_cl_off, d_cl_list, d_xch, d_xmax;
@@ -384,7 +384,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		if (nSf == 0) {   // bias-only state functions: S = bias
 			throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
 		}
-		launch_score_gemm(g, s);
+		if (h->opt_gemm_impl == 1) CUDA_OK(launch_score_gemm_tc(g, s)); else launch_score_gemm(g, s);
 		check_kernel(h, 1);
 	}
 	phase_end(h, "score");
@@ -423,8 +423,9 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 			r.scale = -c.trans_bias_val; r.ones_scale = 0.0; r.mode = 1;
 			r.pair_idx = h->d_tidx.as<uint32_t>() + (size_t)(d - 1) * P; r.pair_ld = L;
 			r.Ew = h->d_E.as<float>() + (size_t)(d - 1) * P; r.e_ld = Lp;
-			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab;
-			launch_reduce_gemm(r, s); check_kernel(h, 1);
+			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl == 1 ? h->opt_k_slab_tc : h->opt_k_slab;
+			if (h->opt_gemm_impl == 1) CUDA_OK(launch_reduce_gemm_tc(r, false, s)); else launch_reduce_gemm(r, s);
+			check_kernel(h, 1);
 		}
 	}
 	phase_end(h, "xi");
@@ -437,8 +438,9 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu;
 		r.scale = 1.0; r.ones_scale = c.state_bias_val; r.mode = 0;
 		r.row_idx = h->d_sidx.as<uint32_t>() + (size_t)d * P;
-		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab;
-		launch_reduce_gemm(r, s); check_kernel(h, 1);
+		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl == 1 ? h->opt_k_slab_tc : h->opt_k_slab;
+		if (h->opt_gemm_impl == 1) CUDA_OK(launch_reduce_gemm_tc(r, true, s)); else launch_reduce_gemm(r, s);
+		check_kernel(h, 1);
 	}
 	EmpiricalParams e{};
 	e.X = h->X(); e.ldx = h->ldx(); e.W = h->W; e.sf0 = c.state_fidx_start; e.nSf = nSf;
@@ -708,6 +710,8 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		if (n == "slots") h->opt_slots = (int)value;
 		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
+		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16
+		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
 		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E
 		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
 		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);

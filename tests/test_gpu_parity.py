@@ -39,7 +39,7 @@ def assert_train_close(got, want, what=""):
 
 
 @pytest.mark.parametrize("name", sorted(TRAIN))
-@pytest.mark.parametrize("impl", ["legacy_u1", "legacy_u4", "cluster", "cluster_u4"])
+@pytest.mark.parametrize("impl", ["legacy_u1", "legacy_u4", "cluster", "cluster_u4", "cluster_ffma_gemm"])
 def test_fwdbwd_matches_reference_golden(name, impl):
     c = TRAIN[name]
     m = gpu(c["cfg"])
@@ -49,6 +49,8 @@ def test_fwdbwd_matches_reference_golden(name, impl):
         m.set_option("slots", int(impl[-1]))
     elif impl == "cluster_u4":
         m.set_option("cluster_slots", 4)
+    elif impl == "cluster_ffma_gemm":
+        m.set_option("gemm_impl", 0)    # fp32 FFMA tiles instead of the tcgen05 split-bf16 GEMMs
     m.set_lambda(c["lam"])
     got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
     assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
@@ -187,7 +189,9 @@ def test_unsupported_geometries_fail_loudly():
 def test_size_independent_properties_full_cfg2_shape():
     """At BASELINE cfg2 size (61 labels, 105 features, ~300-frame utterances): with lambda = 0 every path is
     equally likely, so logZ = T*log(61) - and the gradient's state-bias block sums to zero per frame
-    (sum_c (onehot - gamma) = 0), a checksum that does not need the oracle."""
+    (sum_c (onehot - gamma) = 0), a checksum that does not need the oracle.  The bound on that checksum is
+    1e-5 of the summed magnitudes (2 per frame): the split-bf16 tensor-core GEMM carries ~16 mantissa bits and
+    its fp32 accumulation chain is 2048 frames long."""
     rng = np.random.default_rng(5)
     off, ftrs, labs = synth_batch(rng, 64, 200, 400, 105, 61, 3, 20)
     cfg = make_config("stdframe", n_labs=61, n_base_ftrs=105)
@@ -199,9 +203,10 @@ def test_size_independent_properties_full_cfg2_shape():
     assert np.all(n == 0)
     sidx, _ = m.index_maps()
     bias = g[sidx + 105]
-    assert abs(bias.sum()) < 2e-2
+    bound = 1e-5 * 2 * float(off[-1])
+    assert abs(bias.sum()) < bound
     lam = rng.uniform(-0.25, 0.25, m.lambda_len)
     m.set_lambda(lam)
     g, n, z = m.fwdbwd(off, ftrs, labs)
-    assert abs(g[sidx + 105].sum()) < 2e-2
+    assert abs(g[sidx + 105].sum()) < bound
     assert np.all(n - z < 0)    # log-likelihood of the reference path is negative
