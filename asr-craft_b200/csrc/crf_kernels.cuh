@@ -76,6 +76,26 @@ bool plan_cluster_dp(uint32_t L, uint32_t D, int max_smem_optin, ClusterPlan* pl
 int max_active_clusters(const ClusterPlan& plan);
 cudaError_t launch_cluster_dp(bool backward, const ClusterDpParams& p, const ClusterPlan& plan, cudaStream_t s);
 
+// ---- tensor-core cluster variant (crf_dp_tc.cu): E hi half in TMEM, lo half in smem, tcgen05.mma per frame,
+//      all-gather of the frame vector by bulk DSMEM copies ----
+struct TcDpParams : DpParams {
+	uint32_t CS, CW, K;           // cluster size, label slice per CTA (multiple of 16), padded label count CS*CW
+	uint32_t tmem_cols, ctl_off;  // TMEM columns to allocate, byte offset of the control block in dynamic smem
+	uint32_t n_clusters;
+	const uint32_t* cl_off;       // [n_clusters+1]
+	const uint32_t* cl_list;      // utterance ids in the order each cluster processes them
+	const float* smaxd;           // [N][D] per-duration maxima of S (launch_block_max)
+};
+struct TcDpPlan {
+	uint32_t CS, CW, K, tmem_cols, ctl_off;
+	size_t smem;
+};
+constexpr int TC_DP_SLOTS = 16;
+bool plan_tc_dp(uint32_t L, uint32_t D, int max_smem_optin, TcDpPlan* plan);
+int max_active_tc_clusters(const TcDpPlan& plan);
+cudaError_t launch_tc_dp(bool backward, const TcDpParams& p, const TcDpPlan& plan, cudaStream_t s);
+void launch_block_max(const float* S, const uint32_t* frame_t, float* smaxd, uint32_t N, uint32_t Lp, uint32_t P, uint32_t D, cudaStream_t s);
+
 // ---- TN GEMM with fp64 scatter epilogue:  out[map(i,j)] += scale * sum_n A[n][i]*B[n][j] --------
 struct ReduceGemmParams {
 	const float* A; uint64_t lda;   // rows n in [n0,n1), A row used = n - a_row_shift

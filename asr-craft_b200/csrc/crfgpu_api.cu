@@ -64,10 +64,11 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 1, opt_cluster_slots = 0, opt_gemm_impl = 1; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 1; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
-	DevBuf d_cl_off, d_cl_list, d_xch, d_xmax;
+	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
+	DevBuf d_cl_off, d_cl_list, d_xch, d_xmax, d_smaxd;
 
 	// model tables
 	bool have_lambda = false;
@@ -278,8 +279,36 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// cluster-resident lattice kernels: persistent clusters, utterances dealt longest-first to the least loaded
 	// cluster; inside a cluster the list order is the order slots are (re)filled
 	std::vector<uint32_t> cl_off, cl_list;
-	h->cluster_ok = false;
-	if (h->train_ok && h->opt_dp_impl == 1 && labs && n_utt) {
+	h->cluster_ok = false; h->tc_ok = false;
+	auto deal = [&](uint32_t ncl) {
+		// utterances dealt longest-first to the least loaded cluster; inside a cluster the list order is the order slots are (re)filled
+		std::vector<std::vector<uint32_t>> lists(ncl);
+		std::vector<uint64_t> load(ncl, 0);
+		for (uint32_t i = 0; i < n_utt; i++) {
+			const uint32_t u = order[i];
+			const uint32_t k = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+			lists[k].push_back(u); load[k] += off[u + 1] - off[u];
+		}
+		cl_off.assign(1, 0); cl_list.clear();
+		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
+		upload(h->d_cl_off, cl_off, s); upload(h->d_cl_list, cl_list, s);
+	};
+	if (h->train_ok && h->opt_dp_impl == 2 && labs && n_utt) {
+		// tensor-core cluster kernels: 16 slots per cluster
+		TcDpPlan plan{};
+		if (plan_tc_dp(h->lay.L, c.max_dur, h->max_smem_optin, &plan)) {
+			const int avail_cl = max_active_tc_clusters(plan);
+			if (avail_cl > 0) {
+				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
+				deal(ncl);
+				h->tc_plan = plan; h->n_tc_clusters = ncl; h->tc_ok = true;
+				if (getenv("CRFGPU_VERBOSE"))
+					fprintf(stderr, "[crfgpu] tensor-core lattice plan: CS=%u CW=%u K=%u tmem_cols=%u smem=%zu, %u of %d resident clusters, %u utterances\n",
+					        plan.CS, plan.CW, plan.K, plan.tmem_cols, plan.smem, ncl, avail_cl, n_utt);
+			}
+		}
+	}
+	if (h->train_ok && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
 		ClusterPlan plan{};
 		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
 		if (plan_cluster_dp(h->lay.L, c.max_dur, h->max_smem_optin, &plan, cap)) {
@@ -293,20 +322,11 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 			if (avail_cl > 0) {
 				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + plan.UB - 1) / plan.UB);
-				std::vector<std::vector<uint32_t>> lists(ncl);
-				std::vector<uint64_t> load(ncl, 0);
-				for (uint32_t i = 0; i < n_utt; i++) {
-					const uint32_t u = order[i];
-					const uint32_t k = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
-					lists[k].push_back(u); load[k] += off[u + 1] - off[u];
-				}
-				cl_off.push_back(0);
-				for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
+				deal(ncl);
 				h->plan = plan; h->n_clusters = ncl; h->cluster_ok = true;
 				if (getenv("CRFGPU_VERBOSE"))
 					fprintf(stderr, "[crfgpu] cluster plan: CS=%u CW=%u UB=%d threads=%u smem=%zu, %u of %d resident clusters, %u utterances\n",
 					        plan.CS, plan.CW, plan.UB, plan.threads, plan.smem, ncl, avail_cl, n_utt);
-				upload(h->d_cl_off, cl_off, s); upload(h->d_cl_list, cl_list, s);
 				h->d_xch.ensure(sizeof(float) * (size_t)ncl * 2 * plan.UB * h->Lp + 16);
 				h->d_xmax.ensure(sizeof(float) * (size_t)ncl * 2 * plan.CS * plan.UB + 16);
 			}
@@ -390,7 +410,21 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	phase_end(h, "score");
 
 	DpParams p = dp_params(h);
-	if (h->cluster_ok) {
+	if (h->tc_ok) {
+		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
+		TcDpParams tp{};
+		static_cast<DpParams&>(tp) = p;
+		tp.CS = h->tc_plan.CS; tp.CW = h->tc_plan.CW; tp.K = h->tc_plan.K; tp.tmem_cols = h->tc_plan.tmem_cols; tp.ctl_off = h->tc_plan.ctl_off;
+		tp.n_clusters = h->n_tc_clusters; tp.cl_off = h->d_cl_off.as<uint32_t>(); tp.cl_list = h->d_cl_list.as<uint32_t>();
+		tp.smaxd = h->d_smaxd.as<float>();
+		phase_begin(h, "forward");
+		launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1);
+		CUDA_OK(launch_tc_dp(false, tp, h->tc_plan, s)); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		CUDA_OK(launch_tc_dp(true, tp, h->tc_plan, s)); check_kernel(h, 1);
+		phase_end(h, "backward");
+	} else if (h->cluster_ok) {
 		ClusterDpParams cp{};
 		static_cast<DpParams&>(cp) = p;
 		cp.CS = h->plan.CS; cp.CW = h->plan.CW; cp.CWp = h->plan.CWp; cp.CWt = h->plan.CWt; cp.n_clusters = h->n_clusters;
@@ -543,7 +577,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
-	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax};
+	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(h->stream);
@@ -712,7 +746,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
 		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
-		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E
+		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05
 		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
 		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);
 	});

@@ -38,19 +38,20 @@ def assert_train_close(got, want, what=""):
     assert not bad.any(), f"gradient {what}: {bad.sum()} of {bad.size} entries off, worst {np.abs(g - gw).max():.3e} (|g|max {np.abs(gw).max():.3e})"
 
 
+# lattice kernels: 0 = one CTA per utterance group (E from L2), 1 = cluster-resident E with FFMA, 2 = cluster-resident E with
+# tcgen05 (default); GEMMs: 0 = fp32 FFMA tiles, 1 = tcgen05 split-bf16 (default)
+IMPLS = {"tc": {}, "tc_ffma_gemm": {"gemm_impl": 0}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
+         "legacy_u1": {"dp_impl": 0, "slots": 1}, "legacy_u4": {"dp_impl": 0, "slots": 4, "gemm_impl": 0}}
+
+
 @pytest.mark.parametrize("name", sorted(TRAIN))
-@pytest.mark.parametrize("impl", ["legacy_u1", "legacy_u4", "cluster", "cluster_u4", "cluster_ffma_gemm"])
+@pytest.mark.parametrize("impl", sorted(IMPLS))
 def test_fwdbwd_matches_reference_golden(name, impl):
     c = TRAIN[name]
     m = gpu(c["cfg"])
     assert m.lambda_len == len(c["lam"])
-    if impl.startswith("legacy"):
-        m.set_option("dp_impl", 0)
-        m.set_option("slots", int(impl[-1]))
-    elif impl == "cluster_u4":
-        m.set_option("cluster_slots", 4)
-    elif impl == "cluster_ffma_gemm":
-        m.set_option("gemm_impl", 0)    # fp32 FFMA tiles instead of the tcgen05 split-bf16 GEMMs
+    for k, v in IMPLS[impl].items():
+        m.set_option(k, v)
     m.set_lambda(c["lam"])
     got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
     assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
