@@ -11,14 +11,19 @@
 //     hi + lo.  The hi half lives in TENSOR MEMORY (tcgen05.mma A operand from TMEM, K/2 columns), the lo half in
 //     shared memory, so that the 16-slot frame vectors fit beside it.
 //   * per step:  D[128 x 16] = E_slice[128 x K] * V[K x 16]  as K/16 * 3 tcgen05.mma (hi*hi + hi*lo + lo*hi),
-//     fp32 accumulators in TMEM, ~16 mantissa bits (tools/tc_probe.cu: 3e-6 worst relative error).
+//     fp32 accumulators in TMEM, ~16 mantissa bits (tools/tc_probe.cu: 3e-6 worst relative error).  Measured cost
+//     (tools/mma_bench.cu): 20 cycles per TMEM-sourced and 53 per smem-sourced N=16 MMA, provided the issue loop
+//     lives inside one elect.sync region so that descriptors stay in uniform registers.
 //   * the only exchange is the all-gather of the new frame vector: every CTA writes its slice (already in the
 //     MMA's shared-memory layout, bf16 hi/lo) and pushes it to its CS-1 peers with ONE bulk DSMEM copy each
 //     (cp.async.bulk.shared::cluster, completion counted on the receiver's mbarrier); no cluster barrier and
 //     no max-reduction per frame (tools/dsmem_probe.cu measured 60 cycles/KB for this exchange).
-//   * scales: every frame vector is stored relative to a log scale that is an UPPER BOUND computable one step
-//     ahead from per-duration score maxima and the previous frames' sums, so that entries are <= 1 and the
-//     largest is >= exp(Mmin - Mmax): alpha_t[c] = rho_t + log A_t[c];  S_t[c] + beta_t[c] = base_t + lw_t[c].
+//   * scales: every frame vector is stored relative to a log scale that is an UPPER BOUND of its entries, so entries
+//     are <= 1 and the largest is >= exp(Mmin - Mmax)/L:  alpha_t[c] = rho_t + log A_t[c],
+//     S_t[c] + beta_t[c] = base_t + lw_t[c].  The bound of frame f is computed ONE STEP AHEAD by a dedicated warp from
+//     per-duration score maxima (launch_block_max), the exact sums of the frames gathered so far and, for the one
+//     frame still in flight, an anchored bound (tight bound of that frame + log of its label count), so the scale
+//     bookkeeping is off the critical path and no slack accumulates.
 //   * slots are refilled from the cluster's utterance list as soon as an utterance ends (continuous batching).
 //
 // Forward:   G_t[c] = sum_q A_t[q] E[q][c]   (pushed once per frame, block d of G_t is consumed at t+d)
@@ -40,26 +45,50 @@ using namespace tc05;
 
 namespace {
 
-constexpr int UB = 16;             // slots per cluster == MMA N
-constexpr int DMAX = 32;
-constexpr int N_LANE_THREADS = 256;
-constexpr int N_THREADS = 288;     // 8 lane warps + 1 control warp
+constexpr int UB = TC_DP_SLOTS;        // slots per cluster == MMA N
+constexpr int DMAX = 32;               // scale rings (power of two); max_dur < DMAX
+constexpr int LANE_WARPS = 16;         // 4 per TMEM lane quadrant, each owning SPT slots of its 32 rows
+constexpr int SPT = UB / (LANE_WARPS / 4);
+constexpr int NBK = 4;                 // bookkeeping warps, each owning SPW slots with LPS lanes per slot
+constexpr int SPW = UB / NBK, LPS = 32 / SPW;
+constexpr int MMA_WARP = LANE_WARPS, BK_WARP0 = LANE_WARPS + 1;
+constexpr int N_THREADS = (LANE_WARPS + 1 + NBK) * 32;
+constexpr int BAR_ALL = N_THREADS, BAR_LANES_MMA = (LANE_WARPS + 1) * 32;
 constexpr uint32_t D_COL = 0, EHI_COL = 32;
+static_assert(SPT == 4, "the partial-sum butterfly below is written for 4 slots per thread");
 
 struct Slot {
 	uint32_t utt, off, len, t;     // utt == LAB_BAD: idle
 	double lz;                     // logZ of the utterance (backward)
 };
 
+// what the lane threads need to know about one slot in one step (published by the bookkeeping warp)
+struct LaneCtl {
+	uint32_t flags;    // 1: gathered frame active, 2: produced frame active, 4: forward: keep G of the gathered frame | backward: gathered frame is the tail
+	uint32_t crow;     // element index (frame * Lp) of the gathered frame
+	uint32_t nrow;     // ... of the produced frame
+	uint32_t cn;       // frame index of the gathered frame
+	uint32_t ct;       // t of the gathered frame
+	uint32_t nt;       // forward: t of the produced frame | backward: numNext of the produced frame
+	uint32_t navail;   // forward: labels available in the produced frame | backward: in the gathered frame
+	uint32_t pad;
+};
+
 struct Ctl {
 	uint64_t gather[2], mma_bar;
-	uint32_t tmem, any[2], pad;
-	Slot cur[2][UB], nxt[2][UB];   // [step parity][slot]: frame held by the gathered vector / frame being produced
-	double ring_a[UB][DMAX];       // forward: ghat_t = log sum_c alpha_t   | backward: bl_t = base_t + log sum_c v_t
-	double ring_b[UB][DMAX];       // forward: rho_t                        | backward: base_t
-	float delta[UB][DMAX + 1];     // log-scale correction of duration block d for the vector being produced
-	float rsc[UB][DMAX + 1];       // backward: scale of R for duration d
-	float sg[UB];                  // backward: rho_t + base_t - logZ
+	uint32_t tmem, pad;
+	uint32_t any[2][NBK];
+	// published per step, double-buffered by step parity (the bookkeeping warp runs ahead of the lane threads)
+	LaneCtl lc[2][UB];
+	float delta[2][UB][DMAX + 1];  // log-scale correction of duration block d for the vector being produced
+	float rsc[2][UB][DMAX + 1];    // backward: scale of R for duration d
+	float sg[2][UB];               // backward: rho_t + base_t - logZ
+	// private to the bookkeeping warp
+	Slot fr[4][UB];                // fr[j & 3] = F(j), the frame produced in step j (gathered in step j+1)
+	double ring_a[UB][DMAX];       // forward: ghat_t = log sum_c exp(alpha_t[c]) | backward: bl_t = base_t + log sum_c v_t[c]
+	double ring_b[UB][DMAX];       // forward: rho_t                              | backward: base_t
+	float pre_sm[2][UB][DMAX];     // [j & 1]: forward smaxd[frame of F(j)][d-1] | backward smaxd[frame of F(j) + d][d-1]
+	double pre_rho[UB][DMAX + 1];  // backward: rho_{t-d}, d = 0..D, of the frame about to be gathered
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -70,18 +99,37 @@ __device__ __forceinline__ void cluster_sync_all() {
 	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(N_THREADS) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(N_THREADS) : "memory"); }
-__device__ __forceinline__ float warp_sum(float v) {
+template <int COUNT> __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
+template <int COUNT> __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
+// named barriers: 1 = scales/schedule of the step published (bookkeeping -> everyone), 2 = slice of the new vector written
+// (lanes -> MMA warp), 3 = accumulators complete (MMA warp -> lanes)
+constexpr int BAR_SCALES = 1, BAR_TILE = 2, BAR_ACC = 3;
+
+// reductions over the LPS lanes that share a slot (lane = slot + SPW*h); executed by the whole warp
+__device__ __forceinline__ double slot_max(double v) {
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	for (int o = SPW; o < 32; o <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 	return v;
 }
-__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float slot_sum(float v) {
+#pragma unroll
+	for (int o = SPW; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__device__ __forceinline__ Slot next_frame(const Slot& s, bool bwd) {
+	Slot n = s;
+	if (bwd) n.t = s.t - 1; else n.t = s.t + 1;
+	return n;
+}
+__device__ __forceinline__ bool has_next(const Slot& s, bool bwd) { return s.utt != LAB_BAD && (bwd ? s.t > 0 : s.t + 1 < s.len); }
 
 }  // namespace
 
 size_t tc_dp_ctl_bytes() { return sizeof(Ctl); }
+
+#define TICK(var) const long long var = timing ? clock64() : 0
+#define TACC(slot, a, b) do { if (timing) tacc[slot] += (unsigned long long)((b) - (a)); } while (0)
 
 template <bool BWD>
 __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
@@ -96,28 +144,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t rank = CS > 1 ? cluster_ctarank() : 0, cl = blockIdx.x / CS;
 	const uint32_t c0 = rank * CW;
-	const uint32_t q4 = warp & 3, half = (warp >> 2) & 1;
+	const uint32_t q4 = warp & 3, sub = (warp >> 2) & 3;   // lane warps: TMEM lane quadrant, slot group
 	const uint32_t row = q4 * 32 + lane, c = c0 + row;
-	const bool lane_thread = warp < 8;
+	const bool lane_thread = warp < LANE_WARPS;
 	const bool in_tile = lane_thread && row < CW;          // this thread owns a row of the slice tile
 	const bool row_valid = in_tile && c < L;               // ... that is a real label
 	const uint32_t my_d = row_valid ? c / P + 1 : 0xffffu;
-	const uint32_t list_begin = p.cl_off[cl], list_end = p.cl_off[cl + 1];
 	const float* Msrc = BWD ? p.E : p.ET;                  // rows = my labels, columns = the contracted label
+	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MMA_WARP || warp == BK_WARP0);
+	unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cycle counters, kept in registers and flushed once
 
 	// ---------------------------------------------------------------- setup
 	if (tid == 0) {
 		mbar_init(&ctl->gather[0], 1); mbar_init(&ctl->gather[1], 1); mbar_init(&ctl->mma_bar, 1);
 		fence_mbar_init();
 	}
-	if (warp == 8) tmem_alloc(&ctl->tmem, p.tmem_cols);
+	if (warp == MMA_WARP) tmem_alloc(&ctl->tmem, p.tmem_cols);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem = ctl->tmem;
 	if (lane_thread && q4 * 32 < CW) {
 		// my row of the E slice: hi -> TMEM (8 packed columns per 16-wide k-step), lo -> shared memory (K-major, LBO 128, SBO K*16)
-		const uint32_t KS = K / 16, ks_lo = half ? KS / 2 : 0, ks_hi = half ? KS : KS / 2;
+		const uint32_t KS = K / 16, ks_lo = KS * sub / 4, ks_hi = KS * (sub + 1) / 4;
 		for (uint32_t ks = ks_lo; ks < ks_hi; ks++) {
 			float x[16];
 			const float* src = Msrc + (size_t)c * Lp + ks * 16;
@@ -136,237 +185,373 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 		}
 		tmem_st_wait();
 	}
-	if (warp == 8) {
-		// schedule of step 0: nothing gathered yet, the first UB utterances of the list are produced at their first frame
-		if (lane < UB) {
-			Slot idle{LAB_BAD, 0, 0, 0, 0.0}, n = idle;
-			const uint32_t idx = list_begin + lane;
-			if (idx < list_end) {
-				const uint32_t utt = p.cl_list[idx];
-				n.utt = utt; n.off = p.off[utt]; n.len = p.off[utt + 1] - p.off[utt]; n.t = BWD ? n.len - 1 : 0;
-				if (BWD) n.lz = p.logZ[utt];
-			}
-			ctl->cur[0][lane] = idle; ctl->nxt[0][lane] = n;
-		}
-		if (lane == 0) ctl->any[0] = list_begin < list_end ? 1u : 0u;
-	}
 	fence_proxy_async_smem();
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	if (CS > 1) cluster_sync_all();      // every CTA's mbarriers exist before the first remote completion can arrive
-	uint32_t list_next = min(list_begin + (uint32_t)UB, list_end);
 
-	// ---------------------------------------------------------------- steps
-	uint32_t it = 0;
-	for (;; it++) {
-		const uint32_t pb = it & 1, nb = pb ^ 1;
-		if (!ctl->any[pb]) break;
-		unsigned char* mychunk = bbuf + ((size_t)nb * CS + rank) * CHUNK;
-		if (warp == 8) {
-			// ===================== control warp =====================
-			if (it > 0) {
-				mbar_wait_cluster(&ctl->gather[pb], ((it - 1) >> 1) & 1);
-				if (lane == 0) {
-					tc_fence_after();
-					const uint32_t idesc = idesc_bf16_f32(128, UB, false, false);
-					const uint32_t bb = smem_u32(bbuf + (size_t)pb * CS * CHUNK), eb = smem_u32(elo);
-					const uint32_t ks_per_chunk = CW / 16;
-					uint32_t ks = 0;
-					for (uint32_t j = 0; j < CS; j++) {
-						for (uint32_t k2 = 0; k2 < ks_per_chunk; k2++, ks++) {
-							const uint32_t ba = bb + j * CHUNK + k2 * 1024;
-							const uint64_t vhi = smem_desc(ba, 512, 128), vlo = smem_desc(ba + 256, 512, 128);
-							const uint64_t el = smem_desc(eb + ks * 256, 128, SBO_E);
-							mma_ts(tmem + D_COL, tmem + EHI_COL + ks * 8, vhi, idesc, ks > 0);
-							mma_ts(tmem + D_COL, tmem + EHI_COL + ks * 8, vlo, idesc, true);
-							mma_ss(tmem + D_COL, el, vhi, idesc, true);
-						}
+	if (warp >= BK_WARP0) {
+		// =====================================================================================================
+		// bookkeeping warp.  Iteration j (j = -1, 0, 1, ...) runs during step j of the other warps and
+		//   [1] turns the partial sums gathered in step j into the exact log-sum of F(j-1),
+		//   [2] derives the scale of F(j+1) and publishes everything the lanes need in step j+1,
+		//   [3] schedules F(j+2) and fetches its score maxima.
+		// NBK such warps, each with its own SPW slots; lane = local slot + SPW*h: the LPS lanes of a slot share the duration loops.
+		// =====================================================================================================
+		const uint32_t bw = warp - BK_WARP0, slot = bw * SPW + (lane & (SPW - 1)), h = lane / SPW;
+		// every slot works through its own utterance list (the host balances the lists over all slots of all clusters)
+		const uint32_t list_end = p.cl_off[cl * UB + slot + 1];
+		const Slot idle{LAB_BAD, 0, 0, 0, 0.0};
+		uint32_t list_next = p.cl_off[cl * UB + slot];
+		auto refill = [&](bool want, Slot& out) {
+			if (want && h == 0 && list_next < list_end) {
+				const uint32_t utt = p.cl_list[list_next++];
+				out.utt = utt; out.off = p.off[utt]; out.len = p.off[utt + 1] - p.off[utt]; out.t = BWD ? out.len - 1 : 0;
+				if (BWD) out.lz = p.logZ[utt];
+			}
+		};
+		// what the scale recursions read from global memory (score maxima of a frame; backward: rho of the frames before it) is
+		// loaded into registers right after the frame is scheduled and parked in shared memory only after the current iteration's
+		// scale work, so the latency never shows (lane = duration index)
+		float pf_sm[SPW]; double pf_rho[SPW];
+		auto fetch_sm = [&](uint32_t fidx) {
+#pragma unroll
+			for (int s = 0; s < SPW; s++) {
+				const Slot f = ctl->fr[fidx & 3][bw * SPW + s];
+				pf_sm[s] = -INFINITY;
+				if (f.utt == LAB_BAD) continue;
+				if (!BWD) { if (lane < D) pf_sm[s] = __ldg(p.smaxd + ((size_t)f.off + f.t) * D + lane); }
+				else { const uint32_t d = lane + 1; if (d <= min(f.len - 1 - f.t, D)) pf_sm[s] = __ldg(p.smaxd + ((size_t)f.off + f.t + d) * D + d - 1); }
+			}
+		};
+		auto fetch_rho = [&](uint32_t fidx) {
+#pragma unroll
+			for (int s = 0; s < SPW; s++) {
+				const Slot f = ctl->fr[fidx & 3][bw * SPW + s];
+				pf_rho[s] = 0.0;
+				if (BWD && f.utt != LAB_BAD && lane <= min(f.t, D)) pf_rho[s] = __ldg(p.m + (size_t)f.off + f.t - lane);
+			}
+		};
+		auto park_sm = [&](uint32_t fidx) {
+#pragma unroll
+			for (int s = 0; s < SPW; s++) ctl->pre_sm[fidx & 1][bw * SPW + s][lane] = pf_sm[s];
+		};
+		auto park_rho = [&]() {
+#pragma unroll
+			for (int s = 0; s < SPW; s++) ctl->pre_rho[bw * SPW + s][lane] = pf_rho[s];
+		};
+		// F(-1) idle, F(0) = the first UB utterances of the list at their first frame (iteration -1 schedules F(1))
+		{
+			Slot f0 = idle;
+			refill(true, f0);
+			if (h == 0) { ctl->fr[3][slot] = idle; ctl->fr[0][slot] = f0; }
+			__syncwarp();
+			fetch_sm(0); park_sm(0);
+			if (BWD) { fetch_rho(0); park_rho(); }
+			__syncwarp();
+		}
+		for (int j = -1;; j++) {
+			const uint32_t pb = (uint32_t)j & 1, nb = pb ^ 1;
+			TICK(b0);
+			const Slot fm = ctl->fr[(j - 1) & 3][slot], f0 = ctl->fr[j & 3][slot], f1 = ctl->fr[(j + 1) & 3][slot];
+			// ---- [3] (data-independent, so first) schedule F(j+2) and start fetching its maxima / the forward scales of F(j+1) ----
+			{
+				Slot f2 = idle;
+				const bool cont = has_next(f1, BWD);
+				if (cont) f2 = next_frame(f1, BWD);
+				refill(!cont, f2);
+				if (h == 0) ctl->fr[(j + 2) & 3][slot] = f2;
+				__syncwarp();
+				fetch_sm((uint32_t)(j + 2));
+				if (BWD) fetch_rho((uint32_t)(j + 1));
+			}
+			TICK(b0b); TACC(6, b0, b0b);
+			if (j >= 1) mbar_wait(&ctl->gather[pb], ((j - 1) >> 1) & 1);
+			TICK(b1); TACC(4, b0b, b1);
+			// ---- [1] exact sum of the frame gathered in this step ----
+			if (j >= 1) {
+				float vsum = 0.0f;
+				if (fm.utt != LAB_BAD) {
+					const unsigned char* base = bbuf + (size_t)pb * CS * CHUNK + CW * 64;
+					for (uint32_t r = h; r < CS; r += LPS)
+#pragma unroll
+						for (int q = 0; q < 4; q++) vsum += *reinterpret_cast<const float*>(base + r * CHUNK + (q * 16 + slot) * 4);
+				}
+				vsum = slot_sum(vsum);
+				if (fm.utt != LAB_BAD && h == 0) {
+					if (!BWD) {
+						const bool last = fm.t + 1 == fm.len;
+						// the log scales are references, not results: only logZ needs the accurate logarithm
+						const double ghat = ctl->ring_b[slot][fm.t & (DMAX - 1)] + (last ? log((double)vsum) : (double)__logf(vsum));
+						ctl->ring_a[slot][fm.t & (DMAX - 1)] = ghat;
+						if (last && rank == 0) p.logZ[fm.utt] = ghat;               // computeAlphaSum (:447-462)
+					} else {
+						const bool tail = fm.t + 1 == fm.len;
+						ctl->ring_a[slot][fm.t & (DMAX - 1)] = tail ? 0.0 : ctl->ring_b[slot][fm.t & (DMAX - 1)] + (double)__logf(vsum);
 					}
-					mma_commit(&ctl->mma_bar);
 				}
 				__syncwarp();
 			}
-			Slot c2{LAB_BAD, 0, 0, 0, 0.0}, n2 = c2;
-			bool want_refill = false;
-			if (lane < UB) {
-				const Slot cur = ctl->cur[pb][lane], nxt = ctl->nxt[pb][lane];
-				// ---- scale bookkeeping ----
-				float vsum = 0.0f;
-				if (cur.utt != LAB_BAD) {
-					const unsigned char* base = bbuf + (size_t)pb * CS * CHUNK + CW * 64;
-					for (uint32_t j = 0; j < CS; j++)
-#pragma unroll
-						for (int q = 0; q < 4; q++) vsum += *reinterpret_cast<const float*>(base + j * CHUNK + (q * 16 + lane) * 4);
+			// ---- [2] scale of F(j+1); F(j) (same utterance, one frame earlier in processing order) is still in flight ----
+			const float* sm0 = ctl->pre_sm[pb][slot];      // maxima for F(j)
+			const float* sm1 = ctl->pre_sm[nb][slot];      // maxima for F(j+1)
+			const bool a1 = f1.utt != LAB_BAD, a0 = f0.utt != LAB_BAD;
+			if (!BWD) {
+				const uint32_t t1 = f1.t;
+				double rho = -DBL_MAX, rt = -DBL_MAX;
+				const bool inflight = a1 && t1 > 0;            // F(j) is frame t1-1 of the same utterance
+				const uint32_t t0 = t1 - 1;
+				// tight bound of the in-flight frame t1-1 from exact sums, + log(label count) bounds its log-sum
+				// (shuffles stay outside the per-slot conditions: every lane of the warp must execute them)
+				if (inflight) {
+					for (uint32_t d = 1 + h; d <= min(t0, D); d += LPS) rt = fmax(rt, (double)sm0[d - 1] + p.Mmax + ctl->ring_a[slot][(t0 - d) & (DMAX - 1)]);
+					if (h == 0 && t0 < D) rt = fmax(rt, (double)sm0[t0]);
 				}
-				if (!BWD) {
-					if (cur.utt != LAB_BAD) {
-						const double ghat = ctl->ring_b[lane][cur.t % D] + log((double)vsum);
-						ctl->ring_a[lane][cur.t % D] = ghat;
-						if (cur.t + 1 == cur.len && rank == 0) p.logZ[cur.utt] = ghat;   // computeAlphaSum (:447-462)
-					}
-					if (nxt.utt != LAB_BAD) {
-						const uint32_t t1 = nxt.t;
-						const float* sm = p.smaxd + ((size_t)nxt.off + t1) * D;
-						double rho = -DBL_MAX;
-						for (uint32_t d = 1; d <= min(t1, D); d++) rho = fmax(rho, (double)sm[d - 1] + p.Mmax + ctl->ring_a[lane][(t1 - d) % D]);
-						if (t1 < D) rho = fmax(rho, (double)sm[t1]);            // d == t1+1: the segment starts the utterance, alpha = S
-						for (uint32_t d = 1; d <= D; d++) {
-							float dl = -INFINITY;
-							if (d <= t1) dl = (float)(p.Mmax + ctl->ring_b[lane][(t1 - d) % D] - rho);
-							else if (d == t1 + 1) dl = (float)(-rho);
-							ctl->delta[lane][d] = dl;
-						}
-						ctl->ring_b[lane][t1 % D] = rho;
-						if (rank == 0) p.m[(size_t)nxt.off + t1] = rho;
-					}
-				} else {
-					if (cur.utt != LAB_BAD) {
-						const uint32_t t = cur.t; const size_t n = (size_t)cur.off + t;
-						const bool tail = t + 1 == cur.len;
-						const double base = ctl->ring_b[lane][t % D];
-						ctl->ring_a[lane][t % D] = tail ? 0.0 : base + log((double)vsum);
-						const double rho = p.m[n];
-						ctl->sg[lane] = (float)(rho + base - cur.lz);
-						for (uint32_t d = 1; d <= D; d++)
-							ctl->rsc[lane][d] = (d <= t) ? (float)(base + p.m[n - d] + p.Mmax - cur.lz) : -INFINITY;
-						if (rank == 0) p.bbase[n] = base;
-					}
-					if (nxt.utt != LAB_BAD) {
-						const uint32_t t1 = nxt.t; const size_t n1 = (size_t)nxt.off + t1;
-						const uint32_t numNext = min(nxt.len - 1 - t1, D);
-						double sigma = -DBL_MAX;
-						for (uint32_t d = 1; d <= numNext; d++)
-							sigma = fmax(sigma, (double)p.smaxd[(n1 + d) * D + d - 1] + ctl->ring_a[lane][(t1 + d) % D]);
-						for (uint32_t d = 1; d <= D; d++)
-							ctl->delta[lane][d] = (d <= numNext) ? (float)(ctl->ring_b[lane][(t1 + d) % D] - sigma) : -INFINITY;
-						ctl->ring_b[lane][t1 % D] = numNext ? p.Mmax + sigma : 0.0;   // tail: beta = 0 (setTailBeta)
+				rt = slot_max(rt);
+				if (inflight) {
+					const double ub0 = rt + (double)__logf((float)(P * min(t0 + 1, D)));
+					if (h == 0) rho = (double)sm1[0] + p.Mmax + ub0;
+					for (uint32_t d = 2 + h; d <= min(t1, D); d += LPS) rho = fmax(rho, (double)sm1[d - 1] + p.Mmax + ctl->ring_a[slot][(t1 - d) & (DMAX - 1)]);
+				}
+				if (a1 && h == 0 && t1 < D) rho = fmax(rho, (double)sm1[t1]);       // d == t1+1: the segment starts the utterance, alpha = S
+				rho = slot_max(rho);
+				if (a1) {
+					for (uint32_t d = 1 + h; d <= D; d += LPS) {
+						float dl = -INFINITY;
+						if (d <= t1) dl = (float)(p.Mmax + ctl->ring_b[slot][(t1 - d) & (DMAX - 1)] - rho);
+						else if (d == t1 + 1) dl = (float)(-rho);
+						ctl->delta[nb][slot][d] = dl;
 					}
 				}
-				// ---- schedule of the next step ----
-				c2 = nxt;
-				if (c2.utt != LAB_BAD && (BWD ? c2.t > 0 : c2.t + 1 < c2.len)) { n2 = c2; n2.t = BWD ? c2.t - 1 : c2.t + 1; }
-				else want_refill = true;
+				__syncwarp();
+				if (a1 && h == 0) {
+					ctl->ring_b[slot][t1 & (DMAX - 1)] = rho;
+					if (rank == 0) p.m[(size_t)f1.off + t1] = rho;
+				}
+			} else {
+				const uint32_t t1 = f1.t;
+				const uint32_t nn1 = a1 ? min(f1.len - 1 - t1, D) : 0;
+				double sigma = -DBL_MAX, st = -DBL_MAX;
+				// frame t1+1 = F(j): bound of its bl from the exact bl of the frames behind it
+				const uint32_t nn0 = nn1 ? min(f0.len - 1 - f0.t, D) : 0;
+				for (uint32_t d = 1 + h; d <= nn0; d += LPS) st = fmax(st, (double)sm0[d - 1] + ctl->ring_a[slot][(t1 + 1 + d) & (DMAX - 1)]);
+				st = slot_max(st);
+				if (nn1) {
+					const double ubl0 = nn0 ? p.Mmax + st + (double)__logf((float)(P * nn0)) : 0.0;   // tail frame: S + beta = S exactly
+					if (h == 0) sigma = (double)sm1[0] + ubl0;
+					for (uint32_t d = 2 + h; d <= nn1; d += LPS) sigma = fmax(sigma, (double)sm1[d - 1] + ctl->ring_a[slot][(t1 + d) & (DMAX - 1)]);
+				}
+				sigma = slot_max(sigma);
+				if (a1)
+					for (uint32_t d = 1 + h; d <= D; d += LPS)
+						ctl->delta[nb][slot][d] = (d <= nn1) ? (float)(ctl->ring_b[slot][(t1 + d) & (DMAX - 1)] - sigma) : -INFINITY;
+				// posterior scales of F(j), gathered (and turned into posteriors) in step j+1
+				if (a0) {
+					const double base0 = ctl->ring_b[slot][f0.t & (DMAX - 1)];
+					if (h == 0) {
+						ctl->sg[nb][slot] = (float)(ctl->pre_rho[slot][0] + base0 - f0.lz);
+						if (rank == 0) p.bbase[(size_t)f0.off + f0.t] = base0;
+					}
+					for (uint32_t d = 1 + h; d <= D; d += LPS)
+						ctl->rsc[nb][slot][d] = (d <= f0.t) ? (float)(base0 + ctl->pre_rho[slot][d] + p.Mmax - f0.lz) : -INFINITY;
+				}
+				__syncwarp();
+				if (a1 && h == 0) ctl->ring_b[slot][t1 & (DMAX - 1)] = nn1 ? p.Mmax + sigma : 0.0;   // tail: beta = 0 (setTailBeta)
 			}
-			const uint32_t mask = __ballot_sync(0xffffffffu, want_refill);
-			if (lane < UB) {
-				if (want_refill) {
-					const uint32_t idx = list_next + __popc(mask & ((1u << lane) - 1u));
-					if (idx < list_end) {
-						const uint32_t utt = p.cl_list[idx];
-						n2.utt = utt; n2.off = p.off[utt]; n2.len = p.off[utt + 1] - p.off[utt]; n2.t = BWD ? n2.len - 1 : 0;
-						if (BWD) n2.lz = p.logZ[utt];
-					}
+			if (h == 0) {
+				LaneCtl lc{};
+				lc.flags = (a0 ? 1u : 0u) | (a1 ? 2u : 0u);
+				if (a0) {
+					lc.cn = f0.off + f0.t; lc.crow = lc.cn * Lp; lc.ct = f0.t;
+					if (!BWD) { if (f0.t + 1 < f0.len) lc.flags |= 4u; }
+					else { if (f0.t + 1 == f0.len) lc.flags |= 4u; lc.navail = P * min(f0.t + 1, D); }
 				}
-				ctl->cur[nb][lane] = c2; ctl->nxt[nb][lane] = n2;
+				if (a1) {
+					lc.nrow = (f1.off + f1.t) * Lp;
+					if (!BWD) { lc.nt = f1.t; lc.navail = P * min(f1.t + 1, D); }
+					else lc.nt = min(f1.len - 1 - f1.t, D);
+				}
+				ctl->lc[nb][slot] = lc;
 			}
-			list_next = min(list_next + (uint32_t)__popc(mask), list_end);
-			const uint32_t any = __ballot_sync(0xffffffffu, lane < UB && (c2.utt != LAB_BAD || n2.utt != LAB_BAD));
-			if (lane == 0) ctl->any[nb] = any ? 1u : 0u;
+			const uint32_t any_mine = __ballot_sync(0xffffffffu, a0 || a1);
+			if (lane == 0) ctl->any[nb][bw] = any_mine ? 1u : 0u;
 			__syncwarp();
-			bar_arrive(1);          // scales + next schedule are published
-			bar_sync(2);            // my slice of the new vector is complete in shared memory
-			if (lane == 0) mbar_arrive_expect_tx(&ctl->gather[nb], (CS - 1) * CHUNK);
-			if (lane < CS && lane != rank) {
-				const uint32_t dst = mapa(smem_u32(mychunk), lane), rbar = mapa(smem_u32(&ctl->gather[nb]), lane);
-				asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-				             ::"r"(dst), "r"(smem_u32(mychunk)), "r"(CHUNK), "r"(rbar) : "memory");
-			}
-		} else {
-			// ===================== lane threads: row `row` of the slice, slots half*8 .. half*8+7 =====================
-			float sv[8], aux[8], old[8];
-			uint32_t lab[8];
+			TICK(b2); TACC(5, b1, b2);
+			// all warps meet here once per step (the lanes arrive when they finished the previous step's slice), so every warp
+			// reads the same "anything left" flags and the loops end together
+			bar_sync<BAR_ALL>(BAR_SCALES);
+			uint32_t any = 0;
 #pragma unroll
-			for (int j = 0; j < 8; j++) {
-				const uint32_t s = half * 8 + j;
-				sv[j] = 0.0f; aux[j] = 0.0f; old[j] = 0.0f; lab[j] = LAB_BAD;
-				if (!row_valid) continue;
-				const Slot nxt = ctl->nxt[pb][s];
-				if (!BWD) {
-					if (nxt.utt != LAB_BAD) {
-						const size_t n1 = (size_t)nxt.off + nxt.t;
-						sv[j] = __ldg(p.S + n1 * Lp + c);
-						if (my_d >= 2 && my_d <= nxt.t) old[j] = p.G[(n1 - my_d) * Lp + c];
-					}
-				} else {
-					const Slot cur = ctl->cur[pb][s];
-					if (cur.utt != LAB_BAD) {
-						const size_t n = (size_t)cur.off + cur.t;
-						sv[j] = __ldg(p.S + n * Lp + c); aux[j] = __ldg(p.A + n * Lp + c); lab[j] = __ldg(p.node_lab + n);
-					}
-					if (nxt.utt != LAB_BAD && my_d >= 2 && my_d <= min(nxt.len - 1 - nxt.t, D))
-						old[j] = p.G[((size_t)nxt.off + nxt.t + my_d) * Lp + c];
-				}
-			}
-			bar_sync(1);
-			float g[8];
-#pragma unroll
-			for (int j = 0; j < 8; j++) g[j] = 0.0f;
-			if (it > 0) {
-				mbar_wait(&ctl->mma_bar, (it - 1) & 1);
-				tc_fence_after();
-				tmem_ld8(tmem + ((q4 * 32u) << 16) + D_COL + half * 8, g);
-				tmem_ld_wait();
-				tc_fence_before();
-			}
-#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				const uint32_t s = half * 8 + j;
-				const Slot cur = ctl->cur[pb][s], nxt = ctl->nxt[pb][s];
-				float val = 0.0f;
-				if (!BWD) {
-					if (row_valid) {
-						if (cur.utt != LAB_BAD && cur.t + 1 < cur.len) p.G[((size_t)cur.off + cur.t) * Lp + c] = g[j];
-						if (nxt.utt != LAB_BAD) {
-							const uint32_t t1 = nxt.t;
-							if (c < P * min(t1 + 1, D)) {
-								float lr = sv[j] + ctl->delta[s][my_d];
-								if (my_d <= t1) lr += __logf(my_d == 1 ? g[j] : old[j]);
-								val = __expf(lr);
-							}
-							p.A[((size_t)nxt.off + t1) * Lp + c] = val;
-						}
-					}
-				} else {
-					float lw = -INFINITY;
-					if (row_valid && cur.utt != LAB_BAD) {
-						const uint32_t t = cur.t; const size_t n = (size_t)cur.off + t;
-						float dm = 0.0f, r = 0.0f, uu = 0.0f;
-						if (c < P * min(t + 1, D)) {
-							uu = (t + 1 == cur.len) ? 1.0f : g[j];
-							const float lu = __logf(uu);
-							lw = sv[j] + lu;
-							const float gamma = aux[j] * __expf(lu + ctl->sg[s]);
-							dm = ((lab[j] == c) ? 1.0f : 0.0f) - gamma;
-							if (my_d <= t) r = __expf(lw + ctl->rsc[s][my_d]);
-						}
-						p.Dm[n * Lp + c] = dm; p.R[n * Lp + c] = r;
-						if (p.Uvec) p.Uvec[n * Lp + c] = uu;
-						p.G[n * Lp + c] = lw;          // log-domain S+beta relative to base_t, read back by this thread d frames earlier
-					}
-					if (row_valid && nxt.utt != LAB_BAD && my_d <= min(nxt.len - 1 - nxt.t, D))
-						val = __expf((my_d == 1 ? lw : old[j]) + ctl->delta[s][my_d]);
-				}
-				if (in_tile) {
-					const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-					const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
-					unsigned char* dst = mychunk + (row / 8) * 512 + half * 128 + j * 16 + (row % 8) * 2;
-					*reinterpret_cast<__nv_bfloat16*>(dst) = hi; *reinterpret_cast<__nv_bfloat16*>(dst + 256) = lo;
-				}
-				const float ws = warp_sum(val);
-				if (lane == 0) *reinterpret_cast<float*>(mychunk + CW * 64 + (q4 * 16 + s) * 4) = ws;
-			}
-			fence_proxy_async_smem();
-			bar_arrive(2);
+			for (int w = 0; w < NBK; w++) any |= ctl->any[nb][w];
+			if (!any) break;
+			park_sm((uint32_t)(j + 2));      // overwrites the maxima of F(j), consumed above
+			if (BWD) park_rho();             // ... and the forward scales of F(j)
+			__syncwarp();
 		}
+		if (timing) for (int i = 4; i < 7; i++) p.dbg[i] = tacc[i];   // bookkeeping warp 0
+	} else {
+		// =====================================================================================================
+		// steps
+		// =====================================================================================================
+		uint32_t it = 0;
+		for (;; it++) {
+			const uint32_t pb = it & 1, nb = pb ^ 1;
+			TICK(t0);
+			bar_sync<BAR_ALL>(BAR_SCALES);
+			{
+				uint32_t any = 0;
+#pragma unroll
+				for (int w = 0; w < NBK; w++) any |= ctl->any[pb][w];
+				if (!any) break;
+			}
+			unsigned char* mychunk = bbuf + ((size_t)nb * CS + rank) * CHUNK;
+			if (warp == MMA_WARP) {
+				// ===================== MMA warp: one product per step, then the all-gather of the new slice =====================
+				if (it > 0) {
+					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);
+					TICK(m1); TACC(0, t0, m1);
+					tc_fence_after();
+					if (elect_one()) {
+						// everything the issue loop updates is defined inside the elected region: with exactly one active lane the
+						// compiler keeps descriptors and counters in uniform registers (UIADD3 + UTCHMMA, no R2UR per MMA)
+						const uint32_t idesc = idesc_bf16_f32(128, UB, false, false);
+						uint64_t vhi = smem_desc(smem_u32(bbuf + (size_t)pb * CS * CHUNK), 512, 128);
+						uint64_t el = smem_desc(smem_u32(elo), 128, SBO_E);
+						const uint32_t ks_per_chunk = CW / 16, chunk_skip = (CHUNK - ks_per_chunk * 1024) >> 4;
+						const uint32_t dt = tmem + D_COL;
+						uint32_t ta = tmem + EHI_COL;
+						bool acc = false;
+						for (uint32_t j = 0; j < CS; j++) {
+							for (uint32_t k2 = 0; k2 < ks_per_chunk; k2++) {
+								mma_ts(dt, ta, vhi, idesc, acc);
+								mma_ts(dt, ta, vhi + 16, idesc, true);                  // lo tile = +256 bytes
+								mma_ss(dt, el, vhi, idesc, true);
+								acc = true; vhi += 64; el += 16; ta += 8;               // next k-step: +1024 / +256 bytes, +8 TMEM columns
+							}
+							vhi += chunk_skip;                                          // over the slice's partial sums
+						}
+						mma_commit(&ctl->mma_bar);
+					}
+					__syncwarp();
+					TICK(m2); TACC(1, m1, m2);
+					mbar_wait(&ctl->mma_bar, (it - 1) & 1);          // one polling warp instead of sixteen
+					bar_arrive<BAR_LANES_MMA>(BAR_ACC);                // accumulators are complete
+				}
+				TICK(m3);
+				bar_sync<BAR_LANES_MMA>(BAR_TILE);                      // my slice of the new vector is complete in shared memory
+				if (lane == 0) mbar_arrive_expect_tx(&ctl->gather[nb], (CS - 1) * CHUNK);
+				if (lane < CS && lane != rank) {
+					const uint32_t dst = mapa(smem_u32(mychunk), lane), rbar = mapa(smem_u32(&ctl->gather[nb]), lane);
+					asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					             ::"r"(dst), "r"(smem_u32(mychunk)), "r"(CHUNK), "r"(rbar) : "memory");
+				}
+				TICK(m5); TACC(2, m3, m5);
+				if (timing) tacc[11]++;
+			} else {
+				// ===================== lane threads: row `row` of the slice, slots sub*SPT .. sub*SPT+SPT-1 =====================
+				LaneCtl li[SPT];
+				float sv[SPT], aux[SPT], old[SPT];
+				uint32_t lab[SPT];
+#pragma unroll
+				for (int k = 0; k < SPT; k++) {
+					li[k] = ctl->lc[pb][sub * SPT + k];
+					sv[k] = 0.0f; aux[k] = 0.0f; old[k] = 0.0f; lab[k] = LAB_BAD;
+					if (!row_valid) continue;
+					if (!BWD) {
+						if (li[k].flags & 2u) {
+							sv[k] = __ldg(p.S + li[k].nrow + c);
+							if (my_d >= 2 && my_d <= li[k].nt) old[k] = p.G[li[k].nrow - my_d * Lp + c];
+						}
+					} else {
+						if (li[k].flags & 1u) {
+							sv[k] = __ldg(p.S + li[k].crow + c); aux[k] = __ldg(p.A + li[k].crow + c); lab[k] = __ldg(p.node_lab + li[k].cn);
+						}
+						if ((li[k].flags & 2u) && my_d >= 2 && my_d <= li[k].nt) old[k] = p.G[li[k].nrow + my_d * Lp + c];
+					}
+				}
+				TICK(l1); TACC(7, t0, l1);
+				float g[SPT] = {0.0f, 0.0f, 0.0f, 0.0f};
+				if (it > 0) {
+					bar_sync<BAR_LANES_MMA>(BAR_ACC);
+					tc_fence_after();
+					tmem_ld4(tmem + ((q4 * 32u) << 16) + D_COL + sub * SPT, g);
+					tmem_ld_wait();
+					tc_fence_before();
+				}
+				TICK(l2); TACC(8, l1, l2);
+				float val[SPT];
+#pragma unroll
+				for (int k = 0; k < SPT; k++) {
+					const uint32_t s = sub * SPT + k;
+					val[k] = 0.0f;
+					if (!BWD) {
+						if (row_valid) {
+							if (li[k].flags & 4u) p.G[li[k].crow + c] = g[k];
+							if (li[k].flags & 2u) {
+								if (c < li[k].navail) {
+									float lr = sv[k] + ctl->delta[pb][s][my_d];
+									if (my_d <= li[k].nt) lr += __logf(my_d == 1 ? g[k] : old[k]);
+									val[k] = __expf(lr);
+								}
+								p.A[li[k].nrow + c] = val[k];
+							}
+						}
+					} else {
+						float lw = -INFINITY;
+						if (row_valid && (li[k].flags & 1u)) {
+							float dm = 0.0f, r = 0.0f, uu = 0.0f;
+							if (c < li[k].navail) {
+								uu = (li[k].flags & 4u) ? 1.0f : g[k];
+								const float lu = __logf(uu);
+								lw = sv[k] + lu;
+								const float gamma = aux[k] * __expf(lu + ctl->sg[pb][s]);
+								dm = ((lab[k] == c) ? 1.0f : 0.0f) - gamma;
+								if (my_d <= li[k].ct) r = __expf(lw + ctl->rsc[pb][s][my_d]);
+							}
+							p.Dm[li[k].crow + c] = dm; p.R[li[k].crow + c] = r;
+							if (p.Uvec) p.Uvec[li[k].crow + c] = uu;
+							p.G[li[k].crow + c] = lw;      // log-domain S+beta relative to base_t, read back by this thread d frames earlier
+						}
+						if (row_valid && (li[k].flags & 2u) && my_d <= li[k].nt)
+							val[k] = __expf((my_d == 1 ? lw : old[k]) + ctl->delta[pb][s][my_d]);
+					}
+					if (in_tile) {
+						const __nv_bfloat16 hi = __float2bfloat16_rn(val[k]);
+						const __nv_bfloat16 lo = __float2bfloat16_rn(val[k] - __bfloat162float(hi));
+						unsigned char* dst = mychunk + (row / 8) * 512 + (s / 8) * 128 + (s % 8) * 16 + (row % 8) * 2;
+						*reinterpret_cast<__nv_bfloat16*>(dst) = hi; *reinterpret_cast<__nv_bfloat16*>(dst + 256) = lo;
+					}
+				}
+				// partial sums over my 32 rows of my 4 slots: transposed butterfly (6 shuffles instead of 20)
+				{
+					const bool up16 = lane & 16, up8 = lane & 8;
+					const float a0 = (up16 ? val[2] : val[0]) + __shfl_xor_sync(0xffffffffu, up16 ? val[0] : val[2], 16);
+					const float a1 = (up16 ? val[3] : val[1]) + __shfl_xor_sync(0xffffffffu, up16 ? val[1] : val[3], 16);
+					float b = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+					b += __shfl_xor_sync(0xffffffffu, b, 4);
+					b += __shfl_xor_sync(0xffffffffu, b, 2);
+					b += __shfl_xor_sync(0xffffffffu, b, 1);
+					// lane (bit4, bit3) now holds the sum of slot k = 2*bit4 + bit3
+					if ((lane & 7) == 0) *reinterpret_cast<float*>(mychunk + CW * 64 + (q4 * 16 + sub * SPT + 2 * (lane >> 4) + ((lane >> 3) & 1)) * 4) = b;
+				}
+				TICK(l3); TACC(9, l2, l3);
+				fence_proxy_async_smem();
+				bar_arrive<BAR_LANES_MMA>(BAR_TILE);
+			}
+		}
+		if (timing) {
+			if (warp == MMA_WARP) { for (int i = 0; i < 4; i++) p.dbg[i] = tacc[i]; p.dbg[15] = tacc[11]; }
+			else { for (int i = 7; i < 11; i++) p.dbg[i] = tacc[i]; }
+		}
+		// the vectors pushed during the last executed step are never consumed: wait for them so that no bulk copy is in
+		// flight (into this CTA or out of it) when the cluster retires
+		if (warp == MMA_WARP && it > 0) mbar_wait(&ctl->gather[it & 1], ((it - 1) >> 1) & 1);
 	}
-	// the vectors pushed during the last executed step are never consumed: wait for them so that no bulk copy is in
-	// flight (into this CTA or out of it) when the cluster retires
-	if (warp == 8 && it > 0) mbar_wait_cluster(&ctl->gather[it & 1], ((it - 1) >> 1) & 1);
 	tc_fence_before();
 	__syncthreads();
 	if (CS > 1) cluster_sync_all();
-	if (warp == 8) tmem_dealloc(tmem, p.tmem_cols);
+	if (warp == MMA_WARP) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // per-duration maxima of the state scores: smaxd[n][d-1] = max_y S_n[(d,y)]  (-inf when the block does not exist, d > t+1)
@@ -391,7 +576,7 @@ void launch_block_max(const float* S, const uint32_t* frame_t, float* smaxd, uin
 
 // ------------------------------------------------------------------------------------------------
 bool plan_tc_dp(uint32_t L, uint32_t D, int max_smem_optin, TcDpPlan* plan) {
-	if (D > DMAX) return false;
+	if (D >= DMAX) return false;   // the bookkeeping warp maps durations 0..D onto its 32 lanes
 	for (uint32_t CS = 1; CS <= 8; CS *= 2) {
 		const uint32_t CW = ((L + CS - 1) / CS + 15) / 16 * 16;
 		if (CW > 128) continue;
@@ -432,7 +617,6 @@ int max_active_tc_clusters(const TcDpPlan& plan) {
 	if (configure((void*)dp_tc_kernel<false>, plan, &cfg, attr, 1, nullptr) != cudaSuccess) { cudaGetLastError(); return 0; }
 	int n = 0;
 	if (cudaOccupancyMaxActiveClusters(&n, dp_tc_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
-	// the kernels own the SM's tensor memory while resident: at most 512 / tmem_cols CTAs per SM
 	return n;
 }
 

@@ -76,21 +76,22 @@ bool plan_cluster_dp(uint32_t L, uint32_t D, int max_smem_optin, ClusterPlan* pl
 int max_active_clusters(const ClusterPlan& plan);
 cudaError_t launch_cluster_dp(bool backward, const ClusterDpParams& p, const ClusterPlan& plan, cudaStream_t s);
 
+constexpr int TC_DP_SLOTS = 16;     // utterances advanced in lock-step by one cluster == MMA N
 // ---- tensor-core cluster variant (crf_dp_tc.cu): E hi half in TMEM, lo half in smem, tcgen05.mma per frame,
 //      all-gather of the frame vector by bulk DSMEM copies ----
 struct TcDpParams : DpParams {
 	uint32_t CS, CW, K;           // cluster size, label slice per CTA (multiple of 16), padded label count CS*CW
 	uint32_t tmem_cols, ctl_off;  // TMEM columns to allocate, byte offset of the control block in dynamic smem
 	uint32_t n_clusters;
-	const uint32_t* cl_off;       // [n_clusters+1]
-	const uint32_t* cl_list;      // utterance ids in the order each cluster processes them
+	const uint32_t* cl_off;       // [n_clusters*TC_DP_SLOTS+1] offsets of the per-slot utterance lists
+	const uint32_t* cl_list;      // utterance ids in the order each slot processes them
 	const float* smaxd;           // [N][D] per-duration maxima of S (launch_block_max)
+	unsigned long long* dbg;      // optional [32] cycle counters of cluster 0 / CTA 0 (CRFGPU_DP_TIMING=1), else nullptr
 };
 struct TcDpPlan {
 	uint32_t CS, CW, K, tmem_cols, ctl_off;
 	size_t smem;
 };
-constexpr int TC_DP_SLOTS = 16;
 bool plan_tc_dp(uint32_t L, uint32_t D, int max_smem_optin, TcDpPlan* plan);
 int max_active_tc_clusters(const TcDpPlan& plan);
 cudaError_t launch_tc_dp(bool backward, const TcDpParams& p, const TcDpPlan& plan, cudaStream_t s);

@@ -115,24 +115,29 @@ __global__ void __launch_bounds__(160, 2) score_gemm_tc_kernel(ScoreGemmParams p
 			fence_proxy_async_smem();
 			mbar_arrive(&ring->full[s]);
 		}
-	} else if (lane == 0) {
+	} else {
+		// warp 4: the whole warp walks the ring (uniform descriptors), one elected lane issues
 		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, false, false);
 		for (uint32_t c = 0; c < n_chunks; c++) {
 			const uint32_t s = c % STAGES;
 			mbar_wait(&ring->full[s], (c / STAGES) & 1);
 			tc_fence_after();
 			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+			if (elect_one()) {
 #pragma unroll
-			for (int ks = 0; ks < KC / 16; ks++) {
-				const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
-				const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
-				mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
-				mma_ss(tmem, al, bh, idesc, true);
-				mma_ss(tmem, ah, bl, idesc, true);
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+					mma_ss(tmem, al, bh, idesc, true);
+					mma_ss(tmem, ah, bl, idesc, true);
+				}
+				mma_commit(&ring->empty[s]);
 			}
-			mma_commit(&ring->empty[s]);
+			__syncwarp();
 		}
-		mma_commit(&ring->done);
+		if (elect_one()) mma_commit(&ring->done);
+		__syncwarp();
 	}
 	// ---- epilogue: TMEM -> registers -> (+bias) -> shared transpose -> coalesced rows of S ----
 	if (warp < 4) {
@@ -237,24 +242,29 @@ __global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams
 			fence_proxy_async_smem();
 			mbar_arrive(&ring->full[s]);
 		}
-	} else if (lane == 0) {
+	} else {
+		// warp 4: the whole warp walks the ring (uniform descriptors), one elected lane issues
 		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, true, true);
 		for (uint32_t c = 0; c < n_chunks; c++) {
 			const uint32_t s = c % STAGES;
 			mbar_wait(&ring->full[s], (c / STAGES) & 1);
 			tc_fence_after();
 			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+			if (elect_one()) {
 #pragma unroll
-			for (int ks = 0; ks < KC / 16; ks++) {
-				const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
-				const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
-				mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
-				mma_ss(tmem, al, bh, idesc, true);
-				mma_ss(tmem, ah, bl, idesc, true);
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+					mma_ss(tmem, al, bh, idesc, true);
+					mma_ss(tmem, ah, bl, idesc, true);
+				}
+				mma_commit(&ring->empty[s]);
 			}
-			mma_commit(&ring->empty[s]);
+			__syncwarp();
 		}
-		mma_commit(&ring->done);
+		if (elect_one()) mma_commit(&ring->done);
+		__syncwarp();
 	}
 	// ---- epilogue: lane = M-side column, 64 N-side columns; fp64 atomics into the gradient ----
 	if (warp < 4 && n_chunks) {

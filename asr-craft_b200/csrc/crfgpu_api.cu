@@ -293,14 +293,14 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
 		upload(h->d_cl_off, cl_off, s); upload(h->d_cl_list, cl_list, s);
 	};
-	if (h->train_ok && h->opt_dp_impl == 2 && labs && n_utt) {
+	if (h->train_ok && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
 		// tensor-core cluster kernels: 16 slots per cluster
 		TcDpPlan plan{};
 		if (plan_tc_dp(h->lay.L, c.max_dur, h->max_smem_optin, &plan)) {
 			const int avail_cl = max_active_tc_clusters(plan);
 			if (avail_cl > 0) {
 				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
-				deal(ncl);
+				deal(ncl * TC_DP_SLOTS);         // one list per slot, balanced over all slots of all clusters (longest first)
 				h->tc_plan = plan; h->n_tc_clusters = ncl; h->tc_ok = true;
 				if (getenv("CRFGPU_VERBOSE"))
 					fprintf(stderr, "[crfgpu] tensor-core lattice plan: CS=%u CW=%u K=%u tmem_cols=%u smem=%zu, %u of %d resident clusters, %u utterances\n",
@@ -417,12 +417,25 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		tp.CS = h->tc_plan.CS; tp.CW = h->tc_plan.CW; tp.K = h->tc_plan.K; tp.tmem_cols = h->tc_plan.tmem_cols; tp.ctl_off = h->tc_plan.ctl_off;
 		tp.n_clusters = h->n_tc_clusters; tp.cl_off = h->d_cl_off.as<uint32_t>(); tp.cl_list = h->d_cl_list.as<uint32_t>();
 		tp.smaxd = h->d_smaxd.as<float>();
+		static DevBuf dbg; const bool timing = getenv("CRFGPU_DP_TIMING") != nullptr;
+		if (timing) { dbg.ensure(64 * 8); }
 		phase_begin(h, "forward");
 		launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1);
+		auto report = [&](const char* what) {
+			unsigned long long v[32]; CUDA_OK(cudaMemcpyAsync(v, dbg.p, sizeof(v), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+			const double n = v[15] ? (double)v[15] : 1.0;
+			fprintf(stderr, "[crfgpu] %s: %.0f steps; cycles/step MMA warp: scales+gather-wait %.0f issue %.0f tile-wait+copy %.0f (%.0f) | bookkeeping: gather-wait %.0f scales %.0f schedule+prefetch %.0f | lanes: scales-wait+loads %.0f acc-wait %.0f epilogue %.0f (%.0f)\n",
+			        what, n, v[0] / n, v[1] / n, v[2] / n, v[3] / n, v[4] / n, v[5] / n, v[6] / n, v[7] / n, v[8] / n, v[9] / n, v[10] / n);
+		};
+		tp.dbg = timing ? dbg.as<unsigned long long>() : nullptr;
+		if (timing) CUDA_OK(cudaMemsetAsync(dbg.p, 0, 64 * 8, s));
 		CUDA_OK(launch_tc_dp(false, tp, h->tc_plan, s)); check_kernel(h, 1);
+		if (timing) report("forward");
 		phase_end(h, "forward");
 		phase_begin(h, "backward");
+		if (timing) CUDA_OK(cudaMemsetAsync(dbg.p, 0, 64 * 8, s));
 		CUDA_OK(launch_tc_dp(true, tp, h->tc_plan, s)); check_kernel(h, 1);
+		if (timing) report("backward");
 		phase_end(h, "backward");
 	} else if (h->cluster_ok) {
 		ClusterDpParams cp{};

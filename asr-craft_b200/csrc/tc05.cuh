@@ -86,6 +86,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
 	for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+	uint32_t r[4];
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+	for (int i = 0; i < 4; i++) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 	uint32_t r[16];
 	asm volatile(
@@ -96,6 +102,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 	    : "memory");
 #pragma unroll
 	for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// one lane of a converged warp; the canonical way to issue tcgen05.mma / commit from warp-uniform code (operands that are
+// computed by the whole warp stay in uniform registers; wrapping the issue loop in `if (lane == 0)` instead makes the compiler
+// broadcast every operand through an ELECT/R2UR loop, ~85 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+	uint32_t pred;
+	asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+	return pred != 0;
 }
 
 // ---- descriptors -------------------------------------------------------------------------------
