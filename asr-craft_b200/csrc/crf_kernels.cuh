@@ -118,6 +118,20 @@ void launch_reduce_gemm(const ReduceGemmParams& p, cudaStream_t s);
 // tcgen05 version; m_side_is_b picks which operand's columns ride on the 128-row MMA M side (the wider one should)
 cudaError_t launch_reduce_gemm_tc(const ReduceGemmParams& p, bool m_side_is_b, cudaStream_t s);
 
+// ---- transition-bias expected counts for ALL durations in one pass (crf_tc_gemm.cu) --------------
+// out[pair_idx[q*L + c]] += scale * Ew[q][c] * sum_n A[n-d(c)][q] * R[n][c],  c = (d-1)*P + y
+struct XiGemmParams {
+	const float* A; uint64_t lda;     // [n_frames][L] forward vectors
+	const float* R; uint64_t ldb;     // [n_frames][L] right factors
+	uint32_t n_frames, n0, n1, k_slab;
+	uint32_t L, P, D;
+	const uint32_t* pair_idx;         // [L][L] lambda index of (q,c) or 0xffffffff
+	const float* Ew; uint32_t e_ld;   // E[q][c]
+	double scale;
+	double* out;
+};
+cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s);
+
 // ---- empirical counts and numerators on the reference path -------------------------------------
 struct EmpiricalParams {
 	const float* X; uint64_t ldx;     // window features [N][D][W] (ldx = D*W)

@@ -298,6 +298,168 @@ __global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams
 	if (warp == 4) tmem_dealloc(tmem, BN);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Xi, all durations of a group in ONE pass over the forward vectors:
+//   Xi_d[q][y] = sum_n A[n-d][q] * R[n][(d,y)]        (CRF_StdFeatureMap::computeTransExpF summed over frames, :197-223)
+// One CTA = 128 source labels q x up to XI_G column tiles of R (each with its own duration d = row shift of A) x a frame slab.
+// The A rows of a chunk are staged once, with a halo of `halo` earlier frames, in the MN-major layout whose k rows are a
+// uniform 16 bytes apart, so the operand of duration d is the same tile viewed (halo - d) rows further down:
+// only the descriptor's start address changes.  XI_G accumulator tiles live side by side in TMEM.
+// ------------------------------------------------------------------------------------------------
+constexpr int XI_G = 5, XI_ROWS = 64, XI_STAGES = 3;
+constexpr uint32_t XI_A_TILE = 16 * XI_ROWS * 16;                       // [16 column groups][64 frames][16 B] per hi / lo
+constexpr uint32_t XI_R_TILE = 8 * KC * 16;                             // [8 column groups][32 frames][16 B] per hi / lo
+constexpr uint32_t XI_STAGE = 2 * XI_A_TILE + XI_G * 2 * XI_R_TILE;     // 32 KB + 40 KB
+constexpr uint32_t XI_SMEM = XI_STAGES * XI_STAGE + 1024;
+
+struct XiRing {
+	uint64_t full[XI_STAGES], empty[XI_STAGES], done;
+	uint32_t tmem;
+};
+
+__global__ void __launch_bounds__(160, 1) xi_gemm_tc_kernel(XiGemmParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	XiRing* ring = reinterpret_cast<XiRing*>(smem + XI_STAGES * XI_STAGE);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t ytiles = (p.P + BN - 1) / BN, n_tiles = p.D * ytiles;
+	const uint32_t m0 = blockIdx.x * BM, t0 = blockIdx.y * XI_G, nt = min((uint32_t)XI_G, n_tiles - t0);
+	const uint32_t ns = p.n0 + blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.n1);
+	const uint32_t n_chunks = (ne - ns + KC - 1) / KC;
+	// column tile j of this CTA: duration, first column in R, width
+	auto tile_d = [&](uint32_t j) { return (t0 + j) / ytiles + 1; };
+	auto tile_c0 = [&](uint32_t j) { return ((t0 + j) / ytiles) * p.P + ((t0 + j) % ytiles) * BN; };
+	auto tile_w = [&](uint32_t j) { return min((uint32_t)BN, p.P - ((t0 + j) % ytiles) * BN); };
+	const uint32_t halo = (tile_d(nt - 1) + 7) / 8 * 8;                   // largest shift of the group, rounded to a row group
+	if (tid == 0) {
+		for (int s = 0; s < XI_STAGES; s++) { mbar_init(&ring->full[s], N_PRODUCERS); mbar_init(&ring->empty[s], 1); }
+		mbar_init(&ring->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == 4) tmem_alloc(&ring->tmem, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ring->tmem;
+
+	if (warp < 4) {
+		const bool a_vec2 = ((reinterpret_cast<uintptr_t>(p.A) & 7) == 0) && (p.lda % 2 == 0);
+		const bool r_vec2 = ((reinterpret_cast<uintptr_t>(p.R) & 7) == 0) && (p.ldb % 2 == 0);
+		const uint32_t k8 = lane & 7, rgq = lane >> 3;
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % XI_STAGES, nc = ns + c * KC;
+			if (c >= XI_STAGES) mbar_wait(&ring->empty[s], ((c / XI_STAGES) - 1) & 1);
+			unsigned char* st = smem + s * XI_STAGE;
+			// A rows nc-halo .. nc+KC-1 (row index r in the staged window), 128 columns from m0
+			const uint32_t a_rows = halo + KC;
+			for (uint32_t r0 = 0; r0 < a_rows; r0 += 32) {
+				const uint32_t r = r0 + warp * 8 + k8;
+				const int64_t n = (int64_t)nc - halo + r;
+				const bool ok = r < a_rows && n >= 0 && n < (int64_t)p.n_frames;
+				float x[4][8];
+#pragma unroll
+				for (int it = 0; it < 4; it++) {
+					const uint32_t col = m0 + (it * 4 + rgq) * 8;
+					const float* src = p.A + (uint64_t)(ok ? n : 0) * p.lda + col;
+					if (ok && col + 8 <= p.L) load8(src, true, a_vec2, x[it]);
+					else {
+#pragma unroll
+						for (int j = 0; j < 8; j++) x[it][j] = (ok && col + j < p.L) ? __ldg(src + j) : 0.0f;
+					}
+				}
+				if (r < a_rows) {
+#pragma unroll
+					for (int it = 0; it < 4; it++) {
+						uint4 h, l; split8(x[it], h, l);
+						const uint32_t o = (it * 4 + rgq) * (XI_ROWS * 16) + r * 16;
+						*reinterpret_cast<uint4*>(st + o) = h; *reinterpret_cast<uint4*>(st + XI_A_TILE + o) = l;
+					}
+				}
+			}
+			// R rows nc .. nc+KC-1 of every column tile of the group
+			{
+				const uint32_t n = nc + warp * 8 + k8;
+				const bool ok = n < ne;
+				for (uint32_t j = 0; j < nt; j++) {
+					const uint32_t c0 = tile_c0(j), w = tile_w(j);
+					float x[2][8];
+#pragma unroll
+					for (int it = 0; it < 2; it++) {
+						const uint32_t cc = (it * 4 + rgq) * 8;
+						const float* src = p.R + (uint64_t)(ok ? n : 0) * p.ldb + c0 + cc;
+						if (ok && cc + 8 <= w) load8(src, true, r_vec2 && (c0 % 2 == 0), x[it]);
+						else {
+#pragma unroll
+							for (int jj = 0; jj < 8; jj++) x[it][jj] = (ok && cc + jj < w) ? __ldg(src + jj) : 0.0f;
+						}
+					}
+					unsigned char* rt = st + 2 * XI_A_TILE + j * 2 * XI_R_TILE;
+#pragma unroll
+					for (int it = 0; it < 2; it++) {
+						uint4 h, l; split8(x[it], h, l);
+						const uint32_t o = (it * 4 + rgq) * 512 + (warp * 8 + k8) * 16;
+						*reinterpret_cast<uint4*>(rt + o) = h; *reinterpret_cast<uint4*>(rt + XI_R_TILE + o) = l;
+					}
+				}
+			}
+			fence_proxy_async_smem();
+			mbar_arrive(&ring->full[s]);
+		}
+	} else {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, true, true);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % XI_STAGES;
+			mbar_wait(&ring->full[s], (c / XI_STAGES) & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				const uint32_t base = smem_u32(smem + s * XI_STAGE);
+				for (uint32_t j = 0; j < nt; j++) {
+					const uint32_t a_off = (halo - tile_d(j)) * 16;              // the duration's row shift of A
+					const uint32_t rb = base + 2 * XI_A_TILE + j * 2 * XI_R_TILE;
+#pragma unroll
+					for (int ks = 0; ks < KC / 16; ks++) {
+						const uint64_t ah = smem_desc(base + a_off + ks * 256, 128, XI_ROWS * 16), al = smem_desc(base + XI_A_TILE + a_off + ks * 256, 128, XI_ROWS * 16);
+						const uint64_t bh = smem_desc(rb + ks * 256, 128, 512), bl = smem_desc(rb + XI_R_TILE + ks * 256, 128, 512);
+						mma_ss(tmem + j * BN, ah, bh, idesc, (c | ks) != 0);
+						mma_ss(tmem + j * BN, al, bh, idesc, true);
+						mma_ss(tmem + j * BN, ah, bl, idesc, true);
+					}
+				}
+				mma_commit(&ring->empty[s]);
+			}
+			__syncwarp();
+		}
+		if (elect_one()) mma_commit(&ring->done);
+		__syncwarp();
+	}
+	// ---- epilogue: lane = source label q; per column tile 64 destination labels; fp64 atomics into the gradient ----
+	if (warp < 4 && n_chunks) {
+		mbar_wait(&ring->done, 0);
+		tc_fence_after();
+		const uint32_t q = m0 + warp * 32 + lane;
+		for (uint32_t j = 0; j < nt; j++) {
+			const uint32_t c0 = tile_c0(j), w = tile_w(j);
+#pragma unroll
+			for (int cc = 0; cc < BN; cc += 16) {
+				float v[16];
+				tmem_ld16(tmem + ((warp * 32u) << 16) + j * BN + cc, v);
+				tmem_ld_wait();
+				if (q < p.L) {
+#pragma unroll
+					for (int jj = 0; jj < 16; jj++) {
+						const uint32_t col = cc + jj;
+						if (col >= w || v[jj] == 0.0f) continue;
+						const uint32_t idx = __ldg(p.pair_idx + (uint64_t)q * p.L + c0 + col);
+						if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)__ldg(p.Ew + (uint64_t)q * p.e_ld + c0 + col) * (double)v[jj]);
+					}
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace
 
 cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
@@ -310,6 +472,20 @@ cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
 	}
 	dim3 grid((p.M + BM - 1) / BM, (p.Ncols + BN - 1) / BN);
 	score_gemm_tc_kernel<<<grid, 160, SMEM_BYTES, s>>>(p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s) {
+	if (p.n1 <= p.n0 || !p.L || !p.P || p.D > 32) return p.D > 32 ? cudaErrorInvalidValue : cudaSuccess;
+	static bool attr_done = false;
+	if (!attr_done) {
+		cudaError_t e = cudaFuncSetAttribute(xi_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XI_SMEM);
+		if (e != cudaSuccess) return e;
+		attr_done = true;
+	}
+	const uint32_t n_tiles = p.D * ((p.P + BN - 1) / BN);
+	dim3 grid((p.L + BM - 1) / BM, (n_tiles + XI_G - 1) / XI_G, (p.n1 - p.n0 + p.k_slab - 1) / p.k_slab);
+	xi_gemm_tc_kernel<<<grid, 160, XI_SMEM, s>>>(p);
 	return cudaGetLastError();
 }
 

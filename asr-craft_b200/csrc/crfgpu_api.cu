@@ -460,7 +460,14 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 
 	// K4: expected-minus-empirical counts as two families of reduce-GEMMs
 	phase_begin(h, "xi");
-	if (c.use_trans_bias) {
+	if (c.use_trans_bias && h->opt_gemm_impl == 1 && N > 1) {
+		XiGemmParams x{};
+		x.A = h->d_A.as<float>(); x.lda = Lp; x.R = h->d_R.as<float>(); x.ldb = Lp;
+		x.n_frames = N; x.n0 = 1; x.n1 = N; x.k_slab = h->opt_k_slab_tc;
+		x.L = L; x.P = P; x.D = D; x.pair_idx = h->d_tidx.as<uint32_t>(); x.Ew = h->d_E.as<float>(); x.e_ld = Lp;
+		x.scale = -c.trans_bias_val; x.out = h->d_grad.as<double>();
+		CUDA_OK(launch_xi_gemm_tc(x, s)); check_kernel(h, 1);
+	} else if (c.use_trans_bias) {
 		for (uint32_t d = 1; d <= D; d++) {
 			if (d >= N) break;
 			ReduceGemmParams r{};
@@ -470,9 +477,8 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 			r.scale = -c.trans_bias_val; r.ones_scale = 0.0; r.mode = 1;
 			r.pair_idx = h->d_tidx.as<uint32_t>() + (size_t)(d - 1) * P; r.pair_ld = L;
 			r.Ew = h->d_E.as<float>() + (size_t)(d - 1) * P; r.e_ld = Lp;
-			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl == 1 ? h->opt_k_slab_tc : h->opt_k_slab;
-			if (h->opt_gemm_impl == 1) CUDA_OK(launch_reduce_gemm_tc(r, false, s)); else launch_reduce_gemm(r, s);
-			check_kernel(h, 1);
+			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab;
+			launch_reduce_gemm(r, s); check_kernel(h, 1);
 		}
 	}
 	phase_end(h, "xi");
