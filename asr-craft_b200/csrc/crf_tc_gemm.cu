@@ -5,17 +5,21 @@
 //   score_gemm_tc   S[n][j]      = sum_k X[n][k] * W[j][k] + bias[j]                (GEMM-1, both operands K-major)
 //                   replaces L calls per frame of CRF_StdFeatureMap::computeStateArrayValue
 //                   (CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:65-81)
-//   reduce_gemm_tc  out[map(i,j)] += scale * sum_n A[n-shift][i] * B[n][j]          (GEMM-3 / Xi, both operands MN-major)
-//                   replaces the per-frame scatter of computeStateExpF / computeTransExpF (:130-223) and
+//   reduce_gemm_tc  out[map(i,j)] += scale * sum_n A[n-shift][i] * B[n][j]          (GEMM-3, both operands MN-major)
+//   xi_gemm_tc      the same product for the transition-bias counts, ALL durations of a group in one pass
+//                   replace the per-frame scatter of computeStateExpF / computeTransExpF (:130-223) and
 //                   `grad -= ExpF` (CRF/src/trainers/gradbuilders/CRF_NewGradBuilder.cpp:374-376)
 //
-// Structure of both kernels (one CTA = one 128 x 64 output tile, 160 threads):
-//   warps 0-3  producers: coalesced fp32 loads from HBM/L2 -> split into bf16 hi/lo in registers -> 16-byte stores into
-//              the no-swizzle canonical UMMA layout of a 4-stage ring; later the epilogue (warp w owns TMEM lanes 32w..32w+31)
-//   warp  4    one elected lane issues tcgen05.mma, releases ring stages with tcgen05.commit
-// (a tile that holds, or lies beyond, the constant-1 column takes the per-element path)
+// Structure (one CTA = one 128 x 64 output tile; xi: 128 x up to 5*64):
+//   producer warps  fp32 loads from HBM/L2 -> split into bf16 hi/lo in registers -> stores into the no-swizzle canonical UMMA
+//                   layout of a shared-memory ring.  FOUR LANES SHARE ONE 32-BYTE VECTOR (8 consecutive floats = one
+//                   16-byte row of a bf16 core matrix): every load instruction of a warp reads 8 whole 32-byte sectors and
+//                   every store instruction writes 128 contiguous bytes (no L1 re-fetch of partially used sectors, no
+//                   bank conflicts).  The next chunk's loads are in flight while the current chunk is converted.
+//   MMA warp        one elected lane issues tcgen05.mma, releases ring stages with tcgen05.commit
+//   warps 0-3       run the epilogue afterwards (warp w owns TMEM lanes 32w..32w+31)
 // Register staging (instead of TMA) lets the loaders apply what these operands need on the way: the row shift of the
-// Xi product, the constant-1 bias feature, ragged bounds and 8-byte-aligned window rows.
+// Xi product, the constant-1 bias feature, ragged bounds and the 8-byte alignment of window rows.
 #include "crf_kernels.cuh"
 #include "tc05.cuh"
 
@@ -29,31 +33,62 @@ constexpr int BM = 128, BN = 64, KC = 32, STAGES = 4;
 constexpr uint32_t A_TILE = BM * KC * 2, B_TILE = BN * KC * 2;        // bytes of one bf16 tile
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;             // hi + lo of both operands = 24576
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024;          // + barriers / alignment slack
-constexpr int N_PRODUCERS = 128;
+constexpr int PW = 8, N_PRODUCERS = PW * 32, N_THR = (PW + 1) * 32;   // 8 producer warps + the MMA warp, 2 CTAs per SM
 
 struct Ring {
 	uint64_t full[STAGES], empty[STAGES], done;
 	uint32_t tmem;
 };
 
-__device__ __forceinline__ void load8(const float* p, bool ok, bool vec2, float (&x)[8]) {
-	if (!ok) {
+// two consecutive floats of a row; `valid` of them (0..2) exist, `vec2` = the address is 8-byte aligned
+__device__ __forceinline__ float2 load2(const float* p, uint32_t valid, bool vec2) {
+	if (valid == 2 && vec2) return __ldg(reinterpret_cast<const float2*>(p));
+	float2 v = make_float2(0.0f, 0.0f);
+	if (valid > 0) v.x = __ldg(p);
+	if (valid > 1) v.y = __ldg(p + 1);
+	return v;
+}
+__device__ __forceinline__ uint32_t clamp2(uint32_t pos, uint32_t ext) { return pos >= ext ? 0u : min(2u, ext - pos); }
+// store one float2 as the bf16x2 words of the hi and the lo tile
+__device__ __forceinline__ void store_split(unsigned char* hi_tile, uint32_t lo_off, uint32_t o, float2 v) {
+	uint32_t h, l;
+	split2(v.x, v.y, h, l);
+	*reinterpret_cast<uint32_t*>(hi_tile + o) = h; *reinterpret_cast<uint32_t*>(hi_tile + lo_off + o) = l;
+}
+
+// the MMA warp's walk over the ring: 3 MMAs per 16-wide k-step (hi*hi + lo*hi + hi*lo)
+template <bool MN_MAJOR>
+__device__ __forceinline__ void mma_ring(unsigned char* smem, Ring* ring, uint32_t tmem, uint32_t n_chunks) {
+	constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, MN_MAJOR, MN_MAJOR);
+	for (uint32_t c = 0; c < n_chunks; c++) {
+		const uint32_t s = c % STAGES;
+		mbar_wait(&ring->full[s], (c / STAGES) & 1);
+		tc_fence_after();
+		const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+		if (elect_one()) {
 #pragma unroll
-		for (int j = 0; j < 8; j++) x[j] = 0.0f;
-	} else if (vec2) {
-#pragma unroll
-		for (int j = 0; j < 4; j++) { const float2 v = __ldg(reinterpret_cast<const float2*>(p) + j); x[2 * j] = v.x; x[2 * j + 1] = v.y; }
-	} else {
-#pragma unroll
-		for (int j = 0; j < 8; j++) x[j] = __ldg(p + j);
+			for (int ks = 0; ks < KC / 16; ks++) {
+				const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+				const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+				mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+				mma_ss(tmem, al, bh, idesc, true);
+				mma_ss(tmem, ah, bl, idesc, true);
+			}
+			mma_commit(&ring->empty[s]);
+		}
+		__syncwarp();
 	}
+	if (elect_one()) mma_commit(&ring->done);
+	__syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
 // GEMM-1.  A = X rows (frames) x K features, B = W rows (labels) x K; both K-major.
-// smem vector (row r, k-group g) at (r/8)*512 + g*128 + (r%8)*16   (LBO 128, SBO 512)
+// smem: element (row r, k) of a tile at (r/8)*512 + (k/8)*128 + (r%8)*16 + (k%8)*2   (LBO 128, SBO 512)
+// producer thread = (row sub = lane/4 of a row block, float2 piece = lane%4 of a k-group); warp w owns row blocks w, w+8 of A
+// and row block w of B, all four k-groups of the chunk: 12 float2 per chunk.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(160, 2) score_gemm_tc_kernel(ScoreGemmParams p) {
+__global__ void __launch_bounds__(N_THR, 2) score_gemm_tc_kernel(ScoreGemmParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -64,82 +99,54 @@ __global__ void __launch_bounds__(160, 2) score_gemm_tc_kernel(ScoreGemmParams p
 		mbar_init(&ring->done, 1);
 		fence_mbar_init();
 	}
-	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	if (warp == PW) tmem_alloc(&ring->tmem, BN);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem = ring->tmem;
 
-	if (warp < 4) {
+	if (warp < PW) {
 		const bool a_vec2 = ((reinterpret_cast<uintptr_t>(p.A) & 7) == 0) && (p.lda % 2 == 0);
 		const bool b_vec2 = ((reinterpret_cast<uintptr_t>(p.B) & 7) == 0) && (p.ldb % 2 == 0);
-		const uint32_t r8 = lane & 7, g = lane >> 3;
+		const uint32_t sub = lane >> 2, piece = lane & 3;
+		const uint32_t gm0 = m0 + warp * 8 + sub, gm1 = gm0 + 64, gn = n0 + warp * 8 + sub;
+		const bool ok0 = gm0 < p.M, ok1 = gm1 < p.M, okb = gn < p.Ncols;
+		const float* a0p = p.A + (uint64_t)(ok0 ? gm0 : 0) * p.lda + piece * 2;
+		const float* a1p = p.A + (uint64_t)(ok1 ? gm1 : 0) * p.lda + piece * 2;
+		const float* bp = p.B + (uint64_t)(okb ? gn : 0) * p.ldb + piece * 2;
+		float2 x[12];
+		auto fetch = [&](uint32_t c) {
+#pragma unroll
+			for (uint32_t g = 0; g < 4; g++) {
+				const uint32_t k = c * KC + g * 8, v = clamp2(k + piece * 2, p.K);
+				x[g] = load2(a0p + k, ok0 ? v : 0u, a_vec2);
+				x[4 + g] = load2(a1p + k, ok1 ? v : 0u, a_vec2);
+				x[8 + g] = load2(bp + k, okb ? v : 0u, b_vec2);
+			}
+		};
+		fetch(0);
+		const uint32_t o = warp * 512 + sub * 16 + piece * 4;
 		for (uint32_t c = 0; c < n_chunks; c++) {
-			const uint32_t s = c % STAGES, k0 = c * KC + g * 8;
-			float xa[4][8], xb[2][8];
-			// issue every load of the stage before waiting for the ring slot: the registers are the in-flight buffer
+			const uint32_t s = c % STAGES;
+			uint32_t h[12], l[12];
 #pragma unroll
-			for (int it = 0; it < 4; it++) {
-				const uint32_t r = (it * 4 + warp) * 8 + r8, gm = m0 + r;
-				const float* src = p.A + (uint64_t)gm * p.lda + k0;
-				if (gm < p.M && k0 + 8 <= p.K) load8(src, true, a_vec2, xa[it]);
-				else {
-#pragma unroll
-					for (int j = 0; j < 8; j++) xa[it][j] = (gm < p.M && k0 + j < p.K) ? __ldg(src + j) : 0.0f;
-				}
-			}
-#pragma unroll
-			for (int it = 0; it < 2; it++) {
-				const uint32_t r = (it * 4 + warp) * 8 + r8, gn = n0 + r;
-				const float* src = p.B + (uint64_t)gn * p.ldb + k0;
-				if (gn < p.Ncols && k0 + 8 <= p.K) load8(src, true, b_vec2, xb[it]);
-				else {
-#pragma unroll
-					for (int j = 0; j < 8; j++) xb[it][j] = (gn < p.Ncols && k0 + j < p.K) ? __ldg(src + j) : 0.0f;
-				}
-			}
+			for (int i = 0; i < 12; i++) split2(x[i].x, x[i].y, h[i], l[i]);
+			if (c + 1 < n_chunks) fetch(c + 1);                  // in flight while this chunk is stored and the ring slot awaited
 			if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
 			unsigned char* st = smem + s * STAGE_BYTES;
 #pragma unroll
-			for (int it = 0; it < 4; it++) {
-				uint4 h, l; split8(xa[it], h, l);
-				const uint32_t o = (it * 4 + warp) * 512 + g * 128 + r8 * 16;
-				*reinterpret_cast<uint4*>(st + o) = h; *reinterpret_cast<uint4*>(st + A_TILE + o) = l;
-			}
-#pragma unroll
-			for (int it = 0; it < 2; it++) {
-				uint4 h, l; split8(xb[it], h, l);
-				const uint32_t o = (it * 4 + warp) * 512 + g * 128 + r8 * 16;
-				*reinterpret_cast<uint4*>(st + 2 * A_TILE + o) = h; *reinterpret_cast<uint4*>(st + 2 * A_TILE + B_TILE + o) = l;
+			for (uint32_t g = 0; g < 4; g++) {
+				*reinterpret_cast<uint32_t*>(st + o + g * 128) = h[g]; *reinterpret_cast<uint32_t*>(st + A_TILE + o + g * 128) = l[g];
+				*reinterpret_cast<uint32_t*>(st + o + 8 * 512 + g * 128) = h[4 + g]; *reinterpret_cast<uint32_t*>(st + A_TILE + o + 8 * 512 + g * 128) = l[4 + g];
+				*reinterpret_cast<uint32_t*>(st + 2 * A_TILE + o + g * 128) = h[8 + g]; *reinterpret_cast<uint32_t*>(st + 2 * A_TILE + B_TILE + o + g * 128) = l[8 + g];
 			}
 			fence_proxy_async_smem();
 			mbar_arrive(&ring->full[s]);
 		}
 	} else {
-		// warp 4: the whole warp walks the ring (uniform descriptors), one elected lane issues
-		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, false, false);
-		for (uint32_t c = 0; c < n_chunks; c++) {
-			const uint32_t s = c % STAGES;
-			mbar_wait(&ring->full[s], (c / STAGES) & 1);
-			tc_fence_after();
-			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-			if (elect_one()) {
-#pragma unroll
-				for (int ks = 0; ks < KC / 16; ks++) {
-					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
-					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
-					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
-					mma_ss(tmem, al, bh, idesc, true);
-					mma_ss(tmem, ah, bl, idesc, true);
-				}
-				mma_commit(&ring->empty[s]);
-			}
-			__syncwarp();
-		}
-		if (elect_one()) mma_commit(&ring->done);
-		__syncwarp();
+		mma_ring<false>(smem, ring, tmem, n_chunks);
 	}
-	// ---- epilogue: TMEM -> registers -> (+bias) -> shared transpose -> coalesced rows of S ----
+	// ---- epilogue: TMEM -> registers -> shared transpose -> (+bias) -> coalesced rows of S ----
 	if (warp < 4) {
 		mbar_wait(&ring->done, 0);
 		tc_fence_after();
@@ -156,22 +163,38 @@ __global__ void __launch_bounds__(160, 2) score_gemm_tc_kernel(ScoreGemmParams p
 		tc_fence_before();
 		asm volatile("bar.sync 1, 128;" ::: "memory");
 		const uint32_t ncol = min((uint32_t)BN, p.Ncols - n0);
-		for (uint32_t i = tid; i < BM * BN; i += N_PRODUCERS) {
+		for (uint32_t i = tid; i < BM * BN; i += 128) {
 			const uint32_t r = i / BN, j = i % BN, gm = m0 + r;
 			if (gm < p.M && j < ncol) p.C[(uint64_t)gm * p.ldc + n0 + j] = Cs[r * 65 + j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 4) tmem_dealloc(tmem, BN);
+	if (warp == PW) tmem_dealloc(tmem, BN);
 }
 
 // ------------------------------------------------------------------------------------------------
-// GEMM-3 / Xi.  Both operands are [frames][columns] row-major, i.e. MN-major with the reduction index slow.
-// SWAP = false: MMA M side = p.A columns (I), N side = p.B columns (J)     (Xi: I = L source labels, J = P)
+// GEMM-3.  Both operands are [frames][columns] row-major, i.e. MN-major with the reduction index slow.
+// SWAP = false: MMA M side = p.A columns (I), N side = p.B columns (J)
 // SWAP = true : MMA M side = p.B columns (J), N side = p.A columns (I)     (state weights: J = features, I = P)
 // smem vector (frame k, column group rg) at rg*512 + k*16   (LBO 128 = 8 frames, SBO 512)
+// 4 producer warps, one lane per 32-byte vector (for this operand shape the 4-lanes-per-vector mapping of the other two
+// kernels measured slower: 5.2 vs 3.2 ms per step)
 // ------------------------------------------------------------------------------------------------
+constexpr int V_PRODUCERS = 128;
+__device__ __forceinline__ void load8(const float* p, bool ok, bool vec2, float (&x)[8]) {
+	if (!ok) {
+#pragma unroll
+		for (int j = 0; j < 8; j++) x[j] = 0.0f;
+	} else if (vec2) {
+#pragma unroll
+		for (int j = 0; j < 4; j++) { const float2 v = __ldg(reinterpret_cast<const float2*>(p) + j); x[2 * j] = v.x; x[2 * j + 1] = v.y; }
+	} else {
+#pragma unroll
+		for (int j = 0; j < 8; j++) x[j] = __ldg(p + j);
+	}
+}
+
 template <bool SWAP>
 __global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
@@ -186,7 +209,7 @@ __global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams
 	const uint32_t ns = p.n0 + blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.n1);
 	const uint32_t n_chunks = (ne - ns + KC - 1) / KC;
 	if (tid == 0) {
-		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], N_PRODUCERS); mbar_init(&ring->empty[s], 1); }
+		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], V_PRODUCERS); mbar_init(&ring->empty[s], 1); }
 		mbar_init(&ring->done, 1);
 		fence_mbar_init();
 	}
@@ -305,8 +328,9 @@ __global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams
 // The A rows of a chunk are staged once, with a halo of `halo` earlier frames, in the MN-major layout whose k rows are a
 // uniform 16 bytes apart, so the operand of duration d is the same tile viewed (halo - d) rows further down:
 // only the descriptor's start address changes.  XI_G accumulator tiles live side by side in TMEM.
+// 16 producer warps: the A window has 8 frame blocks x 16 column groups, the R tiles 4 frame blocks x 8 column groups each.
 // ------------------------------------------------------------------------------------------------
-constexpr int XI_G = 5, XI_ROWS = 64, XI_STAGES = 3;
+constexpr int XI_G = 5, XI_ROWS = 64, XI_STAGES = 3, XI_PW = 16, XI_THR = (XI_PW + 1) * 32;
 constexpr uint32_t XI_A_TILE = 16 * XI_ROWS * 16;                       // [16 column groups][64 frames][16 B] per hi / lo
 constexpr uint32_t XI_R_TILE = 8 * KC * 16;                             // [8 column groups][32 frames][16 B] per hi / lo
 constexpr uint32_t XI_STAGE = 2 * XI_A_TILE + XI_G * 2 * XI_R_TILE;     // 32 KB + 40 KB
@@ -317,7 +341,7 @@ struct XiRing {
 	uint32_t tmem;
 };
 
-__global__ void __launch_bounds__(160, 1) xi_gemm_tc_kernel(XiGemmParams p) {
+__global__ void __launch_bounds__(XI_THR, 1) xi_gemm_tc_kernel(XiGemmParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	XiRing* ring = reinterpret_cast<XiRing*>(smem + XI_STAGES * XI_STAGE);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -331,75 +355,69 @@ __global__ void __launch_bounds__(160, 1) xi_gemm_tc_kernel(XiGemmParams p) {
 	auto tile_w = [&](uint32_t j) { return min((uint32_t)BN, p.P - ((t0 + j) % ytiles) * BN); };
 	const uint32_t halo = (tile_d(nt - 1) + 7) / 8 * 8;                   // largest shift of the group, rounded to a row group
 	if (tid == 0) {
-		for (int s = 0; s < XI_STAGES; s++) { mbar_init(&ring->full[s], N_PRODUCERS); mbar_init(&ring->empty[s], 1); }
+		for (int s = 0; s < XI_STAGES; s++) { mbar_init(&ring->full[s], XI_PW * 32); mbar_init(&ring->empty[s], 1); }
 		mbar_init(&ring->done, 1);
 		fence_mbar_init();
 	}
-	if (warp == 4) tmem_alloc(&ring->tmem, 512);
+	if (warp == XI_PW) tmem_alloc(&ring->tmem, 512);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem = ring->tmem;
 
-	if (warp < 4) {
+	if (warp < XI_PW) {
 		const bool a_vec2 = ((reinterpret_cast<uintptr_t>(p.A) & 7) == 0) && (p.lda % 2 == 0);
-		const bool r_vec2 = ((reinterpret_cast<uintptr_t>(p.R) & 7) == 0) && (p.ldb % 2 == 0);
-		const uint32_t k8 = lane & 7, rgq = lane >> 3;
+		const bool r_al = ((reinterpret_cast<uintptr_t>(p.R) & 7) == 0) && (p.ldb % 2 == 0);
+		const uint32_t sub = lane >> 2, piece = lane & 3;
+		const uint32_t a_rows = halo + KC;
+		// A: warp w owns frame block w%8 of the staged window and the column-group half w/8 (8 float2)
+		const uint32_t ar = (warp & 7) * 8 + sub, acg0 = (warp >> 3) * 8;
+		// R: 32 (frame block, column group) cells per column tile, nt*32 in all; warp w owns cells w, w+16, ... (up to 10 float2).
+		// Everything that does not depend on the chunk is worked out once: column offset and how many of my 2 floats exist.
+		uint32_t roff[10], rinfo[10];                          // rinfo: bits 0-1 valid floats, bit 2 8-byte aligned, bit 3 cell exists
+#pragma unroll
+		for (uint32_t i = 0; i < 10; i++) {
+			const uint32_t id = warp + 16 * i, j = id >> 5, cg = id & 7;
+			roff[i] = 0; rinfo[i] = 0;
+			if (j < nt) {
+				const uint32_t c0 = tile_c0(j), cc = cg * 8 + piece * 2;
+				roff[i] = c0 + cc;
+				rinfo[i] = clamp2(cc, tile_w(j)) | ((r_al && (c0 % 2 == 0)) ? 4u : 0u) | 8u;
+			}
+		}
 		for (uint32_t c = 0; c < n_chunks; c++) {
 			const uint32_t s = c % XI_STAGES, nc = ns + c * KC;
-			if (c >= XI_STAGES) mbar_wait(&ring->empty[s], ((c / XI_STAGES) - 1) & 1);
-			unsigned char* st = smem + s * XI_STAGE;
-			// A rows nc-halo .. nc+KC-1 (row index r in the staged window), 128 columns from m0
-			const uint32_t a_rows = halo + KC;
-			for (uint32_t r0 = 0; r0 < a_rows; r0 += 32) {
-				const uint32_t r = r0 + warp * 8 + k8;
-				const int64_t n = (int64_t)nc - halo + r;
-				const bool ok = r < a_rows && n >= 0 && n < (int64_t)p.n_frames;
-				float x[4][8];
+			float2 xa[8], xr[10];
+			{
+				const int64_t n = (int64_t)nc - halo + ar;
+				const bool ok = ar < a_rows && n >= 0 && n < (int64_t)p.n_frames;
+				const float* arow = p.A + (uint64_t)(ok ? n : 0) * p.lda;
 #pragma unroll
-				for (int it = 0; it < 4; it++) {
-					const uint32_t col = m0 + (it * 4 + rgq) * 8;
-					const float* src = p.A + (uint64_t)(ok ? n : 0) * p.lda + col;
-					if (ok && col + 8 <= p.L) load8(src, true, a_vec2, x[it]);
-					else {
-#pragma unroll
-						for (int j = 0; j < 8; j++) x[it][j] = (ok && col + j < p.L) ? __ldg(src + j) : 0.0f;
-					}
-				}
-				if (r < a_rows) {
-#pragma unroll
-					for (int it = 0; it < 4; it++) {
-						uint4 h, l; split8(x[it], h, l);
-						const uint32_t o = (it * 4 + rgq) * (XI_ROWS * 16) + r * 16;
-						*reinterpret_cast<uint4*>(st + o) = h; *reinterpret_cast<uint4*>(st + XI_A_TILE + o) = l;
-					}
+				for (uint32_t g = 0; g < 8; g++) {
+					const uint32_t col = m0 + (acg0 + g) * 8 + piece * 2;
+					xa[g] = load2(arow + col, ok ? clamp2(col, p.L) : 0u, a_vec2);
 				}
 			}
-			// R rows nc .. nc+KC-1 of every column tile of the group
-			{
-				const uint32_t n = nc + warp * 8 + k8;
-				const bool ok = n < ne;
-				for (uint32_t j = 0; j < nt; j++) {
-					const uint32_t c0 = tile_c0(j), w = tile_w(j);
-					float x[2][8];
 #pragma unroll
-					for (int it = 0; it < 2; it++) {
-						const uint32_t cc = (it * 4 + rgq) * 8;
-						const float* src = p.R + (uint64_t)(ok ? n : 0) * p.ldb + c0 + cc;
-						if (ok && cc + 8 <= w) load8(src, true, r_vec2 && (c0 % 2 == 0), x[it]);
-						else {
-#pragma unroll
-							for (int jj = 0; jj < 8; jj++) x[it][jj] = (ok && cc + jj < w) ? __ldg(src + jj) : 0.0f;
-						}
-					}
-					unsigned char* rt = st + 2 * XI_A_TILE + j * 2 * XI_R_TILE;
-#pragma unroll
-					for (int it = 0; it < 2; it++) {
-						uint4 h, l; split8(x[it], h, l);
-						const uint32_t o = (it * 4 + rgq) * 512 + (warp * 8 + k8) * 16;
-						*reinterpret_cast<uint4*>(rt + o) = h; *reinterpret_cast<uint4*>(rt + XI_R_TILE + o) = l;
-					}
+			for (uint32_t i = 0; i < 10; i++) {
+				const uint32_t fb = ((warp + 16 * i) & 31) >> 3;
+				xr[i] = make_float2(0.0f, 0.0f);
+				if (rinfo[i] & 8u) {
+					const uint32_t n = nc + fb * 8 + sub;
+					const bool ok = n < ne;
+					xr[i] = load2(p.R + (uint64_t)(ok ? n : 0) * p.ldb + roff[i], ok ? (rinfo[i] & 3u) : 0u, (rinfo[i] & 4u) != 0);
 				}
+			}
+			if (c >= XI_STAGES) mbar_wait(&ring->empty[s], ((c / XI_STAGES) - 1) & 1);
+			unsigned char* st = smem + s * XI_STAGE;
+			if (ar < a_rows) {
+#pragma unroll
+				for (uint32_t g = 0; g < 8; g++) store_split(st, XI_A_TILE, (acg0 + g) * (XI_ROWS * 16) + ar * 16 + piece * 4, xa[g]);
+			}
+#pragma unroll
+			for (uint32_t i = 0; i < 10; i++) {
+				const uint32_t id = warp + 16 * i, j = id >> 5, fb = (id & 31) >> 3, cg = id & 7;
+				if (j < nt) store_split(st + 2 * XI_A_TILE + j * 2 * XI_R_TILE, XI_R_TILE, cg * 512 + (fb * 8 + sub) * 16 + piece * 4, xr[i]);
 			}
 			fence_proxy_async_smem();
 			mbar_arrive(&ring->full[s]);
@@ -457,7 +475,7 @@ __global__ void __launch_bounds__(160, 1) xi_gemm_tc_kernel(XiGemmParams p) {
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 4) tmem_dealloc(tmem, 512);
+	if (warp == XI_PW) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -471,7 +489,7 @@ cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
 		attr_done = true;
 	}
 	dim3 grid((p.M + BM - 1) / BM, (p.Ncols + BN - 1) / BN);
-	score_gemm_tc_kernel<<<grid, 160, SMEM_BYTES, s>>>(p);
+	score_gemm_tc_kernel<<<grid, N_THR, SMEM_BYTES, s>>>(p);
 	return cudaGetLastError();
 }
 
@@ -485,7 +503,7 @@ cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s) {
 	}
 	const uint32_t n_tiles = p.D * ((p.P + BN - 1) / BN);
 	dim3 grid((p.L + BM - 1) / BM, (n_tiles + XI_G - 1) / XI_G, (p.n1 - p.n0 + p.k_slab - 1) / p.k_slab);
-	xi_gemm_tc_kernel<<<grid, 160, XI_SMEM, s>>>(p);
+	xi_gemm_tc_kernel<<<grid, XI_THR, XI_SMEM, s>>>(p);
 	return cudaGetLastError();
 }
 
