@@ -60,7 +60,12 @@ struct crfgpu_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	uint32_t W = 0;          // window feature width
-	uint32_t Lp = 0;         // padded label stride
+	uint32_t Lp = 0;         // padded label stride of the lattice arrays
+	// label set the lattice kernels run on: the model's labels, or -- for the stdseg_no_dur* models -- the (duration, phone)
+	// expansion with tied weights (same recursions as stdseg; the reference's own stdseg run with tied lambda gives the
+	// identical logZ / numerators)
+	uint32_t Lt = 0; bool tied = false;
+	std::vector<uint32_t> t_sidx, t_tidx;   // lambda indices of the lattice labels / label pairs
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
@@ -129,13 +134,23 @@ void classify(crfgpu_ctx* h) {
 		h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
 		if (c.n_states != 1) { h->train_ok = false; h->train_why = "stdseg with crf_states > 1 throws in the reference (CRF_StateNode.cpp:497-502)"; }
 		if (c.n_labs % c.max_dur != 0) { h->train_ok = false; h->train_why = "stdseg: crf_label_size must be phones * label_maximum_duration"; }
-	} else if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
-		h->train_ok = false; h->train_why = "forward-backward for stdseg_no_dur_no_segtransftr is not implemented on the device yet";
+	} else if (c.model_type == CRFGPU_STDSEG_NO_DUR || c.model_type == CRFGPU_STDSEG_NO_DUR_NO_TRANSFTR || c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
+		// labels = phones, the duration lives in the window features only.  Without transition FEATURES the three no_dur node
+		// families compute the same thing (checked against the reference); CRFDecode accepts only the last one.
+		if (c.model_type != CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
+			h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
+		}
+		if (c.n_states != 1 && c.max_dur != 1) {
+			h->train_ok = false; h->train_why = "forward-backward for N-state segmental models (CRF_StdSegNStateNode*) is not implemented on the device yet";
+		} else if (c.n_states == 1 && (uint64_t)c.n_labs * c.max_dur > 1024) {
+			h->train_ok = false; h->train_why = "forward-backward for stdseg_no_dur* runs on the (duration, phone) expansion, which supports phones * max_dur <= 1024";
+		}
 	} else {
 		h->train_ok = h->decode_ok = false;
-		h->train_why = h->decode_why = "model type not implemented on the device yet (stdseg_no_dur / stdseg_no_dur_no_transftr)";
+		h->train_why = h->decode_why = "unknown model type";
 	}
 	if (h->train_ok && c.n_labs > 1024) { h->train_ok = false; h->train_why = "dense lattice kernels support crf_label_size <= 1024"; }
+	if (h->train_ok && c.model_type != CRFGPU_STDFRAME && c.model_type != CRFGPU_STDSEG && c.n_states == 1 && c.max_dur > 1) h->tied = true;
 	if (h->decode_ok && (c.n_labs > 1024 || c.max_dur > 255)) { h->decode_ok = false; h->decode_why = "Viterbi kernel supports crf_label_size <= 1024 and max duration <= 255"; }
 	if (h->train_ok && c.max_dur > 32) { h->train_ok = false; h->train_why = "lattice kernels support label_maximum_duration <= 32"; }
 }
@@ -153,7 +168,7 @@ void require_decode(crfgpu_ctx* h) {
 void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	if (len != m.len) throw ApiError(CRFGPU_ERR_ARG, "lambda length " + std::to_string(len) + " != feature map length " + std::to_string(m.len));
-	const uint32_t L = m.L, Lp = h->Lp, nSf = m.nSf;
+	const uint32_t L = m.L, Lt = h->Lt, Lp = h->Lp, nSf = m.nSf;
 	cudaStream_t s = h->stream;
 	h->d_lambda.ensure(sizeof(double) * (size_t)len + 16);
 	CUDA_OK(cudaMemcpyAsync(h->d_lambda.p, lam, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, s));
@@ -174,18 +189,29 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 	h->Mmax = Mmax;
 
 	if (h->train_ok) {
-		std::vector<float> Ws((size_t)L * std::max(nSf, 1u)), bias(L, 0.0f), E((size_t)L * Lp, 0.0f), ET((size_t)L * Lp, 0.0f);
-		for (uint32_t cl = 0; cl < L; cl++) {
-			const double* w = lam + m.sidx[cl];
+		// tables over the lattice labels (for tied models label (d,y) reads the weights of phone y)
+		std::vector<float> Ws((size_t)Lt * std::max(nSf, 1u)), bias(Lt, 0.0f), E((size_t)Lt * Lp, 0.0f), ET((size_t)Lt * Lp, 0.0f);
+		double tmax = -DBL_MAX;
+		for (uint32_t q = 0; q < Lt; q++)
+			for (uint32_t cl = 0; cl < Lt; cl++) {
+				const uint32_t ti = h->t_tidx[(size_t)q * Lt + cl];
+				if (ti != CRFGPU_NO_IDX) tmax = std::max(tmax, c.use_trans_bias ? lam[ti] * c.trans_bias_val : 0.0);
+			}
+		if (tmax == -DBL_MAX) tmax = 0.0;
+		h->Mmax = tmax;
+		for (uint32_t cl = 0; cl < Lt; cl++) {
+			const double* w = lam + h->t_sidx[cl];
 			for (uint32_t f = 0; f < nSf; f++) Ws[(size_t)cl * nSf + f] = (float)w[f];
 			if (c.use_state_bias) bias[cl] = (float)(w[nSf] * c.state_bias_val);
 		}
-		for (uint32_t p = 0; p < L; p++)
-			for (uint32_t cl = 0; cl < L; cl++)
-				if (m.tidx[(size_t)p * L + cl] != CRFGPU_NO_IDX) {
-					const float e = (float)std::exp(M[(size_t)p * L + cl] - Mmax);
-					E[(size_t)p * Lp + cl] = e; ET[(size_t)cl * Lp + p] = e;
+		for (uint32_t q = 0; q < Lt; q++)
+			for (uint32_t cl = 0; cl < Lt; cl++) {
+				const uint32_t ti = h->t_tidx[(size_t)q * Lt + cl];
+				if (ti != CRFGPU_NO_IDX) {
+					const float e = (float)std::exp((c.use_trans_bias ? lam[ti] * c.trans_bias_val : 0.0) - tmax);
+					E[(size_t)q * Lp + cl] = e; ET[(size_t)cl * Lp + q] = e;
 				}
+			}
 		upload(h->d_Ws, Ws, s); upload(h->d_bias, bias, s); upload(h->d_E, E, s); upload(h->d_ET, ET, s);
 		CUDA_OK(cudaStreamSynchronize(s));   // host vectors die at scope exit
 	}
@@ -252,7 +278,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 				prev_lab[off[u] + t] = last;
 				if (rec[4 * (size_t)t] != CRFGPU_LAB_BAD) {
 					const uint32_t dur = rec[4 * (size_t)t + 2] - rec[4 * (size_t)t + 1] + 1;
-					const uint32_t lab = (c.model_type == CRFGPU_STDSEG) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
+					const uint32_t lab = (c.model_type == CRFGPU_STDSEG || h->tied) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
 					node_lab[off[u] + t] = lab; last = lab;
 				}
 			}
@@ -296,7 +322,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	if (h->train_ok && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
 		// tensor-core cluster kernels: 16 slots per cluster
 		TcDpPlan plan{};
-		if (plan_tc_dp(h->lay.L, c.max_dur, h->max_smem_optin, &plan)) {
+		if (plan_tc_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
 			const int avail_cl = max_active_tc_clusters(plan);
 			if (avail_cl > 0) {
 				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
@@ -311,12 +337,12 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	if (h->train_ok && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
 		ClusterPlan plan{};
 		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
-		if (plan_cluster_dp(h->lay.L, c.max_dur, h->max_smem_optin, &plan, cap)) {
+		if (plan_cluster_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan, cap)) {
 			int avail_cl = max_active_clusters(plan);
 			// keep every cluster busy: shrink the slot count while there are fewer slot-loads than clusters
 			while (h->opt_cluster_slots <= 0 && plan.UB > 4 && avail_cl > 0 && (n_utt + plan.UB - 1) / plan.UB < (uint32_t)avail_cl) {
 				ClusterPlan smaller{};
-				if (!plan_cluster_dp(h->lay.L, c.max_dur, h->max_smem_optin, &smaller, plan.UB == 32 ? 16 : plan.UB == 16 ? 12 : plan.UB == 12 ? 8 : 4)) break;
+				if (!plan_cluster_dp(h->Lt, c.max_dur, h->max_smem_optin, &smaller, plan.UB == 32 ? 16 : plan.UB == 16 ? 12 : plan.UB == 12 ? 8 : 4)) break;
 				if (smaller.CS != plan.CS) break;
 				plan = smaller; avail_cl = max_active_clusters(plan);
 			}
@@ -364,7 +390,7 @@ __global__ void tail_sums_kernel(const double* numer, const double* logZ, uint32
 DpParams dp_params(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	DpParams p{};
-	p.L = h->lay.L; p.Lp = h->Lp; p.D = c.max_dur; p.P = h->lay.L / c.max_dur;
+	p.L = h->Lt; p.Lp = h->Lp; p.D = c.max_dur; p.P = h->Lt / c.max_dur;
 	p.n_groups = h->n_groups; p.grp_utt = h->d_grp.as<uint32_t>(); p.off = h->d_off.as<uint32_t>();
 	p.S = h->d_S.as<float>(); p.E = h->d_E.as<float>(); p.ET = h->d_ET.as<float>();
 	p.A = h->d_A.as<float>(); p.G = h->d_G.as<float>(); p.m = h->d_m.as<double>(); p.kappa = h->d_kappa.as<double>();
@@ -378,7 +404,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	require_train(h);
 	if (!h->have_labels) throw ApiError(CRFGPU_ERR_ARG, "training needs frame labels");
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
-	const uint32_t N = h->N, L = m.L, Lp = h->Lp, D = c.max_dur, P = L / D, nSf = m.nSf;
+	const uint32_t N = h->N, L = h->Lt, Lp = h->Lp, D = c.max_dur, P = L / D, nSf = m.nSf;
 	cudaStream_t s = h->stream;
 	const size_t NL = (size_t)N * Lp;
 	h->d_S.ensure(sizeof(float) * NL + 16); h->d_A.ensure(sizeof(float) * NL + 16); h->d_G.ensure(sizeof(float) * NL + 16);
@@ -396,7 +422,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	for (uint32_t d = 0; d < D; d++) {
 		ScoreGemmParams g{};
 		g.A = h->X() + (size_t)d * h->W + c.state_fidx_start; g.lda = h->ldx();
-		const bool per_dur = (c.model_type == CRFGPU_STDSEG);
+		const bool per_dur = true;   // the lattice label (d,y) has its own row of the device tables (tied models repeat phone y's weights)
 		g.B = h->d_Ws.as<float>() + (per_dur ? (size_t)d * P * nSf : 0); g.ldb = nSf;
 		g.bias = h->d_bias.as<float>() + (per_dur ? (size_t)d * P : 0);
 		g.C = h->d_S.as<float>() + (size_t)d * P; g.ldc = Lp;
@@ -571,12 +597,24 @@ int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
 		h->cfg = *cfg; h->device = device;
 		h->lay = build_layout(*cfg);
 		h->W = window_width(*cfg);
-		h->Lp = (h->lay.L + 31) / 32 * 32;
 		if (cfg->max_dur == 0) throw ApiError(CRFGPU_ERR_ARG, "the maximum duration of labels must be larger than 0");
 		classify(h);
+		{
+			const uint32_t L0 = h->lay.L, Dd = cfg->max_dur;
+			h->Lt = h->tied ? L0 * Dd : L0;
+			h->Lp = (h->Lt + 31) / 32 * 32;
+			if (!h->tied) { h->t_sidx = h->lay.sidx; h->t_tidx = h->lay.tidx; }
+			else {
+				h->t_sidx.resize(h->Lt); h->t_tidx.resize((size_t)h->Lt * h->Lt);
+				for (uint32_t q = 0; q < h->Lt; q++) {
+					h->t_sidx[q] = h->lay.sidx[q % L0];
+					for (uint32_t cl = 0; cl < h->Lt; cl++) h->t_tidx[(size_t)q * h->Lt + cl] = h->lay.tidx[(size_t)(q % L0) * L0 + cl % L0];
+				}
+			}
+		}
 		CUDA_OK(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 		CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-		upload(h->d_sidx, h->lay.sidx, h->stream); upload(h->d_tidx, h->lay.tidx, h->stream);
+		upload(h->d_sidx, h->t_sidx, h->stream); upload(h->d_tidx, h->t_tidx, h->stream);
 		std::vector<uint32_t> steps = sample_steps(cfg->max_dur);
 		upload(h->d_steps, steps, h->stream);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -744,7 +782,7 @@ int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta) {
 		if (!h || !h->fwdbwd_done || !alpha || !beta) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
 		if (!h->opt_keep_lattice) throw ApiError(CRFGPU_ERR_ARG, "set option keep_lattice=1 before running forward-backward");
 		CUDA_OK(cudaSetDevice(h->device));
-		const size_t n = (size_t)h->N * h->lay.L;
+		const size_t n = (size_t)h->N * h->Lt;
 		DevBuf da, db; da.ensure(sizeof(double) * n + 16); db.ensure(sizeof(double) * n + 16);
 		DpParams p = dp_params(h);
 		launch_dump_alpha_beta(p, h->N, h->d_frame_t.as<uint32_t>(), h->d_frame_len.as<uint32_t>(), da.as<double>(), db.as<double>(), h->stream);

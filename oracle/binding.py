@@ -148,6 +148,40 @@ class OracleLib(_Lib):
     def __init__(self, path=None):
         super().__init__(path or os.path.join(HERE, "libcrforacle.so"))
 
+    def fwdbwd(self, cfg, lam, off, ftrs, labs, n_threads=1):
+        """stdseg_no_dur* training (CRF_StdSegStateNode_WithoutDurLab*, CRF_NewGradBuilder_StdSeg[_NoDur_NoTrans].cpp) is
+        restated through its equivalence with `stdseg` on the (duration, phone) label set with TIED weights: state rows of
+        label (d,y) = rows of phone y, transition (d',y')->(d,y) = transition y'->y (no transition FEATURES).  The reference's
+        own stdseg run with tied lambda reproduces the no_dur logZ / numerators (tests/test_oracle.py pins this restatement to
+        goldens produced by the reference's no_dur node classes)."""
+        if cfg.model_type in (2, 3, 4) and cfg.max_dur > 1 and cfg.n_states == 1 and not cfg.use_trans_ftrs:
+            P, D = cfg.n_labs, cfg.max_dur
+            w = window_width(cfg.n_base_ftrs, D, cfg.extract_seg_ftrs)
+            nS = (cfg.state_fidx_end - cfg.state_fidx_start + 1) + (1 if cfg.use_state_bias else 0)
+            nT = 1 if cfg.use_trans_bias else 0
+            big = Config(1, P * D, cfg.n_base_ftrs, 1, D, P, cfg.extract_seg_ftrs, 1, cfg.state_fidx_start, cfg.state_fidx_end,
+                         0, cfg.trans_fidx_start, cfg.trans_fidx_end, cfg.use_state_bias, cfg.use_trans_bias,
+                         cfg.state_bias_val, cfg.trans_bias_val)
+            L = P * D
+            lam = np.asarray(lam, np.float64)
+            # 1-state layout (CRF_StdFeatureMap.cpp:295,365): label c owns [c*(nS+L*nT), +nS) state weights then L*nT transition weights
+            src = np.empty(L * (nS + L * nT), np.int64)
+            for c in range(L):
+                y = c % P
+                base_s, base_b = y * (nS + P * nT), c * (nS + L * nT)
+                src[base_b:base_b + nS] = np.arange(base_s, base_s + nS)
+                if nT:
+                    src[base_b + nS:base_b + nS + L] = base_s + nS + (np.arange(L) % P)
+            gb, numer, logz = _Lib.fwdbwd(self, big, lam[src], off, ftrs, labs, n_threads)
+            grad = np.zeros(len(lam), np.float64)
+            np.add.at(grad, src, gb)
+            return grad, numer, logz
+        if cfg.model_type in (2, 3, 4) and cfg.max_dur == 1 and not cfg.use_trans_ftrs:
+            # one-frame segments: the no_dur nodes reduce to the frame-level recursions (1 or N states per phone)
+            frame = Config(0, *[getattr(cfg, f[0]) for f in Config._fields_[1:]])
+            return _Lib.fwdbwd(self, frame, lam, off, ftrs, labs, n_threads)
+        return _Lib.fwdbwd(self, cfg, lam, off, ftrs, labs, n_threads)
+
 
 def have_ref():
     return os.path.exists(os.path.join(HERE, "_ref", "libcrfref.so"))

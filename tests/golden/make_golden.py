@@ -151,5 +151,33 @@ def main():
     print("done")
 
 
+def nodur_training():
+    """stdseg_no_dur* training goldens (own file and own RNG so that the older fixtures do not change)."""
+    ref = RefLib()
+    rng = np.random.default_rng(20260202)
+    train = {}
+    off, ftrs, labs = synth(rng, 6, 3, 40, 9, 7, seg_lo=1, seg_hi=6)
+    for mt, D, segf in [("stdseg_no_dur_no_segtransftr", 4, 1), ("stdseg_no_dur_no_segtransftr", 3, 0), ("stdseg_no_dur", 4, 1),
+                        ("stdseg_no_dur_no_transftr", 2, 1), ("stdseg_no_dur_no_segtransftr", 1, 0)]:
+        cfg = make_config(mt, n_labs=7, n_base_ftrs=9, max_dur=D, extract_seg_ftrs=segf)
+        train[f"{mt}_d{D}_s{segf}"] = (cfg, rng.uniform(-0.1, 0.1, ref.lambda_len(cfg)), off, ftrs, labs)
+    offl, ftrsl, labsl = synth(rng, 3, 30, 60, 12, 11, seg_lo=2, seg_hi=14)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=11, n_base_ftrs=12, max_dur=10, extract_seg_ftrs=1)
+    train["nodur_d10_segftr"] = (cfg, rng.uniform(-0.05, 0.05, ref.lambda_len(cfg)), offl, ftrsl, labsl)
+    off3, ftrs3, labs3 = synth(rng, 4, 4, 40, 9, 5, states=3)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=15, n_base_ftrs=9, n_states=3)
+    train["nodur_3state_d1"] = (cfg, rng.uniform(-0.25, 0.25, ref.lambda_len(cfg)), off3, ftrs3, labs3)
+    out = {}
+    for name, (cfg, lam, off, ftrs, labs) in train.items():
+        grad, numer, logz = ref.fwdbwd(cfg, lam, off, ftrs, labs)
+        out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": off, f"{name}/ftrs": ftrs,
+                    f"{name}/labs": labs, f"{name}/grad": grad, f"{name}/numer": numer, f"{name}/logZ": logz})
+        print(f"train {name}: lambda {len(lam)}, logZ {logz[:3]}, |grad|^2 {np.sum(grad ** 2):.12f}")
+    np.savez_compressed(os.path.join(OUT, "train_nodur_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nodur":
+        nodur_training()
+        sys.exit(0)
     main()

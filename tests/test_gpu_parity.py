@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 TRAIN = load_cases("train_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
+NODUR = load_cases("train_nodur_golden.npz")
 
 
 def gpu(cfg):
@@ -48,6 +49,22 @@ IMPLS = {"tc": {}, "tc_ffma_gemm": {"gemm_impl": 0}, "cluster": {"dp_impl": 1}, 
 @pytest.mark.parametrize("impl", sorted(IMPLS))
 def test_fwdbwd_matches_reference_golden(name, impl):
     c = TRAIN[name]
+    m = gpu(c["cfg"])
+    assert m.lambda_len == len(c["lam"])
+    for k, v in IMPLS[impl].items():
+        m.set_option(k, v)
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    m.close()
+
+
+@pytest.mark.parametrize("name", sorted(NODUR))
+@pytest.mark.parametrize("impl", ["tc", "cluster", "legacy_u4"])
+def test_fwdbwd_nodur_matches_reference_golden(name, impl):
+    """stdseg_no_dur* training (the reference's CRF_StdSegStateNode_WithoutDurLab* nodes): the device runs the stdseg
+    recursions on the (duration, phone) label set with tied weights."""
+    c = NODUR[name]
     m = gpu(c["cfg"])
     assert m.lambda_len == len(c["lam"])
     for k, v in IMPLS[impl].items():

@@ -11,6 +11,7 @@ from helpers import load_cases, split_segs, synth_batch
 TRAIN = load_cases("train_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
+NODUR = load_cases("train_nodur_golden.npz")
 
 
 def test_toy_known_answers(oracle):
@@ -31,6 +32,18 @@ def test_train_golden(oracle, name):
     np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
     np.testing.assert_allclose(numer, c["numer"], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", sorted(NODUR))
+def test_train_nodur_golden(oracle, name):
+    """stdseg_no_dur / _no_transftr / _no_segtransftr training: the tied (duration, phone) restatement against goldens
+    produced by the reference's own no_dur node classes and grad builders."""
+    c = NODUR[name]
+    assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
+    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"])
+    np.testing.assert_allclose(logz, c["logZ"], rtol=1e-12)
+    np.testing.assert_allclose(numer, c["numer"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(grad, c["grad"], rtol=1e-9, atol=1e-10)
 
 
 def test_train_threads_match_single(oracle):
