@@ -163,6 +163,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("CRFGPU_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
 
@@ -228,15 +229,22 @@ def run_ours(args):
     pin_n = crf_b200.PinnedBuffer((upg,), np.float64); pin_z = crf_b200.PinnedBuffer((upg,), np.float64)
     out = (pin_g.array, pin_n.array, pin_z.array)
     e2e_steps = max(2, min(args.steps, 5))
+    def e2e_step():
+        if world == 1:
+            m.fwdbwd(off, pin_f.array, pin_l.array, out=out)      # crfgpu_fwdbwd_batch: H2D + kernels + D2H, synchronous
+        else:
+            # the same host-buffer calls split at the collective: H2D (crfgpu_stage_batch), kernels (crfgpu_fwdbwd_staged),
+            # ONE NCCL all-reduce of the gradient (+ scalars) on the handle's stream, D2H (crfgpu_fetch_fwdbwd)
+            m.stage(off, pin_f.array, pin_l.array)
+            m.fwdbwd_staged(); allreduce_grad()
+            m.fetch_fwdbwd(out=out)
+
     for _ in range(2):
-        m.fwdbwd(off, pin_f.array, pin_l.array, out=out)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        m.fwdbwd(off, pin_f.array, pin_l.array, out=out)      # H2D + kernels + D2H, synchronous
-        if world > 1:   # host-side combination of the per-rank gradients, as the drop-in accumulator would do
-            g = torch.from_numpy(pin_g.array).to(f"cuda:{local}", non_blocking=False)
-            dist.all_reduce(g); pin_g.array[...] = g.cpu().numpy()
+        e2e_step()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     te = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
