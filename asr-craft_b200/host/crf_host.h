@@ -1,0 +1,158 @@
+// crf_host.h -- C++ host layer above the C ABI (include/crfgpu.h), mirroring the plug-in surface of ASR-CRaFT for
+// the lattice hot path: same class and member names, argument meaning and error behaviour (std::runtime_error), so
+// that a reference user finds the seams where they expect them.  Reference interfaces (ASR-CRaFT tree):
+//   CRF_FeatureMap_config                      CRF/src/ftrmaps/CRF_FeatureMap.h:24-47
+//   CRF_Model                                  CRF/src/CRF_Model.h:23-84, CRF_Model.cpp:75-87,205-235,290-308
+//   CRF_FeatureStream (nextseg/read/rewind)    CRF/src/io/CRF_FeatureStream.h:35-67, .cpp:71-136
+//   CRF_GradBuilder::create / buildGradient    CRF/src/trainers/gradbuilders/CRF_GradBuilder.h:40-44, .cpp:97-162
+//   CRF_Minibatch_GradAccumulator              CRF/src/trainers/accumulators/CRF_Minibatch_GradAccumulator.h:51-75, .cpp:201-322
+//   CRF_ViterbiDecoder_StdSeg_NoSegTransFtr    CRF/src/decoders/CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398
+// Differences that follow from the device design (documented in INTEGRATION.md):
+//   * the feature stream handed to the builders is the UN-windowed one (what the pfile / ilab hold): one frame of
+//     num_ftrs() floats and one phone label per read(); the segment windows are expanded on the device;
+//   * OpenFst is not available here: the decoder returns the best path as a vector of arcs carrying exactly the fields
+//     the reference puts on its linear FST (ilabel = sub-state label + 1, olabel = phone + 1 or 0) plus the duration.
+#ifndef CRF_HOST_H
+#define CRF_HOST_H
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/crfgpu.h"
+
+typedef uint32_t QNUInt32;
+typedef long QN_SegID;
+enum { QN_SEGID_BAD = -1 };
+#define CRF_LAB_BAD 0xffffffffu
+
+enum ftrmaptype { STDSTATE, STDTRANS, STDSPARSE, STDSPARSETRANS, INFILE };
+enum objfunctype { EXPF, EXPFSOFT, FERR };
+enum modeltype { STDFRAME, STDSEG, STDSEG_NO_DUR, STDSEG_NO_DUR_NO_TRANSFTR, STDSEG_NO_DUR_NO_SEGTRANSFTR };
+
+struct CRF_FeatureMap_config {
+	ftrmaptype map_type;
+	QNUInt32 numLabs;
+	QNUInt32 numFeas;          // width of the WINDOW feature vector (state/trans index ranges refer to it)
+	QNUInt32 numStates;
+	bool useStateFtrs;
+	QNUInt32 stateFidxStart;
+	QNUInt32 stateFidxEnd;
+	bool useTransFtrs;
+	QNUInt32 transFidxStart;
+	QNUInt32 transFidxEnd;
+	bool useStateBias;
+	bool useTransBias;
+	double stateBiasVal;
+	double transBiasVal;
+	QNUInt32 maxDur;
+	QNUInt32 durFtrStart;
+	QNUInt32 nActualLabs;
+};
+
+// Un-windowed frame stream: nextseg() advances to the next utterance (QN_SEGID_BAD at the end), read() returns up to `bs`
+// frames (num_ftrs() floats and one label word each) of the current utterance, 0 when it is exhausted.
+class CRF_FeatureStream {
+public:
+	virtual ~CRF_FeatureStream() {}
+	virtual QN_SegID nextseg() = 0;
+	virtual size_t read(size_t bs, float* fb, QNUInt32* lb) = 0;
+	virtual void rewind() = 0;
+	virtual QNUInt32 num_ftrs() = 0;
+	virtual QNUInt32 num_labs() { return 1; }
+	virtual QNUInt32 num_segs() = 0;
+};
+
+// In-memory ragged batch (what tests and the self-test feed); view(start, n) restricts it to a contiguous utterance range,
+// the rule CRF_FeatureStreamManager uses to shard a corpus over streams (CRF_FeatureStreamManager.cpp:425-464).
+class CRF_MemFeatureStream : public CRF_FeatureStream {
+	std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; QNUInt32 nf;
+	QNUInt32 first, count; long seg; uint32_t pos;
+public:
+	CRF_MemFeatureStream(const std::vector<uint32_t>& frame_off, const std::vector<float>& f, const std::vector<QNUInt32>& l, QNUInt32 n_ftrs);
+	QN_SegID nextseg();
+	size_t read(size_t bs, float* fb, QNUInt32* lb);
+	void rewind();
+	QNUInt32 num_ftrs() { return nf; }
+	QNUInt32 num_segs() { return count; }
+	void view(QNUInt32 startseg, QNUInt32 nsegs);
+};
+
+class CRF_Model {
+protected:
+	QNUInt32 nlabs;
+	std::vector<double> lambda, lambdaAcc;
+	QNUInt32 lab_max_dur, nActualLabs;
+	modeltype model_type;
+	CRF_FeatureMap_config fmap;
+	bool have_map;
+	QNUInt32 n_base_ftrs; bool extract_seg_ftrs;
+	crfgpu_handle handle;
+public:
+	CRF_Model(QNUInt32 num_labs);
+	virtual ~CRF_Model();
+	QNUInt32 getNLabs() { return nlabs; }
+	// createFeatureMap(cfg) + setFeatureMap: fixes the lambda layout and allocates lambda (CRF_Model.cpp:75-87).
+	// n_base_ftrs / extract_seg_ftrs are the window-stream options of CRFTrain (ftr1_window_len == maxDur, ftr1_extract_seg_ftr).
+	virtual void setFeatureMap(const CRF_FeatureMap_config& cfg, QNUInt32 n_base_ftrs, bool extract_seg_ftrs, int device = 0);
+	virtual double* getLambda() { return lambda.data(); }
+	virtual QNUInt32 getLambdaLen() { return (QNUInt32)lambda.size(); }
+	virtual double* getLambdaAcc() { return lambdaAcc.data(); }
+	virtual void setLambda(double* lam, QNUInt32 len);
+	virtual void resetLambda();
+	virtual bool writeToFile(const char* fname);                       // ASCII, one value per line, default ostream precision
+	virtual bool readFromFile(const char* fname);
+	virtual void setLabMaxDur(QNUInt32 d) { lab_max_dur = d; }
+	virtual QNUInt32 getLabMaxDur() { return lab_max_dur; }
+	virtual void setNActualLabs(QNUInt32 n) { nActualLabs = n; }
+	virtual QNUInt32 getNActualLabs() { return nActualLabs; }
+	virtual void setModelType(modeltype m) { model_type = m; }
+	virtual modeltype getModelType() { return model_type; }
+	crfgpu_handle gpu();                                              // the device context of this model (created by setFeatureMap)
+	QNUInt32 baseFtrs() { return n_base_ftrs; }
+};
+
+// per-utterance seam, kept for API parity: grad is ACCUMULATED into, returns the numerator, *Zx_out = logZ
+class CRF_GradBuilder {
+protected:
+	CRF_Model* crf;
+	std::vector<float> ftr_buf; std::vector<QNUInt32> lab_buf; std::vector<double> tmp_grad;
+public:
+	CRF_GradBuilder(CRF_Model* crf_in) : crf(crf_in) {}
+	virtual ~CRF_GradBuilder() {}
+	virtual double buildGradient(CRF_FeatureStream* ftr_strm, double* grad, double* Zx_out);
+	static CRF_GradBuilder* create(CRF_Model* crf_ptr, objfunctype ofunc);
+};
+
+// minibatch seam: one call = `minibatch` utterances through ONE device batch
+class CRF_Minibatch_GradAccumulator {
+protected:
+	CRF_Model* crf; CRF_FeatureStream* strm; QNUInt32 nStreams, minibatch; bool started;
+	std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; std::vector<double> numer, logZ;
+public:
+	CRF_Minibatch_GradAccumulator(CRF_Model* myCrf, CRF_FeatureStream* stream, QNUInt32 myNStreams);
+	virtual ~CRF_Minibatch_GradAccumulator() {}
+	// grad is overwritten with sum(emp - exp) / nStreams_active, *Zx_out = sum logZ, returns sum of numerators
+	virtual double accumulateGradient(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter);
+	void setMinibatch(QNUInt32 mb) { minibatch = mb; }
+	QNUInt32 getNStreams() { return nStreams; }
+	void rewindAllAndNextSegs();
+};
+
+struct CRF_BestPathArc {
+	int ilabel;      // sub-state label + 1
+	int olabel;      // phone + 1 when the segment starts a phone, else 0 (epsilon)
+	QNUInt32 dur;    // frames covered (the reference keeps this in viterbiDurs)
+};
+
+class CRF_ViterbiDecoder_StdSeg_NoSegTransFtr {
+	CRF_FeatureStream* strm; CRF_Model* crf;
+public:
+	CRF_ViterbiDecoder_StdSeg_NoSegTransFtr(CRF_FeatureStream* ftr_strm_in, CRF_Model* crf_in) : strm(ftr_strm_in), crf(crf_in) {}
+	// decodes the CURRENT utterance of the stream (free-phone LM, beam 0); returns the number of frames, like nStateDecode
+	int nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam = 0.0);
+};
+
+#endif

@@ -1,0 +1,117 @@
+// host_selftest -- drives the C++ host layer (crf_host.h) the way CRFTrain / CRFDecode drive the reference classes and checks the
+// results against expected values from a case file written by tests/test_host_cpp.py (goldens of the unmodified reference).
+//   host_selftest <case.txt>      run training (+ Viterbi if the case has a path) on cuda:0, exit 0 on agreement
+//   host_selftest --no-device     verify that the layer fails loudly (std::runtime_error) when there is no CUDA device
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+
+#include "crf_host.h"
+
+static CRF_FeatureMap_config fmap_config(QNUInt32 n_labs, QNUInt32 n_states, QNUInt32 width, QNUInt32 max_dur, QNUInt32 n_act) {
+	// mirrors set_fmap_config (CRFTrain/src/Main.cpp:372-430) for crf_featuremap=stdstate with both biases
+	CRF_FeatureMap_config c;
+	std::memset(&c, 0, sizeof(c));
+	c.map_type = STDSTATE; c.numLabs = n_labs; c.numFeas = width; c.numStates = n_states;
+	c.useStateFtrs = true; c.stateFidxStart = 0; c.stateFidxEnd = width - 1;
+	c.useTransFtrs = false; c.transFidxStart = 0; c.transFidxEnd = width - 1;
+	c.useStateBias = true; c.useTransBias = true; c.stateBiasVal = 1.0; c.transBiasVal = 1.0;
+	c.maxDur = max_dur; c.durFtrStart = 0; c.nActualLabs = n_act;
+	return c;
+}
+
+template <class T> static void read_vec(std::istream& in, std::vector<T>& v, size_t n) {
+	v.resize(n);
+	for (size_t i = 0; i < n; i++) { double x; in >> x; v[i] = (T)x; }
+}
+
+int main(int argc, char** argv) {
+	if (argc < 2) { std::fprintf(stderr, "usage: host_selftest <case.txt> | --no-device\n"); return 2; }
+	try {
+		if (!std::strcmp(argv[1], "--no-device")) {
+			CRF_Model m(4);
+			try { m.setFeatureMap(fmap_config(4, 1, 3, 1, 4), 3, false); }
+			catch (const std::runtime_error& e) { std::printf("failed loudly as expected: %s\n", e.what()); return 0; }
+			std::printf("a CUDA device is present: nothing to check\n");
+			return 0;
+		}
+		std::ifstream in(argv[1]);
+		if (!in.good()) throw std::runtime_error("cannot open case file");
+		QNUInt32 mode, mt, n_labs, n_base, n_states, max_dur, n_act, segf, n_utt, N, len, n_arcs;   // mode 0: training case, 1: decoding case
+		in >> mode >> mt >> n_labs >> n_base >> n_states >> max_dur >> n_act >> segf >> n_utt >> N >> len >> n_arcs;
+		std::vector<uint32_t> off; std::vector<double> lam, logZ, numer, grad; std::vector<float> ftrs; std::vector<QNUInt32> labs;
+		std::vector<int> arcs;
+		read_vec(in, off, n_utt + 1); read_vec(in, lam, len); read_vec(in, ftrs, (size_t)N * n_base); read_vec(in, labs, N);
+		read_vec(in, logZ, n_utt); read_vec(in, numer, n_utt); read_vec(in, grad, len); read_vec(in, arcs, (size_t)n_arcs * 3);
+		if (!in.good() && !in.eof()) throw std::runtime_error("short case file");
+		const QNUInt32 width = max_dur == 1 ? n_base : (segf ? 8 * n_base + max_dur : n_base);
+
+		CRF_Model my_crf(n_labs);
+		my_crf.setLabMaxDur(max_dur); my_crf.setNActualLabs(n_act); my_crf.setModelType((modeltype)mt);
+		my_crf.setFeatureMap(fmap_config(n_labs, n_states, width, max_dur, n_act), n_base, segf != 0);
+		if (my_crf.getLambdaLen() != len) throw std::runtime_error("lambda length differs from the reference's");
+		my_crf.setLambda(lam.data(), len);
+
+		int bad = 0;
+		auto close = [&](double a, double b, double tol, const char* what) {
+			if (std::fabs(a - b) > tol * std::fmax(1.0, std::fabs(b))) { std::printf("MISMATCH %s: %.12g vs %.12g\n", what, a, b); bad++; }
+		};
+		if (mode == 0) {
+			// ---- minibatch seam ----
+			CRF_MemFeatureStream strm(off, ftrs, labs, n_base);
+			CRF_Minibatch_GradAccumulator gaccum(&my_crf, &strm, 1);
+			gaccum.setMinibatch(n_utt);
+			std::vector<double> g(len, 0.0); double Zx = 0.0; QNUInt32 cnt = 0; bool eoi = false;
+			gaccum.rewindAllAndNextSegs();
+			const double num = gaccum.accumulateGradient(g.data(), &Zx, &cnt, &eoi);
+			double zsum = 0, nsum = 0, gmax = 0;
+			for (QNUInt32 u = 0; u < n_utt; u++) { zsum += logZ[u]; nsum += numer[u]; }
+			for (double v : grad) gmax = std::fmax(gmax, std::fabs(v));
+			close(Zx, zsum, 1e-5, "sum logZ"); close(num, nsum, 1e-5, "sum numerator");
+			if (cnt != n_utt || !eoi) { std::printf("MISMATCH uttCount %u eoi %d\n", cnt, (int)eoi); bad++; }
+			for (QNUInt32 i = 0; i < len; i++)
+				if (std::fabs(g[i] - grad[i]) > 1e-4 * gmax + 1e-4 * std::fabs(grad[i])) { if (bad < 5) std::printf("MISMATCH grad[%u]: %.9g vs %.9g\n", i, g[i], grad[i]); bad++; }
+			// ---- per-utterance seam (CRF_GradBuilder::buildGradient accumulates into grad) ----
+			std::unique_ptr<CRF_GradBuilder> gb(CRF_GradBuilder::create(&my_crf, EXPF));
+			std::vector<double> g2(len, 0.0);
+			strm.rewind();
+			QNUInt32 u = 0;
+			while (strm.nextseg() != QN_SEGID_BAD) {
+				double z = 0.0; const double nu = gb->buildGradient(&strm, g2.data(), &z);
+				close(z, logZ[u], 1e-5, "logZ"); close(nu, numer[u], 1e-5, "numerator"); u++;
+			}
+			for (QNUInt32 i = 0; i < len; i++)
+				if (std::fabs(g2[i] - grad[i]) > 1e-4 * gmax + 1e-4 * std::fabs(grad[i])) { if (bad < 5) std::printf("MISMATCH grad2[%u]\n", i); bad++; }
+			// ---- one SGD step as CRF_SGTrainer.cpp:309 and the lossy ASCII checkpoint round trip ----
+			const float lr = 0.008f;
+			for (QNUInt32 i = 0; i < len; i++) my_crf.getLambda()[i] += lr * g[i];
+			std::string path = std::string(argv[1]) + ".weights.out";
+			if (!my_crf.writeToFile(path.c_str())) throw std::runtime_error("writeToFile failed");
+			std::vector<double> before(my_crf.getLambda(), my_crf.getLambda() + len);
+			if (!my_crf.readFromFile(path.c_str())) throw std::runtime_error("readFromFile failed");
+			for (QNUInt32 i = 0; i < len; i++) close(my_crf.getLambda()[i], before[i], 1e-5, "checkpoint round trip");
+			std::remove(path.c_str());
+		}
+		if (mode == 1) {
+			// ---- decode seam: first utterance, free-phone LM, beam 0 ----
+			CRF_MemFeatureStream strm(off, ftrs, std::vector<QNUInt32>(), n_base);
+			strm.nextseg();
+			CRF_ViterbiDecoder_StdSeg_NoSegTransFtr vd(&strm, &my_crf);
+			std::vector<CRF_BestPathArc> path; float cost = 0.0f;
+			const int frames = vd.nStateDecode(&path, &cost);
+			if (frames != (int)(off[1] - off[0]) || path.size() != n_arcs) { std::printf("MISMATCH decode: %d frames, %zu arcs\n", frames, path.size()); bad++; }
+			else for (QNUInt32 k = 0; k < n_arcs; k++)
+				if (path[k].ilabel != arcs[3 * k] || path[k].olabel != arcs[3 * k + 1] || (int)path[k].dur != arcs[3 * k + 2]) { std::printf("MISMATCH arc %u\n", k); bad++; }
+		}
+		if (bad) { std::printf("host_selftest: %d mismatches\n", bad); return 1; }
+		std::printf("host_selftest ok\n");
+		return 0;
+	} catch (const std::exception& e) {
+		std::fprintf(stderr, "host_selftest: %s\n", e.what());
+		return 3;
+	}
+}
