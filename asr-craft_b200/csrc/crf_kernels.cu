@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 	if (n >= p.N) return;
 	const uint32_t t = p.frame_t[n];
 	const uint32_t dmax = min(t + 1, p.D);
-	float* out = p.X + (uint64_t)n * p.D * p.W;
+	float* out = p.X + (uint64_t)n * p.D * p.Wp;
 	const float* cur = p.base + (uint64_t)n * p.F;
 	if (p.seg_ftrs) {
 		for (uint32_t f = threadIdx.x; f < p.F; f += blockDim.x) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 				acc += v;
 				amax = v > amax ? v : amax;
 				amin = v < amin ? v : amin;
-				float* o = out + (uint64_t)(d - 1) * p.W;
+				float* o = out + (uint64_t)(d - 1) * p.Wp;
 #pragma unroll
 				for (int k = 0; k < 5; k++) o[k * p.F + f] = wstart[(uint64_t)p.steps[(d - 1) * 5 + k] * p.F + f];
 				o[5 * p.F + f] = acc / (float)d;
@@ -89,16 +89,18 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 		}
 		for (uint32_t i = threadIdx.x; i < dmax * p.D; i += blockDim.x) {
 			const uint32_t d = i / p.D + 1, k = i % p.D;
-			out[(uint64_t)(d - 1) * p.W + 8 * p.F + k] = (k == d - 1) ? 1.0f : 0.0f;
+			out[(uint64_t)(d - 1) * p.Wp + 8 * p.F + k] = (k == d - 1) ? 1.0f : 0.0f;
 		}
 	} else {
 		for (uint32_t i = threadIdx.x; i < dmax * p.F; i += blockDim.x) {
 			const uint32_t d = i / p.F + 1, f = i % p.F;
-			out[(uint64_t)(d - 1) * p.W + f] = (cur - (uint64_t)(d - 1) * p.F)[f];
+			out[(uint64_t)(d - 1) * p.Wp + f] = (cur - (uint64_t)(d - 1) * p.F)[f];
 		}
 	}
 	// windows that would start before the utterance are never read by the lattice; keep them zero
-	for (uint32_t i = dmax * p.W + threadIdx.x; i < p.D * p.W; i += blockDim.x) out[i] = 0.0f;
+	for (uint32_t i = dmax * p.Wp + threadIdx.x; i < p.D * p.Wp; i += blockDim.x) out[i] = 0.0f;
+	// the pad behind each window
+	for (uint32_t i = threadIdx.x; i < dmax * (p.Wp - p.W); i += blockDim.x) out[(uint64_t)(i / (p.Wp - p.W)) * p.Wp + p.W + i % (p.Wp - p.W)] = 0.0f;
 }
 void launch_expand_windows(const ExpandParams& p, cudaStream_t s) {
 	if (p.N) expand_windows_kernel<<<p.N, 128, 0, s>>>(p);

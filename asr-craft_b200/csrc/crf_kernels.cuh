@@ -14,8 +14,8 @@ struct ExpandParams {
 	const float* base;        // [N][F]
 	const uint32_t* frame_t;  // [N] frame index inside its utterance
 	const uint32_t* steps;    // [D*5] sample offsets (host-computed, see sample_steps())
-	float* X;                 // [N][D][W]
-	uint32_t N, F, D, W;
+	float* X;                 // [N][D][Wp]  (Wp >= W: windows start on 128-byte lines, the pad is zero)
+	uint32_t N, F, D, W, Wp;
 	uint32_t seg_ftrs;        // 1: [5 samples|avg|max|min|one-hot dur], 0: first frame of the window
 };
 void launch_expand_windows(const ExpandParams& p, cudaStream_t s);
