@@ -2,6 +2,7 @@
 // Citations are relative to the ASR-CRaFT tree.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 namespace crfgpu {
@@ -131,6 +132,30 @@ struct XiGemmParams {
 	double* out;
 };
 cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s);
+
+// ---- TMA-fed GEMMs over the window stream, all durations in one launch (crf_tma_gemm.cu) ---------
+struct ScoreTmaParams {
+	const unsigned char* Bt;          // state weights as bf16 hi/lo UMMA tiles, [(d*ntile + jt)*n_chunks + c][8 KB] (split_weight_tiles)
+	const float* bias;                // [D*P] or nullptr
+	float* C; uint32_t ldc;           // S[M][ldc], column (d*P + y)
+	uint32_t M, P, K, D, n_chunks, ntile;
+	float* smaxd;                     // [M][D] per-duration row maxima (-inf where d > t) or nullptr; needs ntile == 1
+	const uint32_t* frame_t;
+};
+struct StateGradTmaParams {
+	const float* Dm; uint32_t ldd;    // [N][ldd], column (d*P + y)
+	uint32_t N, P, D, J, ones_col, k_slab, ntile;
+	double scale, ones_scale;
+	const uint32_t* row_idx;          // [D*P] lambda offset of the label's state block
+	double* out;
+};
+// X must be 16-byte aligned, Wp % 4 == 0, the first state feature a multiple of 4 and the driver must export cuTensorMapEncodeTiled
+bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0);
+uint32_t score_tma_chunks(uint32_t K);
+void split_weight_tiles(const float* Ws, uint32_t P, uint32_t D, uint32_t K, std::vector<unsigned char>* out);   // host side, once per lambda
+// X points at the first state feature of window (frame 0, duration 1)
+cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaParams& p, cudaStream_t s);
+cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const StateGradTmaParams& p, cudaStream_t s);
 
 // ---- empirical counts and numerators on the reference path -------------------------------------
 struct EmpiricalParams {

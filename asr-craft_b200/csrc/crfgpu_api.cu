@@ -70,7 +70,7 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 1; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
@@ -78,7 +78,7 @@ struct crfgpu_ctx {
 
 	// model tables
 	bool have_lambda = false;
-	DevBuf d_lambda, d_sidx, d_tidx, d_Ws, d_bias, d_E, d_ET, d_steps;
+	DevBuf d_lambda, d_sidx, d_tidx, d_Ws, d_Wt, d_bias, d_E, d_ET, d_steps;
 	DevBuf d_Wd, d_crossT, d_negDiag, d_negOff;
 	double Mmax = 0.0;
 
@@ -214,6 +214,11 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 				}
 			}
 		upload(h->d_Ws, Ws, s); upload(h->d_bias, bias, s); upload(h->d_E, E, s); upload(h->d_ET, ET, s);
+		std::vector<unsigned char> tiles;
+		if (c.max_dur > 1 && nSf > 0) {   // bf16 hi/lo UMMA tiles of the state weights for the TMA-fed score GEMM
+			split_weight_tiles(Ws.data(), Lt / c.max_dur, c.max_dur, nSf, &tiles);
+			upload(h->d_Wt, tiles, s);
+		}
 		CUDA_OK(cudaStreamSynchronize(s));   // host vectors die at scope exit
 	}
 	if (h->decode_ok) {
@@ -418,20 +423,27 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	CUDA_OK(cudaMemsetAsync(h->d_numer.p, 0, sizeof(double) * (size_t)h->n_utt, s));
 	if (!N) { h->fwdbwd_done = true; return; }
 
-	// K1: state scores, one GEMM per duration block
+	// K1: state scores.  TMA-fed kernel: all durations in one launch, per-duration maxima fused; otherwise one GEMM per duration block
+	const bool tma = h->opt_gemm_impl == 2 && D > 1 && nSf > 0 && tma_gemm_eligible(h->X() + c.state_fidx_start, D, h->Wp, c.state_fidx_start);
+	bool smax_done = false;
+	if (nSf == 0) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
 	phase_begin(h, "score");
-	for (uint32_t d = 0; d < D; d++) {
+	if (tma) {
+		ScoreTmaParams g{};
+		g.Bt = h->d_Wt.as<unsigned char>(); g.bias = h->d_bias.as<float>(); g.C = h->d_S.as<float>(); g.ldc = Lp;
+		g.M = N; g.P = P; g.K = nSf; g.D = D; g.n_chunks = score_tma_chunks(nSf); g.ntile = (P + 63) / 64;
+		g.frame_t = h->d_frame_t.as<uint32_t>();
+		if (h->tc_ok && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
+		CUDA_OK(launch_score_gemm_tma(h->X() + c.state_fidx_start, h->Wp, g, s));
+		check_kernel(h, 1);
+	} else for (uint32_t d = 0; d < D; d++) {
 		ScoreGemmParams g{};
 		g.A = h->X() + (size_t)d * h->Wp + c.state_fidx_start; g.lda = h->ldx();
-		const bool per_dur = true;   // the lattice label (d,y) has its own row of the device tables (tied models repeat phone y's weights)
-		g.B = h->d_Ws.as<float>() + (per_dur ? (size_t)d * P * nSf : 0); g.ldb = nSf;
-		g.bias = h->d_bias.as<float>() + (per_dur ? (size_t)d * P : 0);
+		g.B = h->d_Ws.as<float>() + (size_t)d * P * nSf; g.ldb = nSf;   // the lattice label (d,y) has its own row of the device tables (tied models repeat phone y's weights)
+		g.bias = h->d_bias.as<float>() + (size_t)d * P;
 		g.C = h->d_S.as<float>() + (size_t)d * P; g.ldc = Lp;
 		g.M = N; g.Ncols = P; g.K = nSf;
-		if (nSf == 0) {   // bias-only state functions: S = bias
-			throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
-		}
-		if (h->opt_gemm_impl == 1) CUDA_OK(launch_score_gemm_tc(g, s)); else launch_score_gemm(g, s);
+		if (h->opt_gemm_impl >= 1) CUDA_OK(launch_score_gemm_tc(g, s)); else launch_score_gemm(g, s);
 		check_kernel(h, 1);
 	}
 	phase_end(h, "score");
@@ -447,7 +459,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		static DevBuf dbg; const bool timing = getenv("CRFGPU_DP_TIMING") != nullptr;
 		if (timing) { dbg.ensure(64 * 8); }
 		phase_begin(h, "forward");
-		launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1);
+		if (!smax_done) { launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1); }
 		auto report = [&](const char* what) {
 			unsigned long long v[32]; CUDA_OK(cudaMemcpyAsync(v, dbg.p, sizeof(v), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
 			const double n = v[15] ? (double)v[15] : 1.0;
@@ -487,7 +499,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 
 	// K4: expected-minus-empirical counts as two families of reduce-GEMMs
 	phase_begin(h, "xi");
-	if (c.use_trans_bias && h->opt_gemm_impl == 1 && N > 1) {
+	if (c.use_trans_bias && h->opt_gemm_impl >= 1 && N > 1) {
 		XiGemmParams x{};
 		x.A = h->d_A.as<float>(); x.lda = Lp; x.R = h->d_R.as<float>(); x.ldb = Lp;
 		x.n_frames = N; x.n0 = 1; x.n1 = N; x.k_slab = h->opt_k_slab_tc;
@@ -510,7 +522,14 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	}
 	phase_end(h, "xi");
 	phase_begin(h, "grad");
-	for (uint32_t d = 0; d < D; d++) {
+	if (tma) {
+		StateGradTmaParams r{};
+		r.Dm = h->d_Dm.as<float>(); r.ldd = Lp; r.N = N; r.P = P; r.D = D; r.J = nSf + (c.use_state_bias ? 1 : 0);
+		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu; r.k_slab = h->opt_k_slab_tma; r.ntile = (P + 63) / 64;
+		r.scale = 1.0; r.ones_scale = c.state_bias_val; r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
+		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, r, s));
+		check_kernel(h, 1);
+	} else for (uint32_t d = 0; d < D; d++) {
 		ReduceGemmParams r{};
 		r.A = h->d_Dm.as<float>() + (size_t)d * P; r.lda = Lp; r.a_row_shift = 0;
 		r.B = h->X() + (size_t)d * h->Wp + c.state_fidx_start; r.ldb = h->ldx();
@@ -518,8 +537,8 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu;
 		r.scale = 1.0; r.ones_scale = c.state_bias_val; r.mode = 0;
 		r.row_idx = h->d_sidx.as<uint32_t>() + (size_t)d * P;
-		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl == 1 ? h->opt_k_slab_tc : h->opt_k_slab;
-		if (h->opt_gemm_impl == 1) CUDA_OK(launch_reduce_gemm_tc(r, true, s)); else launch_reduce_gemm(r, s);
+		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl >= 1 ? h->opt_k_slab_tc : h->opt_k_slab;
+		if (h->opt_gemm_impl >= 1) CUDA_OK(launch_reduce_gemm_tc(r, true, s)); else launch_reduce_gemm(r, s);
 		check_kernel(h, 1);
 	}
 	EmpiricalParams e{};
@@ -600,7 +619,7 @@ int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
 		h->W = window_width(*cfg);
 		// measured on cfg4 (score + state-gradient GEMM ms per step): unpadded 2.01 + 3.18, padded to 8 floats 1.86 + 3.43, to 32 floats
 		// 1.83 + 3.56 -- padding helps the K-major reader and hurts the MN-major one, so the windows stay packed
-		h->Wp = h->W;
+		h->Wp = cfg->max_dur > 1 ? (h->W + 3) / 4 * 4 : h->W;   // 16-byte window rows: TMA-addressable (max_dur == 1 aliases the base stream)
 		if (cfg->max_dur == 0) throw ApiError(CRFGPU_ERR_ARG, "the maximum duration of labels must be larger than 0");
 		classify(h);
 		{
@@ -634,7 +653,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	if (!h) return CRFGPU_OK;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
-	DevBuf* bufs[] = {&h->d_lambda, &h->d_sidx, &h->d_tidx, &h->d_Ws, &h->d_bias, &h->d_E, &h->d_ET, &h->d_steps, &h->d_Wd, &h->d_crossT,
+	DevBuf* bufs[] = {&h->d_lambda, &h->d_sidx, &h->d_tidx, &h->d_Ws, &h->d_Wt, &h->d_bias, &h->d_E, &h->d_ET, &h->d_steps, &h->d_Wd, &h->d_crossT,
 	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
@@ -805,7 +824,8 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		if (n == "slots") h->opt_slots = (int)value;
 		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
-		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16
+		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16, register-staged; 2: + TMA-fed window GEMMs
+		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
 		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05
 		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
