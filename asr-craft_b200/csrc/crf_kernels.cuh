@@ -142,20 +142,30 @@ struct ScoreTmaParams {
 	float* smaxd;                     // [M][D] per-duration row maxima (-inf where d > t) or nullptr; needs ntile == 1
 	const uint32_t* frame_t;
 };
-struct StateGradTmaParams {
-	const float* Dm; uint32_t ldd;    // [N][ldd], column (d*P + y)
-	uint32_t N, P, D, J, ones_col, k_slab, ntile;
+// Frame-reduction GEMMs (both operands [frames][columns], TMA-fed; one launch covers every duration block d):
+//   state gradient  out[row_idx[d*P+y] + j]      += (j == ones_col ? ones_scale : scale) * sum_n X[n][d][j]  * Dm[n][d*P+y]
+//   Xi              out[pair_idx[q*L + d*P+y]]    += scale * Ew[q][d*P+y]                 * sum_n A[n-d-1][q] * R[n][d*P+y]
+constexpr uint32_t FRAME_GEMM_TILE = 61;   // columns of a duration block per CTA (64-wide box minus up to 3 columns of alignment slack)
+struct FrameGemmParams {
+	uint32_t N, P, D, ntile, k_slab;  // frames, phones per duration block, durations, FRAME_GEMM_TILE-column tiles per block, frames per CTA
+	uint32_t Mext;                    // extent of the 128-row side: state features (+ bias) | lattice labels
+	uint32_t ones_col;                // state gradient: index of the constant-1 bias feature or 0xffffffff
 	double scale, ones_scale;
-	const uint32_t* row_idx;          // [D*P] lambda offset of the label's state block
+	const uint32_t* row_idx;          // state gradient: [D*P] lambda offset of the label's state block
+	const uint32_t* pair_idx; uint32_t L; const float* Ew; uint32_t e_ld;   // Xi
 	double* out;
+	uint32_t dbg;                     // debug switches (CRFGPU_DBG)
 };
 // X must be 16-byte aligned, Wp % 4 == 0, the first state feature a multiple of 4 and the driver must export cuTensorMapEncodeTiled
 bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0);
 uint32_t score_tma_chunks(uint32_t K);
 void split_weight_tiles(const float* Ws, uint32_t P, uint32_t D, uint32_t K, std::vector<unsigned char>* out);   // host side, once per lambda
+bool lattice_tma_eligible(const float* a, uint32_t ld);
+// Xi: A, R = lattice arrays [N][ld]
+cudaError_t launch_xi_gemm_tma(const float* A, const float* R, uint32_t ld, const FrameGemmParams& p, cudaStream_t s);
 // X points at the first state feature of window (frame 0, duration 1)
 cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaParams& p, cudaStream_t s);
-cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const StateGradTmaParams& p, cudaStream_t s);
+cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const float* Dm, uint32_t ldd, const FrameGemmParams& p, cudaStream_t s);
 
 // ---- empirical counts and numerators on the reference path -------------------------------------
 struct EmpiricalParams {

@@ -19,6 +19,7 @@
 #include <cuda.h>   // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -71,6 +72,17 @@ __device__ __forceinline__ void load_raw8(const unsigned char* tile, uint32_t ro
 	x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 
+// the same for a 64-column tile held as two boxes when the 8 floats start at an arbitrary column (columns >= 64 read as 0)
+__device__ __forceinline__ void load_raw8_shifted(const unsigned char* tiles, uint32_t row, uint32_t col, float (&x)[8]) {
+	const unsigned char* r = tiles + row * 128;
+	const uint32_t sw = row & 7;
+#pragma unroll
+	for (uint32_t e = 0; e < 8; e++) {
+		const uint32_t cc = col + e;
+		x[e] = cc < 64u ? *reinterpret_cast<const float*>(r + (cc >> 5) * 4096 + ((((cc & 31) >> 2) ^ sw) << 4) + (cc & 3) * 4) : 0.0f;
+	}
+}
+
 __device__ __forceinline__ void setup(Ctl* ctl, uint32_t tid, uint32_t warp, uint32_t alloc_warp, uint32_t op_full_count) {
 	if (tid == 0) {
 		if (smem_u32(ctl) & 127) __trap();
@@ -86,13 +98,13 @@ __device__ __forceinline__ void setup(Ctl* ctl, uint32_t tid, uint32_t warp, uin
 }
 
 template <bool MN_MAJOR>
-__device__ __forceinline__ void mma_walk(unsigned char* smem, Ctl* ctl, uint32_t tmem, uint32_t n_chunks) {
+__device__ __forceinline__ void mma_walk(unsigned char* op, Ctl* ctl, uint32_t tmem, uint32_t n_chunks) {
 	constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, MN_MAJOR, MN_MAJOR);
 	for (uint32_t c = 0; c < n_chunks; c++) {
 		const uint32_t s = c % OS;
 		mbar_wait(&ctl->op_full[s], (c / OS) & 1);
 		tc_fence_after();
-		const uint32_t base = smem_u32(smem + OP_OFF + s * OP_BYTES);
+		const uint32_t base = smem_u32(op + s * OP_BYTES);
 		if (elect_one()) {
 #pragma unroll
 			for (int ks = 0; ks < KC / 16; ks++) {
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tma_kernel(const __grid_
 			if (lane == 0) { mbar_arrive(&ctl->op_full[s]); mbar_arrive(&ctl->raw_empty[r]); }
 		}
 	} else if (warp == CONV_WARPS) {
-		mma_walk<false>(smem, ctl, tmem, n_chunks);
+		mma_walk<false>(smem + OP_OFF, ctl, tmem, n_chunks);
 	} else if (warp == CONV_WARPS + 1) {
 		if (lane == 0) {
 			prefetch_tmap(&tmX);
@@ -209,139 +221,160 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tma_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
-// state_grad_tma: grid (feature tiles of 128, (duration, label tile of 64), frame slabs)
-// MMA M side = window features (MN-major, frames are the reduction index), N side = Dm columns of the duration block.
-// warps 0-7 converters of the TMA'd feature tile, 8-11 register loaders of the Dm tile (its columns start on 4-byte boundaries
-// only; two groups of two warps take alternate chunks so that every load has two chunk-times to land), 12 MMA, 13 TMA
+// frame_gemm_tma: products whose reduction index is the frame, both operands [frames][columns] (MN-major), both TMA-fed.
+//   MODE 0  state gradient: 128-row side = window features of duration block d (3-D map, coordinate d), 64-column side = Dm columns
+//           of block d.  The inner TMA coordinate must be a multiple of 16 bytes (measured: anything else faults), so the box starts at
+//           the aligned column below the block (up to 3 early) and a column tile is 61 wide, which always fits the 64-wide box; the
+//           converters read the tile at the residual offset, columns beyond the tile are masked in the epilogue.
+//   MODE 1  Xi (CRF_StdFeatureMap::computeTransExpF summed over frames, CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:197-223):
+//           128-row side = forward vectors A[n-d][q] -- the duration's row shift is just the TMA row coordinate (negative rows and
+//           columns >= L are zero-filled) --, 64-column side = right factors R[n][(d,y)].
+// grid (128-row tiles, (duration block, 64-column tile), frame slabs); rings: 3 x 16 KB + 2 x 8 KB raw, 2 x 24 KB operands: 112 KB,
+// two CTAs per SM.  warps 0-7 converters, 8 MMA, 9 TMA
 // ------------------------------------------------------------------------------------------------
-constexpr int LOAD_WARPS = 4;
-constexpr int SG_THR = (CONV_WARPS + LOAD_WARPS + 2) * 32;
+constexpr int RM = 3, RN = 2;
+constexpr uint32_t RAWN_BYTES = RAW_BYTES / 2;
+constexpr uint32_t F_RAWN_OFF = RM * RAW_BYTES, F_OP_OFF = F_RAWN_OFF + RN * RAWN_BYTES, F_CTL_OFF = F_OP_OFF + OS * OP_BYTES, F_SMEM = F_CTL_OFF + 128;
+constexpr int FG_THR = (CONV_WARPS + 2) * 32;
 
-__global__ void __launch_bounds__(SG_THR, 2) state_grad_tma_kernel(const __grid_constant__ CUtensorMap tmX, StateGradTmaParams p) {
+struct FCtl {
+	uint64_t m_full[RM], m_empty[RM], n_full[RN], n_empty[RN], op_full[OS], op_empty[OS], done;
+	uint32_t tmem;
+};
+static_assert(sizeof(FCtl) <= 128, "control block");
+
+template <int MODE>
+__global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN, FrameGemmParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
-	Ctl* ctl = reinterpret_cast<Ctl*>(smem + CTL_OFF);
+	FCtl* ctl = reinterpret_cast<FCtl*>(smem + F_CTL_OFF);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t m0 = blockIdx.x * BM, d = blockIdx.y / p.ntile, jt = blockIdx.y % p.ntile;
+	const uint32_t m0 = blockIdx.x * BM, d = blockIdx.y / p.ntile, y0 = (blockIdx.y % p.ntile) * FRAME_GEMM_TILE;
 	const uint32_t ns = blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.N);
 	const uint32_t n_chunks = (ne - ns + KC - 1) / KC;
-	if (tid == 0 && (smem_u32(smem) & 1023)) __trap();
-	setup(ctl, tid, warp, CONV_WARPS + LOAD_WARPS, CONV_WARPS + 2);
+	const uint32_t ncol = min((uint32_t)FRAME_GEMM_TILE, p.P - y0), col0 = d * p.P + y0, sh = col0 & 3;   // the box starts sh columns early
+	if (tid == 0) {
+		if (smem_u32(smem) & 1023) __trap();
+		for (int s = 0; s < RM; s++) { mbar_init(&ctl->m_full[s], 1); mbar_init(&ctl->m_empty[s], CONV_WARPS); }
+		for (int s = 0; s < RN; s++) { mbar_init(&ctl->n_full[s], 1); mbar_init(&ctl->n_empty[s], CONV_WARPS); }
+		for (int s = 0; s < OS; s++) { mbar_init(&ctl->op_full[s], CONV_WARPS); mbar_init(&ctl->op_empty[s], 1); }
+		mbar_init(&ctl->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == CONV_WARPS) tmem_alloc(&ctl->tmem, BN);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
 	const uint32_t tmem = ctl->tmem;
-	const uint32_t y0 = jt * BN, ncol = min((uint32_t)BN, p.P - y0);
 
 	if (warp < CONV_WARPS) {
-		// raw stage = 4 boxes [32 frames][32 features]; unit = (frame k, feature group rg of 8)
-		const uint32_t k = (warp & 3) * 8 + (lane & 7), rg0 = (warp >> 2) * 8 + (lane >> 3) * 2;
+		// unit = (frame k, group of 8 columns): two of the 128-row side and one of the 64-column side per thread
+		const uint32_t k = (warp & 3) * 8 + (lane & 7), rg0 = (warp >> 2) * 8 + (lane >> 3) * 2, cg = (warp >> 2) * 4 + (lane >> 3);
 		for (uint32_t c = 0; c < n_chunks; c++) {
-			const uint32_t r = c % RA, s = c % OS;
-			mbar_wait(&ctl->raw_full[r], (c / RA) & 1);
-			const unsigned char* raw = smem + r * RAW_BYTES;
-			float x[2][8];
+			const uint32_t rm = c % RM, rn = c % RN, s = c % OS;
+			float x[3][8];
+			mbar_wait(&ctl->m_full[rm], (c / RM) & 1);
+			const unsigned char* rawm = smem + rm * RAW_BYTES;
 #pragma unroll
 			for (uint32_t i = 0; i < 2; i++) {
 				const uint32_t rg = rg0 + i;
-				load_raw8(raw + (rg >> 2) * 4096, k, rg & 3, x[i]);
-				const uint32_t rel = p.ones_col - (m0 + rg * 8);          // the constant-1 bias feature (TMA zero-fills beyond the window)
-				if (rel < 8u) {
-					const float one = (ns + c * KC + k < ne) ? 1.0f : 0.0f;
+				load_raw8(rawm + (rg >> 2) * 4096, k, rg & 3, x[i]);
+				if (MODE == 0) {
+					const uint32_t rel = p.ones_col - (m0 + rg * 8);          // the constant-1 bias feature (TMA zero-fills beyond the window)
+					if (rel < 8u) {
+						const float one = (ns + c * KC + k < ne) ? 1.0f : 0.0f;
 #pragma unroll
-					for (uint32_t j = 0; j < 8; j++) if (j == rel) x[i][j] = one;
+						for (uint32_t j = 0; j < 8; j++) if (j == rel) x[i][j] = one;
+					}
 				}
 			}
-			uint4 h[2], l[2];
-			split8(x[0], h[0], l[0]); split8(x[1], h[1], l[1]);
+			mbar_wait(&ctl->n_full[rn], (c / RN) & 1);
+			if (sh == 0) load_raw8(smem + F_RAWN_OFF + rn * RAWN_BYTES + (cg >> 2) * 4096, k, cg & 3, x[2]);
+			else load_raw8_shifted(smem + F_RAWN_OFF + rn * RAWN_BYTES, k, cg * 8 + sh, x[2]);
+			uint4 h[3], l[3];
+#pragma unroll
+			for (int i = 0; i < 3; i++) split8(x[i], h[i], l[i]);
 			if (c >= OS) mbar_wait(&ctl->op_empty[s], ((c / OS) - 1) & 1);
-			unsigned char* st = smem + OP_OFF + s * OP_BYTES;
+			unsigned char* st = smem + F_OP_OFF + s * OP_BYTES;
 #pragma unroll
 			for (uint32_t i = 0; i < 2; i++) {
 				const uint32_t o = (rg0 + i) * 512 + k * 16;
 				*reinterpret_cast<uint4*>(st + o) = h[i]; *reinterpret_cast<uint4*>(st + A_TILE + o) = l[i];
 			}
+			{
+				const uint32_t o = cg * 512 + k * 16;
+				*reinterpret_cast<uint4*>(st + 2 * A_TILE + o) = h[2]; *reinterpret_cast<uint4*>(st + 2 * A_TILE + B_TILE + o) = l[2];
+			}
 			fence_proxy_async_smem();
 			__syncwarp();
-			if (lane == 0) { mbar_arrive(&ctl->op_full[s]); mbar_arrive(&ctl->raw_empty[r]); }
+			if (lane == 0) { mbar_arrive(&ctl->op_full[s]); mbar_arrive(&ctl->m_empty[rm]); mbar_arrive(&ctl->n_empty[rn]); }
 		}
-	} else if (warp < CONV_WARPS + LOAD_WARPS) {
-		// Dm tile [32 frames][64 columns]: unit = (frame, column group of 8); 4 units per thread; group lg owns chunks c = lg (mod 2)
-		const uint32_t lg = (warp - CONV_WARPS) >> 1, lw = (warp - CONV_WARPS) & 1, k8 = lane & 7, cq = lane >> 3;
-		const float* colp = p.Dm + (uint64_t)d * p.P + y0;
-		const bool vec2 = ((reinterpret_cast<uintptr_t>(colp) & 7) == 0) && (p.ldd % 2 == 0);
-		float x[4][8];
-		auto fetch = [&](uint32_t c) {
-#pragma unroll
-			for (uint32_t it = 0; it < 4; it++) {
-				const uint32_t cg = cq + 4 * (it & 1), kk = (lw * 2 + (it >> 1)) * 8 + k8, n = ns + c * KC + kk;
-				const float* src = colp + (uint64_t)n * p.ldd + cg * 8;
-				if (n < ne && cg * 8 + 8 <= ncol) {
-					if (vec2) {
-#pragma unroll
-						for (int j = 0; j < 4; j++) { const float2 v = __ldg(reinterpret_cast<const float2*>(src) + j); x[it][2 * j] = v.x; x[it][2 * j + 1] = v.y; }
-					} else {
-#pragma unroll
-						for (int j = 0; j < 8; j++) x[it][j] = __ldg(src + j);
-					}
-				} else {
-#pragma unroll
-					for (uint32_t j = 0; j < 8; j++) x[it][j] = (n < ne && cg * 8 + j < ncol) ? __ldg(src + j) : 0.0f;
-				}
-			}
-		};
-		if (lg < n_chunks) fetch(lg);
-		for (uint32_t c = lg; c < n_chunks; c += 2) {
+	} else if (warp == CONV_WARPS) {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, true, true);
+		for (uint32_t c = 0; c < n_chunks; c++) {
 			const uint32_t s = c % OS;
-			if (c >= OS) mbar_wait(&ctl->op_empty[s], ((c / OS) - 1) & 1);
-			unsigned char* st = smem + OP_OFF + s * OP_BYTES + 2 * A_TILE;
+			mbar_wait(&ctl->op_full[s], (c / OS) & 1);
+			tc_fence_after();
+			const uint32_t base = smem_u32(smem + F_OP_OFF + s * OP_BYTES);
+			if (elect_one()) {
 #pragma unroll
-			for (uint32_t it = 0; it < 4; it++) {
-				const uint32_t cg = cq + 4 * (it & 1), kk = (lw * 2 + (it >> 1)) * 8 + k8;
-				const uint32_t o = cg * 512 + kk * 16;
-				uint4 h, l;
-				split8(x[it], h, l);
-				*reinterpret_cast<uint4*>(st + o) = h; *reinterpret_cast<uint4*>(st + B_TILE + o) = l;
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+					mma_ss(tmem, al, bh, idesc, true);
+					mma_ss(tmem, ah, bl, idesc, true);
+				}
+				mma_commit(&ctl->op_empty[s]);
 			}
-			fence_proxy_async_smem();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&ctl->op_full[s]);
-			if (c + 2 < n_chunks) fetch(c + 2);
 		}
-	} else if (warp == CONV_WARPS + LOAD_WARPS) {
-		mma_walk<true>(smem, ctl, tmem, n_chunks);
+		if (elect_one()) mma_commit(&ctl->done);
+		__syncwarp();
 	} else {
 		if (lane == 0) {
-			prefetch_tmap(&tmX);
+			prefetch_tmap(&tmM); prefetch_tmap(&tmN);
 			for (uint32_t c = 0; c < n_chunks; c++) {
-				const uint32_t r = c % RA;
-				if (c >= RA) mbar_wait(&ctl->raw_empty[r], ((c / RA) - 1) & 1);
-				mbar_arrive_expect_tx(&ctl->raw_full[r], RAW_BYTES);
+				const uint32_t rm = c % RM, rn = c % RN, n = ns + c * KC;
+				if (c >= RM) mbar_wait(&ctl->m_empty[rm], ((c / RM) - 1) & 1);
+				mbar_arrive_expect_tx(&ctl->m_full[rm], RAW_BYTES);
 #pragma unroll
-				for (uint32_t b = 0; b < 4; b++) tma_load_3d(smem + r * RAW_BYTES + b * 4096, &tmX, m0 + b * 32, d, ns + c * KC, &ctl->raw_full[r]);
+				for (uint32_t b = 0; b < 4; b++)
+					tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmM, m0 + b * 32, MODE == 0 ? d : 0u, MODE == 0 ? n : n - (d + 1), &ctl->m_full[rm]);
+				if (c >= RN) mbar_wait(&ctl->n_empty[rn], ((c / RN) - 1) & 1);
+				mbar_arrive_expect_tx(&ctl->n_full[rn], RAWN_BYTES);
+#pragma unroll
+				for (uint32_t b = 0; b < 2; b++) tma_load_3d(smem + F_RAWN_OFF + rn * RAWN_BYTES + b * 4096, &tmN, (col0 & ~3u) + b * 32, 0, n, &ctl->n_full[rn]);
 			}
 		}
 	}
-	// ---- epilogue: lane = feature j, 64 labels of the duration block; fp64 atomics into the gradient ----
+	// ---- epilogue: lane = row of the 128-row side, 64 columns of the duration block; fp64 atomics into the gradient ----
 	if (warp < 4 && n_chunks) {
 		mbar_wait(&ctl->done, 0);
 		tc_fence_after();
-		const uint32_t gj = m0 + warp * 32 + lane;
-		const double sc = (gj == p.ones_col) ? p.ones_scale : p.scale;
+		const uint32_t gm = m0 + warp * 32 + lane;
+		const double sc = (MODE == 0 && gm == p.ones_col) ? p.ones_scale : p.scale;
 #pragma unroll
 		for (int c0 = 0; c0 < BN; c0 += 16) {
 			float v[16];
 			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
 			tmem_ld_wait();
-			if (gj < p.J) {
+			if (gm < p.Mext) {
 #pragma unroll
 				for (int j = 0; j < 16; j++) {
 					const uint32_t y = c0 + j;
 					if (y >= ncol || v[j] == 0.0f) continue;
-					atomicAdd(&p.out[(uint64_t)__ldg(p.row_idx + d * p.P + y0 + y) + gj], sc * (double)v[j]);
+					if (MODE == 0) atomicAdd(&p.out[(uint64_t)__ldg(p.row_idx + col0 + y) + gm], sc * (double)v[j]);
+					else {
+						const uint32_t idx = __ldg(p.pair_idx + (uint64_t)gm * p.L + col0 + y);
+						if (idx != 0xffffffffu) atomicAdd(&p.out[idx], sc * (double)__ldg(p.Ew + (uint64_t)gm * p.e_ld + col0 + y) * (double)v[j]);
+					}
 				}
 			}
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == CONV_WARPS + LOAD_WARPS) tmem_dealloc(tmem, BN);
+	if (warp == CONV_WARPS) tmem_dealloc(tmem, BN);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -423,19 +456,42 @@ cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaPar
 	return cudaGetLastError();
 }
 
-cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const StateGradTmaParams& p, cudaStream_t s) {
-	if (!p.N || !p.P || !p.J) return cudaSuccess;
-	if (p.k_slab % KC) return cudaErrorInvalidValue;
+static cudaError_t frame_gemm_attrs() {
 	static bool attr_done = false;
 	if (!attr_done) {
-		cudaError_t e = cudaFuncSetAttribute(state_grad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+		cudaError_t e = cudaFuncSetAttribute(frame_gemm_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	CUtensorMap tm;
-	if (!window_map(&tm, X, p.N, p.D, Wp, K, KC, false)) return cudaErrorInvalidValue;
-	dim3 grid((p.J + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	state_grad_tma_kernel<<<grid, SG_THR, SMEM_BYTES, s>>>(tm, p);
+	return cudaSuccess;
+}
+
+bool lattice_tma_eligible(const float* a, uint32_t ld) { return encoder() != nullptr && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0; }
+
+cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const float* Dm, uint32_t ldd, const FrameGemmParams& p, cudaStream_t s) {
+	if (!p.N || !p.P || !p.Mext) return cudaSuccess;
+	if (p.k_slab % KC) return cudaErrorInvalidValue;
+	cudaError_t e = frame_gemm_attrs();
+	if (e != cudaSuccess) return e;
+	// the Dm view ends at column D*P: what a box reads beyond the last block is zero-filled
+	CUtensorMap tm, tn;
+	if (!window_map(&tm, X, p.N, p.D, Wp, K, KC, false) || !window_map(&tn, Dm, p.N, 1, ldd, p.D * p.P, KC, false)) return cudaErrorInvalidValue;
+	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
+	frame_gemm_tma_kernel<0><<<grid, FG_THR, F_SMEM, s>>>(tm, tn, p);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_xi_gemm_tma(const float* A, const float* R, uint32_t ld, const FrameGemmParams& p, cudaStream_t s) {
+	if (!p.N || !p.L) return cudaSuccess;
+	if (p.k_slab % KC) return cudaErrorInvalidValue;
+	cudaError_t e = frame_gemm_attrs();
+	if (e != cudaSuccess) return e;
+	// [N][1][L] views (row stride ld): columns >= L are never read (zero fill), so the pad of the lattice arrays may hold anything
+	CUtensorMap ta, tr;
+	if (!window_map(&ta, A, p.N, 1, ld, p.L, KC, false) || !window_map(&tr, R, p.N, 1, ld, p.L, KC, false)) return cudaErrorInvalidValue;
+	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
+	frame_gemm_tma_kernel<1><<<grid, FG_THR, F_SMEM, s>>>(ta, tr, p);
 	return cudaGetLastError();
 }
 

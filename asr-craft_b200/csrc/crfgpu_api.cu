@@ -70,7 +70,7 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 7; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
@@ -424,7 +424,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	if (!N) { h->fwdbwd_done = true; return; }
 
 	// K1: state scores.  TMA-fed kernel: all durations in one launch, per-duration maxima fused; otherwise one GEMM per duration block
-	const bool tma = h->opt_gemm_impl == 2 && D > 1 && nSf > 0 && tma_gemm_eligible(h->X() + c.state_fidx_start, D, h->Wp, c.state_fidx_start);
+	const bool tma = h->opt_gemm_impl == 2 && (h->opt_tma_mask & 1) && D > 1 && nSf > 0 && tma_gemm_eligible(h->X() + c.state_fidx_start, D, h->Wp, c.state_fidx_start);
 	bool smax_done = false;
 	if (nSf == 0) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
 	phase_begin(h, "score");
@@ -499,7 +499,14 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 
 	// K4: expected-minus-empirical counts as two families of reduce-GEMMs
 	phase_begin(h, "xi");
-	if (c.use_trans_bias && h->opt_gemm_impl >= 1 && N > 1) {
+	const bool lat_tma = h->opt_gemm_impl == 2 && lattice_tma_eligible(h->d_A.as<float>(), Lp) && lattice_tma_eligible(h->d_R.as<float>(), Lp) &&
+	                     lattice_tma_eligible(h->d_Dm.as<float>(), Lp);
+	if (c.use_trans_bias && lat_tma && (h->opt_tma_mask & 4) && N > 1) {
+		FrameGemmParams x{};
+		x.N = N; x.P = P; x.D = D; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = L; x.ones_col = 0xffffffffu;
+		x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = L; x.Ew = h->d_E.as<float>(); x.e_ld = Lp; x.out = h->d_grad.as<double>();
+		CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), Lp, x, s)); check_kernel(h, 1);
+	} else if (c.use_trans_bias && h->opt_gemm_impl >= 1 && N > 1) {
 		XiGemmParams x{};
 		x.A = h->d_A.as<float>(); x.lda = Lp; x.R = h->d_R.as<float>(); x.ldb = Lp;
 		x.n_frames = N; x.n0 = 1; x.n1 = N; x.k_slab = h->opt_k_slab_tc;
@@ -522,12 +529,12 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	}
 	phase_end(h, "xi");
 	phase_begin(h, "grad");
-	if (tma) {
-		StateGradTmaParams r{};
-		r.Dm = h->d_Dm.as<float>(); r.ldd = Lp; r.N = N; r.P = P; r.D = D; r.J = nSf + (c.use_state_bias ? 1 : 0);
-		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu; r.k_slab = h->opt_k_slab_tma; r.ntile = (P + 63) / 64;
-		r.scale = 1.0; r.ones_scale = c.state_bias_val; r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
-		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, r, s));
+	if (tma && lat_tma && (h->opt_tma_mask & 2)) {
+		FrameGemmParams r{};
+		r.N = N; r.P = P; r.D = D; r.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; r.k_slab = h->opt_k_slab_tma; r.Mext = nSf + (c.use_state_bias ? 1 : 0);
+		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu; r.scale = 1.0; r.ones_scale = c.state_bias_val;
+		r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
+		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, h->d_Dm.as<float>(), Lp, r, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
 		ReduceGemmParams r{};
@@ -825,6 +832,8 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
 		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16, register-staged; 2: + TMA-fed window GEMMs
+		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels
+		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }
 		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
 		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05
