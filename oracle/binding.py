@@ -148,13 +148,14 @@ class OracleLib(_Lib):
     def __init__(self, path=None):
         super().__init__(path or os.path.join(HERE, "libcrforacle.so"))
 
-    def fwdbwd(self, cfg, lam, off, ftrs, labs, n_threads=1):
-        """stdseg_no_dur* training (CRF_StdSegStateNode_WithoutDurLab*, CRF_NewGradBuilder_StdSeg[_NoDur_NoTrans].cpp) is
+    def fwdbwd(self, cfg, lam, off, ftrs, labs, n_threads=1, tied=False):
+        """stdseg_no_dur* training has two restatements here.  Default: the native O(P^2 + D*P) recursion of
+        crf_oracle.c::fb_nodur.  tied=True: stdseg_no_dur* training (CRF_StdSegStateNode_WithoutDurLab*, CRF_NewGradBuilder_StdSeg[_NoDur_NoTrans].cpp) is
         restated through its equivalence with `stdseg` on the (duration, phone) label set with TIED weights: state rows of
         label (d,y) = rows of phone y, transition (d',y')->(d,y) = transition y'->y (no transition FEATURES).  The reference's
         own stdseg run with tied lambda reproduces the no_dur logZ / numerators (tests/test_oracle.py pins this restatement to
         goldens produced by the reference's no_dur node classes)."""
-        if cfg.model_type in (2, 3, 4) and cfg.max_dur > 1 and cfg.n_states == 1 and not cfg.use_trans_ftrs:
+        if tied and cfg.model_type in (2, 3, 4) and cfg.max_dur > 1 and cfg.n_states == 1 and not cfg.use_trans_ftrs:
             P, D = cfg.n_labs, cfg.max_dur
             w = window_width(cfg.n_base_ftrs, D, cfg.extract_seg_ftrs)
             nS = (cfg.state_fidx_end - cfg.state_fidx_start + 1) + (1 if cfg.use_state_bias else 0)
@@ -176,7 +177,7 @@ class OracleLib(_Lib):
             grad = np.zeros(len(lam), np.float64)
             np.add.at(grad, src, gb)
             return grad, numer, logz
-        if cfg.model_type in (2, 3, 4) and cfg.max_dur == 1 and not cfg.use_trans_ftrs:
+        if cfg.model_type in (2, 3, 4) and cfg.max_dur == 1 and not cfg.use_trans_ftrs and (tied or cfg.n_states > 1):
             # one-frame segments: the no_dur nodes reduce to the frame-level recursions (1 or N states per phone)
             frame = Config(0, *[getattr(cfg, f[0]) for f in Config._fields_[1:]])
             return _Lib.fwdbwd(self, frame, lam, off, ftrs, labs, n_threads)

@@ -501,6 +501,114 @@ static int fb_stdseg(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	return 0;
 }
 
+/* Segmental `stdseg_no_dur`, `stdseg_no_dur_no_transftr`, `stdseg_no_dur_no_segtransftr` with one state per phone and no transition
+ * FEATURES (labels = phones; the duration lives in the window features only):
+ * CRF_NewGradBuilder_StdSeg_NoDur_NoTrans::buildGradient (CRF/src/trainers/gradbuilders/CRF_NewGradBuilder_StdSeg_NoDur_NoTrans.cpp:65-492)
+ * over CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr (CRF/src/nodes/CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr.cpp:
+ * computeTransMatrix :39-121, computeAlpha :123-333, computeAlphaPlusTrans :1077-1116, computeBeta :395-614, computeExpF :616-1066),
+ * in its native O(P^2 + D*P) form:
+ *   A_t[y]      = logsum_y' (alpha_t[y'] + M[y',y])                       alpha_t[d,y] = S_t[d,y] + A_{t-d}[y]   (= S_t[d,y] when d == t+1)
+ *   alpha_t[y]  = logsum_d alpha_t[d,y]                                    logZ = logsum_y alpha_{T-1}[y]
+ *   B_t[y]      = logsum_d (S_{t+d}[d,y] + beta_{t+d}[y])                  beta_t[y'] = logsum_y (M[y',y] + B_t[y]),  beta_{T-1} = 0
+ *   gamma_t[d,y] = exp(alpha_t[d,y] + beta_t[y] - logZ)                    xi_t[y',y]  = exp(alpha_t[y'] + M[y',y] + B_t[y] - logZ)
+ * Without transition features the three node families give identical results and equal `stdseg` on the (duration, phone) label set
+ * with tied weights (oracle/binding.py keeps that restatement; tests/test_oracle.py checks both against goldens made by the
+ * reference's own no_dur node classes).  alpha/beta dumps: [T][P] (sum over durations). */
+static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
+                    double* grad, double* numer, double* logZ, double* A_out, double* B_out) {
+	const crforacle_config* c = k->c; const fmap_t* m = k->m; const double* lam = k->lam;
+	const uint32_t P = m->L, D = c->max_dur, W = crforacle_window_width(c);
+	if (c->n_states != 1) FAIL("oracle: N-state segmental forward-backward not restated");
+	if (c->use_trans_ftrs || !k->Mconst) FAIL("oracle: no_dur models with transition features not restated");
+	const double* M = k->Mconst;
+	float* X = (float*)malloc(sizeof(float) * (size_t)T * D * W);
+	double* S = (double*)malloc(sizeof(double) * (size_t)T * D * P);      /* [t][d-1][y] */
+	double* AD = (double*)malloc(sizeof(double) * (size_t)T * D * P);     /* alpha_t[d,y] */
+	double* A = (double*)malloc(sizeof(double) * (size_t)T * P);          /* alpha_t[y] */
+	double* AT = (double*)malloc(sizeof(double) * (size_t)T * P);         /* A_t[y] */
+	double* B = (double*)malloc(sizeof(double) * (size_t)T * P);          /* beta_t[y] */
+	double* BV = (double*)malloc(sizeof(double) * (size_t)T * P);         /* B_t[y] */
+	double* acc = (double*)malloc(sizeof(double) * (P > D ? P : D));
+	crforacle_window_ftrs(c, T, x, X);
+	memset(k->ExpF, 0, sizeof(double) * m->len);
+	for (uint32_t t = 0; t < T; t++) {
+		const uint32_t dmax = t + 1 < D ? t + 1 : D;
+		for (uint32_t y = 0; y < P; y++) {
+			for (uint32_t d = 1; d <= dmax; d++) {
+				const double s = state_value(c, m, X + ((size_t)t * D + (d - 1)) * W, lam, y);
+				S[((size_t)t * D + d - 1) * P + y] = s;
+				acc[d - 1] = AD[((size_t)t * D + d - 1) * P + y] = s + (d <= t ? AT[(size_t)(t - d) * P + y] : 0.0);
+			}
+			A[(size_t)t * P + y] = log_add_n(acc, (int)dmax);
+		}
+		for (uint32_t y = 0; y < P; y++) {
+			for (uint32_t q = 0; q < P; q++) acc[q] = A[(size_t)t * P + q] + M[(size_t)q * P + y];
+			AT[(size_t)t * P + y] = log_add_n(acc, (int)P);
+		}
+	}
+	const double Zx = log_add_n(A + (size_t)(T - 1) * P, (int)P);
+	double ll = 0.0;
+	int bad = 0;
+	uint32_t prev_lab = CRFO_LAB_BAD;
+	for (uint32_t t = T; t-- > 0;) {
+		const uint32_t nn = (T - 1 - t) < D ? (T - 1 - t) : D;
+		if (nn == 0) for (uint32_t y = 0; y < P; y++) { B[(size_t)t * P + y] = 0.0; BV[(size_t)t * P + y] = LOG0; }
+		else {
+			for (uint32_t y = 0; y < P; y++) {
+				for (uint32_t d = 1; d <= nn; d++) acc[d - 1] = S[((size_t)(t + d) * D + d - 1) * P + y] + B[(size_t)(t + d) * P + y];
+				BV[(size_t)t * P + y] = log_add_n(acc, (int)nn);
+			}
+			for (uint32_t q = 0; q < P; q++) {
+				for (uint32_t y = 0; y < P; y++) acc[y] = M[(size_t)q * P + y] + BV[(size_t)t * P + y];
+				B[(size_t)t * P + q] = log_add_n(acc, (int)P);
+			}
+		}
+	}
+	for (uint32_t t = 0; t < T && !bad; t++) {
+		const uint32_t* l4 = lab4 + 4 * (size_t)t;
+		const uint32_t dmax = t + 1 < D ? t + 1 : D;
+		const uint32_t lab = l4[0], ldur = (lab != CRFO_LAB_BAD) ? l4[2] - l4[1] + 1 : 0;
+		double tot = 0.0;
+		for (uint32_t d = 1; d <= dmax; d++) {
+			const float* xs = X + ((size_t)t * D + (d - 1)) * W;
+			for (uint32_t y = 0; y < P; y++) {
+				const double ab = exp(AD[((size_t)t * D + d - 1) * P + y] + B[(size_t)t * P + y] - Zx);
+				tot += ab;
+				ll += state_expf(c, m, xs, lam, k->ExpF, grad, ab, (lab != CRFO_LAB_BAD && d == ldur) ? lab : CRFO_LAB_BAD, y);
+			}
+		}
+		if (tot > 1.000001 || tot < -0.000001) bad = 1;
+		/* transitions out of frame t (into the segment that starts at t+1) */
+		if (t + 1 < T) {
+			double ttot = 0.0;
+			for (uint32_t q = 0; q < P; q++)
+				for (uint32_t y = 0; y < P; y++) {
+					const double xi = exp(A[(size_t)t * P + q] + M[(size_t)q * P + y] + BV[(size_t)t * P + y] - Zx);
+					ttot += xi;
+					trans_expf(c, m, NULL, lam, k->ExpF, grad, xi, CRFO_LAB_BAD, CRFO_LAB_BAD, q, y);
+				}
+			if (ttot > 1.000001 || ttot < -0.000001) bad = 1;
+		}
+		/* empirical transition: the reference segment ending here and the one before it */
+		if (lab != CRFO_LAB_BAD) {
+			if (prev_lab != CRFO_LAB_BAD) {
+				uint32_t lc = m->tidx[(size_t)prev_lab * P + lab];
+				if (c->use_trans_bias) { grad[lc] += c->trans_bias_val; ll += lam[lc] * c->trans_bias_val; }
+			}
+			prev_lab = lab;
+		}
+	}
+	if (!bad) {
+		for (uint32_t i = 0; i < m->len; i++) grad[i] -= k->ExpF[i];
+		*numer = ll; *logZ = Zx;
+		if (A_out) memcpy(A_out, A, sizeof(double) * (size_t)T * P);
+		if (B_out) memcpy(B_out, B, sizeof(double) * (size_t)T * P);
+	}
+	free(X); free(S); free(AD); free(A); free(AT); free(B); free(BV); free(acc);
+	if (bad) FAIL("posterior mass check failed (no_dur)");
+	return 0;
+}
+
 static int ctx_init(ctx_t* k, const crforacle_config* c, const fmap_t* m, const double* lam) {
 	k->c = c; k->m = m; k->lam = lam;
 	k->ExpF = (double*)malloc(sizeof(double) * (m->len ? m->len : 1));
@@ -527,6 +635,8 @@ static int fb_one(ctx_t* k, uint32_t T, const float* x, const uint32_t* labs,
 		rc = (c->n_states > 1) ? fb_frame_nstate(k, T, x, lab4, grad, numer, logZ, A, B)
 		                       : fb_frame_1state(k, T, x, lab4, grad, numer, logZ, A, B);
 	} else if (c->model_type == CRFO_STDSEG) rc = fb_stdseg(k, T, x, lab4, grad, numer, logZ, A, B);
+	else if (c->model_type == CRFO_STDSEG_NO_DUR || c->model_type == CRFO_STDSEG_NO_DUR_NO_TRANSFTR || c->model_type == CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR)
+		rc = fb_nodur(k, T, x, lab4, grad, numer, logZ, A, B);
 	else { free(lab4); FAIL("oracle: model type %u forward-backward not restated yet", c->model_type); }
 	free(lab4);
 	return rc;

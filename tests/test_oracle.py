@@ -34,13 +34,14 @@ def test_train_golden(oracle, name):
     np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
 
 
+@pytest.mark.parametrize("tied", [False, True])
 @pytest.mark.parametrize("name", sorted(NODUR))
-def test_train_nodur_golden(oracle, name):
-    """stdseg_no_dur / _no_transftr / _no_segtransftr training: the tied (duration, phone) restatement against goldens
-    produced by the reference's own no_dur node classes and grad builders."""
+def test_train_nodur_golden(oracle, name, tied):
+    """stdseg_no_dur / _no_transftr / _no_segtransftr training: the native O(P^2 + D*P) restatement (fb_nodur) and the tied
+    (duration, phone) restatement, both against goldens produced by the reference's own no_dur node classes and grad builders."""
     c = NODUR[name]
     assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
-    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"])
+    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"], tied=tied)
     np.testing.assert_allclose(logz, c["logZ"], rtol=1e-12)
     np.testing.assert_allclose(numer, c["numer"], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(grad, c["grad"], rtol=1e-9, atol=1e-10)
