@@ -1,0 +1,293 @@
+// Native lattice recursions of the segmental models WITHOUT duration labels (stdseg_no_dur, _no_transftr, _no_segtransftr; one
+// state per phone, transition bias only) for sm_100a -- the O(P^2 + D*P) form that scales to P >= 1000 phones, D = 30.
+//
+// Reference semantics (log domain, fp64): CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr::computeAlpha / computeAlphaPlusTrans /
+// computeBeta / computeExpF (CRF/src/nodes/CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr.cpp:123-333, 1077-1116, 395-614,
+// 616-1066) driven by CRF_NewGradBuilder_StdSeg_NoDur_NoTrans::buildGradient
+// (CRF/src/trainers/gradbuilders/CRF_NewGradBuilder_StdSeg_NoDur_NoTrans.cpp:65-492):
+//   A_t[y]     = logsum_y' (alpha_t[y'] + M[y',y])              alpha_t[d,y] = S_t[d,y] + A_{t-d}[y]   (= S_t[d,y] when d == t+1)
+//   alpha_t[y] = logsum_d alpha_t[d,y]                           logZ = logsum_y alpha_{T-1}[y]
+//   B_t[y]     = logsum_d (S_{t+d}[d,y] + beta_{t+d}[y])         beta_t[y'] = logsum_y (M[y',y] + B_t[y]),  beta_{T-1} = 0
+//   gamma_t[d,y] = exp(alpha_t[d,y] + beta_t[y] - logZ)          xi_t[y',y]  = exp(alpha_t[y'] + M[y',y] + B_t[y] - logZ)
+//
+// Device form (probability domain, one log scale per frame):  alpha_t[y] = rho_t + log a_t[y],  A_t[y] = rho_t + Mmax + LG_t[y] with
+// exp(LG_t[y]) = sum_y' a_t[y'] E[y'][y], E = exp(M - Mmax);  B_t[y] = sigma_t + log bh_t[y],  beta_t[y'] = kappa_t + LB_t[y'] with
+// exp(LB_t[y']) = sum_y E[y'][y] bh_t[y], kappa_t = sigma_t + Mmax.  The scales are upper bounds built from per-duration score maxima
+// and the EXACT log-sums of earlier frames, so every stored value is <= D and nothing overflows.
+//
+// Work split: the P x P matrix is sliced over the CTAs of a GROUP -- CTA pt keeps the 32 columns (forward) / rows (backward) of its
+// phone tile in shared memory for the whole launch -- and UT = 16 utterances advance in lock-step per group.  Per frame:
+//   phase A  (element-wise, D terms per (utterance, phone)): the new vector a_t / bh_t of the CTA's own phones, written to the lattice
+//            array and, transposed ([phone][utterance]), to the group's exchange buffer together with its partial sums;
+//   ONE barrier among the CTAs of the group (a monotonic counter in global memory; the launch is cooperative, so they are co-resident);
+//   phase B  the CTA's 16 x 32 block of the matrix product from the exchanged vector (fp32 FFMA: 8 warps = 8 slices of the contraction
+//            index, 16 accumulators per thread, one shared-memory reduction), LG / LB, and the scale of the next frame -- every CTA
+//            of the group derives the same scale from the same exchanged partial sums, so no second barrier is needed;
+//   phase C  (backward) posteriors of the frame: Dm[n][(d,y)] = [reference segment] - gamma_t[d,y] for the state-gradient GEMM and
+//            R[n+1][y] (phase A) for the Xi GEMM, which both run on the TMA-fed kernels of crf_tma_gemm.cu.
+#include <cooperative_groups.h>
+
+#include <cfloat>
+
+#include "crf_kernels.cuh"
+
+namespace crfgpu {
+
+namespace {
+
+constexpr int UT = NODUR_UT, PT = 32, NTHR = 256, NW = NTHR / 32, RING = 32;
+static_assert(UT == 16 && NW * 2 == UT, "thread mapping: warp w owns utterances 2w, 2w+1 of the batch");
+
+struct Shared {
+	float red[NW][UT][PT];        // partial products of the 8 contraction slices
+	float tileT[PT][UT];          // the CTA's slice of the new vector, [phone][utterance]
+	double g_ring[UT][RING];      // forward: exact log-sum of alpha_t | backward: upper bound of beta_t
+	double s_ring[UT][RING];      // forward: rho_t                    | backward: kappa_t
+	double scale[UT];             // scale of the frame being produced (rho_t | sigma_t)
+	double kap[UT], lz[UT];       // backward: kappa_t of the frame just finished, logZ of the utterance
+	float vsum[UT];
+	uint32_t utt[UT], off[UT], len[UT];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// all CTAs of the group have published their slice of step `gstep`
+__device__ __forceinline__ void group_barrier(uint32_t* ctr, uint32_t target) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(ctr, 1u);
+		while (ld_acquire(ctr) < target) {}
+	}
+	__syncthreads();
+}
+
+}  // namespace
+
+size_t nodur_smem_bytes(uint32_t P) { return sizeof(Shared) + (size_t)((P + 31) / 32 * 32) * (PT + UT) * sizeof(float) + 16; }
+
+template <bool BWD>
+__global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+	float* Et = reinterpret_cast<float*>(smem_raw + (sizeof(Shared) + 15) / 16 * 16);   // [Pk][PT]: Et[k][j] = E[k][y0+j] (fwd) | E[y0+j][k] (bwd)
+	const uint32_t P = p.P, Pp = p.Pp, D = p.D, Pk = (P + 31) / 32 * 32;
+	float* xs = Et + (size_t)Pk * PT;                                                   // [Pk][UT]: the exchanged vector of the step
+	const size_t Lp = p.Lp;
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t g = blockIdx.x / p.npt, pt = blockIdx.x % p.npt, y0 = pt * PT, y = y0 + lane;
+	const bool y_ok = y < P;
+	const float* Msrc = BWD ? p.ET : p.E;
+	for (uint32_t i = tid; i < Pk * PT; i += NTHR) {
+		const uint32_t k = i / PT, j = i % PT;
+		Et[i] = (k < P && y0 + j < P) ? Msrc[(size_t)k * Pp + y0 + j] : 0.0f;
+	}
+	float* xbase = p.xch + (size_t)g * 2 * ((size_t)Pk * UT + (size_t)p.npt * UT);
+	const size_t xstride = (size_t)Pk * UT + (size_t)p.npt * UT;
+	uint32_t* ctr = p.ctr + g;
+	uint32_t gstep = 0;
+	const uint32_t kslice = Pk / NW;     // Pk is a multiple of 32, NW = 8
+
+	for (uint32_t b = p.grp_off[g]; b < p.grp_off[g + 1]; b++) {
+		__syncthreads();
+		if (tid < UT) {
+			const uint32_t u = p.batch_utt[(size_t)b * UT + tid];
+			sh.utt[tid] = u;
+			sh.off[tid] = u != LAB_BAD ? p.off[u] : 0;
+			sh.len[tid] = u != LAB_BAD ? p.off[u + 1] - p.off[u] : 0;
+			if (BWD) sh.lz[tid] = u != LAB_BAD ? p.logZ[u] : 0.0;
+			if (!BWD && u != LAB_BAD) {
+				// alpha_0[1,y] = S_0[1,y]: the first frame is scaled by its score maximum
+				const double r0 = (double)p.smaxd[(size_t)sh.off[tid] * D];
+				sh.scale[tid] = r0; sh.s_ring[tid][0] = r0;
+				if (pt == 0) p.rho[sh.off[tid]] = r0;
+			}
+		}
+		__syncthreads();
+		uint32_t maxlen = 0;
+		for (int u = 0; u < UT; u++) maxlen = max(maxlen, sh.len[u]);
+
+		for (uint32_t step = 0; step < maxlen; step++, gstep++) {
+			const uint32_t t = BWD ? maxlen - 1 - step : step;
+			float* xch = xbase + (gstep & 1) * xstride;
+			// ---------------------------------------------------------------- scale of bh_t (backward)
+			if (BWD) {
+				if (tid < UT) {
+					const uint32_t len = sh.len[tid];
+					if (t + 1 < len) {
+						const uint32_t nn = min(len - 1 - t, D);
+						const size_t n = (size_t)sh.off[tid] + t;
+						double sg = -DBL_MAX;
+						for (uint32_t d = 1; d <= nn; d++) sg = fmax(sg, (double)p.smaxd[(n + d) * D + d - 1] + sh.g_ring[tid][(t + d) & (RING - 1)]);
+						sh.scale[tid] = sg;
+					}
+				}
+				__syncthreads();
+			}
+			// ---------------------------------------------------------------- phase A: my slice of the new vector
+#pragma unroll
+			for (int i = 0; i < 2; i++) {
+				const uint32_t u = warp * 2 + i, len = sh.len[u];
+				const size_t n = (size_t)sh.off[u] + t;
+				float acc = 0.0f;
+				if (!BWD) {
+					if (t < len && y_ok) {
+						const double rt = sh.scale[u];
+						const uint32_t dmax = min(t + 1, D);
+						for (uint32_t d = 1; d <= dmax; d++) {
+							float lr = p.S[n * Lp + (size_t)(d - 1) * P + y];
+							if (d <= t) lr += (float)(sh.s_ring[u][(t - d) & (RING - 1)] + p.Mmax - rt) + p.LG[(n - d) * Pp + y];
+							else lr += (float)(-rt);
+							acc += expf(lr);
+						}
+						p.A[n * Pp + y] = acc;
+					}
+				} else {
+					if (t + 1 < len && y_ok) {
+						const double sg = sh.scale[u];
+						const uint32_t nn = min(len - 1 - t, D);
+						for (uint32_t d = 1; d <= nn; d++)
+							acc += expf(p.S[(n + d) * Lp + (size_t)(d - 1) * P + y] + p.LB[(n + d) * Pp + y] + (float)(sh.s_ring[u][(t + d) & (RING - 1)] - sg));
+						// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: stored with the frame the new segment starts in (row shift 1 of the Xi GEMM)
+						p.R[(n + 1) * Pp + y] = acc * expf((float)(p.rho[n] + p.Mmax + sg - sh.lz[u]));
+					}
+					if (t == 0 && len > 0 && y_ok) p.R[n * Pp + y] = 0.0f;      // no transition enters the first frame
+				}
+				sh.tileT[lane][u] = acc;
+				const float ps = warp_sum(acc);
+				if (lane == 0) __stcg(xch + (size_t)Pk * UT + (size_t)pt * UT + u, ps);
+			}
+			__syncthreads();
+			if (tid < PT * UT / 4) __stcg(reinterpret_cast<float4*>(xch + (size_t)y0 * UT) + tid, reinterpret_cast<const float4*>(&sh.tileT[0][0])[tid]);
+			group_barrier(ctr, (gstep + 1) * p.npt);
+			// ---------------------------------------------------------------- phase B: my block of the matrix product
+			if (tid < UT) {
+				float v = 0.0f;
+				for (uint32_t q = 0; q < p.npt; q++) v += __ldcg(xch + (size_t)Pk * UT + (size_t)q * UT + tid);
+				sh.vsum[tid] = v;
+			}
+			{
+				// the whole exchanged vector in one round trip to L2 (the other CTAs wrote it: bypass L1), then the product from shared memory
+				const float4* xv = reinterpret_cast<const float4*>(xch);
+				float4* xd = reinterpret_cast<float4*>(xs);
+#pragma unroll 8
+				for (uint32_t i = tid; i < Pk * (UT / 4); i += NTHR) xd[i] = __ldcg(xv + i);
+			}
+			__syncthreads();
+			{
+				float acc[UT];
+#pragma unroll
+				for (int u = 0; u < UT; u++) acc[u] = 0.0f;
+				const uint32_t k0 = warp * kslice;
+#pragma unroll 4
+				for (uint32_t k = k0; k < k0 + kslice; k++) {
+					const float e = Et[k * PT + lane];
+					const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)k * UT);
+					const float4 a0 = xr[0], a1 = xr[1], a2 = xr[2], a3 = xr[3];
+					acc[0] = fmaf(a0.x, e, acc[0]); acc[1] = fmaf(a0.y, e, acc[1]); acc[2] = fmaf(a0.z, e, acc[2]); acc[3] = fmaf(a0.w, e, acc[3]);
+					acc[4] = fmaf(a1.x, e, acc[4]); acc[5] = fmaf(a1.y, e, acc[5]); acc[6] = fmaf(a1.z, e, acc[6]); acc[7] = fmaf(a1.w, e, acc[7]);
+					acc[8] = fmaf(a2.x, e, acc[8]); acc[9] = fmaf(a2.y, e, acc[9]); acc[10] = fmaf(a2.z, e, acc[10]); acc[11] = fmaf(a2.w, e, acc[11]);
+					acc[12] = fmaf(a3.x, e, acc[12]); acc[13] = fmaf(a3.y, e, acc[13]); acc[14] = fmaf(a3.z, e, acc[14]); acc[15] = fmaf(a3.w, e, acc[15]);
+				}
+#pragma unroll
+				for (int u = 0; u < UT; u++) sh.red[warp][u][lane] = acc[u];
+			}
+			__syncthreads();
+			float lcur[2];
+#pragma unroll
+			for (int i = 0; i < 2; i++) {
+				const uint32_t u = warp * 2 + i, len = sh.len[u];
+				const size_t n = (size_t)sh.off[u] + t;
+				float s = 0.0f;
+#pragma unroll
+				for (int w = 0; w < NW; w++) s += sh.red[w][u][lane];
+				lcur[i] = 0.0f;
+				if (t < len && y_ok) {
+					if (!BWD) p.LG[n * Pp + y] = logf(s);
+					else { lcur[i] = (t + 1 == len) ? 0.0f : logf(s); p.LB[n * Pp + y] = lcur[i]; }      // setTailBeta: beta_{T-1} = 0
+				}
+			}
+			if (tid < UT) {
+				const uint32_t len = sh.len[tid];
+				const size_t n = (size_t)sh.off[tid] + t;
+				if (t < len) {
+					if (!BWD) {
+						const double gh = sh.scale[tid] + log((double)sh.vsum[tid]);       // exact log-sum of alpha_t
+						sh.g_ring[tid][t & (RING - 1)] = gh;
+						if (t + 1 == len) { if (pt == 0) p.logZ[sh.utt[tid]] = gh; }       // computeAlphaSum
+						else {
+							const uint32_t t1 = t + 1;
+							double r = -DBL_MAX;
+							for (uint32_t d = 1; d <= min(t1, D); d++) r = fmax(r, (double)p.smaxd[(n + 1) * D + d - 1] + p.Mmax + sh.g_ring[tid][(t1 - d) & (RING - 1)]);
+							if (t1 < D) r = fmax(r, (double)p.smaxd[(n + 1) * D + t1]);
+							sh.scale[tid] = r; sh.s_ring[tid][t1 & (RING - 1)] = r;
+							if (pt == 0) p.rho[n + 1] = r;
+						}
+					} else {
+						const bool tail = t + 1 == len;
+						const double kp = tail ? 0.0 : sh.scale[tid] + p.Mmax;
+						sh.kap[tid] = kp; sh.s_ring[tid][t & (RING - 1)] = kp;
+						sh.g_ring[tid][t & (RING - 1)] = tail ? 0.0 : kp + log((double)sh.vsum[tid]);
+					}
+				}
+			}
+			__syncthreads();
+			// ---------------------------------------------------------------- phase C (backward): posteriors of frame t
+			if (BWD) {
+#pragma unroll
+				for (int i = 0; i < 2; i++) {
+					const uint32_t u = warp * 2 + i, len = sh.len[u];
+					if (t >= len || !y_ok) continue;
+					const size_t n = (size_t)sh.off[u] + t;
+					const uint32_t lab = p.node_lab[n], dmax = min(t + 1, D);
+					const double kz = sh.kap[u] - sh.lz[u];
+					for (uint32_t d = 1; d <= D; d++) {
+						const uint32_t col = (d - 1) * P + y;
+						float dm = 0.0f;
+						if (d <= dmax) {
+							float lr = p.S[n * Lp + col] + lcur[i];
+							if (d <= t) lr += (float)(p.rho[n - d] + p.Mmax + kz) + p.LG[(n - d) * Pp + y];
+							else lr += (float)kz;
+							dm = ((lab == col) ? 1.0f : 0.0f) - expf(lr);
+						}
+						p.Dm[n * Lp + col] = dm;
+					}
+				}
+			}
+		}
+	}
+}
+
+int nodur_max_groups(uint32_t P) {
+	int dev = 0, sms = 0, per_sm = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t smem = nodur_smem_bytes(P);
+	if (cudaFuncSetAttribute(nodur_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+	if (cudaFuncSetAttribute(nodur_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nodur_dp_kernel<true>, NTHR, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return 0; }
+	const uint32_t npt = (P + PT - 1) / PT;
+	return (int)((uint32_t)(sms * per_sm) / npt);
+}
+
+cudaError_t launch_nodur_dp(bool backward, const NodurParams& p, cudaStream_t s) {
+	if (!p.n_groups) return cudaSuccess;
+	const size_t smem = nodur_smem_bytes(p.P);
+	cudaError_t e = cudaMemsetAsync(p.ctr, 0, sizeof(uint32_t) * p.n_groups, s);
+	if (e != cudaSuccess) return e;
+	NodurParams q = p;
+	void* args[] = {&q};
+	const void* fn = backward ? (const void*)nodur_dp_kernel<true> : (const void*)nodur_dp_kernel<false>;
+	return cudaLaunchCooperativeKernel(fn, dim3(p.n_groups * p.npt), dim3(NTHR), args, smem, s);
+}
+
+}  // namespace crfgpu

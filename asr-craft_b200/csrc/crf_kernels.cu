@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256) empirical_kernel(EmpiricalParams p) {
 			if (p.use_state_bias) acc += lam[p.nSf] * p.state_bias_val;
 			const uint32_t pl = p.prev_lab[n];
 			if (pl != LAB_BAD && pl < p.L && p.use_trans_bias) {
-				const uint32_t ti = p.tidx[(uint64_t)pl * p.L + lab];
+				const uint32_t ti = (p.tL == p.L) ? p.tidx[(uint64_t)pl * p.L + lab] : p.tidx[(uint64_t)(pl % p.P) * p.tL + lab % p.P];
 				if (ti != 0xffffffffu) {
 					acc += p.lambda[ti] * p.trans_bias_val;
 					atomicAdd(&p.grad[ti], p.trans_bias_val);

@@ -139,9 +139,33 @@ struct ScoreTmaParams {
 	const float* bias;                // [D*P] or nullptr
 	float* C; uint32_t ldc;           // S[M][ldc], column (d*P + y)
 	uint32_t M, P, K, D, n_chunks, ntile;
+	uint32_t shared_w;                // 1: every duration block uses the same weight tiles / bias (labels = phones, stdseg_no_dur*)
 	float* smaxd;                     // [M][D] per-duration row maxima (-inf where d > t) or nullptr; needs ntile == 1
 	const uint32_t* frame_t;
 };
+// ---- native stdseg_no_dur* lattice recursions, O(P^2 + D*P) per frame (crf_dp_nodur.cu) ---------------------------
+constexpr int NODUR_UT = 16;          // utterances that advance in lock-step per group of CTAs
+struct NodurParams {
+	uint32_t P, Pp, D;            // phones, row stride of the P-wide arrays, durations
+	uint64_t Lp;                  // row stride of S / Dm ([N][Lp], column (d-1)*P + y)
+	uint32_t n_groups, npt;       // lock-step groups, CTAs (32-phone tiles) per group
+	const uint32_t* grp_off;      // [n_groups+1] batches of each group
+	const uint32_t* batch_utt;    // [n_batches][NODUR_UT] utterance ids or LAB_BAD
+	const uint32_t* off;          // [n_utt+1]
+	const float* S; const float* smaxd;   // [N][Lp] state scores, [N][D] their per-duration maxima (-inf where d > t+1)
+	const float* E; const float* ET;      // [P][Pp] exp(M - Mmax) and its transpose
+	double Mmax;
+	float* A; float* LG; double* rho;     // forward: a_t [N][Pp], log(a_t E) [N][Pp], scale rho_t [N]
+	double* logZ;                         // [n_utt]
+	float* LB; float* R; float* Dm;       // backward: log(E bh_t) [N][Pp], Xi right factors [N][Pp], [ref] - gamma [N][Lp]
+	const uint32_t* node_lab;             // [N] (dur-1)*P + phone where a reference segment ends, else LAB_BAD
+	float* xch;                           // [n_groups][2][(Pk + npt) * NODUR_UT] exchange buffers, Pk = P rounded up to 32
+	uint32_t* ctr;                        // [n_groups] barrier counters
+};
+size_t nodur_smem_bytes(uint32_t P);
+int nodur_max_groups(uint32_t P);         // co-resident groups of ceil(P/32) CTAs (0: the phone count does not fit)
+cudaError_t launch_nodur_dp(bool backward, const NodurParams& p, cudaStream_t s);
+
 // Frame-reduction GEMMs (both operands [frames][columns], TMA-fed; one launch covers every duration block d):
 //   state gradient  out[row_idx[d*P+y] + j]      += (j == ones_col ? ones_scale : scale) * sum_n X[n][d][j]  * Dm[n][d*P+y]
 //   Xi              out[pair_idx[q*L + d*P+y]]    += scale * Ew[q][d*P+y]                 * sum_n A[n-d-1][q] * R[n][d*P+y]
@@ -175,6 +199,7 @@ struct EmpiricalParams {
 	const uint32_t* prev_lab;         // [N] label of the previous reference segment or LAB_BAD
 	const uint32_t* frame_utt;        // [N] utterance of the frame
 	uint32_t N, L, P;
+	uint32_t tL;                      // side of the transition index table: L, or P when labels fold to phones (native stdseg_no_dur*)
 	const double* lambda;
 	const uint32_t* sidx; const uint32_t* tidx;
 	int use_state_bias, use_trans_bias;

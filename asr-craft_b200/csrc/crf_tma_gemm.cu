@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tma_kernel(const __grid_
 		}
 	} else {
 		if (lane == 0) {
-			const unsigned char* src = p.Bt + ((uint64_t)(d * p.ntile + jt) * n_chunks) * (2 * B_TILE);
+			const unsigned char* src = p.Bt + ((uint64_t)((p.shared_w ? 0u : d) * p.ntile + jt) * n_chunks) * (2 * B_TILE);
 			for (uint32_t c = 0; c < n_chunks; c++) {
 				const uint32_t s = c % OS;
 				if (c >= OS) mbar_wait(&ctl->op_empty[s], ((c / OS) - 1) & 1);
@@ -198,9 +198,9 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tma_kernel(const __grid_
 		tc_fence_before();
 		__syncwarp();
 		const uint32_t y0 = jt * BN, ncol = min((uint32_t)BN, p.P - y0);
-		const uint32_t col0 = d * p.P + y0;
-		const float b0 = (p.bias && lane < ncol) ? __ldg(p.bias + col0 + lane) : 0.0f;
-		const float b1 = (p.bias && lane + 32 < ncol) ? __ldg(p.bias + col0 + lane + 32) : 0.0f;
+		const uint32_t col0 = d * p.P + y0, bcol = (p.shared_w ? 0u : d * p.P) + y0;
+		const float b0 = (p.bias && lane < ncol) ? __ldg(p.bias + bcol + lane) : 0.0f;
+		const float b1 = (p.bias && lane + 32 < ncol) ? __ldg(p.bias + bcol + lane + 32) : 0.0f;
 		for (uint32_t rr = 0; rr < 32; rr++) {
 			const uint32_t rloc = warp * 32 + rr, gm = m0 + rloc;
 			if (gm >= p.M) break;

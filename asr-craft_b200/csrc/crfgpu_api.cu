@@ -66,6 +66,10 @@ struct crfgpu_ctx {
 	// expansion with tied weights (same recursions as stdseg; the reference's own stdseg run with tied lambda gives the
 	// identical logZ / numerators)
 	uint32_t Lt = 0; bool tied = false;
+	// native O(P^2 + D*P) recursion for the same models (crf_dp_nodur.cu): score / posterior columns are (duration, phone), the
+	// transition tables and forward/backward vectors are P wide
+	bool nodur = false; uint32_t Pp = 0; int opt_nodur_impl = 0; int nodur_groups_max = 0; uint32_t n_nodur_groups = 0;
+	DevBuf d_nd_grp, d_nd_batch, d_nd_xch, d_nd_ctr, d_LB;
 	std::vector<uint32_t> t_sidx, t_tidx;   // lambda indices of the lattice labels / label pairs
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
@@ -122,7 +126,7 @@ void check_kernel(crfgpu_ctx* h, int n_launches) {
 // Which paths the device implements for this geometry (anything else fails loudly, never emulated).
 void classify(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
-	h->train_ok = h->decode_ok = true;
+	h->train_ok = h->decode_ok = true; h->tied = h->nodur = false;
 	if (c.use_trans_ftrs) {
 		h->train_ok = h->decode_ok = false;
 		h->train_why = h->decode_why = "transition FEATURES (crf_featuremap=stdtrans) are not implemented on the device yet; "
@@ -143,17 +147,53 @@ void classify(crfgpu_ctx* h) {
 		}
 		if (c.n_states != 1 && c.max_dur != 1) {
 			h->train_ok = false; h->train_why = "forward-backward for N-state segmental models (CRF_StdSegNStateNode*) is not implemented on the device yet";
-		} else if (c.n_states == 1 && (uint64_t)c.n_labs * c.max_dur > 1024) {
-			h->train_ok = false; h->train_why = "forward-backward for stdseg_no_dur* runs on the (duration, phone) expansion, which supports phones * max_dur <= 1024";
+		} else if (c.n_states == 1 && c.max_dur > 1) {
+			// two device paths: the tied (duration, phone) expansion on the dense stdseg kernels (phones * max_dur <= 1024) and the
+			// native O(P^2 + D*P) recursion (any phone count whose matrix slices fit the shared memory of one group of CTAs)
+			const bool tied_ok = (uint64_t)c.n_labs * c.max_dur <= 1024 && c.max_dur <= 32;
+			h->nodur_groups_max = c.max_dur <= 31 ? nodur_max_groups(c.n_labs) : 0;
+			const bool native_ok = h->nodur_groups_max >= 1;
+			if (h->opt_nodur_impl == 1 ? native_ok : (h->opt_nodur_impl == 2 ? false : (!tied_ok && native_ok))) h->nodur = true;
+			else if (tied_ok && h->opt_nodur_impl != 1) h->tied = true;
+			else {
+				h->train_ok = false;
+				h->train_why = "forward-backward for stdseg_no_dur*: the tied (duration, phone) expansion needs phones * max_dur <= 1024, the native "
+				               "recursion max_dur <= 31 and a phone count whose 32-column matrix slices fit shared memory (about 1050 phones)";
+			}
 		}
 	} else {
 		h->train_ok = h->decode_ok = false;
 		h->train_why = h->decode_why = "unknown model type";
 	}
-	if (h->train_ok && c.n_labs > 1024) { h->train_ok = false; h->train_why = "dense lattice kernels support crf_label_size <= 1024"; }
-	if (h->train_ok && c.model_type != CRFGPU_STDFRAME && c.model_type != CRFGPU_STDSEG && c.n_states == 1 && c.max_dur > 1) h->tied = true;
+	if (h->train_ok && !h->nodur && c.n_labs > 1024) { h->train_ok = false; h->train_why = "dense lattice kernels support crf_label_size <= 1024"; }
 	if (h->decode_ok && (c.n_labs > 1024 || c.max_dur > 255)) { h->decode_ok = false; h->decode_why = "Viterbi kernel supports crf_label_size <= 1024 and max duration <= 255"; }
 	if (h->train_ok && c.max_dur > 32) { h->train_ok = false; h->train_why = "lattice kernels support label_maximum_duration <= 32"; }
+}
+
+// lattice label space of the handle (depends on the no_dur implementation chosen by classify) and its lambda index tables
+void setup_label_space(crfgpu_ctx* h) {
+	classify(h);
+	const uint32_t L0 = h->lay.L, Dd = h->cfg.max_dur;
+	h->Lt = (h->tied || h->nodur) ? L0 * Dd : L0;
+	h->Lp = (h->Lt + 31) / 32 * 32;
+	h->Pp = (L0 + 31) / 32 * 32;
+	if (h->nodur) {
+		h->t_sidx.resize(h->Lt);
+		for (uint32_t q = 0; q < h->Lt; q++) h->t_sidx[q] = h->lay.sidx[q % L0];
+		h->t_tidx = h->lay.tidx;                     // P x P
+	} else if (!h->tied) { h->t_sidx = h->lay.sidx; h->t_tidx = h->lay.tidx; }
+	else {
+		h->t_sidx.resize(h->Lt); h->t_tidx.resize((size_t)h->Lt * h->Lt);
+		for (uint32_t q = 0; q < h->Lt; q++) {
+			h->t_sidx[q] = h->lay.sidx[q % L0];
+			for (uint32_t cl = 0; cl < h->Lt; cl++) h->t_tidx[(size_t)q * h->Lt + cl] = h->lay.tidx[(size_t)(q % L0) * L0 + cl % L0];
+		}
+	}
+	h->have_lambda = false; h->fwdbwd_done = false;
+	if (h->stream) {
+		upload(h->d_sidx, h->t_sidx, h->stream); upload(h->d_tidx, h->t_tidx, h->stream);
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+	}
 }
 
 void require_train(crfgpu_ctx* h) {
@@ -190,33 +230,36 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 	h->Mmax = Mmax;
 
 	if (h->train_ok) {
-		// tables over the lattice labels (for tied models label (d,y) reads the weights of phone y)
-		std::vector<float> Ws((size_t)Lt * std::max(nSf, 1u)), bias(Lt, 0.0f), E((size_t)Lt * Lp, 0.0f), ET((size_t)Lt * Lp, 0.0f);
+		// tables over the lattice labels (for tied models label (d,y) reads the weights of phone y; the native no_dur path keeps
+		// P-wide tables and shares them between the duration blocks)
+		const uint32_t Le = h->nodur ? L : Lt, Lpe = h->nodur ? h->Pp : Lp;
+		std::vector<float> Ws((size_t)Le * std::max(nSf, 1u)), bias(Le, 0.0f), E((size_t)Le * Lpe, 0.0f), ET((size_t)Le * Lpe, 0.0f);
 		double tmax = -DBL_MAX;
-		for (uint32_t q = 0; q < Lt; q++)
-			for (uint32_t cl = 0; cl < Lt; cl++) {
-				const uint32_t ti = h->t_tidx[(size_t)q * Lt + cl];
+		for (uint32_t q = 0; q < Le; q++)
+			for (uint32_t cl = 0; cl < Le; cl++) {
+				const uint32_t ti = h->t_tidx[(size_t)q * Le + cl];
 				if (ti != CRFGPU_NO_IDX) tmax = std::max(tmax, c.use_trans_bias ? lam[ti] * c.trans_bias_val : 0.0);
 			}
 		if (tmax == -DBL_MAX) tmax = 0.0;
 		h->Mmax = tmax;
-		for (uint32_t cl = 0; cl < Lt; cl++) {
+		for (uint32_t cl = 0; cl < Le; cl++) {
 			const double* w = lam + h->t_sidx[cl];
 			for (uint32_t f = 0; f < nSf; f++) Ws[(size_t)cl * nSf + f] = (float)w[f];
 			if (c.use_state_bias) bias[cl] = (float)(w[nSf] * c.state_bias_val);
 		}
-		for (uint32_t q = 0; q < Lt; q++)
-			for (uint32_t cl = 0; cl < Lt; cl++) {
-				const uint32_t ti = h->t_tidx[(size_t)q * Lt + cl];
+		for (uint32_t q = 0; q < Le; q++)
+			for (uint32_t cl = 0; cl < Le; cl++) {
+				const uint32_t ti = h->t_tidx[(size_t)q * Le + cl];
 				if (ti != CRFGPU_NO_IDX) {
 					const float e = (float)std::exp((c.use_trans_bias ? lam[ti] * c.trans_bias_val : 0.0) - tmax);
-					E[(size_t)q * Lp + cl] = e; ET[(size_t)cl * Lp + q] = e;
+					E[(size_t)q * Lpe + cl] = e; ET[(size_t)cl * Lpe + q] = e;
 				}
 			}
 		upload(h->d_Ws, Ws, s); upload(h->d_bias, bias, s); upload(h->d_E, E, s); upload(h->d_ET, ET, s);
 		std::vector<unsigned char> tiles;
 		if (c.max_dur > 1 && nSf > 0) {   // bf16 hi/lo UMMA tiles of the state weights for the TMA-fed score GEMM
-			split_weight_tiles(Ws.data(), Lt / c.max_dur, c.max_dur, nSf, &tiles);
+			if (h->nodur) split_weight_tiles(Ws.data(), L, 1, nSf, &tiles);
+			else split_weight_tiles(Ws.data(), Lt / c.max_dur, c.max_dur, nSf, &tiles);
 			upload(h->d_Wt, tiles, s);
 		}
 		CUDA_OK(cudaStreamSynchronize(s));   // host vectors die at scope exit
@@ -284,7 +327,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 				prev_lab[off[u] + t] = last;
 				if (rec[4 * (size_t)t] != CRFGPU_LAB_BAD) {
 					const uint32_t dur = rec[4 * (size_t)t + 2] - rec[4 * (size_t)t + 1] + 1;
-					const uint32_t lab = (c.model_type == CRFGPU_STDSEG || h->tied) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
+					const uint32_t lab = (c.model_type == CRFGPU_STDSEG || h->tied || h->nodur) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
 					node_lab[off[u] + t] = lab; last = lab;
 				}
 			}
@@ -325,7 +368,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
 		upload(h->d_cl_off, cl_off, s); upload(h->d_cl_list, cl_list, s);
 	};
-	if (h->train_ok && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
+	if (h->train_ok && !h->nodur && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
 		// tensor-core cluster kernels: 16 slots per cluster
 		TcDpPlan plan{};
 		if (plan_tc_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
@@ -340,7 +383,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 		}
 	}
-	if (h->train_ok && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
+	if (h->train_ok && !h->nodur && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
 		ClusterPlan plan{};
 		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
 		if (plan_cluster_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan, cap)) {
@@ -363,6 +406,28 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 				h->d_xmax.ensure(sizeof(float) * (size_t)ncl * 2 * plan.CS * plan.UB + 16);
 			}
 		}
+	}
+	std::vector<uint32_t> nd_grp, nd_batch;
+	if (h->train_ok && h->nodur && labs && n_utt) {
+		// native no_dur recursion: batches of NODUR_UT utterances of similar length advance in lock-step; batches are dealt
+		// (longest first) to the least loaded of the co-resident CTA groups
+		const uint32_t nb = (n_utt + NODUR_UT - 1) / NODUR_UT;
+		const uint32_t ng = std::min<uint32_t>((uint32_t)h->nodur_groups_max, nb);
+		std::vector<std::vector<uint32_t>> lists(ng);
+		std::vector<uint64_t> load(ng, 0);
+		for (uint32_t b = 0; b < nb; b++) {
+			const uint32_t u0 = order[(size_t)b * NODUR_UT];
+			const uint32_t k = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+			lists[k].push_back(b); load[k] += off[u0 + 1] - off[u0];
+		}
+		nd_grp.assign(1, 0);
+		for (auto& l : lists) {
+			for (uint32_t b : l)
+				for (uint32_t i = 0; i < NODUR_UT; i++) nd_batch.push_back((size_t)b * NODUR_UT + i < n_utt ? order[(size_t)b * NODUR_UT + i] : CRFGPU_LAB_BAD);
+			nd_grp.push_back((uint32_t)(nd_batch.size() / NODUR_UT));
+		}
+		h->n_nodur_groups = ng;
+		upload(h->d_nd_grp, nd_grp, s); upload(h->d_nd_batch, nd_batch, s);
 	}
 	CUDA_OK(cudaStreamSynchronize(s));   // host staging vectors die here
 
@@ -413,9 +478,14 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	const uint32_t N = h->N, L = h->Lt, Lp = h->Lp, D = c.max_dur, P = L / D, nSf = m.nSf;
 	cudaStream_t s = h->stream;
 	const size_t NL = (size_t)N * Lp;
-	h->d_S.ensure(sizeof(float) * NL + 16); h->d_A.ensure(sizeof(float) * NL + 16); h->d_G.ensure(sizeof(float) * NL + 16);
-	h->d_Dm.ensure(sizeof(float) * NL + 16); h->d_R.ensure(sizeof(float) * NL + 16);
-	if (h->opt_keep_lattice) h->d_Uvec.ensure(sizeof(float) * NL + 16);
+	const size_t NV = h->nodur ? (size_t)N * h->Pp : NL;         // forward/backward vectors: P wide on the native no_dur path
+	h->d_S.ensure(sizeof(float) * NL + 16); h->d_A.ensure(sizeof(float) * NV + 16); h->d_G.ensure(sizeof(float) * NV + 16);
+	h->d_Dm.ensure(sizeof(float) * NL + 16); h->d_R.ensure(sizeof(float) * (NV + (h->nodur ? h->Pp : 0)) + 16);
+	if (h->nodur) h->d_LB.ensure(sizeof(float) * NV + 16);
+	if (h->opt_keep_lattice) {
+		if (h->nodur) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "keep_lattice / crfgpu_fetch_alpha_beta is not implemented for the native stdseg_no_dur* recursion");
+		h->d_Uvec.ensure(sizeof(float) * NL + 16);
+	}
 	h->d_m.ensure(sizeof(double) * (size_t)N + 16); h->d_kappa.ensure(sizeof(double) * (size_t)N + 16); h->d_bbase.ensure(sizeof(double) * (size_t)N + 16);
 	h->d_logZ.ensure(sizeof(double) * (size_t)h->n_utt + 16); h->d_numer.ensure(sizeof(double) * (size_t)h->n_utt + 16);
 	h->d_grad.ensure(sizeof(double) * ((size_t)m.len + 4) + 16);
@@ -432,15 +502,16 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		ScoreTmaParams g{};
 		g.Bt = h->d_Wt.as<unsigned char>(); g.bias = h->d_bias.as<float>(); g.C = h->d_S.as<float>(); g.ldc = Lp;
 		g.M = N; g.P = P; g.K = nSf; g.D = D; g.n_chunks = score_tma_chunks(nSf); g.ntile = (P + 63) / 64;
-		g.frame_t = h->d_frame_t.as<uint32_t>();
-		if (h->tc_ok && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
+		g.frame_t = h->d_frame_t.as<uint32_t>(); g.shared_w = h->nodur ? 1u : 0u;
+		if ((h->tc_ok || h->nodur) && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
 		CUDA_OK(launch_score_gemm_tma(h->X() + c.state_fidx_start, h->Wp, g, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
 		ScoreGemmParams g{};
 		g.A = h->X() + (size_t)d * h->Wp + c.state_fidx_start; g.lda = h->ldx();
-		g.B = h->d_Ws.as<float>() + (size_t)d * P * nSf; g.ldb = nSf;   // the lattice label (d,y) has its own row of the device tables (tied models repeat phone y's weights)
-		g.bias = h->d_bias.as<float>() + (size_t)d * P;
+		// the lattice label (d,y) has its own row of the device tables (tied models repeat phone y's weights; the native no_dur path shares P rows)
+		g.B = h->d_Ws.as<float>() + (h->nodur ? 0 : (size_t)d * P * nSf); g.ldb = nSf;
+		g.bias = h->d_bias.as<float>() + (h->nodur ? 0 : (size_t)d * P);
 		g.C = h->d_S.as<float>() + (size_t)d * P; g.ldc = Lp;
 		g.M = N; g.Ncols = P; g.K = nSf;
 		if (h->opt_gemm_impl >= 1) CUDA_OK(launch_score_gemm_tc(g, s)); else launch_score_gemm(g, s);
@@ -449,7 +520,26 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	phase_end(h, "score");
 
 	DpParams p = dp_params(h);
-	if (h->tc_ok) {
+	if (h->nodur) {
+		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
+		const uint32_t npt = (P + 31) / 32, Pk = npt * 32;
+		h->d_nd_xch.ensure(sizeof(float) * (size_t)h->n_nodur_groups * 2 * ((size_t)Pk + npt) * NODUR_UT + 16);
+		h->d_nd_ctr.ensure(sizeof(uint32_t) * (size_t)h->n_nodur_groups + 16);
+		NodurParams q{};
+		q.P = P; q.Pp = h->Pp; q.D = D; q.Lp = Lp; q.n_groups = h->n_nodur_groups; q.npt = npt;
+		q.grp_off = h->d_nd_grp.as<uint32_t>(); q.batch_utt = h->d_nd_batch.as<uint32_t>(); q.off = h->d_off.as<uint32_t>();
+		q.S = h->d_S.as<float>(); q.smaxd = h->d_smaxd.as<float>(); q.E = h->d_E.as<float>(); q.ET = h->d_ET.as<float>(); q.Mmax = h->Mmax;
+		q.A = h->d_A.as<float>(); q.LG = h->d_G.as<float>(); q.rho = h->d_m.as<double>(); q.logZ = h->d_logZ.as<double>();
+		q.LB = h->d_LB.as<float>(); q.R = h->d_R.as<float>(); q.Dm = h->d_Dm.as<float>(); q.node_lab = h->d_node_lab.as<uint32_t>();
+		q.xch = h->d_nd_xch.as<float>(); q.ctr = h->d_nd_ctr.as<uint32_t>();
+		phase_begin(h, "forward");
+		if (!smax_done) { launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1); }
+		CUDA_OK(launch_nodur_dp(false, q, s)); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		CUDA_OK(launch_nodur_dp(true, q, s)); check_kernel(h, 1);
+		phase_end(h, "backward");
+	} else if (h->tc_ok) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
 		TcDpParams tp{};
 		static_cast<DpParams&>(tp) = p;
@@ -499,8 +589,19 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 
 	// K4: expected-minus-empirical counts as two families of reduce-GEMMs
 	phase_begin(h, "xi");
-	const bool lat_tma = h->opt_gemm_impl == 2 && lattice_tma_eligible(h->d_A.as<float>(), Lp) && lattice_tma_eligible(h->d_R.as<float>(), Lp) &&
+	const uint32_t Lv = h->nodur ? h->Pp : Lp;                  // row stride of the forward / right-factor vectors
+	const bool lat_tma = h->opt_gemm_impl == 2 && lattice_tma_eligible(h->d_A.as<float>(), Lv) && lattice_tma_eligible(h->d_R.as<float>(), Lv) &&
 	                     lattice_tma_eligible(h->d_Dm.as<float>(), Lp);
+	if (h->nodur && !(lat_tma && tma)) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the native stdseg_no_dur* path needs the TMA-fed gradient kernels (gemm_impl 2)");
+	if (h->nodur) {
+		if (c.use_trans_bias && N > 1) {
+			// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: one duration block of P columns with row shift 1
+			FrameGemmParams x{};
+			x.N = N; x.P = P; x.D = 1; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = P; x.ones_col = 0xffffffffu;
+			x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = P; x.Ew = h->d_E.as<float>(); x.e_ld = h->Pp; x.out = h->d_grad.as<double>();
+			CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), h->Pp, x, s)); check_kernel(h, 1);
+		}
+	} else
 	if (c.use_trans_bias && lat_tma && (h->opt_tma_mask & 4) && N > 1) {
 		FrameGemmParams x{};
 		x.N = N; x.P = P; x.D = D; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = L; x.ones_col = 0xffffffffu;
@@ -551,7 +652,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	EmpiricalParams e{};
 	e.X = h->X(); e.ldx = h->ldx(); e.W = h->Wp; e.sf0 = c.state_fidx_start; e.nSf = nSf;
 	e.node_lab = h->d_node_lab.as<uint32_t>(); e.prev_lab = h->d_prev_lab.as<uint32_t>(); e.frame_utt = h->d_frame_utt.as<uint32_t>();
-	e.N = N; e.L = L; e.P = P; e.lambda = h->d_lambda.as<double>(); e.sidx = h->d_sidx.as<uint32_t>(); e.tidx = h->d_tidx.as<uint32_t>();
+	e.N = N; e.L = L; e.P = P; e.tL = h->nodur ? P : L; e.lambda = h->d_lambda.as<double>(); e.sidx = h->d_sidx.as<uint32_t>(); e.tidx = h->d_tidx.as<uint32_t>();
 	e.use_state_bias = c.use_state_bias; e.use_trans_bias = c.use_trans_bias;
 	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
 	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
@@ -628,23 +729,9 @@ int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
 		// 1.83 + 3.56 -- padding helps the K-major reader and hurts the MN-major one, so the windows stay packed
 		h->Wp = cfg->max_dur > 1 ? (h->W + 3) / 4 * 4 : h->W;   // 16-byte window rows: TMA-addressable (max_dur == 1 aliases the base stream)
 		if (cfg->max_dur == 0) throw ApiError(CRFGPU_ERR_ARG, "the maximum duration of labels must be larger than 0");
-		classify(h);
-		{
-			const uint32_t L0 = h->lay.L, Dd = cfg->max_dur;
-			h->Lt = h->tied ? L0 * Dd : L0;
-			h->Lp = (h->Lt + 31) / 32 * 32;
-			if (!h->tied) { h->t_sidx = h->lay.sidx; h->t_tidx = h->lay.tidx; }
-			else {
-				h->t_sidx.resize(h->Lt); h->t_tidx.resize((size_t)h->Lt * h->Lt);
-				for (uint32_t q = 0; q < h->Lt; q++) {
-					h->t_sidx[q] = h->lay.sidx[q % L0];
-					for (uint32_t cl = 0; cl < h->Lt; cl++) h->t_tidx[(size_t)q * h->Lt + cl] = h->lay.tidx[(size_t)(q % L0) * L0 + cl % L0];
-				}
-			}
-		}
-		CUDA_OK(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 		CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-		upload(h->d_sidx, h->t_sidx, h->stream); upload(h->d_tidx, h->t_tidx, h->stream);
+		setup_label_space(h);
+		CUDA_OK(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 		std::vector<uint32_t> steps = sample_steps(cfg->max_dur);
 		upload(h->d_steps, steps, h->stream);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -664,7 +751,8 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
-	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd};
+	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
+	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(h->stream);
@@ -832,6 +920,10 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
 		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16, register-staged; 2: + TMA-fed window GEMMs
+		else if (n == "nodur_impl") {                                    // stdseg_no_dur* lattice: 0 auto, 1 native O(P^2 + D*P), 2 tied (duration, phone) expansion
+			h->opt_nodur_impl = (int)value;
+			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
+		}
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }
 		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }

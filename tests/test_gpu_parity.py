@@ -75,6 +75,35 @@ def test_fwdbwd_nodur_matches_reference_golden(name, impl):
     m.close()
 
 
+@pytest.mark.parametrize("name", sorted(NODUR))
+def test_fwdbwd_nodur_native_matches_reference_golden(name):
+    """The same goldens through the native O(P^2 + D*P) recursion (crf_dp_nodur.cu), which is what large phone sets run on."""
+    c = NODUR[name]
+    m = gpu(c["cfg"])
+    m.set_option("nodur_impl", 1)
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    m.close()
+
+
+@pytest.mark.parametrize("P,D,F,n_utt,t_lo,t_hi,scale", [(48, 10, 12, 40, 5, 90, 0.05), (200, 12, 16, 21, 30, 70, 0.02), (1024, 30, 8, 3, 20, 45, 0.01)])
+def test_fwdbwd_nodur_native_matches_oracle_fresh(oracle, P, D, F, n_utt, t_lo, t_hi, scale):
+    """stdseg_no_dur_no_segtransftr up to the cfg5 geometry (1024 phones, maxDur 30) against the oracle's native restatement;
+    several lock-step batches per group, ragged lengths, phone counts that are not multiples of the 32-phone tiles."""
+    rng = np.random.default_rng(P + D)
+    off, ftrs, labs = synth_batch(rng, n_utt, t_lo, t_hi, F, P, 1, D + 3)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
+    lam = rng.uniform(-scale, scale, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=8)
+    m = gpu(cfg)
+    m.set_option("nodur_impl", 1)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, f"P={P} D={D}")
+    m.close()
+
+
 def test_toy_known_answers_on_gpu():
     c = TRAIN["toy_stdframe"]
     m = gpu(c["cfg"])
