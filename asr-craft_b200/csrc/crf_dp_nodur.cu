@@ -36,6 +36,7 @@ namespace crfgpu {
 namespace {
 
 constexpr int UT = NODUR_UT, PT = 32, NTHR = 256, NW = NTHR / 32, RING = 32;
+constexpr uint32_t DC = 8;          // durations whose loads are in flight together
 static_assert(UT == 16 && NW * 2 == UT, "thread mapping: warp w owns utterances 2w, 2w+1 of the batch");
 
 struct Shared {
@@ -134,6 +135,8 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 				__syncthreads();
 			}
 			// ---------------------------------------------------------------- phase A: my slice of the new vector
+			// the D terms of an entry are independent: their loads are issued DC at a time before any is used, so a (utterance, phone)
+			// entry costs ceil(D / DC) round trips to L2 / HBM instead of D
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
 				const uint32_t u = warp * 2 + i, len = sh.len[u];
@@ -143,11 +146,21 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					if (t < len && y_ok) {
 						const double rt = sh.scale[u];
 						const uint32_t dmax = min(t + 1, D);
-						for (uint32_t d = 1; d <= dmax; d++) {
-							float lr = p.S[n * Lp + (size_t)(d - 1) * P + y];
-							if (d <= t) lr += (float)(sh.s_ring[u][(t - d) & (RING - 1)] + p.Mmax - rt) + p.LG[(n - d) * Pp + y];
-							else lr += (float)(-rt);
-							acc += expf(lr);
+						for (uint32_t d0 = 1; d0 <= dmax; d0 += DC) {
+							float sv[DC], lv[DC];
+#pragma unroll
+							for (uint32_t j = 0; j < DC; j++) {
+								const uint32_t d = d0 + j;
+								sv[j] = d <= dmax ? __ldg(p.S + n * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
+								lv[j] = (d <= dmax && d <= t) ? p.LG[(n - d) * Pp + y] : 0.0f;
+							}
+#pragma unroll
+							for (uint32_t j = 0; j < DC; j++) {
+								const uint32_t d = d0 + j;
+								if (d > dmax) continue;
+								const float sc = (d <= t) ? (float)(sh.s_ring[u][(t - d) & (RING - 1)] + p.Mmax - rt) : (float)(-rt);
+								acc += expf(sv[j] + lv[j] + sc);
+							}
 						}
 						p.A[n * Pp + y] = acc;
 					}
@@ -155,8 +168,21 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					if (t + 1 < len && y_ok) {
 						const double sg = sh.scale[u];
 						const uint32_t nn = min(len - 1 - t, D);
-						for (uint32_t d = 1; d <= nn; d++)
-							acc += expf(p.S[(n + d) * Lp + (size_t)(d - 1) * P + y] + p.LB[(n + d) * Pp + y] + (float)(sh.s_ring[u][(t + d) & (RING - 1)] - sg));
+						for (uint32_t d0 = 1; d0 <= nn; d0 += DC) {
+							float sv[DC], lv[DC];
+#pragma unroll
+							for (uint32_t j = 0; j < DC; j++) {
+								const uint32_t d = d0 + j;
+								sv[j] = d <= nn ? __ldg(p.S + (n + d) * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
+								lv[j] = d <= nn ? p.LB[(n + d) * Pp + y] : 0.0f;
+							}
+#pragma unroll
+							for (uint32_t j = 0; j < DC; j++) {
+								const uint32_t d = d0 + j;
+								if (d > nn) continue;
+								acc += expf(sv[j] + lv[j] + (float)(sh.s_ring[u][(t + d) & (RING - 1)] - sg));
+							}
+						}
 						// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: stored with the frame the new segment starts in (row shift 1 of the Xi GEMM)
 						p.R[(n + 1) * Pp + y] = acc * expf((float)(p.rho[n] + p.Mmax + sg - sh.lz[u]));
 					}
@@ -250,16 +276,23 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					const size_t n = (size_t)sh.off[u] + t;
 					const uint32_t lab = p.node_lab[n], dmax = min(t + 1, D);
 					const double kz = sh.kap[u] - sh.lz[u];
-					for (uint32_t d = 1; d <= D; d++) {
-						const uint32_t col = (d - 1) * P + y;
-						float dm = 0.0f;
-						if (d <= dmax) {
-							float lr = p.S[n * Lp + col] + lcur[i];
-							if (d <= t) lr += (float)(p.rho[n - d] + p.Mmax + kz) + p.LG[(n - d) * Pp + y];
-							else lr += (float)kz;
-							dm = ((lab == col) ? 1.0f : 0.0f) - expf(lr);
+					for (uint32_t d0 = 1; d0 <= D; d0 += DC) {
+						float sv[DC], lv[DC]; double rv[DC];
+#pragma unroll
+						for (uint32_t j = 0; j < DC; j++) {
+							const uint32_t d = d0 + j;
+							sv[j] = d <= dmax ? __ldg(p.S + n * Lp + (size_t)(d - 1) * P + y) : 0.0f;
+							lv[j] = (d <= dmax && d <= t) ? p.LG[(n - d) * Pp + y] : 0.0f;
+							rv[j] = (d <= dmax && d <= t) ? p.rho[n - d] + p.Mmax : 0.0;
 						}
-						p.Dm[n * Lp + col] = dm;
+#pragma unroll
+						for (uint32_t j = 0; j < DC; j++) {
+							const uint32_t d = d0 + j, col = (d - 1) * P + y;
+							if (d > D) continue;
+							float dm = 0.0f;
+							if (d <= dmax) dm = ((lab == col) ? 1.0f : 0.0f) - expf(sv[j] + lcur[i] + lv[j] + (float)(rv[j] + kz));
+							p.Dm[n * Lp + col] = dm;
+						}
 					}
 				}
 			}

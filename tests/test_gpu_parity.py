@@ -184,8 +184,9 @@ def test_viterbi_bit_exact_vs_reference_golden(name):
     m.close()
 
 
-@pytest.mark.parametrize("P,N,D,segf,F", [(61, 3, 1, 0, 105), (61, 1, 1, 0, 105), (48, 1, 10, 1, 12), (20, 3, 4, 1, 9)])
+@pytest.mark.parametrize("P,N,D,segf,F", [(61, 3, 1, 0, 105), (61, 1, 1, 0, 105), (48, 1, 10, 1, 12), (20, 3, 4, 1, 9), (1024, 1, 30, 1, 8)])
 def test_viterbi_bit_exact_vs_oracle_fresh(oracle, P, N, D, segf, F):
+    """the last case is the cfg5 geometry (1024 phones, maxDur 30)"""
     rng = np.random.default_rng(P * 100 + N * 10 + D)
     cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P * N, n_base_ftrs=F, n_states=N, max_dur=D,
                       extract_seg_ftrs=segf)
@@ -257,3 +258,59 @@ def test_size_independent_properties_full_cfg2_shape():
     g, n, z = m.fwdbwd(off, ftrs, labs)
     assert abs(g[sidx + 105].sum()) < bound
     assert np.all(n - z < 0)    # log-likelihood of the reference path is negative
+
+
+def _uniform_segment_stats(T, P, D):
+    """lambda = 0: log(number of labelled segmentations of T frames with segments <= D, P labels each) and the expected
+    number of segments under the uniform distribution over them (log-domain DP, O(T*D))."""
+    logz = np.full(T + 1, -np.inf)
+    logz[0] = 0.0
+    lp = np.log(float(P))
+    for t in range(1, T + 1):
+        prev = logz[max(0, t - D):t]
+        mx = prev.max()
+        logz[t] = lp + mx + np.log(np.exp(prev - mx).sum())
+    exp_segs = 0.0
+    for t in range(T):            # segment ending at frame t (inclusive) with duration d
+        d = np.arange(1, min(t + 1, D) + 1)
+        exp_segs += np.exp(lp + logz[t + 1 - d] + logz[T - 1 - t] - logz[T]).sum()
+    return logz[T], exp_segs
+
+
+def test_size_independent_properties_full_cfg5():
+    """BASELINE cfg5 at full size (64 utterances x 2000 frames, 1024 phones, maxDur 30, 542 segment features) on the native
+    no_dur recursion.  lambda = 0: logZ is the log-count of labelled segmentations, the state-bias gradient of phone y is
+    (#reference segments of y) - E[#segments]/P and the transition-bias gradients sum to (#ref transitions) - (E[#segments] -
+    #utterances), all from a host DP that needs no oracle.  Random lambda: sum of state-bias gradients - sum of transition-bias
+    gradients = 0 (#segments - #transitions = #utterances for the reference path and in expectation) and numerator < logZ."""
+    import workloads
+    P, D = 1024, 30
+    off, ftrs, labs = workloads.cfg5_batch()
+    cfg = crf_b200.make_config(**workloads.cfg5_kwargs())
+    m = crf_b200.CrfGpu(cfg)
+    n_utt, T = len(off) - 1, 2000
+    m.set_lambda(np.zeros(m.lambda_len))
+    g, n, z = m.fwdbwd(off, ftrs, labs)
+    logz, exp_segs = _uniform_segment_stats(T, P, D)
+    np.testing.assert_allclose(z, logz, rtol=1e-6)
+    assert np.all(n == 0)
+    sidx, tidx = m.index_maps()
+    nS = 8 * 64 + D
+    ref_cnt = np.zeros(P)
+    n_ref = 0
+    for u in range(n_utt):
+        r = m.group_labels(labs[off[u]:off[u + 1]])
+        ends = r[:, 0] != 0xffffffff
+        np.add.at(ref_cnt, r[ends, 0].astype(np.int64), 1.0)
+        n_ref += int(ends.sum())
+    bias = g[sidx + nS]
+    np.testing.assert_allclose(bias, ref_cnt - n_utt * exp_segs / P, atol=2e-2)
+    assert abs(bias.sum() - (n_ref - n_utt * exp_segs)) < 1e-4 * n_utt * exp_segs
+    tsum = g[tidx.reshape(-1)].sum()
+    assert abs(tsum - ((n_ref - n_utt) - (n_utt * exp_segs - n_utt))) < 1e-4 * n_utt * exp_segs
+    lam = workloads.lam_for("cfg5", m.lambda_len)
+    m.set_lambda(lam)
+    g, n, z = m.fwdbwd(off, ftrs, labs)
+    assert np.all(np.isfinite(z)) and np.all(n - z < 0)
+    assert abs(g[sidx + nS].sum() - g[tidx.reshape(-1)].sum() - 0.0) < 1e-4 * n_utt * exp_segs
+    m.close()

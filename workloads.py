@@ -87,6 +87,31 @@ def cfg3_batch(n_utt=1680):
     return off, _features(r5, phone)
 
 
+def cfg5_kwargs(n_phones=1024, max_dur=30, n_base_ftrs=64):
+    """stress: segmental CRF without duration labels, 1024 phones, maxDur 30, 8*64+30 = 542 segment features
+    (stdseg_no_dur_no_segtransftr: the stdseg transition table would be (P*D)^2 weights; dim(lambda) = 1024*(543+1024))."""
+    return dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=n_phones, n_base_ftrs=n_base_ftrs, max_dur=max_dur,
+                n_actual_labs=n_phones, extract_seg_ftrs=1)
+
+
+def cfg5_batch(n_utt=64, n_frames=2000, n_phones=1024, max_dur=30, n_base_ftrs=64):
+    """64 utterances x 2000 frames, reference segments dur ~ U{1..30} with no two adjacent phones equal, features U[0,1) (seed 8)."""
+    rng = np.random.default_rng(8)
+    off = (np.arange(n_utt + 1) * n_frames).astype(np.uint32)
+    ftrs = rng.random((n_utt * n_frames, n_base_ftrs), dtype=np.float32)
+    labs = np.empty(n_utt * n_frames, np.uint32)
+    for u in range(n_utt):
+        t, prev = 0, -1
+        while t < n_frames:
+            d = int(rng.integers(1, max_dur + 1))
+            lab = int(rng.integers(0, n_phones))
+            while lab == prev:
+                lab = int(rng.integers(0, n_phones))
+            labs[u * n_frames + t:u * n_frames + min(t + d, n_frames)] = lab
+            prev, t = lab, t + d
+    return off, ftrs, labs
+
+
 def lam_for(name, n):
-    seed, scale = {"cfg2": (3, 0.25), "cfg3": (6, 0.25), "cfg4": (7, 0.01)}[name]
+    seed, scale = {"cfg2": (3, 0.25), "cfg3": (6, 0.25), "cfg4": (7, 0.01), "cfg5": (8, 0.01)}[name]
     return np.random.default_rng(seed).uniform(-scale, scale, n)
