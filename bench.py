@@ -294,6 +294,29 @@ def run_ours(args):
                "frames_per_gpu": int(sub_off[-1])}
         vm.close()
 
+    # ---- stress leg (cfg5: 1024 phones, maxDur 30, 64 utterances x 2000 frames), one GPU, reported beside the headline ----
+    stress = None
+    if world == 1 and not args.no_stress:
+        soff, sftrs, slabs = workloads.cfg5_batch()
+        sm = crf_b200.CrfGpu(crf_b200.make_config(**workloads.cfg5_kwargs()), device=local)
+        sm.set_lambda(workloads.lam_for("cfg5", sm.lambda_len))
+        sm.stage(soff, sftrs, slabs)
+        best = None
+        for _ in range(3):
+            sm.fwdbwd_staged(); sm.synchronize()
+            ph = {k: sm.phase_ms(k) for k in phase_names}
+            best = ph if best is None or sum(ph.values()) < sum(best.values()) else best
+        sm.stage(soff, sftrs)
+        for _ in range(2):
+            sm.viterbi_staged(); sm.synchronize()
+        vs_, vr_ = sm.phase_ms("viterbi_score"), sm.phase_ms("viterbi")
+        sN = float(soff[-1])
+        stress = {"workload": "cfg5 (stdseg_no_dur_no_segtransftr, 1024 phones, maxDur 30, 542 segment features, 64 utterances x 2000 frames)",
+                  "train_frames_per_s": sN / (sum(best.values()) / 1e3), "train_phases_ms": best,
+                  "viterbi_frames_per_s": sN / ((vs_ + vr_) / 1e3), "viterbi_phases_ms": {"score": vs_, "recursion": vr_},
+                  "lambda_len": sm.lambda_len}
+        sm.close()
+
     if rank == 0:
         # per-frame ALGORITHMIC work of cfg4 (SURVEY.md 8d / DESIGN.md section 4).  Every phase sits below the tensor ridge
         # (1388 TFLOP/s / 6.55 TB/s = 212 flop/B): score and state-gradient GEMMs move 34 kB of window features per 1.04 Mflop
@@ -345,7 +368,7 @@ def run_ours(args):
                        "slots_per_cta_option": int(args.slots or 0)},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "steps": e2e_steps, "loglik_check": ll},
-            "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "viterbi": vit}
+            "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "viterbi": vit, "stress": stress}
         print(json.dumps(line))
     for pb in (pin_f, pin_l, pin_g, pin_n, pin_z):
         pb.free()
@@ -365,6 +388,7 @@ def main():
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--no-viterbi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stress", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -30,8 +30,8 @@ def main():
     lines.append("|---|" + "---|" * len(KEYS))
     for r in rows[2:]:
         name = r[ci["Kernel Name"]]
-        short = name.split("(")[0].replace("void ", "").replace("crfgpu::<unnamed>::", "").replace("crfgpu::", "")
-        short = short.replace("(bool)", "")
+        short = name.replace("void ", "").replace("crfgpu::", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "")
+        short = short.replace("(bool)", "").replace("(int)", "").split("(")[0]
         key = (short, r[ci.get("launch__grid_size", 0)])
         if key in seen:
             continue
