@@ -678,25 +678,50 @@ void launch_empirical(const EmpiricalParams& p, cudaStream_t s) {
 // add (no FMA), bias last, then negate and narrow to float
 // (CRF_StdFeatureMap.cpp:65-81; CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:143)
 // =================================================================================================
+// One CTA = VS_ROWS (frame, duration) windows x 256 labels: the windows are staged in shared memory and every weight is loaded
+// once per CTA and applied to all rows, so the kernel is bound by the fp64 pipe instead of by two loads per multiply-add.
+// The accumulation order of every output is unchanged (features in index order, bias last).
+constexpr int VS_ROWS = 8;
 __global__ void __launch_bounds__(256) vit_scores_kernel(VitScoreParams p) {
-	const uint64_t total = (uint64_t)p.N * p.D * p.L;
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-		const uint32_t lab = (uint32_t)(i % p.L);
-		const uint64_t nd = i / p.L;
-		const uint32_t d = (uint32_t)(nd % p.D); const uint64_t n = nd / p.D;
-		if (d > p.frame_t[n]) { p.negS[i] = 0.0f; continue; }
+	extern __shared__ __align__(16) float vs_x[];            // [VS_ROWS][nSf]
+	__shared__ uint32_t row_ok[VS_ROWS];
+	const uint64_t n_rows = (uint64_t)p.N * p.D, r0 = (uint64_t)blockIdx.x * VS_ROWS;
+	for (uint32_t i = 0; i < VS_ROWS; i++) {
+		const uint64_t nd = r0 + i;
+		bool ok = nd < n_rows;
+		uint64_t n = 0; uint32_t d = 0;
+		if (ok) { n = nd / p.D; d = (uint32_t)(nd % p.D); ok = d <= p.frame_t[n]; }
+		if (threadIdx.x == 0) row_ok[i] = ok ? 1u : 0u;
 		const float* x = p.X + n * p.ldx + (uint64_t)d * p.W + p.sf0;
-		double acc = 0.0;
-		for (uint32_t f = 0; f < p.nSf; f++) acc = __dadd_rn(acc, __dmul_rn((double)x[f], p.Wd[(uint64_t)f * p.L + lab]));
-		if (p.use_bias) acc = __dadd_rn(acc, __dmul_rn(p.Wd[(uint64_t)p.nSf * p.L + lab], p.bias_val));
-		p.negS[i] = (float)(-acc);
+		for (uint32_t f = threadIdx.x; f < p.nSf; f += blockDim.x) vs_x[i * p.nSf + f] = ok ? x[f] : 0.0f;
+	}
+	__syncthreads();
+	const uint32_t lab = blockIdx.y * blockDim.x + threadIdx.x;
+	if (lab >= p.L) return;
+	double acc[VS_ROWS];
+#pragma unroll
+	for (int i = 0; i < VS_ROWS; i++) acc[i] = 0.0;
+	for (uint32_t f = 0; f < p.nSf; f++) {
+		const double w = p.Wd[(uint64_t)f * p.L + lab];
+#pragma unroll
+		for (int i = 0; i < VS_ROWS; i++) acc[i] = __dadd_rn(acc[i], __dmul_rn((double)vs_x[i * p.nSf + f], w));
+	}
+	const double wb = p.use_bias ? __dmul_rn(p.Wd[(uint64_t)p.nSf * p.L + lab], p.bias_val) : 0.0;
+#pragma unroll
+	for (int i = 0; i < VS_ROWS; i++) {
+		const uint64_t nd = r0 + i;
+		if (nd >= n_rows) break;
+		const double v = p.use_bias ? __dadd_rn(acc[i], wb) : acc[i];
+		p.negS[nd * p.L + lab] = row_ok[i] ? (float)(-v) : 0.0f;
 	}
 }
 void launch_vit_scores(const VitScoreParams& p, cudaStream_t s) {
-	const uint64_t total = (uint64_t)p.N * p.D * p.L;
-	if (!total) return;
-	uint64_t b = (total + 255) / 256; if (b > 148ull * 32) b = 148ull * 32;
-	vit_scores_kernel<<<(unsigned)b, 256, 0, s>>>(p);
+	const uint64_t n_rows = (uint64_t)p.N * p.D;
+	if (!n_rows || !p.L) return;
+	const size_t smem = sizeof(float) * VS_ROWS * (size_t)(p.nSf ? p.nSf : 1);
+	cudaFuncSetAttribute(vit_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	dim3 grid((unsigned)((n_rows + VS_ROWS - 1) / VS_ROWS), (p.L + 255) / 256);
+	vit_scores_kernel<<<grid, 256, smem, s>>>(p);
 }
 
 // =================================================================================================
@@ -720,6 +745,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	float* Wprev = reinterpret_cast<float*>(smem_raw);   // [L] kept weights of the previous frame
 	float* crossS = Wprev + p.L;                          // [P*P] when it fits, else unused
 	__shared__ uint32_t s_g;        // descriptor of the kept-list order of the previous frame
+	__shared__ uint8_t s_move[256]; // arrival-order descriptors a[s] of the last D start frames (ring; D <= 255)
 	__shared__ int s_best;
 	const uint32_t u = blockIdx.x;
 	const uint32_t L = p.L, P = p.P, NS = p.NS, D = p.D;
@@ -735,7 +761,17 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	const float my_off = (lab < L && k > 0) ? p.negOff[lab] : 0.0f;
 	__syncthreads();
 
+	// the state scores of a node do not depend on the recursion: those of node s+1 are fetched while node s is processed, so the
+	// per-frame chain holds no global-memory round trip (VPF durations in registers, the rest read in place)
+	constexpr uint32_t VPF = 4;
+	float nsv[VPF];
+#pragma unroll
+	for (uint32_t j = 0; j < VPF; j++) nsv[j] = (lab < L && j < D && T > 0) ? p.negS[((uint64_t)off * D + j) * L + lab] : 0.0f;
+
 	for (uint32_t s = 0; s < T; s++) {
+		float nsn[VPF];
+#pragma unroll
+		for (uint32_t j = 0; j < VPF; j++) nsn[j] = (lab < L && j < D && s + 1 < T) ? p.negS[((uint64_t)(off + s + 1) * D + j) * L + lab] : 0.0f;
 		// ---- candidates for segments starting at frame s ----
 		float cw = VIT_INF; int32_t cp = -1;
 		if (lab < L) {
@@ -745,13 +781,22 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				const uint32_t g = s_g;
 				bool seen = false;
 				if (k == 0) {
-					// cross-phone: scan the kept list of frame s-1 in list order; strict '<' keeps the first arrival
-					for (uint32_t i = 0; i < P; i++) {
-						const uint32_t pp = kept_phone(i, P, g);
-						if (NS == 1 && pp == q) continue;   // free-phone LM, 1 state: no arc to the same phone (:1332-1346)
-						const float base = Wprev[pp * NS + NS - 1] + 0.0f;
-						const float cost = base + crossT[(uint64_t)pp * P + q];
-						if (!seen || cost < cw) { cw = cost; cp = (int32_t)(pp * NS + NS - 1); seen = true; }
+					// cross-phone: scan the kept list of frame s-1 in list order; strict '<' keeps the first arrival.  The candidate costs of
+					// 8 list positions are formed independently (their shared-memory loads overlap), then merged in list order.
+					for (uint32_t i0 = 0; i0 < P; i0 += 8) {
+						float cc[8]; int32_t ci[8]; bool ok[8];
+#pragma unroll
+						for (uint32_t j = 0; j < 8; j++) {
+							const uint32_t i = i0 + j;
+							const uint32_t pp = kept_phone(i < P ? i : P - 1, P, g);
+							ok[j] = i < P && !(NS == 1 && pp == q);   // free-phone LM, 1 state: no arc to the same phone (:1332-1346)
+							const float base = Wprev[pp * NS + NS - 1] + 0.0f;
+							cc[j] = base + crossT[(uint64_t)pp * P + q];
+							ci[j] = (int32_t)(pp * NS + NS - 1);
+						}
+#pragma unroll
+						for (uint32_t j = 0; j < 8; j++)
+							if (ok[j] && (!seen || cc[j] < cw)) { cw = cc[j]; cp = ci[j]; seen = true; }
 					}
 				} else seen = true;   // the cross update created the slot with 99999.0 / -1 for inner sub-states
 				// within-phone: self vs advance from the previous sub-state, self only if strictly smaller (:338)
@@ -765,8 +810,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				if (k == 0 && !seen) { cw = w; cp = ptr; }         // no cross arc reached this phone (P == 1)
 				else if (w < cw) { cw = w; cp = ptr; }
 			}
-			candW[(uint64_t)(s % D) * L + lab] = cw;
-			candP[(uint64_t)(s % D) * L + lab] = cp;
+			if (D > 1) { candW[(uint64_t)(s % D) * L + lab] = cw; candP[(uint64_t)(s % D) * L + lab] = cp; }   // read back d-1 frames later
 		}
 		__syncthreads();   // Wprev fully consumed
 		// ---- node s: add state values, best duration per (phone, sub-state); longest duration first ----
@@ -777,7 +821,15 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				const uint32_t s0 = s - d + 1;
 				float w = (d == 1) ? cw : candW[(uint64_t)(s0 % D) * L + lab];
 				const int32_t ptr = (d == 1) ? cp : candP[(uint64_t)(s0 % D) * L + lab];
-				if (w < VIT_INF) w = w + p.negS[((uint64_t)(off + s) * D + (d - 1)) * L + lab];
+				if (w < VIT_INF) {
+					float sv;
+					if (d <= VPF) {
+						sv = nsv[0];
+#pragma unroll
+						for (uint32_t j = 1; j < VPF; j++) if (d == j + 1) sv = nsv[j];
+					} else sv = p.negS[((uint64_t)(off + s) * D + (d - 1)) * L + lab];
+					w = w + sv;
+				}
 				if (d == dmax || w < best) { best = w; bptr = ptr; bdur = d; }
 			}
 			Wprev[lab] = best;
@@ -791,14 +843,16 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 			uint32_t a_s = 0xffu;
 			if (NS == 1 && P > 1 && s >= 1) {
 				const uint32_t j = s >= D ? s - D : 0;
-				const uint32_t aj = j == 0 ? 0xffu : p.gmove[off + j];
+				const uint32_t aj = j == 0 ? 0xffu : s_move[j & 255];
 				a_s = (aj == 0xffu) ? 0u : (aj == 0u ? 1u : 0u);     // head of the list described by aj
 			}
-			p.gmove[off + s] = (uint8_t)a_s;
+			s_move[s & 255] = (uint8_t)a_s;
 			// order of kept(s) feeds the cross scan of frame s+1: kept(s) = a[max(0, s-D+1)]
 			const uint32_t j2 = s + 1 >= D ? s + 1 - D : 0;
-			s_g = (j2 == 0) ? 0xffu : (j2 == s ? a_s : p.gmove[off + j2]);
+			s_g = (j2 == 0) ? 0xffu : (j2 == s ? a_s : s_move[j2 & 255]);
 		}
+#pragma unroll
+		for (uint32_t j = 0; j < VPF; j++) nsv[j] = nsn[j];
 		__syncthreads();
 	}
 	// ---- final argmin over the kept list (first wins) and traceback ----
