@@ -63,47 +63,70 @@ void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t s) {
 // (CRF_InFtrStream_SeqMultiWindow.cpp: sample_ftrs :556-590, avg_ftrs :601-626, max_ftrs :637-666,
 //  min_ftrs :677-706, dur_ftrs :790-812; first_frame_ftrs for the non-segment mode).
 // =================================================================================================
+// One CTA per frame.  The base rows the frame's windows reach back to are fetched with ONE batch of independent loads into shared
+// memory, the D windows are built there (running sum / max / min in the reference's order) and leave the SM as 16-byte vectors of
+// whole rows when the row stride allows it (Wp % 4 == 0: every window row is 16-byte aligned), otherwise element by element.
 __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
-	const uint32_t n = blockIdx.x;
+	extern __shared__ __align__(16) float xw[];             // [D][Wp] windows, then [D][F] base rows (row j = frame n - j)
+	float* rows = xw + (size_t)p.D * p.Wp;
+	const uint32_t n = p.n0 + blockIdx.x;
 	if (n >= p.N) return;
 	const uint32_t t = p.frame_t[n];
 	const uint32_t dmax = min(t + 1, p.D);
-	float* out = p.X + (uint64_t)n * p.D * p.Wp;
 	const float* cur = p.base + (uint64_t)n * p.F;
+	for (uint32_t i = threadIdx.x; i < dmax * p.F; i += blockDim.x) {
+		const uint32_t j = i / p.F, f = i - j * p.F;
+		rows[i] = __ldg(cur - (uint64_t)j * p.F + f);
+	}
+	// windows that would start before the utterance are never read by the lattice; keep them zero
+	for (uint32_t i = dmax * p.Wp + threadIdx.x; i < p.D * p.Wp; i += blockDim.x) xw[i] = 0.0f;
+	__syncthreads();
 	if (p.seg_ftrs) {
 		for (uint32_t f = threadIdx.x; f < p.F; f += blockDim.x) {
-			float acc = 0.0f, amax = cur[f], amin = cur[f];
+			float acc = 0.0f, amax = rows[f], amin = rows[f];
 			for (uint32_t d = 1; d <= dmax; d++) {
-				const float* wstart = cur - (uint64_t)(d - 1) * p.F;   // first frame of the window
-				const float v = wstart[f];
+				// the window of duration d covers frames n-d+1 .. n = rows d-1 .. 0; its first frame is row d-1
+				const float v = rows[(d - 1) * p.F + f];
 				acc += v;
 				amax = v > amax ? v : amax;
 				amin = v < amin ? v : amin;
-				float* o = out + (uint64_t)(d - 1) * p.Wp;
+				float* o = xw + (d - 1) * p.Wp;
 #pragma unroll
-				for (int k = 0; k < 5; k++) o[k * p.F + f] = wstart[(uint64_t)p.steps[(d - 1) * 5 + k] * p.F + f];
+				for (int k = 0; k < 5; k++) o[k * p.F + f] = rows[(d - 1 - p.steps[(d - 1) * 5 + k]) * p.F + f];
 				o[5 * p.F + f] = acc / (float)d;
 				o[6 * p.F + f] = amax;
 				o[7 * p.F + f] = amin;
 			}
 		}
-		for (uint32_t i = threadIdx.x; i < dmax * p.D; i += blockDim.x) {
-			const uint32_t d = i / p.D + 1, k = i % p.D;
-			out[(uint64_t)(d - 1) * p.Wp + 8 * p.F + k] = (k == d - 1) ? 1.0f : 0.0f;
+		// one-hot duration + the pad behind each window
+		const uint32_t tail = p.Wp - 8 * p.F;
+		for (uint32_t i = threadIdx.x; i < dmax * tail; i += blockDim.x) {
+			const uint32_t d = i / tail, j = i - d * tail;
+			xw[d * p.Wp + 8 * p.F + j] = (j == d) ? 1.0f : 0.0f;
 		}
 	} else {
-		for (uint32_t i = threadIdx.x; i < dmax * p.F; i += blockDim.x) {
-			const uint32_t d = i / p.F + 1, f = i % p.F;
-			out[(uint64_t)(d - 1) * p.Wp + f] = (cur - (uint64_t)(d - 1) * p.F)[f];
+		for (uint32_t i = threadIdx.x; i < dmax * p.Wp; i += blockDim.x) {
+			const uint32_t d = i / p.Wp, f = i - d * p.Wp;
+			xw[i] = f < p.F ? rows[d * p.F + f] : 0.0f;
 		}
 	}
-	// windows that would start before the utterance are never read by the lattice; keep them zero
-	for (uint32_t i = dmax * p.Wp + threadIdx.x; i < p.D * p.Wp; i += blockDim.x) out[i] = 0.0f;
-	// the pad behind each window
-	for (uint32_t i = threadIdx.x; i < dmax * (p.Wp - p.W); i += blockDim.x) out[(uint64_t)(i / (p.Wp - p.W)) * p.Wp + p.W + i % (p.Wp - p.W)] = 0.0f;
+	__syncthreads();
+	float* out = p.X + (uint64_t)n * p.D * p.Wp;
+	const uint32_t tot = p.D * p.Wp;
+	if (p.Wp % 4 == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) {
+		float4* o4 = reinterpret_cast<float4*>(out);
+		const float4* s4 = reinterpret_cast<const float4*>(xw);
+		for (uint32_t i = threadIdx.x; i < tot / 4; i += blockDim.x) __stcs(o4 + i, s4[i]);
+	} else {
+		for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) out[i] = xw[i];
+	}
 }
-void launch_expand_windows(const ExpandParams& p, cudaStream_t s) {
-	if (p.N) expand_windows_kernel<<<p.N, 128, 0, s>>>(p);
+void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s) {
+	if (n1 <= p.n0) return;
+	const size_t smem = sizeof(float) * (size_t)p.D * (p.Wp + p.F);
+	static size_t attr = 0;
+	if (smem > attr) { cudaFuncSetAttribute(expand_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+	expand_windows_kernel<<<n1 - p.n0, 128, smem, s>>>(p);
 }
 
 // =================================================================================================

@@ -18,8 +18,9 @@ struct ExpandParams {
 	float* X;                 // [N][D][Wp]  (Wp >= W: windows start on 128-byte lines, the pad is zero)
 	uint32_t N, F, D, W, Wp;
 	uint32_t seg_ftrs;        // 1: [5 samples|avg|max|min|one-hot dur], 0: first frame of the window
+	uint32_t n0;              // first frame of this launch
 };
-void launch_expand_windows(const ExpandParams& p, cudaStream_t s);
+void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s);   // frames [p.n0, n1)
 
 // ---- GEMM-1: state scores  S[n][col0+j] = sum_k A[n][k]*B[j][k] + bias[j] ----------------------
 struct ScoreGemmParams {

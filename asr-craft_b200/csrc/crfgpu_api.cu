@@ -2,6 +2,7 @@
 // buffers, derives the device-side tables from lambda and sequences kernel launches on one stream.
 // There is no CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -58,7 +59,11 @@ struct crfgpu_ctx {
 	crfgpu_config cfg{};
 	Layout lay;
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;       // copy_stream: chunked H2D of the base features, overlapped with the window expansion
+	cudaEvent_t ev_ready = nullptr; std::vector<cudaEvent_t> ev_chunk; std::vector<uint32_t> chunk_end;
+	// page-locked arena for the per-batch index tables: their uploads must not serialise the host with the stream (a copy from pageable
+	// memory first waits for everything queued on its stream)
+	unsigned char* pin = nullptr; size_t pin_cap = 0, pin_used = 0; cudaEvent_t ev_pin = nullptr;
 	uint32_t W = 0;          // window feature width
 	uint32_t Wp = 0;         // stride between the windows of a frame in X (>= W; currently W, see crfgpu_create)
 	uint32_t Lp = 0;         // padded label stride of the lattice arrays
@@ -116,6 +121,17 @@ template <class T>
 void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
 	b.ensure(v.size() * sizeof(T) + 16);
 	if (!v.empty()) CUDA_OK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+// upload through the page-locked arena (truly asynchronous); falls back to the pageable path when the arena is full
+template <class T>
+void upload_async(crfgpu_ctx* h, DevBuf& b, const std::vector<T>& v) {
+	const size_t bytes = v.size() * sizeof(T), at = (h->pin_used + 255) & ~(size_t)255;
+	if (!bytes || at + bytes > h->pin_cap) { upload(b, v, h->stream); return; }
+	b.ensure(bytes + 16);
+	std::memcpy(h->pin + at, v.data(), bytes);
+	h->pin_used = at + bytes;
+	CUDA_OK(cudaMemcpyAsync(b.p, h->pin + at, bytes, cudaMemcpyHostToDevice, h->stream));
 }
 
 void check_kernel(crfgpu_ctx* h, int n_launches) {
@@ -303,13 +319,64 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
 	h->fwdbwd_done = h->viterbi_done = false;
 	h->h_off.assign(off, off + n_utt + 1);
+	{
+		const size_t want = ((size_t)N * 6 + (size_t)n_utt * 24 + 65536) * sizeof(uint32_t);
+		if (!h->ev_pin) CUDA_OK(cudaEventCreateWithFlags(&h->ev_pin, cudaEventDisableTiming));
+		else CUDA_OK(cudaEventSynchronize(h->ev_pin));                  // the previous batch's table uploads have left the arena
+		if (want > h->pin_cap) {
+			if (h->pin) CUDA_OK(cudaFreeHost(h->pin));
+			h->pin = nullptr; h->pin_cap = 0;
+			CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&h->pin), want + want / 4));
+			h->pin_cap = want + want / 4;
+		}
+		h->pin_used = 0;
+	}
 
+	// what the window expansion needs goes through the copy engine ahead of the feature chunks
 	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
 	for (uint32_t u = 0; u < n_utt; u++)
 		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
-	upload(h->d_off, h->h_off, s); upload(h->d_frame_t, frame_t, s); upload(h->d_frame_utt, frame_utt, s); upload(h->d_frame_len, frame_len, s);
+	upload_async(h, h->d_off, h->h_off); upload_async(h, h->d_frame_t, frame_t);
+	// base features: up to 4 chunks cut at utterance boundaries, copied on a second stream FIRST; the main stream expands the windows
+	// of chunk i (they never reach across utterances) while chunk i+1 is still in flight and the host prepares the label tables
 	h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
-	if (N) CUDA_OK(cudaMemcpyAsync(h->d_base.p, ftrs, sizeof(float) * (size_t)N * c.n_base_ftrs, cudaMemcpyHostToDevice, s));
+	if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+	h->chunk_end.clear();
+	if (N) {
+		if (!h->copy_stream) { CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreate(&h->ev_ready)); }
+		CUDA_OK(cudaEventRecord(h->ev_ready, s));                        // everything queued so far may still read the old batch
+		CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+		const uint32_t n_chunks = N >= (1u << 16) ? 4u : 1u;
+		uint32_t u = 0, n_prev = 0;
+		for (uint32_t k = 1; k <= n_chunks; k++) {
+			const uint64_t target = (uint64_t)N * k / n_chunks;
+			while (u < n_utt && off[u + 1] <= target) u++;
+			const uint32_t n_end = (k == n_chunks) ? N : off[u];
+			if (n_end <= n_prev) continue;
+			if (h->ev_chunk.size() <= h->chunk_end.size()) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); h->ev_chunk.push_back(e); }
+			CUDA_OK(cudaMemcpyAsync(h->d_base.as<float>() + (size_t)n_prev * c.n_base_ftrs, ftrs + (size_t)n_prev * c.n_base_ftrs,
+			                        sizeof(float) * (size_t)(n_end - n_prev) * c.n_base_ftrs, cudaMemcpyHostToDevice, h->copy_stream));
+			CUDA_OK(cudaEventRecord(h->ev_chunk[h->chunk_end.size()], h->copy_stream));
+			h->chunk_end.push_back(n_end);
+			n_prev = n_end;
+		}
+	}
+	{
+		if (N) phase_begin(h, "expand");
+		uint32_t n_prev = 0;
+		for (size_t k = 0; k < h->chunk_end.size(); k++) {
+			CUDA_OK(cudaStreamWaitEvent(s, h->ev_chunk[k], 0));
+			if (c.max_dur > 1) {
+				ExpandParams ep{h->d_base.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_steps.as<uint32_t>(), h->d_X.as<float>(),
+				                N, c.n_base_ftrs, c.max_dur, h->W, h->Wp, c.extract_seg_ftrs, n_prev};
+				launch_expand_windows(ep, h->chunk_end[k], s);
+				check_kernel(h, 1);
+			}
+			n_prev = h->chunk_end[k];
+		}
+		if (N) phase_end(h, "expand");
+	}
+	upload_async(h, h->d_frame_utt, frame_utt); upload_async(h, h->d_frame_len, frame_len);
 
 	std::vector<uint32_t> node_lab, prev_lab;
 	if (labs) {
@@ -332,7 +399,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 				}
 			}
 		}
-		upload(h->d_node_lab, node_lab, s); upload(h->d_prev_lab, prev_lab, s);
+		upload_async(h, h->d_node_lab, node_lab); upload_async(h, h->d_prev_lab, prev_lab);
 	}
 	// utterances sorted by length (longest first) so the slots of one CTA finish together; reordering inside a
 	// minibatch does not change the gradient sum
@@ -350,7 +417,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// deal utterances round-robin over the groups so every group gets a similar mix of lengths?  No:
 	// consecutive (similar-length) utterances share a CTA, which minimises idle slots.
 	for (uint32_t i = 0; i < n_utt; i++) grp[i] = order[i];
-	upload(h->d_grp, grp, s);
+	upload_async(h, h->d_grp, grp);
 	// cluster-resident lattice kernels: persistent clusters, utterances dealt longest-first to the least loaded
 	// cluster; inside a cluster the list order is the order slots are (re)filled
 	std::vector<uint32_t> cl_off, cl_list;
@@ -366,7 +433,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		}
 		cl_off.assign(1, 0); cl_list.clear();
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
-		upload(h->d_cl_off, cl_off, s); upload(h->d_cl_list, cl_list, s);
+		upload_async(h, h->d_cl_off, cl_off); upload_async(h, h->d_cl_list, cl_list);
 	};
 	if (h->train_ok && !h->nodur && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
 		// tensor-core cluster kernels: 16 slots per cluster
@@ -427,19 +494,10 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			nd_grp.push_back((uint32_t)(nd_batch.size() / NODUR_UT));
 		}
 		h->n_nodur_groups = ng;
-		upload(h->d_nd_grp, nd_grp, s); upload(h->d_nd_batch, nd_batch, s);
+		upload_async(h, h->d_nd_grp, nd_grp); upload_async(h, h->d_nd_batch, nd_batch);
 	}
-	CUDA_OK(cudaStreamSynchronize(s));   // host staging vectors die here
-
-	if (c.max_dur > 1 && N) {
-		h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
-		phase_begin(h, "expand");
-		ExpandParams ep{h->d_base.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_steps.as<uint32_t>(), h->d_X.as<float>(),
-		                N, c.n_base_ftrs, c.max_dur, h->W, h->Wp, c.extract_seg_ftrs};
-		launch_expand_windows(ep, s);
-		check_kernel(h, 1);
-		phase_end(h, "expand");
-	}
+	// no host-side wait: the table uploads come from the page-locked arena and the kernels of the step queue behind the expansion
+	CUDA_OK(cudaEventRecord(h->ev_pin, s));
 }
 
 // [sum numer, sum logZ, n_utt, 0] behind the gradient so that a multi-GPU driver moves gradient and scalars
@@ -755,6 +813,11 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
+	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+	if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+	if (h->ev_pin) cudaEventDestroy(h->ev_pin);
+	if (h->pin) cudaFreeHost(h->pin);
+	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	cudaStreamDestroy(h->stream);
 	delete h;
 	return CRFGPU_OK;
@@ -833,16 +896,38 @@ int crfgpu_fetch_viterbi(crfgpu_handle h, uint32_t* out_lab, uint32_t* out_dur, 
 
 int crfgpu_fwdbwd_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
                         double* grad, double* numer, double* logZ) {
+	const bool verbose = getenv("CRFGPU_VERBOSE") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+	const auto t0 = now();
+	std::chrono::steady_clock::time_point t1, t2;
 	int rc = guarded([&] {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		CUDA_OK(cudaSetDevice(h->device));
 		require_train(h);
 		if (!frame_labs) throw ApiError(CRFGPU_ERR_ARG, "training needs frame labels");
 		stage_batch(h, n_utt, frame_off, base_ftrs, frame_labs);
+		t1 = now();
 		fwdbwd_staged(h);
+		t2 = now();
 	});
 	if (rc != CRFGPU_OK) return rc;
-	return crfgpu_fetch_fwdbwd(h, grad, numer, logZ);
+	rc = crfgpu_fetch_fwdbwd(h, grad, numer, logZ);
+	if (verbose && h->ev_ready) {
+		fprintf(stderr, "[crfgpu] device timeline from the start of staging (ms):");
+		float t = 0.0f;
+		for (size_t k = 0; k < h->chunk_end.size(); k++) if (cudaEventElapsedTime(&t, h->ev_ready, h->ev_chunk[k]) == cudaSuccess) fprintf(stderr, " H2D chunk %zu done %.3f", k, t);
+		for (const char* ph : {"expand", "score", "grad"}) {
+			auto it = h->phases.find(ph);
+			if (it != h->phases.end() && cudaEventElapsedTime(&t, h->ev_ready, it->second.first) == cudaSuccess) {
+				float t2 = 0.0f; cudaEventElapsedTime(&t2, h->ev_ready, it->second.second);
+				fprintf(stderr, " | %s %.3f..%.3f", ph, t, t2);
+			}
+		}
+		fprintf(stderr, "\n");
+	}
+	if (verbose) fprintf(stderr, "[crfgpu] fwdbwd_batch host timeline: stage (prep + H2D enqueue + sync) %.3f ms, launch %.3f ms, kernels + D2H %.3f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));
+	return rc;
 }
 
 int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
