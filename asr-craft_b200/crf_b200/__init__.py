@@ -67,7 +67,14 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_expand_windows", "crfgpu_group_labels", "crfgpu_stage_batch", "crfgpu_fwdbwd_staged",
            "crfgpu_viterbi_staged", "crfgpu_device_results", "crfgpu_fetch_fwdbwd", "crfgpu_fetch_viterbi",
            "crfgpu_synchronize", "crfgpu_stream", "crfgpu_launch_count", "crfgpu_phase_ms",
-           "crfgpu_fetch_alpha_beta", "crfgpu_set_option", "crfgpu_host_alloc", "crfgpu_host_free"]
+           "crfgpu_fetch_alpha_beta", "crfgpu_set_option", "crfgpu_host_alloc", "crfgpu_host_free",
+           "crfgpu_sgd_update", "crfgpu_get_lambda", "crfgpu_set_train_state"]
+
+
+class Sgd(C.Structure):
+    """crfgpu_sgd (include/crfgpu.h): the per-minibatch update of CRF_SGTrainer.cpp:299-325."""
+    _fields_ = [("lr", C.c_double), ("use_gvar", C.c_uint32), ("inv_square_var", C.c_double),
+                ("use_adagrad", C.c_uint32), ("eta", C.c_double), ("eps", C.c_double)]
 
 
 def load_library(path=None):
@@ -92,6 +99,9 @@ def load_library(path=None):
     lib.crfgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.crfgpu_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.crfgpu_host_free.argtypes = [C.c_void_p]
+    lib.crfgpu_sgd_update.argtypes = [C.c_void_p, C.POINTER(Sgd), C.c_double]
+    lib.crfgpu_get_lambda.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 4
+    lib.crfgpu_set_train_state.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
     _lib = lib
     return lib
 
@@ -164,6 +174,26 @@ class CrfGpu:
     def set_lambda(self, lam):
         lam = np.ascontiguousarray(lam, np.float64)
         self._check(self.lib.crfgpu_set_lambda(self.h, _ptr(lam, C.c_double), C.c_uint32(len(lam))))
+
+    def sgd_update(self, n_active, lr=0.0, use_gvar=0, inv_square_var=0.0, use_adagrad=0, eta=0.0, eps=0.0):
+        """lambda += lr * grad / n_active (or AdaGrad) on the device from the staged gradient; rebuilds the device tables."""
+        opt = Sgd(lr, use_gvar, inv_square_var, use_adagrad, eta, eps)
+        self._check(self.lib.crfgpu_sgd_update(self.h, C.byref(opt), C.c_double(n_active)))
+
+    def get_lambda(self, with_state=False):
+        n = self.lambda_len
+        lam = np.zeros(n, np.float64)
+        if not with_state:
+            self._check(self.lib.crfgpu_get_lambda(self.h, _ptr(lam, C.c_double), None, None, None))
+            return lam
+        acc, sqr, gsq = np.zeros(n), np.zeros(n), np.zeros(n)
+        self._check(self.lib.crfgpu_get_lambda(self.h, _ptr(lam, C.c_double), _ptr(acc, C.c_double), _ptr(sqr, C.c_double),
+                                               _ptr(gsq, C.c_double)))
+        return lam, acc, sqr, gsq
+
+    def set_train_state(self, lambda_acc=None, lambda_sqr_acc=None, grad_sqr_acc=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (lambda_acc, lambda_sqr_acc, grad_sqr_acc)]
+        self._check(self.lib.crfgpu_set_train_state(self.h, *[None if a is None else _ptr(a, C.c_double) for a in arrs]))
 
     # ---- host-buffer calls --------------------------------------------------------------------
     def fwdbwd(self, off, ftrs, labs, out=None):

@@ -136,7 +136,7 @@ cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s);
 
 // ---- TMA-fed GEMMs over the window stream, all durations in one launch (crf_tma_gemm.cu) ---------
 struct ScoreTmaParams {
-	const unsigned char* Bt;          // state weights as bf16 hi/lo UMMA tiles, [(d*ntile + jt)*n_chunks + c][8 KB] (split_weight_tiles)
+	const unsigned char* Bt;          // state weights as bf16 hi/lo UMMA tiles, [(d*ntile + jt)*n_chunks + c][8 KB] (lambda_tables_kernel)
 	const float* bias;                // [D*P] or nullptr
 	float* C; uint32_t ldc;           // S[M][ldc], column (d*P + y)
 	uint32_t M, P, K, D, n_chunks, ntile;
@@ -184,7 +184,6 @@ struct FrameGemmParams {
 // X must be 16-byte aligned, Wp % 4 == 0, the first state feature a multiple of 4 and the driver must export cuTensorMapEncodeTiled
 bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0);
 uint32_t score_tma_chunks(uint32_t K);
-void split_weight_tiles(const float* Ws, uint32_t P, uint32_t D, uint32_t K, std::vector<unsigned char>* out);   // host side, once per lambda
 bool lattice_tma_eligible(const float* a, uint32_t ld);
 // Xi: A, R = lattice arrays [N][ld]
 cudaError_t launch_xi_gemm_tma(const float* A, const float* R, uint32_t ld, const FrameGemmParams& p, cudaStream_t s);
@@ -235,6 +234,28 @@ struct VitParams {
 	uint32_t* out_lab; uint32_t* out_dur; uint32_t* out_phn; uint32_t* n_seg; float* cost;
 };
 void launch_viterbi(const VitParams& p, cudaStream_t s);
+
+// ---- lambda-derived tables and the trainer's update on the device (crf_lambda.cu) -----------------------------------
+struct LambdaTablesParams {
+	const double* lam;
+	// training tables over the lattice labels (null Ws: skip)
+	uint32_t Le, Lpe, nSf;                 // rows of the tables, row stride of E / ET, state features per label
+	const uint32_t* sidx; const uint32_t* tidx;   // [>= Le] state block offsets, [Le*Le] transition indices of the lattice labels
+	int use_state_bias, use_trans_bias; double state_bias_val, trans_bias_val;
+	float* Ws; float* bias; float* E; float* ET;  // E / ET must be zero before the launch
+	double* tmax;                          // device scalar: max transition score (read back by the host as Mmax)
+	unsigned char* Wt; uint32_t wt_P, wt_D, wt_chunks;   // weight tiles of the TMA-fed score GEMM (null: skip)
+	// decoder tables over the model's own labels (null Wd: skip)
+	double* Wd; float* crossT; float* negDiag; float* negOff;
+	const uint32_t* sidx0; const uint32_t* tidx0; uint32_t L0, NS, P0;
+};
+cudaError_t launch_lambda_tables(const LambdaTablesParams& p, cudaStream_t s);
+struct SgdParams {
+	double* lambda; const double* grad; uint64_t len;
+	double n_active, lr; int use_gvar; double inv_square_var; int use_adagrad; double eta, eps;
+	double* grad_sqr_acc; double* lambda_acc; double* lambda_sqr_acc;   // optional (AdaGrad state, averaged-model accumulators)
+};
+cudaError_t launch_sgd_update(const SgdParams& p, cudaStream_t s);
 
 // ---- small helpers ------------------------------------------------------------------------------
 void launch_fill_f32(float* p, uint64_t n, float v, cudaStream_t s);

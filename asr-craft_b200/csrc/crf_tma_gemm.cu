@@ -15,7 +15,7 @@
 //   MMA warp        3 tcgen05.mma per 16-wide k-step (hi*hi + lo*hi + hi*lo) into a TMEM accumulator, commits free the stages
 //   warps 0-3       epilogue
 // The small operand never passes through the converters in the score kernel: the state weights are split into bf16 hi/lo UMMA
-// tiles once per lambda (crfgpu_set_lambda) and land in the operand stage with one 8 KB bulk copy per k-chunk.
+// tiles once per lambda (lambda_tables_kernel, crf_lambda.cu) and land in the operand stage with one 8 KB bulk copy per k-chunk.
 #include <cuda.h>   // CUtensorMap and its enums only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no -lcuda)
 
 #include <cmath>
@@ -403,14 +403,6 @@ bool window_map(CUtensorMap* tm, const float* X, uint32_t N, uint32_t D, uint32_
 	           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-inline uint16_t bf16_rn(float x) {
-	uint32_t u; memcpy(&u, &x, 4);
-	if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
-	u += 0x7fffu + ((u >> 16) & 1u);
-	return (uint16_t)(u >> 16);
-}
-inline float bf16_f(uint16_t h) { const uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
-
 }  // namespace
 
 bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0) {
@@ -418,28 +410,6 @@ bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0) {
 }
 
 uint32_t score_tma_chunks(uint32_t K) { return (K + KC - 1) / KC; }
-
-void split_weight_tiles(const float* Ws, uint32_t P, uint32_t D, uint32_t K, std::vector<unsigned char>* out) {
-	const uint32_t ntile = (P + BN - 1) / BN, n_chunks = score_tma_chunks(K);
-	out->assign((size_t)D * ntile * n_chunks * 2 * B_TILE, 0);
-	for (uint32_t d = 0; d < D; d++)
-		for (uint32_t jt = 0; jt < ntile; jt++)
-			for (uint32_t c = 0; c < n_chunks; c++) {
-				unsigned char* tile = out->data() + ((size_t)(d * ntile + jt) * n_chunks + c) * 2 * B_TILE;
-				for (uint32_t r = 0; r < (uint32_t)BN; r++) {
-					const uint32_t y = jt * BN + r;
-					if (y >= P) break;
-					const float* w = Ws + (size_t)(d * P + y) * K;
-					for (uint32_t kk = 0; kk < (uint32_t)KC; kk++) {
-						const uint32_t k = c * KC + kk;
-						if (k >= K) break;
-						const uint16_t hi = bf16_rn(w[k]), lo = bf16_rn(w[k] - bf16_f(hi));
-						const size_t o = (size_t)(r / 8) * 512 + (kk / 8) * 128 + (r % 8) * 16 + (kk % 8) * 2;
-						memcpy(tile + o, &hi, 2); memcpy(tile + B_TILE + o, &lo, 2);
-					}
-				}
-			}
-}
 
 cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaParams& p, cudaStream_t s) {
 	if (!p.M || !p.P) return cudaSuccess;

@@ -88,7 +88,8 @@ struct crfgpu_ctx {
 	// model tables
 	bool have_lambda = false;
 	DevBuf d_lambda, d_sidx, d_tidx, d_Ws, d_Wt, d_bias, d_E, d_ET, d_steps;
-	DevBuf d_Wd, d_crossT, d_negDiag, d_negOff;
+	DevBuf d_Wd, d_crossT, d_negDiag, d_negOff, d_sidx0, d_tidx0, d_tmax;
+	DevBuf d_lam_acc, d_lam_sqr_acc, d_grad_sqr_acc; bool have_train_state = false;   // crfgpu_sgd_update: accumulators of the averaged model / AdaGrad
 	double Mmax = 0.0;
 
 	// staged batch
@@ -208,6 +209,7 @@ void setup_label_space(crfgpu_ctx* h) {
 	h->have_lambda = false; h->fwdbwd_done = false;
 	if (h->stream) {
 		upload(h->d_sidx, h->t_sidx, h->stream); upload(h->d_tidx, h->t_tidx, h->stream);
+		if (h->decode_ok && (h->tied || h->nodur)) { upload(h->d_sidx0, h->lay.sidx, h->stream); upload(h->d_tidx0, h->lay.tidx, h->stream); }
 		CUDA_OK(cudaStreamSynchronize(h->stream));
 	}
 }
@@ -222,88 +224,58 @@ void require_decode(crfgpu_ctx* h) {
 }
 
 // ---------------------------------------------------------------------------------------------
-void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
+// Everything the kernels read from lambda, derived ON THE DEVICE from d_lambda (crf_lambda.cu): state weights / biases, E = exp(M - Mmax)
+// with M[p][c] = lambda[tidx]*transBiasVal (CRF_StdFeatureMap.cpp:94-110 with no transition features), the weight tiles of the TMA-fed
+// score GEMM and the decoder's tables.  Only the scalar Mmax comes back to the host.
+void derive_tables(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
-	if (len != m.len) throw ApiError(CRFGPU_ERR_ARG, "lambda length " + std::to_string(len) + " != feature map length " + std::to_string(m.len));
 	const uint32_t L = m.L, Lt = h->Lt, Lp = h->Lp, nSf = m.nSf;
 	cudaStream_t s = h->stream;
-	h->d_lambda.ensure(sizeof(double) * (size_t)len + 16);
-	CUDA_OK(cudaMemcpyAsync(h->d_lambda.p, lam, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, s));
-
-	// transition scores: M[p][c] = lambda[tidx]*transBiasVal (CRF_StdFeatureMap.cpp:94-110 with no transition features)
-	std::vector<double> M((size_t)L * L, 0.0);
-	double Mmax = -DBL_MAX;
-	for (uint32_t p = 0; p < L; p++)
-		for (uint32_t cl = 0; cl < L; cl++) {
-			const uint32_t ti = m.tidx[(size_t)p * L + cl];
-			if (ti == CRFGPU_NO_IDX) continue;
-			double v = 0.0;
-			if (c.use_trans_bias) v += lam[ti] * c.trans_bias_val;
-			M[(size_t)p * L + cl] = v;
-			Mmax = std::max(Mmax, v);
-		}
-	if (Mmax == -DBL_MAX) Mmax = 0.0;
-	h->Mmax = Mmax;
-
+	LambdaTablesParams p{};
+	p.lam = h->d_lambda.as<double>(); p.nSf = nSf;
+	p.use_state_bias = c.use_state_bias; p.use_trans_bias = c.use_trans_bias; p.state_bias_val = c.state_bias_val; p.trans_bias_val = c.trans_bias_val;
+	h->d_tmax.ensure(sizeof(double) + 16); p.tmax = h->d_tmax.as<double>();
 	if (h->train_ok) {
 		// tables over the lattice labels (for tied models label (d,y) reads the weights of phone y; the native no_dur path keeps
 		// P-wide tables and shares them between the duration blocks)
 		const uint32_t Le = h->nodur ? L : Lt, Lpe = h->nodur ? h->Pp : Lp;
-		std::vector<float> Ws((size_t)Le * std::max(nSf, 1u)), bias(Le, 0.0f), E((size_t)Le * Lpe, 0.0f), ET((size_t)Le * Lpe, 0.0f);
-		double tmax = -DBL_MAX;
-		for (uint32_t q = 0; q < Le; q++)
-			for (uint32_t cl = 0; cl < Le; cl++) {
-				const uint32_t ti = h->t_tidx[(size_t)q * Le + cl];
-				if (ti != CRFGPU_NO_IDX) tmax = std::max(tmax, c.use_trans_bias ? lam[ti] * c.trans_bias_val : 0.0);
-			}
-		if (tmax == -DBL_MAX) tmax = 0.0;
-		h->Mmax = tmax;
-		for (uint32_t cl = 0; cl < Le; cl++) {
-			const double* w = lam + h->t_sidx[cl];
-			for (uint32_t f = 0; f < nSf; f++) Ws[(size_t)cl * nSf + f] = (float)w[f];
-			if (c.use_state_bias) bias[cl] = (float)(w[nSf] * c.state_bias_val);
-		}
-		for (uint32_t q = 0; q < Le; q++)
-			for (uint32_t cl = 0; cl < Le; cl++) {
-				const uint32_t ti = h->t_tidx[(size_t)q * Le + cl];
-				if (ti != CRFGPU_NO_IDX) {
-					const float e = (float)std::exp((c.use_trans_bias ? lam[ti] * c.trans_bias_val : 0.0) - tmax);
-					E[(size_t)q * Lpe + cl] = e; ET[(size_t)cl * Lpe + q] = e;
-				}
-			}
-		upload(h->d_Ws, Ws, s); upload(h->d_bias, bias, s); upload(h->d_E, E, s); upload(h->d_ET, ET, s);
-		std::vector<unsigned char> tiles;
+		p.Le = Le; p.Lpe = Lpe; p.sidx = h->d_sidx.as<uint32_t>(); p.tidx = h->d_tidx.as<uint32_t>();
+		h->d_Ws.ensure(sizeof(float) * (size_t)Le * std::max(nSf, 1u) + 16); h->d_bias.ensure(sizeof(float) * Le + 16);
+		h->d_E.ensure(sizeof(float) * (size_t)Le * Lpe + 16); h->d_ET.ensure(sizeof(float) * (size_t)Le * Lpe + 16);
+		CUDA_OK(cudaMemsetAsync(h->d_E.p, 0, sizeof(float) * (size_t)Le * Lpe, s)); CUDA_OK(cudaMemsetAsync(h->d_ET.p, 0, sizeof(float) * (size_t)Le * Lpe, s));
+		p.Ws = h->d_Ws.as<float>(); p.bias = h->d_bias.as<float>(); p.E = h->d_E.as<float>(); p.ET = h->d_ET.as<float>();
 		if (c.max_dur > 1 && nSf > 0) {   // bf16 hi/lo UMMA tiles of the state weights for the TMA-fed score GEMM
-			if (h->nodur) split_weight_tiles(Ws.data(), L, 1, nSf, &tiles);
-			else split_weight_tiles(Ws.data(), Lt / c.max_dur, c.max_dur, nSf, &tiles);
-			upload(h->d_Wt, tiles, s);
+			p.wt_P = h->nodur ? L : Lt / c.max_dur; p.wt_D = h->nodur ? 1 : c.max_dur; p.wt_chunks = score_tma_chunks(nSf);
+			h->d_Wt.ensure((size_t)p.wt_D * ((p.wt_P + 63) / 64) * p.wt_chunks * 8192 + 16);
+			p.Wt = h->d_Wt.as<unsigned char>();
 		}
-		CUDA_OK(cudaStreamSynchronize(s));   // host vectors die at scope exit
 	}
 	if (h->decode_ok) {
-		// decoder tables in the reference's arithmetic: double score, negate, narrow to float
-		// (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:286,315,331,458)
-		const uint32_t NS = m.n_states, P = m.n_act;
-		std::vector<double> Wd((size_t)(nSf + 1) * L, 0.0);
-		for (uint32_t cl = 0; cl < L; cl++) {
-			const double* w = lam + m.sidx[cl];
-			for (uint32_t f = 0; f < nSf; f++) Wd[(size_t)f * L + cl] = w[f];
-			if (c.use_state_bias) Wd[(size_t)nSf * L + cl] = w[nSf];
-		}
-		std::vector<float> crossT((size_t)P * P), negDiag(L), negOff(L, 0.0f);
-		for (uint32_t pp = 0; pp < P; pp++)
-			for (uint32_t q = 0; q < P; q++) {
-				const uint32_t pe = pp * NS + NS - 1, cs = q * NS;
-				crossT[(size_t)pp * P + q] = (float)(-1 * M[(size_t)pe * L + cs]);
-			}
-		for (uint32_t l = 0; l < L; l++) {
-			negDiag[l] = (float)(-1 * M[(size_t)l * L + l]);
-			if (l % NS != 0) negOff[l] = (float)(-1 * M[(size_t)(l - 1) * L + l]);
-		}
-		upload(h->d_Wd, Wd, s); upload(h->d_crossT, crossT, s); upload(h->d_negDiag, negDiag, s); upload(h->d_negOff, negOff, s);
+		const bool same = !h->tied && !h->nodur;
+		h->d_Wd.ensure(sizeof(double) * (size_t)(nSf + 1) * L + 16); h->d_crossT.ensure(sizeof(float) * (size_t)m.n_act * m.n_act + 16);
+		h->d_negDiag.ensure(sizeof(float) * L + 16); h->d_negOff.ensure(sizeof(float) * L + 16);
+		p.Wd = h->d_Wd.as<double>(); p.crossT = h->d_crossT.as<float>(); p.negDiag = h->d_negDiag.as<float>(); p.negOff = h->d_negOff.as<float>();
+		p.sidx0 = same ? h->d_sidx.as<uint32_t>() : h->d_sidx0.as<uint32_t>(); p.tidx0 = same ? h->d_tidx.as<uint32_t>() : h->d_tidx0.as<uint32_t>();
+		p.L0 = L; p.NS = m.n_states; p.P0 = m.n_act;
+	}
+	CUDA_OK(launch_lambda_tables(p, s));
+	h->launches += h->train_ok ? 2 : 1;
+	h->Mmax = 0.0;
+	if (h->train_ok) {
+		double t = 0.0;
+		CUDA_OK(cudaMemcpyAsync(&t, h->d_tmax.p, sizeof(double), cudaMemcpyDeviceToHost, s));
 		CUDA_OK(cudaStreamSynchronize(s));
+		h->Mmax = (t == -DBL_MAX) ? 0.0 : t;
 	}
 	h->have_lambda = true;
+}
+
+void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
+	if (len != h->lay.len) throw ApiError(CRFGPU_ERR_ARG, "lambda length " + std::to_string(len) + " != feature map length " + std::to_string(h->lay.len));
+	h->d_lambda.ensure(sizeof(double) * (size_t)len + 16);
+	CUDA_OK(cudaMemcpyAsync(h->d_lambda.p, lam, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice, h->stream));
+	derive_tables(h);
+	CUDA_OK(cudaStreamSynchronize(h->stream));   // the caller may reuse `lam` at once
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -810,7 +782,8 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
-	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB};
+	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -838,6 +811,59 @@ int crfgpu_set_lambda(crfgpu_handle h, const double* lambda, uint32_t len) {
 		if (!h || !lambda) throw ApiError(CRFGPU_ERR_ARG, "null argument");
 		CUDA_OK(cudaSetDevice(h->device));
 		set_lambda(h, lambda, len);
+	});
+}
+
+int crfgpu_sgd_update(crfgpu_handle h, const crfgpu_sgd* opt, double n_active) {
+	return guarded([&] {
+		if (!h || !opt) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		if (!h->fwdbwd_done || !h->have_lambda) throw ApiError(CRFGPU_ERR_ARG, "crfgpu_sgd_update needs a staged gradient (crfgpu_fwdbwd_staged / crfgpu_fwdbwd_batch)");
+		if (!(n_active > 0.0)) throw ApiError(CRFGPU_ERR_ARG, "n_active must be positive");
+		CUDA_OK(cudaSetDevice(h->device));
+		const size_t len = h->lay.len, bytes = sizeof(double) * len;
+		if (!h->have_train_state) {
+			h->d_lam_acc.ensure(bytes + 16); h->d_lam_sqr_acc.ensure(bytes + 16); h->d_grad_sqr_acc.ensure(bytes + 16);
+			CUDA_OK(cudaMemsetAsync(h->d_lam_acc.p, 0, bytes, h->stream)); CUDA_OK(cudaMemsetAsync(h->d_lam_sqr_acc.p, 0, bytes, h->stream));
+			CUDA_OK(cudaMemsetAsync(h->d_grad_sqr_acc.p, 0, bytes, h->stream));
+			h->have_train_state = true;
+		}
+		SgdParams p{};
+		p.lambda = h->d_lambda.as<double>(); p.grad = h->d_grad.as<double>(); p.len = len; p.n_active = n_active; p.lr = opt->lr;
+		p.use_gvar = opt->use_gvar; p.inv_square_var = opt->inv_square_var; p.use_adagrad = opt->use_adagrad; p.eta = opt->eta; p.eps = opt->eps;
+		p.grad_sqr_acc = h->d_grad_sqr_acc.as<double>(); p.lambda_acc = h->d_lam_acc.as<double>(); p.lambda_sqr_acc = h->d_lam_sqr_acc.as<double>();
+		CUDA_OK(launch_sgd_update(p, h->stream)); check_kernel(h, 1);
+		h->fwdbwd_done = false;                   // the gradient has been consumed
+		derive_tables(h);
+	});
+}
+
+int crfgpu_get_lambda(crfgpu_handle h, double* lambda, double* lambda_acc, double* lambda_sqr_acc, double* grad_sqr_acc) {
+	return guarded([&] {
+		if (!h || !h->have_lambda) throw ApiError(CRFGPU_ERR_ARG, "no lambda on the device");
+		CUDA_OK(cudaSetDevice(h->device));
+		const size_t bytes = sizeof(double) * (size_t)h->lay.len;
+		if ((lambda_acc || lambda_sqr_acc || grad_sqr_acc) && !h->have_train_state) throw ApiError(CRFGPU_ERR_ARG, "no training state: crfgpu_sgd_update has not run");
+		if (lambda) CUDA_OK(cudaMemcpyAsync(lambda, h->d_lambda.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+		if (lambda_acc) CUDA_OK(cudaMemcpyAsync(lambda_acc, h->d_lam_acc.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+		if (lambda_sqr_acc) CUDA_OK(cudaMemcpyAsync(lambda_sqr_acc, h->d_lam_sqr_acc.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+		if (grad_sqr_acc) CUDA_OK(cudaMemcpyAsync(grad_sqr_acc, h->d_grad_sqr_acc.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+	});
+}
+
+int crfgpu_set_train_state(crfgpu_handle h, const double* lambda_acc, const double* lambda_sqr_acc, const double* grad_sqr_acc) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		const size_t bytes = sizeof(double) * (size_t)h->lay.len;
+		h->d_lam_acc.ensure(bytes + 16); h->d_lam_sqr_acc.ensure(bytes + 16); h->d_grad_sqr_acc.ensure(bytes + 16);
+		auto put = [&](DevBuf& b, const double* src) {
+			if (src) CUDA_OK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+			else CUDA_OK(cudaMemsetAsync(b.p, 0, bytes, h->stream));
+		};
+		put(h->d_lam_acc, lambda_acc); put(h->d_lam_sqr_acc, lambda_sqr_acc); put(h->d_grad_sqr_acc, grad_sqr_acc);
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+		h->have_train_state = true;
 	});
 }
 

@@ -11,6 +11,9 @@
  *       and CRF_Model::setFeatureMap / setLabMaxDur / setNActualLabs / setModelType  CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:472-517,
  *                                                                                   CRF/src/CRF_Model.cpp:75-87
  *   crfgpu_set_lambda            CRF_Model::getLambda() being read by the nodes     CRF/src/CRF_Model.cpp:105-131
+ *   crfgpu_sgd_update            the per-minibatch update of CRF_SGTrainer::sgtrainMinibatch (SGD / AdaGrad / gvar quirk /
+ *   crfgpu_get_lambda            lambdaAcc, lambdaSqrAcc)                            CRF/src/trainers/CRF_SGTrainer.cpp:299-325
+ *   crfgpu_set_train_state       and the arrays its checkpoints write                CRF/src/trainers/CRF_SGTrainer.cpp:336-380
  *   crfgpu_fwdbwd_batch          CRF_Minibatch_GradAccumulator::accumulateGradient  CRF/src/trainers/accumulators/CRF_Minibatch_GradAccumulator.cpp:201-322
  *                                = a loop of CRF_GradBuilder::buildGradient         CRF/src/trainers/gradbuilders/CRF_GradBuilder.h:40
  *                                (CRF_NewGradBuilder.cpp:48-382, CRF_NewGradBuilder_StdSeg.cpp:31-377)
@@ -85,6 +88,24 @@ int crfgpu_index_maps(crfgpu_handle h, uint32_t* state_idx, uint32_t* trans_idx)
 
 /* Copies lambda (host, double) to the device and derives the device-side tables. */
 int crfgpu_set_lambda(crfgpu_handle h, const double* lambda, uint32_t len);
+
+/* Trainer update on the device, so that lambda never leaves HBM between minibatches: with g = staged gradient / n_active
+ * (CRF_Minibatch_GradAccumulator.cpp:306-308; after an all-reduce the gradient at crfgpu_device_results is the global sum),
+ *   if use_gvar:    g -= g * inv_square_var                      (CRF_SGTrainer.cpp:300-303, the reference's own formula)
+ *   if use_adagrad: gradSqrAcc += g*g; lambda += eta / (sqrt(gradSqrAcc) + eps) * g
+ *   else:           lambda += lr * g                             (lr: the trainer's float learning rate promoted to double)
+ *   lambdaAcc += lambda; lambdaSqrAcc += lambda*lambda           (what the .avg.out checkpoints are built from)
+ * and every lambda-derived device table is rebuilt by a kernel.  The staged gradient is consumed. */
+typedef struct crfgpu_sgd {
+	double lr;
+	uint32_t use_gvar; double inv_square_var;
+	uint32_t use_adagrad; double eta, eps;
+} crfgpu_sgd;
+int crfgpu_sgd_update(crfgpu_handle h, const crfgpu_sgd* opt, double n_active);
+/* Device -> host copies of lambda and (any may be NULL) lambdaAcc, lambdaSqrAcc, gradSqrAcc [lambda_len doubles each]. */
+int crfgpu_get_lambda(crfgpu_handle h, double* lambda, double* lambda_acc, double* lambda_sqr_acc, double* grad_sqr_acc);
+/* Resume: host -> device copies of the accumulators (NULL = zeros). */
+int crfgpu_set_train_state(crfgpu_handle h, const double* lambda_acc, const double* lambda_sqr_acc, const double* grad_sqr_acc);
 
 /* ---- host-buffer entry points (the drop-in calls; H2D + kernels + D2H inside) --------------------
  * grad[lambda_len] is OVERWRITTEN with sum over the batch of (empirical - expected) feature counts,

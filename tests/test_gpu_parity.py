@@ -314,3 +314,59 @@ def test_size_independent_properties_full_cfg5():
     assert np.all(np.isfinite(z)) and np.all(n - z < 0)
     assert abs(g[sidx + nS].sum() - g[tidx.reshape(-1)].sum() - 0.0) < 1e-4 * n_utt * exp_segs
     m.close()
+
+
+@pytest.mark.parametrize("adagrad", [0, 1])
+def test_sgd_update_on_device_matches_reference_rule(adagrad):
+    """crfgpu_sgd_update restates CRF_SGTrainer.cpp:299-325 (grad / n_active, the gvar quirk, SGD or AdaGrad, lambdaAcc /
+    lambdaSqrAcc) on the device and rebuilds every lambda-derived table by a kernel: after two updates lambda and the
+    accumulators equal the host rule applied to the same gradients to 1 ulp, and the next gradient equals the one a fresh handle
+    computes from that lambda through crfgpu_set_lambda."""
+    c = TRAIN["stdseg_d10_segftr"]
+    m = gpu(c["cfg"])
+    lam = c["lam"].copy()
+    m.set_lambda(lam)
+    n_act, lr, eta, eps, isv = 4.0, float(np.float32(0.1)), 0.05, 1e-6, 0.01
+    acc = np.zeros_like(lam); sqr = np.zeros_like(lam); gsq = np.zeros_like(lam)
+    for _ in range(2):
+        g, _, _ = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+        m.sgd_update(n_act, lr=lr, use_gvar=1, inv_square_var=isv, use_adagrad=adagrad, eta=eta, eps=eps)
+        gg = g / n_act
+        gg = gg - gg * isv
+        if adagrad:
+            gsq = gsq + gg * gg
+            lam = lam + eta / (np.sqrt(gsq) + eps) * gg
+        else:
+            lam = lam + lr * gg
+        acc = acc + lam; sqr = sqr + lam * lam
+    got, gacc, gsqr, ggsq = m.get_lambda(with_state=True)
+    np.testing.assert_allclose(got, lam, rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(gacc, acc, rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(gsqr, sqr, rtol=1e-13, atol=1e-16)
+    if adagrad:
+        np.testing.assert_allclose(ggsq, gsq, rtol=1e-13, atol=1e-300)
+    g_dev = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    m2 = gpu(c["cfg"])
+    m2.set_lambda(got)
+    g_host = m2.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    for a, b in zip(g_dev, g_host):      # same tables -> same results up to the order of the fp64 atomics of the GEMM epilogues
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9 * np.abs(b).max())
+    m.close(); m2.close()
+
+
+def test_decode_tables_from_device_lambda_bit_exact(oracle):
+    """Viterbi after an on-device update decodes exactly what the oracle decodes from the fetched lambda."""
+    rng = np.random.default_rng(11)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=12, n_base_ftrs=9, max_dur=4, extract_seg_ftrs=1)
+    off, ftrs, labs = synth_batch(rng, 6, 10, 60, 9, 12, 1, 6)
+    m = gpu(cfg)
+    m.set_lambda(rng.uniform(-0.3, 0.3, m.lambda_len))
+    m.fwdbwd(off, ftrs, labs)
+    m.sgd_update(6.0, lr=0.5)
+    lam = m.get_lambda()
+    segs, cost = m.viterbi(off, ftrs)
+    want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs)
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    m.close()
