@@ -74,10 +74,24 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 	const uint32_t t = p.frame_t[n];
 	const uint32_t dmax = min(t + 1, p.D);
 	const float* cur = p.base + (uint64_t)n * p.F;
-	for (uint32_t i = threadIdx.x; i < dmax * p.F; i += blockDim.x) {
-		const uint32_t j = i / p.F, f = i - j * p.F;
-		rows[i] = __ldg(cur - (uint64_t)j * p.F + f);
+	// rows n, n-1, ... are contiguous in the base stream read backwards: row j, feature f sits at cur[f - j*F].  Eight independent loads per
+	// thread are in flight before the first one is stored.
+	for (uint32_t i0 = 0; i0 < dmax * p.F; i0 += 8 * blockDim.x) {
+		float v[8];
+#pragma unroll
+		for (uint32_t k = 0; k < 8; k++) {
+			const uint32_t i = i0 + k * blockDim.x + threadIdx.x;
+			const uint32_t j = i / p.F, f = i - j * p.F;
+			v[k] = i < dmax * p.F ? __ldg(cur - (uint64_t)j * p.F + f) : 0.0f;
+		}
+#pragma unroll
+		for (uint32_t k = 0; k < 8; k++) {
+			const uint32_t i = i0 + k * blockDim.x + threadIdx.x;
+			if (i < dmax * p.F) rows[i] = v[k];
+		}
 	}
+	uint32_t* stp = reinterpret_cast<uint32_t*>(rows + (size_t)p.D * p.F);     // [D*5] sample offsets, read 5 times per (duration, feature)
+	for (uint32_t i = threadIdx.x; i < p.D * 5; i += blockDim.x) stp[i] = p.steps[i];
 	// windows that would start before the utterance are never read by the lattice; keep them zero
 	for (uint32_t i = dmax * p.Wp + threadIdx.x; i < p.D * p.Wp; i += blockDim.x) xw[i] = 0.0f;
 	__syncthreads();
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 				amin = v < amin ? v : amin;
 				float* o = xw + (d - 1) * p.Wp;
 #pragma unroll
-				for (int k = 0; k < 5; k++) o[k * p.F + f] = rows[(d - 1 - p.steps[(d - 1) * 5 + k]) * p.F + f];
+				for (int k = 0; k < 5; k++) o[k * p.F + f] = rows[(d - 1 - stp[(d - 1) * 5 + k]) * p.F + f];
 				o[5 * p.F + f] = acc / (float)d;
 				o[6 * p.F + f] = amax;
 				o[7 * p.F + f] = amin;
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 }
 void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s) {
 	if (n1 <= p.n0) return;
-	const size_t smem = sizeof(float) * (size_t)p.D * (p.Wp + p.F);
+	const size_t smem = sizeof(float) * (size_t)p.D * (p.Wp + p.F + 5);
 	static size_t attr = 0;
 	if (smem > attr) { cudaFuncSetAttribute(expand_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
 	expand_windows_kernel<<<n1 - p.n0, 128, smem, s>>>(p);
