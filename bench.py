@@ -294,6 +294,41 @@ def run_ours(args):
                "frames_per_gpu": int(sub_off[-1])}
         vm.close()
 
+    # ---- frame-level leg (cfg2: 61 labels, 105 features, the same TIMIT-shaped shard), no collective ----
+    frame = None
+    if not args.no_frame:
+        fm = crf_b200.CrfGpu(crf_b200.make_config(**workloads.cfg2_kwargs()), device=local)
+        fm.set_lambda(workloads.lam_for("cfg2", fm.lambda_len))
+        fstream = torch.cuda.ExternalStream(fm.stream, device=local)
+        fm.stage(off, ftrs, labs)
+        for _ in range(3):
+            fm.fwdbwd_staged()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(fstream):
+            f0.record(fstream)
+        for _ in range(args.steps):
+            fm.fwdbwd_staged()
+        with torch.cuda.stream(fstream):
+            f1.record(fstream)
+        barrier()
+        ft = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        fpin_g = crf_b200.PinnedBuffer((fm.lambda_len,), np.float64)
+        fout = (fpin_g.array, pin_n.array, pin_z.array)
+        for _ in range(2):
+            fm.fwdbwd(off, pin_f.array, pin_l.array, out=fout)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fm.fwdbwd(off, pin_f.array, pin_l.array, out=fout)
+        fe2e = 3 * frames_total / (time.perf_counter() - t0)
+        frame = {"metric": "frame-level CRF fwd-bwd+grad frames/s (cfg2: 61 labels, 105 features, 462 utterances per GPU)",
+                 "value": frames_total * args.steps / (float(ft.item()) / 1e3), "unit": UNIT, "e2e": fe2e,
+                 "phases_ms": {k: fm.phase_ms(k) for k in phase_names}, "lambda_len": fm.lambda_len}
+        fpin_g.free()
+        fm.close()
+
     # ---- stress leg (cfg5: 1024 phones, maxDur 30, 64 utterances x 2000 frames), one GPU, reported beside the headline ----
     stress = None
     if world == 1 and not args.no_stress:
@@ -368,7 +403,7 @@ def run_ours(args):
                        "slots_per_cta_option": int(args.slots or 0)},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "steps": e2e_steps, "loglik_check": ll},
-            "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "viterbi": vit, "stress": stress}
+            "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "viterbi": vit, "frame_crf": frame, "stress": stress}
         print(json.dumps(line))
     for pb in (pin_f, pin_l, pin_g, pin_n, pin_z):
         pb.free()
@@ -389,6 +424,7 @@ def main():
     ap.add_argument("--no-viterbi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
+    ap.add_argument("--no-frame", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
