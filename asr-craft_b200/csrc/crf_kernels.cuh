@@ -140,6 +140,7 @@ struct ScoreTmaParams {
 	const float* bias;                // [D*P] or nullptr
 	float* C; uint32_t ldc;           // S[M][ldc], column (d*P + y)
 	uint32_t M, P, K, D, n_chunks, ntile;
+	uint32_t a_from_tmem;             // 1: window tile through tensor memory (score_gemm_tmem_kernel)
 	uint32_t shared_w;                // 1: every duration block uses the same weight tiles / bias (labels = phones, stdseg_no_dur*)
 	float* smaxd;                     // [M][D] per-duration row maxima (-inf where d > t) or nullptr; needs ntile == 1
 	const uint32_t* frame_t;

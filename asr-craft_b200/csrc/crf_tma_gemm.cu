@@ -221,6 +221,145 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tma_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// score_gemm_tma, A operand from TENSOR MEMORY: the converters write the split window tile with tcgen05.st (thread = frame row,
+// 16 consecutive features = one k-step = 8 packed columns) instead of into shared memory, so that per 16 KB of raw input the CTA moves
+// 52 KB through shared memory (TMA write 16 + converter read 16 + weight tile 8 + MMA reads of the weight tile 12) instead of 92 KB,
+// and the MMAs cost 44 instead of 77 cycles (tools/mma_bench.cu).  TMEM per CTA: 64 accumulator columns + 4 stages x (16 hi + 16 lo)
+// = 192 -> 256 allocated, two CTAs per SM.  Shared memory: 4 x 16 KB raw + 4 x 8 KB weight tiles = 96 KB.
+// warps 0-7 converters (warp w: lane quadrant w % 4, k-step w / 4), 8 MMA, 9 window TMA, 10 weight-tile bulk copies
+// ------------------------------------------------------------------------------------------------
+constexpr int TS = 4;                                               // operand stages (A in TMEM, B in shared memory)
+constexpr uint32_t T_B_OFF = RA * RAW_BYTES, T_CTL_OFF = T_B_OFF + TS * 2 * B_TILE, T_SMEM = T_CTL_OFF + 256;
+constexpr uint32_t T_ACOL = 64, T_COLS = 256;
+
+struct TCtl {
+	uint64_t raw_full[RA], raw_empty[RA], op_full[TS], op_empty[TS], done;
+	uint32_t tmem;
+};
+static_assert(sizeof(TCtl) <= 256, "control block");
+
+__global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid_constant__ CUtensorMap tmX, ScoreTmaParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	TCtl* ctl = reinterpret_cast<TCtl*>(smem + T_CTL_OFF);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t m0 = blockIdx.x * BM, jt = blockIdx.y, d = blockIdx.z;
+	const uint32_t n_chunks = p.n_chunks;
+	if (tid == 0) {
+		if (smem_u32(smem) & 1023) __trap();
+		for (int s = 0; s < RA; s++) { mbar_init(&ctl->raw_full[s], 1); mbar_init(&ctl->raw_empty[s], CONV_WARPS); }
+		for (int s = 0; s < TS; s++) { mbar_init(&ctl->op_full[s], CONV_WARPS + 1); mbar_init(&ctl->op_empty[s], 1); }
+		mbar_init(&ctl->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == CONV_WARPS) tmem_alloc(&ctl->tmem, T_COLS);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ctl->tmem;
+
+	if (warp < CONV_WARPS) {
+		const uint32_t q4 = warp & 3, ks = warp >> 2, row = q4 * 32 + lane;
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t r = c % RA, s = c % TS;
+			mbar_wait(&ctl->raw_full[r], (c / RA) & 1);
+			const unsigned char* raw = smem + r * RAW_BYTES;
+			float x0[8], x1[8];
+			load_raw8(raw, row, 2 * ks, x0);
+			load_raw8(raw, row, 2 * ks + 1, x1);
+			uint4 h0, l0, h1, l1;
+			split8(x0, h0, l0); split8(x1, h1, l1);
+			if (c >= TS) { mbar_wait(&ctl->op_empty[s], ((c / TS) - 1) & 1); tc_fence_after(); }
+			const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w}, lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+			const uint32_t col = tmem + ((q4 * 32u) << 16) + T_ACOL + s * 32 + ks * 8;
+			tmem_st8(col, hi);
+			tmem_st8(col + 16, lo);
+			tmem_st_wait();
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) { mbar_arrive(&ctl->op_full[s]); mbar_arrive(&ctl->raw_empty[r]); }
+		}
+	} else if (warp == CONV_WARPS) {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, false, false);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % TS;
+			mbar_wait(&ctl->op_full[s], (c / TS) & 1);
+			tc_fence_after();
+			const uint32_t bbase = smem_u32(smem + T_B_OFF + s * 2 * B_TILE), acol = tmem + T_ACOL + s * 32;
+			if (elect_one()) {
+#pragma unroll
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t bh = smem_desc(bbase + ks * 256, 128, 512), bl = smem_desc(bbase + B_TILE + ks * 256, 128, 512);
+					mma_ts(tmem, acol + ks * 8, bh, idesc, (c | ks) != 0);
+					mma_ts(tmem, acol + 16 + ks * 8, bh, idesc, true);
+					mma_ts(tmem, acol + ks * 8, bl, idesc, true);
+				}
+				mma_commit(&ctl->op_empty[s]);
+			}
+			__syncwarp();
+		}
+		if (elect_one()) mma_commit(&ctl->done);
+		__syncwarp();
+	} else if (warp == CONV_WARPS + 1) {
+		if (lane == 0) {
+			prefetch_tmap(&tmX);
+			for (uint32_t c = 0; c < n_chunks; c++) {
+				const uint32_t r = c % RA;
+				if (c >= RA) mbar_wait(&ctl->raw_empty[r], ((c / RA) - 1) & 1);
+				mbar_arrive_expect_tx(&ctl->raw_full[r], RAW_BYTES);
+				tma_load_3d(smem + r * RAW_BYTES, &tmX, c * KC, d, m0, &ctl->raw_full[r]);
+			}
+		}
+	} else {
+		if (lane == 0) {
+			const unsigned char* src = p.Bt + ((uint64_t)((p.shared_w ? 0u : d) * p.ntile + jt) * n_chunks) * (2 * B_TILE);
+			for (uint32_t c = 0; c < n_chunks; c++) {
+				const uint32_t s = c % TS;
+				if (c >= TS) mbar_wait(&ctl->op_empty[s], ((c / TS) - 1) & 1);
+				mbar_arrive_expect_tx(&ctl->op_full[s], 2 * B_TILE);
+				bulk_g2s(smem + T_B_OFF + s * 2 * B_TILE, src + (uint64_t)c * (2 * B_TILE), 2 * B_TILE, &ctl->op_full[s]);
+			}
+		}
+	}
+	// ---- epilogue: TMEM -> shared transpose -> (+bias) -> coalesced rows of S, and the row maximum of the duration block ----
+	if (warp < 4) {
+		mbar_wait(&ctl->done, 0);
+		tc_fence_after();
+		float* Cs = reinterpret_cast<float*>(smem);       // [128][65] over the raw ring, idle now
+		const uint32_t row = warp * 32 + lane;
+#pragma unroll
+		for (int c0 = 0; c0 < BN; c0 += 16) {
+			float v[16];
+			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+			tmem_ld_wait();
+#pragma unroll
+			for (int j = 0; j < 16; j++) Cs[row * 65 + c0 + j] = v[j];
+		}
+		tc_fence_before();
+		__syncwarp();
+		const uint32_t y0 = jt * BN, ncol = min((uint32_t)BN, p.P - y0);
+		const uint32_t col0 = d * p.P + y0, bcol = (p.shared_w ? 0u : d * p.P) + y0;
+		const float b0 = (p.bias && lane < ncol) ? __ldg(p.bias + bcol + lane) : 0.0f;
+		const float b1 = (p.bias && lane + 32 < ncol) ? __ldg(p.bias + bcol + lane + 32) : 0.0f;
+		for (uint32_t rr = 0; rr < 32; rr++) {
+			const uint32_t rloc = warp * 32 + rr, gm = m0 + rloc;
+			if (gm >= p.M) break;
+			float mx = -INFINITY;
+			float* crow = p.C + (uint64_t)gm * p.ldc + col0;
+			if (lane < ncol) { const float v = Cs[rloc * 65 + lane] + b0; crow[lane] = v; mx = v; }
+			if (lane + 32 < ncol) { const float v = Cs[rloc * 65 + lane + 32] + b1; crow[lane + 32] = v; mx = fmaxf(mx, v); }
+			if (p.smaxd) {
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+				if (lane == 0) p.smaxd[(uint64_t)gm * p.D + d] = (d <= __ldg(p.frame_t + gm)) ? mx : -INFINITY;
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == CONV_WARPS) tmem_dealloc(tmem, T_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // frame_gemm_tma: products whose reduction index is the frame, both operands [frames][columns] (MN-major), both TMA-fed.
 //   MODE 0  state gradient: 128-row side = window features of duration block d (3-D map, coordinate d), 64-column side = Dm columns
 //           of block d.  The inner TMA coordinate must be a multiple of 16 bytes (measured: anything else faults), so the box starts at
@@ -422,7 +561,15 @@ cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaPar
 	CUtensorMap tm;
 	if (!window_map(&tm, X, p.M, p.D, Wp, p.K, BM, true)) return cudaErrorInvalidValue;
 	dim3 grid((p.M + BM - 1) / BM, p.ntile, p.D);
-	score_gemm_tma_kernel<<<grid, SC_THR, SMEM_BYTES, s>>>(tm, p);
+	if (p.a_from_tmem) {
+		static bool attr2 = false;
+		if (!attr2) {
+			cudaError_t e = cudaFuncSetAttribute(score_gemm_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
+			if (e != cudaSuccess) return e;
+			attr2 = true;
+		}
+		score_gemm_tmem_kernel<<<grid, SC_THR, T_SMEM, s>>>(tm, p);
+	} else score_gemm_tma_kernel<<<grid, SC_THR, SMEM_BYTES, s>>>(tm, p);
 	return cudaGetLastError();
 }
 

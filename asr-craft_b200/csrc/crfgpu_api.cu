@@ -79,7 +79,7 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 7; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 15; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
@@ -532,7 +532,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		ScoreTmaParams g{};
 		g.Bt = h->d_Wt.as<unsigned char>(); g.bias = h->d_bias.as<float>(); g.C = h->d_S.as<float>(); g.ldc = Lp;
 		g.M = N; g.P = P; g.K = nSf; g.D = D; g.n_chunks = score_tma_chunks(nSf); g.ntile = (P + 63) / 64;
-		g.frame_t = h->d_frame_t.as<uint32_t>(); g.shared_w = h->nodur ? 1u : 0u;
+		g.frame_t = h->d_frame_t.as<uint32_t>(); g.shared_w = h->nodur ? 1u : 0u; g.a_from_tmem = (h->opt_tma_mask & 8) ? 1u : 0u;
 		if ((h->tc_ok || h->nodur) && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
 		CUDA_OK(launch_score_gemm_tma(h->X() + c.state_fidx_start, h->Wp, g, s));
 		check_kernel(h, 1);
@@ -1035,7 +1035,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			h->opt_nodur_impl = (int)value;
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
-		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels
+		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 score GEMM's window tile through tensor memory
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }
 		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }

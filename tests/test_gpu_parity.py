@@ -41,7 +41,7 @@ def assert_train_close(got, want, what=""):
 
 # lattice kernels: 0 = one CTA per utterance group (E from L2), 1 = cluster-resident E with FFMA, 2 = cluster-resident E with
 # tcgen05 (default); GEMMs: 0 = fp32 FFMA tiles, 1 = tcgen05 split-bf16 with register-staged operands, 2 = 1 + TMA-fed window GEMMs (default)
-IMPLS = {"tc": {}, "tc_ffma_gemm": {"gemm_impl": 0}, "tc_reg_gemm": {"gemm_impl": 1}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
+IMPLS = {"tc": {}, "tc_ffma_gemm": {"gemm_impl": 0}, "tc_reg_gemm": {"gemm_impl": 1}, "tc_tmem_score": {"tma_mask": 15}, "tc_smem_score": {"tma_mask": 7}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
          "legacy_u1": {"dp_impl": 0, "slots": 1}, "legacy_u4": {"dp_impl": 0, "slots": 4, "gemm_impl": 0}}
 
 
@@ -369,4 +369,46 @@ def test_decode_tables_from_device_lambda_bit_exact(oracle):
     for got, exp in zip(segs, want):
         assert all(np.array_equal(x, y) for x, y in zip(got, exp))
     assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["stdseg", "nodur_native", "nodur_tied", "frame"])
+def test_fwdbwd_edge_lengths_match_oracle(oracle, kind):
+    """Ragged edge cases the reference handles: utterances of 1, 2, 3 frames (shorter than maxDur, so most windows never exist),
+    exactly maxDur frames, and a long one, in one batch; reference segments longer than maxDur are split by the label grouping."""
+    rng = np.random.default_rng(17)
+    lens = np.array([1, 2, 3, 1, 6, 7, 40, 2], np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    F, P, D = 7, 5, 6
+    ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+    labs = np.zeros(int(off[-1]), np.uint32)
+    for u in range(len(lens)):
+        t = int(off[u])
+        while t < off[u + 1]:
+            d = int(rng.integers(1, 12))
+            labs[t:min(t + d, int(off[u + 1]))] = rng.integers(0, P)
+            t += d
+    if kind == "stdseg":
+        cfg = make_config("stdseg", n_labs=P * D, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
+    elif kind == "frame":
+        cfg = make_config("stdframe", n_labs=P, n_base_ftrs=F)
+    else:
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.3, 0.3, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs)
+    m = gpu(cfg)
+    if kind.startswith("nodur"):
+        m.set_option("nodur_impl", 1 if kind == "nodur_native" else 2)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, kind)
+    m.close()
+
+
+def test_empty_batch_is_a_no_op():
+    cfg = make_config("stdseg", n_labs=12, n_base_ftrs=4, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1)
+    m = gpu(cfg)
+    m.set_lambda(np.zeros(m.lambda_len))
+    g, n, z = m.fwdbwd(np.zeros(1, np.uint32), np.zeros((0, 4), np.float32), np.zeros(0, np.uint32))
+    assert not g.any() and len(n) == 0 and len(z) == 0
     m.close()
