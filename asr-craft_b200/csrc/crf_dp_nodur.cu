@@ -47,6 +47,8 @@ struct Shared {
 	double scale[UT];             // scale of the frame being produced (rho_t | sigma_t)
 	double kap[UT], lz[UT];       // backward: kappa_t of the frame just finished, logZ of the utterance
 	float vsum[UT];
+	float scf[UT][RING];          // per-step float scale of duration d: the fp64 differences are formed once per (utterance, duration), not per entry
+	float rcf[UT][RING];          // backward phase C: rho_{t-d} + Mmax + kappa_t - logZ
 	uint32_t utt[UT], off[UT], len[UT];
 };
 
@@ -76,6 +78,8 @@ __device__ __forceinline__ void group_barrier(uint32_t* ctr, uint32_t target) {
 
 size_t nodur_smem_bytes(uint32_t P) { return sizeof(Shared) + (size_t)((P + 31) / 32 * 32) * (PT + UT) * sizeof(float) + 16; }
 
+#define NTICK(i) do { if (timing) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+
 template <bool BWD>
 __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -97,6 +101,9 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	uint32_t* ctr = p.ctr + g;
 	uint32_t gstep = 0;
 	const uint32_t kslice = Pk / NW;     // Pk is a multiple of 32, NW = 8
+	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+	unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	long long tlast = timing ? clock64() : 0;
 
 	for (uint32_t b = p.grp_off[g]; b < p.grp_off[g + 1]; b++) {
 		__syncthreads();
@@ -120,6 +127,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 		for (uint32_t step = 0; step < maxlen; step++, gstep++) {
 			const uint32_t t = BWD ? maxlen - 1 - step : step;
 			float* xch = xbase + (gstep & 1) * xstride;
+			NTICK(7);
 			// ---------------------------------------------------------------- scale of bh_t (backward)
 			if (BWD) {
 				if (tid < UT) {
@@ -135,66 +143,77 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 				__syncthreads();
 			}
 			// ---------------------------------------------------------------- phase A: my slice of the new vector
-			// the D terms of an entry are independent: their loads are issued DC at a time before any is used, so a (utterance, phone)
-			// entry costs ceil(D / DC) round trips to L2 / HBM instead of D
-#pragma unroll
-			for (int i = 0; i < 2; i++) {
-				const uint32_t u = warp * 2 + i, len = sh.len[u];
-				const size_t n = (size_t)sh.off[u] + t;
-				float acc = 0.0f;
-				if (!BWD) {
-					if (t < len && y_ok) {
-						const double rt = sh.scale[u];
-						const uint32_t dmax = min(t + 1, D);
-						for (uint32_t d0 = 1; d0 <= dmax; d0 += DC) {
-							float sv[DC], lv[DC];
-#pragma unroll
-							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j;
-								sv[j] = d <= dmax ? __ldg(p.S + n * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
-								lv[j] = (d <= dmax && d <= t) ? p.LG[(n - d) * Pp + y] : 0.0f;
-							}
-#pragma unroll
-							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j;
-								if (d > dmax) continue;
-								const float sc = (d <= t) ? (float)(sh.s_ring[u][(t - d) & (RING - 1)] + p.Mmax - rt) : (float)(-rt);
-								acc += expf(sv[j] + lv[j] + sc);
-							}
-						}
-						p.A[n * Pp + y] = acc;
-					}
-				} else {
-					if (t + 1 < len && y_ok) {
-						const double sg = sh.scale[u];
-						const uint32_t nn = min(len - 1 - t, D);
-						for (uint32_t d0 = 1; d0 <= nn; d0 += DC) {
-							float sv[DC], lv[DC];
-#pragma unroll
-							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j;
-								sv[j] = d <= nn ? __ldg(p.S + (n + d) * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
-								lv[j] = d <= nn ? p.LB[(n + d) * Pp + y] : 0.0f;
-							}
-#pragma unroll
-							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j;
-								if (d > nn) continue;
-								acc += expf(sv[j] + lv[j] + (float)(sh.s_ring[u][(t + d) & (RING - 1)] - sg));
-							}
-						}
-						// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: stored with the frame the new segment starts in (row shift 1 of the Xi GEMM)
-						p.R[(n + 1) * Pp + y] = acc * expf((float)(p.rho[n] + p.Mmax + sg - sh.lz[u]));
-					}
-					if (t == 0 && len > 0 && y_ok) p.R[n * Pp + y] = 0.0f;      // no transition enters the first frame
+			// float scale per (utterance, duration) for phase A: forward rho_{t-d} + Mmax - rho_t (d <= t) or -rho_t (d == t+1); backward
+			// kappa_{t+d} - sigma_t.  Entries of durations that do not exist are 0 (their score is read as -inf).
+			for (uint32_t i = tid; i < UT * RING; i += NTHR) {
+				const uint32_t u = i / RING, d = i % RING, len = sh.len[u];
+				float v = 0.0f;
+				if (d >= 1 && d <= D) {
+					if (!BWD) { if (t < len && d <= t + 1) v = (d <= t) ? (float)(sh.s_ring[u][(t - d) & (RING - 1)] + p.Mmax - sh.scale[u]) : (float)(-sh.scale[u]); }
+					else if (t + 1 < len && d <= len - 1 - t) v = (float)(sh.s_ring[u][(t + d) & (RING - 1)] - sh.scale[u]);
 				}
-				sh.tileT[lane][u] = acc;
-				const float ps = warp_sum(acc);
-				if (lane == 0) __stcg(xch + (size_t)Pk * UT + (size_t)pt * UT + u, ps);
+				sh.scf[u][d] = v;
 			}
 			__syncthreads();
+			NTICK(0);   // backward: scale
+			// the D terms of an entry are independent: the loads of DC durations of BOTH entries of the thread are issued before any is
+			// used, so a frame costs ceil(D / DC) round trips to L2 / HBM instead of 2 D
+			{
+				const uint32_t u0 = warp * 2;
+				float acc[2] = {0.0f, 0.0f};
+				size_t nf[2]; bool act[2]; uint32_t lim[2];
+#pragma unroll
+				for (int i = 0; i < 2; i++) {
+					const uint32_t len = sh.len[u0 + i];
+					nf[i] = (size_t)sh.off[u0 + i] + t;
+					if (!BWD) { act[i] = t < len && y_ok; lim[i] = min(t + 1, D); }
+					else { act[i] = t + 1 < len && y_ok; lim[i] = act[i] ? min(len - 1 - t, D) : 0; }
+					if (!act[i]) lim[i] = 0;
+				}
+				const uint32_t dtop = max(lim[0], lim[1]);
+				for (uint32_t d0 = 1; d0 <= dtop; d0 += DC) {
+					float sv[2][DC], lv[2][DC];
+#pragma unroll
+					for (int i = 0; i < 2; i++)
+#pragma unroll
+						for (uint32_t j = 0; j < DC; j++) {
+							const uint32_t d = d0 + j;
+							const bool on = d <= lim[i];
+							if (!BWD) {
+								sv[i][j] = on ? __ldg(p.S + nf[i] * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
+								lv[i][j] = (on && d <= t) ? p.LG[(nf[i] - d) * Pp + y] : 0.0f;
+							} else {
+								sv[i][j] = on ? __ldg(p.S + (nf[i] + d) * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
+								lv[i][j] = on ? p.LB[(nf[i] + d) * Pp + y] : 0.0f;
+							}
+						}
+#pragma unroll
+					for (int i = 0; i < 2; i++)
+#pragma unroll
+						for (uint32_t j = 0; j < DC; j++) {
+							const uint32_t d = d0 + j;
+							acc[i] += __expf(sv[i][j] + lv[i][j] + sh.scf[u0 + i][d & (RING - 1)]);     // a term that does not exist has sv = -inf
+						}
+				}
+#pragma unroll
+				for (int i = 0; i < 2; i++) {
+					const uint32_t u = u0 + i, len = sh.len[u];
+					if (!BWD) { if (act[i]) p.A[nf[i] * Pp + y] = acc[i]; }
+					else {
+						// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: stored with the frame the new segment starts in (row shift 1 of the Xi GEMM)
+						if (act[i]) p.R[(nf[i] + 1) * Pp + y] = acc[i] * expf((float)(p.rho[nf[i]] + p.Mmax + sh.scale[u] - sh.lz[u]));
+						if (t == 0 && len > 0 && y_ok) p.R[nf[i] * Pp + y] = 0.0f;      // no transition enters the first frame
+					}
+					sh.tileT[lane][u] = acc[i];
+					const float ps = warp_sum(acc[i]);
+					if (lane == 0) __stcg(xch + (size_t)Pk * UT + (size_t)pt * UT + u, ps);
+				}
+			}
+			__syncthreads();
+			NTICK(1);   // phase A
 			if (tid < PT * UT / 4) __stcg(reinterpret_cast<float4*>(xch + (size_t)y0 * UT) + tid, reinterpret_cast<const float4*>(&sh.tileT[0][0])[tid]);
 			group_barrier(ctr, (gstep + 1) * p.npt);
+			NTICK(2);   // barrier
 			// ---------------------------------------------------------------- phase B: my block of the matrix product
 			if (tid < UT) {
 				float v = 0.0f;
@@ -209,6 +228,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 				for (uint32_t i = tid; i < Pk * (UT / 4); i += NTHR) xd[i] = __ldcg(xv + i);
 			}
 			__syncthreads();
+			NTICK(3);   // staging
 			{
 				float acc[UT];
 #pragma unroll
@@ -228,6 +248,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 				for (int u = 0; u < UT; u++) sh.red[warp][u][lane] = acc[u];
 			}
 			__syncthreads();
+			NTICK(4);   // product
 			float lcur[2];
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
@@ -267,37 +288,57 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 				}
 			}
 			__syncthreads();
+			NTICK(5);   // reduction + scales
 			// ---------------------------------------------------------------- phase C (backward): posteriors of frame t
 			if (BWD) {
+				for (uint32_t i = tid; i < UT * RING; i += NTHR) {
+					const uint32_t u = i / RING, d = i % RING, len = sh.len[u];
+					float v = 0.0f;
+					if (d >= 1 && d <= D && t < len && d <= t + 1) {
+						const double kzu = sh.kap[u] - sh.lz[u];
+						v = (d <= t) ? (float)(p.rho[(size_t)sh.off[u] + t - d] + p.Mmax + kzu) : (float)kzu;
+					}
+					sh.rcf[u][d] = v;
+				}
+				__syncthreads();
+				const uint32_t u0 = warp * 2, dmax = min(t + 1, D);
+				bool act[2]; size_t nf[2]; uint32_t lab[2]; double kz[2];
 #pragma unroll
 				for (int i = 0; i < 2; i++) {
-					const uint32_t u = warp * 2 + i, len = sh.len[u];
-					if (t >= len || !y_ok) continue;
-					const size_t n = (size_t)sh.off[u] + t;
-					const uint32_t lab = p.node_lab[n], dmax = min(t + 1, D);
-					const double kz = sh.kap[u] - sh.lz[u];
+					act[i] = t < sh.len[u0 + i] && y_ok;
+					nf[i] = (size_t)sh.off[u0 + i] + t;
+					lab[i] = act[i] ? p.node_lab[nf[i]] : LAB_BAD;
+					kz[i] = 0.0;
+				}
+				if (act[0] || act[1]) {
 					for (uint32_t d0 = 1; d0 <= D; d0 += DC) {
-						float sv[DC], lv[DC]; double rv[DC];
+						float sv[2][DC], lv[2][DC];
 #pragma unroll
-						for (uint32_t j = 0; j < DC; j++) {
-							const uint32_t d = d0 + j;
-							sv[j] = d <= dmax ? __ldg(p.S + n * Lp + (size_t)(d - 1) * P + y) : 0.0f;
-							lv[j] = (d <= dmax && d <= t) ? p.LG[(n - d) * Pp + y] : 0.0f;
-							rv[j] = (d <= dmax && d <= t) ? p.rho[n - d] + p.Mmax : 0.0;
-						}
+						for (int i = 0; i < 2; i++)
 #pragma unroll
-						for (uint32_t j = 0; j < DC; j++) {
-							const uint32_t d = d0 + j, col = (d - 1) * P + y;
-							if (d > D) continue;
-							float dm = 0.0f;
-							if (d <= dmax) dm = ((lab == col) ? 1.0f : 0.0f) - expf(sv[j] + lcur[i] + lv[j] + (float)(rv[j] + kz));
-							p.Dm[n * Lp + col] = dm;
-						}
+							for (uint32_t j = 0; j < DC; j++) {
+								const uint32_t d = d0 + j;
+								const bool on = act[i] && d <= dmax;
+								sv[i][j] = on ? __ldg(p.S + nf[i] * Lp + (size_t)(d - 1) * P + y) : 0.0f;
+								lv[i][j] = (on && d <= t) ? p.LG[(nf[i] - d) * Pp + y] : 0.0f;
+							}
+#pragma unroll
+						for (int i = 0; i < 2; i++)
+#pragma unroll
+							for (uint32_t j = 0; j < DC; j++) {
+								const uint32_t d = d0 + j, col = (d - 1) * P + y;
+								if (d > D || !act[i]) continue;
+								float dm = 0.0f;
+								if (d <= dmax) dm = ((lab[i] == col) ? 1.0f : 0.0f) - __expf(sv[i][j] + lcur[i] + lv[i][j] + sh.rcf[u0 + i][d & (RING - 1)]);
+								p.Dm[nf[i] * Lp + col] = dm;
+							}
 					}
 				}
 			}
+			NTICK(6);   // phase C
 		}
 	}
+	if (timing) { for (int i = 0; i < 8; i++) p.dbg[i] = tacc[i]; p.dbg[8] = gstep; }
 }
 
 int nodur_max_groups(uint32_t P) {

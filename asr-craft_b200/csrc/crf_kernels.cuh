@@ -163,6 +163,7 @@ struct NodurParams {
 	const uint32_t* node_lab;             // [N] (dur-1)*P + phone where a reference segment ends, else LAB_BAD
 	float* xch;                           // [n_groups][2][(Pk + npt) * NODUR_UT] exchange buffers, Pk = P rounded up to 32
 	uint32_t* ctr;                        // [n_groups] barrier counters
+	unsigned long long* dbg;              // optional [16] cycle counters of CTA 0 (CRFGPU_DP_TIMING=1)
 };
 size_t nodur_smem_bytes(uint32_t P);
 int nodur_max_groups(uint32_t P);         // co-resident groups of ceil(P/32) CTAs (0: the phone count does not fit)

@@ -562,12 +562,22 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		q.A = h->d_A.as<float>(); q.LG = h->d_G.as<float>(); q.rho = h->d_m.as<double>(); q.logZ = h->d_logZ.as<double>();
 		q.LB = h->d_LB.as<float>(); q.R = h->d_R.as<float>(); q.Dm = h->d_Dm.as<float>(); q.node_lab = h->d_node_lab.as<uint32_t>();
 		q.xch = h->d_nd_xch.as<float>(); q.ctr = h->d_nd_ctr.as<uint32_t>();
+		static DevBuf ndbg; const bool ntiming = getenv("CRFGPU_DP_TIMING") != nullptr;
+		if (ntiming) { ndbg.ensure(16 * 8); q.dbg = ndbg.as<unsigned long long>(); }
+		auto nreport = [&](const char* what) {
+			unsigned long long v[16]; CUDA_OK(cudaMemcpyAsync(v, ndbg.p, sizeof(v), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+			const double n = v[8] ? (double)v[8] : 1.0;
+			fprintf(stderr, "[crfgpu] no_dur %s: %.0f steps; cycles/step: scale %.0f phaseA %.0f barrier %.0f staging %.0f product %.0f reduce+scales %.0f phaseC %.0f other %.0f\n",
+			        what, n, v[0] / n, v[1] / n, v[2] / n, v[3] / n, v[4] / n, v[5] / n, v[6] / n, v[7] / n);
+		};
 		phase_begin(h, "forward");
 		if (!smax_done) { launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1); }
 		CUDA_OK(launch_nodur_dp(false, q, s)); check_kernel(h, 1);
+		if (ntiming) nreport("forward");
 		phase_end(h, "forward");
 		phase_begin(h, "backward");
 		CUDA_OK(launch_nodur_dp(true, q, s)); check_kernel(h, 1);
+		if (ntiming) nreport("backward");
 		phase_end(h, "backward");
 	} else if (h->tc_ok) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
