@@ -516,6 +516,151 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tma_kernel(const __grid_
 	if (warp == CONV_WARPS) tmem_dealloc(tmem, BN);
 }
 
+// ------------------------------------------------------------------------------------------------
+// frame_gemm, 128-row operand through TENSOR MEMORY (same idea as score_gemm_tmem_kernel): converter thread = one row of the
+// 128-row side (a window feature / a source label), 16 frames = one k-step; it gathers its 16 values down the raw [frame][column]
+// boxes (a warp reads 32 consecutive columns of one frame: conflict-free through the swizzle) and writes them with tcgen05.st.
+// The 64-column operand still goes through the converters into shared memory (MN-major).  TMEM per CTA: 64 + 4 x 32 = 192 -> 256
+// columns; shared memory 3 x 16 + 2 x 8 KB raw + 4 x 8 KB operand = 96 KB; two CTAs per SM.
+// warps 0-7 converters (warp w: lane quadrant w % 4, k-step w / 4), 8 MMA, 9 TMA
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t G_RAWN_OFF = RM * RAW_BYTES, G_OP_OFF = G_RAWN_OFF + RN * RAWN_BYTES, G_CTL_OFF = G_OP_OFF + TS * 2 * B_TILE, G_SMEM = G_CTL_OFF + 256;
+
+struct GCtl {
+	uint64_t m_full[RM], m_empty[RM], n_full[RN], n_empty[RN], op_full[TS], op_empty[TS], done;
+	uint32_t tmem;
+};
+static_assert(sizeof(GCtl) <= 256, "control block");
+
+template <int MODE>
+__global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN, FrameGemmParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	GCtl* ctl = reinterpret_cast<GCtl*>(smem + G_CTL_OFF);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t m0 = blockIdx.x * BM, d = blockIdx.y / p.ntile, y0 = (blockIdx.y % p.ntile) * FRAME_GEMM_TILE;
+	const uint32_t ns = blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.N);
+	const uint32_t n_chunks = (ne - ns + KC - 1) / KC;
+	const uint32_t ncol = min((uint32_t)FRAME_GEMM_TILE, p.P - y0), col0 = d * p.P + y0, sh = col0 & 3;
+	if (tid == 0) {
+		if (smem_u32(smem) & 1023) __trap();
+		for (int s = 0; s < RM; s++) { mbar_init(&ctl->m_full[s], 1); mbar_init(&ctl->m_empty[s], CONV_WARPS); }
+		for (int s = 0; s < RN; s++) { mbar_init(&ctl->n_full[s], 1); mbar_init(&ctl->n_empty[s], CONV_WARPS); }
+		for (int s = 0; s < TS; s++) { mbar_init(&ctl->op_full[s], CONV_WARPS); mbar_init(&ctl->op_empty[s], 1); }
+		mbar_init(&ctl->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == CONV_WARPS) tmem_alloc(&ctl->tmem, T_COLS);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ctl->tmem;
+
+	if (warp < CONV_WARPS) {
+		const uint32_t q4 = warp & 3, ks = warp >> 2;
+		const uint32_t gm = m0 + q4 * 32 + lane;                                      // my row of the 128-row side
+		const uint32_t k = (warp & 3) * 8 + (lane & 7), cg = (warp >> 2) * 4 + (lane >> 3);   // my unit of the 64-column side
+		const bool is_ones = MODE == 0 && gm == p.ones_col;
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t rm = c % RM, rn = c % RN, s = c % TS;
+			mbar_wait(&ctl->m_full[rm], (c / RM) & 1);
+			const unsigned char* box = smem + rm * RAW_BYTES + q4 * 4096;
+			float x[16];
+#pragma unroll
+			for (uint32_t j = 0; j < 16; j++) {
+				const uint32_t kk = ks * 16 + j;
+				x[j] = *reinterpret_cast<const float*>(box + kk * 128 + ((((lane >> 2) ^ (kk & 7))) << 4) + (lane & 3) * 4);
+				if (is_ones) x[j] = (ns + c * KC + kk < ne) ? 1.0f : 0.0f;              // the constant-1 bias feature (TMA zero-fills beyond the window)
+			}
+			uint32_t hi[8], lo[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+			float xn[8];
+			mbar_wait(&ctl->n_full[rn], (c / RN) & 1);
+			if (sh == 0) load_raw8(smem + G_RAWN_OFF + rn * RAWN_BYTES + (cg >> 2) * 4096, k, cg & 3, xn);
+			else load_raw8_shifted(smem + G_RAWN_OFF + rn * RAWN_BYTES, k, cg * 8 + sh, xn);
+			uint4 hn, ln;
+			split8(xn, hn, ln);
+			if (c >= TS) { mbar_wait(&ctl->op_empty[s], ((c / TS) - 1) & 1); tc_fence_after(); }
+			const uint32_t col = tmem + ((q4 * 32u) << 16) + T_ACOL + s * 32 + ks * 8;
+			tmem_st8(col, hi);
+			tmem_st8(col + 16, lo);
+			unsigned char* st = smem + G_OP_OFF + s * 2 * B_TILE;
+			const uint32_t o = cg * 512 + k * 16;
+			*reinterpret_cast<uint4*>(st + o) = hn; *reinterpret_cast<uint4*>(st + B_TILE + o) = ln;
+			fence_proxy_async_smem();
+			tmem_st_wait();
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) { mbar_arrive(&ctl->op_full[s]); mbar_arrive(&ctl->m_empty[rm]); mbar_arrive(&ctl->n_empty[rn]); }
+		}
+	} else if (warp == CONV_WARPS) {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, false, true);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % TS;
+			mbar_wait(&ctl->op_full[s], (c / TS) & 1);
+			tc_fence_after();
+			const uint32_t bbase = smem_u32(smem + G_OP_OFF + s * 2 * B_TILE), acol = tmem + T_ACOL + s * 32;
+			if (elect_one()) {
+#pragma unroll
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t bh = smem_desc(bbase + ks * 256, 128, 512), bl = smem_desc(bbase + B_TILE + ks * 256, 128, 512);
+					mma_ts(tmem, acol + ks * 8, bh, idesc, (c | ks) != 0);
+					mma_ts(tmem, acol + 16 + ks * 8, bh, idesc, true);
+					mma_ts(tmem, acol + ks * 8, bl, idesc, true);
+				}
+				mma_commit(&ctl->op_empty[s]);
+			}
+			__syncwarp();
+		}
+		if (elect_one()) mma_commit(&ctl->done);
+		__syncwarp();
+	} else {
+		if (lane == 0) {
+			prefetch_tmap(&tmM); prefetch_tmap(&tmN);
+			for (uint32_t c = 0; c < n_chunks; c++) {
+				const uint32_t rm = c % RM, rn = c % RN, n = ns + c * KC;
+				if (c >= RM) mbar_wait(&ctl->m_empty[rm], ((c / RM) - 1) & 1);
+				mbar_arrive_expect_tx(&ctl->m_full[rm], RAW_BYTES);
+#pragma unroll
+				for (uint32_t b = 0; b < 4; b++)
+					tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmM, m0 + b * 32, MODE == 0 ? d : 0u, MODE == 0 ? n : n - (d + 1), &ctl->m_full[rm]);
+				if (c >= RN) mbar_wait(&ctl->n_empty[rn], ((c / RN) - 1) & 1);
+				mbar_arrive_expect_tx(&ctl->n_full[rn], RAWN_BYTES);
+#pragma unroll
+				for (uint32_t b = 0; b < 2; b++) tma_load_3d(smem + G_RAWN_OFF + rn * RAWN_BYTES + b * 4096, &tmN, (col0 & ~3u) + b * 32, 0, n, &ctl->n_full[rn]);
+			}
+		}
+	}
+	// ---- epilogue: lane = row of the 128-row side, 64 columns of the duration block; fp64 atomics into the gradient ----
+	if (warp < 4 && n_chunks) {
+		mbar_wait(&ctl->done, 0);
+		tc_fence_after();
+		const uint32_t gm = m0 + warp * 32 + lane;
+		const double sc = (MODE == 0 && gm == p.ones_col) ? p.ones_scale : p.scale;
+#pragma unroll
+		for (int c0 = 0; c0 < BN; c0 += 16) {
+			float v[16];
+			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+			tmem_ld_wait();
+			if (gm < p.Mext) {
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t y = c0 + j;
+					if (y >= ncol || v[j] == 0.0f) continue;
+					if (MODE == 0) atomicAdd(&p.out[(uint64_t)__ldg(p.row_idx + col0 + y) + gm], sc * (double)v[j]);
+					else {
+						const uint32_t idx = __ldg(p.pair_idx + (uint64_t)gm * p.L + col0 + y);
+						if (idx != 0xffffffffu) atomicAdd(&p.out[idx], sc * (double)__ldg(p.Ew + (uint64_t)gm * p.e_ld + col0 + y) * (double)v[j]);
+					}
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == CONV_WARPS) tmem_dealloc(tmem, T_COLS);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -578,6 +723,8 @@ static cudaError_t frame_gemm_attrs() {
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(frame_gemm_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_gemm_tmem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_gemm_tmem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
@@ -595,7 +742,8 @@ cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const
 	CUtensorMap tm, tn;
 	if (!window_map(&tm, X, p.N, p.D, Wp, K, KC, false) || !window_map(&tn, Dm, p.N, 1, ldd, p.D * p.P, KC, false)) return cudaErrorInvalidValue;
 	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	frame_gemm_tma_kernel<0><<<grid, FG_THR, F_SMEM, s>>>(tm, tn, p);
+	if (p.dbg & 2) frame_gemm_tmem_kernel<0><<<grid, FG_THR, G_SMEM, s>>>(tm, tn, p);
+	else frame_gemm_tma_kernel<0><<<grid, FG_THR, F_SMEM, s>>>(tm, tn, p);
 	return cudaGetLastError();
 }
 
@@ -608,7 +756,8 @@ cudaError_t launch_xi_gemm_tma(const float* A, const float* R, uint32_t ld, cons
 	CUtensorMap ta, tr;
 	if (!window_map(&ta, A, p.N, 1, ld, p.L, KC, false) || !window_map(&tr, R, p.N, 1, ld, p.L, KC, false)) return cudaErrorInvalidValue;
 	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	frame_gemm_tma_kernel<1><<<grid, FG_THR, F_SMEM, s>>>(ta, tr, p);
+	if (p.dbg & 2) frame_gemm_tmem_kernel<1><<<grid, FG_THR, G_SMEM, s>>>(ta, tr, p);
+	else frame_gemm_tma_kernel<1><<<grid, FG_THR, F_SMEM, s>>>(ta, tr, p);
 	return cudaGetLastError();
 }
 

@@ -79,7 +79,7 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 15; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
@@ -639,6 +639,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 			FrameGemmParams x{};
 			x.N = N; x.P = P; x.D = 1; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = P; x.ones_col = 0xffffffffu;
 			x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = P; x.Ew = h->d_E.as<float>(); x.e_ld = h->Pp; x.out = h->d_grad.as<double>();
+			x.dbg = (h->opt_tma_mask & 32) ? 2u : 0u;
 			CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), h->Pp, x, s)); check_kernel(h, 1);
 		}
 	} else
@@ -646,6 +647,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		FrameGemmParams x{};
 		x.N = N; x.P = P; x.D = D; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = L; x.ones_col = 0xffffffffu;
 		x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = L; x.Ew = h->d_E.as<float>(); x.e_ld = Lp; x.out = h->d_grad.as<double>();
+		x.dbg = (h->opt_tma_mask & 32) ? 2u : 0u;
 		CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), Lp, x, s)); check_kernel(h, 1);
 	} else if (c.use_trans_bias && h->opt_gemm_impl >= 1 && N > 1) {
 		XiGemmParams x{};
@@ -675,6 +677,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.N = N; r.P = P; r.D = D; r.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; r.k_slab = h->opt_k_slab_tma; r.Mext = nSf + (c.use_state_bias ? 1 : 0);
 		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu; r.scale = 1.0; r.ones_scale = c.state_bias_val;
 		r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
+		r.dbg = (h->opt_tma_mask & 16) ? 2u : 0u;
 		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, h->d_Dm.as<float>(), Lp, r, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
@@ -1045,7 +1048,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			h->opt_nodur_impl = (int)value;
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
-		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 score GEMM's window tile through tensor memory
+		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }
 		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
