@@ -361,8 +361,8 @@ def run_ours(args):
         flops = {"score": 2.0 * (Fs + 1) * L, "forward": 2.0 * L * L, "backward": 2.0 * L * L, "xi": 2.0 * L * L,
                  "grad": 2.0 * L * (Fs + 1)}
         bytes_ = {"score": 4.0 * D * Fs + 4 * L, "forward": 8.0 * L, "backward": 12.0 * L, "xi": 8.0 * L, "grad": 4.0 * L + 4.0 * D * Fs}
-        kernel_of = {"score": "score_gemm_tma_kernel", "forward": "dp_tc_kernel<0>", "backward": "dp_tc_kernel<1>",
-                     "xi": "frame_gemm_tma_kernel<1>", "grad": "frame_gemm_tma_kernel<0>"}
+        kernel_of = {"score": "score_gemm_tmem_kernel", "forward": "dp_tc_kernel<0>", "backward": "dp_tc_kernel<1>",
+                     "xi": "frame_gemm_tmem_kernel<1>", "grad": "frame_gemm_tmem_kernel<0>"}
         launches_of = {"score": 1, "forward": 1, "backward": 1, "xi": 1, "grad": 1}
         dom = max(phase_names, key=lambda k: phase_acc[k])
         rooflines = {}
