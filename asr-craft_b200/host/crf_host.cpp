@@ -2,6 +2,7 @@
 #include "crf_host.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 
@@ -39,7 +40,7 @@ size_t CRF_MemFeatureStream::read(size_t bs, float* fb, QNUInt32* lb) {
 // ---------------------------------------------------------------------------------------------- model
 CRF_Model::CRF_Model(QNUInt32 num_labs)
     : nlabs(num_labs), lab_max_dur(1), nActualLabs(num_labs), model_type(STDFRAME), have_map(false), n_base_ftrs(0),
-      extract_seg_ftrs(false), handle(nullptr) {}
+      extract_seg_ftrs(false), handle(nullptr), lambdaOnDevice(false) {}
 CRF_Model::~CRF_Model() { if (handle) crfgpu_destroy(handle); }
 
 void CRF_Model::setFeatureMap(const CRF_FeatureMap_config& cfg, QNUInt32 base_ftrs, bool seg_ftrs, int device) {
@@ -98,7 +99,7 @@ double CRF_GradBuilder::buildGradient(CRF_FeatureStream* ftr_strm, double* grad,
 	const uint32_t off[2] = {0, (uint32_t)lab_buf.size()};
 	tmp_grad.assign(crf->getLambdaLen(), 0.0);
 	double numer = 0.0;
-	check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
+	if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
 	check(crfgpu_fwdbwd_batch(crf->gpu(), 1, off, ftr_buf.data(), lab_buf.data(), tmp_grad.data(), &numer, Zx_out), "crfgpu_fwdbwd_batch");
 	for (QNUInt32 i = 0; i < crf->getLambdaLen(); i++) grad[i] += tmp_grad[i];
 	return numer;
@@ -125,7 +126,7 @@ double CRF_Minibatch_GradAccumulator::accumulateGradient(double* grad, double* Z
 	}
 	if (!n) { *isEndOfIter = true; *uttCount = 0; *Zx_out = 0.0; std::fill(grad, grad + crf->getLambdaLen(), 0.0); return 0.0; }
 	numer.assign(n, 0.0); logZ.assign(n, 0.0);
-	check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
+	if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
 	check(crfgpu_fwdbwd_batch(crf->gpu(), n, off.data(), ftrs.data(), labs.data(), grad, numer.data(), logZ.data()), "crfgpu_fwdbwd_batch");
 	double num = 0.0; *Zx_out = 0.0;
 	for (QNUInt32 u = 0; u < n; u++) { num += numer[u]; *Zx_out += logZ[u]; }
@@ -134,6 +135,84 @@ double CRF_Minibatch_GradAccumulator::accumulateGradient(double* grad, double* Z
 	const QNUInt32 nActive = std::min(n, nStreams);
 	for (QNUInt32 i = 0; i < crf->getLambdaLen(); i++) grad[i] /= (double)nActive;
 	return num;
+}
+
+double CRF_Minibatch_GradAccumulator::accumulateGradientOnDevice(double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive) {
+	const QNUInt32 nf = strm->num_ftrs();
+	off.assign(1, 0); ftrs.clear(); labs.clear();
+	std::vector<float> fb(nf); QNUInt32 lb = 0;
+	*isEndOfIter = false;
+	if (!started) rewindAllAndNextSegs();
+	QNUInt32 n = 0;
+	while (n < minibatch && started) {
+		size_t T = 0;
+		while (strm->read(1, fb.data(), &lb) == 1) { ftrs.insert(ftrs.end(), fb.begin(), fb.end()); labs.push_back(lb); T++; }
+		if (!T) throw runtime_error("No features read from this sentence");
+		off.push_back((uint32_t)labs.size()); n++;
+		if (strm->nextseg() == QN_SEGID_BAD) { started = false; *isEndOfIter = true; }
+	}
+	*uttCount = n; *Zx_out = 0.0; *nActive = std::min(n, nStreams);
+	if (!n) { *isEndOfIter = true; return 0.0; }
+	numer.assign(n, 0.0); logZ.assign(n, 0.0);
+	if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
+	check(crfgpu_stage_batch(crf->gpu(), n, off.data(), ftrs.data(), labs.data()), "crfgpu_stage_batch");
+	check(crfgpu_fwdbwd_staged(crf->gpu()), "crfgpu_fwdbwd_staged");
+	check(crfgpu_fetch_fwdbwd(crf->gpu(), nullptr, numer.data(), logZ.data()), "crfgpu_fetch_fwdbwd");   // scalars only: the gradient stays in HBM
+	double num = 0.0;
+	for (QNUInt32 u = 0; u < n; u++) { num += numer[u]; *Zx_out += logZ[u]; }
+	return num;
+}
+
+void CRF_Model::syncLambdaFromDevice() {
+	check(crfgpu_get_lambda(gpu(), lambda.data(), lambdaOnDevice ? lambdaAcc.data() : nullptr, nullptr, nullptr), "crfgpu_get_lambda");
+}
+
+// ---------------------------------------------------------------------------------------------- trainer
+CRF_SGTrainer::CRF_SGTrainer(CRF_Model* crf_in, CRF_FeatureStream* stream, const char* wt_fname)
+    : crf_ptr(crf_in), strm(stream), weight_fname(wt_fname), lr(0.008f), lr_decay_rate(1.0f), maxIters(1), minibatch(1), nStreams(1),
+      useAdagrad(false), eta(1.0), eps(1e-6), useGvar(false), invSquareVar(0.0) {}
+
+static bool write_values(const std::string& fname, const double* v, size_t n) {
+	FILE* f = std::fopen(fname.c_str(), "w");
+	if (!f) return false;
+	for (size_t i = 0; i < n; i++) std::fprintf(f, "%g\n", v[i]);      // default ostream precision: 6 significant digits (CRF_Model.cpp:210-212)
+	return std::fclose(f) == 0;
+}
+
+void CRF_SGTrainer::train() {
+	const QNUInt32 len = crf_ptr->getLambdaLen();
+	CRF_Minibatch_GradAccumulator gaccum(crf_ptr, strm, nStreams);
+	gaccum.setMinibatch(minibatch);
+	check(crfgpu_set_lambda(crf_ptr->gpu(), crf_ptr->getLambda(), len), "crfgpu_set_lambda");
+	check(crfgpu_set_train_state(crf_ptr->gpu(), nullptr, nullptr, nullptr), "crfgpu_set_train_state");
+	crf_ptr->lambdaOnDevice = true;
+	iterLogLi.clear();
+	QNUInt32 accCnt = 0;
+	std::vector<double> avg(len);
+	for (int iCounter = 1; iCounter <= maxIters; iCounter++) {
+		double totLogLi = 0.0; bool eoi = false;
+		gaccum.rewindAllAndNextSegs();
+		while (!eoi) {
+			double Zx = 0.0; QNUInt32 cnt = 0, nActive = 0;
+			const double num = gaccum.accumulateGradientOnDevice(&Zx, &cnt, &eoi, &nActive);
+			if (!cnt) break;
+			totLogLi += num - Zx;
+			crfgpu_sgd opt = {(double)lr, useGvar ? 1u : 0u, invSquareVar, useAdagrad ? 1u : 0u, eta, eps};
+			check(crfgpu_sgd_update(crf_ptr->gpu(), &opt, (double)nActive), "crfgpu_sgd_update");
+			accCnt += cnt;
+		}
+		iterLogLi.push_back(totLogLi);
+		crf_ptr->syncLambdaFromDevice();
+		const std::string base = weight_fname + ".i" + std::to_string(iCounter);
+		if (!crf_ptr->writeToFile((base + ".out").c_str())) throw runtime_error("ERROR! File " + base + ".out unable to be opened for writing.");
+		for (QNUInt32 i = 0; i < len; i++) avg[i] = crf_ptr->getLambdaAcc()[i] / (float)accCnt;      // CRF_SGTrainer.cpp:357
+		if (!write_values(base + ".avg.out", avg.data(), len)) throw runtime_error("ERROR! File " + base + ".avg.out unable to be opened for writing.");
+		{ FILE* f = std::fopen((weight_fname + ".done.train.i" + std::to_string(iCounter)).c_str(), "w"); if (f) std::fclose(f); }
+		if (!useAdagrad) lr *= lr_decay_rate;
+	}
+	if (!crf_ptr->writeToFile(weight_fname.c_str())) throw runtime_error("ERROR! File " + weight_fname + " unable to be opened for writing.");
+	if (accCnt) { for (QNUInt32 i = 0; i < len; i++) avg[i] = crf_ptr->getLambdaAcc()[i] / (float)accCnt; write_values(weight_fname + ".avg.out", avg.data(), len); }
+	crf_ptr->lambdaOnDevice = false;
 }
 
 // ---------------------------------------------------------------------------------------------- decoding

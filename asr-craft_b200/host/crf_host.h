@@ -7,6 +7,7 @@
 //   CRF_GradBuilder::create / buildGradient    CRF/src/trainers/gradbuilders/CRF_GradBuilder.h:40-44, .cpp:97-162
 //   CRF_Minibatch_GradAccumulator              CRF/src/trainers/accumulators/CRF_Minibatch_GradAccumulator.h:51-75, .cpp:201-322
 //   CRF_ViterbiDecoder_StdSeg_NoSegTransFtr    CRF/src/decoders/CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398
+//   CRF_SGTrainer (train loop, update, files)  CRF/src/trainers/CRF_SGTrainer.cpp:99-430, CRF_Trainer.h:35-42
 // Differences that follow from the device design (documented in INTEGRATION.md):
 //   * the feature stream handed to the builders is the UN-windowed one (what the pfile / ilab hold): one frame of
 //     num_ftrs() floats and one phone label per read(); the segment windows are expanded on the device;
@@ -111,6 +112,9 @@ public:
 	virtual void setModelType(modeltype m) { model_type = m; }
 	virtual modeltype getModelType() { return model_type; }
 	crfgpu_handle gpu();                                              // the device context of this model (created by setFeatureMap)
+	// lambda lives on the device between minibatches (CRF_SGTrainer below): accumulateGradient then skips the upload and the
+	// host copy is refreshed by syncLambdaFromDevice() (end of an iteration, before a checkpoint)
+	bool lambdaOnDevice; void syncLambdaFromDevice();
 	QNUInt32 baseFtrs() { return n_base_ftrs; }
 };
 
@@ -137,6 +141,8 @@ public:
 	// grad is overwritten with sum(emp - exp) / nStreams_active, *Zx_out = sum logZ, returns sum of numerators
 	virtual double accumulateGradient(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter);
 	void setMinibatch(QNUInt32 mb) { minibatch = mb; }
+	// the same batch, but the gradient stays on the device for crfgpu_sgd_update (no download, no division): returns sum of numerators
+	virtual double accumulateGradientOnDevice(double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive);
 	QNUInt32 getNStreams() { return nStreams; }
 	void rewindAllAndNextSegs();
 };
@@ -153,6 +159,25 @@ public:
 	CRF_ViterbiDecoder_StdSeg_NoSegTransFtr(CRF_FeatureStream* ftr_strm_in, CRF_Model* crf_in) : strm(ftr_strm_in), crf(crf_in) {}
 	// decodes the CURRENT utterance of the stream (free-phone LM, beam 0); returns the number of frames, like nStateDecode
 	int nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam = 0.0);
+};
+
+// CRF_SGTrainer::train() (CRF/src/trainers/CRF_SGTrainer.cpp:99-430) over the device path: per minibatch one device batch and one
+// crfgpu_sgd_update (lambda += lr * grad / nActiveStreams, lambdaAcc += lambda, optional AdaGrad / gvar), at the end of every iteration
+// the reference's files -- <weights>.i<k>.out, <weights>.i<k>.avg.out (lambdaAcc / (float)accCnt), <weights>.done.train.i<k> -- and the
+// learning-rate decay; finally <weights> and <weights>.avg.out.  lr / lr_decay_rate are floats promoted in the update (CRF_Trainer.h:35-42).
+class CRF_SGTrainer {
+	CRF_Model* crf_ptr; CRF_FeatureStream* strm; std::string weight_fname;
+	float lr, lr_decay_rate; int maxIters; QNUInt32 minibatch, nStreams; bool useAdagrad; double eta, eps; bool useGvar; double invSquareVar;
+public:
+	CRF_SGTrainer(CRF_Model* crf_in, CRF_FeatureStream* stream, const char* wt_fname);
+	void setLR(float v) { lr = v; }
+	void setLRDecayRate(float v) { lr_decay_rate = v; }
+	void setMaxIters(int n) { maxIters = n; }
+	void setMinibatch(QNUInt32 mb, QNUInt32 n_streams) { minibatch = mb; nStreams = n_streams; }
+	void setAdagrad(bool on, double eta_in, double eps_in) { useAdagrad = on; eta = eta_in; eps = eps_in; }
+	void setGaussVar(double gvar) { useGvar = gvar != 0.0; invSquareVar = gvar != 0.0 ? 1.0 / (gvar * gvar) : 0.0; }
+	std::vector<double> iterLogLi;        // per iteration: sum over the corpus of numerator - logZ (what the trainer prints as Iter-Avg LogLi * utts)
+	void train();
 };
 
 #endif

@@ -95,6 +95,42 @@ int main(int argc, char** argv) {
 			if (!my_crf.readFromFile(path.c_str())) throw std::runtime_error("readFromFile failed");
 			for (QNUInt32 i = 0; i < len; i++) close(my_crf.getLambda()[i], before[i], 1e-5, "checkpoint round trip");
 			std::remove(path.c_str());
+			// ---- CRF_SGTrainer::train() with lambda resident on the device: 2 iterations, minibatches of 2 utterances, against the same
+			//      loop run through the host seam (accumulateGradient + `lambda += lr * grad`, CRF_SGTrainer.cpp:309) ----
+			std::vector<double> lam0(len);
+			for (QNUInt32 i = 0; i < len; i++) lam0[i] = lam[i];
+			my_crf.setLambda(lam0.data(), len);
+			const std::string wname = std::string(argv[1]) + ".sgd.weights";
+			CRF_MemFeatureStream tstrm(off, ftrs, labs, n_base);
+			CRF_SGTrainer trainer(&my_crf, &tstrm, wname.c_str());
+			trainer.setLR(0.01f); trainer.setLRDecayRate(0.5f); trainer.setMaxIters(2); trainer.setMinibatch(2, 2);
+			trainer.train();
+			std::vector<double> dev_lam(my_crf.getLambda(), my_crf.getLambda() + len);
+			my_crf.setLambda(lam0.data(), len);
+			CRF_MemFeatureStream hstrm(off, ftrs, labs, n_base);
+			CRF_Minibatch_GradAccumulator hacc(&my_crf, &hstrm, 2);
+			hacc.setMinibatch(2);
+			float hlr = 0.01f; double lmax = 0.0;
+			for (int it = 0; it < 2; it++) {
+				bool end = false;
+				hacc.rewindAllAndNextSegs();
+				while (!end) {
+					double z = 0.0; QNUInt32 c2 = 0;
+					hacc.accumulateGradient(g.data(), &z, &c2, &end);
+					if (!c2) break;
+					for (QNUInt32 i = 0; i < len; i++) my_crf.getLambda()[i] += hlr * g[i];
+				}
+				hlr *= 0.5f;
+			}
+			for (QNUInt32 i = 0; i < len; i++) lmax = std::fmax(lmax, std::fabs(my_crf.getLambda()[i]));
+			for (QNUInt32 i = 0; i < len; i++)
+				if (std::fabs(dev_lam[i] - my_crf.getLambda()[i]) > 1e-9 * lmax) { if (bad < 5) std::printf("MISMATCH sgd lambda[%u]: %.12g vs %.12g\n", i, dev_lam[i], my_crf.getLambda()[i]); bad++; }
+			for (const char* suffix : {".i1.out", ".i1.avg.out", ".done.train.i1", ".i2.out", ".i2.avg.out", ".done.train.i2", "", ".avg.out"}) {
+				const std::string f = wname + suffix;
+				FILE* fp = std::fopen(f.c_str(), "r");
+				if (!fp) { std::printf("MISMATCH missing trainer file %s\n", f.c_str()); bad++; } else { std::fclose(fp); std::remove(f.c_str()); }
+			}
+			if (trainer.iterLogLi.size() != 2 || !(trainer.iterLogLi[1] > trainer.iterLogLi[0])) { std::printf("MISMATCH log-likelihood did not improve\n"); bad++; }
 		}
 		if (mode == 1) {
 			// ---- decode seam: first utterance, free-phone LM, beam 0 ----

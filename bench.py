@@ -284,10 +284,17 @@ def run_ours(args):
         vfr = torch.tensor([float(sub_off[-1])], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(vt, op=dist.ReduceOp.MAX); dist.all_reduce(vfr)
+        vpin = crf_b200.PinnedBuffer(sub_f.shape, np.float32); vpin.array[...] = sub_f      # e2e: H2D from pinned host memory
+        vm.viterbi(sub_off, vpin.array, raw=True)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(3):
-            vm.viterbi(sub_off, sub_f, raw=True)
-        ve2e = 3 * float(sub_off[-1]) * world / (time.perf_counter() - t0)
+            vm.viterbi(sub_off, vpin.array, raw=True)
+        vdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(vdt, op=dist.ReduceOp.MAX)
+        ve2e = 3 * float(vfr.item()) / float(vdt.item())
+        vpin.free()
         vit = {"metric": "Viterbi frames/s (cfg3: 183 labels = 61 phones x 3 states, 210 utterances per GPU)",
                "value": float(vfr.item()) * args.steps / (float(vt.item()) / 1000.0), "unit": UNIT, "e2e": ve2e,
                "score_ms": vm.phase_ms("viterbi_score"), "recursion_ms": vm.phase_ms("viterbi"),
