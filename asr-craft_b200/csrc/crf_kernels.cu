@@ -67,8 +67,13 @@ void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t s) {
 // memory, the D windows are built there (running sum / max / min in the reference's order) and leave the SM as 16-byte vectors of
 // whole rows when the row stride allows it (Wp % 4 == 0: every window row is 16-byte aligned), otherwise element by element.
 __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
-	extern __shared__ __align__(16) float xw[];             // [D][Wp] windows, then [D][F] base rows (row j = frame n - j)
-	float* rows = xw + (size_t)p.D * p.Wp;
+	extern __shared__ __align__(16) float xw_raw[];         // [D][Wp] windows, then [D][F] base rows (row j = frame n - j), then [D*5] offsets
+	// three disjoint regions: telling the compiler so lets it hoist the loads of a duration above the stores of the previous one
+	float* __restrict__ xw = xw_raw;
+	const float* __restrict__ rows = xw_raw + (size_t)p.D * p.Wp;
+	const uint32_t* __restrict__ stp = reinterpret_cast<const uint32_t*>(xw_raw + (size_t)p.D * p.Wp + (size_t)p.D * p.F);
+	float* rows_w = xw_raw + (size_t)p.D * p.Wp;
+	uint32_t* stp_w = reinterpret_cast<uint32_t*>(rows_w + (size_t)p.D * p.F);
 	const uint32_t n = p.n0 + blockIdx.x;
 	if (n >= p.N) return;
 	const uint32_t t = p.frame_t[n];
@@ -76,22 +81,25 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 	const float* cur = p.base + (uint64_t)n * p.F;
 	// rows n, n-1, ... are contiguous in the base stream read backwards: row j, feature f sits at cur[f - j*F].  Eight independent loads per
 	// thread are in flight before the first one is stored.
+	const float inv_f = 1.0f / (float)p.F;
 	for (uint32_t i0 = 0; i0 < dmax * p.F; i0 += 8 * blockDim.x) {
 		float v[8];
 #pragma unroll
 		for (uint32_t k = 0; k < 8; k++) {
 			const uint32_t i = i0 + k * blockDim.x + threadIdx.x;
-			const uint32_t j = i / p.F, f = i - j * p.F;
+			uint32_t j = __float2uint_rz((float)i * inv_f);          // i / F for i < 2^20, corrected below
+			if ((j + 1) * p.F <= i) j++;
+			if (j * p.F > i) j--;
+			const uint32_t f = i - j * p.F;
 			v[k] = i < dmax * p.F ? __ldg(cur - (uint64_t)j * p.F + f) : 0.0f;
 		}
 #pragma unroll
 		for (uint32_t k = 0; k < 8; k++) {
 			const uint32_t i = i0 + k * blockDim.x + threadIdx.x;
-			if (i < dmax * p.F) rows[i] = v[k];
+			if (i < dmax * p.F) rows_w[i] = v[k];
 		}
 	}
-	uint32_t* stp = reinterpret_cast<uint32_t*>(rows + (size_t)p.D * p.F);     // [D*5] sample offsets, read 5 times per (duration, feature)
-	for (uint32_t i = threadIdx.x; i < p.D * 5; i += blockDim.x) stp[i] = p.steps[i];
+	for (uint32_t i = threadIdx.x; i < p.D * 5; i += blockDim.x) stp_w[i] = p.steps[i];
 	// windows that would start before the utterance are never read by the lattice; keep them zero
 	for (uint32_t i = dmax * p.Wp + threadIdx.x; i < p.D * p.Wp; i += blockDim.x) xw[i] = 0.0f;
 	__syncthreads();
@@ -105,8 +113,11 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 				amax = v > amax ? v : amax;
 				amin = v < amin ? v : amin;
 				float* o = xw + (d - 1) * p.Wp;
+				float smp[5];
 #pragma unroll
-				for (int k = 0; k < 5; k++) o[k * p.F + f] = rows[(d - 1 - stp[(d - 1) * 5 + k]) * p.F + f];
+				for (int k = 0; k < 5; k++) smp[k] = rows[(d - 1 - stp[(d - 1) * 5 + k]) * p.F + f];
+#pragma unroll
+				for (int k = 0; k < 5; k++) o[k * p.F + f] = smp[k];
 				o[5 * p.F + f] = acc / (float)d;
 				o[6 * p.F + f] = amax;
 				o[7 * p.F + f] = amin;
