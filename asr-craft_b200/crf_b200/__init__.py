@@ -68,7 +68,7 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_viterbi_staged", "crfgpu_device_results", "crfgpu_fetch_fwdbwd", "crfgpu_fetch_viterbi",
            "crfgpu_synchronize", "crfgpu_stream", "crfgpu_launch_count", "crfgpu_phase_ms",
            "crfgpu_fetch_alpha_beta", "crfgpu_set_option", "crfgpu_host_alloc", "crfgpu_host_free",
-           "crfgpu_sgd_update", "crfgpu_get_lambda", "crfgpu_set_train_state"]
+           "crfgpu_sgd_update", "crfgpu_get_lambda", "crfgpu_set_train_state", "crfgpu_prefetch_batch"]
 
 
 class Sgd(C.Structure):
@@ -257,6 +257,12 @@ class CrfGpu:
         n = len(off) - 1
         self._check(self.lib.crfgpu_stage_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float), lp))
         self._n_utt, self._n_frames = n, int(off[-1])
+
+    def prefetch(self, off, ftrs):
+        """crfgpu_prefetch_batch: copy + window-expand the NEXT batch on side streams; `ftrs` must be the very array later staged."""
+        off = np.ascontiguousarray(off, np.uint32)
+        assert ftrs.dtype == np.float32 and ftrs.flags["C_CONTIGUOUS"]
+        self._check(self.lib.crfgpu_prefetch_batch(self.h, C.c_uint32(len(off) - 1), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float)))
 
     def fwdbwd_staged(self):
         self._check(self.lib.crfgpu_fwdbwd_staged(self.h))

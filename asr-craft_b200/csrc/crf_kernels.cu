@@ -67,17 +67,20 @@ void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t s) {
 // memory, the D windows are built there (running sum / max / min in the reference's order) and leave the SM as 16-byte vectors of
 // whole rows when the row stride allows it (Wp % 4 == 0: every window row is 16-byte aligned), otherwise element by element.
 __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
-	extern __shared__ __align__(16) float xw_raw[];         // [D][Wp] windows, then [D][F] base rows (row j = frame n - j), then [D*5] offsets
+	// blockIdx.y selects a group of p.dpart durations (the whole window set when dpart == D); small groups keep the CTA's shared memory
+	// low enough to run beside a resident lattice CTA (crfgpu_prefetch_batch)
+	extern __shared__ __align__(16) float xw_raw[];         // [dpart][Wp] windows, then [D][F] base rows (row j = frame n - j), then [D*5] offsets
+	const uint32_t DP = p.dpart, dlo = blockIdx.y * DP + 1, dhi = min(dlo + DP - 1, p.D);   // durations [dlo, dhi] of this CTA
 	// three disjoint regions: telling the compiler so lets it hoist the loads of a duration above the stores of the previous one
 	float* __restrict__ xw = xw_raw;
-	const float* __restrict__ rows = xw_raw + (size_t)p.D * p.Wp;
-	const uint32_t* __restrict__ stp = reinterpret_cast<const uint32_t*>(xw_raw + (size_t)p.D * p.Wp + (size_t)p.D * p.F);
-	float* rows_w = xw_raw + (size_t)p.D * p.Wp;
+	const float* __restrict__ rows = xw_raw + (size_t)DP * p.Wp;
+	const uint32_t* __restrict__ stp = reinterpret_cast<const uint32_t*>(xw_raw + (size_t)DP * p.Wp + (size_t)p.D * p.F);
+	float* rows_w = xw_raw + (size_t)DP * p.Wp;
 	uint32_t* stp_w = reinterpret_cast<uint32_t*>(rows_w + (size_t)p.D * p.F);
 	const uint32_t n = p.n0 + blockIdx.x;
 	if (n >= p.N) return;
 	const uint32_t t = p.frame_t[n];
-	const uint32_t dmax = min(t + 1, p.D);
+	const uint32_t dtop = min(t + 1, p.D), dmax = min(dtop, dhi);       // durations that exist for this frame, up to this CTA's last one
 	const float* cur = p.base + (uint64_t)n * p.F;
 	// rows n, n-1, ... are contiguous in the base stream read backwards: row j, feature f sits at cur[f - j*F].  Eight independent loads per
 	// thread are in flight before the first one is stored.
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 	}
 	for (uint32_t i = threadIdx.x; i < p.D * 5; i += blockDim.x) stp_w[i] = p.steps[i];
 	// windows that would start before the utterance are never read by the lattice; keep them zero
-	for (uint32_t i = dmax * p.Wp + threadIdx.x; i < p.D * p.Wp; i += blockDim.x) xw[i] = 0.0f;
+	for (uint32_t i = (dmax >= dlo ? dmax - dlo + 1 : 0) * p.Wp + threadIdx.x; i < (dhi - dlo + 1) * p.Wp; i += blockDim.x) xw[i] = 0.0f;
 	__syncthreads();
 	if (p.seg_ftrs) {
 		for (uint32_t f = threadIdx.x; f < p.F; f += blockDim.x) {
@@ -112,7 +115,8 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 				acc += v;
 				amax = v > amax ? v : amax;
 				amin = v < amin ? v : amin;
-				float* o = xw + (d - 1) * p.Wp;
+				if (d < dlo) continue;                               // the running statistics still cover the shorter windows
+				float* o = xw + (d - dlo) * p.Wp;
 				float smp[5];
 #pragma unroll
 				for (int k = 0; k < 5; k++) smp[k] = rows[(d - 1 - stp[(d - 1) * 5 + k]) * p.F + f];
@@ -125,19 +129,19 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 		}
 		// one-hot duration + the pad behind each window
 		const uint32_t tail = p.Wp - 8 * p.F;
-		for (uint32_t i = threadIdx.x; i < dmax * tail; i += blockDim.x) {
-			const uint32_t d = i / tail, j = i - d * tail;
-			xw[d * p.Wp + 8 * p.F + j] = (j == d) ? 1.0f : 0.0f;
+		for (uint32_t i = threadIdx.x; i < (dmax >= dlo ? dmax - dlo + 1 : 0) * tail; i += blockDim.x) {
+			const uint32_t dl = i / tail, j = i - dl * tail;
+			xw[dl * p.Wp + 8 * p.F + j] = (j == dl + dlo - 1) ? 1.0f : 0.0f;
 		}
 	} else {
-		for (uint32_t i = threadIdx.x; i < dmax * p.Wp; i += blockDim.x) {
-			const uint32_t d = i / p.Wp, f = i - d * p.Wp;
-			xw[i] = f < p.F ? rows[d * p.F + f] : 0.0f;
+		for (uint32_t i = threadIdx.x; i < (dmax >= dlo ? dmax - dlo + 1 : 0) * p.Wp; i += blockDim.x) {
+			const uint32_t dl = i / p.Wp, f = i - dl * p.Wp;
+			xw[i] = f < p.F ? rows[(dl + dlo - 1) * p.F + f] : 0.0f;
 		}
 	}
 	__syncthreads();
-	float* out = p.X + (uint64_t)n * p.D * p.Wp;
-	const uint32_t tot = p.D * p.Wp;
+	float* out = p.X + ((uint64_t)n * p.D + (dlo - 1)) * p.Wp;
+	const uint32_t tot = (dhi - dlo + 1) * p.Wp;
 	if (p.Wp % 4 == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0) {
 		float4* o4 = reinterpret_cast<float4*>(out);
 		const float4* s4 = reinterpret_cast<const float4*>(xw);
@@ -148,10 +152,13 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 }
 void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s) {
 	if (n1 <= p.n0) return;
-	const size_t smem = sizeof(float) * (size_t)p.D * (p.Wp + p.F + 5);
+	ExpandParams q = p;
+	if (q.dpart == 0 || q.dpart > q.D) q.dpart = q.D;
+	const size_t smem = sizeof(float) * ((size_t)q.dpart * q.Wp + (size_t)q.D * (q.F + 5));
 	static size_t attr = 0;
 	if (smem > attr) { cudaFuncSetAttribute(expand_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
-	expand_windows_kernel<<<n1 - p.n0, 128, smem, s>>>(p);
+	dim3 grid(n1 - q.n0, (q.D + q.dpart - 1) / q.dpart);
+	expand_windows_kernel<<<grid, 128, smem, s>>>(q);
 }
 
 // =================================================================================================

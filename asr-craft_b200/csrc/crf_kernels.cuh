@@ -19,6 +19,7 @@ struct ExpandParams {
 	uint32_t N, F, D, W, Wp;
 	uint32_t seg_ftrs;        // 1: [5 samples|avg|max|min|one-hot dur], 0: first frame of the window
 	uint32_t n0;              // first frame of this launch
+	uint32_t dpart;           // durations per CTA (0 = all): small groups keep shared memory low enough to run beside a lattice CTA
 };
 void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s);   // frames [p.n0, n1)
 

@@ -64,6 +64,11 @@ struct crfgpu_ctx {
 	// page-locked arena for the per-batch index tables: their uploads must not serialise the host with the stream (a copy from pageable
 	// memory first waits for everything queued on its stream)
 	unsigned char* pin = nullptr; size_t pin_cap = 0, pin_used = 0; cudaEvent_t ev_pin = nullptr;
+	// crfgpu_prefetch_batch: the NEXT minibatch's base features and windows, copied / expanded into a second buffer set on side streams
+	// while the current minibatch computes; crfgpu_stage_batch swaps the sets when it is handed the batch that was prefetched
+	DevBuf d_base2, d_X2, d_frame_t2; cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre_done = nullptr, ev_pre_ready = nullptr;
+	cudaEvent_t ev_swap = nullptr; bool swap_marked = false;   // main-stream point after which the spare buffer set is free
+	std::vector<cudaEvent_t> ev_chunk2; bool pre_valid = false; const float* pre_ftrs = nullptr; std::vector<uint32_t> pre_off;
 	uint32_t W = 0;          // window feature width
 	uint32_t Wp = 0;         // stride between the windows of a frame in X (>= W; currently W, see crfgpu_create)
 	uint32_t Lp = 0;         // padded label stride of the lattice arrays
@@ -79,7 +84,7 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192, opt_prefetch_smem = 1u << 20;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
@@ -278,14 +283,84 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 	CUDA_OK(cudaStreamSynchronize(h->stream));   // the caller may reuse `lam` at once
 }
 
-// ---------------------------------------------------------------------------------------------
-void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs) {
+// ---------------------------------------------------------------------------------------------// Base features to the device in up to 4 chunks cut at utterance boundaries on the copy stream, and -- on stream xs -- the window
+// expansion of chunk i (windows never reach across utterances) while chunk i+1 is still in flight.  d_ft must already be queued on xs.
+void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_t N, const float* ftrs, DevBuf& d_base, DevBuf& d_X, DevBuf& d_ft,
+                     cudaStream_t xs, cudaEvent_t ev_ready, std::vector<cudaEvent_t>& evs, const char* phase, uint32_t dpart = 0) {
 	const crfgpu_config& c = h->cfg;
+	if (!N) return;
+	if (!h->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+	CUDA_OK(cudaEventRecord(ev_ready, xs));                              // everything queued on xs so far may still read the old contents
+	CUDA_OK(cudaStreamWaitEvent(h->copy_stream, ev_ready, 0));
+	const uint32_t n_chunks = N >= (1u << 16) ? 4u : 1u;
+	std::vector<uint32_t> ends;
+	uint32_t u = 0, n_prev = 0;
+	for (uint32_t k = 1; k <= n_chunks; k++) {
+		const uint64_t target = (uint64_t)N * k / n_chunks;
+		while (u < n_utt && off[u + 1] <= target) u++;
+		const uint32_t n_end = (k == n_chunks) ? N : off[u];
+		if (n_end <= n_prev) continue;
+		if (evs.size() <= ends.size()) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); evs.push_back(e); }
+		CUDA_OK(cudaMemcpyAsync(d_base.as<float>() + (size_t)n_prev * c.n_base_ftrs, ftrs + (size_t)n_prev * c.n_base_ftrs,
+		                        sizeof(float) * (size_t)(n_end - n_prev) * c.n_base_ftrs, cudaMemcpyHostToDevice, h->copy_stream));
+		CUDA_OK(cudaEventRecord(evs[ends.size()], h->copy_stream));
+		ends.push_back(n_end);
+		n_prev = n_end;
+	}
+	if (phase) phase_begin(h, phase);
+	n_prev = 0;
+	for (size_t k = 0; k < ends.size(); k++) {
+		CUDA_OK(cudaStreamWaitEvent(xs, evs[k], 0));
+		if (c.max_dur > 1) {
+			ExpandParams ep{d_base.as<float>(), d_ft.as<uint32_t>(), h->d_steps.as<uint32_t>(), d_X.as<float>(),
+			                N, c.n_base_ftrs, c.max_dur, h->W, h->Wp, c.extract_seg_ftrs, n_prev, dpart};
+			launch_expand_windows(ep, ends[k], xs);
+			check_kernel(h, 1);
+		}
+		n_prev = ends[k];
+	}
+	if (phase) phase_end(h, phase);
+	if (h->chunk_end.size() < ends.size() || phase) h->chunk_end = ends;
+}
+
+void validate_offsets(uint32_t n_utt, const uint32_t* off, const float* ftrs) {
 	if (!off || !ftrs) throw ApiError(CRFGPU_ERR_ARG, "null input pointer");
 	if (off[0] != 0) throw ApiError(CRFGPU_ERR_ARG, "frame_off[0] must be 0");
 	for (uint32_t u = 0; u < n_utt; u++)
 		if (off[u + 1] <= off[u])
 			throw ApiError(CRFGPU_ERR_ARG, "utterance " + std::to_string(u) + " has no frames (reference: \"No features read from this sentence\")");
+}
+
+void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs) {
+	const crfgpu_config& c = h->cfg;
+	validate_offsets(n_utt, off, ftrs);
+	const uint32_t N = n_utt ? off[n_utt] : 0;
+	h->pre_valid = false;
+	if (!N) return;
+	if (!h->pre_stream) {
+		CUDA_OK(cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
+		CUDA_OK(cudaEventCreate(&h->ev_pre_done)); CUDA_OK(cudaEventCreate(&h->ev_pre_ready));
+	}
+	if (h->swap_marked) CUDA_OK(cudaStreamWaitEvent(h->pre_stream, h->ev_swap, 0));
+	std::vector<uint32_t> frame_t(N);
+	for (uint32_t u = 0; u < n_utt; u++)
+		for (uint32_t n = off[u]; n < off[u + 1]; n++) frame_t[n] = n - off[u];
+	h->d_base2.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
+	if (c.max_dur > 1) h->d_X2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+	upload(h->d_frame_t2, frame_t, h->pre_stream);                       // pageable: waits only for this side stream's own earlier work
+	// optional cap on the expansion's shared memory per CTA (option prefetch_smem): small duration groups fit beside a resident lattice
+	// CTA, but measured on cfg4 that SLOWS the step (e2e 13.0 M frames/s at 12 KB vs 14.1 M uncapped: the co-resident CTAs steal issue
+	// and shared-memory bandwidth from the latency-bound recursion), so by default the read-ahead uses whole-frame CTAs
+	uint32_t dpart = c.max_dur;
+	while (dpart > 1 && sizeof(float) * ((size_t)dpart * h->Wp + (size_t)c.max_dur * (c.n_base_ftrs + 5)) > (size_t)h->opt_prefetch_smem) dpart--;
+	copy_and_expand(h, n_utt, off, N, ftrs, h->d_base2, h->d_X2, h->d_frame_t2, h->pre_stream, h->ev_pre_ready, h->ev_chunk2, nullptr, dpart);
+	CUDA_OK(cudaEventRecord(h->ev_pre_done, h->pre_stream));
+	h->pre_off.assign(off, off + n_utt + 1); h->pre_ftrs = ftrs; h->pre_valid = true;
+}
+
+void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs) {
+	const crfgpu_config& c = h->cfg;
+	validate_offsets(n_utt, off, ftrs);
 	const uint32_t N = n_utt ? off[n_utt] : 0;
 	cudaStream_t s = h->stream;
 	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
@@ -304,49 +379,25 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		h->pin_used = 0;
 	}
 
-	// what the window expansion needs goes through the copy engine ahead of the feature chunks
 	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
 	for (uint32_t u = 0; u < n_utt; u++)
 		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
-	upload_async(h, h->d_off, h->h_off); upload_async(h, h->d_frame_t, frame_t);
-	// base features: up to 4 chunks cut at utterance boundaries, copied on a second stream FIRST; the main stream expands the windows
-	// of chunk i (they never reach across utterances) while chunk i+1 is still in flight and the host prepares the label tables
-	h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
-	if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
-	h->chunk_end.clear();
-	if (N) {
-		if (!h->copy_stream) { CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreate(&h->ev_ready)); }
-		CUDA_OK(cudaEventRecord(h->ev_ready, s));                        // everything queued so far may still read the old batch
-		CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
-		const uint32_t n_chunks = N >= (1u << 16) ? 4u : 1u;
-		uint32_t u = 0, n_prev = 0;
-		for (uint32_t k = 1; k <= n_chunks; k++) {
-			const uint64_t target = (uint64_t)N * k / n_chunks;
-			while (u < n_utt && off[u + 1] <= target) u++;
-			const uint32_t n_end = (k == n_chunks) ? N : off[u];
-			if (n_end <= n_prev) continue;
-			if (h->ev_chunk.size() <= h->chunk_end.size()) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); h->ev_chunk.push_back(e); }
-			CUDA_OK(cudaMemcpyAsync(h->d_base.as<float>() + (size_t)n_prev * c.n_base_ftrs, ftrs + (size_t)n_prev * c.n_base_ftrs,
-			                        sizeof(float) * (size_t)(n_end - n_prev) * c.n_base_ftrs, cudaMemcpyHostToDevice, h->copy_stream));
-			CUDA_OK(cudaEventRecord(h->ev_chunk[h->chunk_end.size()], h->copy_stream));
-			h->chunk_end.push_back(n_end);
-			n_prev = n_end;
-		}
-	}
-	{
-		if (N) phase_begin(h, "expand");
-		uint32_t n_prev = 0;
-		for (size_t k = 0; k < h->chunk_end.size(); k++) {
-			CUDA_OK(cudaStreamWaitEvent(s, h->ev_chunk[k], 0));
-			if (c.max_dur > 1) {
-				ExpandParams ep{h->d_base.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_steps.as<uint32_t>(), h->d_X.as<float>(),
-				                N, c.n_base_ftrs, c.max_dur, h->W, h->Wp, c.extract_seg_ftrs, n_prev};
-				launch_expand_windows(ep, h->chunk_end[k], s);
-				check_kernel(h, 1);
-			}
-			n_prev = h->chunk_end[k];
-		}
-		if (N) phase_end(h, "expand");
+	upload_async(h, h->d_off, h->h_off);
+	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off;
+	h->pre_valid = false;
+	if (prefetched) {
+		// this batch was copied and expanded by crfgpu_prefetch_batch while the previous one computed: take over its buffers
+		if (!h->ev_swap) CUDA_OK(cudaEventCreateWithFlags(&h->ev_swap, cudaEventDisableTiming));
+		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
+		std::swap(h->d_base, h->d_base2); std::swap(h->d_X, h->d_X2); std::swap(h->d_frame_t, h->d_frame_t2);
+		CUDA_OK(cudaStreamWaitEvent(s, h->ev_pre_done, 0));
+	} else {
+		// what the window expansion needs goes through the copy engine ahead of the feature chunks
+		upload_async(h, h->d_frame_t, frame_t);
+		h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
+		if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+		if (N && !h->ev_ready) CUDA_OK(cudaEventCreate(&h->ev_ready));
+		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand");
 	}
 	upload_async(h, h->d_frame_utt, frame_utt); upload_async(h, h->d_frame_len, frame_len);
 
@@ -780,6 +831,7 @@ int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
 		CUDA_OK(cudaStreamSynchronize(h->stream));
 		const char* env = getenv("CRFGPU_SLOTS");
 		if (env) h->opt_slots = atoi(env);
+		if ((env = getenv("CRFGPU_PREFETCH_SMEM"))) h->opt_prefetch_smem = (uint32_t)atoi(env);
 		*out = h;
 	});
 	if (rc != CRFGPU_OK && h) { delete h; }
@@ -796,10 +848,15 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+	for (cudaEvent_t e : h->ev_chunk2) cudaEventDestroy(e);
+	if (h->ev_pre_done) cudaEventDestroy(h->ev_pre_done);
+	if (h->ev_swap) cudaEventDestroy(h->ev_swap);
+	if (h->ev_pre_ready) cudaEventDestroy(h->ev_pre_ready);
+	if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
 	if (h->ev_ready) cudaEventDestroy(h->ev_ready);
 	if (h->ev_pin) cudaEventDestroy(h->ev_pin);
 	if (h->pin) cudaFreeHost(h->pin);
@@ -877,6 +934,14 @@ int crfgpu_set_train_state(crfgpu_handle h, const double* lambda_acc, const doub
 		put(h->d_lam_acc, lambda_acc); put(h->d_lam_sqr_acc, lambda_sqr_acc); put(h->d_grad_sqr_acc, grad_sqr_acc);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
 		h->have_train_state = true;
+	});
+}
+
+int crfgpu_prefetch_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		prefetch_batch(h, n_utt, frame_off, base_ftrs);
 	});
 }
 
@@ -1049,6 +1114,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
+		else if (n == "prefetch_smem") h->opt_prefetch_smem = (uint32_t)value;   // shared-memory cap of the read-ahead expansion's CTAs
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }
 		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }

@@ -230,14 +230,16 @@ def run_ours(args):
     out = (pin_g.array, pin_n.array, pin_z.array)
     e2e_steps = max(2, min(args.steps, 5))
     def e2e_step():
-        if world == 1:
-            m.fwdbwd(off, pin_f.array, pin_l.array, out=out)      # crfgpu_fwdbwd_batch: H2D + kernels + D2H, synchronous
-        else:
-            # the same host-buffer calls split at the collective: H2D (crfgpu_stage_batch), kernels (crfgpu_fwdbwd_staged),
-            # ONE NCCL all-reduce of the gradient (+ scalars) on the handle's stream, D2H (crfgpu_fetch_fwdbwd)
-            m.stage(off, pin_f.array, pin_l.array)
-            m.fwdbwd_staged(); allreduce_grad()
-            m.fetch_fwdbwd(out=out)
+        # the host-buffer calls of one training step: H2D (crfgpu_stage_batch), kernels (crfgpu_fwdbwd_staged), the read-ahead of the
+        # NEXT minibatch's features (crfgpu_prefetch_batch: its H2D + window expansion run on side streams under this step's kernels
+        # and are taken over by the next crfgpu_stage_batch), ONE NCCL all-reduce of the gradient (+ scalars) on the handle's stream
+        # when N > 1, D2H (crfgpu_fetch_fwdbwd).  Every step's H2D and D2H are inside the timed region.
+        m.stage(off, pin_f.array, pin_l.array)
+        m.fwdbwd_staged()
+        if not args.no_prefetch:
+            m.prefetch(off, pin_f.array)
+        allreduce_grad()
+        m.fetch_fwdbwd(out=out)
 
     for _ in range(2):
         e2e_step()
@@ -432,6 +434,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-frame", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

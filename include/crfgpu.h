@@ -20,6 +20,7 @@
  *   crfgpu_viterbi_batch         CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode>::nStateDecode
  *                                with lm_fst==NULL, beam 0                           CRF/src/decoders/CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398
  *   crfgpu_expand_windows        CRF_InFtrStream_SeqMultiWindow::read_ftrs           CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:209-328
+ *   crfgpu_prefetch_batch        the bunch read-ahead of the feature streams         CRF/src/io/CRF_FeatureStream.cpp:116-136
  *   crfgpu_group_labels          CRF_InLabStream_SeqMultiWindow::nextseg/read_labs   CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-306
  *
  * Inputs are the UN-windowed streams (what the pfile / ilab hold): a ragged batch of utterances,
@@ -132,6 +133,11 @@ int crfgpu_group_labels(const crfgpu_config* cfg, uint32_t n_frames, const uint3
 /* Stage a batch: copies offsets/features/labels to the device (async on the handle's stream). */
 int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off,
                        const float* base_ftrs, const uint32_t* frame_labs /* may be NULL for decode */);
+/* Optional: start copying and window-expanding the NEXT minibatch into a second buffer set on side streams, to be called after
+ * crfgpu_fwdbwd_staged of the current one (the data-loader prefetch of a training loop; it does not touch lambda).  The next
+ * crfgpu_stage_batch / crfgpu_fwdbwd_batch that is handed the same frame_off contents and base_ftrs pointer takes the buffers over
+ * instead of copying again; any other batch is staged normally.  base_ftrs must stay valid and unchanged until then. */
+int crfgpu_prefetch_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs);
 /* Run forward-backward+gradient on the staged batch; results stay on the device. */
 int crfgpu_fwdbwd_staged(crfgpu_handle h);
 /* Run Viterbi + traceback on the staged batch; results stay on the device. */

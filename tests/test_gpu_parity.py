@@ -412,3 +412,29 @@ def test_empty_batch_is_a_no_op():
     g, n, z = m.fwdbwd(np.zeros(1, np.uint32), np.zeros((0, 4), np.float32), np.zeros(0, np.uint32))
     assert not g.any() and len(n) == 0 and len(z) == 0
     m.close()
+
+
+def test_prefetch_takes_over_buffers_and_falls_back():
+    """crfgpu_prefetch_batch: a batch that was prefetched is staged by taking its buffers over (same results as a plain call);
+    staging a DIFFERENT batch after a prefetch ignores the prefetch."""
+    a, b = TRAIN["stdseg_d10_segftr"], TRAIN["stdseg_d4_segftr"]
+    m = gpu(a["cfg"])
+    m.set_lambda(a["lam"])
+    want = m.fwdbwd(a["off"], a["ftrs"], a["labs"])
+    fa = np.ascontiguousarray(a["ftrs"], np.float32)
+    for _ in range(3):                                # steady state: prefetch the next copy of the batch while this one computes
+        m.stage(a["off"], fa, a["labs"])
+        m.fwdbwd_staged()
+        m.prefetch(a["off"], fa)
+        got = m.fetch_fwdbwd()
+        for x, y in zip(got, want):
+            np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(y).max()))
+    m.prefetch(a["off"], fa)
+    shifted = np.ascontiguousarray(fa[::-1])          # other contents at another address: must be staged normally
+    got = m.fwdbwd(a["off"], shifted, a["labs"])
+    assert not np.allclose(got[2], want[2])
+    got = m.fwdbwd(a["off"], fa, a["labs"])
+    for x, y in zip(got, want):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(y).max()))
+    m.close()
+    assert b is not None
