@@ -798,7 +798,9 @@ __device__ __forceinline__ uint32_t kept_phone(uint32_t i, uint32_t P, uint32_t 
 __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Wprev = reinterpret_cast<float*>(smem_raw);   // [L] kept weights of the previous frame
-	float* crossS = Wprev + p.L;                          // [P*P] when it fits, else unused
+	float* partW = Wprev + p.L;                           // [NS][P] partial cross-phone minima of the frame (all threads share the scan)
+	int32_t* partP = reinterpret_cast<int32_t*>(partW + p.L);   // their back pointers, -1: no candidate in that part of the list
+	float* crossS = partW + 2 * p.L;                      // [P*P] when it fits, else unused
 	__shared__ uint32_t s_g;        // descriptor of the kept-list order of the previous frame
 	__shared__ uint8_t s_move[256]; // arrival-order descriptors a[s] of the last D start frames (ring; D <= 255)
 	__shared__ int s_best;
@@ -814,6 +816,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	const uint32_t q = lab / NS, k = lab % NS;
 	const float my_diag = lab < L ? p.negDiag[lab] : 0.0f;
 	const float my_off = (lab < L && k > 0) ? p.negOff[lab] : 0.0f;
+	if (threadIdx.x == 0) s_g = 0xffu;
 	__syncthreads();
 
 	// the state scores of a node do not depend on the recursion: those of node s+1 are fetched while node s is processed, so the
@@ -827,31 +830,44 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 		float nsn[VPF];
 #pragma unroll
 		for (uint32_t j = 0; j < VPF; j++) nsn[j] = (lab < L && j < D && s + 1 < T) ? p.negS[((uint64_t)(off + s + 1) * D + j) * L + lab] : 0.0f;
+		// ---- cross-phone candidates for segments starting at frame s: the scan of the kept list of frame s-1 is shared by ALL threads
+		//      of the CTA (with N states per phone only every N-th thread owns a start state): thread = (part of the list, target phone);
+		//      strict '<' keeps the first arrival inside a part, and the parts are merged in list order below ----
+		float pw = VIT_INF; int32_t pptr = -1;
+		if (s > 0 && lab < L) {
+			const uint32_t g = s_g, part = lab / P, tq = lab - part * P;
+			const uint32_t chunk = (P + NS - 1) / NS, i_lo = part * chunk, i_hi = min(P, i_lo + chunk);
+			for (uint32_t i0 = i_lo; i0 < i_hi; i0 += 8) {
+				float cc[8]; int32_t ci[8]; bool ok[8];
+#pragma unroll
+				for (uint32_t j = 0; j < 8; j++) {
+					const uint32_t i = i0 + j;
+					const uint32_t pp = kept_phone(i < i_hi ? i : i_hi - 1, P, g);
+					ok[j] = i < i_hi && !(NS == 1 && pp == tq);   // free-phone LM, 1 state: no arc to the same phone (:1332-1346)
+					const float base = Wprev[pp * NS + NS - 1] + 0.0f;
+					cc[j] = base + crossT[pp * P + tq];
+					ci[j] = (int32_t)(pp * NS + NS - 1);
+				}
+#pragma unroll
+				for (uint32_t j = 0; j < 8; j++)
+					if (ok[j] && (pptr < 0 || cc[j] < pw)) { pw = cc[j]; pptr = ci[j]; }
+			}
+			if (NS > 1) { partW[lab] = pw; partP[lab] = pptr; }
+		}
+		if (NS > 1) __syncthreads();        // one state per phone: every thread scanned the whole list for its own phone
 		// ---- candidates for segments starting at frame s ----
 		float cw = VIT_INF; int32_t cp = -1;
 		if (lab < L) {
 			if (s == 0) {
 				if (k == 0) cw = 0.0f + 0.0f;   // lm_start weight 0 + arc weight 0, trans_wt = 0.0 at node 0 (:444-447)
 			} else {
-				const uint32_t g = s_g;
 				bool seen = false;
 				if (k == 0) {
-					// cross-phone: scan the kept list of frame s-1 in list order; strict '<' keeps the first arrival.  The candidate costs of
-					// 8 list positions are formed independently (their shared-memory loads overlap), then merged in list order.
-					for (uint32_t i0 = 0; i0 < P; i0 += 8) {
-						float cc[8]; int32_t ci[8]; bool ok[8];
-#pragma unroll
-						for (uint32_t j = 0; j < 8; j++) {
-							const uint32_t i = i0 + j;
-							const uint32_t pp = kept_phone(i < P ? i : P - 1, P, g);
-							ok[j] = i < P && !(NS == 1 && pp == q);   // free-phone LM, 1 state: no arc to the same phone (:1332-1346)
-							const float base = Wprev[pp * NS + NS - 1] + 0.0f;
-							cc[j] = base + crossT[(uint64_t)pp * P + q];
-							ci[j] = (int32_t)(pp * NS + NS - 1);
-						}
-#pragma unroll
-						for (uint32_t j = 0; j < 8; j++)
-							if (ok[j] && (!seen || cc[j] < cw)) { cw = cc[j]; cp = ci[j]; seen = true; }
+					if (NS == 1) { if (pptr >= 0) { cw = pw; cp = pptr; seen = true; } }
+					else for (uint32_t part = 0; part < NS; part++) {
+						const int32_t qp = partP[part * P + q];
+						const float qw = partW[part * P + q];
+						if (qp >= 0 && (!seen || qw < cw)) { cw = qw; cp = qp; seen = true; }
 					}
 				} else seen = true;   // the cross update created the slot with 99999.0 / -1 for inner sub-states
 				// within-phone: self vs advance from the previous sub-state, self only if strictly smaller (:338)
@@ -892,23 +908,26 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 			p.bd[(uint64_t)(off + s) * L + lab] = (uint8_t)bdur;
 		}
 		__syncthreads();
-		if (threadIdx.x == 0) {
-			// a[s] := descriptor of the ARRIVAL order at start frame s; a[0] = identity.
-			// a[s>=1] (NS==1): head of kept(s-1) moved to the back; kept(s-1) = a[max(0, s-1-D+1)] = a[max(0, s-D)].
-			uint32_t a_s = 0xffu;
-			if (NS == 1 && P > 1 && s >= 1) {
-				const uint32_t j = s >= D ? s - D : 0;
-				const uint32_t aj = j == 0 ? 0xffu : s_move[j & 255];
-				a_s = (aj == 0xffu) ? 0u : (aj == 0u ? 1u : 0u);     // head of the list described by aj
+		// the kept-list order only moves for one state per phone (N > 1: always the identity, s_g stays 0xff): no bookkeeping, no barrier
+		if (NS == 1) {
+			if (threadIdx.x == 0) {
+				// a[s] := descriptor of the ARRIVAL order at start frame s; a[0] = identity.
+				// a[s>=1] (NS==1): head of kept(s-1) moved to the back; kept(s-1) = a[max(0, s-1-D+1)] = a[max(0, s-D)].
+				uint32_t a_s = 0xffu;
+				if (P > 1 && s >= 1) {
+					const uint32_t j = s >= D ? s - D : 0;
+					const uint32_t aj = j == 0 ? 0xffu : s_move[j & 255];
+					a_s = (aj == 0xffu) ? 0u : (aj == 0u ? 1u : 0u);     // head of the list described by aj
+				}
+				s_move[s & 255] = (uint8_t)a_s;
+				// order of kept(s) feeds the cross scan of frame s+1: kept(s) = a[max(0, s-D+1)]
+				const uint32_t j2 = s + 1 >= D ? s + 1 - D : 0;
+				s_g = (j2 == 0) ? 0xffu : (j2 == s ? a_s : s_move[j2 & 255]);
 			}
-			s_move[s & 255] = (uint8_t)a_s;
-			// order of kept(s) feeds the cross scan of frame s+1: kept(s) = a[max(0, s-D+1)]
-			const uint32_t j2 = s + 1 >= D ? s + 1 - D : 0;
-			s_g = (j2 == 0) ? 0xffu : (j2 == s ? a_s : s_move[j2 & 255]);
+			__syncthreads();
 		}
 #pragma unroll
 		for (uint32_t j = 0; j < VPF; j++) nsv[j] = nsn[j];
-		__syncthreads();
 	}
 	// ---- final argmin over the kept list (first wins) and traceback ----
 	if (threadIdx.x == 0) {
@@ -948,7 +967,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	if (!p.n_utt) return;
 	const unsigned threads = (p.L + 31) / 32 * 32;
-	size_t smem = sizeof(float) * p.L;
+	size_t smem = sizeof(float) * 3 * p.L;
 	if ((size_t)p.P * p.P * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * p.P;
 	cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(p);
