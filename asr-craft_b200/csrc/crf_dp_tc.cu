@@ -87,6 +87,8 @@ struct Ctl {
 	Slot fr[4][UB];                // fr[j & 3] = F(j), the frame produced in step j (gathered in step j+1)
 	double ring_a[UB][DMAX];       // forward: ghat_t = log sum_c exp(alpha_t[c]) | backward: bl_t = base_t + log sum_c v_t[c]
 	double ring_b[UB][DMAX];       // forward: rho_t                              | backward: base_t
+	float ring_af[UB][DMAX];       // ring_a narrowed to float: the scale bounds are searched in fp32 (a bound may be off by an ulp of its
+	                               // magnitude -- entries <= 1.001 instead of <= 1 --, what matters is that the chosen scale is then used exactly)
 	float pre_sm[2][UB][DMAX];     // [j & 1]: forward smaxd[frame of F(j)][d-1] | backward smaxd[frame of F(j) + d][d-1]
 	double pre_rho[UB][DMAX + 1];  // backward: rho_{t-d}, d = 0..D, of the frame about to be gathered
 };
@@ -109,6 +111,11 @@ constexpr int BAR_SCALES = 1, BAR_TILE = 2, BAR_ACC = 3;
 __device__ __forceinline__ double slot_max(double v) {
 #pragma unroll
 	for (int o = SPW; o < 32; o <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ float slot_maxf(float v) {
+#pragma unroll
+	for (int o = SPW; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
 	return v;
 }
 __device__ __forceinline__ float slot_sum(float v) {
@@ -284,11 +291,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 						const bool last = fm.t + 1 == fm.len;
 						// the log scales are references, not results: only logZ needs the accurate logarithm
 						const double ghat = ctl->ring_b[slot][fm.t & (DMAX - 1)] + (last ? log((double)vsum) : (double)__logf(vsum));
-						ctl->ring_a[slot][fm.t & (DMAX - 1)] = ghat;
+						ctl->ring_a[slot][fm.t & (DMAX - 1)] = ghat; ctl->ring_af[slot][fm.t & (DMAX - 1)] = (float)ghat;
 						if (last && rank == 0) p.logZ[fm.utt] = ghat;               // computeAlphaSum (:447-462)
 					} else {
 						const bool tail = fm.t + 1 == fm.len;
-						ctl->ring_a[slot][fm.t & (DMAX - 1)] = tail ? 0.0 : ctl->ring_b[slot][fm.t & (DMAX - 1)] + (double)__logf(vsum);
+						const double bl = tail ? 0.0 : ctl->ring_b[slot][fm.t & (DMAX - 1)] + (double)__logf(vsum);
+						ctl->ring_a[slot][fm.t & (DMAX - 1)] = bl; ctl->ring_af[slot][fm.t & (DMAX - 1)] = (float)bl;
 					}
 				}
 				__syncwarp();
@@ -299,23 +307,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 			const bool a1 = f1.utt != LAB_BAD, a0 = f0.utt != LAB_BAD;
 			if (!BWD) {
 				const uint32_t t1 = f1.t;
-				double rho = -DBL_MAX, rt = -DBL_MAX;
+				const float Mmaxf = (float)p.Mmax;
+				float rhof = -INFINITY, rt = -INFINITY;
 				const bool inflight = a1 && t1 > 0;            // F(j) is frame t1-1 of the same utterance
 				const uint32_t t0 = t1 - 1;
 				// tight bound of the in-flight frame t1-1 from exact sums, + log(label count) bounds its log-sum
 				// (shuffles stay outside the per-slot conditions: every lane of the warp must execute them)
 				if (inflight) {
-					for (uint32_t d = 1 + h; d <= min(t0, D); d += LPS) rt = fmax(rt, (double)sm0[d - 1] + p.Mmax + ctl->ring_a[slot][(t0 - d) & (DMAX - 1)]);
-					if (h == 0 && t0 < D) rt = fmax(rt, (double)sm0[t0]);
+					for (uint32_t d = 1 + h; d <= min(t0, D); d += LPS) rt = fmaxf(rt, sm0[d - 1] + Mmaxf + ctl->ring_af[slot][(t0 - d) & (DMAX - 1)]);
+					if (h == 0 && t0 < D) rt = fmaxf(rt, sm0[t0]);
 				}
-				rt = slot_max(rt);
+				rt = slot_maxf(rt);
 				if (inflight) {
-					const double ub0 = rt + (double)__logf((float)(P * min(t0 + 1, D)));
-					if (h == 0) rho = (double)sm1[0] + p.Mmax + ub0;
-					for (uint32_t d = 2 + h; d <= min(t1, D); d += LPS) rho = fmax(rho, (double)sm1[d - 1] + p.Mmax + ctl->ring_a[slot][(t1 - d) & (DMAX - 1)]);
+					const float ub0 = rt + __logf((float)(P * min(t0 + 1, D)));
+					if (h == 0) rhof = sm1[0] + Mmaxf + ub0;
+					for (uint32_t d = 2 + h; d <= min(t1, D); d += LPS) rhof = fmaxf(rhof, sm1[d - 1] + Mmaxf + ctl->ring_af[slot][(t1 - d) & (DMAX - 1)]);
 				}
-				if (a1 && h == 0 && t1 < D) rho = fmax(rho, (double)sm1[t1]);       // d == t1+1: the segment starts the utterance, alpha = S
-				rho = slot_max(rho);
+				if (a1 && h == 0 && t1 < D) rhof = fmaxf(rhof, sm1[t1]);       // d == t1+1: the segment starts the utterance, alpha = S
+				rhof = slot_maxf(rhof);
+				const double rho = (double)rhof;
 				if (a1) {
 					for (uint32_t d = 1 + h; d <= D; d += LPS) {
 						float dl = -INFINITY;
@@ -332,17 +342,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 			} else {
 				const uint32_t t1 = f1.t;
 				const uint32_t nn1 = a1 ? min(f1.len - 1 - t1, D) : 0;
-				double sigma = -DBL_MAX, st = -DBL_MAX;
+				const float Mmaxf = (float)p.Mmax;
+				float sigf = -INFINITY, st = -INFINITY;
 				// frame t1+1 = F(j): bound of its bl from the exact bl of the frames behind it
 				const uint32_t nn0 = nn1 ? min(f0.len - 1 - f0.t, D) : 0;
-				for (uint32_t d = 1 + h; d <= nn0; d += LPS) st = fmax(st, (double)sm0[d - 1] + ctl->ring_a[slot][(t1 + 1 + d) & (DMAX - 1)]);
-				st = slot_max(st);
+				for (uint32_t d = 1 + h; d <= nn0; d += LPS) st = fmaxf(st, sm0[d - 1] + ctl->ring_af[slot][(t1 + 1 + d) & (DMAX - 1)]);
+				st = slot_maxf(st);
 				if (nn1) {
-					const double ubl0 = nn0 ? p.Mmax + st + (double)__logf((float)(P * nn0)) : 0.0;   // tail frame: S + beta = S exactly
-					if (h == 0) sigma = (double)sm1[0] + ubl0;
-					for (uint32_t d = 2 + h; d <= nn1; d += LPS) sigma = fmax(sigma, (double)sm1[d - 1] + ctl->ring_a[slot][(t1 + d) & (DMAX - 1)]);
+					const float ubl0 = nn0 ? Mmaxf + st + __logf((float)(P * nn0)) : 0.0f;   // tail frame: S + beta = S exactly
+					if (h == 0) sigf = sm1[0] + ubl0;
+					for (uint32_t d = 2 + h; d <= nn1; d += LPS) sigf = fmaxf(sigf, sm1[d - 1] + ctl->ring_af[slot][(t1 + d) & (DMAX - 1)]);
 				}
-				sigma = slot_max(sigma);
+				sigf = slot_maxf(sigf);
+				const double sigma = (double)sigf;
 				if (a1)
 					for (uint32_t d = 1 + h; d <= D; d += LPS)
 						ctl->delta[nb][slot][d] = (d <= nn1) ? (float)(ctl->ring_b[slot][(t1 + d) & (DMAX - 1)] - sigma) : -INFINITY;
