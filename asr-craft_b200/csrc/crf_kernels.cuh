@@ -238,6 +238,19 @@ struct VitParams {
 };
 void launch_viterbi(const VitParams& p, cudaStream_t s);
 
+// ---- frame-level CRF with transition FEATURES (stdtrans, one state per label; crf_dp_transftr.cu) ---------------------
+struct TransFtrParams {
+	uint32_t L, Lp, Lq;           // labels (<= 128), row stride of S / A / Dm, row stride of M / Xd (>= L*L)
+	uint32_t n_utt; const uint32_t* off;
+	const float* S; const float* M;       // [N][Lp] state scores, [N][Lq] transition scores M[n][p*L + c] of the frame the arc ENTERS
+	float* A; double* rho;                // forward: alpha normalised to sum 1, its log scale
+	double* logZ; double* numer;          // [n_utt]
+	float* Dm; float* Xd;                 // backward: [ref] - gamma [N][Lp], [ref pair] - xi [N][Lq] (zero on the first frame of an utterance)
+	const uint32_t* labs;                 // [N] reference label per frame
+};
+size_t transftr_smem_bytes(uint32_t L);
+cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStream_t s);
+
 // ---- lambda-derived tables and the trainer's update on the device (crf_lambda.cu) -----------------------------------
 struct LambdaTablesParams {
 	const double* lam;
@@ -248,6 +261,8 @@ struct LambdaTablesParams {
 	float* Ws; float* bias; float* E; float* ET;  // E / ET must be zero before the launch
 	double* tmax;                          // device scalar: max transition score (read back by the host as Mmax)
 	unsigned char* Wt; uint32_t wt_P, wt_D, wt_chunks;   // weight tiles of the TMA-fed score GEMM (null: skip)
+	// transition-FEATURE weights (stdtrans, null Wtr: skip): Wtr[(p*L0 + c)][f] = lambda[tidx0(p,c) + f], tbias = bias weight * transBiasVal
+	float* Wtr; float* tbias; uint32_t nTf;
 	// decoder tables over the model's own labels (null Wd: skip)
 	double* Wd; float* crossT; float* negDiag; float* negOff;
 	const uint32_t* sidx0; const uint32_t* tidx0; uint32_t L0, NS, P0;

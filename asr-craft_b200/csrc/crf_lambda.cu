@@ -79,6 +79,15 @@ __global__ void __launch_bounds__(256) lambda_tables_kernel(LambdaTablesParams p
 			*reinterpret_cast<__nv_bfloat16*>(t) = hi; *reinterpret_cast<__nv_bfloat16*>(t + 4096) = lo;
 		}
 	}
+	if (p.Wtr) {
+		const uint64_t L = p.L0, nw = L * L * p.nTf;
+		for (uint64_t i = tid0; i < nw; i += stride) {
+			const uint64_t pair = i / p.nTf; const uint32_t f = (uint32_t)(i % p.nTf);
+			p.Wtr[i] = (float)p.lam[p.tidx0[pair] + f];
+		}
+		for (uint64_t pair = tid0; pair < L * L; pair += stride)
+			p.tbias[pair] = p.use_trans_bias ? (float)__dmul_rn(p.lam[p.tidx0[pair] + p.nTf], p.trans_bias_val) : 0.0f;
+	}
 	if (p.Wd) {
 		// decoder tables over the MODEL's labels (L0 labels, NS sub-states, P0 phones)
 		const uint32_t L = p.L0, NS = p.NS, P = p.P0;

@@ -78,6 +78,7 @@ struct crfgpu_ctx {
 	uint32_t Lt = 0; bool tied = false;
 	// native O(P^2 + D*P) recursion for the same models (crf_dp_nodur.cu): score / posterior columns are (duration, phone), the
 	// transition tables and forward/backward vectors are P wide
+	bool transftr = false; DevBuf d_Wtr, d_tbias, d_Mall, d_Xd;   // frame-level model with transition FEATURES (crf_dp_transftr.cu)
 	bool nodur = false; uint32_t Pp = 0; int opt_nodur_impl = 0; int nodur_groups_max = 0; uint32_t n_nodur_groups = 0;
 	DevBuf d_nd_grp, d_nd_batch, d_nd_xch, d_nd_ctr, d_LB;
 	std::vector<uint32_t> t_sidx, t_tidx;   // lambda indices of the lattice labels / label pairs
@@ -149,10 +150,14 @@ void check_kernel(crfgpu_ctx* h, int n_launches) {
 void classify(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	h->train_ok = h->decode_ok = true; h->tied = h->nodur = false;
+	h->transftr = false;
 	if (c.use_trans_ftrs) {
-		h->train_ok = h->decode_ok = false;
-		h->train_why = h->decode_why = "transition FEATURES (crf_featuremap=stdtrans) are not implemented on the device yet; "
-		                               "transition bias only";
+		// transition FEATURES (crf_featuremap=stdtrans): implemented for training frame-level models with one state per label
+		h->decode_ok = false; h->decode_why = "decoding with transition FEATURES (crf_featuremap=stdtrans) is not implemented on the device yet";
+		if (c.model_type == CRFGPU_STDFRAME && c.max_dur == 1 && c.n_states == 1 && c.n_labs <= 128 && c.use_state_ftrs) { h->transftr = true; return; }
+		h->train_ok = false;
+		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for frame-level models with one state per "
+		               "label and at most 128 labels; other model types run with transition bias only";
 		return;
 	}
 	if (c.model_type == CRFGPU_STDFRAME) {
@@ -254,6 +259,12 @@ void derive_tables(crfgpu_ctx* h) {
 			h->d_Wt.ensure((size_t)p.wt_D * ((p.wt_P + 63) / 64) * p.wt_chunks * 8192 + 16);
 			p.Wt = h->d_Wt.as<unsigned char>();
 		}
+	}
+	if (h->transftr) {
+		const uint32_t nTf = m.nTf;
+		h->d_Wtr.ensure(sizeof(float) * (size_t)L * L * nTf + 16); h->d_tbias.ensure(sizeof(float) * (size_t)L * L + 16);
+		p.Wtr = h->d_Wtr.as<float>(); p.tbias = h->d_tbias.as<float>(); p.nTf = nTf;
+		p.sidx0 = h->d_sidx.as<uint32_t>(); p.tidx0 = h->d_tidx.as<uint32_t>(); p.L0 = L;
 	}
 	if (h->decode_ok) {
 		const bool same = !h->tied && !h->nodur;
@@ -458,7 +469,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
 		upload_async(h, h->d_cl_off, cl_off); upload_async(h, h->d_cl_list, cl_list);
 	};
-	if (h->train_ok && !h->nodur && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
+	if (h->train_ok && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
 		// tensor-core cluster kernels: 16 slots per cluster
 		TcDpPlan plan{};
 		if (plan_tc_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
@@ -473,7 +484,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 		}
 	}
-	if (h->train_ok && !h->nodur && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
+	if (h->train_ok && !h->nodur && !h->transftr && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
 		ClusterPlan plan{};
 		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
 		if (plan_cluster_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan, cap)) {
@@ -600,6 +611,58 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	}
 	phase_end(h, "score");
 
+	if (h->transftr) {
+		// frame-level model with transition FEATURES: the L*L transition scores of every frame are one more tensor-core GEMM, the
+		// recursions stream them (crf_dp_transftr.cu), and both gradients (with their empirical counts) are reduce-GEMMs
+		const uint32_t Lq = (L * L + 3) / 4 * 4, tf0 = c.trans_fidx_start, nTf = m.nTf;
+		h->d_Mall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_Xd.ensure(sizeof(float) * (size_t)N * Lq + 16);
+		phase_begin(h, "forward");
+		ScoreGemmParams g{};
+		g.A = h->X() + tf0; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = nTf; g.bias = h->d_tbias.as<float>();
+		g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = L * L; g.K = nTf;
+		CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+		TransFtrParams q{};
+		q.L = L; q.Lp = Lp; q.Lq = Lq; q.n_utt = h->n_utt; q.off = h->d_off.as<uint32_t>();
+		q.S = h->d_S.as<float>(); q.M = h->d_Mall.as<float>(); q.A = h->d_A.as<float>(); q.rho = h->d_m.as<double>();
+		q.logZ = h->d_logZ.as<double>(); q.numer = h->d_numer.as<double>(); q.Dm = h->d_Dm.as<float>(); q.Xd = h->d_Xd.as<float>();
+		q.labs = h->d_node_lab.as<uint32_t>();
+		CUDA_OK(launch_transftr_dp(false, q, s)); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		CUDA_OK(launch_transftr_dp(true, q, s)); check_kernel(h, 1);
+		phase_end(h, "backward");
+		phase_begin(h, "xi");
+		{
+			// transition weights: out[tidx(p,c) + f] += sum_n ([ref pair] - xi_n[p][c]) * x_n[tf0 + f]   (computeTransExpF, :197-223)
+			ReduceGemmParams r{};
+			r.A = h->d_Xd.as<float>(); r.lda = Lq; r.a_row_shift = 0;
+			r.B = h->X() + tf0; r.ldb = h->ldx();
+			r.n0 = 0; r.n1 = N; r.I = L * L; r.J = nTf + (c.use_trans_bias ? 1 : 0);
+			r.ones_col = c.use_trans_bias ? nTf : 0xffffffffu;
+			r.scale = 1.0; r.ones_scale = c.trans_bias_val; r.mode = 0;
+			r.row_idx = h->d_tidx.as<uint32_t>();
+			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab_tc;
+			CUDA_OK(launch_reduce_gemm_tc(r, false, s)); check_kernel(h, 1);
+		}
+		phase_end(h, "xi");
+		phase_begin(h, "grad");
+		{
+			ReduceGemmParams r{};
+			r.A = h->d_Dm.as<float>(); r.lda = Lp; r.a_row_shift = 0;
+			r.B = h->X() + c.state_fidx_start; r.ldb = h->ldx();
+			r.n0 = 0; r.n1 = N; r.I = L; r.J = nSf + (c.use_state_bias ? 1 : 0);
+			r.ones_col = c.use_state_bias ? nSf : 0xffffffffu;
+			r.scale = 1.0; r.ones_scale = c.state_bias_val; r.mode = 0;
+			r.row_idx = h->d_sidx.as<uint32_t>();
+			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab_tc;
+			CUDA_OK(launch_reduce_gemm_tc(r, true, s)); check_kernel(h, 1);
+		}
+		tail_sums_kernel<<<1, 256, 0, s>>>(h->d_numer.as<double>(), h->d_logZ.as<double>(), h->n_utt, h->d_grad.as<double>() + m.len);
+		check_kernel(h, 1);
+		phase_end(h, "grad");
+		h->fwdbwd_done = true;
+		return;
+	}
 	DpParams p = dp_params(h);
 	if (h->nodur) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
@@ -848,7 +911,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);

@@ -23,6 +23,7 @@ TRAIN = load_cases("train_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
+TRANSFTR = load_cases("train_transftr_golden.npz")
 
 
 def gpu(cfg):
@@ -224,7 +225,7 @@ def test_window_expansion_bit_exact(name):
 
 def test_unsupported_geometries_fail_loudly():
     with pytest.raises(crf_b200.CrfGpuError) as ei:
-        m = gpu(make_config("stdframe", n_labs=5, n_base_ftrs=4, use_trans_ftrs=1))
+        m = gpu(make_config("stdseg", n_labs=10, n_base_ftrs=4, max_dur=2, n_actual_labs=5, use_trans_ftrs=1))
         m.set_lambda(np.zeros(m.lambda_len))
         m.fwdbwd([0, 3], np.zeros((3, 4), np.float32), np.zeros(3, np.uint32))
     assert ei.value.code == 2
@@ -438,3 +439,30 @@ def test_prefetch_takes_over_buffers_and_falls_back():
         np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(y).max()))
     m.close()
     assert b is not None
+
+
+@pytest.mark.parametrize("name", sorted(TRANSFTR))
+def test_fwdbwd_transition_features_match_reference_golden(name):
+    """crf_featuremap=stdtrans on frame-level models: transition scores as a tensor-core GEMM, streamed recursions, both gradients
+    as reduce-GEMMs (crf_dp_transftr.cu), against goldens produced by the reference."""
+    c = TRANSFTR[name]
+    m = gpu(c["cfg"])
+    assert m.lambda_len == len(c["lam"])
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    m.close()
+
+
+def test_fwdbwd_transition_features_cfg2_shape_matches_oracle(oracle):
+    """61 labels, 105 features for states and transitions (the cfg2 geometry with stdtrans: dim(lambda) = 61*(106 + 61*106))."""
+    rng = np.random.default_rng(23)
+    off, ftrs, labs = synth_batch(rng, 5, 8, 40, 105, 61, 2, 9)
+    cfg = make_config("stdframe", n_labs=61, n_base_ftrs=105, use_trans_ftrs=1)
+    lam = rng.uniform(-0.02, 0.02, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=4)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, "stdtrans cfg2 shape")
+    m.close()

@@ -12,6 +12,7 @@ TRAIN = load_cases("train_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
+TRANSFTR = load_cases("train_transftr_golden.npz")
 
 
 def test_toy_known_answers(oracle):
@@ -45,6 +46,17 @@ def test_train_nodur_golden(oracle, name, tied):
     np.testing.assert_allclose(logz, c["logZ"], rtol=1e-12)
     np.testing.assert_allclose(numer, c["numer"], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(grad, c["grad"], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", sorted(TRANSFTR))
+def test_train_transftr_golden(oracle, name):
+    """frame-level CRFs with transition FEATURES (stdtrans) against goldens produced by the reference (make_golden_transftr.py)."""
+    c = TRANSFTR[name]
+    assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
+    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"])
+    np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
+    np.testing.assert_allclose(numer, c["numer"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
 
 
 def test_train_threads_match_single(oracle):
