@@ -182,7 +182,7 @@ struct FrameGemmParams {
 	const uint32_t* row_idx;          // state gradient: [D*P] lambda offset of the label's state block
 	const uint32_t* pair_idx; uint32_t L; const float* Ew; uint32_t e_ld;   // Xi
 	double* out;
-	uint32_t dbg;                     // bit 1: 128-row operand through tensor memory (frame_gemm_tmem_kernel)
+	uint32_t a_from_tmem;             // 1: 128-row operand through tensor memory (frame_gemm_tmem_kernel)
 };
 // X must be 16-byte aligned, Wp % 4 == 0, the first state feature a multiple of 4 and the driver must export cuTensorMapEncodeTiled
 bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0);

@@ -742,7 +742,7 @@ cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const
 	CUtensorMap tm, tn;
 	if (!window_map(&tm, X, p.N, p.D, Wp, K, KC, false) || !window_map(&tn, Dm, p.N, 1, ldd, p.D * p.P, KC, false)) return cudaErrorInvalidValue;
 	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	if (p.dbg & 2) frame_gemm_tmem_kernel<0><<<grid, FG_THR, G_SMEM, s>>>(tm, tn, p);
+	if (p.a_from_tmem) frame_gemm_tmem_kernel<0><<<grid, FG_THR, G_SMEM, s>>>(tm, tn, p);
 	else frame_gemm_tma_kernel<0><<<grid, FG_THR, F_SMEM, s>>>(tm, tn, p);
 	return cudaGetLastError();
 }
@@ -756,7 +756,7 @@ cudaError_t launch_xi_gemm_tma(const float* A, const float* R, uint32_t ld, cons
 	CUtensorMap ta, tr;
 	if (!window_map(&ta, A, p.N, 1, ld, p.L, KC, false) || !window_map(&tr, R, p.N, 1, ld, p.L, KC, false)) return cudaErrorInvalidValue;
 	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	if (p.dbg & 2) frame_gemm_tmem_kernel<1><<<grid, FG_THR, G_SMEM, s>>>(ta, tr, p);
+	if (p.a_from_tmem) frame_gemm_tmem_kernel<1><<<grid, FG_THR, G_SMEM, s>>>(ta, tr, p);
 	else frame_gemm_tma_kernel<1><<<grid, FG_THR, F_SMEM, s>>>(ta, tr, p);
 	return cudaGetLastError();
 }

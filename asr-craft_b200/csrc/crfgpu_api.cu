@@ -753,7 +753,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 			FrameGemmParams x{};
 			x.N = N; x.P = P; x.D = 1; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = P; x.ones_col = 0xffffffffu;
 			x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = P; x.Ew = h->d_E.as<float>(); x.e_ld = h->Pp; x.out = h->d_grad.as<double>();
-			x.dbg = (h->opt_tma_mask & 32) ? 2u : 0u;
+			x.a_from_tmem = (h->opt_tma_mask & 32) ? 1u : 0u;
 			CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), h->Pp, x, s)); check_kernel(h, 1);
 		}
 	} else
@@ -761,7 +761,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		FrameGemmParams x{};
 		x.N = N; x.P = P; x.D = D; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = L; x.ones_col = 0xffffffffu;
 		x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = L; x.Ew = h->d_E.as<float>(); x.e_ld = Lp; x.out = h->d_grad.as<double>();
-		x.dbg = (h->opt_tma_mask & 32) ? 2u : 0u;
+		x.a_from_tmem = (h->opt_tma_mask & 32) ? 1u : 0u;
 		CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), Lp, x, s)); check_kernel(h, 1);
 	} else if (c.use_trans_bias && h->opt_gemm_impl >= 1 && N > 1) {
 		XiGemmParams x{};
@@ -791,7 +791,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.N = N; r.P = P; r.D = D; r.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; r.k_slab = h->opt_k_slab_tma; r.Mext = nSf + (c.use_state_bias ? 1 : 0);
 		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu; r.scale = 1.0; r.ones_scale = c.state_bias_val;
 		r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
-		r.dbg = (h->opt_tma_mask & 16) ? 2u : 0u;
+		r.a_from_tmem = (h->opt_tma_mask & 16) ? 1u : 0u;
 		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, h->d_Dm.as<float>(), Lp, r, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
