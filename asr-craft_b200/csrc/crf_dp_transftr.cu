@@ -178,4 +178,185 @@ cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStrea
 	return cudaGetLastError();
 }
 
+
+// =================================================================================================
+// Segmental model WITHOUT duration labels and WITH transition features (stdseg_no_dur_no_segtransftr + stdtrans: the production TIMIT
+// recipe, demo/segmental-timit-demo.cfg.in:11-48).  Reference: CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr
+// (CRF/src/nodes/CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr.cpp: computeTransMatrix :39-121 -- M_t[y'][y] from the duration-1
+// window of frame t --, computeAlpha :123-333, computeAlphaPlusTrans :1077-1116, computeBeta :395-614, computeExpF :616-1066 -- the
+// transition counts of node t use node t+1's features and the NEXT reference label) driven by CRF_NewGradBuilder_StdSeg_NoDur_NoTrans.
+//   A_t[y]     = logsum_y' (alpha_t[y'] + M_{t+1}[y'][y])         alpha_t[d,y] = S_t[d,y] + A_{t-d}[y]   (= S_t[d,y] when d == t+1)
+//   B_t[y]     = logsum_d (S_{t+d}[d,y] + beta_{t+d}[y])          beta_t[y'] = logsum_y (M_{t+1}[y'][y] + B_t[y])
+//   gamma_t[d,y] = exp(alpha_t[d,y] + beta_t[y] - logZ)           xi_t[y'][y]  = exp(alpha_t[y'] + M_{t+1}[y'][y] + B_t[y] - logZ)
+// One CTA per utterance, thread = phone (<= 128), M_{t+1} prefetched with cp.async, alpha_t normalised to sum 1 with a running
+// log scale rho_t, the D-term sums formed as float log-sum-exps of differences of the (double) scales.
+// =================================================================================================
+namespace {
+
+constexpr uint32_t ND_RING = 32;     // max_dur <= 31
+
+__global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams p) {
+	extern __shared__ __align__(16) float sm[];
+	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
+	double* rring = reinterpret_cast<double*>(sm);            // [ND_RING] rho_t (first: 8-byte aligned)
+	float* Ms = sm + 2 * ND_RING;                // [2][P][Ps]
+	float* av = Ms + 2 * P * Ps;                 // [P] alpha_t (sum 1)
+	float* lgh = av + P;                         // [ND_RING][P] log A_t[y] - rho_t of the last D frames
+	float* scratch = lgh + ND_RING * P;          // [8]
+	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
+	double num = 0.0;
+	if (T > 1) prefetch_matrix(Ms + P * Ps, p.M + (size_t)(off + 1) * p.Lq, P, Ps);       // M_1 -> buffer 1
+	for (uint32_t t = 0; t < T; t++) {
+		const size_t n = (size_t)off + t;
+		const uint32_t dmax = min(t + 1, D);
+		const double rref = t > 0 ? rring[(t - 1) & (ND_RING - 1)] : 0.0;
+		// w[y] = log sum_d exp(S_t[d,y] + A_{t-d}[y] - rref)
+		float w = -INFINITY;
+		if (y < P) {
+			float lt[ND_RING];
+			float mx = -INFINITY;
+			for (uint32_t d = 1; d <= dmax; d++) {
+				float v = p.S[n * p.Lp + (size_t)(d - 1) * P + y];
+				if (d <= t) v += lgh[((t - d) & (ND_RING - 1)) * P + y] + (float)(rring[(t - d) & (ND_RING - 1)] - rref);
+				else v += (float)(-rref);
+				lt[d - 1] = v; mx = fmaxf(mx, v);
+			}
+			float sacc = 0.0f;
+			for (uint32_t d = 1; d <= dmax; d++) sacc += __expf(lt[d - 1] - mx);
+			w = mx + __logf(sacc);
+		}
+		const float wmax = block_max(w, scratch);
+		const float a = y < P ? __expf(w - wmax) : 0.0f;
+		const float asum = block_sum(a, scratch);
+		const double rho = rref + (double)wmax + (double)__logf(asum);
+		if (y < P) { av[y] = a / asum; p.A[n * p.Pp + y] = a / asum; }
+		if (y == 0) { rring[t & (ND_RING - 1)] = rho; p.rho[n] = rho; }
+		// numerator: state score of the reference segment ending here
+		const uint32_t lab = p.node_lab[n];
+		if (y == 0 && lab != LAB_BAD) num += (double)p.S[n * p.Lp + lab];
+		__syncthreads();
+		if (t + 1 < T) {
+			// A_t[y] = rho_t + lgh_t[y],  lgh_t[y] = mmax + log sum_q alpha_t[q] exp(M_{t+1}[q][y] - mmax)
+			float* Mn = Ms + ((t + 1) & 1) * P * Ps;
+			cp_async_wait_all();
+			__syncthreads();
+			if (t + 2 < T) prefetch_matrix(Ms + (t & 1) * P * Ps, p.M + (n + 2) * p.Lq, P, Ps);
+			float m = -INFINITY;
+			for (uint32_t i = y; i < P * P; i += TF_THR) m = fmaxf(m, Mn[(i / P) * Ps + i % P]);
+			const float mmax = block_max(m, scratch);
+			if (y < P) {
+				float v = 0.0f;
+				for (uint32_t q = 0; q < P; q++) v = fmaf(av[q], __expf(Mn[q * Ps + y] - mmax), v);
+				const float l = mmax + __logf(v);
+				lgh[(t & (ND_RING - 1)) * P + y] = l; p.LG[n * p.Pp + y] = l;
+			}
+			if (y == 0 && lab != LAB_BAD) { const uint32_t nl = p.next_lab[n]; if (nl != LAB_BAD) num += (double)Mn[(lab % P) * Ps + nl]; }
+			__syncthreads();
+		}
+	}
+	if (y == 0) { p.logZ[u] = T ? rring[(T - 1) & (ND_RING - 1)] : 0.0; p.numer[u] = num; }
+}
+
+__global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams p) {
+	extern __shared__ __align__(16) float sm[];
+	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
+	double* kring = reinterpret_cast<double*>(sm);            // [ND_RING] kappa_t (first: 8-byte aligned)
+	float* Ms = sm + 2 * ND_RING;                // [2][P][Ps]
+	float* av = Ms + 2 * P * Ps;                 // [P] alpha_t
+	float* lbh = av + P;                         // [ND_RING][P] beta_t[y] - kappa_t of the last D frames
+	float* ev = lbh + ND_RING * P;               // [P] exp(B_t[y] - its maximum)
+	float* scratch = ev + P;                     // [8]
+	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
+	const double lz = p.logZ[u];
+	if (T > 1) prefetch_matrix(Ms + ((T - 1) & 1) * P * Ps, p.M + (size_t)(off + T - 1) * p.Lq, P, Ps);    // M_{T-1}
+	for (uint32_t t = T; t-- > 0;) {
+		const size_t n = (size_t)off + t;
+		const uint32_t nn = min(T - 1 - t, D), dmax = min(t + 1, D);
+		const uint32_t lab = p.node_lab[n];
+		float lb = 0.0f;                         // beta_t[y] - kappa_t; tail: beta = 0
+		double kappa = 0.0;
+		if (nn > 0) {
+			// w[y] = B_t[y] - kref = log sum_d exp(S_{t+d}[d,y] + beta_{t+d}[y] - kref)
+			const double kref = kring[(t + 1) & (ND_RING - 1)];
+			float w = -INFINITY;
+			if (y < P) {
+				float lt[ND_RING];
+				float mx = -INFINITY;
+				for (uint32_t d = 1; d <= nn; d++) {
+					const float v = p.S[(n + d) * p.Lp + (size_t)(d - 1) * P + y] + lbh[((t + d) & (ND_RING - 1)) * P + y] + (float)(kring[(t + d) & (ND_RING - 1)] - kref);
+					lt[d - 1] = v; mx = fmaxf(mx, v);
+				}
+				float sacc = 0.0f;
+				for (uint32_t d = 1; d <= nn; d++) sacc += __expf(lt[d - 1] - mx);
+				w = mx + __logf(sacc);
+			}
+			const float wmax = block_max(w, scratch);
+			float* Mn = Ms + ((t + 1) & 1) * P * Ps;     // M_{t+1}
+			cp_async_wait_all();
+			__syncthreads();
+			if (t > 0) prefetch_matrix(Ms + (t & 1) * P * Ps, p.M + n * p.Lq, P, Ps);      // M_t for the next step
+			float m = -INFINITY;
+			for (uint32_t i = y; i < P * P; i += TF_THR) m = fmaxf(m, Mn[(i / P) * Ps + i % P]);
+			const float mmax = block_max(m, scratch);
+			if (y < P) { ev[y] = __expf(w - wmax); av[y] = p.A[n * p.Pp + y]; }
+			__syncthreads();
+			// E[q][yy] = exp(M_{t+1}[q][yy] - mmax) * ev[yy] in place;
+			// xi_t[q][yy] = exp(alpha_t[q] + M_{t+1}[q][yy] + B_t[yy] - logZ) = alpha^_t[q] E[q][yy] exp(rho_t + mmax + kref + wmax - logZ)
+			// (a segment boundary after frame t has probability <= 1: the posteriors are NOT renormalised per frame)
+			for (uint32_t i = y; i < P * P; i += TF_THR) {
+				const uint32_t q = i / P, yy = i - q * P;
+				Mn[q * Ps + yy] = __expf(Mn[q * Ps + yy] - mmax) * ev[yy];
+			}
+			__syncthreads();
+			const float xscale = __expf((float)(p.rho[n] + (double)mmax + kref + (double)wmax - lz));
+			const uint32_t nl = lab != LAB_BAD ? p.next_lab[n] : LAB_BAD, lq = lab != LAB_BAD ? lab % P : LAB_BAD;
+			float* xrow = p.Xd + (n + 1) * p.Lq;         // stored with the frame whose duration-1 window carries the transition features
+			for (uint32_t i = y; i < P * P; i += TF_THR) {
+				const uint32_t q = i / P, yy = i - q * P;
+				xrow[i] = ((q == lq && yy == nl) ? 1.0f : 0.0f) - av[q] * Mn[q * Ps + yy] * xscale;
+			}
+			float bn = 0.0f;
+			if (y < P) for (uint32_t yy = 0; yy < P; yy++) bn += Mn[y * Ps + yy];
+			const float bmax = block_max(y < P ? bn : 0.0f, scratch);
+			lb = y < P ? __logf(bn / bmax) : 0.0f;
+			kappa = kref + (double)mmax + (double)wmax + (double)__logf(bmax);
+		} else if (T > 1) {
+			// tail frame of a multi-frame utterance: nothing to wait for, M_{T-1} stays in flight for the next step
+		}
+		if (y < P) lbh[(t & (ND_RING - 1)) * P + y] = lb;
+		if (y == 0) kring[t & (ND_RING - 1)] = kappa;
+		if (t == 0) for (uint32_t i = y; i < P * P; i += TF_THR) p.Xd[n * p.Lq + i] = 0.0f;      // no transition enters the first frame
+		// gamma_t[d,y] = exp(S_t[d,y] + A_{t-d}[y] + beta_t[y] - logZ): the scalar part (rho_{t-d} + kappa_t - logZ) is formed in double
+		if (y < P) {
+			for (uint32_t d = 1; d <= D; d++) {
+				const uint32_t col = (d - 1) * P + y;
+				float dm = 0.0f;
+				if (d <= dmax) {
+					float v = p.S[n * p.Lp + col] + lb;
+					if (d <= t) v += p.LG[(n - d) * p.Pp + y] + (float)(p.rho[n - d] + kappa - lz);
+					else v += (float)(kappa - lz);
+					dm = ((lab == col) ? 1.0f : 0.0f) - __expf(v);
+				}
+				p.Dm[n * p.Lp + col] = dm;
+			}
+		}
+		__syncthreads();
+	}
+}
+
+}  // namespace
+
+size_t nodur_tf_smem_bytes(uint32_t P) { return sizeof(float) * ((size_t)2 * P * (P | 1u) + (size_t)(2 + ND_RING) * P + 16) + sizeof(double) * ND_RING + 16; }
+
+cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s) {
+	if (!p.n_utt) return cudaSuccess;
+	const size_t smem = nodur_tf_smem_bytes(p.P);
+	cudaError_t e = cudaFuncSetAttribute(backward ? (const void*)nodur_tf_backward_kernel : (const void*)nodur_tf_forward_kernel,
+	                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	if (backward) nodur_tf_backward_kernel<<<p.n_utt, TF_THR, smem, s>>>(p);
+	else nodur_tf_forward_kernel<<<p.n_utt, TF_THR, smem, s>>>(p);
+	return cudaGetLastError();
+}
+
 }  // namespace crfgpu

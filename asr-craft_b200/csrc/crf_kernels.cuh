@@ -248,6 +248,18 @@ struct TransFtrParams {
 	float* Dm; float* Xd;                 // backward: [ref] - gamma [N][Lp], [ref pair] - xi [N][Lq] (zero on the first frame of an utterance)
 	const uint32_t* labs;                 // [N] reference label per frame
 };
+// segmental model without duration labels + transition features (stdseg_no_dur_no_segtransftr with stdtrans)
+struct NodurTfParams {
+	uint32_t P, Pp, D; uint64_t Lp; uint32_t Lq;   // phones (<= 128), stride of the P-wide arrays, durations (<= 31), stride of S / Dm, stride of M / Xd
+	uint32_t n_utt; const uint32_t* off;
+	const float* S; const float* M;               // [N][Lp] scores of (d,y); [N][Lq] M_n[y'][y] from frame n's duration-1 window
+	float* A; float* LG; double* rho;             // forward: alpha_t (sum 1), log A_t[y] - rho_t, log scale
+	double* logZ; double* numer;
+	float* Dm; float* Xd;                         // backward: [ref] - gamma [N][Lp], [ref pair] - xi stored at the frame the new segment starts in
+	const uint32_t* node_lab; const uint32_t* next_lab;   // (dur-1)*P + phone where a reference segment ends; phone of the NEXT reference segment there
+};
+size_t nodur_tf_smem_bytes(uint32_t P);
+cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s);
 size_t transftr_smem_bytes(uint32_t L);
 cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStream_t s);
 

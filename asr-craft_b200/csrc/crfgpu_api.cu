@@ -78,6 +78,7 @@ struct crfgpu_ctx {
 	uint32_t Lt = 0; bool tied = false;
 	// native O(P^2 + D*P) recursion for the same models (crf_dp_nodur.cu): score / posterior columns are (duration, phone), the
 	// transition tables and forward/backward vectors are P wide
+	bool nodur_tf = false; DevBuf d_next_lab;                       // segmental no_dur model with transition features (nodur && nodur_tf)
 	bool transftr = false; DevBuf d_Wtr, d_tbias, d_Mall, d_Xd;   // frame-level model with transition FEATURES (crf_dp_transftr.cu)
 	bool nodur = false; uint32_t Pp = 0; int opt_nodur_impl = 0; int nodur_groups_max = 0; uint32_t n_nodur_groups = 0;
 	DevBuf d_nd_grp, d_nd_batch, d_nd_xch, d_nd_ctr, d_LB;
@@ -150,14 +151,18 @@ void check_kernel(crfgpu_ctx* h, int n_launches) {
 void classify(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	h->train_ok = h->decode_ok = true; h->tied = h->nodur = false;
-	h->transftr = false;
+	h->transftr = h->nodur_tf = false;
 	if (c.use_trans_ftrs) {
 		// transition FEATURES (crf_featuremap=stdtrans): implemented for training frame-level models with one state per label
 		h->decode_ok = false; h->decode_why = "decoding with transition FEATURES (crf_featuremap=stdtrans) is not implemented on the device yet";
 		if (c.model_type == CRFGPU_STDFRAME && c.max_dur == 1 && c.n_states == 1 && c.n_labs <= 128 && c.use_state_ftrs) { h->transftr = true; return; }
+		// ... and for the segmental production recipe: no duration labels, transition features from the duration-1 window
+		if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.n_states == 1 && c.max_dur > 1 && c.max_dur <= 31 && c.n_labs <= 128 && c.use_state_ftrs) {
+			h->nodur = h->nodur_tf = true; return;
+		}
 		h->train_ok = false;
-		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for frame-level models with one state per "
-		               "label and at most 128 labels; other model types run with transition bias only";
+		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for one state per label and at most 128 labels, "
+		               "in frame-level models and in stdseg_no_dur_no_segtransftr (max_dur <= 31); other model types run with transition bias only";
 		return;
 	}
 	if (c.model_type == CRFGPU_STDFRAME) {
@@ -260,7 +265,7 @@ void derive_tables(crfgpu_ctx* h) {
 			p.Wt = h->d_Wt.as<unsigned char>();
 		}
 	}
-	if (h->transftr) {
+	if (h->transftr || h->nodur_tf) {
 		const uint32_t nTf = m.nTf;
 		h->d_Wtr.ensure(sizeof(float) * (size_t)L * L * nTf + 16); h->d_tbias.ensure(sizeof(float) * (size_t)L * L + 16);
 		p.Wtr = h->d_Wtr.as<float>(); p.tbias = h->d_tbias.as<float>(); p.nTf = nTf;
@@ -434,6 +439,17 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 		}
 		upload_async(h, h->d_node_lab, node_lab); upload_async(h, h->d_prev_lab, prev_lab);
+		if (h->nodur_tf) {
+			// phone of the NEXT reference segment at every frame where a reference segment ends (the builder's next_lab,
+			// CRF_NewGradBuilder_StdSeg_NoDur_NoTrans.cpp:436-446)
+			std::vector<uint32_t> next_lab(N, CRFGPU_LAB_BAD);
+			for (uint32_t u = 0; u < n_utt; u++) {
+				uint32_t nxt = CRFGPU_LAB_BAD;
+				for (uint32_t n = off[u + 1]; n-- > off[u];)
+					if (node_lab[n] != CRFGPU_LAB_BAD) { next_lab[n] = nxt; nxt = node_lab[n] % c.n_actual_labs; }
+			}
+			upload_async(h, h->d_next_lab, next_lab);
+		}
 	}
 	// utterances sorted by length (longest first) so the slots of one CTA finish together; reordering inside a
 	// minibatch does not change the gradient sum
@@ -509,7 +525,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		}
 	}
 	std::vector<uint32_t> nd_grp, nd_batch;
-	if (h->train_ok && h->nodur && labs && n_utt) {
+	if (h->train_ok && h->nodur && !h->nodur_tf && labs && n_utt) {
 		// native no_dur recursion: batches of NODUR_UT utterances of similar length advance in lock-step; batches are dealt
 		// (longest first) to the least loaded of the co-resident CTA groups
 		const uint32_t nb = (n_utt + NODUR_UT - 1) / NODUR_UT;
@@ -664,7 +680,26 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		return;
 	}
 	DpParams p = dp_params(h);
-	if (h->nodur) {
+	const uint32_t Lq = (P * P + 3) / 4 * 4;        // nodur_tf: row stride of the per-frame transition scores
+	if (h->nodur_tf) {
+		const uint32_t tf0 = c.trans_fidx_start, nTf = m.nTf;
+		h->d_Mall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_Xd.ensure(sizeof(float) * (size_t)N * Lq + 16);
+		phase_begin(h, "forward");
+		ScoreGemmParams g{};      // M_n[y'][y] from the duration-1 window of frame n
+		g.A = h->X() + tf0; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = nTf; g.bias = h->d_tbias.as<float>();
+		g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = P * P; g.K = nTf;
+		CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+		NodurTfParams q{};
+		q.P = P; q.Pp = h->Pp; q.D = D; q.Lp = Lp; q.Lq = Lq; q.n_utt = h->n_utt; q.off = h->d_off.as<uint32_t>();
+		q.S = h->d_S.as<float>(); q.M = h->d_Mall.as<float>(); q.A = h->d_A.as<float>(); q.LG = h->d_G.as<float>(); q.rho = h->d_m.as<double>();
+		q.logZ = h->d_logZ.as<double>(); q.numer = h->d_numer.as<double>(); q.Dm = h->d_Dm.as<float>(); q.Xd = h->d_Xd.as<float>();
+		q.node_lab = h->d_node_lab.as<uint32_t>(); q.next_lab = h->d_next_lab.as<uint32_t>();
+		CUDA_OK(launch_nodur_tf_dp(false, q, s)); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		CUDA_OK(launch_nodur_tf_dp(true, q, s)); check_kernel(h, 1);
+		phase_end(h, "backward");
+	} else if (h->nodur) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
 		const uint32_t npt = (P + 31) / 32, Pk = npt * 32;
 		h->d_nd_xch.ensure(sizeof(float) * (size_t)h->n_nodur_groups * 2 * ((size_t)Pk + npt) * NODUR_UT + 16);
@@ -747,7 +782,18 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	const bool lat_tma = h->opt_gemm_impl == 2 && lattice_tma_eligible(h->d_A.as<float>(), Lv) && lattice_tma_eligible(h->d_R.as<float>(), Lv) &&
 	                     lattice_tma_eligible(h->d_Dm.as<float>(), Lp);
 	if (h->nodur && !(lat_tma && tma)) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the native stdseg_no_dur* path needs the TMA-fed gradient kernels (gemm_impl 2)");
-	if (h->nodur) {
+	if (h->nodur_tf) {
+		// transition weights: out[tidx(y',y) + f] += sum_n ([ref pair] - xi)[n][y'][y] * x_{n,1}[tf0 + f]  (duration-1 window of frame n)
+		ReduceGemmParams r{};
+		r.A = h->d_Xd.as<float>(); r.lda = Lq; r.a_row_shift = 0;
+		r.B = h->X() + c.trans_fidx_start; r.ldb = h->ldx();
+		r.n0 = 0; r.n1 = N; r.I = P * P; r.J = m.nTf + (c.use_trans_bias ? 1 : 0);
+		r.ones_col = c.use_trans_bias ? m.nTf : 0xffffffffu;
+		r.scale = 1.0; r.ones_scale = c.trans_bias_val; r.mode = 0;
+		r.row_idx = h->d_tidx.as<uint32_t>();
+		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab_tc;
+		CUDA_OK(launch_reduce_gemm_tc(r, false, s)); check_kernel(h, 1);
+	} else if (h->nodur) {
 		if (c.use_trans_bias && N > 1) {
 			// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: one duration block of P columns with row shift 1
 			FrameGemmParams x{};
@@ -813,7 +859,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	e.use_state_bias = c.use_state_bias; e.use_trans_bias = c.use_trans_bias;
 	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
 	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
-	launch_empirical(e, s); check_kernel(h, 1);
+	if (!h->nodur_tf) { launch_empirical(e, s); check_kernel(h, 1); }      // nodur_tf: numerators come from the forward kernel, counts from Dm / Xd
 	tail_sums_kernel<<<1, 256, 0, s>>>(h->d_numer.as<double>(), h->d_logZ.as<double>(), h->n_utt, h->d_grad.as<double>() + m.len);
 	check_kernel(h, 1);
 	phase_end(h, "grad");
@@ -911,7 +957,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);

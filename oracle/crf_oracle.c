@@ -519,8 +519,9 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	const crforacle_config* c = k->c; const fmap_t* m = k->m; const double* lam = k->lam;
 	const uint32_t P = m->L, D = c->max_dur, W = crforacle_window_width(c);
 	if (c->n_states != 1) FAIL("oracle: N-state segmental forward-backward not restated");
-	if (c->use_trans_ftrs || !k->Mconst) FAIL("oracle: no_dur models with transition features not restated");
-	const double* M = k->Mconst;
+	/* transition FEATURES are restated for stdseg_no_dur_no_segtransftr only: M_t[y'][y] comes from the duration-1 window of the frame
+	 * the new segment starts in (CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr::computeTransMatrix :39-121) */
+	if (c->use_trans_ftrs && c->model_type != CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR) FAIL("oracle: transition features restated for stdseg_no_dur_no_segtransftr only");
 	float* X = (float*)malloc(sizeof(float) * (size_t)T * D * W);
 	double* S = (double*)malloc(sizeof(double) * (size_t)T * D * P);      /* [t][d-1][y] */
 	double* AD = (double*)malloc(sizeof(double) * (size_t)T * D * P);     /* alpha_t[d,y] */
@@ -528,9 +529,15 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	double* AT = (double*)malloc(sizeof(double) * (size_t)T * P);         /* A_t[y] */
 	double* B = (double*)malloc(sizeof(double) * (size_t)T * P);          /* beta_t[y] */
 	double* BV = (double*)malloc(sizeof(double) * (size_t)T * P);         /* B_t[y] */
+	double* Mt = k->Mconst ? NULL : (double*)malloc(sizeof(double) * (size_t)T * P * P);   /* M_t[y'][y] of the frame the segment starts in */
 	double* acc = (double*)malloc(sizeof(double) * (P > D ? P : D));
 	crforacle_window_ftrs(c, T, x, X);
 	memset(k->ExpF, 0, sizeof(double) * m->len);
+#define MAT(t) (k->Mconst ? k->Mconst : Mt + (size_t)(t) * P * P)
+	if (Mt)
+		for (uint32_t t = 0; t < T; t++)
+			for (uint32_t q = 0; q < P; q++) for (uint32_t y = 0; y < P; y++)
+				Mt[((size_t)t * P + q) * P + y] = trans_value(c, m, X + (size_t)t * D * W, lam, q, y);
 	for (uint32_t t = 0; t < T; t++) {
 		const uint32_t dmax = t + 1 < D ? t + 1 : D;
 		for (uint32_t y = 0; y < P; y++) {
@@ -541,19 +548,22 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 			}
 			A[(size_t)t * P + y] = log_add_n(acc, (int)dmax);
 		}
-		for (uint32_t y = 0; y < P; y++) {
-			for (uint32_t q = 0; q < P; q++) acc[q] = A[(size_t)t * P + q] + M[(size_t)q * P + y];
-			AT[(size_t)t * P + y] = log_add_n(acc, (int)P);
+		if (t + 1 < T) {
+			const double* M = MAT(t + 1);
+			for (uint32_t y = 0; y < P; y++) {
+				for (uint32_t q = 0; q < P; q++) acc[q] = A[(size_t)t * P + q] + M[(size_t)q * P + y];
+				AT[(size_t)t * P + y] = log_add_n(acc, (int)P);
+			}
 		}
 	}
 	const double Zx = log_add_n(A + (size_t)(T - 1) * P, (int)P);
 	double ll = 0.0;
 	int bad = 0;
-	uint32_t prev_lab = CRFO_LAB_BAD;
 	for (uint32_t t = T; t-- > 0;) {
 		const uint32_t nn = (T - 1 - t) < D ? (T - 1 - t) : D;
 		if (nn == 0) for (uint32_t y = 0; y < P; y++) { B[(size_t)t * P + y] = 0.0; BV[(size_t)t * P + y] = LOG0; }
 		else {
+			const double* M = MAT(t + 1);
 			for (uint32_t y = 0; y < P; y++) {
 				for (uint32_t d = 1; d <= nn; d++) acc[d - 1] = S[((size_t)(t + d) * D + d - 1) * P + y] + B[(size_t)(t + d) * P + y];
 				BV[(size_t)t * P + y] = log_add_n(acc, (int)nn);
@@ -578,33 +588,32 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 			}
 		}
 		if (tot > 1.000001 || tot < -0.000001) bad = 1;
-		/* transitions out of frame t (into the segment that starts at t+1) */
+		/* transitions out of frame t into the segment that starts at t+1, with the features of frame t+1's duration-1 window; the
+		 * reference pair is (segment ending here, next reference segment) -- computeExpF :737-792 and the builder's next_lab (:436-453) */
 		if (t + 1 < T) {
+			const double* M = MAT(t + 1);
+			const float* xn = X + (size_t)(t + 1) * D * W;
+			uint32_t next_lab = CRFO_LAB_BAD;
+			for (uint32_t u = t + 1; u < T; u++) { next_lab = lab4[4 * (size_t)u]; if (next_lab != CRFO_LAB_BAD) break; }
 			double ttot = 0.0;
 			for (uint32_t q = 0; q < P; q++)
 				for (uint32_t y = 0; y < P; y++) {
 					const double xi = exp(A[(size_t)t * P + q] + M[(size_t)q * P + y] + BV[(size_t)t * P + y] - Zx);
 					ttot += xi;
-					trans_expf(c, m, NULL, lam, k->ExpF, grad, xi, CRFO_LAB_BAD, CRFO_LAB_BAD, q, y);
+					const int match = lab != CRFO_LAB_BAD && next_lab != CRFO_LAB_BAD && q == lab && y == next_lab;
+					ll += trans_expf(c, m, xn, lam, k->ExpF, grad, xi, match ? lab : CRFO_LAB_BAD, match ? next_lab : CRFO_LAB_BAD, q, y);
 				}
 			if (ttot > 1.000001 || ttot < -0.000001) bad = 1;
 		}
-		/* empirical transition: the reference segment ending here and the one before it */
-		if (lab != CRFO_LAB_BAD) {
-			if (prev_lab != CRFO_LAB_BAD) {
-				uint32_t lc = m->tidx[(size_t)prev_lab * P + lab];
-				if (c->use_trans_bias) { grad[lc] += c->trans_bias_val; ll += lam[lc] * c->trans_bias_val; }
-			}
-			prev_lab = lab;
-		}
 	}
+#undef MAT
 	if (!bad) {
 		for (uint32_t i = 0; i < m->len; i++) grad[i] -= k->ExpF[i];
 		*numer = ll; *logZ = Zx;
 		if (A_out) memcpy(A_out, A, sizeof(double) * (size_t)T * P);
 		if (B_out) memcpy(B_out, B, sizeof(double) * (size_t)T * P);
 	}
-	free(X); free(S); free(AD); free(A); free(AT); free(B); free(BV); free(acc);
+	free(X); free(S); free(AD); free(A); free(AT); free(B); free(BV); free(Mt); free(acc);
 	if (bad) FAIL("posterior mass check failed (no_dur)");
 	return 0;
 }

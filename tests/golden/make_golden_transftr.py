@@ -32,6 +32,21 @@ def main():
     off2, ftrs2, labs2 = synth(rng, 4, 20, 70, 13, 20, seg_lo=1, seg_hi=5)
     cfg = make_config("stdframe", n_labs=20, n_base_ftrs=13, use_trans_ftrs=1, trans_fidx=(0, 12), state_fidx=(3, 12))
     cases["frame_transftr_20labs"] = (cfg, rng.uniform(-0.1, 0.1, ref.lambda_len(cfg)), off2, ftrs2, labs2)
+    # segmental models without duration labels: transition features from the duration-1 window of the frame the new segment starts in
+    # (CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr; the production TIMIT recipe, demo/segmental-timit-demo.cfg.in:11-48)
+    off3, ftrs3, labs3 = synth(rng, 5, 1, 45, 6, 7, seg_lo=1, seg_hi=9)
+    w = 8 * 6 + 4
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=7, n_base_ftrs=6, max_dur=4, n_actual_labs=7, extract_seg_ftrs=1,
+                      use_trans_ftrs=1, trans_fidx=(0, w - 1))
+    cases["nodur_transftr_d4_all"] = (cfg, rng.uniform(-0.05, 0.05, ref.lambda_len(cfg)), off3, ftrs3, labs3)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=7, n_base_ftrs=6, max_dur=4, n_actual_labs=7, extract_seg_ftrs=1,
+                      use_trans_ftrs=1, trans_fidx=(6, 17), state_fidx=(0, 8 * 6 - 1), use_trans_bias=0)
+    cases["nodur_transftr_d4_slice_nobias"] = (cfg, rng.uniform(-0.05, 0.05, ref.lambda_len(cfg)), off3, ftrs3, labs3)
+    off4, ftrs4, labs4 = synth(rng, 3, 25, 60, 5, 12, seg_lo=2, seg_hi=14)
+    w = 8 * 5 + 10
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=12, n_base_ftrs=5, max_dur=10, n_actual_labs=12, extract_seg_ftrs=1,
+                      use_trans_ftrs=1, trans_fidx=(0, 5 * 5 - 1))
+    cases["nodur_transftr_d10"] = (cfg, rng.uniform(-0.03, 0.03, ref.lambda_len(cfg)), off4, ftrs4, labs4)
     out = {}
     for name, (cfg, lam, off, ftrs, labs) in cases.items():
         grad, numer, logz = ref.fwdbwd(cfg, lam, off, ftrs, labs)

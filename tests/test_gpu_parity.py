@@ -454,6 +454,24 @@ def test_fwdbwd_transition_features_match_reference_golden(name):
     m.close()
 
 
+def test_fwdbwd_nodur_transition_features_timit_recipe_shape(oracle):
+    """stdseg_no_dur_no_segtransftr + stdtrans at the shape of the production TIMIT recipe (48 phones, maxDur 10, transition features
+    from the duration-1 window), against the oracle's native restatement (pinned to goldens from the reference's no_dur nodes)."""
+    rng = np.random.default_rng(29)
+    F, P, D = 13, 48, 10
+    off, ftrs, labs = synth_batch(rng, 6, 5, 60, F, P, 1, 14)
+    w = 8 * F + D
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1,
+                      use_trans_ftrs=1, trans_fidx=(0, 5 * F - 1), state_fidx=(0, w - 1))
+    lam = rng.uniform(-0.02, 0.02, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=6)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, "no_dur stdtrans")
+    m.close()
+
+
 def test_fwdbwd_transition_features_cfg2_shape_matches_oracle(oracle):
     """61 labels, 105 features for states and transitions (the cfg2 geometry with stdtrans: dim(lambda) = 61*(106 + 61*106))."""
     rng = np.random.default_rng(23)
