@@ -808,14 +808,15 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	const uint32_t L = p.L, P = p.P, NS = p.NS, D = p.D;
 	const uint32_t off = p.off[u], T = p.off[u + 1] - p.off[u];
 	const uint32_t lab = threadIdx.x;
-	const bool cross_in_smem = ((size_t)P * P * sizeof(float) <= 96 * 1024);
+	const bool cross_in_smem = p.negMt == nullptr && ((size_t)P * P * sizeof(float) <= 96 * 1024);
 	if (cross_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) crossS[i] = p.crossT[i];
 	const float* crossT = cross_in_smem ? crossS : p.crossT;
+	const bool per_frame = p.negMt != nullptr;      // transition FEATURES: the tables of the frame a segment starts in (global memory)
 	float* candW = p.candW + (uint64_t)u * D * L;
 	int32_t* candP = p.candP + (uint64_t)u * D * L;
 	const uint32_t q = lab / NS, k = lab % NS;
-	const float my_diag = lab < L ? p.negDiag[lab] : 0.0f;
-	const float my_off = (lab < L && k > 0) ? p.negOff[lab] : 0.0f;
+	float my_diag = (lab < L && p.negMt == nullptr) ? p.negDiag[lab] : 0.0f;
+	float my_off = (lab < L && k > 0 && p.negMt == nullptr) ? p.negOff[lab] : 0.0f;
 	if (threadIdx.x == 0) s_g = 0xffu;
 	__syncthreads();
 
@@ -833,6 +834,11 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 		// ---- cross-phone candidates for segments starting at frame s: the scan of the kept list of frame s-1 is shared by ALL threads
 		//      of the CTA (with N states per phone only every N-th thread owns a start state): thread = (part of the list, target phone);
 		//      strict '<' keeps the first arrival inside a part, and the parts are merged in list order below ----
+		if (per_frame && s > 0) {
+			const float* tb = p.negMt + (uint64_t)(off + s) * p.E;
+			crossT = tb;
+			if (lab < L) { my_diag = tb[P * P + lab]; my_off = k > 0 ? tb[P * P + L + lab] : 0.0f; }
+		}
 		float pw = VIT_INF; int32_t pptr = -1;
 		if (s > 0 && lab < L) {
 			const uint32_t g = s_g, part = lab / P, tq = lab - part * P;
@@ -968,7 +974,7 @@ void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	if (!p.n_utt) return;
 	const unsigned threads = (p.L + 31) / 32 * 32;
 	size_t smem = sizeof(float) * 3 * p.L;
-	if ((size_t)p.P * p.P * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * p.P;
+	if (p.negMt == nullptr && (size_t)p.P * p.P * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * p.P;
 	cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(p);
 }

@@ -230,6 +230,7 @@ struct VitParams {
 	const float* crossT;              // [P][P]  crossT[pp*P+q] = (float)(-M[end(pp)][start(q)])
 	const float* negDiag;             // [L]     (float)(-M[l][l])
 	const float* negOff;              // [L]     (float)(-M[l-1][l]) for sub-state > 0
+	const float* negMt; uint32_t E;   // transition FEATURES: per-frame table [N][E], E = P*P + 2L: crossT | negDiag | negOff of the frame (else nullptr)
 	float* candW; int32_t* candP;     // [n_utt][D][L] rings of candidates per start frame
 	float* keptW;                     // [n_utt][2][L]
 	uint16_t* bp; uint8_t* bd;        // [N][L] back pointer (label or 0xffff) and duration
@@ -275,6 +276,8 @@ struct LambdaTablesParams {
 	unsigned char* Wt; uint32_t wt_P, wt_D, wt_chunks;   // weight tiles of the TMA-fed score GEMM (null: skip)
 	// transition-FEATURE weights (stdtrans, null Wtr: skip): Wtr[(p*L0 + c)][f] = lambda[tidx0(p,c) + f], tbias = bias weight * transBiasVal
 	float* Wtr; float* tbias; uint32_t nTf;
+	// decoder transition-FEATURE weights (null WdT: skip): WdT[f*vtE + e] = lambda[vt_base[e] + f] for the vtE = P*P + 2L decoder pairs
+	double* WdT; const uint32_t* vt_base; uint32_t vtE;
 	// decoder tables over the model's own labels (null Wd: skip)
 	double* Wd; float* crossT; float* negDiag; float* negOff;
 	const uint32_t* sidx0; const uint32_t* tidx0; uint32_t L0, NS, P0;

@@ -88,6 +88,14 @@ __global__ void __launch_bounds__(256) lambda_tables_kernel(LambdaTablesParams p
 		for (uint64_t pair = tid0; pair < L * L; pair += stride)
 			p.tbias[pair] = p.use_trans_bias ? (float)__dmul_rn(p.lam[p.tidx0[pair] + p.nTf], p.trans_bias_val) : 0.0f;
 	}
+	if (p.WdT) {
+		const uint64_t nw = (uint64_t)(p.nTf + 1) * p.vtE;
+		for (uint64_t i = tid0; i < nw; i += stride) {
+			const uint32_t f = (uint32_t)(i / p.vtE), e = (uint32_t)(i % p.vtE);
+			const uint32_t b = p.vt_base[e];
+			p.WdT[i] = (b != 0xffffffffu && (f < p.nTf || p.use_trans_bias)) ? p.lam[b + f] : 0.0;
+		}
+	}
 	if (p.Wd) {
 		// decoder tables over the MODEL's labels (L0 labels, NS sub-states, P0 phones)
 		const uint32_t L = p.L0, NS = p.NS, P = p.P0;

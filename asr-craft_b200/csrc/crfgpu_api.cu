@@ -78,6 +78,7 @@ struct crfgpu_ctx {
 	uint32_t Lt = 0; bool tied = false;
 	// native O(P^2 + D*P) recursion for the same models (crf_dp_nodur.cu): score / posterior columns are (duration, phone), the
 	// transition tables and forward/backward vectors are P wide
+	DevBuf d_WdT, d_vt_base, d_negMt; uint32_t vtE = 0;              // decoding with transition features: per-frame transition tables
 	bool nodur_tf = false; DevBuf d_next_lab;                       // segmental no_dur model with transition features (nodur && nodur_tf)
 	bool transftr = false; DevBuf d_Wtr, d_tbias, d_Mall, d_Xd;   // frame-level model with transition FEATURES (crf_dp_transftr.cu)
 	bool nodur = false; uint32_t Pp = 0; int opt_nodur_impl = 0; int nodur_groups_max = 0; uint32_t n_nodur_groups = 0;
@@ -154,7 +155,10 @@ void classify(crfgpu_ctx* h) {
 	h->transftr = h->nodur_tf = false;
 	if (c.use_trans_ftrs) {
 		// transition FEATURES (crf_featuremap=stdtrans): implemented for training frame-level models with one state per label
-		h->decode_ok = false; h->decode_why = "decoding with transition FEATURES (crf_featuremap=stdtrans) is not implemented on the device yet";
+		// decoding: the decoder's transition tables become per-frame tables (fp64 scores in the reference's order, one row per frame)
+		if (c.model_type != CRFGPU_STDFRAME && c.model_type != CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
+			h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
+		} else if (c.n_labs > 1024 || c.max_dur > 255) { h->decode_ok = false; h->decode_why = "Viterbi kernel supports crf_label_size <= 1024 and max duration <= 255"; }
 		if (c.model_type == CRFGPU_STDFRAME && c.max_dur == 1 && c.n_states == 1 && c.n_labs <= 128 && c.use_state_ftrs) { h->transftr = true; return; }
 		// ... and for the segmental production recipe: no duration labels, transition features from the duration-1 window
 		if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.n_states == 1 && c.max_dur > 1 && c.max_dur <= 31 && c.n_labs <= 128 && c.use_state_ftrs) {
@@ -225,6 +229,19 @@ void setup_label_space(crfgpu_ctx* h) {
 	if (h->stream) {
 		upload(h->d_sidx, h->t_sidx, h->stream); upload(h->d_tidx, h->t_tidx, h->stream);
 		if (h->decode_ok && (h->tied || h->nodur)) { upload(h->d_sidx0, h->lay.sidx, h->stream); upload(h->d_tidx0, h->lay.tidx, h->stream); }
+		if (h->decode_ok && h->cfg.use_trans_ftrs) {
+			// the decoder's transition pairs: end(pp) -> start(q) for all phone pairs, self loops, advance arcs (the same pairs the
+			// constant tables crossT / negDiag / negOff hold for bias-only transitions)
+			const Layout& m = h->lay; const uint32_t L = m.L, NS = m.n_states, P = m.n_act;
+			std::vector<uint32_t> base((size_t)P * P + 2 * L, CRFGPU_NO_IDX);
+			for (uint32_t pp = 0; pp < P; pp++) for (uint32_t q = 0; q < P; q++) base[(size_t)pp * P + q] = m.tidx[(size_t)(pp * NS + NS - 1) * L + q * NS];
+			for (uint32_t l = 0; l < L; l++) {
+				base[(size_t)P * P + l] = m.tidx[(size_t)l * L + l];
+				if (l % NS != 0) base[(size_t)P * P + L + l] = m.tidx[(size_t)(l - 1) * L + l];
+			}
+			h->vtE = (uint32_t)base.size();
+			upload(h->d_vt_base, base, h->stream);
+		}
 		CUDA_OK(cudaStreamSynchronize(h->stream));
 	}
 }
@@ -270,6 +287,10 @@ void derive_tables(crfgpu_ctx* h) {
 		h->d_Wtr.ensure(sizeof(float) * (size_t)L * L * nTf + 16); h->d_tbias.ensure(sizeof(float) * (size_t)L * L + 16);
 		p.Wtr = h->d_Wtr.as<float>(); p.tbias = h->d_tbias.as<float>(); p.nTf = nTf;
 		p.sidx0 = h->d_sidx.as<uint32_t>(); p.tidx0 = h->d_tidx.as<uint32_t>(); p.L0 = L;
+	}
+	if (h->decode_ok && c.use_trans_ftrs) {
+		h->d_WdT.ensure(sizeof(double) * (size_t)(m.nTf + 1) * h->vtE + 16);
+		p.WdT = h->d_WdT.as<double>(); p.vt_base = h->d_vt_base.as<uint32_t>(); p.vtE = h->vtE; p.nTf = m.nTf;
 	}
 	if (h->decode_ok) {
 		const bool same = !h->tied && !h->nodur;
@@ -884,10 +905,20 @@ void viterbi_staged(crfgpu_ctx* h) {
 	vs.negS = h->d_negS.as<float>();
 	launch_vit_scores(vs, s); check_kernel(h, 1);
 	phase_end(h, "viterbi_score");
+	if (c.use_trans_ftrs) {
+		// (float)(-M_n[p][c]) of every frame's decoder pairs from its duration-1 window, in the reference's fp64 arithmetic
+		h->d_negMt.ensure(sizeof(float) * (size_t)N * h->vtE + 16);
+		VitScoreParams ts{};
+		ts.X = h->X(); ts.ldx = h->ldx(); ts.W = h->Wp; ts.sf0 = c.trans_fidx_start; ts.nSf = m.nTf; ts.N = N; ts.D = 1; ts.L = h->vtE;
+		ts.frame_t = h->d_frame_t.as<uint32_t>(); ts.Wd = h->d_WdT.as<double>(); ts.use_bias = c.use_trans_bias; ts.bias_val = c.trans_bias_val;
+		ts.negS = h->d_negMt.as<float>();
+		launch_vit_scores(ts, s); check_kernel(h, 1);
+	}
 	phase_begin(h, "viterbi");
 	VitParams v{};
 	v.n_utt = h->n_utt; v.L = L; v.P = P; v.NS = NS; v.D = D; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
 	v.crossT = h->d_crossT.as<float>(); v.negDiag = h->d_negDiag.as<float>(); v.negOff = h->d_negOff.as<float>();
+	v.negMt = c.use_trans_ftrs ? h->d_negMt.as<float>() : nullptr; v.E = h->vtE;
 	v.candW = h->d_candW.as<float>(); v.candP = h->d_candP.as<int32_t>(); v.keptW = nullptr;
 	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
 	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
@@ -957,7 +988,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);

@@ -55,6 +55,29 @@ def main():
         print(f"{name}: lambda {len(lam)}, logZ {logz[:3]}, |grad|^2 {np.sum(grad ** 2):.12f}")
     np.savez_compressed(os.path.join(OUT, "train_transftr_golden.npz"), **out)
 
+    # ---- decoding with transition features (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr over nodes whose transMatrix comes from the
+    #      duration-1 window of the frame the segment starts in) ----
+    out = {}
+    lens = [1, 2, 3, 5, 9, 30, 47]
+    voff = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    for (P, N, D, segf) in [(5, 1, 1, 0), (5, 3, 1, 0), (7, 1, 3, 1), (4, 3, 2, 1), (6, 1, 5, 1)]:
+        w = 4 if (D == 1 or not segf) else 8 * 4 + D
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P * N, n_base_ftrs=4, n_states=N, max_dur=D, extract_seg_ftrs=segf,
+                          use_trans_ftrs=1, trans_fidx=(0, min(w, 12) - 1))
+        n = ref.lambda_len(cfg)
+        vf = rng.random((int(voff[-1]), 4), dtype=np.float32)
+        qf = (np.round(vf * 2) / 2).astype(np.float32)
+        for kind, lam, f in [("rand", rng.uniform(-0.5, 0.5, n), vf), ("ties", np.zeros(n), vf), ("quant", np.round(rng.uniform(-1, 1, n) * 2) / 2, qf)]:
+            name = f"{kind}_P{P}N{N}D{D}s{segf}"
+            segs, cost, logz = ref.viterbi(cfg, lam, voff, f)
+            nseg = np.array([len(sg[0]) for sg in segs], np.uint32)
+            out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": voff, f"{name}/ftrs": f,
+                        f"{name}/nseg": nseg, f"{name}/cost": cost, f"{name}/logZ": logz,
+                        f"{name}/lab": np.concatenate([sg[0] for sg in segs]), f"{name}/dur": np.concatenate([sg[1] for sg in segs]),
+                        f"{name}/phn": np.concatenate([sg[2] for sg in segs])})
+    print("viterbi cases with transition features:", len(out) // 10)
+    np.savez_compressed(os.path.join(OUT, "viterbi_transftr_golden.npz"), **out)
+
 
 if __name__ == "__main__":
     main()

@@ -24,6 +24,7 @@ VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
+VIT_TF = load_cases("viterbi_transftr_golden.npz")
 
 
 def gpu(cfg):
@@ -483,4 +484,39 @@ def test_fwdbwd_transition_features_cfg2_shape_matches_oracle(oracle):
     m.set_lambda(lam)
     got = m.fwdbwd(off, ftrs, labs)
     assert_train_close(got, want, "stdtrans cfg2 shape")
+    m.close()
+
+
+@pytest.mark.parametrize("name", sorted(VIT_TF))
+def test_viterbi_transition_features_bit_exact_vs_reference_golden(name):
+    """decoding with crf_featuremap=stdtrans: per-frame decoder tables from fp64 scores in the reference's order"""
+    c = VIT_TF[name]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    segs, cost = m.viterbi(c["off"], c["ftrs"])
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s[0]) for s in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp)), name
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32)), name
+    m.close()
+
+
+def test_viterbi_transition_features_recipe_shape_vs_oracle(oracle):
+    """48 phones, maxDur 10, transition features from the duration-1 window (the TIMIT recipe's decode), bit-exact against the oracle"""
+    rng = np.random.default_rng(31)
+    F, P, D = 13, 48, 10
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=1,
+                      use_trans_ftrs=1, trans_fidx=(0, 5 * F - 1))
+    lens = rng.integers(1, 90, 9)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+    lam = rng.uniform(-0.25, 0.25, oracle.lambda_len(cfg))
+    want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    segs, cost = m.viterbi(off, ftrs)
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
     m.close()

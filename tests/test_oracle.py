@@ -13,6 +13,7 @@ VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
+VIT_TF = load_cases("viterbi_transftr_golden.npz")
 
 
 def test_toy_known_answers(oracle):
@@ -57,6 +58,17 @@ def test_train_transftr_golden(oracle, name):
     np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
     np.testing.assert_allclose(numer, c["numer"], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", sorted(VIT_TF))
+def test_viterbi_transftr_golden_bit_exact(oracle, name):
+    """decoding with transition FEATURES against the reference decoder (goldens of make_golden_transftr.py)"""
+    c = VIT_TF[name]
+    segs, cost, _ = oracle.viterbi(c["cfg"], c["lam"], c["off"], c["ftrs"])
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
 
 
 def test_train_threads_match_single(oracle):
