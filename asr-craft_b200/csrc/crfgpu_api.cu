@@ -181,9 +181,9 @@ void classify(crfgpu_ctx* h) {
 		if (c.model_type != CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
 			h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
 		}
-		if (c.n_states != 1 && c.max_dur != 1) {
-			h->train_ok = false; h->train_why = "forward-backward for N-state segmental models (CRF_StdSegNStateNode*) is not implemented on the device yet";
-		} else if (c.n_states == 1 && c.max_dur > 1) {
+		if (c.max_dur > 1) {
+			// (N states per phone -- CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr -- make every sub-state a segment of its own over
+			// the N-state map's legal pairs: the same recursions with E = 0 on the illegal pairs)
 			// two device paths: the tied (duration, phone) expansion on the dense stdseg kernels (phones * max_dur <= 1024) and the
 			// native O(P^2 + D*P) recursion (any phone count whose matrix slices fit the shared memory of one group of CTAs)
 			const bool tied_ok = (uint64_t)c.n_labs * c.max_dur <= 1024 && c.max_dur <= 32;

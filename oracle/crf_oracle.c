@@ -518,7 +518,11 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
                     double* grad, double* numer, double* logZ, double* A_out, double* B_out) {
 	const crforacle_config* c = k->c; const fmap_t* m = k->m; const double* lam = k->lam;
 	const uint32_t P = m->L, D = c->max_dur, W = crforacle_window_width(c);
-	if (c->n_states != 1) FAIL("oracle: N-state segmental forward-backward not restated");
+	/* N states per phone (CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr): every sub-state is a segment of its own and only the
+	 * legal pairs of the N-state map exist -- self (diagTransMatrix), end state -> start state (denseTransMatrix) and k-1 -> k
+	 * (offDiagTransMatrix), computeAlphaPlusTrans :1161-1268, computeBeta :450-718, computeExpF :719-1160 */
+	if (c->n_states != 1 && c->use_trans_ftrs) FAIL("oracle: N-state segmental forward-backward with transition features not restated");
+#define LEGAL(q, y) (m->tidx[(size_t)(q) * P + (y)] != CRFO_NO_IDX)
 	/* transition FEATURES are restated for stdseg_no_dur_no_segtransftr only: M_t[y'][y] comes from the duration-1 window of the frame
 	 * the new segment starts in (CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr::computeTransMatrix :39-121) */
 	if (c->use_trans_ftrs && c->model_type != CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR) FAIL("oracle: transition features restated for stdseg_no_dur_no_segtransftr only");
@@ -529,11 +533,16 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	double* AT = (double*)malloc(sizeof(double) * (size_t)T * P);         /* A_t[y] */
 	double* B = (double*)malloc(sizeof(double) * (size_t)T * P);          /* beta_t[y] */
 	double* BV = (double*)malloc(sizeof(double) * (size_t)T * P);         /* B_t[y] */
-	double* Mt = k->Mconst ? NULL : (double*)malloc(sizeof(double) * (size_t)T * P * P);   /* M_t[y'][y] of the frame the segment starts in */
+	double* Mt = (k->Mconst || !c->use_trans_ftrs) ? NULL : (double*)malloc(sizeof(double) * (size_t)T * P * P);   /* M_t[y'][y] of the frame the segment starts in */
 	double* acc = (double*)malloc(sizeof(double) * (P > D ? P : D));
+	double* Mn = NULL;
 	crforacle_window_ftrs(c, T, x, X);
 	memset(k->ExpF, 0, sizeof(double) * m->len);
-#define MAT(t) (k->Mconst ? k->Mconst : Mt + (size_t)(t) * P * P)
+	if (!k->Mconst && !c->use_trans_ftrs) {   /* N-state, bias only: one matrix, illegal pairs never read */
+		Mn = (double*)malloc(sizeof(double) * (size_t)P * P);
+		for (uint32_t q = 0; q < P; q++) for (uint32_t y = 0; y < P; y++) Mn[(size_t)q * P + y] = LEGAL(q, y) ? trans_value(c, m, NULL, lam, q, y) : 0.0;
+	}
+#define MAT(t) (k->Mconst ? k->Mconst : (Mn ? Mn : Mt + (size_t)(t) * P * P))
 	if (Mt)
 		for (uint32_t t = 0; t < T; t++)
 			for (uint32_t q = 0; q < P; q++) for (uint32_t y = 0; y < P; y++)
@@ -551,8 +560,9 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 		if (t + 1 < T) {
 			const double* M = MAT(t + 1);
 			for (uint32_t y = 0; y < P; y++) {
-				for (uint32_t q = 0; q < P; q++) acc[q] = A[(size_t)t * P + q] + M[(size_t)q * P + y];
-				AT[(size_t)t * P + y] = log_add_n(acc, (int)P);
+				int na = 0;
+				for (uint32_t q = 0; q < P; q++) if (LEGAL(q, y)) acc[na++] = A[(size_t)t * P + q] + M[(size_t)q * P + y];
+				AT[(size_t)t * P + y] = log_add_n(acc, na);
 			}
 		}
 	}
@@ -569,8 +579,9 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 				BV[(size_t)t * P + y] = log_add_n(acc, (int)nn);
 			}
 			for (uint32_t q = 0; q < P; q++) {
-				for (uint32_t y = 0; y < P; y++) acc[y] = M[(size_t)q * P + y] + BV[(size_t)t * P + y];
-				B[(size_t)t * P + q] = log_add_n(acc, (int)P);
+				int na = 0;
+				for (uint32_t y = 0; y < P; y++) if (LEGAL(q, y)) acc[na++] = M[(size_t)q * P + y] + BV[(size_t)t * P + y];
+				B[(size_t)t * P + q] = log_add_n(acc, na);
 			}
 		}
 	}
@@ -598,6 +609,7 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 			double ttot = 0.0;
 			for (uint32_t q = 0; q < P; q++)
 				for (uint32_t y = 0; y < P; y++) {
+					if (!LEGAL(q, y)) continue;
 					const double xi = exp(A[(size_t)t * P + q] + M[(size_t)q * P + y] + BV[(size_t)t * P + y] - Zx);
 					ttot += xi;
 					const int match = lab != CRFO_LAB_BAD && next_lab != CRFO_LAB_BAD && q == lab && y == next_lab;
@@ -607,13 +619,14 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 		}
 	}
 #undef MAT
+#undef LEGAL
 	if (!bad) {
 		for (uint32_t i = 0; i < m->len; i++) grad[i] -= k->ExpF[i];
 		*numer = ll; *logZ = Zx;
 		if (A_out) memcpy(A_out, A, sizeof(double) * (size_t)T * P);
 		if (B_out) memcpy(B_out, B, sizeof(double) * (size_t)T * P);
 	}
-	free(X); free(S); free(AD); free(A); free(AT); free(B); free(BV); free(Mt); free(acc);
+	free(X); free(S); free(AD); free(A); free(AT); free(B); free(BV); free(Mt); free(Mn); free(acc);
 	if (bad) FAIL("posterior mass check failed (no_dur)");
 	return 0;
 }

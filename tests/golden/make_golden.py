@@ -176,7 +176,35 @@ def nodur_training():
     np.savez_compressed(os.path.join(OUT, "train_nodur_golden.npz"), **out)
 
 
+def nodur_nstate_training():
+    """N-state segmental training (CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr): every sub-state is a segment of its own."""
+    ref = RefLib()
+    rng = np.random.default_rng(20260303)
+    train = {}
+    off, ftrs, labs = synth(rng, 5, 6, 45, 8, 5, seg_lo=3, seg_hi=12, states=3)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=15, n_base_ftrs=8, n_states=3, max_dur=4, extract_seg_ftrs=1)
+    train["nstate3_p5_d4_segftr"] = (cfg, rng.uniform(-0.1, 0.1, ref.lambda_len(cfg)), off, ftrs, labs)
+    cfg = make_config("stdseg_no_dur_no_transftr", n_labs=15, n_base_ftrs=8, n_states=3, max_dur=3, extract_seg_ftrs=0)
+    train["nstate3_p5_d3_notransftr"] = (cfg, rng.uniform(-0.1, 0.1, ref.lambda_len(cfg)), off, ftrs, labs)
+    off2, ftrs2, labs2 = synth(rng, 4, 3, 30, 6, 4, seg_lo=1, seg_hi=9, states=2)   # short phones skip sub-states: illegal reference pairs
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=8, n_base_ftrs=6, n_states=2, max_dur=3, extract_seg_ftrs=1)
+    train["nstate2_p4_d3_skips"] = (cfg, rng.uniform(-0.2, 0.2, ref.lambda_len(cfg)), off2, ftrs2, labs2)
+    off3, ftrs3, labs3 = synth(rng, 3, 30, 70, 10, 6, seg_lo=6, seg_hi=30, states=3)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=18, n_base_ftrs=10, n_states=3, max_dur=10, extract_seg_ftrs=1)
+    train["nstate3_p6_d10_segftr"] = (cfg, rng.uniform(-0.05, 0.05, ref.lambda_len(cfg)), off3, ftrs3, labs3)
+    out = {}
+    for name, (cfg, lam, off, ftrs, labs) in train.items():
+        grad, numer, logz = ref.fwdbwd(cfg, lam, off, ftrs, labs)
+        out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": off, f"{name}/ftrs": ftrs,
+                    f"{name}/labs": labs, f"{name}/grad": grad, f"{name}/numer": numer, f"{name}/logZ": logz})
+        print(f"train {name}: lambda {len(lam)}, logZ {logz[:3]}, numer {numer[:3]}, |grad|^2 {np.sum(grad ** 2):.12f}")
+    np.savez_compressed(os.path.join(OUT, "train_nodur_nstate_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nstate":
+        nodur_nstate_training()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "nodur":
         nodur_training()
         sys.exit(0)

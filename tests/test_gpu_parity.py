@@ -23,6 +23,7 @@ TRAIN = load_cases("train_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
+NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 
@@ -520,3 +521,42 @@ def test_viterbi_transition_features_recipe_shape_vs_oracle(oracle):
         assert all(np.array_equal(x, y) for x, y in zip(got, exp))
     assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
     m.close()
+
+
+@pytest.mark.parametrize("name", sorted(NSTATE))
+@pytest.mark.parametrize("impl", ["native", "tied_tc", "tied_cluster"])
+def test_fwdbwd_nodur_nstate_matches_reference_golden(name, impl):
+    """N states per phone in stdseg_no_dur_no_[seg]transftr (CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr): the native recursion
+    and the tied (duration, label) expansion, both with E = 0 on the pairs the N-state map does not have."""
+    c = NSTATE[name]
+    m = gpu(c["cfg"])
+    assert m.lambda_len == len(c["lam"])
+    if impl == "native":
+        m.set_option("nodur_impl", 1)
+    else:
+        m.set_option("nodur_impl", 2)
+        for k, v in IMPLS[impl[5:]].items():
+            m.set_option(k, v)
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    m.close()
+
+
+@pytest.mark.parametrize("P,NS,D,F,n_utt", [(48, 3, 10, 12, 24), (61, 3, 6, 10, 9), (100, 2, 4, 8, 6)])
+def test_fwdbwd_nodur_nstate_matches_oracle_fresh(oracle, P, NS, D, F, n_utt):
+    """the TIMIT phone sets with 3 states per phone (144 / 183 labels) against the oracle, native recursion and (where it fits) tied"""
+    rng = np.random.default_rng(P * NS + D)
+    off, ftrs, labs = synth_batch(rng, n_utt, 8, 80, F, P, 3, 3 * D, states=NS)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P * NS, n_base_ftrs=F, n_states=NS, max_dur=D, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.05, 0.05, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=8)
+    for impl in (1, 2):
+        if impl == 2 and P * NS * D > 1024:
+            continue
+        m = gpu(cfg)
+        m.set_option("nodur_impl", impl)
+        m.set_lambda(lam)
+        got = m.fwdbwd(off, ftrs, labs)
+        assert_train_close(got, want, f"P={P} NS={NS} D={D} impl={impl}")
+        m.close()

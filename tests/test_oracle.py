@@ -12,6 +12,7 @@ TRAIN = load_cases("train_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
 WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
+NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 
@@ -47,6 +48,18 @@ def test_train_nodur_golden(oracle, name, tied):
     np.testing.assert_allclose(logz, c["logZ"], rtol=1e-12)
     np.testing.assert_allclose(numer, c["numer"], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(grad, c["grad"], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", sorted(NSTATE))
+def test_train_nodur_nstate_golden(oracle, name):
+    """N states per phone in the segmental no_dur models (CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr): every sub-state is a
+    segment of its own; goldens from the reference (make_golden.py nstate), one of them with reference paths that skip sub-states."""
+    c = NSTATE[name]
+    assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
+    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"])
+    np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
+    np.testing.assert_allclose(numer, c["numer"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
 
 
 @pytest.mark.parametrize("name", sorted(TRANSFTR))
