@@ -738,7 +738,8 @@ void launch_empirical(const EmpiricalParams& p, cudaStream_t s) {
 // The accumulation order of every output is unchanged (features in index order, bias last).
 constexpr int VS_ROWS = 8;
 __global__ void __launch_bounds__(256) vit_scores_kernel(VitScoreParams p) {
-	extern __shared__ __align__(16) float vs_x[];            // [VS_ROWS][nSf]
+	extern __shared__ __align__(16) double vs_x[];           // [nSf][VS_ROWS], widened once per CTA (the float -> double conversion runs
+	                                                         // at a quarter of the fp64 multiply-add rate, so it must not sit in the inner loop)
 	__shared__ uint32_t row_ok[VS_ROWS];
 	const uint64_t n_rows = (uint64_t)p.N * p.D, r0 = (uint64_t)blockIdx.x * VS_ROWS;
 	for (uint32_t i = 0; i < VS_ROWS; i++) {
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(256) vit_scores_kernel(VitScoreParams p) {
 		if (ok) { n = nd / p.D; d = (uint32_t)(nd % p.D); ok = d <= p.frame_t[n]; }
 		if (threadIdx.x == 0) row_ok[i] = ok ? 1u : 0u;
 		const float* x = p.X + n * p.ldx + (uint64_t)d * p.W + p.sf0;
-		for (uint32_t f = threadIdx.x; f < p.nSf; f += blockDim.x) vs_x[i * p.nSf + f] = ok ? x[f] : 0.0f;
+		for (uint32_t f = threadIdx.x; f < p.nSf; f += blockDim.x) vs_x[f * VS_ROWS + i] = ok ? (double)x[f] : 0.0;
 	}
 	__syncthreads();
 	const uint32_t lab = blockIdx.y * blockDim.x + threadIdx.x;
@@ -759,7 +760,11 @@ __global__ void __launch_bounds__(256) vit_scores_kernel(VitScoreParams p) {
 	for (uint32_t f = 0; f < p.nSf; f++) {
 		const double w = p.Wd[(uint64_t)f * p.L + lab];
 #pragma unroll
-		for (int i = 0; i < VS_ROWS; i++) acc[i] = __dadd_rn(acc[i], __dmul_rn((double)vs_x[i * p.nSf + f], w));
+		for (int i = 0; i < VS_ROWS; i += 2) {
+			const double2 xv = *reinterpret_cast<const double2*>(vs_x + f * VS_ROWS + i);     // broadcast, two windows per load
+			acc[i] = __dadd_rn(acc[i], __dmul_rn(xv.x, w));
+			acc[i + 1] = __dadd_rn(acc[i + 1], __dmul_rn(xv.y, w));
+		}
 	}
 	const double wb = p.use_bias ? __dmul_rn(p.Wd[(uint64_t)p.nSf * p.L + lab], p.bias_val) : 0.0;
 #pragma unroll
@@ -773,7 +778,7 @@ __global__ void __launch_bounds__(256) vit_scores_kernel(VitScoreParams p) {
 void launch_vit_scores(const VitScoreParams& p, cudaStream_t s) {
 	const uint64_t n_rows = (uint64_t)p.N * p.D;
 	if (!n_rows || !p.L) return;
-	const size_t smem = sizeof(float) * VS_ROWS * (size_t)(p.nSf ? p.nSf : 1);
+	const size_t smem = sizeof(double) * VS_ROWS * (size_t)(p.nSf ? p.nSf : 1);
 	cudaFuncSetAttribute(vit_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	dim3 grid((unsigned)((n_rows + VS_ROWS - 1) / VS_ROWS), (p.L + 255) / 256);
 	vit_scores_kernel<<<grid, 256, smem, s>>>(p);

@@ -239,6 +239,27 @@ struct VitParams {
 };
 void launch_viterbi(const VitParams& p, cudaStream_t s);
 
+// ---- Viterbi for large phone sets, one state per phone: cross-phone table sliced over a group of CTAs (crf_viterbi_group.cu) ----
+constexpr int VITG_UT = 16;           // utterances that advance in lock-step per group
+struct VitGroupParams {
+	uint32_t n_utt, P, D;             // one state per phone: labels = phones
+	uint32_t n_batches, n_groups, npt;  // batches of VITG_UT utterances dealt to the groups; CTAs per group = ceil(P / 32)
+	const uint32_t* off;
+	const uint32_t* slot_utt;         // [n_batches][VITG_UT] utterance ids or 0xffffffff
+	const float* negS;                // [N][D][P]
+	const float* crossT;              // [P][P]
+	const float* negDiag;             // [P]
+	float* candW; int32_t* candP;     // [n_utt][D][P] rings of candidates per start frame
+	uint16_t* bp; uint8_t* bd;        // [N][P]
+	float* xch;                       // [n_groups][2][Pk][VITG_UT] kept costs of the frame, Pk = P rounded up to 32
+	float* finalW;                    // [n_utt][P] kept costs of every utterance's last frame
+	uint32_t* ctr;                    // [n_groups] arrival counters
+	uint32_t* out_lab; uint32_t* out_dur; uint32_t* out_phn; uint32_t* n_seg; float* cost;
+};
+size_t vitg_smem_bytes(uint32_t P);
+int vitg_max_groups(uint32_t P);      // groups of ceil(P/32) CTAs that are co-resident (0: the slices do not fit shared memory)
+cudaError_t launch_viterbi_group(const VitGroupParams& p, cudaStream_t s);
+
 // ---- frame-level CRF with transition FEATURES (stdtrans, one state per label; crf_dp_transftr.cu) ---------------------
 struct TransFtrParams {
 	uint32_t L, Lp, Lq;           // labels (<= 128), row stride of S / A / Dm, row stride of M / Xd (>= L*L)

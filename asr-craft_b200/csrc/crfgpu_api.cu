@@ -109,6 +109,7 @@ struct crfgpu_ctx {
 	bool fwdbwd_done = false;
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
+	DevBuf d_vg_slots, d_vg_xch, d_vg_final, d_vg_ctr; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	bool viterbi_done = false;
 
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
@@ -914,6 +915,41 @@ void viterbi_staged(crfgpu_ctx* h) {
 		ts.negS = h->d_negMt.as<float>();
 		launch_vit_scores(ts, s); check_kernel(h, 1);
 	}
+	// large phone sets with one state per phone and constant transition tables: the cross-phone table sliced over groups of CTAs,
+	// 16 utterances in lock-step per group (crf_viterbi_group.cu); opt_vit_impl 1 forces one CTA per utterance, 2 forces the groups
+	const bool vg_fit = NS == 1 && !c.use_trans_ftrs && P >= 2 && L == P;
+	const bool vg_auto = vg_fit && (size_t)P * P * sizeof(float) > 96 * 1024;
+	if (vg_fit && (h->opt_vit_impl == 2 || (h->opt_vit_impl == 0 && vg_auto))) {
+		const int gmax = vitg_max_groups(P);
+		if (gmax >= 1) {
+			phase_begin(h, "viterbi");
+			std::vector<uint32_t> order(h->n_utt);
+			std::iota(order.begin(), order.end(), 0u);
+			const std::vector<uint32_t>& ho = h->h_off;
+			std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ho[a + 1] - ho[a] > ho[b + 1] - ho[b]; });
+			VitGroupParams g{};
+			g.n_utt = h->n_utt; g.P = P; g.D = D; g.npt = (P + 31) / 32;
+			g.n_batches = (h->n_utt + VITG_UT - 1) / VITG_UT;
+			g.n_groups = std::min<uint32_t>((uint32_t)gmax, g.n_batches);
+			std::vector<uint32_t> slots((size_t)g.n_batches * VITG_UT, 0xffffffffu);
+			for (uint32_t i = 0; i < h->n_utt; i++) slots[i] = order[i];
+			upload_async(h, h->d_vg_slots, slots);
+			const uint32_t Pk = (P + 31) / 32 * 32;
+			h->d_vg_xch.ensure(sizeof(float) * (size_t)g.n_groups * 2 * Pk * VITG_UT + 16);
+			h->d_vg_final.ensure(sizeof(float) * (size_t)h->n_utt * P + 16); h->d_vg_ctr.ensure(sizeof(uint32_t) * g.n_groups + 16);
+			g.off = h->d_off.as<uint32_t>(); g.slot_utt = h->d_vg_slots.as<uint32_t>(); g.negS = h->d_negS.as<float>();
+			g.crossT = h->d_crossT.as<float>(); g.negDiag = h->d_negDiag.as<float>();
+			g.candW = h->d_candW.as<float>(); g.candP = h->d_candP.as<int32_t>(); g.bp = h->d_bp.as<uint16_t>(); g.bd = h->d_bd.as<uint8_t>();
+			g.xch = h->d_vg_xch.as<float>(); g.finalW = h->d_vg_final.as<float>(); g.ctr = h->d_vg_ctr.as<uint32_t>();
+			g.out_lab = h->d_olab.as<uint32_t>(); g.out_dur = h->d_odur.as<uint32_t>(); g.out_phn = h->d_ophn.as<uint32_t>();
+			g.n_seg = h->d_nseg.as<uint32_t>(); g.cost = h->d_cost.as<float>();
+			CUDA_OK(launch_viterbi_group(g, s)); check_kernel(h, 2);
+			phase_end(h, "viterbi");
+			h->viterbi_done = true;
+			return;
+		}
+		if (h->opt_vit_impl == 2) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "group-sliced Viterbi: the table slices of this phone count do not fit shared memory");
+	}
 	phase_begin(h, "viterbi");
 	VitParams v{};
 	v.n_utt = h->n_utt; v.L = L; v.P = P; v.NS = NS; v.D = D; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
@@ -1253,6 +1289,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			h->opt_nodur_impl = (int)value;
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
+		else if (n == "vit_impl") h->opt_vit_impl = (int)value;          // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
 		else if (n == "prefetch_smem") h->opt_prefetch_smem = (uint32_t)value;   // shared-memory cap of the read-ahead expansion's CTAs
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }

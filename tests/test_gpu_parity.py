@@ -560,3 +560,59 @@ def test_fwdbwd_nodur_nstate_matches_oracle_fresh(oracle, P, NS, D, F, n_utt):
         got = m.fwdbwd(off, ftrs, labs)
         assert_train_close(got, want, f"P={P} NS={NS} D={D} impl={impl}")
         m.close()
+
+
+def _one_state_viterbi_goldens():
+    return sorted(n for n, c in VIT.items() if c["cfg"].n_states == 1 and c["cfg"].n_labs >= 2 and not c["cfg"].use_trans_ftrs)
+
+
+@pytest.mark.parametrize("name", _one_state_viterbi_goldens())
+def test_viterbi_group_sliced_bit_exact_vs_reference_golden(name):
+    """every one-state golden (ties, quantised weights, D = 1..3) through the group-sliced recursion (crf_viterbi_group.cu),
+    which large phone sets run on by default"""
+    c = VIT[name]
+    m = gpu(c["cfg"])
+    m.set_option("vit_impl", 2)
+    m.set_lambda(c["lam"])
+    segs, cost = m.viterbi(c["off"], c["ftrs"])
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s[0]) for s in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp)), name
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32)), name
+    m.close()
+
+
+@pytest.mark.parametrize("P,D,F,n_utt,t_hi", [(2, 1, 4, 5, 40), (33, 2, 6, 19, 70), (61, 10, 12, 40, 130), (200, 12, 8, 37, 90), (1024, 30, 8, 21, 140)])
+def test_viterbi_group_sliced_matches_single_cta_and_oracle(oracle, P, D, F, n_utt, t_hi):
+    """group-sliced recursion == one CTA per utterance == oracle, bit for bit: several batches of 16 per group, ragged lengths
+    (including single frames), phone counts off the 32-phone tiles, random / all-ties / quantised weights"""
+    rng = np.random.default_rng(P * 7 + D)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=1 if D > 1 else 0)
+    lens = rng.integers(1, t_hi, n_utt)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    for lam_kind in ("random", "ties", "quantised"):
+        n = oracle.lambda_len(cfg)
+        ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+        if lam_kind == "random":
+            lam = rng.uniform(-0.25, 0.25, n)
+        elif lam_kind == "ties":
+            lam = np.zeros(n)
+        else:
+            lam = np.round(rng.uniform(-1, 1, n) * 2) / 2
+            ftrs = (np.round(ftrs * 2) / 2).astype(np.float32)
+        res = {}
+        for impl in (1, 2):
+            m = gpu(cfg)
+            m.set_option("vit_impl", impl)
+            m.set_lambda(lam)
+            res[impl] = m.viterbi(off, ftrs)
+            m.close()
+        for a, b in zip(res[1][0], res[2][0]):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), lam_kind
+        assert np.array_equal(res[1][1].view(np.uint32), res[2][1].view(np.uint32)), lam_kind
+        if P <= 200 or lam_kind == "random":
+            want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs)
+            for got, exp in zip(res[2][0], want):
+                assert all(np.array_equal(x, y) for x, y in zip(got, exp)), lam_kind
+            assert np.array_equal(res[2][1].view(np.uint32), wcost.view(np.uint32)), lam_kind
