@@ -36,7 +36,7 @@ namespace crfgpu {
 namespace {
 
 constexpr int UT = NODUR_UT, PT = 32, NTHR = 256, NW = NTHR / 32, RING = 32;
-constexpr uint32_t DC = 8;          // durations whose loads are in flight together
+constexpr uint32_t DC = 10;         // durations whose loads are in flight together
 static_assert(UT == 16 && NW * 2 == UT, "thread mapping: warp w owns utterances 2w, 2w+1 of the batch");
 
 struct Shared {
@@ -161,38 +161,42 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 			{
 				const uint32_t u0 = warp * 2;
 				float acc[2] = {0.0f, 0.0f};
-				size_t nf[2]; bool act[2]; uint32_t lim[2];
+				size_t nf[2]; bool act[2]; uint32_t lim[2], limL[2];
+				// base pointers once per frame and 32-bit offsets per duration (64-bit index arithmetic per load made this phase
+				// instruction-bound); entries that do not exist read element 0 of their row and are replaced after the load
+				const float* Sq[2]; const float* Lq[2];
 #pragma unroll
 				for (int i = 0; i < 2; i++) {
 					const uint32_t len = sh.len[u0 + i];
 					nf[i] = (size_t)sh.off[u0 + i] + t;
-					if (!BWD) { act[i] = t < len && y_ok; lim[i] = min(t + 1, D); }
-					else { act[i] = t + 1 < len && y_ok; lim[i] = act[i] ? min(len - 1 - t, D) : 0; }
-					if (!act[i]) lim[i] = 0;
+					if (!BWD) { act[i] = t < len && y_ok; lim[i] = act[i] ? min(t + 1, D) : 0; limL[i] = act[i] ? min(t, D) : 0; }
+					else { act[i] = t + 1 < len && y_ok; lim[i] = act[i] ? min(len - 1 - t, D) : 0; limL[i] = lim[i]; }
+					Sq[i] = p.S + (act[i] ? nf[i] * Lp + y : 0);
+					Lq[i] = (BWD ? p.LB : p.LG) + (act[i] ? nf[i] * Pp + y : 0);
 				}
 				const uint32_t dtop = max(lim[0], lim[1]);
+				const uint32_t s_step = BWD ? Lp + P : P;      // forward: S[n][(d-1)P + y]; backward: S[n+d][(d-1)P + y]
 				for (uint32_t d0 = 1; d0 <= dtop; d0 += DC) {
 					float sv[2][DC], lv[2][DC];
 #pragma unroll
-					for (int i = 0; i < 2; i++)
+					for (uint32_t j = 0; j < DC; j++) {
+						const uint32_t d = d0 + j;
+						const uint32_t o_s = BWD ? d * s_step - P : (d - 1) * s_step, o_l = d * Pp;
 #pragma unroll
-						for (uint32_t j = 0; j < DC; j++) {
-							const uint32_t d = d0 + j;
-							const bool on = d <= lim[i];
-							if (!BWD) {
-								sv[i][j] = on ? __ldg(p.S + nf[i] * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
-								lv[i][j] = (on && d <= t) ? p.LG[(nf[i] - d) * Pp + y] : 0.0f;
-							} else {
-								sv[i][j] = on ? __ldg(p.S + (nf[i] + d) * Lp + (size_t)(d - 1) * P + y) : -INFINITY;
-								lv[i][j] = on ? p.LB[(nf[i] + d) * Pp + y] : 0.0f;
-							}
+						for (int i = 0; i < 2; i++) {
+							const bool on = d <= lim[i], onL = d <= limL[i];
+							const float sx = __ldg(Sq[i] + (on ? o_s : 0u));
+							const float lx = BWD ? Lq[i][onL ? o_l : 0u] : *(Lq[i] - (onL ? o_l : 0u));
+							sv[i][j] = on ? sx : -INFINITY;      // a term that does not exist contributes exp(-inf) = 0
+							lv[i][j] = onL ? lx : 0.0f;          // forward, d == t+1: the segment starts the utterance
 						}
+					}
 #pragma unroll
 					for (int i = 0; i < 2; i++)
 #pragma unroll
 						for (uint32_t j = 0; j < DC; j++) {
 							const uint32_t d = d0 + j;
-							acc[i] += __expf(sv[i][j] + lv[i][j] + sh.scf[u0 + i][d & (RING - 1)]);     // a term that does not exist has sv = -inf
+							acc[i] += __expf(sv[i][j] + lv[i][j] + sh.scf[u0 + i][d & (RING - 1)]);
 						}
 				}
 #pragma unroll
@@ -311,26 +315,36 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					kz[i] = 0.0;
 				}
 				if (act[0] || act[1]) {
+					const float* Sq[2]; const float* Lq[2]; float* Dq[2];
+#pragma unroll
+					for (int i = 0; i < 2; i++) {
+						Sq[i] = p.S + (act[i] ? nf[i] * Lp + y : 0);
+						Lq[i] = p.LG + (act[i] ? nf[i] * Pp + y : 0);
+						Dq[i] = p.Dm + (act[i] ? nf[i] * Lp + y : 0);
+					}
+					const uint32_t dL = min(t, D);
 					for (uint32_t d0 = 1; d0 <= D; d0 += DC) {
 						float sv[2][DC], lv[2][DC];
 #pragma unroll
-						for (int i = 0; i < 2; i++)
+						for (uint32_t j = 0; j < DC; j++) {
+							const uint32_t d = d0 + j, o_s = (d - 1) * P, o_l = d * Pp;
 #pragma unroll
-							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j;
-								const bool on = act[i] && d <= dmax;
-								sv[i][j] = on ? __ldg(p.S + nf[i] * Lp + (size_t)(d - 1) * P + y) : 0.0f;
-								lv[i][j] = (on && d <= t) ? p.LG[(nf[i] - d) * Pp + y] : 0.0f;
+							for (int i = 0; i < 2; i++) {
+								const bool on = act[i] && d <= dmax, onL = act[i] && d <= dL;
+								sv[i][j] = __ldg(Sq[i] + (on ? o_s : 0u));
+								const float lx = *(Lq[i] - (onL ? o_l : 0u));
+								lv[i][j] = onL ? lx : 0.0f;
 							}
+						}
 #pragma unroll
 						for (int i = 0; i < 2; i++)
 #pragma unroll
 							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j, col = (d - 1) * P + y;
+								const uint32_t d = d0 + j, o_s = (d - 1) * P;
 								if (d > D || !act[i]) continue;
 								float dm = 0.0f;
-								if (d <= dmax) dm = ((lab[i] == col) ? 1.0f : 0.0f) - __expf(sv[i][j] + lcur[i] + lv[i][j] + sh.rcf[u0 + i][d & (RING - 1)]);
-								p.Dm[nf[i] * Lp + col] = dm;
+								if (d <= dmax) dm = ((lab[i] == o_s + y) ? 1.0f : 0.0f) - __expf(sv[i][j] + lcur[i] + lv[i][j] + sh.rcf[u0 + i][d & (RING - 1)]);
+								Dq[i][o_s] = dm;
 							}
 					}
 				}

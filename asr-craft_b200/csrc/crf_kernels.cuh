@@ -249,11 +249,12 @@ struct VitGroupParams {
 	const float* negS;                // [N][D][P]
 	const float* crossT;              // [P][P]
 	const float* negDiag;             // [P]
-	float* candW; int32_t* candP;     // [n_utt][D][P] rings of candidates per start frame
+	float2* cand;                     // [n_utt][D][P] ring of candidates per start frame: (cost, back pointer as int bits)
 	uint16_t* bp; uint8_t* bd;        // [N][P]
 	float* xch;                       // [n_groups][2][Pk][VITG_UT] kept costs of the frame, Pk = P rounded up to 32
 	float* finalW;                    // [n_utt][P] kept costs of every utterance's last frame
 	uint32_t* ctr;                    // [n_groups] arrival counters
+	unsigned long long* dbg;          // CRFGPU_DP_TIMING: cycle counters of CTA 0 (else nullptr)
 	uint32_t* out_lab; uint32_t* out_dur; uint32_t* out_phn; uint32_t* n_seg; float* cost;
 };
 size_t vitg_smem_bytes(uint32_t P);

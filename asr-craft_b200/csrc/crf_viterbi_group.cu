@@ -41,6 +41,8 @@ __device__ __forceinline__ uint32_t kept_desc(uint32_t s, uint32_t D) { const ui
 
 }  // namespace
 
+#define VTICK(i) do { if (timing) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+
 size_t vitg_smem_bytes(uint32_t P) { return (size_t)((P + 31) / 32 * 32) * (PT + UT) * sizeof(float) + 16; }
 
 __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p) {
@@ -62,6 +64,9 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 	float* xch0 = p.xch + (size_t)grp * 2 * Pk * UT;
 	uint32_t gstep = 0;      // arrivals of this CTA so far
 	__syncthreads();
+	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+	unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	long long tlast = timing ? clock64() : 0;
 
 	for (uint32_t batch = grp; batch < p.n_batches; batch += p.n_groups) {
 		if (gstep) {    // every CTA of the group has left the previous batch (its exchange buffers are free again)
@@ -84,46 +89,71 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 			// ---- durations >= 2 of node s (candidates of earlier start frames), longest first; and the duration-1 score ----
 			float best[2], ns1[2]; int32_t bptr[2]; uint32_t bdur[2]; bool act[2];
 			const uint32_t dmax = min(s + 1, D);
+			// base pointers once per frame, 32-bit offsets inside the frame's block of scores / the utterance's ring; entries that are
+			// not active read entry 0 of the arrays (harmless) and write nothing
+			const float* sp[2]; const float2* ring[2];
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
 				const uint32_t u = u0 + i;
 				act[i] = s < s_len[u] && y_ok;
-				best[i] = 0.0f; bptr[i] = -1; bdur[i] = 0; ns1[i] = 0.0f;
-				if (act[i]) {
-					const size_t row = (size_t)(s_off[u] + s) * D;
-					ns1[i] = __ldg(p.negS + row * P + y);
-					const float* cwp = p.candW + (size_t)s_utt[u] * D * P + y;
-					const int32_t* cpp = p.candP + (size_t)s_utt[u] * D * P + y;
-					for (uint32_t dh = dmax; dh >= 2;) {
-						float w[DC], sv[DC]; int32_t pr[DC];
+				best[i] = CUDART_INF_F; bptr[i] = -1; bdur[i] = 0;      // the first (longest) duration always wins against +inf: "d == dmax ||"
+				sp[i] = p.negS + (act[i] ? (size_t)(s_off[u] + s) * D * P + y : 0);
+				ring[i] = p.cand + (act[i] ? (size_t)s_utt[u] * D * P + y : 0);
+				ns1[i] = __ldg(sp[i]);
+			}
+			if (dmax >= 2 && (act[0] || act[1])) {
+				// k = d - 1 runs from dmax - 1 down to 1; the candidates of start frame s - k sit in ring slot (slot - k) mod D.
+				// The loads of DC durations of BOTH entries are issued before any is used.
+				uint32_t k = dmax - 1;
+				int32_t sl = (int32_t)slot - (int32_t)k; if (sl < 0) sl += (int32_t)D;
+				for (; k >= DC; k -= DC) {
+					float2 cv[2][DC]; float sv[2][DC];
+#pragma unroll
+					for (uint32_t j = 0; j < DC; j++) {
+						int32_t slj = sl + (int32_t)j; if (slj >= (int32_t)D) slj -= (int32_t)D;
+						const uint32_t o_r = (uint32_t)slj * P, o_s = (k - j) * P;
+#pragma unroll
+						for (int i = 0; i < 2; i++) { cv[i][j] = ring[i][o_r]; sv[i][j] = __ldg(sp[i] + o_s); }
+					}
+#pragma unroll
+					for (int i = 0; i < 2; i++)
 #pragma unroll
 						for (uint32_t j = 0; j < DC; j++) {
-							const bool on = dh >= 2 + j;
-							const uint32_t d = dh - j;                                           // meaningful when on
-							const uint32_t sl = slot >= d - 1 ? slot - (d - 1) : slot + D - (d - 1);   // (s - d + 1) % D
-							w[j] = on ? cwp[(size_t)sl * P] : VINF;
-							pr[j] = on ? cpp[(size_t)sl * P] : -1;
-							sv[j] = on ? __ldg(p.negS + (row + d - 1) * P + y) : 0.0f;
+							float ww = cv[i][j].x;
+							if (ww < VINF) ww = ww + sv[i][j];
+							if (ww < best[i]) { best[i] = ww; bptr[i] = __float_as_int(cv[i][j].y); bdur[i] = k - j + 1; }
 						}
+					sl += (int32_t)DC; if (sl >= (int32_t)D) sl -= (int32_t)D;
+				}
+				if (k >= 1) {      // k, ..., 1
+					float2 cv[2][DC]; float sv[2][DC];
+#pragma unroll
+					for (uint32_t j = 0; j < DC; j++) {
+						const bool on = j < k;
+						int32_t slj = sl + (int32_t)j; if (slj >= (int32_t)D) slj -= (int32_t)D;
+						const uint32_t o_r = on ? (uint32_t)slj * P : 0, o_s = on ? (k - j) * P : 0;
+#pragma unroll
+						for (int i = 0; i < 2; i++) { cv[i][j] = ring[i][o_r]; sv[i][j] = __ldg(sp[i] + o_s); }
+					}
+#pragma unroll
+					for (int i = 0; i < 2; i++)
 #pragma unroll
 						for (uint32_t j = 0; j < DC; j++) {
-							if (dh >= 2 + j) {
-								const uint32_t d = dh - j;
-								float ww = w[j];
-								if (ww < VINF) ww = ww + sv[j];
-								if (d == dmax || ww < best[i]) { best[i] = ww; bptr[i] = pr[j]; bdur[i] = d; }
+							if (j < k) {
+								float ww = cv[i][j].x;
+								if (ww < VINF) ww = ww + sv[i][j];
+								if (ww < best[i]) { best[i] = ww; bptr[i] = __float_as_int(cv[i][j].y); bdur[i] = k - j + 1; }
 							}
 						}
-						if (dh < 2 + DC) break;
-						dh -= DC;
-					}
 				}
 			}
+			VTICK(0);   // durations >= 2
 			// ---- cross-phone candidates for segments starting at frame s ----
 			float cw[2] = {0.0f, 0.0f}; int32_t cp[2] = {-1, -1};     // s == 0: lm_start weight 0 + arc weight 0 (:444-447)
 			if (s > 0) {
 				if (tid == 0) while (ld_acquire_u32(ctr) < gstep * p.npt) {}
 				__syncthreads();
+				VTICK(1);   // barrier wait
 				{
 					const float4* xv = reinterpret_cast<const float4*>(xch0 + (size_t)((s - 1) & 1) * Pk * UT);
 					float4* xd = reinterpret_cast<float4*>(xs);
@@ -131,28 +161,59 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 					for (uint32_t i = tid; i < Pk * (UT / 4); i += NTHR) xd[i] = __ldcg(xv + i);
 				}
 				__syncthreads();
+				VTICK(2);   // staging
 				const uint32_t g = kept_desc(s - 1, D);
 				float pw0 = CUDART_INF_F, pw1 = CUDART_INF_F; int32_t q0 = -1, q1 = -1;
-				const float* xw = xs + u0;
+				const float* xw = xs + u0;          // the published costs already carry the reference's "+ 0.0f" (see the publish step)
 				const float* cs = crossS + lane;
+				constexpr int32_t TAG = 0x40000000;   // q = TAG | first phone of an 8-phone block: the index inside the block is resolved after the scan
 				auto checked = [&](uint32_t pp) {
 					if (pp != y) {     // free-phone LM, one state per phone: no arc to the same phone (:1332-1346)
 						const float c = cs[(size_t)pp * PT];
 						const float2 w = *reinterpret_cast<const float2*>(xw + (size_t)pp * UT);
-						const float c0 = (w.x + 0.0f) + c, c1 = (w.y + 0.0f) + c;
+						const float c0 = w.x + c, c1 = w.y + c;
 						if (c0 < pw0) { pw0 = c0; q0 = (int32_t)pp; }
 						if (c1 < pw1) { pw1 = c1; q1 = (int32_t)pp; }
 					}
 				};
+				// blocks of 8 phones: the block minimum (a tree of FMNMX, no index bookkeeping) replaces the running minimum only if
+				// strictly smaller, so the FIRST block that attains the final minimum is remembered and the first phone inside it that
+				// attains it is found afterwards -- the same winner as the element-by-element scan with strict '<'
 				auto range = [&](uint32_t a, uint32_t b) {
-#pragma unroll 8
-					for (uint32_t pp = a; pp < b; pp++) {
+					uint32_t pp = a;
+					for (; pp + 8 <= b; pp += 8) {
+						float c0[8], c1[8];
+#pragma unroll
+						for (int j = 0; j < 8; j++) {
+							const float c = cs[(size_t)(pp + j) * PT];
+							const float2 w = *reinterpret_cast<const float2*>(xw + (size_t)(pp + j) * UT);
+							c0[j] = w.x + c; c1[j] = w.y + c;
+						}
+						const float m0 = fminf(fminf(fminf(c0[0], c0[1]), fminf(c0[2], c0[3])), fminf(fminf(c0[4], c0[5]), fminf(c0[6], c0[7])));
+						const float m1 = fminf(fminf(fminf(c1[0], c1[1]), fminf(c1[2], c1[3])), fminf(fminf(c1[4], c1[5]), fminf(c1[6], c1[7])));
+						if (m0 < pw0) { pw0 = m0; q0 = TAG | (int32_t)pp; }
+						if (m1 < pw1) { pw1 = m1; q1 = TAG | (int32_t)pp; }
+					}
+					for (; pp < b; pp++) {
 						const float c = cs[(size_t)pp * PT];
 						const float2 w = *reinterpret_cast<const float2*>(xw + (size_t)pp * UT);
-						const float c0 = (w.x + 0.0f) + c, c1 = (w.y + 0.0f) + c;
+						const float c0 = w.x + c, c1 = w.y + c;
 						if (c0 < pw0) { pw0 = c0; q0 = (int32_t)pp; }
 						if (c1 < pw1) { pw1 = c1; q1 = (int32_t)pp; }
 					}
+				};
+				auto resolve = [&](float& pw, int32_t q, int which) -> int32_t {
+					if (q < TAG) return q;
+					const uint32_t b0 = (uint32_t)(q & ~TAG);
+					int32_t r = -1; float v = pw;
+#pragma unroll
+					for (int j = 7; j >= 0; j--) {
+						const float c = cs[(size_t)(b0 + j) * PT];
+						const float w = xw[(size_t)(b0 + j) * UT + which];
+						if (w + c == pw) { r = (int32_t)(b0 + j); v = w + c; }
+					}
+					pw = v;      // the winner's own value (fminf may have picked the other sign of a zero)
+					return r;
 				};
 				// increasing phone order with g moved to the back; phones 0, 1 (possible g) and the CTA's own tile (possible target) checked
 				if (g != 0u) checked(0);
@@ -162,6 +223,7 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 				for (uint32_t pp = t_lo; pp < t_hi; pp++) checked(pp);
 				if (t_hi < P) range(max(t_hi, 2u), P);
 				if (g != 0xffu) checked(g);
+				q0 = resolve(pw0, q0, 0); q1 = resolve(pw1, q1, 1);
 				// within-phone: the self transition, taken only if strictly smaller than the cross candidate (first arrival wins)
 				cw[0] = pw0; cp[0] = q0; cw[1] = pw1; cp[1] = q1;
 #pragma unroll
@@ -170,12 +232,13 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 					if (cp[i] < 0 || n1 < cw[i]) { cw[i] = n1; cp[i] = (int32_t)y; }
 				}
 			}
+			VTICK(3);   // scan
 			// ---- node s: duration 1 joins the durations formed above; back pointers; the kept cost of the frame ----
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
 				const uint32_t u = u0 + i;
 				if (act[i]) {
-					if (D > 1) { p.candW[((size_t)s_utt[u] * D + slot) * P + y] = cw[i]; p.candP[((size_t)s_utt[u] * D + slot) * P + y] = cp[i]; }
+					if (D > 1) p.cand[((size_t)s_utt[u] * D + slot) * P + y] = make_float2(cw[i], __int_as_float(cp[i]));
 					float w1 = cw[i];
 					if (w1 < VINF) w1 = w1 + ns1[i];
 					if (dmax == 1 || w1 < best[i]) { best[i] = w1; bptr[i] = cp[i]; bdur[i] = 1; }
@@ -185,7 +248,7 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 					p.bd[n] = (uint8_t)bdur[i];
 					if (s + 1 == s_len[u]) p.finalW[(size_t)s_utt[u] * P + y] = best[i];
 				}
-				tileT[lane][u] = wprev[i];
+				tileT[lane][u] = wprev[i] + 0.0f;     // the cross-phone scan reads (kept cost + 0.0f) (the LM arc weight of the free-phone loop)
 			}
 			__syncthreads();
 			// ---- publish the CTA's slice of the kept costs and arrive ----
@@ -193,10 +256,12 @@ __global__ void __launch_bounds__(NTHR, 1) viterbi_group_kernel(VitGroupParams p
 				__stcg(reinterpret_cast<float4*>(xch0 + (size_t)(s & 1) * Pk * UT + (size_t)y0 * UT) + tid, reinterpret_cast<const float4*>(&tileT[0][0])[tid]);
 			__syncthreads();
 			if (tid == 0) { __threadfence(); atomicAdd(ctr, 1u); }
+			VTICK(4);   // node update + publish
 			gstep++;
 			slot = slot + 1 == D ? 0 : slot + 1;
 		}
 	}
+	if (timing) { for (int i = 0; i < 8; i++) p.dbg[i] = tacc[i]; p.dbg[8] = gstep; }
 }
 
 // final argmin over the kept list of the last frame (first in list order wins) and traceback, one warp per utterance

@@ -109,7 +109,7 @@ struct crfgpu_ctx {
 	bool fwdbwd_done = false;
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
-	DevBuf d_vg_slots, d_vg_xch, d_vg_final, d_vg_ctr; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
+	DevBuf d_vg_slots, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	bool viterbi_done = false;
 
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
@@ -939,11 +939,19 @@ void viterbi_staged(crfgpu_ctx* h) {
 			h->d_vg_final.ensure(sizeof(float) * (size_t)h->n_utt * P + 16); h->d_vg_ctr.ensure(sizeof(uint32_t) * g.n_groups + 16);
 			g.off = h->d_off.as<uint32_t>(); g.slot_utt = h->d_vg_slots.as<uint32_t>(); g.negS = h->d_negS.as<float>();
 			g.crossT = h->d_crossT.as<float>(); g.negDiag = h->d_negDiag.as<float>();
-			g.candW = h->d_candW.as<float>(); g.candP = h->d_candP.as<int32_t>(); g.bp = h->d_bp.as<uint16_t>(); g.bd = h->d_bd.as<uint8_t>();
+			h->d_vg_cand.ensure(sizeof(float2) * (size_t)h->n_utt * D * P + 16); g.cand = h->d_vg_cand.as<float2>(); g.bp = h->d_bp.as<uint16_t>(); g.bd = h->d_bd.as<uint8_t>();
 			g.xch = h->d_vg_xch.as<float>(); g.finalW = h->d_vg_final.as<float>(); g.ctr = h->d_vg_ctr.as<uint32_t>();
 			g.out_lab = h->d_olab.as<uint32_t>(); g.out_dur = h->d_odur.as<uint32_t>(); g.out_phn = h->d_ophn.as<uint32_t>();
 			g.n_seg = h->d_nseg.as<uint32_t>(); g.cost = h->d_cost.as<float>();
+			static DevBuf vdbg; const bool vtiming = getenv("CRFGPU_DP_TIMING") != nullptr;
+			if (vtiming) { vdbg.ensure(16 * 8); g.dbg = vdbg.as<unsigned long long>(); }
 			CUDA_OK(launch_viterbi_group(g, s)); check_kernel(h, 2);
+			if (vtiming) {
+				unsigned long long v[16]; CUDA_OK(cudaMemcpyAsync(v, vdbg.p, sizeof(v), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+				const double n = v[8] ? (double)v[8] : 1.0;
+				fprintf(stderr, "[crfgpu] group viterbi: %llu steps; cycles/step: dur>=2 %.0f wait %.0f staging %.0f scan %.0f update+publish %.0f\n",
+				        v[8], v[0] / n, v[1] / n, v[2] / n, v[3] / n, v[4] / n);
+			}
 			phase_end(h, "viterbi");
 			h->viterbi_done = true;
 			return;
