@@ -3,6 +3,7 @@
 #include "crf_kernels.cuh"
 
 #include <cfloat>
+#include <math_constants.h>
 
 namespace crfgpu {
 
@@ -805,7 +806,8 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	float* Wprev = reinterpret_cast<float*>(smem_raw);   // [L] kept weights of the previous frame
 	float* partW = Wprev + p.L;                           // [NS][P] partial cross-phone minima of the frame (all threads share the scan)
 	int32_t* partP = reinterpret_cast<int32_t*>(partW + p.L);   // their back pointers, -1: no candidate in that part of the list
-	float* crossS = partW + 2 * p.L;                      // [P*P] when it fits, else unused
+	float* We = partW + 2 * p.L;                          // [P] kept weight of every phone's END state + 0.0f (the LM arc weight of the free-phone loop)
+	float* crossS = We + p.P;                             // [P][Pt] when it fits, TRANSPOSED: crossS[tq*Pt + pp] = crossT[pp][tq], Pt = P | 1
 	__shared__ uint32_t s_g;        // descriptor of the kept-list order of the previous frame
 	__shared__ uint8_t s_move[256]; // arrival-order descriptors a[s] of the last D start frames (ring; D <= 255)
 	__shared__ int s_best;
@@ -813,17 +815,28 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	const uint32_t L = p.L, P = p.P, NS = p.NS, D = p.D;
 	const uint32_t off = p.off[u], T = p.off[u + 1] - p.off[u];
 	const uint32_t lab = threadIdx.x;
-	const bool cross_in_smem = p.negMt == nullptr && ((size_t)P * P * sizeof(float) <= 96 * 1024);
-	if (cross_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) crossS[i] = p.crossT[i];
-	const float* crossT = cross_in_smem ? crossS : p.crossT;
+	const uint32_t Pt = P | 1u;      // odd row stride: the rows of 32 consecutive target phones start in 32 different banks
+	const bool cross_in_smem = p.negMt == nullptr && ((size_t)P * Pt * sizeof(float) <= 96 * 1024);
+	if (cross_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) crossS[(i % P) * Pt + i / P] = p.crossT[i];
+	const float* crossT = p.crossT;      // global table (per-frame tables replace it below); the shared-memory copy is crossS
 	const bool per_frame = p.negMt != nullptr;      // transition FEATURES: the tables of the frame a segment starts in (global memory)
 	float* candW = p.candW + (uint64_t)u * D * L;
 	int32_t* candP = p.candP + (uint64_t)u * D * L;
 	const uint32_t q = lab / NS, k = lab % NS;
+	// cross-phone scan: thread = (part of the kept list, target phone); constant over the frames
+	// (p.Ppad = P rounded up to the warp size when NS * Ppad threads fit the CTA, so that no warp straddles two parts of the list and
+	// runs both loops; else P)
+	const uint32_t part = threadIdx.x / p.Ppad, tq = threadIdx.x - part * p.Ppad;
+	const bool scan_ok = part < NS && tq < P;
+	const uint32_t chunk = (P + NS - 1) / NS, i_lo = min(P, part * chunk), i_hi = min(P, i_lo + chunk);
 	float my_diag = (lab < L && p.negMt == nullptr) ? p.negDiag[lab] : 0.0f;
 	float my_off = (lab < L && k > 0 && p.negMt == nullptr) ? p.negOff[lab] : 0.0f;
 	if (threadIdx.x == 0) s_g = 0xffu;
 	__syncthreads();
+	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+	unsigned long long tacc[4] = {0, 0, 0, 0};
+	long long tlast = timing ? clock64() : 0;
+#define VKTICK(i) do { if (timing) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
 
 	// the state scores of a node do not depend on the recursion: those of node s+1 are fetched while node s is processed, so the
 	// per-frame chain holds no global-memory round trip (VPF durations in registers, the rest read in place)
@@ -844,27 +857,46 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 			crossT = tb;
 			if (lab < L) { my_diag = tb[P * P + lab]; my_off = k > 0 ? tb[P * P + L + lab] : 0.0f; }
 		}
+		VKTICK(3);   // loop top: prefetch issue (+ list bookkeeping of the previous frame)
 		float pw = VIT_INF; int32_t pptr = -1;
-		if (s > 0 && lab < L) {
-			const uint32_t g = s_g, part = lab / P, tq = lab - part * P;
-			const uint32_t chunk = (P + NS - 1) / NS, i_lo = part * chunk, i_hi = min(P, i_lo + chunk);
-			for (uint32_t i0 = i_lo; i0 < i_hi; i0 += 8) {
-				float cc[8]; int32_t ci[8]; bool ok[8];
-#pragma unroll
-				for (uint32_t j = 0; j < 8; j++) {
-					const uint32_t i = i0 + j;
-					const uint32_t pp = kept_phone(i < i_hi ? i : i_hi - 1, P, g);
-					ok[j] = i < i_hi && !(NS == 1 && pp == tq);   // free-phone LM, 1 state: no arc to the same phone (:1332-1346)
-					const float base = Wprev[pp * NS + NS - 1] + 0.0f;
-					cc[j] = base + crossT[pp * P + tq];
-					ci[j] = (int32_t)(pp * NS + NS - 1);
+		if (s > 0 && scan_ok) {
+			const uint32_t g = s_g;
+			// the table pointer keeps its address space (shared or global) in each instantiation, the per-thread part of the index is
+			// hoisted out of the frame loop, and the two list orders have their own loops: per element this is two loads, two adds and
+			// one compare-select (generic loads and per-element list arithmetic made the scan 70 % of the frame)
+			// The scan is bound by instruction issue (a few warps per scheduler), so it is written for the fewest instructions per list
+			// entry: We[] already carries "+ 0.0f", the shared-memory table is transposed (one row per target phone: consecutive entries at
+			// consecutive addresses, immediate offsets after unrolling), and the running minimum starts at +inf -- every real candidate is
+			// finite, so that equals the reference's "the first candidate is always taken".
+			auto scan = [&](const float* ct, const uint32_t stride) {     // entry pp of the target phone's column at ct[pp * stride]
+				pw = CUDART_INF_F;
+				if (NS > 1) {
+					// N states per phone: the kept list is always in phone order (s_g stays 0xff) and every phone may follow every phone
+#pragma unroll 4
+					for (uint32_t pp = i_lo; pp < i_hi; pp++) {
+						const float cc = We[pp] + ct[(size_t)pp * stride];
+						if (cc < pw) { pw = cc; pptr = (int32_t)pp; }
+					}
+				} else {
+					// one state per phone: increasing phone order with phone g (if any) moved to the back; no arc to the same phone (:1332-1346)
+#pragma unroll 4
+					for (uint32_t pp = 0; pp < P; pp++) {
+						const float cc = We[pp] + ct[(size_t)pp * stride];
+						if (pp != tq && pp != g && cc < pw) { pw = cc; pptr = (int32_t)pp; }
+					}
+					if (g != 0xffu && g != tq) {
+						const float cc = We[g] + ct[(size_t)g * stride];
+						if (cc < pw) { pw = cc; pptr = (int32_t)g; }
+					}
 				}
-#pragma unroll
-				for (uint32_t j = 0; j < 8; j++)
-					if (ok[j] && (pptr < 0 || cc[j] < pw)) { pw = cc[j]; pptr = ci[j]; }
-			}
-			if (NS > 1) { partW[lab] = pw; partP[lab] = pptr; }
+				if (pptr < 0) pw = VIT_INF;                       // no candidate (P == 1)
+				else pptr = pptr * (int32_t)NS + (int32_t)NS - 1;   // the phone's end state
+			};
+			if (cross_in_smem) scan(crossS + (size_t)tq * Pt, 1u);
+			else scan(crossT + tq, P);
+			if (NS > 1) { partW[part * P + tq] = pw; partP[part * P + tq] = pptr; }
 		}
+		VKTICK(0);   // cross-phone scan
 		if (NS > 1) __syncthreads();        // one state per phone: every thread scanned the whole list for its own phone
 		// ---- candidates for segments starting at frame s ----
 		float cw = VIT_INF; int32_t cp = -1;
@@ -894,6 +926,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 			}
 			if (D > 1) { candW[(uint64_t)(s % D) * L + lab] = cw; candP[(uint64_t)(s % D) * L + lab] = cp; }   // read back d-1 frames later
 		}
+		VKTICK(1);   // merge + within-phone candidates
 		__syncthreads();   // Wprev fully consumed
 		// ---- node s: add state values, best duration per (phone, sub-state); longest duration first ----
 		if (lab < L) {
@@ -915,10 +948,12 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				if (d == dmax || w < best) { best = w; bptr = ptr; bdur = d; }
 			}
 			Wprev[lab] = best;
+			if (k == NS - 1) We[q] = best + 0.0f;
 			p.bp[(uint64_t)(off + s) * L + lab] = bptr < 0 ? (uint16_t)0xffff : (uint16_t)bptr;
 			p.bd[(uint64_t)(off + s) * L + lab] = (uint8_t)bdur;
 		}
 		__syncthreads();
+		VKTICK(2);   // node update + barrier
 		// the kept-list order only moves for one state per phone (N > 1: always the identity, s_g stays 0xff): no bookkeeping, no barrier
 		if (NS == 1) {
 			if (threadIdx.x == 0) {
@@ -940,6 +975,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 #pragma unroll
 		for (uint32_t j = 0; j < VPF; j++) nsv[j] = nsn[j];
 	}
+	if (timing) { for (int i = 0; i < 4; i++) p.dbg[i] = tacc[i]; p.dbg[4] = T; }
 	// ---- final argmin over the kept list (first wins) and traceback ----
 	if (threadIdx.x == 0) {
 		uint32_t nseg = 0; float minw = VIT_INF; int best = -1;
@@ -977,11 +1013,14 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 }
 void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	if (!p.n_utt) return;
-	const unsigned threads = (p.L + 31) / 32 * 32;
-	size_t smem = sizeof(float) * 3 * p.L;
-	if (p.negMt == nullptr && (size_t)p.P * p.P * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * p.P;
+	VitParams q = p;
+	const uint32_t Pw = (p.P + 31) / 32 * 32;
+	q.Ppad = (p.NS > 1 && p.NS * Pw <= 1024) ? Pw : p.P;
+	const unsigned threads = (std::max(p.L, p.NS * q.Ppad) + 31) / 32 * 32;
+	size_t smem = sizeof(float) * (3 * (size_t)p.L + p.P);
+	if (p.negMt == nullptr && (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
 	cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(p);
+	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(q);
 }
 
 }  // namespace crfgpu

@@ -225,6 +225,7 @@ void launch_vit_scores(const VitScoreParams& p, cudaStream_t s);
 
 struct VitParams {
 	uint32_t n_utt, L, P, NS, D;
+	uint32_t Ppad;                    // set by launch_viterbi: thread = (part of the kept list) * Ppad + target phone in the cross-phone scan
 	const uint32_t* off;
 	const float* negS;                // [N][D][L]
 	const float* crossT;              // [P][P]  crossT[pp*P+q] = (float)(-M[end(pp)][start(q)])
@@ -235,6 +236,7 @@ struct VitParams {
 	float* keptW;                     // [n_utt][2][L]
 	uint16_t* bp; uint8_t* bd;        // [N][L] back pointer (label or 0xffff) and duration
 	uint8_t* gmove;                   // [N] which phone was moved to the back of the kept list (0xff none)
+	unsigned long long* dbg;          // CRFGPU_DP_TIMING: cycle counters of CTA 0 (else nullptr)
 	uint32_t* out_lab; uint32_t* out_dur; uint32_t* out_phn; uint32_t* n_seg; float* cost;
 };
 void launch_viterbi(const VitParams& p, cudaStream_t s);

@@ -967,7 +967,14 @@ void viterbi_staged(crfgpu_ctx* h) {
 	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
 	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
 	v.n_seg = h->d_nseg.as<uint32_t>(); v.cost = h->d_cost.as<float>();
+	static DevBuf kdbg; const bool ktiming = getenv("CRFGPU_DP_TIMING") != nullptr;
+	if (ktiming) { kdbg.ensure(8 * 8); v.dbg = kdbg.as<unsigned long long>(); }
 	launch_viterbi(v, s); check_kernel(h, 1);
+	if (ktiming) {
+		unsigned long long t[8]; CUDA_OK(cudaMemcpyAsync(t, kdbg.p, sizeof(t), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+		const double n = t[4] ? (double)t[4] : 1.0;
+		fprintf(stderr, "[crfgpu] viterbi (utterance 0, %llu frames); cycles/frame: top %.0f scan %.0f candidates %.0f node %.0f\n", t[4], t[3] / n, t[0] / n, t[1] / n, t[2] / n);
+	}
 	phase_end(h, "viterbi");
 	h->viterbi_done = true;
 }
