@@ -110,6 +110,7 @@ struct crfgpu_ctx {
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
 	DevBuf d_vg_slots, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
+	int opt_frame_impl = 0;
 	bool viterbi_done = false;
 
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
@@ -750,6 +751,15 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		CUDA_OK(launch_nodur_dp(true, q, s)); check_kernel(h, 1);
 		if (ntiming) nreport("backward");
 		phase_end(h, "backward");
+	} else if (D == 1 && L <= 64 && !h->tied && h->opt_dp_impl == 2 && h->opt_frame_impl != 1) {
+		// frame-level models with at most 64 labels: one warp per utterance, the transition matrix in registers (crf_dp_frame.cu);
+		// d_grp holds the utterances longest first, so the four warps of a CTA carry similar lengths
+		phase_begin(h, "forward");
+		CUDA_OK(launch_frame_dp(false, p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		CUDA_OK(launch_frame_dp(true, p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
+		phase_end(h, "backward");
 	} else if (h->tc_ok) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
 		TcDpParams tp{};
@@ -1304,6 +1314,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			h->opt_nodur_impl = (int)value;
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
+		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per utterance (crf_dp_frame.cu), 1 the cluster lattice kernels
 		else if (n == "vit_impl") h->opt_vit_impl = (int)value;          // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
 		else if (n == "prefetch_smem") h->opt_prefetch_smem = (uint32_t)value;   // shared-memory cap of the read-ahead expansion's CTAs
