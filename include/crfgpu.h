@@ -161,8 +161,16 @@ double crfgpu_phase_ms(crfgpu_handle h, const char* phase);
  * alpha/beta [sum T][n_labs] as doubles (entries the reference never computes are -DBL_MAX). */
 int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta);
 
-/* Tuning / debug switches: "slots" (utterances per CTA in the lattice kernels: 0 auto,1,2,4,8),
- * "k_slab" (frames per CTA in the reduce-GEMMs), "keep_lattice" (1: keep what crfgpu_fetch_alpha_beta needs). */
+/* Tuning / debug switches (results do not depend on them beyond the stated tolerance; decoding stays bit-exact):
+ *  "slots" (utterances per CTA in the one-CTA lattice kernels: 0 auto,1,2,4,8), "k_slab" / "k_slab_tc" / "k_slab_tma" / "k_slab_xi"
+ *  (frames per CTA in the reduce-GEMMs), "keep_lattice" (1: keep what crfgpu_fetch_alpha_beta needs),
+ *  "dp_impl" (dense lattice: 0 one CTA per utterance group, 1 cluster-resident FFMA, 2 cluster-resident tcgen05 = default),
+ *  "frame_impl" (frame-level models with <= 64 labels: 0 one warp per utterance = default, 1 the cluster lattice kernels),
+ *  "nodur_impl" (stdseg_no_dur*: 0 auto, 1 native O(P^2 + D*P) recursion, 2 tied (duration, label) expansion; set_lambda again after it),
+ *  "vit_impl" (Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 transition table sliced over groups of CTAs -- one state per phone),
+ *  "gemm_impl" / "tma_mask" (which GEMM kernels run: FFMA, register-staged tcgen05, TMA-fed tcgen05 with the 128-row operand in TMEM),
+ *  "cluster_slots", "prefetch_smem".  Environment: CRFGPU_VERBOSE (plans, device timeline), CRFGPU_DP_TIMING (cycle counters of the
+ *  recursion kernels on stderr). */
 int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value);
 
 /* Pinned host memory helpers for callers that want asynchronous copies. */
