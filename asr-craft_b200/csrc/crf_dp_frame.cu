@@ -66,11 +66,13 @@ __device__ __forceinline__ void matvec(const float (&Mreg)[2][64], const float* 
 
 }  // namespace
 
-template <bool BWD>
-__global__ void __launch_bounds__(FW * 32) frame_dp_kernel(DpParams p, const uint32_t* __restrict__ utt_list, uint32_t n_utt) {
-	__shared__ __align__(16) float vec_s[FW][64];
+// BWD = false: forward.  BWD = true: backward; FUSED = true also forms the posteriors Dm / R of every frame (needs the forward pass
+// to have finished), FUSED = false only runs the beta chain and stores u_t, bbase_t for frame_post_kernel -- the two chains of an
+// utterance are independent given the scores, so they can then run side by side in one launch.
+template <bool BWD, bool FUSED>
+__device__ __forceinline__ void frame_dp_body(const DpParams& p, const uint32_t* __restrict__ utt_list, uint32_t n_utt, uint32_t cta, float (*vec_s)[64]) {
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t slot = blockIdx.x * FW + warp;
+	const uint32_t slot = cta * FW + warp;
 	if (slot >= n_utt) return;                               // whole warps leave: no CTA-wide barrier below
 	const uint32_t utt = utt_list[slot];
 	const uint32_t L = p.L, Lp = p.Lp;
@@ -130,6 +132,43 @@ __global__ void __launch_bounds__(FW * 32) frame_dp_kernel(DpParams p, const uin
 		}
 		const float zs = wsum(a[0] + a[1]);
 		if (lane == 0) p.logZ[utt] = m + log((double)zs);
+	} else if (!FUSED) {
+		// the beta chain alone: w~_t = exp(S_t - sref) u_t 2^-e;  u_t and bbase_t are what the posteriors need
+		float sv[2], sn[2] = {-INFINITY, -INFINITY};
+		load_s(T - 1, sv);
+		if (T > 1) load_s(T - 2, sn);
+		// last frame: beta = 0 (setTailBeta): u = 1, bbase = 0
+		float sref = wmax(fmaxf(sv[0], sv[1]));
+		float w[2] = {__expf(sv[0] - sref), __expf(sv[1] - sref)};
+		double kap = (double)sref;
+		{
+			const size_t n = (size_t)off + T - 1;
+			float* Ur = p.Uvec + n * Lp;
+			if (pad0) Ur[c0] = ok0 ? 1.0f : 0.0f;
+			if (pad1) Ur[c1] = ok1 ? 1.0f : 0.0f;
+			if (lane == 0) { p.bbase[n] = 0.0; p.kappa[n] = kap; }
+		}
+		for (uint32_t t = T - 1; t-- > 0;) {
+			sv[0] = sn[0]; sv[1] = sn[1];
+			if (t >= 1) load_s(t - 1, sn);
+			vec[c0] = w[0]; vec[c1] = w[1];
+			__syncwarp();
+			const float mxprev = wmax(fmaxf(w[0], w[1]));
+			sref = wmax(fmaxf(sv[0], sv[1]));
+			const float es0 = __expf(sv[0] - sref), es1 = __expf(sv[1] - sref);
+			float u[2];
+			matvec(Mreg, vec, u);
+			__syncwarp();
+			int e; const float sc = pow2_scale(mxprev, &e);
+			w[0] = u[0] * es0 * sc; w[1] = u[1] * es1 * sc;      // es = 0 on the padding labels
+			const double bbase = kap + p.Mmax;
+			kap = bbase + (double)sref + (double)e * LN2;
+			const size_t n = (size_t)off + t;
+			float* Ur = p.Uvec + n * Lp;
+			if (pad0) Ur[c0] = u[0];                               // rows / columns of E beyond L are zero: u = 0 there
+			if (pad1) Ur[c1] = u[1];
+			if (lane == 0) { p.bbase[n] = bbase; p.kappa[n] = kap; }
+		}
 	} else {
 		const double logZ = p.logZ[utt];
 		// frame state prefetched one frame ahead: scores, alpha, its scales, the reference label
@@ -183,11 +222,58 @@ __global__ void __launch_bounds__(FW * 32) frame_dp_kernel(DpParams p, const uin
 	}
 }
 
+template <bool BWD>
+__global__ void __launch_bounds__(FW * 32) frame_dp_kernel(DpParams p, const uint32_t* __restrict__ utt_list, uint32_t n_utt) {
+	__shared__ __align__(16) float vec_s[FW][64];
+	frame_dp_body<BWD, true>(p, utt_list, n_utt, blockIdx.x, vec_s);
+}
+// both chains in one launch: even CTAs run the forward recursion, odd CTAs the beta chain of the same four utterances.  The launch
+// asks for enough dynamic shared memory that ONE CTA is resident per SM: each of its four warps then has a scheduler to itself (a
+// frame is ~350 issue slots of a ~700-cycle chain -- a second warp on the scheduler lengthens the chain), the utterance list is
+// longest first, so the longest chains start first and the short ones fill in behind them.
+__global__ void __launch_bounds__(FW * 32) frame_dp_pair_kernel(DpParams p, const uint32_t* __restrict__ utt_list, uint32_t n_utt) {
+	__shared__ __align__(16) float vec_s[FW][64];
+	if ((blockIdx.x & 1u) == 0) frame_dp_body<false, true>(p, utt_list, n_utt, blockIdx.x >> 1, vec_s);
+	else frame_dp_body<true, false>(p, utt_list, n_utt, blockIdx.x >> 1, vec_s);
+}
+// posteriors of every frame from the two finished chains (no recursion: one thread per frame and label)
+//   gamma_t[c] = A_t[c] u_t[c] exp(m_t + bbase_t - logZ),   R_t[c] = u_t[c] exp(S_t[c] + bbase_t + m_{t-1} + Mmax - logZ), 0 on the first frame
+__global__ void __launch_bounds__(256) frame_post_kernel(DpParams p, const uint32_t* __restrict__ frame_t, const uint32_t* __restrict__ frame_utt, uint32_t N) {
+	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	const uint32_t Lp = p.Lp;
+	if (i >= (uint64_t)N * Lp) return;
+	const uint64_t n = i / Lp; const uint32_t c = (uint32_t)(i - n * Lp);
+	float dm = 0.0f, r = 0.0f;
+	if (c < p.L) {
+		const double lz = p.logZ[frame_utt[n]], bb = p.bbase[n];
+		const float u = p.Uvec[i];
+		const float gamma = p.A[i] * u * expf((float)(p.m[n] + bb - lz));
+		dm = ((p.node_lab[n] == c) ? 1.0f : 0.0f) - gamma;
+		if (frame_t[n] > 0) r = u * expf(__ldg(p.S + i) + (float)(bb + p.m[n - 1] + p.Mmax - lz));
+	}
+	p.Dm[i] = dm; p.R[i] = r;
+}
+
 cudaError_t launch_frame_dp(bool backward, const DpParams& p, const uint32_t* utt_list, uint32_t n_utt, cudaStream_t s) {
 	if (!n_utt) return cudaSuccess;
 	const unsigned grid = (n_utt + FW - 1) / FW;
 	if (backward) frame_dp_kernel<true><<<grid, FW * 32, 0, s>>>(p, utt_list, n_utt);
 	else frame_dp_kernel<false><<<grid, FW * 32, 0, s>>>(p, utt_list, n_utt);
+	return cudaGetLastError();
+}
+cudaError_t launch_frame_dp_pair(const DpParams& p, const uint32_t* utt_list, uint32_t n_utt, cudaStream_t s) {
+	if (!n_utt) return cudaSuccess;
+	const unsigned G = (n_utt + FW - 1) / FW;
+	const int excl = 120 * 1024;      // more than half of an SM's shared memory: one CTA per SM
+	cudaError_t e = cudaFuncSetAttribute(frame_dp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, excl);
+	if (e != cudaSuccess) return e;
+	frame_dp_pair_kernel<<<2 * G, FW * 32, excl, s>>>(p, utt_list, n_utt);
+	return cudaGetLastError();
+}
+cudaError_t launch_frame_post(const DpParams& p, const uint32_t* frame_t, const uint32_t* frame_utt, uint32_t N, cudaStream_t s) {
+	if (!N) return cudaSuccess;
+	const uint64_t total = (uint64_t)N * p.Lp;
+	frame_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p, frame_t, frame_utt, N);
 	return cudaGetLastError();
 }
 

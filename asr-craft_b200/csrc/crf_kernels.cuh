@@ -63,6 +63,9 @@ void launch_backward(const DpParams& p, int U, cudaStream_t s);
 // frame-level models (D == 1) with at most 64 labels: one warp per utterance, E in registers (crf_dp_frame.cu); utt_list = the
 // utterance ids in the order the warps take them
 cudaError_t launch_frame_dp(bool backward, const DpParams& p, const uint32_t* utt_list, uint32_t n_utt, cudaStream_t s);
+// both chains in one launch (the beta chain stores u_t in p.Uvec and bbase_t), then the posteriors Dm / R of all frames
+cudaError_t launch_frame_dp_pair(const DpParams& p, const uint32_t* utt_list, uint32_t n_utt, cudaStream_t s);
+cudaError_t launch_frame_post(const DpParams& p, const uint32_t* frame_t, const uint32_t* frame_utt, uint32_t N, cudaStream_t s);
 
 // ---- cluster-resident variant (crf_dp_cluster.cu): E sliced over the CTAs of a thread-block cluster ----
 struct ClusterDpParams : DpParams {

@@ -754,12 +754,24 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	} else if (D == 1 && L <= 64 && !h->tied && h->opt_dp_impl == 2 && h->opt_frame_impl != 1) {
 		// frame-level models with at most 64 labels: one warp per utterance, the transition matrix in registers (crf_dp_frame.cu);
 		// d_grp holds the utterances longest first, so the four warps of a CTA carry similar lengths
-		phase_begin(h, "forward");
-		CUDA_OK(launch_frame_dp(false, p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
-		phase_end(h, "forward");
-		phase_begin(h, "backward");
-		CUDA_OK(launch_frame_dp(true, p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
-		phase_end(h, "backward");
+		if (h->opt_frame_impl == 2) {     // the two chains one after the other, posteriors fused into the backward pass
+			phase_begin(h, "forward");
+			CUDA_OK(launch_frame_dp(false, p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
+			phase_end(h, "forward");
+			phase_begin(h, "backward");
+			CUDA_OK(launch_frame_dp(true, p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
+			phase_end(h, "backward");
+		} else {
+			// the alpha and beta chains of an utterance are independent given the scores: both run in ONE launch (the step is bound by the
+			// longest utterance's chain, not by throughput), then the posteriors of all frames are formed without any recursion
+			h->d_Uvec.ensure(sizeof(float) * NL + 16); p.Uvec = h->d_Uvec.as<float>();
+			phase_begin(h, "forward");
+			CUDA_OK(launch_frame_dp_pair(p, h->d_grp.as<uint32_t>(), h->n_utt, s)); check_kernel(h, 1);
+			phase_end(h, "forward");
+			phase_begin(h, "backward");
+			CUDA_OK(launch_frame_post(p, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), N, s)); check_kernel(h, 1);
+			phase_end(h, "backward");
+		}
 	} else if (h->tc_ok) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
 		TcDpParams tp{};
@@ -1314,7 +1326,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			h->opt_nodur_impl = (int)value;
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
-		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per utterance (crf_dp_frame.cu), 1 the cluster lattice kernels
+		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per chain, both chains in one launch (crf_dp_frame.cu), 2 the chains one after the other, 1 the cluster lattice kernels
 		else if (n == "vit_impl") h->opt_vit_impl = (int)value;          // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
 		else if (n == "prefetch_smem") h->opt_prefetch_smem = (uint32_t)value;   // shared-memory cap of the read-ahead expansion's CTAs

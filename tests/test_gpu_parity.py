@@ -44,7 +44,7 @@ def assert_train_close(got, want, what=""):
 
 # lattice kernels: 0 = one CTA per utterance group (E from L2), 1 = cluster-resident E with FFMA, 2 = cluster-resident E with
 # tcgen05 (default); GEMMs: 0 = fp32 FFMA tiles, 1 = tcgen05 split-bf16 with register-staged operands, 2 = 1 + TMA-fed window GEMMs (default)
-IMPLS = {"tc": {}, "tc_frame_lattice": {"frame_impl": 1}, "tc_ffma_gemm": {"gemm_impl": 0}, "tc_reg_gemm": {"gemm_impl": 1}, "tc_tmem_all": {"tma_mask": 63}, "tc_smem_all": {"tma_mask": 7}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
+IMPLS = {"tc": {}, "tc_frame_lattice": {"frame_impl": 1}, "frame_sequential": {"frame_impl": 2}, "tc_ffma_gemm": {"gemm_impl": 0}, "tc_reg_gemm": {"gemm_impl": 1}, "tc_tmem_all": {"tma_mask": 63}, "tc_smem_all": {"tma_mask": 7}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
          "legacy_u1": {"dp_impl": 0, "slots": 1}, "legacy_u4": {"dp_impl": 0, "slots": 4, "gemm_impl": 0}}
 
 
