@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	__shared__ uint32_t s_g;        // descriptor of the kept-list order of the previous frame
 	__shared__ uint8_t s_move[256]; // arrival-order descriptors a[s] of the last D start frames (ring; D <= 255)
 	__shared__ int s_best;
-	const uint32_t u = blockIdx.x;
+	const uint32_t u = p.order ? p.order[blockIdx.x] : blockIdx.x;      // longest utterances first
 	const uint32_t L = p.L, P = p.P, NS = p.NS, D = p.D;
 	const uint32_t off = p.off[u], T = p.off[u + 1] - p.off[u];
 	const uint32_t lab = threadIdx.x;
@@ -977,8 +977,12 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	}
 	if (timing) { for (int i = 0; i < 4; i++) p.dbg[i] = tacc[i]; p.dbg[4] = T; }
 	// ---- final argmin over the kept list (first wins) and traceback ----
+	// The walk is one dependent load per segment; from global memory that was 0.3 us per segment (a fifth of the kernel at cfg3).
+	// The CTA now copies the back-pointer rows of a WINDOW of frames into shared memory (coalesced, all threads), thread 0 walks
+	// inside the window at shared-memory latency, and the segments (found last to first) are reversed by all threads at the end.
+	__shared__ int s_end, s_cur; __shared__ uint32_t s_nseg;
 	if (threadIdx.x == 0) {
-		uint32_t nseg = 0; float minw = VIT_INF; int best = -1;
+		float minw = VIT_INF; int best = -1;
 		if (T > 0) {
 			const uint32_t g = s_g;
 			for (uint32_t i = 0; i < P; i++) {
@@ -986,30 +990,57 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				const float w = Wprev[e];
 				if (w < minw) { minw = w; best = (int)e; }
 			}
-			if (best >= 0) {
-				int end = (int)T - 1; int cur = best;
-				uint32_t* ol = p.out_lab + off; uint32_t* od = p.out_dur + off; uint32_t* op = p.out_phn + off;
-				while (end >= 0) {
-					const uint32_t d = p.bd[(uint64_t)(off + end) * L + cur];
-					const uint16_t prev = p.bp[(uint64_t)(off + end) * L + cur];
-					const int start = end + 1 - (int)d;
-					ol[nseg] = (uint32_t)cur; od[nseg] = d;
-					if (start == 0) op[nseg] = (uint32_t)cur / NS;
-					else op[nseg] = ((uint32_t)cur % NS == 0 && (int)prev != cur) ? (uint32_t)cur / NS : LAB_BAD;
-					nseg++;
-					if (start == 0) break;
-					cur = (int)prev; end = start - 1;
-				}
-				for (uint32_t i = 0; i < nseg / 2; i++) {
-					uint32_t a;
-					a = ol[i]; ol[i] = ol[nseg - 1 - i]; ol[nseg - 1 - i] = a;
-					a = od[i]; od[i] = od[nseg - 1 - i]; od[nseg - 1 - i] = a;
-					a = op[i]; op[i] = op[nseg - 1 - i]; op[nseg - 1 - i] = a;
-				}
-			}
 		}
-		p.n_seg[u] = nseg; p.cost[u] = minw;
+		p.cost[u] = minw;
+		s_cur = best; s_end = best >= 0 ? (int)T - 1 : -1; s_nseg = 0;
 	}
+	__syncthreads();                       // the recursion's shared memory is free from here on
+	// window buffers: the rows lo..end of bp / bd are ONE contiguous byte range each; it is copied in 16-byte vectors from the
+	// 16-byte-aligned address below its start, so the data sits `shift` bytes into the (aligned) buffer
+	const size_t bp_cap = ((size_t)p.tbW * L * 2 + 47) / 16 * 16;
+	unsigned char* bpw_raw = smem_raw;                                   // [<= tbW * L * 2 + 32]
+	unsigned char* bdw_raw = smem_raw + bp_cap;                          // [<= tbW * L + 32]
+	auto copy_window = [&](unsigned char* dst, const unsigned char* src, size_t nbytes) -> uint32_t {
+		const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+		const uint4* sv = reinterpret_cast<const uint4*>(src - shift);
+		const uint32_t nvec = (uint32_t)((shift + nbytes + 15) / 16);
+		for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = sv[i];
+		return shift;
+	};
+	uint32_t* ol = p.out_lab + off; uint32_t* od = p.out_dur + off; uint32_t* op = p.out_phn + off;
+	while (s_end >= 0) {
+		const int end0 = s_end, lo = max(0, end0 - (int)p.tbW + 1);
+		const size_t cnt = (size_t)(end0 - lo + 1) * L;
+		const uint32_t sh_p = copy_window(bpw_raw, reinterpret_cast<const unsigned char*>(p.bp + (uint64_t)(off + lo) * L), cnt * 2);
+		const uint32_t sh_d = copy_window(bdw_raw, p.bd + (uint64_t)(off + lo) * L, cnt);
+		const uint16_t* bpw = reinterpret_cast<const uint16_t*>(bpw_raw + sh_p);     // 2-byte aligned: bp rows are
+		const uint8_t* bdw = bdw_raw + sh_d;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			int end = end0, cur = s_cur; uint32_t nseg = s_nseg;
+			while (end >= lo) {
+				const uint32_t d = bdw[(uint32_t)(end - lo) * L + cur];
+				const uint16_t prev = bpw[(uint32_t)(end - lo) * L + cur];
+				const int start = end + 1 - (int)d;
+				ol[nseg] = (uint32_t)cur; od[nseg] = d;
+				if (start == 0) op[nseg] = (uint32_t)cur / NS;
+				else op[nseg] = ((uint32_t)cur % NS == 0 && (int)prev != cur) ? (uint32_t)cur / NS : LAB_BAD;
+				nseg++;
+				if (start == 0) { end = -1; break; }
+				cur = (int)prev; end = start - 1;
+			}
+			s_end = end; s_cur = cur; s_nseg = nseg;
+		}
+		__syncthreads();
+	}
+	const uint32_t nseg = s_nseg;
+	for (uint32_t i = threadIdx.x; i < nseg / 2; i += blockDim.x) {
+		uint32_t a;
+		a = ol[i]; ol[i] = ol[nseg - 1 - i]; ol[nseg - 1 - i] = a;
+		a = od[i]; od[i] = od[nseg - 1 - i]; od[nseg - 1 - i] = a;
+		a = op[i]; op[i] = op[nseg - 1 - i]; op[nseg - 1 - i] = a;
+	}
+	if (threadIdx.x == 0) p.n_seg[u] = nseg;
 }
 void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	if (!p.n_utt) return;
@@ -1019,6 +1050,9 @@ void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	const unsigned threads = (std::max(p.L, p.NS * q.Ppad) + 31) / 32 * 32;
 	size_t smem = sizeof(float) * (3 * (size_t)p.L + p.P);
 	if (p.negMt == nullptr && (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
+	// traceback window: rows of back pointers (2 + 1 bytes per label) of as many frames as fit 48 KB, at least 8
+	q.tbW = std::max<uint32_t>(8u, (48u * 1024u) / (3u * p.L));
+	smem = std::max(smem, ((size_t)q.tbW * p.L * 2 + 47) / 16 * 16 + (size_t)q.tbW * p.L + 48);
 	cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(q);
 }

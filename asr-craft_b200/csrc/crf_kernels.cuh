@@ -231,6 +231,8 @@ void launch_vit_scores(const VitScoreParams& p, cudaStream_t s);
 
 struct VitParams {
 	uint32_t n_utt, L, P, NS, D;
+	const uint32_t* order;            // [n_utt] utterance handled by CTA i (longest first), or nullptr = identity
+	uint32_t tbW;                     // set by launch_viterbi: frames per traceback window in shared memory
 	uint32_t Ppad;                    // set by launch_viterbi: thread = (part of the kept list) * Ppad + target phone in the cross-phone scan
 	const uint32_t* off;
 	const float* negS;                // [N][D][L]

@@ -109,7 +109,7 @@ struct crfgpu_ctx {
 	bool fwdbwd_done = false;
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
-	DevBuf d_vg_slots, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
+	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	int opt_frame_impl = 0;
 	bool viterbi_done = false;
 
@@ -491,6 +491,11 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// consecutive (similar-length) utterances share a CTA, which minimises idle slots.
 	for (uint32_t i = 0; i < n_utt; i++) grp[i] = order[i];
 	upload_async(h, h->d_grp, grp);
+	{   // the same order padded to a multiple of 16 with LAB_BAD: lock-step batches of the group Viterbi, launch order of the per-utterance kernels
+		std::vector<uint32_t> o16((n_utt + 15) / 16 * 16, CRFGPU_LAB_BAD);
+		for (uint32_t i = 0; i < n_utt; i++) o16[i] = order[i];
+		upload_async(h, h->d_order16, o16);
+	}
 	// cluster-resident lattice kernels: persistent clusters, utterances dealt longest-first to the least loaded
 	// cluster; inside a cluster the list order is the order slots are (re)filled
 	std::vector<uint32_t> cl_off, cl_list;
@@ -945,21 +950,14 @@ void viterbi_staged(crfgpu_ctx* h) {
 		const int gmax = vitg_max_groups(P);
 		if (gmax >= 1) {
 			phase_begin(h, "viterbi");
-			std::vector<uint32_t> order(h->n_utt);
-			std::iota(order.begin(), order.end(), 0u);
-			const std::vector<uint32_t>& ho = h->h_off;
-			std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ho[a + 1] - ho[a] > ho[b + 1] - ho[b]; });
 			VitGroupParams g{};
 			g.n_utt = h->n_utt; g.P = P; g.D = D; g.npt = (P + 31) / 32;
 			g.n_batches = (h->n_utt + VITG_UT - 1) / VITG_UT;
 			g.n_groups = std::min<uint32_t>((uint32_t)gmax, g.n_batches);
-			std::vector<uint32_t> slots((size_t)g.n_batches * VITG_UT, 0xffffffffu);
-			for (uint32_t i = 0; i < h->n_utt; i++) slots[i] = order[i];
-			upload_async(h, h->d_vg_slots, slots);
 			const uint32_t Pk = (P + 31) / 32 * 32;
 			h->d_vg_xch.ensure(sizeof(float) * (size_t)g.n_groups * 2 * Pk * VITG_UT + 16);
 			h->d_vg_final.ensure(sizeof(float) * (size_t)h->n_utt * P + 16); h->d_vg_ctr.ensure(sizeof(uint32_t) * g.n_groups + 16);
-			g.off = h->d_off.as<uint32_t>(); g.slot_utt = h->d_vg_slots.as<uint32_t>(); g.negS = h->d_negS.as<float>();
+			g.off = h->d_off.as<uint32_t>(); g.slot_utt = h->d_order16.as<uint32_t>(); g.negS = h->d_negS.as<float>();
 			g.crossT = h->d_crossT.as<float>(); g.negDiag = h->d_negDiag.as<float>();
 			h->d_vg_cand.ensure(sizeof(float2) * (size_t)h->n_utt * D * P + 16); g.cand = h->d_vg_cand.as<float2>(); g.bp = h->d_bp.as<uint16_t>(); g.bd = h->d_bd.as<uint8_t>();
 			g.xch = h->d_vg_xch.as<float>(); g.finalW = h->d_vg_final.as<float>(); g.ctr = h->d_vg_ctr.as<uint32_t>();
@@ -989,6 +987,7 @@ void viterbi_staged(crfgpu_ctx* h) {
 	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
 	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
 	v.n_seg = h->d_nseg.as<uint32_t>(); v.cost = h->d_cost.as<float>();
+	v.order = h->d_order16.as<uint32_t>();      // longest utterances first
 	static DevBuf kdbg; const bool ktiming = getenv("CRFGPU_DP_TIMING") != nullptr;
 	if (ktiming) { kdbg.ensure(8 * 8); v.dbg = kdbg.as<unsigned long long>(); }
 	launch_viterbi(v, s); check_kernel(h, 1);
