@@ -239,19 +239,25 @@ __global__ void __launch_bounds__(FW * 32) frame_dp_pair_kernel(DpParams p, cons
 // posteriors of every frame from the two finished chains (no recursion: one thread per frame and label)
 //   gamma_t[c] = A_t[c] u_t[c] exp(m_t + bbase_t - logZ),   R_t[c] = u_t[c] exp(S_t[c] + bbase_t + m_{t-1} + Mmax - logZ), 0 on the first frame
 __global__ void __launch_bounds__(256) frame_post_kernel(DpParams p, const uint32_t* __restrict__ frame_t, const uint32_t* __restrict__ frame_utt, uint32_t N) {
-	const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-	const uint32_t Lp = p.Lp;
-	if (i >= (uint64_t)N * Lp) return;
-	const uint64_t n = i / Lp; const uint32_t c = (uint32_t)(i - n * Lp);
-	float dm = 0.0f, r = 0.0f;
-	if (c < p.L) {
-		const double lz = p.logZ[frame_utt[n]], bb = p.bbase[n];
-		const float u = p.Uvec[i];
-		const float gamma = p.A[i] * u * expf((float)(p.m[n] + bb - lz));
-		dm = ((p.node_lab[n] == c) ? 1.0f : 0.0f) - gamma;
-		if (frame_t[n] > 0) r = u * expf(__ldg(p.S + i) + (float)(bb + p.m[n - 1] + p.Mmax - lz));
+	// one warp per frame: the frame's scalars (two exponentials' arguments) once per lane, columns lane and lane + 32
+	const uint64_t n = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31, Lp = p.Lp;
+	if (n >= N) return;
+	const double lz = p.logZ[frame_utt[n]], bb = p.bbase[n];
+	const float gsc = expf((float)(p.m[n] + bb - lz));
+	const bool first = frame_t[n] == 0;
+	const float rarg = first ? 0.0f : (float)(bb + p.m[n - 1] + p.Mmax - lz);
+	const uint32_t lab = p.node_lab[n];
+	const size_t row = (size_t)n * Lp;
+	for (uint32_t c = lane; c < Lp; c += 32) {
+		float dm = 0.0f, r = 0.0f;
+		if (c < p.L) {
+			const float u = p.Uvec[row + c];
+			dm = ((lab == c) ? 1.0f : 0.0f) - p.A[row + c] * u * gsc;
+			if (!first) r = u * expf(__ldg(p.S + row + c) + rarg);
+		}
+		p.Dm[row + c] = dm; p.R[row + c] = r;
 	}
-	p.Dm[i] = dm; p.R[i] = r;
 }
 
 cudaError_t launch_frame_dp(bool backward, const DpParams& p, const uint32_t* utt_list, uint32_t n_utt, cudaStream_t s) {
@@ -264,16 +270,19 @@ cudaError_t launch_frame_dp(bool backward, const DpParams& p, const uint32_t* ut
 cudaError_t launch_frame_dp_pair(const DpParams& p, const uint32_t* utt_list, uint32_t n_utt, cudaStream_t s) {
 	if (!n_utt) return cudaSuccess;
 	const unsigned G = (n_utt + FW - 1) / FW;
-	const int excl = 120 * 1024;      // more than half of an SM's shared memory: one CTA per SM
-	cudaError_t e = cudaFuncSetAttribute(frame_dp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, excl);
+	// up to two CTAs per SM the launch is as long as its longest chain: ask for more than half of an SM's shared memory so that every
+	// CTA has its SM to itself; larger batches are a matter of throughput and share the SMs
+	int dev = 0, sms = 0;
+	cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const int excl = (sms > 0 && 2 * G <= 2u * (unsigned)sms) ? 120 * 1024 : 0;
+	cudaError_t e = cudaFuncSetAttribute(frame_dp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
 	if (e != cudaSuccess) return e;
 	frame_dp_pair_kernel<<<2 * G, FW * 32, excl, s>>>(p, utt_list, n_utt);
 	return cudaGetLastError();
 }
 cudaError_t launch_frame_post(const DpParams& p, const uint32_t* frame_t, const uint32_t* frame_utt, uint32_t N, cudaStream_t s) {
 	if (!N) return cudaSuccess;
-	const uint64_t total = (uint64_t)N * p.Lp;
-	frame_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p, frame_t, frame_utt, N);
+	frame_post_kernel<<<(unsigned)(((uint64_t)N * 32 + 255) / 256), 256, 0, s>>>(p, frame_t, frame_utt, N);
 	return cudaGetLastError();
 }
 
