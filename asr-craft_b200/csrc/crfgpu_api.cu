@@ -110,7 +110,7 @@ struct crfgpu_ctx {
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
 	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
-	int opt_frame_impl = 0;
+	int opt_frame_impl = 0; bool frame_path = false;
 	bool viterbi_done = false;
 
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
@@ -500,6 +500,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// cluster; inside a cluster the list order is the order slots are (re)filled
 	std::vector<uint32_t> cl_off, cl_list;
 	h->cluster_ok = false; h->tc_ok = false;
+	// frame-level models with at most 64 labels run one warp per chain (crf_dp_frame.cu): no cluster plan, no slot lists
+	h->frame_path = c.max_dur == 1 && h->Lt <= 64 && !h->tied && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && h->opt_frame_impl != 1;
 	auto deal = [&](uint32_t ncl) {
 		// utterances dealt longest-first to the least loaded cluster; inside a cluster the list order is the order slots are (re)filled
 		std::vector<std::vector<uint32_t>> lists(ncl);
@@ -513,7 +515,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
 		upload_async(h, h->d_cl_off, cl_off); upload_async(h, h->d_cl_list, cl_list);
 	};
-	if (h->train_ok && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
+	if (h->train_ok && !h->frame_path && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
 		// tensor-core cluster kernels: 16 slots per cluster
 		TcDpPlan plan{};
 		if (plan_tc_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
@@ -528,7 +530,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 		}
 	}
-	if (h->train_ok && !h->nodur && !h->transftr && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
+	if (h->train_ok && !h->frame_path && !h->nodur && !h->transftr && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
 		ClusterPlan plan{};
 		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
 		if (plan_cluster_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan, cap)) {
@@ -756,7 +758,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		CUDA_OK(launch_nodur_dp(true, q, s)); check_kernel(h, 1);
 		if (ntiming) nreport("backward");
 		phase_end(h, "backward");
-	} else if (D == 1 && L <= 64 && !h->tied && h->opt_dp_impl == 2 && h->opt_frame_impl != 1) {
+	} else if (h->frame_path) {
 		// frame-level models with at most 64 labels: one warp per utterance, the transition matrix in registers (crf_dp_frame.cu);
 		// d_grp holds the utterances longest first, so the four warps of a CTA carry similar lengths
 		if (h->opt_frame_impl == 2) {     // the two chains one after the other, posteriors fused into the backward pass
