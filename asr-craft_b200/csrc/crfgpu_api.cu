@@ -710,6 +710,13 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		return;
 	}
 	DpParams p = dp_params(h);
+	// frames per CTA in the reduce-GEMMs.  The defaults are tuned on cfg4 (10 duration blocks of CTAs); a frame-level model has one
+	// block, so the same slabs would leave most SMs idle (cfg2: 17 and 68 CTAs): one to two slabs per SM instead
+	uint32_t ks_xi = h->opt_k_slab_xi, ks_tc = h->opt_k_slab_tc;
+	if (D == 1 && N) {
+		ks_xi = std::min(ks_xi, std::max(512u, (N / 148u + 31u) / 32u * 32u));
+		ks_tc = std::min(ks_tc, std::max(256u, (N / 296u + 31u) / 32u * 32u));
+	}
 	const uint32_t Lq = (P * P + 3) / 4 * 4;        // nodur_tf: row stride of the per-frame transition scores
 	if (h->nodur_tf) {
 		const uint32_t tf0 = c.trans_fidx_start, nTf = m.nTf;
@@ -856,7 +863,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	} else
 	if (c.use_trans_bias && lat_tma && (h->opt_tma_mask & 4) && N > 1) {
 		FrameGemmParams x{};
-		x.N = N; x.P = P; x.D = D; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = h->opt_k_slab_xi; x.Mext = L; x.ones_col = 0xffffffffu;
+		x.N = N; x.P = P; x.D = D; x.ntile = (P + FRAME_GEMM_TILE - 1) / FRAME_GEMM_TILE; x.k_slab = ks_xi; x.Mext = L; x.ones_col = 0xffffffffu;
 		x.scale = -c.trans_bias_val; x.pair_idx = h->d_tidx.as<uint32_t>(); x.L = L; x.Ew = h->d_E.as<float>(); x.e_ld = Lp; x.out = h->d_grad.as<double>();
 		x.a_from_tmem = (h->opt_tma_mask & 32) ? 1u : 0u;
 		CUDA_OK(launch_xi_gemm_tma(h->d_A.as<float>(), h->d_R.as<float>(), Lp, x, s)); check_kernel(h, 1);
@@ -899,7 +906,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu;
 		r.scale = 1.0; r.ones_scale = c.state_bias_val; r.mode = 0;
 		r.row_idx = h->d_sidx.as<uint32_t>() + (size_t)d * P;
-		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl >= 1 ? h->opt_k_slab_tc : h->opt_k_slab;
+		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_gemm_impl >= 1 ? ks_tc : h->opt_k_slab;
 		if (h->opt_gemm_impl >= 1) CUDA_OK(launch_reduce_gemm_tc(r, true, s)); else launch_reduce_gemm(r, s);
 		check_kernel(h, 1);
 	}

@@ -4,7 +4,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "asr-craft_b200"))
 import numpy as np, crf_b200, workloads
-n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 462
+n_utt = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 462
 transftr = "--transftr" in sys.argv        # crf_featuremap=stdtrans: 105 transition features per label pair
 off, ftrs, labs = workloads.timit_train_batch(0, n_utt)
 kw = workloads.cfg2_kwargs()
@@ -12,6 +12,9 @@ if transftr:
     kw["use_trans_ftrs"] = 1
 m = crf_b200.CrfGpu(crf_b200.make_config(**kw))
 m.set_lambda(np.random.default_rng(3).uniform(-0.02, 0.02, m.lambda_len) if transftr else workloads.lam_for("cfg2", m.lambda_len))
+for a in sys.argv[1:]:                     # name=value pairs go to crfgpu_set_option
+    if "=" in a:
+        k, v = a.split("="); m.set_option(k, int(v))
 m.stage(off, ftrs, labs)
 names = ["score", "forward", "backward", "xi", "grad"]
 best = None
