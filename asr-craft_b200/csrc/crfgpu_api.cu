@@ -12,6 +12,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -111,6 +112,7 @@ struct crfgpu_ctx {
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
 	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	int opt_frame_impl = 0; bool frame_path = false;
+	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
 
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
@@ -262,6 +264,7 @@ void require_decode(crfgpu_ctx* h) {
 // with M[p][c] = lambda[tidx]*transBiasVal (CRF_StdFeatureMap.cpp:94-110 with no transition features), the weight tiles of the TMA-fed
 // score GEMM and the decoder's tables.  Only the scalar Mmax comes back to the host.
 void derive_tables(crfgpu_ctx* h) {
+	h->vit_score_ready = false;              // scores launched ahead by crfgpu_stage_batch belong to the previous lambda
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t L = m.L, Lt = h->Lt, Lp = h->Lp, nSf = m.nSf;
 	cudaStream_t s = h->stream;
@@ -325,13 +328,14 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 // ---------------------------------------------------------------------------------------------// Base features to the device in up to 4 chunks cut at utterance boundaries on the copy stream, and -- on stream xs -- the window
 // expansion of chunk i (windows never reach across utterances) while chunk i+1 is still in flight.  d_ft must already be queued on xs.
 void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_t N, const float* ftrs, DevBuf& d_base, DevBuf& d_X, DevBuf& d_ft,
-                     cudaStream_t xs, cudaEvent_t ev_ready, std::vector<cudaEvent_t>& evs, const char* phase, uint32_t dpart = 0) {
+                     cudaStream_t xs, cudaEvent_t ev_ready, std::vector<cudaEvent_t>& evs, const char* phase, uint32_t dpart = 0,
+                     const std::function<void(uint32_t, uint32_t)>* after_chunk = nullptr) {
 	const crfgpu_config& c = h->cfg;
 	if (!N) return;
 	if (!h->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	CUDA_OK(cudaEventRecord(ev_ready, xs));                              // everything queued on xs so far may still read the old contents
 	CUDA_OK(cudaStreamWaitEvent(h->copy_stream, ev_ready, 0));
-	const uint32_t n_chunks = N >= (1u << 16) ? 4u : 1u;
+	const uint32_t n_chunks = N >= (1u << 14) ? 4u : 1u;
 	std::vector<uint32_t> ends;
 	uint32_t u = 0, n_prev = 0;
 	for (uint32_t k = 1; k <= n_chunks; k++) {
@@ -356,6 +360,7 @@ void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_
 			launch_expand_windows(ep, ends[k], xs);
 			check_kernel(h, 1);
 		}
+		if (after_chunk) (*after_chunk)(n_prev, ends[k]);      // work on the frames of this chunk while the next one is in flight
 		n_prev = ends[k];
 	}
 	if (phase) phase_end(h, phase);
@@ -403,7 +408,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	const uint32_t N = n_utt ? off[n_utt] : 0;
 	cudaStream_t s = h->stream;
 	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
-	h->fwdbwd_done = h->viterbi_done = false;
+	h->fwdbwd_done = h->viterbi_done = false; h->vit_score_ready = false;
 	h->h_off.assign(off, off + n_utt + 1);
 	{
 		const size_t want = ((size_t)N * 6 + (size_t)n_utt * 24 + 65536) * sizeof(uint32_t);
@@ -436,7 +441,20 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
 		if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
 		if (N && !h->ev_ready) CUDA_OK(cudaEventCreate(&h->ev_ready));
-		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand");
+		// a decode batch (no labels): the decoder's fp64 state scores of a chunk are launched as soon as the chunk has arrived, so the
+		// scoring runs under the remaining H2D copies instead of behind them
+		std::function<void(uint32_t, uint32_t)> score_chunk = [&](uint32_t n0, uint32_t n1) {
+			const Layout& m = h->lay;
+			VitScoreParams vs{};
+			vs.X = h->X() + (size_t)n0 * h->ldx(); vs.ldx = h->ldx(); vs.W = h->Wp; vs.sf0 = c.state_fidx_start; vs.nSf = m.nSf; vs.N = n1 - n0; vs.D = c.max_dur; vs.L = m.L;
+			vs.frame_t = h->d_frame_t.as<uint32_t>() + n0; vs.Wd = h->d_Wd.as<double>(); vs.use_bias = c.use_state_bias; vs.bias_val = c.state_bias_val;
+			vs.negS = h->d_negS.as<float>() + (size_t)n0 * c.max_dur * m.L;
+			launch_vit_scores(vs, s); check_kernel(h, 1);
+		};
+		const bool eager_vit = !labs && N && h->decode_ok && h->have_lambda && h->lay.nSf > 0;
+		if (eager_vit) h->d_negS.ensure(sizeof(float) * (size_t)N * c.max_dur * h->lay.L + 16);
+		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand", 0, eager_vit ? &score_chunk : nullptr);
+		h->vit_score_ready = eager_vit;
 	}
 	upload_async(h, h->d_frame_utt, frame_utt); upload_async(h, h->d_frame_len, frame_len);
 
@@ -935,13 +953,14 @@ void viterbi_staged(crfgpu_ctx* h) {
 	h->d_olab.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_odur.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_ophn.ensure(sizeof(uint32_t) * (size_t)N + 16);
 	h->d_nseg.ensure(sizeof(uint32_t) * (size_t)h->n_utt + 16); h->d_cost.ensure(sizeof(float) * (size_t)h->n_utt + 16);
 	if (!N) { h->viterbi_done = true; return; }
-	phase_begin(h, "viterbi_score");
+	const bool scored = h->vit_score_ready;      // launched chunk by chunk by crfgpu_stage_batch for this batch and this lambda
+	h->vit_score_ready = false;
+	if (!scored) phase_begin(h, "viterbi_score");
 	VitScoreParams vs{};
 	vs.X = h->X(); vs.ldx = h->ldx(); vs.W = h->Wp; vs.sf0 = c.state_fidx_start; vs.nSf = m.nSf; vs.N = N; vs.D = D; vs.L = L;
 	vs.frame_t = h->d_frame_t.as<uint32_t>(); vs.Wd = h->d_Wd.as<double>(); vs.use_bias = c.use_state_bias; vs.bias_val = c.state_bias_val;
 	vs.negS = h->d_negS.as<float>();
-	launch_vit_scores(vs, s); check_kernel(h, 1);
-	phase_end(h, "viterbi_score");
+	if (!scored) { launch_vit_scores(vs, s); check_kernel(h, 1); phase_end(h, "viterbi_score"); }
 	if (c.use_trans_ftrs) {
 		// (float)(-M_n[p][c]) of every frame's decoder pairs from its duration-1 window, in the reference's fp64 arithmetic
 		h->d_negMt.ensure(sizeof(float) * (size_t)N * h->vtE + 16);
