@@ -270,6 +270,20 @@ class CrfGpu:
     def viterbi_staged(self):
         self._check(self.lib.crfgpu_viterbi_staged(self.h))
 
+    def fetch_viterbi(self, off):
+        """crfgpu_fetch_viterbi after viterbi_staged(): (segments per utterance, path costs) like viterbi()"""
+        off = np.ascontiguousarray(off, np.uint32)
+        n, tot = len(off) - 1, int(off[-1])
+        lab = np.zeros(tot, np.uint32); dur = np.zeros(tot, np.uint32); phn = np.zeros(tot, np.uint32)
+        nseg = np.zeros(n, np.uint32); cost = np.zeros(n, np.float32)
+        self._check(self.lib.crfgpu_fetch_viterbi(self.h, _ptr(lab, C.c_uint32), _ptr(dur, C.c_uint32), _ptr(phn, C.c_uint32),
+                                                  _ptr(nseg, C.c_uint32), _ptr(cost, C.c_float)))
+        segs = []
+        for u in range(n):
+            b, k = int(off[u]), int(nseg[u])
+            segs.append((lab[b:b + k].copy(), dur[b:b + k].copy(), phn[b:b + k].copy()))
+        return segs, cost
+
     def synchronize(self):
         self._check(self.lib.crfgpu_synchronize(self.h))
 

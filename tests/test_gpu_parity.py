@@ -616,3 +616,35 @@ def test_viterbi_group_sliced_matches_single_cta_and_oracle(oracle, P, D, F, n_u
             for got, exp in zip(res[2][0], want):
                 assert all(np.array_equal(x, y) for x, y in zip(got, exp)), lam_kind
             assert np.array_equal(res[2][1].view(np.uint32), wcost.view(np.uint32)), lam_kind
+
+
+def test_viterbi_multi_chunk_staging_bit_exact_vs_oracle(oracle):
+    """a decode batch big enough for crfgpu_stage_batch to copy it in four chunks (>= 16384 frames): the decoder's fp64 scores are
+    launched chunk by chunk behind the copies, and the paths must still be the oracle's bit for bit"""
+    rng = np.random.default_rng(77)
+    P, NS, D, F = 5, 3, 2, 6
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P * NS, n_base_ftrs=F, n_states=NS, max_dur=D, extract_seg_ftrs=1)
+    lens = rng.integers(150, 400, 80)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    assert off[-1] >= 16384
+    ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+    lam = rng.uniform(-0.25, 0.25, oracle.lambda_len(cfg))
+    want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    for _ in range(2):      # second call: the read-after-restage path
+        segs, cost = m.viterbi(off, ftrs)
+        for got, exp in zip(segs, want):
+            assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+        assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    # a new lambda after staging must not reuse the scores launched by the staging call
+    lam2 = rng.uniform(-0.25, 0.25, oracle.lambda_len(cfg))
+    want2, wcost2, _ = oracle.viterbi(cfg, lam2, off, ftrs)
+    m.stage(off, ftrs)
+    m.set_lambda(lam2)
+    m.viterbi_staged()
+    segs, cost = m.fetch_viterbi(off)
+    for got, exp in zip(segs, want2):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost2.view(np.uint32))
+    m.close()
