@@ -98,9 +98,11 @@ __device__ __forceinline__ void frame_dp_body(const DpParams& p, const uint32_t*
 	};
 
 	if (!BWD) {
-		float sv[2], sn[2] = {-INFINITY, -INFINITY};
+		// scores two frames ahead: one frame (~700 cycles) does not cover a miss to HBM
+		float sv[2], sn[2] = {-INFINITY, -INFINITY}, sn2[2] = {-INFINITY, -INFINITY};
 		load_s(0, sv);
 		if (T > 1) load_s(1, sn);
+		if (T > 2) load_s(2, sn2);
 		// frame 0: alpha = S (computeFirstAlpha)
 		float sref = wmax(fmaxf(sv[0], sv[1]));
 		float a[2] = {__expf(sv[0] - sref), __expf(sv[1] - sref)};
@@ -112,8 +114,8 @@ __device__ __forceinline__ void frame_dp_body(const DpParams& p, const uint32_t*
 			if (lane == 0) p.m[off] = m;
 		}
 		for (uint32_t t = 1; t < T; t++) {
-			sv[0] = sn[0]; sv[1] = sn[1];
-			if (t + 1 < T) load_s(t + 1, sn);
+			sv[0] = sn[0]; sv[1] = sn[1]; sn[0] = sn2[0]; sn[1] = sn2[1];
+			if (t + 2 < T) load_s(t + 2, sn2);
 			vec[c0] = a[0]; vec[c1] = a[1];
 			__syncwarp();
 			const float mxprev = wmax(fmaxf(a[0], a[1]));          // beside the product, not behind it
@@ -134,9 +136,10 @@ __device__ __forceinline__ void frame_dp_body(const DpParams& p, const uint32_t*
 		if (lane == 0) p.logZ[utt] = m + log((double)zs);
 	} else if (!FUSED) {
 		// the beta chain alone: w~_t = exp(S_t - sref) u_t 2^-e;  u_t and bbase_t are what the posteriors need
-		float sv[2], sn[2] = {-INFINITY, -INFINITY};
+		float sv[2], sn[2] = {-INFINITY, -INFINITY}, sn2[2] = {-INFINITY, -INFINITY};
 		load_s(T - 1, sv);
 		if (T > 1) load_s(T - 2, sn);
+		if (T > 2) load_s(T - 3, sn2);
 		// last frame: beta = 0 (setTailBeta): u = 1, bbase = 0
 		float sref = wmax(fmaxf(sv[0], sv[1]));
 		float w[2] = {__expf(sv[0] - sref), __expf(sv[1] - sref)};
@@ -149,8 +152,8 @@ __device__ __forceinline__ void frame_dp_body(const DpParams& p, const uint32_t*
 			if (lane == 0) { p.bbase[n] = 0.0; p.kappa[n] = kap; }
 		}
 		for (uint32_t t = T - 1; t-- > 0;) {
-			sv[0] = sn[0]; sv[1] = sn[1];
-			if (t >= 1) load_s(t - 1, sn);
+			sv[0] = sn[0]; sv[1] = sn[1]; sn[0] = sn2[0]; sn[1] = sn2[1];
+			if (t >= 2) load_s(t - 2, sn2);
 			vec[c0] = w[0]; vec[c1] = w[1];
 			__syncwarp();
 			const float mxprev = wmax(fmaxf(w[0], w[1]));
