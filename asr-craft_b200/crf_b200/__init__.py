@@ -68,7 +68,11 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_viterbi_staged", "crfgpu_device_results", "crfgpu_fetch_fwdbwd", "crfgpu_fetch_viterbi",
            "crfgpu_synchronize", "crfgpu_stream", "crfgpu_launch_count", "crfgpu_phase_ms",
            "crfgpu_fetch_alpha_beta", "crfgpu_set_option", "crfgpu_host_alloc", "crfgpu_host_free",
-           "crfgpu_sgd_update", "crfgpu_get_lambda", "crfgpu_set_train_state", "crfgpu_prefetch_batch"]
+           "crfgpu_sgd_update", "crfgpu_get_lambda", "crfgpu_set_train_state", "crfgpu_prefetch_batch",
+           "crfgpu_comm_unique_id", "crfgpu_comm_init_rank", "crfgpu_comm_init_all", "crfgpu_comm_destroy", "crfgpu_comm_size",
+           "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
+           "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info"]
+COMM_ID_BYTES = 128
 
 
 class Sgd(C.Structure):
@@ -102,6 +106,18 @@ def load_library(path=None):
     lib.crfgpu_sgd_update.argtypes = [C.c_void_p, C.POINTER(Sgd), C.c_double]
     lib.crfgpu_get_lambda.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 4
     lib.crfgpu_set_train_state.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3
+    lib.crfgpu_comm_unique_id.argtypes = [C.c_void_p]
+    lib.crfgpu_comm_init_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.crfgpu_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    for name in ("crfgpu_comm_destroy", "crfgpu_comm_size", "crfgpu_allreduce_grad"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.crfgpu_fetch_tail.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.crfgpu_shard_views.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.crfgpu_minibatch_share.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.crfgpu_minibatch_share.restype = C.c_uint32
+    lib.crfgpu_balance_utts.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.crfgpu_plan_info.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+    lib.crfgpu_plan_info.restype = C.c_uint32
     _lib = lib
     return lib
 
@@ -129,6 +145,51 @@ class PinnedBuffer:
             self.array = None
             self.lib.crfgpu_host_free(self.ptr)
             self.ptr = None
+
+
+def _host_check(rc):
+    if rc:
+        raise CrfGpuError(rc, load_library().crfgpu_last_error().decode())
+
+
+def shard_views(n_utt, n_streams):
+    """crfgpu_shard_views: the reference's contiguous corpus views (first, count) per stream."""
+    first = np.zeros(n_streams, np.uint32); count = np.zeros(n_streams, np.uint32)
+    _host_check(load_library().crfgpu_shard_views(n_utt, n_streams, _ptr(first, C.c_uint32), _ptr(count, C.c_uint32)))
+    return first, count
+
+
+def minibatch_share(minibatch, n_streams, stream):
+    return int(load_library().crfgpu_minibatch_share(minibatch, n_streams, stream))
+
+
+def balance_utts(n_frames, n_ranks):
+    """crfgpu_balance_utts: rank of every utterance of one global minibatch (equal counts, frames balanced, longest first)."""
+    n_frames = np.ascontiguousarray(n_frames, np.uint32)
+    out = np.zeros(len(n_frames), np.uint32)
+    _host_check(load_library().crfgpu_balance_utts(len(n_frames), _ptr(n_frames, C.c_uint32), n_ranks, _ptr(out, C.c_uint32)))
+    return out
+
+
+def comm_unique_id():
+    """128 bytes rank 0 hands to the other ranks (crfgpu_comm_unique_id)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _host_check(load_library().crfgpu_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init_all(models):
+    """One process, one handle per device: crfgpu_comm_init_all."""
+    arr = (C.c_void_p * len(models))(*[m.h for m in models])
+    _host_check(load_library().crfgpu_comm_init_all(arr, len(models)))
+
+
+def group_start():
+    _host_check(load_library().crfgpu_group_start())
+
+
+def group_end():
+    _host_check(load_library().crfgpu_group_end())
 
 
 class CrfGpu:
@@ -307,6 +368,32 @@ class CrfGpu:
         b = np.zeros((self._n_frames, L), np.float64)
         self._check(self.lib.crfgpu_fetch_alpha_beta(self.h, _ptr(a, C.c_double), _ptr(b, C.c_double)))
         return a, b
+
+    # ---- multi-GPU ----------------------------------------------------------------------------
+    def comm_init_rank(self, n_ranks, rank, id128):
+        buf = C.create_string_buffer(bytes(id128), COMM_ID_BYTES)
+        self._check(self.lib.crfgpu_comm_init_rank(self.h, n_ranks, rank, buf))
+
+    def comm_destroy(self):
+        self._check(self.lib.crfgpu_comm_destroy(self.h))
+
+    @property
+    def comm_size(self):
+        return int(self.lib.crfgpu_comm_size(self.h))
+
+    def allreduce_grad(self):
+        """ONE ncclAllReduce(sum) over the staged gradient + [sum numer, sum logZ, n_utt, 0], in place, on the handle's stream."""
+        self._check(self.lib.crfgpu_allreduce_grad(self.h))
+
+    def fetch_tail(self):
+        t = np.zeros(4, np.float64)
+        self._check(self.lib.crfgpu_fetch_tail(self.h, _ptr(t, C.c_double)))
+        return t
+
+    def plan_info(self):
+        buf = C.create_string_buffer(2048)
+        n = self.lib.crfgpu_plan_info(self.h, buf, 2048)
+        return buf.raw[:n].decode()
 
     def phase_ms(self, name):
         return float(self.lib.crfgpu_phase_ms(self.h, name.encode()))

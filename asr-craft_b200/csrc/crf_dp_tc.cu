@@ -60,6 +60,10 @@ static_assert(SPT == 4, "the partial-sum butterfly below is written for 4 slots 
 struct Slot {
 	uint32_t utt, off, len, t;     // utt == LAB_BAD: idle
 	double lz;                     // logZ of the utterance (backward)
+	double sc;                     // log scale of THIS frame (forward rho_t, backward base_t), stashed with the schedule entry when it is
+	                               // derived: step [1] must not read it back from ring_b, because a slot that was refilled in between has
+	                               // already stored the NEW utterance's scale of frame 0 there -- the same ring index whenever
+	                               // (len - 1) % DMAX == 0 (that aliasing made logZ of such utterances wrong: 1.5 % on the cfg4 bench shard)
 };
 
 // what the lane threads need to know about one slot in one step (published by the bookkeeping warp)
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 		const uint32_t bw = warp - BK_WARP0, slot = bw * SPW + (lane & (SPW - 1)), h = lane / SPW;
 		// every slot works through its own utterance list (the host balances the lists over all slots of all clusters)
 		const uint32_t list_end = p.cl_off[cl * UB + slot + 1];
-		const Slot idle{LAB_BAD, 0, 0, 0, 0.0};
+		const Slot idle{LAB_BAD, 0, 0, 0, 0.0, 0.0};
 		uint32_t list_next = p.cl_off[cl * UB + slot];
 		auto refill = [&](bool want, Slot& out) {
 			if (want && h == 0 && list_next < list_end) {
@@ -290,12 +294,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 					if (!BWD) {
 						const bool last = fm.t + 1 == fm.len;
 						// the log scales are references, not results: only logZ needs the accurate logarithm
-						const double ghat = ctl->ring_b[slot][fm.t & (DMAX - 1)] + (last ? log((double)vsum) : (double)__logf(vsum));
+						const double ghat = fm.sc + (last ? log((double)vsum) : (double)__logf(vsum));
 						ctl->ring_a[slot][fm.t & (DMAX - 1)] = ghat; ctl->ring_af[slot][fm.t & (DMAX - 1)] = (float)ghat;
 						if (last && rank == 0) p.logZ[fm.utt] = ghat;               // computeAlphaSum (:447-462)
 					} else {
 						const bool tail = fm.t + 1 == fm.len;
-						const double bl = tail ? 0.0 : ctl->ring_b[slot][fm.t & (DMAX - 1)] + (double)__logf(vsum);
+						const double bl = tail ? 0.0 : fm.sc + (double)__logf(vsum);
 						ctl->ring_a[slot][fm.t & (DMAX - 1)] = bl; ctl->ring_af[slot][fm.t & (DMAX - 1)] = (float)bl;
 					}
 				}
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 				__syncwarp();
 				if (a1 && h == 0) {
 					ctl->ring_b[slot][t1 & (DMAX - 1)] = rho;
+					ctl->fr[(j + 1) & 3][slot].sc = rho;
 					if (rank == 0) p.m[(size_t)f1.off + t1] = rho;
 				}
 			} else {
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 						ctl->delta[nb][slot][d] = (d <= nn1) ? (float)(ctl->ring_b[slot][(t1 + d) & (DMAX - 1)] - sigma) : -INFINITY;
 				// posterior scales of F(j), gathered (and turned into posteriors) in step j+1
 				if (a0) {
-					const double base0 = ctl->ring_b[slot][f0.t & (DMAX - 1)];
+					const double base0 = f0.sc;
 					if (h == 0) {
 						ctl->sg[nb][slot] = (float)(ctl->pre_rho[slot][0] + base0 - f0.lz);
 						if (rank == 0) p.bbase[(size_t)f0.off + f0.t] = base0;
@@ -369,7 +374,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_tc_kernel(TcDpParams p) {
 						ctl->rsc[nb][slot][d] = (d <= f0.t) ? (float)(base0 + ctl->pre_rho[slot][d] + p.Mmax - f0.lz) : -INFINITY;
 				}
 				__syncwarp();
-				if (a1 && h == 0) ctl->ring_b[slot][t1 & (DMAX - 1)] = nn1 ? p.Mmax + sigma : 0.0;   // tail: beta = 0 (setTailBeta)
+				if (a1 && h == 0) {
+					const double base1 = nn1 ? p.Mmax + sigma : 0.0;   // tail: beta = 0 (setTailBeta)
+					ctl->ring_b[slot][t1 & (DMAX - 1)] = base1;
+					ctl->fr[(j + 1) & 3][slot].sc = base1;
+				}
 			}
 			if (h == 0) {
 				LaneCtl lc{};

@@ -1,6 +1,8 @@
 #include "crf_layout.h"
 
+#include <algorithm>
 #include <cmath>
+#include <numeric>
 #include <stdexcept>
 
 namespace crfgpu {
@@ -105,6 +107,37 @@ std::vector<uint32_t> sample_steps(uint32_t D) {
 		}
 	}
 	return steps;
+}
+
+void shard_views(uint32_t n_utt, uint32_t n_streams, uint32_t* first, uint32_t* count) {
+	const uint32_t per = n_streams ? n_utt / n_streams : 0;
+	for (uint32_t i = 0; i < n_streams; i++) {
+		first[i] = i * per;
+		count[i] = (i + 1 == n_streams) ? n_utt - i * per : per;     // view(i*nseg_per_child, last ? QN_ALL : nseg_per_child)
+	}
+}
+
+uint32_t minibatch_share(uint32_t minibatch, uint32_t n_streams, uint32_t stream) {
+	if (minibatch == 0 || minibatch == 0xffffffffu) return 0xffffffffu;    // setMinibatch(0): "totally batch"
+	return minibatch / n_streams + (stream < minibatch % n_streams ? 1u : 0u);
+}
+
+void balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t* rank_of) {
+	if (!n_ranks) return;
+	std::vector<uint32_t> order(n_utt);
+	std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return n_frames[a] > n_frames[b]; });
+	std::vector<uint64_t> load(n_ranks, 0);
+	std::vector<uint32_t> cnt(n_ranks, 0);
+	const uint32_t cap_lo = n_utt / n_ranks, n_hi = n_utt % n_ranks;   // ranks 0..n_hi-1 may take one more
+	for (uint32_t u : order) {
+		uint32_t best = n_ranks;
+		for (uint32_t r = 0; r < n_ranks; r++) {
+			if (cnt[r] >= cap_lo + (r < n_hi ? 1u : 0u)) continue;
+			if (best == n_ranks || load[r] < load[best]) best = r;
+		}
+		rank_of[u] = best; load[best] += n_frames[u]; cnt[best]++;
+	}
 }
 
 }  // namespace crfgpu

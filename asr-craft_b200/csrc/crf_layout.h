@@ -36,4 +36,14 @@ void group_labels(uint32_t max_dur, uint32_t n_frames, const uint32_t* frame_lab
 // Computed on the host with the reference's own float arithmetic so the device never re-derives it.
 std::vector<uint32_t> sample_steps(uint32_t max_dur);
 
+// Sharding rules of the data-parallel training seam.
+// shard_views: stream i of n_streams owns [i*floor(n/n_streams), (i+1)*floor(n/n_streams)), the last one also the remainder
+// (CRF/src/io/CRF_FeatureStreamManager.cpp:425-464).
+void shard_views(uint32_t n_utt, uint32_t n_streams, uint32_t* first, uint32_t* count);
+// minibatch_share: utterances stream i takes per minibatch (CRF_Minibatch_GradAccumulator.cpp:229-257); 0 = whole view.
+uint32_t minibatch_share(uint32_t minibatch, uint32_t n_streams, uint32_t stream);
+// balance_utts: utterances of ONE global minibatch dealt to n_ranks devices with equal counts (+-1), longest first onto the rank
+// with the fewest frames so far among those that still have room.
+void balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t* rank_of);
+
 }  // namespace crfgpu

@@ -16,6 +16,8 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "../../include/crfgpu.h"
 #include "crf_kernels.cuh"
@@ -88,10 +90,11 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192, opt_prefetch_smem = 1u << 20;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_max_clusters = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192, opt_prefetch_smem = 1u << 20;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
+	uint64_t locksteps = 0;   // frames of the longest slot / cluster list of the staged batch = dependent steps of the lattice kernels
 	DevBuf d_cl_off, d_cl_list, d_xch, d_xmax, d_smaxd;
 
 	// model tables
@@ -116,6 +119,7 @@ struct crfgpu_ctx {
 	bool viterbi_done = false;
 
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
+	ncclComm_t comm = nullptr; int comm_nranks = 0, comm_rank = 0;   // crfgpu_comm_init_*: the communicator crfgpu_allreduce_grad runs on
 
 	const float* X() const { return (cfg.max_dur == 1) ? d_base.as<float>() : d_X.as<float>(); }
 	uint64_t ldx() const { return (uint64_t)cfg.max_dur * Wp; }
@@ -517,7 +521,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// cluster-resident lattice kernels: persistent clusters, utterances dealt longest-first to the least loaded
 	// cluster; inside a cluster the list order is the order slots are (re)filled
 	std::vector<uint32_t> cl_off, cl_list;
-	h->cluster_ok = false; h->tc_ok = false;
+	h->cluster_ok = false; h->tc_ok = false; h->locksteps = 0;
+	for (uint32_t u = 0; u < n_utt; u++) h->locksteps = std::max<uint64_t>(h->locksteps, off[u + 1] - off[u]);   // one chain per utterance unless a plan below deals lists
 	// frame-level models with at most 64 labels run one warp per chain (crf_dp_frame.cu): no cluster plan, no slot lists
 	h->frame_path = c.max_dur == 1 && h->Lt <= 64 && !h->tied && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && h->opt_frame_impl != 1;
 	auto deal = [&](uint32_t ncl) {
@@ -529,6 +534,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			const uint32_t k = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
 			lists[k].push_back(u); load[k] += off[u + 1] - off[u];
 		}
+		h->locksteps = load.empty() ? 0 : *std::max_element(load.begin(), load.end());
 		cl_off.assign(1, 0); cl_list.clear();
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
 		upload_async(h, h->d_cl_off, cl_off); upload_async(h, h->d_cl_list, cl_list);
@@ -539,7 +545,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		if (plan_tc_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
 			const int avail_cl = max_active_tc_clusters(plan);
 			if (avail_cl > 0) {
-				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
+				uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
+				if (h->opt_max_clusters > 0) ncl = std::min<uint32_t>(ncl, (uint32_t)h->opt_max_clusters);   // tests: few clusters force slot refills on small batches
 				deal(ncl * TC_DP_SLOTS);         // one list per slot, balanced over all slots of all clusters (longest first)
 				h->tc_plan = plan; h->n_tc_clusters = ncl; h->tc_ok = true;
 				if (getenv("CRFGPU_VERBOSE"))
@@ -561,7 +568,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 				plan = smaller; avail_cl = max_active_clusters(plan);
 			}
 			if (avail_cl > 0) {
-				const uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + plan.UB - 1) / plan.UB);
+				uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + plan.UB - 1) / plan.UB);
+				if (h->opt_max_clusters > 0) ncl = std::min<uint32_t>(ncl, (uint32_t)h->opt_max_clusters);
 				deal(ncl);
 				h->plan = plan; h->n_clusters = ncl; h->cluster_ok = true;
 				if (getenv("CRFGPU_VERBOSE"))
@@ -1028,6 +1036,79 @@ void viterbi_staged(crfgpu_ctx* h) {
 	h->viterbi_done = true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (dlopen) so that libcrfgpu.so itself loads on a box without NCCL and a process that already carries an NCCL
+// (e.g. PyTorch's bundled one) shares it.  Only the lambda-gradient all-reduce of the training seam uses it
+// (CRF_Minibatch_GradAccumulator.cpp:277-308 sums the per-stream gradients and scalars serially on the host).
+struct NcclApi {
+	void* lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+NcclApi& nccl() {
+	static NcclApi api;
+	if (api.lib) return api;
+	const char* names[] = {getenv("CRFGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+	for (const char* n : names) { if (n && *n && (api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break; }
+	if (!api.lib) throw ApiError(CRFGPU_ERR_UNSUPPORTED, std::string("NCCL is not loadable (libnccl.so.2; set CRFGPU_NCCL_LIB): ") + (dlerror() ? dlerror() : ""));
+	auto sym = [&](const char* n) { void* f = dlsym(api.lib, n); if (!f) { api.lib = nullptr; throw ApiError(CRFGPU_ERR_UNSUPPORTED, std::string("NCCL lacks ") + n); } return f; };
+	api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+	api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+	api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+	api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+	api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+	api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+	api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+	api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+	api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+	return api;
+}
+#define NCCL_OK(expr)                                                                                   \
+	do {                                                                                                \
+		ncclResult_t r_ = (expr);                                                                       \
+		if (r_ != ncclSuccess)                                                                          \
+			throw ApiError(CRFGPU_ERR_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(r_));     \
+	} while (0)
+
+void comm_release(crfgpu_ctx* h) {
+	if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; h->comm_nranks = 0; h->comm_rank = 0; }
+}
+
+// one line of text: which kernels run for the staged batch (crfgpu_plan_info)
+std::string plan_text(crfgpu_ctx* h) {
+	const crfgpu_config& c = h->cfg;
+	char b[512];
+	std::string s;
+	snprintf(b, sizeof b, "model_type=%u labels=%u lattice_labels=%u max_dur=%u states=%u batch=%u utts/%u frames; ", c.model_type, h->lay.L, h->Lt, c.max_dur, h->lay.n_states, h->n_utt, h->N);
+	s += b;
+	if (!h->train_ok) s += "train: unsupported (" + h->train_why + "); ";
+	else if (!h->have_labels) s += "train: no labels staged; ";
+	else if (h->transftr) s += "lattice=transftr_forward/backward_kernel (one CTA per utterance, per-frame transition scores); ";
+	else if (h->nodur_tf) s += "lattice=nodur_tf_forward/backward_kernel (one CTA per utterance, per-frame transition scores); ";
+	else if (h->nodur) { snprintf(b, sizeof b, "lattice=nodur_dp_kernel (native O(P^2+D*P), %u groups x %u CTAs, 16 utterances in lock-step); ", h->n_nodur_groups, (h->lay.L + 31) / 32); s += b; }
+	else if (h->frame_path) s += h->opt_frame_impl == 2 ? "lattice=frame_dp_kernel (one warp per utterance, chains one after the other); " : "lattice=frame_dp_pair_kernel+frame_post_kernel (one warp per chain); ";
+	else if (h->tc_ok) { snprintf(b, sizeof b, "lattice=dp_tc_kernel (tcgen05, cluster of %u CTAs x %u labels, %u clusters x 16 slots%s); ", h->tc_plan.CS, h->tc_plan.CW, h->n_tc_clusters, h->tied ? ", tied (duration, phone) expansion" : ""); s += b; }
+	else if (h->cluster_ok) { snprintf(b, sizeof b, "lattice=cluster_dp_kernel (FFMA fallback: the tcgen05 plan does not hold this geometry or dp_impl=1; cluster of %u CTAs, %u clusters x %d slots); ", h->plan.CS, h->n_clusters, h->plan.UB); s += b; }
+	else { snprintf(b, sizeof b, "lattice=forward/backward_kernel (FFMA fallback, E from L2, %d slots per CTA); ", h->U); s += b; }
+	snprintf(b, sizeof b, "locksteps=%llu; ", (unsigned long long)h->locksteps); s += b;
+	s += h->opt_gemm_impl == 2 ? "gemm=tcgen05 (TMA-fed where the window stream is TMA-addressable, else register-staged); " : h->opt_gemm_impl == 1 ? "gemm=tcgen05 register-staged; " : "gemm=FFMA; ";
+	if (!h->decode_ok) s += "decode: unsupported (" + h->decode_why + ")";
+	else {
+		const uint32_t P = h->lay.n_act;
+		const bool vg = h->lay.n_states == 1 && !c.use_trans_ftrs && P >= 2 && h->lay.L == P && (h->opt_vit_impl == 2 || (h->opt_vit_impl == 0 && (size_t)P * P * sizeof(float) > 96 * 1024));
+		s += vg ? "decode=viterbi_group_kernel (table sliced over CTA groups)" : "decode=viterbi_kernel (one CTA per utterance)";
+	}
+	if (h->comm) { snprintf(b, sizeof b, "; comm=nccl rank %d of %d", h->comm_rank, h->comm_nranks); s += b; }
+	return s;
+}
+
 template <class F>
 int guarded(F&& f) {
 	try { f(); return CRFGPU_OK; }
@@ -1082,6 +1163,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	if (!h) return CRFGPU_OK;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
+	try { comm_release(h); } catch (...) {}
 	DevBuf* bufs[] = {&h->d_lambda, &h->d_sidx, &h->d_tidx, &h->d_Ws, &h->d_Wt, &h->d_bias, &h->d_E, &h->d_ET, &h->d_steps, &h->d_Wd, &h->d_crossT,
 	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
@@ -1362,8 +1444,101 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
 		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05
 		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
+		else if (n == "max_clusters") h->opt_max_clusters = (int)value;   // cap on the resident clusters of the lattice kernels (0 = all): a small cap makes every slot work through a long utterance list
 		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);
 	});
+}
+
+// ---- multi-GPU: the one exchange step of the training path --------------------------------------------------------------------
+int crfgpu_comm_unique_id(void* id128) {
+	return guarded([&] {
+		if (!id128) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		static_assert(sizeof(ncclUniqueId) == CRFGPU_COMM_ID_BYTES, "id size");
+		ncclUniqueId id;
+		NCCL_OK(nccl().GetUniqueId(&id));
+		std::memcpy(id128, &id, sizeof(id));
+	});
+}
+
+int crfgpu_comm_init_rank(crfgpu_handle h, int n_ranks, int rank, const void* id128) {
+	return guarded([&] {
+		if (!h || !id128) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw ApiError(CRFGPU_ERR_ARG, "rank out of range");
+		CUDA_OK(cudaSetDevice(h->device));
+		comm_release(h);
+		ncclUniqueId id;
+		std::memcpy(&id, id128, sizeof(id));
+		NCCL_OK(nccl().CommInitRank(&h->comm, n_ranks, id, rank));
+		h->comm_nranks = n_ranks; h->comm_rank = rank;
+	});
+}
+
+int crfgpu_comm_init_all(crfgpu_handle* handles, int n) {
+	return guarded([&] {
+		if (!handles || n < 1) throw ApiError(CRFGPU_ERR_ARG, "null argument");
+		std::vector<int> devs(n);
+		for (int i = 0; i < n; i++) {
+			if (!handles[i]) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+			devs[i] = handles[i]->device;
+			for (int j = 0; j < i; j++) if (devs[j] == devs[i]) throw ApiError(CRFGPU_ERR_ARG, "crfgpu_comm_init_all needs one handle per DEVICE (two handles share device " + std::to_string(devs[i]) + ")");
+			if (handles[i]->lay.len != handles[0]->lay.len) throw ApiError(CRFGPU_ERR_ARG, "the handles of one communicator must share the model geometry");
+			comm_release(handles[i]);
+		}
+		std::vector<ncclComm_t> comms(n);
+		NCCL_OK(nccl().CommInitAll(comms.data(), n, devs.data()));
+		for (int i = 0; i < n; i++) { handles[i]->comm = comms[i]; handles[i]->comm_nranks = n; handles[i]->comm_rank = i; }
+	});
+}
+
+int crfgpu_comm_destroy(crfgpu_handle h) {
+	return guarded([&] { if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle"); CUDA_OK(cudaSetDevice(h->device)); comm_release(h); });
+}
+
+int crfgpu_comm_size(crfgpu_handle h) { return h ? (h->comm ? h->comm_nranks : 0) : 0; }
+
+int crfgpu_group_start(void) { return guarded([&] { NCCL_OK(nccl().GroupStart()); }); }
+int crfgpu_group_end(void) { return guarded([&] { NCCL_OK(nccl().GroupEnd()); }); }
+
+int crfgpu_allreduce_grad(crfgpu_handle h) {
+	return guarded([&] {
+		if (!h || !h->fwdbwd_done) throw ApiError(CRFGPU_ERR_ARG, "crfgpu_allreduce_grad needs a staged gradient (crfgpu_fwdbwd_staged)");
+		if (!h->comm) throw ApiError(CRFGPU_ERR_ARG, "no communicator: call crfgpu_comm_init_rank / crfgpu_comm_init_all first");
+		CUDA_OK(cudaSetDevice(h->device));
+		// gradient + [sum numer, sum logZ, n_utt, 0] in ONE collective, in place, ordered on the handle's stream behind the gradient kernels
+		NCCL_OK(nccl().AllReduce(h->d_grad.p, h->d_grad.p, (size_t)h->lay.len + 4, ncclDouble, ncclSum, h->comm, h->stream));
+		h->launches += 1;
+	});
+}
+
+int crfgpu_fetch_tail(crfgpu_handle h, double* tail4) {
+	return guarded([&] {
+		if (!h || !h->fwdbwd_done || !tail4) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
+		CUDA_OK(cudaSetDevice(h->device));
+		CUDA_OK(cudaMemcpyAsync(tail4, h->d_grad.as<double>() + h->lay.len, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+	});
+}
+
+int crfgpu_shard_views(uint32_t n_utt, uint32_t n_streams, uint32_t* first, uint32_t* count) {
+	return guarded([&] {
+		if (!first || !count || !n_streams) throw ApiError(CRFGPU_ERR_ARG, "null argument / zero streams");
+		shard_views(n_utt, n_streams, first, count);
+	});
+}
+uint32_t crfgpu_minibatch_share(uint32_t minibatch, uint32_t n_streams, uint32_t stream) { return n_streams ? minibatch_share(minibatch, n_streams, stream) : 0; }
+int crfgpu_balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t* rank_of) {
+	return guarded([&] {
+		if ((n_utt && (!n_frames || !rank_of)) || !n_ranks) throw ApiError(CRFGPU_ERR_ARG, "null argument / zero ranks");
+		balance_utts(n_utt, n_frames, n_ranks, rank_of);
+	});
+}
+
+uint32_t crfgpu_plan_info(crfgpu_handle h, char* buf, uint32_t cap) {
+	if (!h || !buf || !cap) return 0;
+	std::string s = plan_text(h);
+	const uint32_t n = (uint32_t)std::min<size_t>(s.size(), cap - 1);
+	std::memcpy(buf, s.data(), n); buf[n] = 0;
+	return n;
 }
 
 int crfgpu_host_alloc(void** p, uint64_t bytes) {

@@ -22,6 +22,10 @@
  *   crfgpu_expand_windows        CRF_InFtrStream_SeqMultiWindow::read_ftrs           CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:209-328
  *   crfgpu_prefetch_batch        the bunch read-ahead of the feature streams         CRF/src/io/CRF_FeatureStream.cpp:116-136
  *   crfgpu_group_labels          CRF_InLabStream_SeqMultiWindow::nextseg/read_labs   CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-306
+ *   crfgpu_comm_* /              the serial sum of the per-stream gradients and scalars CRF/src/trainers/accumulators/CRF_Minibatch_GradAccumulator.cpp:277-298
+ *   crfgpu_allreduce_grad        (one NCCL all-reduce of lambda_len+4 doubles per minibatch; the caller keeps the "/ nStreams_active" of :306-308)
+ *   crfgpu_shard_views /         the contiguous per-stream corpus views and the per-stream minibatch shares
+ *   crfgpu_balance_utts          CRF/src/io/CRF_FeatureStreamManager.cpp:425-464, CRF_Minibatch_GradAccumulator.cpp:229-257
  *
  * Inputs are the UN-windowed streams (what the pfile / ilab hold): a ragged batch of utterances,
  * `frame_off[n_utt+1]` frame offsets, `base_ftrs[sum T][n_base_ftrs]` floats and one phone label per
@@ -172,6 +176,46 @@ int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta);
  *  "cluster_slots", "prefetch_smem".  Environment: CRFGPU_VERBOSE (plans, device timeline), CRFGPU_DP_TIMING (cycle counters of the
  *  recursion kernels on stderr). */
 int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value);
+
+/* ---- multi-GPU training: one process (or host thread) per GPU, one handle each ----------------------------------------------
+ * The data-parallel exchange of the reference is the serial host sum of nStreams gradients (CRF_Minibatch_GradAccumulator.cpp:277-298);
+ * here it is ONE ncclAllReduce(sum) over the staged device gradient and its tail [sum numer, sum logZ, n_utt, 0], issued on the
+ * handle's stream behind the gradient kernels, so crfgpu_sgd_update can consume the global sum without a host round trip.
+ * NCCL is loaded with dlopen("libnccl.so.2") on first use (CRFGPU_NCCL_LIB overrides the name); CRFGPU_ERR_UNSUPPORTED if absent.
+ *   multi-process:  rank 0 calls crfgpu_comm_unique_id, ships the 128 bytes to the other ranks by any means (file, MPI, torch
+ *                   broadcast ...), every rank calls crfgpu_comm_init_rank;
+ *   one process:    crfgpu_comm_init_all over one handle per device; collectives of several handles issued by ONE thread must be
+ *                   bracketed by crfgpu_group_start / crfgpu_group_end (ncclGroupStart/End). */
+#define CRFGPU_COMM_ID_BYTES 128
+int crfgpu_comm_unique_id(void* id128);
+int crfgpu_comm_init_rank(crfgpu_handle h, int n_ranks, int rank, const void* id128);
+int crfgpu_comm_init_all(crfgpu_handle* handles, int n);
+int crfgpu_comm_destroy(crfgpu_handle h);
+int crfgpu_comm_size(crfgpu_handle h);            /* ranks of the handle's communicator, 0 if none */
+int crfgpu_group_start(void);
+int crfgpu_group_end(void);
+/* In-place all-reduce (sum) of the staged gradient + tail over the handle's communicator; asynchronous on crfgpu_stream(h). */
+int crfgpu_allreduce_grad(crfgpu_handle h);
+/* The 4 tail doubles behind the staged gradient: [sum numer, sum logZ, n_utt, 0] (global sums after crfgpu_allreduce_grad). */
+int crfgpu_fetch_tail(crfgpu_handle h, double* tail4);
+
+/* Host-side sharding rules (no device work).
+ * crfgpu_shard_views: the reference's contiguous corpus views -- stream i of n_streams owns utterances
+ *   [i*floor(n/n_streams), (i+1)*floor(n/n_streams)), the last stream also the remainder (CRF_FeatureStreamManager.cpp:425-464);
+ *   writes first[n_streams] and count[n_streams].
+ * crfgpu_minibatch_share: utterances stream i takes per minibatch, floor(mb/n_streams) + (i < mb % n_streams)
+ *   (CRF_Minibatch_GradAccumulator.cpp:229-257); minibatch 0 = the whole view (0xffffffff is returned).
+ * crfgpu_balance_utts: assignment of the utterances of ONE global minibatch to n_ranks devices, equal counts (+-1), longest-first
+ *   onto the rank with the fewest frames so far -- membership of the minibatch is untouched and the gradient sum is order-free
+ *   (SURVEY.md 8e), only the device that computes an utterance changes; writes rank_of[n_utt]. */
+int crfgpu_shard_views(uint32_t n_utt, uint32_t n_streams, uint32_t* first, uint32_t* count);
+uint32_t crfgpu_minibatch_share(uint32_t minibatch, uint32_t n_streams, uint32_t stream);
+int crfgpu_balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t* rank_of);
+
+/* Which kernels the handle runs for the staged batch, as one line of text: lattice implementation and its plan (clusters, slots,
+ * lock-steps = frames of the longest slot list), GEMM family, Viterbi variant -- so that no geometry changes implementation
+ * without the caller being able to see it.  Returns the number of bytes written (without the NUL), 0 on error. */
+uint32_t crfgpu_plan_info(crfgpu_handle h, char* buf, uint32_t cap);
 
 /* Pinned host memory helpers for callers that want asynchronous copies. */
 int crfgpu_host_alloc(void** p, uint64_t bytes);

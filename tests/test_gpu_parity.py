@@ -648,3 +648,138 @@ def test_viterbi_multi_chunk_staging_bit_exact_vs_oracle(oracle):
         assert all(np.array_equal(x, y) for x, y in zip(got, exp))
     assert np.array_equal(cost.view(np.uint32), wcost2.view(np.uint32))
     m.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Slot refill (continuous batching) of the lattice kernels.  A cluster's 16 slots each work through their own utterance
+# list; lists hold more than one utterance only when the batch has more utterances than slots (240 on a B200 for cfg4), so
+# "max_clusters" = 1 makes EVERY slot refill many times on a small batch.  Round 1 shipped a kernel whose bookkeeping warp
+# read the old utterance's last scale from a ring entry the refilled utterance had already overwritten (wrong logZ whenever
+# (len - 1) % 32 == 0) and no test reached the refill path: these do, with those lengths over-represented.
+def _refill_lengths(rng, n_utt, t_hi):
+    special = np.array([1, 1, 2, 33, 33, 65, 97, 129, 32, 34, 64, 66], np.int64)
+    special = special[special <= t_hi]
+    lens = rng.integers(1, t_hi + 1, n_utt)
+    k = min(len(lens) // 2, 4 * len(special))
+    lens[rng.permutation(n_utt)[:k]] = rng.choice(special, k)
+    return lens
+
+
+def _labelled_batch(rng, lens, F, P, seg_hi, states=1):
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+    labs = np.zeros(int(off[-1]), np.uint32)
+    for u in range(len(lens)):
+        t, prev = int(off[u]), -1
+        while t < off[u + 1]:
+            d = int(rng.integers(1, seg_hi + 1))
+            lab = int(rng.integers(0, P))
+            while lab == prev and P > 1:
+                lab = int(rng.integers(0, P))
+            e = min(t + d, int(off[u + 1]))
+            if states == 1:
+                labs[t:e] = lab
+            else:
+                n = e - t
+                labs[t:e] = lab * states + np.minimum(np.arange(n) * states // max(n, 1), states - 1)
+            prev, t = lab, e
+    return off, ftrs, labs
+
+
+REFILL_KINDS = {
+    # kind: (config kwargs, options, n_utt, t_hi, lambda scale)
+    "stdseg_tc": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {}, 640, 200, 0.3),
+    "stdseg_tc_long": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {}, 96, 800, 0.3),
+    "stdseg_cluster_ffma": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {"dp_impl": 1}, 640, 200, 0.3),
+    "stdseg_d10": (dict(model_type="stdseg", n_labs=50, n_base_ftrs=6, max_dur=10, n_actual_labs=5, extract_seg_ftrs=1), {}, 320, 150, 0.1),
+    "nodur_tied": (dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=6, n_base_ftrs=5, max_dur=4, n_actual_labs=6, extract_seg_ftrs=1), {"nodur_impl": 2}, 400, 150, 0.3),
+    "nodur_nstate_tied": (dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=9, n_base_ftrs=5, n_states=3, max_dur=3, extract_seg_ftrs=1), {"nodur_impl": 2}, 400, 150, 0.3),
+    "frame_on_lattice": (dict(model_type="stdframe", n_labs=7, n_base_ftrs=5), {"frame_impl": 1}, 640, 200, 0.5),
+    "frame3state_on_lattice": (dict(model_type="stdframe", n_labs=12, n_base_ftrs=5, n_states=3), {"frame_impl": 1}, 400, 150, 0.5),
+}
+
+
+@pytest.mark.parametrize("kind", sorted(REFILL_KINDS))
+def test_slot_refill_matches_oracle(oracle, kind):
+    kw, opts, n_utt, t_hi, scale = REFILL_KINDS[kind]
+    rng = np.random.default_rng(sum(map(ord, kind)))
+    lens = _refill_lengths(rng, n_utt, t_hi)
+    states = kw.get("n_states", 1)
+    P = kw.get("n_actual_labs", kw["n_labs"] // states) if kw["model_type"] != "stdframe" else kw["n_labs"] // states
+    off, ftrs, labs = _labelled_batch(rng, lens, kw["n_base_ftrs"], P, 2 * kw.get("max_dur", 1) + 2, states)
+    cfg = make_config(**kw)
+    lam = rng.uniform(-scale, scale, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=8)
+    m = gpu(cfg)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    m.set_option("max_clusters", 1)          # 16 slots (tcgen05) / one cluster (FFMA) for the whole batch: every slot refills ~n_utt/16 times
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, kind)
+    # the same batch with all clusters resident (one or two utterances per slot): same per-utterance results
+    m.set_option("max_clusters", 0)
+    got2 = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got2, want, kind + " (all clusters)")
+    m.close()
+
+
+def test_slot_refill_cfg4_geometry_matches_oracle(oracle):
+    """cfg4's own geometry (610 labels: clusters of 8 CTAs, E in tensor memory) with every slot refilled: 64 short utterances
+    on ONE cluster, lengths 1, 33 and 65 among them."""
+    rng = np.random.default_rng(610)
+    lens = rng.integers(1, 40, 64)
+    lens[[3, 17, 40]] = 1
+    lens[[5, 21, 33, 50]] = 33
+    lens[[9]] = 65
+    off, ftrs, labs = _labelled_batch(rng, lens, 105, 61, 14)
+    cfg = make_config("stdseg", n_labs=610, n_base_ftrs=105, max_dur=10, n_actual_labs=61, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.01, 0.01, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=8)
+    m = gpu(cfg)
+    m.set_option("max_clusters", 1)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, "cfg4 geometry, one cluster")
+    m.close()
+
+
+def block_relative_errors(g, gw, sidx):
+    """worst |g - gw| per label block of lambda (a label's state weights + its incoming transition weights), relative to the block's
+    own largest entry -- tighter than one tolerance scaled by the global maximum"""
+    starts = np.sort(np.asarray(sidx, np.int64))
+    bounds = np.concatenate([starts, [len(gw)]])
+    out = np.zeros(len(starts))
+    for i in range(len(starts)):
+        a, b = bounds[i], bounds[i + 1]
+        out[i] = np.abs(g[a:b] - gw[a:b]).max() / max(np.abs(gw[a:b]).max(), 1e-300)
+    return out
+
+
+def test_cfg4_bench_shard_matches_reference_golden():
+    """THE bench workload (cfg4 on workloads.timit_train_batch(0, 462), 138 137 frames, the minibatch rank 0 times) against the
+    golden the unmodified reference produced for it (tests/golden/make_golden_cfg4_shard0.py): per-utterance numerator and logZ
+    to 1e-5 relative, the 891 210-entry gradient to 1e-4 (element-wise against the global maximum, per label block against the
+    block's own maximum, and in relative L2 norm), log-likelihood sum to 1e-6 relative."""
+    import json
+    import os
+    import workloads
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "cfg4_shard0_golden.npz"))
+    pin = json.load(open(os.path.join(GOLDEN, "cfg4_shard0_pin.json")))
+    off, ftrs, labs = workloads.timit_train_batch(0, 462)
+    m = crf_b200.CrfGpu(crf_b200.make_config(**workloads.cfg4_kwargs()))
+    m.set_lambda(workloads.lam_for("cfg4", m.lambda_len))
+    g, n, lz = m.fwdbwd(off, ftrs, labs)
+    gw = z["grad32"].astype(np.float64)
+    assert_train_close((g, n, lz), (gw, z["numer"], z["logZ"]), "cfg4 bench shard 0")
+    ll = float((n - lz).sum())
+    assert abs(ll - pin["loglik"]) <= 1e-6 * abs(pin["loglik"]), (ll, pin["loglik"])
+    rel_l2 = np.linalg.norm(g - gw) / np.linalg.norm(gw)
+    sidx, _ = m.index_maps()
+    blk = block_relative_errors(g, gw, sidx)
+    print(f"cfg4 shard 0: loglik {ll:.6f} (golden {pin['loglik']:.6f}), gradient rel-L2 error {rel_l2:.3e}, worst label block {blk.max():.3e}")
+    assert rel_l2 <= 1e-4
+    assert blk.max() <= 2e-4
+    assert abs(np.sum(g * g) - pin["grad_sq"]) <= 2e-4 * pin["grad_sq"]
+    m.close()
