@@ -71,7 +71,8 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_sgd_update", "crfgpu_get_lambda", "crfgpu_set_train_state", "crfgpu_prefetch_batch",
            "crfgpu_comm_unique_id", "crfgpu_comm_init_rank", "crfgpu_comm_init_all", "crfgpu_comm_destroy", "crfgpu_comm_size",
            "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
-           "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info"]
+           "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info",
+           "crfgpu_fetch_posterior_mass"]
 COMM_ID_BYTES = 128
 
 
@@ -352,9 +353,8 @@ class CrfGpu:
         if out is None:
             out = (np.zeros(self.lambda_len, np.float64), np.zeros(self._n_utt, np.float64),
                    np.zeros(self._n_utt, np.float64))
-        grad, numer, logz = out
-        self._check(self.lib.crfgpu_fetch_fwdbwd(self.h, _ptr(grad, C.c_double), _ptr(numer, C.c_double),
-                                                 _ptr(logz, C.c_double)))
+        grad, numer, logz = out          # any may be None: that array stays on the device
+        self._check(self.lib.crfgpu_fetch_fwdbwd(self.h, *[None if a is None else _ptr(a, C.c_double) for a in (grad, numer, logz)]))
         return grad, numer, logz
 
     def device_results(self):
@@ -394,6 +394,11 @@ class CrfGpu:
         buf = C.create_string_buffer(2048)
         n = self.lib.crfgpu_plan_info(self.h, buf, 2048)
         return buf.raw[:n].decode()
+
+    def fetch_posterior_mass(self):
+        out = np.zeros(self._n_frames, np.float32)
+        self._check(self.lib.crfgpu_fetch_posterior_mass(self.h, _ptr(out, C.c_float)))
+        return out
 
     def phase_ms(self, name):
         return float(self.lib.crfgpu_phase_ms(self.h, name.encode()))

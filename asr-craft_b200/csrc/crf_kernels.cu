@@ -610,6 +610,39 @@ void launch_dump_alpha_beta(const DpParams& p, uint32_t N, const uint32_t* frame
 }
 
 // =================================================================================================
+// Posterior-mass assertion of the nodes' computeExpF: mass_n = sum_c gamma_n(c) = [a reference label sits on frame n] - sum_c Dm[n][c].
+// Frame-level nodes throw unless 0.9 <= mass <= 1.1 (CRF_StdStateNode.cpp:252-275, CRF_StdNStateNode.cpp); segmental nodes -- where the
+// mass is the probability that a segment ENDS on the frame -- unless -1e-6 <= mass <= 1.000001 (CRF_StdSegStateNode.cpp:417-436); the
+// device holds posteriors in fp32 and sums up to 1024 of them, so its segmental band is [-tol, 1 + tol] with tol = 1e-3.  NaN counts as a
+// violation.  One warp per frame; violating frames are counted into *n_bad (the 4th tail scalar behind the gradient, so that it is
+// all-reduced with it), mass[] is kept for crfgpu_fetch_posterior_mass.
+// =================================================================================================
+__global__ void __launch_bounds__(256) posterior_mass_kernel(const float* Dm, uint64_t ld, uint32_t L, const uint32_t* node_lab, uint32_t N,
+                                                             float lo, float hi, float* mass, double* n_bad) {
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+	uint32_t bad = 0;
+	for (uint32_t n = w; n < N; n += nw) {
+		const float* row = Dm + (uint64_t)n * ld;
+		float sum = 0.0f;
+		for (uint32_t c = lane; c < L; c += 32) sum += row[c];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+		const float m = ((node_lab[n] != LAB_BAD) ? 1.0f : 0.0f) - sum;
+		if (lane == 0) {
+			mass[n] = m;
+			if (!(m >= lo && m <= hi)) bad++;
+		}
+	}
+	if (lane == 0 && bad) atomicAdd(n_bad, (double)bad);
+}
+void launch_posterior_mass(const float* Dm, uint64_t ld, uint32_t L, const uint32_t* node_lab, uint32_t N, float lo, float hi, float* mass,
+                           double* n_bad, cudaStream_t s) {
+	if (!N) return;
+	unsigned blocks = (N + 7) / 8; if (blocks > 148 * 8) blocks = 148 * 8;
+	posterior_mass_kernel<<<blocks, 256, 0, s>>>(Dm, ld, L, node_lab, N, lo, hi, mass, n_bad);
+}
+
+// =================================================================================================
 // Reduce-GEMM: out[map(i,j)] += scale * sum_n A[n-shift][i] * B[n][j]   (fp32 tiles, fp64 atomics)
 // replaces the per-frame scatter of CRF_StdFeatureMap::computeStateExpF / computeTransExpF
 // (CRF/src/ftrmaps/CRF_StdFeatureMap.cpp:130-223) and `grad -= ExpF` (CRF_NewGradBuilder.cpp:374-376).

@@ -322,6 +322,10 @@ struct SgdParams {
 };
 cudaError_t launch_sgd_update(const SgdParams& p, cudaStream_t s);
 
+// ---- posterior-mass assertion of computeExpF (CRF_StdStateNode.cpp:252-275, CRF_StdSegStateNode.cpp:417-436) ----
+void launch_posterior_mass(const float* Dm, uint64_t ld, uint32_t L, const uint32_t* node_lab, uint32_t N, float lo, float hi, float* mass,
+                           double* n_bad, cudaStream_t s);
+
 // ---- small helpers ------------------------------------------------------------------------------
 void launch_fill_f32(float* p, uint64_t n, float v, cudaStream_t s);
 void launch_fill_f64(double* p, uint64_t n, double v, cudaStream_t s);

@@ -109,7 +109,8 @@ struct crfgpu_ctx {
 	std::vector<uint32_t> h_off;
 	DevBuf d_off, d_base, d_frame_t, d_frame_utt, d_frame_len, d_node_lab, d_prev_lab, d_grp;
 	uint32_t n_groups = 0; int U = 1;
-	DevBuf d_X, d_S, d_A, d_G, d_m, d_kappa, d_bbase, d_Uvec, d_Dm, d_R, d_logZ, d_numer, d_grad;
+	DevBuf d_X, d_S, d_A, d_G, d_m, d_kappa, d_bbase, d_Uvec, d_Dm, d_R, d_logZ, d_numer, d_grad, d_mass;
+	int opt_mass_check = 1;
 	bool fwdbwd_done = false;
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
@@ -618,7 +619,7 @@ __global__ void tail_sums_kernel(const double* numer, const double* logZ, uint32
 	if (threadIdx.x == 0) {
 		double ta = 0.0, tb = 0.0;
 		for (uint32_t w = 0; w < blockDim.x / 32; w++) { ta += sn[w]; tb += sz[w]; }
-		tail[0] = ta; tail[1] = tb; tail[2] = (double)n_utt; tail[3] = 0.0;
+		tail[0] = ta; tail[1] = tb; tail[2] = (double)n_utt;      // tail[3] = frames that failed the posterior-mass assertion (posterior_mass_kernel)
 	}
 }
 
@@ -944,6 +945,14 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
 	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
 	if (!h->nodur_tf) { launch_empirical(e, s); check_kernel(h, 1); }      // nodur_tf: numerators come from the forward kernel, counts from Dm / Xd
+	if (h->opt_mass_check) {
+		// the nodes' posterior-mass assertion (frame-level: 0.9..1.1, segmental: the probability that a segment ends here, 0..1)
+		h->d_mass.ensure(sizeof(float) * (size_t)N + 16);
+		const bool seg = D > 1;
+		launch_posterior_mass(h->d_Dm.as<float>(), Lp, L, h->d_node_lab.as<uint32_t>(), N, seg ? -1e-3f : 0.9f, seg ? 1.001f : 1.1f,
+		                      h->d_mass.as<float>(), h->d_grad.as<double>() + m.len + 3, s);
+		check_kernel(h, 1);
+	}
 	tail_sums_kernel<<<1, 256, 0, s>>>(h->d_numer.as<double>(), h->d_logZ.as<double>(), h->n_utt, h->d_grad.as<double>() + m.len);
 	check_kernel(h, 1);
 	phase_end(h, "grad");
@@ -1109,6 +1118,22 @@ std::string plan_text(crfgpu_ctx* h) {
 	return s;
 }
 
+// what the reference throws for from inside the nodes (runtime_error "Probability sums greater / less than ...", overflow_error from
+// CRF_LogMath) surfaces here as CRFGPU_ERR_NUMERIC when the results are read
+void tail_numeric(const double* tail4) {
+	if (!std::isfinite(tail4[0]) || !std::isfinite(tail4[1]))
+		throw ApiError(CRFGPU_ERR_NUMERIC, "non-finite numerator / log partition function in this batch (empty or overflowed log-sum)");
+	if (tail4[3] != 0.0)
+		throw ApiError(CRFGPU_ERR_NUMERIC, "computeExpF: posterior probability sums outside the reference's band on " + std::to_string((long long)tail4[3]) +
+		                                   " frame(s) (CRF_StdStateNode.cpp:252-275 / CRF_StdSegStateNode.cpp:417-436); crfgpu_fetch_posterior_mass shows them");
+}
+void check_tail_numeric(crfgpu_ctx* h) {
+	double t[4];
+	CUDA_OK(cudaMemcpyAsync(t, h->d_grad.as<double>() + h->lay.len, sizeof(t), cudaMemcpyDeviceToHost, h->stream));
+	CUDA_OK(cudaStreamSynchronize(h->stream));
+	if (h->N) tail_numeric(t);
+}
+
 template <class F>
 int guarded(F&& f) {
 	try { f(); return CRFGPU_OK; }
@@ -1167,7 +1192,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	DevBuf* bufs[] = {&h->d_lambda, &h->d_sidx, &h->d_tidx, &h->d_Ws, &h->d_Wt, &h->d_bias, &h->d_E, &h->d_ET, &h->d_steps, &h->d_Wd, &h->d_crossT,
 	                  &h->d_negDiag, &h->d_negOff, &h->d_off, &h->d_base, &h->d_frame_t, &h->d_frame_utt, &h->d_frame_len, &h->d_node_lab,
 	                  &h->d_prev_lab, &h->d_grp, &h->d_X, &h->d_S, &h->d_A, &h->d_G, &h->d_m, &h->d_kappa, &h->d_bbase, &h->d_Uvec, &h->d_Dm,
-	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
+	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_mass, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
 	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
@@ -1303,6 +1328,7 @@ int crfgpu_fetch_fwdbwd(crfgpu_handle h, double* grad, double* numer, double* lo
 		// reference throws from logE/expE (CRF_LogMath.cpp:192-224)
 		if (logZ) for (uint32_t u = 0; u < h->n_utt; u++)
 			if (!std::isfinite(logZ[u])) throw ApiError(CRFGPU_ERR_NUMERIC, "non-finite log partition function for utterance " + std::to_string(u));
+		check_tail_numeric(h);
 	});
 }
 
@@ -1406,6 +1432,16 @@ double crfgpu_phase_ms(crfgpu_handle h, const char* phase) {
 	return ms;
 }
 
+int crfgpu_fetch_posterior_mass(crfgpu_handle h, float* mass) {
+	return guarded([&] {
+		if (!h || !h->fwdbwd_done || !mass) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
+		if (!h->opt_mass_check || h->transftr) throw ApiError(CRFGPU_ERR_ARG, "the posterior-mass pass did not run for this batch");
+		CUDA_OK(cudaSetDevice(h->device));
+		if (h->N) CUDA_OK(cudaMemcpyAsync(mass, h->d_mass.p, sizeof(float) * (size_t)h->N, cudaMemcpyDeviceToHost, h->stream));
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+	});
+}
+
 int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta) {
 	return guarded([&] {
 		if (!h || !h->fwdbwd_done || !alpha || !beta) throw ApiError(CRFGPU_ERR_ARG, "no forward-backward results staged");
@@ -1444,6 +1480,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
 		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05
 		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
+		else if (n == "mass_check") h->opt_mass_check = value != 0;       // 0 skips the posterior-mass assertion pass (one read of the posterior array)
 		else if (n == "max_clusters") h->opt_max_clusters = (int)value;   // cap on the resident clusters of the lattice kernels (0 = all): a small cap makes every slot work through a long utterance list
 		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);
 	});
@@ -1516,6 +1553,7 @@ int crfgpu_fetch_tail(crfgpu_handle h, double* tail4) {
 		CUDA_OK(cudaSetDevice(h->device));
 		CUDA_OK(cudaMemcpyAsync(tail4, h->d_grad.as<double>() + h->lay.len, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
 		CUDA_OK(cudaStreamSynchronize(h->stream));
+		tail_numeric(tail4);
 	});
 }
 

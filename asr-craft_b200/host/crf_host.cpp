@@ -2,9 +2,11 @@
 #include "crf_host.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <sstream>
 
 using std::runtime_error;
 using std::string;
@@ -16,22 +18,31 @@ static void check(int rc, const char* what) {
 // ---------------------------------------------------------------------------------------------- stream
 CRF_MemFeatureStream::CRF_MemFeatureStream(const std::vector<uint32_t>& frame_off, const std::vector<float>& f,
                                            const std::vector<QNUInt32>& l, QNUInt32 n_ftrs)
-    : off(frame_off), ftrs(f), labs(l), nf(n_ftrs), first(0), count((QNUInt32)frame_off.size() - 1), seg(-1), pos(0) {}
+    : nf(n_ftrs), first(0), count((QNUInt32)frame_off.size() - 1), seg(-1), pos(0) {
+	auto data = std::make_shared<Data>();
+	data->off = frame_off; data->ftrs = f; data->labs = l;
+	d = data;
+}
 
 void CRF_MemFeatureStream::view(QNUInt32 startseg, QNUInt32 nsegs) { first = startseg; count = nsegs; rewind(); }
+CRF_FeatureStream* CRF_MemFeatureStream::newView(QNUInt32 startseg, QNUInt32 nsegs) {
+	CRF_MemFeatureStream* v = new CRF_MemFeatureStream(*this);      // shares the data block
+	v->view(first + startseg, nsegs);
+	return v;
+}
 void CRF_MemFeatureStream::rewind() { seg = -1; pos = 0; }
 QN_SegID CRF_MemFeatureStream::nextseg() {
 	if (seg + 1 >= (long)count) { seg = count; return QN_SEGID_BAD; }
-	seg++; pos = off[first + seg];
+	seg++; pos = d->off[first + seg];
 	return seg;
 }
 size_t CRF_MemFeatureStream::read(size_t bs, float* fb, QNUInt32* lb) {
 	if (seg < 0 || seg >= (long)count) return 0;
-	const uint32_t end = off[first + seg + 1];
+	const uint32_t end = d->off[first + seg + 1];
 	const size_t n = std::min<size_t>(bs, end - pos);
 	if (n) {
-		std::memcpy(fb, &ftrs[(size_t)pos * nf], n * nf * sizeof(float));
-		if (lb) for (size_t i = 0; i < n; i++) lb[i] = labs.empty() ? CRF_LAB_BAD : labs[pos + i];
+		std::memcpy(fb, &d->ftrs[(size_t)pos * nf], n * nf * sizeof(float));
+		if (lb) for (size_t i = 0; i < n; i++) lb[i] = d->labs.empty() ? CRF_LAB_BAD : d->labs[pos + i];
 	}
 	pos += (uint32_t)n;
 	return n;
@@ -40,13 +51,13 @@ size_t CRF_MemFeatureStream::read(size_t bs, float* fb, QNUInt32* lb) {
 // ---------------------------------------------------------------------------------------------- model
 CRF_Model::CRF_Model(QNUInt32 num_labs)
     : nlabs(num_labs), lab_max_dur(1), nActualLabs(num_labs), model_type(STDFRAME), have_map(false), n_base_ftrs(0),
-      extract_seg_ftrs(false), handle(nullptr), lambdaOnDevice(false) {}
-CRF_Model::~CRF_Model() { if (handle) crfgpu_destroy(handle); }
+      extract_seg_ftrs(false), init_present(0), init_iter(0), lambdaOnDevice(false) {}
+CRF_Model::~CRF_Model() { for (crfgpu_handle h : handles) crfgpu_destroy(h); }
 
 void CRF_Model::setFeatureMap(const CRF_FeatureMap_config& cfg, QNUInt32 base_ftrs, bool seg_ftrs, int device) {
 	if (cfg.map_type != STDSTATE && cfg.map_type != STDTRANS) throw runtime_error("only the dense feature maps are implemented on the device (stdstate, stdtrans)");
 	fmap = cfg; have_map = true; n_base_ftrs = base_ftrs; extract_seg_ftrs = seg_ftrs;
-	crfgpu_config c;
+	crfgpu_config& c = dev_cfg;
 	std::memset(&c, 0, sizeof(c));
 	c.model_type = (uint32_t)model_type; c.n_labs = cfg.numLabs; c.n_base_ftrs = base_ftrs; c.n_states = cfg.numStates;
 	c.max_dur = lab_max_dur; c.n_actual_labs = nActualLabs; c.extract_seg_ftrs = seg_ftrs ? 1 : 0;
@@ -56,33 +67,63 @@ void CRF_Model::setFeatureMap(const CRF_FeatureMap_config& cfg, QNUInt32 base_ft
 	c.state_bias_val = cfg.stateBiasVal; c.trans_bias_val = cfg.transBiasVal;
 	if (crfgpu_window_width(&c) != cfg.numFeas)
 		throw runtime_error("CRF_FeatureMap_config::numFeas does not match the window width of the feature stream");
-	if (handle) { crfgpu_destroy(handle); handle = nullptr; }
-	check(crfgpu_create(&c, device, &handle), "crfgpu_create");
-	lambda.assign(crfgpu_lambda_len(handle), 0.0);
+	for (crfgpu_handle h : handles) crfgpu_destroy(h);
+	handles.clear();
+	crfgpu_handle h = nullptr;
+	check(crfgpu_create(&c, device, &h), "crfgpu_create");
+	handles.push_back(h);
+	lambda.assign(crfgpu_lambda_len(h), 0.0);
 	lambdaAcc.assign(lambda.size(), 0.0);
+	gradSqrAcc.assign(lambda.size(), 0.0);
 }
-crfgpu_handle CRF_Model::gpu() {
-	if (!handle) throw runtime_error("CRF_Model: setFeatureMap has not been called");
-	return handle;
+void CRF_Model::addDevices(const std::vector<int>& devices) {
+	if (handles.empty()) throw runtime_error("CRF_Model: setFeatureMap has not been called");
+	for (int dv : devices) {
+		crfgpu_handle h = nullptr;
+		check(crfgpu_create(&dev_cfg, dv, &h), "crfgpu_create");
+		handles.push_back(h);
+	}
+	if (handles.size() > 1) check(crfgpu_comm_init_all(handles.data(), (int)handles.size()), "crfgpu_comm_init_all");
+}
+crfgpu_handle CRF_Model::gpu(size_t i) {
+	if (i >= handles.size()) throw runtime_error("CRF_Model: setFeatureMap has not been called");
+	return handles[i];
+}
+void CRF_Model::pushLambdaToDevices() {
+	for (crfgpu_handle h : handles) check(crfgpu_set_lambda(h, lambda.data(), (uint32_t)lambda.size()), "crfgpu_set_lambda");
 }
 void CRF_Model::setLambda(double* lam, QNUInt32 len) {
 	if (len != lambda.size()) throw runtime_error("CRF_Model::setLambda: length mismatch");
 	std::copy(lam, lam + len, lambda.begin());
 }
 void CRF_Model::resetLambda() { std::fill(lambda.begin(), lambda.end(), 0.0); }
-bool CRF_Model::writeToFile(const char* fname) {
+bool CRF_Model::writeToFile(const char* fname, double* lam, QNUInt32 ll) {
 	std::ofstream ofile(fname);
-	if (!ofile.good()) return false;
-	for (double v : lambda) ofile << v << std::endl;      // default precision, as CRF_Model.cpp:210-212
+	if (!ofile.is_open()) throw runtime_error(string("CRF_Model::writeToFile() caught exception: cannot open the file:\n") + fname);   // CRF_Model.cpp:270-276
+	for (QNUInt32 i = 0; i < ll; i++) ofile << lam[i] << std::endl;      // default ostream precision: 6 significant digits (CRF_Model.cpp:253-255)
+	if (ofile.bad()) throw runtime_error(string("CRF_Model::writeToFile() caught exception: errors when writing the weights to the file:\n") + fname);
 	return true;
 }
-bool CRF_Model::readFromFile(const char* fname) {
+bool CRF_Model::writeToFile(const char* fname) { return writeToFile(fname, lambda.data(), (QNUInt32)lambda.size()); }
+static bool read_values(const char* fname, std::vector<double>& v) {
 	std::ifstream ifile(fname);
-	if (!ifile.good()) return false;
-	size_t i = 0; double v;
-	while (i < lambda.size() && (ifile >> v)) lambda[i++] = v;
-	return i == lambda.size();
+	if (!ifile.is_open()) return false;
+	for (size_t i = 0; i < v.size(); i++) {      // one value per line; a short file leaves the rest untouched, like the reference's getline loop
+		string s;
+		std::getline(ifile, s);
+		std::istringstream iss(s);
+		iss >> std::dec >> v[i];
+	}
+	return true;
 }
+bool CRF_Model::readFromFile(const char* fname) { return read_values(fname, lambda); }
+bool CRF_Model::readAverageFromFile(const char* fname, int present) {
+	init_present = (QNUInt32)present;
+	if (!read_values(fname, lambdaAcc)) return false;
+	if (present > 0) for (double& v : lambdaAcc) v = v * present;
+	return true;
+}
+bool CRF_Model::readGradSqrAccFromFile(const char* fname) { return read_values(fname, gradSqrAcc); }
 
 // ---------------------------------------------------------------------------------------------- training
 CRF_GradBuilder* CRF_GradBuilder::create(CRF_Model* crf_ptr, objfunctype ofunc) {
@@ -90,12 +131,27 @@ CRF_GradBuilder* CRF_GradBuilder::create(CRF_Model* crf_ptr, objfunctype ofunc) 
 	return new CRF_GradBuilder(crf_ptr);
 }
 
+// all frames of the current utterance of `s` appended to the batch; returns the frame count
+static size_t read_utterance(CRF_FeatureStream* s, std::vector<float>& ftrs, std::vector<QNUInt32>* labs) {
+	const QNUInt32 nf = s->num_ftrs();
+	const size_t chunk = 256;
+	size_t T = 0;
+	for (;;) {
+		const size_t f0 = ftrs.size(), l0 = labs ? labs->size() : 0;
+		ftrs.resize(f0 + chunk * nf);
+		if (labs) labs->resize(l0 + chunk);
+		const size_t n = s->read(chunk, ftrs.data() + f0, labs ? labs->data() + l0 : nullptr);
+		ftrs.resize(f0 + n * nf);
+		if (labs) labs->resize(l0 + n);
+		T += n;
+		if (n < chunk) break;
+	}
+	return T;
+}
+
 double CRF_GradBuilder::buildGradient(CRF_FeatureStream* ftr_strm, double* grad, double* Zx_out) {
-	const QNUInt32 nf = ftr_strm->num_ftrs();
 	ftr_buf.clear(); lab_buf.clear();
-	std::vector<float> fb(nf); QNUInt32 lb = 0;
-	while (ftr_strm->read(1, fb.data(), &lb) == 1) { ftr_buf.insert(ftr_buf.end(), fb.begin(), fb.end()); lab_buf.push_back(lb); }
-	if (lab_buf.empty()) throw runtime_error("No features read from this sentence");       // CRF_NewGradBuilder.cpp
+	if (!read_utterance(ftr_strm, ftr_buf, &lab_buf)) throw runtime_error("No features read from this sentence");       // CRF_NewGradBuilder.cpp
 	const uint32_t off[2] = {0, (uint32_t)lab_buf.size()};
 	tmp_grad.assign(crf->getLambdaLen(), 0.0);
 	double numer = 0.0;
@@ -106,130 +162,213 @@ double CRF_GradBuilder::buildGradient(CRF_FeatureStream* ftr_strm, double* grad,
 }
 
 CRF_Minibatch_GradAccumulator::CRF_Minibatch_GradAccumulator(CRF_Model* myCrf, CRF_FeatureStream* stream, QNUInt32 myNStreams)
-    : crf(myCrf), strm(stream), nStreams(myNStreams), minibatch(myNStreams), started(false) {}
-
-void CRF_Minibatch_GradAccumulator::rewindAllAndNextSegs() { strm->rewind(); started = strm->nextseg() != QN_SEGID_BAD; }
-
-double CRF_Minibatch_GradAccumulator::accumulateGradient(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter) {
-	const QNUInt32 nf = strm->num_ftrs();
-	off.assign(1, 0); ftrs.clear(); labs.clear();
-	std::vector<float> fb(nf); QNUInt32 lb = 0;
-	*isEndOfIter = false;
-	if (!started) rewindAllAndNextSegs();
-	QNUInt32 n = 0;
-	while (n < minibatch && started) {
-		size_t T = 0;
-		while (strm->read(1, fb.data(), &lb) == 1) { ftrs.insert(ftrs.end(), fb.begin(), fb.end()); labs.push_back(lb); T++; }
-		if (!T) throw runtime_error("No features read from this sentence");
-		off.push_back((uint32_t)labs.size()); n++;
-		if (strm->nextseg() == QN_SEGID_BAD) { started = false; *isEndOfIter = true; }
+    : crf(myCrf), nStreams(myNStreams), minibatch(CRF_UINT32_MAX) {
+	if (!stream) throw runtime_error("CRF_Minibatch_GradAccumulator: Cannot open the feature stream");
+	if (!nStreams) throw runtime_error("CRF_Minibatch_GradAccumulator: the number of streams must be positive");
+	if (nStreams == 1) { ftrStrms.push_back(stream); owned.push_back(false); }
+	else {
+		// the contiguous views of CRF_FeatureStreamManager.cpp:425-464
+		std::vector<uint32_t> first(nStreams), count(nStreams);
+		check(crfgpu_shard_views(stream->num_segs(), nStreams, first.data(), count.data()), "crfgpu_shard_views");
+		for (QNUInt32 s = 0; s < nStreams; s++) {
+			CRF_FeatureStream* v = stream->newView(first[s], count[s]);
+			if (!v) throw runtime_error("CRF_Minibatch_GradAccumulator: Cannot get the child feature stream (the stream does not implement newView)");
+			ftrStrms.push_back(v); owned.push_back(true);
+		}
 	}
-	if (!n) { *isEndOfIter = true; *uttCount = 0; *Zx_out = 0.0; std::fill(grad, grad + crf->getLambdaLen(), 0.0); return 0.0; }
-	numer.assign(n, 0.0); logZ.assign(n, 0.0);
-	if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
-	check(crfgpu_fwdbwd_batch(crf->gpu(), n, off.data(), ftrs.data(), labs.data(), grad, numer.data(), logZ.data()), "crfgpu_fwdbwd_batch");
-	double num = 0.0; *Zx_out = 0.0;
-	for (QNUInt32 u = 0; u < n; u++) { num += numer[u]; *Zx_out += logZ[u]; }
-	*uttCount = n;
-	// the reference divides the summed gradient by the number of ACTIVE streams, not by the utterance count (.cpp:306-308)
-	const QNUInt32 nActive = std::min(n, nStreams);
-	for (QNUInt32 i = 0; i < crf->getLambdaLen(); i++) grad[i] /= (double)nActive;
-	return num;
+	strmsSegids.assign(nStreams, QN_SEGID_BAD);
+	dev.resize(crf->nDevices());
+}
+CRF_Minibatch_GradAccumulator::~CRF_Minibatch_GradAccumulator() {
+	for (size_t s = 0; s < ftrStrms.size(); s++) if (owned[s]) delete ftrStrms[s];
 }
 
-double CRF_Minibatch_GradAccumulator::accumulateGradientOnDevice(double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive) {
-	const QNUInt32 nf = strm->num_ftrs();
-	off.assign(1, 0); ftrs.clear(); labs.clear();
-	std::vector<float> fb(nf); QNUInt32 lb = 0;
-	*isEndOfIter = false;
-	if (!started) rewindAllAndNextSegs();
-	QNUInt32 n = 0;
-	while (n < minibatch && started) {
-		size_t T = 0;
-		while (strm->read(1, fb.data(), &lb) == 1) { ftrs.insert(ftrs.end(), fb.begin(), fb.end()); labs.push_back(lb); T++; }
-		if (!T) throw runtime_error("No features read from this sentence");
-		off.push_back((uint32_t)labs.size()); n++;
-		if (strm->nextseg() == QN_SEGID_BAD) { started = false; *isEndOfIter = true; }
+void CRF_Minibatch_GradAccumulator::setMinibatch(QNUInt32 mb) {
+	if (mb < nStreams)      // also catches 0: the reference tests this first, so its "0 = totally batch" branch is unreachable (.cpp:175-187)
+		throw runtime_error("CRF_Minibatch_GradAccumulator::setMinibatch() Error: minibatch size (" + std::to_string(mb) + ") is less than the number of threads (" + std::to_string(nStreams) + ").");
+	minibatch = mb == 0 ? CRF_UINT32_MAX : mb;
+}
+
+void CRF_Minibatch_GradAccumulator::rewindAllAndNextSegs() {
+	for (QNUInt32 s = 0; s < nStreams; s++) { ftrStrms[s]->rewind(); strmsSegids[s] = ftrStrms[s]->nextseg(); }
+}
+
+QNUInt32 CRF_Minibatch_GradAccumulator::planShares(QNUInt32 mb, QNUInt32 n, const std::vector<bool>& atEnd, std::vector<QNUInt32>* share) {
+	share->assign(n, 0);
+	QNUInt32 active = 0;
+	for (QNUInt32 s = 0; s < n; s++) {
+		if (atEnd[s]) continue;
+		(*share)[s] = crfgpu_minibatch_share(mb, n, s);       // floor(mb/n) + (s < mb % n); CRF_UINT32_MAX = the rest of the view
+		active++;
 	}
-	*uttCount = n; *Zx_out = 0.0; *nActive = std::min(n, nStreams);
-	if (!n) { *isEndOfIter = true; return 0.0; }
-	numer.assign(n, 0.0); logZ.assign(n, 0.0);
-	if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
-	check(crfgpu_stage_batch(crf->gpu(), n, off.data(), ftrs.data(), labs.data()), "crfgpu_stage_batch");
-	check(crfgpu_fwdbwd_staged(crf->gpu()), "crfgpu_fwdbwd_staged");
-	check(crfgpu_fetch_fwdbwd(crf->gpu(), nullptr, numer.data(), logZ.data()), "crfgpu_fetch_fwdbwd");   // scalars only: the gradient stays in HBM
-	double num = 0.0;
-	for (QNUInt32 u = 0; u < n; u++) { num += numer[u]; *Zx_out += logZ[u]; }
-	return num;
+	return active;
+}
+
+double CRF_Minibatch_GradAccumulator::runBatch(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActiveOut) {
+	const size_t nDev = crf->nDevices();
+	if (minibatch < nStreams) throw runtime_error("CRF_Minibatch_GradAccumulator::accumulateGradient() Error: minibatch size is less than the number of threads.");
+	std::vector<bool> atEnd(nStreams);
+	for (QNUInt32 s = 0; s < nStreams; s++) atEnd[s] = strmsSegids[s] == QN_SEGID_BAD;
+	std::vector<QNUInt32> share;
+	const QNUInt32 nActive = planShares(minibatch, nStreams, atEnd, &share);
+	if (!nActive)
+		throw runtime_error("All feature streams are at the end! You don't have any utterances or you forget to rewind all the streams.\n"
+		                    "For the latter case, run rewindAllAndNextSegs().");
+	for (DevBatch& b : dev) { b.off.assign(1, 0); b.ftrs.clear(); b.labs.clear(); }
+	QNUInt32 total = 0;
+	for (QNUInt32 s = 0; s < nStreams; s++) {
+		if (atEnd[s]) continue;
+		DevBatch& b = dev[s % nDev];
+		QNUInt32 cnt = 0;
+		do {       // the thread's do-while (.cpp:46-96): at least one utterance, stop at the share or at the end of the view
+			if (!read_utterance(ftrStrms[s], b.ftrs, &b.labs)) throw runtime_error("No features read from this sentence");
+			b.off.push_back((uint32_t)b.labs.size());
+			cnt++;
+			strmsSegids[s] = ftrStrms[s]->nextseg();
+			if (cnt >= share[s]) break;
+		} while (strmsSegids[s] != QN_SEGID_BAD);
+		total += cnt;
+	}
+	static const float no_f = 0.0f; static const uint32_t no_l = 0;
+	for (size_t d = 0; d < nDev; d++) {
+		DevBatch& b = dev[d];
+		crfgpu_handle h = crf->gpu(d);
+		if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(h, crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
+		const uint32_t n = (uint32_t)b.off.size() - 1;      // may be 0 on a device whose streams are exhausted: it still joins the all-reduce
+		check(crfgpu_stage_batch(h, n, b.off.data(), n ? b.ftrs.data() : &no_f, n ? b.labs.data() : &no_l), "crfgpu_stage_batch");
+		check(crfgpu_fwdbwd_staged(h), "crfgpu_fwdbwd_staged");          // asynchronous: the devices compute side by side
+	}
+	if (nDev > 1) {
+		check(crfgpu_group_start(), "crfgpu_group_start");
+		for (size_t d = 0; d < nDev; d++) check(crfgpu_allreduce_grad(crf->gpu(d)), "crfgpu_allreduce_grad");
+		check(crfgpu_group_end(), "crfgpu_group_end");
+	}
+	double tail[4];
+	check(crfgpu_fetch_tail(crf->gpu(0), tail), "crfgpu_fetch_tail");       // [sum numer, sum logZ, n_utt, 0] over ALL devices
+	if (!std::isfinite(tail[1]) || !std::isfinite(tail[0]))
+		throw std::overflow_error("non-finite log partition function in this minibatch (the reference throws from CRF_LogMath)");
+	if ((QNUInt32)tail[2] != total) throw runtime_error("CRF_Minibatch_GradAccumulator: utterance count of the device batches differs from the host's");
+	if (grad) {
+		check(crfgpu_fetch_fwdbwd(crf->gpu(0), grad, nullptr, nullptr), "crfgpu_fetch_fwdbwd");
+		// averaging the gradient over streams, not utterances (.cpp:306-308)
+		for (QNUInt32 i = 0; i < crf->getLambdaLen(); i++) grad[i] /= nActive;
+	}
+	QNUInt32 nEnd = 0;
+	for (QNUInt32 s = 0; s < nStreams; s++) if (strmsSegids[s] == QN_SEGID_BAD) nEnd++;
+	*isEndOfIter = nEnd == nStreams;
+	*uttCount = total; *Zx_out = tail[1];
+	if (nActiveOut) *nActiveOut = nActive;
+	return tail[0];
+}
+
+double CRF_Minibatch_GradAccumulator::accumulateGradient(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter) {
+	return runBatch(grad, Zx_out, uttCount, isEndOfIter, nullptr);
+}
+double CRF_Minibatch_GradAccumulator::accumulateGradientOnDevice(double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive) {
+	return runBatch(nullptr, Zx_out, uttCount, isEndOfIter, nActive);
 }
 
 void CRF_Model::syncLambdaFromDevice() {
-	check(crfgpu_get_lambda(gpu(), lambda.data(), lambdaOnDevice ? lambdaAcc.data() : nullptr, nullptr, nullptr), "crfgpu_get_lambda");
+	check(crfgpu_get_lambda(gpu(), lambda.data(), lambdaOnDevice ? lambdaAcc.data() : nullptr, nullptr, lambdaOnDevice ? gradSqrAcc.data() : nullptr), "crfgpu_get_lambda");
 }
 
 // ---------------------------------------------------------------------------------------------- trainer
 CRF_SGTrainer::CRF_SGTrainer(CRF_Model* crf_in, CRF_FeatureStream* stream, const char* wt_fname)
     : crf_ptr(crf_in), strm(stream), weight_fname(wt_fname), lr(0.008f), lr_decay_rate(1.0f), maxIters(1), minibatch(1), nStreams(1),
-      useAdagrad(false), eta(1.0), eps(1e-6), useGvar(false), invSquareVar(0.0) {}
+      useAdagrad(false), eta(1.0), eps(1e-6), useGvar(false), gvar(0.0f), presentations(0) {}
 
-static bool write_values(const std::string& fname, const double* v, size_t n) {
-	FILE* f = std::fopen(fname.c_str(), "w");
-	if (!f) return false;
-	for (size_t i = 0; i < n; i++) std::fprintf(f, "%g\n", v[i]);      // default ostream precision: 6 significant digits (CRF_Model.cpp:210-212)
-	return std::fclose(f) == 0;
-}
+static void touch(const std::string& f) { std::ofstream o(f.c_str()); if (!o.is_open()) std::fprintf(stderr, "ERROR: cannot touch the done file %s\n", f.c_str()); }
 
 void CRF_SGTrainer::train() {
 	const QNUInt32 len = crf_ptr->getLambdaLen();
+	const size_t found = weight_fname.find_last_of('/');
+	const std::string weight_dir = found == std::string::npos ? "." : weight_fname.substr(0, found);     // CRF_Trainer.cpp:24-30
+	int iCounter = (int)crf_ptr->getInitIter();
+	for (int i = 0; i < iCounter; ++i) strm->rewind();      // keeps a random-order generator in step with the interrupted run (:88-93); a no-op for seq order
 	CRF_Minibatch_GradAccumulator gaccum(crf_ptr, strm, nStreams);
 	gaccum.setMinibatch(minibatch);
-	check(crfgpu_set_lambda(crf_ptr->gpu(), crf_ptr->getLambda(), len), "crfgpu_set_lambda");
-	check(crfgpu_set_train_state(crf_ptr->gpu(), nullptr, nullptr, nullptr), "crfgpu_set_train_state");
+	// lambda and the trainer's accumulators move to every device once; a resumed run carries lambdaAcc (average x presentations) and the
+	// AdaGrad sums in (CRF_SGTrainer.cpp:133-145), lambdaSqrAcc restarts at zero as in the reference (:131,149)
+	crf_ptr->pushLambdaToDevices();
+	for (size_t d = 0; d < crf_ptr->nDevices(); d++)
+		check(crfgpu_set_train_state(crf_ptr->gpu(d), crf_ptr->getLambdaAcc(), nullptr, crf_ptr->getGradSqrAcc()), "crfgpu_set_train_state");
 	crf_ptr->lambdaOnDevice = true;
 	iterLogLi.clear();
-	QNUInt32 accCnt = 0;
-	std::vector<double> avg(len);
-	for (int iCounter = 1; iCounter <= maxIters; iCounter++) {
-		double totLogLi = 0.0; bool eoi = false;
-		gaccum.rewindAllAndNextSegs();
-		while (!eoi) {
-			double Zx = 0.0; QNUInt32 cnt = 0, nActive = 0;
-			const double num = gaccum.accumulateGradientOnDevice(&Zx, &cnt, &eoi, &nActive);
-			if (!cnt) break;
-			totLogLi += num - Zx;
-			crfgpu_sgd opt = {(double)lr, useGvar ? 1u : 0u, invSquareVar, useAdagrad ? 1u : 0u, eta, eps};
-			check(crfgpu_sgd_update(crf_ptr->gpu(), &opt, (double)nActive), "crfgpu_sgd_update");
-			accCnt += cnt;
-		}
+	int accCnt = (int)crf_ptr->getPresentations();
+	std::vector<double> avg(len, 0.0);
+	float invSquareVar = 0.0f;
+	if (useGvar) invSquareVar = 1 / gvar;                   // float, and 1/gvar not 1/gvar^2: the reference's own arithmetic (:164-167)
+	gaccum.rewindAllAndNextSegs();
+	double totLogLi = 0.0;
+	while (iCounter < maxIters) {
+		double Zx = 0.0; QNUInt32 cnt = 0, nActive = 0; bool eoi = false;
+		const double num = gaccum.accumulateGradientOnDevice(&Zx, &cnt, &eoi, &nActive);
+		totLogLi += num - Zx;
+		crfgpu_sgd opt = {(double)lr, useGvar ? 1u : 0u, (double)invSquareVar, useAdagrad ? 1u : 0u, eta, eps};
+		for (size_t d = 0; d < crf_ptr->nDevices(); d++)      // every device applies the identical update to its copy of lambda
+			check(crfgpu_sgd_update(crf_ptr->gpu(d), &opt, (double)nActive), "crfgpu_sgd_update");
+		accCnt += (int)cnt; presentations = accCnt;
+		if (!eoi) continue;
 		iterLogLi.push_back(totLogLi);
 		crf_ptr->syncLambdaFromDevice();
 		const std::string base = weight_fname + ".i" + std::to_string(iCounter);
-		if (!crf_ptr->writeToFile((base + ".out").c_str())) throw runtime_error("ERROR! File " + base + ".out unable to be opened for writing.");
+		crf_ptr->writeToFile((base + ".out").c_str());
 		for (QNUInt32 i = 0; i < len; i++) avg[i] = crf_ptr->getLambdaAcc()[i] / (float)accCnt;      // CRF_SGTrainer.cpp:357
-		if (!write_values(base + ".avg.out", avg.data(), len)) throw runtime_error("ERROR! File " + base + ".avg.out unable to be opened for writing.");
-		{ FILE* f = std::fopen((weight_fname + ".done.train.i" + std::to_string(iCounter)).c_str(), "w"); if (f) std::fclose(f); }
+		crf_ptr->writeToFile((base + ".avg.out").c_str(), avg.data(), len);
+		if (useAdagrad) crf_ptr->writeToFile((base + ".gradSqrAcc.out").c_str(), crf_ptr->getGradSqrAcc(), len);      // :370-381
+		gaccum.rewindAllAndNextSegs();
+		touch(weight_dir + "/.done.train.i" + std::to_string(iCounter));
+		iCounter++;
+		totLogLi = 0.0;
 		if (!useAdagrad) lr *= lr_decay_rate;
 	}
-	if (!crf_ptr->writeToFile(weight_fname.c_str())) throw runtime_error("ERROR! File " + weight_fname + " unable to be opened for writing.");
-	if (accCnt) { for (QNUInt32 i = 0; i < len; i++) avg[i] = crf_ptr->getLambdaAcc()[i] / (float)accCnt; write_values(weight_fname + ".avg.out", avg.data(), len); }
+	crf_ptr->writeToFile(weight_fname.c_str());
+	crf_ptr->writeToFile((weight_fname + ".avg.out").c_str(), avg.data(), len);
+	touch(weight_dir + "/.done.train");
 	crf_ptr->lambdaOnDevice = false;
 }
 
 // ---------------------------------------------------------------------------------------------- decoding
+static void arcs_from_segments(const uint32_t* lab, const uint32_t* dur, const uint32_t* phn, uint32_t nseg, std::vector<CRF_BestPathArc>* result) {
+	result->clear();
+	for (uint32_t k = 0; k < nseg; k++)
+		result->push_back(CRF_BestPathArc{(int)lab[k] + 1, phn[k] == CRFGPU_LAB_BAD ? 0 : (int)phn[k] + 1, dur[k]});
+}
+
 int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam) {
 	if (beam > 0.0) throw runtime_error("beam pruning / LM-constrained decoding is not implemented on the device (free-phone LM, beam 0 only)");
-	const QNUInt32 nf = strm->num_ftrs();
-	std::vector<float> f, fb(nf);
-	while (strm->read(1, fb.data(), nullptr) == 1) f.insert(f.end(), fb.begin(), fb.end());
-	const uint32_t T = (uint32_t)(f.size() / nf);
+	std::vector<float> f;
+	const uint32_t T = (uint32_t)read_utterance(strm, f, nullptr);
 	if (!T) throw runtime_error("No features read from this sentence");
 	const uint32_t off[2] = {0, T};
 	std::vector<uint32_t> lab(T), dur(T), phn(T); uint32_t nseg = 0; float cost = 0.0f;
 	check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
 	check(crfgpu_viterbi_batch(crf->gpu(), 1, off, f.data(), lab.data(), dur.data(), phn.data(), &nseg, &cost), "crfgpu_viterbi_batch");
-	result->clear();
-	for (uint32_t k = 0; k < nseg; k++)
-		result->push_back(CRF_BestPathArc{(int)lab[k] + 1, phn[k] == CRFGPU_LAB_BAD ? 0 : (int)phn[k] + 1, dur[k]});
+	arcs_from_segments(lab.data(), dur.data(), phn.data(), nseg, result);
 	if (path_cost) *path_cost = cost;
 	return (int)T;
+}
+
+size_t CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecodeBatch(size_t max_utts, std::vector<std::vector<CRF_BestPathArc>>* results,
+                                                                   std::vector<float>* path_costs, std::vector<int>* n_frames, bool* stream_end) {
+	std::vector<float> f; std::vector<uint32_t> off(1, 0);
+	if (stream_end) *stream_end = false;
+	while (off.size() - 1 < max_utts) {
+		const size_t T = read_utterance(strm, f, nullptr);
+		if (!T) throw runtime_error("No features read from this sentence");
+		off.push_back(off.back() + (uint32_t)T);
+		if (strm->nextseg() == QN_SEGID_BAD) { if (stream_end) *stream_end = true; break; }
+	}
+	const uint32_t n = (uint32_t)off.size() - 1, N = off.back();
+	std::vector<uint32_t> lab(N), dur(N), phn(N), nseg(n); std::vector<float> cost(n);
+	check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");      // once per batch, not per utterance
+	check(crfgpu_viterbi_batch(crf->gpu(), n, off.data(), f.data(), lab.data(), dur.data(), phn.data(), nseg.data(), cost.data()), "crfgpu_viterbi_batch");
+	results->assign(n, std::vector<CRF_BestPathArc>());
+	if (n_frames) n_frames->assign(n, 0);
+	for (uint32_t u = 0; u < n; u++) {
+		arcs_from_segments(&lab[off[u]], &dur[off[u]], &phn[off[u]], nseg[u], &(*results)[u]);
+		if (n_frames) (*n_frames)[u] = (int)(off[u + 1] - off[u]);
+	}
+	if (path_costs) *path_costs = cost;
+	return n;
 }

@@ -18,6 +18,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -64,12 +65,17 @@ public:
 	virtual QNUInt32 num_ftrs() = 0;
 	virtual QNUInt32 num_labs() { return 1; }
 	virtual QNUInt32 num_segs() = 0;
+	// A new stream over the contiguous utterance range [startseg, startseg + nsegs) of this one -- what
+	// CRF_FeatureStreamManager::getChild(i)->trn_stream->view(...) hands every training thread (CRF_FeatureStreamManager.cpp:425-464).
+	// The caller owns the result; nullptr = this stream cannot be split (then only nStreams == 1 is possible).
+	virtual CRF_FeatureStream* newView(QNUInt32 /*startseg*/, QNUInt32 /*nsegs*/) { return nullptr; }
 };
 
 // In-memory ragged batch (what tests and the self-test feed); view(start, n) restricts it to a contiguous utterance range,
 // the rule CRF_FeatureStreamManager uses to shard a corpus over streams (CRF_FeatureStreamManager.cpp:425-464).
 class CRF_MemFeatureStream : public CRF_FeatureStream {
-	std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; QNUInt32 nf;
+	struct Data { std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; };
+	std::shared_ptr<const Data> d; QNUInt32 nf;
 	QNUInt32 first, count; long seg; uint32_t pos;
 public:
 	CRF_MemFeatureStream(const std::vector<uint32_t>& frame_off, const std::vector<float>& f, const std::vector<QNUInt32>& l, QNUInt32 n_ftrs);
@@ -79,18 +85,21 @@ public:
 	QNUInt32 num_ftrs() { return nf; }
 	QNUInt32 num_segs() { return count; }
 	void view(QNUInt32 startseg, QNUInt32 nsegs);
+	CRF_FeatureStream* newView(QNUInt32 startseg, QNUInt32 nsegs);     // shares the data, own position
 };
 
 class CRF_Model {
 protected:
 	QNUInt32 nlabs;
-	std::vector<double> lambda, lambdaAcc;
+	std::vector<double> lambda, lambdaAcc, gradSqrAcc;
 	QNUInt32 lab_max_dur, nActualLabs;
 	modeltype model_type;
 	CRF_FeatureMap_config fmap;
 	bool have_map;
 	QNUInt32 n_base_ftrs; bool extract_seg_ftrs;
-	crfgpu_handle handle;
+	std::vector<crfgpu_handle> handles;       // one device context per GPU (handles[0] created by setFeatureMap)
+	crfgpu_config dev_cfg;
+	QNUInt32 init_present, init_iter;         // resume state (CRF_Model.cpp:29,323,487-507)
 public:
 	CRF_Model(QNUInt32 num_labs);
 	virtual ~CRF_Model();
@@ -101,17 +110,32 @@ public:
 	virtual double* getLambda() { return lambda.data(); }
 	virtual QNUInt32 getLambdaLen() { return (QNUInt32)lambda.size(); }
 	virtual double* getLambdaAcc() { return lambdaAcc.data(); }
+	virtual double* getGradSqrAcc() { return gradSqrAcc.data(); }      // AdaGrad accumulator (CRF_Model.h:42)
 	virtual void setLambda(double* lam, QNUInt32 len);
 	virtual void resetLambda();
 	virtual bool writeToFile(const char* fname);                       // ASCII, one value per line, default ostream precision
+	virtual bool writeToFile(const char* fname, double* lam, QNUInt32 ll);   // any vector in the same format (CRF_Model.cpp:248-279)
 	virtual bool readFromFile(const char* fname);
+	// resume (CRF_Model.cpp:323-372, CRFTrain/src/Main.cpp:611-630): the average file times `present` refills lambdaAcc
+	virtual bool readAverageFromFile(const char* fname, int present);
+	virtual bool readGradSqrAccFromFile(const char* fname);
+	virtual QNUInt32 getPresentations() { return init_present; }
+	// resume from the state a finished train() left in this object (lambda, lambdaAcc, gradSqrAcc) instead of from the lossy ASCII files
+	void resumeFromMemory(QNUInt32 presentations, QNUInt32 start_iter) { init_present = presentations; init_iter = start_iter; }
+	virtual void setInitIter(QNUInt32 start_iter) { init_iter = start_iter; }
+	virtual QNUInt32 getInitIter() { return init_iter; }
 	virtual void setLabMaxDur(QNUInt32 d) { lab_max_dur = d; }
 	virtual QNUInt32 getLabMaxDur() { return lab_max_dur; }
 	virtual void setNActualLabs(QNUInt32 n) { nActualLabs = n; }
 	virtual QNUInt32 getNActualLabs() { return nActualLabs; }
 	virtual void setModelType(modeltype m) { model_type = m; }
 	virtual modeltype getModelType() { return model_type; }
-	crfgpu_handle gpu();                                              // the device context of this model (created by setFeatureMap)
+	crfgpu_handle gpu(size_t i = 0);                                  // the device context(s) of this model (the first is created by setFeatureMap)
+	// Data-parallel training over several GPUs of one box from ONE process: one more device context per listed device and an NCCL
+	// communicator over all of them (crfgpu_comm_init_all).  The accumulator then maps stream s to device s % nDevices().
+	void addDevices(const std::vector<int>& devices);
+	size_t nDevices() { return handles.size(); }
+	void pushLambdaToDevices();                                       // crfgpu_set_lambda on every device context
 	// lambda lives on the device between minibatches (CRF_SGTrainer below): accumulateGradient then skips the upload and the
 	// host copy is refreshed by syncLambdaFromDevice() (end of an iteration, before a checkpoint)
 	bool lambdaOnDevice; void syncLambdaFromDevice();
@@ -130,21 +154,33 @@ public:
 	static CRF_GradBuilder* create(CRF_Model* crf_ptr, objfunctype ofunc);
 };
 
-// minibatch seam: one call = `minibatch` utterances through ONE device batch
+// minibatch seam (CRF_Minibatch_GradAccumulator.cpp:112-322).  nStreams contiguous views of the corpus, one per training thread in the
+// reference; per call stream i contributes floor(minibatch / nStreams) (+1 for the first minibatch % nStreams streams) utterances -- at
+// least one, a stream stops early at the end of its view -- and the summed gradient is divided by the number of streams that were
+// NOT yet exhausted when the call started.  Here stream s is computed on device s % nDevices (all streams of one device form ONE
+// device batch), and with several devices the per-device sums are combined by ONE NCCL all-reduce (crfgpu_allreduce_grad).
+#define CRF_UINT32_MAX 0xffffffffu
 class CRF_Minibatch_GradAccumulator {
 protected:
-	CRF_Model* crf; CRF_FeatureStream* strm; QNUInt32 nStreams, minibatch; bool started;
-	std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; std::vector<double> numer, logZ;
+	CRF_Model* crf; QNUInt32 nStreams, minibatch;
+	std::vector<CRF_FeatureStream*> ftrStrms; std::vector<bool> owned; std::vector<QN_SegID> strmsSegids;
+	struct DevBatch { std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; };
+	std::vector<DevBatch> dev;
+	double runBatch(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive);
 public:
+	// `stream` is the whole training corpus; for myNStreams > 1 it is split with newView() by the reference's view rule
 	CRF_Minibatch_GradAccumulator(CRF_Model* myCrf, CRF_FeatureStream* stream, QNUInt32 myNStreams);
-	virtual ~CRF_Minibatch_GradAccumulator() {}
+	virtual ~CRF_Minibatch_GradAccumulator();
 	// grad is overwritten with sum(emp - exp) / nStreams_active, *Zx_out = sum logZ, returns sum of numerators
 	virtual double accumulateGradient(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter);
-	void setMinibatch(QNUInt32 mb) { minibatch = mb; }
-	// the same batch, but the gradient stays on the device for crfgpu_sgd_update (no download, no division): returns sum of numerators
+	// minibatch < nStreams is an error (the reference prints and exits, .cpp:175-181); the default is the whole view per call
+	void setMinibatch(QNUInt32 mb);
+	// the same batch, but the (all-reduced) gradient stays on the device(s) for crfgpu_sgd_update (no download, no division)
 	virtual double accumulateGradientOnDevice(double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive);
 	QNUInt32 getNStreams() { return nStreams; }
 	void rewindAllAndNextSegs();
+	// utterances each stream takes in the next call and the divisor, from the streams' end flags (pure host rule, exposed for tests)
+	static QNUInt32 planShares(QNUInt32 minibatch, QNUInt32 nStreams, const std::vector<bool>& atEnd, std::vector<QNUInt32>* share);
 };
 
 struct CRF_BestPathArc {
@@ -159,15 +195,26 @@ public:
 	CRF_ViterbiDecoder_StdSeg_NoSegTransFtr(CRF_FeatureStream* ftr_strm_in, CRF_Model* crf_in) : strm(ftr_strm_in), crf(crf_in) {}
 	// decodes the CURRENT utterance of the stream (free-phone LM, beam 0); returns the number of frames, like nStateDecode
 	int nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam = 0.0);
+	// The decode loop of CRFDecode (Main.cpp:1064-1112: one decoder object per utterance) as ONE device batch: decodes up to max_utts
+	// utterances from the current one on (advancing the stream with nextseg()), lambda uploaded once; returns the utterances decoded.
+	// results[u] / path_costs[u] / n_frames[u] are what nStateDecode returns for utterance u.
+	// *stream_end is set when the stream has no further utterance (nextseg() returned QN_SEGID_BAD).
+	size_t nStateDecodeBatch(size_t max_utts, std::vector<std::vector<CRF_BestPathArc>>* results, std::vector<float>* path_costs, std::vector<int>* n_frames,
+	                         bool* stream_end = nullptr);
 };
 
 // CRF_SGTrainer::train() (CRF/src/trainers/CRF_SGTrainer.cpp:99-430) over the device path: per minibatch one device batch and one
 // crfgpu_sgd_update (lambda += lr * grad / nActiveStreams, lambdaAcc += lambda, optional AdaGrad / gvar), at the end of every iteration
 // the reference's files -- <weights>.i<k>.out, <weights>.i<k>.avg.out (lambdaAcc / (float)accCnt), <weights>.done.train.i<k> -- and the
 // learning-rate decay; finally <weights> and <weights>.avg.out.  lr / lr_decay_rate are floats promoted in the update (CRF_Trainer.h:35-42).
+// Iterations are numbered from CRF_Model::getInitIter() (0 unless resuming) while < maxIters (CRF_SGTrainer.cpp:86,203); with AdaGrad
+// every iteration also writes <weights>.i<k>.gradSqrAcc.out (:370-381); the done markers are <dir of weights>/.done.train.i<k> and
+// <dir>/.done.train (CRF_Trainer.cpp:144-179).  Resume = readFromFile + readAverageFromFile(avg, presentations) [+ readGradSqrAccFromFile]
+// + setInitIter(k) on the model before train(), exactly the CRFTrain options init_weight_file / avg_weight_file / avg_weight_present /
+// grad_sqr_acc_file / init_iter (CRFTrain/src/Main.cpp:599-630).
 class CRF_SGTrainer {
 	CRF_Model* crf_ptr; CRF_FeatureStream* strm; std::string weight_fname;
-	float lr, lr_decay_rate; int maxIters; QNUInt32 minibatch, nStreams; bool useAdagrad; double eta, eps; bool useGvar; double invSquareVar;
+	float lr, lr_decay_rate; int maxIters; QNUInt32 minibatch, nStreams; bool useAdagrad; double eta, eps; bool useGvar; float gvar;
 public:
 	CRF_SGTrainer(CRF_Model* crf_in, CRF_FeatureStream* stream, const char* wt_fname);
 	void setLR(float v) { lr = v; }
@@ -175,7 +222,8 @@ public:
 	void setMaxIters(int n) { maxIters = n; }
 	void setMinibatch(QNUInt32 mb, QNUInt32 n_streams) { minibatch = mb; nStreams = n_streams; }
 	void setAdagrad(bool on, double eta_in, double eps_in) { useAdagrad = on; eta = eta_in; eps = eps_in; }
-	void setGaussVar(double gvar) { useGvar = gvar != 0.0; invSquareVar = gvar != 0.0 ? 1.0 / (gvar * gvar) : 0.0; }
+	void setGaussVar(float gvar_in) { gvar = gvar_in; if (gvar != 0.0) useGvar = true; }     // CRF_Trainer.cpp:106-111; the update uses float 1/gvar (CRF_SGTrainer.cpp:164-167)
+	int presentations;                    // utterances presented so far (accCnt): what a resumed run passes as avg_weight_present
 	std::vector<double> iterLogLi;        // per iteration: sum over the corpus of numerator - logZ (what the trainer prints as Iter-Avg LogLi * utts)
 	void train();
 };

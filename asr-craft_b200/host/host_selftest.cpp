@@ -1,6 +1,14 @@
 // host_selftest -- drives the C++ host layer (crf_host.h) the way CRFTrain / CRFDecode drive the reference classes and checks the
 // results against expected values from a case file written by tests/test_host_cpp.py (goldens of the unmodified reference).
 //   host_selftest <case.txt>      run training (+ Viterbi if the case has a path) on cuda:0, exit 0 on agreement
+//   host_selftest <case.txt> acc <nStreams> <minibatch> <nDevices>
+//                                 one epoch through CRF_Minibatch_GradAccumulator::accumulateGradient with nStreams corpus views on
+//                                 nDevices GPUs; every minibatch's [uttCount, endOfIter, numerator, Zx, grad...] is appended (doubles)
+//                                 to <case.txt>.acc.bin for the caller to compare with the reference's rule
+//   host_selftest <case.txt> resume
+//                                 AdaGrad training: 2 iterations in one run == 1 iteration, then a resumed second one
+//   host_selftest --plan <n_utt> <nStreams> <minibatch>
+//                                 no device: prints the minibatch composition of one epoch ("stream:first+count ..." per call, "/nActive")
 //   host_selftest --no-device     verify that the layer fails loudly (std::runtime_error) when there is no CUDA device
 #include <cmath>
 #include <cstdio>
@@ -39,6 +47,28 @@ int main(int argc, char** argv) {
 			std::printf("a CUDA device is present: nothing to check\n");
 			return 0;
 		}
+		if (!std::strcmp(argv[1], "--plan")) {
+			if (argc < 5) throw std::runtime_error("--plan <n_utt> <nStreams> <minibatch>");
+			const QNUInt32 n = (QNUInt32)std::atoi(argv[2]), ns = (QNUInt32)std::atoi(argv[3]), mb = (QNUInt32)std::atoi(argv[4]);
+			if (mb < ns) throw std::runtime_error("minibatch size is less than the number of threads");
+			std::vector<uint32_t> first(ns), count(ns), pos(ns, 0);
+			if (crfgpu_shard_views(n, ns, first.data(), count.data()) != CRFGPU_OK) throw std::runtime_error(crfgpu_last_error());
+			for (;;) {
+				std::vector<bool> atEnd(ns);
+				for (QNUInt32 s = 0; s < ns; s++) atEnd[s] = pos[s] >= count[s];
+				std::vector<QNUInt32> share;
+				const QNUInt32 act = CRF_Minibatch_GradAccumulator::planShares(mb, ns, atEnd, &share);
+				if (!act) break;
+				for (QNUInt32 s = 0; s < ns; s++) {
+					if (atEnd[s]) continue;
+					const QNUInt32 take = std::min<QNUInt32>(std::max<QNUInt32>(share[s], 1), count[s] - pos[s]);
+					std::printf("%u:%u+%u ", s, first[s] + pos[s], take);
+					pos[s] += take;
+				}
+				std::printf("/%u\n", act);
+			}
+			return 0;
+		}
 		std::ifstream in(argv[1]);
 		if (!in.good()) throw std::runtime_error("cannot open case file");
 		QNUInt32 mode, mt, n_labs, n_base, n_states, max_dur, n_act, segf, n_utt, N, len, n_arcs;   // mode 0: training case, 1: decoding case
@@ -60,6 +90,84 @@ int main(int argc, char** argv) {
 		auto close = [&](double a, double b, double tol, const char* what) {
 			if (std::fabs(a - b) > tol * std::fmax(1.0, std::fabs(b))) { std::printf("MISMATCH %s: %.12g vs %.12g\n", what, a, b); bad++; }
 		};
+		const std::string sub = argc > 2 ? argv[2] : "";
+		if (sub == "acc") {
+			if (argc < 6) throw std::runtime_error("acc <nStreams> <minibatch> <nDevices>");
+			const QNUInt32 ns = (QNUInt32)std::atoi(argv[3]), mb = (QNUInt32)std::atoi(argv[4]); const int nd = std::atoi(argv[5]);
+			if (nd > 1) { std::vector<int> more; for (int d = 1; d < nd; d++) more.push_back(d); my_crf.addDevices(more); }
+			CRF_MemFeatureStream strm(off, ftrs, labs, n_base);
+			CRF_Minibatch_GradAccumulator gaccum(&my_crf, &strm, ns);
+			gaccum.setMinibatch(mb);
+			gaccum.rewindAllAndNextSegs();
+			FILE* out = std::fopen((std::string(argv[1]) + ".acc.bin").c_str(), "wb");
+			if (!out) throw std::runtime_error("cannot write the .acc.bin file");
+			std::vector<double> g(len); bool eoi = false; int calls = 0;
+			while (!eoi) {
+				double Zx = 0.0; QNUInt32 cnt = 0;
+				const double num = gaccum.accumulateGradient(g.data(), &Zx, &cnt, &eoi);
+				const double head[4] = {(double)cnt, eoi ? 1.0 : 0.0, num, Zx};
+				std::fwrite(head, sizeof(double), 4, out); std::fwrite(g.data(), sizeof(double), len, out);
+				calls++;
+			}
+			std::fclose(out);
+			// one more call without a rewind must fail loudly (the reference prints "All feature streams are at the end!" and exits)
+			bool threw = false;
+			try { double Zx; QNUInt32 cnt; gaccum.accumulateGradient(g.data(), &Zx, &cnt, &eoi); } catch (const std::runtime_error&) { threw = true; }
+			if (!threw) { std::printf("MISMATCH: accumulateGradient past the end of every stream did not throw\n"); return 1; }
+			std::printf("host_selftest ok (%d minibatches)\n", calls);
+			return 0;
+		}
+		if (sub == "resume") {
+			// AdaGrad, 2 iterations: (A) one run; (B) one iteration, then a second trainer resumed from the state left in the model
+			// (CRFTrain's init_iter / avg_weight_present / grad_sqr_acc_file resume, CRFTrain/src/Main.cpp:599-630); (C) resumed from the FILES
+			const std::string wname = std::string(argv[1]) + ".resume.weights";
+			auto run = [&](CRF_Model& m, int from, int to, int present) {
+				CRF_MemFeatureStream tstrm(off, ftrs, labs, n_base);
+				m.resumeFromMemory((QNUInt32)present, (QNUInt32)from);
+				CRF_SGTrainer t(&m, &tstrm, wname.c_str());
+				t.setMaxIters(to); t.setMinibatch(3, 2); t.setAdagrad(true, 0.05, 1e-6); t.setGaussVar(50.0f);
+				t.train();
+				return t.presentations;
+			};
+			std::vector<double> lam0(lam);
+			my_crf.setLambda(lam0.data(), len);
+			std::fill(my_crf.getLambdaAcc(), my_crf.getLambdaAcc() + len, 0.0); std::fill(my_crf.getGradSqrAcc(), my_crf.getGradSqrAcc() + len, 0.0);
+			run(my_crf, 0, 2, 0);
+			std::vector<double> A(my_crf.getLambda(), my_crf.getLambda() + len), Aacc(my_crf.getLambdaAcc(), my_crf.getLambdaAcc() + len);
+			my_crf.setLambda(lam0.data(), len);
+			std::fill(my_crf.getLambdaAcc(), my_crf.getLambdaAcc() + len, 0.0); std::fill(my_crf.getGradSqrAcc(), my_crf.getGradSqrAcc() + len, 0.0);
+			const int present = run(my_crf, 0, 1, 0);
+			if (present != (int)n_utt) { std::printf("MISMATCH presentations %d\n", present); bad++; }
+			{ FILE* fp = std::fopen((wname + ".i0.gradSqrAcc.out").c_str(), "r"); if (!fp) { std::printf("MISMATCH missing .i0.gradSqrAcc.out\n"); bad++; } else std::fclose(fp); }
+			run(my_crf, 1, 2, present);
+			double lmax = 0.0;
+			for (QNUInt32 i = 0; i < len; i++) lmax = std::fmax(lmax, std::fabs(A[i]));
+			for (QNUInt32 i = 0; i < len; i++) {
+				if (std::fabs(my_crf.getLambda()[i] - A[i]) > 1e-13 * lmax) { if (bad < 5) std::printf("MISMATCH resumed lambda[%u]: %.15g vs %.15g\n", i, my_crf.getLambda()[i], A[i]); bad++; }
+				if (std::fabs(my_crf.getLambdaAcc()[i] - Aacc[i]) > 1e-12 * std::fmax(1.0, std::fabs(Aacc[i]))) { if (bad < 5) std::printf("MISMATCH resumed lambdaAcc[%u]\n", i); bad++; }
+			}
+			// (C) through the 6-digit ASCII files of iteration 0, as CRFTrain resumes: same trajectory up to the files' rounding
+			CRF_Model m2(n_labs);
+			m2.setLabMaxDur(max_dur); m2.setNActualLabs(n_act); m2.setModelType((modeltype)mt);
+			m2.setFeatureMap(fmap_config(n_labs, n_states, width, max_dur, n_act), n_base, segf != 0);
+			if (!m2.readFromFile((wname + ".i0.out").c_str()) || !m2.readAverageFromFile((wname + ".i0.avg.out").c_str(), present) ||
+			    !m2.readGradSqrAccFromFile((wname + ".i0.gradSqrAcc.out").c_str())) throw std::runtime_error("cannot read the iteration-0 files back");
+			m2.setInitIter(1);
+			{
+				CRF_MemFeatureStream tstrm(off, ftrs, labs, n_base);
+				CRF_SGTrainer t(&m2, &tstrm, wname.c_str());
+				t.setMaxIters(2); t.setMinibatch(3, 2); t.setAdagrad(true, 0.05, 1e-6); t.setGaussVar(50.0f);
+				t.train();
+			}
+			for (QNUInt32 i = 0; i < len; i++)
+				if (std::fabs(m2.getLambda()[i] - A[i]) > 1e-3 * lmax) { if (bad < 5) std::printf("MISMATCH file-resumed lambda[%u]: %.9g vs %.9g\n", i, m2.getLambda()[i], A[i]); bad++; }
+			const std::string wdir = wname.find_last_of('/') == std::string::npos ? "." : wname.substr(0, wname.find_last_of('/'));
+			for (const std::string& f : {wname + ".i0.out", wname + ".i0.avg.out", wname + ".i0.gradSqrAcc.out", wdir + "/.done.train.i0", wname + ".i1.out", wname + ".i1.avg.out",
+			                             wname + ".i1.gradSqrAcc.out", wdir + "/.done.train.i1", wname, wname + ".avg.out", wdir + "/.done.train"}) std::remove(f.c_str());
+			if (bad) { std::printf("host_selftest: %d mismatches\n", bad); return 1; }
+			std::printf("host_selftest ok\n");
+			return 0;
+		}
 		if (mode == 0) {
 			// ---- minibatch seam ----
 			CRF_MemFeatureStream strm(off, ftrs, labs, n_base);
@@ -125,8 +233,10 @@ int main(int argc, char** argv) {
 			for (QNUInt32 i = 0; i < len; i++) lmax = std::fmax(lmax, std::fabs(my_crf.getLambda()[i]));
 			for (QNUInt32 i = 0; i < len; i++)
 				if (std::fabs(dev_lam[i] - my_crf.getLambda()[i]) > 1e-9 * lmax) { if (bad < 5) std::printf("MISMATCH sgd lambda[%u]: %.12g vs %.12g\n", i, dev_lam[i], my_crf.getLambda()[i]); bad++; }
-			for (const char* suffix : {".i1.out", ".i1.avg.out", ".done.train.i1", ".i2.out", ".i2.avg.out", ".done.train.i2", "", ".avg.out"}) {
-				const std::string f = wname + suffix;
+			// iterations are numbered from init_iter = 0 (CRF_SGTrainer.cpp:86,203); done markers live in the weight file's directory
+			const std::string wdir = wname.find_last_of('/') == std::string::npos ? "." : wname.substr(0, wname.find_last_of('/'));
+			for (const std::string& f : {wname + ".i0.out", wname + ".i0.avg.out", wdir + "/.done.train.i0", wname + ".i1.out", wname + ".i1.avg.out",
+			                             wdir + "/.done.train.i1", wname, wname + ".avg.out", wdir + "/.done.train"}) {
 				FILE* fp = std::fopen(f.c_str(), "r");
 				if (!fp) { std::printf("MISMATCH missing trainer file %s\n", f.c_str()); bad++; } else { std::fclose(fp); std::remove(f.c_str()); }
 			}
@@ -142,6 +252,21 @@ int main(int argc, char** argv) {
 			if (frames != (int)(off[1] - off[0]) || path.size() != n_arcs) { std::printf("MISMATCH decode: %d frames, %zu arcs\n", frames, path.size()); bad++; }
 			else for (QNUInt32 k = 0; k < n_arcs; k++)
 				if (path[k].ilabel != arcs[3 * k] || path[k].olabel != arcs[3 * k + 1] || (int)path[k].dur != arcs[3 * k + 2]) { std::printf("MISMATCH arc %u\n", k); bad++; }
+			// ---- the whole stream as device batches of 3 utterances: utterance 0 must decode as above, the stream must end where it ends ----
+			strm.rewind(); strm.nextseg();
+			std::vector<std::vector<CRF_BestPathArc>> all; bool end = false; size_t done = 0;
+			while (!end) {
+				std::vector<std::vector<CRF_BestPathArc>> res; std::vector<float> costs; std::vector<int> nfr;
+				done += vd.nStateDecodeBatch(3, &res, &costs, &nfr, &end);
+				for (size_t u = 0; u < res.size(); u++) {
+					if (nfr[u] != (int)(off[all.size() + 1] - off[all.size()])) { std::printf("MISMATCH batch decode frame count\n"); bad++; }
+					if (all.empty() && (res[u].size() != path.size() || costs[u] != cost)) { std::printf("MISMATCH batch decode of utterance 0\n"); bad++; }
+					all.push_back(res[u]);
+				}
+			}
+			if (done != n_utt) { std::printf("MISMATCH batch decode: %zu of %u utterances\n", done, n_utt); bad++; }
+			for (size_t k = 0; k < path.size() && k < all[0].size(); k++)
+				if (all[0][k].ilabel != path[k].ilabel || all[0][k].olabel != path[k].olabel || all[0][k].dur != path[k].dur) { std::printf("MISMATCH batch arc %zu\n", k); bad++; }
 		}
 		if (bad) { std::printf("host_selftest: %d mismatches\n", bad); return 1; }
 		std::printf("host_selftest ok\n");

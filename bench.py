@@ -5,13 +5,23 @@
 
 Workload (config.workload = "cfg4"): segmental CRF `stdseg`, 61 phones x maxDur 10 (610 labels), 850 segment
 features from 105 base features, TIMIT-shaped utterances (real lengths / segment boundaries, synthetic features
-and labels).  One STEP = forward-backward + gradient over one minibatch of --utts-per-gpu (462 =
-3696/8) utterances per GPU; rank r owns the contiguous utterance range [r*462,(r+1)*462) (the reference's
-contiguous-view rule, CRF_FeatureStreamManager.cpp:425-464) and the lambda-gradient (+3 scalars) is combined
-with ONE NCCL all-reduce per step.  `value` = frames of all ranks / max-over-ranks device time with the batch
-already resident in HBM; `e2e` = the same metric through the host-buffer C-ABI call crfgpu_fwdbwd_batch with
-pinned host inputs (H2D of base features + labels, D2H of gradient/numerator/logZ inside the timed region).
-The JSON line also carries the Viterbi leg (cfg3: 183 labels, 1680 utterances) under "viterbi".
+and labels).  One STEP = forward-backward + gradient over one global minibatch of N x --utts-per-gpu
+utterances (default 462 = 3696/8 per GPU: the whole corpus is one minibatch at N = 8): the global minibatch is the union
+of the ranks' contiguous corpus views (CRF_FeatureStreamManager.cpp:425-464), its utterances are dealt to the ranks
+length-balanced (crfgpu_balance_utts: membership of the minibatch unchanged, the gradient sum is order-free; --contiguous
+keeps the reference's own placement) and the lambda-gradient (+3 scalars) is combined with ONE NCCL all-reduce per step
+issued by the product (crfgpu_allreduce_grad).  `value` = frames of all ranks / max-over-ranks device time with the batch
+already resident in HBM; `e2e` = the trainer's step through the C ABI with HOST buffers: crfgpu_stage_batch (H2D from pinned
+memory) -> crfgpu_fwdbwd_staged -> crfgpu_prefetch_batch (next minibatch) -> crfgpu_allreduce_grad -> crfgpu_sgd_update
+(lambda += lr * grad / N on the device, tables rebuilt) -> D2H of the numerators / logZ, every step inside the timed region.
+
+PARITY GATE: before anything is timed every leg is checked against pins produced by the unmodified reference / the C
+restatement (tests/golden/bench_pins.npz, cfg4_shard0_pin.json): per-utterance log-likelihood sums of the very minibatch
+being timed (rel 1e-5), Viterbi path CRCs and float costs (bit-exact).  A mismatch prints the evidence and exits 3.
+
+Other lines of the same JSON object: "minibatch_sweep" (64 and 148 utterances per GPU, SURVEY.md 8d's crf_bunch_size =
+64 x nGPU), "viterbi" (cfg3: 183 labels, all 1680/N utterances per GPU) with its own roofline and CPU baseline,
+"frame_crf" (cfg2), "stress" (cfg5, N = 1 only).
 """
 import argparse
 import json
@@ -20,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -31,6 +42,7 @@ import workloads  # noqa: E402
 
 METRIC = "seg-CRF fwd-bwd+grad frames/s (TIMIT shape)"
 UNIT = "frames/s"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def load_peaks():
@@ -85,7 +97,59 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------ pins
+class Pins:
+    """Per-utterance results of the reference / the C restatement for the bench workloads (tests/golden/make_bench_pins.py)."""
+
+    def __init__(self):
+        self.z = {}
+        p = os.path.join(GOLDEN, "bench_pins.npz")
+        if os.path.exists(p):
+            self.z = dict(np.load(p))
+        g0 = os.path.join(GOLDEN, "cfg4_shard0_golden.npz")
+        if "cfg4/logZ" not in self.z and os.path.exists(g0):      # at least bench shard 0, produced by the reference itself
+            z0 = np.load(g0)
+            numer, logz = np.zeros(3696), np.zeros(3696)
+            numer[:462], logz[:462] = z0["numer"], z0["logZ"]
+            self.z["cfg4/numer"], self.z["cfg4/logZ"] = numer, logz
+
+    def loglik(self, name, ids):
+        """(sum(numer - logZ) over the utterances, True) or (None, False) when a pin is missing for any of them"""
+        k = name + "/logZ"
+        if k not in self.z:
+            return None, False
+        ids = np.asarray(list(ids), np.int64)
+        z, n = self.z[k][ids], self.z[name + "/numer"][ids]
+        if np.any(z == 0.0):
+            return None, False
+        return float(np.sum(n - z)), True
+
+    def check_loglik(self, name, ids, numer, logz, what, rtol=1e-5):
+        got = float(np.sum(numer - logz))
+        want, have = self.loglik(name, ids)
+        rec = {"what": what, "loglik": got, "pinned": want, "ok": None}
+        if have:
+            z, n = self.z[name + "/logZ"][np.asarray(list(ids), np.int64)], self.z[name + "/numer"][np.asarray(list(ids), np.int64)]
+            worst = float(np.max(np.abs(logz - z) / np.maximum(1.0, np.abs(z))))
+            rec.update(ok=bool(abs(got - want) <= rtol * abs(want) and worst <= rtol and np.allclose(numer, n, rtol=rtol, atol=rtol)),
+                       worst_rel_logZ=worst)
+        return rec
+
+
+def path_crc(lab, dur, phn):
+    return zlib.crc32(np.ascontiguousarray(phn, np.uint32).tobytes(),
+                      zlib.crc32(np.ascontiguousarray(dur, np.uint32).tobytes(), zlib.crc32(np.ascontiguousarray(lab, np.uint32).tobytes())))
+
+
+def fail_parity(records):
+    sys.stderr.write("bench.py: PARITY GATE FAILED -- nothing is reported for a path that computes the wrong answer\n")
+    for r in records:
+        sys.stderr.write(json.dumps(r) + "\n")
+    sys.stderr.flush()
+    os._exit(3)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
 def cpu_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -102,11 +166,11 @@ def cpu_baseline_lib():
     return OracleLib(), "port"
 
 
-def cpu_sample(cores, frames_per_utt):
-    """Bounded sample of cfg4: the first `cores` utterances of the shard, truncated to frames_per_utt frames."""
-    off, ftrs, labs = workloads.timit_train_batch(0, cores)
-    keep = np.concatenate([np.arange(off[u], min(off[u] + frames_per_utt, off[u + 1])) for u in range(cores)])
-    lens = [min(frames_per_utt, int(off[u + 1] - off[u])) for u in range(cores)]
+def cpu_sample(n_utt, frames_per_utt):
+    """Bounded sample of cfg4: the first n_utt utterances of the shard, truncated to frames_per_utt frames."""
+    off, ftrs, labs = workloads.timit_train_batch(0, n_utt)
+    keep = np.concatenate([np.arange(off[u], min(off[u] + frames_per_utt, off[u + 1])) for u in range(n_utt)])
+    lens = [min(frames_per_utt, int(off[u + 1] - off[u])) for u in range(n_utt)]
     return np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32), ftrs[keep], labs[keep]
 
 
@@ -114,6 +178,40 @@ def time_cpu(lib, cfg, lam, off, ftrs, labs, threads):
     t0 = time.perf_counter()
     lib.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=threads)
     return time.perf_counter() - t0
+
+
+_VIT_DATA = None      # (off, ftrs) of cfg3, set in the parent before the workers are forked (copy-on-write)
+
+
+def _vit_worker(args):
+    first, n, fpu = args
+    from oracle.binding import make_config
+    lib, _ = cpu_baseline_lib()
+    cfg = make_config(**workloads.cfg3_kwargs())
+    lam = workloads.lam_for("cfg3", lib.lambda_len(cfg))
+    off, ftrs = _VIT_DATA
+    keep = np.concatenate([np.arange(off[u], min(off[u] + fpu, off[u + 1])) for u in range(first, first + n)])
+    lens = [min(fpu, int(off[u + 1] - off[u])) for u in range(first, first + n)]
+    so = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    f = np.ascontiguousarray(ftrs[keep])
+    t0 = time.perf_counter()
+    lib.viterbi(cfg, lam, so, f)
+    return int(so[-1]), time.perf_counter() - t0
+
+
+def cpu_viterbi_baseline(cores, data, utts_per_core=4, fpu=300):
+    """The reference decoder (nStateDecode, one decoder object per utterance, single-threaded as in CRFDecode) on `cores` forked
+    processes side by side, a bounded sample of cfg3; value = frames of all processes / the slowest process's decode time."""
+    import multiprocessing as mp
+    global _VIT_DATA
+    _VIT_DATA = data
+    _, kind = cpu_baseline_lib()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_vit_worker, [(c * utts_per_core, utts_per_core, fpu) for c in range(cores)])
+    frames, slowest = sum(r[0] for r in res), max(r[1] for r in res)
+    return {"value": frames / slowest, "unit": UNIT, "cores": cores, "kind": kind,
+            "one_thread": {"value": res[0][0] / res[0][1], "unit": UNIT, "cores": 1},
+            "sample": f"{cores} processes x {utts_per_core} utterances x first {fpu} frames ({frames} frames), slowest process {slowest:.1f} s"}
 
 
 def run_reference_arm(args):
@@ -145,12 +243,7 @@ def run_reference_arm(args):
         "gpu_launches": 0}))
 
 
-# ------------------------------------------------------------------------------------------------
-class _DevArray:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
+# ------------------------------------------------------------------------------------------------ ours
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -162,84 +255,128 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CRFGPU_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))      # plumbing: barriers, max-over-ranks, the 128-byte communicator id
     peaks = load_peaks()
-
-    upg = args.utts_per_gpu
-    off, ftrs, labs = workloads.timit_train_batch(rank * upg, upg)
-    frames_local = int(off[-1])
-    cfg = crf_b200.make_config(**workloads.cfg4_kwargs())
-    m = crf_b200.CrfGpu(cfg, device=local)
-    lam = workloads.lam_for("cfg4", m.lambda_len)
-    m.set_lambda(lam)
-    if args.slots:
-        m.set_option("slots", args.slots)
-    stream = torch.cuda.ExternalStream(m.stream, device=local)
-    n_ext = m.lambda_len + 4
+    pins = Pins()
+    gate = []          # parity records of this rank
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+
+    def gather_list(x):
+        if world == 1:
+            return [x]
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
+    utt_len, _, _ = workloads.timit_shape()
+
+    def my_utts(upg):
+        """utterance ids of this rank for a global minibatch of world x upg utterances"""
+        glob = np.arange(world * upg)                       # union of the ranks' next upg utterances = the first world*upg of the corpus views
+        if world == 1 or args.contiguous:
+            return glob[rank * upg:(rank + 1) * upg]
+        rank_of = crf_b200.balance_utts(utt_len[glob].astype(np.uint32), world)
+        return glob[rank_of == rank]
+
+    cfg = crf_b200.make_config(**workloads.cfg4_kwargs())
+    m = crf_b200.CrfGpu(cfg, device=local)
+    lam = workloads.lam_for("cfg4", m.lambda_len)
+    m.set_lambda(lam)
+    if world > 1:
+        # the product's own communicator: rank 0 creates the id, torch.distributed only ships its 128 bytes
+        idt = torch.zeros(crf_b200.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.tensor(list(crf_b200.comm_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        m.comm_init_rank(world, rank, bytes(idt.cpu().numpy().tobytes()))
+    stream = torch.cuda.ExternalStream(m.stream, device=local)
+
     def allreduce_grad():
         if world > 1:
-            gptr, _, _ = m.device_results()
-            g = torch.as_tensor(_DevArray(gptr, n_ext), device=f"cuda:{local}")
-            with torch.cuda.stream(stream):
-                dist.all_reduce(g)
+            m.allreduce_grad()
 
-    # ---- device-resident timing ("value") ----
-    m.stage(off, ftrs, labs)
-    for _ in range(args.warmup):
-        m.fwdbwd_staged(); allreduce_grad()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = m.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def timed_resident(model, steps, step_fn):
+        st = torch.cuda.ExternalStream(model.stream, device=local)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record(st)
+        for _ in range(steps):
+            step_fn()
+        with torch.cuda.stream(st):
+            e1.record(st)
+        barrier()
+        return reduce_max(e0.elapsed_time(e1))
+
     phase_names = ["score", "forward", "backward", "xi", "grad"]
-    phase_acc = {k: 0.0 for k in phase_names}
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-    for _ in range(args.steps):
-        m.fwdbwd_staged(); allreduce_grad()
-    with torch.cuda.stream(stream):
-        e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = m.launch_count - l0
-    for k in phase_names:   # per-phase device time of the last step (CUDA events on the launching stream)
-        phase_acc[k] = m.phase_ms(k)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-    fr = torch.tensor([frames_local], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(fr)
-    ms_max, frames_total = float(t.item()), float(fr.item())
-    value = frames_total * args.steps / (ms_max / 1000.0)
 
-    # ---- end-to-end through the host-buffer C ABI ("e2e") ----
+    def cfg4_leg(upg, steps, warmup, headline):
+        ids = my_utts(upg)
+        off, ftrs, labs = workloads.timit_train_utts(ids)
+        frames_local = int(off[-1])
+        # ---- parity gate: the minibatch about to be timed, through the host-buffer call ----
+        _, n, z = m.fwdbwd(off, ftrs, labs)
+        gate.append(pins.check_loglik("cfg4", ids, n, z, f"cfg4 fwd-bwd, {upg} utterances/GPU, rank {rank}"))
+        if gate[-1]["ok"] is False:
+            fail_parity(gate)
+        m.stage(off, ftrs, labs)
+        for _ in range(warmup):
+            m.fwdbwd_staged(); allreduce_grad()
+        sampler = ClockSampler(local)
+        if rank == 0 and headline:
+            sampler.start()
+        l0 = m.launch_count
+        ms = timed_resident(m, steps, lambda: (m.fwdbwd_staged(), allreduce_grad()))
+        launches = m.launch_count - l0
+        clocks = sampler.stop() if rank == 0 and headline else None
+        phases = {k: m.phase_ms(k) for k in phase_names}
+        frames_total = reduce_sum(frames_local)
+        plans = gather_list(m.plan_info())
+        fr = gather_list(frames_local)
+        res = {"utts_per_gpu": upg, "value": frames_total * steps / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+               "frames_per_gpu": fr, "locksteps_per_gpu": [int(p.split("locksteps=")[1].split(";")[0]) for p in plans],
+               "phases_ms": phases, "loglik": gate[-1]["loglik"], "loglik_pinned": gate[-1]["pinned"], "parity_ok": gate[-1]["ok"]}
+        return res, (ids, off, ftrs, labs, frames_local, frames_total, launches, clocks, plans)
+
+    upg = args.utts_per_gpu
+    head, (ids, off, ftrs, labs, frames_local, frames_total, launches, clocks, plans) = cfg4_leg(upg, args.steps, args.warmup, True)
+    ms_per_step, value, phase_acc = head["ms_per_step"], head["value"], head["phases_ms"]
+
+    # ---- end-to-end: the trainer's step through the C ABI with host buffers ----
     pin_f = crf_b200.PinnedBuffer(ftrs.shape, np.float32); pin_f.array[...] = ftrs
     pin_l = crf_b200.PinnedBuffer(labs.shape, np.uint32); pin_l.array[...] = labs
-    pin_g = crf_b200.PinnedBuffer((m.lambda_len,), np.float64)
-    pin_n = crf_b200.PinnedBuffer((upg,), np.float64); pin_z = crf_b200.PinnedBuffer((upg,), np.float64)
-    out = (pin_g.array, pin_n.array, pin_z.array)
+    pin_n = crf_b200.PinnedBuffer((len(ids),), np.float64); pin_z = crf_b200.PinnedBuffer((len(ids),), np.float64)
     e2e_steps = max(2, min(args.steps, 5))
+    # a real update every step (update kernel + rebuild of every lambda-derived table); the rate is tiny so that the timed workload stays
+    # the pinned one: one step moves the log-likelihood by lr * |grad|^2 / N = 1e-13 * 2.7e10 = 0.003 of -571 721
+    e2e_lr = 1e-13
+
     def e2e_step():
-        # the host-buffer calls of one training step: H2D (crfgpu_stage_batch), kernels (crfgpu_fwdbwd_staged), the read-ahead of the
-        # NEXT minibatch's features (crfgpu_prefetch_batch: its H2D + window expansion run on side streams under this step's kernels
-        # and are taken over by the next crfgpu_stage_batch), ONE NCCL all-reduce of the gradient (+ scalars) on the handle's stream
-        # when N > 1, D2H (crfgpu_fetch_fwdbwd).  Every step's H2D and D2H are inside the timed region.
-        m.stage(off, pin_f.array, pin_l.array)
+        m.stage(off, pin_f.array, pin_l.array)                 # H2D of this minibatch (taken over from the read-ahead after the first step)
         m.fwdbwd_staged()
         if not args.no_prefetch:
-            m.prefetch(off, pin_f.array)
-        allreduce_grad()
-        m.fetch_fwdbwd(out=out)
+            m.prefetch(off, pin_f.array)                       # read-ahead of the NEXT minibatch: H2D + window expansion on side streams
+        allreduce_grad()                                       # ONE ncclAllReduce on the handle's stream (N > 1)
+        m.fetch_fwdbwd(out=(None, pin_n.array, pin_z.array))   # D2H of the step's result: per-utterance numerators and logZ
+        m.sgd_update(float(world), lr=e2e_lr)                  # lambda += lr * grad / nStreams_active on the device, every table rebuilt
 
     for _ in range(2):
         e2e_step()
@@ -248,94 +385,101 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = frames_total * e2e_steps / float(te.item())
+    e2e_dt = reduce_max(time.perf_counter() - t0)
+    e2e_value = frames_total * e2e_steps / e2e_dt
+    gate.append(pins.check_loglik("cfg4", ids, pin_n.array, pin_z.array, f"cfg4 e2e last step, rank {rank}", rtol=1e-5))   # lambda moved by 7 updates of lr 1e-13
+    if gate[-1]["ok"] is False:
+        fail_parity(gate)
     h2d = int(ftrs.nbytes + labs.nbytes + off.nbytes + 3 * 4 * frames_local + 2 * 4 * frames_local)  # + derived per-frame index/label tables
-    d2h = int(8 * (m.lambda_len + 2 * upg))
-    ll = float(np.sum(pin_n.array - pin_z.array))
+    d2h = int(8 * 2 * len(ids))
+    m.set_lambda(lam)
 
-    # ---- Viterbi leg (cfg3), N=1 shard per rank, no collective ----
+    # ---- minibatch sweep (crf_bunch_size = 64 x nGPU) ----
+    sweep = []
+    for u in [int(x) for x in args.sweep.split(",") if x]:
+        if u == upg:
+            continue
+        r, _ = cfg4_leg(u, max(3, args.steps // 2), 3, False)
+        sweep.append(r)
+
+    # ---- Viterbi leg (cfg3), all 1680/N utterances per rank, no collective ----
     vit = None
     if not args.no_viterbi:
         vcfg = crf_b200.make_config(**workloads.cfg3_kwargs())
         voff, vftrs = workloads.cfg3_batch(1680)
-        per = 1680 // 8
-        lo, hi = rank * per, (rank + 1) * per
+        per = 1680 // world
+        lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else 1680
         sub_off = (voff[lo:hi + 1] - voff[lo]).astype(np.uint32)
         sub_f = vftrs[int(voff[lo]):int(voff[hi])]
         vm = crf_b200.CrfGpu(vcfg, device=local)
         vm.set_lambda(workloads.lam_for("cfg3", vm.lambda_len))
-        vstream = torch.cuda.ExternalStream(vm.stream, device=local)
+        segs, cost = vm.viterbi(sub_off, sub_f)
+        rec = {"what": f"cfg3 Viterbi, utterances {lo}..{hi - 1}, rank {rank}", "ok": None}
+        if "cfg3/crc" in pins.z:
+            crc = np.array([path_crc(*s) for s in segs], np.uint32)
+            rec["paths_equal"] = int(np.sum(crc == pins.z["cfg3/crc"][lo:hi])); rec["n"] = hi - lo
+            rec["costs_bit_equal"] = bool(np.array_equal(cost.view(np.uint32), pins.z["cfg3/cost"][lo:hi].view(np.uint32)))
+            rec["ok"] = bool(rec["paths_equal"] == hi - lo and rec["costs_bit_equal"])
+            rec["cost_sum"] = float(cost.astype(np.float64).sum())
+        gate.append(rec)
+        if rec["ok"] is False:
+            fail_parity(gate)
         vm.stage(sub_off, sub_f)
         for _ in range(3):
             vm.viterbi_staged()
-        barrier()
-        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(vstream):
-            v0.record(vstream)
-        for _ in range(args.steps):
-            vm.viterbi_staged()
-        with torch.cuda.stream(vstream):
-            v1.record(vstream)
-        barrier()
-        vms = v0.elapsed_time(v1)
-        vt = torch.tensor([vms], dtype=torch.float64, device=f"cuda:{local}")
-        vfr = torch.tensor([float(sub_off[-1])], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(vt, op=dist.ReduceOp.MAX); dist.all_reduce(vfr)
+        vms = timed_resident(vm, args.steps, vm.viterbi_staged)
+        vfr = reduce_sum(float(sub_off[-1]))
         vpin = crf_b200.PinnedBuffer(sub_f.shape, np.float32); vpin.array[...] = sub_f      # e2e: H2D from pinned host memory
         vm.viterbi(sub_off, vpin.array, raw=True)
         barrier()
         t0 = time.perf_counter()
         for _ in range(3):
             vm.viterbi(sub_off, vpin.array, raw=True)
-        vdt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(vdt, op=dist.ReduceOp.MAX)
-        ve2e = 3 * float(vfr.item()) / float(vdt.item())
+        ve2e = 3 * vfr / reduce_max(time.perf_counter() - t0)
         vpin.free()
-        vit = {"metric": "Viterbi frames/s (cfg3: 183 labels = 61 phones x 3 states, 210 utterances per GPU)",
-               "value": float(vfr.item()) * args.steps / (float(vt.item()) / 1000.0), "unit": UNIT, "e2e": ve2e,
-               "score_ms": vm.phase_ms("viterbi_score"), "recursion_ms": vm.phase_ms("viterbi"),
-               "frames_per_gpu": int(sub_off[-1])}
+        sc_ms, rc_ms = vm.phase_ms("viterbi_score"), vm.phase_ms("viterbi")
+        Lv, Fv, nfr = 183, 105, float(sub_off[-1])
+        # algorithmic bytes per frame: scoring reads the 4F-byte frame and writes 4L scores; the recursion reads 4L scores,
+        # writes a 2-byte back pointer + 1-byte duration per label and reads T of them back in the traceback
+        vb = {"vit_scores_kernel": (4.0 * Fv + 4.0 * Lv, sc_ms), "viterbi_kernel": (4.0 * Lv + 3.0 * Lv + 3.0, rc_ms)}
+        dom = max(vb, key=lambda k: vb[k][1])
+        vroof = {"kernel": dom, "bound": "hbm", "achieved": vb[dom][0] * nfr / (vb[dom][1] / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "traffic": None, "launch_ms": vb[dom][1],
+                 "note": "latency chain: one CTA per utterance walks its frames in order (778 dependent frames in the longest utterance); "
+                         "the fp64 scoring kernel is bound by the DMUL+DADD rate the reference's summation order imposes"}
+        vroof["frac"] = vroof["achieved"] / peaks["hbm_gbs"]
+        vit = {"metric": "Viterbi frames/s (cfg3: 183 labels = 61 phones x 3 states, all 1680 utterances / N per GPU)",
+               "value": vfr * args.steps / (vms / 1000.0), "unit": UNIT, "e2e": ve2e, "score_ms": sc_ms, "recursion_ms": rc_ms,
+               "frames_per_gpu": int(sub_off[-1]), "utts_per_gpu": hi - lo, "parity": rec, "roofline": vroof}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            vit["cpu_baseline"] = cpu_viterbi_baseline(cpu_threads(), (voff, vftrs))
         vm.close()
 
-    # ---- frame-level leg (cfg2: 61 labels, 105 features, the same TIMIT-shaped shard), no collective ----
+    # ---- frame-level leg (cfg2: 61 labels, 105 features, the same TIMIT-shaped minibatch), no collective ----
     frame = None
     if not args.no_frame:
         fm = crf_b200.CrfGpu(crf_b200.make_config(**workloads.cfg2_kwargs()), device=local)
         fm.set_lambda(workloads.lam_for("cfg2", fm.lambda_len))
-        fstream = torch.cuda.ExternalStream(fm.stream, device=local)
+        _, n2, z2 = fm.fwdbwd(off, ftrs, labs)
+        gate.append(pins.check_loglik("cfg2", ids, n2, z2, f"cfg2 frame-level fwd-bwd, rank {rank}"))
+        if gate[-1]["ok"] is False:
+            fail_parity(gate)
         fm.stage(off, ftrs, labs)
         for _ in range(3):
             fm.fwdbwd_staged()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(fstream):
-            f0.record(fstream)
-        for _ in range(args.steps):
-            fm.fwdbwd_staged()
-        with torch.cuda.stream(fstream):
-            f1.record(fstream)
-        barrier()
-        ft = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
-        fpin_g = crf_b200.PinnedBuffer((fm.lambda_len,), np.float64)
-        fout = (fpin_g.array, pin_n.array, pin_z.array)
+        fms = timed_resident(fm, args.steps, fm.fwdbwd_staged)
+        pin_g = crf_b200.PinnedBuffer((fm.lambda_len,), np.float64)
+        fout = (pin_g.array, pin_n.array, pin_z.array)
         for _ in range(2):
             fm.fwdbwd(off, pin_f.array, pin_l.array, out=fout)
         t0 = time.perf_counter()
         for _ in range(3):
             fm.fwdbwd(off, pin_f.array, pin_l.array, out=fout)
-        fe2e = 3 * frames_total / (time.perf_counter() - t0)
-        frame = {"metric": "frame-level CRF fwd-bwd+grad frames/s (cfg2: 61 labels, 105 features, 462 utterances per GPU)",
-                 "value": frames_total * args.steps / (float(ft.item()) / 1e3), "unit": UNIT, "e2e": fe2e,
-                 "phases_ms": {k: fm.phase_ms(k) for k in phase_names}, "lambda_len": fm.lambda_len}
-        fpin_g.free()
+        fe2e = 3 * frames_total / reduce_max(time.perf_counter() - t0)
+        frame = {"metric": f"frame-level CRF fwd-bwd+grad frames/s (cfg2: 61 labels, 105 features, {upg} utterances per GPU)",
+                 "value": frames_total * args.steps / (fms / 1e3), "unit": UNIT, "e2e": fe2e,
+                 "phases_ms": {k: fm.phase_ms(k) for k in phase_names}, "lambda_len": fm.lambda_len, "parity": gate[-1]}
+        pin_g.free()
         fm.close()
 
     # ---- stress leg (cfg5: 1024 phones, maxDur 30, 64 utterances x 2000 frames), one GPU, reported beside the headline ----
@@ -358,9 +502,10 @@ def run_ours(args):
         stress = {"workload": "cfg5 (stdseg_no_dur_no_segtransftr, 1024 phones, maxDur 30, 542 segment features, 64 utterances x 2000 frames)",
                   "train_frames_per_s": sN / (sum(best.values()) / 1e3), "train_phases_ms": best,
                   "viterbi_frames_per_s": sN / ((vs_ + vr_) / 1e3), "viterbi_phases_ms": {"score": vs_, "recursion": vr_},
-                  "lambda_len": sm.lambda_len}
+                  "lambda_len": sm.lambda_len, "plan": sm.plan_info()}
         sm.close()
 
+    all_gate = [r for g in gather_list(gate) for r in g]
     if rank == 0:
         # per-frame ALGORITHMIC work of cfg4 (SURVEY.md 8d / DESIGN.md section 4).  Every phase sits below the tensor ridge
         # (1388 TFLOP/s / 6.55 TB/s = 212 flop/B): score and state-gradient GEMMs move 34 kB of window features per 1.04 Mflop
@@ -372,13 +517,12 @@ def run_ours(args):
         bytes_ = {"score": 4.0 * D * Fs + 4 * L, "forward": 8.0 * L, "backward": 12.0 * L, "xi": 8.0 * L, "grad": 4.0 * L + 4.0 * D * Fs}
         kernel_of = {"score": "score_gemm_tmem_kernel", "forward": "dp_tc_kernel<0>", "backward": "dp_tc_kernel<1>",
                      "xi": "frame_gemm_tmem_kernel<1>", "grad": "frame_gemm_tmem_kernel<0>"}
-        launches_of = {"score": 1, "forward": 1, "backward": 1, "xi": 1, "grad": 1}
         dom = max(phase_names, key=lambda k: phase_acc[k])
         rooflines = {}
         for k in phase_names:
             sec = max(phase_acc[k], 1e-6) / 1000.0
             rooflines[k] = {"ms": phase_acc[k], "tflops": flops[k] * frames_local / sec / 1e12,
-                            "gbs": bytes_[k] * frames_local / sec / 1e9, "kernel": kernel_of[k], "launches": launches_of[k]}
+                            "gbs": bytes_[k] * frames_local / sec / 1e9, "kernel": kernel_of[k], "launches": 1}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):      # DRAM read+write bytes of ONE launch from the committed ncu --set full capture
@@ -386,10 +530,11 @@ def run_ours(args):
         ach = rooflines[dom]["gbs"]
         roof = {"kernel": kernel_of[dom], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
-                "algorithmic_bytes_per_launch": bytes_[dom] * frames_local / launches_of[dom],
-                "launch_ms": phase_acc[dom] / launches_of[dom], "launches_per_step": launches_of[dom],
-                "peak_source": peaks["source"], "tensor_tflops": rooflines[dom]["tflops"]}
-        # CPU baseline beside it (bounded sample, N=1 only)
+                "algorithmic_bytes_per_launch": bytes_[dom] * frames_local,
+                "launch_ms": phase_acc[dom], "launches_per_step": 1,
+                "peak_source": peaks["source"], "tensor_tflops": rooflines[dom]["tflops"],
+                "note": "a dependent chain of lock-steps (locksteps_per_gpu), not a stream: latency-bound, see DESIGN.md section 4"}
+        # CPU baseline beside it (bounded sample, N=1 only): the reference's own pthread fan-out on all host threads, and one thread
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle.binding import make_config as omake
@@ -399,22 +544,35 @@ def run_ours(args):
             fpu = 96
             coff, cftrs, clabs = cpu_sample(cores, fpu)
             sec = time_cpu(lib, ocfg, lam, coff, cftrs, clabs, cores)
+            o1, f1, l1 = cpu_sample(1, 160)
+            sec1 = time_cpu(lib, ocfg, lam, o1, f1, l1, 1)
             cpu = {"value": int(coff[-1]) / sec, "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": f"{cores} utterances x first {fpu} frames ({int(coff[-1])} frames), {cores} pthreads, {sec:.1f} s"}
+                   "sample": f"{cores} utterances x first {fpu} frames ({int(coff[-1])} frames), {cores} pthreads, {sec:.1f} s",
+                   "one_thread": {"value": int(o1[-1]) / sec1, "unit": UNIT, "cores": 1, "sample": f"1 utterance x first {int(o1[-1])} frames, {sec1:.1f} s"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3->f32 (every GEMM-shaped product is three bf16 tcgen05 MMAs on hi/lo splits with fp32 accumulation, ~16 mantissa bits; "
+                     "log scales, logZ and the gradient sums in f64)",
+            "data": "synthetic",
             "config": {"workload": "cfg4", "model_type": "stdseg", "phones": 61, "max_dur": 10, "labels": 610, "base_ftrs": 105,
-                       "seg_ftrs": 850, "lambda_len": m.lambda_len, "utts_per_gpu": upg, "frames_per_gpu": frames_local,
-                       "sharding": "contiguous utterance ranges, one NCCL all-reduce of lambda_len+4 doubles per step",
+                       "seg_ftrs": 850, "lambda_len": m.lambda_len, "utts_per_gpu": upg, "global_minibatch": upg * world,
+                       "frames_per_gpu": head["frames_per_gpu"], "locksteps_per_gpu": head["locksteps_per_gpu"],
+                       "sharding": ("contiguous corpus views" if (args.contiguous or world == 1) else
+                                    "global minibatch = union of the ranks' contiguous views, dealt to ranks length-balanced (crfgpu_balance_utts)")
+                                   + "; one ncclAllReduce of lambda_len+4 doubles per step (crfgpu_allreduce_grad)",
                        "l2": "inputs_exceed_l2 (4.8 GB of window features + 5 x 0.36 GB lattice arrays per step vs 126 MB L2)",
-                       "slots_per_cta_option": int(args.slots or 0)},
-            "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                      "steps": e2e_steps, "loglik_check": ll},
-            "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "viterbi": vit, "frame_crf": frame, "stress": stress}
+                       "plan": plans[0], "nccl_ranks": m.comm_size if world > 1 else 1},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "step": "stage(H2D) + fwdbwd + prefetch(next) + allreduce + D2H(numer, logZ) + sgd_update(lr 1e-13) through the C ABI",
+                    "loglik_check": float(np.sum(pin_n.array - pin_z.array))},
+            "parity_gate": {"ok": all(r["ok"] is not False for r in all_gate), "unpinned": [r["what"] for r in all_gate if r["ok"] is None],
+                            "cfg4_loglik": head["loglik"], "cfg4_loglik_pinned": head["loglik_pinned"], "records": all_gate if world == 1 else all_gate[:8]},
+            "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "minibatch_sweep": sweep,
+            "viterbi": vit, "frame_crf": frame, "stress": stress}
         print(json.dumps(line))
-    for pb in (pin_f, pin_l, pin_g, pin_n, pin_z):
+    for pb in (pin_f, pin_l, pin_n, pin_z):
         pb.free()
     m.close()
     if world > 1:
@@ -429,7 +587,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts-per-gpu", type=int, default=462)
-    ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--sweep", default="64,148", help="further minibatch sizes (utterances per GPU) reported under minibatch_sweep")
+    ap.add_argument("--contiguous", action="store_true", help="keep the reference's contiguous placement instead of the length-balanced one")
     ap.add_argument("--no-viterbi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")

@@ -165,6 +165,13 @@ double crfgpu_phase_ms(crfgpu_handle h, const char* phase);
  * alpha/beta [sum T][n_labs] as doubles (entries the reference never computes are -DBL_MAX). */
 int crfgpu_fetch_alpha_beta(crfgpu_handle h, double* alpha, double* beta);
 
+/* The posterior-mass assertion of the nodes' computeExpF (CRF_StdStateNode.cpp:252-275, CRF_StdSegStateNode.cpp:417-436) runs on the device
+ * after every forward-backward: mass[n] = sum over labels of the posterior of frame n (frame-level models: 1; segmental models: the
+ * probability that a segment ends on frame n).  Frames outside the reference's band (frame-level 0.9..1.1; segmental 0..1, +-1e-3 for the
+ * device's fp32 posteriors) or NaN make crfgpu_fetch_fwdbwd / crfgpu_fetch_tail / crfgpu_fwdbwd_batch return CRFGPU_ERR_NUMERIC, the way
+ * the reference throws.  This call returns the masses themselves [sum T floats] (test / diagnosis access). */
+int crfgpu_fetch_posterior_mass(crfgpu_handle h, float* mass);
+
 /* Tuning / debug switches (results do not depend on them beyond the stated tolerance; decoding stays bit-exact):
  *  "slots" (utterances per CTA in the one-CTA lattice kernels: 0 auto,1,2,4,8), "k_slab" / "k_slab_tc" / "k_slab_tma" / "k_slab_xi"
  *  (frames per CTA in the reduce-GEMMs), "keep_lattice" (1: keep what crfgpu_fetch_alpha_beta needs),

@@ -783,3 +783,94 @@ def test_cfg4_bench_shard_matches_reference_golden():
     assert blk.max() <= 2e-4
     assert abs(np.sum(g * g) - pin["grad_sq"]) <= 2e-4 * pin["grad_sq"]
     m.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CRF_LogMath / computeExpF error semantics: the reference throws overflow_error for NaN / Inf / empty log-sums and
+# runtime_error when the posterior masses of a frame leave its band; the C ABI reports CRFGPU_ERR_NUMERIC.
+def test_posterior_mass_matches_oracle(oracle):
+    """sum over labels of the frame posteriors, from the device's own posterior array, against the oracle's alpha / beta: the probability
+    that a segment ends on the frame (segmental) and 1 (frame-level)"""
+    import ctypes as C
+    rng = np.random.default_rng(19)
+    off, ftrs, labs = synth_batch(rng, 1, 43, 43, 8, 6, 1, 9)
+    cfg = make_config("stdseg", n_labs=6 * 4, n_base_ftrs=8, max_dur=4, n_actual_labs=6, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.3, 0.3, oracle.lambda_len(cfg))
+    T, L = int(off[-1]), 24
+    a = np.zeros((T, L)); b = np.zeros((T, L)); g = np.zeros(len(lam)); nu = np.zeros(1); z = np.zeros(1)
+    P = lambda x, t: x.ctypes.data_as(C.POINTER(t))
+    rc = oracle.lib.crforacle_fwdbwd_dump(C.byref(cfg), P(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(T), P(ftrs, C.c_float),
+                                          P(labs, C.c_uint32), P(g, C.c_double), P(nu, C.c_double), P(z, C.c_double), P(a, C.c_double), P(b, C.c_double))
+    assert rc == 0
+    with np.errstate(over="ignore"):
+        want = np.where((a > -1e300) & (b > -1e300), np.exp(np.minimum(a + b - z[0], 0.0)), 0.0).sum(axis=1)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    m.fwdbwd(off, ftrs, labs)
+    mass = m.fetch_posterior_mass()
+    np.testing.assert_allclose(mass, want, atol=2e-5)
+    assert abs(mass[-1] - 1.0) < 1e-5 and mass.min() >= -1e-6 and mass.max() <= 1 + 1e-5      # every path ends on the last frame
+    m.close()
+    off, ftrs, labs = synth_batch(rng, 6, 1, 80, 105, 61, 2, 9)
+    m = gpu(make_config("stdframe", n_labs=61, n_base_ftrs=105))
+    m.set_lambda(rng.uniform(-0.25, 0.25, m.lambda_len))
+    m.fwdbwd(off, ftrs, labs)
+    np.testing.assert_allclose(m.fetch_posterior_mass(), 1.0, atol=2e-5)
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["stdseg", "frame", "nodur_native", "frame_lattice"])
+def test_nan_features_return_numeric_error_and_handle_survives(oracle, kind):
+    """a NaN in one frame poisons that utterance's lattice: the reference throws from CRF_LogMath, the device reports CRFGPU_ERR_NUMERIC
+    (non-finite logZ and posterior masses outside the band) -- and the same handle computes the next, clean batch correctly"""
+    rng = np.random.default_rng(23)
+    F, P, D = 7, 5, 3
+    off, ftrs, labs = synth_batch(rng, 5, 4, 30, F, P, 1, 5)
+    if kind == "stdseg":
+        cfg = make_config("stdseg", n_labs=P * D, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
+    elif kind == "nodur_native":
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
+    else:
+        cfg = make_config("stdframe", n_labs=P, n_base_ftrs=F)
+    lam = rng.uniform(-0.3, 0.3, oracle.lambda_len(cfg))
+    m = gpu(cfg)
+    if kind == "nodur_native":
+        m.set_option("nodur_impl", 1)
+    if kind == "frame_lattice":
+        m.set_option("frame_impl", 1)
+    m.set_lambda(lam)
+    bad = ftrs.copy()
+    bad[int(off[2]) + 1, 3] = np.nan
+    with pytest.raises(crf_b200.CrfGpuError) as ei:
+        m.fwdbwd(off, bad, labs)
+    assert ei.value.code == 4, str(ei.value)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, oracle.fwdbwd(cfg, lam, off, ftrs, labs), kind)
+    m.close()
+
+
+def test_overflowing_lambda_returns_numeric_error():
+    """weights that leave the double range in the reference (expE throws overflow_error): CRFGPU_ERR_NUMERIC"""
+    rng = np.random.default_rng(29)
+    off, ftrs, labs = synth_batch(rng, 3, 5, 20, 6, 4, 1, 4)
+    m = gpu(make_config("stdseg", n_labs=8, n_base_ftrs=6, max_dur=2, n_actual_labs=4, extract_seg_ftrs=1))
+    lam = np.zeros(m.lambda_len)
+    lam[:] = np.inf
+    m.set_lambda(lam)
+    with pytest.raises(crf_b200.CrfGpuError) as ei:
+        m.fwdbwd(off, ftrs, labs)
+    assert ei.value.code == 4
+    m.close()
+
+
+def test_plan_info_names_the_kernels():
+    c = TRAIN["stdseg_d10_segftr"]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    info = m.plan_info()
+    assert "lattice=dp_tc_kernel" in info and "locksteps=" in info and "decode:" in info
+    m.set_option("dp_impl", 1)
+    m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert "FFMA fallback" in m.plan_info()
+    m.close()

@@ -38,10 +38,15 @@ def timit_train_batch(first_utt=0, n_utt=3696, n_phones=N_PHONES):
     """Utterances [first_utt, first_utt+n_utt) of the TIMIT-shaped train set: real lengths and segment
     boundaries, phone ids U{0..n_phones-1} with no two adjacent segments equal (seed 9), features seed 2.
     Labels and features of an utterance do not depend on which slice is requested."""
+    return timit_train_utts(range(first_utt, first_utt + n_utt), n_phones)
+
+
+def timit_train_utts(ids, n_phones=N_PHONES):
+    """The same utterances by id (any subset, in the given order): what a rank of a length-balanced global minibatch stages."""
     utt_len, seg_cnt, seg_dur = timit_shape()
     seg_start = np.concatenate([[0], np.cumsum(seg_cnt)])
-    sel = range(first_utt, first_utt + n_utt)
-    lens = utt_len[first_utt:first_utt + n_utt]
+    sel = list(ids)
+    lens = utt_len[np.asarray(sel, np.int64)] if len(sel) else np.zeros(0, np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
     labs = np.empty(int(off[-1]), np.uint32)
     ftrs = np.empty((int(off[-1]), N_BASE_FTRS), np.float32)
