@@ -106,6 +106,25 @@ int max_active_tc_clusters(const TcDpPlan& plan);
 cudaError_t launch_tc_dp(bool backward, const TcDpParams& p, const TcDpPlan& plan, cudaStream_t s);
 void launch_block_max(const float* S, const uint32_t* frame_t, float* smaxd, uint32_t N, uint32_t Lp, uint32_t P, uint32_t D, cudaStream_t s);
 
+// ---- contraction-sliced tensor-core variant (crf_dp_ks.cu): CTA r keeps E[:, slice r] of ALL label rows (hi and lo halves in TMEM) and
+//      multiplies it with its own slice of the frame vector; the partial products are reduce-scattered by bulk DSMEM copies ----
+struct KsDpParams : DpParams {
+	uint32_t CS, CW, K, MT;       // cluster size, contraction slice per CTA (multiple of 16, <= 128), padded label count CS*CW, 128-row tiles
+	uint32_t tmem_cols, recv_off, vbuf_off, ps_off, ctl_off;   // TMEM columns to allocate, byte offsets in dynamic shared memory
+	uint32_t n_clusters;
+	const uint32_t* cl_off;       // [n_clusters*TC_DP_SLOTS+1] offsets of the per-slot utterance lists
+	const uint32_t* cl_list;      // utterance ids in the order each slot processes them
+	const float* smaxd;           // [N][D] per-duration maxima of S
+	unsigned long long* dbg;      // optional [32] cycle counters of cluster 0 / CTA 0 (CRFGPU_DP_TIMING=1), else nullptr
+};
+struct KsDpPlan {
+	uint32_t CS, CW, K, MT, tmem_cols, recv_off, vbuf_off, ps_off, ctl_off;
+	size_t smem;
+};
+bool plan_ks_dp(uint32_t L, uint32_t D, int max_smem_optin, KsDpPlan* plan);
+int max_active_ks_clusters(const KsDpPlan& plan);
+cudaError_t launch_ks_dp(bool backward, const KsDpParams& p, const KsDpPlan& plan, cudaStream_t s);
+
 // ---- TN GEMM with fp64 scatter epilogue:  out[map(i,j)] += scale * sum_n A[n][i]*B[n][j] --------
 struct ReduceGemmParams {
 	const float* A; uint64_t lda;   // rows n in [n0,n1), A row used = n - a_row_shift

@@ -90,10 +90,11 @@ struct crfgpu_ctx {
 	bool train_ok = false, decode_ok = false;
 	std::string train_why, decode_why;
 	uint64_t launches = 0;
-	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 2, opt_cluster_slots = 0, opt_max_clusters = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192, opt_prefetch_smem = 1u << 20;
+	int opt_slots = 0, opt_keep_lattice = 0, opt_dp_impl = 3, opt_cluster_slots = 0, opt_max_clusters = 0, opt_gemm_impl = 2, opt_tma_mask = 63; uint32_t opt_k_slab = 1024, opt_k_slab_tc = 2048, opt_k_slab_tma = 4096, opt_k_slab_xi = 8192, opt_prefetch_smem = 1u << 20;
 	int max_smem_optin = 0;
 	bool cluster_ok = false; ClusterPlan plan{}; uint32_t n_clusters = 0;
 	bool tc_ok = false; TcDpPlan tc_plan{}; uint32_t n_tc_clusters = 0;
+	bool ks_ok = false; KsDpPlan ks_plan{}; uint32_t n_ks_clusters = 0;   // contraction-sliced tcgen05 lattice kernels (crf_dp_ks.cu): the default where the geometry fits
 	uint64_t locksteps = 0;   // frames of the longest slot / cluster list of the staged batch = dependent steps of the lattice kernels
 	DevBuf d_cl_off, d_cl_list, d_xch, d_xmax, d_smaxd;
 
@@ -522,10 +523,10 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	// cluster-resident lattice kernels: persistent clusters, utterances dealt longest-first to the least loaded
 	// cluster; inside a cluster the list order is the order slots are (re)filled
 	std::vector<uint32_t> cl_off, cl_list;
-	h->cluster_ok = false; h->tc_ok = false; h->locksteps = 0;
+	h->cluster_ok = false; h->tc_ok = false; h->ks_ok = false; h->locksteps = 0;
 	for (uint32_t u = 0; u < n_utt; u++) h->locksteps = std::max<uint64_t>(h->locksteps, off[u + 1] - off[u]);   // one chain per utterance unless a plan below deals lists
 	// frame-level models with at most 64 labels run one warp per chain (crf_dp_frame.cu): no cluster plan, no slot lists
-	h->frame_path = c.max_dur == 1 && h->Lt <= 64 && !h->tied && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && h->opt_frame_impl != 1;
+	h->frame_path = c.max_dur == 1 && h->Lt <= 64 && !h->tied && !h->nodur && !h->transftr && h->opt_dp_impl >= 2 && h->opt_frame_impl != 1;
 	auto deal = [&](uint32_t ncl) {
 		// utterances dealt longest-first to the least loaded cluster; inside a cluster the list order is the order slots are (re)filled
 		std::vector<std::vector<uint32_t>> lists(ncl);
@@ -540,15 +541,32 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		for (auto& l : lists) { cl_list.insert(cl_list.end(), l.begin(), l.end()); cl_off.push_back((uint32_t)cl_list.size()); }
 		upload_async(h, h->d_cl_off, cl_off); upload_async(h, h->d_cl_list, cl_list);
 	};
-	if (h->train_ok && !h->frame_path && !h->nodur && !h->transftr && h->opt_dp_impl == 2 && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32)) {   // the lane threads index the lattice arrays with 32 bits
-		// tensor-core cluster kernels: 16 slots per cluster
+	const bool lattice_tc = h->train_ok && !h->frame_path && !h->nodur && !h->transftr && labs && n_utt && (uint64_t)N * h->Lp < (1ull << 32);   // the lane threads index the lattice arrays with 32 bits
+	if (lattice_tc && h->opt_dp_impl == 3) {
+		// contraction-sliced tensor-core kernels: 16 slots per cluster, E entirely in tensor memory
+		KsDpPlan plan{};
+		if (plan_ks_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
+			const int avail_cl = max_active_ks_clusters(plan);
+			if (avail_cl > 0) {
+				uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
+				if (h->opt_max_clusters > 0) ncl = std::min<uint32_t>(ncl, (uint32_t)h->opt_max_clusters);   // tests: few clusters force slot refills on small batches
+				deal(ncl * TC_DP_SLOTS);         // one list per slot, balanced over all slots of all clusters (longest first)
+				h->ks_plan = plan; h->n_ks_clusters = ncl; h->ks_ok = true;
+				if (getenv("CRFGPU_VERBOSE"))
+					fprintf(stderr, "[crfgpu] contraction-sliced lattice plan: CS=%u CW=%u K=%u MT=%u tmem_cols=%u smem=%zu, %u of %d resident clusters, %u utterances\n",
+					        plan.CS, plan.CW, plan.K, plan.MT, plan.tmem_cols, plan.smem, ncl, avail_cl, n_utt);
+			}
+		}
+	}
+	if (lattice_tc && !h->ks_ok && h->opt_dp_impl >= 2) {
+		// output-sliced tensor-core kernels (crf_dp_tc.cu): geometries whose tiles do not fit tensor memory whole
 		TcDpPlan plan{};
 		if (plan_tc_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan)) {
 			const int avail_cl = max_active_tc_clusters(plan);
 			if (avail_cl > 0) {
 				uint32_t ncl = std::min<uint32_t>((uint32_t)avail_cl, (n_utt + TC_DP_SLOTS - 1) / TC_DP_SLOTS);
-				if (h->opt_max_clusters > 0) ncl = std::min<uint32_t>(ncl, (uint32_t)h->opt_max_clusters);   // tests: few clusters force slot refills on small batches
-				deal(ncl * TC_DP_SLOTS);         // one list per slot, balanced over all slots of all clusters (longest first)
+				if (h->opt_max_clusters > 0) ncl = std::min<uint32_t>(ncl, (uint32_t)h->opt_max_clusters);
+				deal(ncl * TC_DP_SLOTS);
 				h->tc_plan = plan; h->n_tc_clusters = ncl; h->tc_ok = true;
 				if (getenv("CRFGPU_VERBOSE"))
 					fprintf(stderr, "[crfgpu] tensor-core lattice plan: CS=%u CW=%u K=%u tmem_cols=%u smem=%zu, %u of %d resident clusters, %u utterances\n",
@@ -556,7 +574,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 		}
 	}
-	if (h->train_ok && !h->frame_path && !h->nodur && !h->transftr && (h->opt_dp_impl == 1 || (h->opt_dp_impl == 2 && !h->tc_ok)) && labs && n_utt) {
+	if (h->train_ok && !h->frame_path && !h->nodur && !h->transftr && (h->opt_dp_impl == 1 || (h->opt_dp_impl >= 2 && !h->tc_ok && !h->ks_ok)) && labs && n_utt) {
 		ClusterPlan plan{};
 		int cap = h->opt_cluster_slots > 0 ? h->opt_cluster_slots : 32;
 		if (plan_cluster_dp(h->Lt, c.max_dur, h->max_smem_optin, &plan, cap)) {
@@ -668,7 +686,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		g.Bt = h->d_Wt.as<unsigned char>(); g.bias = h->d_bias.as<float>(); g.C = h->d_S.as<float>(); g.ldc = Lp;
 		g.M = N; g.P = P; g.K = nSf; g.D = D; g.n_chunks = score_tma_chunks(nSf); g.ntile = (P + 63) / 64;
 		g.frame_t = h->d_frame_t.as<uint32_t>(); g.shared_w = h->nodur ? 1u : 0u; g.a_from_tmem = (h->opt_tma_mask & 8) ? 1u : 0u;
-		if ((h->tc_ok || h->nodur) && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
+		if ((h->tc_ok || h->ks_ok || h->nodur) && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
 		CUDA_OK(launch_score_gemm_tma(h->X() + c.state_fidx_start, h->Wp, g, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
@@ -813,6 +831,34 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 			CUDA_OK(launch_frame_post(p, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), N, s)); check_kernel(h, 1);
 			phase_end(h, "backward");
 		}
+	} else if (h->ks_ok) {
+		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
+		KsDpParams kp{};
+		static_cast<DpParams&>(kp) = p;
+		kp.CS = h->ks_plan.CS; kp.CW = h->ks_plan.CW; kp.K = h->ks_plan.K; kp.MT = h->ks_plan.MT; kp.tmem_cols = h->ks_plan.tmem_cols;
+		kp.recv_off = h->ks_plan.recv_off; kp.vbuf_off = h->ks_plan.vbuf_off; kp.ps_off = h->ks_plan.ps_off; kp.ctl_off = h->ks_plan.ctl_off;
+		kp.n_clusters = h->n_ks_clusters; kp.cl_off = h->d_cl_off.as<uint32_t>(); kp.cl_list = h->d_cl_list.as<uint32_t>();
+		kp.smaxd = h->d_smaxd.as<float>();
+		static DevBuf kdbg2; const bool timing = getenv("CRFGPU_DP_TIMING") != nullptr;
+		if (timing) { kdbg2.ensure(64 * 8); }
+		auto report = [&](const char* what) {
+			unsigned long long v[32]; CUDA_OK(cudaMemcpyAsync(v, kdbg2.p, sizeof(v), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+			const double n = v[15] ? (double)v[15] : 1.0;
+			fprintf(stderr, "[crfgpu] %s (contraction-sliced): %.0f steps; cycles/step MMA warp: scales-wait+issue %.0f mma-wait %.0f scatter-wait+push+reduce-wait %.0f tile-wait+push %.0f | bookkeeping: sums-wait %.0f scales %.0f schedule+prefetch %.0f | lanes: scales-wait+loads %.0f acc-wait+scatter %.0f recv-wait+sum %.0f epilogue %.0f\n",
+			        what, n, v[1] / n, v[0] / n, v[2] / n, v[3] / n, v[4] / n, v[5] / n, v[6] / n, v[7] / n, v[8] / n, v[10] / n, v[9] / n);
+		};
+		kp.dbg = timing ? kdbg2.as<unsigned long long>() : nullptr;
+		phase_begin(h, "forward");
+		if (!smax_done) { launch_block_max(h->d_S.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_smaxd.as<float>(), N, Lp, P, D, s); check_kernel(h, 1); }
+		if (timing) CUDA_OK(cudaMemsetAsync(kdbg2.p, 0, 64 * 8, s));
+		CUDA_OK(launch_ks_dp(false, kp, h->ks_plan, s)); check_kernel(h, 1);
+		if (timing) report("forward");
+		phase_end(h, "forward");
+		phase_begin(h, "backward");
+		if (timing) CUDA_OK(cudaMemsetAsync(kdbg2.p, 0, 64 * 8, s));
+		CUDA_OK(launch_ks_dp(true, kp, h->ks_plan, s)); check_kernel(h, 1);
+		if (timing) report("backward");
+		phase_end(h, "backward");
 	} else if (h->tc_ok) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
 		TcDpParams tp{};
@@ -1103,6 +1149,7 @@ std::string plan_text(crfgpu_ctx* h) {
 	else if (h->nodur_tf) s += "lattice=nodur_tf_forward/backward_kernel (one CTA per utterance, per-frame transition scores); ";
 	else if (h->nodur) { snprintf(b, sizeof b, "lattice=nodur_dp_kernel (native O(P^2+D*P), %u groups x %u CTAs, 16 utterances in lock-step); ", h->n_nodur_groups, (h->lay.L + 31) / 32); s += b; }
 	else if (h->frame_path) s += h->opt_frame_impl == 2 ? "lattice=frame_dp_kernel (one warp per utterance, chains one after the other); " : "lattice=frame_dp_pair_kernel+frame_post_kernel (one warp per chain); ";
+	else if (h->ks_ok) { snprintf(b, sizeof b, "lattice=dp_ks_kernel (tcgen05, contraction-sliced: cluster of %u CTAs x %u labels, %u M-tiles in tensor memory, %u clusters x 16 slots%s); ", h->ks_plan.CS, h->ks_plan.CW, h->ks_plan.MT, h->n_ks_clusters, h->tied ? ", tied (duration, phone) expansion" : ""); s += b; }
 	else if (h->tc_ok) { snprintf(b, sizeof b, "lattice=dp_tc_kernel (tcgen05, cluster of %u CTAs x %u labels, %u clusters x 16 slots%s); ", h->tc_plan.CS, h->tc_plan.CW, h->n_tc_clusters, h->tied ? ", tied (duration, phone) expansion" : ""); s += b; }
 	else if (h->cluster_ok) { snprintf(b, sizeof b, "lattice=cluster_dp_kernel (FFMA fallback: the tcgen05 plan does not hold this geometry or dp_impl=1; cluster of %u CTAs, %u clusters x %d slots); ", h->plan.CS, h->n_clusters, h->plan.UB); s += b; }
 	else { snprintf(b, sizeof b, "lattice=forward/backward_kernel (FFMA fallback, E from L2, %d slots per CTA); ", h->U); s += b; }
@@ -1478,7 +1525,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }
 		else if (n == "k_slab_tma") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tma must be a multiple of 32"); h->opt_k_slab_tma = (uint32_t)value; }
 		else if (n == "k_slab_tc") { if (value < 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_tc must be >= 32"); h->opt_k_slab_tc = (uint32_t)value; }
-		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05
+		else if (n == "dp_impl") h->opt_dp_impl = (int)value;            // 0: one CTA per utterance group, E from L2; 1: cluster-resident E, FFMA; 2: cluster-resident E, tcgen05, output labels sliced; 3 (default): tcgen05, contraction sliced, E whole in tensor memory
 		else if (n == "cluster_slots") h->opt_cluster_slots = (int)value; // utterance slots per cluster (4,8,12,16,32; 0 auto)
 		else if (n == "mass_check") h->opt_mass_check = value != 0;       // 0 skips the posterior-mass assertion pass (one read of the posterior array)
 		else if (n == "max_clusters") h->opt_max_clusters = (int)value;   // cap on the resident clusters of the lattice kernels (0 = all): a small cap makes every slot work through a long utterance list

@@ -43,8 +43,8 @@ def assert_train_close(got, want, what=""):
 
 
 # lattice kernels: 0 = one CTA per utterance group (E from L2), 1 = cluster-resident E with FFMA, 2 = cluster-resident E with
-# tcgen05 (default); GEMMs: 0 = fp32 FFMA tiles, 1 = tcgen05 split-bf16 with register-staged operands, 2 = 1 + TMA-fed window GEMMs (default)
-IMPLS = {"tc": {}, "tc_frame_lattice": {"frame_impl": 1}, "frame_sequential": {"frame_impl": 2}, "tc_ffma_gemm": {"gemm_impl": 0}, "tc_reg_gemm": {"gemm_impl": 1}, "tc_tmem_all": {"tma_mask": 63}, "tc_smem_all": {"tma_mask": 7}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
+# tcgen05, output labels sliced over the cluster, 3 = tcgen05, contraction index sliced, E whole in tensor memory (default); GEMMs: 0 = fp32 FFMA tiles, 1 = tcgen05 split-bf16 with register-staged operands, 2 = 1 + TMA-fed window GEMMs (default)
+IMPLS = {"tc": {}, "tc_msplit": {"dp_impl": 2}, "tc_frame_lattice": {"frame_impl": 1}, "tc_msplit_frame_lattice": {"dp_impl": 2, "frame_impl": 1}, "frame_sequential": {"frame_impl": 2}, "tc_ffma_gemm": {"gemm_impl": 0}, "tc_reg_gemm": {"gemm_impl": 1}, "tc_tmem_all": {"tma_mask": 63}, "tc_smem_all": {"tma_mask": 7}, "cluster": {"dp_impl": 1}, "cluster_u4": {"dp_impl": 1, "cluster_slots": 4},
          "legacy_u1": {"dp_impl": 0, "slots": 1}, "legacy_u4": {"dp_impl": 0, "slots": 4, "gemm_impl": 0}}
 
 
@@ -691,6 +691,10 @@ REFILL_KINDS = {
     "stdseg_tc": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {}, 640, 200, 0.3),
     "stdseg_tc_long": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {}, 96, 800, 0.3),
     "stdseg_cluster_ffma": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {"dp_impl": 1}, 640, 200, 0.3),
+    "stdseg_tc_msplit": (dict(model_type="stdseg", n_labs=12, n_base_ftrs=5, max_dur=3, n_actual_labs=4, extract_seg_ftrs=1), {"dp_impl": 2}, 640, 200, 0.3),
+    "stdseg_d10_msplit": (dict(model_type="stdseg", n_labs=50, n_base_ftrs=6, max_dur=10, n_actual_labs=5, extract_seg_ftrs=1), {"dp_impl": 2}, 320, 150, 0.1),
+    "stdseg_200labels": (dict(model_type="stdseg", n_labs=200, n_base_ftrs=4, max_dur=4, n_actual_labs=50, extract_seg_ftrs=1), {}, 96, 60, 0.1),
+    "stdseg_200labels_msplit": (dict(model_type="stdseg", n_labs=200, n_base_ftrs=4, max_dur=4, n_actual_labs=50, extract_seg_ftrs=1), {"dp_impl": 2}, 96, 60, 0.1),
     "stdseg_d10": (dict(model_type="stdseg", n_labs=50, n_base_ftrs=6, max_dur=10, n_actual_labs=5, extract_seg_ftrs=1), {}, 320, 150, 0.1),
     "nodur_tied": (dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=6, n_base_ftrs=5, max_dur=4, n_actual_labs=6, extract_seg_ftrs=1), {"nodur_impl": 2}, 400, 150, 0.3),
     "nodur_nstate_tied": (dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=9, n_base_ftrs=5, n_states=3, max_dur=3, extract_seg_ftrs=1), {"nodur_impl": 2}, 400, 150, 0.3),
@@ -724,7 +728,8 @@ def test_slot_refill_matches_oracle(oracle, kind):
     m.close()
 
 
-def test_slot_refill_cfg4_geometry_matches_oracle(oracle):
+@pytest.mark.parametrize("dp_impl", [3, 2])
+def test_slot_refill_cfg4_geometry_matches_oracle(oracle, dp_impl):
     """cfg4's own geometry (610 labels: clusters of 8 CTAs, E in tensor memory) with every slot refilled: 64 short utterances
     on ONE cluster, lengths 1, 33 and 65 among them."""
     rng = np.random.default_rng(610)
@@ -737,9 +742,11 @@ def test_slot_refill_cfg4_geometry_matches_oracle(oracle):
     lam = rng.uniform(-0.01, 0.01, oracle.lambda_len(cfg))
     want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=8)
     m = gpu(cfg)
+    m.set_option("dp_impl", dp_impl)
     m.set_option("max_clusters", 1)
     m.set_lambda(lam)
     got = m.fwdbwd(off, ftrs, labs)
+    assert ("dp_ks_kernel" if dp_impl == 3 else "dp_tc_kernel") in m.plan_info()
     assert_train_close(got, want, "cfg4 geometry, one cluster")
     m.close()
 
@@ -756,7 +763,8 @@ def block_relative_errors(g, gw, sidx):
     return out
 
 
-def test_cfg4_bench_shard_matches_reference_golden():
+@pytest.mark.parametrize("dp_impl", [3, 2])
+def test_cfg4_bench_shard_matches_reference_golden(dp_impl):
     """THE bench workload (cfg4 on workloads.timit_train_batch(0, 462), 138 137 frames, the minibatch rank 0 times) against the
     golden the unmodified reference produced for it (tests/golden/make_golden_cfg4_shard0.py): per-utterance numerator and logZ
     to 1e-5 relative, the 891 210-entry gradient to 1e-4 (element-wise against the global maximum, per label block against the
@@ -769,6 +777,7 @@ def test_cfg4_bench_shard_matches_reference_golden():
     pin = json.load(open(os.path.join(GOLDEN, "cfg4_shard0_pin.json")))
     off, ftrs, labs = workloads.timit_train_batch(0, 462)
     m = crf_b200.CrfGpu(crf_b200.make_config(**workloads.cfg4_kwargs()))
+    m.set_option("dp_impl", dp_impl)
     m.set_lambda(workloads.lam_for("cfg4", m.lambda_len))
     g, n, lz = m.fwdbwd(off, ftrs, labs)
     gw = z["grad32"].astype(np.float64)
@@ -869,7 +878,10 @@ def test_plan_info_names_the_kernels():
     m.set_lambda(c["lam"])
     m.fwdbwd(c["off"], c["ftrs"], c["labs"])
     info = m.plan_info()
-    assert "lattice=dp_tc_kernel" in info and "locksteps=" in info and "decode:" in info
+    assert "lattice=dp_ks_kernel" in info and "locksteps=" in info and "decode:" in info
+    m.set_option("dp_impl", 2)
+    m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert "lattice=dp_tc_kernel" in m.plan_info()
     m.set_option("dp_impl", 1)
     m.fwdbwd(c["off"], c["ftrs"], c["labs"])
     assert "FFMA fallback" in m.plan_info()
