@@ -10,10 +10,11 @@
 // tensor memory (cfg4: 5 tiles x 80 columns = 400 of 512 TMEM columns, 80 more for the accumulators) -- and multiplies them with ITS OWN
 // slice of V, which its own lane threads produced in the previous step:
 //   * per step 5 tiles x 5 k-steps x 3 = 75 tcgen05.mma, every A operand from TMEM (20 instead of 53 cycles): 1.5 k cycles;
-//   * the partial products are REDUCE-SCATTERED: the lane threads read their accumulator rows (tcgen05.ld), store them by destination
-//     slice and the MMA warp pushes slice r' to CTA r' with one bulk DSMEM copy (the same 5 KB per peer the all-gather moved); the
-//     owner sums the 8 partials of its 80 rows and runs the usual epilogue (log, + score, + scale, exp, bf16 hi/lo split) straight into
-//     its local MMA operand buffer -- no vector ever has to be gathered;
+//   * the partial products are REDUCE-SCATTERED tile by tile while the later tiles are still being multiplied: the lane threads read
+//     their accumulator rows (tcgen05.ld) as soon as a tile's commit arrives and send each row's 4 slots straight to the owner of the
+//     row with one remote store that counts its bytes on the owner's mbarrier (st.async, 16 B per thread and tile); the owner sums the
+//     8 partials of its 80 rows and runs the usual epilogue (log, + score, + scale, exp, bf16 hi/lo split) straight into its local MMA
+//     operand buffer -- no vector ever has to be gathered, nothing is staged, no copy-issuing warp sits in the chain;
 //   * only the 64 partial sums per CTA that the scale bookkeeping needs travel to every peer (256 B, off the critical path).
 // No shared-memory E half (100 KB freed), no operand fetch from shared memory in the product.  Scales, slot refill, masking and the
 // lane-thread arithmetic are those of crf_dp_tc.cu.  Geometries whose tiles do not fit tensor memory (more than 640 padded labels)
@@ -37,9 +38,9 @@ constexpr int LANE_WARPS = 16;         // 4 per TMEM lane quadrant, each owning 
 constexpr int SPT = UB / (LANE_WARPS / 4);
 constexpr int NBK = 4;                 // bookkeeping warps, each owning SPW slots with LPS lanes per slot
 constexpr int SPW = UB / NBK, LPS = 32 / SPW;
-constexpr int MMA_WARP = LANE_WARPS, BK_WARP0 = LANE_WARPS + 1;
-constexpr int N_THREADS = (LANE_WARPS + 1 + NBK) * 32;
-constexpr int BAR_ALL = N_THREADS, BAR_LANES_MMA = (LANE_WARPS + 1) * 32;
+constexpr int MMA_WARP = LANE_WARPS, COMM_WARP = LANE_WARPS + 1, BK_WARP0 = LANE_WARPS + 2;
+constexpr int N_THREADS = (LANE_WARPS + 2 + NBK) * 32;
+constexpr int BAR_ALL = N_THREADS, BAR_LANES_1 = (LANE_WARPS + 1) * 32, BAR_LANES_2 = (LANE_WARPS + 2) * 32;   // lane threads + one / both service warps
 constexpr int MT_MAX = 5;                // M-tiles of 128 label rows (plan: MT * (CW + 16) <= 512 TMEM columns)
 constexpr uint32_t PS_BYTES = 256;       // [4 lane quadrants][16 slots] partial sums of one CTA
 static_assert(SPT == 4, "the partial-sum butterfly below is written for 4 slots per thread");
@@ -66,7 +67,7 @@ struct LaneCtl {
 };
 
 struct Ctl {
-	uint64_t gather[2], psg[2], mma_bar;      // gather: partial products of my slice arrived | psg: partial sums of every CTA arrived
+	uint64_t gather[2], psg[2], mma_bar[5];   // gather: partial products of my slice arrived | psg: partial sums of every CTA arrived | one commit per M-tile
 	uint32_t tmem, pad;
 	uint32_t any[2][NBK];
 	// published per step, double-buffered by step parity (the bookkeeping warp runs ahead of the lane threads)
@@ -95,9 +96,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <int COUNT> __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
 template <int COUNT> __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
 // named barriers: 1 = scales/schedule of the step published (bookkeeping -> everyone), 2 = my slice of the new vector written
-// (lanes -> MMA warp), 3 = accumulators complete (MMA warp -> lanes), 4 = partial products stored by destination (lanes -> MMA warp),
-// 5 = partial products of my slice arrived from every peer (MMA warp -> lanes)
-constexpr int BAR_SCALES = 1, BAR_TILE = 2, BAR_ACC = 3, BAR_SEND = 4, BAR_RECV = 5;
+// (lanes -> MMA and communication warps), 3 = partial products of my slice arrived from every peer (communication warp -> lanes)
+constexpr int BAR_SCALES = 1, BAR_TILE = 2, BAR_RECV = 3;
 
 // reductions over the LPS lanes that share a slot (lane = slot + SPW*h); executed by the whole warp
 __device__ __forceinline__ double slot_max_unused(double v) {
@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 	const uint32_t L = p.L, Lp = p.Lp, P = p.P, D = p.D, CS = p.CS, CW = p.CW, K = p.K;
 	const uint32_t MT = p.MT, KS = CW / 16;
 	const uint32_t CH = CW * 64;                           // one slice x 16 slots: fp32 partial products [4 slot quads][CW rows][4], or the bf16 hi/lo operand tile
-	unsigned char* sendb = smem;                           // [2][CS][CH] partial products by destination slice (double-buffered: see the push)
-	unsigned char* recvb = smem + p.recv_off;              // [2][CS][CH] partial products of MY slice by source CTA
+	unsigned char* recvb = smem + p.recv_off;              // [2][CS][CH] partial products of MY slice by source CTA (double-buffered: a peer may be one step ahead)
 	unsigned char* vbuf = smem + p.vbuf_off;               // [CH] my slice of the frame vector as the MMA's B operand (hi/lo, K-major)
 	unsigned char* psb = smem + p.ps_off;                  // [2][CS][PS_BYTES] partial sums of every CTA's slice
 	Ctl* ctl = reinterpret_cast<Ctl*>(smem + p.ctl_off);
@@ -146,22 +145,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t rank = CS > 1 ? cluster_ctarank() : 0, cl = blockIdx.x / CS;
 	const uint32_t c0 = rank * CW;
-	const uint32_t q4 = warp & 3, sub = (warp >> 2) & 3;   // lane warps: TMEM lane quadrant, slot group
-	const uint32_t row = q4 * 32 + lane, c = c0 + row;
+	// lane warps have TWO identities.  Reading accumulators (tcgen05.ld) ties a warp to the TMEM lane quadrant warp % 4: (q4, ssub) = the 32
+	// accumulator rows and the 4 slot columns it scatters.  The epilogue reads its sums from shared memory, so its rows are free to choose:
+	// the RW = ceil(CW / 32) row groups of the 4 slot quads are dealt to warps 0 .. 4 RW - 1 in order, which spreads the busy warps evenly
+	// over the four SM sub-partitions (cfg4: 12 busy warps, 3 per sub-partition; tied to the quadrants it was 4 + 4 + 4 + 0 and the
+	// epilogue is bound by instruction issue)
+	const uint32_t q4 = warp & 3, ssub = (warp >> 2) & 3;
+	const uint32_t RW = (CW + 31) / 32;
+	const uint32_t sub = warp / RW, rgrp = warp - sub * RW;    // epilogue: slot quad, row group
+	const uint32_t srow = q4 * 32 + lane;                      // accumulator row inside a tile
+	const uint32_t row = rgrp * 32 + lane, c = c0 + row;       // epilogue: row of my slice, label
 	const bool lane_thread = warp < LANE_WARPS;
-	const bool in_tile = lane_thread && row < CW;          // this thread owns a row of the slice tile
-	const bool row_valid = in_tile && c < L;               // ... that is a real label
+	const bool epi_warp = lane_thread && sub < 4;              // this warp has epilogue work
+	const bool in_tile = epi_warp && row < CW;                 // this thread owns a row of the slice tile
+	const bool row_valid = in_tile && c < L;                   // ... that is a real label
 	const uint32_t my_d = row_valid ? c / P + 1 : 0xffffu;
+	const uint32_t inv20 = ((1u << 20) + CW - 1) / CW;         // R / CW == (R * inv20) >> 20 for R < 1024 (no integer division in the step loop)
 	const float* Msrc = BWD ? p.E : p.ET;                  // rows = my labels, columns = the contracted label
-	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MMA_WARP || warp == BK_WARP0);
+	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == MMA_WARP || warp == COMM_WARP || warp == BK_WARP0);
 	unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cycle counters, kept in registers and flushed once
 
 	// ---------------------------------------------------------------- setup
 	if (tid == 0) {
-		mbar_init(&ctl->gather[0], 1); mbar_init(&ctl->gather[1], 1); mbar_init(&ctl->psg[0], 1); mbar_init(&ctl->psg[1], 1); mbar_init(&ctl->mma_bar, 1);
+		mbar_init(&ctl->gather[0], 1); mbar_init(&ctl->gather[1], 1); mbar_init(&ctl->psg[0], 1); mbar_init(&ctl->psg[1], 1);
+		for (int i = 0; i < MT_MAX; i++) mbar_init(&ctl->mma_bar[i], 1);
 		fence_mbar_init();
 	}
 	if (warp == MMA_WARP) tmem_alloc(&ctl->tmem, p.tmem_cols);
+	for (uint32_t i = tid; i < 2 * CS * PS_BYTES / 4; i += N_THREADS) reinterpret_cast<float*>(psb)[i] = 0.0f;   // row groups without a warp stay 0
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
@@ -170,8 +181,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 		// tile i, k-step ks of my contraction slice: row R = 128 i + my lane of E (backward) / E^T (forward), 16 contracted labels from
 		// c0 + 16 ks on; hi and lo halves both into TENSOR MEMORY (8 packed columns each per k-step).  The four warps of a lane quadrant
 		// share the (tile, k-step) pairs.
-		for (uint32_t pr = sub; pr < MT * KS; pr += 4) {
-			const uint32_t i = pr / KS, ks = pr % KS, R = i * 128 + row;
+		for (uint32_t pr = ssub; pr < MT * KS; pr += 4) {
+			const uint32_t i = pr / KS, ks = pr % KS, R = i * 128 + srow;
 			float x[16];
 			const float* src = Msrc + (size_t)R * Lp + c0 + ks * 16;
 #pragma unroll
@@ -419,9 +430,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 			}
 			unsigned char* myps = psb + ((size_t)nb * CS + rank) * PS_BYTES;
 			unsigned char* recv_pb = recvb + (size_t)pb * CS * CH;
-			unsigned char* send_pb = sendb + (size_t)pb * CS * CH;
+			// tile order of this step: CTA r starts with the tile that holds the first rows of slice r + 1, so that at any moment the CTAs of
+			// the cluster push to DIFFERENT destinations and every destination receives a steady trickle instead of 7 chunks at once
+			const uint32_t i0 = CS > 1 ? ((rank + 1) % CS) * CW / 128 : 0;
 			if (warp == MMA_WARP) {
-				// ===================== MMA warp: the product of my contraction slice, then the reduce-scatter of its partial products =====================
+				// ===================== MMA warp: the product of my contraction slice, one commit per M-tile =====================
 				if (it > 0) {
 					// my slice of the vector was completed by my own lane threads (BAR_TILE at the end of the previous step)
 					tc_fence_after();
@@ -430,9 +443,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 						// compiler keeps descriptors and counters in uniform registers (UIADD3 + UTCHMMA, no R2UR per MMA)
 						const uint32_t idesc = idesc_bf16_f32(128, UB, false, false);
 						const uint64_t v0 = smem_desc(smem_u32(vbuf), 512, 128);
-						uint32_t ta = tmem + E_COL;
-						for (uint32_t i = 0; i < MT; i++) {
+						uint32_t i = i0;
+						for (uint32_t jj = 0; jj < MT; jj++) {
 							const uint32_t dt = tmem + i * 16;
+							uint32_t ta = tmem + E_COL + i * CW;
 							uint64_t vhi = v0;
 							bool acc = false;
 							for (uint32_t k2 = 0; k2 < KS; k2++) {
@@ -441,31 +455,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 								mma_ts(dt, ta + CW / 2, vhi, idesc, true);              // E_lo * V_hi
 								acc = true; vhi += 64; ta += 8;                         // next k-step: +1024 bytes, +8 TMEM columns
 							}
-							ta += CW / 2;                                               // over the tile's lo half
+							mma_commit(&ctl->mma_bar[jj]);                              // the lane threads pick tile jj up as soon as it is complete
+							i = (i + 1 == MT) ? 0 : i + 1;
 						}
-						mma_commit(&ctl->mma_bar);
 					}
 					__syncwarp();
 					TICK(m2); TACC(1, t0, m2);
-					mbar_wait(&ctl->mma_bar, (it - 1) & 1);          // one polling warp instead of sixteen
-					bar_arrive<BAR_LANES_MMA>(BAR_ACC);                // accumulators are complete
-					TICK(m2b); TACC(0, m2, m2b);
-					bar_sync<BAR_LANES_MMA>(BAR_SEND);                 // partial products are stored by destination slice
-					// reduce-scatter: slice r' of my partial products goes to CTA r' (its receive buffer [pb][my rank]).  The send buffer is
-					// double-buffered: I overwrite buffer pb again two steps on, after every peer's NEXT push has reached me -- which it issued
-					// only after this push had arrived there.
+				}
+				bar_sync<BAR_LANES_2>(BAR_TILE);                        // my slice of the new vector (local MMA operand) is complete
+				if (timing) tacc[11]++;
+			} else if (warp == COMM_WARP) {
+				// ===================== communication warp: reduce-scatter of the partial products, tile by tile =====================
+				if (it > 0) {
+					// slice r' of my partial products goes to CTA r' (its receive buffer [pb][my rank]) as soon as every tile that holds rows
+					// of it has been stored.  The send buffer is double-buffered: I overwrite buffer pb again two steps on, after every peer's
+					// NEXT push has reached me -- which it issued only after this push had arrived there.
+					// the partial products of my slice arrive as remote stores of the peers' lane threads, each counting its bytes on gather[pb]
 					if (lane == 0) mbar_arrive_expect_tx(&ctl->gather[pb], (CS - 1) * CH);
-					if (lane < CS && lane != rank) {
-						const uint32_t dst = mapa(smem_u32(recv_pb + (size_t)rank * CH), lane), rbar = mapa(smem_u32(&ctl->gather[pb]), lane);
-						asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-						             ::"r"(dst), "r"(smem_u32(send_pb + (size_t)lane * CH)), "r"(CH), "r"(rbar) : "memory");
-					}
+					TICK(c1); TACC(0, t0, c1);
 					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);  // the partial products of my slice from every peer
-					bar_arrive<BAR_LANES_MMA>(BAR_RECV);
-					TICK(m3); TACC(2, m2b, m3);
+					bar_arrive<BAR_LANES_1>(BAR_RECV);
+					TICK(c2); TACC(2, c1, c2);
 				}
 				TICK(m4);
-				bar_sync<BAR_LANES_MMA>(BAR_TILE);                      // my slice of the new vector (local MMA operand) and its partial sums are complete
+				bar_sync<BAR_LANES_2>(BAR_TILE);                        // the partial sums of my slice are complete
 				// the only thing every CTA needs from every other: 64 partial sums for the scale bookkeeping
 				if (lane == 0) mbar_arrive_expect_tx(&ctl->psg[nb], (CS - 1) * PS_BYTES);
 				if (lane < CS && lane != rank) {
@@ -474,15 +487,47 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 					             ::"r"(dst), "r"(smem_u32(myps)), "r"(PS_BYTES), "r"(rbar) : "memory");
 				}
 				TICK(m5); TACC(3, m4, m5);
-				if (timing) tacc[11]++;
 			} else {
 				// ===================== lane threads: row `row` of the slice, slots sub*SPT .. sub*SPT+SPT-1 =====================
+				TICK(l1); TACC(7, t0, l1);
+				float g[SPT] = {0.0f, 0.0f, 0.0f, 0.0f};
+				if (it > 0) {
+					// my accumulator rows, tile by tile as the MMA warp completes them (row R = 128 i + row of the full product, my 4 slots),
+					// stored by destination slice: [slot quad][row in slice][4 slots] so that consecutive lanes write consecutive 16 bytes
+					uint32_t i = i0;
+					const uint32_t gbar = smem_u32(&ctl->gather[pb]);
+					for (uint32_t jj = 0; jj < MT; jj++) {
+						mbar_wait(&ctl->mma_bar[jj], (it - 1) & 1);
+						tc_fence_after();
+						float pa[4];
+						tmem_ld4(tmem + ((q4 * 32u) << 16) + i * 16 + ssub * SPT, pa);
+						tmem_ld_wait();
+						const uint32_t R = i * 128 + srow;
+						if (R < K) {
+							// straight from the registers into the owner's receive buffer [pb][my rank]: a remote store that counts its 16
+							// bytes on the owner's mbarrier (st.async); no staging buffer, no proxy fence, no hand-over to a copy-issuing warp
+							const uint32_t rd = (R * inv20) >> 20, rr = R - rd * CW;
+							unsigned char* lp = recv_pb + rank * CH + (ssub * CW + rr) * 16;
+							if (rd == rank) *reinterpret_cast<float4*>(lp) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+							else {
+								const uint32_t ra = mapa(smem_u32(lp), rd), rb = mapa(gbar, rd);
+								asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+								             ::"r"(ra), "f"(pa[0]), "f"(pa[1]), "f"(pa[2]), "f"(pa[3]), "r"(rb) : "memory");
+							}
+						}
+						i = (i + 1 == MT) ? 0 : i + 1;
+					}
+					tc_fence_before();
+				}
+				TICK(l1b); TACC(8, l1, l1b);
+				// what the epilogue reads from global memory is requested only now: the proxy fences of the scatter above would otherwise
+				// wait for these loads (MEMBAR), and the exchange that follows hides their latency just as well
 				LaneCtl li[SPT];
 				float sv[SPT], aux[SPT], old[SPT];
 				uint32_t lab[SPT];
 #pragma unroll
 				for (int k = 0; k < SPT; k++) {
-					li[k] = ctl->lc[pb][sub * SPT + k];
+					li[k] = ctl->lc[pb][(sub & 3) * SPT + k];
 					sv[k] = 0.0f; aux[k] = 0.0f; old[k] = 0.0f; lab[k] = LAB_BAD;
 					if (!row_valid) continue;
 					if (!BWD) {
@@ -497,41 +542,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 						if ((li[k].flags & 2u) && my_d >= 2 && my_d <= li[k].nt) old[k] = p.G[li[k].nrow + my_d * Lp + c];
 					}
 				}
-				TICK(l1); TACC(7, t0, l1);
-				float g[SPT] = {0.0f, 0.0f, 0.0f, 0.0f};
 				if (it > 0) {
-					bar_sync<BAR_LANES_MMA>(BAR_ACC);
-					tc_fence_after();
-					// my accumulator rows of every tile (row R = 128 i + row of the full product, my 4 slots), stored by destination slice:
-					// [slot quad][row in slice][4 slots] so that consecutive lanes write consecutive 16 bytes
-					// (21 warps leave 80 registers per thread -- one SM sub-partition carries 6 of them --, so the tiles go through the registers one
-					// at a time: the next load is in flight while the previous tile is stored)
-					float pa[4], pb4[4];
-					tmem_ld4(tmem + ((q4 * 32u) << 16) + sub * SPT, pa);
-#pragma unroll
-					for (int i = 0; i < MT_MAX; i++) {
-						if ((uint32_t)i >= MT) break;
-						tmem_ld_wait();
-						const float4 cur = make_float4(pa[0], pa[1], pa[2], pa[3]);
-						if ((uint32_t)i + 1 < MT) { tmem_ld4(tmem + ((q4 * 32u) << 16) + (i + 1) * 16 + sub * SPT, pb4); }
-						const uint32_t R = i * 128 + row;
-						if (R < K) {
-							const uint32_t rd = R / CW, rr = R - rd * CW;
-							unsigned char* dstb = (rd == rank ? recv_pb : send_pb) + (size_t)rd * CH + ((size_t)sub * CW + rr) * 16;
-							*reinterpret_cast<float4*>(dstb) = cur;
-						}
-						if ((uint32_t)i + 1 < MT) {
-							tmem_ld_wait();
-#pragma unroll
-							for (int q = 0; q < 4; q++) pa[q] = pb4[q];
-						}
-					}
-					tc_fence_before();
-					fence_proxy_async_smem();
-					bar_arrive<BAR_LANES_MMA>(BAR_SEND);
-					TICK(l1b); TACC(8, l1, l1b);
-					bar_sync<BAR_LANES_MMA>(BAR_RECV);
-					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);    // already complete (the MMA warp polled it): every reader's own acquire of the peers' bulk copies
+					bar_sync<BAR_LANES_1>(BAR_RECV);
+					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);    // already complete (the communication warp polled it): every reader's own acquire of the peers' bulk copies
 					if (in_tile) {
 						const unsigned char* src = recv_pb + ((size_t)sub * CW + row) * 16;
 						for (uint32_t r = 0; r < CS; r++) {
@@ -542,41 +555,38 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 					TICK(l2); TACC(10, l1b, l2);
 				}
 				TICK(l2c);
-				float val[SPT];
+				// phase A: everything the NEXT step waits for -- the new vector entries into the local MMA operand, their partial sums -- and
+				// the barrier; phase B (below): the global stores.  The proxy fence in front of the barrier is a MEMBAR that waits for every
+				// outstanding memory operation of the thread: with the stores issued first it held the whole step up until they had reached L2.
+				// The arithmetic is written with selects instead of branches so that the compiler interleaves the four slots' dependent chains
+				// (log -> add -> exp -> convert): with a branch per slot they ran one after the other.
+				float val[SPT], st0[SPT], st1[SPT], st2[SPT];
+				const uint32_t dd = row_valid ? my_d : 1u;                  // safe index into the per-duration tables
 #pragma unroll
 				for (int k = 0; k < SPT; k++) {
-					const uint32_t s = sub * SPT + k;
-					val[k] = 0.0f;
+					const uint32_t s = (sub & 3) * SPT + k;
+					const float dl = ctl->delta[pb][s][dd];
+					st0[k] = 0.0f; st1[k] = 0.0f; st2[k] = 0.0f;
 					if (!BWD) {
-						if (row_valid) {
-							if (li[k].flags & 4u) p.G[li[k].crow + c] = g[k];
-							if (li[k].flags & 2u) {
-								if (c < li[k].navail) {
-									float lr = sv[k] + ctl->delta[pb][s][my_d];
-									if (my_d <= li[k].nt) lr += __logf(my_d == 1 ? g[k] : old[k]);
-									val[k] = __expf(lr);
-								}
-								p.A[li[k].nrow + c] = val[k];
-							}
-						}
+						const bool prod = row_valid && (li[k].flags & 2u) && c < li[k].navail;
+						const bool use_log = prod && my_d <= li[k].nt;
+						const float lg = __logf(use_log ? (my_d == 1 ? g[k] : old[k]) : 1.0f);
+						const float e = __expf(sv[k] + dl + lg);
+						val[k] = prod ? e : 0.0f;
 					} else {
-						float lw = -INFINITY;
-						if (row_valid && (li[k].flags & 1u)) {
-							float dm = 0.0f, r = 0.0f, uu = 0.0f;
-							if (c < li[k].navail) {
-								uu = (li[k].flags & 4u) ? 1.0f : g[k];
-								const float lu = __logf(uu);
-								lw = sv[k] + lu;
-								const float gamma = aux[k] * __expf(lu + ctl->sg[pb][s]);
-								dm = ((lab[k] == c) ? 1.0f : 0.0f) - gamma;
-								if (my_d <= li[k].ct) r = __expf(lw + ctl->rsc[pb][s][my_d]);
-							}
-							p.Dm[li[k].crow + c] = dm; p.R[li[k].crow + c] = r;
-							if (p.Uvec) p.Uvec[li[k].crow + c] = uu;
-							p.G[li[k].crow + c] = lw;      // log-domain S+beta relative to base_t, read back by this thread d frames earlier
-						}
-						if (row_valid && (li[k].flags & 2u) && my_d <= li[k].nt)
-							val[k] = __expf((my_d == 1 ? lw : old[k]) + ctl->delta[pb][s][my_d]);
+						const bool a0 = row_valid && (li[k].flags & 1u) && c < li[k].navail;
+						const float uu = a0 ? ((li[k].flags & 4u) ? 1.0f : g[k]) : 0.0f;
+						const float lu = __logf(a0 ? uu : 1.0f);
+						const float lw = a0 ? sv[k] + lu : -INFINITY;
+						const float gamma = aux[k] * __expf(lu + ctl->sg[pb][s]);
+						const float er = __expf(lw + ctl->rsc[pb][s][dd]);
+						st0[k] = a0 ? ((lab[k] == c) ? 1.0f : 0.0f) - gamma : 0.0f;     // Dm
+						st1[k] = (a0 && my_d <= li[k].ct) ? er : 0.0f;                     // R
+						st2[k] = uu;
+						sv[k] = lw;                                                         // G: log-domain S+beta relative to base_t
+						const bool a1 = row_valid && (li[k].flags & 2u) && my_d <= li[k].nt;
+						const float ev = __expf((my_d == 1 ? lw : old[k]) + dl);
+						val[k] = a1 ? ev : 0.0f;
 					}
 					if (in_tile) {
 						const __nv_bfloat16 hi = __float2bfloat16_rn(val[k]);
@@ -595,20 +605,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 					b += __shfl_xor_sync(0xffffffffu, b, 2);
 					b += __shfl_xor_sync(0xffffffffu, b, 1);
 					// lane (bit4, bit3) now holds the sum of slot k = 2*bit4 + bit3
-					if ((lane & 7) == 0) *reinterpret_cast<float*>(myps + (q4 * 16 + sub * SPT + 2 * (lane >> 4) + ((lane >> 3) & 1)) * 4) = b;
+					if (epi_warp && (lane & 7) == 0) *reinterpret_cast<float*>(myps + (rgrp * 16 + sub * SPT + 2 * (lane >> 4) + ((lane >> 3) & 1)) * 4) = b;
 				}
 				TICK(l3); TACC(9, l2c, l3);
 				fence_proxy_async_smem();
-				bar_arrive<BAR_LANES_MMA>(BAR_TILE);
+				bar_arrive<BAR_LANES_2>(BAR_TILE);
+				// phase B: the lattice arrays (read back by later steps of this thread, by the other direction and by the gradient GEMMs)
+				if (row_valid) {
+#pragma unroll
+					for (int k = 0; k < SPT; k++) {
+						if (!BWD) {
+							if (li[k].flags & 4u) p.G[li[k].crow + c] = g[k];
+							if (li[k].flags & 2u) p.A[li[k].nrow + c] = val[k];
+						} else if (li[k].flags & 1u) {
+							p.Dm[li[k].crow + c] = st0[k]; p.R[li[k].crow + c] = st1[k];
+							if (p.Uvec) p.Uvec[li[k].crow + c] = st2[k];
+							p.G[li[k].crow + c] = sv[k];      // read back by this thread d frames earlier
+						}
+					}
+				}
 			}
 		}
 		if (timing) {
-			if (warp == MMA_WARP) { for (int i = 0; i < 4; i++) p.dbg[i] = tacc[i]; p.dbg[15] = tacc[11]; }
+			if (warp == MMA_WARP) { p.dbg[1] = tacc[1]; p.dbg[15] = tacc[11]; }
+			else if (warp == COMM_WARP) { p.dbg[0] = tacc[0]; p.dbg[2] = tacc[2]; p.dbg[3] = tacc[3]; }
 			else { for (int i = 7; i < 11; i++) p.dbg[i] = tacc[i]; }
 		}
 		// the partial sums pushed during the last executed step are never consumed: wait for them so that no bulk copy is in
 		// flight (into this CTA or out of it) when the cluster retires
-		if (warp == MMA_WARP && it > 0) mbar_wait(&ctl->psg[it & 1], ((it - 1) >> 1) & 1);
+		if (warp == COMM_WARP && it > 0) mbar_wait(&ctl->psg[it & 1], ((it - 1) >> 1) & 1);
 	}
 	tc_fence_before();
 	__syncthreads();
@@ -629,7 +654,7 @@ bool plan_ks_dp(uint32_t L, uint32_t D, int max_smem_optin, KsDpPlan* plan) {
 		if (need > 512) continue;
 		uint32_t cols = 32; while (cols < need) cols *= 2;
 		const size_t CH = (size_t)CW * 64;
-		const size_t recv_off = 2 * CS * CH, vbuf_off = recv_off + 2 * CS * CH;
+		const size_t recv_off = 0, vbuf_off = recv_off + 2 * CS * CH;
 		size_t ps_off = vbuf_off + CH;
 		ps_off = (ps_off + 127) / 128 * 128;
 		const size_t ctl_off = (ps_off + 2 * CS * PS_BYTES + 127) / 128 * 128;
