@@ -97,7 +97,7 @@ template <int COUNT> __device__ __forceinline__ void bar_sync(int id) { asm vola
 template <int COUNT> __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
 // named barriers: 1 = scales/schedule of the step published (bookkeeping -> everyone), 2 = my slice of the new vector written
 // (lanes -> MMA and communication warps), 3 = partial products of my slice arrived from every peer (communication warp -> lanes)
-constexpr int BAR_SCALES = 1, BAR_TILE = 2, BAR_RECV = 3;
+constexpr int BAR_SCALES = 1, BAR_TILE = 2;
 
 // reductions over the LPS lanes that share a slot (lane = slot + SPW*h); executed by the whole warp
 __device__ __forceinline__ double slot_max_unused(double v) {
@@ -471,11 +471,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 					// of it has been stored.  The send buffer is double-buffered: I overwrite buffer pb again two steps on, after every peer's
 					// NEXT push has reached me -- which it issued only after this push had arrived there.
 					// the partial products of my slice arrive as remote stores of the peers' lane threads, each counting its bytes on gather[pb]
-					if (lane == 0) mbar_arrive_expect_tx(&ctl->gather[pb], (CS - 1) * CH);
+					if (lane == 0) mbar_arrive_expect_tx(&ctl->gather[pb], CS * CH);
 					TICK(c1); TACC(0, t0, c1);
-					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);  // the partial products of my slice from every peer
-					bar_arrive<BAR_LANES_1>(BAR_RECV);
-					TICK(c2); TACC(2, c1, c2);
 				}
 				TICK(m4);
 				bar_sync<BAR_LANES_2>(BAR_TILE);                        // the partial sums of my slice are complete
@@ -507,13 +504,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 							// straight from the registers into the owner's receive buffer [pb][my rank]: a remote store that counts its 16
 							// bytes on the owner's mbarrier (st.async); no staging buffer, no proxy fence, no hand-over to a copy-issuing warp
 							const uint32_t rd = (R * inv20) >> 20, rr = R - rd * CW;
+							// (the rows of my own slice take the same route, to my own buffer and barrier: one completion covers everything the
+							// epilogue threads -- which are not the threads that stored -- are about to read)
 							unsigned char* lp = recv_pb + rank * CH + (ssub * CW + rr) * 16;
-							if (rd == rank) *reinterpret_cast<float4*>(lp) = make_float4(pa[0], pa[1], pa[2], pa[3]);
-							else {
-								const uint32_t ra = mapa(smem_u32(lp), rd), rb = mapa(gbar, rd);
-								asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
-								             ::"r"(ra), "f"(pa[0]), "f"(pa[1]), "f"(pa[2]), "f"(pa[3]), "r"(rb) : "memory");
-							}
+							const uint32_t ra = mapa(smem_u32(lp), rd), rb = mapa(gbar, rd);
+							asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+							             ::"r"(ra), "f"(pa[0]), "f"(pa[1]), "f"(pa[2]), "f"(pa[3]), "r"(rb) : "memory");
 						}
 						i = (i + 1 == MT) ? 0 : i + 1;
 					}
@@ -543,8 +539,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dp_ks_kernel(KsDpParams p) {
 					}
 				}
 				if (it > 0) {
-					bar_sync<BAR_LANES_1>(BAR_RECV);
-					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);    // already complete (the communication warp polled it): every reader's own acquire of the peers' bulk copies
+					mbar_wait(&ctl->gather[pb], ((it - 1) >> 1) & 1);    // the partial products of my slice from every peer (each reader polls: no hand-over hop)
 					if (in_tile) {
 						const unsigned char* src = recv_pb + ((size_t)sub * CW + row) * 16;
 						for (uint32_t r = 0; r < CS; r++) {
