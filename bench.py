@@ -387,6 +387,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_dt = reduce_max(time.perf_counter() - t0)
     e2e_value = frames_total * e2e_steps / e2e_dt
+    e2e_loglik = float(np.sum(pin_n.array - pin_z.array))
     gate.append(pins.check_loglik("cfg4", ids, pin_n.array, pin_z.array, f"cfg4 e2e last step, rank {rank}", rtol=1e-5))   # lambda moved by 7 updates of lr 1e-13
     if gate[-1]["ok"] is False:
         fail_parity(gate)
@@ -515,7 +516,8 @@ def run_ours(args):
         flops = {"score": 2.0 * (Fs + 1) * L, "forward": 2.0 * L * L, "backward": 2.0 * L * L, "xi": 2.0 * L * L,
                  "grad": 2.0 * L * (Fs + 1)}
         bytes_ = {"score": 4.0 * D * Fs + 4 * L, "forward": 8.0 * L, "backward": 12.0 * L, "xi": 8.0 * L, "grad": 4.0 * L + 4.0 * D * Fs}
-        kernel_of = {"score": "score_gemm_tmem_kernel", "forward": "dp_tc_kernel<0>", "backward": "dp_tc_kernel<1>",
+        lat = "dp_ks_kernel" if "dp_ks_kernel" in plans[0] else ("dp_tc_kernel" if "dp_tc_kernel" in plans[0] else "lattice kernel")
+        kernel_of = {"score": "score_gemm_tmem_kernel", "forward": lat + "<0>", "backward": lat + "<1>",
                      "xi": "frame_gemm_tmem_kernel<1>", "grad": "frame_gemm_tmem_kernel<0>"}
         dom = max(phase_names, key=lambda k: phase_acc[k])
         rooflines = {}
@@ -566,7 +568,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "step": "stage(H2D) + fwdbwd + prefetch(next) + allreduce + D2H(numer, logZ) + sgd_update(lr 1e-13) through the C ABI",
-                    "loglik_check": float(np.sum(pin_n.array - pin_z.array))},
+                    "loglik_check": e2e_loglik},
             "parity_gate": {"ok": all(r["ok"] is not False for r in all_gate), "unpinned": [r["what"] for r in all_gate if r["ok"] is None],
                             "cfg4_loglik": head["loglik"], "cfg4_loglik_pinned": head["loglik_pinned"], "records": all_gate if world == 1 else all_gate[:8]},
             "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "minibatch_sweep": sweep,
