@@ -151,13 +151,57 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 		for (uint32_t i = threadIdx.x; i < tot; i += blockDim.x) out[i] = xw[i];
 	}
 }
+// =================================================================================================
+// "Virtual windows" for the training GEMMs.  Five of the eight feature blocks of a segment window are SAMPLED FRAMES -- plain rows of the
+// base stream at an offset that depends only on (duration, sample) -- so the score and state-gradient GEMMs read them as row-shifted TMA
+// boxes of a PADDED copy of the base stream and only the three aggregate blocks (average, maximum, minimum over the window's frames,
+// CRF_InFtrStream_SeqMultiWindow.cpp:592-706) are materialised: [N][D][Wa] with Wa = roundup(3F + 1, 32) instead of [N][D][8F + D]
+// (cfg4: 12.8 instead of 34 kB per frame).  The one-hot duration block (:790-812) is 1 exactly at the window's own duration: it enters the
+// scores through a per-(duration, label) bias and the gradient through the constant-1 row that also counts the bias.
+// =================================================================================================
+__global__ void __launch_bounds__(256) pad_base_kernel(const float* base, float* base2, uint32_t n0, uint32_t n1, uint32_t F, uint32_t Fp) {
+	const uint64_t tot = (uint64_t)(n1 - n0) * Fp;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < tot; i += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t n = n0 + i / Fp; const uint32_t f = (uint32_t)(i % Fp);
+		base2[n * Fp + f] = f < F ? __ldg(base + n * F + f) : 0.0f;
+	}
+}
+// one CTA per frame: running sum / maximum / minimum over the window's frames in the reference's order (longest reach last), exactly the
+// arithmetic of expand_windows_kernel for these three blocks
+__global__ void __launch_bounds__(128) expand_agg_kernel(const float* base, const uint32_t* frame_t, float* Xa, uint32_t N, uint32_t F, uint32_t D, uint32_t Wa, uint32_t n0) {
+	const uint32_t n = n0 + blockIdx.x;
+	if (n >= N) return;
+	const uint32_t dmax = min(__ldg(frame_t + n) + 1, D);
+	float* out = Xa + (uint64_t)n * D * Wa;
+	const float* cur = base + (uint64_t)n * F;
+	for (uint32_t f = threadIdx.x; f < F; f += blockDim.x) {
+		float acc = 0.0f, amax = 0.0f, amin = 0.0f;
+		for (uint32_t d = 1; d <= D; d++) {
+			float* o = out + (uint64_t)(d - 1) * Wa;
+			if (d <= dmax) {
+				const float v = __ldg(cur - (uint64_t)(d - 1) * F + f);
+				acc += v;
+				amax = (d == 1 || v > amax) ? v : amax;
+				amin = (d == 1 || v < amin) ? v : amin;
+				o[f] = acc / (float)d; o[F + f] = amax; o[2 * F + f] = amin;
+			} else { o[f] = 0.0f; o[F + f] = 0.0f; o[2 * F + f] = 0.0f; }
+		}
+	}
+	for (uint32_t i = threadIdx.x; i < D * (Wa - 3 * F); i += blockDim.x) out[(uint64_t)(i / (Wa - 3 * F)) * Wa + 3 * F + i % (Wa - 3 * F)] = 0.0f;
+}
+void launch_virtual_windows(const float* base, const uint32_t* frame_t, float* base2, float* Xa, uint32_t N, uint32_t F, uint32_t Fp, uint32_t D,
+                            uint32_t Wa, uint32_t n0, uint32_t n1, cudaStream_t s) {
+	if (n1 <= n0) return;
+	pad_base_kernel<<<148 * 4, 256, 0, s>>>(base, base2, n0, n1, F, Fp);
+	expand_agg_kernel<<<n1 - n0, 128, 0, s>>>(base, frame_t, Xa, N, F, D, Wa, n0);
+}
+
 void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s) {
 	if (n1 <= p.n0) return;
 	ExpandParams q = p;
 	if (q.dpart == 0 || q.dpart > q.D) q.dpart = q.D;
 	const size_t smem = sizeof(float) * ((size_t)q.dpart * q.Wp + (size_t)q.D * (q.F + 5));
-	static size_t attr = 0;
-	if (smem > attr) { cudaFuncSetAttribute(expand_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = smem; }
+	cudaFuncSetAttribute(expand_windows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device, so no process-wide cache
 	dim3 grid(n1 - q.n0, (q.D + q.dpart - 1) / q.dpart);
 	expand_windows_kernel<<<grid, 128, smem, s>>>(q);
 }
@@ -737,10 +781,22 @@ __global__ void __launch_bounds__(256) empirical_kernel(EmpiricalParams p) {
 		const uint32_t lab = p.node_lab[n];
 		if (lab == LAB_BAD || lab >= p.L) continue;
 		const uint32_t d = lab / p.P;   // duration block (0-based); 0 for frame-level models
-		const float* x = p.X + (uint64_t)n * p.ldx + (uint64_t)d * p.W + p.sf0;
 		const double* lam = p.lambda + p.sidx[lab];
 		double acc = 0.0;
-		for (uint32_t f = lane; f < p.nSf; f += 32) acc += lam[f] * (double)x[f];
+		if (!p.virt) {
+			const float* x = p.X + (uint64_t)n * p.ldx + (uint64_t)d * p.W + p.sf0;
+			for (uint32_t f = lane; f < p.nSf; f += 32) acc += lam[f] * (double)x[f];
+		} else {
+			// the window rebuilt from its parts: five sampled base rows, the aggregate array, the one-hot duration feature
+			const uint32_t F = p.F;
+			for (uint32_t b = 0; b < 5; b++) {
+				const float* x = p.base + ((uint64_t)n - d + p.steps[d * 5 + b]) * F;
+				for (uint32_t f = lane; f < F; f += 32) acc += lam[b * F + f] * (double)x[f];
+			}
+			const float* xa = p.X + ((uint64_t)n * p.D + d) * p.W;
+			for (uint32_t f = lane; f < 3 * F; f += 32) acc += lam[5 * F + f] * (double)xa[f];
+			if (lane == 0) acc += lam[8 * F + d];
+		}
 		acc = warp_sum_d(acc);
 		if (lane == 0) {
 			if (p.use_state_bias) acc += lam[p.nSf] * p.state_bias_val;

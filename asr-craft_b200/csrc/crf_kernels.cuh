@@ -22,6 +22,10 @@ struct ExpandParams {
 	uint32_t dpart;           // durations per CTA (0 = all): small groups keep shared memory low enough to run beside a lattice CTA
 };
 void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s);   // frames [p.n0, n1)
+// virtual windows of the training GEMMs: padded base stream base2[N][Fp] and the aggregate blocks Xa[N][D][Wa] (avg | max | min | zero pad)
+// of frames [n0, n1); the five sampled-frame blocks are read from base2 at row shifts, the one-hot block rides in the bias
+void launch_virtual_windows(const float* base, const uint32_t* frame_t, float* base2, float* Xa, uint32_t N, uint32_t F, uint32_t Fp, uint32_t D,
+                            uint32_t Wa, uint32_t n0, uint32_t n1, cudaStream_t s);
 
 // ---- GEMM-1: state scores  S[n][col0+j] = sum_k A[n][k]*B[j][k] + bias[j] ----------------------
 struct ScoreGemmParams {
@@ -170,6 +174,11 @@ struct ScoreTmaParams {
 	uint32_t shared_w;                // 1: every duration block uses the same weight tiles / bias (labels = phones, stdseg_no_dur*)
 	float* smaxd;                     // [M][D] per-duration row maxima (-inf where d > t) or nullptr; needs ntile == 1
 	const uint32_t* frame_t;
+	// virtual windows (virt = 1, needs a_from_tmem): the five sampled-frame blocks are row shifts of the padded base stream base2[M][cpb*32],
+	// X holds only avg | max | min; chunks = 5 * cpb + ceil(width of X / 32) in that order (the weight tiles follow it), bias is [D*P]
+	uint32_t virt, cpb;
+	const float* base2;
+	const uint32_t* steps;            // [D*5] sample offsets (sample_steps())
 };
 // ---- native stdseg_no_dur* lattice recursions, O(P^2 + D*P) per frame (crf_dp_nodur.cu) ---------------------------
 constexpr int NODUR_UT = 16;          // utterances that advance in lock-step per group of CTAs
@@ -208,6 +217,12 @@ struct FrameGemmParams {
 	const uint32_t* pair_idx; uint32_t L; const float* Ew; uint32_t e_ld;   // Xi
 	double* out;
 	uint32_t a_from_tmem;             // 1: 128-row operand through tensor memory (frame_gemm_tmem_kernel)
+	// state gradient over virtual windows (virt = 1, needs a_from_tmem): 128-row tiles = tpb per sampled-frame block (rows of base2[N][Fp] at
+	// a row shift) + the tiles of the aggregate array; lambda row of feature f of block b = b*F + f, of aggregate column a = 5F + a; the
+	// constant-1 row sits at aggregate column 3F and counts into the bias (ones_col) and into the one-hot duration weight 8F + d
+	uint32_t virt, tpb, F, Fp;
+	const float* base2;
+	const uint32_t* steps;
 };
 // X must be 16-byte aligned, Wp % 4 == 0, the first state feature a multiple of 4 and the driver must export cuTensorMapEncodeTiled
 bool tma_gemm_eligible(const float* X, uint32_t D, uint32_t Wp, uint32_t sf0);
@@ -234,6 +249,8 @@ struct EmpiricalParams {
 	double state_bias_val, trans_bias_val;
 	double* grad;                     // transition-bias empirical counts are added here
 	double* numer;                    // [n_utt]
+	// virtual windows: X = aggregate array [N][D][W] (avg | max | min), base = un-windowed stream [N][F], steps = sample offsets [D*5]
+	uint32_t virt, F, D; const float* base; const uint32_t* steps;
 };
 void launch_empirical(const EmpiricalParams& p, cudaStream_t s);
 
@@ -325,6 +342,9 @@ struct LambdaTablesParams {
 	float* Ws; float* bias; float* E; float* ET;  // E / ET must be zero before the launch
 	double* tmax;                          // device scalar: max transition score (read back by the host as Mmax)
 	unsigned char* Wt; uint32_t wt_P, wt_D, wt_chunks;   // weight tiles of the TMA-fed score GEMM (null: skip)
+	// virtual windows (wt_virt): chunk c < 5*wt_cpb holds features [32 (c % cpb), +32) of sampled-frame block c / cpb (zero beyond F), the
+	// chunks behind them the aggregate columns 5F ...; bias_dy[d*wt_P + y] = state bias + the one-hot duration weight lambda[sidx + 8F + d]
+	uint32_t wt_virt, wt_cpb, wt_F, wt_Dd; float* bias_dy;
 	// transition-FEATURE weights (stdtrans, null Wtr: skip): Wtr[(p*L0 + c)][f] = lambda[tidx0(p,c) + f], tbias = bias weight * transBiasVal
 	float* Wtr; float* tbias; uint32_t nTf;
 	// decoder transition-FEATURE weights (null WdT: skip): WdT[f*vtE + e] = lambda[vt_base[e] + f] for the vtE = P*P + 2L decoder pairs

@@ -71,12 +71,28 @@ __global__ void __launch_bounds__(256) lambda_tables_kernel(LambdaTablesParams p
 			const uint32_t kk = (uint32_t)(i & 31), r = (uint32_t)((i >> 5) & 63);
 			const uint64_t tile = i >> 11;
 			const uint32_t c = (uint32_t)(tile % p.wt_chunks), jt = (uint32_t)((tile / p.wt_chunks) % ntile), d = (uint32_t)(tile / ((uint64_t)p.wt_chunks * ntile));
-			const uint32_t y = jt * 64 + r, k = c * 32 + kk;
+			const uint32_t y = jt * 64 + r;
+			uint32_t k = c * 32 + kk;
+			if (p.wt_virt) {
+				// chunk order of the virtual windows -> feature index inside the window (0xffffffff: padding)
+				if (c < 5 * p.wt_cpb) { const uint32_t b = c / p.wt_cpb, f = (c - b * p.wt_cpb) * 32 + kk; k = f < p.wt_F ? b * p.wt_F + f : 0xffffffffu; }
+				else { const uint32_t a = (c - 5 * p.wt_cpb) * 32 + kk; k = a < 3 * p.wt_F ? 5 * p.wt_F + a : 0xffffffffu; }
+			}
 			float w = 0.0f;
 			if (y < p.wt_P && k < p.nSf) w = (float)p.lam[p.sidx[d * p.wt_P + y] + k];
 			const __nv_bfloat16 hi = __float2bfloat16_rn(w), lo = __float2bfloat16_rn(w - __bfloat162float(hi));
 			unsigned char* t = p.Wt + tile * 8192 + (r / 8) * 512 + (kk / 8) * 128 + (r % 8) * 16 + (kk % 8) * 2;
 			*reinterpret_cast<__nv_bfloat16*>(t) = hi; *reinterpret_cast<__nv_bfloat16*>(t + 4096) = lo;
+		}
+	}
+	if (p.bias_dy) {
+		// per-(duration, label) bias of the virtual windows: the state bias + the weight of the one-hot duration feature of duration d
+		const uint64_t n = (uint64_t)p.wt_Dd * p.wt_P;
+		for (uint64_t i = tid0; i < n; i += stride) {
+			const uint32_t d = (uint32_t)(i / p.wt_P), y = (uint32_t)(i % p.wt_P);
+			const uint32_t sb = p.sidx[(p.wt_D == 1 ? 0 : d * p.wt_P) + y];
+			const double b = p.use_state_bias ? __dmul_rn(p.lam[sb + p.nSf], p.state_bias_val) : 0.0;
+			p.bias_dy[i] = (float)(b + p.lam[sb + 8 * p.wt_F + d]);
 		}
 	}
 	if (p.Wtr) {

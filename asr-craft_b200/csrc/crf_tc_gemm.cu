@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(XI_THR, 1) xi_gemm_tc_kernel(XiGemmParams p) {
 
 cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
 	if (!p.M || !p.Ncols) return cudaSuccess;
-	static bool attr_done = false;
+	bool attr_done = false;      // (function attributes are per device: no process-wide cache, a multi-GPU process configures each one)
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(score_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
 		if (e != cudaSuccess) return e;
@@ -495,7 +495,7 @@ cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
 
 cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s) {
 	if (p.n1 <= p.n0 || !p.L || !p.P || p.D > 32) return p.D > 32 ? cudaErrorInvalidValue : cudaSuccess;
-	static bool attr_done = false;
+	bool attr_done = false;      // (function attributes are per device: no process-wide cache, a multi-GPU process configures each one)
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(xi_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XI_SMEM);
 		if (e != cudaSuccess) return e;
@@ -509,7 +509,7 @@ cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s) {
 
 cudaError_t launch_reduce_gemm_tc(const ReduceGemmParams& p, bool m_side_is_b, cudaStream_t s) {
 	if (p.n1 <= p.n0 || !p.I || !p.J) return cudaSuccess;
-	static bool attr_done = false;
+	bool attr_done = false;      // (function attributes are per device: no process-wide cache, a multi-GPU process configures each one)
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(reduce_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(reduce_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);

@@ -238,7 +238,7 @@ struct TCtl {
 };
 static_assert(sizeof(TCtl) <= 256, "control block");
 
-__global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid_constant__ CUtensorMap tmX, ScoreTmaParams p) {
+__global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, ScoreTmaParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	TCtl* ctl = reinterpret_cast<TCtl*>(smem + T_CTL_OFF);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -302,11 +302,21 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid
 	} else if (warp == CONV_WARPS + 1) {
 		if (lane == 0) {
 			prefetch_tmap(&tmX);
+			if (p.virt) prefetch_tmap(&tmB);
 			for (uint32_t c = 0; c < n_chunks; c++) {
 				const uint32_t r = c % RA;
 				if (c >= RA) mbar_wait(&ctl->raw_empty[r], ((c / RA) - 1) & 1);
 				mbar_arrive_expect_tx(&ctl->raw_full[r], RAW_BYTES);
-				tma_load_3d(smem + r * RAW_BYTES, &tmX, c * KC, d, m0, &ctl->raw_full[r]);
+				if (!p.virt) tma_load_3d(smem + r * RAW_BYTES, &tmX, c * KC, d, m0, &ctl->raw_full[r]);
+				else if (c < 5 * p.cpb) {
+					// a sampled-frame block of the window = a ROW SHIFT of the (padded) base stream: the window of duration d+1 that ends on
+					// frame n starts on frame n - d and its b-th sample sits steps[d][b] frames further on
+					// (CRF_InFtrStream_SeqMultiWindow::sample_ftrs).  Rows before the batch are zero-filled by the TMA unit; rows of the
+					// previous utterance belong to windows that do not exist (d > t) and are never read downstream.
+					const uint32_t b = c / p.cpb;
+					const uint32_t shift = __ldg(p.steps + d * 5 + b) - d;
+					tma_load_3d(smem + r * RAW_BYTES, &tmB, (c - b * p.cpb) * KC, 0, m0 + shift, &ctl->raw_full[r]);
+				} else tma_load_3d(smem + r * RAW_BYTES, &tmX, (c - 5 * p.cpb) * KC, d, m0, &ctl->raw_full[r]);      // avg | max | min, materialised
 			}
 		}
 	} else {
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid
 		tc_fence_before();
 		__syncwarp();
 		const uint32_t y0 = jt * BN, ncol = min((uint32_t)BN, p.P - y0);
-		const uint32_t col0 = d * p.P + y0, bcol = (p.shared_w ? 0u : d * p.P) + y0;
+		const uint32_t col0 = d * p.P + y0, bcol = ((p.shared_w && !p.virt) ? 0u : d * p.P) + y0;   // virt: bias per (d,y), it carries the one-hot duration weight
 		const float b0 = (p.bias && lane < ncol) ? __ldg(p.bias + bcol + lane) : 0.0f;
 		const float b1 = (p.bias && lane + 32 < ncol) ? __ldg(p.bias + bcol + lane + 32) : 0.0f;
 		for (uint32_t rr = 0; rr < 32; rr++) {
@@ -533,11 +543,26 @@ struct GCtl {
 static_assert(sizeof(GCtl) <= 256, "control block");
 
 template <int MODE>
-__global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN, FrameGemmParams p) {
+__global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN, const __grid_constant__ CUtensorMap tmB, FrameGemmParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
 	GCtl* ctl = reinterpret_cast<GCtl*>(smem + G_CTL_OFF);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t m0 = blockIdx.x * BM, d = blockIdx.y / p.ntile, y0 = (blockIdx.y % p.ntile) * FRAME_GEMM_TILE;
+	const uint32_t d = blockIdx.y / p.ntile, y0 = (blockIdx.y % p.ntile) * FRAME_GEMM_TILE;
+	// virtual windows (MODE 0, p.virt): the 128-row tiles walk the window in BLOCKS -- tile mt < 5 tpb is rows [f0, f0 + 128) of sampled-frame
+	// block b (a row shift of the padded base stream), the others are rows of the materialised avg | max | min array; lam_row = index of
+	// tile row 0 inside the label's state-weight block of lambda, vrows = rows of the tile that are real features
+	uint32_t m0 = blockIdx.x * BM, vb = 0xffffffffu, vshift = 0, lam_row = m0, vrows = BM;
+	if (MODE == 0 && p.virt) {
+		const uint32_t mt = blockIdx.x;
+		if (mt < 5 * p.tpb) {
+			vb = mt / p.tpb; m0 = (mt - vb * p.tpb) * BM;
+			vshift = __ldg(p.steps + d * 5 + vb) - d;
+			lam_row = vb * p.F + m0; vrows = p.F > m0 ? min((uint32_t)BM, p.F - m0) : 0u;
+		} else {
+			m0 = (mt - 5 * p.tpb) * BM;
+			lam_row = 5 * p.F + m0; vrows = 3 * p.F > m0 ? min((uint32_t)BM, 3 * p.F - m0) : 0u;
+		}
+	}
 	const uint32_t ns = blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.N);
 	const uint32_t n_chunks = (ne - ns + KC - 1) / KC;
 	const uint32_t ncol = min((uint32_t)FRAME_GEMM_TILE, p.P - y0), col0 = d * p.P + y0, sh = col0 & 3;
@@ -559,7 +584,7 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 		const uint32_t q4 = warp & 3, ks = warp >> 2;
 		const uint32_t gm = m0 + q4 * 32 + lane;                                      // my row of the 128-row side
 		const uint32_t k = (warp & 3) * 8 + (lane & 7), cg = (warp >> 2) * 4 + (lane >> 3);   // my unit of the 64-column side
-		const bool is_ones = MODE == 0 && gm == p.ones_col;
+		const bool is_ones = MODE == 0 && (p.virt ? (vb == 0xffffffffu && gm == 3 * p.F) : gm == p.ones_col);
 		for (uint32_t c = 0; c < n_chunks; c++) {
 			const uint32_t rm = c % RM, rn = c % RN, s = c % TS;
 			mbar_wait(&ctl->m_full[rm], (c / RM) & 1);
@@ -622,8 +647,10 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 				if (c >= RM) mbar_wait(&ctl->m_empty[rm], ((c / RM) - 1) & 1);
 				mbar_arrive_expect_tx(&ctl->m_full[rm], RAW_BYTES);
 #pragma unroll
-				for (uint32_t b = 0; b < 4; b++)
-					tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmM, m0 + b * 32, MODE == 0 ? d : 0u, MODE == 0 ? n : n - (d + 1), &ctl->m_full[rm]);
+				for (uint32_t b = 0; b < 4; b++) {
+					if (MODE == 0 && p.virt && vb != 0xffffffffu) tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmB, m0 + b * 32, 0, n + vshift, &ctl->m_full[rm]);
+					else tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmM, m0 + b * 32, MODE == 0 ? d : 0u, MODE == 0 ? n : n - (d + 1), &ctl->m_full[rm]);
+				}
 				if (c >= RN) mbar_wait(&ctl->n_empty[rn], ((c / RN) - 1) & 1);
 				mbar_arrive_expect_tx(&ctl->n_full[rn], RAWN_BYTES);
 #pragma unroll
@@ -636,18 +663,25 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 		mbar_wait(&ctl->done, 0);
 		tc_fence_after();
 		const uint32_t gm = m0 + warp * 32 + lane;
-		const double sc = (MODE == 0 && gm == p.ones_col) ? p.ones_scale : p.scale;
+		const bool v_ones = MODE == 0 && p.virt && vb == 0xffffffffu && gm == 3 * p.F;      // sum_n Dm: the bias count AND the one-hot duration count
+		const bool row_ok = (MODE == 0 && p.virt) ? (warp * 32 + lane < vrows || v_ones) : gm < p.Mext;
+		const uint32_t lrow = (MODE == 0 && p.virt) ? (v_ones ? p.ones_col : lam_row + warp * 32 + lane) : gm;
+		const double sc = (MODE == 0 && (p.virt ? v_ones : gm == p.ones_col)) ? p.ones_scale : p.scale;
 #pragma unroll
 		for (int c0 = 0; c0 < BN; c0 += 16) {
 			float v[16];
 			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
 			tmem_ld_wait();
-			if (gm < p.Mext) {
+			if (row_ok) {
 #pragma unroll
 				for (int j = 0; j < 16; j++) {
 					const uint32_t y = c0 + j;
 					if (y >= ncol || v[j] == 0.0f) continue;
-					if (MODE == 0) atomicAdd(&p.out[(uint64_t)__ldg(p.row_idx + col0 + y) + gm], sc * (double)v[j]);
+					if (MODE == 0) {
+						const uint64_t rb = __ldg(p.row_idx + col0 + y);
+						if (!v_ones || p.ones_col != 0xffffffffu) atomicAdd(&p.out[rb + lrow], sc * (double)v[j]);
+						if (v_ones) atomicAdd(&p.out[rb + 8 * p.F + d], p.scale * (double)v[j]);          // the window's one-hot duration feature is 1 exactly at d
+					}
 					else {
 						const uint32_t idx = __ldg(p.pair_idx + (uint64_t)gm * p.L + col0 + y);
 						if (idx != 0xffffffffu) atomicAdd(&p.out[idx], sc * (double)__ldg(p.Ew + (uint64_t)gm * p.e_ld + col0 + y) * (double)v[j]);
@@ -697,29 +731,32 @@ uint32_t score_tma_chunks(uint32_t K) { return (K + KC - 1) / KC; }
 
 cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaParams& p, cudaStream_t s) {
 	if (!p.M || !p.P) return cudaSuccess;
-	static bool attr_done = false;
+	bool attr_done = false;      // (function attributes are per device: no process-wide cache, a multi-GPU process configures each one)
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(score_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	CUtensorMap tm;
-	if (!window_map(&tm, X, p.M, p.D, Wp, p.K, BM, true)) return cudaErrorInvalidValue;
+	CUtensorMap tm, tb;
+	// virtual windows: X is the aggregate array [M][D][Wp] (avg | max | min), base2 the padded base stream [M][cpb * 32]
+	if (!window_map(&tm, X, p.M, p.D, Wp, p.virt ? Wp : p.K, BM, true)) return cudaErrorInvalidValue;
+	if (p.virt) { if (!p.a_from_tmem || !window_map(&tb, p.base2, p.M, 1, p.cpb * KC, p.cpb * KC, BM, false)) return cudaErrorInvalidValue; }
+	else tb = tm;
 	dim3 grid((p.M + BM - 1) / BM, p.ntile, p.D);
 	if (p.a_from_tmem) {
-		static bool attr2 = false;
+		bool attr2 = false;
 		if (!attr2) {
 			cudaError_t e = cudaFuncSetAttribute(score_gemm_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM);
 			if (e != cudaSuccess) return e;
 			attr2 = true;
 		}
-		score_gemm_tmem_kernel<<<grid, SC_THR, T_SMEM, s>>>(tm, p);
+		score_gemm_tmem_kernel<<<grid, SC_THR, T_SMEM, s>>>(tm, tb, p);
 	} else score_gemm_tma_kernel<<<grid, SC_THR, SMEM_BYTES, s>>>(tm, p);
 	return cudaGetLastError();
 }
 
 static cudaError_t frame_gemm_attrs() {
-	static bool attr_done = false;
+	bool attr_done = false;      // (function attributes are per device: no process-wide cache, a multi-GPU process configures each one)
 	if (!attr_done) {
 		cudaError_t e = cudaFuncSetAttribute(frame_gemm_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(frame_gemm_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
@@ -739,10 +776,16 @@ cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const
 	cudaError_t e = frame_gemm_attrs();
 	if (e != cudaSuccess) return e;
 	// the Dm view ends at column D*P: what a box reads beyond the last block is zero-filled
-	CUtensorMap tm, tn;
-	if (!window_map(&tm, X, p.N, p.D, Wp, K, KC, false) || !window_map(&tn, Dm, p.N, 1, ldd, p.D * p.P, KC, false)) return cudaErrorInvalidValue;
-	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	if (p.a_from_tmem) frame_gemm_tmem_kernel<0><<<grid, FG_THR, G_SMEM, s>>>(tm, tn, p);
+	CUtensorMap tm, tn, tb;
+	if (!window_map(&tm, X, p.N, p.D, Wp, p.virt ? Wp : K, KC, false) || !window_map(&tn, Dm, p.N, 1, ldd, p.D * p.P, KC, false)) return cudaErrorInvalidValue;
+	uint32_t mtiles = (p.Mext + BM - 1) / BM;
+	if (p.virt) {
+		// virtual windows: X = aggregate array (avg | max | min, the constant-1 row right behind), base2 = padded base stream [N][Fp]
+		if (!p.a_from_tmem || !window_map(&tb, p.base2, p.N, 1, p.Fp, p.Fp, KC, false)) return cudaErrorInvalidValue;
+		mtiles = 5 * p.tpb + (3 * p.F + 1 + BM - 1) / BM;
+	} else tb = tm;
+	dim3 grid(mtiles, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
+	if (p.a_from_tmem) frame_gemm_tmem_kernel<0><<<grid, FG_THR, G_SMEM, s>>>(tm, tn, tb, p);
 	else frame_gemm_tma_kernel<0><<<grid, FG_THR, F_SMEM, s>>>(tm, tn, p);
 	return cudaGetLastError();
 }
@@ -756,7 +799,7 @@ cudaError_t launch_xi_gemm_tma(const float* A, const float* R, uint32_t ld, cons
 	CUtensorMap ta, tr;
 	if (!window_map(&ta, A, p.N, 1, ld, p.L, KC, false) || !window_map(&tr, R, p.N, 1, ld, p.L, KC, false)) return cudaErrorInvalidValue;
 	dim3 grid((p.Mext + BM - 1) / BM, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
-	if (p.a_from_tmem) frame_gemm_tmem_kernel<1><<<grid, FG_THR, G_SMEM, s>>>(ta, tr, p);
+	if (p.a_from_tmem) frame_gemm_tmem_kernel<1><<<grid, FG_THR, G_SMEM, s>>>(ta, tr, ta, p);
 	else frame_gemm_tma_kernel<1><<<grid, FG_THR, F_SMEM, s>>>(ta, tr, p);
 	return cudaGetLastError();
 }

@@ -69,10 +69,12 @@ struct crfgpu_ctx {
 	unsigned char* pin = nullptr; size_t pin_cap = 0, pin_used = 0; cudaEvent_t ev_pin = nullptr;
 	// crfgpu_prefetch_batch: the NEXT minibatch's base features and windows, copied / expanded into a second buffer set on side streams
 	// while the current minibatch computes; crfgpu_stage_batch swaps the sets when it is handed the batch that was prefetched
-	DevBuf d_base2, d_X2, d_frame_t2; cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre_done = nullptr, ev_pre_ready = nullptr;
+	DevBuf d_base2, d_X2, d_frame_t2, d_bpad2, d_Xa2; bool pre_virt = false; cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre_done = nullptr, ev_pre_ready = nullptr;
 	cudaEvent_t ev_swap = nullptr; bool swap_marked = false;   // main-stream point after which the spare buffer set is free
 	std::vector<cudaEvent_t> ev_chunk2; bool pre_valid = false; const float* pre_ftrs = nullptr; std::vector<uint32_t> pre_off;
 	uint32_t W = 0;          // window feature width
+	// virtual windows of the training GEMMs (see launch_virtual_windows): padded base stream [N][Fp] + aggregate blocks [N][D][Wa]
+	bool virt = false, x_virt_valid = false, x_full_valid = false; int opt_virt = 1; uint32_t Fp = 0, Wa = 0; DevBuf d_bpad, d_Xa, d_bias_dy;
 	uint32_t Wp = 0;         // stride between the windows of a frame in X (>= W; currently W, see crfgpu_create)
 	uint32_t Lp = 0;         // padded label stride of the lattice arrays
 	// label set the lattice kernels run on: the model's labels, or -- for the stdseg_no_dur* models -- the (duration, phone)
@@ -217,6 +219,18 @@ void classify(crfgpu_ctx* h) {
 }
 
 // lattice label space of the handle (depends on the no_dur implementation chosen by classify) and its lambda index tables
+// virtual windows: segment windows whose whole width is the state-feature range, no transition features, TMA-fed tcgen05 GEMMs with the
+// 128-row operand through tensor memory.  The weight tiles follow the virtual chunk order, so the tables are derived again when an option
+// flips the decision (crfgpu_set_option).
+bool decide_virt(crfgpu_ctx* h) {
+	const crfgpu_config& c = h->cfg;
+	const bool was = h->virt;
+	h->Fp = (c.n_base_ftrs + 31) / 32 * 32; h->Wa = (3 * c.n_base_ftrs + 1 + 31) / 32 * 32;
+	h->virt = h->opt_virt && h->train_ok && c.max_dur > 1 && c.extract_seg_ftrs && !c.use_trans_ftrs && c.use_state_ftrs && c.state_fidx_start == 0 &&
+	          c.state_fidx_end + 1 == h->W && h->opt_gemm_impl == 2 && (h->opt_tma_mask & 27) == 27 && tma_gemm_eligible(nullptr, c.max_dur, h->Wa, 0);
+	return was != h->virt;
+}
+
 void setup_label_space(crfgpu_ctx* h) {
 	classify(h);
 	const uint32_t L0 = h->lay.L, Dd = h->cfg.max_dur;
@@ -236,6 +250,7 @@ void setup_label_space(crfgpu_ctx* h) {
 		}
 	}
 	h->have_lambda = false; h->fwdbwd_done = false;
+	decide_virt(h);
 	if (h->stream) {
 		upload(h->d_sidx, h->t_sidx, h->stream); upload(h->d_tidx, h->t_tidx, h->stream);
 		if (h->decode_ok && (h->tied || h->nodur)) { upload(h->d_sidx0, h->lay.sidx, h->stream); upload(h->d_tidx0, h->lay.tidx, h->stream); }
@@ -289,6 +304,10 @@ void derive_tables(crfgpu_ctx* h) {
 		p.Ws = h->d_Ws.as<float>(); p.bias = h->d_bias.as<float>(); p.E = h->d_E.as<float>(); p.ET = h->d_ET.as<float>();
 		if (c.max_dur > 1 && nSf > 0) {   // bf16 hi/lo UMMA tiles of the state weights for the TMA-fed score GEMM
 			p.wt_P = h->nodur ? L : Lt / c.max_dur; p.wt_D = h->nodur ? 1 : c.max_dur; p.wt_chunks = score_tma_chunks(nSf);
+			if (h->virt) {
+				p.wt_virt = 1; p.wt_cpb = h->Fp / 32; p.wt_F = c.n_base_ftrs; p.wt_Dd = c.max_dur; p.wt_chunks = 5 * p.wt_cpb + h->Wa / 32;
+				h->d_bias_dy.ensure(sizeof(float) * (size_t)c.max_dur * p.wt_P + 16); p.bias_dy = h->d_bias_dy.as<float>();
+			}
 			h->d_Wt.ensure((size_t)p.wt_D * ((p.wt_P + 63) / 64) * p.wt_chunks * 8192 + 16);
 			p.Wt = h->d_Wt.as<unsigned char>();
 		}
@@ -333,9 +352,10 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 
 // ---------------------------------------------------------------------------------------------// Base features to the device in up to 4 chunks cut at utterance boundaries on the copy stream, and -- on stream xs -- the window
 // expansion of chunk i (windows never reach across utterances) while chunk i+1 is still in flight.  d_ft must already be queued on xs.
+// virt: the virtual-window form (padded base stream d_bp + aggregate blocks d_Xa) instead of the full windows d_X.
 void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_t N, const float* ftrs, DevBuf& d_base, DevBuf& d_X, DevBuf& d_ft,
                      cudaStream_t xs, cudaEvent_t ev_ready, std::vector<cudaEvent_t>& evs, const char* phase, uint32_t dpart = 0,
-                     const std::function<void(uint32_t, uint32_t)>* after_chunk = nullptr) {
+                     const std::function<void(uint32_t, uint32_t)>* after_chunk = nullptr, bool virt = false, DevBuf* d_bp = nullptr, DevBuf* d_Xa = nullptr) {
 	const crfgpu_config& c = h->cfg;
 	if (!N) return;
 	if (!h->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -360,7 +380,10 @@ void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_
 	n_prev = 0;
 	for (size_t k = 0; k < ends.size(); k++) {
 		CUDA_OK(cudaStreamWaitEvent(xs, evs[k], 0));
-		if (c.max_dur > 1) {
+		if (c.max_dur > 1 && virt) {
+			launch_virtual_windows(d_base.as<float>(), d_ft.as<uint32_t>(), d_bp->as<float>(), d_Xa->as<float>(), N, c.n_base_ftrs, h->Fp, c.max_dur, h->Wa, n_prev, ends[k], xs);
+			check_kernel(h, 2);
+		} else if (c.max_dur > 1) {
 			ExpandParams ep{d_base.as<float>(), d_ft.as<uint32_t>(), h->d_steps.as<uint32_t>(), d_X.as<float>(),
 			                N, c.n_base_ftrs, c.max_dur, h->W, h->Wp, c.extract_seg_ftrs, n_prev, dpart};
 			launch_expand_windows(ep, ends[k], xs);
@@ -396,14 +419,17 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 	for (uint32_t u = 0; u < n_utt; u++)
 		for (uint32_t n = off[u]; n < off[u + 1]; n++) frame_t[n] = n - off[u];
 	h->d_base2.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
-	if (c.max_dur > 1) h->d_X2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+	h->pre_virt = h->virt;                                               // the read-ahead of a training loop: the form the training GEMMs read
+	if (h->pre_virt) { h->d_bpad2.ensure(sizeof(float) * (size_t)N * h->Fp + 16); h->d_Xa2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wa + 16); }
+	else if (c.max_dur > 1) h->d_X2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
 	upload(h->d_frame_t2, frame_t, h->pre_stream);                       // pageable: waits only for this side stream's own earlier work
 	// optional cap on the expansion's shared memory per CTA (option prefetch_smem): small duration groups fit beside a resident lattice
 	// CTA, but measured on cfg4 that SLOWS the step (e2e 13.0 M frames/s at 12 KB vs 14.1 M uncapped: the co-resident CTAs steal issue
 	// and shared-memory bandwidth from the latency-bound recursion), so by default the read-ahead uses whole-frame CTAs
 	uint32_t dpart = c.max_dur;
 	while (dpart > 1 && sizeof(float) * ((size_t)dpart * h->Wp + (size_t)c.max_dur * (c.n_base_ftrs + 5)) > (size_t)h->opt_prefetch_smem) dpart--;
-	copy_and_expand(h, n_utt, off, N, ftrs, h->d_base2, h->d_X2, h->d_frame_t2, h->pre_stream, h->ev_pre_ready, h->ev_chunk2, nullptr, dpart);
+	copy_and_expand(h, n_utt, off, N, ftrs, h->d_base2, h->d_X2, h->d_frame_t2, h->pre_stream, h->ev_pre_ready, h->ev_chunk2, nullptr, dpart, nullptr,
+	                h->pre_virt, &h->d_bpad2, &h->d_Xa2);
 	CUDA_OK(cudaEventRecord(h->ev_pre_done, h->pre_stream));
 	h->pre_off.assign(off, off + n_utt + 1); h->pre_ftrs = ftrs; h->pre_valid = true;
 }
@@ -433,19 +459,23 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	for (uint32_t u = 0; u < n_utt; u++)
 		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
 	upload_async(h, h->d_off, h->h_off);
-	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off;
+	const bool want_virt = h->virt && labs != nullptr;                   // training batches of eligible models stage the virtual-window form
+	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off && h->pre_virt == want_virt;
 	h->pre_valid = false;
+	h->x_virt_valid = want_virt; h->x_full_valid = !want_virt;
 	if (prefetched) {
 		// this batch was copied and expanded by crfgpu_prefetch_batch while the previous one computed: take over its buffers
 		if (!h->ev_swap) CUDA_OK(cudaEventCreateWithFlags(&h->ev_swap, cudaEventDisableTiming));
 		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
 		std::swap(h->d_base, h->d_base2); std::swap(h->d_X, h->d_X2); std::swap(h->d_frame_t, h->d_frame_t2);
+		std::swap(h->d_bpad, h->d_bpad2); std::swap(h->d_Xa, h->d_Xa2);
 		CUDA_OK(cudaStreamWaitEvent(s, h->ev_pre_done, 0));
 	} else {
 		// what the window expansion needs goes through the copy engine ahead of the feature chunks
 		upload_async(h, h->d_frame_t, frame_t);
 		h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
-		if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+		if (want_virt && N) { h->d_bpad.ensure(sizeof(float) * (size_t)N * h->Fp + 16); h->d_Xa.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wa + 16); }
+		else if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
 		if (N && !h->ev_ready) CUDA_OK(cudaEventCreate(&h->ev_ready));
 		// a decode batch (no labels): the decoder's fp64 state scores of a chunk are launched as soon as the chunk has arrived, so the
 		// scoring runs under the remaining H2D copies instead of behind them
@@ -459,7 +489,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		};
 		const bool eager_vit = !labs && N && h->decode_ok && h->have_lambda && h->lay.nSf > 0;
 		if (eager_vit) h->d_negS.ensure(sizeof(float) * (size_t)N * c.max_dur * h->lay.L + 16);
-		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand", 0, eager_vit ? &score_chunk : nullptr);
+		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand", 0, eager_vit ? &score_chunk : nullptr,
+		                want_virt, &h->d_bpad, &h->d_Xa);
 		h->vit_score_ready = eager_vit;
 	}
 	upload_async(h, h->d_frame_utt, frame_utt); upload_async(h, h->d_frame_len, frame_len);
@@ -641,6 +672,27 @@ __global__ void tail_sums_kernel(const double* numer, const double* logZ, uint32
 	}
 }
 
+// The window arrays of the staged batch in the form the next consumer reads, rebuilt from the resident base stream when the batch was
+// staged in the other form (a decode call on a training batch, an option changed between staging and the call).
+void ensure_windows(crfgpu_ctx* h, bool want_virt) {
+	const crfgpu_config& c = h->cfg;
+	if (c.max_dur == 1 || !h->N) return;
+	cudaStream_t s = h->stream;
+	if (want_virt && !h->x_virt_valid) {
+		h->d_bpad.ensure(sizeof(float) * (size_t)h->N * h->Fp + 16); h->d_Xa.ensure(sizeof(float) * (size_t)h->N * c.max_dur * h->Wa + 16);
+		launch_virtual_windows(h->d_base.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_bpad.as<float>(), h->d_Xa.as<float>(), h->N, c.n_base_ftrs, h->Fp, c.max_dur, h->Wa, 0, h->N, s);
+		check_kernel(h, 2);
+		h->x_virt_valid = true;
+	} else if (!want_virt && !h->x_full_valid) {
+		h->d_X.ensure(sizeof(float) * (size_t)h->N * c.max_dur * h->Wp + 16);
+		ExpandParams ep{h->d_base.as<float>(), h->d_frame_t.as<uint32_t>(), h->d_steps.as<uint32_t>(), h->d_X.as<float>(),
+		                h->N, c.n_base_ftrs, c.max_dur, h->W, h->Wp, c.extract_seg_ftrs, 0, 0};
+		launch_expand_windows(ep, h->N, s);
+		check_kernel(h, 1);
+		h->x_full_valid = true;
+	}
+}
+
 DpParams dp_params(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	DpParams p{};
@@ -677,7 +729,9 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	if (!N) { h->fwdbwd_done = true; return; }
 
 	// K1: state scores.  TMA-fed kernel: all durations in one launch, per-duration maxima fused; otherwise one GEMM per duration block
-	const bool tma = h->opt_gemm_impl == 2 && (h->opt_tma_mask & 1) && D > 1 && nSf > 0 && tma_gemm_eligible(h->X() + c.state_fidx_start, D, h->Wp, c.state_fidx_start);
+	const bool virt = h->virt;                                    // virtual windows: sampled-frame blocks as row shifts of the padded base stream
+	ensure_windows(h, virt);
+	const bool tma = virt || (h->opt_gemm_impl == 2 && (h->opt_tma_mask & 1) && D > 1 && nSf > 0 && tma_gemm_eligible(h->X() + c.state_fidx_start, D, h->Wp, c.state_fidx_start));
 	bool smax_done = false;
 	if (nSf == 0) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
 	phase_begin(h, "score");
@@ -687,6 +741,11 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		g.M = N; g.P = P; g.K = nSf; g.D = D; g.n_chunks = score_tma_chunks(nSf); g.ntile = (P + 63) / 64;
 		g.frame_t = h->d_frame_t.as<uint32_t>(); g.shared_w = h->nodur ? 1u : 0u; g.a_from_tmem = (h->opt_tma_mask & 8) ? 1u : 0u;
 		if ((h->tc_ok || h->ks_ok || h->nodur) && g.ntile == 1) { h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16); g.smaxd = h->d_smaxd.as<float>(); smax_done = true; }
+		if (virt) {
+			g.virt = 1; g.cpb = h->Fp / 32; g.base2 = h->d_bpad.as<float>(); g.steps = h->d_steps.as<uint32_t>();
+			g.bias = h->d_bias_dy.as<float>(); g.n_chunks = 5 * g.cpb + h->Wa / 32;
+			CUDA_OK(launch_score_gemm_tma(h->d_Xa.as<float>(), h->Wa, g, s));
+		} else
 		CUDA_OK(launch_score_gemm_tma(h->X() + c.state_fidx_start, h->Wp, g, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
@@ -912,6 +971,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	const uint32_t Lv = h->nodur ? h->Pp : Lp;                  // row stride of the forward / right-factor vectors
 	const bool lat_tma = h->opt_gemm_impl == 2 && lattice_tma_eligible(h->d_A.as<float>(), Lv) && lattice_tma_eligible(h->d_R.as<float>(), Lv) &&
 	                     lattice_tma_eligible(h->d_Dm.as<float>(), Lp);
+	if (virt && !(lat_tma && tma)) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "internal: the virtual-window form needs the TMA-fed gradient kernels");
 	if (h->nodur && !(lat_tma && tma)) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the native stdseg_no_dur* path needs the TMA-fed gradient kernels (gemm_impl 2)");
 	if (h->nodur_tf) {
 		// transition weights: out[tidx(y',y) + f] += sum_n ([ref pair] - xi)[n][y'][y] * x_{n,1}[tf0 + f]  (duration-1 window of frame n)
@@ -969,6 +1029,10 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.ones_col = c.use_state_bias ? nSf : 0xffffffffu; r.scale = 1.0; r.ones_scale = c.state_bias_val;
 		r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
 		r.a_from_tmem = (h->opt_tma_mask & 16) ? 1u : 0u;
+		if (virt) {
+			r.virt = 1; r.F = c.n_base_ftrs; r.Fp = h->Fp; r.tpb = (c.n_base_ftrs + 127) / 128; r.base2 = h->d_bpad.as<float>(); r.steps = h->d_steps.as<uint32_t>();
+			CUDA_OK(launch_state_grad_tma(h->d_Xa.as<float>(), h->Wa, nSf, h->d_Dm.as<float>(), Lp, r, s));
+		} else
 		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, h->d_Dm.as<float>(), Lp, r, s));
 		check_kernel(h, 1);
 	} else for (uint32_t d = 0; d < D; d++) {
@@ -990,6 +1054,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	e.use_state_bias = c.use_state_bias; e.use_trans_bias = c.use_trans_bias;
 	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
 	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
+	if (virt) { e.virt = 1; e.F = c.n_base_ftrs; e.D = D; e.base = h->d_base.as<float>(); e.steps = h->d_steps.as<uint32_t>(); e.X = h->d_Xa.as<float>(); e.W = h->Wa; }
 	if (!h->nodur_tf) { launch_empirical(e, s); check_kernel(h, 1); }      // nodur_tf: numerators come from the forward kernel, counts from Dm / Xd
 	if (h->opt_mass_check) {
 		// the nodes' posterior-mass assertion (frame-level: 0.9..1.1, segmental: the probability that a segment ends here, 0..1)
@@ -1007,6 +1072,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 
 void viterbi_staged(crfgpu_ctx* h) {
 	require_decode(h);
+	ensure_windows(h, false);
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t N = h->N, L = m.L, D = c.max_dur, NS = m.n_states, P = m.n_act;
 	cudaStream_t s = h->stream;
@@ -1242,7 +1308,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_mass, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1513,6 +1579,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		if (n == "slots") h->opt_slots = (int)value;
 		else if (n == "k_slab") { if (value < 16) throw ApiError(CRFGPU_ERR_ARG, "k_slab must be >= 16"); h->opt_k_slab = (uint32_t)value; }
 		else if (n == "keep_lattice") h->opt_keep_lattice = value != 0;
+		else if (n == "virt_windows") h->opt_virt = value != 0;           // 0: the training GEMMs read fully materialised windows (34 kB per cfg4 frame instead of 12.8)
 		else if (n == "gemm_impl") h->opt_gemm_impl = (int)value;        // 0: fp32 FFMA tiles; 1: tcgen05 split-bf16, register-staged; 2: + TMA-fed window GEMMs
 		else if (n == "nodur_impl") {                                    // stdseg_no_dur* lattice: 0 auto, 1 native O(P^2 + D*P), 2 tied (duration, phone) expansion
 			h->opt_nodur_impl = (int)value;
@@ -1530,6 +1597,10 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		else if (n == "mass_check") h->opt_mass_check = value != 0;       // 0 skips the posterior-mass assertion pass (one read of the posterior array)
 		else if (n == "max_clusters") h->opt_max_clusters = (int)value;   // cap on the resident clusters of the lattice kernels (0 = all): a small cap makes every slot work through a long utterance list
 		else throw ApiError(CRFGPU_ERR_ARG, "unknown option " + n);
+		if ((n == "virt_windows" || n == "gemm_impl" || n == "tma_mask") && decide_virt(h) && h->have_lambda) {
+			CUDA_OK(cudaSetDevice(h->device));
+			derive_tables(h);                                              // the weight tiles follow the chunk order of the window form
+		}
 	});
 }
 
