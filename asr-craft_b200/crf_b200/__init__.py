@@ -32,27 +32,42 @@ class Config(C.Structure):
                 ("use_state_ftrs", C.c_uint32), ("state_fidx_start", C.c_uint32), ("state_fidx_end", C.c_uint32),
                 ("use_trans_ftrs", C.c_uint32), ("trans_fidx_start", C.c_uint32), ("trans_fidx_end", C.c_uint32),
                 ("use_state_bias", C.c_uint32), ("use_trans_bias", C.c_uint32),
-                ("state_bias_val", C.c_double), ("trans_bias_val", C.c_double)]
+                ("state_bias_val", C.c_double), ("trans_bias_val", C.c_double),
+                # context frames of stream 1, optional joined second stream (ftr1_* / ftr2_* of CRFTrain)
+                ("left_ctx", C.c_uint32), ("right_ctx", C.c_uint32), ("boundary_delta", C.c_uint32),
+                ("n_base_ftrs2", C.c_uint32), ("extract_seg_ftrs2", C.c_uint32), ("left_ctx2", C.c_uint32),
+                ("right_ctx2", C.c_uint32), ("boundary_delta2", C.c_uint32)]
 
 
-def window_width(n_base_ftrs, max_dur, extract_seg_ftrs):
-    if max_dur == 1 or not extract_seg_ftrs:
-        return n_base_ftrs
-    return 8 * n_base_ftrs + max_dur
+def window_width(n_base_ftrs, max_dur, extract_seg_ftrs, left_ctx=0, right_ctx=0, boundary_delta=0):
+    """width of one stream's window vector (CRF_InFtrStream_SeqMultiWindow ctor, .cpp:47-117)"""
+    if max_dur == 1:
+        return (left_ctx + 1 + right_ctx) * n_base_ftrs
+    if extract_seg_ftrs:
+        return 8 * n_base_ftrs + max_dur + (left_ctx + right_ctx) * n_base_ftrs
+    if boundary_delta:
+        return min(left_ctx, right_ctx + 1) * n_base_ftrs
+    return (left_ctx + 1 + right_ctx) * n_base_ftrs
 
 
 def make_config(model_type="stdframe", n_labs=0, n_base_ftrs=0, n_states=1, max_dur=1, n_actual_labs=None,
                 extract_seg_ftrs=0, use_trans_ftrs=0, state_fidx=None, trans_fidx=None,
-                use_state_bias=1, use_trans_bias=1, state_bias_val=1.0, trans_bias_val=1.0):
+                use_state_bias=1, use_trans_bias=1, state_bias_val=1.0, trans_bias_val=1.0,
+                left_ctx=0, right_ctx=0, boundary_delta=0, n_base_ftrs2=0, extract_seg_ftrs2=0, left_ctx2=0, right_ctx2=0,
+                boundary_delta2=0):
     """Same defaults as CRFTrain's set_fmap_config (CRFTrain/src/Main.cpp:372-430)."""
-    w = window_width(n_base_ftrs, max_dur, extract_seg_ftrs)
+    w = window_width(n_base_ftrs, max_dur, extract_seg_ftrs, left_ctx, right_ctx, boundary_delta)
+    if n_base_ftrs2:
+        w += window_width(n_base_ftrs2, max_dur, extract_seg_ftrs2, left_ctx2, right_ctx2, boundary_delta2)
     if n_actual_labs is None:
         n_actual_labs = n_labs // max_dur if model_type == "stdseg" else n_labs
     s0, s1 = state_fidx if state_fidx is not None else (0, w - 1)
     t0, t1 = trans_fidx if trans_fidx is not None else (0, w - 1)
     return Config(MODEL_TYPES[model_type], n_labs, n_base_ftrs, n_states, max_dur, n_actual_labs,
                   int(extract_seg_ftrs), 1, s0, s1, int(use_trans_ftrs), t0, t1,
-                  int(use_state_bias), int(use_trans_bias), state_bias_val, trans_bias_val)
+                  int(use_state_bias), int(use_trans_bias), state_bias_val, trans_bias_val,
+                  int(left_ctx), int(right_ctx), int(boundary_delta), int(n_base_ftrs2), int(extract_seg_ftrs2),
+                  int(left_ctx2), int(right_ctx2), int(boundary_delta2))
 
 
 def copy_config(cfg):
@@ -72,7 +87,8 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_comm_unique_id", "crfgpu_comm_init_rank", "crfgpu_comm_init_all", "crfgpu_comm_destroy", "crfgpu_comm_size",
            "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
            "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info",
-           "crfgpu_fetch_posterior_mass"]
+           "crfgpu_fetch_posterior_mass", "crfgpu_stage_batch2", "crfgpu_fwdbwd_batch2", "crfgpu_viterbi_batch2",
+           "crfgpu_expand_windows2"]
 COMM_ID_BYTES = 128
 
 
@@ -258,7 +274,9 @@ class CrfGpu:
         self._check(self.lib.crfgpu_set_train_state(self.h, *[None if a is None else _ptr(a, C.c_double) for a in arrs]))
 
     # ---- host-buffer calls --------------------------------------------------------------------
-    def fwdbwd(self, off, ftrs, labs, out=None):
+    def fwdbwd(self, off, ftrs, labs, out=None, ftrs2=None):
+        """ftrs2: the joined second stream (crfgpu_fwdbwd_batch2); with context frames stream s has
+        off[u] + u * (left_ctx_s + right_ctx_s) rows before utterance u"""
         off = np.ascontiguousarray(off, np.uint32)
         ftrs = np.ascontiguousarray(ftrs, np.float32)
         labs = np.ascontiguousarray(labs, np.uint32)
@@ -266,24 +284,32 @@ class CrfGpu:
         if out is None:
             out = (np.zeros(self.lambda_len, np.float64), np.zeros(n, np.float64), np.zeros(n, np.float64))
         grad, numer, logz = out
-        self._check(self.lib.crfgpu_fwdbwd_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
-                                                 _ptr(labs, C.c_uint32), _ptr(grad, C.c_double),
-                                                 _ptr(numer, C.c_double), _ptr(logz, C.c_double)))
+        if ftrs2 is not None:
+            ftrs2 = np.ascontiguousarray(ftrs2, np.float32)
+            self._check(self.lib.crfgpu_fwdbwd_batch2(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float), _ptr(ftrs2, C.c_float),
+                                                      _ptr(labs, C.c_uint32), _ptr(grad, C.c_double),
+                                                      _ptr(numer, C.c_double), _ptr(logz, C.c_double)))
+        else:
+            self._check(self.lib.crfgpu_fwdbwd_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
+                                                     _ptr(labs, C.c_uint32), _ptr(grad, C.c_double),
+                                                     _ptr(numer, C.c_double), _ptr(logz, C.c_double)))
         self._n_utt, self._n_frames = n, int(off[-1])
         return grad, numer, logz
 
-    def viterbi(self, off, ftrs, raw=False):
+    def viterbi(self, off, ftrs, raw=False, ftrs2=None):
         off = np.ascontiguousarray(off, np.uint32)
         ftrs = np.ascontiguousarray(ftrs, np.float32)
+        f2 = None if ftrs2 is None else np.ascontiguousarray(ftrs2, np.float32)
         n, tot = len(off) - 1, int(off[-1])
         lab = np.zeros(tot, np.uint32)
         dur = np.zeros(tot, np.uint32)
         phn = np.zeros(tot, np.uint32)
         nseg = np.zeros(n, np.uint32)
         cost = np.zeros(n, np.float32)
-        self._check(self.lib.crfgpu_viterbi_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
-                                                  _ptr(lab, C.c_uint32), _ptr(dur, C.c_uint32), _ptr(phn, C.c_uint32),
-                                                  _ptr(nseg, C.c_uint32), _ptr(cost, C.c_float)))
+        self._check(self.lib.crfgpu_viterbi_batch2(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
+                                                   None if f2 is None else _ptr(f2, C.c_float),
+                                                   _ptr(lab, C.c_uint32), _ptr(dur, C.c_uint32), _ptr(phn, C.c_uint32),
+                                                   _ptr(nseg, C.c_uint32), _ptr(cost, C.c_float)))
         self._n_utt, self._n_frames = n, tot
         if raw:
             return lab, dur, phn, nseg, cost
@@ -293,12 +319,15 @@ class CrfGpu:
             segs.append((lab[b:b + k].copy(), dur[b:b + k].copy(), phn[b:b + k].copy()))
         return segs, cost
 
-    def expand_windows(self, ftrs):
+    def expand_windows(self, ftrs, ftrs2=None):
+        """ftrs: [left_ctx + T + right_ctx][n_base_ftrs]; ftrs2 likewise for the joined second stream -> [T][max_dur][width]"""
         ftrs = np.ascontiguousarray(ftrs, np.float32)
-        T = ftrs.shape[0]
-        w = window_width(self.cfg.n_base_ftrs, self.cfg.max_dur, self.cfg.extract_seg_ftrs)
+        f2 = None if ftrs2 is None else np.ascontiguousarray(ftrs2, np.float32)
+        T = ftrs.shape[0] - self.cfg.left_ctx - self.cfg.right_ctx
+        w = int(self.lib.crfgpu_window_width(C.byref(self.cfg)))
         out = np.zeros((T, self.cfg.max_dur, w), np.float32)
-        self._check(self.lib.crfgpu_expand_windows(self.h, C.c_uint32(T), _ptr(ftrs, C.c_float), _ptr(out, C.c_float)))
+        self._check(self.lib.crfgpu_expand_windows2(self.h, C.c_uint32(T), _ptr(ftrs, C.c_float), None if f2 is None else _ptr(f2, C.c_float),
+                                                    _ptr(out, C.c_float)))
         return out
 
     def group_labels(self, labs):
@@ -309,15 +338,17 @@ class CrfGpu:
         return out
 
     # ---- device-resident calls ----------------------------------------------------------------
-    def stage(self, off, ftrs, labs=None):
+    def stage(self, off, ftrs, labs=None, ftrs2=None):
         off = np.ascontiguousarray(off, np.uint32)
         ftrs = np.ascontiguousarray(ftrs, np.float32)
+        f2 = None if ftrs2 is None else np.ascontiguousarray(ftrs2, np.float32)
         lp = None
         if labs is not None:
             labs = np.ascontiguousarray(labs, np.uint32)
             lp = _ptr(labs, C.c_uint32)
         n = len(off) - 1
-        self._check(self.lib.crfgpu_stage_batch(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float), lp))
+        self._check(self.lib.crfgpu_stage_batch2(self.h, C.c_uint32(n), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
+                                                 None if f2 is None else _ptr(f2, C.c_float), lp))
         self._n_utt, self._n_frames = n, int(off[-1])
 
     def prefetch(self, off, ftrs):

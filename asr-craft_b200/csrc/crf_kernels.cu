@@ -196,6 +196,65 @@ void launch_virtual_windows(const float* base, const uint32_t* frame_t, float* b
 	expand_agg_kernel<<<n1 - n0, 128, 0, s>>>(base, frame_t, Xa, N, F, D, Wa, n0);
 }
 
+// =================================================================================================
+// General window expansion: context frames around the window, boundary deltas, a second stream joined behind the first
+// (CRF_InFtrStream_SeqMultiWindow::read_ftrs, CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:325-471: first_frame_left_ctx_ftrs :897-935 |
+// sample / avg / max / min / dur or first_frame_ftrs :1017-1048 | last_frame_right_ctx_ftrs :977-1015 (segment features) or
+// first_frame_right_ctx_ftrs :937-975, or boundary_delta_ftrs :1050-1110 alone; QN_InFtrStream_JoinFtrs puts stream 2's vector behind
+// stream 1's).  One CTA per frame, one thread per output element: a gather with the reference's running sum / max / min order.
+// Labelled frame t of utterance u is row  n + u (lc + rc) + lc  of a stream with lc + rc context frames per utterance.
+// =================================================================================================
+__global__ void __launch_bounds__(256) expand_joined_kernel(ExpandJoinedParams p) {
+	const uint32_t n = blockIdx.x;
+	if (n >= p.N) return;
+	const uint32_t t = __ldg(p.frame_t + n), u = __ldg(p.frame_utt + n);
+	const uint32_t dmax = min(t + 1, p.D);
+	float* out = p.X + (uint64_t)n * p.D * p.Wp;
+	for (uint32_t i = threadIdx.x; i < p.D * p.Wp; i += blockDim.x) {
+		const uint32_t d0 = i / p.Wp;            // duration - 1
+		uint32_t j = i - d0 * p.Wp;
+		float v = 0.0f;
+		if (d0 < dmax) {
+			const uint32_t d = d0 + 1;
+			for (uint32_t q = 0; q < p.n_parts; q++) {
+				const JoinedPart& a = p.part[q];
+				if (j >= a.width) { j -= a.width; continue; }
+				const uint32_t F = a.F;
+				const int64_t last = (int64_t)n + (int64_t)u * (a.lc + a.rc) + a.lc, first = last - d0;   // rows of the window's last / first frame
+				const uint32_t k = j / F, f = j - k * F;
+				const float* x = a.x + f;
+				if (a.bdelta && !(p.D > 1 && a.seg)) {
+					const float l = __ldg(x + (first - 1 - k) * F), r = __ldg(x + (first + k) * F);
+					v = l >= r ? l - r : r - l;
+				} else if (k < a.lc) v = __ldg(x + (first - a.lc + k) * F);
+				else if (p.D == 1 || !a.seg) v = __ldg(x + (first + (k - a.lc)) * F);      // the first frame, then its right context
+				else {
+					const uint32_t b = k - a.lc;                                              // block inside the segment-feature body
+					if (b < 5) v = __ldg(x + (first + __ldg(p.steps + d0 * 5 + b)) * F);
+					else if (b < 8) {
+						float acc = 0.0f, amax = 0.0f, amin = 0.0f;
+						for (uint32_t e = 0; e < d; e++) {                                    // from the last frame back to the first, as the reference
+							const float w = __ldg(x + (last - e) * F);
+							acc += w; amax = (e == 0 || w > amax) ? w : amax; amin = (e == 0 || w < amin) ? w : amin;
+						}
+						v = b == 5 ? acc / (float)d : (b == 6 ? amax : amin);
+					} else {
+						const uint32_t jj = j - (a.lc + 8) * F;                               // one-hot duration, then the right context of the last frame
+						if (jj < p.D) v = jj == d0 ? 1.0f : 0.0f;
+						else { const uint32_t kk = (jj - p.D) / F, ff = (jj - p.D) - kk * F; v = __ldg(a.x + ff + (last + 1 + kk) * F); }
+					}
+				}
+				break;
+			}
+		}
+		out[i] = v;
+	}
+}
+void launch_expand_joined(const ExpandJoinedParams& p, cudaStream_t s) {
+	if (!p.N) return;
+	expand_joined_kernel<<<p.N, 256, 0, s>>>(p);
+}
+
 void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s) {
 	if (n1 <= p.n0) return;
 	ExpandParams q = p;

@@ -27,6 +27,19 @@ void launch_expand_windows(const ExpandParams& p, uint32_t n1, cudaStream_t s); 
 void launch_virtual_windows(const float* base, const uint32_t* frame_t, float* base2, float* Xa, uint32_t N, uint32_t F, uint32_t Fp, uint32_t D,
                             uint32_t Wa, uint32_t n0, uint32_t n1, cudaStream_t s);
 
+// ---- window streams with context frames and / or a joined second stream (general path; crfgpu_*2 entry points) -----------------------
+struct JoinedPart {
+	const float* x;           // the stream's frames, lc + T + rc rows per utterance
+	uint32_t F, seg, lc, rc, bdelta, width;
+};
+struct ExpandJoinedParams {
+	JoinedPart part[2]; uint32_t n_parts;
+	const uint32_t* frame_t; const uint32_t* frame_utt; const uint32_t* steps;
+	float* X;                 // [N][D][Wp]
+	uint32_t N, D, Wp;
+};
+void launch_expand_joined(const ExpandJoinedParams& p, cudaStream_t s);
+
 // ---- GEMM-1: state scores  S[n][col0+j] = sum_k A[n][k]*B[j][k] + bias[j] ----------------------
 struct ScoreGemmParams {
 	const float* A; uint64_t lda;     // [M][K] row stride lda (window features of one duration)

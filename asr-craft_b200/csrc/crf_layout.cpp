@@ -7,11 +7,21 @@
 
 namespace crfgpu {
 
-uint32_t window_width(const crfgpu_config& c) {
-	// CRF_InFtrStream_SeqMultiWindow ctor (CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:50-125), no context frames
-	if (c.max_dur == 1 || !c.extract_seg_ftrs) return c.n_base_ftrs;
-	return 8 * c.n_base_ftrs + c.max_dur;
+uint32_t stream_width(uint32_t F, uint32_t D, uint32_t seg, uint32_t lc, uint32_t rc, uint32_t bdelta) {
+	// CRF_InFtrStream_SeqMultiWindow ctor (CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:47-117)
+	if (D == 1) return (lc + 1 + rc) * F;
+	if (seg) return 8 * F + D + (lc + rc) * F;              // left context | sample x5 | avg | max | min | one-hot duration | right context
+	if (bdelta) return std::min(lc, rc + 1) * F;            // |left - right| of the frame pairs around the window's first frame
+	return (lc + 1 + rc) * F;                               // left context | first frame | right context
 }
+
+uint32_t window_width(const crfgpu_config& c) {
+	uint32_t w = stream_width(c.n_base_ftrs, c.max_dur, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta);
+	if (c.n_base_ftrs2) w += stream_width(c.n_base_ftrs2, c.max_dur, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2);   // joined behind the first
+	return w;
+}
+
+bool has_context_or_join(const crfgpu_config& c) { return c.left_ctx || c.right_ctx || c.boundary_delta || c.n_base_ftrs2; }
 
 Layout build_layout(const crfgpu_config& c) {
 	Layout m;

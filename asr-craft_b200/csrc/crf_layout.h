@@ -26,6 +26,10 @@ struct Layout {
 Layout build_layout(const crfgpu_config& c);
 
 uint32_t window_width(const crfgpu_config& c);
+// one stream's share of the window vector (CRF_InFtrStream_SeqMultiWindow ctor, CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:47-117)
+uint32_t stream_width(uint32_t n_base_ftrs, uint32_t max_dur, uint32_t seg_ftrs, uint32_t left_ctx, uint32_t right_ctx, uint32_t boundary_delta);
+// context frames on stream 1, boundary deltas or a joined second stream: the windows are built by expand_joined_kernel
+bool has_context_or_join(const crfgpu_config& c);
 
 // CRF_InLabStream_SeqMultiWindow (CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-306): per frame
 // (label,start,end,broken) on the frame where a (possibly split) reference segment ends, else LAB_BAD x4.

@@ -125,7 +125,9 @@ struct crfgpu_ctx {
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> phases;
 	ncclComm_t comm = nullptr; int comm_nranks = 0, comm_rank = 0;   // crfgpu_comm_init_*: the communicator crfgpu_allreduce_grad runs on
 
-	const float* X() const { return (cfg.max_dur == 1) ? d_base.as<float>() : d_X.as<float>(); }
+	// context frames / boundary deltas / joined second stream (crfgpu_*2): the windows are always materialised by expand_joined_kernel
+	bool joined = false; DevBuf d_baseB;
+	const float* X() const { return (cfg.max_dur == 1 && !joined) ? d_base.as<float>() : d_X.as<float>(); }
 	uint64_t ldx() const { return (uint64_t)cfg.max_dur * Wp; }
 };
 
@@ -226,7 +228,7 @@ bool decide_virt(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	const bool was = h->virt;
 	h->Fp = (c.n_base_ftrs + 31) / 32 * 32; h->Wa = (3 * c.n_base_ftrs + 1 + 31) / 32 * 32;
-	h->virt = h->opt_virt && h->train_ok && c.max_dur > 1 && c.extract_seg_ftrs && !c.use_trans_ftrs && c.use_state_ftrs && c.state_fidx_start == 0 &&
+	h->virt = h->opt_virt && !h->joined && h->train_ok && c.max_dur > 1 && c.extract_seg_ftrs && !c.use_trans_ftrs && c.use_state_ftrs && c.state_fidx_start == 0 &&
 	          c.state_fidx_end + 1 == h->W && h->opt_gemm_impl == 2 && (h->opt_tma_mask & 27) == 27 && tma_gemm_eligible(nullptr, c.max_dur, h->Wa, 0);
 	return was != h->virt;
 }
@@ -409,7 +411,7 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 	validate_offsets(n_utt, off, ftrs);
 	const uint32_t N = n_utt ? off[n_utt] : 0;
 	h->pre_valid = false;
-	if (!N) return;
+	if (!N || h->joined) return;                                         // joined / context windows are staged by crfgpu_stage_batch2 only
 	if (!h->pre_stream) {
 		CUDA_OK(cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
 		CUDA_OK(cudaEventCreate(&h->ev_pre_done)); CUDA_OK(cudaEventCreate(&h->ev_pre_ready));
@@ -434,9 +436,10 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 	h->pre_off.assign(off, off + n_utt + 1); h->pre_ftrs = ftrs; h->pre_valid = true;
 }
 
-void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs) {
+void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs, const float* ftrs2 = nullptr) {
 	const crfgpu_config& c = h->cfg;
 	validate_offsets(n_utt, off, ftrs);
+	if (c.n_base_ftrs2 && !ftrs2) throw ApiError(CRFGPU_ERR_ARG, "the model joins a second feature stream: use the crfgpu_*2 entry points and pass it");
 	const uint32_t N = n_utt ? off[n_utt] : 0;
 	cudaStream_t s = h->stream;
 	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
@@ -455,15 +458,42 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		h->pin_used = 0;
 	}
 
+	upload_async(h, h->d_off, h->h_off);
 	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
 	for (uint32_t u = 0; u < n_utt; u++)
 		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
-	upload_async(h, h->d_off, h->h_off);
 	const bool want_virt = h->virt && labs != nullptr;                   // training batches of eligible models stage the virtual-window form
 	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off && h->pre_virt == want_virt;
 	h->pre_valid = false;
 	h->x_virt_valid = want_virt; h->x_full_valid = !want_virt;
-	if (prefetched) {
+	if (h->joined) {
+		// general window streams: both streams go to the device whole, one gather kernel builds the joined windows
+		upload_async(h, h->d_frame_t, frame_t); upload_async(h, h->d_frame_utt, frame_utt);
+		const size_t n1 = (size_t)N + (size_t)n_utt * (c.left_ctx + c.right_ctx), n2 = (size_t)N + (size_t)n_utt * (c.left_ctx2 + c.right_ctx2);
+		h->d_base.ensure(sizeof(float) * n1 * c.n_base_ftrs + 16);
+		if (N) CUDA_OK(cudaMemcpyAsync(h->d_base.p, ftrs, sizeof(float) * n1 * c.n_base_ftrs, cudaMemcpyHostToDevice, s));
+		if (c.n_base_ftrs2) {
+			h->d_baseB.ensure(sizeof(float) * n2 * c.n_base_ftrs2 + 16);
+			if (N) CUDA_OK(cudaMemcpyAsync(h->d_baseB.p, ftrs2, sizeof(float) * n2 * c.n_base_ftrs2, cudaMemcpyHostToDevice, s));
+		}
+		if (N) {
+			h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+			phase_begin(h, "expand");
+			ExpandJoinedParams ep{};
+			ep.part[0] = JoinedPart{h->d_base.as<float>(), c.n_base_ftrs, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta,
+			                        stream_width(c.n_base_ftrs, c.max_dur, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta)};
+			ep.n_parts = 1;
+			if (c.n_base_ftrs2) {
+				ep.part[1] = JoinedPart{h->d_baseB.as<float>(), c.n_base_ftrs2, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2,
+				                        stream_width(c.n_base_ftrs2, c.max_dur, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2)};
+				ep.n_parts = 2;
+			}
+			ep.frame_t = h->d_frame_t.as<uint32_t>(); ep.frame_utt = h->d_frame_utt.as<uint32_t>(); ep.steps = h->d_steps.as<uint32_t>();
+			ep.X = h->d_X.as<float>(); ep.N = N; ep.D = c.max_dur; ep.Wp = h->Wp;
+			launch_expand_joined(ep, s); check_kernel(h, 1);
+			phase_end(h, "expand");
+		}
+	} else if (prefetched) {
 		// this batch was copied and expanded by crfgpu_prefetch_batch while the previous one computed: take over its buffers
 		if (!h->ev_swap) CUDA_OK(cudaEventCreateWithFlags(&h->ev_swap, cudaEventDisableTiming));
 		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
@@ -493,7 +523,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		                want_virt, &h->d_bpad, &h->d_Xa);
 		h->vit_score_ready = eager_vit;
 	}
-	upload_async(h, h->d_frame_utt, frame_utt); upload_async(h, h->d_frame_len, frame_len);
+	if (!h->joined) upload_async(h, h->d_frame_utt, frame_utt);
+	upload_async(h, h->d_frame_len, frame_len);
 
 	std::vector<uint32_t> node_lab, prev_lab;
 	if (labs) {
@@ -1278,6 +1309,11 @@ int crfgpu_create(const crfgpu_config* cfg, int device, crfgpu_handle* out) {
 		h->cfg = *cfg; h->device = device;
 		h->lay = build_layout(*cfg);
 		h->W = window_width(*cfg);
+		h->joined = has_context_or_join(*cfg);
+		if (cfg->boundary_delta && cfg->max_dur > 1 && cfg->extract_seg_ftrs) throw ApiError(CRFGPU_ERR_ARG, "extract_segment_features must be false to use boundary_delta_ftrs.");
+		if (cfg->n_base_ftrs2 && cfg->boundary_delta2 && cfg->max_dur > 1 && cfg->extract_seg_ftrs2) throw ApiError(CRFGPU_ERR_ARG, "extract_segment_features must be false to use boundary_delta_ftrs.");
+		if ((cfg->boundary_delta || (cfg->n_base_ftrs2 && cfg->boundary_delta2)) && cfg->max_dur == 1)
+			throw ApiError(CRFGPU_ERR_UNSUPPORTED, "boundary delta features with window length 1 (the reference leaves most of that window vector unwritten)");
 		// measured on cfg4 (score + state-gradient GEMM ms per step): unpadded 2.01 + 3.18, padded to 8 floats 1.86 + 3.43, to 32 floats
 		// 1.83 + 3.56 -- padding helps the K-major reader and hurts the MN-major one, so the windows stay packed
 		h->Wp = cfg->max_dur > 1 ? (h->W + 3) / 4 * 4 : h->W;   // 16-byte window rows: TMA-addressable (max_dur == 1 aliases the base stream)
@@ -1308,7 +1344,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_mass, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1413,6 +1449,14 @@ int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_of
 	});
 }
 
+int crfgpu_stage_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2, const uint32_t* frame_labs) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		stage_batch(h, n_utt, frame_off, base_ftrs, frame_labs, base_ftrs2);
+	});
+}
+
 int crfgpu_fwdbwd_staged(crfgpu_handle h) {
 	return guarded([&] { if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle"); CUDA_OK(cudaSetDevice(h->device)); fwdbwd_staged(h); });
 }
@@ -1461,6 +1505,11 @@ int crfgpu_fetch_viterbi(crfgpu_handle h, uint32_t* out_lab, uint32_t* out_dur, 
 
 int crfgpu_fwdbwd_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
                         double* grad, double* numer, double* logZ) {
+	return crfgpu_fwdbwd_batch2(h, n_utt, frame_off, base_ftrs, nullptr, frame_labs, grad, numer, logZ);
+}
+
+int crfgpu_fwdbwd_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                         const uint32_t* frame_labs, double* grad, double* numer, double* logZ) {
 	const bool verbose = getenv("CRFGPU_VERBOSE") != nullptr;
 	auto now = [] { return std::chrono::steady_clock::now(); };
 	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -1471,7 +1520,7 @@ int crfgpu_fwdbwd_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_o
 		CUDA_OK(cudaSetDevice(h->device));
 		require_train(h);
 		if (!frame_labs) throw ApiError(CRFGPU_ERR_ARG, "training needs frame labels");
-		stage_batch(h, n_utt, frame_off, base_ftrs, frame_labs);
+		stage_batch(h, n_utt, frame_off, base_ftrs, frame_labs, base_ftrs2);
 		t1 = now();
 		fwdbwd_staged(h);
 		t2 = now();
@@ -1497,11 +1546,16 @@ int crfgpu_fwdbwd_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_o
 
 int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
                          uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg, float* path_cost) {
+	return crfgpu_viterbi_batch2(h, n_utt, frame_off, base_ftrs, nullptr, out_lab, out_dur, out_phn, n_seg, path_cost);
+}
+
+int crfgpu_viterbi_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                          uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg, float* path_cost) {
 	int rc = guarded([&] {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		CUDA_OK(cudaSetDevice(h->device));
 		require_decode(h);
-		stage_batch(h, n_utt, frame_off, base_ftrs, nullptr);
+		stage_batch(h, n_utt, frame_off, base_ftrs, nullptr, base_ftrs2);
 		viterbi_staged(h);
 	});
 	if (rc != CRFGPU_OK) return rc;
@@ -1509,12 +1563,16 @@ int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_
 }
 
 int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out) {
+	return crfgpu_expand_windows2(h, n_frames, base_ftrs, nullptr, out);
+}
+
+int crfgpu_expand_windows2(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, const float* base_ftrs2, float* out) {
 	return guarded([&] {
 		if (!h || !base_ftrs || !out) throw ApiError(CRFGPU_ERR_ARG, "null argument");
 		CUDA_OK(cudaSetDevice(h->device));
 		const uint32_t off[2] = {0, n_frames};
 		if (!n_frames) return;
-		stage_batch(h, 1, off, base_ftrs, nullptr);
+		stage_batch(h, 1, off, base_ftrs, nullptr, base_ftrs2);
 		CUDA_OK(cudaMemcpy2DAsync(out, sizeof(float) * h->W, h->X(), sizeof(float) * h->Wp, sizeof(float) * h->W,
 		                          (size_t)n_frames * h->cfg.max_dur, cudaMemcpyDeviceToHost, h->stream));
 		CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -20,6 +20,9 @@
  *   crfgpu_viterbi_batch         CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode>::nStateDecode
  *                                with lm_fst==NULL, beam 0                           CRF/src/decoders/CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398
  *   crfgpu_expand_windows        CRF_InFtrStream_SeqMultiWindow::read_ftrs           CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:209-328
+ *   crfgpu_*2                    the same calls for models whose window stream has context frames (first_frame_left_ctx_ftrs,
+ *                                first/last_frame_right_ctx_ftrs, boundary_delta_ftrs, .cpp:897-1110) and / or a second stream joined
+ *                                behind the first (CRF_FeatureStreamManager::join, CRF/src/io/CRF_FeatureStreamManager.cpp:482-500)
  *   crfgpu_prefetch_batch        the bunch read-ahead of the feature streams         CRF/src/io/CRF_FeatureStream.cpp:116-136
  *   crfgpu_group_labels          CRF_InLabStream_SeqMultiWindow::nextseg/read_labs   CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-306
  *   crfgpu_comm_* /              the serial sum of the per-stream gradients and scalars CRF/src/trainers/accumulators/CRF_Minibatch_GradAccumulator.cpp:277-298
@@ -76,6 +79,15 @@ typedef struct crfgpu_config {
 	uint32_t use_trans_ftrs, trans_fidx_start, trans_fidx_end;   /* crf_featuremap=stdtrans: training of one-state models with <= 128 labels, frame-level or stdseg_no_dur_no_segtransftr; decoding for those two model kinds at any state count */
 	uint32_t use_state_bias, use_trans_bias;
 	double state_bias_val, trans_bias_val;
+	/* Context frames of feature stream 1 (ftr1_left_context_len, ftr1_right_context_len, ftr1_use_boundary_delta_ftr;
+	 * CRFTrain/src/Main.cpp:508-515, CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:47-117): the stream then carries
+	 * left_ctx + right_ctx more frames per utterance than there are labelled frames (a padded pfile). */
+	uint32_t left_ctx, right_ctx, boundary_delta;
+	/* Optional second feature stream whose windows are joined behind those of the first (ftr2_*; CRFTrain/src/Main.cpp:516-526,
+	 * CRF_FeatureStream::join, CRF/src/io/CRF_FeatureStream.cpp:172-184).  n_base_ftrs2 == 0: absent.  The TIMIT recipe
+	 * (demo/segmental-timit-demo.cfg.in:16-33) takes its 1162 state features from stream 1 (segment features of 144 inputs, maxDur 10)
+	 * and its 1872 transition features from stream 2 (13 context frames x 144 around the first frame of the window). */
+	uint32_t n_base_ftrs2, extract_seg_ftrs2, left_ctx2, right_ctx2, boundary_delta2;
 } crfgpu_config;
 
 typedef struct crfgpu_ctx* crfgpu_handle;
@@ -129,6 +141,21 @@ int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_
 
 /* Window features for one utterance, out[(t*max_dur + d-1)*window_width ...]; slots with d > t+1 are zero. */
 int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out);
+
+/* ---- models with context frames and / or a joined second feature stream -------------------------------------------------------
+ * frame_off[] are the offsets of the LABELLED frames, as everywhere else.  Stream s (1 or 2) carries left_ctx_s + right_ctx_s more
+ * frames per utterance: utterance u's rows start at row frame_off[u] + u * (left_ctx_s + right_ctx_s) of base_ftrs_s and number
+ * T_u + left_ctx_s + right_ctx_s; labelled frame t of the utterance is row left_ctx_s + t of them (nextseg(),
+ * CRF_InFtrStream_SeqMultiWindow.cpp:163-199).  base_ftrs2 is ignored (may be NULL) when the configuration has no second stream.
+ * Without context frames and without a second stream these calls equal the ones above. */
+int crfgpu_stage_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                        const uint32_t* frame_labs /* may be NULL for decode */);
+int crfgpu_fwdbwd_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                         const uint32_t* frame_labs, double* grad, double* numer, double* logZ);
+int crfgpu_viterbi_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                          uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg, float* path_cost);
+/* base_ftrs: [left_ctx + n_frames + right_ctx][n_base_ftrs], base_ftrs2 likewise with the second stream's context lengths */
+int crfgpu_expand_windows2(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, const float* base_ftrs2, float* out);
 /* (label,start,end,broken) records per frame or CRFGPU_LAB_BAD x4 (host-side, no device work). */
 int crfgpu_group_labels(const crfgpu_config* cfg, uint32_t n_frames, const uint32_t* frame_labs, uint32_t* out4);
 

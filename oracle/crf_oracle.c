@@ -153,29 +153,56 @@ static double trans_expf(const crforacle_config* c, const fmap_t* m, const float
 /* ------------------------------------------------------------------------------------------
  * window streams
  * ---------------------------------------------------------------------------------------- */
-uint32_t crforacle_window_width(const crforacle_config* c) {
-	/* CRF_InFtrStream_SeqMultiWindow ctor, CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:50-125 (no context frames) */
-	if (c->max_dur == 1 || !c->extract_seg_ftrs) return c->n_base_ftrs;
-	return 8 * c->n_base_ftrs + c->max_dur;
+/* width of one stream's window vector: CRF_InFtrStream_SeqMultiWindow ctor, CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:47-117 */
+static uint32_t part_width(uint32_t F, uint32_t D, uint32_t seg, uint32_t lc, uint32_t rc, uint32_t bdelta) {
+	if (D == 1) return (lc + 1 + rc) * F;
+	if (seg) return 8 * F + D + (lc + rc) * F;
+	if (bdelta) { uint32_t both = lc < rc + 1 ? lc : rc + 1; return both * F; }
+	return (lc + 1 + rc) * F;
 }
+uint32_t crforacle_window_width(const crforacle_config* c) {
+	uint32_t w = part_width(c->n_base_ftrs, c->max_dur, c->extract_seg_ftrs, c->left_ctx, c->right_ctx, c->boundary_delta);
+	/* QN_InFtrStream_JoinFtrs (QuickNet3, version unpinned by the reference): the frames of the second stream behind those of the first */
+	if (c->n_base_ftrs2) w += part_width(c->n_base_ftrs2, c->max_dur, c->extract_seg_ftrs2, c->left_ctx2, c->right_ctx2, c->boundary_delta2);
+	return w;
+}
+static int has_ext(const crforacle_config* c) { return c->left_ctx || c->right_ctx || c->boundary_delta || c->n_base_ftrs2; }
 
-/* One (t,d) window.  x points at the utterance's base frames [T][F]; window covers frames t-d+1..t.
- * CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp: read_ftrs :209-328, sample_ftrs :556-590,
- * avg_ftrs :601-626, max_ftrs :637-666, min_ftrs :677-706, dur_ftrs :790-812, first_frame_ftrs. */
-static void window_one(const crforacle_config* c, const float* x, uint32_t t, uint32_t d, float* out) {
-	uint32_t F = c->n_base_ftrs, D = c->max_dur;
-	const float* start = x + (size_t)(t - d + 1) * F;
-	if (D == 1 || !c->extract_seg_ftrs) { memcpy(out, start, F * sizeof(float)); return; }
+/* One (t,d) window of one stream.  x points at the utterance's frames of that stream, [lc + T + rc][F]: labelled frame t is row lc + t
+ * (nextseg: cur_line = top_margin + left_context_len, :163-199); the window covers labelled frames t-d+1..t.
+ * CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp: read_ftrs :325-471 = [left context of the FIRST frame | body | right context], body =
+ * sample_ftrs :556-607 | avg_ftrs :609-655 | max_ftrs :657-706 | min_ftrs :708-757 | dur_ftrs :850-895 (segment features) or
+ * first_frame_ftrs :1017-1048; the right context hangs on the LAST frame with segment features (last_frame_right_ctx_ftrs :977-1015)
+ * and on the first frame otherwise (first_frame_right_ctx_ftrs :937-975); boundary_delta_ftrs :1050-1110 replaces all of it. */
+static void window_part(uint32_t F, uint32_t D, uint32_t seg, uint32_t lc, uint32_t rc, uint32_t bdelta,
+                        const float* x, uint32_t t, uint32_t d, float* out) {
+	const float* first = x + (size_t)(lc + t - d + 1) * F;     /* first frame of the window */
+	const float* last = x + (size_t)(lc + t) * F;
+	if (bdelta && !(D > 1 && seg)) {
+		uint32_t both = lc < rc + 1 ? lc : rc + 1;
+		for (uint32_t i = 0; i < both; i++) {
+			const float* l = first - (size_t)(i + 1) * F; const float* r = first + (size_t)i * F;
+			for (uint32_t f = 0; f < F; f++) out[(size_t)i * F + f] = l[f] >= r[f] ? l[f] - r[f] : r[f] - l[f];
+		}
+		return;
+	}
+	memcpy(out, first - (size_t)lc * F, (size_t)lc * F * sizeof(float));      /* first_frame_left_ctx_ftrs :897-935 */
+	out += (size_t)lc * F;
+	if (D == 1 || !seg) {
+		memcpy(out, first, F * sizeof(float)); out += F;
+		memcpy(out, first + F, (size_t)rc * F * sizeof(float));
+		return;
+	}
 	/* 5 sampled frames at the 10/30/50/70/90 % points; float arithmetic as in the reference */
 	float one_tenth = d * 0.1;
 	for (int i = 1, k = 0; i < 10; i += 2, k++) {
 		uint32_t step = (uint32_t)ceil(one_tenth * i) - 1;
-		memcpy(out + (size_t)k * F, start + (size_t)step * F, F * sizeof(float));
+		memcpy(out + (size_t)k * F, first + (size_t)step * F, F * sizeof(float));
 	}
 	float* avg = out + 5 * (size_t)F; float* mx = avg + F; float* mn = mx + F; float* du = mn + F;
 	/* running statistics accumulate from the LAST frame of the window back to the first */
 	for (uint32_t f = 0; f < F; f++) {
-		const float* p = x + (size_t)t * F + f;
+		const float* p = last + f;
 		float acc = 0.0f, amax = *p, amin = *p;
 		for (uint32_t k = 1; k <= d; k++) {
 			float v = *p;
@@ -187,15 +214,22 @@ static void window_one(const crforacle_config* c, const float* x, uint32_t t, ui
 		avg[f] = acc / d; mx[f] = amax; mn[f] = amin;
 	}
 	for (uint32_t k = 1; k <= D; k++) du[k - 1] = (k == d) ? 1.0f : 0.0f;
+	memcpy(du + D, last + F, (size_t)rc * F * sizeof(float));
 }
 
-int crforacle_window_ftrs(const crforacle_config* c, uint32_t T, const float* base, float* out) {
+int crforacle_window_ftrs2(const crforacle_config* c, uint32_t T, const float* base, const float* base2, float* out) {
 	uint32_t W = crforacle_window_width(c), D = c->max_dur;
+	uint32_t W1 = part_width(c->n_base_ftrs, D, c->extract_seg_ftrs, c->left_ctx, c->right_ctx, c->boundary_delta);
+	if (c->n_base_ftrs2 && !base2) FAIL("the configuration joins a second feature stream but none was passed");
 	for (uint32_t t = 0; t < T; t++)
-		for (uint32_t d = 1; d <= D && d <= t + 1; d++)
-			window_one(c, base, t, d, out + ((size_t)t * D + (d - 1)) * W);
+		for (uint32_t d = 1; d <= D && d <= t + 1; d++) {
+			float* o = out + ((size_t)t * D + (d - 1)) * W;
+			window_part(c->n_base_ftrs, D, c->extract_seg_ftrs, c->left_ctx, c->right_ctx, c->boundary_delta, base, t, d, o);
+			if (c->n_base_ftrs2) window_part(c->n_base_ftrs2, D, c->extract_seg_ftrs2, c->left_ctx2, c->right_ctx2, c->boundary_delta2, base2, t, d, o + W1);
+		}
 	return 0;
 }
+int crforacle_window_ftrs(const crforacle_config* c, uint32_t T, const float* base, float* out) { return crforacle_window_ftrs2(c, T, base, NULL, out); }
 
 /* CRF_InLabStream_SeqMultiWindow::groupLabels / nextseg / read_labs,
  * CRF/src/io/CRF_InLabStream_SeqMultiWindow.cpp:51-110, 119-196, 246-306 */
@@ -243,6 +277,7 @@ typedef struct {
 	const crforacle_config* c; const fmap_t* m; const double* lam;
 	double* ExpF;     /* [len] scratch */
 	double* Mconst;   /* [L*L] transition scores when they do not depend on the frame, else NULL */
+	const float* x2;  /* the utterance's frames of the joined second stream (or NULL) */
 } ctx_t;
 
 /* Frame-level, 1 state/label: CRF_NewGradBuilder::buildGradient (CRF/src/trainers/gradbuilders/CRF_NewGradBuilder.cpp:48-382)
@@ -250,7 +285,7 @@ typedef struct {
 static int fb_frame_1state(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
                            double* grad, double* numer, double* logZ, double* A_out, double* B_out) {
 	const crforacle_config* c = k->c; const fmap_t* m = k->m; const double* lam = k->lam;
-	uint32_t L = m->L, F = c->n_base_ftrs;
+	uint32_t L = m->L, F = crforacle_window_width(c);   /* = n_base_ftrs without context frames / joined streams; else x is the expanded window matrix (fb_one) */
 	double* S = (double*)malloc(sizeof(double) * (size_t)T * L);
 	double* A = (double*)malloc(sizeof(double) * (size_t)T * L);
 	double* B = (double*)malloc(sizeof(double) * (size_t)T * L);
@@ -320,7 +355,7 @@ static int fb_frame_1state(ctx_t* k, uint32_t T, const float* x, const uint32_t*
 static int fb_frame_nstate(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
                            double* grad, double* numer, double* logZ, double* A_out, double* B_out) {
 	const crforacle_config* c = k->c; const fmap_t* m = k->m; const double* lam = k->lam;
-	uint32_t L = m->L, F = c->n_base_ftrs, N = m->nStates, P = m->nAct;
+	uint32_t L = m->L, F = crforacle_window_width(c), N = m->nStates, P = m->nAct;
 	size_t per = (size_t)2 * L + (size_t)P * P;
 	double* S = (double*)malloc(sizeof(double) * (size_t)T * L);
 	double* A = (double*)malloc(sizeof(double) * (size_t)T * L);
@@ -422,7 +457,7 @@ static int fb_stdseg(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	double* acc = (double*)malloc(sizeof(double) * (L > D * P ? L : D * P));
 	double* tmpB = (double*)malloc(sizeof(double) * L);
 	uint32_t* nodeLab = (uint32_t*)malloc(sizeof(uint32_t) * T);
-	crforacle_window_ftrs(c, T, x, X);
+	crforacle_window_ftrs2(c, T, x, k->x2, X);
 	memset(k->ExpF, 0, sizeof(double) * m->len);
 	for (size_t i = 0; i < (size_t)T * L; i++) { A[i] = LOG0; B[i] = LOG0; }
 #define AVAIL(t) (P * (((t) + 1 < D) ? (t) + 1 : D))
@@ -536,7 +571,7 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	double* Mt = (k->Mconst || !c->use_trans_ftrs) ? NULL : (double*)malloc(sizeof(double) * (size_t)T * P * P);   /* M_t[y'][y] of the frame the segment starts in */
 	double* acc = (double*)malloc(sizeof(double) * (P > D ? P : D));
 	double* Mn = NULL;
-	crforacle_window_ftrs(c, T, x, X);
+	crforacle_window_ftrs2(c, T, x, k->x2, X);
 	memset(k->ExpF, 0, sizeof(double) * m->len);
 	if (!k->Mconst && !c->use_trans_ftrs) {   /* N-state, bias only: one matrix, illegal pairs never read */
 		Mn = (double*)malloc(sizeof(double) * (size_t)P * P);
@@ -632,6 +667,7 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 }
 
 static int ctx_init(ctx_t* k, const crforacle_config* c, const fmap_t* m, const double* lam) {
+	k->x2 = NULL;
 	k->c = c; k->m = m; k->lam = lam;
 	k->ExpF = (double*)malloc(sizeof(double) * (m->len ? m->len : 1));
 	k->Mconst = NULL;
@@ -654,8 +690,15 @@ static int fb_one(ctx_t* k, uint32_t T, const float* x, const uint32_t* labs,
 	int rc;
 	if (c->model_type == CRFO_STDFRAME) {
 		if (c->max_dur != 1) { free(lab4); FAIL("stdframe requires max_dur==1"); }
+		float* Xw = NULL;
+		if (has_ext(c)) {   /* context frames / joined stream: the frame-level recursions read the expanded window vectors */
+			Xw = (float*)malloc(sizeof(float) * (size_t)T * crforacle_window_width(c));
+			if (crforacle_window_ftrs2(c, T, x, k->x2, Xw)) { free(Xw); free(lab4); return 1; }
+			x = Xw;
+		}
 		rc = (c->n_states > 1) ? fb_frame_nstate(k, T, x, lab4, grad, numer, logZ, A, B)
 		                       : fb_frame_1state(k, T, x, lab4, grad, numer, logZ, A, B);
+		free(Xw);
 	} else if (c->model_type == CRFO_STDSEG) rc = fb_stdseg(k, T, x, lab4, grad, numer, logZ, A, B);
 	else if (c->model_type == CRFO_STDSEG_NO_DUR || c->model_type == CRFO_STDSEG_NO_DUR_NO_TRANSFTR || c->model_type == CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR)
 		rc = fb_nodur(k, T, x, lab4, grad, numer, logZ, A, B);
@@ -666,9 +709,12 @@ static int fb_one(ctx_t* k, uint32_t T, const float* x, const uint32_t* labs,
 
 typedef struct {
 	const crforacle_config* c; const fmap_t* m; const double* lam;
-	uint32_t n_utt; const uint32_t* off; const float* ftrs; const uint32_t* labs;
+	uint32_t n_utt; const uint32_t* off; const float* ftrs; const float* ftrs2; uint32_t u0; const uint32_t* labs;
 	double* grad; double* numer; double* logZ; int rc; char err[512];
 } shard_t;
+
+/* first row of utterance u (absolute index) in a stream that carries lc + rc context frames per utterance */
+static size_t stream_row(const uint32_t* off_abs, uint32_t u_abs, uint32_t lc, uint32_t rc) { return (size_t)off_abs[0] + (size_t)u_abs * (lc + rc); }
 
 static void* shard_run(void* p) {
 	shard_t* s = (shard_t*)p;
@@ -676,7 +722,9 @@ static void* shard_run(void* p) {
 	s->rc = 0;
 	for (uint32_t u = 0; u < s->n_utt && !s->rc; u++) {
 		uint32_t T = s->off[u + 1] - s->off[u];
-		s->rc = fb_one(&k, T, s->ftrs + (size_t)s->off[u] * s->c->n_base_ftrs, s->labs + s->off[u],
+		const crforacle_config* c = s->c;
+		k.x2 = s->ftrs2 ? s->ftrs2 + stream_row(s->off + u, s->u0 + u, c->left_ctx2, c->right_ctx2) * c->n_base_ftrs2 : NULL;
+		s->rc = fb_one(&k, T, s->ftrs + stream_row(s->off + u, s->u0 + u, c->left_ctx, c->right_ctx) * c->n_base_ftrs, s->labs + s->off[u],
 		               s->grad, &s->numer[u], &s->logZ[u], NULL, NULL);
 	}
 	if (s->rc) memcpy(s->err, g_err, sizeof s->err);
@@ -687,6 +735,13 @@ static void* shard_run(void* p) {
 int crforacle_fwdbwd_mt(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
                         uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs,
                         double* grad, double* numer, double* logZ, uint32_t n_threads) {
+	return crforacle_fwdbwd_mt2(c, lambda, lambda_len, n_utt, off, ftrs, NULL, labs, grad, numer, logZ, n_threads);
+}
+
+int crforacle_fwdbwd_mt2(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                         uint32_t n_utt, const uint32_t* off, const float* ftrs, const float* ftrs2, const uint32_t* labs,
+                         double* grad, double* numer, double* logZ, uint32_t n_threads) {
+	if (c->n_base_ftrs2 && !ftrs2) FAIL("the configuration joins a second feature stream but none was passed");
 	fmap_t m; if (fmap_build(c, &m)) return 1;
 	if (m.len != lambda_len) { uint32_t l = m.len; fmap_free(&m); FAIL("lambda length mismatch: map has %u, caller passed %u", l, lambda_len); }
 	if (n_threads < 1) n_threads = 1;
@@ -697,7 +752,7 @@ int crforacle_fwdbwd_mt(const crforacle_config* c, const double* lambda, uint32_
 	for (uint32_t i = 0; i < n_threads; i++) {
 		uint32_t start = i * per, cnt = (i == n_threads - 1) ? n_utt - start : per;
 		sh[i].c = c; sh[i].m = &m; sh[i].lam = lambda; sh[i].n_utt = cnt; sh[i].off = off + start;
-		sh[i].ftrs = ftrs; sh[i].labs = labs; sh[i].numer = numer + start; sh[i].logZ = logZ + start;
+		sh[i].ftrs = ftrs; sh[i].ftrs2 = c->n_base_ftrs2 ? ftrs2 : NULL; sh[i].u0 = start; sh[i].labs = labs; sh[i].numer = numer + start; sh[i].logZ = logZ + start;
 		sh[i].grad = (n_threads == 1) ? grad : (double*)calloc(lambda_len ? lambda_len : 1, sizeof(double));
 	}
 	if (n_threads == 1) shard_run(&sh[0]);
@@ -720,6 +775,7 @@ int crforacle_fwdbwd_dump(const crforacle_config* c, const double* lambda, uint3
                           double* grad, double* numer, double* logZ, double* alpha, double* beta) {
 	fmap_t m; if (fmap_build(c, &m)) return 1;
 	if (m.len != lambda_len) { fmap_free(&m); FAIL("lambda length mismatch"); }
+	if (c->n_base_ftrs2) { fmap_free(&m); FAIL("crforacle_fwdbwd_dump takes one feature stream"); }
 	ctx_t k; ctx_init(&k, c, &m, lambda);
 	int rc = fb_one(&k, T, ftrs, labs, grad, numer, logZ, alpha, beta);
 	ctx_free(&k); fmap_free(&m);
@@ -748,12 +804,12 @@ int crforacle_fwdbwd_dump(const crforacle_config* c, const double* lambda, uint3
 typedef struct { float w; int ptr; } cand_t;  /* ptr = previous (phone*N+sub) or -1 */
 
 static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double* lam,
-                       uint32_t T, const float* x, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,
+                       uint32_t T, const float* x, const float* x2, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,
                        uint32_t* n_seg, float* path_cost) {
 	uint32_t L = m->L, N = m->nStates, P = m->nAct, D = c->max_dur, W = crforacle_window_width(c);
 	if (T == 0) FAIL("empty utterance");
 	float* X = (float*)malloc(sizeof(float) * (size_t)T * D * W);
-	crforacle_window_ftrs(c, T, x, X);
+	crforacle_window_ftrs2(c, T, x, x2, X);
 	/* candidates for segments starting at frame s: C[s][lab] */
 	cand_t* C = (cand_t*)malloc(sizeof(cand_t) * (size_t)T * L);
 	float* Wt = (float*)malloc(sizeof(float) * (size_t)T * L);        /* kept weights per frame */
@@ -883,6 +939,14 @@ int crforacle_viterbi(const crforacle_config* c, const double* lambda, uint32_t 
                       uint32_t n_utt, const uint32_t* off, const float* ftrs,
                       uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                       float* path_cost, double* logZ) {
+	return crforacle_viterbi2(c, lambda, lambda_len, n_utt, off, ftrs, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
+int crforacle_viterbi2(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                       uint32_t n_utt, const uint32_t* off, const float* ftrs, const float* ftrs2,
+                       uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                       float* path_cost, double* logZ) {
+	if (c->n_base_ftrs2 && !ftrs2) FAIL("the configuration joins a second feature stream but none was passed");
 	if (c->model_type != CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR && c->model_type != CRFO_STDFRAME)
 		FAIL("viterbi: only stdframe / stdseg_no_dur_no_segtransftr are accepted (CRFDecode/src/Main.cpp:1065-1076)");
 	fmap_t m; if (fmap_build(c, &m)) return 1;
@@ -890,7 +954,8 @@ int crforacle_viterbi(const crforacle_config* c, const double* lambda, uint32_t 
 	int rc = 0;
 	for (uint32_t u = 0; u < n_utt && !rc; u++) {
 		uint32_t T = off[u + 1] - off[u];
-		rc = viterbi_one(c, &m, lambda, T, ftrs + (size_t)off[u] * c->n_base_ftrs,
+		rc = viterbi_one(c, &m, lambda, T, ftrs + stream_row(off + u, u, c->left_ctx, c->right_ctx) * c->n_base_ftrs,
+		                 c->n_base_ftrs2 ? ftrs2 + stream_row(off + u, u, c->left_ctx2, c->right_ctx2) * c->n_base_ftrs2 : NULL,
 		                 out_lab + off[u], out_dur + off[u], out_phn + off[u], &n_seg[u], &path_cost[u]);
 		if (logZ) logZ[u] = 0.0;
 	}

@@ -44,6 +44,11 @@ typedef struct crforacle_config {
 	uint32_t use_trans_ftrs, trans_fidx_start, trans_fidx_end;
 	uint32_t use_state_bias, use_trans_bias;
 	double state_bias_val, trans_bias_val;
+	/* context frames of feature stream 1 (ftr1_left_context_len / ftr1_right_context_len / ftr1_use_boundary_delta_ftr,
+	 * CRFTrain/src/Main.cpp:508-515): the stream then carries left_ctx + right_ctx more frames per utterance than there are labels */
+	uint32_t left_ctx, right_ctx, boundary_delta;
+	/* optional second feature stream joined behind the first (ftr2_*, CRFTrain/src/Main.cpp:516-526); n_base_ftrs2 == 0: absent */
+	uint32_t n_base_ftrs2, extract_seg_ftrs2, left_ctx2, right_ctx2, boundary_delta2;
 } crforacle_config;
 
 const char* crforacle_last_error(void);
@@ -56,6 +61,8 @@ int crforacle_lambda_len(const crforacle_config* c, uint32_t* out);
 int crforacle_index_maps(const crforacle_config* c, uint32_t* state_idx, uint32_t* trans_idx);
 
 int crforacle_window_ftrs(const crforacle_config* c, uint32_t n_frames, const float* base_ftrs, float* out);
+/* joined / context windows: stream s holds T + left_ctx_s + right_ctx_s frames for an utterance of T labelled frames (base2 may be NULL) */
+int crforacle_window_ftrs2(const crforacle_config* c, uint32_t n_frames, const float* base_ftrs, const float* base_ftrs2, float* out);
 int crforacle_window_labs(const crforacle_config* c, uint32_t n_frames, const uint32_t* frame_labs, uint32_t* out4);
 
 /* grad accumulated into (caller zeroes); numer/logZ per utterance.  n_threads shards utterances
@@ -63,6 +70,16 @@ int crforacle_window_labs(const crforacle_config* c, uint32_t n_frames, const ui
 int crforacle_fwdbwd_mt(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
                         uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
                         double* grad, double* numer, double* logZ, uint32_t n_threads);
+
+/* The same with the second feature stream: utterance u's rows of stream s start at row frame_off[u] + u * (left_ctx_s + right_ctx_s)
+ * and number T_u + left_ctx_s + right_ctx_s (the padded pfile of the TIMIT recipe, demo/segmental-timit-demo.cfg.in:16-33) */
+int crforacle_fwdbwd_mt2(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                         uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2, const uint32_t* frame_labs,
+                         double* grad, double* numer, double* logZ, uint32_t n_threads);
+int crforacle_viterbi2(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                       uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                       uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                       float* path_cost, double* logZ);
 
 /* Same as crforacle_fwdbwd_mt(…,1) for one utterance, additionally returning alpha/beta
  * ([T][n_labs] doubles, entries the reference never computes are set to -DBL_MAX = LOG0). */

@@ -59,6 +59,9 @@ struct crfref_config {
 	uint32_t use_trans_ftrs, trans_fidx_start, trans_fidx_end;
 	uint32_t use_state_bias, use_trans_bias;
 	double state_bias_val, trans_bias_val;
+	/* ftr1 context options and the optional joined second stream (CRFTrain/src/Main.cpp:508-526); same order as crforacle_config */
+	uint32_t left_ctx, right_ctx, boundary_delta;
+	uint32_t n_base_ftrs2, extract_seg_ftrs2, left_ctx2, right_ctx2, boundary_delta2;
 };
 
 }  // extern "C"
@@ -179,13 +182,25 @@ struct ModelBundle {
 	~ModelBundle() { delete crf; delete fcfg; }
 };
 
+/* Offsets of a stream that carries lc + rc context frames per utterance: utterance u (absolute index u0 + u) starts at row
+ * off[u] + (u0 + u) * (lc + rc) and has T_u + lc + rc rows. */
+std::vector<uint32_t> padded_offsets(const uint32_t* off, size_t nutt, size_t u0, uint32_t ctx) {
+	std::vector<uint32_t> o(nutt + 1);
+	for (size_t u = 0; u <= nutt; u++) o[u] = off[u] + (uint32_t)((u0 + u) * ctx);
+	return o;
+}
+
 struct Streams {
-	MemFtrStream memF; MemLabStream* memL;
-	CRF_InFtrStream_SeqMultiWindow winF; CRF_InLabStream_SeqMultiWindow* winL;
-	CRF_FeatureStream* fs;
-	Streams(const crfref_config* c, const float* ftrs, const uint32_t* labs, const uint32_t* off, size_t nutt)
-		: memF(ftrs, off, nutt, c->n_base_ftrs), memL(NULL),
-		  winF(0, "f", memF, c->max_dur, 0, 0, 0, 0, c->extract_seg_ftrs != 0, false), winL(NULL), fs(NULL) {
+	std::vector<uint32_t> off1, off2;
+	MemFtrStream memF; MemFtrStream* memF2; MemLabStream* memL;
+	CRF_InFtrStream_SeqMultiWindow winF; CRF_InFtrStream_SeqMultiWindow* winF2; CRF_InLabStream_SeqMultiWindow* winL;
+	CRF_FeatureStream* fs; CRF_FeatureStream* fs1; CRF_FeatureStream* fs2;
+	/* u0 = absolute index of the first utterance (the shards of crfref_fwdbwd_mt index the shared frame arrays) */
+	Streams(const crfref_config* c, const float* ftrs, const float* ftrs2, const uint32_t* labs, const uint32_t* off, size_t nutt, size_t u0 = 0)
+		: off1(padded_offsets(off, nutt, u0, c->left_ctx + c->right_ctx)), off2(padded_offsets(off, nutt, u0, c->left_ctx2 + c->right_ctx2)),
+		  memF(ftrs, off1.data(), nutt, c->n_base_ftrs), memF2(NULL), memL(NULL),
+		  winF(0, "f", memF, c->max_dur, 0, 0, c->left_ctx, c->right_ctx, c->extract_seg_ftrs != 0, c->boundary_delta != 0), winF2(NULL), winL(NULL),
+		  fs(NULL), fs1(NULL), fs2(NULL) {
 		if (labs) {
 			memL = new MemLabStream(labs, off, nutt);
 			/* input buffer large enough to hold a whole utterance, so no chunk boundary is ever hit */
@@ -194,19 +209,28 @@ struct Streams {
 		} else {
 			fs = new CRF_FeatureStream(&winF);
 		}
+		if (c->n_base_ftrs2) {
+			/* the second stream is windowed on its own and joined behind the first: CRF_FeatureStreamManager::join
+			 * (CRF/src/io/CRF_FeatureStreamManager.cpp:482-500) -> CRF_FeatureStream::join (CRF/src/io/CRF_FeatureStream.cpp:172-184) */
+			if (!ftrs2) throw std::runtime_error("the configuration joins a second feature stream but none was passed");
+			memF2 = new MemFtrStream(ftrs2, off2.data(), nutt, c->n_base_ftrs2);
+			winF2 = new CRF_InFtrStream_SeqMultiWindow(0, "f2", *memF2, c->max_dur, 0, 0, c->left_ctx2, c->right_ctx2, c->extract_seg_ftrs2 != 0, c->boundary_delta2 != 0);
+			fs1 = fs; fs2 = new CRF_FeatureStream(winF2);
+			fs = fs1->join(fs2);
+		}
 	}
-	~Streams() { delete fs; delete winL; delete memL; }
+	~Streams() { delete fs; if (fs1) { delete fs1; delete fs2; } delete winF2; delete memF2; delete winL; delete memL; }
 };
 
 struct ShardArgs {
 	const crfref_config* cfg; CRF_Model* crf;
-	const float* ftrs; const uint32_t* labs; const uint32_t* off; size_t nutt;
+	const float* ftrs; const float* ftrs2; const uint32_t* labs; const uint32_t* off; size_t nutt, u0;
 	double* grad; double* numer; double* logZ; std::string err;
 };
 
 void run_shard(ShardArgs* a) {
 	try {
-		Streams st(a->cfg, a->ftrs, a->labs, a->off, a->nutt);
+		Streams st(a->cfg, a->ftrs, a->ftrs2, a->labs, a->off, a->nutt, a->u0);
 		CRF_GradBuilder* gb = CRF_GradBuilder::create(a->crf, EXPF);
 		st.fs->rewind();
 		size_t u = 0;
@@ -222,9 +246,17 @@ void run_shard(ShardArgs* a) {
 
 void* shard_thread(void* p) { run_shard((ShardArgs*)p); return NULL; }
 
+size_t part_width(size_t F, size_t D, bool seg, size_t lc, size_t rc, bool bdelta) {
+	/* CRF_InFtrStream_SeqMultiWindow ctor (CRF/src/io/CRF_InFtrStream_SeqMultiWindow.cpp:47-117); cross-checked against num_ftrs() of the live streams below */
+	if (D == 1) return (lc + 1 + rc) * F;
+	if (seg) return 8 * F + D + (lc + rc) * F;
+	if (bdelta) return (lc < rc + 1 ? lc : rc + 1) * F;
+	return (lc + 1 + rc) * F;
+}
 size_t window_width(const crfref_config* c) {
-	if (c->max_dur == 1) return c->n_base_ftrs;
-	return c->extract_seg_ftrs ? 8 * (size_t)c->n_base_ftrs + c->max_dur : c->n_base_ftrs;
+	size_t w = part_width(c->n_base_ftrs, c->max_dur, c->extract_seg_ftrs != 0, c->left_ctx, c->right_ctx, c->boundary_delta != 0);
+	if (c->n_base_ftrs2) w += part_width(c->n_base_ftrs2, c->max_dur, c->extract_seg_ftrs2 != 0, c->left_ctx2, c->right_ctx2, c->boundary_delta2 != 0);
+	return w;
 }
 
 /* Subclass used only to observe the decoder's per-frame survivors, so the (label,duration)
@@ -269,9 +301,9 @@ int crfref_lambda_len(const crfref_config* c, uint32_t* out) {
 }
 
 /* grad is accumulated into (caller zeroes), numer/logZ are per utterance. */
-int crfref_fwdbwd_mt(const crfref_config* c, const double* lambda, uint32_t lambda_len,
-                     uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
-                     double* grad, double* numer, double* logZ, uint32_t n_threads) {
+int crfref_fwdbwd_mt2(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                      uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2, const uint32_t* frame_labs,
+                      double* grad, double* numer, double* logZ, uint32_t n_threads) {
 	try {
 		Quiet q;
 		ModelBundle mb(c, window_width(c), lambda, lambda_len);
@@ -284,7 +316,7 @@ int crfref_fwdbwd_mt(const crfref_config* c, const double* lambda, uint32_t lamb
 			size_t start = i * per, cnt = (i == n_threads - 1) ? n_utt - start : per;
 			sh[i].cfg = c; sh[i].crf = mb.crf;
 			/* offsets stay absolute: the shard's streams index the shared frame arrays */
-			sh[i].ftrs = base_ftrs; sh[i].labs = frame_labs; sh[i].off = frame_off + start; sh[i].nutt = cnt;
+			sh[i].ftrs = base_ftrs; sh[i].ftrs2 = base_ftrs2; sh[i].labs = frame_labs; sh[i].off = frame_off + start; sh[i].nutt = cnt; sh[i].u0 = start;
 			sh[i].numer = numer + start; sh[i].logZ = logZ + start;
 			if (n_threads == 1) sh[i].grad = grad;
 			else { sgrad[i].assign(lambda_len, 0.0); sh[i].grad = sgrad[i].data(); }
@@ -303,6 +335,12 @@ int crfref_fwdbwd_mt(const crfref_config* c, const double* lambda, uint32_t lamb
 	} catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
+int crfref_fwdbwd_mt(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                     uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
+                     double* grad, double* numer, double* logZ, uint32_t n_threads) {
+	return crfref_fwdbwd_mt2(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, NULL, frame_labs, grad, numer, logZ, n_threads);
+}
+
 int crfref_fwdbwd(const crfref_config* c, const double* lambda, uint32_t lambda_len,
                   uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs,
                   double* grad, double* numer, double* logZ) {
@@ -313,14 +351,14 @@ int crfref_fwdbwd(const crfref_config* c, const double* lambda, uint32_t lambda_
  * segment per frame), segments of utterance u start at frame_off[u]; n_seg[u] segments are valid.
  * out_lab = sub-state label (ilabel-1), out_phn = phone emitted on that arc (olabel-1, or
  * 0xffffffff when none), path_cost = float cost of the winning hypothesis, logZ = final weight. */
-int crfref_viterbi(const crfref_config* c, const double* lambda, uint32_t lambda_len,
-                   uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
-                   uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
-                   float* path_cost, double* logZ) {
+int crfref_viterbi2(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                    uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                    uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                    float* path_cost, double* logZ) {
 	try {
 		Quiet q;
 		ModelBundle mb(c, window_width(c), lambda, lambda_len);
-		Streams st(c, base_ftrs, NULL, frame_off, n_utt);
+		Streams st(c, base_ftrs, base_ftrs2, NULL, frame_off, n_utt);
 		st.fs->rewind();
 		for (uint32_t u = 0; u < n_utt; u++) {
 			if (st.fs->nextseg() == QN_SEGID_BAD) throw std::runtime_error("stream ended early");
@@ -375,6 +413,13 @@ int crfref_viterbi(const crfref_config* c, const double* lambda, uint32_t lambda
 	} catch (std::exception& e) { g_err = e.what(); return 1; }
 }
 
+int crfref_viterbi(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                   uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
+                   uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                   float* path_cost, double* logZ) {
+	return crfref_viterbi2(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
 /* Older frame-level decoder; one label per frame. */
 int crfref_viterbi_old(const crfref_config* c, const double* lambda, uint32_t lambda_len,
                        uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, uint32_t* out_lab) {
@@ -382,7 +427,7 @@ int crfref_viterbi_old(const crfref_config* c, const double* lambda, uint32_t la
 		Quiet q;
 		crfref_config cc = *c; cc.model_type = STDFRAME;
 		ModelBundle mb(&cc, window_width(&cc), lambda, lambda_len);
-		Streams st(&cc, base_ftrs, NULL, frame_off, n_utt);
+		Streams st(&cc, base_ftrs, NULL, NULL, frame_off, n_utt);
 		st.fs->rewind();
 		for (uint32_t u = 0; u < n_utt; u++) {
 			if (st.fs->nextseg() == QN_SEGID_BAD) throw std::runtime_error("stream ended early");
@@ -405,18 +450,18 @@ int crfref_viterbi_old(const crfref_config* c, const double* lambda, uint32_t la
 /* Expanded window features exactly as buildGradient receives them: for frame t the windows of
  * duration 1..min(t+1,max_dur) ending at t, each window_width floats, written at
  * out[(frame_off_in_utt*max_dur + (d-1)) * width]; unused (t,d) slots are left untouched. */
-int crfref_window_ftrs(const crfref_config* c, uint32_t n_frames, const float* base_ftrs, float* out) {
+int crfref_window_ftrs2(const crfref_config* c, uint32_t n_frames, const float* base_ftrs, const float* base_ftrs2, float* out) {
 	try {
 		Quiet q;
 		uint32_t off[2] = {0, n_frames};
-		MemFtrStream memF(base_ftrs, off, 1, c->n_base_ftrs);
-		CRF_InFtrStream_SeqMultiWindow winF(0, "f", memF, c->max_dur, 0, 0, 0, 0, c->extract_seg_ftrs != 0, false);
-		size_t w = winF.num_ftrs();
-		if (winF.nextseg() == QN_SEGID_BAD) throw std::runtime_error("no segment");
+		Streams st(c, base_ftrs, base_ftrs2, NULL, off, 1);
+		size_t w = st.fs->num_ftrs();
+		if (w != window_width(c)) throw std::runtime_error("window width formula disagrees with the reference streams");
+		if (st.fs->nextseg() == QN_SEGID_BAD) throw std::runtime_error("no segment");
 		std::vector<float> buf(w * c->max_dur);
 		size_t bunch = 1, t = 0;
 		for (;;) {
-			size_t n = winF.read_ftrs(bunch, buf.data());
+			size_t n = st.fs->read(bunch, buf.data(), NULL);
 			if (n == 0) break;
 			memcpy(out + (size_t)t * c->max_dur * w, buf.data(), n * w * sizeof(float));
 			t++;
@@ -426,6 +471,7 @@ int crfref_window_ftrs(const crfref_config* c, uint32_t n_frames, const float* b
 		return 0;
 	} catch (std::exception& e) { g_err = e.what(); return 1; }
 }
+int crfref_window_ftrs(const crfref_config* c, uint32_t n_frames, const float* base_ftrs, float* out) { return crfref_window_ftrs2(c, n_frames, base_ftrs, NULL, out); }
 
 /* Per-frame 4-word label records (lab,start,end,broken) or CRF_LAB_BAD x4. */
 int crfref_window_labs(const crfref_config* c, uint32_t n_frames, const uint32_t* frame_labs, uint32_t* out4) {

@@ -57,19 +57,37 @@ public:
 	virtual QN_SegID set_pos(size_t segno, size_t frameno) = 0;
 };
 
-/* CRF_FeatureStream::join() (CRF/src/io/CRF_FeatureStream.cpp:172-184) names this class; the
- * oracle never joins streams, so the methods abort if reached. */
+/* CRF_FeatureStream::join() (CRF/src/io/CRF_FeatureStream.cpp:172-184) names this QuickNet3 class (version unpinned by the
+ * reference, sources absent).  Its published behaviour, restated from the call sites: the two streams advance together segment by
+ * segment and frame by frame, and every frame read is the first stream's feature vector followed by the second's. */
 class QN_InFtrStream_JoinFtrs : public QN_InFtrStream {
+	QN_InFtrStream& a_; QN_InFtrStream& b_;
+	float* ta_; float* tb_; size_t cap_;
 public:
-	QN_InFtrStream_JoinFtrs(int, const char*, QN_InFtrStream&, QN_InFtrStream&) {}
-	size_t num_ftrs() { abort(); }
-	QN_SegID nextseg() { abort(); }
-	size_t read_ftrs(size_t, float*) { abort(); }
-	int rewind() { abort(); }
-	size_t num_segs() { abort(); }
-	size_t num_frames(size_t = QN_ALL) { abort(); }
-	int get_pos(size_t*, size_t*) { abort(); }
-	QN_SegID set_pos(size_t, size_t) { abort(); }
+	QN_InFtrStream_JoinFtrs(int, const char*, QN_InFtrStream& a, QN_InFtrStream& b) : a_(a), b_(b), ta_(NULL), tb_(NULL), cap_(0) {}
+	~QN_InFtrStream_JoinFtrs() { free(ta_); free(tb_); }
+	size_t num_ftrs() { return a_.num_ftrs() + b_.num_ftrs(); }
+	QN_SegID nextseg() {
+		QN_SegID x = a_.nextseg(), y = b_.nextseg();
+		if (x != y) { fputs("QN_InFtrStream_JoinFtrs: the joined streams disagree on the segment id\n", stderr); abort(); }
+		return x;
+	}
+	size_t read_ftrs(size_t cnt, float* ftrs) {
+		const size_t wa = a_.num_ftrs(), wb = b_.num_ftrs();
+		if (cnt > cap_) { free(ta_); free(tb_); cap_ = cnt; ta_ = (float*)malloc(cap_ * wa * sizeof(float)); tb_ = (float*)malloc(cap_ * wb * sizeof(float)); }
+		const size_t na = a_.read_ftrs(cnt, ta_), nb = b_.read_ftrs(cnt, tb_);
+		if (na != nb) { fputs("QN_InFtrStream_JoinFtrs: the joined streams disagree on the frame count\n", stderr); abort(); }
+		for (size_t i = 0; i < na; i++) {
+			memcpy(ftrs + i * (wa + wb), ta_ + i * wa, wa * sizeof(float));
+			memcpy(ftrs + i * (wa + wb) + wa, tb_ + i * wb, wb * sizeof(float));
+		}
+		return na;
+	}
+	int rewind() { int x = a_.rewind(); int y = b_.rewind(); return (x == QN_OK && y == QN_OK) ? QN_OK : QN_BAD; }
+	size_t num_segs() { return a_.num_segs(); }
+	size_t num_frames(size_t segno = QN_ALL) { return a_.num_frames(segno); }
+	int get_pos(size_t* s, size_t* f) { return a_.get_pos(s, f); }
+	QN_SegID set_pos(size_t s, size_t f) { b_.set_pos(s, f); return a_.set_pos(s, f); }
 };
 
 enum { QN_LOG_PER_RUN = 1, QN_LOG_PER_EPOCH, QN_LOG_PER_SENT, QN_LOG_PER_BUNCH };

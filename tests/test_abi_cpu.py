@@ -32,13 +32,21 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_matches_oracle_layout():
     from oracle.binding import Config as OConfig
     assert [f[0] for f in OConfig._fields_] == [f[0] for f in crf_b200.Config._fields_]
-    assert C.sizeof(OConfig) == C.sizeof(crf_b200.Config) == 15 * 4 + 4 + 16
+    assert C.sizeof(OConfig) == C.sizeof(crf_b200.Config) == 15 * 4 + 4 + 16 + 8 * 4   # 15 words, pad, 2 doubles, 8 context / joined-stream words
 
 
 def test_window_width():
     lib = crf_b200.load_library()
     for (F, D, seg, want) in [(105, 1, 0, 105), (105, 10, 1, 850), (64, 30, 1, 542), (9, 3, 0, 9)]:
         cfg = crf_b200.make_config("stdseg", n_labs=D * 2, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=seg)
+        assert lib.crfgpu_window_width(C.byref(cfg)) == want
+    # the TIMIT recipe (demo/segmental-timit-demo.cfg.in:16-33): 1162 state + 1872 transition features
+    cfg = crf_b200.make_config("stdseg_no_dur_no_segtransftr", n_labs=48, n_base_ftrs=144, max_dur=10, extract_seg_ftrs=1,
+                               n_base_ftrs2=144, left_ctx2=6, right_ctx2=6)
+    assert lib.crfgpu_window_width(C.byref(cfg)) == 1162 + 1872
+    for kw, want in [(dict(max_dur=4, extract_seg_ftrs=1, left_ctx=2, right_ctx=3), 56), (dict(max_dur=3, left_ctx=3, right_ctx=1, boundary_delta=1), 8),
+                     (dict(max_dur=1, left_ctx=2, right_ctx=2), 20)]:
+        cfg = crf_b200.make_config("stdseg_no_dur_no_segtransftr" if kw["max_dur"] > 1 else "stdframe", n_labs=5, n_base_ftrs=4, **kw)
         assert lib.crfgpu_window_width(C.byref(cfg)) == want
 
 

@@ -26,6 +26,7 @@ NODUR = load_cases("train_nodur_golden.npz")
 NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
+JOINED = load_cases("joined_golden.npz")
 
 
 def gpu(cfg):
@@ -885,4 +886,76 @@ def test_plan_info_names_the_kernels():
     m.set_option("dp_impl", 1)
     m.fwdbwd(c["off"], c["ftrs"], c["labs"])
     assert "FFMA fallback" in m.plan_info()
+    m.close()
+
+
+# ---- window streams with context frames / boundary deltas / a joined second stream (crfgpu_*2) ----------------------------------
+def f2_of(c):
+    return c["ftrs2"] if c["cfg"].n_base_ftrs2 else None
+
+
+@pytest.mark.parametrize("name", sorted(k for k in JOINED if k.startswith("win_")))
+def test_joined_windows_bit_exact(name):
+    """expand_joined_kernel against the reference's own window streams (CRF_InFtrStream_SeqMultiWindow with context frames, joined by
+    QN_InFtrStream_JoinFtrs; goldens of make_golden_joined.py)"""
+    c = JOINED[name]
+    m = gpu(c["cfg"])
+    got = m.expand_windows(c["ftrs"], f2_of(c))
+    assert got.shape == c["win"].shape
+    assert np.array_equal(got.view(np.uint32), c["win"].view(np.uint32))
+    m.close()
+
+
+@pytest.mark.parametrize("name", sorted(k for k in JOINED if k.startswith("train_")))
+def test_joined_fwdbwd_matches_reference_golden(name):
+    c = JOINED[name]
+    m = gpu(c["cfg"])
+    assert m.lambda_len == len(c["lam"])
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"], ftrs2=f2_of(c))
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    # staged path gives the same
+    m.stage(c["off"], c["ftrs"], c["labs"], ftrs2=f2_of(c)); m.fwdbwd_staged()
+    assert_train_close(m.fetch_fwdbwd(), (c["grad"], c["numer"], c["logZ"]), name + " staged")
+    m.close()
+
+
+@pytest.mark.parametrize("name", sorted(k for k in JOINED if k.startswith("vit_")))
+def test_joined_viterbi_bit_exact(name):
+    c = JOINED[name]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    segs, cost = m.viterbi(c["off"], c["ftrs"], ftrs2=f2_of(c))
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s_[0]) for s_ in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
+    m.close()
+
+
+def test_timit_recipe_shape_matches_oracle(oracle):
+    """The production TIMIT recipe at its real shape (demo/segmental-timit-demo.cfg.in:11-48): stdseg_no_dur_no_segtransftr + stdtrans,
+    48 phones, maxDur 10, stream 1 = 144 inputs -> 1162 segment features (state), stream 2 = the same inputs padded by 6 frames on
+    each side -> 13 x 144 = 1872 context features (transition); training and decoding against the oracle."""
+    rng = np.random.default_rng(48)
+    P, D, F = 48, 10, 144
+    off, _, labs = synth_batch(rng, 5, 20, 90, 1, P, 2, 14)
+    n = int(off[-1])
+    f1 = rng.random((n, F), dtype=np.float32)
+    f2 = rng.random((n + 12 * (len(off) - 1), F), dtype=np.float32)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1,
+                      n_base_ftrs2=F, left_ctx2=6, right_ctx2=6, use_trans_ftrs=1, state_fidx=(0, 1161), trans_fidx=(1162, 3033))
+    lam = rng.uniform(-0.01, 0.01, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, f1, labs, n_threads=8, ftrs2=f2)
+    m = gpu(cfg)
+    assert m.lambda_len == len(lam) == 48 * 1163 + 48 * 48 * 1873
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, f1, labs, ftrs2=f2)
+    assert_train_close(got, want, "TIMIT recipe shape")
+    segs, cost = m.viterbi(off, f1, ftrs2=f2)
+    wsegs, wcost, _ = oracle.viterbi(cfg, lam, off, f1, f2)
+    for a, b in zip(segs, wsegs):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
     m.close()

@@ -15,6 +15,41 @@ NODUR = load_cases("train_nodur_golden.npz")
 NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
+JOINED = load_cases("joined_golden.npz")
+
+
+def f2_of(c):
+    return c["ftrs2"] if c["cfg"].n_base_ftrs2 else None
+
+
+@pytest.mark.parametrize("name", sorted(k for k in JOINED if k.startswith("win_")))
+def test_joined_window_golden_bit_exact(oracle, name):
+    """context frames / boundary deltas / joined second stream: window vectors against the reference's own streams (make_golden_joined.py)"""
+    c = JOINED[name]
+    got = np.nan_to_num(oracle.window_ftrs(c["cfg"], c["ftrs"], f2_of(c)), nan=0.0)
+    assert np.array_equal(got.view(np.uint32), c["win"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", sorted(k for k in JOINED if k.startswith("train_")))
+def test_joined_train_golden(oracle, name):
+    """training over joined / context window streams (incl. the TIMIT recipe's layout: state features from stream 1's segment
+    features, transition features from stream 2's context frames) against goldens produced by the reference"""
+    c = JOINED[name]
+    assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
+    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"], ftrs2=f2_of(c))
+    np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
+    np.testing.assert_allclose(numer, c["numer"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", sorted(k for k in JOINED if k.startswith("vit_")))
+def test_joined_viterbi_golden_bit_exact(oracle, name):
+    c = JOINED[name]
+    segs, cost, _ = oracle.viterbi(c["cfg"], c["lam"], c["off"], c["ftrs"], f2_of(c))
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
 
 
 def test_toy_known_answers(oracle):
