@@ -72,6 +72,8 @@ struct crfgpu_ctx {
 	DevBuf d_base2, d_X2, d_frame_t2, d_bpad2, d_Xa2; bool pre_virt = false; cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre_done = nullptr, ev_pre_ready = nullptr;
 	cudaEvent_t ev_swap = nullptr; bool swap_marked = false;   // main-stream point after which the spare buffer set is free
 	std::vector<cudaEvent_t> ev_chunk2; bool pre_valid = false; const float* pre_ftrs = nullptr; std::vector<uint32_t> pre_off;
+	// ... and, when the read-ahead was handed the labels too (crfgpu_prefetch_train_batch), the per-frame index / label tables of that batch
+	DevBuf d_frame_utt2, d_frame_len2, d_node_lab2, d_prev_lab2, d_next_lab2; const uint32_t* pre_labs = nullptr; bool pre_tabs = false;
 	uint32_t W = 0;          // window feature width
 	// virtual windows of the training GEMMs (see launch_virtual_windows): padded base stream [N][Fp] + aggregate blocks [N][D][Wa]
 	bool virt = false, x_virt_valid = false, x_full_valid = false; int opt_virt = 1; uint32_t Fp = 0, Wa = 0; DevBuf d_bpad, d_Xa, d_bias_dy;
@@ -395,7 +397,7 @@ void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_
 		n_prev = ends[k];
 	}
 	if (phase) phase_end(h, phase);
-	if (h->chunk_end.size() < ends.size() || phase) h->chunk_end = ends;
+	if (phase) h->chunk_end = ends;      // the chunk list of the timed (non-read-ahead) staging: indexes ev_chunk in the verbose timeline
 }
 
 void validate_offsets(uint32_t n_utt, const uint32_t* off, const float* ftrs) {
@@ -406,7 +408,42 @@ void validate_offsets(uint32_t n_utt, const uint32_t* off, const float* ftrs) {
 			throw ApiError(CRFGPU_ERR_ARG, "utterance " + std::to_string(u) + " has no frames (reference: \"No features read from this sentence\")");
 }
 
-void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs) {
+// node label = (dur-1)*nActualLabs + phone on the frame where a reference segment ends (CRF_NewGradBuilder_StdSeg.cpp:172-187);
+// prev_lab = label of the preceding reference segment (:343-351).  Frame-level models label every frame (window length 1 cuts every
+// run into 1-frame pieces).  next_lab (transition-feature no_dur models only): phone of the NEXT reference segment at every frame where
+// a reference segment ends (the builder's next_lab, CRF_NewGradBuilder_StdSeg_NoDur_NoTrans.cpp:436-446)
+void build_label_tables(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const uint32_t* labs, std::vector<uint32_t>& node_lab,
+                        std::vector<uint32_t>& prev_lab, std::vector<uint32_t>& next_lab) {
+	const crfgpu_config& c = h->cfg;
+	const uint32_t N = n_utt ? off[n_utt] : 0;
+	node_lab.assign(N, CRFGPU_LAB_BAD); prev_lab.assign(N, CRFGPU_LAB_BAD);
+	std::vector<uint32_t> rec;
+	for (uint32_t u = 0; u < n_utt; u++) {
+		const uint32_t T = off[u + 1] - off[u];
+		rec.resize((size_t)T * 4);
+		group_labels(c.max_dur, T, labs + off[u], rec.data());
+		uint32_t last = CRFGPU_LAB_BAD;
+		for (uint32_t t = 0; t < T; t++) {
+			prev_lab[off[u] + t] = last;
+			if (rec[4 * (size_t)t] != CRFGPU_LAB_BAD) {
+				const uint32_t dur = rec[4 * (size_t)t + 2] - rec[4 * (size_t)t + 1] + 1;
+				const uint32_t lab = (c.model_type == CRFGPU_STDSEG || h->tied || h->nodur) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
+				node_lab[off[u] + t] = lab; last = lab;
+			}
+		}
+	}
+	next_lab.clear();
+	if (h->nodur_tf) {
+		next_lab.assign(N, CRFGPU_LAB_BAD);
+		for (uint32_t u = 0; u < n_utt; u++) {
+			uint32_t nxt = CRFGPU_LAB_BAD;
+			for (uint32_t n = off[u + 1]; n-- > off[u];)
+				if (node_lab[n] != CRFGPU_LAB_BAD) { next_lab[n] = nxt; nxt = node_lab[n] % c.n_actual_labs; }
+		}
+	}
+}
+
+void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs = nullptr) {
 	const crfgpu_config& c = h->cfg;
 	validate_offsets(n_utt, off, ftrs);
 	const uint32_t N = n_utt ? off[n_utt] : 0;
@@ -417,14 +454,25 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 		CUDA_OK(cudaEventCreate(&h->ev_pre_done)); CUDA_OK(cudaEventCreate(&h->ev_pre_ready));
 	}
 	if (h->swap_marked) CUDA_OK(cudaStreamWaitEvent(h->pre_stream, h->ev_swap, 0));
-	std::vector<uint32_t> frame_t(N);
+	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
 	for (uint32_t u = 0; u < n_utt; u++)
-		for (uint32_t n = off[u]; n < off[u + 1]; n++) frame_t[n] = n - off[u];
+		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
 	h->d_base2.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
 	h->pre_virt = h->virt;                                               // the read-ahead of a training loop: the form the training GEMMs read
 	if (h->pre_virt) { h->d_bpad2.ensure(sizeof(float) * (size_t)N * h->Fp + 16); h->d_Xa2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wa + 16); }
 	else if (c.max_dur > 1) h->d_X2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
 	upload(h->d_frame_t2, frame_t, h->pre_stream);                       // pageable: waits only for this side stream's own earlier work
+	h->pre_tabs = false; h->pre_labs = labs;
+	if (labs) {
+		// the label-derived tables of the next minibatch, built while this one computes (about 1 ms of host work per cfg4 minibatch
+		// that crfgpu_stage_batch would otherwise do with the device idle)
+		std::vector<uint32_t> node_lab, prev_lab, next_lab;
+		build_label_tables(h, n_utt, off, labs, node_lab, prev_lab, next_lab);
+		upload(h->d_frame_utt2, frame_utt, h->pre_stream); upload(h->d_frame_len2, frame_len, h->pre_stream);
+		upload(h->d_node_lab2, node_lab, h->pre_stream); upload(h->d_prev_lab2, prev_lab, h->pre_stream);
+		if (!next_lab.empty()) upload(h->d_next_lab2, next_lab, h->pre_stream);
+		h->pre_tabs = true;
+	}
 	// optional cap on the expansion's shared memory per CTA (option prefetch_smem): small duration groups fit beside a resident lattice
 	// CTA, but measured on cfg4 that SLOWS the step (e2e 13.0 M frames/s at 12 KB vs 14.1 M uncapped: the co-resident CTAs steal issue
 	// and shared-memory bandwidth from the latency-bound recursion), so by default the read-ahead uses whole-frame CTAs
@@ -464,7 +512,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
 	const bool want_virt = h->virt && labs != nullptr;                   // training batches of eligible models stage the virtual-window form
 	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off && h->pre_virt == want_virt;
-	h->pre_valid = false;
+	const bool tabs_ready = prefetched && !h->joined && h->pre_tabs && labs != nullptr && h->pre_labs == labs;   // index / label tables already on the device
+	h->pre_valid = false; h->pre_tabs = false;
 	h->x_virt_valid = want_virt; h->x_full_valid = !want_virt;
 	if (h->joined) {
 		// general window streams: both streams go to the device whole, one gather kernel builds the joined windows
@@ -499,6 +548,10 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
 		std::swap(h->d_base, h->d_base2); std::swap(h->d_X, h->d_X2); std::swap(h->d_frame_t, h->d_frame_t2);
 		std::swap(h->d_bpad, h->d_bpad2); std::swap(h->d_Xa, h->d_Xa2);
+		if (tabs_ready) {
+			std::swap(h->d_frame_utt, h->d_frame_utt2); std::swap(h->d_frame_len, h->d_frame_len2);
+			std::swap(h->d_node_lab, h->d_node_lab2); std::swap(h->d_prev_lab, h->d_prev_lab2); std::swap(h->d_next_lab, h->d_next_lab2);
+		}
 		CUDA_OK(cudaStreamWaitEvent(s, h->ev_pre_done, 0));
 	} else {
 		// what the window expansion needs goes through the copy engine ahead of the feature chunks
@@ -523,42 +576,14 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		                want_virt, &h->d_bpad, &h->d_Xa);
 		h->vit_score_ready = eager_vit;
 	}
-	if (!h->joined) upload_async(h, h->d_frame_utt, frame_utt);
-	upload_async(h, h->d_frame_len, frame_len);
+	if (!h->joined && !tabs_ready) upload_async(h, h->d_frame_utt, frame_utt);
+	if (!tabs_ready) upload_async(h, h->d_frame_len, frame_len);
 
-	std::vector<uint32_t> node_lab, prev_lab;
-	if (labs) {
-		// node label = (dur-1)*nActualLabs + phone on the frame where a reference segment ends
-		// (CRF_NewGradBuilder_StdSeg.cpp:172-187); prev_lab = label of the preceding reference segment (:343-351).
-		// Frame-level models label every frame (window length 1 cuts every run into 1-frame pieces).
-		node_lab.assign(N, CRFGPU_LAB_BAD); prev_lab.assign(N, CRFGPU_LAB_BAD);
-		std::vector<uint32_t> rec;
-		for (uint32_t u = 0; u < n_utt; u++) {
-			const uint32_t T = off[u + 1] - off[u];
-			rec.resize((size_t)T * 4);
-			group_labels(c.max_dur, T, labs + off[u], rec.data());
-			uint32_t last = CRFGPU_LAB_BAD;
-			for (uint32_t t = 0; t < T; t++) {
-				prev_lab[off[u] + t] = last;
-				if (rec[4 * (size_t)t] != CRFGPU_LAB_BAD) {
-					const uint32_t dur = rec[4 * (size_t)t + 2] - rec[4 * (size_t)t + 1] + 1;
-					const uint32_t lab = (c.model_type == CRFGPU_STDSEG || h->tied || h->nodur) ? c.n_actual_labs * (dur - 1) + rec[4 * (size_t)t] : rec[4 * (size_t)t];
-					node_lab[off[u] + t] = lab; last = lab;
-				}
-			}
-		}
+	if (labs && !tabs_ready) {
+		std::vector<uint32_t> node_lab, prev_lab, next_lab;
+		build_label_tables(h, n_utt, off, labs, node_lab, prev_lab, next_lab);
 		upload_async(h, h->d_node_lab, node_lab); upload_async(h, h->d_prev_lab, prev_lab);
-		if (h->nodur_tf) {
-			// phone of the NEXT reference segment at every frame where a reference segment ends (the builder's next_lab,
-			// CRF_NewGradBuilder_StdSeg_NoDur_NoTrans.cpp:436-446)
-			std::vector<uint32_t> next_lab(N, CRFGPU_LAB_BAD);
-			for (uint32_t u = 0; u < n_utt; u++) {
-				uint32_t nxt = CRFGPU_LAB_BAD;
-				for (uint32_t n = off[u + 1]; n-- > off[u];)
-					if (node_lab[n] != CRFGPU_LAB_BAD) { next_lab[n] = nxt; nxt = node_lab[n] % c.n_actual_labs; }
-			}
-			upload_async(h, h->d_next_lab, next_lab);
-		}
+		if (!next_lab.empty()) upload_async(h, h->d_next_lab, next_lab);
 	}
 	// utterances sorted by length (longest first) so the slots of one CTA finish together; reordering inside a
 	// minibatch does not change the gradient sum
@@ -1344,7 +1369,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_mass, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1441,6 +1466,14 @@ int crfgpu_prefetch_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame
 	});
 }
 
+int crfgpu_prefetch_train_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		prefetch_batch(h, n_utt, frame_off, base_ftrs, frame_labs);
+	});
+}
+
 int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs) {
 	return guarded([&] {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
@@ -1530,7 +1563,7 @@ int crfgpu_fwdbwd_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_
 	if (verbose && h->ev_ready) {
 		fprintf(stderr, "[crfgpu] device timeline from the start of staging (ms):");
 		float t = 0.0f;
-		for (size_t k = 0; k < h->chunk_end.size(); k++) if (cudaEventElapsedTime(&t, h->ev_ready, h->ev_chunk[k]) == cudaSuccess) fprintf(stderr, " H2D chunk %zu done %.3f", k, t);
+		for (size_t k = 0; k < std::min(h->chunk_end.size(), h->ev_chunk.size()); k++) if (cudaEventElapsedTime(&t, h->ev_ready, h->ev_chunk[k]) == cudaSuccess) fprintf(stderr, " H2D chunk %zu done %.3f", k, t);
 		for (const char* ph : {"expand", "score", "grad"}) {
 			auto it = h->phases.find(ph);
 			if (it != h->phases.end() && cudaEventElapsedTime(&t, h->ev_ready, it->second.first) == cudaSuccess) {

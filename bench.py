@@ -373,7 +373,7 @@ def run_ours(args):
         m.stage(off, pin_f.array, pin_l.array)                 # H2D of this minibatch (taken over from the read-ahead after the first step)
         m.fwdbwd_staged()
         if not args.no_prefetch:
-            m.prefetch(off, pin_f.array)                       # read-ahead of the NEXT minibatch: H2D + window expansion on side streams
+            m.prefetch(off, pin_f.array, pin_l.array)          # read-ahead of the NEXT minibatch: H2D, window expansion and label tables on side streams
         allreduce_grad()                                       # ONE ncclAllReduce on the handle's stream (N > 1)
         m.fetch_fwdbwd(out=(None, pin_n.array, pin_z.array))   # D2H of the step's result: per-utterance numerators and logZ
         m.sgd_update(float(world), lr=e2e_lr)                  # lambda += lr * grad / nStreams_active on the device, every table rebuilt

@@ -169,6 +169,11 @@ int crfgpu_stage_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_of
  * crfgpu_stage_batch / crfgpu_fwdbwd_batch that is handed the same frame_off contents and base_ftrs pointer takes the buffers over
  * instead of copying again; any other batch is staged normally.  base_ftrs must stay valid and unchanged until then. */
 int crfgpu_prefetch_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs);
+/* The same read-ahead for a training loop that also hands over the labels of the next minibatch: the per-frame index and label tables
+ * (reference-segment labels of CRF_InLabStream_SeqMultiWindow's grouping, previous / next segment labels) are built on the host and
+ * copied while the current minibatch computes, so that the crfgpu_stage_batch that takes the batch over (same frame_off contents, same
+ * base_ftrs and frame_labs pointers) has no per-frame host work left. */
+int crfgpu_prefetch_train_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs);
 /* Run forward-backward+gradient on the staged batch; results stay on the device. */
 int crfgpu_fwdbwd_staged(crfgpu_handle h);
 /* Run Viterbi + traceback on the staged batch; results stay on the device. */

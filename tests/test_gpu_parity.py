@@ -444,6 +444,34 @@ def test_prefetch_takes_over_buffers_and_falls_back():
     assert b is not None
 
 
+@pytest.mark.parametrize("case", ["stdseg_d10_segftr", "frame_1state"])
+def test_prefetch_train_batch_hands_over_label_tables(case):
+    """crfgpu_prefetch_train_batch: the read-ahead also builds and copies the label tables; the staged batch gives the plain call's
+    results, and a batch staged with OTHER labels (another array) rebuilds its tables instead of taking the prefetched ones."""
+    a = TRAIN[case]
+    m = gpu(a["cfg"])
+    m.set_lambda(a["lam"])
+    want = m.fwdbwd(a["off"], a["ftrs"], a["labs"])
+    fa, la = np.ascontiguousarray(a["ftrs"], np.float32), np.ascontiguousarray(a["labs"], np.uint32)
+    for _ in range(3):
+        m.stage(a["off"], fa, la)
+        m.fwdbwd_staged()
+        m.prefetch(a["off"], fa, la)
+        got = m.fetch_fwdbwd()
+        for x, y in zip(got, want):
+            np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(y).max()))
+    # same features, different labels at another address: the prefetched label tables must not be used
+    m.prefetch(a["off"], fa, la)
+    lb = la.copy(); lb[:] = la[::-1]
+    m.stage(a["off"], fa, lb); m.fwdbwd_staged()
+    got_b = m.fetch_fwdbwd()
+    want_b = m.fwdbwd(a["off"], a["ftrs"], lb)
+    for x, y in zip(got_b, want_b):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(y).max()))
+    assert not np.allclose(got_b[1], want[1])
+    m.close()
+
+
 @pytest.mark.parametrize("name", sorted(TRANSFTR))
 def test_fwdbwd_transition_features_match_reference_golden(name):
     """crf_featuremap=stdtrans on frame-level models: transition scores as a tensor-core GEMM, streamed recursions, both gradients
