@@ -123,7 +123,7 @@ __device__ __forceinline__ void mma_walk(unsigned char* op, Ctl* ctl, uint32_t t
 }
 
 // ------------------------------------------------------------------------------------------------
-// score_gemm_tma: grid (frame tiles of 128, label tiles of 64 inside a duration, durations)
+// score_gemm_tma: grid (durations, label tiles of 64 inside a duration, frame tiles of 128)
 // warps 0-7 converters, 8 MMA, 9 window TMA, 10 weight-tile bulk copies
 // ------------------------------------------------------------------------------------------------
 constexpr int SC_THR = (CONV_WARPS + 3) * 32;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tma_kernel(const __grid_
 	extern __shared__ __align__(1024) unsigned char smem[];
 	Ctl* ctl = reinterpret_cast<Ctl*>(smem + CTL_OFF);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t m0 = blockIdx.x * BM, jt = blockIdx.y, d = blockIdx.z;
+	const uint32_t d = blockIdx.x, jt = blockIdx.y, m0 = blockIdx.z * BM;   // durations of one frame tile run back to back: they share the base rows and the rows of S
 	const uint32_t n_chunks = p.n_chunks;
 	if (tid == 0 && (smem_u32(smem) & 1023)) __trap();
 	setup(ctl, tid, warp, CONV_WARPS, CONV_WARPS + 1);
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid
 	extern __shared__ __align__(1024) unsigned char smem[];
 	TCtl* ctl = reinterpret_cast<TCtl*>(smem + T_CTL_OFF);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t m0 = blockIdx.x * BM, jt = blockIdx.y, d = blockIdx.z;
+	const uint32_t d = blockIdx.x, jt = blockIdx.y, m0 = blockIdx.z * BM;   // durations of one frame tile run back to back: they share the base rows and the rows of S
 	const uint32_t n_chunks = p.n_chunks;
 	if (tid == 0) {
 		if (smem_u32(smem) & 1023) __trap();
@@ -742,7 +742,8 @@ cudaError_t launch_score_gemm_tma(const float* X, uint32_t Wp, const ScoreTmaPar
 	if (!window_map(&tm, X, p.M, p.D, Wp, p.virt ? Wp : p.K, BM, true)) return cudaErrorInvalidValue;
 	if (p.virt) { if (!p.a_from_tmem || !window_map(&tb, p.base2, p.M, 1, p.cpb * KC, p.cpb * KC, BM, false)) return cudaErrorInvalidValue; }
 	else tb = tm;
-	dim3 grid((p.M + BM - 1) / BM, p.ntile, p.D);
+	dim3 grid(p.D, p.ntile, (p.M + BM - 1) / BM);
+	if (grid.z > 65535u) return cudaErrorInvalidValue;      // 8.3 M frames per launch
 	if (p.a_from_tmem) {
 		bool attr2 = false;
 		if (!attr2) {
