@@ -330,38 +330,42 @@ __global__ void __launch_bounds__(SC_THR, 2) score_gemm_tmem_kernel(const __grid
 			}
 		}
 	}
-	// ---- epilogue: TMEM -> shared transpose -> (+bias) -> coalesced rows of S, and the row maximum of the duration block ----
+	// ---- epilogue: thread = frame row: its 64 accumulators (+bias) and their maximum straight from tensor memory, then a shared-memory
+	// transpose so that the rows of S leave as coalesced stores.  (The row maximum used to be a 5-shuffle reduction inside a per-row loop:
+	// 32 dependent iterations per warp, a quarter of the CTA's lifetime with the other seven warps idle.)
 	if (warp < 4) {
+		const uint32_t y0 = jt * BN, ncol = min((uint32_t)BN, p.P - y0);
+		const uint32_t col0 = d * p.P + y0, bcol = ((p.shared_w && !p.virt) ? 0u : d * p.P) + y0;   // virt: bias per (d,y), it carries the one-hot duration weight
+		float* Cs = reinterpret_cast<float*>(smem);       // [128][65] over the raw ring, idle once the last MMA has committed
+		float* sb = reinterpret_cast<float*>(smem + T_B_OFF);   // the tile's biases, over the weight ring (idle as well)
 		mbar_wait(&ctl->done, 0);
 		tc_fence_after();
-		float* Cs = reinterpret_cast<float*>(smem);       // [128][65] over the raw ring, idle now
-		const uint32_t row = warp * 32 + lane;
+		if (warp == 0) { sb[lane] = (p.bias && lane < ncol) ? __ldg(p.bias + bcol + lane) : 0.0f; sb[lane + 32] = (p.bias && lane + 32 < ncol) ? __ldg(p.bias + bcol + lane + 32) : 0.0f; }
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		const uint32_t row = warp * 32 + lane, gmr = m0 + row;
+		float mx = -INFINITY;
 #pragma unroll
 		for (int c0 = 0; c0 < BN; c0 += 16) {
 			float v[16];
 			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
 			tmem_ld_wait();
 #pragma unroll
-			for (int j = 0; j < 16; j++) Cs[row * 65 + c0 + j] = v[j];
+			for (int j = 0; j < 16; j++) {
+				const float x = v[j] + sb[c0 + j];
+				Cs[row * 65 + c0 + j] = x;
+				if ((uint32_t)(c0 + j) < ncol) mx = fmaxf(mx, x);
+			}
 		}
 		tc_fence_before();
+		if (p.smaxd && gmr < p.M) p.smaxd[(uint64_t)gmr * p.D + d] = (d <= __ldg(p.frame_t + gmr)) ? mx : -INFINITY;
 		__syncwarp();
-		const uint32_t y0 = jt * BN, ncol = min((uint32_t)BN, p.P - y0);
-		const uint32_t col0 = d * p.P + y0, bcol = ((p.shared_w && !p.virt) ? 0u : d * p.P) + y0;   // virt: bias per (d,y), it carries the one-hot duration weight
-		const float b0 = (p.bias && lane < ncol) ? __ldg(p.bias + bcol + lane) : 0.0f;
-		const float b1 = (p.bias && lane + 32 < ncol) ? __ldg(p.bias + bcol + lane + 32) : 0.0f;
-		for (uint32_t rr = 0; rr < 32; rr++) {
-			const uint32_t rloc = warp * 32 + rr, gm = m0 + rloc;
-			if (gm >= p.M) break;
-			float mx = -INFINITY;
-			float* crow = p.C + (uint64_t)gm * p.ldc + col0;
-			if (lane < ncol) { const float v = Cs[rloc * 65 + lane] + b0; crow[lane] = v; mx = v; }
-			if (lane + 32 < ncol) { const float v = Cs[rloc * 65 + lane + 32] + b1; crow[lane + 32] = v; mx = fmaxf(mx, v); }
-			if (p.smaxd) {
-#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-				if (lane == 0) p.smaxd[(uint64_t)gm * p.D + d] = (d <= __ldg(p.frame_t + gm)) ? mx : -INFINITY;
-			}
+		const uint32_t nrow = min(32u, p.M > m0 + warp * 32 ? p.M - (m0 + warp * 32) : 0u);
+#pragma unroll 4
+		for (uint32_t rr = 0; rr < nrow; rr++) {
+			const uint32_t rloc = warp * 32 + rr;
+			float* crow = p.C + (uint64_t)(m0 + rloc) * p.ldc + col0;
+			if (lane < ncol) crow[lane] = Cs[rloc * 65 + lane];
+			if (lane + 32 < ncol) crow[lane + 32] = Cs[rloc * 65 + lane + 32];
 		}
 	}
 	tc_fence_before();
