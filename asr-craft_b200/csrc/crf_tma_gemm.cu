@@ -589,6 +589,10 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 		const uint32_t gm = m0 + q4 * 32 + lane;                                      // my row of the 128-row side
 		const uint32_t k = (warp & 3) * 8 + (lane & 7), cg = (warp >> 2) * 4 + (lane >> 3);   // my unit of the 64-column side
 		const bool is_ones = MODE == 0 && (p.virt ? (vb == 0xffffffffu && gm == 3 * p.F) : gm == p.ones_col);
+		// byte offset of my column inside raw row kk of the swizzled box: 16-byte chunk (lane >> 2) ^ (kk & 7), word lane & 3
+		uint32_t xoff[8];
+#pragma unroll
+		for (uint32_t j = 0; j < 8; j++) xoff[j] = (((lane >> 2) ^ j) << 4) + (lane & 3) * 4;
 		for (uint32_t c = 0; c < n_chunks; c++) {
 			const uint32_t rm = c % RM, rn = c % RN, s = c % TS;
 			mbar_wait(&ctl->m_full[rm], (c / RM) & 1);
@@ -597,8 +601,11 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 #pragma unroll
 			for (uint32_t j = 0; j < 16; j++) {
 				const uint32_t kk = ks * 16 + j;
-				x[j] = *reinterpret_cast<const float*>(box + kk * 128 + ((((lane >> 2) ^ (kk & 7))) << 4) + (lane & 3) * 4);
-				if (is_ones) x[j] = (ns + c * KC + kk < ne) ? 1.0f : 0.0f;              // the constant-1 bias feature (TMA zero-fills beyond the window)
+				x[j] = *reinterpret_cast<const float*>(box + kk * 128 + xoff[j & 7]);
+			}
+			if (is_ones) {                                                              // one lane of one warp of the tile that holds the bias row
+#pragma unroll
+				for (uint32_t j = 0; j < 16; j++) x[j] = (ns + c * KC + ks * 16 + j < ne) ? 1.0f : 0.0f;   // the constant-1 bias feature (TMA zero-fills beyond the window)
 			}
 			uint32_t hi[8], lo[8];
 #pragma unroll
