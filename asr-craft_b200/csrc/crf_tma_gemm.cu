@@ -72,14 +72,28 @@ __device__ __forceinline__ void load_raw8(const unsigned char* tile, uint32_t ro
 	x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
 
-// the same for a 64-column tile held as two boxes when the 8 floats start at an arbitrary column (columns >= 64 read as 0)
-__device__ __forceinline__ void load_raw8_shifted(const unsigned char* tiles, uint32_t row, uint32_t col, float (&x)[8]) {
+// the same for a 64-column tile held as two boxes when the 8 floats start `sh` (1..3, the same for the whole CTA) columns behind the
+// aligned column col4 (a multiple of 4): three aligned 16-byte loads and a register selection instead of eight scalar loads with their
+// own swizzle arithmetic (columns >= 64 read as 0)
+__device__ __forceinline__ void load_raw8_shifted(const unsigned char* tiles, uint32_t row, uint32_t col4, uint32_t sh, float (&x)[8]) {
 	const unsigned char* r = tiles + row * 128;
-	const uint32_t sw = row & 7;
+	const uint32_t sw = row & 7, q = col4 >> 2;                     // first aligned 16-byte chunk (0..15 over the two boxes)
+	float4 v[3];
 #pragma unroll
-	for (uint32_t e = 0; e < 8; e++) {
-		const uint32_t cc = col + e;
-		x[e] = cc < 64u ? *reinterpret_cast<const float*>(r + (cc >> 5) * 4096 + ((((cc & 31) >> 2) ^ sw) << 4) + (cc & 3) * 4) : 0.0f;
+	for (uint32_t i = 0; i < 3; i++) {
+		const uint32_t qi = q + i;
+		v[i] = qi < 16u ? *reinterpret_cast<const float4*>(r + (qi >> 3) * 4096 + (((qi & 7) ^ sw) << 4)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
+	const float f[12] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w, v[2].x, v[2].y, v[2].z, v[2].w};
+	if (sh == 1) {
+#pragma unroll
+		for (int e = 0; e < 8; e++) x[e] = f[e + 1];
+	} else if (sh == 2) {
+#pragma unroll
+		for (int e = 0; e < 8; e++) x[e] = f[e + 2];
+	} else {
+#pragma unroll
+		for (int e = 0; e < 8; e++) x[e] = f[e + 3];
 	}
 }
 
@@ -442,7 +456,7 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tma_kernel(const __grid_
 			}
 			mbar_wait(&ctl->n_full[rn], (c / RN) & 1);
 			if (sh == 0) load_raw8(smem + F_RAWN_OFF + rn * RAWN_BYTES + (cg >> 2) * 4096, k, cg & 3, x[2]);
-			else load_raw8_shifted(smem + F_RAWN_OFF + rn * RAWN_BYTES, k, cg * 8 + sh, x[2]);
+			else load_raw8_shifted(smem + F_RAWN_OFF + rn * RAWN_BYTES, k, cg * 8, sh, x[2]);
 			uint4 h[3], l[3];
 #pragma unroll
 			for (int i = 0; i < 3; i++) split8(x[i], h[i], l[i]);
@@ -613,7 +627,7 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 			float xn[8];
 			mbar_wait(&ctl->n_full[rn], (c / RN) & 1);
 			if (sh == 0) load_raw8(smem + G_RAWN_OFF + rn * RAWN_BYTES + (cg >> 2) * 4096, k, cg & 3, xn);
-			else load_raw8_shifted(smem + G_RAWN_OFF + rn * RAWN_BYTES, k, cg * 8 + sh, xn);
+			else load_raw8_shifted(smem + G_RAWN_OFF + rn * RAWN_BYTES, k, cg * 8, sh, xn);
 			uint4 hn, ln;
 			split8(xn, hn, ln);
 			if (c >= TS) { mbar_wait(&ctl->op_empty[s], ((c / TS) - 1) & 1); tc_fence_after(); }
