@@ -230,8 +230,9 @@ struct FrameGemmParams {
 	const uint32_t* pair_idx; uint32_t L; const float* Ew; uint32_t e_ld;   // Xi
 	double* out;
 	uint32_t a_from_tmem;             // 1: 128-row operand through tensor memory (frame_gemm_tmem_kernel)
-	// state gradient over virtual windows (virt = 1, needs a_from_tmem): 128-row tiles = tpb per sampled-frame block (rows of base2[N][Fp] at
-	// a row shift) + the tiles of the aggregate array; lambda row of feature f of block b = b*F + f, of aggregate column a = 5F + a; the
+	// state gradient over virtual windows (virt = 1, needs a_from_tmem): 128-row tiles = tpb sampled tiles (four 32-feature units each; unit
+	// u = features [32 (u % upb), +32) of sampled-frame block u / upb, upb = Fp / 32: rows of base2[N][Fp] at the block's row shift) + the
+	// tiles of the aggregate array; lambda row of feature f of block b = b*F + f, of aggregate column a = 5F + a; the
 	// constant-1 row sits at aggregate column 3F and counts into the bias (ones_col) and into the one-hot duration weight 8F + d
 	uint32_t virt, tpb, F, Fp;
 	const float* base2;

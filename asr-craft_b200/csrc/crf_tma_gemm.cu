@@ -566,19 +566,23 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 	GCtl* ctl = reinterpret_cast<GCtl*>(smem + G_CTL_OFF);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t d = blockIdx.y / p.ntile, y0 = (blockIdx.y % p.ntile) * FRAME_GEMM_TILE;
-	// virtual windows (MODE 0, p.virt): the 128-row tiles walk the window in BLOCKS -- tile mt < 5 tpb is rows [f0, f0 + 128) of sampled-frame
-	// block b (a row shift of the padded base stream), the others are rows of the materialised avg | max | min array; lam_row = index of
-	// tile row 0 inside the label's state-weight block of lambda, vrows = rows of the tile that are real features
-	uint32_t m0 = blockIdx.x * BM, vb = 0xffffffffu, vshift = 0, lam_row = m0, vrows = BM;
+	// virtual windows (MODE 0, p.virt): the five sampled-frame blocks are walked in UNITS of 32 features -- unit u = 32 consecutive features
+	// of block u / upb (a row shift of the padded base stream, upb = Fp / 32 units per block); a 128-row tile holds four consecutive units
+	// (each of its four TMA boxes has its own block and shift, so narrow streams waste no tile: F = 64 -> 10 units = 3 tiles, not 5), the
+	// first p.tpb tiles are sampled tiles, the others rows of the materialised avg | max | min array.  Per warp quadrant / epilogue warp
+	// (32 rows = one unit): lam_row = index of its row 0 inside the label's state-weight block of lambda, vrows = its real feature rows.
+	uint32_t m0 = blockIdx.x * BM, vb = 0xffffffffu, lam_row = m0 + (warp & 3) * 32, vrows = 32;
+	const uint32_t upb = (MODE == 0 && p.virt) ? p.Fp / 32 : 1;
 	if (MODE == 0 && p.virt) {
 		const uint32_t mt = blockIdx.x;
-		if (mt < 5 * p.tpb) {
-			vb = mt / p.tpb; m0 = (mt - vb * p.tpb) * BM;
-			vshift = __ldg(p.steps + d * 5 + vb) - d;
-			lam_row = vb * p.F + m0; vrows = p.F > m0 ? min((uint32_t)BM, p.F - m0) : 0u;
+		if (mt < p.tpb) {
+			const uint32_t u = mt * 4 + (warp & 3), blk = u / upb, foff = (u - blk * upb) * 32;
+			vb = 0;                                                              // a sampled tile
+			lam_row = blk * p.F + foff; vrows = (blk < 5 && p.F > foff) ? min(32u, p.F - foff) : 0u;
 		} else {
-			m0 = (mt - 5 * p.tpb) * BM;
-			lam_row = 5 * p.F + m0; vrows = 3 * p.F > m0 ? min((uint32_t)BM, 3 * p.F - m0) : 0u;
+			m0 = (mt - p.tpb) * BM;
+			const uint32_t r0 = m0 + (warp & 3) * 32;
+			lam_row = 5 * p.F + r0; vrows = 3 * p.F > r0 ? min(32u, 3 * p.F - r0) : 0u;
 		}
 	}
 	const uint32_t ns = blockIdx.z * p.k_slab, ne = min(ns + p.k_slab, p.N);
@@ -667,13 +671,25 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 	} else {
 		if (lane == 0) {
 			prefetch_tmap(&tmM); prefetch_tmap(&tmN);
+			// sampled tiles: unit of each of the four boxes -> (feature offset, row shift); units behind the fifth block read beyond the
+			// stream's last row, which the TMA unit zero-fills
+			uint32_t ufoff[4] = {0, 0, 0, 0}, usft[4] = {0, 0, 0, 0}; bool ulive[4] = {false, false, false, false};
+			if (MODE == 0 && p.virt && vb != 0xffffffffu) {
+				prefetch_tmap(&tmB);
+#pragma unroll
+				for (uint32_t b = 0; b < 4; b++) {
+					const uint32_t u = blockIdx.x * 4 + b, blk = u / upb;
+					ufoff[b] = (u - blk * upb) * 32; ulive[b] = blk < 5;
+					usft[b] = ulive[b] ? __ldg(p.steps + d * 5 + blk) - d : 0u;
+				}
+			}
 			for (uint32_t c = 0; c < n_chunks; c++) {
 				const uint32_t rm = c % RM, rn = c % RN, n = ns + c * KC;
 				if (c >= RM) mbar_wait(&ctl->m_empty[rm], ((c / RM) - 1) & 1);
 				mbar_arrive_expect_tx(&ctl->m_full[rm], RAW_BYTES);
 #pragma unroll
 				for (uint32_t b = 0; b < 4; b++) {
-					if (MODE == 0 && p.virt && vb != 0xffffffffu) tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmB, m0 + b * 32, 0, n + vshift, &ctl->m_full[rm]);
+					if (MODE == 0 && p.virt && vb != 0xffffffffu) tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmB, ufoff[b], 0, ulive[b] ? n + usft[b] : p.N, &ctl->m_full[rm]);
 					else tma_load_3d(smem + rm * RAW_BYTES + b * 4096, &tmM, m0 + b * 32, MODE == 0 ? d : 0u, MODE == 0 ? n : n - (d + 1), &ctl->m_full[rm]);
 				}
 				if (c >= RN) mbar_wait(&ctl->n_empty[rn], ((c / RN) - 1) & 1);
@@ -689,8 +705,8 @@ __global__ void __launch_bounds__(FG_THR, 2) frame_gemm_tmem_kernel(const __grid
 		tc_fence_after();
 		const uint32_t gm = m0 + warp * 32 + lane;
 		const bool v_ones = MODE == 0 && p.virt && vb == 0xffffffffu && gm == 3 * p.F;      // sum_n Dm: the bias count AND the one-hot duration count
-		const bool row_ok = (MODE == 0 && p.virt) ? (warp * 32 + lane < vrows || v_ones) : gm < p.Mext;
-		const uint32_t lrow = (MODE == 0 && p.virt) ? (v_ones ? p.ones_col : lam_row + warp * 32 + lane) : gm;
+		const bool row_ok = (MODE == 0 && p.virt) ? (lane < vrows || v_ones) : gm < p.Mext;
+		const uint32_t lrow = (MODE == 0 && p.virt) ? (v_ones ? p.ones_col : lam_row + lane) : gm;
 		const double sc = (MODE == 0 && (p.virt ? v_ones : gm == p.ones_col)) ? p.ones_scale : p.scale;
 #pragma unroll
 		for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -808,7 +824,7 @@ cudaError_t launch_state_grad_tma(const float* X, uint32_t Wp, uint32_t K, const
 	if (p.virt) {
 		// virtual windows: X = aggregate array (avg | max | min, the constant-1 row right behind), base2 = padded base stream [N][Fp]
 		if (!p.a_from_tmem || !window_map(&tb, p.base2, p.N, 1, p.Fp, p.Fp, KC, false)) return cudaErrorInvalidValue;
-		mtiles = 5 * p.tpb + (3 * p.F + 1 + BM - 1) / BM;
+		mtiles = p.tpb + (3 * p.F + 1 + BM - 1) / BM;         // p.tpb = sampled tiles = ceil(5 * (Fp / 32) / 4)
 	} else tb = tm;
 	dim3 grid(mtiles, p.D * p.ntile, (p.N + p.k_slab - 1) / p.k_slab);
 	if (p.a_from_tmem) frame_gemm_tmem_kernel<0><<<grid, FG_THR, G_SMEM, s>>>(tm, tn, tb, p);

@@ -1086,7 +1086,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		r.row_idx = h->d_sidx.as<uint32_t>(); r.out = h->d_grad.as<double>();
 		r.a_from_tmem = (h->opt_tma_mask & 16) ? 1u : 0u;
 		if (virt) {
-			r.virt = 1; r.F = c.n_base_ftrs; r.Fp = h->Fp; r.tpb = (c.n_base_ftrs + 127) / 128; r.base2 = h->d_bpad.as<float>(); r.steps = h->d_steps.as<uint32_t>();
+			r.virt = 1; r.F = c.n_base_ftrs; r.Fp = h->Fp; r.tpb = (5 * (h->Fp / 32) + 3) / 4; r.base2 = h->d_bpad.as<float>(); r.steps = h->d_steps.as<uint32_t>();
 			CUDA_OK(launch_state_grad_tma(h->d_Xa.as<float>(), h->Wa, nSf, h->d_Dm.as<float>(), Lp, r, s));
 		} else
 		CUDA_OK(launch_state_grad_tma(h->X() + c.state_fidx_start, h->Wp, nSf, h->d_Dm.as<float>(), Lp, r, s));
