@@ -509,13 +509,16 @@ def run_ours(args):
     all_gate = [r for g in gather_list(gate) for r in g]
     if rank == 0:
         # per-frame ALGORITHMIC work of cfg4 (SURVEY.md 8d / DESIGN.md section 4).  Every phase sits below the tensor ridge
-        # (1388 TFLOP/s / 6.55 TB/s = 212 flop/B): score and state-gradient GEMMs move 34 kB of window features per 1.04 Mflop
-        # (29 flop/B), the transition-gradient GEMM 2*L^2 flop per 8*L bytes (152 flop/B), the lattice recursions are streams
+        # (1388 TFLOP/s / 6.55 TB/s = 212 flop/B): score and state-gradient GEMMs move 15.7 kB of window data per 1.04 Mflop
+        # (66 flop/B), the transition-gradient GEMM 2*L^2 flop per 8*L bytes (152 flop/B), the lattice recursions are streams
         # of 4*L-byte frame vectors -> the bound of every kernel is HBM, and `achieved` is algorithmic bytes / measured time.
-        L, P, D, Fs = 610, 61, 10, 850
+        L, P, D, Fs, F = 610, 61, 10, 850, 105
         flops = {"score": 2.0 * (Fs + 1) * L, "forward": 2.0 * L * L, "backward": 2.0 * L * L, "xi": 2.0 * L * L,
                  "grad": 2.0 * L * (Fs + 1)}
-        bytes_ = {"score": 4.0 * D * Fs + 4 * L, "forward": 8.0 * L, "backward": 12.0 * L, "xi": 8.0 * L, "grad": 4.0 * L + 4.0 * D * Fs}
+        # window GEMMs over the VIRTUAL windows: per frame D rows of the aggregate array (avg | max | min, 3F + 1
+        # floats padded to 32) + one row of the padded base stream (the five sampled-frame blocks are row shifts of it) + the label vector
+        win = 4.0 * D * ((3 * F + 1 + 31) // 32 * 32) + 4.0 * ((F + 31) // 32 * 32)
+        bytes_ = {"score": win + 4 * L, "forward": 8.0 * L, "backward": 12.0 * L, "xi": 8.0 * L, "grad": 4.0 * L + win}
         lat = "dp_ks_kernel" if "dp_ks_kernel" in plans[0] else ("dp_tc_kernel" if "dp_tc_kernel" in plans[0] else "lattice kernel")
         kernel_of = {"score": "score_gemm_tmem_kernel", "forward": lat + "<0>", "backward": lat + "<1>",
                      "xi": "frame_gemm_tmem_kernel<1>", "grad": "frame_gemm_tmem_kernel<0>"}
@@ -563,7 +566,7 @@ def run_ours(args):
                        "sharding": ("contiguous corpus views" if (args.contiguous or world == 1) else
                                     "global minibatch = union of the ranks' contiguous views, dealt to ranks length-balanced (crfgpu_balance_utts)")
                                    + "; one ncclAllReduce of lambda_len+4 doubles per step (crfgpu_allreduce_grad)",
-                       "l2": "inputs_exceed_l2 (4.8 GB of window features + 5 x 0.36 GB lattice arrays per step vs 126 MB L2)",
+                       "l2": "inputs_exceed_l2 (1.8 GB of window aggregates + 5 x 0.36 GB lattice arrays per step vs 126 MB L2)",
                        "plan": plans[0], "nccl_ranks": m.comm_size if world > 1 else 1},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
