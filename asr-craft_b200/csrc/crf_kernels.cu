@@ -949,6 +949,7 @@ __device__ __forceinline__ uint32_t kept_phone(uint32_t i, uint32_t P, uint32_t 
 	return i < g ? i : i + 1;
 }
 
+template <bool HAS_LM>
 __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Wprev = reinterpret_cast<float*>(smem_raw);   // [L] kept weights of the previous frame
@@ -966,6 +967,13 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	const uint32_t Pt = P | 1u;      // odd row stride: the rows of 32 consecutive target phones start in 32 different banks
 	const bool cross_in_smem = p.negMt == nullptr && ((size_t)P * Pt * sizeof(float) <= 96 * 1024);
 	if (cross_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) crossS[(i % P) * Pt + i / P] = p.crossT[i];
+	// phone-bigram LM (one state per phone): the weight of arc pp -> tq is added to the expanding hypothesis BEFORE the transition score,
+	// float by float -- (prev + lm) + trans, expandCrossStateFromPrevNode :629 / crossStateTransUpdate :467 -- so We[] then holds the raw
+	// kept weights (the "+ 0.0f" of the free-phone loop IS this add).  The table sits behind the cross table in shared memory when both fit.
+	constexpr bool has_lm = HAS_LM;       // compile-time: the free-phone instantiation is the kernel it was before the LM existed
+	const bool lm_in_smem = has_lm && cross_in_smem && (2 * (size_t)P * Pt * sizeof(float) <= 96 * 1024);
+	float* lmS = crossS + (size_t)P * Pt;
+	if (lm_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) lmS[(i / P) * Pt + i % P] = p.lm_bigT[i];
 	const float* crossT = p.crossT;      // global table (per-frame tables replace it below); the shared-memory copy is crossS
 	const bool per_frame = p.negMt != nullptr;      // transition FEATURES: the tables of the frame a segment starts in (global memory)
 	float* candW = p.candW + (uint64_t)u * D * L;
@@ -1018,7 +1026,19 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 			// finite, so that equals the reference's "the first candidate is always taken".
 			auto scan = [&](const float* ct, const uint32_t stride) {     // entry pp of the target phone's column at ct[pp * stride]
 				pw = CUDART_INF_F;
-				if (NS > 1) {
+				if (has_lm) {
+					// one state per phone with LM weights: the same list order, two adds per entry
+					const float* lr = lm_in_smem ? lmS + (size_t)tq * Pt : p.lm_bigT + (size_t)tq * P;
+#pragma unroll 4
+					for (uint32_t pp = 0; pp < P; pp++) {
+						const float cc = (We[pp] + lr[pp]) + ct[(size_t)pp * stride];
+						if (pp != tq && pp != g && cc < pw) { pw = cc; pptr = (int32_t)pp; }
+					}
+					if (g != 0xffu && g != tq) {
+						const float cc = (We[g] + lr[g]) + ct[(size_t)g * stride];
+						if (cc < pw) { pw = cc; pptr = (int32_t)g; }
+					}
+				} else if (NS > 1) {
 					// N states per phone: the kept list is always in phone order (s_g stays 0xff) and every phone may follow every phone
 #pragma unroll 4
 					for (uint32_t pp = i_lo; pp < i_hi; pp++) {
@@ -1050,7 +1070,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 		float cw = VIT_INF; int32_t cp = -1;
 		if (lab < L) {
 			if (s == 0) {
-				if (k == 0) cw = 0.0f + 0.0f;   // lm_start weight 0 + arc weight 0, trans_wt = 0.0 at node 0 (:444-447)
+				if (k == 0) cw = (0.0f + (has_lm ? __ldg(p.lm_start + q) : 0.0f)) + 0.0f;   // lm_start hypothesis 0 + arc weight, trans_wt = 0.0 at node 0 (:444-447)
 			} else {
 				bool seen = false;
 				if (k == 0) {
@@ -1096,7 +1116,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				if (d == dmax || w < best) { best = w; bptr = ptr; bdur = d; }
 			}
 			Wprev[lab] = best;
-			if (k == NS - 1) We[q] = best + 0.0f;
+			if (k == NS - 1) We[q] = has_lm ? best : best + 0.0f;
 			p.bp[(uint64_t)(off + s) * L + lab] = bptr < 0 ? (uint16_t)0xffff : (uint16_t)bptr;
 			p.bd[(uint64_t)(off + s) * L + lab] = (uint8_t)bdur;
 		}
@@ -1134,8 +1154,11 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 		if (T > 0) {
 			const uint32_t g = s_g;
 			for (uint32_t i = 0; i < P; i++) {
-				const uint32_t e = kept_phone(i, P, g) * NS + NS - 1;
-				const float w = Wprev[e];
+				// free-phone LM: kept-list order, first wins.  Input LM: the decoder's finalStateSet, ordered by LM state = phone, weight =
+				// hypothesis + final weight of its state, states that are not final left out (expandFinalNode :746-758, :2138-2153)
+				const uint32_t e = (has_lm ? i : kept_phone(i, P, g)) * NS + NS - 1;
+				float w = Wprev[e];
+				if (has_lm) { const float fw = __ldg(p.lm_final + i); if (isinf(fw)) continue; w = w + fw; }
 				if (w < minw) { minw = w; best = (int)e; }
 			}
 		}
@@ -1197,12 +1220,20 @@ void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	q.Ppad = (p.NS > 1 && p.NS * Pw <= 1024) ? Pw : p.P;
 	const unsigned threads = (std::max(p.L, p.NS * q.Ppad) + 31) / 32 * 32;
 	size_t smem = sizeof(float) * (3 * (size_t)p.L + p.P);
-	if (p.negMt == nullptr && (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
+	if (p.negMt == nullptr && (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) {
+		smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
+		if (p.lm_bigT != nullptr && 2 * (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
+	}
 	// traceback window: rows of back pointers (2 + 1 bytes per label) of as many frames as fit 48 KB, at least 8
 	q.tbW = std::max<uint32_t>(8u, (48u * 1024u) / (3u * p.L));
 	smem = std::max(smem, ((size_t)q.tbW * p.L * 2 + 47) / 16 * 16 + (size_t)q.tbW * p.L + 48);
-	cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	viterbi_kernel<<<p.n_utt, threads, smem, s>>>(q);
+	if (p.lm_bigT != nullptr) {
+		cudaFuncSetAttribute(viterbi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		viterbi_kernel<true><<<p.n_utt, threads, smem, s>>>(q);
+	} else {
+		cudaFuncSetAttribute(viterbi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		viterbi_kernel<false><<<p.n_utt, threads, smem, s>>>(q);
+	}
 }
 
 }  // namespace crfgpu

@@ -290,6 +290,9 @@ struct VitParams {
 	const float* negDiag;             // [L]     (float)(-M[l][l])
 	const float* negOff;              // [L]     (float)(-M[l-1][l]) for sub-state > 0
 	const float* negMt; uint32_t E;   // transition FEATURES: per-frame table [N][E], E = P*P + 2L: crossT | negDiag | negOff of the frame (else nullptr)
+	// phone-bigram language model (one state per phone; nullptr = the decoder's free-phone LM with weight 0 on every arc):
+	// lm_start[P], lm_bigT[to * P + from] (TRANSPOSED like the shared-memory cross table), lm_final[P] (+inf = not a final state)
+	const float* lm_start; const float* lm_bigT; const float* lm_final;
 	float* candW; int32_t* candP;     // [n_utt][D][L] rings of candidates per start frame
 	float* keptW;                     // [n_utt][2][L]
 	uint16_t* bp; uint8_t* bd;        // [N][L] back pointer (label or 0xffff) and duration

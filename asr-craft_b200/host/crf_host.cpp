@@ -335,8 +335,21 @@ static void arcs_from_segments(const uint32_t* lab, const uint32_t* dur, const u
 		result->push_back(CRF_BestPathArc{(int)lab[k] + 1, phn[k] == CRFGPU_LAB_BAD ? 0 : (int)phn[k] + 1, dur[k]});
 }
 
+void CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::setLm(const CRF_PhoneBigramLm* lm_fst) {
+	if (!lm_fst) { check(crfgpu_set_phone_lm(crf->gpu(), nullptr, nullptr, nullptr), "crfgpu_set_phone_lm"); return; }
+	const size_t P = lm_fst->start.size();
+	if (lm_fst->bigram.size() != P * P || lm_fst->final_wt.size() != P) throw runtime_error("CRF_PhoneBigramLm: start[P], bigram[P*P], final_wt[P] expected");
+	check(crfgpu_set_phone_lm(crf->gpu(), lm_fst->start.data(), lm_fst->bigram.data(), lm_fst->final_wt.data()), "crfgpu_set_phone_lm");
+}
+
+int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPathArc>* result, const CRF_PhoneBigramLm* lm_fst, float* path_cost, double beam) {
+	setLm(lm_fst);
+	struct Drop { CRF_ViterbiDecoder_StdSeg_NoSegTransFtr* d; ~Drop() { try { d->setLm(nullptr); } catch (...) {} } } drop{this};   // the LM belongs to this call, as in the reference
+	return nStateDecode(result, path_cost, beam);
+}
+
 int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam) {
-	if (beam > 0.0) throw runtime_error("beam pruning / LM-constrained decoding is not implemented on the device (free-phone LM, beam 0 only)");
+	if (beam > 0.0) throw runtime_error("beam pruning is not implemented on the device (beam 0 only)");
 	std::vector<float> f;
 	const uint32_t T = (uint32_t)read_utterance(strm, f, nullptr);
 	if (!T) throw runtime_error("No features read from this sentence");

@@ -189,12 +189,23 @@ struct CRF_BestPathArc {
 	QNUInt32 dur;    // frames covered (the reference keeps this in viterbiDurs)
 };
 
+// The language models the device decodes against (nStateDecode's lm_fst): complete phone-bigram LMs in the topology of the decoder's own
+// free-phone LM (createFreePhoneLmFst, CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1270-1348), one state per phone.  Costs = the arc
+// weights an OpenFst LM of that shape carries: start[q] on start -> q, bigram[p*P + q] on p -> q (p != q), final_wt[p] (+inf: not final).
+struct CRF_PhoneBigramLm {
+	std::vector<float> start, bigram, final_wt;
+};
+
 class CRF_ViterbiDecoder_StdSeg_NoSegTransFtr {
 	CRF_FeatureStream* strm; CRF_Model* crf;
 public:
 	CRF_ViterbiDecoder_StdSeg_NoSegTransFtr(CRF_FeatureStream* ftr_strm_in, CRF_Model* crf_in) : strm(ftr_strm_in), crf(crf_in) {}
 	// decodes the CURRENT utterance of the stream (free-phone LM, beam 0); returns the number of frames, like nStateDecode
 	int nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam = 0.0);
+	// the same against a language model (the reference's nStateDecode(result, lm_fst, ...), .cpp:1369-1372); path_cost includes the final weight
+	int nStateDecode(std::vector<CRF_BestPathArc>* result, const CRF_PhoneBigramLm* lm_fst, float* path_cost, double beam = 0.0);
+	// the LM later nStateDecode / nStateDecodeBatch calls decode against (nullptr: the free-phone LM)
+	void setLm(const CRF_PhoneBigramLm* lm_fst);
 	// The decode loop of CRFDecode (Main.cpp:1064-1112: one decoder object per utterance) as ONE device batch: decodes up to max_utts
 	// utterances from the current one on (advancing the stream with nextseg()), lambda uploaded once; returns the utterances decoded.
 	// results[u] / path_costs[u] / n_frames[u] are what nStateDecode returns for utterance u.

@@ -252,6 +252,29 @@ int main(int argc, char** argv) {
 			if (frames != (int)(off[1] - off[0]) || path.size() != n_arcs) { std::printf("MISMATCH decode: %d frames, %zu arcs\n", frames, path.size()); bad++; }
 			else for (QNUInt32 k = 0; k < n_arcs; k++)
 				if (path[k].ilabel != arcs[3 * k] || path[k].olabel != arcs[3 * k + 1] || (int)path[k].dur != arcs[3 * k + 2]) { std::printf("MISMATCH arc %u\n", k); bad++; }
+			// ---- LM seam (one state per phone): nStateDecode(result, lm_fst, ...).  A bigram LM whose every weight is 0 is the free-phone LM
+			//      with explicit weights: same arcs and cost; a prohibitive cost on every arc INTO the first phone of the free path (and on
+			//      starting with it) must change the path; the LM belongs to the call, so a plain decode afterwards is the free one again ----
+			if (n_states == 1 && n_labs > 2) {
+				CRF_PhoneBigramLm lm; lm.start.assign(n_labs, 0.0f); lm.bigram.assign((size_t)n_labs * n_labs, 0.0f); lm.final_wt.assign(n_labs, 0.0f);
+				std::vector<CRF_BestPathArc> p0; float c0 = 0.0f;
+				strm.rewind(); strm.nextseg();
+				vd.nStateDecode(&p0, &lm, &c0);
+				if (p0.size() != path.size() || c0 != cost) { std::printf("MISMATCH zero-weight LM: %zu arcs cost %.9g vs %zu arcs cost %.9g\n", p0.size(), c0, path.size(), cost); bad++; }
+				const int first = path[0].ilabel - 1;
+				lm.start[first] = 5000.0f;
+				for (QNUInt32 q = 0; q < n_labs; q++) lm.bigram[(size_t)q * n_labs + first] = 5000.0f;
+				std::vector<CRF_BestPathArc> p1; float c1 = 0.0f;
+				strm.rewind(); strm.nextseg();
+				vd.nStateDecode(&p1, &lm, &c1);
+				bool uses = false;
+				for (const CRF_BestPathArc& a : p1) uses = uses || a.ilabel - 1 == first;
+				if (uses || !(c1 > cost)) { std::printf("MISMATCH penalised LM: phone %d still on the path or cost %.9g not above %.9g\n", first, c1, cost); bad++; }
+				std::vector<CRF_BestPathArc> p2; float c2 = 0.0f;
+				strm.rewind(); strm.nextseg();
+				vd.nStateDecode(&p2, &c2);
+				if (p2.size() != path.size() || c2 != cost) { std::printf("MISMATCH the LM outlived its call\n"); bad++; }
+			}
 			// ---- the whole stream as device batches of 3 utterances: utterance 0 must decode as above, the stream must end where it ends ----
 			strm.rewind(); strm.nextseg();
 			std::vector<std::vector<CRF_BestPathArc>> all; bool end = false; size_t done = 0;

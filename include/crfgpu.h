@@ -139,6 +139,16 @@ int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_
                          uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                          float* path_cost);
 
+/* Decoding against a phone-bigram language model (nStateDecode's lm_fst, CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-1372, for the
+ * class of LMs that has the topology of the decoder's own free-phone LM, createFreePhoneLmFst :1270-1348, with one state per phone:
+ * state "the last phone was p", an arc p -> q for every q != p, every phone state possibly final).  lm_start[P] = weight of the arc
+ * start -> q, lm_bigram[from*P + to] = weight of the arc from -> to (diagonal unused; every other entry finite: the LM must be complete),
+ * lm_final[P] = final weight of state p (+inf: not final).  Weights are costs (negative log probabilities) added float by float where
+ * the reference adds them -- (hypothesis + arc) + transition -- and the best final hypothesis is taken over the LM states in state
+ * order with the final weight added (expandFinalNode :746-758, :2138-2153); path_cost then includes it.  All three NULL drops the LM.
+ * Epsilon / back-off arcs, word-level LMs, beam pruning and lattice output are not implemented (CRFGPU_ERR_UNSUPPORTED). */
+int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_bigram, const float* lm_final);
+
 /* Window features for one utterance, out[(t*max_dur + d-1)*window_width ...]; slots with d > t+1 are zero. */
 int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out);
 

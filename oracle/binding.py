@@ -112,8 +112,9 @@ class _Lib:
                                            C.c_uint32(n_threads)))
         return grad, numer, logz
 
-    def viterbi(self, cfg, lam, off, ftrs, ftrs2=None):
-        """Returns list of (labels, durs, phones) per utterance, path costs, logZ."""
+    def viterbi(self, cfg, lam, off, ftrs, ftrs2=None, lm=None):
+        """Returns list of (labels, durs, phones) per utterance, path costs, logZ.  lm = (start[P], bigram[P][P], final[P]) float32:
+        a phone-bigram LM in the topology of the decoder's free-phone LM (one state per phone)."""
         f2 = np.ascontiguousarray(ftrs2, np.float32) if ftrs2 is not None else None
         lam = np.ascontiguousarray(lam, np.float64)
         off = np.ascontiguousarray(off, np.uint32)
@@ -126,8 +127,10 @@ class _Lib:
         nseg = np.zeros(n, np.uint32)
         cost = np.zeros(n, np.float32)
         logz = np.zeros(n, np.float64)
-        self._check(self._fn("viterbi2")(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(n),
+        lms = [None, None, None] if lm is None else [np.ascontiguousarray(a, np.float32) for a in lm]
+        self._check(self._fn("viterbi_lm")(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(n),
                                         _p(off, C.c_uint32), _p(ftrs, C.c_float), _p(f2, C.c_float) if f2 is not None else None,
+                                        *[None if a is None else _p(a, C.c_float) for a in lms],
                                         _p(lab, C.c_uint32),
                                         _p(dur, C.c_uint32), _p(phn, C.c_uint32), _p(nseg, C.c_uint32),
                                         _p(cost, C.c_float), _p(logz, C.c_double)))

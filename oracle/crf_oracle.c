@@ -803,8 +803,16 @@ int crforacle_fwdbwd_dump(const crforacle_config* c, const double* lambda, uint3
 
 typedef struct { float w; int ptr; } cand_t;  /* ptr = previous (phone*N+sub) or -1 */
 
+/* lm_start / lm_bigram / lm_final (all NULL: the decoder's own free-phone LM): a phone-bigram LM in the free-phone LM's topology (one
+ * state per phone; createFreePhoneLmFst .cpp:1270-1348) with a weight on every arc and a final weight per phone state:
+ *  - the arc weight is added to the expanding hypothesis BEFORE the transition score, float by float: (prev + lm) + trans
+ *    (expandCrossStateFromPrevNode :629, crossStateTransUpdate :467);
+ *  - with an input LM the final hypothesis is the minimum over the finalStateSet -- ordered by LM state id, i.e. by phone --
+ *    of weight + final weight (expandFinalNode :746-758, addToFinalSet :929-946, selection :2138-2153); that sum is the path cost. */
+typedef struct { const float* start; const float* bigram; const float* fin; } phone_lm_t;
+
 static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double* lam,
-                       uint32_t T, const float* x, const float* x2, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,
+                       uint32_t T, const float* x, const float* x2, const phone_lm_t* lm, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,
                        uint32_t* n_seg, float* path_cost) {
 	uint32_t L = m->L, N = m->nStates, P = m->nAct, D = c->max_dur, W = crforacle_window_width(c);
 	if (T == 0) FAIL("empty utterance");
@@ -832,7 +840,7 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 		if (s == 0) {
 			for (uint32_t q = 0; q < P; q++) {
 				arr[q] = q;
-				for (uint32_t k = 0; k < N; k++) { Cs[q * N + k].w = (k == 0) ? 0.0f + 0.0f : VINF; Cs[q * N + k].ptr = -1; }
+				for (uint32_t k = 0; k < N; k++) { Cs[q * N + k].w = (k == 0) ? (0.0f + (lm ? lm->start[q] : 0.0f)) + 0.0f : VINF; Cs[q * N + k].ptr = -1; }
 			}
 		} else {
 			/* transition scores of node s from its dur-1 window (…WithoutSegTransFtr.cpp:39-74) */
@@ -845,9 +853,9 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 			/* cross-phone candidates, in kept-list order x LM-arc order */
 			for (uint32_t i = 0; i < P; i++) {
 				uint32_t pp = ord[i], pend = pp * N + N - 1;
-				float base = Wp[pend] + 0.0f;   /* + LM arc weight 0 */
 				for (uint32_t q = 0; q < P; q++) {
 					if (N == 1 && q == pp) continue;     /* free-phone LM, 1 state: no self arc (.cpp:1332-1346) */
+					float base = Wp[pend] + (lm ? lm->bigram[(size_t)pp * P + q] : 0.0f);   /* + LM arc weight (0 in the free-phone LM) */
 					float tw = NEGM(pend, q * N);
 					float cost = base + tw;
 					if (!seen[q]) { seen[q] = 1; arr[narr++] = q; Cs[q * N].w = cost; Cs[q * N].ptr = (int)pend; }
@@ -900,8 +908,11 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 		const uint32_t* ord = order + (size_t)(T - 1) * P;
 		float minw = VINF; int best = -1;
 		for (uint32_t i = 0; i < P; i++) {
-			uint32_t e = ord[i] * N + N - 1;
+			/* no LM: kept-list order; with an LM: LM-state order = phone order, final weights added, states that are not final skipped */
+			uint32_t q = lm ? i : ord[i], e = q * N + N - 1;
+			if (lm && isinf(lm->fin[q])) continue;
 			float w = Wt[(size_t)(T - 1) * L + e];
+			if (lm) w = w + lm->fin[q];
 			if (w < minw) { minw = w; best = (int)e; }
 		}
 		*path_cost = minw;
@@ -946,6 +957,17 @@ int crforacle_viterbi2(const crforacle_config* c, const double* lambda, uint32_t
                        uint32_t n_utt, const uint32_t* off, const float* ftrs, const float* ftrs2,
                        uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                        float* path_cost, double* logZ) {
+	return crforacle_viterbi_lm(c, lambda, lambda_len, n_utt, off, ftrs, ftrs2, NULL, NULL, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
+int crforacle_viterbi_lm(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                         uint32_t n_utt, const uint32_t* off, const float* ftrs, const float* ftrs2,
+                         const float* lm_start, const float* lm_bigram, const float* lm_final,
+                         uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                         float* path_cost, double* logZ) {
+	phone_lm_t lmv = {lm_start, lm_bigram, lm_final};
+	const phone_lm_t* lm = lm_start ? &lmv : NULL;
+	if (lm && (c->n_states != 1 || !lm_bigram || !lm_final)) FAIL("the phone-bigram LM needs one state per phone and all three weight arrays");
 	if (c->n_base_ftrs2 && !ftrs2) FAIL("the configuration joins a second feature stream but none was passed");
 	if (c->model_type != CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR && c->model_type != CRFO_STDFRAME)
 		FAIL("viterbi: only stdframe / stdseg_no_dur_no_segtransftr are accepted (CRFDecode/src/Main.cpp:1065-1076)");
@@ -955,7 +977,7 @@ int crforacle_viterbi2(const crforacle_config* c, const double* lambda, uint32_t
 	for (uint32_t u = 0; u < n_utt && !rc; u++) {
 		uint32_t T = off[u + 1] - off[u];
 		rc = viterbi_one(c, &m, lambda, T, ftrs + stream_row(off + u, u, c->left_ctx, c->right_ctx) * c->n_base_ftrs,
-		                 c->n_base_ftrs2 ? ftrs2 + stream_row(off + u, u, c->left_ctx2, c->right_ctx2) * c->n_base_ftrs2 : NULL,
+		                 c->n_base_ftrs2 ? ftrs2 + stream_row(off + u, u, c->left_ctx2, c->right_ctx2) * c->n_base_ftrs2 : NULL, lm,
 		                 out_lab + off[u], out_dur + off[u], out_phn + off[u], &n_seg[u], &path_cost[u]);
 		if (logZ) logZ[u] = 0.0;
 	}

@@ -81,6 +81,14 @@ int crforacle_viterbi2(const crforacle_config* c, const double* lambda, uint32_t
                        uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                        float* path_cost, double* logZ);
 
+/* Decoding against a phone-bigram LM (one state per phone): lm_start[P], lm_bigram[P*P] at [from*P + to] (diagonal unused),
+ * lm_final[P] (+inf: not a final state); path_cost then includes the final weight.  All three NULL = crforacle_viterbi2. */
+int crforacle_viterbi_lm(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                         uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                         const float* lm_start, const float* lm_bigram, const float* lm_final,
+                         uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                         float* path_cost, double* logZ);
+
 /* Same as crforacle_fwdbwd_mt(…,1) for one utterance, additionally returning alpha/beta
  * ([T][n_labs] doubles, entries the reference never computes are set to -DBL_MAX = LOG0). */
 int crforacle_fwdbwd_dump(const crforacle_config* c, const double* lambda, uint32_t lambda_len,

@@ -267,7 +267,7 @@ size_t window_width(const crfref_config* c) {
 class ObservedDecoder : public CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode> {
 public:
 	std::vector<std::vector<uint> > phnIds; std::vector<std::vector<int> > ptrs; std::vector<std::vector<uint> > durs;
-	std::vector<float> finalWts;
+	std::vector<float> finalWts; std::vector<uint> finalStates;
 	ObservedDecoder(CRF_FeatureStream* f, CRF_Model* m) : CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode>(f, m) {}
 	void pruning(uint nodeCnt, double beam) {
 		CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode>::pruning(nodeCnt, beam);
@@ -278,6 +278,7 @@ public:
 	}
 	void expandFinalNode(uint finalNodeCnt, VectorFst<StdArc>* lm, double beam) {
 		finalWts = *this->prevViterbiWts_nStates;
+		finalStates = *this->prevViterbiStateIds;
 		CRF_ViterbiDecoder_StdSeg_NoSegTransFtr<CRF_ViterbiNode>::expandFinalNode(finalNodeCnt, lm, beam);
 	}
 	uint nStatesPerPhone() { return this->nStates; }
@@ -351,20 +352,33 @@ int crfref_fwdbwd(const crfref_config* c, const double* lambda, uint32_t lambda_
  * segment per frame), segments of utterance u start at frame_off[u]; n_seg[u] segments are valid.
  * out_lab = sub-state label (ilabel-1), out_phn = phone emitted on that arc (olabel-1, or
  * 0xffffffff when none), path_cost = float cost of the winning hypothesis, logZ = final weight. */
-int crfref_viterbi2(const crfref_config* c, const double* lambda, uint32_t lambda_len,
-                    uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
-                    uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
-                    float* path_cost, double* logZ) {
+/* Phone-bigram language model handed to nStateDecode as its lm_fst (one state per phone only): the topology of the decoder's own
+ * free-phone LM (createFreePhoneLmFst, .cpp:1270-1348: state 0 = start, state p + 1 = "the last phone was p", an arc to every OTHER phone,
+ * every phone state final) with a weight on every arc -- lm_start[q], lm_bigram[p*P + q] (the diagonal is unused) -- and a final weight
+ * lm_final[p].  All three NULL: lm_fst == NULL. */
+static int viterbi_impl(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                        uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                        const float* lm_start, const float* lm_bigram, const float* lm_final,
+                        uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                        float* path_cost, double* logZ) {
 	try {
 		Quiet q;
 		ModelBundle mb(c, window_width(c), lambda, lambda_len);
 		Streams st(c, base_ftrs, base_ftrs2, NULL, frame_off, n_utt);
+		VectorFst<StdArc> lm; const bool have_lm = lm_start != NULL;
+		if (have_lm) {
+			if (c->n_states != 1) throw std::runtime_error("the phone-bigram LM topology needs one state per phone");
+			const int P = (int)c->n_labs;
+			int s0 = lm.AddState(); lm.SetStart(s0);
+			for (int p = 0; p < P; p++) { int sp = lm.AddState(); lm.AddArc(s0, StdArc(p + 1, p + 1, lm_start[p], sp)); lm.SetFinal(sp, lm_final[p]); }
+			for (int p = 0; p < P; p++) for (int r = 0; r < P; r++) if (r != p) lm.AddArc(p + 1, StdArc(r + 1, r + 1, lm_bigram[(size_t)p * P + r], r + 1));
+		}
 		st.fs->rewind();
 		for (uint32_t u = 0; u < n_utt; u++) {
 			if (st.fs->nextseg() == QN_SEGID_BAD) throw std::runtime_error("stream ended early");
 			ObservedDecoder vd(st.fs, mb.crf);   /* one decoder per utterance, CRFDecode/src/Main.cpp:1064-1112 */
 			VectorFst<StdArc> best, full;
-			int T = vd.nStateDecode(&best, NULL, &full, 0.0);
+			int T = vd.nStateDecode(&best, have_lm ? &lm : NULL, &full, 0.0);
 			if ((uint32_t)T != frame_off[u + 1] - frame_off[u]) throw std::runtime_error("decoder frame count mismatch");
 			/* walk the reference's own linear best-path FST */
 			std::vector<uint32_t> labs, phns; double zx = 0.0;
@@ -380,9 +394,21 @@ int crfref_viterbi2(const crfref_config* c, const double* lambda, uint32_t lambd
 			 * (same rule as CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:2156-2171, 2204-2349) */
 			uint nS = vd.nStatesPerPhone();
 			float minw = 99999.0; int min_idx = -1;
-			for (size_t idx = 0; idx * nS < vd.finalWts.size(); idx++) {
-				int e = (int)(idx * nS + nS - 1);
-				if (vd.finalWts[e] < minw) { minw = vd.finalWts[e]; min_idx = e; }
+			if (!have_lm) {
+				for (size_t idx = 0; idx * nS < vd.finalWts.size(); idx++) {
+					int e = (int)(idx * nS + nS - 1);
+					if (vd.finalWts[e] < minw) { minw = vd.finalWts[e]; min_idx = e; }
+				}
+			} else {
+				/* with an input LM the decoder takes the minimum over its finalStateSet -- ordered by LM state id, weight = hypothesis weight
+				 * + final weight of its LM state (expandFinalNode :746-758, addToFinalSet :929-946, selection :2138-2153) */
+				for (int sid = 0; sid < lm.NumStates(); sid++)
+					for (size_t idx = 0; idx < vd.finalStates.size(); idx++) {
+						if ((int)vd.finalStates[idx] != sid || lm.Final(sid) == TropicalWeight::Zero()) continue;
+						int e = (int)(idx * nS + nS - 1);
+						float w = vd.finalWts[e] + lm.Final(sid).Value();
+						if (w < minw) { minw = w; min_idx = e; }
+					}
 			}
 			std::vector<uint32_t> tl, td;
 			int end = T - 1;
@@ -417,7 +443,22 @@ int crfref_viterbi(const crfref_config* c, const double* lambda, uint32_t lambda
                    uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
                    uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                    float* path_cost, double* logZ) {
-	return crfref_viterbi2(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, NULL, NULL, NULL, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
+int crfref_viterbi2(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                    uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                    uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                    float* path_cost, double* logZ) {
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, NULL, NULL, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
+int crfref_viterbi_lm(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                      uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                      const float* lm_start, const float* lm_bigram, const float* lm_final,
+                      uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                      float* path_cost, double* logZ) {
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, lm_start, lm_bigram, lm_final, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
 }
 
 /* Older frame-level decoder; one label per frame. */

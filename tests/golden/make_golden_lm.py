@@ -1,0 +1,58 @@
+"""Generates tests/golden/viterbi_lm_golden.npz from the UNMODIFIED reference (oracle/_ref/libcrfref.so): nStateDecode with an input
+language model (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398, lm_fst != NULL) for the class of LMs the device implements --
+complete phone-bigram LMs in the topology of the decoder's own free-phone LM (one state per phone; createFreePhoneLmFst :1270-1348):
+random costs, quantised costs (ties in every frame), phone states that are not final, with and without transition features.
+
+    python tests/golden/make_golden_lm.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle.binding import RefLib, make_config  # noqa: E402
+from make_golden_joined import cfg_to_array  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = RefLib()
+    rng = np.random.default_rng(20261019)
+    out = {}
+    lens = [1, 2, 3, 5, 9, 30, 47, 120]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    n = 0
+    for (P, D, seg, tf) in [(5, 1, 0, 0), (7, 3, 1, 0), (6, 5, 1, 0), (6, 4, 1, 1), (48, 10, 1, 0)]:
+        w = 4 if (D == 1 or not seg) else 8 * 4 + D
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=4, max_dur=D, extract_seg_ftrs=seg,
+                          use_trans_ftrs=tf, trans_fidx=(0, min(w, 12) - 1))
+        nl = ref.lambda_len(cfg)
+        f = rng.random((int(off[-1]), 4), dtype=np.float32)
+        qf = (np.round(f * 2) / 2).astype(np.float32)
+        for kind in ("rand", "quant", "nofinal"):
+            lam = rng.uniform(-0.5, 0.5, nl)
+            st = rng.uniform(0, 3, P).astype(np.float32); bg = rng.uniform(0, 3, (P, P)).astype(np.float32); fin = rng.uniform(0, 2, P).astype(np.float32)
+            x = f
+            if kind == "quant":
+                lam = np.round(rng.uniform(-1, 1, nl) * 2) / 2
+                st, bg, fin, x = np.round(st), np.round(bg), np.round(fin), qf
+            if kind == "nofinal":
+                fin[::2] = np.inf
+            segs, cost, _ = ref.viterbi(cfg, lam, off, x, lm=(st, bg, fin))
+            name = f"{kind}_P{P}D{D}s{seg}t{tf}"
+            nseg = np.array([len(sg[0]) for sg in segs], np.uint32)
+            out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": off, f"{name}/ftrs": x,
+                        f"{name}/lm_start": st, f"{name}/lm_bigram": bg, f"{name}/lm_final": fin, f"{name}/nseg": nseg, f"{name}/cost": cost,
+                        f"{name}/lab": np.concatenate([sg[0] for sg in segs]), f"{name}/dur": np.concatenate([sg[1] for sg in segs]),
+                        f"{name}/phn": np.concatenate([sg[2] for sg in segs])})
+            n += 1
+    print("LM-constrained Viterbi cases:", n)
+    np.savez_compressed(os.path.join(OUT, "viterbi_lm_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

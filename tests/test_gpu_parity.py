@@ -27,6 +27,7 @@ NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 JOINED = load_cases("joined_golden.npz")
+VIT_LM = load_cases("viterbi_lm_golden.npz")
 
 
 def gpu(cfg):
@@ -986,4 +987,65 @@ def test_timit_recipe_shape_matches_oracle(oracle):
     for a, b in zip(segs, wsegs):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
     assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    m.close()
+
+
+# ---- decoding against a phone-bigram language model (crfgpu_set_phone_lm) --------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(VIT_LM))
+def test_viterbi_phone_lm_bit_exact(name):
+    """nStateDecode with an input lm_fst for complete phone-bigram LMs (one state per phone): labels, durations, emitted phones and the
+    float path cost (final weight included) against the reference's decoder; dropping the LM restores the free-phone result"""
+    c = VIT_LM[name]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    free, free_cost = m.viterbi(c["off"], c["ftrs"])
+    m.set_phone_lm(c["lm_start"], c["lm_bigram"], c["lm_final"])
+    segs, cost = m.viterbi(c["off"], c["ftrs"])
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s_[0]) for s_ in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
+    m.set_phone_lm()
+    again, again_cost = m.viterbi(c["off"], c["ftrs"])
+    assert np.array_equal(again_cost.view(np.uint32), free_cost.view(np.uint32))
+    for a, b in zip(again, free):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    m.close()
+
+
+def test_phone_lm_matches_oracle_at_timit_size(oracle):
+    """61 phones, maxDur 10, 105-dim segment features, a smoothed random bigram: the device against the oracle on ragged utterances"""
+    rng = np.random.default_rng(61)
+    P, D, F = 61, 10, 105
+    off, ftrs, _ = synth_batch(rng, 24, 30, 400, F, P, 2, 14)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.05, 0.05, oracle.lambda_len(cfg))
+    prob = rng.dirichlet(np.ones(P) * 0.5, P) * 0.9 + 0.1 / P
+    bg = (-np.log(prob)).astype(np.float32); st = (-np.log(rng.dirichlet(np.ones(P)))).astype(np.float32); fin = rng.uniform(0, 1, P).astype(np.float32)
+    wsegs, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs, lm=(st, bg, fin))
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    m.set_phone_lm(st, bg, fin)
+    segs, cost = m.viterbi(off, ftrs)
+    for a, b in zip(segs, wsegs):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    m.close()
+
+
+def test_phone_lm_rejects_what_is_not_implemented():
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=12, n_base_ftrs=4, n_states=3, max_dur=1)
+    m = gpu(cfg)
+    P = 4
+    with pytest.raises(crf_b200.CrfGpuError) as e:
+        m.set_phone_lm(np.zeros(P, np.float32), np.zeros((P, P), np.float32), np.zeros(P, np.float32))
+    assert e.value.code == 2          # N states per phone: the free-phone LM returns to the start state through epsilon arcs
+    m.close()
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=5, n_base_ftrs=4, max_dur=2, extract_seg_ftrs=1)
+    m = gpu(cfg)
+    bg = np.zeros((5, 5), np.float32); bg[1, 3] = np.inf
+    with pytest.raises(crf_b200.CrfGpuError) as e:
+        m.set_phone_lm(np.zeros(5, np.float32), bg, np.zeros(5, np.float32))
+    assert e.value.code == 2          # a missing arc
     m.close()

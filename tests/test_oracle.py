@@ -16,6 +16,20 @@ NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 JOINED = load_cases("joined_golden.npz")
+VIT_LM = load_cases("viterbi_lm_golden.npz")
+
+
+@pytest.mark.parametrize("name", sorted(VIT_LM))
+def test_viterbi_lm_golden_bit_exact(oracle, name):
+    """decoding against a phone-bigram LM: the oracle against the reference's nStateDecode driven with an input lm_fst
+    (goldens of make_golden_lm.py: random / quantised costs, non-final phone states, transition features)"""
+    c = VIT_LM[name]
+    segs, cost, _ = oracle.viterbi(c["cfg"], c["lam"], c["off"], c["ftrs"], lm=(c["lm_start"], c["lm_bigram"], c["lm_final"]))
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s_[0]) for s_ in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
 
 
 def f2_of(c):
