@@ -51,7 +51,8 @@ size_t CRF_MemFeatureStream::read(size_t bs, float* fb, QNUInt32* lb) {
 // ---------------------------------------------------------------------------------------------- model
 CRF_Model::CRF_Model(QNUInt32 num_labs)
     : nlabs(num_labs), lab_max_dur(1), nActualLabs(num_labs), model_type(STDFRAME), have_map(false), n_base_ftrs(0),
-      extract_seg_ftrs(false), init_present(0), init_iter(0), lambdaOnDevice(false) {}
+      extract_seg_ftrs(false), n_base_ftrs2(0), left_ctx2(0), right_ctx2(0), extract_seg_ftrs2(false), boundary_delta2(false),
+      init_present(0), init_iter(0), lambdaOnDevice(false) {}
 CRF_Model::~CRF_Model() { for (crfgpu_handle h : handles) crfgpu_destroy(h); }
 
 void CRF_Model::setFeatureMap(const CRF_FeatureMap_config& cfg, QNUInt32 base_ftrs, bool seg_ftrs, int device) {
@@ -65,6 +66,8 @@ void CRF_Model::setFeatureMap(const CRF_FeatureMap_config& cfg, QNUInt32 base_ft
 	c.use_trans_ftrs = cfg.useTransFtrs; c.trans_fidx_start = cfg.transFidxStart; c.trans_fidx_end = cfg.transFidxEnd;
 	c.use_state_bias = cfg.useStateBias; c.use_trans_bias = cfg.useTransBias;
 	c.state_bias_val = cfg.stateBiasVal; c.trans_bias_val = cfg.transBiasVal;
+	c.n_base_ftrs2 = n_base_ftrs2; c.extract_seg_ftrs2 = extract_seg_ftrs2 ? 1 : 0; c.left_ctx2 = left_ctx2; c.right_ctx2 = right_ctx2;
+	c.boundary_delta2 = boundary_delta2 ? 1 : 0;
 	if (crfgpu_window_width(&c) != cfg.numFeas)
 		throw runtime_error("CRF_FeatureMap_config::numFeas does not match the window width of the feature stream");
 	for (crfgpu_handle h : handles) crfgpu_destroy(h);
@@ -149,14 +152,26 @@ static size_t read_utterance(CRF_FeatureStream* s, std::vector<float>& ftrs, std
 	return T;
 }
 
+CRF_FeatureStream* CRF_FeatureStream::join(CRF_FeatureStream* in_stream) { return new CRF_JoinedFeatureStream(this, in_stream); }
+
+// the current utterance of the joined second stream (when the model has one) appended to ftrs2
+static void read_second(CRF_Model* crf, CRF_FeatureStream* s, std::vector<float>& ftrs2) {
+	if (!crf->secondStreamFtrs()) return;
+	CRF_FeatureStream* b = s->joinedStream();
+	if (!b) throw runtime_error("the model was configured with a second feature stream (setSecondStream): hand a joined stream (CRF_FeatureStream::join) to the builders / decoder");
+	if (b->num_ftrs() != crf->secondStreamFtrs()) throw runtime_error("width of the joined second stream differs from setSecondStream's");
+	if (!read_utterance(b, ftrs2, nullptr)) throw runtime_error("No features read from this sentence (second stream)");
+}
+
 double CRF_GradBuilder::buildGradient(CRF_FeatureStream* ftr_strm, double* grad, double* Zx_out) {
-	ftr_buf.clear(); lab_buf.clear();
+	ftr_buf.clear(); lab_buf.clear(); ftr2_buf.clear();
 	if (!read_utterance(ftr_strm, ftr_buf, &lab_buf)) throw runtime_error("No features read from this sentence");       // CRF_NewGradBuilder.cpp
+	read_second(crf, ftr_strm, ftr2_buf);
 	const uint32_t off[2] = {0, (uint32_t)lab_buf.size()};
 	tmp_grad.assign(crf->getLambdaLen(), 0.0);
 	double numer = 0.0;
 	if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
-	check(crfgpu_fwdbwd_batch(crf->gpu(), 1, off, ftr_buf.data(), lab_buf.data(), tmp_grad.data(), &numer, Zx_out), "crfgpu_fwdbwd_batch");
+	check(crfgpu_fwdbwd_batch2(crf->gpu(), 1, off, ftr_buf.data(), ftr2_buf.empty() ? nullptr : ftr2_buf.data(), lab_buf.data(), tmp_grad.data(), &numer, Zx_out), "crfgpu_fwdbwd_batch");
 	for (QNUInt32 i = 0; i < crf->getLambdaLen(); i++) grad[i] += tmp_grad[i];
 	return numer;
 }
@@ -214,7 +229,7 @@ double CRF_Minibatch_GradAccumulator::runBatch(double* grad, double* Zx_out, QNU
 	if (!nActive)
 		throw runtime_error("All feature streams are at the end! You don't have any utterances or you forget to rewind all the streams.\n"
 		                    "For the latter case, run rewindAllAndNextSegs().");
-	for (DevBatch& b : dev) { b.off.assign(1, 0); b.ftrs.clear(); b.labs.clear(); }
+	for (DevBatch& b : dev) { b.off.assign(1, 0); b.ftrs.clear(); b.ftrs2.clear(); b.labs.clear(); }
 	QNUInt32 total = 0;
 	for (QNUInt32 s = 0; s < nStreams; s++) {
 		if (atEnd[s]) continue;
@@ -222,6 +237,7 @@ double CRF_Minibatch_GradAccumulator::runBatch(double* grad, double* Zx_out, QNU
 		QNUInt32 cnt = 0;
 		do {       // the thread's do-while (.cpp:46-96): at least one utterance, stop at the share or at the end of the view
 			if (!read_utterance(ftrStrms[s], b.ftrs, &b.labs)) throw runtime_error("No features read from this sentence");
+			read_second(crf, ftrStrms[s], b.ftrs2);
 			b.off.push_back((uint32_t)b.labs.size());
 			cnt++;
 			strmsSegids[s] = ftrStrms[s]->nextseg();
@@ -235,7 +251,7 @@ double CRF_Minibatch_GradAccumulator::runBatch(double* grad, double* Zx_out, QNU
 		crfgpu_handle h = crf->gpu(d);
 		if (!crf->lambdaOnDevice) check(crfgpu_set_lambda(h, crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
 		const uint32_t n = (uint32_t)b.off.size() - 1;      // may be 0 on a device whose streams are exhausted: it still joins the all-reduce
-		check(crfgpu_stage_batch(h, n, b.off.data(), n ? b.ftrs.data() : &no_f, n ? b.labs.data() : &no_l), "crfgpu_stage_batch");
+		check(crfgpu_stage_batch2(h, n, b.off.data(), n ? b.ftrs.data() : &no_f, (n && !b.ftrs2.empty()) ? b.ftrs2.data() : &no_f, n ? b.labs.data() : &no_l), "crfgpu_stage_batch");
 		check(crfgpu_fwdbwd_staged(h), "crfgpu_fwdbwd_staged");          // asynchronous: the devices compute side by side
 	}
 	if (nDev > 1) {
@@ -353,10 +369,11 @@ int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPa
 	std::vector<float> f;
 	const uint32_t T = (uint32_t)read_utterance(strm, f, nullptr);
 	if (!T) throw runtime_error("No features read from this sentence");
+	std::vector<float> f2; read_second(crf, strm, f2);
 	const uint32_t off[2] = {0, T};
 	std::vector<uint32_t> lab(T), dur(T), phn(T); uint32_t nseg = 0; float cost = 0.0f;
 	check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");
-	check(crfgpu_viterbi_batch(crf->gpu(), 1, off, f.data(), lab.data(), dur.data(), phn.data(), &nseg, &cost), "crfgpu_viterbi_batch");
+	check(crfgpu_viterbi_batch2(crf->gpu(), 1, off, f.data(), f2.empty() ? nullptr : f2.data(), lab.data(), dur.data(), phn.data(), &nseg, &cost), "crfgpu_viterbi_batch");
 	arcs_from_segments(lab.data(), dur.data(), phn.data(), nseg, result);
 	if (path_cost) *path_cost = cost;
 	return (int)T;
@@ -364,18 +381,19 @@ int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPa
 
 size_t CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecodeBatch(size_t max_utts, std::vector<std::vector<CRF_BestPathArc>>* results,
                                                                    std::vector<float>* path_costs, std::vector<int>* n_frames, bool* stream_end) {
-	std::vector<float> f; std::vector<uint32_t> off(1, 0);
+	std::vector<float> f, f2; std::vector<uint32_t> off(1, 0);
 	if (stream_end) *stream_end = false;
 	while (off.size() - 1 < max_utts) {
 		const size_t T = read_utterance(strm, f, nullptr);
 		if (!T) throw runtime_error("No features read from this sentence");
+		read_second(crf, strm, f2);
 		off.push_back(off.back() + (uint32_t)T);
 		if (strm->nextseg() == QN_SEGID_BAD) { if (stream_end) *stream_end = true; break; }
 	}
 	const uint32_t n = (uint32_t)off.size() - 1, N = off.back();
 	std::vector<uint32_t> lab(N), dur(N), phn(N), nseg(n); std::vector<float> cost(n);
 	check(crfgpu_set_lambda(crf->gpu(), crf->getLambda(), crf->getLambdaLen()), "crfgpu_set_lambda");      // once per batch, not per utterance
-	check(crfgpu_viterbi_batch(crf->gpu(), n, off.data(), f.data(), lab.data(), dur.data(), phn.data(), nseg.data(), cost.data()), "crfgpu_viterbi_batch");
+	check(crfgpu_viterbi_batch2(crf->gpu(), n, off.data(), f.data(), f2.empty() ? nullptr : f2.data(), lab.data(), dur.data(), phn.data(), nseg.data(), cost.data()), "crfgpu_viterbi_batch");
 	results->assign(n, std::vector<CRF_BestPathArc>());
 	if (n_frames) n_frames->assign(n, 0);
 	for (uint32_t u = 0; u < n; u++) {

@@ -69,6 +69,30 @@ public:
 	// CRF_FeatureStreamManager::getChild(i)->trn_stream->view(...) hands every training thread (CRF_FeatureStreamManager.cpp:425-464).
 	// The caller owns the result; nullptr = this stream cannot be split (then only nStreams == 1 is possible).
 	virtual CRF_FeatureStream* newView(QNUInt32 /*startseg*/, QNUInt32 /*nsegs*/) { return nullptr; }
+	// CRF_FeatureStream::join (CRF/src/io/CRF_FeatureStream.cpp:172-184): a new stream whose frames are this stream's followed by
+	// in_stream's ("the streams must match segment-wise and frame-wise"; here in_stream may carry the left + right context frames the
+	// model's second window stream is configured with, CRF_Model::setSecondStream).  The result reads like this stream (features,
+	// labels, segments) and hands the second one out through joinedStream(); it advances and rewinds both.  The caller owns it.
+	virtual CRF_FeatureStream* join(CRF_FeatureStream* in_stream);
+	virtual CRF_FeatureStream* joinedStream() { return nullptr; }
+};
+
+class CRF_JoinedFeatureStream : public CRF_FeatureStream {
+	CRF_FeatureStream* a; CRF_FeatureStream* b; bool own;
+public:
+	CRF_JoinedFeatureStream(CRF_FeatureStream* first, CRF_FeatureStream* second, bool owns = false) : a(first), b(second), own(owns) {}
+	~CRF_JoinedFeatureStream() { if (own) { delete a; delete b; } }
+	QN_SegID nextseg() { const QN_SegID x = a->nextseg(), y = b->nextseg(); if ((x == QN_SEGID_BAD) != (y == QN_SEGID_BAD)) throw std::runtime_error("joined feature streams disagree on the number of segments"); return x; }
+	size_t read(size_t bs, float* fb, QNUInt32* lb) { return a->read(bs, fb, lb); }
+	void rewind() { a->rewind(); b->rewind(); }
+	QNUInt32 num_ftrs() { return a->num_ftrs(); }
+	QNUInt32 num_segs() { return a->num_segs(); }
+	CRF_FeatureStream* newView(QNUInt32 startseg, QNUInt32 nsegs) {
+		CRF_FeatureStream* va = a->newView(startseg, nsegs); CRF_FeatureStream* vb = b->newView(startseg, nsegs);
+		if (!va || !vb) { delete va; delete vb; return nullptr; }
+		return new CRF_JoinedFeatureStream(va, vb, true);
+	}
+	CRF_FeatureStream* joinedStream() { return b; }
 };
 
 // In-memory ragged batch (what tests and the self-test feed); view(start, n) restricts it to a contiguous utterance range,
@@ -97,6 +121,7 @@ protected:
 	CRF_FeatureMap_config fmap;
 	bool have_map;
 	QNUInt32 n_base_ftrs; bool extract_seg_ftrs;
+	QNUInt32 n_base_ftrs2, left_ctx2, right_ctx2; bool extract_seg_ftrs2, boundary_delta2;     // second window stream (0 features: none)
 	std::vector<crfgpu_handle> handles;       // one device context per GPU (handles[0] created by setFeatureMap)
 	crfgpu_config dev_cfg;
 	QNUInt32 init_present, init_iter;         // resume state (CRF_Model.cpp:29,323,487-507)
@@ -126,6 +151,14 @@ public:
 	virtual QNUInt32 getInitIter() { return init_iter; }
 	virtual void setLabMaxDur(QNUInt32 d) { lab_max_dur = d; }
 	virtual QNUInt32 getLabMaxDur() { return lab_max_dur; }
+	// The second feature stream of CRFTrain / CRFDecode (ftr2_file with ftr2_window_len == maxDur, ftr2_left_context_len,
+	// ftr2_right_context_len, ftr2_extract_seg_ftr, ftr2_use_boundary_delta_ftr; CRFTrain/src/Main.cpp:516-526), joined behind the first:
+	// call BEFORE setFeatureMap, like setLabMaxDur.  The streams handed to the builders / decoder must then be joined ones
+	// (CRF_FeatureStream::join) whose second stream carries left_ctx + right_ctx more frames per utterance (the padded pfile).
+	virtual void setSecondStream(QNUInt32 n_base_ftrs2_in, bool extract_seg_ftrs2_in, QNUInt32 left_ctx, QNUInt32 right_ctx, bool boundary_delta = false) {
+		n_base_ftrs2 = n_base_ftrs2_in; extract_seg_ftrs2 = extract_seg_ftrs2_in; left_ctx2 = left_ctx; right_ctx2 = right_ctx; boundary_delta2 = boundary_delta;
+	}
+	QNUInt32 secondStreamFtrs() { return n_base_ftrs2; }
 	virtual void setNActualLabs(QNUInt32 n) { nActualLabs = n; }
 	virtual QNUInt32 getNActualLabs() { return nActualLabs; }
 	virtual void setModelType(modeltype m) { model_type = m; }
@@ -146,7 +179,7 @@ public:
 class CRF_GradBuilder {
 protected:
 	CRF_Model* crf;
-	std::vector<float> ftr_buf; std::vector<QNUInt32> lab_buf; std::vector<double> tmp_grad;
+	std::vector<float> ftr_buf, ftr2_buf; std::vector<QNUInt32> lab_buf; std::vector<double> tmp_grad;
 public:
 	CRF_GradBuilder(CRF_Model* crf_in) : crf(crf_in) {}
 	virtual ~CRF_GradBuilder() {}
@@ -164,7 +197,7 @@ class CRF_Minibatch_GradAccumulator {
 protected:
 	CRF_Model* crf; QNUInt32 nStreams, minibatch;
 	std::vector<CRF_FeatureStream*> ftrStrms; std::vector<bool> owned; std::vector<QN_SegID> strmsSegids;
-	struct DevBatch { std::vector<uint32_t> off; std::vector<float> ftrs; std::vector<QNUInt32> labs; };
+	struct DevBatch { std::vector<uint32_t> off; std::vector<float> ftrs, ftrs2; std::vector<QNUInt32> labs; };
 	std::vector<DevBatch> dev;
 	double runBatch(double* grad, double* Zx_out, QNUInt32* uttCount, bool* isEndOfIter, QNUInt32* nActive);
 public:

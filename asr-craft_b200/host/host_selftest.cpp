@@ -78,11 +78,26 @@ int main(int argc, char** argv) {
 		read_vec(in, off, n_utt + 1); read_vec(in, lam, len); read_vec(in, ftrs, (size_t)N * n_base); read_vec(in, labs, N);
 		read_vec(in, logZ, n_utt); read_vec(in, numer, n_utt); read_vec(in, grad, len); read_vec(in, arcs, (size_t)n_arcs * 3);
 		if (!in.good() && !in.eof()) throw std::runtime_error("short case file");
-		const QNUInt32 width = max_dur == 1 ? n_base : (segf ? 8 * n_base + max_dur : n_base);
+		QNUInt32 width = max_dur == 1 ? n_base : (segf ? 8 * n_base + max_dur : n_base);
+		// optional trailer: a second feature stream joined behind the first (the TIMIT recipe's layout) and the feature ranges of the map
+		QNUInt32 n_base2 = 0, segf2 = 0, lc2 = 0, rc2 = 0, bd2 = 0, use_tf = 0, sf0 = 0, sf1 = 0, tf0 = 0, tf1 = 0, N2 = 0;
+		std::vector<float> ftrs2; std::vector<uint32_t> off2;
+		if (in >> n_base2 >> segf2 >> lc2 >> rc2 >> bd2 >> use_tf >> sf0 >> sf1 >> tf0 >> tf1 >> N2) {
+			read_vec(in, ftrs2, (size_t)N2 * n_base2);
+			for (QNUInt32 u = 0; u <= n_utt; u++) off2.push_back(off[u] + u * (lc2 + rc2));
+			if (off2.back() != N2) throw std::runtime_error("second stream: frame count does not match the context lengths");
+			width += max_dur == 1 ? (lc2 + 1 + rc2) * n_base2 : (segf2 ? 8 * n_base2 + max_dur + (lc2 + rc2) * n_base2 : (bd2 ? std::min(lc2, rc2 + 1) : lc2 + 1 + rc2) * n_base2);
+		}
 
 		CRF_Model my_crf(n_labs);
 		my_crf.setLabMaxDur(max_dur); my_crf.setNActualLabs(n_act); my_crf.setModelType((modeltype)mt);
-		my_crf.setFeatureMap(fmap_config(n_labs, n_states, width, max_dur, n_act), n_base, segf != 0);
+		CRF_FeatureMap_config fcfg = fmap_config(n_labs, n_states, width, max_dur, n_act);
+		if (n_base2) {
+			my_crf.setSecondStream(n_base2, segf2 != 0, lc2, rc2, bd2 != 0);
+			fcfg.stateFidxStart = sf0; fcfg.stateFidxEnd = sf1;
+			if (use_tf) { fcfg.map_type = STDTRANS; fcfg.useTransFtrs = true; fcfg.transFidxStart = tf0; fcfg.transFidxEnd = tf1; }
+		}
+		my_crf.setFeatureMap(fcfg, n_base, segf != 0);
 		if (my_crf.getLambdaLen() != len) throw std::runtime_error("lambda length differs from the reference's");
 		my_crf.setLambda(lam.data(), len);
 
@@ -91,6 +106,57 @@ int main(int argc, char** argv) {
 			if (std::fabs(a - b) > tol * std::fmax(1.0, std::fabs(b))) { std::printf("MISMATCH %s: %.12g vs %.12g\n", what, a, b); bad++; }
 		};
 		const std::string sub = argc > 2 ? argv[2] : "";
+		if (n_base2) {
+			// ---- joined second stream: minibatch seam over two views of the JOINED stream, per-utterance seam, decode seam ----
+			CRF_MemFeatureStream s1(off, ftrs, labs.empty() ? std::vector<QNUInt32>(N, 0) : labs, n_base);
+			CRF_MemFeatureStream s2(off2, ftrs2, std::vector<QNUInt32>(N2, 0), n_base2);
+			std::unique_ptr<CRF_FeatureStream> js(s1.join(&s2));
+			if (mode == 0) {
+				CRF_Minibatch_GradAccumulator gaccum(&my_crf, js.get(), 2);
+				std::vector<double> g(len, 0.0), gsum(len, 0.0); double Zx = 0.0, zacc = 0.0, nacc = 0.0; QNUInt32 cnt = 0, tot = 0; bool eoi = false;
+				gaccum.setMinibatch(4);
+				gaccum.rewindAllAndNextSegs();
+				while (!eoi) {
+					const double num = gaccum.accumulateGradient(g.data(), &Zx, &cnt, &eoi);
+					// undo the division by the active streams so that the minibatches add up to the golden's batch gradient
+					const double nact = std::min<QNUInt32>(2, cnt);       // two views whose sizes differ by at most one, shares of two utterances: both active unless ONE utterance is left
+					for (QNUInt32 i = 0; i < len; i++) gsum[i] += g[i] * nact;
+					zacc += Zx; nacc += num; tot += cnt;
+				}
+				double zsum = 0, nsum = 0, gmax = 0;
+				for (QNUInt32 u = 0; u < n_utt; u++) { zsum += logZ[u]; nsum += numer[u]; }
+				for (double v : grad) gmax = std::fmax(gmax, std::fabs(v));
+				close(zacc, zsum, 1e-5, "sum logZ (joined)"); close(nacc, nsum, 1e-5, "sum numerator (joined)");
+				if (tot != n_utt) { std::printf("MISMATCH joined uttCount %u\n", tot); bad++; }
+				for (QNUInt32 i = 0; i < len; i++)
+					if (std::fabs(gsum[i] - grad[i]) > 1e-4 * gmax + 1e-4 * std::fabs(grad[i])) { if (bad < 5) std::printf("MISMATCH joined grad[%u]: %.9g vs %.9g\n", i, gsum[i], grad[i]); bad++; }
+				std::unique_ptr<CRF_GradBuilder> gb(CRF_GradBuilder::create(&my_crf, EXPF));
+				std::vector<double> g2(len, 0.0);
+				js->rewind();
+				QNUInt32 u = 0;
+				while (js->nextseg() != QN_SEGID_BAD) {
+					double z = 0.0; const double nu = gb->buildGradient(js.get(), g2.data(), &z);
+					close(z, logZ[u], 1e-5, "logZ (joined)"); close(nu, numer[u], 1e-5, "numerator (joined)"); u++;
+				}
+				for (QNUInt32 i = 0; i < len; i++)
+					if (std::fabs(g2[i] - grad[i]) > 1e-4 * gmax + 1e-4 * std::fabs(grad[i])) { if (bad < 5) std::printf("MISMATCH joined grad2[%u]\n", i); bad++; }
+			} else {
+				js->rewind(); js->nextseg();
+				CRF_ViterbiDecoder_StdSeg_NoSegTransFtr vd(js.get(), &my_crf);
+				std::vector<CRF_BestPathArc> path; float cost = 0.0f;
+				const int frames = vd.nStateDecode(&path, &cost);
+				if (frames != (int)(off[1] - off[0]) || path.size() != n_arcs) { std::printf("MISMATCH joined decode: %d frames, %zu arcs\n", frames, path.size()); bad++; }
+				else for (QNUInt32 k = 0; k < n_arcs; k++)
+					if (path[k].ilabel != arcs[3 * k] || path[k].olabel != arcs[3 * k + 1] || (int)path[k].dur != arcs[3 * k + 2]) { std::printf("MISMATCH joined arc %u\n", k); bad++; }
+				js->rewind(); js->nextseg();
+				std::vector<std::vector<CRF_BestPathArc>> res; std::vector<float> costs; std::vector<int> nfr; bool end = false;
+				const size_t done = vd.nStateDecodeBatch(n_utt, &res, &costs, &nfr, &end);
+				if (done != n_utt || !end || res[0].size() != path.size() || costs[0] != cost) { std::printf("MISMATCH joined batch decode\n"); bad++; }
+			}
+			if (bad) { std::printf("host_selftest: %d mismatches\n", bad); return 1; }
+			std::printf("host_selftest ok (joined streams)\n");
+			return 0;
+		}
 		if (sub == "acc") {
 			if (argc < 6) throw std::runtime_error("acc <nStreams> <minibatch> <nDevices>");
 			const QNUInt32 ns = (QNUInt32)std::atoi(argv[3]), mb = (QNUInt32)std::atoi(argv[4]); const int nd = std::atoi(argv[5]);

@@ -14,6 +14,7 @@ EXE = os.path.join(ROOT, "asr-craft_b200", "host", "host_selftest")
 TRAIN = load_cases("train_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
 VIT = load_cases("viterbi_golden.npz")
+JOINED = load_cases("joined_golden.npz")
 
 
 def write_case(path, c, decode_arcs=None):
@@ -27,6 +28,11 @@ def write_case(path, c, decode_arcs=None):
         for a in (c["off"], c["lam"], c["ftrs"].ravel(), c.get("labs", np.zeros(N)), c.get("logZ", np.zeros(n_utt))[:n_utt],
                   c.get("numer", np.zeros(n_utt)), grad, np.asarray(arcs).ravel()):
             f.write(" ".join(repr(float(x)) for x in np.asarray(a, np.float64)) + "\n")
+        if cfg.n_base_ftrs2:      # trailer: the joined second stream and the feature ranges of the map
+            f2 = c["ftrs2"]
+            f.write(f"{cfg.n_base_ftrs2} {cfg.extract_seg_ftrs2} {cfg.left_ctx2} {cfg.right_ctx2} {cfg.boundary_delta2} {cfg.use_trans_ftrs} "
+                    f"{cfg.state_fidx_start} {cfg.state_fidx_end} {cfg.trans_fidx_start} {cfg.trans_fidx_end} {f2.shape[0]}\n")
+            f.write(" ".join(repr(float(x)) for x in f2.ravel()) + "\n")
 
 
 def test_host_layer_fails_loudly_without_device():
@@ -56,6 +62,23 @@ def test_host_layer_decoding_matches_reference_golden(tmp_path, name):
     write_case(path, c, arcs)
     r = subprocess.run([EXE, path], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "host_selftest ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["train_nodur_joined_recipe", "train_nodur_joined_bdelta", "train_frame_joined_transftr", "vit_rand_P7N1D3c2", "vit_quant_P4N3D2c1"])
+def test_host_layer_joined_streams_match_reference_golden(tmp_path, name):
+    """the C++ host layer over a JOINED stream (CRF_FeatureStream::join; CRF_Model::setSecondStream = CRFTrain's ftr2_* options): the
+    minibatch seam over two views, the per-utterance seam and the decode seam against goldens produced by the reference with two
+    window streams (the TIMIT recipe's layout: transition features from the context frames of the padded second stream)"""
+    c = JOINED[name]
+    arcs = None
+    if name.startswith("vit_"):
+        lab, dur, phn = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])[0]
+        arcs = np.stack([lab.astype(np.int64) + 1, np.where(phn == 0xffffffff, 0, phn.astype(np.int64) + 1), dur.astype(np.int64)], axis=1)
+    path = str(tmp_path / "case.txt")
+    write_case(path, c, arcs)
+    r = subprocess.run([EXE, path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_selftest ok (joined streams)" in r.stdout, r.stdout + r.stderr
 
 
 # ---------------------------------------------------------------------------------------------------------------------
