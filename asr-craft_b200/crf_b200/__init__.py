@@ -88,7 +88,7 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
            "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info",
            "crfgpu_fetch_posterior_mass", "crfgpu_stage_batch2", "crfgpu_fwdbwd_batch2", "crfgpu_viterbi_batch2",
-           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm"]
+           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm"]
 COMM_ID_BYTES = 128
 
 
@@ -274,12 +274,14 @@ class CrfGpu:
         self._check(self.lib.crfgpu_set_train_state(self.h, *[None if a is None else _ptr(a, C.c_double) for a in arrs]))
 
     def set_phone_lm(self, start=None, bigram=None, final=None):
-        """crfgpu_set_phone_lm: complete phone-bigram LM (costs) for decoding, one state per phone; no arguments drop it."""
+        """crfgpu_set_phone_lm: complete phone-bigram LM (costs) for decoding, one state per phone; no arguments drop it.
+        With N > 1 states per phone the arguments are (unigram[P], exit[P], final[P]): crfgpu_set_phone_unigram_lm."""
         if start is None:
             self._check(self.lib.crfgpu_set_phone_lm(self.h, None, None, None))
             return
         a = [np.ascontiguousarray(x, np.float32) for x in (start, bigram, final)]
-        self._check(self.lib.crfgpu_set_phone_lm(self.h, *[_ptr(x, C.c_float) for x in a]))
+        fn = self.lib.crfgpu_set_phone_lm if self.cfg.n_states == 1 else self.lib.crfgpu_set_phone_unigram_lm
+        self._check(fn(self.h, *[_ptr(x, C.c_float) for x in a]))
 
     # ---- host-buffer calls --------------------------------------------------------------------
     def fwdbwd(self, off, ftrs, labs, out=None, ftrs2=None):

@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	// float by float -- (prev + lm) + trans, expandCrossStateFromPrevNode :629 / crossStateTransUpdate :467 -- so We[] then holds the raw
 	// kept weights (the "+ 0.0f" of the free-phone loop IS this add).  The table sits behind the cross table in shared memory when both fit.
 	constexpr bool has_lm = HAS_LM;       // compile-time: the free-phone instantiation is the kernel it was before the LM existed
-	const bool lm_in_smem = has_lm && cross_in_smem && (2 * (size_t)P * Pt * sizeof(float) <= 96 * 1024);
+	const bool lm_in_smem = has_lm && NS == 1 && cross_in_smem && (2 * (size_t)P * Pt * sizeof(float) <= 96 * 1024);
 	float* lmS = crossS + (size_t)P * Pt;
 	if (lm_in_smem) for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) lmS[(i / P) * Pt + i % P] = p.lm_bigT[i];
 	const float* crossT = p.crossT;      // global table (per-frame tables replace it below); the shared-memory copy is crossS
@@ -1026,7 +1026,16 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 			// finite, so that equals the reference's "the first candidate is always taken".
 			auto scan = [&](const float* ct, const uint32_t stride) {     // entry pp of the target phone's column at ct[pp * stride]
 				pw = CUDART_INF_F;
-				if (has_lm) {
+				if (has_lm && NS > 1) {
+					// N states per phone: the hypothesis returns to the LM's start state through the epsilon arc of its phone (exit cost, already
+					// in We[]) and leaves it on the unigram arc of the target phone: (prev + exit) + unigram, then the transition score
+					const float uq = __ldg(p.lm_start + tq);
+#pragma unroll 4
+					for (uint32_t pp = i_lo; pp < i_hi; pp++) {
+						const float cc = (We[pp] + uq) + ct[(size_t)pp * stride];
+						if (cc < pw) { pw = cc; pptr = (int32_t)pp; }
+					}
+				} else if (has_lm) {
 					// one state per phone with LM weights: the same list order, two adds per entry
 					const float* lr = lm_in_smem ? lmS + (size_t)tq * Pt : p.lm_bigT + (size_t)tq * P;
 #pragma unroll 4
@@ -1116,7 +1125,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				if (d == dmax || w < best) { best = w; bptr = ptr; bdur = d; }
 			}
 			Wprev[lab] = best;
-			if (k == NS - 1) We[q] = has_lm ? best : best + 0.0f;
+			if (k == NS - 1) We[q] = has_lm ? (NS == 1 ? best : best + __ldg(p.lm_exit + q)) : best + 0.0f;
 			p.bp[(uint64_t)(off + s) * L + lab] = bptr < 0 ? (uint16_t)0xffff : (uint16_t)bptr;
 			p.bd[(uint64_t)(off + s) * L + lab] = (uint8_t)bdur;
 		}
@@ -1227,7 +1236,7 @@ void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	// traceback window: rows of back pointers (2 + 1 bytes per label) of as many frames as fit 48 KB, at least 8
 	q.tbW = std::max<uint32_t>(8u, (48u * 1024u) / (3u * p.L));
 	smem = std::max(smem, ((size_t)q.tbW * p.L * 2 + 47) / 16 * 16 + (size_t)q.tbW * p.L + 48);
-	if (p.lm_bigT != nullptr) {
+	if (p.lm_start != nullptr) {
 		cudaFuncSetAttribute(viterbi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		viterbi_kernel<true><<<p.n_utt, threads, smem, s>>>(q);
 	} else {

@@ -121,7 +121,7 @@ struct crfgpu_ctx {
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
 	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	int opt_frame_impl = 0; bool frame_path = false;
-	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final;   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
+	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit;   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
 	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
 
@@ -1158,7 +1158,6 @@ void viterbi_staged(crfgpu_ctx* h) {
 	}
 	// large phone sets with one state per phone and constant transition tables: the cross-phone table sliced over groups of CTAs,
 	// 16 utterances in lock-step per group (crf_viterbi_group.cu); opt_vit_impl 1 forces one CTA per utterance, 2 forces the groups
-	if (h->have_lm && NS != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the phone-bigram LM is implemented for one state per phone");
 	const bool vg_fit = NS == 1 && !c.use_trans_ftrs && P >= 2 && L == P && !h->have_lm;      // (LM weights: the per-utterance kernel)
 	const bool vg_auto = vg_fit && (size_t)P * P * sizeof(float) > 96 * 1024;
 	if (vg_fit && (h->opt_vit_impl == 2 || (h->opt_vit_impl == 0 && vg_auto))) {
@@ -1198,7 +1197,10 @@ void viterbi_staged(crfgpu_ctx* h) {
 	v.n_utt = h->n_utt; v.L = L; v.P = P; v.NS = NS; v.D = D; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
 	v.crossT = h->d_crossT.as<float>(); v.negDiag = h->d_negDiag.as<float>(); v.negOff = h->d_negOff.as<float>();
 	v.negMt = c.use_trans_ftrs ? h->d_negMt.as<float>() : nullptr; v.E = h->vtE;
-	if (h->have_lm) { v.lm_start = h->d_lm_start.as<float>(); v.lm_bigT = h->d_lm_bigT.as<float>(); v.lm_final = h->d_lm_final.as<float>(); }
+	if (h->have_lm) {
+		v.lm_start = h->d_lm_start.as<float>(); v.lm_final = h->d_lm_final.as<float>();
+		if (NS == 1) v.lm_bigT = h->d_lm_bigT.as<float>(); else v.lm_exit = h->d_lm_exit.as<float>();
+	}
 	v.candW = h->d_candW.as<float>(); v.candP = h->d_candP.as<int32_t>(); v.keptW = nullptr;
 	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
 	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
@@ -1372,7 +1374,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_mass, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1615,6 +1617,23 @@ int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_
 		}
 		for (uint32_t a = 0; a < P; a++) if (!std::isfinite(st[a])) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the phone-bigram LM must have a finite start weight for every phone");
 		upload(h->d_lm_start, st, h->stream); upload(h->d_lm_bigT, bt, h->stream); upload(h->d_lm_final, fin, h->stream);
+		CUDA_OK(cudaStreamSynchronize(h->stream));
+		h->have_lm = true; h->viterbi_done = false;
+	});
+}
+
+int crfgpu_set_phone_unigram_lm(crfgpu_handle h, const float* lm_unigram, const float* lm_exit, const float* lm_final) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		if (!lm_unigram && !lm_exit && !lm_final) { h->have_lm = false; return; }
+		if (!lm_unigram || !lm_exit || !lm_final) throw ApiError(CRFGPU_ERR_ARG, "the phone-unigram LM needs all three weight arrays (or none, to drop it)");
+		if (!h->decode_ok) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "decoding: " + h->decode_why);
+		if (h->lay.n_states < 2) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the unigram + exit-cost LM has the topology of the reference's N-state free-phone LM (epsilon arcs back to the start state); with one state per phone use crfgpu_set_phone_lm");
+		const uint32_t P = h->lay.n_act;
+		std::vector<float> un(lm_unigram, lm_unigram + P), ex(lm_exit, lm_exit + P), fin(lm_final, lm_final + P);
+		for (uint32_t a = 0; a < P; a++) if (!std::isfinite(un[a]) || !std::isfinite(ex[a])) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the phone-unigram LM must have a finite unigram and exit cost for every phone");
+		upload(h->d_lm_start, un, h->stream); upload(h->d_lm_exit, ex, h->stream); upload(h->d_lm_final, fin, h->stream);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
 		h->have_lm = true; h->viterbi_done = false;
 	});

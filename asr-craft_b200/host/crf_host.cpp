@@ -354,6 +354,11 @@ static void arcs_from_segments(const uint32_t* lab, const uint32_t* dur, const u
 void CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::setLm(const CRF_PhoneBigramLm* lm_fst) {
 	if (!lm_fst) { check(crfgpu_set_phone_lm(crf->gpu(), nullptr, nullptr, nullptr), "crfgpu_set_phone_lm"); return; }
 	const size_t P = lm_fst->start.size();
+	if (crf->numStates() > 1) {      // N states per phone: unigram costs + the exit costs of the epsilon arcs back to the LM's start state
+		if (lm_fst->bigram.size() != P || lm_fst->final_wt.size() != P) throw runtime_error("CRF_PhoneBigramLm (N states per phone): start[P] = unigram costs, bigram[P] = exit costs, final_wt[P] expected");
+		check(crfgpu_set_phone_unigram_lm(crf->gpu(), lm_fst->start.data(), lm_fst->bigram.data(), lm_fst->final_wt.data()), "crfgpu_set_phone_unigram_lm");
+		return;
+	}
 	if (lm_fst->bigram.size() != P * P || lm_fst->final_wt.size() != P) throw runtime_error("CRF_PhoneBigramLm: start[P], bigram[P*P], final_wt[P] expected");
 	check(crfgpu_set_phone_lm(crf->gpu(), lm_fst->start.data(), lm_fst->bigram.data(), lm_fst->final_wt.data()), "crfgpu_set_phone_lm");
 }

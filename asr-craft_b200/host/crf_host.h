@@ -159,6 +159,7 @@ public:
 		n_base_ftrs2 = n_base_ftrs2_in; extract_seg_ftrs2 = extract_seg_ftrs2_in; left_ctx2 = left_ctx; right_ctx2 = right_ctx; boundary_delta2 = boundary_delta;
 	}
 	QNUInt32 secondStreamFtrs() { return n_base_ftrs2; }
+	QNUInt32 numStates() { return have_map ? fmap.numStates : 1; }
 	virtual void setNActualLabs(QNUInt32 n) { nActualLabs = n; }
 	virtual QNUInt32 getNActualLabs() { return nActualLabs; }
 	virtual void setModelType(modeltype m) { model_type = m; }
@@ -225,6 +226,8 @@ struct CRF_BestPathArc {
 // The language models the device decodes against (nStateDecode's lm_fst): complete phone-bigram LMs in the topology of the decoder's own
 // free-phone LM (createFreePhoneLmFst, CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1270-1348), one state per phone.  Costs = the arc
 // weights an OpenFst LM of that shape carries: start[q] on start -> q, bigram[p*P + q] on p -> q (p != q), final_wt[p] (+inf: not final).
+// With N > 1 states per phone the reference's free-phone LM returns from every phone state to the start state through an epsilon arc:
+// start[q] = unigram cost of the arc start -> q, bigram[p] (P values) = exit cost of phone p's epsilon arc (a phone insertion penalty).
 struct CRF_PhoneBigramLm {
 	std::vector<float> start, bigram, final_wt;
 };

@@ -148,6 +148,11 @@ int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_
  * order with the final weight added (expandFinalNode :746-758, :2138-2153); path_cost then includes it.  All three NULL drops the LM.
  * Epsilon / back-off arcs, word-level LMs, beam pruning and lattice output are not implemented (CRFGPU_ERR_UNSUPPORTED). */
 int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_bigram, const float* lm_final);
+/* The same for models with N > 1 states per phone, whose free-phone LM in the reference returns from every phone state to the start
+ * state through an epsilon arc and leaves it again on one arc per phone (:1313-1330): lm_unigram[P] = cost of the arc start -> q (also
+ * paid by the first phone), lm_exit[P] = cost of the epsilon arc of phone p (a phone insertion penalty when all equal), lm_final[P] as
+ * above.  Added where the reference adds them: ((hypothesis + exit) + unigram) + transition. */
+int crfgpu_set_phone_unigram_lm(crfgpu_handle h, const float* lm_unigram, const float* lm_exit, const float* lm_final);
 
 /* Window features for one utterance, out[(t*max_dur + d-1)*window_width ...]; slots with d > t+1 are zero. */
 int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out);

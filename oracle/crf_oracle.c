@@ -807,6 +807,9 @@ typedef struct { float w; int ptr; } cand_t;  /* ptr = previous (phone*N+sub) or
  * state per phone; createFreePhoneLmFst .cpp:1270-1348) with a weight on every arc and a final weight per phone state:
  *  - the arc weight is added to the expanding hypothesis BEFORE the transition score, float by float: (prev + lm) + trans
  *    (expandCrossStateFromPrevNode :629, crossStateTransUpdate :467);
+ *  - N states per phone: lm_start = unigram costs, lm_bigram = P exit costs on the epsilon arcs back to the LM's start state (the topology
+ *    of the N-state free-phone LM, .cpp:1313-1330); the epsilon closure keeps one entry per (start state, previous phone), expanded in
+ *    the order the hypotheses were visited (:640-733), i.e. the kept-list order the free-phone path already follows;
  *  - with an input LM the final hypothesis is the minimum over the finalStateSet -- ordered by LM state id, i.e. by phone --
  *    of weight + final weight (expandFinalNode :746-758, addToFinalSet :929-946, selection :2138-2153); that sum is the path cost. */
 typedef struct { const float* start; const float* bigram; const float* fin; } phone_lm_t;
@@ -855,7 +858,9 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 				uint32_t pp = ord[i], pend = pp * N + N - 1;
 				for (uint32_t q = 0; q < P; q++) {
 					if (N == 1 && q == pp) continue;     /* free-phone LM, 1 state: no self arc (.cpp:1332-1346) */
-					float base = Wp[pend] + (lm ? lm->bigram[(size_t)pp * P + q] : 0.0f);   /* + LM arc weight (0 in the free-phone LM) */
+					/* + LM arc weight (0 in the free-phone LM).  N states per phone: the hypothesis first takes the epsilon arc back to the LM's
+					 * start state (exit cost of phone pp), then the unigram arc of q: two float adds in that order (:597, :686) */
+					float base = !lm ? Wp[pend] + 0.0f : (N == 1 ? Wp[pend] + lm->bigram[(size_t)pp * P + q] : (Wp[pend] + lm->bigram[pp]) + lm->start[q]);
 					float tw = NEGM(pend, q * N);
 					float cost = base + tw;
 					if (!seen[q]) { seen[q] = 1; arr[narr++] = q; Cs[q * N].w = cost; Cs[q * N].ptr = (int)pend; }
@@ -967,7 +972,7 @@ int crforacle_viterbi_lm(const crforacle_config* c, const double* lambda, uint32
                          float* path_cost, double* logZ) {
 	phone_lm_t lmv = {lm_start, lm_bigram, lm_final};
 	const phone_lm_t* lm = lm_start ? &lmv : NULL;
-	if (lm && (c->n_states != 1 || !lm_bigram || !lm_final)) FAIL("the phone-bigram LM needs one state per phone and all three weight arrays");
+	if (lm && (!lm_bigram || !lm_final)) FAIL("the phone LM needs all three weight arrays");
 	if (c->n_base_ftrs2 && !ftrs2) FAIL("the configuration joins a second feature stream but none was passed");
 	if (c->model_type != CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR && c->model_type != CRFO_STDFRAME)
 		FAIL("viterbi: only stdframe / stdseg_no_dur_no_segtransftr are accepted (CRFDecode/src/Main.cpp:1065-1076)");

@@ -355,7 +355,8 @@ int crfref_fwdbwd(const crfref_config* c, const double* lambda, uint32_t lambda_
 /* Phone-bigram language model handed to nStateDecode as its lm_fst (one state per phone only): the topology of the decoder's own
  * free-phone LM (createFreePhoneLmFst, .cpp:1270-1348: state 0 = start, state p + 1 = "the last phone was p", an arc to every OTHER phone,
  * every phone state final) with a weight on every arc -- lm_start[q], lm_bigram[p*P + q] (the diagonal is unused) -- and a final weight
- * lm_final[p].  All three NULL: lm_fst == NULL. */
+ * lm_final[p].  N states per phone: lm_start = unigram costs, lm_bigram = P exit costs on the epsilon arcs back to the start state.
+ * All three NULL: lm_fst == NULL. */
 static int viterbi_impl(const crfref_config* c, const double* lambda, uint32_t lambda_len,
                         uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
                         const float* lm_start, const float* lm_bigram, const float* lm_final,
@@ -367,11 +368,16 @@ static int viterbi_impl(const crfref_config* c, const double* lambda, uint32_t l
 		Streams st(c, base_ftrs, base_ftrs2, NULL, frame_off, n_utt);
 		VectorFst<StdArc> lm; const bool have_lm = lm_start != NULL;
 		if (have_lm) {
-			if (c->n_states != 1) throw std::runtime_error("the phone-bigram LM topology needs one state per phone");
-			const int P = (int)c->n_labs;
+			const int P = (int)(c->n_labs / c->n_states);
 			int s0 = lm.AddState(); lm.SetStart(s0);
 			for (int p = 0; p < P; p++) { int sp = lm.AddState(); lm.AddArc(s0, StdArc(p + 1, p + 1, lm_start[p], sp)); lm.SetFinal(sp, lm_final[p]); }
-			for (int p = 0; p < P; p++) for (int r = 0; r < P; r++) if (r != p) lm.AddArc(p + 1, StdArc(r + 1, r + 1, lm_bigram[(size_t)p * P + r], r + 1));
+			if (c->n_states == 1) {
+				for (int p = 0; p < P; p++) for (int r = 0; r < P; r++) if (r != p) lm.AddArc(p + 1, StdArc(r + 1, r + 1, lm_bigram[(size_t)p * P + r], r + 1));
+			} else {
+				/* N states per phone: the free-phone LM's own topology (.cpp:1313-1330) -- every phone state returns to the start state through
+				 * an epsilon arc, here with the phone's EXIT cost lm_bigram[p] (P values), and leaves it again on the unigram arcs lm_start[q] */
+				for (int p = 0; p < P; p++) lm.AddArc(p + 1, StdArc(0, 0, lm_bigram[p], s0));
+			}
 		}
 		st.fs->rewind();
 		for (uint32_t u = 0; u < n_utt; u++) {

@@ -1,7 +1,9 @@
 """Generates tests/golden/viterbi_lm_golden.npz from the UNMODIFIED reference (oracle/_ref/libcrfref.so): nStateDecode with an input
 language model (CRF_ViterbiDecoder_StdSeg_NoSegTransFtr.cpp:1369-2398, lm_fst != NULL) for the class of LMs the device implements --
 complete phone-bigram LMs in the topology of the decoder's own free-phone LM (one state per phone; createFreePhoneLmFst :1270-1348):
-random costs, quantised costs (ties in every frame), phone states that are not final, with and without transition features.
+random costs, quantised costs (ties in every frame), phone states that are not final, with and without transition features; and, for N states
+per phone, unigram + exit-cost LMs in the topology of the N-state free-phone LM (epsilon arcs back to the start state; a plain phone
+insertion penalty among them).
 
     python tests/golden/make_golden_lm.py
 """
@@ -47,6 +49,31 @@ def main():
             nseg = np.array([len(sg[0]) for sg in segs], np.uint32)
             out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": off, f"{name}/ftrs": x,
                         f"{name}/lm_start": st, f"{name}/lm_bigram": bg, f"{name}/lm_final": fin, f"{name}/nseg": nseg, f"{name}/cost": cost,
+                        f"{name}/lab": np.concatenate([sg[0] for sg in segs]), f"{name}/dur": np.concatenate([sg[1] for sg in segs]),
+                        f"{name}/phn": np.concatenate([sg[2] for sg in segs])})
+            n += 1
+    # N states per phone: unigram + exit costs in the topology of the N-state free-phone LM (epsilon arcs back to the start state)
+    for (P, N, D, seg) in [(5, 3, 1, 0), (4, 3, 2, 1), (6, 2, 3, 1), (61, 3, 1, 0)]:
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P * N, n_base_ftrs=4, n_states=N, max_dur=D, extract_seg_ftrs=seg)
+        nl = ref.lambda_len(cfg)
+        f = rng.random((int(off[-1]), 4), dtype=np.float32)
+        qf = (np.round(f * 2) / 2).astype(np.float32)
+        for kind in ("rand", "quant", "nofinal", "penalty"):
+            lam = rng.uniform(-0.5, 0.5, nl)
+            uni = rng.uniform(0, 3, P).astype(np.float32); ex = rng.uniform(0, 3, P).astype(np.float32); fin = rng.uniform(0, 2, P).astype(np.float32)
+            x = f
+            if kind == "quant":
+                lam = np.round(rng.uniform(-1, 1, nl) * 2) / 2
+                uni, ex, fin, x = np.round(uni), np.round(ex), np.round(fin), qf
+            if kind == "nofinal":
+                fin[::2] = np.inf
+            if kind == "penalty":      # a plain phone insertion penalty
+                uni[:] = 0.0; ex[:] = 1.5; fin[:] = 0.0
+            segs, cost, _ = ref.viterbi(cfg, lam, off, x, lm=(uni, ex, fin))
+            name = f"{kind}_P{P}N{N}D{D}s{seg}"
+            nseg = np.array([len(sg[0]) for sg in segs], np.uint32)
+            out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": off, f"{name}/ftrs": x,
+                        f"{name}/lm_start": uni, f"{name}/lm_bigram": ex, f"{name}/lm_final": fin, f"{name}/nseg": nseg, f"{name}/cost": cost,
                         f"{name}/lab": np.concatenate([sg[0] for sg in segs]), f"{name}/dur": np.concatenate([sg[1] for sg in segs]),
                         f"{name}/phn": np.concatenate([sg[2] for sg in segs])})
             n += 1
