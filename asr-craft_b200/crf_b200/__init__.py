@@ -88,7 +88,7 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
            "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info",
            "crfgpu_fetch_posterior_mass", "crfgpu_stage_batch2", "crfgpu_fwdbwd_batch2", "crfgpu_viterbi_batch2",
-           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm"]
+           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm", "crfgpu_set_beam"]
 COMM_ID_BYTES = 128
 
 
@@ -272,6 +272,10 @@ class CrfGpu:
     def set_train_state(self, lambda_acc=None, lambda_sqr_acc=None, grad_sqr_acc=None):
         arrs = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (lambda_acc, lambda_sqr_acc, grad_sqr_acc)]
         self._check(self.lib.crfgpu_set_train_state(self.h, *[None if a is None else _ptr(a, C.c_double) for a in arrs]))
+
+    def set_beam(self, beam):
+        """crfgpu_set_beam: beam pruning of the decoder (0 = off)"""
+        self._check(self.lib.crfgpu_set_beam(self.h, C.c_double(beam)))
 
     def set_phone_lm(self, start=None, bigram=None, final=None):
         """crfgpu_set_phone_lm: complete phone-bigram LM (costs) for decoding, one state per phone; no arguments drop it.

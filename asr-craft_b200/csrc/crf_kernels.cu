@@ -942,14 +942,14 @@ void launch_vit_scores(const VitScoreParams& p, cudaStream_t s) {
 // All costs are float with the finite sentinel 99999.0; candidate order reproduces the reference's
 // first-arrival-wins tie-breaks (see DESIGN.md "Viterbi exactness").
 // =================================================================================================
-__device__ __forceinline__ uint32_t kept_phone(uint32_t i, uint32_t P, uint32_t g) {
-	// i-th phone of the kept list described by g: identity if g==0xff, else increasing order with g moved last
-	if (g == 0xffu) return i;
+__device__ __forceinline__ uint32_t kept_phone(uint32_t i, uint32_t P, uint32_t g, uint32_t none = 0xffu) {
+	// i-th phone of the kept list described by g: identity if g is the "none" sentinel, else increasing order with g moved last
+	if (g == none) return i;
 	if (i + 1 == P) return g;
 	return i < g ? i : i + 1;
 }
 
-template <bool HAS_LM>
+template <bool HAS_LM, bool BEAM>
 __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	float* Wprev = reinterpret_cast<float*>(smem_raw);   // [L] kept weights of the previous frame
@@ -960,6 +960,18 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	__shared__ uint32_t s_g;        // descriptor of the kept-list order of the previous frame
 	__shared__ uint8_t s_move[256]; // arrival-order descriptors a[s] of the last D start frames (ring; D <= 255)
 	__shared__ int s_best;
+	// beam pruning (BEAM, one state per phone): a node keeps the hypotheses whose weight is < min_weight + beam (a float against a double
+	// sum, pruning() .cpp:1013-1100) and only kept hypotheses are expanded -- across phones (:573; a pruned phone's entry of We[] is +inf,
+	// so it never wins the scan and the list order of the others is untouched) and within the phone -- or end the path.  Every kept
+	// hypothesis still reaches every other phone, so every phone has a candidate at every start frame and the kept list is the closed-form
+	// order with the pruned phones left out; its HEAD (the phone whose own candidate arrives last at the next start frame) is the first
+	// kept phone in that order, found from the warps' ballots.
+	__shared__ float s_wmin[32];
+	__shared__ uint32_t s_keptmask[32];
+	__shared__ uint32_t s_move_w[256];     // BEAM: the arrival-order descriptors are phone ids (any phone can head a pruned list), 0xffffffff = identity
+	__shared__ uint32_t s_gw;
+	constexpr uint32_t GNONE = BEAM ? 0xffffffffu : 0xffu;
+	bool my_kept = true; float my_best = 0.0f;
 	const uint32_t u = p.order ? p.order[blockIdx.x] : blockIdx.x;      // longest utterances first
 	const uint32_t L = p.L, P = p.P, NS = p.NS, D = p.D;
 	const uint32_t off = p.off[u], T = p.off[u + 1] - p.off[u];
@@ -987,7 +999,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	const uint32_t chunk = (P + NS - 1) / NS, i_lo = min(P, part * chunk), i_hi = min(P, i_lo + chunk);
 	float my_diag = (lab < L && p.negMt == nullptr) ? p.negDiag[lab] : 0.0f;
 	float my_off = (lab < L && k > 0 && p.negMt == nullptr) ? p.negOff[lab] : 0.0f;
-	if (threadIdx.x == 0) s_g = 0xffu;
+	if (threadIdx.x == 0) { s_g = 0xffu; s_gw = 0xffffffffu; }
 	__syncthreads();
 	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 	unsigned long long tacc[4] = {0, 0, 0, 0};
@@ -1016,7 +1028,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 		VKTICK(3);   // loop top: prefetch issue (+ list bookkeeping of the previous frame)
 		float pw = VIT_INF; int32_t pptr = -1;
 		if (s > 0 && scan_ok) {
-			const uint32_t g = s_g;
+			const uint32_t g = BEAM ? s_gw : s_g;
 			// the table pointer keeps its address space (shared or global) in each instantiation, the per-thread part of the index is
 			// hoisted out of the frame loop, and the two list orders have their own loops: per element this is two loads, two adds and
 			// one compare-select (generic loads and per-element list arithmetic made the scan 70 % of the frame)
@@ -1043,7 +1055,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 						const float cc = (We[pp] + lr[pp]) + ct[(size_t)pp * stride];
 						if (pp != tq && pp != g && cc < pw) { pw = cc; pptr = (int32_t)pp; }
 					}
-					if (g != 0xffu && g != tq) {
+					if (g != GNONE && g != tq) {
 						const float cc = (We[g] + lr[g]) + ct[(size_t)g * stride];
 						if (cc < pw) { pw = cc; pptr = (int32_t)g; }
 					}
@@ -1061,7 +1073,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 						const float cc = We[pp] + ct[(size_t)pp * stride];
 						if (pp != tq && pp != g && cc < pw) { pw = cc; pptr = (int32_t)pp; }
 					}
-					if (g != 0xffu && g != tq) {
+					if (g != GNONE && g != tq) {
 						const float cc = We[g] + ct[(size_t)g * stride];
 						if (cc < pw) { pw = cc; pptr = (int32_t)g; }
 					}
@@ -1091,15 +1103,17 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 					}
 				} else seen = true;   // the cross update created the slot with 99999.0 / -1 for inner sub-states
 				// within-phone: self vs advance from the previous sub-state, self only if strictly smaller (:338)
-				float w; int32_t ptr;
-				const float n1 = Wprev[lab] + my_diag;
-				if (k == 0) { w = n1; ptr = (int32_t)lab; }
-				else {
-					const float n2 = Wprev[lab - 1] + my_off;
-					if (n1 < n2) { w = n1; ptr = (int32_t)lab; } else { w = n2; ptr = (int32_t)lab - 1; }
+				if (!BEAM || my_kept) {                              // (a pruned hypothesis is not expanded)
+					float w; int32_t ptr;
+					const float n1 = Wprev[lab] + my_diag;
+					if (k == 0) { w = n1; ptr = (int32_t)lab; }
+					else {
+						const float n2 = Wprev[lab - 1] + my_off;
+						if (n1 < n2) { w = n1; ptr = (int32_t)lab; } else { w = n2; ptr = (int32_t)lab - 1; }
+					}
+					if (k == 0 && !seen) { cw = w; cp = ptr; }         // no cross arc reached this phone (P == 1, or it is the only kept one)
+					else if (w < cw) { cw = w; cp = ptr; }
 				}
-				if (k == 0 && !seen) { cw = w; cp = ptr; }         // no cross arc reached this phone (P == 1)
-				else if (w < cw) { cw = w; cp = ptr; }
 			}
 			if (D > 1) { candW[(uint64_t)(s % D) * L + lab] = cw; candP[(uint64_t)(s % D) * L + lab] = cp; }   // read back d-1 frames later
 		}
@@ -1125,14 +1139,47 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				if (d == dmax || w < best) { best = w; bptr = ptr; bdur = d; }
 			}
 			Wprev[lab] = best;
-			if (k == NS - 1) We[q] = has_lm ? (NS == 1 ? best : best + __ldg(p.lm_exit + q)) : best + 0.0f;
+			if (!BEAM && k == NS - 1) We[q] = has_lm ? (NS == 1 ? best : best + __ldg(p.lm_exit + q)) : best + 0.0f;
+			if (BEAM) my_best = best;
 			p.bp[(uint64_t)(off + s) * L + lab] = bptr < 0 ? (uint16_t)0xffff : (uint16_t)bptr;
 			p.bd[(uint64_t)(off + s) * L + lab] = (uint8_t)bdur;
+		}
+		if (BEAM) {
+			// minimum over the node (findMinWeight), then the kept flags and their ballots
+			float mn = lab < L ? my_best : CUDART_INF_F;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+			if ((threadIdx.x & 31) == 0) s_wmin[threadIdx.x >> 5] = mn;
+			__syncthreads();
+			const uint32_t nw = (blockDim.x + 31) / 32;
+			float bm = (threadIdx.x & 31) < nw ? s_wmin[threadIdx.x & 31] : CUDART_INF_F;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) bm = fminf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+			my_kept = lab < L && (double)my_best < (double)bm + p.beam;
+			const uint32_t bal = __ballot_sync(0xffffffffu, my_kept);
+			if ((threadIdx.x & 31) == 0) s_keptmask[threadIdx.x >> 5] = bal;
+			if (lab < L) We[q] = my_kept ? (has_lm ? my_best : my_best + 0.0f) : CUDART_INF_F;
 		}
 		__syncthreads();
 		VKTICK(2);   // node update + barrier
 		// the kept-list order only moves for one state per phone (N > 1: always the identity, s_g stays 0xff): no bookkeeping, no barrier
-		if (NS == 1) {
+		if (BEAM) {
+			if (threadIdx.x == 0) {
+				// order of kept(s) = a[max(0, s-D+1)] with the pruned phones left out; its head = the first kept phone in that order =
+				// the smallest kept phone unless that is the one the descriptor moves to the back
+				const uint32_t j2 = s + 1 >= D ? s + 1 - D : 0;
+				const uint32_t g2 = (j2 == 0) ? 0xffffffffu : s_move_w[j2 & 255];
+				uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
+				for (uint32_t w = 0; w < (P + 31) / 32 && m2 == 0xffffffffu; w++) {
+					uint32_t b = s_keptmask[w];
+					while (b && m2 == 0xffffffffu) { const uint32_t i = w * 32 + (uint32_t)__ffs((int)b) - 1; b &= b - 1; if (m1 == 0xffffffffu) m1 = i; else m2 = i; }
+				}
+				const uint32_t head = (m1 != g2 || m2 == 0xffffffffu) ? m1 : m2;
+				s_move_w[(s + 1) & 255] = P > 1 ? head : 0xffffffffu;      // a[s+1]: ascending with the head of kept(s) arriving last
+				s_gw = g2;                                                  // order of kept(s) feeds the cross scan of frame s+1
+			}
+			__syncthreads();
+		} else if (NS == 1) {
 			if (threadIdx.x == 0) {
 				// a[s] := descriptor of the ARRIVAL order at start frame s; a[0] = identity.
 				// a[s>=1] (NS==1): head of kept(s-1) moved to the back; kept(s-1) = a[max(0, s-1-D+1)] = a[max(0, s-D)].
@@ -1161,11 +1208,12 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	if (threadIdx.x == 0) {
 		float minw = VIT_INF; int best = -1;
 		if (T > 0) {
-			const uint32_t g = s_g;
+			const uint32_t g = BEAM ? s_gw : s_g;
 			for (uint32_t i = 0; i < P; i++) {
 				// free-phone LM: kept-list order, first wins.  Input LM: the decoder's finalStateSet, ordered by LM state = phone, weight =
 				// hypothesis + final weight of its state, states that are not final left out (expandFinalNode :746-758, :2138-2153)
-				const uint32_t e = (has_lm ? i : kept_phone(i, P, g)) * NS + NS - 1;
+				const uint32_t ph = has_lm ? i : kept_phone(i, P, g, GNONE), e = ph * NS + NS - 1;
+				if (BEAM && !((s_keptmask[ph >> 5] >> (ph & 31)) & 1u)) continue;      // pruned at the last node
 				float w = Wprev[e];
 				if (has_lm) { const float fw = __ldg(p.lm_final + i); if (isinf(fw)) continue; w = w + fw; }
 				if (w < minw) { minw = w; best = (int)e; }
@@ -1236,13 +1284,15 @@ void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	// traceback window: rows of back pointers (2 + 1 bytes per label) of as many frames as fit 48 KB, at least 8
 	q.tbW = std::max<uint32_t>(8u, (48u * 1024u) / (3u * p.L));
 	smem = std::max(smem, ((size_t)q.tbW * p.L * 2 + 47) / 16 * 16 + (size_t)q.tbW * p.L + 48);
-	if (p.lm_start != nullptr) {
-		cudaFuncSetAttribute(viterbi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		viterbi_kernel<true><<<p.n_utt, threads, smem, s>>>(q);
-	} else {
-		cudaFuncSetAttribute(viterbi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		viterbi_kernel<false><<<p.n_utt, threads, smem, s>>>(q);
-	}
+	auto go = [&](auto kern) {
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		kern<<<p.n_utt, threads, smem, s>>>(q);
+	};
+	const bool lm = p.lm_start != nullptr, beam = p.beam > 0.0;      // (beam: one state per phone, checked by the caller)
+	if (lm && beam) go(viterbi_kernel<true, true>);
+	else if (lm) go(viterbi_kernel<true, false>);
+	else if (beam) go(viterbi_kernel<false, true>);
+	else go(viterbi_kernel<false, false>);
 }
 
 }  // namespace crfgpu

@@ -293,6 +293,7 @@ struct VitParams {
 	// phone-bigram language model (one state per phone; nullptr = the decoder's free-phone LM with weight 0 on every arc):
 	// lm_start[P], lm_bigT[to * P + from] (TRANSPOSED like the shared-memory cross table), lm_final[P] (+inf = not a final state)
 	const float* lm_start; const float* lm_bigT; const float* lm_final;
+	double beam;                      // > 0: beam pruning (pruning(), .cpp:976-1106; one state per phone): a node keeps the hypotheses with weight < min + beam
 	const float* lm_exit;             // N states per phone (lm_bigT then nullptr): cost of the epsilon arc phone state -> LM start state; lm_start = unigram costs
 	float* candW; int32_t* candP;     // [n_utt][D][L] rings of candidates per start frame
 	float* keptW;                     // [n_utt][2][L]

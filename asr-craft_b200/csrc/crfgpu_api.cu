@@ -121,7 +121,7 @@ struct crfgpu_ctx {
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
 	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	int opt_frame_impl = 0; bool frame_path = false;
-	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit;   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
+	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit; double beam = 0.0;   // crfgpu_set_beam   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
 	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
 
@@ -1158,7 +1158,8 @@ void viterbi_staged(crfgpu_ctx* h) {
 	}
 	// large phone sets with one state per phone and constant transition tables: the cross-phone table sliced over groups of CTAs,
 	// 16 utterances in lock-step per group (crf_viterbi_group.cu); opt_vit_impl 1 forces one CTA per utterance, 2 forces the groups
-	const bool vg_fit = NS == 1 && !c.use_trans_ftrs && P >= 2 && L == P && !h->have_lm;      // (LM weights: the per-utterance kernel)
+	if (h->beam > 0.0 && NS != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "beam pruning is implemented for one state per phone (with N states a pruned node can leave phones without any candidate, and the hypothesis order becomes data-dependent)");
+	const bool vg_fit = NS == 1 && !c.use_trans_ftrs && P >= 2 && L == P && !h->have_lm && !(h->beam > 0.0);      // (LM weights / beam: the per-utterance kernel)
 	const bool vg_auto = vg_fit && (size_t)P * P * sizeof(float) > 96 * 1024;
 	if (vg_fit && (h->opt_vit_impl == 2 || (h->opt_vit_impl == 0 && vg_auto))) {
 		const int gmax = vitg_max_groups(P);
@@ -1197,6 +1198,7 @@ void viterbi_staged(crfgpu_ctx* h) {
 	v.n_utt = h->n_utt; v.L = L; v.P = P; v.NS = NS; v.D = D; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
 	v.crossT = h->d_crossT.as<float>(); v.negDiag = h->d_negDiag.as<float>(); v.negOff = h->d_negOff.as<float>();
 	v.negMt = c.use_trans_ftrs ? h->d_negMt.as<float>() : nullptr; v.E = h->vtE;
+	v.beam = h->beam;
 	if (h->have_lm) {
 		v.lm_start = h->d_lm_start.as<float>(); v.lm_final = h->d_lm_final.as<float>();
 		if (NS == 1) v.lm_bigT = h->d_lm_bigT.as<float>(); else v.lm_exit = h->d_lm_exit.as<float>();
@@ -1619,6 +1621,15 @@ int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_
 		upload(h->d_lm_start, st, h->stream); upload(h->d_lm_bigT, bt, h->stream); upload(h->d_lm_final, fin, h->stream);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
 		h->have_lm = true; h->viterbi_done = false;
+	});
+}
+
+int crfgpu_set_beam(crfgpu_handle h, double beam) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		if (!(beam >= 0.0) || !std::isfinite(beam)) throw ApiError(CRFGPU_ERR_ARG, "the beam must be a finite number >= 0 (0 = no pruning)");
+		if (beam > 0.0 && h->lay.n_states != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "beam pruning is implemented for one state per phone");
+		h->beam = beam; h->viterbi_done = false;
 	});
 }
 

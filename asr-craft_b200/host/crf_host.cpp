@@ -370,7 +370,7 @@ int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPa
 }
 
 int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam) {
-	if (beam > 0.0) throw runtime_error("beam pruning is not implemented on the device (beam 0 only)");
+	check(crfgpu_set_beam(crf->gpu(), beam), "crfgpu_set_beam");      // input_beam of nStateDecode (one state per phone; 0 = no pruning)
 	std::vector<float> f;
 	const uint32_t T = (uint32_t)read_utterance(strm, f, nullptr);
 	if (!T) throw runtime_error("No features read from this sentence");
@@ -385,7 +385,8 @@ int CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecode(std::vector<CRF_BestPa
 }
 
 size_t CRF_ViterbiDecoder_StdSeg_NoSegTransFtr::nStateDecodeBatch(size_t max_utts, std::vector<std::vector<CRF_BestPathArc>>* results,
-                                                                   std::vector<float>* path_costs, std::vector<int>* n_frames, bool* stream_end) {
+                                                                   std::vector<float>* path_costs, std::vector<int>* n_frames, bool* stream_end, double beam) {
+	check(crfgpu_set_beam(crf->gpu(), beam), "crfgpu_set_beam");
 	std::vector<float> f, f2; std::vector<uint32_t> off(1, 0);
 	if (stream_end) *stream_end = false;
 	while (off.size() - 1 < max_utts) {

@@ -236,7 +236,8 @@ class CRF_ViterbiDecoder_StdSeg_NoSegTransFtr {
 	CRF_FeatureStream* strm; CRF_Model* crf;
 public:
 	CRF_ViterbiDecoder_StdSeg_NoSegTransFtr(CRF_FeatureStream* ftr_strm_in, CRF_Model* crf_in) : strm(ftr_strm_in), crf(crf_in) {}
-	// decodes the CURRENT utterance of the stream (free-phone LM, beam 0); returns the number of frames, like nStateDecode
+	// decodes the CURRENT utterance of the stream (free-phone LM); returns the number of frames, like nStateDecode.  beam > 0: the
+	// reference's beam pruning (one state per phone)
 	int nStateDecode(std::vector<CRF_BestPathArc>* result, float* path_cost, double beam = 0.0);
 	// the same against a language model (the reference's nStateDecode(result, lm_fst, ...), .cpp:1369-1372); path_cost includes the final weight
 	int nStateDecode(std::vector<CRF_BestPathArc>* result, const CRF_PhoneBigramLm* lm_fst, float* path_cost, double beam = 0.0);
@@ -247,7 +248,7 @@ public:
 	// results[u] / path_costs[u] / n_frames[u] are what nStateDecode returns for utterance u.
 	// *stream_end is set when the stream has no further utterance (nextseg() returned QN_SEGID_BAD).
 	size_t nStateDecodeBatch(size_t max_utts, std::vector<std::vector<CRF_BestPathArc>>* results, std::vector<float>* path_costs, std::vector<int>* n_frames,
-	                         bool* stream_end = nullptr);
+	                         bool* stream_end = nullptr, double beam = 0.0);
 };
 
 // CRF_SGTrainer::train() (CRF/src/trainers/CRF_SGTrainer.cpp:99-430) over the device path: per minibatch one device batch and one

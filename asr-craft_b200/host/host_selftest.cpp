@@ -340,6 +340,14 @@ int main(int argc, char** argv) {
 				strm.rewind(); strm.nextseg();
 				vd.nStateDecode(&p2, &c2);
 				if (p2.size() != path.size() || c2 != cost) { std::printf("MISMATCH the LM outlived its call\n"); bad++; }
+				// beam: a huge beam prunes nothing, a tiny one can only lose paths, beam 0 afterwards is the unpruned decode again
+				std::vector<CRF_BestPathArc> p3; float c3 = 0.0f, c4 = 0.0f, c5 = 0.0f;
+				strm.rewind(); strm.nextseg(); vd.nStateDecode(&p3, &c3, 1e6);
+				if (p3.size() != path.size() || c3 != cost) { std::printf("MISMATCH beam 1e6 changed the path\n"); bad++; }
+				strm.rewind(); strm.nextseg(); p3.clear(); vd.nStateDecode(&p3, &c4, 1e-3);
+				if (c4 < cost) { std::printf("MISMATCH a pruned decode is cheaper than the full one\n"); bad++; }
+				strm.rewind(); strm.nextseg(); p3.clear(); vd.nStateDecode(&p3, &c5);
+				if (c5 != cost) { std::printf("MISMATCH the beam outlived its call\n"); bad++; }
 			}
 			// ---- the whole stream as device batches of 3 utterances: utterance 0 must decode as above, the stream must end where it ends ----
 			strm.rewind(); strm.nextseg();

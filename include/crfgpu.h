@@ -153,6 +153,10 @@ int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_
  * paid by the first phone), lm_exit[P] = cost of the epsilon arc of phone p (a phone insertion penalty when all equal), lm_final[P] as
  * above.  Added where the reference adds them: ((hypothesis + exit) + unigram) + transition. */
 int crfgpu_set_phone_unigram_lm(crfgpu_handle h, const float* lm_unigram, const float* lm_exit, const float* lm_final);
+/* nStateDecode's input_beam (one state per phone): after every frame the decoder drops the hypotheses whose weight is not below the frame's
+ * minimum + beam (pruning(), .cpp:976-1106) and expands only the survivors (:573); 0 = no pruning (the default).  The results are the
+ * reference's for the same beam, bit for bit.  min_hyps / max_hyps / beam_inc are accepted by the reference's signature and never used. */
+int crfgpu_set_beam(crfgpu_handle h, double beam);
 
 /* Window features for one utterance, out[(t*max_dur + d-1)*window_width ...]; slots with d > t+1 are zero. */
 int crfgpu_expand_windows(crfgpu_handle h, uint32_t n_frames, const float* base_ftrs, float* out);

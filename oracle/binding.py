@@ -112,7 +112,7 @@ class _Lib:
                                            C.c_uint32(n_threads)))
         return grad, numer, logz
 
-    def viterbi(self, cfg, lam, off, ftrs, ftrs2=None, lm=None):
+    def viterbi(self, cfg, lam, off, ftrs, ftrs2=None, lm=None, beam=0.0):
         """Returns list of (labels, durs, phones) per utterance, path costs, logZ.  lm = (start[P], bigram[P][P], final[P]) float32:
         a phone-bigram LM in the topology of the decoder's free-phone LM (one state per phone)."""
         f2 = np.ascontiguousarray(ftrs2, np.float32) if ftrs2 is not None else None
@@ -128,9 +128,9 @@ class _Lib:
         cost = np.zeros(n, np.float32)
         logz = np.zeros(n, np.float64)
         lms = [None, None, None] if lm is None else [np.ascontiguousarray(a, np.float32) for a in lm]
-        self._check(self._fn("viterbi_lm")(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(n),
+        self._check(self._fn("viterbi_beam")(C.byref(cfg), _p(lam, C.c_double), C.c_uint32(len(lam)), C.c_uint32(n),
                                         _p(off, C.c_uint32), _p(ftrs, C.c_float), _p(f2, C.c_float) if f2 is not None else None,
-                                        *[None if a is None else _p(a, C.c_float) for a in lms],
+                                        *[None if a is None else _p(a, C.c_float) for a in lms], C.c_double(beam),
                                         _p(lab, C.c_uint32),
                                         _p(dur, C.c_uint32), _p(phn, C.c_uint32), _p(nseg, C.c_uint32),
                                         _p(cost, C.c_float), _p(logz, C.c_double)))

@@ -812,7 +812,11 @@ typedef struct { float w; int ptr; } cand_t;  /* ptr = previous (phone*N+sub) or
  *    the order the hypotheses were visited (:640-733), i.e. the kept-list order the free-phone path already follows;
  *  - with an input LM the final hypothesis is the minimum over the finalStateSet -- ordered by LM state id, i.e. by phone --
  *    of weight + final weight (expandFinalNode :746-758, addToFinalSet :929-946, selection :2138-2153); that sum is the path cost. */
-typedef struct { const float* start; const float* bigram; const float* fin; } phone_lm_t;
+typedef struct { const float* start; const float* bigram; const float* fin; double beam; } phone_lm_t;
+/* beam > 0 (one state per phone): pruning() (.cpp:976-1106) keeps the hypotheses of a node whose weight is < min_weight + beam (float
+ * against a double sum); only kept hypotheses are expanded (cross-phone, :573, and within-phone) and may end the path.  In the free-phone
+ * / bigram topology every kept hypothesis still reaches every other phone, so every phone has a candidate at every start frame and the
+ * kept list is the closed-form order with the pruned phones left out. */
 
 static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double* lam,
                        uint32_t T, const float* x, const float* x2, const phone_lm_t* lm, uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn,
@@ -828,6 +832,10 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 	uint32_t* bd = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)T * L);
 	uint32_t* order = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)T * P);  /* kept-list phone order per frame */
 	uint32_t* arrive = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)T * P); /* arrival order of slots created at frame s */
+	uint8_t* kept = (uint8_t*)malloc((size_t)T * P);                        /* beam pruning: phone survives node t */
+	const double beam = lm ? lm->beam : 0.0;
+	if (lm && !lm->start) lm = NULL;                                        /* beam without an input LM */
+	if (beam > 0.0 && N != 1) { free(X); free(C); free(Wt); free(bp); free(bd); free(order); free(arrive); free(kept); FAIL("oracle: beam pruning restated for one state per phone only"); }
 	/* (float)(-M[p,c]) for the legal pairs, precomputed when transitions carry no features */
 	float* negM = NULL;
 	if (!c->use_trans_ftrs) {
@@ -850,12 +858,14 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 			const float* xs = X + ((size_t)s * D) * W;
 			const float* Wp = Wt + (size_t)(s - 1) * L;
 			const uint32_t* ord = order + (size_t)(s - 1) * P;
+			const uint8_t* kp = kept + (size_t)(s - 1) * P;
 			uint32_t narr = 0;
 			uint8_t* seen = (uint8_t*)calloc(P, 1);
 			for (uint32_t q = 0; q < P; q++) for (uint32_t k = 0; k < N; k++) { Cs[q * N + k].w = VINF; Cs[q * N + k].ptr = -1; }
 			/* cross-phone candidates, in kept-list order x LM-arc order */
 			for (uint32_t i = 0; i < P; i++) {
 				uint32_t pp = ord[i], pend = pp * N + N - 1;
+				if (!kp[pp]) continue;                   /* pruned at node s-1 */
 				for (uint32_t q = 0; q < P; q++) {
 					if (N == 1 && q == pp) continue;     /* free-phone LM, 1 state: no self arc (.cpp:1332-1346) */
 					/* + LM arc weight (0 in the free-phone LM).  N states per phone: the hypothesis first takes the epsilon arc back to the LM's
@@ -870,6 +880,7 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 			/* within-phone candidates, in kept-list order */
 			for (uint32_t i = 0; i < P; i++) {
 				uint32_t q = ord[i];
+				if (!kp[q]) continue;
 				int fresh = !seen[q];
 				if (fresh) { seen[q] = 1; arr[narr++] = q; }
 				for (uint32_t k = 0; k < N; k++) {
@@ -904,6 +915,12 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 			}
 			Wt[(size_t)t * L + lab] = best; bp[(size_t)t * L + lab] = bptr; bd[(size_t)t * L + lab] = bdur;
 		}
+		/* pruning (.cpp:976-1106): min over the node, keep weight < min + beam (the sum in double) */
+		{
+			float mn = VINF;
+			for (uint32_t q = 0; q < P; q++) { float bw = Wt[(size_t)t * L + q * N]; for (uint32_t k = 1; k < N; k++) if (Wt[(size_t)t * L + q * N + k] < bw) bw = Wt[(size_t)t * L + q * N + k]; if (bw < mn) mn = bw; }
+			for (uint32_t q = 0; q < P; q++) kept[(size_t)t * P + q] = (beam <= 0.0) ? 1 : ((double)Wt[(size_t)t * L + q] < (double)mn + beam);
+		}
 		/* kept-list order = arrival order of the slots inserted earliest into node t */
 		uint32_t sfirst = t + 1 >= D ? t + 1 - D : 0;
 		memcpy(order + (size_t)t * P, arrive + (size_t)sfirst * P, sizeof(uint32_t) * P);
@@ -915,6 +932,7 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 		for (uint32_t i = 0; i < P; i++) {
 			/* no LM: kept-list order; with an LM: LM-state order = phone order, final weights added, states that are not final skipped */
 			uint32_t q = lm ? i : ord[i], e = q * N + N - 1;
+			if (!kept[(size_t)(T - 1) * P + q]) continue;
 			if (lm && isinf(lm->fin[q])) continue;
 			float w = Wt[(size_t)(T - 1) * L + e];
 			if (lm) w = w + lm->fin[q];
@@ -947,7 +965,7 @@ static int viterbi_one(const crforacle_config* c, const fmap_t* m, const double*
 			*n_seg = ns;
 		}
 	}
-	free(X); free(C); free(Wt); free(bp); free(bd); free(order); free(arrive); free(negM);
+	free(X); free(C); free(Wt); free(bp); free(bd); free(order); free(arrive); free(negM); free(kept);
 	return rc;
 }
 
@@ -970,9 +988,18 @@ int crforacle_viterbi_lm(const crforacle_config* c, const double* lambda, uint32
                          const float* lm_start, const float* lm_bigram, const float* lm_final,
                          uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                          float* path_cost, double* logZ) {
-	phone_lm_t lmv = {lm_start, lm_bigram, lm_final};
-	const phone_lm_t* lm = lm_start ? &lmv : NULL;
-	if (lm && (!lm_bigram || !lm_final)) FAIL("the phone LM needs all three weight arrays");
+	return crforacle_viterbi_beam(c, lambda, lambda_len, n_utt, off, ftrs, ftrs2, lm_start, lm_bigram, lm_final, 0.0, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
+int crforacle_viterbi_beam(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                           uint32_t n_utt, const uint32_t* off, const float* ftrs, const float* ftrs2,
+                           const float* lm_start, const float* lm_bigram, const float* lm_final, double beam,
+                           uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                           float* path_cost, double* logZ) {
+	phone_lm_t lmv = {lm_start, lm_bigram, lm_final, beam};
+	const phone_lm_t* lm = (lm_start || beam > 0.0) ? &lmv : NULL;
+	if (lm_start && (!lm_bigram || !lm_final)) FAIL("the phone LM needs all three weight arrays");
+
 	if (c->n_base_ftrs2 && !ftrs2) FAIL("the configuration joins a second feature stream but none was passed");
 	if (c->model_type != CRFO_STDSEG_NO_DUR_NO_SEGTRANSFTR && c->model_type != CRFO_STDFRAME)
 		FAIL("viterbi: only stdframe / stdseg_no_dur_no_segtransftr are accepted (CRFDecode/src/Main.cpp:1065-1076)");

@@ -89,6 +89,13 @@ int crforacle_viterbi_lm(const crforacle_config* c, const double* lambda, uint32
                          uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                          float* path_cost, double* logZ);
 
+/* ... with beam pruning (nStateDecode's input_beam > 0; one state per phone): hypotheses of a node with weight >= min + beam are dropped */
+int crforacle_viterbi_beam(const crforacle_config* c, const double* lambda, uint32_t lambda_len,
+                           uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                           const float* lm_start, const float* lm_bigram, const float* lm_final, double beam,
+                           uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                           float* path_cost, double* logZ);
+
 /* Same as crforacle_fwdbwd_mt(…,1) for one utterance, additionally returning alpha/beta
  * ([T][n_labs] doubles, entries the reference never computes are set to -DBL_MAX = LOG0). */
 int crforacle_fwdbwd_dump(const crforacle_config* c, const double* lambda, uint32_t lambda_len,

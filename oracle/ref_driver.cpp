@@ -359,7 +359,7 @@ int crfref_fwdbwd(const crfref_config* c, const double* lambda, uint32_t lambda_
  * All three NULL: lm_fst == NULL. */
 static int viterbi_impl(const crfref_config* c, const double* lambda, uint32_t lambda_len,
                         uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
-                        const float* lm_start, const float* lm_bigram, const float* lm_final,
+                        const float* lm_start, const float* lm_bigram, const float* lm_final, double beam,
                         uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                         float* path_cost, double* logZ) {
 	try {
@@ -384,7 +384,7 @@ static int viterbi_impl(const crfref_config* c, const double* lambda, uint32_t l
 			if (st.fs->nextseg() == QN_SEGID_BAD) throw std::runtime_error("stream ended early");
 			ObservedDecoder vd(st.fs, mb.crf);   /* one decoder per utterance, CRFDecode/src/Main.cpp:1064-1112 */
 			VectorFst<StdArc> best, full;
-			int T = vd.nStateDecode(&best, have_lm ? &lm : NULL, &full, 0.0);
+			int T = vd.nStateDecode(&best, have_lm ? &lm : NULL, &full, beam);
 			if ((uint32_t)T != frame_off[u + 1] - frame_off[u]) throw std::runtime_error("decoder frame count mismatch");
 			/* walk the reference's own linear best-path FST */
 			std::vector<uint32_t> labs, phns; double zx = 0.0;
@@ -449,14 +449,14 @@ int crfref_viterbi(const crfref_config* c, const double* lambda, uint32_t lambda
                    uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs,
                    uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                    float* path_cost, double* logZ) {
-	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, NULL, NULL, NULL, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, NULL, NULL, NULL, NULL, 0.0, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
 }
 
 int crfref_viterbi2(const crfref_config* c, const double* lambda, uint32_t lambda_len,
                     uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
                     uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                     float* path_cost, double* logZ) {
-	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, NULL, NULL, NULL, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, NULL, NULL, NULL, 0.0, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
 }
 
 int crfref_viterbi_lm(const crfref_config* c, const double* lambda, uint32_t lambda_len,
@@ -464,7 +464,15 @@ int crfref_viterbi_lm(const crfref_config* c, const double* lambda, uint32_t lam
                       const float* lm_start, const float* lm_bigram, const float* lm_final,
                       uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
                       float* path_cost, double* logZ) {
-	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, lm_start, lm_bigram, lm_final, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, lm_start, lm_bigram, lm_final, 0.0, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
+}
+
+int crfref_viterbi_beam(const crfref_config* c, const double* lambda, uint32_t lambda_len,
+                        uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                        const float* lm_start, const float* lm_bigram, const float* lm_final, double beam,
+                        uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg,
+                        float* path_cost, double* logZ) {
+	return viterbi_impl(c, lambda, lambda_len, n_utt, frame_off, base_ftrs, base_ftrs2, lm_start, lm_bigram, lm_final, beam, out_lab, out_dur, out_phn, n_seg, path_cost, logZ);
 }
 
 /* Older frame-level decoder; one label per frame. */

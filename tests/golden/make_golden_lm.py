@@ -77,6 +77,34 @@ def main():
                         f"{name}/lab": np.concatenate([sg[0] for sg in segs]), f"{name}/dur": np.concatenate([sg[1] for sg in segs]),
                         f"{name}/phn": np.concatenate([sg[2] for sg in segs])})
             n += 1
+    # beam pruning (nStateDecode's input_beam > 0), one state per phone, with the free-phone LM and with a bigram LM
+    nb = 0
+    for (P, D, seg) in [(5, 1, 0), (7, 3, 1), (6, 5, 1), (20, 4, 1), (48, 10, 1)]:
+        w = 4 if (D == 1 or not seg) else 8 * 4 + D
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=4, max_dur=D, extract_seg_ftrs=seg)
+        nl = ref.lambda_len(cfg)
+        f = rng.random((int(off[-1]), 4), dtype=np.float32)
+        qf = (np.round(f * 2) / 2).astype(np.float32)
+        for kind in ("rand", "quant"):
+            lam = rng.uniform(-0.5, 0.5, nl)
+            st = rng.uniform(0, 3, P).astype(np.float32); bg = rng.uniform(0, 3, (P, P)).astype(np.float32); fin = rng.uniform(0, 2, P).astype(np.float32)
+            x = f
+            if kind == "quant":
+                lam = np.round(rng.uniform(-1, 1, nl) * 2) / 2
+                st, bg, fin, x = np.round(st), np.round(bg), np.round(fin), qf
+            for use_lm in (0, 1):
+                for beam in (0.5, 2.0):
+                    lm = (st, bg, fin) if use_lm else None
+                    segs, cost, _ = ref.viterbi(cfg, lam, off, x, lm=lm, beam=beam)
+                    name = f"beam{beam}_{kind}_P{P}D{D}s{seg}lm{use_lm}"
+                    nseg = np.array([len(sg[0]) for sg in segs], np.uint32)
+                    out.update({f"{name}/cfg": cfg_to_array(cfg), f"{name}/lam": lam, f"{name}/off": off, f"{name}/ftrs": x, f"{name}/beam": np.array([beam]),
+                                f"{name}/lm_start": st if use_lm else np.zeros(0, np.float32), f"{name}/lm_bigram": bg if use_lm else np.zeros(0, np.float32),
+                                f"{name}/lm_final": fin if use_lm else np.zeros(0, np.float32), f"{name}/nseg": nseg, f"{name}/cost": cost,
+                                f"{name}/lab": np.concatenate([sg[0] for sg in segs] + [np.zeros(0, np.uint32)]), f"{name}/dur": np.concatenate([sg[1] for sg in segs] + [np.zeros(0, np.uint32)]),
+                                f"{name}/phn": np.concatenate([sg[2] for sg in segs] + [np.zeros(0, np.uint32)])})
+                    nb += 1
+    print("beam-pruned Viterbi cases:", nb)
     print("LM-constrained Viterbi cases:", n)
     np.savez_compressed(os.path.join(OUT, "viterbi_lm_golden.npz"), **out)
 

@@ -28,6 +28,8 @@ TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 JOINED = load_cases("joined_golden.npz")
 VIT_LM = load_cases("viterbi_lm_golden.npz")
+VIT_BEAM = {k: v for k, v in VIT_LM.items() if k.startswith("beam")}
+VIT_LM = {k: v for k, v in VIT_LM.items() if not k.startswith("beam")}
 
 
 def gpu(cfg):
@@ -1052,4 +1054,46 @@ def test_phone_lm_rejects_what_is_not_implemented():
     with pytest.raises(crf_b200.CrfGpuError) as e:
         m.set_phone_lm(np.zeros(5, np.float32), bg, np.zeros(5, np.float32))
     assert e.value.code == 2          # a missing arc
+    m.close()
+
+
+@pytest.mark.parametrize("name", sorted(VIT_BEAM))
+def test_viterbi_beam_bit_exact(name):
+    """crfgpu_set_beam: the decoder's beam pruning (pruning(), expansion threshold) with the free-phone LM and with a bigram LM against the
+    reference's nStateDecode with the same beam -- labels, durations, emitted phones, float cost; beam 0 afterwards is the unpruned result"""
+    c = VIT_BEAM[name]
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    if len(c["lm_start"]):
+        m.set_phone_lm(c["lm_start"], c["lm_bigram"], c["lm_final"])
+    full, full_cost = m.viterbi(c["off"], c["ftrs"])
+    m.set_beam(float(c["beam"][0]))
+    segs, cost = m.viterbi(c["off"], c["ftrs"])
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s_[0]) for s_ in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
+    assert np.all(cost >= full_cost)                     # pruning can only lose paths
+    m.set_beam(0.0)
+    again, again_cost = m.viterbi(c["off"], c["ftrs"])
+    assert np.array_equal(again_cost.view(np.uint32), full_cost.view(np.uint32))
+    m.close()
+
+
+def test_beam_matches_oracle_at_timit_size(oracle):
+    rng = np.random.default_rng(62)
+    P, D, F = 61, 10, 105
+    off, ftrs, _ = synth_batch(rng, 16, 30, 300, F, P, 2, 14)
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=1)
+    lam = rng.uniform(-0.05, 0.05, oracle.lambda_len(cfg))
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    for beam in (0.3, 1.0, 4.0):
+        wsegs, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs, beam=beam)
+        m.set_beam(beam)
+        segs, cost = m.viterbi(off, ftrs)
+        for a, b in zip(segs, wsegs):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
     m.close()

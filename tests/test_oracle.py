@@ -17,6 +17,8 @@ TRANSFTR = load_cases("train_transftr_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 JOINED = load_cases("joined_golden.npz")
 VIT_LM = load_cases("viterbi_lm_golden.npz")
+VIT_BEAM = {k: v for k, v in VIT_LM.items() if k.startswith("beam")}
+VIT_LM = {k: v for k, v in VIT_LM.items() if not k.startswith("beam")}
 
 
 @pytest.mark.parametrize("name", sorted(VIT_LM))
@@ -228,3 +230,16 @@ def test_viterbi_vs_reference_live(oracle, reflib, P, N, D, segf):
         for a, b in zip(s1, s2):
             assert all(np.array_equal(x, y) for x, y in zip(a, b))
         assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", sorted(VIT_BEAM))
+def test_viterbi_beam_golden_bit_exact(oracle, name):
+    """beam pruning (one state per phone, free-phone and bigram LM): the oracle against the reference's nStateDecode with input_beam > 0"""
+    c = VIT_BEAM[name]
+    lm = (c["lm_start"], c["lm_bigram"], c["lm_final"]) if len(c["lm_start"]) else None
+    segs, cost, _ = oracle.viterbi(c["cfg"], c["lam"], c["off"], c["ftrs"], lm=lm, beam=float(c["beam"][0]))
+    want = split_segs(c["lab"], c["dur"], c["phn"], c["nseg"])
+    assert [len(s_[0]) for s_ in segs] == [int(k) for k in c["nseg"]]
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), c["cost"].view(np.uint32))
