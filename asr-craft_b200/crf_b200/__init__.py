@@ -88,7 +88,7 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
            "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info",
            "crfgpu_fetch_posterior_mass", "crfgpu_stage_batch2", "crfgpu_fwdbwd_batch2", "crfgpu_viterbi_batch2",
-           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm", "crfgpu_set_beam"]
+           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm", "crfgpu_set_beam", "crfgpu_balance_utts_cost"]
 COMM_ID_BYTES = 128
 
 
@@ -185,6 +185,16 @@ def balance_utts(n_frames, n_ranks):
     n_frames = np.ascontiguousarray(n_frames, np.uint32)
     out = np.zeros(len(n_frames), np.uint32)
     _host_check(load_library().crfgpu_balance_utts(len(n_frames), _ptr(n_frames, C.c_uint32), n_ranks, _ptr(out, C.c_uint32)))
+    return out
+
+
+def balance_utts_cost(n_frames, n_ranks, n_slots, step_frames):
+    """crfgpu_balance_utts_cost: rank of every utterance of one global minibatch by the time model step_frames * lock-steps + frames"""
+    n_frames = np.ascontiguousarray(n_frames, np.uint32)
+    out = np.zeros(len(n_frames), np.uint32)
+    lib = load_library()
+    lib.crfgpu_balance_utts_cost.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_double, C.POINTER(C.c_uint32)]
+    _host_check(lib.crfgpu_balance_utts_cost(len(n_frames), _ptr(n_frames, C.c_uint32), n_ranks, n_slots, float(step_frames), _ptr(out, C.c_uint32)))
     return out
 
 

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
 #include <numeric>
 #include <stdexcept>
 
@@ -147,6 +148,33 @@ void balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, ui
 			if (best == n_ranks || load[r] < load[best]) best = r;
 		}
 		rank_of[u] = best; load[best] += n_frames[u]; cnt[best]++;
+	}
+}
+
+void balance_utts_cost(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t n_slots, double step_frames, uint32_t* rank_of) {
+	if (!n_ranks) return;
+	if (!n_slots) n_slots = 1;
+	std::vector<uint32_t> order(n_utt);
+	std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return n_frames[a] > n_frames[b]; });
+	// Every rank deals ITS utterances longest first to the least loaded of its n_slots slots (crfgpu_stage_batch), and the global order
+	// here is longest first too -- so the slot loads of a rank can be carried along exactly: a min-heap of slot loads per rank, the new
+	// utterance lands on the rank's least loaded slot, lock-steps = the largest slot load.
+	std::vector<std::vector<uint64_t>> heap(n_ranks, std::vector<uint64_t>(n_slots, 0));      // min-heaps (std::greater)
+	std::vector<uint64_t> load(n_ranks, 0), steps(n_ranks, 0);
+	for (uint32_t u : order) {
+		uint32_t best = 0; double bc = 0.0;
+		for (uint32_t r = 0; r < n_ranks; r++) {
+			const uint64_t st = std::max<uint64_t>(steps[r], heap[r].front() + n_frames[u]);
+			const double c = step_frames * (double)st + (double)(load[r] + n_frames[u]);
+			if (r == 0 || c < bc) { best = r; bc = c; }
+		}
+		std::vector<uint64_t>& h = heap[best];
+		std::pop_heap(h.begin(), h.end(), std::greater<uint64_t>());
+		h.back() += n_frames[u];
+		steps[best] = std::max(steps[best], h.back());
+		std::push_heap(h.begin(), h.end(), std::greater<uint64_t>());
+		rank_of[u] = best; load[best] += n_frames[u];
 	}
 }
 

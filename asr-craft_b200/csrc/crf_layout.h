@@ -49,5 +49,12 @@ uint32_t minibatch_share(uint32_t minibatch, uint32_t n_streams, uint32_t stream
 // balance_utts: utterances of ONE global minibatch dealt to n_ranks devices with equal counts (+-1), longest first onto the rank
 // with the fewest frames so far among those that still have room.
 void balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t* rank_of);
+// balance_utts_cost: the same deal by a TIME model instead of equal counts.  The lattice kernels are a dependent chain of lock-steps whose
+// number is the largest load of the rank's n_slots slots under its own longest-first dealing (carried along exactly), the rest of the step
+// streams the rank's frames; with
+// step_frames = cost of one lock-step in units of the per-frame cost, a rank costs step_frames * lock-steps + frames.  Utterances go,
+// longest first, to the rank that is cheapest afterwards: a rank that holds one of the corpus' longest utterances ends up with fewer
+// frames.  Membership of the global minibatch -- hence the gradient -- is unchanged; counts per rank differ.
+void balance_utts_cost(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t n_slots, double step_frames, uint32_t* rank_of);
 
 }  // namespace crfgpu

@@ -1835,6 +1835,13 @@ int crfgpu_balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ran
 	});
 }
 
+int crfgpu_balance_utts_cost(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t n_slots, double step_frames, uint32_t* rank_of) {
+	return guarded([&] {
+		if ((n_utt && (!n_frames || !rank_of)) || !n_ranks || !(step_frames >= 0.0)) throw ApiError(CRFGPU_ERR_ARG, "crfgpu_balance_utts_cost: bad argument");
+		balance_utts_cost(n_utt, n_frames, n_ranks, n_slots, step_frames, rank_of);
+	});
+}
+
 uint32_t crfgpu_plan_info(crfgpu_handle h, char* buf, uint32_t cap) {
 	if (!h || !buf || !cap) return 0;
 	std::string s = plan_text(h);

@@ -328,10 +328,46 @@ def run_ours(args):
 
     phase_names = ["score", "forward", "backward", "xi", "grad"]
 
+    placement = {}
+
     def cfg4_leg(upg, steps, warmup, headline):
         ids = my_utts(upg)
         off, ftrs, labs = workloads.timit_train_utts(ids)
         frames_local = int(off[-1])
+        if world > 1 and not args.contiguous and not args.count_balanced:
+            # Placement by a time model (crfgpu_balance_utts_cost).  The lattice kernels are a dependent chain whose length is the LONGEST
+            # utterance a rank holds (or its largest slot load), the rest of the step streams the rank's frames: a rank that holds one of
+            # the corpus' longest utterances should get fewer frames.  The model's one constant -- the cost of a lock-step in units of
+            # the per-frame cost -- is bracketed by this minibatch's own phase times (average cost per lock-step / per frame on the
+            # count-balanced placement = an upper bound of the marginal ratio) and the candidates are TIMED: the fastest placement of
+            # the global minibatch wins (membership, hence the gradient, is the same for all of them).
+            def trial(ids_t):
+                o, f, l = workloads.timit_train_utts(ids_t)
+                m.stage(o, f, l)
+                for _ in range(2):
+                    m.fwdbwd_staged(); allreduce_grad()
+                return timed_resident(m, 3, lambda: (m.fwdbwd_staged(), allreduce_grad())) / 3.0
+            t_count = trial(ids)
+            ph = {k: m.phase_ms(k) for k in phase_names}
+            plan = m.plan_info()
+            ls = int(plan.split("locksteps=")[1].split(";")[0])
+            slots = 16 * int(plan.split(" clusters x 16 slots")[0].split()[-1]) if " clusters x 16 slots" in plan else 240
+            upper = ((ph["forward"] + ph["backward"]) / max(ls, 1)) / ((ph["score"] + ph["xi"] + ph["grad"]) / max(frames_local, 1))
+            upper = reduce_sum(upper) / world
+            glob = np.arange(world * upg)
+            best = (t_count, None, ids)
+            tried = {"count_balanced": t_count}
+            for frac in (0.3, 0.5, 0.7, 1.0):
+                rank_of = crf_b200.balance_utts_cost(utt_len[glob].astype(np.uint32), world, slots, frac * upper)
+                ids_c = glob[rank_of == rank]
+                t_c = trial(ids_c)
+                tried[f"step_frames={frac * upper:.0f}"] = t_c
+                if t_c < best[0]:
+                    best = (t_c, frac * upper, ids_c)
+            ids = best[2]
+            off, ftrs, labs = workloads.timit_train_utts(ids)
+            frames_local = int(off[-1])
+            placement[upg] = {"chosen": "count_balanced" if best[1] is None else f"step_frames={best[1]:.0f}", "slots": slots, "trial_ms_per_step": tried}
         # ---- parity gate: the minibatch about to be timed, through the host-buffer call ----
         _, n, z = m.fwdbwd(off, ftrs, labs)
         gate.append(pins.check_loglik("cfg4", ids, n, z, f"cfg4 fwd-bwd, {upg} utterances/GPU, rank {rank}"))
@@ -352,7 +388,7 @@ def run_ours(args):
         plans = gather_list(m.plan_info())
         fr = gather_list(frames_local)
         res = {"utts_per_gpu": upg, "value": frames_total * steps / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-               "frames_per_gpu": fr, "locksteps_per_gpu": [int(p.split("locksteps=")[1].split(";")[0]) for p in plans],
+               "frames_per_gpu": fr, "utts_on_gpu": gather_list(len(ids)), "locksteps_per_gpu": [int(p.split("locksteps=")[1].split(";")[0]) for p in plans],
                "phases_ms": phases, "loglik": gate[-1]["loglik"], "loglik_pinned": gate[-1]["pinned"], "parity_ok": gate[-1]["ok"]}
         return res, (ids, off, ftrs, labs, frames_local, frames_total, launches, clocks, plans)
 
@@ -562,9 +598,12 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "cfg4", "model_type": "stdseg", "phones": 61, "max_dur": 10, "labels": 610, "base_ftrs": 105,
                        "seg_ftrs": 850, "lambda_len": m.lambda_len, "utts_per_gpu": upg, "global_minibatch": upg * world,
-                       "frames_per_gpu": head["frames_per_gpu"], "locksteps_per_gpu": head["locksteps_per_gpu"],
+                       "frames_per_gpu": head["frames_per_gpu"], "utts_on_gpu": head["utts_on_gpu"], "locksteps_per_gpu": head["locksteps_per_gpu"],
+                       "placement_model": placement.get(upg),
                        "sharding": ("contiguous corpus views" if (args.contiguous or world == 1) else
-                                    "global minibatch = union of the ranks' contiguous views, dealt to ranks length-balanced (crfgpu_balance_utts)")
+                                    "global minibatch = union of the ranks' contiguous views, dealt to ranks " +
+                                    ("with equal counts and balanced frame totals (crfgpu_balance_utts)" if args.count_balanced else
+                                     "by the time model step_frames x lock-steps + frames, its constant measured on this minibatch (crfgpu_balance_utts_cost)"))
                                    + "; one ncclAllReduce of lambda_len+4 doubles per step (crfgpu_allreduce_grad)",
                        "l2": "inputs_exceed_l2 (1.8 GB of window aggregates + 5 x 0.36 GB lattice arrays per step vs 126 MB L2)",
                        "plan": plans[0], "nccl_ranks": m.comm_size if world > 1 else 1},
@@ -594,6 +633,7 @@ def main():
     ap.add_argument("--utts-per-gpu", type=int, default=462)
     ap.add_argument("--sweep", default="64,148", help="further minibatch sizes (utterances per GPU) reported under minibatch_sweep")
     ap.add_argument("--contiguous", action="store_true", help="keep the reference's contiguous placement instead of the length-balanced one")
+    ap.add_argument("--count-balanced", action="store_true", help="N > 1: equal utterance counts per rank with balanced frame totals (crfgpu_balance_utts) instead of the time-model placement (crfgpu_balance_utts_cost)")
     ap.add_argument("--no-viterbi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")

@@ -269,6 +269,13 @@ int crfgpu_fetch_tail(crfgpu_handle h, double* tail4);
 int crfgpu_shard_views(uint32_t n_utt, uint32_t n_streams, uint32_t* first, uint32_t* count);
 uint32_t crfgpu_minibatch_share(uint32_t minibatch, uint32_t n_streams, uint32_t stream);
 int crfgpu_balance_utts(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t* rank_of);
+/* The same deal by a time model instead of equal counts: cost of a rank = step_frames * lock-steps + frames, lock-steps = the largest
+ * load of the rank's n_slots slots when it deals its utterances longest first to the least loaded slot, as crfgpu_stage_batch does (the
+ * model carries those loads along exactly) -- the lattice kernels are a dependent chain of lock-steps (n_slots = utterances a device
+ * advances side by side: resident clusters x 16, see crfgpu_plan_info), everything else streams the frames;
+ * step_frames = measured time of one lock-step / measured time per frame of the rest of the step.  A rank holding one of the corpus'
+ * longest utterances gets fewer frames.  Membership of the global minibatch is unchanged. */
+int crfgpu_balance_utts_cost(uint32_t n_utt, const uint32_t* n_frames, uint32_t n_ranks, uint32_t n_slots, double step_frames, uint32_t* rank_of);
 
 /* Which kernels the handle runs for the staged batch, as one line of text: lattice implementation and its plan (clusters, slots,
  * lock-steps = frames of the longest slot list), GEMM family, Viterbi variant -- so that no geometry changes implementation

@@ -85,3 +85,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "crf_oracle" not in text and "libcrforacle" not in text and "libcrfref" not in text, os.path.join(dp, f)
+
+
+def test_balance_rules_of_one_global_minibatch():
+    """crfgpu_balance_utts (equal counts, balanced frames) and crfgpu_balance_utts_cost (time model: step_frames x lock-steps + frames):
+    both keep the membership of the minibatch; the time model gives the rank that holds the longest utterance the fewest frames and never
+    a worse modelled step than the count-balanced deal."""
+    import workloads
+    utt_len, _, _ = workloads.timit_shape()
+    for world in (2, 4, 8):
+        lens = utt_len[:world * 462].astype(np.uint32)
+        by_count = crf_b200.balance_utts(lens, world)
+        by_cost = crf_b200.balance_utts_cost(lens, world, 240, 440.0)
+        for ro in (by_count, by_cost):
+            assert ro.min() == 0 and ro.max() == world - 1 and len(ro) == len(lens)
+        assert all((by_count == r).sum() == 462 for r in range(world))
+
+        def model(ro):
+            return max(440.0 * max(int(lens[ro == r].max()), -(-int(lens[ro == r].sum()) // 240)) + int(lens[ro == r].sum()) for r in range(world))
+        assert model(by_cost) <= model(by_count)
+        frames = [int(lens[by_cost == r].sum()) for r in range(world)]
+        longest_rank = int(by_cost[np.argmax(lens)])
+        assert frames[longest_rank] == min(frames)
+    # degenerate inputs
+    assert list(crf_b200.balance_utts_cost(np.array([5, 9, 2], np.uint32), 1, 16, 100.0)) == [0, 0, 0]
+    assert len(crf_b200.balance_utts_cost(np.zeros(0, np.uint32), 3, 16, 100.0)) == 0
