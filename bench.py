@@ -531,10 +531,26 @@ def run_ours(args):
             sm.fwdbwd_staged(); sm.synchronize()
             ph = {k: sm.phase_ms(k) for k in phase_names}
             best = ph if best is None or sum(ph.values()) < sum(best.values()) else best
+        # parity of the stress leg: the pinned utterances (the first few of the batch; the whole batch is hours of CPU) against the oracle
+        _, sn, sz = sm.fetch_fwdbwd()
+        npin = len(pins.z["cfg5/logZ"]) if "cfg5/logZ" in pins.z else 0
+        if npin:
+            gate.append(pins.check_loglik("cfg5", range(npin), sn[:npin], sz[:npin], f"cfg5 fwd-bwd, pinned utterances 0..{npin - 1} of 64"))
+            if gate[-1]["ok"] is False:
+                fail_parity(gate)
         sm.stage(soff, sftrs)
         for _ in range(2):
             sm.viterbi_staged(); sm.synchronize()
         vs_, vr_ = sm.phase_ms("viterbi_score"), sm.phase_ms("viterbi")
+        if npin and "cfg5/crc" in pins.z:
+            ssegs, scost = sm.fetch_viterbi(soff)
+            crc = np.array([path_crc(*sg) for sg in ssegs[:npin]], np.uint32)
+            rec = {"what": f"cfg5 Viterbi, pinned utterances 0..{npin - 1} of 64", "paths_equal": int(np.sum(crc == pins.z["cfg5/crc"])), "n": npin,
+                   "costs_bit_equal": bool(np.array_equal(scost[:npin].view(np.uint32), pins.z["cfg5/cost"].view(np.uint32)))}
+            rec["ok"] = bool(rec["paths_equal"] == npin and rec["costs_bit_equal"])
+            gate.append(rec)
+            if not rec["ok"]:
+                fail_parity(gate)
         sN = float(soff[-1])
         stress = {"workload": "cfg5 (stdseg_no_dur_no_segtransftr, 1024 phones, maxDur 30, 542 segment features, 64 utterances x 2000 frames)",
                   "train_frames_per_s": sN / (sum(best.values()) / 1e3), "train_phases_ms": best,

@@ -11,6 +11,9 @@ records which.  Output tests/golden/bench_pins.npz:
   cfg3/cost, cfg3/crc     per utterance of workloads.cfg3_batch(1680): float path cost and CRC-32 of the (label, duration, phone)
                           segment arrays of the best path (3-state Viterbi, lam_for("cfg3"))
 
+  cfg5/numer, cfg5/logZ,  the stress leg (1024 phones, maxDur 30, 2000-frame utterances): the first CFG5_PINNED utterances of
+  cfg5/cost, cfg5/crc     workloads.cfg5_batch() -- training numerator / logZ and the Viterbi path CRC / cost (the whole batch is hours of CPU)
+
 Utterances are independent given lambda, so the work is cut into chunks that run in forked worker processes.
 
     python tests/golden/make_bench_pins.py [n_procs] [cfg4|cfg2|cfg3 ...]      (cfg4: ~45 min on 6 cores, cfg2 / cfg3: minutes)
@@ -67,6 +70,21 @@ def vit_chunk(args):
     return first, cost, np.array([path_crc(*s) for s in segs], np.uint32)
 
 
+CFG5_PINNED = 4
+
+
+def cfg5_chunk(u):
+    lib, _ = lib_and_kind()
+    cfg = make_config(**workloads.cfg5_kwargs())
+    lam = workloads.lam_for("cfg5", lib.lambda_len(cfg))
+    off, ftrs, labs = workloads.cfg5_batch()
+    a, b = int(off[u]), int(off[u + 1])
+    sub = np.array([0, b - a], np.uint32)
+    _, numer, logz = lib.fwdbwd(cfg, lam, sub, ftrs[a:b], labs[a:b], n_threads=1)
+    segs, cost, _ = lib.viterbi(cfg, lam, sub, ftrs[a:b])
+    return u, numer[0], logz[0], cost[0], path_crc(*segs[0])
+
+
 def main():
     procs = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     what = sys.argv[2:] or ["cfg2", "cfg3", "cfg4"]
@@ -95,6 +113,12 @@ def main():
                 for first, c, h in pool.imap_unordered(vit_chunk, jobs):
                     cost[first:first + len(c)] = c; crc[first:first + len(h)] = h
                 out["cfg3/cost"], out["cfg3/crc"] = cost, crc
+            elif name == "cfg5":
+                numer, logz = np.zeros(CFG5_PINNED), np.zeros(CFG5_PINNED)
+                cost, crc = np.zeros(CFG5_PINNED, np.float32), np.zeros(CFG5_PINNED, np.uint32)
+                for u, n, z, c, h in pool.imap_unordered(cfg5_chunk, range(CFG5_PINNED)):
+                    numer[u], logz[u], cost[u], crc[u] = n, z, c, h
+                out["cfg5/numer"], out["cfg5/logZ"], out["cfg5/cost"], out["cfg5/crc"] = numer, logz, cost, crc
             out[name + "/producer"] = np.array(kind)
             np.savez_compressed(OUT, **out)
             print(f"{name}: done in {time.time() - t0:.0f} s ({kind})", flush=True)
