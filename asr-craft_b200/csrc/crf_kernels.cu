@@ -929,8 +929,11 @@ void launch_vit_scores(const VitScoreParams& p, cudaStream_t s) {
 	if (!n_rows || !p.L) return;
 	const size_t smem = sizeof(double) * VS_ROWS * (size_t)(p.nSf ? p.nSf : 1);
 	cudaFuncSetAttribute(vit_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	dim3 grid((unsigned)((n_rows + VS_ROWS - 1) / VS_ROWS), (p.L + 255) / 256);
-	vit_scores_kernel<<<grid, 256, smem, s>>>(p);
+	// thread = label: label sets below 256 get a CTA of their own size (cfg3: 183 labels -> 192 threads instead of 256 with 73 idle ones,
+	// so more windows are resident per SM to hide the fp64 pipe's latency)
+	const unsigned threads = p.L >= 256 ? 256u : (p.L + 31) / 32 * 32;
+	dim3 grid((unsigned)((n_rows + VS_ROWS - 1) / VS_ROWS), (p.L + threads - 1) / threads);
+	vit_scores_kernel<<<grid, threads, smem, s>>>(p);
 }
 
 // =================================================================================================
