@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 			const uint32_t y = p.labs[n];
 			if (y < L) {
 				num += (double)p.S[n * p.Lp + y];
-				if (t > 0) { const uint32_t yp = p.labs[n - 1]; if (yp < L) num += (double)Mt[yp * Ls + y]; }
+				if (t > 0) { const uint32_t yp = p.labs[n - 1]; if (yp < L && p.tidx[yp * L + y] != 0xffffffffu) num += (double)Mt[yp * Ls + y]; }
 			}
 		}
 		__syncthreads();
@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 			part += av[q] * e;
 		}
 		const float xsum = block_sum(part, scratch);                            // sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc]
-		const uint32_t yp = p.labs[n - 1];
+		uint32_t yp = p.labs[n - 1];
+		if (yp < L && y < L && p.tidx[yp * L + y] == 0xffffffffu) yp = LAB_BAD;      // a reference pair the N-state map does not have
 		const float inv = 1.0f / xsum;
 		for (uint32_t i = c; i < L * L; i += TF_THR) {
 			const uint32_t q = i / L, cc = i - q * L;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 				const float l = mmax + __logf(v);
 				lgh[(t & (ND_RING - 1)) * P + y] = l; p.LG[n * p.Pp + y] = l;
 			}
-			if (y == 0 && lab != LAB_BAD) { const uint32_t nl = p.next_lab[n]; if (nl != LAB_BAD) num += (double)Mn[(lab % P) * Ps + nl]; }
+			if (y == 0 && lab != LAB_BAD) { const uint32_t nl = p.next_lab[n]; if (nl != LAB_BAD && p.tidx[(lab % P) * P + nl] != 0xffffffffu) num += (double)Mn[(lab % P) * Ps + nl]; }
 			__syncthreads();
 		}
 	}
@@ -309,7 +310,9 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			}
 			__syncthreads();
 			const float xscale = __expf((float)(p.rho[n] + (double)mmax + kref + (double)wmax - lz));
-			const uint32_t nl = lab != LAB_BAD ? p.next_lab[n] : LAB_BAD, lq = lab != LAB_BAD ? lab % P : LAB_BAD;
+			uint32_t nl = lab != LAB_BAD ? p.next_lab[n] : LAB_BAD;
+			const uint32_t lq = lab != LAB_BAD ? lab % P : LAB_BAD;
+			if (nl != LAB_BAD && p.tidx[lq * P + nl] == 0xffffffffu) nl = LAB_BAD;       // a reference pair the N-state map does not have
 			float* xrow = p.Xd + (n + 1) * p.Lq;         // stored with the frame whose duration-1 window carries the transition features
 			for (uint32_t i = y; i < P * P; i += TF_THR) {
 				const uint32_t q = i / P, yy = i - q * P;

@@ -159,6 +159,19 @@ __global__ void __launch_bounds__(128) expand_windows_kernel(ExpandParams p) {
 // (cfg4: 12.8 instead of 34 kB per frame).  The one-hot duration block (:790-812) is 1 exactly at the window's own duration: it enters the
 // scores through a per-(duration, label) bias and the gradient through the constant-1 row that also counts the bias.
 // =================================================================================================
+// per-frame index tables of a ragged batch from its utterance offsets: frame_t = position inside the utterance, frame_utt = utterance,
+// frame_len = its length (the host used to build and upload 12 bytes per frame before the first feature byte could leave)
+__global__ void __launch_bounds__(256) frame_tables_kernel(const uint32_t* __restrict__ off, uint32_t n_utt, uint32_t N, uint32_t* ft, uint32_t* fu, uint32_t* fl) {
+	const uint32_t n = blockIdx.x * 256 + threadIdx.x;
+	if (n >= N) return;
+	uint32_t lo = 0, hi = n_utt;             // the utterance u with off[u] <= n < off[u+1]
+	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(off + mid) <= n) lo = mid; else hi = mid; }
+	const uint32_t o = __ldg(off + lo);
+	if (ft) ft[n] = n - o;
+	if (fu) fu[n] = lo;
+	if (fl) fl[n] = __ldg(off + lo + 1) - o;
+}
+
 __global__ void __launch_bounds__(256) pad_base_kernel(const float* base, float* base2, uint32_t n0, uint32_t n1, uint32_t F, uint32_t Fp) {
 	const uint64_t tot = (uint64_t)(n1 - n0) * Fp;
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < tot; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -813,7 +826,7 @@ __global__ void __launch_bounds__(256) reduce_gemm_kernel(ReduceGemmParams p) {
 			if (v == 0.0) continue;
 			if (p.mode == 0) {
 				const double sc = (gj == p.ones_col) ? p.ones_scale : p.scale;
-				atomicAdd(&p.out[(uint64_t)p.row_idx[gi] + gj], sc * v);
+				if (p.row_idx[gi] != 0xffffffffu) atomicAdd(&p.out[(uint64_t)p.row_idx[gi] + gj], sc * v);
 			} else {
 				const uint32_t idx = p.pair_idx[(uint64_t)gi * p.pair_ld + gj];
 				if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)p.Ew[(uint64_t)gi * p.e_ld + gj] * v);
@@ -1273,6 +1286,11 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 	}
 	if (threadIdx.x == 0) p.n_seg[u] = nseg;
 }
+void launch_frame_tables(const uint32_t* off, uint32_t n_utt, uint32_t N, uint32_t* ft, uint32_t* fu, uint32_t* fl, cudaStream_t s) {
+	if (!N) return;
+	frame_tables_kernel<<<(N + 255) / 256, 256, 0, s>>>(off, n_utt, N, ft, fu, fl);
+}
+
 void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	if (!p.n_utt) return;
 	VitParams q = p;

@@ -303,6 +303,8 @@ struct VitParams {
 	uint32_t* out_lab; uint32_t* out_dur; uint32_t* out_phn; uint32_t* n_seg; float* cost;
 };
 void launch_viterbi(const VitParams& p, cudaStream_t s);
+// frame_t / frame_utt / frame_len (any may be null) of a ragged batch from its device-resident utterance offsets [n_utt + 1]
+void launch_frame_tables(const uint32_t* off, uint32_t n_utt, uint32_t N, uint32_t* ft, uint32_t* fu, uint32_t* fl, cudaStream_t s);
 
 // ---- Viterbi for large phone sets, one state per phone: cross-phone table sliced over a group of CTAs (crf_viterbi_group.cu) ----
 constexpr int VITG_UT = 16;           // utterances that advance in lock-step per group
@@ -335,6 +337,7 @@ struct TransFtrParams {
 	double* logZ; double* numer;          // [n_utt]
 	float* Dm; float* Xd;                 // backward: [ref] - gamma [N][Lp], [ref pair] - xi [N][Lq] (zero on the first frame of an utterance)
 	const uint32_t* labs;                 // [N] reference label per frame
+	const uint32_t* tidx;                 // [L][L] lambda index of the pair, 0xffffffff on the illegal pairs of an N-state map (their M is -inf)
 };
 // segmental model without duration labels + transition features (stdseg_no_dur_no_segtransftr with stdtrans)
 struct NodurTfParams {
@@ -345,6 +348,7 @@ struct NodurTfParams {
 	double* logZ; double* numer;
 	float* Dm; float* Xd;                         // backward: [ref] - gamma [N][Lp], [ref pair] - xi stored at the frame the new segment starts in
 	const uint32_t* node_lab; const uint32_t* next_lab;   // (dur-1)*P + phone where a reference segment ends; phone of the NEXT reference segment there
+	const uint32_t* tidx;                         // [P][P] lambda index of the pair, 0xffffffff on the illegal pairs of an N-state map (their M is -inf)
 };
 size_t nodur_tf_smem_bytes(uint32_t P);
 cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s);

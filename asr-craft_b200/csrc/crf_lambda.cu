@@ -99,10 +99,12 @@ __global__ void __launch_bounds__(256) lambda_tables_kernel(LambdaTablesParams p
 		const uint64_t L = p.L0, nw = L * L * p.nTf;
 		for (uint64_t i = tid0; i < nw; i += stride) {
 			const uint64_t pair = i / p.nTf; const uint32_t f = (uint32_t)(i % p.nTf);
-			p.Wtr[i] = (float)p.lam[p.tidx0[pair] + f];
+			const uint32_t b = p.tidx0[pair];
+			p.Wtr[i] = b != 0xffffffffu ? (float)p.lam[b + f] : 0.0f;
 		}
 		for (uint64_t pair = tid0; pair < L * L; pair += stride)
-			p.tbias[pair] = p.use_trans_bias ? (float)__dmul_rn(p.lam[p.tidx0[pair] + p.nTf], p.trans_bias_val) : 0.0f;
+			// illegal pairs of an N-state map: score -inf, so that exp(M - max) is an exact 0 in the recursions
+			p.tbias[pair] = p.tidx0[pair] == 0xffffffffu ? -INFINITY : (p.use_trans_bias ? (float)__dmul_rn(p.lam[p.tidx0[pair] + p.nTf], p.trans_bias_val) : 0.0f);
 	}
 	if (p.WdT) {
 		const uint64_t nw = (uint64_t)(p.nTf + 1) * p.vtE;

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(160, 2) reduce_gemm_tc_kernel(ReduceGemmParams
 					const uint32_t gi = SWAP ? gn : gm, gj = SWAP ? gm : gn;
 					if (p.mode == 0) {
 						const double sc = (gj == p.ones_col) ? p.ones_scale : p.scale;
-						atomicAdd(&p.out[(uint64_t)__ldg(p.row_idx + gi) + gj], sc * (double)v[j]);
+						const uint32_t ri = __ldg(p.row_idx + gi);
+						if (ri != 0xffffffffu) atomicAdd(&p.out[(uint64_t)ri + gj], sc * (double)v[j]);
 					} else {
 						const uint32_t idx = __ldg(p.pair_idx + (uint64_t)gi * p.pair_ld + gj);
 						if (idx != 0xffffffffu) atomicAdd(&p.out[idx], p.scale * (double)__ldg(p.Ew + (uint64_t)gi * p.e_ld + gj) * (double)v[j]);

@@ -119,9 +119,11 @@ struct crfgpu_ctx {
 	bool fwdbwd_done = false;
 	// viterbi
 	DevBuf d_negS, d_candW, d_candP, d_bp, d_bd, d_gmove, d_olab, d_odur, d_ophn, d_nseg, d_cost;
+	int opt_vit_eager = 1;   // decode batches: the recursion of each H2D chunk's utterances launched by crfgpu_stage_batch (0: by viterbi_staged, all at once)
 	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	int opt_frame_impl = 0; bool frame_path = false;
 	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit; double beam = 0.0;   // crfgpu_set_beam   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
+	bool vit_rec_ready = false; DevBuf d_vorder, d_off2;   // ... and the recursion of each chunk's utterances behind its scores (d_vorder: the chunks' utterances, longest first)
 	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
 
@@ -176,13 +178,15 @@ void classify(crfgpu_ctx* h) {
 		if (c.model_type != CRFGPU_STDFRAME && c.model_type != CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) {
 			h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
 		} else if (c.n_labs > 1024 || c.max_dur > 255) { h->decode_ok = false; h->decode_why = "Viterbi kernel supports crf_label_size <= 1024 and max duration <= 255"; }
-		if (c.model_type == CRFGPU_STDFRAME && c.max_dur == 1 && c.n_states == 1 && c.n_labs <= 128 && c.use_state_ftrs) { h->transftr = true; return; }
+		// (N states per label: the illegal pairs of the N-state map score -inf, CRF_StdNStateNode.cpp:65-108)
+		if ((c.model_type == CRFGPU_STDFRAME || c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) && c.max_dur == 1 && c.n_labs <= 128 && c.use_state_ftrs) { h->transftr = true; return; }
 		// ... and for the segmental production recipe: no duration labels, transition features from the duration-1 window
-		if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.n_states == 1 && c.max_dur > 1 && c.max_dur <= 31 && c.n_labs <= 128 && c.use_state_ftrs) {
+		// (N states per phone: CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr.cpp:38-80, every sub-state a segment of its own)
+		if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.max_dur > 1 && c.max_dur <= 31 && c.n_labs <= 128 && c.use_state_ftrs) {
 			h->nodur = h->nodur_tf = true; return;
 		}
 		h->train_ok = false;
-		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for one state per label and at most 128 labels, "
+		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for at most 128 labels (phones x states), "
 		               "in frame-level models and in stdseg_no_dur_no_segtransftr (max_dur <= 31); other model types run with transition bias only";
 		return;
 	}
@@ -290,7 +294,7 @@ void require_decode(crfgpu_ctx* h) {
 // with M[p][c] = lambda[tidx]*transBiasVal (CRF_StdFeatureMap.cpp:94-110 with no transition features), the weight tiles of the TMA-fed
 // score GEMM and the decoder's tables.  Only the scalar Mmax comes back to the host.
 void derive_tables(crfgpu_ctx* h) {
-	h->vit_score_ready = false;              // scores launched ahead by crfgpu_stage_batch belong to the previous lambda
+	h->vit_score_ready = h->vit_rec_ready = false;              // scores / paths launched ahead by crfgpu_stage_batch belong to the previous lambda
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t L = m.L, Lt = h->Lt, Lp = h->Lp, nSf = m.nSf;
 	cudaStream_t s = h->stream;
@@ -455,21 +459,24 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 		CUDA_OK(cudaEventCreate(&h->ev_pre_done)); CUDA_OK(cudaEventCreate(&h->ev_pre_ready));
 	}
 	if (h->swap_marked) CUDA_OK(cudaStreamWaitEvent(h->pre_stream, h->ev_swap, 0));
-	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
-	for (uint32_t u = 0; u < n_utt; u++)
-		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
 	h->d_base2.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
 	h->pre_virt = h->virt;                                               // the read-ahead of a training loop: the form the training GEMMs read
 	if (h->pre_virt) { h->d_bpad2.ensure(sizeof(float) * (size_t)N * h->Fp + 16); h->d_Xa2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wa + 16); }
 	else if (c.max_dur > 1) h->d_X2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
-	upload(h->d_frame_t2, frame_t, h->pre_stream);                       // pageable: waits only for this side stream's own earlier work
+	// per-frame index tables: built on the device from the utterance offsets (launch_frame_tables)
+	h->pre_off.assign(off, off + n_utt + 1);
+	upload(h->d_off2, h->pre_off, h->pre_stream);                        // pageable: waits only for this side stream's own earlier work
+	h->d_frame_t2.ensure(sizeof(uint32_t) * (size_t)N + 16);
+	if (labs) { h->d_frame_utt2.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_frame_len2.ensure(sizeof(uint32_t) * (size_t)N + 16); }
+	launch_frame_tables(h->d_off2.as<uint32_t>(), n_utt, N, h->d_frame_t2.as<uint32_t>(), labs ? h->d_frame_utt2.as<uint32_t>() : nullptr,
+	                    labs ? h->d_frame_len2.as<uint32_t>() : nullptr, h->pre_stream);
+	check_kernel(h, 1);
 	h->pre_tabs = false; h->pre_labs = labs;
 	if (labs) {
 		// the label-derived tables of the next minibatch, built while this one computes (about 1 ms of host work per cfg4 minibatch
 		// that crfgpu_stage_batch would otherwise do with the device idle)
 		std::vector<uint32_t> node_lab, prev_lab, next_lab;
 		build_label_tables(h, n_utt, off, labs, node_lab, prev_lab, next_lab);
-		upload(h->d_frame_utt2, frame_utt, h->pre_stream); upload(h->d_frame_len2, frame_len, h->pre_stream);
 		upload(h->d_node_lab2, node_lab, h->pre_stream); upload(h->d_prev_lab2, prev_lab, h->pre_stream);
 		if (!next_lab.empty()) upload(h->d_next_lab2, next_lab, h->pre_stream);
 		h->pre_tabs = true;
@@ -482,7 +489,44 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 	copy_and_expand(h, n_utt, off, N, ftrs, h->d_base2, h->d_X2, h->d_frame_t2, h->pre_stream, h->ev_pre_ready, h->ev_chunk2, nullptr, dpart, nullptr,
 	                h->pre_virt, &h->d_bpad2, &h->d_Xa2);
 	CUDA_OK(cudaEventRecord(h->ev_pre_done, h->pre_stream));
-	h->pre_off.assign(off, off + n_utt + 1); h->pre_ftrs = ftrs; h->pre_valid = true;
+	h->pre_ftrs = ftrs; h->pre_valid = true;
+}
+
+// ---- decoder plumbing shared by crfgpu_stage_batch (recursion launched chunk by chunk behind the H2D copies) and viterbi_staged ----
+void ensure_decode_buffers(crfgpu_ctx* h) {
+	const uint32_t N = h->N, L = h->lay.L, D = h->cfg.max_dur;
+	h->d_negS.ensure(sizeof(float) * (size_t)N * D * L + 16);
+	h->d_candW.ensure(sizeof(float) * (size_t)h->n_utt * D * L + 16); h->d_candP.ensure(sizeof(int32_t) * (size_t)h->n_utt * D * L + 16);
+	h->d_bp.ensure(sizeof(uint16_t) * (size_t)N * L + 16); h->d_bd.ensure((size_t)N * L + 16); h->d_gmove.ensure((size_t)N + 16);
+	h->d_olab.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_odur.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_ophn.ensure(sizeof(uint32_t) * (size_t)N + 16);
+	h->d_nseg.ensure(sizeof(uint32_t) * (size_t)h->n_utt + 16); h->d_cost.ensure(sizeof(float) * (size_t)h->n_utt + 16);
+}
+// large phone sets with one state per phone and constant transition tables: the cross-phone table sliced over groups of CTAs,
+// 16 utterances in lock-step per group (crf_viterbi_group.cu); opt_vit_impl 1 forces one CTA per utterance, 2 forces the groups
+bool vit_wants_groups(const crfgpu_ctx* h) {
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	const uint32_t L = m.L, NS = m.n_states, P = m.n_act;
+	const bool vg_fit = NS == 1 && !c.use_trans_ftrs && P >= 2 && L == P && !h->have_lm && !(h->beam > 0.0);      // (LM weights / beam: the per-utterance kernel)
+	const bool vg_auto = vg_fit && (size_t)P * P * sizeof(float) > 96 * 1024;
+	return vg_fit && (h->opt_vit_impl == 2 || (h->opt_vit_impl == 0 && vg_auto));
+}
+// the per-utterance kernel's parameters; order / n_utt are left to the caller (all utterances, or the utterances of one H2D chunk)
+VitParams vit_params(crfgpu_ctx* h) {
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	VitParams v{};
+	v.L = m.L; v.P = m.n_act; v.NS = m.n_states; v.D = c.max_dur; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
+	v.crossT = h->d_crossT.as<float>(); v.negDiag = h->d_negDiag.as<float>(); v.negOff = h->d_negOff.as<float>();
+	v.negMt = c.use_trans_ftrs ? h->d_negMt.as<float>() : nullptr; v.E = h->vtE;
+	v.beam = h->beam;
+	if (h->have_lm) {
+		v.lm_start = h->d_lm_start.as<float>(); v.lm_final = h->d_lm_final.as<float>();
+		if (m.n_states == 1) v.lm_bigT = h->d_lm_bigT.as<float>(); else v.lm_exit = h->d_lm_exit.as<float>();
+	}
+	v.candW = h->d_candW.as<float>(); v.candP = h->d_candP.as<int32_t>(); v.keptW = nullptr;
+	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
+	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
+	v.n_seg = h->d_nseg.as<uint32_t>(); v.cost = h->d_cost.as<float>();
+	return v;
 }
 
 void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs, const float* ftrs2 = nullptr) {
@@ -492,7 +536,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	const uint32_t N = n_utt ? off[n_utt] : 0;
 	cudaStream_t s = h->stream;
 	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
-	h->fwdbwd_done = h->viterbi_done = false; h->vit_score_ready = false;
+	h->fwdbwd_done = h->viterbi_done = false; h->vit_score_ready = h->vit_rec_ready = false;
 	h->h_off.assign(off, off + n_utt + 1);
 	{
 		const size_t want = ((size_t)N * 6 + (size_t)n_utt * 24 + 65536) * sizeof(uint32_t);
@@ -508,9 +552,16 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	}
 
 	upload_async(h, h->d_off, h->h_off);
-	std::vector<uint32_t> frame_t(N), frame_utt(N), frame_len(N);
-	for (uint32_t u = 0; u < n_utt; u++)
-		for (uint32_t n = off[u]; n < off[u + 1]; n++) { frame_t[n] = n - off[u]; frame_utt[n] = u; frame_len[n] = off[u + 1] - off[u]; }
+	// per-frame index tables (position in the utterance, utterance, its length): one small kernel over the offsets instead of 12 bytes
+	// per frame of host loops and uploads ahead of the first feature byte
+	auto frame_tables = [&](bool with_t) {
+		if (!N) return;
+		if (with_t) h->d_frame_t.ensure(sizeof(uint32_t) * (size_t)N + 16);
+		h->d_frame_utt.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_frame_len.ensure(sizeof(uint32_t) * (size_t)N + 16);
+		launch_frame_tables(h->d_off.as<uint32_t>(), n_utt, N, with_t ? h->d_frame_t.as<uint32_t>() : nullptr, h->d_frame_utt.as<uint32_t>(),
+		                    h->d_frame_len.as<uint32_t>(), s);
+		check_kernel(h, 1);
+	};
 	const bool want_virt = h->virt && labs != nullptr;                   // training batches of eligible models stage the virtual-window form
 	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off && h->pre_virt == want_virt;
 	const bool tabs_ready = prefetched && !h->joined && h->pre_tabs && labs != nullptr && h->pre_labs == labs;   // index / label tables already on the device
@@ -518,7 +569,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	h->x_virt_valid = want_virt; h->x_full_valid = !want_virt;
 	if (h->joined) {
 		// general window streams: both streams go to the device whole, one gather kernel builds the joined windows
-		upload_async(h, h->d_frame_t, frame_t); upload_async(h, h->d_frame_utt, frame_utt);
+		frame_tables(true);
 		const size_t n1 = (size_t)N + (size_t)n_utt * (c.left_ctx + c.right_ctx), n2 = (size_t)N + (size_t)n_utt * (c.left_ctx2 + c.right_ctx2);
 		h->d_base.ensure(sizeof(float) * n1 * c.n_base_ftrs + 16);
 		if (N) CUDA_OK(cudaMemcpyAsync(h->d_base.p, ftrs, sizeof(float) * n1 * c.n_base_ftrs, cudaMemcpyHostToDevice, s));
@@ -554,15 +605,17 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			std::swap(h->d_node_lab, h->d_node_lab2); std::swap(h->d_prev_lab, h->d_prev_lab2); std::swap(h->d_next_lab, h->d_next_lab2);
 		}
 		CUDA_OK(cudaStreamWaitEvent(s, h->ev_pre_done, 0));
+		if (!tabs_ready) frame_tables(false);
 	} else {
 		// what the window expansion needs goes through the copy engine ahead of the feature chunks
-		upload_async(h, h->d_frame_t, frame_t);
+		frame_tables(true);
 		h->d_base.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
 		if (want_virt && N) { h->d_bpad.ensure(sizeof(float) * (size_t)N * h->Fp + 16); h->d_Xa.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wa + 16); }
 		else if (c.max_dur > 1 && N) h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
 		if (N && !h->ev_ready) CUDA_OK(cudaEventCreate(&h->ev_ready));
 		// a decode batch (no labels): the decoder's fp64 state scores of a chunk are launched as soon as the chunk has arrived, so the
 		// scoring runs under the remaining H2D copies instead of behind them
+		bool eager_rec = false; uint32_t u_next = 0;
 		std::function<void(uint32_t, uint32_t)> score_chunk = [&](uint32_t n0, uint32_t n1) {
 			const Layout& m = h->lay;
 			VitScoreParams vs{};
@@ -570,15 +623,33 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			vs.frame_t = h->d_frame_t.as<uint32_t>() + n0; vs.Wd = h->d_Wd.as<double>(); vs.use_bias = c.use_state_bias; vs.bias_val = c.state_bias_val;
 			vs.negS = h->d_negS.as<float>() + (size_t)n0 * c.max_dur * m.L;
 			launch_vit_scores(vs, s); check_kernel(h, 1);
+			if (!eager_rec) return;
+			// ... and the recursion over the utterances of this chunk (chunks end at utterance boundaries), longest first
+			uint32_t u1 = u_next;
+			while (u1 < n_utt && off[u1] < n1) u1++;
+			const uint32_t cnt = u1 - u_next;
+			const size_t bytes = sizeof(uint32_t) * cnt, at = (h->pin_used + 255) & ~(size_t)255;
+			if (at + bytes > h->pin_cap) throw ApiError(CRFGPU_ERR_CUDA, "internal: the page-locked table arena is too small for the decode order");
+			uint32_t* ord = reinterpret_cast<uint32_t*>(h->pin + at);
+			std::iota(ord, ord + cnt, u_next);
+			std::stable_sort(ord, ord + cnt, [&](uint32_t a, uint32_t b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
+			h->pin_used = at + bytes;
+			CUDA_OK(cudaMemcpyAsync(h->d_vorder.as<uint32_t>() + u_next, ord, bytes, cudaMemcpyHostToDevice, s));
+			VitParams v = vit_params(h);
+			v.order = h->d_vorder.as<uint32_t>() + u_next; v.n_utt = cnt;
+			launch_viterbi(v, s); check_kernel(h, 1);
+			u_next = u1;
 		};
 		const bool eager_vit = !labs && N && h->decode_ok && h->have_lambda && h->lay.nSf > 0;
+		// the per-utterance recursion needs nothing but the state scores and the constant tables: it follows chunk by chunk as well
+		// (not with per-frame transition tables, the group-sliced kernel, or a geometry viterbi_staged refuses)
+		eager_rec = eager_vit && !c.use_trans_ftrs && !vit_wants_groups(h) && !(h->beam > 0.0 && h->lay.n_states != 1) && !getenv("CRFGPU_DP_TIMING") && h->opt_vit_eager;
 		if (eager_vit) h->d_negS.ensure(sizeof(float) * (size_t)N * c.max_dur * h->lay.L + 16);
+		if (eager_rec) { ensure_decode_buffers(h); h->d_vorder.ensure(sizeof(uint32_t) * (size_t)n_utt + 16); }
 		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand", 0, eager_vit ? &score_chunk : nullptr,
 		                want_virt, &h->d_bpad, &h->d_Xa);
-		h->vit_score_ready = eager_vit;
+		h->vit_score_ready = eager_vit; h->vit_rec_ready = eager_rec;
 	}
-	if (!h->joined && !tabs_ready) upload_async(h, h->d_frame_utt, frame_utt);
-	if (!tabs_ready) upload_async(h, h->d_frame_len, frame_len);
 
 	if (labs && !tabs_ready) {
 		std::vector<uint32_t> node_lab, prev_lab, next_lab;
@@ -832,7 +903,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		q.L = L; q.Lp = Lp; q.Lq = Lq; q.n_utt = h->n_utt; q.off = h->d_off.as<uint32_t>();
 		q.S = h->d_S.as<float>(); q.M = h->d_Mall.as<float>(); q.A = h->d_A.as<float>(); q.rho = h->d_m.as<double>();
 		q.logZ = h->d_logZ.as<double>(); q.numer = h->d_numer.as<double>(); q.Dm = h->d_Dm.as<float>(); q.Xd = h->d_Xd.as<float>();
-		q.labs = h->d_node_lab.as<uint32_t>();
+		q.labs = h->d_node_lab.as<uint32_t>(); q.tidx = h->d_tidx.as<uint32_t>();
 		CUDA_OK(launch_transftr_dp(false, q, s)); check_kernel(h, 1);
 		phase_end(h, "forward");
 		phase_begin(h, "backward");
@@ -891,7 +962,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		q.P = P; q.Pp = h->Pp; q.D = D; q.Lp = Lp; q.Lq = Lq; q.n_utt = h->n_utt; q.off = h->d_off.as<uint32_t>();
 		q.S = h->d_S.as<float>(); q.M = h->d_Mall.as<float>(); q.A = h->d_A.as<float>(); q.LG = h->d_G.as<float>(); q.rho = h->d_m.as<double>();
 		q.logZ = h->d_logZ.as<double>(); q.numer = h->d_numer.as<double>(); q.Dm = h->d_Dm.as<float>(); q.Xd = h->d_Xd.as<float>();
-		q.node_lab = h->d_node_lab.as<uint32_t>(); q.next_lab = h->d_next_lab.as<uint32_t>();
+		q.node_lab = h->d_node_lab.as<uint32_t>(); q.next_lab = h->d_next_lab.as<uint32_t>(); q.tidx = h->d_tidx.as<uint32_t>();
 		CUDA_OK(launch_nodur_tf_dp(false, q, s)); check_kernel(h, 1);
 		phase_end(h, "forward");
 		phase_begin(h, "backward");
@@ -1133,14 +1204,13 @@ void viterbi_staged(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t N = h->N, L = m.L, D = c.max_dur, NS = m.n_states, P = m.n_act;
 	cudaStream_t s = h->stream;
-	h->d_negS.ensure(sizeof(float) * (size_t)N * D * L + 16);
-	h->d_candW.ensure(sizeof(float) * (size_t)h->n_utt * D * L + 16); h->d_candP.ensure(sizeof(int32_t) * (size_t)h->n_utt * D * L + 16);
-	h->d_bp.ensure(sizeof(uint16_t) * (size_t)N * L + 16); h->d_bd.ensure((size_t)N * L + 16); h->d_gmove.ensure((size_t)N + 16);
-	h->d_olab.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_odur.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_ophn.ensure(sizeof(uint32_t) * (size_t)N + 16);
-	h->d_nseg.ensure(sizeof(uint32_t) * (size_t)h->n_utt + 16); h->d_cost.ensure(sizeof(float) * (size_t)h->n_utt + 16);
+	ensure_decode_buffers(h);
 	if (!N) { h->viterbi_done = true; return; }
+	if (h->beam > 0.0 && NS != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "beam pruning is implemented for one state per phone (with N states a pruned node can leave phones without any candidate, and the hypothesis order becomes data-dependent)");
 	const bool scored = h->vit_score_ready;      // launched chunk by chunk by crfgpu_stage_batch for this batch and this lambda
-	h->vit_score_ready = false;
+	const bool walked = scored && h->vit_rec_ready;   // ... and so were the recursions of each chunk's utterances
+	h->vit_score_ready = h->vit_rec_ready = false;
+	if (walked) { h->viterbi_done = true; return; }
 	if (!scored) phase_begin(h, "viterbi_score");
 	VitScoreParams vs{};
 	vs.X = h->X(); vs.ldx = h->ldx(); vs.W = h->Wp; vs.sf0 = c.state_fidx_start; vs.nSf = m.nSf; vs.N = N; vs.D = D; vs.L = L;
@@ -1156,12 +1226,7 @@ void viterbi_staged(crfgpu_ctx* h) {
 		ts.negS = h->d_negMt.as<float>();
 		launch_vit_scores(ts, s); check_kernel(h, 1);
 	}
-	// large phone sets with one state per phone and constant transition tables: the cross-phone table sliced over groups of CTAs,
-	// 16 utterances in lock-step per group (crf_viterbi_group.cu); opt_vit_impl 1 forces one CTA per utterance, 2 forces the groups
-	if (h->beam > 0.0 && NS != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "beam pruning is implemented for one state per phone (with N states a pruned node can leave phones without any candidate, and the hypothesis order becomes data-dependent)");
-	const bool vg_fit = NS == 1 && !c.use_trans_ftrs && P >= 2 && L == P && !h->have_lm && !(h->beam > 0.0);      // (LM weights / beam: the per-utterance kernel)
-	const bool vg_auto = vg_fit && (size_t)P * P * sizeof(float) > 96 * 1024;
-	if (vg_fit && (h->opt_vit_impl == 2 || (h->opt_vit_impl == 0 && vg_auto))) {
+	if (vit_wants_groups(h)) {
 		const int gmax = vitg_max_groups(P);
 		if (gmax >= 1) {
 			phase_begin(h, "viterbi");
@@ -1194,19 +1259,8 @@ void viterbi_staged(crfgpu_ctx* h) {
 		if (h->opt_vit_impl == 2) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "group-sliced Viterbi: the table slices of this phone count do not fit shared memory");
 	}
 	phase_begin(h, "viterbi");
-	VitParams v{};
-	v.n_utt = h->n_utt; v.L = L; v.P = P; v.NS = NS; v.D = D; v.off = h->d_off.as<uint32_t>(); v.negS = h->d_negS.as<float>();
-	v.crossT = h->d_crossT.as<float>(); v.negDiag = h->d_negDiag.as<float>(); v.negOff = h->d_negOff.as<float>();
-	v.negMt = c.use_trans_ftrs ? h->d_negMt.as<float>() : nullptr; v.E = h->vtE;
-	v.beam = h->beam;
-	if (h->have_lm) {
-		v.lm_start = h->d_lm_start.as<float>(); v.lm_final = h->d_lm_final.as<float>();
-		if (NS == 1) v.lm_bigT = h->d_lm_bigT.as<float>(); else v.lm_exit = h->d_lm_exit.as<float>();
-	}
-	v.candW = h->d_candW.as<float>(); v.candP = h->d_candP.as<int32_t>(); v.keptW = nullptr;
-	v.bp = h->d_bp.as<uint16_t>(); v.bd = h->d_bd.as<uint8_t>(); v.gmove = h->d_gmove.as<uint8_t>();
-	v.out_lab = h->d_olab.as<uint32_t>(); v.out_dur = h->d_odur.as<uint32_t>(); v.out_phn = h->d_ophn.as<uint32_t>();
-	v.n_seg = h->d_nseg.as<uint32_t>(); v.cost = h->d_cost.as<float>();
+	VitParams v = vit_params(h);
+	v.n_utt = h->n_utt;
 	v.order = h->d_order16.as<uint32_t>();      // longest utterances first
 	static DevBuf kdbg; const bool ktiming = getenv("CRFGPU_DP_TIMING") != nullptr;
 	if (ktiming) { kdbg.ensure(8 * 8); v.dbg = kdbg.as<unsigned long long>(); }
@@ -1376,7 +1430,8 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_R, &h->d_logZ, &h->d_numer, &h->d_grad, &h->d_mass, &h->d_negS, &h->d_candW, &h->d_candP, &h->d_bp, &h->d_bd, &h->d_gmove,
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
-	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt};
+	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt,
+	                  &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1591,22 +1646,44 @@ int crfgpu_viterbi_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_
 
 int crfgpu_viterbi_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
                           uint32_t* out_lab, uint32_t* out_dur, uint32_t* out_phn, uint32_t* n_seg, float* path_cost) {
+	const bool verbose = getenv("CRFGPU_VERBOSE") != nullptr;
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+	const auto t0 = now();
+	std::chrono::steady_clock::time_point t1, t2;
 	int rc = guarded([&] {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		CUDA_OK(cudaSetDevice(h->device));
 		require_decode(h);
 		stage_batch(h, n_utt, frame_off, base_ftrs, nullptr, base_ftrs2);
+		t1 = now();
 		viterbi_staged(h);
+		t2 = now();
 	});
 	if (rc != CRFGPU_OK) return rc;
-	return crfgpu_fetch_viterbi(h, out_lab, out_dur, out_phn, n_seg, path_cost);
+	rc = crfgpu_fetch_viterbi(h, out_lab, out_dur, out_phn, n_seg, path_cost);
+	if (verbose && h->ev_ready) {
+		fprintf(stderr, "[crfgpu] device timeline from the start of staging (ms):");
+		float t = 0.0f;
+		for (size_t k = 0; k < std::min(h->chunk_end.size(), h->ev_chunk.size()); k++) if (cudaEventElapsedTime(&t, h->ev_ready, h->ev_chunk[k]) == cudaSuccess) fprintf(stderr, " H2D chunk %zu done %.3f", k, t);
+		for (const char* ph : {"expand", "viterbi_score", "viterbi"}) {
+			auto it = h->phases.find(ph);
+			if (it != h->phases.end() && cudaEventElapsedTime(&t, h->ev_ready, it->second.first) == cudaSuccess) {
+				float t2 = 0.0f; cudaEventElapsedTime(&t2, h->ev_ready, it->second.second);
+				fprintf(stderr, " | %s %.3f..%.3f", ph, t, t2);
+			}
+		}
+		fprintf(stderr, "\n");
+	}
+	if (verbose) fprintf(stderr, "[crfgpu] viterbi_batch host timeline: stage (prep + H2D enqueue) %.3f ms, launch %.3f ms, kernels + D2H %.3f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));
+	return rc;
 }
 
 int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_bigram, const float* lm_final) {
 	return guarded([&] {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		CUDA_OK(cudaSetDevice(h->device));
-		if (!lm_start && !lm_bigram && !lm_final) { h->have_lm = false; return; }
+		if (!lm_start && !lm_bigram && !lm_final) { h->have_lm = false; h->vit_rec_ready = false; return; }
 		if (!lm_start || !lm_bigram || !lm_final) throw ApiError(CRFGPU_ERR_ARG, "the phone-bigram LM needs all three weight arrays (or none, to drop it)");
 		if (!h->decode_ok) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "decoding: " + h->decode_why);
 		if (h->lay.n_states != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the phone-bigram LM is implemented for one state per phone (the N-state free-phone LM of the reference returns to its start state through epsilon arcs)");
@@ -1620,7 +1697,7 @@ int crfgpu_set_phone_lm(crfgpu_handle h, const float* lm_start, const float* lm_
 		for (uint32_t a = 0; a < P; a++) if (!std::isfinite(st[a])) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the phone-bigram LM must have a finite start weight for every phone");
 		upload(h->d_lm_start, st, h->stream); upload(h->d_lm_bigT, bt, h->stream); upload(h->d_lm_final, fin, h->stream);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
-		h->have_lm = true; h->viterbi_done = false;
+		h->have_lm = true; h->viterbi_done = false; h->vit_rec_ready = false;
 	});
 }
 
@@ -1629,7 +1706,7 @@ int crfgpu_set_beam(crfgpu_handle h, double beam) {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		if (!(beam >= 0.0) || !std::isfinite(beam)) throw ApiError(CRFGPU_ERR_ARG, "the beam must be a finite number >= 0 (0 = no pruning)");
 		if (beam > 0.0 && h->lay.n_states != 1) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "beam pruning is implemented for one state per phone");
-		h->beam = beam; h->viterbi_done = false;
+		h->beam = beam; h->viterbi_done = false; h->vit_rec_ready = false;
 	});
 }
 
@@ -1637,7 +1714,7 @@ int crfgpu_set_phone_unigram_lm(crfgpu_handle h, const float* lm_unigram, const 
 	return guarded([&] {
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		CUDA_OK(cudaSetDevice(h->device));
-		if (!lm_unigram && !lm_exit && !lm_final) { h->have_lm = false; return; }
+		if (!lm_unigram && !lm_exit && !lm_final) { h->have_lm = false; h->vit_rec_ready = false; return; }
 		if (!lm_unigram || !lm_exit || !lm_final) throw ApiError(CRFGPU_ERR_ARG, "the phone-unigram LM needs all three weight arrays (or none, to drop it)");
 		if (!h->decode_ok) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "decoding: " + h->decode_why);
 		if (h->lay.n_states < 2) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the unigram + exit-cost LM has the topology of the reference's N-state free-phone LM (epsilon arcs back to the start state); with one state per phone use crfgpu_set_phone_lm");
@@ -1646,7 +1723,7 @@ int crfgpu_set_phone_unigram_lm(crfgpu_handle h, const float* lm_unigram, const 
 		for (uint32_t a = 0; a < P; a++) if (!std::isfinite(un[a]) || !std::isfinite(ex[a])) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the phone-unigram LM must have a finite unigram and exit cost for every phone");
 		upload(h->d_lm_start, un, h->stream); upload(h->d_lm_exit, ex, h->stream); upload(h->d_lm_final, fin, h->stream);
 		CUDA_OK(cudaStreamSynchronize(h->stream));
-		h->have_lm = true; h->viterbi_done = false;
+		h->have_lm = true; h->viterbi_done = false; h->vit_rec_ready = false;
 	});
 }
 
@@ -1732,7 +1809,8 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
 		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per chain, both chains in one launch (crf_dp_frame.cu), 2 the chains one after the other, 1 the cluster lattice kernels
-		else if (n == "vit_impl") h->opt_vit_impl = (int)value;          // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
+		else if (n == "vit_eager") h->opt_vit_eager = value != 0.0 ? 1 : 0;
+		else if (n == "vit_impl") { h->opt_vit_impl = (int)value; h->vit_rec_ready = false; }         // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
 		else if (n == "prefetch_smem") h->opt_prefetch_smem = (uint32_t)value;   // shared-memory cap of the read-ahead expansion's CTAs
 		else if (n == "k_slab_xi") { if (value < 32 || value % 32) throw ApiError(CRFGPU_ERR_ARG, "k_slab_xi must be a multiple of 32"); h->opt_k_slab_xi = (uint32_t)value; }

@@ -556,7 +556,6 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	/* N states per phone (CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr): every sub-state is a segment of its own and only the
 	 * legal pairs of the N-state map exist -- self (diagTransMatrix), end state -> start state (denseTransMatrix) and k-1 -> k
 	 * (offDiagTransMatrix), computeAlphaPlusTrans :1161-1268, computeBeta :450-718, computeExpF :719-1160 */
-	if (c->n_states != 1 && c->use_trans_ftrs) FAIL("oracle: N-state segmental forward-backward with transition features not restated");
 #define LEGAL(q, y) (m->tidx[(size_t)(q) * P + (y)] != CRFO_NO_IDX)
 	/* transition FEATURES are restated for stdseg_no_dur_no_segtransftr only: M_t[y'][y] comes from the duration-1 window of the frame
 	 * the new segment starts in (CRF_StdSegStateNode_WithoutDurLab_WithoutSegTransFtr::computeTransMatrix :39-121) */
@@ -581,7 +580,7 @@ static int fb_nodur(ctx_t* k, uint32_t T, const float* x, const uint32_t* lab4,
 	if (Mt)
 		for (uint32_t t = 0; t < T; t++)
 			for (uint32_t q = 0; q < P; q++) for (uint32_t y = 0; y < P; y++)
-				Mt[((size_t)t * P + q) * P + y] = trans_value(c, m, X + (size_t)t * D * W, lam, q, y);
+				Mt[((size_t)t * P + q) * P + y] = LEGAL(q, y) ? trans_value(c, m, X + (size_t)t * D * W, lam, q, y) : 0.0;   /* N states: legal pairs only */
 	for (uint32_t t = 0; t < T; t++) {
 		const uint32_t dmax = t + 1 < D ? t + 1 : D;
 		for (uint32_t y = 0; y < P; y++) {

@@ -25,6 +25,7 @@ WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
 NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
+TRANSFTR_NS = load_cases("train_transftr_nstate_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 JOINED = load_cases("joined_golden.npz")
 VIT_LM = load_cases("viterbi_lm_golden.npz")
@@ -480,6 +481,20 @@ def test_fwdbwd_transition_features_match_reference_golden(name):
     """crf_featuremap=stdtrans on frame-level models: transition scores as a tensor-core GEMM, streamed recursions, both gradients
     as reduce-GEMMs (crf_dp_transftr.cu), against goldens produced by the reference."""
     c = TRANSFTR[name]
+    m = gpu(c["cfg"])
+    assert m.lambda_len == len(c["lam"])
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name)
+    m.close()
+
+
+@pytest.mark.parametrize("name", sorted(TRANSFTR_NS))
+def test_fwdbwd_transition_features_nstate_match_reference_golden(name):
+    """crf_featuremap=stdtrans with N states per label (frame-level CRF_StdNStateNode and the segmental
+    CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr): the illegal pairs of the N-state map score -inf in the per-frame transition
+    matrices and carry no gradient rows; against goldens produced by the reference."""
+    c = TRANSFTR_NS[name]
     m = gpu(c["cfg"])
     assert m.lambda_len == len(c["lam"])
     m.set_lambda(c["lam"])

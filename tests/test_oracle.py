@@ -14,6 +14,7 @@ WIN = load_cases("window_golden.npz")
 NODUR = load_cases("train_nodur_golden.npz")
 NSTATE = load_cases("train_nodur_nstate_golden.npz")
 TRANSFTR = load_cases("train_transftr_golden.npz")
+TRANSFTR_NS = load_cases("train_transftr_nstate_golden.npz")
 VIT_TF = load_cases("viterbi_transftr_golden.npz")
 JOINED = load_cases("joined_golden.npz")
 VIT_LM = load_cases("viterbi_lm_golden.npz")
@@ -117,6 +118,18 @@ def test_train_nodur_nstate_golden(oracle, name):
 def test_train_transftr_golden(oracle, name):
     """frame-level CRFs with transition FEATURES (stdtrans) against goldens produced by the reference (make_golden_transftr.py)."""
     c = TRANSFTR[name]
+    assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
+    grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"])
+    np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
+    np.testing.assert_allclose(numer, c["numer"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(grad, c["grad"], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", sorted(TRANSFTR_NS))
+def test_train_transftr_nstate_golden(oracle, name):
+    """transition FEATURES with N states per label, frame-level (CRF_StdNStateNode) and segmental without duration labels
+    (CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr), against goldens produced by the reference (make_golden_transftr_nstate.py)."""
+    c = TRANSFTR_NS[name]
     assert oracle.lambda_len(c["cfg"]) == len(c["lam"])
     grad, numer, logz = oracle.fwdbwd(c["cfg"], c["lam"], c["off"], c["ftrs"], c["labs"])
     np.testing.assert_allclose(logz, c["logZ"], rtol=1e-13)
