@@ -123,6 +123,7 @@ struct crfgpu_ctx {
 	DevBuf d_order16, d_vg_xch, d_vg_final, d_vg_ctr, d_vg_cand; int opt_vit_impl = 0;   // group-sliced Viterbi (large phone sets)
 	int opt_frame_impl = 0; bool frame_path = false;
 	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit; double beam = 0.0;   // crfgpu_set_beam   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
+	std::vector<cudaStream_t> rec_stream; std::vector<cudaEvent_t> ev_scored, ev_walked;   // one side stream per chunk: the chunks' recursions are latency chains and run beside each other
 	bool vit_rec_ready = false; DevBuf d_vorder, d_off2;   // ... and the recursion of each chunk's utterances behind its scores (d_vorder: the chunks' utterances, longest first)
 	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
@@ -364,13 +365,14 @@ void set_lambda(crfgpu_ctx* h, const double* lam, uint32_t len) {
 // virt: the virtual-window form (padded base stream d_bp + aggregate blocks d_Xa) instead of the full windows d_X.
 void copy_and_expand(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, uint32_t N, const float* ftrs, DevBuf& d_base, DevBuf& d_X, DevBuf& d_ft,
                      cudaStream_t xs, cudaEvent_t ev_ready, std::vector<cudaEvent_t>& evs, const char* phase, uint32_t dpart = 0,
-                     const std::function<void(uint32_t, uint32_t)>* after_chunk = nullptr, bool virt = false, DevBuf* d_bp = nullptr, DevBuf* d_Xa = nullptr) {
+                     const std::function<void(uint32_t, uint32_t)>* after_chunk = nullptr, bool virt = false, DevBuf* d_bp = nullptr, DevBuf* d_Xa = nullptr,
+                     uint32_t want_chunks = 4) {
 	const crfgpu_config& c = h->cfg;
 	if (!N) return;
 	if (!h->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 	CUDA_OK(cudaEventRecord(ev_ready, xs));                              // everything queued on xs so far may still read the old contents
 	CUDA_OK(cudaStreamWaitEvent(h->copy_stream, ev_ready, 0));
-	const uint32_t n_chunks = N >= (1u << 14) ? 4u : 1u;
+	const uint32_t n_chunks = N >= (1u << 14) ? want_chunks : 1u;
 	std::vector<uint32_t> ends;
 	uint32_t u = 0, n_prev = 0;
 	for (uint32_t k = 1; k <= n_chunks; k++) {
@@ -615,7 +617,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		if (N && !h->ev_ready) CUDA_OK(cudaEventCreate(&h->ev_ready));
 		// a decode batch (no labels): the decoder's fp64 state scores of a chunk are launched as soon as the chunk has arrived, so the
 		// scoring runs under the remaining H2D copies instead of behind them
-		bool eager_rec = false; uint32_t u_next = 0;
+		bool eager_rec = false; uint32_t u_next = 0, k_chunk = 0;
 		std::function<void(uint32_t, uint32_t)> score_chunk = [&](uint32_t n0, uint32_t n1) {
 			const Layout& m = h->lay;
 			VitScoreParams vs{};
@@ -634,11 +636,22 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			std::iota(ord, ord + cnt, u_next);
 			std::stable_sort(ord, ord + cnt, [&](uint32_t a, uint32_t b) { return off[a + 1] - off[a] > off[b + 1] - off[b]; });
 			h->pin_used = at + bytes;
-			CUDA_OK(cudaMemcpyAsync(h->d_vorder.as<uint32_t>() + u_next, ord, bytes, cudaMemcpyHostToDevice, s));
+			// a recursion lasts as long as its longest utterance however few utterances it walks: every chunk's launch gets a stream of
+			// its own, so that it neither delays the next chunk's scores nor waits for the previous chunk's paths
+			if (h->rec_stream.size() <= k_chunk) {
+				cudaStream_t st; CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); h->rec_stream.push_back(st);
+				cudaEvent_t e0, e1; CUDA_OK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+				h->ev_scored.push_back(e0); h->ev_walked.push_back(e1);
+			}
+			cudaStream_t rs = h->rec_stream[k_chunk];
+			CUDA_OK(cudaEventRecord(h->ev_scored[k_chunk], s));
+			CUDA_OK(cudaStreamWaitEvent(rs, h->ev_scored[k_chunk], 0));
+			CUDA_OK(cudaMemcpyAsync(h->d_vorder.as<uint32_t>() + u_next, ord, bytes, cudaMemcpyHostToDevice, rs));
 			VitParams v = vit_params(h);
 			v.order = h->d_vorder.as<uint32_t>() + u_next; v.n_utt = cnt;
-			launch_viterbi(v, s); check_kernel(h, 1);
-			u_next = u1;
+			launch_viterbi(v, rs); check_kernel(h, 1);
+			CUDA_OK(cudaEventRecord(h->ev_walked[k_chunk], rs));
+			u_next = u1; k_chunk++;
 		};
 		const bool eager_vit = !labs && N && h->decode_ok && h->have_lambda && h->lay.nSf > 0;
 		// the per-utterance recursion needs nothing but the state scores and the constant tables: it follows chunk by chunk as well
@@ -647,7 +660,8 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		if (eager_vit) h->d_negS.ensure(sizeof(float) * (size_t)N * c.max_dur * h->lay.L + 16);
 		if (eager_rec) { ensure_decode_buffers(h); h->d_vorder.ensure(sizeof(uint32_t) * (size_t)n_utt + 16); }
 		copy_and_expand(h, n_utt, off, N, ftrs, h->d_base, h->d_X, h->d_frame_t, s, h->ev_ready, h->ev_chunk, "expand", 0, eager_vit ? &score_chunk : nullptr,
-		                want_virt, &h->d_bpad, &h->d_Xa);
+		                want_virt, &h->d_bpad, &h->d_Xa, eager_rec ? 8u : 4u);
+		for (uint32_t k = 0; k < k_chunk; k++) CUDA_OK(cudaStreamWaitEvent(s, h->ev_walked[k], 0));      // the batch's paths: behind every chunk's recursion
 		h->vit_score_ready = eager_vit; h->vit_rec_ready = eager_rec;
 	}
 
@@ -1444,6 +1458,9 @@ int crfgpu_destroy(crfgpu_handle h) {
 	if (h->ev_pin) cudaEventDestroy(h->ev_pin);
 	if (h->pin) cudaFreeHost(h->pin);
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+	for (cudaStream_t st : h->rec_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+	for (cudaEvent_t e : h->ev_scored) cudaEventDestroy(e);
+	for (cudaEvent_t e : h->ev_walked) cudaEventDestroy(e);
 	cudaStreamDestroy(h->stream);
 	delete h;
 	return CRFGPU_OK;

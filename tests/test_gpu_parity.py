@@ -694,6 +694,50 @@ def test_viterbi_multi_chunk_staging_bit_exact_vs_oracle(oracle):
     for got, exp in zip(segs, want2):
         assert all(np.array_equal(x, y) for x, y in zip(got, exp))
     assert np.array_equal(cost.view(np.uint32), wcost2.view(np.uint32))
+    # the recursion launched by viterbi_staged for the whole batch (option vit_eager 0) instead of per chunk on side streams
+    m.set_option("vit_eager", 0)
+    segs, cost = m.viterbi(off, ftrs)
+    for got, exp in zip(segs, want2):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost2.view(np.uint32))
+    m.close()
+
+
+def test_viterbi_eager_paths_dropped_when_beam_or_lm_change(oracle):
+    """crfgpu_stage_batch launches the recursion of a decode batch chunk by chunk; a beam or a phone LM set between staging and
+    crfgpu_viterbi_staged must not be answered with those paths"""
+    rng = np.random.default_rng(78)
+    P, D, F = 9, 2, 5
+    cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=1)
+    lens = rng.integers(150, 400, 70)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    assert off[-1] >= 16384
+    ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
+    lam = rng.uniform(-0.5, 0.5, oracle.lambda_len(cfg))
+    lm = (rng.uniform(0, 2, P).astype(np.float32), rng.uniform(0, 2, (P, P)).astype(np.float32), rng.uniform(0, 2, P).astype(np.float32))
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    m.stage(off, ftrs)
+    m.set_phone_lm(*lm)
+    m.viterbi_staged()
+    segs, cost = m.fetch_viterbi(off)
+    want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs, lm=lm)
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    m.stage(off, ftrs)
+    m.set_beam(3.0)
+    m.viterbi_staged()
+    segs, cost = m.fetch_viterbi(off)
+    want, wcost, _ = oracle.viterbi(cfg, lam, off, ftrs, lm=lm, beam=3.0)
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
+    # ... and a batch staged with both set takes the per-chunk route with them
+    segs, cost = m.viterbi(off, ftrs)
+    for got, exp in zip(segs, want):
+        assert all(np.array_equal(x, y) for x, y in zip(got, exp))
+    assert np.array_equal(cost.view(np.uint32), wcost.view(np.uint32))
     m.close()
 
 
