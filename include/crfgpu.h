@@ -230,6 +230,9 @@ int crfgpu_fetch_posterior_mass(crfgpu_handle h, float* mass);
  *  "frame_impl" (frame-level models with <= 64 labels: 0 one warp per utterance = default, 1 the cluster lattice kernels),
  *  "nodur_impl" (stdseg_no_dur*: 0 auto, 1 native O(P^2 + D*P) recursion, 2 tied (duration, label) expansion; set_lambda again after it),
  *  "vit_impl" (Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 transition table sliced over groups of CTAs -- one state per phone),
+ *  "vit_eager" (decode batches: 1 = default, crfgpu_stage_batch launches the recursion of each H2D chunk's utterances behind the chunk on
+ *  a side stream; 0 = one launch for the whole batch in crfgpu_viterbi_staged), "virt_windows" (0: the training GEMMs read fully
+ *  materialised windows),
  *  "gemm_impl" / "tma_mask" (which GEMM kernels run: FFMA, register-staged tcgen05, TMA-fed tcgen05 with the 128-row operand in TMEM),
  *  "cluster_slots", "prefetch_smem".  Environment: CRFGPU_VERBOSE (plans, device timeline), CRFGPU_DP_TIMING (cycle counters of the
  *  recursion kernels on stderr). */
