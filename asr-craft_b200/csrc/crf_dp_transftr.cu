@@ -22,7 +22,9 @@ namespace crfgpu {
 
 namespace {
 
-constexpr int TF_THR = 128;
+// CTA sizes: thread = label.  128 threads up to 128 labels, 192 beyond (the double-buffered L x L tile bounds the label count by shared memory:
+// 169 labels frame-level, 160 segmental)
+constexpr int TF_MAX_THR = 192;
 
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -30,6 +32,7 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+template <int TF_THR>
 __device__ __forceinline__ float block_max(float v, float* scratch) {
 	for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
 	__syncthreads();
@@ -39,6 +42,7 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 	for (int w = 1; w < TF_THR / 32; w++) r = fmaxf(r, scratch[w]);
 	return r;
 }
+template <int TF_THR>
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	__syncthreads();
@@ -50,11 +54,13 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 }
 
 // the L x L scores of frame n into a shared-memory matrix with odd row stride Ls (columns AND rows conflict-free)
+template <int TF_THR>
 __device__ __forceinline__ void prefetch_matrix(float* dst, const float* src, uint32_t L, uint32_t Ls) {
 	for (uint32_t i = threadIdx.x; i < L * L; i += TF_THR) { const uint32_t p = i / L, c = i - p * L; cp_async4(dst + p * Ls + c, src + i); }
 	cp_async_commit();
 }
 
+template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t L = p.L, Ls = L | 1u;
@@ -63,7 +69,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 	float* scratch = a_prev + L;                 // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
 	double rho = 0.0, num = 0.0;
-	if (T > 1) prefetch_matrix(Ms + L * Ls, p.M + (size_t)(off + 1) * p.Lq, L, Ls);       // frame 1 -> buffer 1
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + L * Ls, p.M + (size_t)(off + 1) * p.Lq, L, Ls);       // frame 1 -> buffer 1
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
 		float* Mt = Ms + (t & 1) * L * Ls;
@@ -74,19 +80,19 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 		else {
 			cp_async_wait_all();
 			__syncthreads();
-			if (t + 1 < T) prefetch_matrix(Ms + ((t + 1) & 1) * L * Ls, p.M + (n + 1) * p.Lq, L, Ls);
+			if (t + 1 < T) prefetch_matrix<TF_THR>(Ms + ((t + 1) & 1) * L * Ls, p.M + (n + 1) * p.Lq, L, Ls);
 			float m = -INFINITY;
 			for (uint32_t i = c; i < L * L; i += TF_THR) m = fmaxf(m, Mt[(i / L) * Ls + i % L]);
-			mmax = block_max(m, scratch);
+			mmax = block_max<TF_THR>(m, scratch);
 			if (c < L) {
 				float v = 0.0f;
 				for (uint32_t q = 0; q < L; q++) v = fmaf(a_prev[q], __expf(Mt[q * Ls + c] - mmax), v);
 				w = __logf(v) + s;
 			}
 		}
-		const float wmax = block_max(w, scratch);
+		const float wmax = block_max<TF_THR>(w, scratch);
 		const float a = c < L ? __expf(w - wmax) : 0.0f;
-		const float asum = block_sum(a, scratch);
+		const float asum = block_sum<TF_THR>(a, scratch);
 		rho += (double)mmax + (double)wmax + (double)__logf(asum);
 		if (c < L) { a_prev[c] = a / asum; p.A[n * p.Lp + c] = a / asum; }
 		if (c == 0) {
@@ -103,6 +109,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 	if (c == 0) { p.logZ[u] = rho; p.numer[u] = num; }       // sum_c a_{T-1}[c] = 1: alpha_{T-1} sums to exp(rho)
 }
 
+template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t L = p.L, Ls = L | 1u;
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 	float* scratch = av + L;                     // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
 	if (c < L) b[c] = 1.0f;                      // setTailBeta
-	if (T > 1) prefetch_matrix(Ms + ((T - 1) & 1) * L * Ls, p.M + (size_t)(off + T - 1) * p.Lq, L, Ls);
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.M + (size_t)(off + T - 1) * p.Lq, L, Ls);
 	__syncthreads();
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		// gamma_t = A_t * b_t / sum
 		const float a = c < L ? p.A[n * p.Lp + c] : 0.0f;
 		const float g = c < L ? a * b[c] : 0.0f;
-		const float gsum = block_sum(g, scratch);
+		const float gsum = block_sum<TF_THR>(g, scratch);
 		if (c < L) p.Dm[n * p.Lp + c] = ((y == c) ? 1.0f : 0.0f) - g / gsum;
 		float* xrow = p.Xd + n * p.Lq;
 		if (t == 0) {
@@ -131,13 +138,13 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		float* Mt = Ms + (t & 1) * L * Ls;
 		cp_async_wait_all();
 		__syncthreads();
-		if (t > 1) prefetch_matrix(Ms + ((t - 1) & 1) * L * Ls, p.M + (n - 1) * p.Lq, L, Ls);
+		if (t > 1) prefetch_matrix<TF_THR>(Ms + ((t - 1) & 1) * L * Ls, p.M + (n - 1) * p.Lq, L, Ls);
 		// E_t = exp(M_t - mmax) in place
 		float m = -INFINITY;
 		for (uint32_t i = c; i < L * L; i += TF_THR) m = fmaxf(m, Mt[(i / L) * Ls + i % L]);
-		const float mmax = block_max(m, scratch);
+		const float mmax = block_max<TF_THR>(m, scratch);
 		const float s = c < L ? p.S[n * p.Lp + c] : -INFINITY;
-		const float smax = block_max(s, scratch);
+		const float smax = block_max<TF_THR>(s, scratch);
 		if (c < L) { wv[c] = __expf(s - smax) * b[c]; av[c] = p.A[(n - 1) * p.Lp + c]; }
 		__syncthreads();
 		float part = 0.0f;
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 			Mt[q * Ls + cc] = e;
 			part += av[q] * e;
 		}
-		const float xsum = block_sum(part, scratch);                            // sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc]
+		const float xsum = block_sum<TF_THR>(part, scratch);                            // sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc]
 		uint32_t yp = p.labs[n - 1];
 		if (yp < L && y < L && p.tidx[yp * L + y] == 0xffffffffu) yp = LAB_BAD;      // a reference pair the N-state map does not have
 		const float inv = 1.0f / xsum;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		// beta_{t-1}[q] = sum_cc E_t[q][cc] w_t[cc], max-normalised
 		float bn = 0.0f;
 		if (c < L) for (uint32_t cc = 0; cc < L; cc++) bn += Mt[c * Ls + cc];
-		const float bmax = block_max(c < L ? bn : 0.0f, scratch);
+		const float bmax = block_max<TF_THR>(c < L ? bn : 0.0f, scratch);
 		if (c < L) b[c] = bn / bmax;
 		__syncthreads();
 	}
@@ -171,12 +178,15 @@ size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * L *
 cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStream_t s) {
 	if (!p.n_utt) return cudaSuccess;
 	const size_t smem = transftr_smem_bytes(p.L);
-	cudaError_t e = cudaFuncSetAttribute(backward ? (const void*)transftr_backward_kernel : (const void*)transftr_forward_kernel,
-	                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
-	if (backward) transftr_backward_kernel<<<p.n_utt, TF_THR, smem, s>>>(p);
-	else transftr_forward_kernel<<<p.n_utt, TF_THR, smem, s>>>(p);
-	return cudaGetLastError();
+	if (p.L > (uint32_t)TF_MAX_THR) return cudaErrorInvalidValue;
+	auto go = [&](auto kern, int thr) -> cudaError_t {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		kern<<<p.n_utt, thr, smem, s>>>(p);
+		return cudaGetLastError();
+	};
+	if (p.L <= 128) return backward ? go(transftr_backward_kernel<128>, 128) : go(transftr_forward_kernel<128>, 128);
+	return backward ? go(transftr_backward_kernel<TF_MAX_THR>, TF_MAX_THR) : go(transftr_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
 }
 
 
@@ -196,6 +206,7 @@ namespace {
 
 constexpr uint32_t ND_RING = 32;     // max_dur <= 31
 
+template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 	float* scratch = lgh + ND_RING * P;          // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
 	double num = 0.0;
-	if (T > 1) prefetch_matrix(Ms + P * Ps, p.M + (size_t)(off + 1) * p.Lq, P, Ps);       // M_1 -> buffer 1
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + P * Ps, p.M + (size_t)(off + 1) * p.Lq, P, Ps);       // M_1 -> buffer 1
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
 		const uint32_t dmax = min(t + 1, D);
@@ -226,9 +237,9 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 			for (uint32_t d = 1; d <= dmax; d++) sacc += __expf(lt[d - 1] - mx);
 			w = mx + __logf(sacc);
 		}
-		const float wmax = block_max(w, scratch);
+		const float wmax = block_max<TF_THR>(w, scratch);
 		const float a = y < P ? __expf(w - wmax) : 0.0f;
-		const float asum = block_sum(a, scratch);
+		const float asum = block_sum<TF_THR>(a, scratch);
 		const double rho = rref + (double)wmax + (double)__logf(asum);
 		if (y < P) { av[y] = a / asum; p.A[n * p.Pp + y] = a / asum; }
 		if (y == 0) { rring[t & (ND_RING - 1)] = rho; p.rho[n] = rho; }
@@ -241,10 +252,10 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 			float* Mn = Ms + ((t + 1) & 1) * P * Ps;
 			cp_async_wait_all();
 			__syncthreads();
-			if (t + 2 < T) prefetch_matrix(Ms + (t & 1) * P * Ps, p.M + (n + 2) * p.Lq, P, Ps);
+			if (t + 2 < T) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.M + (n + 2) * p.Lq, P, Ps);
 			float m = -INFINITY;
 			for (uint32_t i = y; i < P * P; i += TF_THR) m = fmaxf(m, Mn[(i / P) * Ps + i % P]);
-			const float mmax = block_max(m, scratch);
+			const float mmax = block_max<TF_THR>(m, scratch);
 			if (y < P) {
 				float v = 0.0f;
 				for (uint32_t q = 0; q < P; q++) v = fmaf(av[q], __expf(Mn[q * Ps + y] - mmax), v);
@@ -258,6 +269,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 	if (y == 0) { p.logZ[u] = T ? rring[(T - 1) & (ND_RING - 1)] : 0.0; p.numer[u] = num; }
 }
 
+template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
@@ -269,7 +281,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 	float* scratch = ev + P;                     // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
 	const double lz = p.logZ[u];
-	if (T > 1) prefetch_matrix(Ms + ((T - 1) & 1) * P * Ps, p.M + (size_t)(off + T - 1) * p.Lq, P, Ps);    // M_{T-1}
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * P * Ps, p.M + (size_t)(off + T - 1) * p.Lq, P, Ps);    // M_{T-1}
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
 		const uint32_t nn = min(T - 1 - t, D), dmax = min(t + 1, D);
@@ -291,14 +303,14 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 				for (uint32_t d = 1; d <= nn; d++) sacc += __expf(lt[d - 1] - mx);
 				w = mx + __logf(sacc);
 			}
-			const float wmax = block_max(w, scratch);
+			const float wmax = block_max<TF_THR>(w, scratch);
 			float* Mn = Ms + ((t + 1) & 1) * P * Ps;     // M_{t+1}
 			cp_async_wait_all();
 			__syncthreads();
-			if (t > 0) prefetch_matrix(Ms + (t & 1) * P * Ps, p.M + n * p.Lq, P, Ps);      // M_t for the next step
+			if (t > 0) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.M + n * p.Lq, P, Ps);      // M_t for the next step
 			float m = -INFINITY;
 			for (uint32_t i = y; i < P * P; i += TF_THR) m = fmaxf(m, Mn[(i / P) * Ps + i % P]);
-			const float mmax = block_max(m, scratch);
+			const float mmax = block_max<TF_THR>(m, scratch);
 			if (y < P) { ev[y] = __expf(w - wmax); av[y] = p.A[n * p.Pp + y]; }
 			__syncthreads();
 			// E[q][yy] = exp(M_{t+1}[q][yy] - mmax) * ev[yy] in place;
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			}
 			float bn = 0.0f;
 			if (y < P) for (uint32_t yy = 0; yy < P; yy++) bn += Mn[y * Ps + yy];
-			const float bmax = block_max(y < P ? bn : 0.0f, scratch);
+			const float bmax = block_max<TF_THR>(y < P ? bn : 0.0f, scratch);
 			lb = y < P ? __logf(bn / bmax) : 0.0f;
 			kappa = kref + (double)mmax + (double)wmax + (double)__logf(bmax);
 		} else if (T > 1) {
@@ -354,12 +366,15 @@ size_t nodur_tf_smem_bytes(uint32_t P) { return sizeof(float) * ((size_t)2 * P *
 cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s) {
 	if (!p.n_utt) return cudaSuccess;
 	const size_t smem = nodur_tf_smem_bytes(p.P);
-	cudaError_t e = cudaFuncSetAttribute(backward ? (const void*)nodur_tf_backward_kernel : (const void*)nodur_tf_forward_kernel,
-	                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return e;
-	if (backward) nodur_tf_backward_kernel<<<p.n_utt, TF_THR, smem, s>>>(p);
-	else nodur_tf_forward_kernel<<<p.n_utt, TF_THR, smem, s>>>(p);
-	return cudaGetLastError();
+	if (p.P > (uint32_t)TF_MAX_THR) return cudaErrorInvalidValue;
+	auto go = [&](auto kern, int thr) -> cudaError_t {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		kern<<<p.n_utt, thr, smem, s>>>(p);
+		return cudaGetLastError();
+	};
+	if (p.P <= 128) return backward ? go(nodur_tf_backward_kernel<128>, 128) : go(nodur_tf_forward_kernel<128>, 128);
+	return backward ? go(nodur_tf_backward_kernel<TF_MAX_THR>, TF_MAX_THR) : go(nodur_tf_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
 }
 
 }  // namespace crfgpu

@@ -169,6 +169,7 @@ void check_kernel(crfgpu_ctx* h, int n_launches) {
 }
 
 // Which paths the device implements for this geometry (anything else fails loudly, never emulated).
+constexpr size_t TF_SMEM_MAX = 227 * 1024;      // dynamic shared memory one CTA can opt into on sm_100
 void classify(crfgpu_ctx* h) {
 	const crfgpu_config& c = h->cfg;
 	h->train_ok = h->decode_ok = true; h->tied = h->nodur = false;
@@ -180,15 +181,16 @@ void classify(crfgpu_ctx* h) {
 			h->decode_ok = false; h->decode_why = "CRFDecode accepts only stdframe / stdseg_no_dur_no_segtransftr (CRFDecode/src/Main.cpp:1065-1076)";
 		} else if (c.n_labs > 1024 || c.max_dur > 255) { h->decode_ok = false; h->decode_why = "Viterbi kernel supports crf_label_size <= 1024 and max duration <= 255"; }
 		// (N states per label: the illegal pairs of the N-state map score -inf, CRF_StdNStateNode.cpp:65-108)
-		if ((c.model_type == CRFGPU_STDFRAME || c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) && c.max_dur == 1 && c.n_labs <= 128 && c.use_state_ftrs) { h->transftr = true; return; }
+		if ((c.model_type == CRFGPU_STDFRAME || c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR) && c.max_dur == 1 && c.n_labs <= 192 && transftr_smem_bytes(c.n_labs) <= TF_SMEM_MAX && c.use_state_ftrs) { h->transftr = true; return; }
 		// ... and for the segmental production recipe: no duration labels, transition features from the duration-1 window
 		// (N states per phone: CRF_StdSegNStateNode_WithoutDurLab_WithoutSegTransFtr.cpp:38-80, every sub-state a segment of its own)
-		if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.max_dur > 1 && c.max_dur <= 31 && c.n_labs <= 128 && c.use_state_ftrs) {
+		if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.max_dur > 1 && c.max_dur <= 31 && c.n_labs <= 192 && nodur_tf_smem_bytes(c.n_labs) <= TF_SMEM_MAX && c.use_state_ftrs) {
 			h->nodur = h->nodur_tf = true; return;
 		}
 		h->train_ok = false;
-		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for at most 128 labels (phones x states), "
-		               "in frame-level models and in stdseg_no_dur_no_segtransftr (max_dur <= 31); other model types run with transition bias only";
+		h->train_why = "transition FEATURES (crf_featuremap=stdtrans) are implemented on the device for frame-level models up to 169 labels (phones x states) "
+		               "and for stdseg_no_dur_no_segtransftr up to 161 labels, max_dur <= 31 (the double-buffered per-frame label x label matrix must fit "
+		               "shared memory); other model types run with transition bias only";
 		return;
 	}
 	if (c.model_type == CRFGPU_STDFRAME) {

@@ -76,7 +76,7 @@ typedef struct crfgpu_config {
 	uint32_t n_actual_labs;     /* num_actual_labs */
 	uint32_t extract_seg_ftrs;  /* ftr1_extract_seg_ftr: windows carry [5 samples|avg|max|min|one-hot dur] */
 	uint32_t use_state_ftrs, state_fidx_start, state_fidx_end;   /* indices into the WINDOW feature vector, inclusive */
-	uint32_t use_trans_ftrs, trans_fidx_start, trans_fidx_end;   /* crf_featuremap=stdtrans: training with <= 128 labels (phones x states), frame-level or stdseg_no_dur_no_segtransftr; decoding for those two model kinds up to 1024 labels */
+	uint32_t use_trans_ftrs, trans_fidx_start, trans_fidx_end;   /* crf_featuremap=stdtrans: training with <= 169 labels (phones x states) frame-level, <= 161 in stdseg_no_dur_no_segtransftr; decoding for those two model kinds up to 1024 labels */
 	uint32_t use_state_bias, use_trans_bias;
 	double state_bias_val, trans_bias_val;
 	/* Context frames of feature stream 1 (ftr1_left_context_len, ftr1_right_context_len, ftr1_use_boundary_delta_ftr;

@@ -535,6 +535,45 @@ def test_fwdbwd_transition_features_cfg2_shape_matches_oracle(oracle):
     m.close()
 
 
+@pytest.mark.parametrize("kind", ["frame_144", "frame_169", "nodur_144_d10", "nodur_161_d3", "frame_170_refused", "nodur_162_refused"])
+def test_fwdbwd_transition_features_beyond_128_labels(oracle, kind):
+    """stdtrans past 128 labels (48 phones x 3 states = 144 is the TIMIT recipe with crf_states 3): 192-thread CTAs, the label count
+    bounded by the double-buffered L x L tile in shared memory (169 frame-level, 161 segmental); one more label is refused loudly."""
+    rng = np.random.default_rng(144)
+    F = 6
+    if kind.endswith("refused"):
+        cfg = (make_config("stdframe", n_labs=170, n_base_ftrs=F, use_trans_ftrs=1) if kind.startswith("frame") else
+               make_config("stdseg_no_dur_no_segtransftr", n_labs=162, n_base_ftrs=F, max_dur=3, extract_seg_ftrs=1, use_trans_ftrs=1, trans_fidx=(0, 5)))
+        m = gpu(cfg)
+        m.set_lambda(np.zeros(m.lambda_len))
+        off, ftrs, labs = synth_batch(rng, 2, 5, 9, F, 100, 1, 3)
+        with pytest.raises(crf_b200.CrfGpuError) as e:
+            m.fwdbwd(off, ftrs, labs)
+        assert e.value.code == 2      # CRFGPU_ERR_UNSUPPORTED
+        m.close()
+        return
+    if kind == "frame_144":
+        off, ftrs, labs = synth_batch(rng, 4, 20, 60, F, 48, 3, 9, states=3)
+        cfg = make_config("stdframe", n_labs=144, n_base_ftrs=F, n_states=3, use_trans_ftrs=1)
+    elif kind == "frame_169":
+        off, ftrs, labs = synth_batch(rng, 3, 10, 40, F, 169, 1, 5)
+        cfg = make_config("stdframe", n_labs=169, n_base_ftrs=F, use_trans_ftrs=1, trans_fidx=(1, 4))
+    elif kind == "nodur_144_d10":
+        off, ftrs, labs = synth_batch(rng, 3, 30, 70, F, 48, 6, 30, states=3)
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=144, n_base_ftrs=F, n_states=3, max_dur=10, extract_seg_ftrs=1,
+                          use_trans_ftrs=1, trans_fidx=(0, 5 * F - 1))
+    else:
+        off, ftrs, labs = synth_batch(rng, 3, 10, 40, F, 161, 1, 6)
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=161, n_base_ftrs=F, max_dur=3, extract_seg_ftrs=1, use_trans_ftrs=1, trans_fidx=(0, 11))
+    lam = rng.uniform(-0.05, 0.05, oracle.lambda_len(cfg))
+    want = oracle.fwdbwd(cfg, lam, off, ftrs, labs, n_threads=4)
+    m = gpu(cfg)
+    m.set_lambda(lam)
+    got = m.fwdbwd(off, ftrs, labs)
+    assert_train_close(got, want, kind)
+    m.close()
+
+
 @pytest.mark.parametrize("name", sorted(VIT_TF))
 def test_viterbi_transition_features_bit_exact_vs_reference_golden(name):
     """decoding with crf_featuremap=stdtrans: per-frame decoder tables from fp64 scores in the reference's order"""
