@@ -287,72 +287,68 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 						const bool tail = t + 1 == len;
 						const double kp = tail ? 0.0 : sh.scale[tid] + p.Mmax;
 						sh.kap[tid] = kp; sh.s_ring[tid][t & (RING - 1)] = kp;
+						if (pt == 0) p.kappa[n] = kp;                                         // for the posterior pass
 						sh.g_ring[tid][t & (RING - 1)] = tail ? 0.0 : kp + log((double)sh.vsum[tid]);
 					}
 				}
 			}
 			__syncthreads();
 			NTICK(5);   // reduction + scales
-			// ---------------------------------------------------------------- phase C (backward): posteriors of frame t
-			if (BWD) {
-				for (uint32_t i = tid; i < UT * RING; i += NTHR) {
-					const uint32_t u = i / RING, d = i % RING, len = sh.len[u];
-					float v = 0.0f;
-					if (d >= 1 && d <= D && t < len && d <= t + 1) {
-						const double kzu = sh.kap[u] - sh.lz[u];
-						v = (d <= t) ? (float)(p.rho[(size_t)sh.off[u] + t - d] + p.Mmax + kzu) : (float)kzu;
-					}
-					sh.rcf[u][d] = v;
-				}
-				__syncthreads();
-				const uint32_t u0 = warp * 2, dmax = min(t + 1, D);
-				bool act[2]; size_t nf[2]; uint32_t lab[2]; double kz[2];
-#pragma unroll
-				for (int i = 0; i < 2; i++) {
-					act[i] = t < sh.len[u0 + i] && y_ok;
-					nf[i] = (size_t)sh.off[u0 + i] + t;
-					lab[i] = act[i] ? p.node_lab[nf[i]] : LAB_BAD;
-					kz[i] = 0.0;
-				}
-				if (act[0] || act[1]) {
-					const float* Sq[2]; const float* Lq[2]; float* Dq[2];
-#pragma unroll
-					for (int i = 0; i < 2; i++) {
-						Sq[i] = p.S + (act[i] ? nf[i] * Lp + y : 0);
-						Lq[i] = p.LG + (act[i] ? nf[i] * Pp + y : 0);
-						Dq[i] = p.Dm + (act[i] ? nf[i] * Lp + y : 0);
-					}
-					const uint32_t dL = min(t, D);
-					for (uint32_t d0 = 1; d0 <= D; d0 += DC) {
-						float sv[2][DC], lv[2][DC];
-#pragma unroll
-						for (uint32_t j = 0; j < DC; j++) {
-							const uint32_t d = d0 + j, o_s = (d - 1) * P, o_l = d * Pp;
-#pragma unroll
-							for (int i = 0; i < 2; i++) {
-								const bool on = act[i] && d <= dmax, onL = act[i] && d <= dL;
-								sv[i][j] = __ldg(Sq[i] + (on ? o_s : 0u));
-								const float lx = *(Lq[i] - (onL ? o_l : 0u));
-								lv[i][j] = onL ? lx : 0.0f;
-							}
-						}
-#pragma unroll
-						for (int i = 0; i < 2; i++)
-#pragma unroll
-							for (uint32_t j = 0; j < DC; j++) {
-								const uint32_t d = d0 + j, o_s = (d - 1) * P;
-								if (d > D || !act[i]) continue;
-								float dm = 0.0f;
-								if (d <= dmax) dm = ((lab[i] == o_s + y) ? 1.0f : 0.0f) - __expf(sv[i][j] + lcur[i] + lv[i][j] + sh.rcf[u0 + i][d & (RING - 1)]);
-								Dq[i][o_s] = dm;
-							}
-					}
-				}
-			}
-			NTICK(6);   // phase C
+			NTICK(6);   // (phase C: the posteriors are a pass of their own behind the recursion, nodur_post_kernel)
 		}
 	}
 	if (timing) { for (int i = 0; i < 8; i++) p.dbg[i] = tacc[i]; p.dbg[8] = gstep; }
+}
+
+// Posteriors of the native no_dur recursion, a pass of its own behind the backward recursion (they feed nothing of the chain: inside the
+// lock-step loop they were 21 k of the 56 k cycles per step at cfg5):
+//   Dm[n][(d,y)] = [reference segment (d,y) ends at n] - gamma_t[d,y],
+//   gamma_t[d,y] = exp(S_t[d,y] + A_{t-d}[y] + beta_t[y] - logZ) = exp(S + LB_t[y] + LG_{t-d}[y] + (rho_{t-d} + Mmax + kappa_t - logZ))
+// (d <= t; d == t+1: the segment starts the utterance, exp(S + LB_t[y] + (kappa_t - logZ))); durations that do not exist get 0.
+// One CTA per (frame, 256-phone tile): the scalar part per duration in fp64 by the first warp, then D coalesced rows.
+__global__ void __launch_bounds__(256) nodur_post_kernel(NodurParams p, const uint32_t* __restrict__ frame_t, const uint32_t* __restrict__ frame_utt) {
+	__shared__ float rcf[RING];
+	const uint32_t n = blockIdx.x, y = blockIdx.y * 256 + threadIdx.x;
+	const uint32_t t = frame_t[n], P = p.P, D = p.D, dmax = min(t + 1, D);
+	if (threadIdx.x < RING) {
+		const uint32_t d = threadIdx.x;
+		float v = 0.0f;
+		if (d >= 1 && d <= dmax) {
+			const double kzu = p.kappa[n] - p.logZ[frame_utt[n]];
+			v = (d <= t) ? (float)(p.rho[(size_t)n - d] + p.Mmax + kzu) : (float)kzu;
+		}
+		rcf[d] = v;
+	}
+	__syncthreads();
+	if (y >= P) return;
+	const uint32_t lab = p.node_lab[n];
+	const float lcur = p.LB[(size_t)n * p.Pp + y];
+	const float* Sq = p.S + (size_t)n * p.Lp + y;
+	float* Dq = p.Dm + (size_t)n * p.Lp + y;
+	const float* Lq = p.LG + (size_t)n * p.Pp + y;
+	for (uint32_t d0 = 1; d0 <= D; d0 += DC) {
+		float sv[DC], lv[DC];
+#pragma unroll
+		for (uint32_t j = 0; j < DC; j++) {
+			const uint32_t d = d0 + j;
+			const bool on = d <= dmax, onL = d <= min(t, D);
+			sv[j] = on ? __ldg(Sq + (size_t)(d - 1) * P) : 0.0f;
+			lv[j] = onL ? *(Lq - (size_t)d * p.Pp) : 0.0f;
+		}
+#pragma unroll
+		for (uint32_t j = 0; j < DC; j++) {
+			const uint32_t d = d0 + j, o_s = (d - 1) * P;
+			if (d > D) continue;
+			float dm = 0.0f;
+			if (d <= dmax) dm = ((lab == o_s + y) ? 1.0f : 0.0f) - __expf(sv[j] + lcur + lv[j] + rcf[d & (RING - 1)]);
+			Dq[o_s] = dm;
+		}
+	}
+}
+
+void launch_nodur_post(const NodurParams& p, const uint32_t* frame_t, const uint32_t* frame_utt, uint32_t N, cudaStream_t s) {
+	if (!N) return;
+	nodur_post_kernel<<<dim3(N, (p.P + 255) / 256), 256, 0, s>>>(p, frame_t, frame_utt);
 }
 
 int nodur_max_groups(uint32_t P) {

@@ -207,7 +207,8 @@ struct NodurParams {
 	double Mmax;
 	float* A; float* LG; double* rho;     // forward: a_t [N][Pp], log(a_t E) [N][Pp], scale rho_t [N]
 	double* logZ;                         // [n_utt]
-	float* LB; float* R; float* Dm;       // backward: log(E bh_t) [N][Pp], Xi right factors [N][Pp], [ref] - gamma [N][Lp]
+	float* LB; float* R; float* Dm;       // backward: log(E bh_t) [N][Pp], Xi right factors [N][Pp], [ref] - gamma [N][Lp] (Dm: nodur_post_kernel)
+	double* kappa;                        // [N] backward scale kappa_t of every frame (read by the posterior pass)
 	const uint32_t* node_lab;             // [N] (dur-1)*P + phone where a reference segment ends, else LAB_BAD
 	float* xch;                           // [n_groups][2][(Pk + npt) * NODUR_UT] exchange buffers, Pk = P rounded up to 32
 	uint32_t* ctr;                        // [n_groups] barrier counters
@@ -216,6 +217,7 @@ struct NodurParams {
 size_t nodur_smem_bytes(uint32_t P);
 int nodur_max_groups(uint32_t P);         // co-resident groups of ceil(P/32) CTAs (0: the phone count does not fit)
 cudaError_t launch_nodur_dp(bool backward, const NodurParams& p, cudaStream_t s);
+void launch_nodur_post(const NodurParams& p, const uint32_t* frame_t, const uint32_t* frame_utt, uint32_t N, cudaStream_t s);   // Dm = [ref] - gamma, behind the backward recursion
 
 // Frame-reduction GEMMs (both operands [frames][columns], TMA-fed; one launch covers every duration block d):
 //   state gradient  out[row_idx[d*P+y] + j]      += (j == ones_col ? ones_scale : scale) * sum_n X[n][d][j]  * Dm[n][d*P+y]

@@ -995,7 +995,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		q.S = h->d_S.as<float>(); q.smaxd = h->d_smaxd.as<float>(); q.E = h->d_E.as<float>(); q.ET = h->d_ET.as<float>(); q.Mmax = h->Mmax;
 		q.A = h->d_A.as<float>(); q.LG = h->d_G.as<float>(); q.rho = h->d_m.as<double>(); q.logZ = h->d_logZ.as<double>();
 		q.LB = h->d_LB.as<float>(); q.R = h->d_R.as<float>(); q.Dm = h->d_Dm.as<float>(); q.node_lab = h->d_node_lab.as<uint32_t>();
-		q.xch = h->d_nd_xch.as<float>(); q.ctr = h->d_nd_ctr.as<uint32_t>();
+		q.xch = h->d_nd_xch.as<float>(); q.ctr = h->d_nd_ctr.as<uint32_t>(); q.kappa = h->d_kappa.as<double>();
 		static DevBuf ndbg; const bool ntiming = getenv("CRFGPU_DP_TIMING") != nullptr;
 		if (ntiming) { ndbg.ensure(16 * 8); q.dbg = ndbg.as<unsigned long long>(); }
 		auto nreport = [&](const char* what) {
@@ -1012,6 +1012,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		phase_begin(h, "backward");
 		CUDA_OK(launch_nodur_dp(true, q, s)); check_kernel(h, 1);
 		if (ntiming) nreport("backward");
+		launch_nodur_post(q, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), N, s); check_kernel(h, 1);      // Dm = [ref] - gamma
 		phase_end(h, "backward");
 	} else if (h->frame_path) {
 		// frame-level models with at most 64 labels: one warp per utterance, the transition matrix in registers (crf_dp_frame.cu);
