@@ -26,6 +26,7 @@
 //   phase C  (backward) posteriors of the frame: Dm[n][(d,y)] = [reference segment] - gamma_t[d,y] for the state-gradient GEMM and
 //            R[n+1][y] (phase A) for the Xi GEMM, which both run on the TMA-fed kernels of crf_tma_gemm.cu.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include <cfloat>
 
@@ -41,7 +42,7 @@ static_assert(UT == 16 && NW * 2 == UT, "thread mapping: warp w owns utterances 
 
 struct Shared {
 	float red[NW][UT][PT];        // partial products of the 8 contraction slices
-	float tileT[PT][UT];          // the CTA's slice of the new vector, [phone][utterance]
+	float tileU[UT][PT];          // the CTA's slice of the new vector, [utterance][phone]
 	double g_ring[UT][RING];      // forward: exact log-sum of alpha_t | backward: upper bound of beta_t
 	double s_ring[UT][RING];      // forward: rho_t                    | backward: kappa_t
 	double scale[UT];             // scale of the frame being produced (rho_t | sigma_t)
@@ -63,6 +64,17 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
 	return v;
 }
 
+// (x, y) -> packed bf16 pairs: hi = round-to-nearest halves, lo = the halves of the remainders (x in the low 16 bits)
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+	const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+	const __nv_bfloat162 l = __floats2bfloat162_rn(x - __low2float(h), y - __high2float(h));
+	hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // all CTAs of the group have published their slice of step `gstep`
 __device__ __forceinline__ void group_barrier(uint32_t* ctr, uint32_t target) {
 	__syncthreads();
@@ -76,7 +88,7 @@ __device__ __forceinline__ void group_barrier(uint32_t* ctr, uint32_t target) {
 
 }  // namespace
 
-size_t nodur_smem_bytes(uint32_t P) { return sizeof(Shared) + (size_t)((P + 31) / 32 * 32) * (PT + UT) * sizeof(float) + 16; }
+size_t nodur_smem_bytes(uint32_t P) { return sizeof(Shared) + (size_t)((P + 31) / 32 * 32) * PT * sizeof(float) + 32; }
 
 #define NTICK(i) do { if (timing) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
 
@@ -84,23 +96,31 @@ template <bool BWD>
 __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
-	float* Et = reinterpret_cast<float*>(smem_raw + (sizeof(Shared) + 15) / 16 * 16);   // [Pk][PT]: Et[k][j] = E[k][y0+j] (fwd) | E[y0+j][k] (bwd)
-	const uint32_t P = p.P, Pp = p.Pp, D = p.D, Pk = (P + 31) / 32 * 32;
-	float* xs = Et + (size_t)Pk * PT;                                                   // [Pk][UT]: the exchanged vector of the step
+	// B operand of the product, E[k][y0+j] (fwd) | E[y0+j][k] (bwd), as bf16 hi / lo halves in mma.sync fragment order:
+	// Ef[(ks * 4 + nt) * 32 + lane] = {hi(k 2t,2t+1), hi(k 2t+8,2t+9), lo(..), lo(..)} of column nt * 8 + g, k relative to 16 ks
+	uint4* Ef = reinterpret_cast<uint4*>(smem_raw + (sizeof(Shared) + 15) / 16 * 16);
+	const uint32_t P = p.P, Pp = p.Pp, D = p.D, Pk = (P + 31) / 32 * 32, n_ks = Pk / 16;
 	const size_t Lp = p.Lp;
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t g = blockIdx.x / p.npt, pt = blockIdx.x % p.npt, y0 = pt * PT, y = y0 + lane;
 	const bool y_ok = y < P;
 	const float* Msrc = BWD ? p.ET : p.E;
-	for (uint32_t i = tid; i < Pk * PT; i += NTHR) {
-		const uint32_t k = i / PT, j = i % PT;
-		Et[i] = (k < P && y0 + j < P) ? Msrc[(size_t)k * Pp + y0 + j] : 0.0f;
+	for (uint32_t i = tid; i < n_ks * 4 * 32; i += NTHR) {
+		const uint32_t ks = i >> 7, nt = (i >> 5) & 3, ln = i & 31, fg = ln >> 2, ft = ln & 3, j = nt * 8 + fg;
+		float v[4];
+#pragma unroll
+		for (int e = 0; e < 4; e++) {
+			const uint32_t k = ks * 16 + 2 * ft + (e & 1) + (e >> 1) * 8;
+			v[e] = (k < P && y0 + j < P) ? Msrc[(size_t)k * Pp + y0 + j] : 0.0f;
+		}
+		uint4 w;
+		split2(v[0], v[1], w.x, w.z); split2(v[2], v[3], w.y, w.w);
+		Ef[i] = w;
 	}
 	float* xbase = p.xch + (size_t)g * 2 * ((size_t)Pk * UT + (size_t)p.npt * UT);
 	const size_t xstride = (size_t)Pk * UT + (size_t)p.npt * UT;
 	uint32_t* ctr = p.ctr + g;
 	uint32_t gstep = 0;
-	const uint32_t kslice = Pk / NW;     // Pk is a multiple of 32, NW = 8
 	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
 	unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	long long tlast = timing ? clock64() : 0;
@@ -208,14 +228,15 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 						if (act[i]) p.R[(nf[i] + 1) * Pp + y] = acc[i] * expf((float)(p.rho[nf[i]] + p.Mmax + sh.scale[u] - sh.lz[u]));
 						if (t == 0 && len > 0 && y_ok) p.R[nf[i] * Pp + y] = 0.0f;      // no transition enters the first frame
 					}
-					sh.tileT[lane][u] = acc[i];
+					sh.tileU[u][lane] = acc[i];
 					const float ps = warp_sum(acc[i]);
 					if (lane == 0) __stcg(xch + (size_t)Pk * UT + (size_t)pt * UT + u, ps);
 				}
 			}
 			__syncthreads();
 			NTICK(1);   // phase A
-			if (tid < PT * UT / 4) __stcg(reinterpret_cast<float4*>(xch + (size_t)y0 * UT) + tid, reinterpret_cast<const float4*>(&sh.tileT[0][0])[tid]);
+			// exchange layout [utterance][Pk]: the A fragments of the product are float2 loads straight from L2
+			if (tid < PT * UT / 4) __stcg(reinterpret_cast<float4*>(xch + (size_t)(tid >> 3) * Pk + y0) + (tid & 7), reinterpret_cast<const float4*>(&sh.tileU[0][0])[tid]);
 			group_barrier(ctr, (gstep + 1) * p.npt);
 			NTICK(2);   // barrier
 			// ---------------------------------------------------------------- phase B: my block of the matrix product
@@ -224,32 +245,56 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 				for (uint32_t q = 0; q < p.npt; q++) v += __ldcg(xch + (size_t)Pk * UT + (size_t)q * UT + tid);
 				sh.vsum[tid] = v;
 			}
+			NTICK(3);   // staging (none: the operand fragments come straight from L2)
 			{
-				// the whole exchanged vector in one round trip to L2 (the other CTAs wrote it: bypass L1), then the product from shared memory
-				const float4* xv = reinterpret_cast<const float4*>(xch);
-				float4* xd = reinterpret_cast<float4*>(xs);
-#pragma unroll 8
-				for (uint32_t i = tid; i < Pk * (UT / 4); i += NTHR) xd[i] = __ldcg(xv + i);
-			}
-			__syncthreads();
-			NTICK(3);   // staging
-			{
-				float acc[UT];
+				// the CTA's 16 x 32 block of the product on the tensor cores: mma.sync m16n8k16, rows = utterances, columns = the tile's
+				// phones, bf16 hi/lo splits of both operands (hi*hi + hi*lo + lo*hi, fp32 accumulation: ~16 mantissa bits like every other
+				// GEMM-shaped product here); warp w takes the k-steps w, w + 8, ... and the partial blocks are summed through shared memory.
+				// All A fragments of a warp's k-steps (the exchanged vector, written by the other CTAs: L1 bypassed) are requested before
+				// the first is used: one round trip to L2 per step.
+				float acc[4][4];
 #pragma unroll
-				for (int u = 0; u < UT; u++) acc[u] = 0.0f;
-				const uint32_t k0 = warp * kslice;
-#pragma unroll 4
-				for (uint32_t k = k0; k < k0 + kslice; k++) {
-					const float e = Et[k * PT + lane];
-					const float4* xr = reinterpret_cast<const float4*>(xs + (size_t)k * UT);
-					const float4 a0 = xr[0], a1 = xr[1], a2 = xr[2], a3 = xr[3];
-					acc[0] = fmaf(a0.x, e, acc[0]); acc[1] = fmaf(a0.y, e, acc[1]); acc[2] = fmaf(a0.z, e, acc[2]); acc[3] = fmaf(a0.w, e, acc[3]);
-					acc[4] = fmaf(a1.x, e, acc[4]); acc[5] = fmaf(a1.y, e, acc[5]); acc[6] = fmaf(a1.z, e, acc[6]); acc[7] = fmaf(a1.w, e, acc[7]);
-					acc[8] = fmaf(a2.x, e, acc[8]); acc[9] = fmaf(a2.y, e, acc[9]); acc[10] = fmaf(a2.z, e, acc[10]); acc[11] = fmaf(a2.w, e, acc[11]);
-					acc[12] = fmaf(a3.x, e, acc[12]); acc[13] = fmaf(a3.y, e, acc[13]); acc[14] = fmaf(a3.z, e, acc[14]); acc[15] = fmaf(a3.w, e, acc[15]);
+				for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+					for (int e = 0; e < 4; e++) acc[nt][e] = 0.0f;
+				const uint32_t fg = lane >> 2, ft = lane & 3;
+				constexpr uint32_t KB = 9;      // k-steps per warp and pass (P <= 1152 in one pass)
+				for (uint32_t ks0 = warp; ks0 < n_ks; ks0 += NW * KB) {
+					float2 av[KB][4];
+#pragma unroll
+					for (uint32_t j = 0; j < KB; j++) {
+						const uint32_t ks = ks0 + j * NW;
+						if (ks < n_ks) {
+							const float* r0 = xch + (size_t)fg * Pk + ks * 16 + 2 * ft;
+							av[j][0] = __ldcg(reinterpret_cast<const float2*>(r0));
+							av[j][1] = __ldcg(reinterpret_cast<const float2*>(r0 + (size_t)8 * Pk));
+							av[j][2] = __ldcg(reinterpret_cast<const float2*>(r0 + 8));
+							av[j][3] = __ldcg(reinterpret_cast<const float2*>(r0 + (size_t)8 * Pk + 8));
+						}
+					}
+#pragma unroll
+					for (uint32_t j = 0; j < KB; j++) {
+						const uint32_t ks = ks0 + j * NW;
+						if (ks < n_ks) {      // (warp-uniform)
+							uint32_t ah[4], al[4];
+#pragma unroll
+							for (int e = 0; e < 4; e++) split2(av[j][e].x, av[j][e].y, ah[e], al[e]);
+							const uint4* bf = Ef + (size_t)ks * 128 + lane;
+#pragma unroll
+							for (int nt = 0; nt < 4; nt++) {
+								const uint4 b = bf[nt * 32];
+								mma_bf16(acc[nt], ah, b.x, b.y);
+								mma_bf16(acc[nt], ah, b.z, b.w);
+								mma_bf16(acc[nt], al, b.x, b.y);
+							}
+						}
+					}
 				}
 #pragma unroll
-				for (int u = 0; u < UT; u++) sh.red[warp][u][lane] = acc[u];
+				for (int nt = 0; nt < 4; nt++) {
+					*reinterpret_cast<float2*>(&sh.red[warp][fg][nt * 8 + 2 * ft]) = make_float2(acc[nt][0], acc[nt][1]);
+					*reinterpret_cast<float2*>(&sh.red[warp][fg + 8][nt * 8 + 2 * ft]) = make_float2(acc[nt][2], acc[nt][3]);
+				}
 			}
 			__syncthreads();
 			NTICK(4);   // product
