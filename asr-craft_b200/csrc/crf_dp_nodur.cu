@@ -46,10 +46,8 @@ struct Shared {
 	double g_ring[UT][RING];      // forward: exact log-sum of alpha_t | backward: upper bound of beta_t
 	double s_ring[UT][RING];      // forward: rho_t                    | backward: kappa_t
 	double scale[UT];             // scale of the frame being produced (rho_t | sigma_t)
-	double kap[UT], lz[UT];       // backward: kappa_t of the frame just finished, logZ of the utterance
-	float vsum[UT];
+	double lz[UT];                // backward: logZ of the utterance
 	float scf[UT][RING];          // per-step float scale of duration d: the fp64 differences are formed once per (utterance, duration), not per entry
-	float rcf[UT][RING];          // backward phase C: rho_{t-d} + Mmax + kappa_t - logZ
 	uint32_t utt[UT], off[UT], len[UT];
 };
 
@@ -88,11 +86,11 @@ __device__ __forceinline__ void group_barrier(uint32_t* ctr, uint32_t target) {
 
 }  // namespace
 
-size_t nodur_smem_bytes(uint32_t P) { return sizeof(Shared) + (size_t)((P + 31) / 32 * 32) * PT * sizeof(float) + 32; }
+size_t nodur_smem_bytes(uint32_t P) { return sizeof(Shared) + (size_t)((P + 31) / 32 * 32) * PT * sizeof(float) + sizeof(float) * RING * UT * PT + 32; }
 
 #define NTICK(i) do { if (timing) { const long long now_ = clock64(); tacc[i] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
 
-template <bool BWD>
+template <bool BWD, int DR>
 __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -100,6 +98,9 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	// Ef[(ks * 4 + nt) * 32 + lane] = {hi(k 2t,2t+1), hi(k 2t+8,2t+9), lo(..), lo(..)} of column nt * 8 + g, k relative to 16 ks
 	uint4* Ef = reinterpret_cast<uint4*>(smem_raw + (sizeof(Shared) + 15) / 16 * 16);
 	const uint32_t P = p.P, Pp = p.Pp, D = p.D, Pk = (P + 31) / 32 * 32, n_ks = Pk / 16;
+	// the CTA's own slice of log(a_t E) (forward) / log(E bh_t) (backward) of the last RING frames: phase A reads its D history terms
+	// here instead of the lattice arrays in global memory
+	float* hist = reinterpret_cast<float*>(Ef + (size_t)n_ks * 128);                     // [RING][UT][PT]
 	const size_t Lp = p.Lp;
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t g = blockIdx.x / p.npt, pt = blockIdx.x % p.npt, y0 = pt * PT, y = y0 + lane;
@@ -124,6 +125,67 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
 	unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	long long tlast = timing ? clock64() : 0;
+	// Everything that belongs to ONE utterance of the batch -- scales, rings, the float scale terms of phase A -- is kept by the warp that
+	// owns the utterance in phases A and B (warp w: utterances 2w, 2w + 1; lane = duration - 1 for the D-term maxima), so the
+	// bookkeeping needs no block-wide barrier and no single-thread loops over D.
+	const uint32_t u0 = warp * 2;
+	const uint32_t s_step = BWD ? (uint32_t)Lp + P : P;      // forward: S[n][(d-1)P + y]; backward: S[n+d][(d-1)P + y]
+	// values that do not depend on the recursion are requested one step ahead and wait in registers: the D score terms of both
+	// entries of the thread, the score maxima that bound the next scale, the forward scale of the frame (backward: Xi factor)
+	float sn[2][DR]; float sm[2]; double rh[2];
+	const float* const Sg = p.S;
+	auto prefetch = [&](uint32_t tt, uint32_t maxlen) {
+#pragma unroll
+		for (int i = 0; i < 2; i++) {
+			const uint32_t u = u0 + i, len = sh.len[u];
+			const bool in = tt < maxlen;                          // (tt wraps to 0xffffffff behind the last backward step)
+			bool a; uint32_t lm;
+			if (!BWD) { a = in && tt < len; lm = a ? min(tt + 1, D) : 0; }
+			else { a = in && tt + 1 < len; lm = a ? min(len - 1 - tt, D) : 0; }
+			const size_t n = (size_t)sh.off[u] + (a ? tt : 0);
+			const float* q = Sg + (n + (BWD ? 1 : 0)) * Lp + (y_ok ? y : 0);     // the d = 1 term; one pointer increment per duration
+			const uint32_t lmy = y_ok ? lm : 0;
+#pragma unroll
+			for (uint32_t d = 1; d <= (uint32_t)DR; d++) {
+				sn[i][d - 1] = d <= lmy ? __ldg(q) : -INFINITY;      // a term that does not exist contributes exp(-inf) = 0
+				q += s_step;
+			}
+			// lane = d - 1: forward smaxd[n][d-1] (d <= min(tt + 1, D)); backward smaxd[n + d][d - 1] (d <= min(len - 1 - tt, D))
+			sm[i] = lane < lm ? __ldg(p.smaxd + (BWD ? (n + lane + 1) * D + lane : n * D + lane)) : 0.0f;
+			rh[i] = (BWD && a) ? p.rho[n] : 0.0;
+		}
+	};
+	// scale of step tt and the float scale terms of its phase A, for utterance u = u0 + i (whole warp; lane = d - 1 / d)
+	auto next_scale = [&](uint32_t tt, int i) {
+		const uint32_t u = u0 + i, len = sh.len[u];
+		__syncwarp();
+		if (!BWD) {
+			// rho_tt = max_d (smaxd_tt[d] + Mmax + exact log-sum of alpha_{tt-d}), the segment that starts the utterance without history
+			const bool a = tt < len;
+			const uint32_t d = lane + 1;
+			double c = -DBL_MAX;
+			if (a && d <= min(tt, D)) c = (double)sm[i] + p.Mmax + sh.g_ring[u][(tt - d) & (RING - 1)];
+			else if (a && d == tt + 1 && tt < D) c = (double)sm[i];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+			if (a && lane == 0) { sh.scale[u] = c; sh.s_ring[u][tt & (RING - 1)] = c; if (pt == 0) p.rho[(size_t)sh.off[u] + tt] = c; }
+			float v = 0.0f;      // scf[u][lane]: rho_{tt-d} + Mmax - rho_tt (d <= tt) or -rho_tt (d == tt+1), d = lane
+			if (a && lane >= 1 && lane <= D && lane <= tt + 1) v = (lane <= tt) ? (float)(sh.s_ring[u][(tt - lane) & (RING - 1)] + p.Mmax - c) : (float)(-c);
+			sh.scf[u][lane] = v;
+		} else {
+			const bool a = tt + 1 < len && tt < len;              // (tt may have wrapped)
+			const uint32_t d = lane + 1, nn = a ? min(len - 1 - tt, D) : 0;
+			double c = -DBL_MAX;
+			if (d <= nn) c = (double)sm[i] + sh.g_ring[u][(tt + d) & (RING - 1)];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+			if (a && lane == 0) sh.scale[u] = c;
+			float v = 0.0f;      // scf[u][lane]: kappa_{tt+d} - sigma_tt, d = lane
+			if (a && lane >= 1 && lane <= nn) v = (float)(sh.s_ring[u][(tt + lane) & (RING - 1)] - c);
+			sh.scf[u][lane] = v;
+		}
+		__syncwarp();
+	};
 
 	for (uint32_t b = p.grp_off[g]; b < p.grp_off[g + 1]; b++) {
 		__syncthreads();
@@ -133,91 +195,42 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 			sh.off[tid] = u != LAB_BAD ? p.off[u] : 0;
 			sh.len[tid] = u != LAB_BAD ? p.off[u + 1] - p.off[u] : 0;
 			if (BWD) sh.lz[tid] = u != LAB_BAD ? p.logZ[u] : 0.0;
-			if (!BWD && u != LAB_BAD) {
-				// alpha_0[1,y] = S_0[1,y]: the first frame is scaled by its score maximum
-				const double r0 = (double)p.smaxd[(size_t)sh.off[tid] * D];
-				sh.scale[tid] = r0; sh.s_ring[tid][0] = r0;
-				if (pt == 0) p.rho[sh.off[tid]] = r0;
-			}
 		}
 		__syncthreads();
 		uint32_t maxlen = 0;
 		for (int u = 0; u < UT; u++) maxlen = max(maxlen, sh.len[u]);
+		if (maxlen == 0) continue;
+		{
+			// first step of the batch: its score terms, and (forward) alpha_0[1,y] = S_0[1,y] scaled by the score maximum of frame 0
+			const uint32_t t_first = BWD ? maxlen - 1 : 0;
+			prefetch(t_first, maxlen);
+			next_scale(t_first, 0); next_scale(t_first, 1);
+		}
 
 		for (uint32_t step = 0; step < maxlen; step++, gstep++) {
 			const uint32_t t = BWD ? maxlen - 1 - step : step;
+			const uint32_t t_next = BWD ? t - 1 : t + 1;          // (wraps behind the last backward step: prefetch / next_scale switch off)
 			float* xch = xbase + (gstep & 1) * xstride;
 			NTICK(7);
-			// ---------------------------------------------------------------- scale of bh_t (backward)
-			if (BWD) {
-				if (tid < UT) {
-					const uint32_t len = sh.len[tid];
-					if (t + 1 < len) {
-						const uint32_t nn = min(len - 1 - t, D);
-						const size_t n = (size_t)sh.off[tid] + t;
-						double sg = -DBL_MAX;
-						for (uint32_t d = 1; d <= nn; d++) sg = fmax(sg, (double)p.smaxd[(n + d) * D + d - 1] + sh.g_ring[tid][(t + d) & (RING - 1)]);
-						sh.scale[tid] = sg;
-					}
-				}
-				__syncthreads();
-			}
 			// ---------------------------------------------------------------- phase A: my slice of the new vector
-			// float scale per (utterance, duration) for phase A: forward rho_{t-d} + Mmax - rho_t (d <= t) or -rho_t (d == t+1); backward
-			// kappa_{t+d} - sigma_t.  Entries of durations that do not exist are 0 (their score is read as -inf).
-			for (uint32_t i = tid; i < UT * RING; i += NTHR) {
-				const uint32_t u = i / RING, d = i % RING, len = sh.len[u];
-				float v = 0.0f;
-				if (d >= 1 && d <= D) {
-					if (!BWD) { if (t < len && d <= t + 1) v = (d <= t) ? (float)(sh.s_ring[u][(t - d) & (RING - 1)] + p.Mmax - sh.scale[u]) : (float)(-sh.scale[u]); }
-					else if (t + 1 < len && d <= len - 1 - t) v = (float)(sh.s_ring[u][(t + d) & (RING - 1)] - sh.scale[u]);
-				}
-				sh.scf[u][d] = v;
-			}
-			__syncthreads();
-			NTICK(0);   // backward: scale
-			// the D terms of an entry are independent: the loads of DC durations of BOTH entries of the thread are issued before any is
-			// used, so a frame costs ceil(D / DC) round trips to L2 / HBM instead of 2 D
+			//   forward  a_t[y]  = sum_d exp(S_t[d,y] + LG_{t-d}[y] + (rho_{t-d} + Mmax - rho_t))   (d == t+1: exp(S_t[d,y] - rho_t))
+			//   backward bh_t[y] = sum_d exp(S_{t+d}[d,y] + LB_{t+d}[y] + (kappa_{t+d} - sigma_t))
 			{
-				const uint32_t u0 = warp * 2;
 				float acc[2] = {0.0f, 0.0f};
-				size_t nf[2]; bool act[2]; uint32_t lim[2], limL[2];
-				// base pointers once per frame and 32-bit offsets per duration (64-bit index arithmetic per load made this phase
-				// instruction-bound); entries that do not exist read element 0 of their row and are replaced after the load
-				const float* Sq[2]; const float* Lq[2];
+				size_t nf[2]; bool act[2];
 #pragma unroll
 				for (int i = 0; i < 2; i++) {
-					const uint32_t len = sh.len[u0 + i];
-					nf[i] = (size_t)sh.off[u0 + i] + t;
-					if (!BWD) { act[i] = t < len && y_ok; lim[i] = act[i] ? min(t + 1, D) : 0; limL[i] = act[i] ? min(t, D) : 0; }
-					else { act[i] = t + 1 < len && y_ok; lim[i] = act[i] ? min(len - 1 - t, D) : 0; limL[i] = lim[i]; }
-					Sq[i] = p.S + (act[i] ? nf[i] * Lp + y : 0);
-					Lq[i] = (BWD ? p.LB : p.LG) + (act[i] ? nf[i] * Pp + y : 0);
-				}
-				const uint32_t dtop = max(lim[0], lim[1]);
-				const uint32_t s_step = BWD ? Lp + P : P;      // forward: S[n][(d-1)P + y]; backward: S[n+d][(d-1)P + y]
-				for (uint32_t d0 = 1; d0 <= dtop; d0 += DC) {
-					float sv[2][DC], lv[2][DC];
+					const uint32_t u = u0 + i, len = sh.len[u];
+					nf[i] = (size_t)sh.off[u] + t;
+					uint32_t limL;
+					if (!BWD) { act[i] = t < len && y_ok; limL = act[i] ? min(t, D) : 0; }
+					else { act[i] = t + 1 < len && y_ok; limL = act[i] ? min(len - 1 - t, D) : 0; }
+					const float* hq = hist + (size_t)u * PT + lane;
 #pragma unroll
-					for (uint32_t j = 0; j < DC; j++) {
-						const uint32_t d = d0 + j;
-						const uint32_t o_s = BWD ? d * s_step - P : (d - 1) * s_step, o_l = d * Pp;
-#pragma unroll
-						for (int i = 0; i < 2; i++) {
-							const bool on = d <= lim[i], onL = d <= limL[i];
-							const float sx = __ldg(Sq[i] + (on ? o_s : 0u));
-							const float lx = BWD ? Lq[i][onL ? o_l : 0u] : *(Lq[i] - (onL ? o_l : 0u));
-							sv[i][j] = on ? sx : -INFINITY;      // a term that does not exist contributes exp(-inf) = 0
-							lv[i][j] = onL ? lx : 0.0f;          // forward, d == t+1: the segment starts the utterance
-						}
+					for (uint32_t d = 1; d <= (uint32_t)DR; d++) {
+						const float lx = d <= limL ? hq[(size_t)((BWD ? t + d : t - d) & (RING - 1)) * (UT * PT)] : 0.0f;   // forward, d == t+1: the segment starts the utterance
+						acc[i] += __expf(sn[i][d - 1] + lx + sh.scf[u][d & (RING - 1)]);
 					}
-#pragma unroll
-					for (int i = 0; i < 2; i++)
-#pragma unroll
-						for (uint32_t j = 0; j < DC; j++) {
-							const uint32_t d = d0 + j;
-							acc[i] += __expf(sv[i][j] + lv[i][j] + sh.scf[u0 + i][d & (RING - 1)]);
-						}
 				}
 #pragma unroll
 				for (int i = 0; i < 2; i++) {
@@ -225,7 +238,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					if (!BWD) { if (act[i]) p.A[nf[i] * Pp + y] = acc[i]; }
 					else {
 						// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: stored with the frame the new segment starts in (row shift 1 of the Xi GEMM)
-						if (act[i]) p.R[(nf[i] + 1) * Pp + y] = acc[i] * expf((float)(p.rho[nf[i]] + p.Mmax + sh.scale[u] - sh.lz[u]));
+						if (act[i]) p.R[(nf[i] + 1) * Pp + y] = acc[i] * expf((float)(rh[i] + p.Mmax + sh.scale[u] - sh.lz[u]));
 						if (t == 0 && len > 0 && y_ok) p.R[nf[i] * Pp + y] = 0.0f;      // no transition enters the first frame
 					}
 					sh.tileU[u][lane] = acc[i];
@@ -240,12 +253,16 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 			group_barrier(ctr, (gstep + 1) * p.npt);
 			NTICK(2);   // barrier
 			// ---------------------------------------------------------------- phase B: my block of the matrix product
-			if (tid < UT) {
-				float v = 0.0f;
-				for (uint32_t q = 0; q < p.npt; q++) v += __ldcg(xch + (size_t)Pk * UT + (size_t)q * UT + tid);
-				sh.vsum[tid] = v;
-			}
-			NTICK(3);   // staging (none: the operand fragments come straight from L2)
+			// the partial sums of the exchanged vector (one per CTA of the group and utterance), requested ahead of the product
+			float vpart[2][2];
+#pragma unroll
+			for (int i = 0; i < 2; i++)
+#pragma unroll
+				for (int h2 = 0; h2 < 2; h2++) {
+					const uint32_t q = lane + 32 * h2;
+					vpart[i][h2] = q < p.npt ? __ldcg(xch + (size_t)Pk * UT + (size_t)q * UT + u0 + i) : 0.0f;
+				}
+			NTICK(3);
 			{
 				// the CTA's 16 x 32 block of the product on the tensor cores: mma.sync m16n8k16, rows = utterances, columns = the tile's
 				// phones, bf16 hi/lo splits of both operands (hi*hi + hi*lo + lo*hi, fp32 accumulation: ~16 mantissa bits like every other
@@ -272,6 +289,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 							av[j][3] = __ldcg(reinterpret_cast<const float2*>(r0 + (size_t)8 * Pk + 8));
 						}
 					}
+					NTICK(0);   // operand requests issued
 #pragma unroll
 					for (uint32_t j = 0; j < KB; j++) {
 						const uint32_t ks = ks0 + j * NW;
@@ -290,6 +308,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 						}
 					}
 				}
+				NTICK(6);   // operands arrived, split, multiplied
 #pragma unroll
 				for (int nt = 0; nt < 4; nt++) {
 					*reinterpret_cast<float2*>(&sh.red[warp][fg][nt * 8 + 2 * ft]) = make_float2(acc[nt][0], acc[nt][1]);
@@ -298,48 +317,37 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 			}
 			__syncthreads();
 			NTICK(4);   // product
-			float lcur[2];
+			prefetch(t_next, maxlen);      // in flight across the reduction and the scale bookkeeping (requested earlier, the 62 values would
+			                               // sit in registers through the product and serialise its operand loads)
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
-				const uint32_t u = warp * 2 + i, len = sh.len[u];
+				const uint32_t u = u0 + i, len = sh.len[u];
 				const size_t n = (size_t)sh.off[u] + t;
 				float s = 0.0f;
 #pragma unroll
 				for (int w = 0; w < NW; w++) s += sh.red[w][u][lane];
-				lcur[i] = 0.0f;
-				if (t < len && y_ok) {
-					if (!BWD) p.LG[n * Pp + y] = logf(s);
-					else { lcur[i] = (t + 1 == len) ? 0.0f : logf(s); p.LB[n * Pp + y] = lcur[i]; }      // setTailBeta: beta_{T-1} = 0
-				}
-			}
-			if (tid < UT) {
-				const uint32_t len = sh.len[tid];
-				const size_t n = (size_t)sh.off[tid] + t;
 				if (t < len) {
+					const bool tail = BWD && t + 1 == len;                          // setTailBeta: beta_{T-1} = 0
+					const float l = tail ? 0.0f : logf(s);
+					hist[(size_t)(t & (RING - 1)) * (UT * PT) + (size_t)u * PT + lane] = l;
+					if (y_ok) (BWD ? p.LB : p.LG)[n * Pp + y] = l;
+					// per-utterance bookkeeping by the whole warp (every lane holds the same values; lane 0 stores)
+					const double vs = (double)warp_sum(vpart[i][0] + vpart[i][1]);
 					if (!BWD) {
-						const double gh = sh.scale[tid] + log((double)sh.vsum[tid]);       // exact log-sum of alpha_t
-						sh.g_ring[tid][t & (RING - 1)] = gh;
-						if (t + 1 == len) { if (pt == 0) p.logZ[sh.utt[tid]] = gh; }       // computeAlphaSum
-						else {
-							const uint32_t t1 = t + 1;
-							double r = -DBL_MAX;
-							for (uint32_t d = 1; d <= min(t1, D); d++) r = fmax(r, (double)p.smaxd[(n + 1) * D + d - 1] + p.Mmax + sh.g_ring[tid][(t1 - d) & (RING - 1)]);
-							if (t1 < D) r = fmax(r, (double)p.smaxd[(n + 1) * D + t1]);
-							sh.scale[tid] = r; sh.s_ring[tid][t1 & (RING - 1)] = r;
-							if (pt == 0) p.rho[n + 1] = r;
-						}
+						const double gh = sh.scale[u] + log(vs);                      // exact log-sum of alpha_t
+						if (lane == 0) { sh.g_ring[u][t & (RING - 1)] = gh; if (t + 1 == len && pt == 0) p.logZ[sh.utt[u]] = gh; }   // computeAlphaSum
 					} else {
-						const bool tail = t + 1 == len;
-						const double kp = tail ? 0.0 : sh.scale[tid] + p.Mmax;
-						sh.kap[tid] = kp; sh.s_ring[tid][t & (RING - 1)] = kp;
-						if (pt == 0) p.kappa[n] = kp;                                         // for the posterior pass
-						sh.g_ring[tid][t & (RING - 1)] = tail ? 0.0 : kp + log((double)sh.vsum[tid]);
+						const double kp = tail ? 0.0 : sh.scale[u] + p.Mmax;
+						if (lane == 0) {
+							sh.s_ring[u][t & (RING - 1)] = kp;
+							if (pt == 0) p.kappa[n] = kp;                               // for the posterior pass
+							sh.g_ring[u][t & (RING - 1)] = tail ? 0.0 : kp + log(vs);
+						}
 					}
 				}
+				next_scale(t_next, i);
 			}
-			__syncthreads();
 			NTICK(5);   // reduction + scales
-			NTICK(6);   // (phase C: the posteriors are a pass of their own behind the recursion, nodur_post_kernel)
 		}
 	}
 	if (timing) { for (int i = 0; i < 8; i++) p.dbg[i] = tacc[i]; p.dbg[8] = gstep; }
@@ -396,26 +404,40 @@ void launch_nodur_post(const NodurParams& p, const uint32_t* frame_t, const uint
 	nodur_post_kernel<<<dim3(N, (p.P + 255) / 256), 256, 0, s>>>(p, frame_t, frame_utt);
 }
 
+namespace {
+// the instantiation whose unrolled duration loops cover max_dur (the D terms of an entry wait in registers)
+template <bool BWD>
+const void* nodur_fn(uint32_t D) {
+	if (D <= 4) return (const void*)nodur_dp_kernel<BWD, 4>;
+	if (D <= 10) return (const void*)nodur_dp_kernel<BWD, 10>;
+	if (D <= 16) return (const void*)nodur_dp_kernel<BWD, 16>;
+	return (const void*)nodur_dp_kernel<BWD, 31>;
+}
+}  // namespace
+
 int nodur_max_groups(uint32_t P) {
 	int dev = 0, sms = 0, per_sm = 0;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const size_t smem = nodur_smem_bytes(P);
-	if (cudaFuncSetAttribute(nodur_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-	if (cudaFuncSetAttribute(nodur_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nodur_dp_kernel<true>, NTHR, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return 0; }
+	for (uint32_t D : {4u, 10u, 16u, 31u}) {
+		if (cudaFuncSetAttribute(nodur_fn<false>(D), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+		if (cudaFuncSetAttribute(nodur_fn<true>(D), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+	}
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nodur_fn<true>(31), NTHR, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return 0; }
 	const uint32_t npt = (P + PT - 1) / PT;
 	return (int)((uint32_t)(sms * per_sm) / npt);
 }
 
 cudaError_t launch_nodur_dp(bool backward, const NodurParams& p, cudaStream_t s) {
 	if (!p.n_groups) return cudaSuccess;
+	if (p.D > 31) return cudaErrorInvalidValue;
 	const size_t smem = nodur_smem_bytes(p.P);
 	cudaError_t e = cudaMemsetAsync(p.ctr, 0, sizeof(uint32_t) * p.n_groups, s);
 	if (e != cudaSuccess) return e;
 	NodurParams q = p;
 	void* args[] = {&q};
-	const void* fn = backward ? (const void*)nodur_dp_kernel<true> : (const void*)nodur_dp_kernel<false>;
+	const void* fn = backward ? nodur_fn<true>(p.D) : nodur_fn<false>(p.D);
 	return cudaLaunchCooperativeKernel(fn, dim3(p.n_groups * p.npt), dim3(NTHR), args, smem, s);
 }
 

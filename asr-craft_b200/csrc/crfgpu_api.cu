@@ -1001,7 +1001,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		auto nreport = [&](const char* what) {
 			unsigned long long v[16]; CUDA_OK(cudaMemcpyAsync(v, ndbg.p, sizeof(v), cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
 			const double n = v[8] ? (double)v[8] : 1.0;
-			fprintf(stderr, "[crfgpu] no_dur %s: %.0f steps; cycles/step: scale %.0f phaseA %.0f barrier %.0f staging %.0f product %.0f reduce+scales %.0f phaseC %.0f other %.0f\n",
+			fprintf(stderr, "[crfgpu] no_dur %s: %.0f steps; cycles/step: operand requests %.0f phaseA %.0f barrier %.0f partial-sum requests %.0f store+sync %.0f reduce+scales+prefetch %.0f multiply %.0f other %.0f\n",
 			        what, n, v[0] / n, v[1] / n, v[2] / n, v[3] / n, v[4] / n, v[5] / n, v[6] / n, v[7] / n);
 		};
 		phase_begin(h, "forward");
