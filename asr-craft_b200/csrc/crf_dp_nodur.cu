@@ -42,7 +42,7 @@ static_assert(UT == 16 && NW * 2 == UT, "thread mapping: warp w owns utterances 
 
 struct Shared {
 	float red[NW][UT][PT];        // partial products of the 8 contraction slices
-	float tileU[UT][PT];          // the CTA's slice of the new vector, [utterance][phone]
+	float tileF[UT * PT];         // the CTA's slice of the new vector in the A-fragment order of the product (frag_index)
 	double g_ring[UT][RING];      // forward: exact log-sum of alpha_t | backward: upper bound of beta_t
 	double s_ring[UT][RING];      // forward: rho_t                    | backward: kappa_t
 	double scale[UT];             // scale of the frame being produced (rho_t | sigma_t)
@@ -71,6 +71,14 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
 	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
 	             : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Exchange layout = A-fragment order of mma.sync m16n8k16 (rows = utterances, k = phone): element (u, k) of k-step ks = k / 16 sits at
+// float ((ks * 4 + e) * 32 + lane) * 2 + (k & 1) with e = u / 8 + 2 * ((k % 16) / 8), lane = (u % 8) * 4 + (k % 8) / 2 -- so the four
+// float2 operand loads of a k-step are 256 contiguous bytes per warp, and a CTA's 32-phone tile (two k-steps) is one 2 KB block.
+__device__ __forceinline__ uint32_t frag_index(uint32_t u, uint32_t j) {      // j = phone inside the 32-phone tile
+	const uint32_t ks = j >> 4, kk = j & 15;
+	return (((ks * 4 + (u >> 3) + 2 * (kk >> 3)) * 32 + (u & 7) * 4 + ((kk & 7) >> 1)) << 1) + (kk & 1);
 }
 
 // all CTAs of the group have published their slice of step `gstep`
@@ -106,6 +114,7 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	const uint32_t g = blockIdx.x / p.npt, pt = blockIdx.x % p.npt, y0 = pt * PT, y = y0 + lane;
 	const bool y_ok = y < P;
 	const float* Msrc = BWD ? p.ET : p.E;
+	const float* const Sg = p.S;
 	for (uint32_t i = tid; i < n_ks * 4 * 32; i += NTHR) {
 		const uint32_t ks = i >> 7, nt = (i >> 5) & 3, ln = i & 31, fg = ln >> 2, ft = ln & 3, j = nt * 8 + fg;
 		float v[4];
@@ -133,7 +142,6 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 	// values that do not depend on the recursion are requested one step ahead and wait in registers: the D score terms of both
 	// entries of the thread, the score maxima that bound the next scale, the forward scale of the frame (backward: Xi factor)
 	float sn[2][DR]; float sm[2]; double rh[2];
-	const float* const Sg = p.S;
 	auto prefetch = [&](uint32_t tt, uint32_t maxlen) {
 #pragma unroll
 		for (int i = 0; i < 2; i++) {
@@ -153,6 +161,23 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 			// lane = d - 1: forward smaxd[n][d-1] (d <= min(tt + 1, D)); backward smaxd[n + d][d - 1] (d <= min(len - 1 - tt, D))
 			sm[i] = lane < lm ? __ldg(p.smaxd + (BWD ? (n + lane + 1) * D + lane : n * D + lane)) : 0.0f;
 			rh[i] = (BWD && a) ? p.rho[n] : 0.0;
+		}
+	};
+	// ... and one step before that their lines are pulled from DRAM into L2 (lane = d - 1 asks for the 128-byte line of duration d): all
+	// CTAs request their 60 KB of scores at the same point of the lock-step, 8 MB in a burst that ran at the HBM rate for 4 k cycles
+	// when the register loads met DRAM themselves; requested here, the transfer hides behind the barrier and the product
+	auto prefetch_l2 = [&](uint32_t tt, uint32_t maxlen) {
+#pragma unroll
+		for (int i = 0; i < 2; i++) {
+			const uint32_t u = u0 + i, len = sh.len[u];
+			const bool in = tt < maxlen;
+			uint32_t lm;
+			if (!BWD) lm = (in && tt < len) ? min(tt + 1, D) : 0;
+			else lm = (in && tt + 1 < len) ? min(len - 1 - tt, D) : 0;
+			if (lane < lm) {
+				const float* q = Sg + ((size_t)sh.off[u] + tt + (BWD ? 1 : 0)) * Lp + y0 + (size_t)lane * s_step;
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+			}
 		}
 	};
 	// scale of step tt and the float scale terms of its phase A, for utterance u = u0 + i (whole warp; lane = d - 1 / d)
@@ -241,15 +266,16 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 						if (act[i]) p.R[(nf[i] + 1) * Pp + y] = acc[i] * expf((float)(rh[i] + p.Mmax + sh.scale[u] - sh.lz[u]));
 						if (t == 0 && len > 0 && y_ok) p.R[nf[i] * Pp + y] = 0.0f;      // no transition enters the first frame
 					}
-					sh.tileU[u][lane] = acc[i];
+					sh.tileF[frag_index(u, lane)] = acc[i];
 					const float ps = warp_sum(acc[i]);
 					if (lane == 0) __stcg(xch + (size_t)Pk * UT + (size_t)pt * UT + u, ps);
 				}
 			}
+			prefetch_l2(t_next, maxlen);
 			__syncthreads();
 			NTICK(1);   // phase A
-			// exchange layout [utterance][Pk]: the A fragments of the product are float2 loads straight from L2
-			if (tid < PT * UT / 4) __stcg(reinterpret_cast<float4*>(xch + (size_t)(tid >> 3) * Pk + y0) + (tid & 7), reinterpret_cast<const float4*>(&sh.tileU[0][0])[tid]);
+			// the tile in fragment order: one contiguous 2 KB block of the exchange buffer
+			if (tid < PT * UT / 4) __stcg(reinterpret_cast<float4*>(xch + (size_t)y0 * UT) + tid, reinterpret_cast<const float4*>(&sh.tileF[0])[tid]);
 			group_barrier(ctr, (gstep + 1) * p.npt);
 			NTICK(2);   // barrier
 			// ---------------------------------------------------------------- phase B: my block of the matrix product
@@ -282,11 +308,9 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					for (uint32_t j = 0; j < KB; j++) {
 						const uint32_t ks = ks0 + j * NW;
 						if (ks < n_ks) {
-							const float* r0 = xch + (size_t)fg * Pk + ks * 16 + 2 * ft;
-							av[j][0] = __ldcg(reinterpret_cast<const float2*>(r0));
-							av[j][1] = __ldcg(reinterpret_cast<const float2*>(r0 + (size_t)8 * Pk));
-							av[j][2] = __ldcg(reinterpret_cast<const float2*>(r0 + 8));
-							av[j][3] = __ldcg(reinterpret_cast<const float2*>(r0 + (size_t)8 * Pk + 8));
+							const float2* r0 = reinterpret_cast<const float2*>(xch) + (size_t)ks * 128 + lane;
+#pragma unroll
+							for (int e = 0; e < 4; e++) av[j][e] = __ldcg(r0 + e * 32);
 						}
 					}
 					NTICK(0);   // operand requests issued
@@ -332,16 +356,19 @@ __global__ void __launch_bounds__(NTHR, 1) nodur_dp_kernel(NodurParams p) {
 					hist[(size_t)(t & (RING - 1)) * (UT * PT) + (size_t)u * PT + lane] = l;
 					if (y_ok) (BWD ? p.LB : p.LG)[n * Pp + y] = l;
 					// per-utterance bookkeeping by the whole warp (every lane holds the same values; lane 0 stores)
-					const double vs = (double)warp_sum(vpart[i][0] + vpart[i][1]);
+					// log of the vector's sum in float: a scale is only the reference its own frame is stored against (the entries are formed
+					// from the scales exactly as stored), so this rounding does not accumulate over the frames -- the fp64 log cost more than
+					// the whole reduction
+					const double lvs = (double)logf(warp_sum(vpart[i][0] + vpart[i][1]));
 					if (!BWD) {
-						const double gh = sh.scale[u] + log(vs);                      // exact log-sum of alpha_t
+						const double gh = sh.scale[u] + lvs;                          // log-sum of alpha_t
 						if (lane == 0) { sh.g_ring[u][t & (RING - 1)] = gh; if (t + 1 == len && pt == 0) p.logZ[sh.utt[u]] = gh; }   // computeAlphaSum
 					} else {
 						const double kp = tail ? 0.0 : sh.scale[u] + p.Mmax;
 						if (lane == 0) {
 							sh.s_ring[u][t & (RING - 1)] = kp;
 							if (pt == 0) p.kappa[n] = kp;                               // for the posterior pass
-							sh.g_ring[u][t & (RING - 1)] = tail ? 0.0 : kp + log(vs);
+							sh.g_ring[u][t & (RING - 1)] = tail ? 0.0 : kp + lvs;
 						}
 					}
 				}
