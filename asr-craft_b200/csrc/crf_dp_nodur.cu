@@ -16,15 +16,20 @@
 // and the EXACT log-sums of earlier frames, so every stored value is <= D and nothing overflows.
 //
 // Work split: the P x P matrix is sliced over the CTAs of a GROUP -- CTA pt keeps the 32 columns (forward) / rows (backward) of its
-// phone tile in shared memory for the whole launch -- and UT = 16 utterances advance in lock-step per group.  Per frame:
-//   phase A  (element-wise, D terms per (utterance, phone)): the new vector a_t / bh_t of the CTA's own phones, written to the lattice
-//            array and, transposed ([phone][utterance]), to the group's exchange buffer together with its partial sums;
+// phone tile in shared memory for the whole launch, pre-split into bf16 hi / lo halves in mma.sync fragment order -- and UT = 16
+// utterances advance in lock-step per group.  Per lock-step:
+//   phase A  (element-wise, D terms per (utterance, phone)): the new vector a_t / bh_t of the CTA's own phones from score terms that
+//            wait in registers (requested a step ahead, their lines pulled into L2 a phase before that), history terms in a
+//            shared-memory ring and float scale terms formed once per (utterance, duration); written to the lattice array and, in the
+//            A-fragment order of the product, to the group's exchange buffer together with its partial sums;
 //   ONE barrier among the CTAs of the group (a monotonic counter in global memory; the launch is cooperative, so they are co-resident);
-//   phase B  the CTA's 16 x 32 block of the matrix product from the exchanged vector (fp32 FFMA: 8 warps = 8 slices of the contraction
-//            index, 16 accumulators per thread, one shared-memory reduction), LG / LB, and the scale of the next frame -- every CTA
-//            of the group derives the same scale from the same exchanged partial sums, so no second barrier is needed;
-//   phase C  (backward) posteriors of the frame: Dm[n][(d,y)] = [reference segment] - gamma_t[d,y] for the state-gradient GEMM and
-//            R[n+1][y] (phase A) for the Xi GEMM, which both run on the TMA-fed kernels of crf_tma_gemm.cu.
+//   phase B  the CTA's 16 x 32 block of the matrix product from the exchanged vector on the tensor cores (mma.sync m16n8k16, bf16
+//            hi/lo splits, 8 warps = 8 interleaved slices of the contraction index, one shared-memory reduction), LG / LB, and the
+//            scale of the next frame -- every CTA of the group derives the same scale from the same exchanged partial sums, so no
+//            second barrier is needed; the per-utterance bookkeeping is done by the warp that owns the utterance, lane = duration.
+//   The posteriors Dm[n][(d,y)] = [reference segment] - gamma_t[d,y] for the state-gradient GEMM are a pass of their own behind the
+//   backward recursion (nodur_post_kernel); R[n+1][y] (phase A) feeds the Xi GEMM; both GEMMs run on the TMA-fed kernels of
+//   crf_tma_gemm.cu.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
