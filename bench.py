@@ -558,6 +558,45 @@ def run_ours(args):
                   "lambda_len": sm.lambda_len, "plan": sm.plan_info()}
         sm.close()
 
+    # ---- production-recipe leg (stdseg_no_dur_no_segtransftr + stdtrans at the TIMIT demo's shape), one GPU ----
+    recipe = None
+    if world == 1 and not args.no_recipe:
+        roff, rf1, rf2, rlabs = workloads.recipe_batch()
+        rm = crf_b200.CrfGpu(crf_b200.make_config(**workloads.recipe_kwargs()), device=local)
+        rm.set_lambda(workloads.lam_for("recipe", rm.lambda_len))
+        rm.stage(roff, rf1, rlabs, ftrs2=rf2)
+        rbest = None
+        for _ in range(3):
+            rm.fwdbwd_staged(); rm.synchronize()
+            ph = {k: rm.phase_ms(k) for k in phase_names}
+            rbest = ph if rbest is None or sum(ph.values()) < sum(rbest.values()) else rbest
+        _, rn, rz = rm.fetch_fwdbwd()
+        npin = len(pins.z["recipe/logZ"]) if "recipe/logZ" in pins.z else 0
+        if npin:
+            gate.append(pins.check_loglik("recipe", range(npin), rn[:npin], rz[:npin], f"recipe fwd-bwd, pinned utterances 0..{npin - 1} of {len(roff) - 1}"))
+            if gate[-1]["ok"] is False:
+                fail_parity(gate)
+        rm.stage(roff, rf1, ftrs2=rf2)
+        for _ in range(2):
+            rm.viterbi_staged(); rm.synchronize()
+        rvs, rvr = rm.phase_ms("viterbi_score"), rm.phase_ms("viterbi")
+        if npin and "recipe/crc" in pins.z:
+            rsegs, rcost = rm.fetch_viterbi(roff)
+            crc = np.array([path_crc(*sg) for sg in rsegs[:npin]], np.uint32)
+            rec = {"what": f"recipe Viterbi, pinned utterances 0..{npin - 1} of {len(roff) - 1}", "paths_equal": int(np.sum(crc == pins.z["recipe/crc"])), "n": npin,
+                   "costs_bit_equal": bool(np.array_equal(rcost[:npin].view(np.uint32), pins.z["recipe/cost"].view(np.uint32)))}
+            rec["ok"] = bool(rec["paths_equal"] == npin and rec["costs_bit_equal"])
+            gate.append(rec)
+            if not rec["ok"]:
+                fail_parity(gate)
+        rN = float(roff[-1])
+        recipe = {"workload": "TIMIT recipe shape (stdseg_no_dur_no_segtransftr + stdtrans, 48 phones, maxDur 10, 1162 state features from stream 1, "
+                              f"1872 transition features from 13 context frames of stream 2; {len(roff) - 1} utterances = {int(rN)} frames, device-resident)",
+                  "train_frames_per_s": rN / (sum(rbest.values()) / 1e3), "train_phases_ms": rbest,
+                  "viterbi_frames_per_s": rN / ((rvs + rvr) / 1e3), "viterbi_phases_ms": {"score": rvs, "recursion": rvr},
+                  "lambda_len": rm.lambda_len, "plan": rm.plan_info()}
+        rm.close()
+
     all_gate = [r for g in gather_list(gate) for r in g]
     if rank == 0:
         # per-frame ALGORITHMIC work of cfg4 (SURVEY.md 8d / DESIGN.md section 4).  Every phase sits below the tensor ridge
@@ -630,7 +669,7 @@ def run_ours(args):
             "parity_gate": {"ok": all(r["ok"] is not False for r in all_gate), "unpinned": [r["what"] for r in all_gate if r["ok"] is None],
                             "cfg4_loglik": head["loglik"], "cfg4_loglik_pinned": head["loglik_pinned"], "records": all_gate if world == 1 else all_gate[:8]},
             "gpu_launches": int(launches), "roofline": roof, "phases": rooflines, "cpu_baseline": cpu, "minibatch_sweep": sweep,
-            "viterbi": vit, "frame_crf": frame, "stress": stress}
+            "viterbi": vit, "frame_crf": frame, "stress": stress, "recipe": recipe}
         print(json.dumps(line))
     for pb in (pin_f, pin_l, pin_n, pin_z):
         pb.free()
@@ -653,6 +692,7 @@ def main():
     ap.add_argument("--no-viterbi", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
+    ap.add_argument("--no-recipe", action="store_true", help="skip the production-recipe leg (transition features, joined streams)")
     ap.add_argument("--no-frame", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true")
     args = ap.parse_args()

@@ -13,6 +13,8 @@ records which.  Output tests/golden/bench_pins.npz:
 
   cfg5/numer, cfg5/logZ,  the stress leg (1024 phones, maxDur 30, 2000-frame utterances): the first CFG5_PINNED utterances of
   cfg5/cost, cfg5/crc     workloads.cfg5_batch() -- training numerator / logZ and the Viterbi path CRC / cost (the whole batch is hours of CPU)
+  recipe/numer, .../logZ, the production TIMIT recipe's shape (48 phones, maxDur 10, 1162 state + 1872 transition features, joined streams):
+  recipe/cost, recipe/crc the first RECIPE_PINNED utterances of workloads.recipe_batch(), training and Viterbi
 
 Utterances are independent given lambda, so the work is cut into chunks that run in forked worker processes.
 
@@ -85,6 +87,19 @@ def cfg5_chunk(u):
     return u, numer[0], logz[0], cost[0], path_crc(*segs[0])
 
 
+RECIPE_PINNED = 4
+
+
+def recipe_chunk(u):
+    lib, _ = lib_and_kind()
+    cfg = make_config(**workloads.recipe_kwargs())
+    lam = workloads.lam_for("recipe", lib.lambda_len(cfg))
+    sub, f1, f2, labs = workloads.recipe_utt(*workloads.recipe_batch(), u)
+    _, numer, logz = lib.fwdbwd(cfg, lam, sub, f1, labs, n_threads=1, ftrs2=f2)
+    segs, cost, _ = lib.viterbi(cfg, lam, sub, f1, f2)
+    return u, numer[0], logz[0], cost[0], path_crc(*segs[0])
+
+
 def main():
     procs = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     what = sys.argv[2:] or ["cfg2", "cfg3", "cfg4"]
@@ -119,6 +134,12 @@ def main():
                 for u, n, z, c, h in pool.imap_unordered(cfg5_chunk, range(CFG5_PINNED)):
                     numer[u], logz[u], cost[u], crc[u] = n, z, c, h
                 out["cfg5/numer"], out["cfg5/logZ"], out["cfg5/cost"], out["cfg5/crc"] = numer, logz, cost, crc
+            elif name == "recipe":
+                numer, logz = np.zeros(RECIPE_PINNED), np.zeros(RECIPE_PINNED)
+                cost, crc = np.zeros(RECIPE_PINNED, np.float32), np.zeros(RECIPE_PINNED, np.uint32)
+                for u, n, z, c, h in pool.imap_unordered(recipe_chunk, range(RECIPE_PINNED)):
+                    numer[u], logz[u], cost[u], crc[u] = n, z, c, h
+                out["recipe/numer"], out["recipe/logZ"], out["recipe/cost"], out["recipe/crc"] = numer, logz, cost, crc
             out[name + "/producer"] = np.array(kind)
             np.savez_compressed(OUT, **out)
             print(f"{name}: done in {time.time() - t0:.0f} s ({kind})", flush=True)

@@ -117,6 +117,51 @@ def cfg5_batch(n_utt=64, n_frames=2000, n_phones=1024, max_dur=30, n_base_ftrs=6
     return off, ftrs, labs
 
 
+RECIPE_PHONES, RECIPE_FTRS, RECIPE_DUR, RECIPE_CTX = 48, 144, 10, 6
+
+
+def recipe_kwargs():
+    """The production TIMIT recipe (demo/segmental-timit-demo.cfg.in:11-48): stdseg_no_dur_no_segtransftr + stdtrans,
+    48 phones, maxDur 10; stream 1 = 144 inputs -> 8*144 + 10 = 1162 segment features (state features), stream 2 = the same inputs
+    padded by 6 frames on each side -> 13*144 = 1872 context features (transition features); dim(lambda) = 48*1163 + 48^2*1873."""
+    w1, w2 = 8 * RECIPE_FTRS + RECIPE_DUR, (2 * RECIPE_CTX + 1) * RECIPE_FTRS
+    return dict(model_type="stdseg_no_dur_no_segtransftr", n_labs=RECIPE_PHONES, n_base_ftrs=RECIPE_FTRS, max_dur=RECIPE_DUR,
+                n_actual_labs=RECIPE_PHONES, extract_seg_ftrs=1, n_base_ftrs2=RECIPE_FTRS, left_ctx2=RECIPE_CTX, right_ctx2=RECIPE_CTX,
+                use_trans_ftrs=1, state_fidx=(0, w1 - 1), trans_fidx=(w1, w1 + w2 - 1))
+
+
+def recipe_batch(n_utt=128):
+    """The first n_utt utterances of the TIMIT-shaped train set (real lengths and segment boundaries) with 48 phone ids drawn like the
+    other workloads (seed 9), stream 1 U[0,1) (seed 11), stream 2 U[0,1) with 6 context frames on each side of every utterance (seed 12).
+    Returns off, ftrs1, ftrs2, labs."""
+    utt_len, seg_cnt, seg_dur = timit_shape()
+    seg_start = np.concatenate([[0], np.cumsum(seg_cnt)])
+    lens = utt_len[:n_utt]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    labs = np.empty(int(off[-1]), np.uint32)
+    for u in range(n_utt):
+        rl = np.random.default_rng([9, u])
+        durs = seg_dur[seg_start[u]:seg_start[u + 1]]
+        phones = np.empty(len(durs), np.int64)
+        prev = -1
+        for i in range(len(durs)):
+            p = int(rl.integers(0, RECIPE_PHONES))
+            while p == prev:
+                p = int(rl.integers(0, RECIPE_PHONES))
+            phones[i] = prev = p
+        labs[off[u]:off[u + 1]] = np.repeat(phones, durs)
+    f1 = np.random.default_rng(11).random((int(off[-1]), RECIPE_FTRS), dtype=np.float32)
+    f2 = np.random.default_rng(12).random((int(off[-1]) + 2 * RECIPE_CTX * n_utt, RECIPE_FTRS), dtype=np.float32)
+    return off, f1, f2, labs
+
+
+def recipe_utt(off, f1, f2, labs, u):
+    """utterance u of a recipe batch as a batch of its own (stream 2 carries its own context frames)"""
+    a, b = int(off[u]), int(off[u + 1])
+    a2, b2 = a + 2 * RECIPE_CTX * u, b + 2 * RECIPE_CTX * (u + 1)
+    return np.array([0, b - a], np.uint32), f1[a:b], f2[a2:b2], labs[a:b]
+
+
 def lam_for(name, n):
-    seed, scale = {"cfg2": (3, 0.25), "cfg3": (6, 0.25), "cfg4": (7, 0.01), "cfg5": (8, 0.01)}[name]
+    seed, scale = {"cfg2": (3, 0.25), "cfg3": (6, 0.25), "cfg4": (7, 0.01), "cfg5": (8, 0.01), "recipe": (10, 0.01)}[name]
     return np.random.default_rng(seed).uniform(-scale, scale, n)
