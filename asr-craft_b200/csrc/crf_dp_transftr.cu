@@ -53,6 +53,20 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 	return r;
 }
 
+// Pre-pass over all frames, fully parallel: E_n = exp(M_n - max M_n) and the row maximum.  Inside the recursions that was L*L exp per
+// frame on the dependent chain (48 of them per thread and frame in the forward matrix-vector product alone).
+__global__ void __launch_bounds__(256) transftr_exp_kernel(const float* __restrict__ M, float* __restrict__ E, float* __restrict__ rowmax, uint32_t N, uint32_t LL, uint32_t Lq) {
+	const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= N) return;
+	const float* m = M + (size_t)warp * Lq;
+	float* e = E + (size_t)warp * Lq;
+	float mx = -INFINITY;
+	for (uint32_t i = lane; i < LL; i += 32) mx = fmaxf(mx, m[i]);
+	for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	for (uint32_t i = lane; i < LL; i += 32) e[i] = __expf(m[i] - mx);
+	if (lane == 0) rowmax[warp] = mx;
+}
+
 // the L x L scores of frame n into a shared-memory matrix with odd row stride Ls (columns AND rows conflict-free)
 template <int TF_THR>
 __device__ __forceinline__ void prefetch_matrix(float* dst, const float* src, uint32_t L, uint32_t Ls) {
@@ -69,7 +83,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 	float* scratch = a_prev + L;                 // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
 	double rho = 0.0, num = 0.0;
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + L * Ls, p.M + (size_t)(off + 1) * p.Lq, L, Ls);       // frame 1 -> buffer 1
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + L * Ls, p.E + (size_t)(off + 1) * p.Lq, L, Ls);       // frame 1 -> buffer 1
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
 		float* Mt = Ms + (t & 1) * L * Ls;
@@ -80,13 +94,12 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 		else {
 			cp_async_wait_all();
 			__syncthreads();
-			if (t + 1 < T) prefetch_matrix<TF_THR>(Ms + ((t + 1) & 1) * L * Ls, p.M + (n + 1) * p.Lq, L, Ls);
-			float m = -INFINITY;
-			for (uint32_t i = c; i < L * L; i += TF_THR) m = fmaxf(m, Mt[(i / L) * Ls + i % L]);
-			mmax = block_max<TF_THR>(m, scratch);
+			if (t + 1 < T) prefetch_matrix<TF_THR>(Ms + ((t + 1) & 1) * L * Ls, p.E + (n + 1) * p.Lq, L, Ls);
+			mmax = p.rowmax[n];
 			if (c < L) {
 				float v = 0.0f;
-				for (uint32_t q = 0; q < L; q++) v = fmaf(a_prev[q], __expf(Mt[q * Ls + c] - mmax), v);
+#pragma unroll 8
+				for (uint32_t q = 0; q < L; q++) v = fmaf(a_prev[q], Mt[q * Ls + c], v);      // Mt = exp(M_t - mmax) from the pre-pass
 				w = __logf(v) + s;
 			}
 		}
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 			const uint32_t y = p.labs[n];
 			if (y < L) {
 				num += (double)p.S[n * p.Lp + y];
-				if (t > 0) { const uint32_t yp = p.labs[n - 1]; if (yp < L && p.tidx[yp * L + y] != 0xffffffffu) num += (double)Mt[yp * Ls + y]; }
+				if (t > 0) { const uint32_t yp = p.labs[n - 1]; if (yp < L && p.tidx[yp * L + y] != 0xffffffffu) num += (double)p.M[n * p.Lq + yp * L + y]; }
 			}
 		}
 		__syncthreads();
@@ -120,7 +133,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 	float* scratch = av + L;                     // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
 	if (c < L) b[c] = 1.0f;                      // setTailBeta
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.M + (size_t)(off + T - 1) * p.Lq, L, Ls);
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.E + (size_t)(off + T - 1) * p.Lq, L, Ls);
 	__syncthreads();
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
@@ -138,11 +151,8 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		float* Mt = Ms + (t & 1) * L * Ls;
 		cp_async_wait_all();
 		__syncthreads();
-		if (t > 1) prefetch_matrix<TF_THR>(Ms + ((t - 1) & 1) * L * Ls, p.M + (n - 1) * p.Lq, L, Ls);
-		// E_t = exp(M_t - mmax) in place
-		float m = -INFINITY;
-		for (uint32_t i = c; i < L * L; i += TF_THR) m = fmaxf(m, Mt[(i / L) * Ls + i % L]);
-		const float mmax = block_max<TF_THR>(m, scratch);
+		if (t > 1) prefetch_matrix<TF_THR>(Ms + ((t - 1) & 1) * L * Ls, p.E + (n - 1) * p.Lq, L, Ls);
+		// Mt = E_t = exp(M_t - max) from the pre-pass (the normalisations below are scale-free)
 		const float s = c < L ? p.S[n * p.Lp + c] : -INFINITY;
 		const float smax = block_max<TF_THR>(s, scratch);
 		if (c < L) { wv[c] = __expf(s - smax) * b[c]; av[c] = p.A[(n - 1) * p.Lp + c]; }
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		float part = 0.0f;
 		for (uint32_t i = c; i < L * L; i += TF_THR) {
 			const uint32_t q = i / L, cc = i - q * L;
-			const float e = __expf(Mt[q * Ls + cc] - mmax) * wv[cc];          // E_t[q][cc] * w_t[cc]
+			const float e = Mt[q * Ls + cc] * wv[cc];                         // E_t[q][cc] * w_t[cc]
 			Mt[q * Ls + cc] = e;
 			part += av[q] * e;
 		}
@@ -172,6 +182,11 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 }
 
 }  // namespace
+
+void launch_transftr_exp(const float* M, float* E, float* rowmax, uint32_t N, uint32_t LL, uint32_t Lq, cudaStream_t s) {
+	if (!N) return;
+	transftr_exp_kernel<<<(N + 7) / 8, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);
+}
 
 size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * L * (L | 1u) + 3 * (size_t)L + 16); }
 
@@ -217,24 +232,38 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 	float* scratch = lgh + ND_RING * P;          // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
 	double num = 0.0;
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + P * Ps, p.M + (size_t)(off + 1) * p.Lq, P, Ps);       // M_1 -> buffer 1
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + P * Ps, p.E + (size_t)(off + 1) * p.Lq, P, Ps);       // exp(M_1 - max) -> buffer 1
+	// the score terms of a frame do not depend on the recursion: those of frame t+1 are requested while frame t is processed
+	float sv[ND_RING];
+#pragma unroll
+	for (uint32_t d = 1; d < ND_RING; d++) sv[d] = (y < P && T > 0 && d <= min(1u, D)) ? p.S[(size_t)off * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
 		const uint32_t dmax = min(t + 1, D);
+		float sn[ND_RING];
+		{
+			const uint32_t dn = (t + 1 < T && y < P) ? min(t + 2, D) : 0;
+#pragma unroll
+			for (uint32_t d = 1; d < ND_RING; d++) sn[d] = d <= dn ? p.S[(n + 1) * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
+		}
 		const double rref = t > 0 ? rring[(t - 1) & (ND_RING - 1)] : 0.0;
 		// w[y] = log sum_d exp(S_t[d,y] + A_{t-d}[y] - rref)
 		float w = -INFINITY;
 		if (y < P) {
 			float lt[ND_RING];
 			float mx = -INFINITY;
-			for (uint32_t d = 1; d <= dmax; d++) {
-				float v = p.S[n * p.Lp + (size_t)(d - 1) * P + y];
-				if (d <= t) v += lgh[((t - d) & (ND_RING - 1)) * P + y] + (float)(rring[(t - d) & (ND_RING - 1)] - rref);
-				else v += (float)(-rref);
-				lt[d - 1] = v; mx = fmaxf(mx, v);
+#pragma unroll
+			for (uint32_t d = 1; d < ND_RING; d++) {
+				if (d <= dmax) {
+					float v = sv[d];
+					if (d <= t) v += lgh[((t - d) & (ND_RING - 1)) * P + y] + (float)(rring[(t - d) & (ND_RING - 1)] - rref);
+					else v += (float)(-rref);
+					lt[d - 1] = v; mx = fmaxf(mx, v);
+				}
 			}
 			float sacc = 0.0f;
-			for (uint32_t d = 1; d <= dmax; d++) sacc += __expf(lt[d - 1] - mx);
+#pragma unroll
+			for (uint32_t d = 1; d < ND_RING; d++) if (d <= dmax) sacc += __expf(lt[d - 1] - mx);
 			w = mx + __logf(sacc);
 		}
 		const float wmax = block_max<TF_THR>(w, scratch);
@@ -252,19 +281,20 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 			float* Mn = Ms + ((t + 1) & 1) * P * Ps;
 			cp_async_wait_all();
 			__syncthreads();
-			if (t + 2 < T) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.M + (n + 2) * p.Lq, P, Ps);
-			float m = -INFINITY;
-			for (uint32_t i = y; i < P * P; i += TF_THR) m = fmaxf(m, Mn[(i / P) * Ps + i % P]);
-			const float mmax = block_max<TF_THR>(m, scratch);
+			if (t + 2 < T) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.E + (n + 2) * p.Lq, P, Ps);
+			const float mmax = p.rowmax[n + 1];
 			if (y < P) {
 				float v = 0.0f;
-				for (uint32_t q = 0; q < P; q++) v = fmaf(av[q], __expf(Mn[q * Ps + y] - mmax), v);
+#pragma unroll 8
+				for (uint32_t q = 0; q < P; q++) v = fmaf(av[q], Mn[q * Ps + y], v);           // Mn = exp(M_{t+1} - mmax) from the pre-pass
 				const float l = mmax + __logf(v);
 				lgh[(t & (ND_RING - 1)) * P + y] = l; p.LG[n * p.Pp + y] = l;
 			}
-			if (y == 0 && lab != LAB_BAD) { const uint32_t nl = p.next_lab[n]; if (nl != LAB_BAD && p.tidx[(lab % P) * P + nl] != 0xffffffffu) num += (double)Mn[(lab % P) * Ps + nl]; }
+			if (y == 0 && lab != LAB_BAD) { const uint32_t nl = p.next_lab[n]; if (nl != LAB_BAD && p.tidx[(lab % P) * P + nl] != 0xffffffffu) num += (double)p.M[(n + 1) * p.Lq + (lab % P) * P + nl]; }
 			__syncthreads();
 		}
+#pragma unroll
+		for (uint32_t d = 1; d < ND_RING; d++) sv[d] = sn[d];
 	}
 	if (y == 0) { p.logZ[u] = T ? rring[(T - 1) & (ND_RING - 1)] : 0.0; p.numer[u] = num; }
 }
@@ -281,11 +311,20 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 	float* scratch = ev + P;                     // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
 	const double lz = p.logZ[u];
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * P * Ps, p.M + (size_t)(off + T - 1) * p.Lq, P, Ps);    // M_{T-1}
+	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * P * Ps, p.E + (size_t)(off + T - 1) * p.Lq, P, Ps);    // exp(M_{T-1} - max)
+	// the score terms S_{t+d}[d,y] of a frame do not depend on the recursion: those of frame t-1 are requested while frame t is processed
+	float sv[ND_RING], sn[ND_RING];
+#pragma unroll
+	for (uint32_t d = 1; d < ND_RING; d++) sv[d] = 0.0f;      // the tail frame has no successor terms
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
-		const uint32_t nn = min(T - 1 - t, D), dmax = min(t + 1, D);
+		const uint32_t nn = min(T - 1 - t, D);
 		const uint32_t lab = p.node_lab[n];
+		{
+			const uint32_t dn = (t > 0 && y < P) ? min(T - t, D) : 0;      // frame t-1: d <= T-1-(t-1)
+#pragma unroll
+			for (uint32_t d = 1; d < ND_RING; d++) sn[d] = d <= dn ? p.S[(n - 1 + d) * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
+		}
 		float lb = 0.0f;                         // beta_t[y] - kappa_t; tail: beta = 0
 		double kappa = 0.0;
 		if (nn > 0) {
@@ -295,22 +334,24 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			if (y < P) {
 				float lt[ND_RING];
 				float mx = -INFINITY;
-				for (uint32_t d = 1; d <= nn; d++) {
-					const float v = p.S[(n + d) * p.Lp + (size_t)(d - 1) * P + y] + lbh[((t + d) & (ND_RING - 1)) * P + y] + (float)(kring[(t + d) & (ND_RING - 1)] - kref);
-					lt[d - 1] = v; mx = fmaxf(mx, v);
+#pragma unroll
+				for (uint32_t d = 1; d < ND_RING; d++) {
+					if (d <= nn) {
+						const float v = sv[d] + lbh[((t + d) & (ND_RING - 1)) * P + y] + (float)(kring[(t + d) & (ND_RING - 1)] - kref);
+						lt[d - 1] = v; mx = fmaxf(mx, v);
+					}
 				}
 				float sacc = 0.0f;
-				for (uint32_t d = 1; d <= nn; d++) sacc += __expf(lt[d - 1] - mx);
+#pragma unroll
+				for (uint32_t d = 1; d < ND_RING; d++) if (d <= nn) sacc += __expf(lt[d - 1] - mx);
 				w = mx + __logf(sacc);
 			}
 			const float wmax = block_max<TF_THR>(w, scratch);
 			float* Mn = Ms + ((t + 1) & 1) * P * Ps;     // M_{t+1}
 			cp_async_wait_all();
 			__syncthreads();
-			if (t > 0) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.M + n * p.Lq, P, Ps);      // M_t for the next step
-			float m = -INFINITY;
-			for (uint32_t i = y; i < P * P; i += TF_THR) m = fmaxf(m, Mn[(i / P) * Ps + i % P]);
-			const float mmax = block_max<TF_THR>(m, scratch);
+			if (t > 0) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.E + n * p.Lq, P, Ps);      // exp(M_t - max) for the next step
+			const float mmax = p.rowmax[n + 1];
 			if (y < P) { ev[y] = __expf(w - wmax); av[y] = p.A[n * p.Pp + y]; }
 			__syncthreads();
 			// E[q][yy] = exp(M_{t+1}[q][yy] - mmax) * ev[yy] in place;
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			// (a segment boundary after frame t has probability <= 1: the posteriors are NOT renormalised per frame)
 			for (uint32_t i = y; i < P * P; i += TF_THR) {
 				const uint32_t q = i / P, yy = i - q * P;
-				Mn[q * Ps + yy] = __expf(Mn[q * Ps + yy] - mmax) * ev[yy];
+				Mn[q * Ps + yy] = Mn[q * Ps + yy] * ev[yy];
 			}
 			__syncthreads();
 			const float xscale = __expf((float)(p.rho[n] + (double)mmax + kref + (double)wmax - lz));
@@ -341,20 +382,12 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 		if (y < P) lbh[(t & (ND_RING - 1)) * P + y] = lb;
 		if (y == 0) kring[t & (ND_RING - 1)] = kappa;
 		if (t == 0) for (uint32_t i = y; i < P * P; i += TF_THR) p.Xd[n * p.Lq + i] = 0.0f;      // no transition enters the first frame
-		// gamma_t[d,y] = exp(S_t[d,y] + A_{t-d}[y] + beta_t[y] - logZ): the scalar part (rho_{t-d} + kappa_t - logZ) is formed in double
-		if (y < P) {
-			for (uint32_t d = 1; d <= D; d++) {
-				const uint32_t col = (d - 1) * P + y;
-				float dm = 0.0f;
-				if (d <= dmax) {
-					float v = p.S[n * p.Lp + col] + lb;
-					if (d <= t) v += p.LG[(n - d) * p.Pp + y] + (float)(p.rho[n - d] + kappa - lz);
-					else v += (float)(kappa - lz);
-					dm = ((lab == col) ? 1.0f : 0.0f) - __expf(v);
-				}
-				p.Dm[n * p.Lp + col] = dm;
-			}
-		}
+		// gamma_t[d,y] = exp(S_t[d,y] + A_{t-d}[y] + beta_t[y] - logZ) feeds nothing of this chain: beta_t[y] - kappa_t and kappa_t are
+		// stored, and Dm = [ref] - gamma is the posterior pass of the native no_dur path behind this kernel (launch_nodur_post, Mmax = 0)
+		if (y < P) p.LB[n * p.Pp + y] = lb;
+		if (y == 0) p.kappa[n] = kappa;
+#pragma unroll
+		for (uint32_t d = 1; d < ND_RING; d++) sv[d] = sn[d];
 		__syncthreads();
 	}
 }

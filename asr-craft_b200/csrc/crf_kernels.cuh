@@ -335,6 +335,7 @@ struct TransFtrParams {
 	uint32_t L, Lp, Lq;           // labels (<= 128), row stride of S / A / Dm, row stride of M / Xd (>= L*L)
 	uint32_t n_utt; const uint32_t* off;
 	const float* S; const float* M;       // [N][Lp] state scores, [N][Lq] transition scores M[n][p*L + c] of the frame the arc ENTERS
+	const float* E; const float* rowmax;  // [N][Lq] exp(M_n - max M_n) and [N] that maximum (launch_transftr_exp)
 	float* A; double* rho;                // forward: alpha normalised to sum 1, its log scale
 	double* logZ; double* numer;          // [n_utt]
 	float* Dm; float* Xd;                 // backward: [ref] - gamma [N][Lp], [ref pair] - xi [N][Lq] (zero on the first frame of an utterance)
@@ -346,9 +347,11 @@ struct NodurTfParams {
 	uint32_t P, Pp, D; uint64_t Lp; uint32_t Lq;   // phones (<= 128), stride of the P-wide arrays, durations (<= 31), stride of S / Dm, stride of M / Xd
 	uint32_t n_utt; const uint32_t* off;
 	const float* S; const float* M;               // [N][Lp] scores of (d,y); [N][Lq] M_n[y'][y] from frame n's duration-1 window
+	const float* E; const float* rowmax;          // [N][Lq] exp(M_n - max M_n) and [N] that maximum (launch_transftr_exp)
 	float* A; float* LG; double* rho;             // forward: alpha_t (sum 1), log A_t[y] - rho_t, log scale
 	double* logZ; double* numer;
-	float* Dm; float* Xd;                         // backward: [ref] - gamma [N][Lp], [ref pair] - xi stored at the frame the new segment starts in
+	float* Dm; float* Xd;                         // [ref] - gamma [N][Lp] (written by launch_nodur_post); backward: [ref pair] - xi stored at the frame the new segment starts in
+	float* LB; double* kappa;                     // backward: beta_t[y] - kappa_t [N][Pp] and kappa_t [N] for the posterior pass
 	const uint32_t* node_lab; const uint32_t* next_lab;   // (dur-1)*P + phone where a reference segment ends; phone of the NEXT reference segment there
 	const uint32_t* tidx;                         // [P][P] lambda index of the pair, 0xffffffff on the illegal pairs of an N-state map (their M is -inf)
 };
@@ -356,6 +359,8 @@ size_t nodur_tf_smem_bytes(uint32_t P);
 cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s);
 size_t transftr_smem_bytes(uint32_t L);
 cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStream_t s);
+// E_n = exp(M_n - max M_n), rowmax[n] = max M_n for every frame (rows of LL entries, stride Lq): the exp of the recursions, taken off their chains
+void launch_transftr_exp(const float* M, float* E, float* rowmax, uint32_t N, uint32_t LL, uint32_t Lq, cudaStream_t s);
 
 // ---- lambda-derived tables and the trainer's update on the device (crf_lambda.cu) -----------------------------------
 struct LambdaTablesParams {

@@ -87,6 +87,7 @@ struct crfgpu_ctx {
 	// transition tables and forward/backward vectors are P wide
 	DevBuf d_WdT, d_vt_base, d_negMt; uint32_t vtE = 0;              // decoding with transition features: per-frame transition tables
 	bool nodur_tf = false; DevBuf d_next_lab;                       // segmental no_dur model with transition features (nodur && nodur_tf)
+	DevBuf d_Eall, d_rowmax;                                        // exp(M_n - max M_n) of every frame and the maxima (launch_transftr_exp)
 	bool transftr = false; DevBuf d_Wtr, d_tbias, d_Mall, d_Xd;   // frame-level model with transition FEATURES (crf_dp_transftr.cu)
 	bool nodur = false; uint32_t Pp = 0; int opt_nodur_impl = 0; int nodur_groups_max = 0; uint32_t n_nodur_groups = 0;
 	DevBuf d_nd_grp, d_nd_batch, d_nd_xch, d_nd_ctr, d_LB;
@@ -915,7 +916,10 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		g.A = h->X() + tf0; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = nTf; g.bias = h->d_tbias.as<float>();
 		g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = L * L; g.K = nTf;
 		CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+		h->d_Eall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_rowmax.ensure(sizeof(float) * (size_t)N + 16);
+		launch_transftr_exp(h->d_Mall.as<float>(), h->d_Eall.as<float>(), h->d_rowmax.as<float>(), N, L * L, Lq, s); check_kernel(h, 1);
 		TransFtrParams q{};
+		q.E = h->d_Eall.as<float>(); q.rowmax = h->d_rowmax.as<float>();
 		q.L = L; q.Lp = Lp; q.Lq = Lq; q.n_utt = h->n_utt; q.off = h->d_off.as<uint32_t>();
 		q.S = h->d_S.as<float>(); q.M = h->d_Mall.as<float>(); q.A = h->d_A.as<float>(); q.rho = h->d_m.as<double>();
 		q.logZ = h->d_logZ.as<double>(); q.numer = h->d_numer.as<double>(); q.Dm = h->d_Dm.as<float>(); q.Xd = h->d_Xd.as<float>();
@@ -973,16 +977,29 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		ScoreGemmParams g{};      // M_n[y'][y] from the duration-1 window of frame n
 		g.A = h->X() + tf0; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = nTf; g.bias = h->d_tbias.as<float>();
 		g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = P * P; g.K = nTf;
+		phase_begin(h, "trans_score");      // (nested in "forward": the transition-score GEMM and its exp pre-pass on their own)
 		CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+		h->d_Eall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_rowmax.ensure(sizeof(float) * (size_t)N + 16);
+		launch_transftr_exp(h->d_Mall.as<float>(), h->d_Eall.as<float>(), h->d_rowmax.as<float>(), N, P * P, Lq, s); check_kernel(h, 1);
+		phase_end(h, "trans_score");
 		NodurTfParams q{};
+		q.E = h->d_Eall.as<float>(); q.rowmax = h->d_rowmax.as<float>();
 		q.P = P; q.Pp = h->Pp; q.D = D; q.Lp = Lp; q.Lq = Lq; q.n_utt = h->n_utt; q.off = h->d_off.as<uint32_t>();
 		q.S = h->d_S.as<float>(); q.M = h->d_Mall.as<float>(); q.A = h->d_A.as<float>(); q.LG = h->d_G.as<float>(); q.rho = h->d_m.as<double>();
 		q.logZ = h->d_logZ.as<double>(); q.numer = h->d_numer.as<double>(); q.Dm = h->d_Dm.as<float>(); q.Xd = h->d_Xd.as<float>();
 		q.node_lab = h->d_node_lab.as<uint32_t>(); q.next_lab = h->d_next_lab.as<uint32_t>(); q.tidx = h->d_tidx.as<uint32_t>();
+		q.LB = h->d_LB.as<float>(); q.kappa = h->d_kappa.as<double>();
 		CUDA_OK(launch_nodur_tf_dp(false, q, s)); check_kernel(h, 1);
 		phase_end(h, "forward");
 		phase_begin(h, "backward");
 		CUDA_OK(launch_nodur_tf_dp(true, q, s)); check_kernel(h, 1);
+		{   // Dm = [ref] - gamma: the posterior pass of the native no_dur path (this recursion keeps no Mmax in its scales)
+			NodurParams pp{};
+			pp.P = P; pp.Pp = h->Pp; pp.D = D; pp.Lp = Lp; pp.S = h->d_S.as<float>(); pp.LG = h->d_G.as<float>(); pp.LB = h->d_LB.as<float>();
+			pp.rho = h->d_m.as<double>(); pp.kappa = h->d_kappa.as<double>(); pp.logZ = h->d_logZ.as<double>(); pp.Mmax = 0.0;
+			pp.node_lab = h->d_node_lab.as<uint32_t>(); pp.Dm = h->d_Dm.as<float>();
+			launch_nodur_post(pp, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), N, s); check_kernel(h, 1);
+		}
 		phase_end(h, "backward");
 	} else if (h->nodur) {
 		h->d_smaxd.ensure(sizeof(float) * (size_t)N * D + 16);
@@ -1448,7 +1465,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
 	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt,
-	                  &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
+	                  &h->d_Eall, &h->d_rowmax, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
