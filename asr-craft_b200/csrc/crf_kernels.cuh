@@ -48,6 +48,7 @@ struct ScoreGemmParams {
 	float* C; uint32_t ldc;           // [M][ldc], written at column offset applied by the caller
 	uint32_t M, Ncols, K;
 	const uint32_t* frame_t; uint32_t min_t;  // rows with frame_t[n] < min_t are skipped (window d needs t >= d-1)
+	uint32_t n_fast;                  // set by launch_score_gemm_tc: column tiles run fastest in the grid (see there)
 };
 void launch_score_gemm(const ScoreGemmParams& p, cudaStream_t s);          // fp32 FFMA tiles (round-1 baseline)
 cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s); // tcgen05, split-bf16 operands (crf_tc_gemm.cu)

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(N_THR, 2) score_gemm_tc_kernel(ScoreGemmParams
 	extern __shared__ __align__(1024) unsigned char smem[];
 	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+	const uint32_t m0 = (p.n_fast ? blockIdx.y : blockIdx.x) * BM, n0 = (p.n_fast ? blockIdx.x : blockIdx.y) * BN;
 	const uint32_t n_chunks = (p.K + KC - 1) / KC;
 	if (tid == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], N_PRODUCERS); mbar_init(&ring->empty[s], 1); }
@@ -489,8 +489,14 @@ cudaError_t launch_score_gemm_tc(const ScoreGemmParams& p, cudaStream_t s) {
 		if (e != cudaSuccess) return e;
 		attr_done = true;
 	}
-	dim3 grid((p.M + BM - 1) / BM, (p.Ncols + BN - 1) / BN);
-	score_gemm_tc_kernel<<<grid, N_THR, SMEM_BYTES, s>>>(p);
+	// Many column tiles (the transition-score GEMM: labels^2 columns): the column tiles of one row tile run back to back, so the row
+	// tile of X -- strided rows, far more bytes than the weights -- is read from DRAM once and from L2 by the other column tiles
+	// (recipe shape, 36 column tiles: 10.9 GB of DRAM reads per launch with the row tiles fastest, profiles/r2v_recipe_kernels_full.md)
+	const uint32_t mt = (p.M + BM - 1) / BM, nt = (p.Ncols + BN - 1) / BN;
+	ScoreGemmParams q = p;
+	q.n_fast = (nt > 1 && mt <= 65535) ? 1u : 0u;
+	dim3 grid(q.n_fast ? nt : mt, q.n_fast ? mt : nt);
+	score_gemm_tc_kernel<<<grid, N_THR, SMEM_BYTES, s>>>(q);
 	return cudaGetLastError();
 }
 
