@@ -180,6 +180,27 @@ def time_cpu(lib, cfg, lam, off, ftrs, labs, threads):
     return time.perf_counter() - t0
 
 
+def cpu_recipe_baseline(threads, fpu=32):
+    """The reference's buildGradient at the production recipe's shape on `threads` host threads: the first `threads` utterances of
+    workloads.recipe_batch(), each truncated to its first fpu frames (stream 2 keeps its 6 + 6 context frames per utterance)."""
+    from oracle.binding import make_config
+    lib, kind = cpu_baseline_lib()
+    cfg = make_config(**workloads.recipe_kwargs())
+    lam = workloads.lam_for("recipe", lib.lambda_len(cfg))
+    off, f1, f2, labs = workloads.recipe_batch(threads)
+    ctx = 2 * workloads.RECIPE_CTX
+    lens = [min(fpu, int(off[u + 1] - off[u])) for u in range(threads)]
+    so = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    k1 = np.concatenate([np.arange(int(off[u]), int(off[u]) + lens[u]) for u in range(threads)])
+    k2 = np.concatenate([np.arange(int(off[u]) + ctx * u, int(off[u]) + ctx * u + lens[u] + ctx) for u in range(threads)])
+    a1, a2, al = np.ascontiguousarray(f1[k1]), np.ascontiguousarray(f2[k2]), np.ascontiguousarray(labs[k1])
+    t0 = time.perf_counter()
+    lib.fwdbwd(cfg, lam, so, a1, al, n_threads=threads, ftrs2=a2)
+    dt = time.perf_counter() - t0
+    return {"value": float(so[-1]) / dt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{threads} utterances x first {fpu} frames ({int(so[-1])} frames), {threads} pthreads, {dt:.1f} s"}
+
+
 _VIT_DATA = None      # (off, ftrs) of cfg3, set in the parent before the workers are forked (copy-on-write)
 
 
@@ -596,6 +617,8 @@ def run_ours(args):
                   "viterbi_frames_per_s": rN / ((rvs + rvr) / 1e3), "viterbi_phases_ms": {"score": rvs, "recursion": rvr},
                   "lambda_len": rm.lambda_len, "plan": rm.plan_info()}
         rm.close()
+        if rank == 0 and not args.no_cpu:
+            recipe["cpu_baseline"] = cpu_recipe_baseline(cpu_threads())
 
     all_gate = [r for g in gather_list(gate) for r in g]
     if rank == 0:
