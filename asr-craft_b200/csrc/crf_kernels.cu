@@ -218,49 +218,53 @@ void launch_virtual_windows(const float* base, const uint32_t* frame_t, float* b
 // Labelled frame t of utterance u is row  n + u (lc + rc) + lc  of a stream with lc + rc context frames per utterance.
 // =================================================================================================
 __global__ void __launch_bounds__(256) expand_joined_kernel(ExpandJoinedParams p) {
+	// One CTA per frame, one thread per window COLUMN, the durations as the inner loop: which stream / block / feature a column is
+	// is worked out once (it is the same for every duration), and the average / maximum / minimum blocks grow by one frame per
+	// duration in the reference's own order (from the window's last frame back to its first) instead of being re-summed per duration.
 	const uint32_t n = blockIdx.x;
 	if (n >= p.N) return;
 	const uint32_t t = __ldg(p.frame_t + n), u = __ldg(p.frame_utt + n);
 	const uint32_t dmax = min(t + 1, p.D);
 	float* out = p.X + (uint64_t)n * p.D * p.Wp;
-	for (uint32_t i = threadIdx.x; i < p.D * p.Wp; i += blockDim.x) {
-		const uint32_t d0 = i / p.Wp;            // duration - 1
-		uint32_t j = i - d0 * p.Wp;
-		float v = 0.0f;
-		if (d0 < dmax) {
-			const uint32_t d = d0 + 1;
-			for (uint32_t q = 0; q < p.n_parts; q++) {
-				const JoinedPart& a = p.part[q];
-				if (j >= a.width) { j -= a.width; continue; }
-				const uint32_t F = a.F;
-				const int64_t last = (int64_t)n + (int64_t)u * (a.lc + a.rc) + a.lc, first = last - d0;   // rows of the window's last / first frame
-				const uint32_t k = j / F, f = j - k * F;
-				const float* x = a.x + f;
-				if (a.bdelta && !(p.D > 1 && a.seg)) {
+	for (uint32_t j0 = threadIdx.x; j0 < p.Wp; j0 += blockDim.x) {
+		uint32_t j = j0; int q = -1;
+		for (uint32_t qq = 0; qq < p.n_parts; qq++) { if (j < p.part[qq].width) { q = (int)qq; break; } j -= p.part[qq].width; }
+		if (q < 0) {                                       // padding behind the joined vector
+			for (uint32_t d0 = 0; d0 < p.D; d0++) out[(uint64_t)d0 * p.Wp + j0] = 0.0f;
+			continue;
+		}
+		const JoinedPart& a = p.part[q];
+		const uint32_t F = a.F, k = j / F, f = j - k * F;
+		const float* x = a.x + f;
+		const int64_t last = (int64_t)n + (int64_t)u * (a.lc + a.rc) + a.lc;      // row of the window's last frame
+		// columns no kernel reads in windows longer than one frame (the transition features of a model whose transition scores come
+		// from the duration-1 window): zeros instead of the gather
+		const bool d1_only = p.keep_hi != 0 && (j0 < p.keep_lo || j0 >= p.keep_hi);
+		const bool delta = a.bdelta && !(p.D > 1 && a.seg);
+		const bool body = !delta && k >= a.lc && !(p.D == 1 || !a.seg);
+		const uint32_t b = body ? k - a.lc : 0;                                    // block inside the segment-feature body
+		const uint32_t jj = j - (a.lc + 8) * F;                                     // (b >= 8) one-hot duration, then the right context of the last frame
+		float acc = 0.0f, amax = 0.0f, amin = 0.0f;
+		for (uint32_t d0 = 0; d0 < p.D; d0++) {
+			float v = 0.0f;
+			if (d0 < dmax && !(d1_only && d0 >= 1)) {
+				const uint32_t d = d0 + 1;
+				const int64_t first = last - d0;                                        // row of the window's first frame
+				if (delta) {
 					const float l = __ldg(x + (first - 1 - k) * F), r = __ldg(x + (first + k) * F);
 					v = l >= r ? l - r : r - l;
 				} else if (k < a.lc) v = __ldg(x + (first - a.lc + k) * F);
-				else if (p.D == 1 || !a.seg) v = __ldg(x + (first + (k - a.lc)) * F);      // the first frame, then its right context
-				else {
-					const uint32_t b = k - a.lc;                                              // block inside the segment-feature body
-					if (b < 5) v = __ldg(x + (first + __ldg(p.steps + d0 * 5 + b)) * F);
-					else if (b < 8) {
-						float acc = 0.0f, amax = 0.0f, amin = 0.0f;
-						for (uint32_t e = 0; e < d; e++) {                                    // from the last frame back to the first, as the reference
-							const float w = __ldg(x + (last - e) * F);
-							acc += w; amax = (e == 0 || w > amax) ? w : amax; amin = (e == 0 || w < amin) ? w : amin;
-						}
-						v = b == 5 ? acc / (float)d : (b == 6 ? amax : amin);
-					} else {
-						const uint32_t jj = j - (a.lc + 8) * F;                               // one-hot duration, then the right context of the last frame
-						if (jj < p.D) v = jj == d0 ? 1.0f : 0.0f;
-						else { const uint32_t kk = (jj - p.D) / F, ff = (jj - p.D) - kk * F; v = __ldg(a.x + ff + (last + 1 + kk) * F); }
-					}
-				}
-				break;
+				else if (!body) v = __ldg(x + (first + (k - a.lc)) * F);                 // the first frame, then its right context
+				else if (b < 5) v = __ldg(x + (first + __ldg(p.steps + d0 * 5 + b)) * F);
+				else if (b < 8) {
+					const float w = __ldg(x + first * F);                                  // the frame this duration adds
+					acc += w; amax = (d0 == 0 || w > amax) ? w : amax; amin = (d0 == 0 || w < amin) ? w : amin;
+					v = b == 5 ? acc / (float)d : (b == 6 ? amax : amin);
+				} else if (jj < p.D) v = jj == d0 ? 1.0f : 0.0f;
+				else { const uint32_t kk = (jj - p.D) / F, ff = (jj - p.D) - kk * F; v = __ldg(a.x + ff + (last + 1 + kk) * F); }
 			}
+			out[(uint64_t)d0 * p.Wp + j0] = v;
 		}
-		out[i] = v;
 	}
 }
 void launch_expand_joined(const ExpandJoinedParams& p, cudaStream_t s) {

@@ -37,6 +37,7 @@ struct ExpandJoinedParams {
 	const uint32_t* frame_t; const uint32_t* frame_utt; const uint32_t* steps;
 	float* X;                 // [N][D][Wp]
 	uint32_t N, D, Wp;
+	uint32_t keep_lo, keep_hi; // keep_hi != 0: only the columns [keep_lo, keep_hi) are materialised in windows longer than one frame (zeros elsewhere)
 };
 void launch_expand_joined(const ExpandJoinedParams& p, cudaStream_t s);
 

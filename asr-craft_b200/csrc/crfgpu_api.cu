@@ -126,6 +126,7 @@ struct crfgpu_ctx {
 	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit; double beam = 0.0;   // crfgpu_set_beam   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
 	std::vector<cudaStream_t> rec_stream; std::vector<cudaEvent_t> ev_scored, ev_walked;   // one side stream per chunk: the chunks' recursions are latency chains and run beside each other
 	bool vit_rec_ready = false; DevBuf d_vorder, d_off2;   // ... and the recursion of each chunk's utterances behind its scores (d_vorder: the chunks' utterances, longest first)
+	bool full_windows = false;      // crfgpu_expand_windows: gather every column of every window (no duration-1-only ranges)
 	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
 
@@ -596,6 +597,11 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 			}
 			ep.frame_t = h->d_frame_t.as<uint32_t>(); ep.frame_utt = h->d_frame_utt.as<uint32_t>(); ep.steps = h->d_steps.as<uint32_t>();
 			ep.X = h->d_X.as<float>(); ep.N = N; ep.D = c.max_dur; ep.Wp = h->Wp;
+			// stdseg_no_dur_no_segtransftr + stdtrans: the transition scores (training and decoding) read the duration-1 window only, so in
+			// the longer windows only the state-feature range is gathered -- 62 % of the recipe's 121 kB per frame are transition columns
+			if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.use_trans_ftrs && c.use_state_ftrs && c.max_dur > 1 && !h->full_windows) {
+				ep.keep_lo = c.state_fidx_start; ep.keep_hi = c.state_fidx_end + 1;
+			}
 			launch_expand_joined(ep, s); check_kernel(h, 1);
 			phase_end(h, "expand");
 		}
@@ -1774,7 +1780,9 @@ int crfgpu_expand_windows2(crfgpu_handle h, uint32_t n_frames, const float* base
 		CUDA_OK(cudaSetDevice(h->device));
 		const uint32_t off[2] = {0, n_frames};
 		if (!n_frames) return;
-		stage_batch(h, 1, off, base_ftrs, nullptr, base_ftrs2);
+		h->full_windows = true;                       // the caller reads every column of every window back
+		try { stage_batch(h, 1, off, base_ftrs, nullptr, base_ftrs2); } catch (...) { h->full_windows = false; throw; }
+		h->full_windows = false;
 		CUDA_OK(cudaMemcpy2DAsync(out, sizeof(float) * h->W, h->X(), sizeof(float) * h->Wp, sizeof(float) * h->W,
 		                          (size_t)n_frames * h->cfg.max_dur, cudaMemcpyDeviceToHost, h->stream));
 		CUDA_OK(cudaStreamSynchronize(h->stream));

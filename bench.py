@@ -609,6 +609,34 @@ def run_ours(args):
             gate.append(pins.check_loglik("recipe", range(npin), rn[:npin], rz[:npin], f"recipe fwd-bwd, pinned utterances 0..{npin - 1} of {len(roff) - 1}"))
             if gate[-1]["ok"] is False:
                 fail_parity(gate)
+        # end to end: the trainer's step with host buffers -- both streams over PCIe, joined windows built on the device, fwd-bwd + gradient,
+        # D2H of numerators / logZ, lambda update on the device (no read-ahead: joined streams are staged by crfgpu_stage_batch2 only)
+        rp1 = crf_b200.PinnedBuffer(rf1.shape, np.float32); rp1.array[...] = rf1
+        rp2 = crf_b200.PinnedBuffer(rf2.shape, np.float32); rp2.array[...] = rf2
+        rpl = crf_b200.PinnedBuffer(rlabs.shape, np.uint32); rpl.array[...] = rlabs
+        rpn = crf_b200.PinnedBuffer((len(roff) - 1,), np.float64); rpz = crf_b200.PinnedBuffer((len(roff) - 1,), np.float64)
+
+        def r_step():
+            rm.stage(roff, rp1.array, rpl.array, ftrs2=rp2.array)
+            rm.fwdbwd_staged()
+            rm.fetch_fwdbwd(out=(None, rpn.array, rpz.array))
+            rm.sgd_update(1.0, lr=1e-13)
+
+        for _ in range(2):
+            r_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r_step()
+        torch.cuda.synchronize()
+        re2e = 3 * float(roff[-1]) / (time.perf_counter() - t0)
+        if npin:
+            gate.append(pins.check_loglik("recipe", range(npin), rpn.array[:npin], rpz.array[:npin], "recipe e2e last step, pinned utterances", rtol=1e-5))
+            if gate[-1]["ok"] is False:
+                fail_parity(gate)
+        rh2d = int(rf1.nbytes + rf2.nbytes + rlabs.nbytes + roff.nbytes + 3 * 4 * int(roff[-1]))
+        for pb in (rp1, rp2, rpl, rpn, rpz):
+            pb.free()
+        rm.set_lambda(workloads.lam_for("recipe", rm.lambda_len))
         rm.stage(roff, rf1, ftrs2=rf2)
         for _ in range(2):
             rm.viterbi_staged(); rm.synchronize()
@@ -626,6 +654,7 @@ def run_ours(args):
         recipe = {"workload": "TIMIT recipe shape (stdseg_no_dur_no_segtransftr + stdtrans, 48 phones, maxDur 10, 1162 state features from stream 1, "
                               f"1872 transition features from 13 context frames of stream 2; {len(roff) - 1} utterances = {int(rN)} frames, device-resident)",
                   "train_frames_per_s": rN / (sum(rbest.values()) / 1e3), "train_phases_ms": rbest,
+                  "train_e2e_frames_per_s": re2e, "h2d_bytes_per_step": rh2d, "expand_ms": rm.phase_ms("expand"),
                   "viterbi_frames_per_s": rN / ((rvs + rvr) / 1e3), "viterbi_phases_ms": {"score": rvs, "recursion": rvr},
                   "lambda_len": rm.lambda_len, "plan": rm.plan_info()}
         rm.close()
