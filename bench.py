@@ -657,6 +657,17 @@ def run_ours(args):
                   "train_e2e_frames_per_s": re2e, "h2d_bytes_per_step": rh2d, "expand_ms": rm.phase_ms("expand"),
                   "viterbi_frames_per_s": rN / ((rvs + rvr) / 1e3), "viterbi_phases_ms": {"score": rvs, "recursion": rvr},
                   "lambda_len": rm.lambda_len, "plan": rm.plan_info()}
+        # the leg's dominant kernel is tensor-bound ("the only genuinely tensor-bound GEMM"): the transition-gradient
+        # reduce-GEMM [P^2 x frames] . [frames x (Ft + 1)], every product three bf16 MMAs (hi*hi + hi*lo + lo*hi)
+        rP, rFt = workloads.RECIPE_PHONES, (2 * workloads.RECIPE_CTX + 1) * workloads.RECIPE_FTRS
+        xi_flop = 2.0 * rN * rP * rP * (rFt + 1)
+        xi_ms = rbest["xi"]
+        recipe["roofline"] = {"kernel": "reduce_gemm_tc_kernel<0>", "bound": "tensor", "achieved": 3.0 * xi_flop / (xi_ms / 1e3) / 1e12,
+                              "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None, "launch_ms": xi_ms,
+                              "fp32_equivalent_tflops": xi_flop / (xi_ms / 1e3) / 1e12, "peak_source": peaks["source"],
+                              "note": "achieved counts the three bf16 MMAs of every fp32-equivalent product; the kernel is the register-staged "
+                                      "tcgen05 GEMM (producer warps convert strided fp32 rows), see DESIGN.md section 4"}
+        recipe["roofline"]["frac"] = recipe["roofline"]["achieved"] / peaks["bf16_tflops_sustained"]
         rm.close()
         if rank == 0 and not args.no_cpu:
             recipe["cpu_baseline"] = cpu_recipe_baseline(cpu_threads())
