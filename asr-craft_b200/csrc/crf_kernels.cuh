@@ -165,6 +165,18 @@ void launch_reduce_gemm(const ReduceGemmParams& p, cudaStream_t s);
 // tcgen05 version; m_side_is_b picks which operand's columns ride on the 128-row MMA M side (the wider one should)
 cudaError_t launch_reduce_gemm_tc(const ReduceGemmParams& p, bool m_side_is_b, cudaStream_t s);
 
+// the same product from pre-split, pre-tiled operands (launch_tile_mn), fed by bulk copies: out[row_idx[i] + j] += scale * sum_n A[n][i] * B[n][j]
+struct TiledReduceParams {
+	const unsigned char* At; const unsigned char* Bt;   // tiles of the M side (128 columns of A) and the N side (64 columns of B)
+	uint32_t N, I, J;                 // frames, columns of A (output rows), columns of B (output columns, the ones column included)
+	uint32_t ones_col; double scale, ones_scale;
+	const uint32_t* row_idx; double* out;
+	uint32_t n_mt, n_nt, n_chunks, slab_chunks;         // set by the launcher
+};
+size_t tiled_operand_bytes(uint32_t N, uint32_t ncols, uint32_t T);      // T = 128 (M side) or 64 (N side)
+cudaError_t launch_tile_mn(const float* src, uint64_t ld, uint32_t ncols, uint32_t ones_col, uint32_t N, bool m_side, unsigned char* dst, cudaStream_t s);
+cudaError_t launch_reduce_gemm_tiled(const TiledReduceParams& p, cudaStream_t s);
+
 // ---- transition-bias expected counts for ALL durations in one pass (crf_tc_gemm.cu) --------------
 // out[pair_idx[q*L + c]] += scale * Ew[q][c] * sum_n A[n-d(c)][q] * R[n][c],  c = (d-1)*P + y
 struct XiGemmParams {

@@ -20,6 +20,8 @@
 //   warps 0-3       run the epilogue afterwards (warp w owns TMEM lanes 32w..32w+31)
 // Register staging (instead of TMA) lets the loaders apply what these operands need on the way: the row shift of the
 // Xi product, the constant-1 bias feature, ragged bounds and the 8-byte alignment of window rows.
+#include <algorithm>
+
 #include "crf_kernels.cuh"
 #include "tc05.cuh"
 
@@ -511,6 +513,147 @@ cudaError_t launch_xi_gemm_tc(const XiGemmParams& p, cudaStream_t s) {
 	const uint32_t n_tiles = p.D * ((p.P + BN - 1) / BN);
 	dim3 grid((p.L + BM - 1) / BM, (n_tiles + XI_G - 1) / XI_G, (p.n1 - p.n0 + p.k_slab - 1) / p.k_slab);
 	xi_gemm_tc_kernel<<<grid, XI_THR, XI_SMEM, s>>>(p);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same product from operands that are ALREADY split and tiled (labels^2 rows: the transition-feature gradient, 342 Gflop at the
+// TIMIT recipe's shape).  The register-staged kernel above spends its time in its four producer warps (strided fp32 loads, split,
+// shared-memory stores: tensor pipe 9 %, profiles/r2v_recipe_kernels_full.md); here a tiling pass writes both operands once as bf16
+// hi / lo halves in the byte order of the shared-memory tiles -- [column group][frame of the chunk][8 columns] per 32-frame chunk
+// and column tile, hi then lo -- so a ring stage is two bulk copies (cp.async.bulk, 16 KB + 8 KB) issued by one thread, and every
+// operand byte crosses L2 -> shared memory exactly as the MMA reads it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// src[n][col0 + c], c < ncols (column ones_col reads as the constant 1), n < N  ->  tiles of T columns x 32 frames:
+// dst + ((chunk * n_ct + ct) * 2 + {hi, lo}) * T * 64 bytes, element (column group cg, frame kk, j) at cg * 512 + kk * 16 + j * 2.
+// lane = frame of the chunk (a thread reads whole 32-byte sectors of its row, a warp writes 512 contiguous bytes), warp = column groups.
+template <int T>
+__global__ void __launch_bounds__(256) tile_mn_kernel(const float* __restrict__ src, uint64_t ld, uint32_t ncols, uint32_t ones_col, uint32_t N, unsigned char* __restrict__ dst, uint32_t n_ct) {
+	const uint32_t chunk = blockIdx.x, ct = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t n = chunk * KC + lane;
+	const bool vec2 = ((reinterpret_cast<uintptr_t>(src) & 7) == 0) && (ld % 2 == 0);
+	unsigned char* hi = dst + ((size_t)chunk * n_ct + ct) * 2 * (T * 64);
+	for (uint32_t cg = warp; cg < T / 8; cg += 8) {
+		const uint32_t col = ct * T + cg * 8;
+		float x[8];
+		const float* r = src + (uint64_t)n * ld + col;
+		if (n < N && col + 8 <= ncols && ones_col >= col + 8) load8(r, true, vec2, x);
+		else {
+#pragma unroll
+			for (int j = 0; j < 8; j++) x[j] = (n >= N || col + j >= ncols) ? 0.0f : (col + j == ones_col ? 1.0f : __ldg(r + j));
+		}
+		uint4 h, l; split8(x, h, l);
+		const uint32_t o = cg * 512 + lane * 16;
+		*reinterpret_cast<uint4*>(hi + o) = h; *reinterpret_cast<uint4*>(hi + T * 64 + o) = l;
+	}
+}
+
+__global__ void __launch_bounds__(192, 2) reduce_gemm_tiled_kernel(TiledReduceParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t mt = blockIdx.x, nt = blockIdx.y, m0 = mt * BM, n0 = nt * BN;
+	const uint32_t c_lo = blockIdx.z * p.slab_chunks, c_hi = min(c_lo + p.slab_chunks, p.n_chunks);
+	const uint32_t n_chunks = c_hi - c_lo;
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
+		mbar_init(&ring->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ring->tmem;
+	if (warp == 5) {
+		if (lane == 0) {
+			for (uint32_t c = 0; c < n_chunks; c++) {
+				const uint32_t s = c % STAGES;
+				if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
+				unsigned char* st = smem + s * STAGE_BYTES;
+				mbar_arrive_expect_tx(&ring->full[s], STAGE_BYTES);
+				bulk_g2s(st, p.At + ((size_t)(c_lo + c) * p.n_mt + mt) * (2 * A_TILE), 2 * A_TILE, &ring->full[s]);
+				bulk_g2s(st + 2 * A_TILE, p.Bt + ((size_t)(c_lo + c) * p.n_nt + nt) * (2 * B_TILE), 2 * B_TILE, &ring->full[s]);
+			}
+		}
+		__syncwarp();
+	} else if (warp == 4) {
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, true, true);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % STAGES;
+			mbar_wait(&ring->full[s], (c / STAGES) & 1);
+			tc_fence_after();
+			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+			if (elect_one()) {
+#pragma unroll
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+					mma_ss(tmem, al, bh, idesc, true);
+					mma_ss(tmem, ah, bl, idesc, true);
+				}
+				mma_commit(&ring->empty[s]);
+			}
+			__syncwarp();
+		}
+		if (elect_one()) mma_commit(&ring->done);
+		__syncwarp();
+	}
+	// ---- epilogue: lane = M-side column (output row), 64 N-side columns; fp64 atomics into the gradient ----
+	if (warp < 4 && n_chunks) {
+		mbar_wait(&ring->done, 0);
+		tc_fence_after();
+		const uint32_t gm = m0 + warp * 32 + lane;
+		const uint32_t ri = gm < p.I ? __ldg(p.row_idx + gm) : 0xffffffffu;
+#pragma unroll
+		for (int c0 = 0; c0 < BN; c0 += 16) {
+			float v[16];
+			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+			tmem_ld_wait();
+			if (ri != 0xffffffffu) {
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t gn = n0 + c0 + j;
+					if (gn >= p.J || v[j] == 0.0f) continue;
+					const double sc = (gn == p.ones_col) ? p.ones_scale : p.scale;
+					atomicAdd(&p.out[(uint64_t)ri + gn], sc * (double)v[j]);
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 4) tmem_dealloc(tmem, BN);
+}
+
+size_t tiled_operand_bytes(uint32_t N, uint32_t ncols, uint32_t T) { return (size_t)((N + KC - 1) / KC) * ((ncols + T - 1) / T) * 2 * ((size_t)T * 64); }
+
+cudaError_t launch_tile_mn(const float* src, uint64_t ld, uint32_t ncols, uint32_t ones_col, uint32_t N, bool m_side, unsigned char* dst, cudaStream_t s) {
+	if (!N || !ncols) return cudaSuccess;
+	const uint32_t T = m_side ? BM : BN, n_ct = (ncols + T - 1) / T;
+	dim3 grid((N + KC - 1) / KC, n_ct);
+	if (m_side) tile_mn_kernel<BM><<<grid, 256, 0, s>>>(src, ld, ncols, ones_col, N, dst, n_ct);
+	else tile_mn_kernel<BN><<<grid, 256, 0, s>>>(src, ld, ncols, ones_col, N, dst, n_ct);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_gemm_tiled(const TiledReduceParams& p0, cudaStream_t s) {
+	if (!p0.N || !p0.I || !p0.J) return cudaSuccess;
+	cudaError_t e = cudaFuncSetAttribute(reduce_gemm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+	if (e != cudaSuccess) return e;
+	TiledReduceParams p = p0;
+	p.n_mt = (p.I + BM - 1) / BM; p.n_nt = (p.J + BN - 1) / BN; p.n_chunks = (p.N + KC - 1) / KC;
+	// frame slabs only until the grid is about six waves of 2 CTAs per SM: every slab ends in up to 8192 fp64 atomics per CTA
+	const uint32_t tiles = p.n_mt * p.n_nt, slabs = std::max(1u, std::min(p.n_chunks, (6u * 296u + tiles - 1) / tiles));
+	p.slab_chunks = (p.n_chunks + slabs - 1) / slabs;
+	dim3 grid(p.n_mt, p.n_nt, (p.n_chunks + p.slab_chunks - 1) / p.slab_chunks);
+	reduce_gemm_tiled_kernel<<<grid, 192, SMEM_BYTES, s>>>(p);
 	return cudaGetLastError();
 }
 

@@ -87,6 +87,7 @@ struct crfgpu_ctx {
 	// transition tables and forward/backward vectors are P wide
 	DevBuf d_WdT, d_vt_base, d_negMt; uint32_t vtE = 0;              // decoding with transition features: per-frame transition tables
 	bool nodur_tf = false; DevBuf d_next_lab;                       // segmental no_dur model with transition features (nodur && nodur_tf)
+	DevBuf d_XdT, d_XtT; int opt_tf_tiled = 1;                     // transition-feature gradient from pre-split, pre-tiled operands (launch_reduce_gemm_tiled)
 	DevBuf d_Eall, d_rowmax;                                        // exp(M_n - max M_n) of every frame and the maxima (launch_transftr_exp)
 	bool transftr = false; DevBuf d_Wtr, d_tbias, d_Mall, d_Xd;   // frame-level model with transition FEATURES (crf_dp_transftr.cu)
 	bool nodur = false; uint32_t Pp = 0; int opt_nodur_impl = 0; int nodur_groups_max = 0; uint32_t n_nodur_groups = 0;
@@ -857,6 +858,33 @@ DpParams dp_params(crfgpu_ctx* h) {
 	return p;
 }
 
+// transition-feature gradient: out[tidx(pair) + f] += sum_n Xd[n][pair] * x_n[tf0 + f] (+ the bias as a constant-1 column), pairs = I.
+// Default: both operands split into bf16 hi / lo and tiled once (launch_tile_mn), the product fed by bulk copies; option tf_tiled 0:
+// the register-staged kernel on the fp32 arrays.
+void trans_gradient_gemm(crfgpu_ctx* h, uint32_t N, uint32_t I, uint32_t Lq, cudaStream_t s) {
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	const uint32_t nTf = m.nTf, J = nTf + (c.use_trans_bias ? 1 : 0), ones = c.use_trans_bias ? nTf : 0xffffffffu;
+	if (h->opt_tf_tiled) {
+		h->d_XdT.ensure(tiled_operand_bytes(N, I, 128) + 16); h->d_XtT.ensure(tiled_operand_bytes(N, J, 64) + 16);
+		CUDA_OK(launch_tile_mn(h->d_Xd.as<float>(), Lq, I, 0xffffffffu, N, true, h->d_XdT.as<unsigned char>(), s)); check_kernel(h, 1);
+		CUDA_OK(launch_tile_mn(h->X() + c.trans_fidx_start, h->ldx(), J, ones, N, false, h->d_XtT.as<unsigned char>(), s)); check_kernel(h, 1);
+		TiledReduceParams t{};
+		t.At = h->d_XdT.as<unsigned char>(); t.Bt = h->d_XtT.as<unsigned char>(); t.N = N; t.I = I; t.J = J;
+		t.ones_col = ones; t.scale = 1.0; t.ones_scale = c.trans_bias_val; t.row_idx = h->d_tidx.as<uint32_t>(); t.out = h->d_grad.as<double>();
+		CUDA_OK(launch_reduce_gemm_tiled(t, s)); check_kernel(h, 1);
+		return;
+	}
+	ReduceGemmParams r{};
+	r.A = h->d_Xd.as<float>(); r.lda = Lq; r.a_row_shift = 0;
+	r.B = h->X() + c.trans_fidx_start; r.ldb = h->ldx();
+	r.n0 = 0; r.n1 = N; r.I = I; r.J = J;
+	r.ones_col = ones;
+	r.scale = 1.0; r.ones_scale = c.trans_bias_val; r.mode = 0;
+	r.row_idx = h->d_tidx.as<uint32_t>();
+	r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab_tc;
+	CUDA_OK(launch_reduce_gemm_tc(r, false, s)); check_kernel(h, 1);
+}
+
 void fwdbwd_staged(crfgpu_ctx* h) {
 	require_train(h);
 	if (!h->have_labels) throw ApiError(CRFGPU_ERR_ARG, "training needs frame labels");
@@ -938,15 +966,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		phase_begin(h, "xi");
 		{
 			// transition weights: out[tidx(p,c) + f] += sum_n ([ref pair] - xi_n[p][c]) * x_n[tf0 + f]   (computeTransExpF, :197-223)
-			ReduceGemmParams r{};
-			r.A = h->d_Xd.as<float>(); r.lda = Lq; r.a_row_shift = 0;
-			r.B = h->X() + tf0; r.ldb = h->ldx();
-			r.n0 = 0; r.n1 = N; r.I = L * L; r.J = nTf + (c.use_trans_bias ? 1 : 0);
-			r.ones_col = c.use_trans_bias ? nTf : 0xffffffffu;
-			r.scale = 1.0; r.ones_scale = c.trans_bias_val; r.mode = 0;
-			r.row_idx = h->d_tidx.as<uint32_t>();
-			r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab_tc;
-			CUDA_OK(launch_reduce_gemm_tc(r, false, s)); check_kernel(h, 1);
+			trans_gradient_gemm(h, N, L * L, Lq, s);
 		}
 		phase_end(h, "xi");
 		phase_begin(h, "grad");
@@ -1143,15 +1163,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	if (h->nodur && !(lat_tma && tma)) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "the native stdseg_no_dur* path needs the TMA-fed gradient kernels (gemm_impl 2)");
 	if (h->nodur_tf) {
 		// transition weights: out[tidx(y',y) + f] += sum_n ([ref pair] - xi)[n][y'][y] * x_{n,1}[tf0 + f]  (duration-1 window of frame n)
-		ReduceGemmParams r{};
-		r.A = h->d_Xd.as<float>(); r.lda = Lq; r.a_row_shift = 0;
-		r.B = h->X() + c.trans_fidx_start; r.ldb = h->ldx();
-		r.n0 = 0; r.n1 = N; r.I = P * P; r.J = m.nTf + (c.use_trans_bias ? 1 : 0);
-		r.ones_col = c.use_trans_bias ? m.nTf : 0xffffffffu;
-		r.scale = 1.0; r.ones_scale = c.trans_bias_val; r.mode = 0;
-		r.row_idx = h->d_tidx.as<uint32_t>();
-		r.out = h->d_grad.as<double>(); r.k_slab = h->opt_k_slab_tc;
-		CUDA_OK(launch_reduce_gemm_tc(r, false, s)); check_kernel(h, 1);
+		trans_gradient_gemm(h, N, P * P, Lq, s);
 	} else if (h->nodur) {
 		if (c.use_trans_bias && N > 1) {
 			// xi_t[y',y] = a_t[y'] E[y'][y] R_{t+1}[y]: one duration block of P columns with row shift 1
@@ -1471,7 +1483,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
 	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt,
-	                  &h->d_Eall, &h->d_rowmax, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
+	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1854,6 +1866,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
 		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per chain, both chains in one launch (crf_dp_frame.cu), 2 the chains one after the other, 1 the cluster lattice kernels
+		else if (n == "tf_tiled") h->opt_tf_tiled = value != 0 ? 1 : 0;     // transition-feature gradient: 1 pre-tiled operands + bulk copies, 0 register-staged kernel
 		else if (n == "vit_eager") h->opt_vit_eager = value != 0.0 ? 1 : 0;
 		else if (n == "vit_impl") { h->opt_vit_impl = (int)value; h->vit_rec_ready = false; }         // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
