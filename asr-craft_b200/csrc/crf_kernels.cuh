@@ -177,6 +177,17 @@ size_t tiled_operand_bytes(uint32_t N, uint32_t ncols, uint32_t T);      // T = 
 cudaError_t launch_tile_mn(const float* src, uint64_t ld, uint32_t ncols, uint32_t ones_col, uint32_t N, bool m_side, unsigned char* dst, cudaStream_t s);
 cudaError_t launch_reduce_gemm_tiled(const TiledReduceParams& p, cudaStream_t s);
 
+// K-major twin: C[n][c] = sum_k A[n][k] * B[c][k] + bias[c] from operands tiled by launch_tile_k (rows x 32-feature chunks)
+struct TiledScoreParams {
+	const unsigned char* At; const unsigned char* Bt;   // tiles of A (128-row tiles of the frames) and of B (64-row tiles of the weight rows)
+	const float* bias; float* C; uint32_t ldc;
+	uint32_t M, Ncols, K;
+	uint32_t n_kc;                    // set by the launcher
+};
+size_t tiled_k_operand_bytes(uint32_t rows, uint32_t K, uint32_t T);     // T = 128 (A) or 64 (B)
+cudaError_t launch_tile_k(const float* src, uint64_t ld, uint32_t rows, uint32_t K, bool m_side, unsigned char* dst, cudaStream_t s);
+cudaError_t launch_score_gemm_tiled(const TiledScoreParams& p, cudaStream_t s);
+
 // ---- transition-bias expected counts for ALL durations in one pass (crf_tc_gemm.cu) --------------
 // out[pair_idx[q*L + c]] += scale * Ew[q][c] * sum_n A[n-d(c)][q] * R[n][c],  c = (d-1)*P + y
 struct XiGemmParams {

@@ -632,6 +632,111 @@ __global__ void __launch_bounds__(192, 2) reduce_gemm_tiled_kernel(TiledReducePa
 	if (warp == 4) tmem_dealloc(tmem, BN);
 }
 
+// K-major twin for the transition SCORES  M[n][c] = sum_k X[n][k] * W[c][k] + bias[c]  (labels^2 columns): rows x 32-feature chunks of
+// both operands as tiles in the byte order of score_gemm_tc_kernel's shared-memory tiles -- element (row r, k) at
+// (r / 8) * 512 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2, hi then lo -- at dst + ((row tile * n_kc + chunk) * 2 + {hi, lo}) * T * 64.
+// lane = row of a 32-row block (whole 32-byte sectors per thread, 128-byte runs per 8 lanes), warp = (row block, k group).
+template <int T>
+__global__ void __launch_bounds__(256) tile_k_kernel(const float* __restrict__ src, uint64_t ld, uint32_t rows, uint32_t K, unsigned char* __restrict__ dst, uint32_t n_kc) {
+	const uint32_t rt = blockIdx.x, kc = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const bool vec2 = ((reinterpret_cast<uintptr_t>(src) & 7) == 0) && (ld % 2 == 0);
+	unsigned char* hi = dst + ((size_t)rt * n_kc + kc) * 2 * (T * 64);
+	for (uint32_t w = warp; w < (T / 32) * 4; w += 8) {
+		const uint32_t rb = w >> 2, kg = w & 3, r = rb * 32 + lane, row = rt * T + r, k = kc * KC + kg * 8;
+		float x[8];
+		const float* p = src + (uint64_t)row * ld + k;
+		if (row < rows && k + 8 <= K) load8(p, true, vec2, x);
+		else {
+#pragma unroll
+			for (int j = 0; j < 8; j++) x[j] = (row < rows && k + j < K) ? __ldg(p + j) : 0.0f;
+		}
+		uint4 h, l; split8(x, h, l);
+		const uint32_t o = (r >> 3) * 512 + kg * 128 + (r & 7) * 16;
+		*reinterpret_cast<uint4*>(hi + o) = h; *reinterpret_cast<uint4*>(hi + T * 64 + o) = l;
+	}
+}
+
+__global__ void __launch_bounds__(192, 2) score_gemm_tiled_kernel(TiledScoreParams p) {
+	extern __shared__ __align__(1024) unsigned char smem[];
+	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
+	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t nt = blockIdx.x, mt = blockIdx.y, m0 = mt * BM, n0 = nt * BN;      // column tiles fastest: the row tile of X stays in L2
+	const uint32_t n_chunks = p.n_kc;
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
+		mbar_init(&ring->done, 1);
+		fence_mbar_init();
+	}
+	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem = ring->tmem;
+	if (warp == 5) {
+		if (lane == 0) {
+			for (uint32_t c = 0; c < n_chunks; c++) {
+				const uint32_t s = c % STAGES;
+				if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
+				unsigned char* st = smem + s * STAGE_BYTES;
+				mbar_arrive_expect_tx(&ring->full[s], STAGE_BYTES);
+				bulk_g2s(st, p.At + ((size_t)mt * p.n_kc + c) * (2 * A_TILE), 2 * A_TILE, &ring->full[s]);
+				bulk_g2s(st + 2 * A_TILE, p.Bt + ((size_t)nt * p.n_kc + c) * (2 * B_TILE), 2 * B_TILE, &ring->full[s]);
+			}
+		}
+		__syncwarp();
+	} else if (warp == 4) {
+		mma_ring<false>(smem, ring, tmem, n_chunks);
+	}
+	// ---- epilogue: TMEM -> registers -> shared transpose -> (+bias) -> coalesced rows of the score matrix ----
+	if (warp < 4) {
+		mbar_wait(&ring->done, 0);
+		tc_fence_after();
+		float* Cs = reinterpret_cast<float*>(smem);       // [128][65], the ring is idle now
+		const uint32_t row = warp * 32 + lane;
+#pragma unroll
+		for (int c0 = 0; c0 < BN; c0 += 16) {
+			float v[16];
+			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
+			tmem_ld_wait();
+#pragma unroll
+			for (int j = 0; j < 16; j++) Cs[row * 65 + c0 + j] = v[j];
+		}
+		tc_fence_before();
+		asm volatile("bar.sync 1, 128;" ::: "memory");
+		const uint32_t ncol = min((uint32_t)BN, p.Ncols - n0);
+		for (uint32_t i = tid; i < BM * BN; i += 128) {
+			const uint32_t r = i / BN, j = i % BN, gm = m0 + r;
+			if (gm < p.M && j < ncol) p.C[(uint64_t)gm * p.ldc + n0 + j] = Cs[r * 65 + j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 4) tmem_dealloc(tmem, BN);
+}
+
+size_t tiled_k_operand_bytes(uint32_t rows, uint32_t K, uint32_t T) { return (size_t)((rows + T - 1) / T) * ((K + KC - 1) / KC) * 2 * ((size_t)T * 64); }
+
+cudaError_t launch_tile_k(const float* src, uint64_t ld, uint32_t rows, uint32_t K, bool m_side, unsigned char* dst, cudaStream_t s) {
+	if (!rows || !K) return cudaSuccess;
+	const uint32_t T = m_side ? BM : BN, n_kc = (K + KC - 1) / KC;
+	dim3 grid((rows + T - 1) / T, n_kc);
+	if (m_side) tile_k_kernel<BM><<<grid, 256, 0, s>>>(src, ld, rows, K, dst, n_kc);
+	else tile_k_kernel<BN><<<grid, 256, 0, s>>>(src, ld, rows, K, dst, n_kc);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_score_gemm_tiled(const TiledScoreParams& p0, cudaStream_t s) {
+	if (!p0.M || !p0.Ncols || !p0.K) return cudaSuccess;
+	cudaError_t e = cudaFuncSetAttribute(score_gemm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+	if (e != cudaSuccess) return e;
+	TiledScoreParams p = p0;
+	p.n_kc = (p.K + KC - 1) / KC;
+	const uint32_t mt = (p.M + BM - 1) / BM, nt = (p.Ncols + BN - 1) / BN;
+	if (mt > 65535) return cudaErrorInvalidValue;
+	score_gemm_tiled_kernel<<<dim3(nt, mt), 192, SMEM_BYTES, s>>>(p);
+	return cudaGetLastError();
+}
+
 size_t tiled_operand_bytes(uint32_t N, uint32_t ncols, uint32_t T) { return (size_t)((N + KC - 1) / KC) * ((ncols + T - 1) / T) * 2 * ((size_t)T * 64); }
 
 cudaError_t launch_tile_mn(const float* src, uint64_t ld, uint32_t ncols, uint32_t ones_col, uint32_t N, bool m_side, unsigned char* dst, cudaStream_t s) {

@@ -87,6 +87,7 @@ struct crfgpu_ctx {
 	// transition tables and forward/backward vectors are P wide
 	DevBuf d_WdT, d_vt_base, d_negMt; uint32_t vtE = 0;              // decoding with transition features: per-frame transition tables
 	bool nodur_tf = false; DevBuf d_next_lab;                       // segmental no_dur model with transition features (nodur && nodur_tf)
+	DevBuf d_XtK, d_WtrT;                                           // ... and the transition scores: X slice and weights as K-major tiles (launch_tile_k)
 	DevBuf d_XdT, d_XtT; int opt_tf_tiled = 1;                     // transition-feature gradient from pre-split, pre-tiled operands (launch_reduce_gemm_tiled)
 	DevBuf d_Eall, d_rowmax;                                        // exp(M_n - max M_n) of every frame and the maxima (launch_transftr_exp)
 	bool transftr = false; DevBuf d_Wtr, d_tbias, d_Mall, d_Xd;   // frame-level model with transition FEATURES (crf_dp_transftr.cu)
@@ -346,6 +347,12 @@ void derive_tables(crfgpu_ctx* h) {
 		p.L0 = L; p.NS = m.n_states; p.P0 = m.n_act;
 	}
 	CUDA_OK(launch_lambda_tables(p, s));
+	if ((h->transftr || h->nodur_tf) && h->opt_tf_tiled) {
+		// the transition weights once more as bf16 hi / lo tiles in the byte order of the score GEMM's shared-memory tiles
+		h->d_WtrT.ensure(tiled_k_operand_bytes(L * L, m.nTf, 64) + 16);
+		CUDA_OK(launch_tile_k(h->d_Wtr.as<float>(), m.nTf, L * L, m.nTf, false, h->d_WtrT.as<unsigned char>(), s));
+		h->launches++;
+	}
 	h->launches += h->train_ok ? 2 : 1;
 	h->Mmax = 0.0;
 	if (h->train_ok) {
@@ -861,6 +868,24 @@ DpParams dp_params(crfgpu_ctx* h) {
 // transition-feature gradient: out[tidx(pair) + f] += sum_n Xd[n][pair] * x_n[tf0 + f] (+ the bias as a constant-1 column), pairs = I.
 // Default: both operands split into bf16 hi / lo and tiled once (launch_tile_mn), the product fed by bulk copies; option tf_tiled 0:
 // the register-staged kernel on the fp32 arrays.
+// transition scores of every frame: M[n][pair] = x_n(trans slice) . lambda_t[pair] + bias[pair] (-inf on the pairs an N-state map lacks)
+void trans_score_gemm(crfgpu_ctx* h, uint32_t N, uint32_t I, uint32_t Lq, cudaStream_t s) {
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	if (h->opt_tf_tiled) {
+		h->d_XtK.ensure(tiled_k_operand_bytes(N, m.nTf, 128) + 16);
+		CUDA_OK(launch_tile_k(h->X() + c.trans_fidx_start, h->ldx(), N, m.nTf, true, h->d_XtK.as<unsigned char>(), s)); check_kernel(h, 1);
+		TiledScoreParams t{};
+		t.At = h->d_XtK.as<unsigned char>(); t.Bt = h->d_WtrT.as<unsigned char>(); t.bias = h->d_tbias.as<float>();
+		t.C = h->d_Mall.as<float>(); t.ldc = Lq; t.M = N; t.Ncols = I; t.K = m.nTf;
+		CUDA_OK(launch_score_gemm_tiled(t, s)); check_kernel(h, 1);
+		return;
+	}
+	ScoreGemmParams g{};
+	g.A = h->X() + c.trans_fidx_start; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = m.nTf; g.bias = h->d_tbias.as<float>();
+	g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = I; g.K = m.nTf;
+	CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+}
+
 void trans_gradient_gemm(crfgpu_ctx* h, uint32_t N, uint32_t I, uint32_t Lq, cudaStream_t s) {
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t nTf = m.nTf, J = nTf + (c.use_trans_bias ? 1 : 0), ones = c.use_trans_bias ? nTf : 0xffffffffu;
@@ -946,10 +971,7 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		const uint32_t Lq = (L * L + 3) / 4 * 4, tf0 = c.trans_fidx_start, nTf = m.nTf;
 		h->d_Mall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_Xd.ensure(sizeof(float) * (size_t)N * Lq + 16);
 		phase_begin(h, "forward");
-		ScoreGemmParams g{};
-		g.A = h->X() + tf0; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = nTf; g.bias = h->d_tbias.as<float>();
-		g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = L * L; g.K = nTf;
-		CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+		trans_score_gemm(h, N, L * L, Lq, s);
 		h->d_Eall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_rowmax.ensure(sizeof(float) * (size_t)N + 16);
 		launch_transftr_exp(h->d_Mall.as<float>(), h->d_Eall.as<float>(), h->d_rowmax.as<float>(), N, L * L, Lq, s); check_kernel(h, 1);
 		TransFtrParams q{};
@@ -1000,11 +1022,8 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		const uint32_t tf0 = c.trans_fidx_start, nTf = m.nTf;
 		h->d_Mall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_Xd.ensure(sizeof(float) * (size_t)N * Lq + 16);
 		phase_begin(h, "forward");
-		ScoreGemmParams g{};      // M_n[y'][y] from the duration-1 window of frame n
-		g.A = h->X() + tf0; g.lda = h->ldx(); g.B = h->d_Wtr.as<float>(); g.ldb = nTf; g.bias = h->d_tbias.as<float>();
-		g.C = h->d_Mall.as<float>(); g.ldc = Lq; g.M = N; g.Ncols = P * P; g.K = nTf;
 		phase_begin(h, "trans_score");      // (nested in "forward": the transition-score GEMM and its exp pre-pass on their own)
-		CUDA_OK(launch_score_gemm_tc(g, s)); check_kernel(h, 1);
+		trans_score_gemm(h, N, P * P, Lq, s);      // M_n[y'][y] from the duration-1 window of frame n
 		h->d_Eall.ensure(sizeof(float) * (size_t)N * Lq + 16); h->d_rowmax.ensure(sizeof(float) * (size_t)N + 16);
 		launch_transftr_exp(h->d_Mall.as<float>(), h->d_Eall.as<float>(), h->d_rowmax.as<float>(), N, P * P, Lq, s); check_kernel(h, 1);
 		phase_end(h, "trans_score");
@@ -1483,7 +1502,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
 	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt,
-	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
+	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_XtK, &h->d_WtrT, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1866,7 +1885,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
 		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per chain, both chains in one launch (crf_dp_frame.cu), 2 the chains one after the other, 1 the cluster lattice kernels
-		else if (n == "tf_tiled") h->opt_tf_tiled = value != 0 ? 1 : 0;     // transition-feature gradient: 1 pre-tiled operands + bulk copies, 0 register-staged kernel
+		else if (n == "tf_tiled") { h->opt_tf_tiled = value != 0 ? 1 : 0; h->have_lambda = false; }      // transition-feature GEMMs: 1 pre-tiled operands + bulk copies, 0 register-staged kernels (set_lambda again: the weight tiles belong to the tiled path)
 		else if (n == "vit_eager") h->opt_vit_eager = value != 0.0 ? 1 : 0;
 		else if (n == "vit_impl") { h->opt_vit_impl = (int)value; h->vit_rec_ready = false; }         // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
