@@ -15,6 +15,7 @@
 // Xd = [ref pair] - xi, so that the state and transition gradients (and their empirical counts) are two more tensor-core GEMMs
 // (launch_reduce_gemm_tc).  gamma and xi are normalised by their own per-frame sums, which are 1 in exact arithmetic.
 #include <cfloat>
+#include <type_traits>
 
 #include "crf_kernels.cuh"
 
@@ -70,7 +71,14 @@ __global__ void __launch_bounds__(256) transftr_exp_kernel(const float* __restri
 // the L x L scores of frame n into a shared-memory matrix with odd row stride Ls (columns AND rows conflict-free)
 template <int TF_THR>
 __device__ __forceinline__ void prefetch_matrix(float* dst, const float* src, uint32_t L, uint32_t Ls) {
-	for (uint32_t i = threadIdx.x; i < L * L; i += TF_THR) { const uint32_t p = i / L, c = i - p * L; cp_async4(dst + p * Ls + c, src + i); }
+	// (row, column) of element i advance by a constant step with a carry: one division per call instead of one per element
+	uint32_t r = threadIdx.x / L, c = threadIdx.x - r * L;
+	const uint32_t dr = TF_THR / L, dc = TF_THR - dr * L;
+	for (uint32_t i = threadIdx.x; i < L * L; i += TF_THR) {
+		cp_async4(dst + r * Ls + c, src + i);
+		c += dc; r += dr;
+		if (c >= L) { c -= L; r++; }
+	}
 	cp_async_commit();
 }
 
@@ -132,6 +140,8 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 	float* av = wv + L;                          // [L] alpha_{t-1}
 	float* scratch = av + L;                     // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
+	// (pair of element i = c + k * TF_THR of the L x L matrix: a constant step with a carry, no division per element)
+	const uint32_t q_first = c / L, c_first = c - q_first * L, dq_ = TF_THR / L, dc_ = TF_THR - dq_ * L;
 	if (c < L) b[c] = 1.0f;                      // setTailBeta
 	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.E + (size_t)(off + T - 1) * p.Lq, L, Ls);
 	__syncthreads();
@@ -158,19 +168,23 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		if (c < L) { wv[c] = __expf(s - smax) * b[c]; av[c] = p.A[(n - 1) * p.Lp + c]; }
 		__syncthreads();
 		float part = 0.0f;
+		uint32_t q = q_first, cc = c_first;
 		for (uint32_t i = c; i < L * L; i += TF_THR) {
-			const uint32_t q = i / L, cc = i - q * L;
 			const float e = Mt[q * Ls + cc] * wv[cc];                         // E_t[q][cc] * w_t[cc]
 			Mt[q * Ls + cc] = e;
 			part += av[q] * e;
+			cc += dc_; q += dq_;
+			if (cc >= L) { cc -= L; q++; }
 		}
 		const float xsum = block_sum<TF_THR>(part, scratch);                            // sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc]
 		uint32_t yp = p.labs[n - 1];
 		if (yp < L && y < L && p.tidx[yp * L + y] == 0xffffffffu) yp = LAB_BAD;      // a reference pair the N-state map does not have
 		const float inv = 1.0f / xsum;
+		q = q_first; cc = c_first;
 		for (uint32_t i = c; i < L * L; i += TF_THR) {
-			const uint32_t q = i / L, cc = i - q * L;
 			xrow[i] = ((q == yp && cc == y) ? 1.0f : 0.0f) - av[q] * Mt[q * Ls + cc] * inv;
+			cc += dc_; q += dq_;
+			if (cc >= L) { cc -= L; q++; }
 		}
 		// beta_{t-1}[q] = sum_cc E_t[q][cc] w_t[cc], max-normalised
 		float bn = 0.0f;
@@ -221,7 +235,7 @@ namespace {
 
 constexpr uint32_t ND_RING = 32;     // max_dur <= 31
 
-template <int TF_THR>
+template <int TF_THR, int DR>
 __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
@@ -231,12 +245,11 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 	float* lgh = av + P;                         // [ND_RING][P] log A_t[y] - rho_t of the last D frames
 	float* scratch = lgh + ND_RING * P;          // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
-	double num = 0.0;
 	if (T > 1) prefetch_matrix<TF_THR>(Ms + P * Ps, p.E + (size_t)(off + 1) * p.Lq, P, Ps);       // exp(M_1 - max) -> buffer 1
 	// the score terms of a frame do not depend on the recursion: those of frame t+1 are requested while frame t is processed
 	float sv[ND_RING];
 #pragma unroll
-	for (uint32_t d = 1; d < ND_RING; d++) sv[d] = (y < P && T > 0 && d <= min(1u, D)) ? p.S[(size_t)off * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
+	for (uint32_t d = 1; d <= (uint32_t)DR; d++) sv[d] = (y < P && T > 0 && d <= min(1u, D)) ? p.S[(size_t)off * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
 		const uint32_t dmax = min(t + 1, D);
@@ -244,8 +257,9 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 		{
 			const uint32_t dn = (t + 1 < T && y < P) ? min(t + 2, D) : 0;
 #pragma unroll
-			for (uint32_t d = 1; d < ND_RING; d++) sn[d] = d <= dn ? p.S[(n + 1) * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
+			for (uint32_t d = 1; d <= (uint32_t)DR; d++) sn[d] = d <= dn ? p.S[(n + 1) * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
 		}
+		const float mmax = t + 1 < T ? p.rowmax[n + 1] : 0.0f;      // (requested here: used behind the matrix-vector product)
 		const double rref = t > 0 ? rring[(t - 1) & (ND_RING - 1)] : 0.0;
 		// w[y] = log sum_d exp(S_t[d,y] + A_{t-d}[y] - rref)
 		float w = -INFINITY;
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 			float lt[ND_RING];
 			float mx = -INFINITY;
 #pragma unroll
-			for (uint32_t d = 1; d < ND_RING; d++) {
+			for (uint32_t d = 1; d <= (uint32_t)DR; d++) {
 				if (d <= dmax) {
 					float v = sv[d];
 					if (d <= t) v += lgh[((t - d) & (ND_RING - 1)) * P + y] + (float)(rring[(t - d) & (ND_RING - 1)] - rref);
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 			}
 			float sacc = 0.0f;
 #pragma unroll
-			for (uint32_t d = 1; d < ND_RING; d++) if (d <= dmax) sacc += __expf(lt[d - 1] - mx);
+			for (uint32_t d = 1; d <= (uint32_t)DR; d++) if (d <= dmax) sacc += __expf(lt[d - 1] - mx);
 			w = mx + __logf(sacc);
 		}
 		const float wmax = block_max<TF_THR>(w, scratch);
@@ -272,9 +286,8 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 		const double rho = rref + (double)wmax + (double)__logf(asum);
 		if (y < P) { av[y] = a / asum; p.A[n * p.Pp + y] = a / asum; }
 		if (y == 0) { rring[t & (ND_RING - 1)] = rho; p.rho[n] = rho; }
-		// numerator: state score of the reference segment ending here
-		const uint32_t lab = p.node_lab[n];
-		if (y == 0 && lab != LAB_BAD) num += (double)p.S[n * p.Lp + lab];
+		// (the numerator -- scores of the reference path -- is three dependent global loads per segment for one thread: a pass of its
+		// own, nodur_tf_numer_kernel, instead of a stall of the whole CTA at the frame's barrier)
 		__syncthreads();
 		if (t + 1 < T) {
 			// A_t[y] = rho_t + lgh_t[y],  lgh_t[y] = mmax + log sum_q alpha_t[q] exp(M_{t+1}[q][y] - mmax)
@@ -282,7 +295,6 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 			cp_async_wait_all();
 			__syncthreads();
 			if (t + 2 < T) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.E + (n + 2) * p.Lq, P, Ps);
-			const float mmax = p.rowmax[n + 1];
 			if (y < P) {
 				float v = 0.0f;
 #pragma unroll 8
@@ -290,16 +302,37 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 				const float l = mmax + __logf(v);
 				lgh[(t & (ND_RING - 1)) * P + y] = l; p.LG[n * p.Pp + y] = l;
 			}
-			if (y == 0 && lab != LAB_BAD) { const uint32_t nl = p.next_lab[n]; if (nl != LAB_BAD && p.tidx[(lab % P) * P + nl] != 0xffffffffu) num += (double)p.M[(n + 1) * p.Lq + (lab % P) * P + nl]; }
 			__syncthreads();
 		}
 #pragma unroll
-		for (uint32_t d = 1; d < ND_RING; d++) sv[d] = sn[d];
+		for (uint32_t d = 1; d <= (uint32_t)DR; d++) sv[d] = sn[d];
 	}
-	if (y == 0) { p.logZ[u] = T ? rring[(T - 1) & (ND_RING - 1)] : 0.0; p.numer[u] = num; }
+	if (y == 0) p.logZ[u] = T ? rring[(T - 1) & (ND_RING - 1)] : 0.0;
 }
 
-template <int TF_THR>
+// numerator of an utterance: state scores of the reference segments + transition scores between consecutive reference segments (taken
+// from the frame the next segment starts in); one warp per utterance, lanes stride the frames, fixed summation order
+__global__ void __launch_bounds__(128) nodur_tf_numer_kernel(NodurTfParams p) {
+	const uint32_t u = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (u >= p.n_utt) return;
+	const uint32_t off = p.off[u], T = p.off[u + 1] - off, P = p.P;
+	double acc = 0.0;
+	for (uint32_t t = lane; t < T; t += 32) {
+		const size_t n = (size_t)off + t;
+		const uint32_t lab = p.node_lab[n];
+		if (lab == LAB_BAD) continue;
+		acc += (double)p.S[n * p.Lp + lab];
+		if (t + 1 < T) {
+			const uint32_t nl = p.next_lab[n];
+			if (nl != LAB_BAD && p.tidx[(lab % P) * P + nl] != 0xffffffffu) acc += (double)p.M[(n + 1) * p.Lq + (lab % P) * P + nl];
+		}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) p.numer[u] = acc;
+}
+
+template <int TF_THR, int DR>
 __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
@@ -311,19 +344,27 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 	float* scratch = ev + P;                     // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
 	const double lz = p.logZ[u];
+	// (pair of element i = y + k * TF_THR of the P x P matrix: a constant step with a carry, no division per element)
+	const uint32_t q_first = y / P, y_first = y - q_first * P, dq_ = TF_THR / P, dy_ = TF_THR - dq_ * P;
 	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * P * Ps, p.E + (size_t)(off + T - 1) * p.Lq, P, Ps);    // exp(M_{T-1} - max)
 	// the score terms S_{t+d}[d,y] of a frame do not depend on the recursion: those of frame t-1 are requested while frame t is processed
 	float sv[ND_RING], sn[ND_RING];
 #pragma unroll
-	for (uint32_t d = 1; d < ND_RING; d++) sv[d] = 0.0f;      // the tail frame has no successor terms
+	for (uint32_t d = 1; d <= (uint32_t)DR; d++) sv[d] = 0.0f;      // the tail frame has no successor terms
+	// ... and so are the frame's labels, forward scale, matrix maximum and alpha entry (none is needed at the tail frame)
+	uint32_t lab = LAB_BAD, c_nl = LAB_BAD; double c_rho = 0.0; float c_mmax = 0.0f, c_av = 0.0f;
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
 		const uint32_t nn = min(T - 1 - t, D);
-		const uint32_t lab = p.node_lab[n];
+		uint32_t n_lab = LAB_BAD, n_nl = LAB_BAD; double n_rho = 0.0; float n_mmax = 0.0f, n_av = 0.0f;
+		if (t > 0) {
+			n_lab = p.node_lab[n - 1]; n_nl = p.next_lab[n - 1]; n_rho = p.rho[n - 1]; n_mmax = p.rowmax[n];
+			n_av = y < P ? p.A[(n - 1) * p.Pp + y] : 0.0f;
+		}
 		{
 			const uint32_t dn = (t > 0 && y < P) ? min(T - t, D) : 0;      // frame t-1: d <= T-1-(t-1)
 #pragma unroll
-			for (uint32_t d = 1; d < ND_RING; d++) sn[d] = d <= dn ? p.S[(n - 1 + d) * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
+			for (uint32_t d = 1; d <= (uint32_t)DR; d++) sn[d] = d <= dn ? p.S[(n - 1 + d) * p.Lp + (size_t)(d - 1) * P + y] : 0.0f;
 		}
 		float lb = 0.0f;                         // beta_t[y] - kappa_t; tail: beta = 0
 		double kappa = 0.0;
@@ -335,7 +376,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 				float lt[ND_RING];
 				float mx = -INFINITY;
 #pragma unroll
-				for (uint32_t d = 1; d < ND_RING; d++) {
+				for (uint32_t d = 1; d <= (uint32_t)DR; d++) {
 					if (d <= nn) {
 						const float v = sv[d] + lbh[((t + d) & (ND_RING - 1)) * P + y] + (float)(kring[(t + d) & (ND_RING - 1)] - kref);
 						lt[d - 1] = v; mx = fmaxf(mx, v);
@@ -343,7 +384,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 				}
 				float sacc = 0.0f;
 #pragma unroll
-				for (uint32_t d = 1; d < ND_RING; d++) if (d <= nn) sacc += __expf(lt[d - 1] - mx);
+				for (uint32_t d = 1; d <= (uint32_t)DR; d++) if (d <= nn) sacc += __expf(lt[d - 1] - mx);
 				w = mx + __logf(sacc);
 			}
 			const float wmax = block_max<TF_THR>(w, scratch);
@@ -351,25 +392,29 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			cp_async_wait_all();
 			__syncthreads();
 			if (t > 0) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.E + n * p.Lq, P, Ps);      // exp(M_t - max) for the next step
-			const float mmax = p.rowmax[n + 1];
-			if (y < P) { ev[y] = __expf(w - wmax); av[y] = p.A[n * p.Pp + y]; }
+			const float mmax = c_mmax;
+			if (y < P) { ev[y] = __expf(w - wmax); av[y] = c_av; }
 			__syncthreads();
 			// E[q][yy] = exp(M_{t+1}[q][yy] - mmax) * ev[yy] in place;
 			// xi_t[q][yy] = exp(alpha_t[q] + M_{t+1}[q][yy] + B_t[yy] - logZ) = alpha^_t[q] E[q][yy] exp(rho_t + mmax + kref + wmax - logZ)
 			// (a segment boundary after frame t has probability <= 1: the posteriors are NOT renormalised per frame)
+			uint32_t q = q_first, yy = y_first;
 			for (uint32_t i = y; i < P * P; i += TF_THR) {
-				const uint32_t q = i / P, yy = i - q * P;
 				Mn[q * Ps + yy] = Mn[q * Ps + yy] * ev[yy];
+				yy += dy_; q += dq_;
+				if (yy >= P) { yy -= P; q++; }
 			}
 			__syncthreads();
-			const float xscale = __expf((float)(p.rho[n] + (double)mmax + kref + (double)wmax - lz));
-			uint32_t nl = lab != LAB_BAD ? p.next_lab[n] : LAB_BAD;
+			const float xscale = __expf((float)(c_rho + (double)mmax + kref + (double)wmax - lz));
+			uint32_t nl = lab != LAB_BAD ? c_nl : LAB_BAD;
 			const uint32_t lq = lab != LAB_BAD ? lab % P : LAB_BAD;
 			if (nl != LAB_BAD && p.tidx[lq * P + nl] == 0xffffffffu) nl = LAB_BAD;       // a reference pair the N-state map does not have
 			float* xrow = p.Xd + (n + 1) * p.Lq;         // stored with the frame whose duration-1 window carries the transition features
+			q = q_first; yy = y_first;
 			for (uint32_t i = y; i < P * P; i += TF_THR) {
-				const uint32_t q = i / P, yy = i - q * P;
 				xrow[i] = ((q == lq && yy == nl) ? 1.0f : 0.0f) - av[q] * Mn[q * Ps + yy] * xscale;
+				yy += dy_; q += dq_;
+				if (yy >= P) { yy -= P; q++; }
 			}
 			float bn = 0.0f;
 			if (y < P) for (uint32_t yy = 0; yy < P; yy++) bn += Mn[y * Ps + yy];
@@ -387,7 +432,8 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 		if (y < P) p.LB[n * p.Pp + y] = lb;
 		if (y == 0) p.kappa[n] = kappa;
 #pragma unroll
-		for (uint32_t d = 1; d < ND_RING; d++) sv[d] = sn[d];
+		for (uint32_t d = 1; d <= (uint32_t)DR; d++) sv[d] = sn[d];
+		lab = n_lab; c_nl = n_nl; c_rho = n_rho; c_mmax = n_mmax; c_av = n_av;
 		__syncthreads();
 	}
 }
@@ -406,8 +452,17 @@ cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream
 		kern<<<p.n_utt, thr, smem, s>>>(p);
 		return cudaGetLastError();
 	};
-	if (p.P <= 128) return backward ? go(nodur_tf_backward_kernel<128>, 128) : go(nodur_tf_forward_kernel<128>, 128);
-	return backward ? go(nodur_tf_backward_kernel<TF_MAX_THR>, TF_MAX_THR) : go(nodur_tf_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
+	if (!backward) nodur_tf_numer_kernel<<<(p.n_utt + 3) / 4, 128, 0, s>>>(p);      // the numerators: a pass of their own beside the forward chain
+	// instantiation whose unrolled duration loops cover max_dur (the D score terms of a frame wait in registers)
+	auto pick = [&](auto dr) -> cudaError_t {
+		constexpr int DR = decltype(dr)::value;
+		if (p.P <= 128) return backward ? go(nodur_tf_backward_kernel<128, DR>, 128) : go(nodur_tf_forward_kernel<128, DR>, 128);
+		return backward ? go(nodur_tf_backward_kernel<TF_MAX_THR, DR>, TF_MAX_THR) : go(nodur_tf_forward_kernel<TF_MAX_THR, DR>, TF_MAX_THR);
+	};
+	if (p.D <= 4) return pick(std::integral_constant<int, 4>{});
+	if (p.D <= 10) return pick(std::integral_constant<int, 10>{});
+	if (p.D <= 16) return pick(std::integral_constant<int, 16>{});
+	return pick(std::integral_constant<int, 31>{});
 }
 
 }  // namespace crfgpu
