@@ -1033,6 +1033,30 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 #pragma unroll
 	for (uint32_t j = 0; j < VPF; j++) nsv[j] = (lab < L && j < D && T > 0) ? p.negS[((uint64_t)off * D + j) * L + lab] : 0.0f;
 
+	// transition FEATURES: the cross-phone table of frame s+1 is copied (transposed like the constant table) into the other half of a
+	// double buffer while frame s is processed, its self-loop / advance entries wait in registers: the scan reads shared memory instead
+	// of 48 rounds to L2 per frame
+	const bool pf_smem = per_frame && (2 * (size_t)P * Pt * sizeof(float) <= 96 * 1024);
+	auto fetch_table = [&](uint32_t frame) {      // row `frame` of negMt -> buffer frame & 1 (cp.async, 4 bytes per element)
+		const float* tb = p.negMt + (uint64_t)(off + frame) * p.E;
+		float* dst = crossS + (size_t)(frame & 1) * P * Pt;
+		uint32_t r = threadIdx.x / P, c = threadIdx.x - r * P;      // element i = r * P + c -> dst[c * Pt + r]
+		const uint32_t dr = blockDim.x / P, dc = blockDim.x - dr * P;
+		for (uint32_t i = threadIdx.x; i < P * P; i += blockDim.x) {
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + (size_t)c * Pt + r)), "l"(tb + i) : "memory");
+			c += dc; r += dr;
+			if (c >= P) { c -= P; r++; }
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	float nx_diag = 0.0f, nx_off = 0.0f;
+	if (pf_smem && T > 1) {
+		fetch_table(1);
+		const float* tb = p.negMt + (uint64_t)(off + 1) * p.E;
+		if (lab < L) { nx_diag = tb[P * P + lab]; nx_off = k > 0 ? tb[P * P + L + lab] : 0.0f; }
+	}
+	const float* crossF = crossS;
+
 	for (uint32_t s = 0; s < T; s++) {
 		float nsn[VPF];
 #pragma unroll
@@ -1040,7 +1064,17 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 		// ---- cross-phone candidates for segments starting at frame s: the scan of the kept list of frame s-1 is shared by ALL threads
 		//      of the CTA (with N states per phone only every N-th thread owns a start state): thread = (part of the list, target phone);
 		//      strict '<' keeps the first arrival inside a part, and the parts are merged in list order below ----
-		if (per_frame && s > 0) {
+		if (pf_smem && s > 0) {
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			__syncthreads();                                     // the table of frame s is complete; the other buffer was last read in frame s-1
+			crossF = crossS + (size_t)(s & 1) * P * Pt;
+			my_diag = nx_diag; my_off = nx_off;
+			if (s + 1 < T) {
+				fetch_table(s + 1);
+				const float* tb = p.negMt + (uint64_t)(off + s + 1) * p.E;
+				if (lab < L) { nx_diag = tb[P * P + lab]; nx_off = k > 0 ? tb[P * P + L + lab] : 0.0f; }
+			}
+		} else if (per_frame && s > 0) {
 			const float* tb = p.negMt + (uint64_t)(off + s) * p.E;
 			crossT = tb;
 			if (lab < L) { my_diag = tb[P * P + lab]; my_off = k > 0 ? tb[P * P + L + lab] : 0.0f; }
@@ -1102,6 +1136,7 @@ __global__ void __launch_bounds__(1024) viterbi_kernel(VitParams p) {
 				else pptr = pptr * (int32_t)NS + (int32_t)NS - 1;   // the phone's end state
 			};
 			if (cross_in_smem) scan(crossS + (size_t)tq * Pt, 1u);
+			else if (pf_smem) scan(crossF + (size_t)tq * Pt, 1u);
 			else scan(crossT + tq, P);
 			if (NS > 1) { partW[part * P + tq] = pw; partP[part * P + tq] = pptr; }
 		}
@@ -1302,6 +1337,7 @@ void launch_viterbi(const VitParams& p, cudaStream_t s) {
 	q.Ppad = (p.NS > 1 && p.NS * Pw <= 1024) ? Pw : p.P;
 	const unsigned threads = (std::max(p.L, p.NS * q.Ppad) + 31) / 32 * 32;
 	size_t smem = sizeof(float) * (3 * (size_t)p.L + p.P);
+	if (p.negMt != nullptr && 2 * (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) smem += 2 * sizeof(float) * (size_t)p.P * (p.P | 1u);   // per-frame tables: double buffer
 	if (p.negMt == nullptr && (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) {
 		smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
 		if (p.lm_bigT != nullptr && 2 * (size_t)p.P * (p.P | 1u) * sizeof(float) <= 96 * 1024) smem += sizeof(float) * (size_t)p.P * (p.P | 1u);
