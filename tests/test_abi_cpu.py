@@ -110,3 +110,18 @@ def test_balance_rules_of_one_global_minibatch():
     # degenerate inputs
     assert list(crf_b200.balance_utts_cost(np.array([5, 9, 2], np.uint32), 1, 16, 100.0)) == [0, 0, 0]
     assert len(crf_b200.balance_utts_cost(np.zeros(0, np.uint32), 3, 16, 100.0)) == 0
+
+
+def test_recipe_workload_and_pins():
+    """the production-recipe leg of bench.py: geometry of the workload and the pins the leg is gated on (made by the reference itself,
+    tests/golden/make_bench_pins.py recipe)"""
+    import workloads
+    kw = workloads.recipe_kwargs()
+    assert kw["state_fidx"] == (0, 1161) and kw["trans_fidx"] == (1162, 3033)
+    off, f1, f2, labs = workloads.recipe_batch(3)
+    assert f1.shape == (int(off[-1]), 144) and f2.shape == (int(off[-1]) + 12 * 3, 144) and labs.max() < 48
+    so, a1, a2, al = workloads.recipe_utt(off, f1, f2, labs, 1)
+    assert a1.shape[0] == int(so[-1]) and a2.shape[0] == int(so[-1]) + 12 and np.array_equal(a1, f1[int(off[1]):int(off[2])])
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_pins.npz"))
+    for k in ("recipe/numer", "recipe/logZ", "recipe/cost", "recipe/crc"):
+        assert k in z and len(z[k]) == 4

@@ -503,6 +503,23 @@ def test_fwdbwd_transition_features_nstate_match_reference_golden(name):
     m.close()
 
 
+@pytest.mark.parametrize("name", ["frame_transftr_20labs", "nodur_transftr_d10"])
+def test_fwdbwd_transition_features_register_staged_gemms(name):
+    """option tf_tiled 0: the labels^2 GEMMs on the register-staged kernels (fp32 operands) instead of the pre-tiled bf16 operands fed
+    by bulk copies -- both routes against the reference's golden"""
+    c = TRANSFTR[name]
+    m = gpu(c["cfg"])
+    m.set_option("tf_tiled", 0)
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name + " tf_tiled=0")
+    m.set_option("tf_tiled", 1)
+    m.set_lambda(c["lam"])
+    got = m.fwdbwd(c["off"], c["ftrs"], c["labs"])
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name + " tf_tiled=1")
+    m.close()
+
+
 def test_fwdbwd_nodur_transition_features_timit_recipe_shape(oracle):
     """stdseg_no_dur_no_segtransftr + stdtrans at the shape of the production TIMIT recipe (48 phones, maxDur 10, transition features
     from the duration-1 window), against the oracle's native restatement (pinned to goldens from the reference's no_dur nodes)."""
