@@ -88,7 +88,7 @@ SYMBOLS = ["crfgpu_last_error", "crfgpu_create", "crfgpu_destroy", "crfgpu_windo
            "crfgpu_group_start", "crfgpu_group_end", "crfgpu_allreduce_grad", "crfgpu_fetch_tail",
            "crfgpu_shard_views", "crfgpu_minibatch_share", "crfgpu_balance_utts", "crfgpu_plan_info",
            "crfgpu_fetch_posterior_mass", "crfgpu_stage_batch2", "crfgpu_fwdbwd_batch2", "crfgpu_viterbi_batch2",
-           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm", "crfgpu_set_beam", "crfgpu_balance_utts_cost"]
+           "crfgpu_expand_windows2", "crfgpu_prefetch_train_batch", "crfgpu_prefetch_train_batch2", "crfgpu_set_phone_lm", "crfgpu_set_phone_unigram_lm", "crfgpu_set_beam", "crfgpu_balance_utts_cost"]
 COMM_ID_BYTES = 128
 
 
@@ -375,12 +375,17 @@ class CrfGpu:
                                                  None if f2 is None else _ptr(f2, C.c_float), lp))
         self._n_utt, self._n_frames = n, int(off[-1])
 
-    def prefetch(self, off, ftrs, labs=None):
-        """crfgpu_prefetch_batch / crfgpu_prefetch_train_batch: copy + window-expand the NEXT batch on side streams (with labs: its
-        label tables too); `ftrs` (and `labs`) must be the very arrays later staged."""
+    def prefetch(self, off, ftrs, labs=None, ftrs2=None):
+        """crfgpu_prefetch_batch / crfgpu_prefetch_train_batch[2]: copy + window-expand the NEXT batch on side streams (with labs: its
+        label tables too); `ftrs` (`ftrs2`, `labs`) must be the very arrays later staged."""
         off = np.ascontiguousarray(off, np.uint32)
         assert ftrs.dtype == np.float32 and ftrs.flags["C_CONTIGUOUS"]
-        if labs is None:
+        if ftrs2 is not None:
+            assert ftrs2.dtype == np.float32 and ftrs2.flags["C_CONTIGUOUS"]
+            assert labs is None or (labs.dtype == np.uint32 and labs.flags["C_CONTIGUOUS"])
+            self._check(self.lib.crfgpu_prefetch_train_batch2(self.h, C.c_uint32(len(off) - 1), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float),
+                                                              _ptr(ftrs2, C.c_float), None if labs is None else _ptr(labs, C.c_uint32)))
+        elif labs is None:
             self._check(self.lib.crfgpu_prefetch_batch(self.h, C.c_uint32(len(off) - 1), _ptr(off, C.c_uint32), _ptr(ftrs, C.c_float)))
         else:
             assert labs.dtype == np.uint32 and labs.flags["C_CONTIGUOUS"]

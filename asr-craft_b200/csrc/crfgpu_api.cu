@@ -69,6 +69,7 @@ struct crfgpu_ctx {
 	unsigned char* pin = nullptr; size_t pin_cap = 0, pin_used = 0; cudaEvent_t ev_pin = nullptr;
 	// crfgpu_prefetch_batch: the NEXT minibatch's base features and windows, copied / expanded into a second buffer set on side streams
 	// while the current minibatch computes; crfgpu_stage_batch swaps the sets when it is handed the batch that was prefetched
+	DevBuf d_baseB2; const float* pre_ftrs2 = nullptr;             // (second stream of a joined model)
 	DevBuf d_base2, d_X2, d_frame_t2, d_bpad2, d_Xa2; bool pre_virt = false; cudaStream_t pre_stream = nullptr; cudaEvent_t ev_pre_done = nullptr, ev_pre_ready = nullptr;
 	cudaEvent_t ev_swap = nullptr; bool swap_marked = false;   // main-stream point after which the spare buffer set is free
 	std::vector<cudaEvent_t> ev_chunk2; bool pre_valid = false; const float* pre_ftrs = nullptr; std::vector<uint32_t> pre_off;
@@ -462,17 +463,72 @@ void build_label_tables(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, cons
 	}
 }
 
-void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs = nullptr) {
+// joined / context window streams of a batch: both streams to the device whole, one gather kernel builds the windows (on stream st,
+// into the given buffer set: the staged one or the read-ahead's spare one)
+void stage_joined(crfgpu_ctx* h, uint32_t n_utt, uint32_t N, const float* ftrs, const float* ftrs2, DevBuf& base, DevBuf& baseB, DevBuf& X,
+                  const uint32_t* d_ft, const uint32_t* d_fu, cudaStream_t st) {
+	const crfgpu_config& c = h->cfg;
+	if (!N) return;
+	const size_t n1 = (size_t)N + (size_t)n_utt * (c.left_ctx + c.right_ctx), n2 = (size_t)N + (size_t)n_utt * (c.left_ctx2 + c.right_ctx2);
+	base.ensure(sizeof(float) * n1 * c.n_base_ftrs + 16);
+	CUDA_OK(cudaMemcpyAsync(base.p, ftrs, sizeof(float) * n1 * c.n_base_ftrs, cudaMemcpyHostToDevice, st));
+	if (c.n_base_ftrs2) {
+		baseB.ensure(sizeof(float) * n2 * c.n_base_ftrs2 + 16);
+		CUDA_OK(cudaMemcpyAsync(baseB.p, ftrs2, sizeof(float) * n2 * c.n_base_ftrs2, cudaMemcpyHostToDevice, st));
+	}
+	X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
+	ExpandJoinedParams ep{};
+	ep.part[0] = JoinedPart{base.as<float>(), c.n_base_ftrs, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta,
+	                        stream_width(c.n_base_ftrs, c.max_dur, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta)};
+	ep.n_parts = 1;
+	if (c.n_base_ftrs2) {
+		ep.part[1] = JoinedPart{baseB.as<float>(), c.n_base_ftrs2, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2,
+		                        stream_width(c.n_base_ftrs2, c.max_dur, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2)};
+		ep.n_parts = 2;
+	}
+	ep.frame_t = d_ft; ep.frame_utt = d_fu; ep.steps = h->d_steps.as<uint32_t>();
+	ep.X = X.as<float>(); ep.N = N; ep.D = c.max_dur; ep.Wp = h->Wp;
+	// stdseg_no_dur_no_segtransftr + stdtrans: the transition scores (training and decoding) read the duration-1 window only, so in
+	// the longer windows only the state-feature range is gathered -- 62 % of the recipe's 121 kB per frame are transition columns
+	if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.use_trans_ftrs && c.use_state_ftrs && c.max_dur > 1 && !h->full_windows) {
+		ep.keep_lo = c.state_fidx_start; ep.keep_hi = c.state_fidx_end + 1;
+	}
+	launch_expand_joined(ep, st); check_kernel(h, 1);
+}
+
+void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs = nullptr, const float* ftrs2 = nullptr) {
 	const crfgpu_config& c = h->cfg;
 	validate_offsets(n_utt, off, ftrs);
 	const uint32_t N = n_utt ? off[n_utt] : 0;
 	h->pre_valid = false;
-	if (!N || h->joined) return;                                         // joined / context windows are staged by crfgpu_stage_batch2 only
+	if (!N) return;
+	if (h->joined && c.n_base_ftrs2 && !ftrs2) return;                    // a joined model without its second stream: nothing to read ahead
 	if (!h->pre_stream) {
 		CUDA_OK(cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
 		CUDA_OK(cudaEventCreate(&h->ev_pre_done)); CUDA_OK(cudaEventCreate(&h->ev_pre_ready));
 	}
 	if (h->swap_marked) CUDA_OK(cudaStreamWaitEvent(h->pre_stream, h->ev_swap, 0));
+	if (h->joined) {
+		// joined / context window streams (crfgpu_prefetch_train_batch2): the whole staging of crfgpu_stage_batch2 on the side stream,
+		// into the spare buffer set
+		h->pre_off.assign(off, off + n_utt + 1);
+		upload(h->d_off2, h->pre_off, h->pre_stream);
+		h->d_frame_t2.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_frame_utt2.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_frame_len2.ensure(sizeof(uint32_t) * (size_t)N + 16);
+		launch_frame_tables(h->d_off2.as<uint32_t>(), n_utt, N, h->d_frame_t2.as<uint32_t>(), h->d_frame_utt2.as<uint32_t>(), h->d_frame_len2.as<uint32_t>(), h->pre_stream);
+		check_kernel(h, 1);
+		stage_joined(h, n_utt, N, ftrs, ftrs2, h->d_base2, h->d_baseB2, h->d_X2, h->d_frame_t2.as<uint32_t>(), h->d_frame_utt2.as<uint32_t>(), h->pre_stream);
+		h->pre_tabs = false; h->pre_labs = labs;
+		if (labs) {
+			std::vector<uint32_t> node_lab, prev_lab, next_lab;
+			build_label_tables(h, n_utt, off, labs, node_lab, prev_lab, next_lab);
+			upload(h->d_node_lab2, node_lab, h->pre_stream); upload(h->d_prev_lab2, prev_lab, h->pre_stream);
+			if (!next_lab.empty()) upload(h->d_next_lab2, next_lab, h->pre_stream);
+			h->pre_tabs = true;
+		}
+		CUDA_OK(cudaEventRecord(h->ev_pre_done, h->pre_stream));
+		h->pre_virt = false; h->pre_ftrs = ftrs; h->pre_ftrs2 = ftrs2; h->pre_valid = true;
+		return;
+	}
 	h->d_base2.ensure(sizeof(float) * (size_t)N * c.n_base_ftrs + 16);
 	h->pre_virt = h->virt;                                               // the read-ahead of a training loop: the form the training GEMMs read
 	if (h->pre_virt) { h->d_bpad2.ensure(sizeof(float) * (size_t)N * h->Fp + 16); h->d_Xa2.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wa + 16); }
@@ -578,53 +634,40 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	};
 	const bool want_virt = h->virt && labs != nullptr;                   // training batches of eligible models stage the virtual-window form
 	const bool prefetched = h->pre_valid && N && h->pre_ftrs == ftrs && h->pre_off == h->h_off && h->pre_virt == want_virt;
-	const bool tabs_ready = prefetched && !h->joined && h->pre_tabs && labs != nullptr && h->pre_labs == labs;   // index / label tables already on the device
+	bool joined_tabs = false;
+	const bool tabs_ready0 = prefetched && !h->joined && h->pre_tabs && labs != nullptr && h->pre_labs == labs;   // index / label tables already on the device
+	const bool had_tabs = h->pre_tabs;
 	h->pre_valid = false; h->pre_tabs = false;
 	h->x_virt_valid = want_virt; h->x_full_valid = !want_virt;
-	if (h->joined) {
+	const bool joined_ahead = h->joined && prefetched && h->pre_ftrs2 == ftrs2;      // this joined batch was read ahead (crfgpu_prefetch_train_batch2)
+	if (h->joined && joined_ahead) {
+		if (!h->ev_swap) CUDA_OK(cudaEventCreateWithFlags(&h->ev_swap, cudaEventDisableTiming));
+		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
+		std::swap(h->d_base, h->d_base2); std::swap(h->d_baseB, h->d_baseB2); std::swap(h->d_X, h->d_X2);
+		std::swap(h->d_frame_t, h->d_frame_t2); std::swap(h->d_frame_utt, h->d_frame_utt2); std::swap(h->d_frame_len, h->d_frame_len2);
+		if (had_tabs && labs != nullptr && h->pre_labs == labs) {
+			std::swap(h->d_node_lab, h->d_node_lab2); std::swap(h->d_prev_lab, h->d_prev_lab2); std::swap(h->d_next_lab, h->d_next_lab2);
+			joined_tabs = true;
+		}
+		CUDA_OK(cudaStreamWaitEvent(s, h->ev_pre_done, 0));
+	} else if (h->joined) {
 		// general window streams: both streams go to the device whole, one gather kernel builds the joined windows
 		frame_tables(true);
-		const size_t n1 = (size_t)N + (size_t)n_utt * (c.left_ctx + c.right_ctx), n2 = (size_t)N + (size_t)n_utt * (c.left_ctx2 + c.right_ctx2);
-		h->d_base.ensure(sizeof(float) * n1 * c.n_base_ftrs + 16);
-		if (N) CUDA_OK(cudaMemcpyAsync(h->d_base.p, ftrs, sizeof(float) * n1 * c.n_base_ftrs, cudaMemcpyHostToDevice, s));
-		if (c.n_base_ftrs2) {
-			h->d_baseB.ensure(sizeof(float) * n2 * c.n_base_ftrs2 + 16);
-			if (N) CUDA_OK(cudaMemcpyAsync(h->d_baseB.p, ftrs2, sizeof(float) * n2 * c.n_base_ftrs2, cudaMemcpyHostToDevice, s));
-		}
-		if (N) {
-			h->d_X.ensure(sizeof(float) * (size_t)N * c.max_dur * h->Wp + 16);
-			phase_begin(h, "expand");
-			ExpandJoinedParams ep{};
-			ep.part[0] = JoinedPart{h->d_base.as<float>(), c.n_base_ftrs, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta,
-			                        stream_width(c.n_base_ftrs, c.max_dur, c.extract_seg_ftrs, c.left_ctx, c.right_ctx, c.boundary_delta)};
-			ep.n_parts = 1;
-			if (c.n_base_ftrs2) {
-				ep.part[1] = JoinedPart{h->d_baseB.as<float>(), c.n_base_ftrs2, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2,
-				                        stream_width(c.n_base_ftrs2, c.max_dur, c.extract_seg_ftrs2, c.left_ctx2, c.right_ctx2, c.boundary_delta2)};
-				ep.n_parts = 2;
-			}
-			ep.frame_t = h->d_frame_t.as<uint32_t>(); ep.frame_utt = h->d_frame_utt.as<uint32_t>(); ep.steps = h->d_steps.as<uint32_t>();
-			ep.X = h->d_X.as<float>(); ep.N = N; ep.D = c.max_dur; ep.Wp = h->Wp;
-			// stdseg_no_dur_no_segtransftr + stdtrans: the transition scores (training and decoding) read the duration-1 window only, so in
-			// the longer windows only the state-feature range is gathered -- 62 % of the recipe's 121 kB per frame are transition columns
-			if (c.model_type == CRFGPU_STDSEG_NO_DUR_NO_SEGTRANSFTR && c.use_trans_ftrs && c.use_state_ftrs && c.max_dur > 1 && !h->full_windows) {
-				ep.keep_lo = c.state_fidx_start; ep.keep_hi = c.state_fidx_end + 1;
-			}
-			launch_expand_joined(ep, s); check_kernel(h, 1);
-			phase_end(h, "expand");
-		}
+		phase_begin(h, "expand");
+		stage_joined(h, n_utt, N, ftrs, ftrs2, h->d_base, h->d_baseB, h->d_X, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), s);
+		phase_end(h, "expand");
 	} else if (prefetched) {
 		// this batch was copied and expanded by crfgpu_prefetch_batch while the previous one computed: take over its buffers
 		if (!h->ev_swap) CUDA_OK(cudaEventCreateWithFlags(&h->ev_swap, cudaEventDisableTiming));
 		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
 		std::swap(h->d_base, h->d_base2); std::swap(h->d_X, h->d_X2); std::swap(h->d_frame_t, h->d_frame_t2);
 		std::swap(h->d_bpad, h->d_bpad2); std::swap(h->d_Xa, h->d_Xa2);
-		if (tabs_ready) {
+		if (tabs_ready0) {
 			std::swap(h->d_frame_utt, h->d_frame_utt2); std::swap(h->d_frame_len, h->d_frame_len2);
 			std::swap(h->d_node_lab, h->d_node_lab2); std::swap(h->d_prev_lab, h->d_prev_lab2); std::swap(h->d_next_lab, h->d_next_lab2);
 		}
 		CUDA_OK(cudaStreamWaitEvent(s, h->ev_pre_done, 0));
-		if (!tabs_ready) frame_tables(false);
+		if (!tabs_ready0) frame_tables(false);
 	} else {
 		// what the window expansion needs goes through the copy engine ahead of the feature chunks
 		frame_tables(true);
@@ -682,6 +725,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		h->vit_score_ready = eager_vit; h->vit_rec_ready = eager_rec;
 	}
 
+	const bool tabs_ready = tabs_ready0 || joined_tabs;
 	if (labs && !tabs_ready) {
 		std::vector<uint32_t> node_lab, prev_lab, next_lab;
 		build_label_tables(h, n_utt, off, labs, node_lab, prev_lab, next_lab);
@@ -1502,7 +1546,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
 	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt,
-	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_XtK, &h->d_WtrT, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
+	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_XtK, &h->d_WtrT, &h->d_baseB2, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1607,6 +1651,14 @@ int crfgpu_prefetch_train_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t*
 		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
 		CUDA_OK(cudaSetDevice(h->device));
 		prefetch_batch(h, n_utt, frame_off, base_ftrs, frame_labs);
+	});
+}
+
+int crfgpu_prefetch_train_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2, const uint32_t* frame_labs) {
+	return guarded([&] {
+		if (!h) throw ApiError(CRFGPU_ERR_ARG, "null handle");
+		CUDA_OK(cudaSetDevice(h->device));
+		prefetch_batch(h, n_utt, frame_off, base_ftrs, frame_labs, base_ftrs2);
 	});
 }
 

@@ -610,15 +610,17 @@ def run_ours(args):
             if gate[-1]["ok"] is False:
                 fail_parity(gate)
         # end to end: the trainer's step with host buffers -- both streams over PCIe, joined windows built on the device, fwd-bwd + gradient,
-        # D2H of numerators / logZ, lambda update on the device (no read-ahead: joined streams are staged by crfgpu_stage_batch2 only)
+        # D2H of numerators / logZ, lambda update on the device, read-ahead of the next minibatch (crfgpu_prefetch_train_batch2)
         rp1 = crf_b200.PinnedBuffer(rf1.shape, np.float32); rp1.array[...] = rf1
         rp2 = crf_b200.PinnedBuffer(rf2.shape, np.float32); rp2.array[...] = rf2
         rpl = crf_b200.PinnedBuffer(rlabs.shape, np.uint32); rpl.array[...] = rlabs
         rpn = crf_b200.PinnedBuffer((len(roff) - 1,), np.float64); rpz = crf_b200.PinnedBuffer((len(roff) - 1,), np.float64)
 
         def r_step():
-            rm.stage(roff, rp1.array, rpl.array, ftrs2=rp2.array)
+            rm.stage(roff, rp1.array, rpl.array, ftrs2=rp2.array)     # taken over from the read-ahead after the first step
             rm.fwdbwd_staged()
+            if not args.no_prefetch:
+                rm.prefetch(roff, rp1.array, rpl.array, ftrs2=rp2.array)   # the NEXT minibatch: copies, joined windows, label tables on the side stream
             rm.fetch_fwdbwd(out=(None, rpn.array, rpz.array))
             rm.sgd_update(1.0, lr=1e-13)
 

@@ -193,6 +193,11 @@ int crfgpu_prefetch_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame
  * copied while the current minibatch computes, so that the crfgpu_stage_batch that takes the batch over (same frame_off contents, same
  * base_ftrs and frame_labs pointers) has no per-frame host work left. */
 int crfgpu_prefetch_train_batch(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const uint32_t* frame_labs);
+/* ... and of a model with context frames / a joined second stream (crfgpu_stage_batch2's layout of both streams; frame_labs may be
+ * NULL): copies, joined windows and label tables of the NEXT minibatch on the side stream, taken over by crfgpu_stage_batch2 /
+ * crfgpu_fwdbwd_batch2 when handed the same pointers and offsets. */
+int crfgpu_prefetch_train_batch2(crfgpu_handle h, uint32_t n_utt, const uint32_t* frame_off, const float* base_ftrs, const float* base_ftrs2,
+                                 const uint32_t* frame_labs);
 /* Run forward-backward+gradient on the staged batch; results stay on the device. */
 int crfgpu_fwdbwd_staged(crfgpu_handle h);
 /* Run Viterbi + traceback on the staged batch; results stay on the device. */

@@ -476,6 +476,38 @@ def test_prefetch_train_batch_hands_over_label_tables(case):
     m.close()
 
 
+@pytest.mark.parametrize("name", ["train_nodur_joined_recipe", "train_frame_joined_transftr", "train_stdseg_ctx"])
+def test_prefetch_train_batch2_joined_streams(name):
+    """crfgpu_prefetch_train_batch2: the read-ahead of a model with context frames / a joined second stream -- both streams, the joined
+    windows and the label tables on the side stream; the staged batch gives the reference's golden, a batch at other addresses (or
+    with other labels) is staged normally."""
+    c = JOINED[name]
+    f2 = f2_of(c)
+    m = gpu(c["cfg"])
+    m.set_lambda(c["lam"])
+    fa, la = np.ascontiguousarray(c["ftrs"], np.float32), np.ascontiguousarray(c["labs"], np.uint32)
+    fb = None if f2 is None else np.ascontiguousarray(f2, np.float32)
+    if fb is None:      # (context frames only: the read-ahead entry point takes the first stream alone)
+        fb = np.zeros((1, 1), np.float32)
+    two = c["cfg"].n_base_ftrs2 > 0
+    for _ in range(3):
+        m.stage(c["off"], fa, la, ftrs2=fb if two else None)
+        m.fwdbwd_staged()
+        m.prefetch(c["off"], fa, la, ftrs2=fb)
+        got = m.fetch_fwdbwd()
+        assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name + " read ahead")
+    # other labels at another address: the windows are taken over, the label tables rebuilt
+    m.prefetch(c["off"], fa, la, ftrs2=fb)
+    lb = la.copy()
+    got = m.fwdbwd(c["off"], fa, lb, ftrs2=fb if two else None)
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name + " other label array")
+    # other features at another address: staged normally
+    m.prefetch(c["off"], fa, la, ftrs2=fb)
+    got = m.fwdbwd(c["off"], fa.copy(), la, ftrs2=fb if two else None)
+    assert_train_close(got, (c["grad"], c["numer"], c["logZ"]), name + " other feature array")
+    m.close()
+
+
 @pytest.mark.parametrize("name", sorted(TRANSFTR))
 def test_fwdbwd_transition_features_match_reference_golden(name):
     """crf_featuremap=stdtrans on frame-level models: transition scores as a tensor-core GEMM, streamed recursions, both gradients
