@@ -594,7 +594,7 @@ def run_ours(args):
     # ---- production-recipe leg (stdseg_no_dur_no_segtransftr + stdtrans at the TIMIT demo's shape), one GPU ----
     recipe = None
     if world == 1 and not args.no_recipe:
-        roff, rf1, rf2, rlabs = workloads.recipe_batch()
+        roff, rf1, rf2, rlabs = workloads.recipe_batch(args.recipe_utts)      # the headline's minibatch shape by default: the first 462 TIMIT-shaped utterances
         rm = crf_b200.CrfGpu(crf_b200.make_config(**workloads.recipe_kwargs()), device=local)
         rm.set_lambda(workloads.lam_for("recipe", rm.lambda_len))
         rm.stage(roff, rf1, rlabs, ftrs2=rf2)
@@ -622,7 +622,7 @@ def run_ours(args):
             if not args.no_prefetch:
                 rm.prefetch(roff, rp1.array, rpl.array, ftrs2=rp2.array)   # the NEXT minibatch: copies, joined windows, label tables on the side stream
             rm.fetch_fwdbwd(out=(None, rpn.array, rpz.array))
-            rm.sgd_update(1.0, lr=1e-13)
+            rm.sgd_update(1.0, lr=1e-16)      # a real update (every lambda-derived table rebuilt); the rate keeps the timed workload the pinned one
 
         for _ in range(2):
             r_step()
@@ -770,6 +770,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-recipe", action="store_true", help="skip the production-recipe leg (transition features, joined streams)")
+    ap.add_argument("--recipe-utts", type=int, default=462, help="utterances of the production-recipe leg's minibatch")
     ap.add_argument("--no-frame", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true")
     args = ap.parse_args()
