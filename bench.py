@@ -656,7 +656,7 @@ def run_ours(args):
         recipe = {"workload": "TIMIT recipe shape (stdseg_no_dur_no_segtransftr + stdtrans, 48 phones, maxDur 10, 1162 state features from stream 1, "
                               f"1872 transition features from 13 context frames of stream 2; {len(roff) - 1} utterances = {int(rN)} frames, device-resident)",
                   "train_frames_per_s": rN / (sum(rbest.values()) / 1e3), "train_phases_ms": rbest,
-                  "train_e2e_frames_per_s": re2e, "h2d_bytes_per_step": rh2d, "expand_ms": rm.phase_ms("expand"),
+                  "train_e2e_frames_per_s": re2e, "h2d_bytes_per_step": rh2d,
                   "viterbi_frames_per_s": rN / ((rvs + rvr) / 1e3), "viterbi_phases_ms": {"score": rvs, "recursion": rvr},
                   "lambda_len": rm.lambda_len, "plan": rm.plan_info()}
         # the leg's dominant kernel is tensor-bound ("the only genuinely tensor-bound GEMM"): the transition-gradient
