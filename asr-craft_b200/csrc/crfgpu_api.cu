@@ -88,6 +88,7 @@ struct crfgpu_ctx {
 	// transition tables and forward/backward vectors are P wide
 	DevBuf d_WdT, d_vt_base, d_negMt; uint32_t vtE = 0;              // decoding with transition features: per-frame transition tables
 	bool nodur_tf = false; DevBuf d_next_lab;                       // segmental no_dur model with transition features (nodur && nodur_tf)
+	DevBuf d_XtK2, d_XtT2; bool x_tiles_valid = false, pre_tiles = false;   // the X tiles of a joined training batch are made at staging (read-ahead: into the spare set)
 	DevBuf d_XtK, d_WtrT;                                           // ... and the transition scores: X slice and weights as K-major tiles (launch_tile_k)
 	DevBuf d_XdT, d_XtT; int opt_tf_tiled = 1;                     // transition-feature gradient from pre-split, pre-tiled operands (launch_reduce_gemm_tiled)
 	DevBuf d_Eall, d_rowmax;                                        // exp(M_n - max M_n) of every frame and the maxima (launch_transftr_exp)
@@ -465,8 +466,18 @@ void build_label_tables(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, cons
 
 // joined / context window streams of a batch: both streams to the device whole, one gather kernel builds the windows (on stream st,
 // into the given buffer set: the staged one or the read-ahead's spare one)
+// the transition slice of the duration-1 windows as bf16 hi / lo tiles for the two labels^2 GEMMs (K-major for the scores, frame-major
+// with the constant-1 bias column for the gradient): they depend on the windows only, so a training batch gets them at staging
+void tile_trans_slice(crfgpu_ctx* h, uint32_t N, const float* X, DevBuf& XtK, DevBuf& XtT, cudaStream_t st) {
+	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
+	const uint32_t J = m.nTf + (c.use_trans_bias ? 1 : 0), ones = c.use_trans_bias ? m.nTf : 0xffffffffu;
+	XtK.ensure(tiled_k_operand_bytes(N, m.nTf, 128) + 16); XtT.ensure(tiled_operand_bytes(N, J, 64) + 16);
+	CUDA_OK(launch_tile_k(X + c.trans_fidx_start, (uint64_t)c.max_dur * h->Wp, N, m.nTf, true, XtK.as<unsigned char>(), st)); check_kernel(h, 1);
+	CUDA_OK(launch_tile_mn(X + c.trans_fidx_start, (uint64_t)c.max_dur * h->Wp, J, ones, N, false, XtT.as<unsigned char>(), st)); check_kernel(h, 1);
+}
+
 void stage_joined(crfgpu_ctx* h, uint32_t n_utt, uint32_t N, const float* ftrs, const float* ftrs2, DevBuf& base, DevBuf& baseB, DevBuf& X,
-                  const uint32_t* d_ft, const uint32_t* d_fu, cudaStream_t st) {
+                  const uint32_t* d_ft, const uint32_t* d_fu, cudaStream_t st, DevBuf* XtK = nullptr, DevBuf* XtT = nullptr) {
 	const crfgpu_config& c = h->cfg;
 	if (!N) return;
 	const size_t n1 = (size_t)N + (size_t)n_utt * (c.left_ctx + c.right_ctx), n2 = (size_t)N + (size_t)n_utt * (c.left_ctx2 + c.right_ctx2);
@@ -494,6 +505,7 @@ void stage_joined(crfgpu_ctx* h, uint32_t n_utt, uint32_t N, const float* ftrs, 
 		ep.keep_lo = c.state_fidx_start; ep.keep_hi = c.state_fidx_end + 1;
 	}
 	launch_expand_joined(ep, st); check_kernel(h, 1);
+	if (XtK && XtT) tile_trans_slice(h, N, X.as<float>(), *XtK, *XtT, st);
 }
 
 void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float* ftrs, const uint32_t* labs = nullptr, const float* ftrs2 = nullptr) {
@@ -516,7 +528,9 @@ void prefetch_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const fl
 		h->d_frame_t2.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_frame_utt2.ensure(sizeof(uint32_t) * (size_t)N + 16); h->d_frame_len2.ensure(sizeof(uint32_t) * (size_t)N + 16);
 		launch_frame_tables(h->d_off2.as<uint32_t>(), n_utt, N, h->d_frame_t2.as<uint32_t>(), h->d_frame_utt2.as<uint32_t>(), h->d_frame_len2.as<uint32_t>(), h->pre_stream);
 		check_kernel(h, 1);
-		stage_joined(h, n_utt, N, ftrs, ftrs2, h->d_base2, h->d_baseB2, h->d_X2, h->d_frame_t2.as<uint32_t>(), h->d_frame_utt2.as<uint32_t>(), h->pre_stream);
+		h->pre_tiles = labs != nullptr && (h->transftr || h->nodur_tf) && h->opt_tf_tiled;
+		stage_joined(h, n_utt, N, ftrs, ftrs2, h->d_base2, h->d_baseB2, h->d_X2, h->d_frame_t2.as<uint32_t>(), h->d_frame_utt2.as<uint32_t>(), h->pre_stream,
+		             h->pre_tiles ? &h->d_XtK2 : nullptr, h->pre_tiles ? &h->d_XtT2 : nullptr);
 		h->pre_tabs = false; h->pre_labs = labs;
 		if (labs) {
 			std::vector<uint32_t> node_lab, prev_lab, next_lab;
@@ -607,6 +621,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 	cudaStream_t s = h->stream;
 	h->n_utt = n_utt; h->N = N; h->have_labels = labs != nullptr;
 	h->fwdbwd_done = h->viterbi_done = false; h->vit_score_ready = h->vit_rec_ready = false;
+	h->x_tiles_valid = false;
 	h->h_off.assign(off, off + n_utt + 1);
 	{
 		const size_t want = ((size_t)N * 6 + (size_t)n_utt * 24 + 65536) * sizeof(uint32_t);
@@ -645,6 +660,7 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		CUDA_OK(cudaEventRecord(h->ev_swap, s)); h->swap_marked = true;   // work queued before this point is the last reader of the set handed back
 		std::swap(h->d_base, h->d_base2); std::swap(h->d_baseB, h->d_baseB2); std::swap(h->d_X, h->d_X2);
 		std::swap(h->d_frame_t, h->d_frame_t2); std::swap(h->d_frame_utt, h->d_frame_utt2); std::swap(h->d_frame_len, h->d_frame_len2);
+		if (h->pre_tiles && h->opt_tf_tiled) { std::swap(h->d_XtK, h->d_XtK2); std::swap(h->d_XtT, h->d_XtT2); h->x_tiles_valid = true; }
 		if (had_tabs && labs != nullptr && h->pre_labs == labs) {
 			std::swap(h->d_node_lab, h->d_node_lab2); std::swap(h->d_prev_lab, h->d_prev_lab2); std::swap(h->d_next_lab, h->d_next_lab2);
 			joined_tabs = true;
@@ -654,7 +670,10 @@ void stage_batch(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, const float
 		// general window streams: both streams go to the device whole, one gather kernel builds the joined windows
 		frame_tables(true);
 		phase_begin(h, "expand");
-		stage_joined(h, n_utt, N, ftrs, ftrs2, h->d_base, h->d_baseB, h->d_X, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), s);
+		const bool tiles = labs != nullptr && N && (h->transftr || h->nodur_tf) && h->opt_tf_tiled;
+		stage_joined(h, n_utt, N, ftrs, ftrs2, h->d_base, h->d_baseB, h->d_X, h->d_frame_t.as<uint32_t>(), h->d_frame_utt.as<uint32_t>(), s,
+		             tiles ? &h->d_XtK : nullptr, tiles ? &h->d_XtT : nullptr);
+		h->x_tiles_valid = tiles;
 		phase_end(h, "expand");
 	} else if (prefetched) {
 		// this batch was copied and expanded by crfgpu_prefetch_batch while the previous one computed: take over its buffers
@@ -916,8 +935,7 @@ DpParams dp_params(crfgpu_ctx* h) {
 void trans_score_gemm(crfgpu_ctx* h, uint32_t N, uint32_t I, uint32_t Lq, cudaStream_t s) {
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	if (h->opt_tf_tiled) {
-		h->d_XtK.ensure(tiled_k_operand_bytes(N, m.nTf, 128) + 16);
-		CUDA_OK(launch_tile_k(h->X() + c.trans_fidx_start, h->ldx(), N, m.nTf, true, h->d_XtK.as<unsigned char>(), s)); check_kernel(h, 1);
+		if (!h->x_tiles_valid) { tile_trans_slice(h, N, h->X(), h->d_XtK, h->d_XtT, s); h->x_tiles_valid = true; }      // (batches staged without the tiles)
 		TiledScoreParams t{};
 		t.At = h->d_XtK.as<unsigned char>(); t.Bt = h->d_WtrT.as<unsigned char>(); t.bias = h->d_tbias.as<float>();
 		t.C = h->d_Mall.as<float>(); t.ldc = Lq; t.M = N; t.Ncols = I; t.K = m.nTf;
@@ -934,9 +952,9 @@ void trans_gradient_gemm(crfgpu_ctx* h, uint32_t N, uint32_t I, uint32_t Lq, cud
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t nTf = m.nTf, J = nTf + (c.use_trans_bias ? 1 : 0), ones = c.use_trans_bias ? nTf : 0xffffffffu;
 	if (h->opt_tf_tiled) {
-		h->d_XdT.ensure(tiled_operand_bytes(N, I, 128) + 16); h->d_XtT.ensure(tiled_operand_bytes(N, J, 64) + 16);
+		h->d_XdT.ensure(tiled_operand_bytes(N, I, 128) + 16);
 		CUDA_OK(launch_tile_mn(h->d_Xd.as<float>(), Lq, I, 0xffffffffu, N, true, h->d_XdT.as<unsigned char>(), s)); check_kernel(h, 1);
-		CUDA_OK(launch_tile_mn(h->X() + c.trans_fidx_start, h->ldx(), J, ones, N, false, h->d_XtT.as<unsigned char>(), s)); check_kernel(h, 1);
+		if (!h->x_tiles_valid) { tile_trans_slice(h, N, h->X(), h->d_XtK, h->d_XtT, s); h->x_tiles_valid = true; }
 		TiledReduceParams t{};
 		t.At = h->d_XdT.as<unsigned char>(); t.Bt = h->d_XtT.as<unsigned char>(); t.N = N; t.I = I; t.J = J;
 		t.ones_col = ones; t.scale = 1.0; t.ones_scale = c.trans_bias_val; t.row_idx = h->d_tidx.as<uint32_t>(); t.out = h->d_grad.as<double>();
@@ -1546,7 +1564,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	                  &h->d_olab, &h->d_odur, &h->d_ophn, &h->d_nseg, &h->d_cost, &h->d_cl_off, &h->d_cl_list, &h->d_xch, &h->d_xmax, &h->d_smaxd,
 	                  &h->d_nd_grp, &h->d_nd_batch, &h->d_nd_xch, &h->d_nd_ctr, &h->d_LB,
 	                  &h->d_sidx0, &h->d_tidx0, &h->d_tmax, &h->d_lam_acc, &h->d_lam_sqr_acc, &h->d_grad_sqr_acc, &h->d_base2, &h->d_X2, &h->d_frame_t2, &h->d_bpad, &h->d_Xa, &h->d_bias_dy, &h->d_baseB, &h->d_lm_start, &h->d_lm_bigT, &h->d_lm_final, &h->d_lm_exit, &h->d_frame_utt2, &h->d_frame_len2, &h->d_node_lab2, &h->d_prev_lab2, &h->d_next_lab2, &h->d_bpad2, &h->d_Xa2, &h->d_Wtr, &h->d_tbias, &h->d_Mall, &h->d_Xd, &h->d_next_lab, &h->d_WdT, &h->d_vt_base, &h->d_negMt,
-	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_XtK, &h->d_WtrT, &h->d_baseB2, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
+	                  &h->d_Eall, &h->d_rowmax, &h->d_XdT, &h->d_XtT, &h->d_XtK, &h->d_WtrT, &h->d_baseB2, &h->d_XtK2, &h->d_XtT2, &h->d_order16, &h->d_vg_xch, &h->d_vg_final, &h->d_vg_ctr, &h->d_vg_cand, &h->d_vorder, &h->d_off2};
 	for (DevBuf* b : bufs) b->release();
 	for (auto& kv : h->phases) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
@@ -1937,7 +1955,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 			setup_label_space(h);                                          // new label space: crfgpu_set_lambda must be called again
 		}
 		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per chain, both chains in one launch (crf_dp_frame.cu), 2 the chains one after the other, 1 the cluster lattice kernels
-		else if (n == "tf_tiled") { h->opt_tf_tiled = value != 0 ? 1 : 0; h->have_lambda = false; }      // transition-feature GEMMs: 1 pre-tiled operands + bulk copies, 0 register-staged kernels (set_lambda again: the weight tiles belong to the tiled path)
+		else if (n == "tf_tiled") { h->opt_tf_tiled = value != 0 ? 1 : 0; h->have_lambda = false; h->x_tiles_valid = false; }      // transition-feature GEMMs: 1 pre-tiled operands + bulk copies, 0 register-staged kernels (set_lambda again: the weight tiles belong to the tiled path)
 		else if (n == "vit_eager") h->opt_vit_eager = value != 0.0 ? 1 : 0;
 		else if (n == "vit_impl") { h->opt_vit_impl = (int)value; h->vit_rec_ready = false; }         // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory
