@@ -130,6 +130,7 @@ struct crfgpu_ctx {
 	bool have_lm = false; DevBuf d_lm_start, d_lm_bigT, d_lm_final, d_lm_exit; double beam = 0.0;   // crfgpu_set_beam   // phone-bigram LM of the decoder (crfgpu_set_phone_lm)
 	std::vector<cudaStream_t> rec_stream; std::vector<cudaEvent_t> ev_scored, ev_walked;   // one side stream per chunk: the chunks' recursions are latency chains and run beside each other
 	bool vit_rec_ready = false; DevBuf d_vorder, d_off2;   // ... and the recursion of each chunk's utterances behind its scores (d_vorder: the chunks' utterances, longest first)
+	cudaStream_t aux_stream = nullptr; cudaEvent_t ev_aux_go = nullptr, ev_aux_done = nullptr; int opt_aux_empirical = 1;   // empirical counts beside the recursions
 	bool full_windows = false;      // crfgpu_expand_windows: gather every column of every window (no duration-1-only ranges)
 	bool vit_score_ready = false;   // the decoder's fp64 scores of the staged batch were launched chunk by chunk behind the H2D copies
 	bool viterbi_done = false;
@@ -1000,6 +1001,30 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 	const bool tma = virt || (h->opt_gemm_impl == 2 && (h->opt_tma_mask & 1) && D > 1 && nSf > 0 && tma_gemm_eligible(h->X() + c.state_fidx_start, D, h->Wp, c.state_fidx_start));
 	bool smax_done = false;
 	if (nSf == 0) throw ApiError(CRFGPU_ERR_UNSUPPORTED, "models without state features are not implemented on the device");
+	// the empirical counts and numerators (labels, windows and lambda only) do not wait for anything the recursions produce: on a side
+	// stream they run beside the score GEMM and the lattice kernels (which leave 28 SMs idle) instead of behind the state gradient
+	auto make_emp = [&]() {
+		EmpiricalParams e{};
+		e.X = h->X(); e.ldx = h->ldx(); e.W = h->Wp; e.sf0 = c.state_fidx_start; e.nSf = nSf;
+		e.node_lab = h->d_node_lab.as<uint32_t>(); e.prev_lab = h->d_prev_lab.as<uint32_t>(); e.frame_utt = h->d_frame_utt.as<uint32_t>();
+		e.N = N; e.L = L; e.P = P; e.tL = h->nodur ? P : L; e.lambda = h->d_lambda.as<double>(); e.sidx = h->d_sidx.as<uint32_t>(); e.tidx = h->d_tidx.as<uint32_t>();
+		e.use_state_bias = c.use_state_bias; e.use_trans_bias = c.use_trans_bias;
+		e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
+		e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
+		if (virt) { e.virt = 1; e.F = c.n_base_ftrs; e.D = D; e.base = h->d_base.as<float>(); e.steps = h->d_steps.as<uint32_t>(); e.X = h->d_Xa.as<float>(); e.W = h->Wa; }
+		return e;
+	};
+	const bool emp_early = h->opt_aux_empirical && !h->nodur_tf && !h->transftr;
+	if (emp_early) {
+		if (!h->aux_stream) {
+			CUDA_OK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+			CUDA_OK(cudaEventCreateWithFlags(&h->ev_aux_go, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&h->ev_aux_done, cudaEventDisableTiming));
+		}
+		CUDA_OK(cudaEventRecord(h->ev_aux_go, s));                  // behind the memsets of the gradient / numerators and the windows
+		CUDA_OK(cudaStreamWaitEvent(h->aux_stream, h->ev_aux_go, 0));
+		launch_empirical(make_emp(), h->aux_stream); check_kernel(h, 1);
+		CUDA_OK(cudaEventRecord(h->ev_aux_done, h->aux_stream));
+	}
 	phase_begin(h, "score");
 	if (tma) {
 		ScoreTmaParams g{};
@@ -1308,15 +1333,8 @@ void fwdbwd_staged(crfgpu_ctx* h) {
 		if (h->opt_gemm_impl >= 1) CUDA_OK(launch_reduce_gemm_tc(r, true, s)); else launch_reduce_gemm(r, s);
 		check_kernel(h, 1);
 	}
-	EmpiricalParams e{};
-	e.X = h->X(); e.ldx = h->ldx(); e.W = h->Wp; e.sf0 = c.state_fidx_start; e.nSf = nSf;
-	e.node_lab = h->d_node_lab.as<uint32_t>(); e.prev_lab = h->d_prev_lab.as<uint32_t>(); e.frame_utt = h->d_frame_utt.as<uint32_t>();
-	e.N = N; e.L = L; e.P = P; e.tL = h->nodur ? P : L; e.lambda = h->d_lambda.as<double>(); e.sidx = h->d_sidx.as<uint32_t>(); e.tidx = h->d_tidx.as<uint32_t>();
-	e.use_state_bias = c.use_state_bias; e.use_trans_bias = c.use_trans_bias;
-	e.state_bias_val = c.state_bias_val; e.trans_bias_val = c.trans_bias_val;
-	e.grad = h->d_grad.as<double>(); e.numer = h->d_numer.as<double>();
-	if (virt) { e.virt = 1; e.F = c.n_base_ftrs; e.D = D; e.base = h->d_base.as<float>(); e.steps = h->d_steps.as<uint32_t>(); e.X = h->d_Xa.as<float>(); e.W = h->Wa; }
-	if (!h->nodur_tf) { launch_empirical(e, s); check_kernel(h, 1); }      // nodur_tf: numerators come from the forward kernel, counts from Dm / Xd
+	if (emp_early) CUDA_OK(cudaStreamWaitEvent(s, h->ev_aux_done, 0));      // the empirical counts ran beside the recursions
+	else if (!h->nodur_tf) { launch_empirical(make_emp(), s); check_kernel(h, 1); }      // nodur_tf: numerators come from the forward kernel, counts from Dm / Xd
 	if (h->opt_mass_check) {
 		// the nodes' posterior-mass assertion (frame-level: 0.9..1.1, segmental: the probability that a segment ends here, 0..1)
 		h->d_mass.ensure(sizeof(float) * (size_t)N + 16);
@@ -1577,6 +1595,7 @@ int crfgpu_destroy(crfgpu_handle h) {
 	if (h->ev_pin) cudaEventDestroy(h->ev_pin);
 	if (h->pin) cudaFreeHost(h->pin);
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+	if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->ev_aux_go); cudaEventDestroy(h->ev_aux_done); }
 	for (cudaStream_t st : h->rec_stream) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
 	for (cudaEvent_t e : h->ev_scored) cudaEventDestroy(e);
 	for (cudaEvent_t e : h->ev_walked) cudaEventDestroy(e);
@@ -1956,6 +1975,7 @@ int crfgpu_set_option(crfgpu_handle h, const char* name, int64_t value) {
 		}
 		else if (n == "frame_impl") h->opt_frame_impl = (int)value;      // frame-level models with <= 64 labels: 0 one warp per chain, both chains in one launch (crf_dp_frame.cu), 2 the chains one after the other, 1 the cluster lattice kernels
 		else if (n == "tf_tiled") { h->opt_tf_tiled = value != 0 ? 1 : 0; h->have_lambda = false; h->x_tiles_valid = false; }      // transition-feature GEMMs: 1 pre-tiled operands + bulk copies, 0 register-staged kernels (set_lambda again: the weight tiles belong to the tiled path)
+		else if (n == "aux_empirical") h->opt_aux_empirical = value != 0 ? 1 : 0;      // empirical counts on a side stream beside the recursions (1) or behind the state gradient (0)
 		else if (n == "vit_eager") h->opt_vit_eager = value != 0.0 ? 1 : 0;
 		else if (n == "vit_impl") { h->opt_vit_impl = (int)value; h->vit_rec_ready = false; }         // Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 table sliced over groups of CTAs (one state per phone)
 		else if (n == "tma_mask") h->opt_tma_mask = (int)value;          // debug: 1 score, 2 state gradient, 4 Xi through the TMA-fed kernels, 8 / 16 / 32 the 128-row operand of the score / state-gradient / Xi GEMM through tensor memory

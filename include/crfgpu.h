@@ -235,6 +235,8 @@ int crfgpu_fetch_posterior_mass(crfgpu_handle h, float* mass);
  *  "frame_impl" (frame-level models with <= 64 labels: 0 one warp per utterance = default, 1 the cluster lattice kernels),
  *  "nodur_impl" (stdseg_no_dur*: 0 auto, 1 native O(P^2 + D*P) recursion, 2 tied (duration, label) expansion; set_lambda again after it),
  *  "vit_impl" (Viterbi recursion: 0 auto, 1 one CTA per utterance, 2 transition table sliced over groups of CTAs -- one state per phone),
+ *  "aux_empirical" (1 = default: the empirical counts / numerators run on a side stream beside the score GEMM and the recursions; 0: behind
+ *  the state gradient),
  *  "tf_tiled" (transition-feature GEMMs: 1 = default, operands split into bf16 hi / lo and tiled once, ring stages by bulk copies; 0 = the
  *  register-staged kernels on the fp32 arrays; set_lambda again after it),
  *  "vit_eager" (decode batches: 1 = default, crfgpu_stage_batch launches the recursion of each H2D chunk's utterances behind the chunk on
