@@ -167,7 +167,7 @@ cudaError_t launch_reduce_gemm_tc(const ReduceGemmParams& p, bool m_side_is_b, c
 
 // the same product from pre-split, pre-tiled operands (launch_tile_mn), fed by bulk copies: out[row_idx[i] + j] += scale * sum_n A[n][i] * B[n][j]
 struct TiledReduceParams {
-	const unsigned char* At; const unsigned char* Bt;   // tiles of the M side (128 columns of A) and the N side (64 columns of B)
+	const unsigned char* At; const unsigned char* Bt;   // 128-column tiles of A (M side) and of B (N side)
 	uint32_t N, I, J;                 // frames, columns of A (output rows), columns of B (output columns, the ones column included)
 	uint32_t ones_col; double scale, ones_scale;
 	const uint32_t* row_idx; double* out;
@@ -179,7 +179,7 @@ cudaError_t launch_reduce_gemm_tiled(const TiledReduceParams& p, cudaStream_t s)
 
 // K-major twin: C[n][c] = sum_k A[n][k] * B[c][k] + bias[c] from operands tiled by launch_tile_k (rows x 32-feature chunks)
 struct TiledScoreParams {
-	const unsigned char* At; const unsigned char* Bt;   // tiles of A (128-row tiles of the frames) and of B (64-row tiles of the weight rows)
+	const unsigned char* At; const unsigned char* Bt;   // 128-row tiles of A (frames) and of B (weight rows)
 	const float* bias; float* C; uint32_t ldc;
 	uint32_t M, Ncols, K;
 	uint32_t n_kc;                    // set by the launcher

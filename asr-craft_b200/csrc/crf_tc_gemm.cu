@@ -553,19 +553,24 @@ __global__ void __launch_bounds__(256) tile_mn_kernel(const float* __restrict__ 
 	}
 }
 
+// tiles of the bulk-copy-fed kernels: 128 x 128 outputs (both operands as 128-wide tiles: half the L2 -> shared-memory traffic per MMA of
+// the 128 x 64 tiles of the register-staged kernels), three ring stages of 32 KB, two CTAs per SM
+constexpr int TBN = 128, TSTAGES = 3;
+constexpr uint32_t TB_TILE = TBN * KC * 2, TSTAGE = 2 * A_TILE + 2 * TB_TILE, TSMEM = TSTAGES * TSTAGE + 1024;
+
 __global__ void __launch_bounds__(192, 2) reduce_gemm_tiled_kernel(TiledReduceParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
-	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
+	Ring* ring = reinterpret_cast<Ring*>(smem + TSTAGES * TSTAGE);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t mt = blockIdx.x, nt = blockIdx.y, m0 = mt * BM, n0 = nt * BN;
+	const uint32_t mt = blockIdx.x, nt = blockIdx.y, m0 = mt * BM, n0 = nt * TBN;
 	const uint32_t c_lo = blockIdx.z * p.slab_chunks, c_hi = min(c_lo + p.slab_chunks, p.n_chunks);
 	const uint32_t n_chunks = c_hi - c_lo;
 	if (tid == 0) {
-		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
+		for (int s = 0; s < TSTAGES; s++) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
 		mbar_init(&ring->done, 1);
 		fence_mbar_init();
 	}
-	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	if (warp == 4) tmem_alloc(&ring->tmem, TBN);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
@@ -573,27 +578,27 @@ __global__ void __launch_bounds__(192, 2) reduce_gemm_tiled_kernel(TiledReducePa
 	if (warp == 5) {
 		if (lane == 0) {
 			for (uint32_t c = 0; c < n_chunks; c++) {
-				const uint32_t s = c % STAGES;
-				if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
-				unsigned char* st = smem + s * STAGE_BYTES;
-				mbar_arrive_expect_tx(&ring->full[s], STAGE_BYTES);
+				const uint32_t s = c % TSTAGES;
+				if (c >= TSTAGES) mbar_wait(&ring->empty[s], ((c / TSTAGES) - 1) & 1);
+				unsigned char* st = smem + s * TSTAGE;
+				mbar_arrive_expect_tx(&ring->full[s], TSTAGE);
 				bulk_g2s(st, p.At + ((size_t)(c_lo + c) * p.n_mt + mt) * (2 * A_TILE), 2 * A_TILE, &ring->full[s]);
-				bulk_g2s(st + 2 * A_TILE, p.Bt + ((size_t)(c_lo + c) * p.n_nt + nt) * (2 * B_TILE), 2 * B_TILE, &ring->full[s]);
+				bulk_g2s(st + 2 * A_TILE, p.Bt + ((size_t)(c_lo + c) * p.n_nt + nt) * (2 * TB_TILE), 2 * TB_TILE, &ring->full[s]);
 			}
 		}
 		__syncwarp();
 	} else if (warp == 4) {
-		constexpr uint32_t idesc = idesc_bf16_f32(BM, BN, true, true);
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, TBN, true, true);
 		for (uint32_t c = 0; c < n_chunks; c++) {
-			const uint32_t s = c % STAGES;
-			mbar_wait(&ring->full[s], (c / STAGES) & 1);
+			const uint32_t s = c % TSTAGES;
+			mbar_wait(&ring->full[s], (c / TSTAGES) & 1);
 			tc_fence_after();
-			const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+			const uint32_t base = smem_u32(smem + s * TSTAGE);
 			if (elect_one()) {
 #pragma unroll
 				for (int ks = 0; ks < KC / 16; ks++) {
 					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
-					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + B_TILE + ks * 256, 128, 512);
+					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + TB_TILE + ks * 256, 128, 512);
 					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
 					mma_ss(tmem, al, bh, idesc, true);
 					mma_ss(tmem, ah, bl, idesc, true);
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(192, 2) reduce_gemm_tiled_kernel(TiledReducePa
 		const uint32_t gm = m0 + warp * 32 + lane;
 		const uint32_t ri = gm < p.I ? __ldg(p.row_idx + gm) : 0xffffffffu;
 #pragma unroll
-		for (int c0 = 0; c0 < BN; c0 += 16) {
+		for (int c0 = 0; c0 < TBN; c0 += 16) {
 			float v[16];
 			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
 			tmem_ld_wait();
@@ -629,7 +634,7 @@ __global__ void __launch_bounds__(192, 2) reduce_gemm_tiled_kernel(TiledReducePa
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 4) tmem_dealloc(tmem, BN);
+	if (warp == 4) tmem_dealloc(tmem, TBN);
 }
 
 // K-major twin for the transition SCORES  M[n][c] = sum_k X[n][k] * W[c][k] + bias[c]  (labels^2 columns): rows x 32-feature chunks of
@@ -658,16 +663,16 @@ __global__ void __launch_bounds__(256) tile_k_kernel(const float* __restrict__ s
 
 __global__ void __launch_bounds__(192, 2) score_gemm_tiled_kernel(TiledScoreParams p) {
 	extern __shared__ __align__(1024) unsigned char smem[];
-	Ring* ring = reinterpret_cast<Ring*>(smem + STAGES * STAGE_BYTES);
+	Ring* ring = reinterpret_cast<Ring*>(smem + TSTAGES * TSTAGE);
 	const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const uint32_t nt = blockIdx.x, mt = blockIdx.y, m0 = mt * BM, n0 = nt * BN;      // column tiles fastest: the row tile of X stays in L2
+	const uint32_t nt = blockIdx.x, mt = blockIdx.y, m0 = mt * BM, n0 = nt * TBN;      // column tiles fastest: the row tile of X stays in L2
 	const uint32_t n_chunks = p.n_kc;
 	if (tid == 0) {
-		for (int s = 0; s < STAGES; s++) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
+		for (int s = 0; s < TSTAGES; s++) { mbar_init(&ring->full[s], 1); mbar_init(&ring->empty[s], 1); }
 		mbar_init(&ring->done, 1);
 		fence_mbar_init();
 	}
-	if (warp == 4) tmem_alloc(&ring->tmem, BN);
+	if (warp == 4) tmem_alloc(&ring->tmem, TBN);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
@@ -675,43 +680,63 @@ __global__ void __launch_bounds__(192, 2) score_gemm_tiled_kernel(TiledScorePara
 	if (warp == 5) {
 		if (lane == 0) {
 			for (uint32_t c = 0; c < n_chunks; c++) {
-				const uint32_t s = c % STAGES;
-				if (c >= STAGES) mbar_wait(&ring->empty[s], ((c / STAGES) - 1) & 1);
-				unsigned char* st = smem + s * STAGE_BYTES;
-				mbar_arrive_expect_tx(&ring->full[s], STAGE_BYTES);
+				const uint32_t s = c % TSTAGES;
+				if (c >= TSTAGES) mbar_wait(&ring->empty[s], ((c / TSTAGES) - 1) & 1);
+				unsigned char* st = smem + s * TSTAGE;
+				mbar_arrive_expect_tx(&ring->full[s], TSTAGE);
 				bulk_g2s(st, p.At + ((size_t)mt * p.n_kc + c) * (2 * A_TILE), 2 * A_TILE, &ring->full[s]);
-				bulk_g2s(st + 2 * A_TILE, p.Bt + ((size_t)nt * p.n_kc + c) * (2 * B_TILE), 2 * B_TILE, &ring->full[s]);
+				bulk_g2s(st + 2 * A_TILE, p.Bt + ((size_t)nt * p.n_kc + c) * (2 * TB_TILE), 2 * TB_TILE, &ring->full[s]);
 			}
 		}
 		__syncwarp();
 	} else if (warp == 4) {
-		mma_ring<false>(smem, ring, tmem, n_chunks);
+		constexpr uint32_t idesc = idesc_bf16_f32(BM, TBN, false, false);
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			const uint32_t s = c % TSTAGES;
+			mbar_wait(&ring->full[s], (c / TSTAGES) & 1);
+			tc_fence_after();
+			const uint32_t base = smem_u32(smem + s * TSTAGE);
+			if (elect_one()) {
+#pragma unroll
+				for (int ks = 0; ks < KC / 16; ks++) {
+					const uint64_t ah = smem_desc(base + ks * 256, 128, 512), al = smem_desc(base + A_TILE + ks * 256, 128, 512);
+					const uint64_t bh = smem_desc(base + 2 * A_TILE + ks * 256, 128, 512), bl = smem_desc(base + 2 * A_TILE + TB_TILE + ks * 256, 128, 512);
+					mma_ss(tmem, ah, bh, idesc, (c | ks) != 0);
+					mma_ss(tmem, al, bh, idesc, true);
+					mma_ss(tmem, ah, bl, idesc, true);
+				}
+				mma_commit(&ring->empty[s]);
+			}
+			__syncwarp();
+		}
+		if (elect_one()) mma_commit(&ring->done);
+		__syncwarp();
 	}
 	// ---- epilogue: TMEM -> registers -> shared transpose -> (+bias) -> coalesced rows of the score matrix ----
 	if (warp < 4) {
 		mbar_wait(&ring->done, 0);
 		tc_fence_after();
-		float* Cs = reinterpret_cast<float*>(smem);       // [128][65], the ring is idle now
+		float* Cs = reinterpret_cast<float*>(smem);       // [128][TBN + 1], the ring is idle now
 		const uint32_t row = warp * 32 + lane;
 #pragma unroll
-		for (int c0 = 0; c0 < BN; c0 += 16) {
+		for (int c0 = 0; c0 < TBN; c0 += 16) {
 			float v[16];
 			tmem_ld16(tmem + ((warp * 32u) << 16) + c0, v);
 			tmem_ld_wait();
 #pragma unroll
-			for (int j = 0; j < 16; j++) Cs[row * 65 + c0 + j] = v[j];
+			for (int j = 0; j < 16; j++) Cs[row * (TBN + 1) + c0 + j] = v[j];
 		}
 		tc_fence_before();
 		asm volatile("bar.sync 1, 128;" ::: "memory");
-		const uint32_t ncol = min((uint32_t)BN, p.Ncols - n0);
-		for (uint32_t i = tid; i < BM * BN; i += 128) {
-			const uint32_t r = i / BN, j = i % BN, gm = m0 + r;
-			if (gm < p.M && j < ncol) p.C[(uint64_t)gm * p.ldc + n0 + j] = Cs[r * 65 + j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
+		const uint32_t ncol = min((uint32_t)TBN, p.Ncols - n0);
+		for (uint32_t i = tid; i < BM * TBN; i += 128) {
+			const uint32_t r = i / TBN, j = i % TBN, gm = m0 + r;
+			if (gm < p.M && j < ncol) p.C[(uint64_t)gm * p.ldc + n0 + j] = Cs[r * (TBN + 1) + j] + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f);
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 4) tmem_dealloc(tmem, BN);
+	if (warp == 4) tmem_dealloc(tmem, TBN);
 }
 
 size_t tiled_k_operand_bytes(uint32_t rows, uint32_t K, uint32_t T) { return (size_t)((rows + T - 1) / T) * ((K + KC - 1) / KC) * 2 * ((size_t)T * 64); }
@@ -727,13 +752,13 @@ cudaError_t launch_tile_k(const float* src, uint64_t ld, uint32_t rows, uint32_t
 
 cudaError_t launch_score_gemm_tiled(const TiledScoreParams& p0, cudaStream_t s) {
 	if (!p0.M || !p0.Ncols || !p0.K) return cudaSuccess;
-	cudaError_t e = cudaFuncSetAttribute(score_gemm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+	cudaError_t e = cudaFuncSetAttribute(score_gemm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSMEM);
 	if (e != cudaSuccess) return e;
 	TiledScoreParams p = p0;
 	p.n_kc = (p.K + KC - 1) / KC;
-	const uint32_t mt = (p.M + BM - 1) / BM, nt = (p.Ncols + BN - 1) / BN;
+	const uint32_t mt = (p.M + BM - 1) / BM, nt = (p.Ncols + TBN - 1) / TBN;
 	if (mt > 65535) return cudaErrorInvalidValue;
-	score_gemm_tiled_kernel<<<dim3(nt, mt), 192, SMEM_BYTES, s>>>(p);
+	score_gemm_tiled_kernel<<<dim3(nt, mt), 192, TSMEM, s>>>(p);
 	return cudaGetLastError();
 }
 
@@ -741,7 +766,7 @@ size_t tiled_operand_bytes(uint32_t N, uint32_t ncols, uint32_t T) { return (siz
 
 cudaError_t launch_tile_mn(const float* src, uint64_t ld, uint32_t ncols, uint32_t ones_col, uint32_t N, bool m_side, unsigned char* dst, cudaStream_t s) {
 	if (!N || !ncols) return cudaSuccess;
-	const uint32_t T = m_side ? BM : BN, n_ct = (ncols + T - 1) / T;
+	const uint32_t T = m_side ? BM : BN, n_ct = (ncols + T - 1) / T;      // (the bulk-copy-fed GEMMs take 128-wide tiles on both sides)
 	dim3 grid((N + KC - 1) / KC, n_ct);
 	if (m_side) tile_mn_kernel<BM><<<grid, 256, 0, s>>>(src, ld, ncols, ones_col, N, dst, n_ct);
 	else tile_mn_kernel<BN><<<grid, 256, 0, s>>>(src, ld, ncols, ones_col, N, dst, n_ct);
@@ -750,15 +775,15 @@ cudaError_t launch_tile_mn(const float* src, uint64_t ld, uint32_t ncols, uint32
 
 cudaError_t launch_reduce_gemm_tiled(const TiledReduceParams& p0, cudaStream_t s) {
 	if (!p0.N || !p0.I || !p0.J) return cudaSuccess;
-	cudaError_t e = cudaFuncSetAttribute(reduce_gemm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+	cudaError_t e = cudaFuncSetAttribute(reduce_gemm_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSMEM);
 	if (e != cudaSuccess) return e;
 	TiledReduceParams p = p0;
-	p.n_mt = (p.I + BM - 1) / BM; p.n_nt = (p.J + BN - 1) / BN; p.n_chunks = (p.N + KC - 1) / KC;
+	p.n_mt = (p.I + BM - 1) / BM; p.n_nt = (p.J + TBN - 1) / TBN; p.n_chunks = (p.N + KC - 1) / KC;
 	// frame slabs only until the grid is about six waves of 2 CTAs per SM: every slab ends in up to 8192 fp64 atomics per CTA
 	const uint32_t tiles = p.n_mt * p.n_nt, slabs = std::max(1u, std::min(p.n_chunks, (6u * 296u + tiles - 1) / tiles));
 	p.slab_chunks = (p.n_chunks + slabs - 1) / slabs;
 	dim3 grid(p.n_mt, p.n_nt, (p.n_chunks + p.slab_chunks - 1) / p.slab_chunks);
-	reduce_gemm_tiled_kernel<<<grid, 192, SMEM_BYTES, s>>>(p);
+	reduce_gemm_tiled_kernel<<<grid, 192, TSMEM, s>>>(p);
 	return cudaGetLastError();
 }
 

@@ -352,8 +352,8 @@ void derive_tables(crfgpu_ctx* h) {
 	CUDA_OK(launch_lambda_tables(p, s));
 	if ((h->transftr || h->nodur_tf) && h->opt_tf_tiled) {
 		// the transition weights once more as bf16 hi / lo tiles in the byte order of the score GEMM's shared-memory tiles
-		h->d_WtrT.ensure(tiled_k_operand_bytes(L * L, m.nTf, 64) + 16);
-		CUDA_OK(launch_tile_k(h->d_Wtr.as<float>(), m.nTf, L * L, m.nTf, false, h->d_WtrT.as<unsigned char>(), s));
+		h->d_WtrT.ensure(tiled_k_operand_bytes(L * L, m.nTf, 128) + 16);
+		CUDA_OK(launch_tile_k(h->d_Wtr.as<float>(), m.nTf, L * L, m.nTf, true, h->d_WtrT.as<unsigned char>(), s));
 		h->launches++;
 	}
 	h->launches += h->train_ok ? 2 : 1;
@@ -472,9 +472,9 @@ void build_label_tables(crfgpu_ctx* h, uint32_t n_utt, const uint32_t* off, cons
 void tile_trans_slice(crfgpu_ctx* h, uint32_t N, const float* X, DevBuf& XtK, DevBuf& XtT, cudaStream_t st) {
 	const crfgpu_config& c = h->cfg; const Layout& m = h->lay;
 	const uint32_t J = m.nTf + (c.use_trans_bias ? 1 : 0), ones = c.use_trans_bias ? m.nTf : 0xffffffffu;
-	XtK.ensure(tiled_k_operand_bytes(N, m.nTf, 128) + 16); XtT.ensure(tiled_operand_bytes(N, J, 64) + 16);
+	XtK.ensure(tiled_k_operand_bytes(N, m.nTf, 128) + 16); XtT.ensure(tiled_operand_bytes(N, J, 128) + 16);
 	CUDA_OK(launch_tile_k(X + c.trans_fidx_start, (uint64_t)c.max_dur * h->Wp, N, m.nTf, true, XtK.as<unsigned char>(), st)); check_kernel(h, 1);
-	CUDA_OK(launch_tile_mn(X + c.trans_fidx_start, (uint64_t)c.max_dur * h->Wp, J, ones, N, false, XtT.as<unsigned char>(), st)); check_kernel(h, 1);
+	CUDA_OK(launch_tile_mn(X + c.trans_fidx_start, (uint64_t)c.max_dur * h->Wp, J, ones, N, true, XtT.as<unsigned char>(), st)); check_kernel(h, 1);
 }
 
 void stage_joined(crfgpu_ctx* h, uint32_t n_utt, uint32_t N, const float* ftrs, const float* ftrs2, DevBuf& base, DevBuf& baseB, DevBuf& X,
