@@ -1481,6 +1481,8 @@ std::string plan_text(crfgpu_ctx* h) {
 	else if (!h->have_labels) s += "train: no labels staged; ";
 	else if (h->transftr) s += "lattice=transftr_forward/backward_kernel (one CTA per utterance, per-frame transition scores); ";
 	else if (h->nodur_tf) s += "lattice=nodur_tf_forward/backward_kernel (one CTA per utterance, per-frame transition scores); ";
+	if (h->transftr || h->nodur_tf) s += h->opt_tf_tiled ? "labels^2 GEMMs=score_gemm_tiled/reduce_gemm_tiled_kernel (pre-split bf16 tiles, bulk copies); "
+	                                                      : "labels^2 GEMMs=score_gemm_tc/reduce_gemm_tc_kernel (register-staged); ";
 	else if (h->nodur) { snprintf(b, sizeof b, "lattice=nodur_dp_kernel (native O(P^2+D*P), %u groups x %u CTAs, 16 utterances in lock-step); ", h->n_nodur_groups, (h->lay.L + 31) / 32); s += b; }
 	else if (h->frame_path) s += h->opt_frame_impl == 2 ? "lattice=frame_dp_kernel (one warp per utterance, chains one after the other); " : "lattice=frame_dp_pair_kernel+frame_post_kernel (one warp per chain); ";
 	else if (h->ks_ok) { snprintf(b, sizeof b, "lattice=dp_ks_kernel (tcgen05, contraction-sliced: cluster of %u CTAs x %u labels, %u M-tiles in tensor memory, %u clusters x 16 slots%s); ", h->ks_plan.CS, h->ks_plan.CW, h->ks_plan.MT, h->n_ks_clusters, h->tied ? ", tied (duration, phone) expansion" : ""); s += b; }
