@@ -90,20 +90,22 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 	float* a_prev = sm + 2 * L * Ls;             // [L]
 	float* scratch = a_prev + L;                 // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
-	double rho = 0.0, num = 0.0;
+	double rho = 0.0;
 	if (T > 1) prefetch_matrix<TF_THR>(Ms + L * Ls, p.E + (size_t)(off + 1) * p.Lq, L, Ls);       // frame 1 -> buffer 1
+	// the frame's score and matrix maximum do not depend on the recursion: those of frame t+1 are requested while frame t is processed
+	float s_next = (c < L && T > 0) ? p.S[(size_t)off * p.Lp + c] : 0.0f, mmax_next = 0.0f;
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
 		float* Mt = Ms + (t & 1) * L * Ls;
 		float w = -INFINITY;
-		const float s = c < L ? p.S[n * p.Lp + c] : 0.0f;
-		float mmax = 0.0f;
+		const float s = s_next;
+		float mmax = mmax_next;
+		if (t + 1 < T) { s_next = c < L ? p.S[(n + 1) * p.Lp + c] : 0.0f; mmax_next = p.rowmax[n + 1]; }
 		if (t == 0) { if (c < L) w = s; }
 		else {
 			cp_async_wait_all();
 			__syncthreads();
 			if (t + 1 < T) prefetch_matrix<TF_THR>(Ms + ((t + 1) & 1) * L * Ls, p.E + (n + 1) * p.Lq, L, Ls);
-			mmax = p.rowmax[n];
 			if (c < L) {
 				float v = 0.0f;
 #pragma unroll 8
@@ -116,18 +118,29 @@ __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams
 		const float asum = block_sum<TF_THR>(a, scratch);
 		rho += (double)mmax + (double)wmax + (double)__logf(asum);
 		if (c < L) { a_prev[c] = a / asum; p.A[n * p.Lp + c] = a / asum; }
-		if (c == 0) {
-			p.rho[n] = rho;
-			// numerator on the reference path: state score of the frame's label + transition score from the previous frame's label
-			const uint32_t y = p.labs[n];
-			if (y < L) {
-				num += (double)p.S[n * p.Lp + y];
-				if (t > 0) { const uint32_t yp = p.labs[n - 1]; if (yp < L && p.tidx[yp * L + y] != 0xffffffffu) num += (double)p.M[n * p.Lq + yp * L + y]; }
-			}
-		}
+		if (c == 0) p.rho[n] = rho;      // (the numerator -- dependent global loads of ONE thread per frame -- is a pass of its own: transftr_numer_kernel)
 		__syncthreads();
 	}
-	if (c == 0) { p.logZ[u] = rho; p.numer[u] = num; }       // sum_c a_{T-1}[c] = 1: alpha_{T-1} sums to exp(rho)
+	if (c == 0) p.logZ[u] = rho;       // sum_c a_{T-1}[c] = 1: alpha_{T-1} sums to exp(rho)
+}
+
+// numerator of an utterance on the reference path: state score of every frame's label + transition score from the previous frame's
+// label (pairs an N-state map lacks count nothing); one warp per utterance, lanes stride the frames, fixed summation order
+__global__ void __launch_bounds__(128) transftr_numer_kernel(TransFtrParams p) {
+	const uint32_t u = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (u >= p.n_utt) return;
+	const uint32_t off = p.off[u], T = p.off[u + 1] - off, L = p.L;
+	double acc = 0.0;
+	for (uint32_t t = lane; t < T; t += 32) {
+		const size_t n = (size_t)off + t;
+		const uint32_t y = p.labs[n];
+		if (y >= L) continue;
+		acc += (double)p.S[n * p.Lp + y];
+		if (t > 0) { const uint32_t yp = p.labs[n - 1]; if (yp < L && p.tidx[yp * L + y] != 0xffffffffu) acc += (double)p.M[n * p.Lq + yp * L + y]; }
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) p.numer[u] = acc;
 }
 
 template <int TF_THR>
@@ -145,11 +158,16 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 	if (c < L) b[c] = 1.0f;                      // setTailBeta
 	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.E + (size_t)(off + T - 1) * p.Lq, L, Ls);
 	__syncthreads();
+	// the frame's label, alpha entry and score do not depend on the recursion: those of frame t-1 are requested while frame t is processed
+	uint32_t y_cur = T ? p.labs[(size_t)off + T - 1] : LAB_BAD;
+	float a_cur = (c < L && T) ? p.A[((size_t)off + T - 1) * p.Lp + c] : 0.0f, s_cur = (c < L && T) ? p.S[((size_t)off + T - 1) * p.Lp + c] : -INFINITY;
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
-		const uint32_t y = p.labs[n];
+		const uint32_t y = y_cur;
+		uint32_t y_prev = LAB_BAD; float a_prev1 = 0.0f, s_prev = -INFINITY;
+		if (t > 0) { y_prev = p.labs[n - 1]; if (c < L) { a_prev1 = p.A[(n - 1) * p.Lp + c]; s_prev = p.S[(n - 1) * p.Lp + c]; } }
 		// gamma_t = A_t * b_t / sum
-		const float a = c < L ? p.A[n * p.Lp + c] : 0.0f;
+		const float a = a_cur;
 		const float g = c < L ? a * b[c] : 0.0f;
 		const float gsum = block_sum<TF_THR>(g, scratch);
 		if (c < L) p.Dm[n * p.Lp + c] = ((y == c) ? 1.0f : 0.0f) - g / gsum;
@@ -163,9 +181,9 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		__syncthreads();
 		if (t > 1) prefetch_matrix<TF_THR>(Ms + ((t - 1) & 1) * L * Ls, p.E + (n - 1) * p.Lq, L, Ls);
 		// Mt = E_t = exp(M_t - max) from the pre-pass (the normalisations below are scale-free)
-		const float s = c < L ? p.S[n * p.Lp + c] : -INFINITY;
+		const float s = s_cur;
 		const float smax = block_max<TF_THR>(s, scratch);
-		if (c < L) { wv[c] = __expf(s - smax) * b[c]; av[c] = p.A[(n - 1) * p.Lp + c]; }
+		if (c < L) { wv[c] = __expf(s - smax) * b[c]; av[c] = a_prev1; }
 		__syncthreads();
 		float part = 0.0f;
 		uint32_t q = q_first, cc = c_first;
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 			if (cc >= L) { cc -= L; q++; }
 		}
 		const float xsum = block_sum<TF_THR>(part, scratch);                            // sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc]
-		uint32_t yp = p.labs[n - 1];
+		uint32_t yp = y_prev;
 		if (yp < L && y < L && p.tidx[yp * L + y] == 0xffffffffu) yp = LAB_BAD;      // a reference pair the N-state map does not have
 		const float inv = 1.0f / xsum;
 		q = q_first; cc = c_first;
@@ -191,6 +209,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		if (c < L) for (uint32_t cc = 0; cc < L; cc++) bn += Mt[c * Ls + cc];
 		const float bmax = block_max<TF_THR>(c < L ? bn : 0.0f, scratch);
 		if (c < L) b[c] = bn / bmax;
+		y_cur = y_prev; a_cur = a_prev1; s_cur = s_prev;
 		__syncthreads();
 	}
 }
@@ -214,8 +233,9 @@ cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStrea
 		kern<<<p.n_utt, thr, smem, s>>>(p);
 		return cudaGetLastError();
 	};
-	if (p.L <= 128) return backward ? go(transftr_backward_kernel<128>, 128) : go(transftr_forward_kernel<128>, 128);
-	return backward ? go(transftr_backward_kernel<TF_MAX_THR>, TF_MAX_THR) : go(transftr_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
+	if (backward) return p.L <= 128 ? go(transftr_backward_kernel<128>, 128) : go(transftr_backward_kernel<TF_MAX_THR>, TF_MAX_THR);
+	transftr_numer_kernel<<<(p.n_utt + 3) / 4, 128, 0, s>>>(p);          // reads S, M, labs only: ahead of the recursion on the same stream
+	return p.L <= 128 ? go(transftr_forward_kernel<128>, 128) : go(transftr_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
 }
 
 
