@@ -15,6 +15,7 @@
 // Xd = [ref pair] - xi, so that the state and transition gradients (and their empirical counts) are two more tensor-core GEMMs
 // (launch_reduce_gemm_tc).  gamma and xi are normalised by their own per-frame sums, which are 1 in exact arithmetic.
 #include <cfloat>
+#include <cstdlib>
 #include <type_traits>
 
 #include "crf_kernels.cuh"
@@ -66,6 +67,33 @@ __global__ void __launch_bounds__(256) transftr_exp_kernel(const float* __restri
 	for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
 	for (uint32_t i = lane; i < LL; i += 32) e[i] = __expf(m[i] - mx);
 	if (lane == 0) rowmax[warp] = mx;
+}
+
+// The same pre-pass with ONE read of M: a CTA per row, the row's RPT * 256 elements wait in registers between the maximum and the
+// exponentials (the warp-per-row kernel above reads every row twice, and with 8 rows of 15 KB per CTA and 8 CTAs per SM the second
+// read misses L1 and L2: ncu 4.1 GB read for 2.0 GB of scores, profiles/r2z4_frame_transftr_kernels_full.md).  Same values bit for bit.
+template <int RPT>
+__global__ void __launch_bounds__(256) transftr_exp_row_kernel(const float* __restrict__ M, float* __restrict__ E, float* __restrict__ rowmax, uint32_t N, uint32_t LL, uint32_t Lq) {
+	__shared__ float wmax[2][8];
+	uint32_t it = 0;
+	for (uint32_t n = blockIdx.x; n < N; n += gridDim.x, it ^= 1) {
+		const float* m = M + (size_t)n * Lq;
+		float* e = E + (size_t)n * Lq;
+		float x[RPT], mx = -INFINITY;
+#pragma unroll
+		for (int j = 0; j < RPT; j++) { const uint32_t i = threadIdx.x + j * 256; x[j] = i < LL ? __ldcs(m + i) : -INFINITY; }
+#pragma unroll
+		for (int j = 0; j < RPT; j++) mx = fmaxf(mx, x[j]);
+		for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		if ((threadIdx.x & 31) == 0) wmax[it][threadIdx.x >> 5] = mx;
+		__syncthreads();      // (one barrier per row: the other half of wmax is only rewritten behind the next row's barrier)
+		float r = wmax[it][0];
+#pragma unroll
+		for (int w = 1; w < 8; w++) r = fmaxf(r, wmax[it][w]);
+#pragma unroll
+		for (int j = 0; j < RPT; j++) { const uint32_t i = threadIdx.x + j * 256; if (i < LL) e[i] = __expf(x[j] - r); }
+		if (threadIdx.x == 0) rowmax[n] = r;
+	}
 }
 
 // the L x L scores of frame n into a shared-memory matrix with odd row stride Ls (columns AND rows conflict-free)
@@ -218,7 +246,11 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 
 void launch_transftr_exp(const float* M, float* E, float* rowmax, uint32_t N, uint32_t LL, uint32_t Lq, cudaStream_t s) {
 	if (!N) return;
-	transftr_exp_kernel<<<(N + 7) / 8, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);
+	const uint32_t grid = N < 148u * 8u ? N : 148u * 8u;      // rows strided over the resident CTAs
+	if (LL <= 256u * 10u) transftr_exp_row_kernel<10><<<grid, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);       // up to 50 labels (the recipe's 48 phones)
+	else if (LL <= 256u * 16u) transftr_exp_row_kernel<16><<<grid, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);  // up to 64 labels
+	else if (LL <= 256u * 40u) transftr_exp_row_kernel<40><<<grid, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);  // up to 101 labels
+	else transftr_exp_kernel<<<(N + 7) / 8, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);
 }
 
 size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * L * (L | 1u) + 3 * (size_t)L + 16); }
@@ -233,9 +265,12 @@ cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStrea
 		kern<<<p.n_utt, thr, smem, s>>>(p);
 		return cudaGetLastError();
 	};
-	if (backward) return p.L <= 128 ? go(transftr_backward_kernel<128>, 128) : go(transftr_backward_kernel<TF_MAX_THR>, TF_MAX_THR);
+	// up to 128 labels: 256 threads share the L x L loops of the backward step (2.11 -> 1.68 ms at 64 utterances, 2.94 -> 2.77 ms at 462);
+	// the forward step has no such loop beyond the matrix prefetch: 256 threads only while every CTA has an SM's issue slots to itself
+	if (backward) return p.L <= 128 ? go(transftr_backward_kernel<256>, 256) : go(transftr_backward_kernel<TF_MAX_THR>, TF_MAX_THR);
 	transftr_numer_kernel<<<(p.n_utt + 3) / 4, 128, 0, s>>>(p);          // reads S, M, labs only: ahead of the recursion on the same stream
-	return p.L <= 128 ? go(transftr_forward_kernel<128>, 128) : go(transftr_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
+	if (p.L > 128) return go(transftr_forward_kernel<TF_MAX_THR>, TF_MAX_THR);
+	return p.n_utt <= 2 * 148 ? go(transftr_forward_kernel<256>, 256) : go(transftr_forward_kernel<128>, 128);
 }
 
 
@@ -476,6 +511,7 @@ cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream
 	// instantiation whose unrolled duration loops cover max_dur (the D score terms of a frame wait in registers)
 	auto pick = [&](auto dr) -> cudaError_t {
 		constexpr int DR = decltype(dr)::value;
+		// (256 threads measured slower here: recursion 1.47 -> 1.79 ms forward, 2.78 -> 3.03 ms backward at the recipe's shape)
 		if (p.P <= 128) return backward ? go(nodur_tf_backward_kernel<128, DR>, 128) : go(nodur_tf_forward_kernel<128, DR>, 128);
 		return backward ? go(nodur_tf_backward_kernel<TF_MAX_THR, DR>, TF_MAX_THR) : go(nodur_tf_forward_kernel<TF_MAX_THR, DR>, TF_MAX_THR);
 	};
