@@ -171,72 +171,91 @@ __global__ void __launch_bounds__(128) transftr_numer_kernel(TransFtrParams p) {
 	if (lane == 0) p.numer[u] = acc;
 }
 
+// One step of the backward recursion needs three reductions over the CTA -- sum_{q,c} alpha_{t-1}[q] E_t[q][c] w_t[c] (the normaliser of
+// xi_t), the maximum of the new beta vector, and the maximum of the NEXT frame's scores (data-independent, in registers one frame
+// ahead) -- and they are ONE pass with one barrier: the scratch words are only rewritten behind the step's closing barrier.
+template <int TF_THR>
+__device__ __forceinline__ void block_sum_max_max(float& s, float& m1, float& m2, float* scratch) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		s += __shfl_xor_sync(0xffffffffu, s, o);
+		m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+		m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+	}
+	if ((threadIdx.x & 31) == 0) { scratch[threadIdx.x >> 5] = s; scratch[8 + (threadIdx.x >> 5)] = m1; scratch[16 + (threadIdx.x >> 5)] = m2; }
+	__syncthreads();
+	s = scratch[0]; m1 = scratch[8]; m2 = scratch[16];
+#pragma unroll
+	for (int w = 1; w < TF_THR / 32; w++) { s += scratch[w]; m1 = fmaxf(m1, scratch[8 + w]); m2 = fmaxf(m2, scratch[16 + w]); }
+}
+
 template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParams p) {
 	extern __shared__ __align__(16) float sm[];
 	const uint32_t L = p.L, Ls = L | 1u;
 	float* Ms = sm;                              // [2][L][Ls]
-	float* b = sm + 2 * L * Ls;                  // [L] beta_t, max-normalised
-	float* wv = b + L;                           // [L] exp(S_t - smax) * b_t
+	float* b = sm + 2 * L * Ls;                  // [L] row sums of the step = beta_{t-1} before its normalisation (row threads -> label threads)
+	float* wv = b + L;                           // [L] exp(S_t - smax) * beta_t
 	float* av = wv + L;                          // [L] alpha_{t-1}
-	float* scratch = av + L;                     // [8]
+	float* scratch = av + L;                     // [24]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
 	// (pair of element i = c + k * TF_THR of the L x L matrix: a constant step with a carry, no division per element)
 	const uint32_t q_first = c / L, c_first = c - q_first * L, dq_ = TF_THR / L, dc_ = TF_THR - dq_ * L;
-	if (c < L) b[c] = 1.0f;                      // setTailBeta
+	// second identity of a thread: TPR threads share row rq of the matrix (E_t[rq][.] * w_t summed over the row IS beta_{t-1}[rq]:
+	// the row sums fall out of the pass that scales the matrix, not out of a loop of their own over L dependent additions)
+	const uint32_t TPR = TF_THR / L >= 4 ? 4u : TF_THR / L >= 2 ? 2u : 1u;
+	const uint32_t rq = c / TPR, rpart = c - rq * TPR;
+	const bool row_ok = rq < L;
 	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.E + (size_t)(off + T - 1) * p.Lq, L, Ls);
-	__syncthreads();
+	if (!T) return;
 	// the frame's label, alpha entry and score do not depend on the recursion: those of frame t-1 are requested while frame t is processed
-	uint32_t y_cur = T ? p.labs[(size_t)off + T - 1] : LAB_BAD;
-	float a_cur = (c < L && T) ? p.A[((size_t)off + T - 1) * p.Lp + c] : 0.0f, s_cur = (c < L && T) ? p.S[((size_t)off + T - 1) * p.Lp + c] : -INFINITY;
+	uint32_t y_cur = p.labs[(size_t)off + T - 1];
+	float a_cur = c < L ? p.A[((size_t)off + T - 1) * p.Lp + c] : 0.0f, s_cur = c < L ? p.S[((size_t)off + T - 1) * p.Lp + c] : -INFINITY;
+	float bc = c < L ? 1.0f : 0.0f;                              // beta_t[c], max-normalised (setTailBeta)
+	float gsum = block_sum<TF_THR>(a_cur * bc, scratch);         // sum_c alpha_t[c] beta_t[c]
+	float smax = block_max<TF_THR>(s_cur, scratch);
+	__syncthreads();
 	for (uint32_t t = T; t-- > 0;) {
 		const size_t n = (size_t)off + t;
 		const uint32_t y = y_cur;
 		uint32_t y_prev = LAB_BAD; float a_prev1 = 0.0f, s_prev = -INFINITY;
 		if (t > 0) { y_prev = p.labs[n - 1]; if (c < L) { a_prev1 = p.A[(n - 1) * p.Lp + c]; s_prev = p.S[(n - 1) * p.Lp + c]; } }
 		// gamma_t = A_t * b_t / sum
-		const float a = a_cur;
-		const float g = c < L ? a * b[c] : 0.0f;
-		const float gsum = block_sum<TF_THR>(g, scratch);
-		if (c < L) p.Dm[n * p.Lp + c] = ((y == c) ? 1.0f : 0.0f) - g / gsum;
+		if (c < L) p.Dm[n * p.Lp + c] = ((y == c) ? 1.0f : 0.0f) - a_cur * bc / gsum;
 		float* xrow = p.Xd + n * p.Lq;
 		if (t == 0) {
 			for (uint32_t i = c; i < L * L; i += TF_THR) xrow[i] = 0.0f;      // no transition enters the first frame
 			break;
 		}
 		float* Mt = Ms + (t & 1) * L * Ls;
+		if (c < L) { wv[c] = __expf(s_cur - smax) * bc; av[c] = a_prev1; }
 		cp_async_wait_all();
 		__syncthreads();
 		if (t > 1) prefetch_matrix<TF_THR>(Ms + ((t - 1) & 1) * L * Ls, p.E + (n - 1) * p.Lq, L, Ls);
-		// Mt = E_t = exp(M_t - max) from the pre-pass (the normalisations below are scale-free)
-		const float s = s_cur;
-		const float smax = block_max<TF_THR>(s, scratch);
-		if (c < L) { wv[c] = __expf(s - smax) * b[c]; av[c] = a_prev1; }
-		__syncthreads();
-		float part = 0.0f;
-		uint32_t q = q_first, cc = c_first;
-		for (uint32_t i = c; i < L * L; i += TF_THR) {
-			const float e = Mt[q * Ls + cc] * wv[cc];                         // E_t[q][cc] * w_t[cc]
-			Mt[q * Ls + cc] = e;
-			part += av[q] * e;
-			cc += dc_; q += dq_;
-			if (cc >= L) { cc -= L; q++; }
+		// Mt = E_t = exp(M_t - max) from the pre-pass (the normalisations below are scale-free) -> E_t[q][cc] * w_t[cc] in place
+		float rs = 0.0f;
+		if (row_ok) {
+			float* mrow = Mt + rq * Ls;
+#pragma unroll 4
+			for (uint32_t cc = rpart; cc < L; cc += TPR) { const float e = mrow[cc] * wv[cc]; mrow[cc] = e; rs += e; }
 		}
-		const float xsum = block_sum<TF_THR>(part, scratch);                            // sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc]
+		for (uint32_t o = 1; o < TPR; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+		if (row_ok && rpart == 0) b[rq] = rs;
+		// xsum = sum_{q,cc} alpha_{t-1}[q] E_t[q][cc] w_t[cc];  bmax = max_q beta_{t-1}[q];  the next frame's score maximum
+		float xsum = (row_ok && rpart == 0) ? av[rq] * rs : 0.0f, bmax = row_ok ? rs : 0.0f, smax_next = s_prev;
+		block_sum_max_max<TF_THR>(xsum, bmax, smax_next, scratch);
 		uint32_t yp = y_prev;
 		if (yp < L && y < L && p.tidx[yp * L + y] == 0xffffffffu) yp = LAB_BAD;      // a reference pair the N-state map does not have
 		const float inv = 1.0f / xsum;
-		q = q_first; cc = c_first;
+		uint32_t q = q_first, cc = c_first;
 		for (uint32_t i = c; i < L * L; i += TF_THR) {
 			xrow[i] = ((q == yp && cc == y) ? 1.0f : 0.0f) - av[q] * Mt[q * Ls + cc] * inv;
 			cc += dc_; q += dq_;
 			if (cc >= L) { cc -= L; q++; }
 		}
-		// beta_{t-1}[q] = sum_cc E_t[q][cc] w_t[cc], max-normalised
-		float bn = 0.0f;
-		if (c < L) for (uint32_t cc = 0; cc < L; cc++) bn += Mt[c * Ls + cc];
-		const float bmax = block_max<TF_THR>(c < L ? bn : 0.0f, scratch);
-		if (c < L) b[c] = bn / bmax;
+		// beta_{t-1}, max-normalised; sum_q alpha_{t-1}[q] beta_{t-1}[q] is the xi normaliser over the same maximum
+		bc = c < L ? b[c] / bmax : 0.0f;
+		gsum = xsum / bmax; smax = smax_next;
 		y_cur = y_prev; a_cur = a_prev1; s_cur = s_prev;
 		__syncthreads();
 	}
@@ -253,7 +272,7 @@ void launch_transftr_exp(const float* M, float* E, float* rowmax, uint32_t N, ui
 	else transftr_exp_kernel<<<(N + 7) / 8, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);
 }
 
-size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * L * (L | 1u) + 3 * (size_t)L + 16); }
+size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * L * (L | 1u) + 3 * (size_t)L + 32); }
 
 cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStream_t s) {
 	if (!p.n_utt) return cudaSuccess;
