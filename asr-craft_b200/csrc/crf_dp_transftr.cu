@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "crf_kernels.cuh"
+#include "tc05.cuh"
 
 namespace crfgpu {
 
@@ -110,34 +111,46 @@ __device__ __forceinline__ void prefetch_matrix(float* dst, const float* src, ui
 	cp_async_commit();
 }
 
+// The frame-level kernels keep the matrix DENSE in shared memory -- exactly the Lq floats of the frame's row in global memory -- so a
+// frame is ONE bulk copy issued by one thread and counted on an mbarrier (cp.async.bulk), instead of L * L / threads 4-byte cp.async
+// with their index arithmetic per thread (about 40 % of the forward step's instructions at 61 labels).
+__device__ __forceinline__ void bulk_matrix(float* dst, const float* src, uint32_t Lq, uint64_t* bar) {
+	tc05::mbar_arrive_expect_tx(bar, Lq * 4u);
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(tc05::smem_u32(dst)), "l"(src), "r"(Lq * 4u), "r"(tc05::smem_u32(bar)) : "memory");
+}
+
 template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) transftr_forward_kernel(TransFtrParams p) {
 	extern __shared__ __align__(16) float sm[];
-	const uint32_t L = p.L, Ls = L | 1u;
-	float* Ms = sm;                              // [2][L][Ls]
-	float* a_prev = sm + 2 * L * Ls;             // [L]
+	const uint32_t L = p.L, Lq = p.Lq;
+	float* Ms = sm;                              // [2][Lq] dense: element (q, c) at q * L + c
+	float* a_prev = sm + 2 * Lq;                 // [L]
 	float* scratch = a_prev + L;                 // [8]
+	__shared__ uint64_t mbar[2];                 // matrix of frame t >= 1 arrived in buffer t & 1 (use (t - 1) >> 1 of that buffer: frame 0 has no matrix)
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, c = threadIdx.x;
 	double rho = 0.0;
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + L * Ls, p.E + (size_t)(off + 1) * p.Lq, L, Ls);       // frame 1 -> buffer 1
+	if (c == 0) { tc05::mbar_init(&mbar[0], 1); tc05::mbar_init(&mbar[1], 1); tc05::fence_mbar_init(); }
+	__syncthreads();
+	if (c == 0 && T > 1) bulk_matrix(Ms + Lq, p.E + (size_t)(off + 1) * Lq, Lq, &mbar[1]);       // frame 1 -> buffer 1
 	// the frame's score and matrix maximum do not depend on the recursion: those of frame t+1 are requested while frame t is processed
 	float s_next = (c < L && T > 0) ? p.S[(size_t)off * p.Lp + c] : 0.0f, mmax_next = 0.0f;
 	for (uint32_t t = 0; t < T; t++) {
 		const size_t n = (size_t)off + t;
-		float* Mt = Ms + (t & 1) * L * Ls;
+		float* Mt = Ms + (t & 1) * Lq;
 		float w = -INFINITY;
 		const float s = s_next;
 		float mmax = mmax_next;
 		if (t + 1 < T) { s_next = c < L ? p.S[(n + 1) * p.Lp + c] : 0.0f; mmax_next = p.rowmax[n + 1]; }
 		if (t == 0) { if (c < L) w = s; }
 		else {
-			cp_async_wait_all();
-			__syncthreads();
-			if (t + 1 < T) prefetch_matrix<TF_THR>(Ms + ((t + 1) & 1) * L * Ls, p.E + (n + 1) * p.Lq, L, Ls);
+			// (the other buffer was last read in step t-1, which every thread left through the step's closing barrier)
+			if (c == 0 && t + 1 < T) bulk_matrix(Ms + ((t + 1) & 1) * Lq, p.E + (n + 1) * Lq, Lq, &mbar[(t + 1) & 1]);
+			tc05::mbar_wait(&mbar[t & 1], ((t - 1) >> 1) & 1);
 			if (c < L) {
 				float v = 0.0f;
 #pragma unroll 8
-				for (uint32_t q = 0; q < L; q++) v = fmaf(a_prev[q], Mt[q * Ls + c], v);      // Mt = exp(M_t - mmax) from the pre-pass
+				for (uint32_t q = 0; q < L; q++) v = fmaf(a_prev[q], Mt[q * L + c], v);      // Mt = exp(M_t - mmax) from the pre-pass
 				w = __logf(v) + s;
 			}
 		}
@@ -192,9 +205,10 @@ __device__ __forceinline__ void block_sum_max_max(float& s, float& m1, float& m2
 template <int TF_THR>
 __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParams p) {
 	extern __shared__ __align__(16) float sm[];
-	const uint32_t L = p.L, Ls = L | 1u;
-	float* Ms = sm;                              // [2][L][Ls]
-	float* b = sm + 2 * L * Ls;                  // [L] row sums of the step = beta_{t-1} before its normalisation (row threads -> label threads)
+	const uint32_t L = p.L, Lq = p.Lq;
+	float* Ms = sm;                              // [2][Lq] dense: element (q, c) at q * L + c
+	__shared__ uint64_t mbar[2];                 // matrix of frame t arrived in buffer t & 1 (use (T - 1 - t) >> 1 of that buffer)
+	float* b = sm + 2 * Lq;                      // [L] row sums of the step = beta_{t-1} before its normalisation (row threads -> label threads)
 	float* wv = b + L;                           // [L] exp(S_t - smax) * beta_t
 	float* av = wv + L;                          // [L] alpha_{t-1}
 	float* scratch = av + L;                     // [24]
@@ -206,8 +220,12 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 	const uint32_t TPR = TF_THR / L >= 4 ? 4u : TF_THR / L >= 2 ? 2u : 1u;
 	const uint32_t rq = c / TPR, rpart = c - rq * TPR;
 	const bool row_ok = rq < L;
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * L * Ls, p.E + (size_t)(off + T - 1) * p.Lq, L, Ls);
+	// rows of an even label count all start in the same few banks: row rq then starts its pass rq columns further on (wrapping round)
+	const uint32_t r_first = row_ok ? (rpart + ((L & 1u) ? 0u : rq)) % L : 0u, r_cnt = (row_ok && rpart < L) ? (L - rpart + TPR - 1) / TPR : 0u;
 	if (!T) return;
+	if (c == 0) { tc05::mbar_init(&mbar[0], 1); tc05::mbar_init(&mbar[1], 1); tc05::fence_mbar_init(); }
+	__syncthreads();
+	if (c == 0 && T > 1) bulk_matrix(Ms + ((T - 1) & 1) * Lq, p.E + (size_t)(off + T - 1) * Lq, Lq, &mbar[(T - 1) & 1]);
 	// the frame's label, alpha entry and score do not depend on the recursion: those of frame t-1 are requested while frame t is processed
 	uint32_t y_cur = p.labs[(size_t)off + T - 1];
 	float a_cur = c < L ? p.A[((size_t)off + T - 1) * p.Lp + c] : 0.0f, s_cur = c < L ? p.S[((size_t)off + T - 1) * p.Lp + c] : -INFINITY;
@@ -227,17 +245,22 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 			for (uint32_t i = c; i < L * L; i += TF_THR) xrow[i] = 0.0f;      // no transition enters the first frame
 			break;
 		}
-		float* Mt = Ms + (t & 1) * L * Ls;
+		float* Mt = Ms + (t & 1) * Lq;
 		if (c < L) { wv[c] = __expf(s_cur - smax) * bc; av[c] = a_prev1; }
-		cp_async_wait_all();
+		// (the other buffer was last touched in step t+1, which every thread left through the step's closing barrier behind its proxy fence)
+		if (c == 0 && t > 1) bulk_matrix(Ms + ((t - 1) & 1) * Lq, p.E + (n - 1) * Lq, Lq, &mbar[(t - 1) & 1]);
+		tc05::mbar_wait(&mbar[t & 1], ((T - 1 - t) >> 1) & 1);
 		__syncthreads();
-		if (t > 1) prefetch_matrix<TF_THR>(Ms + ((t - 1) & 1) * L * Ls, p.E + (n - 1) * p.Lq, L, Ls);
 		// Mt = E_t = exp(M_t - max) from the pre-pass (the normalisations below are scale-free) -> E_t[q][cc] * w_t[cc] in place
 		float rs = 0.0f;
-		if (row_ok) {
-			float* mrow = Mt + rq * Ls;
+		{
+			float* mrow = Mt + rq * L;
+			uint32_t cc = r_first;
 #pragma unroll 4
-			for (uint32_t cc = rpart; cc < L; cc += TPR) { const float e = mrow[cc] * wv[cc]; mrow[cc] = e; rs += e; }
+			for (uint32_t k = 0; k < r_cnt; k++) {
+				const float e = mrow[cc] * wv[cc]; mrow[cc] = e; rs += e;
+				cc += TPR; if (cc >= L) cc -= L;
+			}
 		}
 		for (uint32_t o = 1; o < TPR; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
 		if (row_ok && rpart == 0) b[rq] = rs;
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		const float inv = 1.0f / xsum;
 		uint32_t q = q_first, cc = c_first;
 		for (uint32_t i = c; i < L * L; i += TF_THR) {
-			xrow[i] = ((q == yp && cc == y) ? 1.0f : 0.0f) - av[q] * Mt[q * Ls + cc] * inv;
+			xrow[i] = ((q == yp && cc == y) ? 1.0f : 0.0f) - av[q] * Mt[i] * inv;
 			cc += dc_; q += dq_;
 			if (cc >= L) { cc -= L; q++; }
 		}
@@ -257,6 +280,7 @@ __global__ void __launch_bounds__(TF_THR) transftr_backward_kernel(TransFtrParam
 		bc = c < L ? b[c] / bmax : 0.0f;
 		gsum = xsum / bmax; smax = smax_next;
 		y_cur = y_prev; a_cur = a_prev1; s_cur = s_prev;
+		tc05::fence_proxy_async_smem();      // this step's in-place scaling (generic stores) before the bulk copy that reuses the buffer
 		__syncthreads();
 	}
 }
@@ -272,7 +296,7 @@ void launch_transftr_exp(const float* M, float* E, float* rowmax, uint32_t N, ui
 	else transftr_exp_kernel<<<(N + 7) / 8, 256, 0, s>>>(M, E, rowmax, N, LL, Lq);
 }
 
-size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * L * (L | 1u) + 3 * (size_t)L + 32); }
+size_t transftr_smem_bytes(uint32_t L) { return sizeof(float) * ((size_t)2 * ((L * L + 3) / 4 * 4) + 3 * (size_t)L + 32); }      // two dense matrices of Lq floats + the vectors
 
 cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStream_t s) {
 	if (!p.n_utt) return cudaSuccess;
