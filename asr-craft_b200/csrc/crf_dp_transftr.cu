@@ -11,7 +11,7 @@
 //
 // Device plan: the L*L transition scores of every frame are ONE tensor-core GEMM [frames x features] . [features x L*L]
 // (launch_score_gemm_tc, crf_tc_gemm.cu) into M[N][L*L]; the recursions below stream that matrix, one CTA per utterance, the
-// next frame's matrix prefetched with cp.async while the current one is used; the posteriors leave as Dm = [ref] - gamma and
+// next frame's matrix fetched with one bulk copy (cp.async.bulk, mbarrier) while the current one is used; the posteriors leave as Dm = [ref] - gamma and
 // Xd = [ref pair] - xi, so that the state and transition gradients (and their empirical counts) are two more tensor-core GEMMs
 // (launch_reduce_gemm_tc).  gamma and xi are normalised by their own per-frame sums, which are 1 in exact arithmetic.
 #include <cfloat>
@@ -28,12 +28,6 @@ namespace {
 // CTA sizes: thread = label.  128 threads up to 128 labels, 192 beyond (the double-buffered L x L tile bounds the label count by shared memory:
 // 169 labels frame-level, 160 segmental)
 constexpr int TF_MAX_THR = 192;
-
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int TF_THR>
 __device__ __forceinline__ float block_max(float v, float* scratch) {
@@ -97,21 +91,7 @@ __global__ void __launch_bounds__(256) transftr_exp_row_kernel(const float* __re
 	}
 }
 
-// the L x L scores of frame n into a shared-memory matrix with odd row stride Ls (columns AND rows conflict-free)
-template <int TF_THR>
-__device__ __forceinline__ void prefetch_matrix(float* dst, const float* src, uint32_t L, uint32_t Ls) {
-	// (row, column) of element i advance by a constant step with a carry: one division per call instead of one per element
-	uint32_t r = threadIdx.x / L, c = threadIdx.x - r * L;
-	const uint32_t dr = TF_THR / L, dc = TF_THR - dr * L;
-	for (uint32_t i = threadIdx.x; i < L * L; i += TF_THR) {
-		cp_async4(dst + r * Ls + c, src + i);
-		c += dc; r += dr;
-		if (c >= L) { c -= L; r++; }
-	}
-	cp_async_commit();
-}
-
-// The frame-level kernels keep the matrix DENSE in shared memory -- exactly the Lq floats of the frame's row in global memory -- so a
+// The recursions keep the frame's matrix DENSE in shared memory -- exactly the Lq floats of the frame's row in global memory -- so a
 // frame is ONE bulk copy issued by one thread and counted on an mbarrier (cp.async.bulk), instead of L * L / threads 4-byte cp.async
 // with their index arithmetic per thread (about 40 % of the forward step's instructions at 61 labels).
 __device__ __forceinline__ void bulk_matrix(float* dst, const float* src, uint32_t Lq, uint64_t* bar) {
@@ -326,7 +306,7 @@ cudaError_t launch_transftr_dp(bool backward, const TransFtrParams& p, cudaStrea
 //   A_t[y]     = logsum_y' (alpha_t[y'] + M_{t+1}[y'][y])         alpha_t[d,y] = S_t[d,y] + A_{t-d}[y]   (= S_t[d,y] when d == t+1)
 //   B_t[y]     = logsum_d (S_{t+d}[d,y] + beta_{t+d}[y])          beta_t[y'] = logsum_y (M_{t+1}[y'][y] + B_t[y])
 //   gamma_t[d,y] = exp(alpha_t[d,y] + beta_t[y] - logZ)           xi_t[y'][y]  = exp(alpha_t[y'] + M_{t+1}[y'][y] + B_t[y] - logZ)
-// One CTA per utterance, thread = phone (<= 128), M_{t+1} prefetched with cp.async, alpha_t normalised to sum 1 with a running
+// One CTA per utterance, thread = phone (<= 128), M_{t+1} fetched ahead with one bulk copy, alpha_t normalised to sum 1 with a running
 // log scale rho_t, the D-term sums formed as float log-sum-exps of differences of the (double) scales.
 // =================================================================================================
 namespace {
@@ -336,14 +316,17 @@ constexpr uint32_t ND_RING = 32;     // max_dur <= 31
 template <int TF_THR, int DR>
 __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams p) {
 	extern __shared__ __align__(16) float sm[];
-	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
+	const uint32_t P = p.P, D = p.D, Lq = p.Lq;
 	double* rring = reinterpret_cast<double*>(sm);            // [ND_RING] rho_t (first: 8-byte aligned)
-	float* Ms = sm + 2 * ND_RING;                // [2][P][Ps]
-	float* av = Ms + 2 * P * Ps;                 // [P] alpha_t (sum 1)
+	float* Ms = sm + 2 * ND_RING;                // [2][Lq] dense (element (q, y) at q * P + y): a frame is one bulk copy, as in the frame-level kernels
+	float* av = Ms + 2 * Lq;                     // [P] alpha_t (sum 1)
+	__shared__ uint64_t mbar[2];                 // matrix of frame f >= 1 arrived in buffer f & 1 (use (f - 1) >> 1 of that buffer)
 	float* lgh = av + P;                         // [ND_RING][P] log A_t[y] - rho_t of the last D frames
 	float* scratch = lgh + ND_RING * P;          // [8]
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + P * Ps, p.E + (size_t)(off + 1) * p.Lq, P, Ps);       // exp(M_1 - max) -> buffer 1
+	if (y == 0) { tc05::mbar_init(&mbar[0], 1); tc05::mbar_init(&mbar[1], 1); tc05::fence_mbar_init(); }
+	__syncthreads();
+	if (y == 0 && T > 1) bulk_matrix(Ms + Lq, p.E + (size_t)(off + 1) * Lq, Lq, &mbar[1]);       // exp(M_1 - max) -> buffer 1
 	// the score terms of a frame do not depend on the recursion: those of frame t+1 are requested while frame t is processed
 	float sv[ND_RING];
 #pragma unroll
@@ -389,14 +372,14 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_forward_kernel(NodurTfParams 
 		__syncthreads();
 		if (t + 1 < T) {
 			// A_t[y] = rho_t + lgh_t[y],  lgh_t[y] = mmax + log sum_q alpha_t[q] exp(M_{t+1}[q][y] - mmax)
-			float* Mn = Ms + ((t + 1) & 1) * P * Ps;
-			cp_async_wait_all();
-			__syncthreads();
-			if (t + 2 < T) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.E + (n + 2) * p.Lq, P, Ps);
+			float* Mn = Ms + ((t + 1) & 1) * Lq;
+			// (buffer t & 1 held frame t's matrix, last read in step t-1, which every thread left through the step's closing barrier)
+			if (y == 0 && t + 2 < T) bulk_matrix(Ms + (t & 1) * Lq, p.E + (n + 2) * Lq, Lq, &mbar[t & 1]);
+			tc05::mbar_wait(&mbar[(t + 1) & 1], (t >> 1) & 1);
 			if (y < P) {
 				float v = 0.0f;
 #pragma unroll 8
-				for (uint32_t q = 0; q < P; q++) v = fmaf(av[q], Mn[q * Ps + y], v);           // Mn = exp(M_{t+1} - mmax) from the pre-pass
+				for (uint32_t q = 0; q < P; q++) v = fmaf(av[q], Mn[q * P + y], v);           // Mn = exp(M_{t+1} - mmax) from the pre-pass
 				const float l = mmax + __logf(v);
 				lgh[(t & (ND_RING - 1)) * P + y] = l; p.LG[n * p.Pp + y] = l;
 			}
@@ -433,10 +416,11 @@ __global__ void __launch_bounds__(128) nodur_tf_numer_kernel(NodurTfParams p) {
 template <int TF_THR, int DR>
 __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams p) {
 	extern __shared__ __align__(16) float sm[];
-	const uint32_t P = p.P, D = p.D, Ps = P | 1u;
+	const uint32_t P = p.P, D = p.D, Lq = p.Lq;
 	double* kring = reinterpret_cast<double*>(sm);            // [ND_RING] kappa_t (first: 8-byte aligned)
-	float* Ms = sm + 2 * ND_RING;                // [2][P][Ps]
-	float* av = Ms + 2 * P * Ps;                 // [P] alpha_t
+	float* Ms = sm + 2 * ND_RING;                // [2][Lq] dense (element (q, y) at q * P + y): a frame is one bulk copy
+	float* av = Ms + 2 * Lq;                     // [P] alpha_t
+	__shared__ uint64_t mbar[2];                 // matrix of frame f arrived in buffer f & 1 (use (T - 1 - f) >> 1 of that buffer)
 	float* lbh = av + P;                         // [ND_RING][P] beta_t[y] - kappa_t of the last D frames
 	float* ev = lbh + ND_RING * P;               // [P] exp(B_t[y] - its maximum)
 	float* scratch = ev + P;                     // [8]
@@ -444,7 +428,11 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 	const double lz = p.logZ[u];
 	// (pair of element i = y + k * TF_THR of the P x P matrix: a constant step with a carry, no division per element)
 	const uint32_t q_first = y / P, y_first = y - q_first * P, dq_ = TF_THR / P, dy_ = TF_THR - dq_ * P;
-	if (T > 1) prefetch_matrix<TF_THR>(Ms + ((T - 1) & 1) * P * Ps, p.E + (size_t)(off + T - 1) * p.Lq, P, Ps);    // exp(M_{T-1} - max)
+	if (y == 0) { tc05::mbar_init(&mbar[0], 1); tc05::mbar_init(&mbar[1], 1); tc05::fence_mbar_init(); }
+	__syncthreads();
+	if (y == 0 && T > 1) bulk_matrix(Ms + ((T - 1) & 1) * Lq, p.E + (size_t)(off + T - 1) * Lq, Lq, &mbar[(T - 1) & 1]);    // exp(M_{T-1} - max)
+	// row y of an even phone count starts y columns further on (wrapping round): the rows of a dense matrix would share their banks
+	const uint32_t row_first = (P & 1u) ? 0u : (y < P ? y : 0u);
 	// the score terms S_{t+d}[d,y] of a frame do not depend on the recursion: those of frame t-1 are requested while frame t is processed
 	float sv[ND_RING], sn[ND_RING];
 #pragma unroll
@@ -486,10 +474,10 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 				w = mx + __logf(sacc);
 			}
 			const float wmax = block_max<TF_THR>(w, scratch);
-			float* Mn = Ms + ((t + 1) & 1) * P * Ps;     // M_{t+1}
-			cp_async_wait_all();
-			__syncthreads();
-			if (t > 0) prefetch_matrix<TF_THR>(Ms + (t & 1) * P * Ps, p.E + n * p.Lq, P, Ps);      // exp(M_t - max) for the next step
+			float* Mn = Ms + ((t + 1) & 1) * Lq;     // M_{t+1}
+			// exp(M_t - max) for the next step (buffer t & 1 was last touched in step t+1, left through its closing barrier behind the proxy fence)
+			if (y == 0 && t > 0) bulk_matrix(Ms + (t & 1) * Lq, p.E + n * Lq, Lq, &mbar[t & 1]);
+			tc05::mbar_wait(&mbar[(t + 1) & 1], ((T - 2 - t) >> 1) & 1);
 			const float mmax = c_mmax;
 			if (y < P) { ev[y] = __expf(w - wmax); av[y] = c_av; }
 			__syncthreads();
@@ -498,7 +486,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			// (a segment boundary after frame t has probability <= 1: the posteriors are NOT renormalised per frame)
 			uint32_t q = q_first, yy = y_first;
 			for (uint32_t i = y; i < P * P; i += TF_THR) {
-				Mn[q * Ps + yy] = Mn[q * Ps + yy] * ev[yy];
+				Mn[i] = Mn[i] * ev[yy];
 				yy += dy_; q += dq_;
 				if (yy >= P) { yy -= P; q++; }
 			}
@@ -510,12 +498,12 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			float* xrow = p.Xd + (n + 1) * p.Lq;         // stored with the frame whose duration-1 window carries the transition features
 			q = q_first; yy = y_first;
 			for (uint32_t i = y; i < P * P; i += TF_THR) {
-				xrow[i] = ((q == lq && yy == nl) ? 1.0f : 0.0f) - av[q] * Mn[q * Ps + yy] * xscale;
+				xrow[i] = ((q == lq && yy == nl) ? 1.0f : 0.0f) - av[q] * Mn[i] * xscale;
 				yy += dy_; q += dq_;
 				if (yy >= P) { yy -= P; q++; }
 			}
 			float bn = 0.0f;
-			if (y < P) for (uint32_t yy = 0; yy < P; yy++) bn += Mn[y * Ps + yy];
+			if (y < P) { uint32_t yy = row_first; for (uint32_t k = 0; k < P; k++) { bn += Mn[y * P + yy]; if (++yy == P) yy = 0; } }
 			const float bmax = block_max<TF_THR>(y < P ? bn : 0.0f, scratch);
 			lb = y < P ? __logf(bn / bmax) : 0.0f;
 			kappa = kref + (double)mmax + (double)wmax + (double)__logf(bmax);
@@ -532,13 +520,19 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 #pragma unroll
 		for (uint32_t d = 1; d <= (uint32_t)DR; d++) sv[d] = sn[d];
 		lab = n_lab; c_nl = n_nl; c_rho = n_rho; c_mmax = n_mmax; c_av = n_av;
+		tc05::fence_proxy_async_smem();      // this step's in-place scaling (generic stores) before the bulk copy that reuses the buffer
 		__syncthreads();
 	}
 }
 
 }  // namespace
 
-size_t nodur_tf_smem_bytes(uint32_t P) { return sizeof(float) * ((size_t)2 * P * (P | 1u) + (size_t)(2 + ND_RING) * P + 16) + sizeof(double) * ND_RING + 16; }
+// (two dense matrices of Lq floats; the admission rule keeps the odd-stride size of the cp.async version for even phone counts, so the
+// documented limit -- 161 labels -- stays what the tests pin)
+size_t nodur_tf_smem_bytes(uint32_t P) {
+	const size_t Lq = ((size_t)P * P + 3) / 4 * 4, old = (size_t)P * (P | 1u);
+	return sizeof(float) * (2 * (Lq > old ? Lq : old) + (size_t)(2 + ND_RING) * P + 16) + sizeof(double) * ND_RING + 16;
+}
 
 cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s) {
 	if (!p.n_utt) return cudaSuccess;
