@@ -380,14 +380,14 @@ def test_decode_tables_from_device_lambda_bit_exact(oracle):
     m.close()
 
 
-@pytest.mark.parametrize("kind", ["stdseg", "nodur_native", "nodur_tied", "frame"])
+@pytest.mark.parametrize("kind", ["stdseg", "nodur_native", "nodur_tied", "frame", "frame_transftr", "frame_transftr_even", "nodur_transftr"])
 def test_fwdbwd_edge_lengths_match_oracle(oracle, kind):
     """Ragged edge cases the reference handles: utterances of 1, 2, 3 frames (shorter than maxDur, so most windows never exist),
     exactly maxDur frames, and a long one, in one batch; reference segments longer than maxDur are split by the label grouping."""
     rng = np.random.default_rng(17)
     lens = np.array([1, 2, 3, 1, 6, 7, 40, 2], np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
-    F, P, D = 7, 5, 6
+    F, P, D = 7, (6 if kind in ("frame_transftr_even", "nodur_transftr") else 5), 6
     ftrs = rng.random((int(off[-1]), F), dtype=np.float32)
     labs = np.zeros(int(off[-1]), np.uint32)
     for u in range(len(lens)):
@@ -400,6 +400,10 @@ def test_fwdbwd_edge_lengths_match_oracle(oracle, kind):
         cfg = make_config("stdseg", n_labs=P * D, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
     elif kind == "frame":
         cfg = make_config("stdframe", n_labs=P, n_base_ftrs=F)
+    elif kind.startswith("frame_transftr"):      # (the bulk-copied matrix of the transition-feature recursions: no copy at all for one frame)
+        cfg = make_config("stdframe", n_labs=P, n_base_ftrs=F, use_trans_ftrs=1)
+    elif kind == "nodur_transftr":
+        cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, extract_seg_ftrs=1, use_trans_ftrs=1, trans_fidx=(0, F - 1))
     else:
         cfg = make_config("stdseg_no_dur_no_segtransftr", n_labs=P, n_base_ftrs=F, max_dur=D, n_actual_labs=P, extract_seg_ftrs=1)
     lam = rng.uniform(-0.3, 0.3, oracle.lambda_len(cfg))
