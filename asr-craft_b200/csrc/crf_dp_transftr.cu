@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 	__shared__ uint64_t mbar[2];                 // matrix of frame f arrived in buffer f & 1 (use (T - 1 - f) >> 1 of that buffer)
 	float* lbh = av + P;                         // [ND_RING][P] beta_t[y] - kappa_t of the last D frames
 	float* ev = lbh + ND_RING * P;               // [P] exp(B_t[y] - its maximum)
-	float* scratch = ev + P;                     // [8]
+	float* scratch = ev + P;                     // [16]
+	float* rsum = scratch + 16;                  // [P] row sums of the scaled matrix (row threads -> phone threads)
 	const uint32_t u = blockIdx.x, off = p.off[u], T = p.off[u + 1] - off, y = threadIdx.x;
 	const double lz = p.logZ[u];
 	// (pair of element i = y + k * TF_THR of the P x P matrix: a constant step with a carry, no division per element)
@@ -431,8 +432,13 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 	if (y == 0) { tc05::mbar_init(&mbar[0], 1); tc05::mbar_init(&mbar[1], 1); tc05::fence_mbar_init(); }
 	__syncthreads();
 	if (y == 0 && T > 1) bulk_matrix(Ms + ((T - 1) & 1) * Lq, p.E + (size_t)(off + T - 1) * Lq, Lq, &mbar[(T - 1) & 1]);    // exp(M_{T-1} - max)
-	// row y of an even phone count starts y columns further on (wrapping round): the rows of a dense matrix would share their banks
-	const uint32_t row_first = (P & 1u) ? 0u : (y < P ? y : 0u);
+	// second identity of a thread, as in the frame-level kernel: TPR threads share row rq of the matrix, whose sum over the scaled row IS
+	// beta_t[rq] before its normalisation; row rq of an even phone count starts rq columns further on (wrapping round): the rows of a
+	// dense matrix would share their banks
+	const uint32_t TPR = TF_THR / P >= 4 ? 4u : TF_THR / P >= 2 ? 2u : 1u;
+	const uint32_t rq = y / TPR, rpart = y - rq * TPR;
+	const bool row_ok = rq < P;
+	const uint32_t r_first = row_ok ? (rpart + ((P & 1u) ? 0u : rq)) % P : 0u, r_cnt = (row_ok && rpart < P) ? (P - rpart + TPR - 1) / TPR : 0u;
 	// the score terms S_{t+d}[d,y] of a frame do not depend on the recursion: those of frame t-1 are requested while frame t is processed
 	float sv[ND_RING], sn[ND_RING];
 #pragma unroll
@@ -484,13 +490,29 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 			// E[q][yy] = exp(M_{t+1}[q][yy] - mmax) * ev[yy] in place;
 			// xi_t[q][yy] = exp(alpha_t[q] + M_{t+1}[q][yy] + B_t[yy] - logZ) = alpha^_t[q] E[q][yy] exp(rho_t + mmax + kref + wmax - logZ)
 			// (a segment boundary after frame t has probability <= 1: the posteriors are NOT renormalised per frame)
-			uint32_t q = q_first, yy = y_first;
-			for (uint32_t i = y; i < P * P; i += TF_THR) {
-				Mn[i] = Mn[i] * ev[yy];
-				yy += dy_; q += dq_;
-				if (yy >= P) { yy -= P; q++; }
+			float rs = 0.0f;
+			{
+				float* mrow = Mn + rq * P;
+				uint32_t cc = r_first;
+#pragma unroll 4
+				for (uint32_t k = 0; k < r_cnt; k++) {
+					const float e = mrow[cc] * ev[cc]; mrow[cc] = e; rs += e;
+					cc += TPR; if (cc >= P) cc -= P;
+				}
 			}
+			for (uint32_t o = 1; o < TPR; o <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+			if (row_ok && rpart == 0) rsum[rq] = rs;
+			// maximum of the row sums: one barrier, which also publishes the scaled matrix and the row sums (scratch[8..15] is only
+			// rewritten behind the step's closing barrier)
+			float bmax = row_ok ? rs : 0.0f;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+			if ((threadIdx.x & 31) == 0) scratch[8 + (threadIdx.x >> 5)] = bmax;
 			__syncthreads();
+			bmax = scratch[8];
+#pragma unroll
+			for (int w = 1; w < TF_THR / 32; w++) bmax = fmaxf(bmax, scratch[8 + w]);
+			uint32_t q = q_first, yy = y_first;
 			const float xscale = __expf((float)(c_rho + (double)mmax + kref + (double)wmax - lz));
 			uint32_t nl = lab != LAB_BAD ? c_nl : LAB_BAD;
 			const uint32_t lq = lab != LAB_BAD ? lab % P : LAB_BAD;
@@ -502,10 +524,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 				yy += dy_; q += dq_;
 				if (yy >= P) { yy -= P; q++; }
 			}
-			float bn = 0.0f;
-			if (y < P) { uint32_t yy = row_first; for (uint32_t k = 0; k < P; k++) { bn += Mn[y * P + yy]; if (++yy == P) yy = 0; } }
-			const float bmax = block_max<TF_THR>(y < P ? bn : 0.0f, scratch);
-			lb = y < P ? __logf(bn / bmax) : 0.0f;
+			lb = y < P ? __logf(rsum[y] / bmax) : 0.0f;
 			kappa = kref + (double)mmax + (double)wmax + (double)__logf(bmax);
 		} else if (T > 1) {
 			// tail frame of a multi-frame utterance: nothing to wait for, M_{T-1} stays in flight for the next step
@@ -531,7 +550,7 @@ __global__ void __launch_bounds__(TF_THR) nodur_tf_backward_kernel(NodurTfParams
 // documented limit -- 161 labels -- stays what the tests pin)
 size_t nodur_tf_smem_bytes(uint32_t P) {
 	const size_t Lq = ((size_t)P * P + 3) / 4 * 4, old = (size_t)P * (P | 1u);
-	return sizeof(float) * (2 * (Lq > old ? Lq : old) + (size_t)(2 + ND_RING) * P + 16) + sizeof(double) * ND_RING + 16;
+	return sizeof(float) * (2 * (Lq > old ? Lq : old) + (size_t)(3 + ND_RING) * P + 16) + sizeof(double) * ND_RING + 16;
 }
 
 cudaError_t launch_nodur_tf_dp(bool backward, const NodurTfParams& p, cudaStream_t s) {
